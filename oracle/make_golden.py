@@ -1,0 +1,149 @@
+#!/usr/bin/env python
+"""TEST INFRASTRUCTURE — generate tests/golden/ from the UNMODIFIED reference binary.
+
+Run in the build container (where /root/reference exists):
+    make -C oracle ref && python oracle/make_golden.py
+
+For every case below it writes tests/golden/<case>/
+    case.json        parameters, the exact reference command line, toolchain stamp
+    genome.fa.gz     the synthetic genome given to the reference
+    seqN.reads.gz    what the reference wrote to <prefix>_NNNN.fq.gz (FASTQ) or .bam (SAM text, header included)
+    seqN.maf.gz      what it wrote to <prefix>_NNNN.maf.gz
+    seqN.ref.gz      <prefix>_NNNN.ref
+    stderr.txt       the reference's stderr (parameter / reference / simulation stats blocks)
+    marks.npy        draw index after each (read, pass), from the interposed rand() log
+    ndraws.txt       total rand() calls
+    rand_head.npy    first 64 draws (pins the glibc rand() restatement for this seed)
+The draw log itself is not committed (it is regenerated from the seed by oracle/glibc_rand.c).
+"""
+import gzip
+import hashlib
+import json
+import os
+import platform
+import subprocess
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+from oracle import refrun as R  # noqa: E402
+
+GOLDEN = os.path.join(os.path.dirname(HERE), "tests", "golden")
+DATA = R.REF_DATA
+
+G_PLAIN = dict(seed=1, contigs=[("chrA", 20000), ("chrB", 5000)])
+G_QUIRK = dict(seed=2, contigs=[("c1", 30000), ("c2", 150), ("c3", 8000)], n_runs=6, hp_plants=40,
+               lowercase_frac=0.1, iupac=5)
+
+CASES = {
+    # name: (method, model, genome spec, depth, seed, extra CLI args, oracle kwargs)
+    "qs_rsii_basic": ("qshmm", "QSHMM-RSII.model", G_PLAIN, 5, 42,
+                      ["--length-mean", "1000", "--length-sd", "700"],
+                      dict(len_mean=1000.0, len_sd=700.0)),
+    "qs_rsii_quirks": ("qshmm", "QSHMM-RSII.model", G_QUIRK, 4, 7,
+                       ["--length-mean", "800", "--length-sd", "600"],
+                       dict(len_mean=800.0, len_sd=600.0)),
+    "qs_ont_hpbias": ("qshmm", "QSHMM-ONT.model", G_QUIRK, 3, 9,
+                      ["--length-mean", "800", "--length-sd", "600", "--hp-del-bias", "4",
+                       "--difference-ratio", "39:24:36"],
+                      dict(len_mean=800.0, len_sd=600.0, hp_del_bias=4.0, ratio=(39, 24, 36))),
+    "err_onthq_basic": ("errhmm", "ERRHMM-ONT-HQ.model", G_QUIRK, 4, 11,
+                        ["--length-mean", "800", "--length-sd", "600"],
+                        dict(len_mean=800.0, len_sd=600.0)),
+    "err_sequel_hiacc": ("errhmm", "ERRHMM-SEQUEL.model", G_QUIRK, 4, 13,
+                         ["--length-mean", "800", "--length-sd", "600", "--accuracy-mean", "0.98",
+                          "--hp-del-bias", "2.5"],
+                         dict(len_mean=800.0, len_sd=600.0, accuracy_mean=0.98, accuracy_mean_set=True,
+                              hp_del_bias=2.5)),
+    "err_sequel_multipass": ("errhmm", "ERRHMM-SEQUEL.model", G_PLAIN, 2, 5,
+                             ["--length-mean", "800", "--length-sd", "600", "--pass-num", "3"],
+                             dict(len_mean=800.0, len_sd=600.0, pass_num=3)),
+    "qs_rsii_multipass": ("qshmm", "QSHMM-RSII.model", G_PLAIN, 2, 6,
+                          ["--length-mean", "800", "--length-sd", "600", "--pass-num", "2", "--id-prefix", "XY"],
+                          dict(len_mean=800.0, len_sd=600.0, pass_num=2, id_prefix="XY")),
+    "qs_rsii_fixedlen": ("qshmm", "QSHMM-RSII.model", G_PLAIN, 3, 21,
+                         ["--length-mean", "500", "--length-sd", "0", "--accuracy-mean", "0.9",
+                          "--length-min", "50", "--length-max", "5000"],
+                         dict(len_mean=500.0, len_sd=0.0, accuracy_mean=0.9, accuracy_mean_set=True,
+                              len_min=50, len_max=5000)),
+}
+
+
+def toolchain_stamp():
+    gxx = subprocess.run(["g++", "--version"], stdout=subprocess.PIPE).stdout.decode().splitlines()[0]
+    libc = " ".join(platform.libc_ver())
+    with open(R.REF_SRC, "rb") as f:
+        sha = hashlib.sha256(f.read()).hexdigest()
+    return {"gxx": gxx, "libc": libc, "flags": "-O2", "reference_sha256": sha, "machine": platform.machine()}
+
+
+def gz_write(path, data):
+    with gzip.GzipFile(path, "wb", mtime=0) as f:
+        f.write(data)
+
+
+def main():
+    assert R.build_reference(), "reference source not present: run this in the build container"
+    stamp = toolchain_stamp()
+    for name, (method, model, gspec, depth, seed, extra, okw) in CASES.items():
+        d = os.path.join(GOLDEN, name)
+        os.makedirs(d, exist_ok=True)
+        contigs = R.synth_genome(**gspec)
+        fa = os.path.join(d, "genome.fa")
+        R.write_fasta(fa, contigs)
+        args = ["--strategy", "wgs", "--method", method, "--" + method, os.path.join(DATA, model),
+                "--genome", fa, "--depth", str(depth), "--seed", str(seed)] + extra
+        plain = R.run_reference(args, logrand=False)
+        logged = R.run_reference(args, logrand=True)
+        assert plain["returncode"] == 0, plain["stderr"]
+        assert plain["files"] == logged["files"], "interposed rand() changed the reference's output"
+        pass_num = okw.get("pass_num", 1)
+        for i in range(1, len(contigs) + 1):
+            reads = plain["files"]["out_%04d.%s" % (i, "fq.gz" if pass_num == 1 else "bam")]
+            gz_write(os.path.join(d, "seq%d.reads.gz" % i), reads)
+            gz_write(os.path.join(d, "seq%d.maf.gz" % i), plain["files"]["out_%04d.maf.gz" % i])
+            gz_write(os.path.join(d, "seq%d.ref.gz" % i), plain["files"]["out_%04d.ref" % i])
+        with open(fa, "rb") as f:
+            gz_write(fa + ".gz", f.read())
+        os.remove(fa)
+        stderr = plain["stderr"].replace(fa, "genome.fa")
+        with open(os.path.join(d, "stderr.txt"), "w") as f:
+            f.write(stderr)
+        np.save(os.path.join(d, "marks.npy"), logged["marks"])
+        np.save(os.path.join(d, "rand_head.npy"), logged["draws"][:64])
+        with open(os.path.join(d, "ndraws.txt"), "w") as f:
+            f.write("%d\n" % len(logged["draws"]))
+        case = dict(name=name, method=method, model=model, depth=depth, seed=seed, extra_args=extra,
+                    oracle_kwargs=okw, genome_spec=gspec, n_seq=len(contigs), pass_num=pass_num,
+                    toolchain=stamp,
+                    command="pbsim --strategy wgs --method %s --%s data/%s --genome genome.fa --depth %s --seed %d %s"
+                            % (method, method, model, depth, seed, " ".join(extra)))
+        with open(os.path.join(d, "case.json"), "w") as f:
+            json.dump(case, f, indent=1, sort_keys=True)
+        print("golden", name, {k: len(v) for k, v in plain["files"].items() if not k.endswith(".ref")},
+              "draws", len(logged["draws"]))
+
+    # the reference's data/*.model files are INPUT DATA of the path (HMM parameters), not code;
+    # carried gz-compressed so that the -m gpu tests and bench.py can run where /root/reference is absent
+    mdir = os.path.join(GOLDEN, "models")
+    os.makedirs(mdir, exist_ok=True)
+    for fn in sorted(os.listdir(DATA)):
+        if fn.endswith(".model"):
+            with open(os.path.join(DATA, fn), "rb") as f:
+                gz_write(os.path.join(mdir, fn + ".gz"), f.read())
+
+    # glibc rand() known answers taken from the system libc here
+    import ctypes
+    libc = ctypes.CDLL(None)
+    kat = {}
+    for seed in (0, 1, 42, 2024, 4294967295):
+        libc.srand(ctypes.c_uint(seed))
+        kat[str(seed)] = [int(libc.rand()) for _ in range(400)]
+    with open(os.path.join(GOLDEN, "glibc_rand_kat.json"), "w") as f:
+        json.dump({"libc": stamp["libc"], "values": kat}, f)
+
+
+if __name__ == "__main__":
+    main()

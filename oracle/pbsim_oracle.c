@@ -1,0 +1,1176 @@
+/* TEST INFRASTRUCTURE — CPU oracle for the PBSIM3 read-generation hot path.
+ * See pbsim_oracle.h for the role of this file and how its parity is pinned.
+ *
+ * Every function cites the lines of /root/reference/src/pbsim.cpp ("ref:") whose
+ * behaviour it restates.  The restatement is structured around a draw source with
+ * purpose-named draws so that the same control flow serves three modes:
+ *   glibc   srand(seed)/rand() restated (glibc_rand.c): reproduces the reference
+ *   replay  the same, but reading a captured draw log
+ *   philox  the engine's counter-addressed Philox4x32-10 stream (no reference
+ *           counterpart; statistical parity only) — see DESIGN.md for addressing.
+ */
+#include "pbsim_oracle.h"
+#include "philox.h"
+
+#include <limits.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define LINE_MAX_BYTES 10240 /* ref: BUF_SIZE :20 */
+#define NACC (ORC_ACC_MAX + 1)
+#define NST (ORC_STATE_MAX + 1)
+
+/* ------------------------------------------------------------------ buffers */
+typedef struct {
+  char *p;
+  int64_t n, cap;
+} buf_t;
+
+static void buf_reserve(buf_t *b, int64_t extra) {
+  if (b->n + extra <= b->cap) return;
+  int64_t cap = b->cap ? b->cap : 1 << 16;
+  while (cap < b->n + extra) cap *= 2;
+  b->p = (char *)realloc(b->p, (size_t)cap);
+  b->cap = cap;
+}
+static void buf_put(buf_t *b, const void *src, int64_t n) {
+  buf_reserve(b, n);
+  memcpy(b->p + b->n, src, (size_t)n);
+  b->n += n;
+}
+static void buf_puts(buf_t *b, const char *s) { buf_put(b, s, (int64_t)strlen(s)); }
+static void buf_pad(buf_t *b, int n) {
+  while (n-- > 0) buf_put(b, " ", 1);
+}
+static void buf_long(buf_t *b, const char *pre, long v, const char *post) {
+  char tmp[64];
+  snprintf(tmp, sizeof tmp, "%s%ld%s", pre, v, post);
+  buf_puts(b, tmp);
+}
+
+/* ------------------------------------------------------------------ draw source */
+enum { RNG_GLIBC = 0, RNG_REPLAY = 1, RNG_PHILOX = 2 };
+
+typedef struct {
+  int mode;
+  orc_glibc_rand_t g;
+  const int32_t *log;
+  int64_t nlog;
+  int64_t cur; /* draws consumed (stream modes) */
+  int32_t *rec;
+  int64_t rec_cap;
+  int exhausted;
+  /* philox */
+  uint32_t key[2];
+  uint32_t read_id, pass, pos;
+  uint32_t w[4];  /* block 0 of the current position */
+  uint32_t xw[4]; /* cached extra block */
+  uint32_t xblk;
+} rng_t;
+
+static uint32_t stream_next(rng_t *r) {
+  int32_t v;
+  if (r->mode == RNG_GLIBC) {
+    v = orc_glibc_rand(&r->g);
+    if (r->cur >= r->rec_cap) {
+      r->rec_cap = r->rec_cap ? r->rec_cap * 2 : 1 << 20;
+      r->rec = (int32_t *)realloc(r->rec, (size_t)r->rec_cap * sizeof(int32_t));
+    }
+    r->rec[r->cur] = v;
+  } else {
+    if (r->cur >= r->nlog) {
+      r->exhausted = 1;
+      v = 0;
+    } else {
+      v = r->log[r->cur];
+    }
+  }
+  r->cur++;
+  return (uint32_t)v;
+}
+
+static inline uint32_t mulhi32(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
+
+static void philox_at(const rng_t *r, uint32_t pos, uint32_t blk, uint32_t domain, uint32_t out[4]) {
+  uint32_t ctr[4];
+  ctr[0] = pos;
+  ctr[1] = blk | (r->pass << 16);
+  ctr[2] = r->read_id;
+  ctr[3] = domain;
+  orc_philox4x32_10(ctr, r->key, out);
+}
+
+/* planner draws (ref: :2174, :2183, :2189) */
+static void d_plan_begin(rng_t *r, uint32_t read_id) {
+  r->read_id = read_id;
+  r->pass = 0;
+  if (r->mode == RNG_PHILOX) philox_at(r, 0, 0, 0, r->w);
+}
+static uint32_t d_plan_len(rng_t *r, uint32_t mod) {
+  return r->mode == RNG_PHILOX ? mulhi32(r->w[0], mod) : stream_next(r) % mod;
+}
+static uint32_t d_plan_acc(rng_t *r, uint32_t mod) {
+  return r->mode == RNG_PHILOX ? mulhi32(r->w[1], mod) : stream_next(r) % mod;
+}
+static uint64_t d_plan_off(rng_t *r, uint64_t span) {
+  if (r->mode == RNG_PHILOX) {
+    uint64_t u = ((uint64_t)r->w[2] << 32) | r->w[3];
+    return (uint64_t)(((unsigned __int128)u * span) >> 64);
+  }
+  return (uint64_t)stream_next(r) % span;
+}
+
+/* per-position draws */
+static void d_begin(rng_t *r, uint32_t pass, uint32_t pos) {
+  r->pass = pass;
+  r->pos = pos;
+  r->xblk = 0;
+  if (r->mode == RNG_PHILOX) philox_at(r, pos, 0, 1, r->w);
+}
+static uint32_t d_w0(rng_t *r, uint32_t mod) { /* state / freq draw */
+  return r->mode == RNG_PHILOX ? mulhi32(r->w[0], mod) : stream_next(r) % mod;
+}
+static uint32_t d_w1(rng_t *r, uint32_t mod) {
+  return r->mode == RNG_PHILOX ? mulhi32(r->w[1], mod) : stream_next(r) % mod;
+}
+static uint32_t d_w2(rng_t *r, uint32_t mod) {
+  return r->mode == RNG_PHILOX ? mulhi32(r->w[2], mod) : stream_next(r) % mod;
+}
+static uint32_t d_w3(rng_t *r, uint32_t mod) {
+  return r->mode == RNG_PHILOX ? mulhi32(r->w[3], mod) : stream_next(r) % mod;
+}
+static uint32_t d_choice3(rng_t *r) {
+  return r->mode == RNG_PHILOX ? ((r->w[0] & 0xFFFu) * 3u) >> 12 : stream_next(r) % 3;
+}
+static uint32_t d_choice4(rng_t *r) {
+  return r->mode == RNG_PHILOX ? (r->w[0] >> 12) & 3u : stream_next(r) % 4;
+}
+static uint32_t d_choice8(rng_t *r) {
+  return r->mode == RNG_PHILOX ? r->w[1] & 7u : stream_next(r) % 8;
+}
+static uint32_t d_mag3(rng_t *r) { /* errhmm: rand()%3+1 (ref: :3895) */
+  return r->mode == RNG_PHILOX ? (((r->w[3] & 0xFFFu) * 3u) >> 12) + 1 : stream_next(r) % 3 + 1;
+}
+/* qshmm deletion draw number j (0-based) after the current position (ref: :2270) */
+static uint32_t d_del(rng_t *r, uint32_t j) {
+  if (r->mode != RNG_PHILOX) return stream_next(r) % 1000000;
+  if (j == 0) return mulhi32(r->w[3], 1000000);
+  {
+    uint32_t blk = 1 + (j - 1) / 4;
+    if (blk != r->xblk) {
+      philox_at(r, r->pos, blk, 1, r->xw);
+      r->xblk = blk;
+    }
+    return mulhi32(r->xw[(j - 1) % 4], 1000000);
+  }
+}
+
+/* ------------------------------------------------------------------ context */
+struct orc_ctx {
+  char err[256];
+  /* parameters */
+  int method, pass_num;
+  double accuracy_mean;
+  long len_min, len_max;
+  double len_mean, len_sd;
+  long sub_ratio, ins_ratio, del_ratio;
+  double sub_rate, ins_rate, del_rate;
+  double hp_del_bias_opt;
+  char id_prefix[256];
+  /* model, laid out flat exactly like the reference's arrays so that out-of-range
+   * state numbers alias the same cells (ref: struct qshmm_t/errhmm_t :160-178) */
+  double *ip;   /* [NACC][NST] */
+  double *ep;   /* [NACC][NST][94] (errhmm: [NACC][NST][4]) */
+  double *tp;   /* [NACC][NST][NST] */
+  int ep_cols;
+  int exist[NACC];
+  int state_max[NACC];
+  int acc_min, acc_max;
+  int model_loaded;
+  /* Phred / uniform tables (ref: :546-578) */
+  double qc_prob[ORC_NQV];
+  double uni_ep[NACC][ORC_NQV];
+  long sub_thre[ORC_NQV], ins_thre[ORC_NQV], del_thre[ORC_NQV];
+  /* quantised tables, 1-based like the reference */
+  long *prob2len;  /* [100001] */
+  long *prob2acc;  /* [100001] */
+  long len_rand_value, accuracy_rand_value;
+  long tab_acc_lo, tab_acc_hi;
+  /* qshmm (resolution 100) and freq2qc (1000) */
+  uint8_t (*qs_init)[101];         /* [NACC][101] */
+  uint8_t (*qs_emis)[NST][101];    /* [NACC][NST][101] */
+  uint8_t (*qs_tran)[NST][101];
+  uint8_t (*qs_freq)[1001];        /* [NACC][1001] */
+  long mod_init[NACC], mod_freq[NACC];
+  long mod_emis[NACC][NST], mod_tran[NACC][NST];
+  /* errhmm (resolution 1000) */
+  uint8_t (*er_init)[1001];        /* [NACC][1001] */
+  uint8_t (*er_emis)[NST][1001];
+  uint8_t (*er_tran)[NST][1001];
+  long er_del[NACC][NST];
+  int tables_built;
+  /* genome */
+  char *seq;
+  int16_t *hp; /* hp[-1] is readable: allocated with one leading cell */
+  int16_t *hp_alloc;
+  int64_t glen;
+  int seq_num;
+  long hpfreq[12];  /* [11] aliases hp_del_bias[0] in the reference build, see set_sequence */
+  double bias[12];
+  /* window scratch */
+  char *w_seq, *read_seq, *qual, *maf_seq, *maf_ref;
+  int16_t *w_hp_alloc, *w_hp;
+  int64_t w_cap;
+  /* draw source */
+  rng_t rng;
+  /* outputs */
+  buf_t out_reads, out_maf;
+  orc_stats_t st;
+  int64_t *freq_len;
+  int64_t freq_len_n;
+  int64_t *freq_acc;
+  orc_readinfo_t *info;
+  int64_t info_n, info_cap;
+};
+
+static int fail(orc_ctx *c, const char *msg) {
+  snprintf(c->err, sizeof c->err, "%s", msg);
+  return -1;
+}
+
+orc_ctx *orc_new(void) {
+  orc_ctx *c = (orc_ctx *)calloc(1, sizeof(orc_ctx));
+  int i, j;
+  double prob, rate;
+  c->ip = (double *)calloc((size_t)NACC * NST, sizeof(double));
+  c->tp = (double *)calloc((size_t)NACC * NST * NST, sizeof(double));
+  c->prob2len = (long *)calloc(100001, sizeof(long));
+  c->prob2acc = (long *)calloc(100001, sizeof(long));
+  c->qs_init = calloc(NACC, sizeof(*c->qs_init));
+  c->qs_emis = calloc(NACC, sizeof(*c->qs_emis));
+  c->qs_tran = calloc(NACC, sizeof(*c->qs_tran));
+  c->qs_freq = calloc(NACC, sizeof(*c->qs_freq));
+  c->er_init = calloc(NACC, sizeof(*c->er_init));
+  c->er_emis = calloc(NACC, sizeof(*c->er_emis));
+  c->er_tran = calloc(NACC, sizeof(*c->er_tran));
+  c->freq_acc = (int64_t *)calloc(100001, sizeof(int64_t));
+  strcpy(c->id_prefix, "S");
+  /* ref: :546-549  qc[i].prob = pow(10, (double)i / -10) */
+  for (i = 0; i <= 93; i++) c->qc_prob[i] = pow(10, (double)i / -10);
+  /* ref: :558-578  uniform error probability: two adjacent QVs whose mean error is 1-acc/100 */
+  for (i = 0; i <= ORC_ACC_MAX; i++) {
+    for (j = 0; j <= 93; j++) c->uni_ep[i][j] = 0;
+    if (i == ORC_ACC_MAX) {
+      c->uni_ep[i][93] = 1.0;
+      continue;
+    }
+    prob = 1.0 - i / 100.0;
+    for (j = 0; j <= 93; j++) {
+      if (prob == c->qc_prob[j]) {
+        c->uni_ep[i][j] = 1.0;
+        break;
+      } else if (prob > c->qc_prob[j]) {
+        rate = (prob - c->qc_prob[j]) / (c->qc_prob[j - 1] - c->qc_prob[j]);
+        c->uni_ep[i][j - 1] = rate;
+        c->uni_ep[i][j] = 1 - rate;
+        break;
+      }
+    }
+  }
+  for (i = 1; i <= 10; i++) c->bias[i] = 1; /* ref: :673-676 */
+  return c;
+}
+
+void orc_free(orc_ctx *c) {
+  if (!c) return;
+  free(c->ip); free(c->ep); free(c->tp);
+  free(c->prob2len); free(c->prob2acc);
+  free(c->qs_init); free(c->qs_emis); free(c->qs_tran); free(c->qs_freq);
+  free(c->er_init); free(c->er_emis); free(c->er_tran);
+  free(c->seq); free(c->hp_alloc);
+  free(c->w_seq); free(c->read_seq); free(c->qual); free(c->maf_seq); free(c->maf_ref); free(c->w_hp_alloc);
+  free(c->rng.rec);
+  free(c->out_reads.p); free(c->out_maf.p);
+  free(c->freq_len); free(c->freq_acc); free(c->info);
+  free(c);
+}
+
+const char *orc_error(orc_ctx *c) { return c->err; }
+
+void orc_philox_block(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+  orc_philox4x32_10(ctr, key, out);
+}
+
+/* ref: the C++ functional cast int(x) on a double; x86-64 cvttsd2si yields INT_MIN for
+ * NaN / out-of-range, which is what the reference build observes. */
+static long trunc_int(double x) {
+  if (!(x > -2147483649.0 && x < 2147483648.0)) return (long)INT_MIN;
+  return (long)(int)x;
+}
+
+int orc_set_params(orc_ctx *c, int method, int pass_num, double accuracy_mean,
+                   long len_min, long len_max, double len_mean, double len_sd,
+                   long sub_ratio, long ins_ratio, long del_ratio,
+                   double hp_del_bias, const char *id_prefix) {
+  long sum;
+  int i;
+  c->method = method;
+  c->pass_num = pass_num;
+  c->accuracy_mean = accuracy_mean;
+  c->len_min = len_min;
+  c->len_max = len_max;
+  c->len_mean = len_mean;
+  c->len_sd = len_sd;
+  c->sub_ratio = sub_ratio;
+  c->ins_ratio = ins_ratio;
+  c->del_ratio = del_ratio;
+  c->hp_del_bias_opt = hp_del_bias;
+  snprintf(c->id_prefix, sizeof c->id_prefix, "%s", id_prefix ? id_prefix : "S");
+  /* ref: :1561-1564 */
+  sum = sub_ratio + ins_ratio + del_ratio;
+  c->sub_rate = (double)sub_ratio / sum;
+  c->ins_rate = (double)ins_ratio / sum;
+  c->del_rate = (double)del_ratio / sum;
+  /* ref: set_mut :5474-5479 */
+  for (i = 0; i <= 93; i++) {
+    c->sub_thre[i] = trunc_int((c->qc_prob[i] * c->sub_rate) * 1000000 + 0.5);
+    c->ins_thre[i] = trunc_int((c->qc_prob[i] * (c->sub_rate + c->ins_rate)) * 1000000 + 0.5);
+    c->del_thre[i] = trunc_int((c->qc_prob[i] * c->del_rate) / (1 + c->qc_prob[i] * c->del_rate) * 1000000 + 0.5);
+  }
+  free(c->freq_len);
+  c->freq_len_n = 2 * len_max + 2; /* the reference indexes freq_len[len] unguarded (:2300) */
+  c->freq_len = (int64_t *)calloc((size_t)c->freq_len_n, sizeof(int64_t));
+  c->tables_built = 0;
+  return 0;
+}
+
+/* ref: set_qshmm :5570-5634, set_errhmm :5640-5714.  Format:
+ *   <acc> IP <state> <p> | <acc> EP <state> <p...> (0-based columns) | <acc> TP <state> <p...> (1-based) */
+int orc_load_model(orc_ctx *c, const char *path) {
+  FILE *fp = fopen(path, "r");
+  char *line, *tok;
+  int accuracy, state, num, i;
+  int64_t ep_cells, tp_cells, ip_cells, idx;
+  if (!fp) return fail(c, "ERROR: Cannot open file (model)");
+  c->ep_cols = (c->method == ORC_METHOD_ERR) ? 4 : 94;
+  free(c->ep);
+  ep_cells = (int64_t)NACC * NST * c->ep_cols;
+  tp_cells = (int64_t)NACC * NST * NST;
+  ip_cells = (int64_t)NACC * NST;
+  c->ep = (double *)calloc((size_t)ep_cells, sizeof(double));
+  memset(c->ip, 0, (size_t)ip_cells * sizeof(double));
+  memset(c->tp, 0, (size_t)tp_cells * sizeof(double));
+  for (i = 0; i < NACC; i++) {
+    c->exist[i] = 0;
+    c->state_max[i] = 0;
+  }
+  c->acc_min = 100;
+  c->acc_max = 0;
+  line = (char *)malloc(LINE_MAX_BYTES);
+  while (fgets(line, LINE_MAX_BYTES, fp) != NULL) {
+    size_t n = strlen(line);
+    if (n && line[n - 1] == '\n') line[n - 1] = '\0';
+    tok = strtok(line, " ");
+    if (!tok) continue;
+    accuracy = atoi(tok);
+    if (accuracy < 0 || accuracy > ORC_ACC_MAX) { fclose(fp); free(line); return fail(c, "model: accuracy out of range"); }
+    c->exist[accuracy] = 1;
+    if (c->acc_min > accuracy) c->acc_min = accuracy;
+    if (c->acc_max < accuracy) c->acc_max = accuracy;
+    tok = strtok(NULL, " ");
+    if (!tok) continue;
+    if (strcmp(tok, "IP") == 0) {
+      tok = strtok(NULL, " ");
+      state = atoi(tok);
+      tok = strtok(NULL, " ");
+      idx = (int64_t)accuracy * NST + state;
+      if (idx < 0 || idx >= ip_cells) { fclose(fp); free(line); return fail(c, "model: IP index outside the reference array"); }
+      c->ip[idx] = atof(tok);
+      c->state_max[accuracy] = state; /* ref: :5686 (errhmm only uses it) */
+    } else if (strcmp(tok, "EP") == 0) {
+      tok = strtok(NULL, " ");
+      state = atoi(tok);
+      num = 0;
+      tok = strtok(NULL, " ");
+      while (tok != NULL) {
+        idx = ((int64_t)accuracy * NST + state) * c->ep_cols + num;
+        if (idx < 0 || idx >= ep_cells) { fclose(fp); free(line); return fail(c, "model: EP index outside the reference array"); }
+        c->ep[idx] = atof(tok);
+        num++;
+        tok = strtok(NULL, " ");
+      }
+    } else if (strcmp(tok, "TP") == 0) {
+      tok = strtok(NULL, " ");
+      state = atoi(tok);
+      num = 0;
+      tok = strtok(NULL, " ");
+      while (tok != NULL) {
+        num++;
+        idx = ((int64_t)accuracy * NST + state) * NST + num;
+        if (idx < 0 || idx >= tp_cells) { fclose(fp); free(line); return fail(c, "model: TP index outside the reference array"); }
+        c->tp[idx] = atof(tok);
+        tok = strtok(NULL, " ");
+      }
+    }
+  }
+  free(line);
+  fclose(fp);
+  c->model_loaded = 1;
+  c->tables_built = 0;
+  return 0;
+}
+
+#define IP(a, s) c->ip[(int64_t)(a) * NST + (s)]
+#define EP(a, s, k) c->ep[((int64_t)(a) * NST + (s)) * c->ep_cols + (k)]
+#define TP(a, s, k) c->tp[((int64_t)(a) * NST + (s)) * NST + (k)]
+
+/* ref: the table builders inlined at the top of simulate_by_qshmm (:1991-2170) and
+ * simulate_by_errhmm (:3633-3789).  Quantised CDFs: walk outcomes in index order, skip
+ * zero-probability outcomes, end = int(cum*R + 0.5) clamped to R, fill (start..end],
+ * stop once end >= R; the row modulus is the last `end` (stale when a row is empty, as
+ * in the reference, because end_wk is one function-scope variable). */
+int orc_build_tables(orc_ctx *c) {
+  long i, j, k, l;
+  double variance, kappa, theta, gam, mean;
+  double len_prob_total, freq_total, accuracy_prob_total, cum;
+  long start_wk, end_wk = 0;
+  long accuracy_min, accuracy_max;
+
+  if (!c->model_loaded) return fail(c, "model not loaded");
+
+  /* length distribution (ref: :1991-2027) */
+  variance = pow(c->len_sd, 2);
+  kappa = pow(c->len_mean, 2) / variance;
+  theta = variance / c->len_mean;
+  gam = tgamma(kappa);
+  if (c->len_sd == 0.0) {
+    c->prob2len[1] = trunc_int(c->len_mean + 0.5);
+    c->len_rand_value = 1;
+  } else {
+    start_wk = 1;
+    len_prob_total = 0.0;
+    for (i = c->len_min; i <= c->len_max; i++) {
+      len_prob_total += pow((double)i, kappa - 1) * exp((double)(-1 * i) / theta) / pow(theta, kappa) / gam;
+      end_wk = trunc_int(len_prob_total * 100000 + 0.5);
+      if (end_wk > 100000) end_wk = 100000;
+      for (j = start_wk; j <= end_wk; j++) c->prob2len[j] = i;
+      if (end_wk >= 100000) break;
+      start_wk = end_wk + 1;
+    }
+    c->len_rand_value = end_wk;
+  }
+  if (c->pass_num == 1 && c->len_rand_value < 1)
+    return fail(c, "ERROR: length parameters are not appropriate.");
+
+  /* accuracy distribution (ref: :2029-2064) */
+  mean = c->accuracy_mean * 100;
+  accuracy_max = (long)floor(mean * 1.05);
+  accuracy_min = (long)floor(mean * 0.75);
+  if (accuracy_max > 100) accuracy_max = 100;
+  freq_total = 0.0;
+  for (i = accuracy_min; i <= accuracy_max; i++) freq_total += exp(0.22 * i);
+  start_wk = 1;
+  accuracy_prob_total = 0.0;
+  for (i = accuracy_min; i <= accuracy_max; i++) {
+    accuracy_prob_total += exp(0.22 * i) / freq_total;
+    end_wk = trunc_int(accuracy_prob_total * 100000 + 0.5);
+    if (end_wk > 100000) end_wk = 100000;
+    for (j = start_wk; j <= end_wk; j++) c->prob2acc[j] = i;
+    if (end_wk >= 100000) break;
+    start_wk = end_wk + 1;
+  }
+  c->accuracy_rand_value = end_wk;
+  if (c->accuracy_rand_value < 1) return fail(c, "ERROR: accuracy parameters are not appropriate.");
+  c->tab_acc_lo = accuracy_min;
+  c->tab_acc_hi = accuracy_max;
+
+  if (c->method == ORC_METHOD_QS) {
+    /* ref: :2066-2170 */
+    for (i = accuracy_min; i <= accuracy_max; i++) {
+      if (c->exist[i] == 1) {
+        start_wk = 1;
+        cum = 0.0;
+        for (j = 1; j <= ORC_STATE_MAX; j++) {
+          if (IP(i, j) == 0) continue;
+          cum += IP(i, j);
+          end_wk = trunc_int(cum * 100 + 0.5);
+          if (end_wk > 100) end_wk = 100;
+          for (k = start_wk; k <= end_wk; k++) c->qs_init[i][k] = (uint8_t)j;
+          if (end_wk >= 100) break;
+          start_wk = end_wk + 1;
+        }
+        c->mod_init[i] = end_wk;
+        for (j = 1; j <= ORC_STATE_MAX; j++) {
+          start_wk = 1;
+          cum = 0.0;
+          for (k = 0; k <= 93; k++) {
+            if (EP(i, j, k) == 0) continue;
+            cum += EP(i, j, k);
+            end_wk = trunc_int(cum * 100 + 0.5);
+            if (end_wk > 100) end_wk = 100;
+            for (l = start_wk; l <= end_wk; l++) c->qs_emis[i][j][l] = (uint8_t)k;
+            if (end_wk >= 100) break;
+            start_wk = end_wk + 1;
+          }
+          c->mod_emis[i][j] = end_wk;
+        }
+        for (j = 1; j <= ORC_STATE_MAX; j++) {
+          start_wk = 1;
+          cum = 0.0;
+          for (k = 1; k <= ORC_STATE_MAX; k++) {
+            if (TP(i, j, k) == 0) continue;
+            cum += TP(i, j, k);
+            end_wk = trunc_int(cum * 100 + 0.5);
+            if (end_wk > 100) end_wk = 100;
+            for (l = start_wk; l <= end_wk; l++) c->qs_tran[i][j][l] = (uint8_t)k;
+            if (end_wk >= 100) break;
+            start_wk = end_wk + 1;
+          }
+          c->mod_tran[i][j] = end_wk;
+        }
+      } else {
+        start_wk = 1;
+        cum = 0.0;
+        for (j = 0; j <= 93; j++) {
+          if (c->uni_ep[i][j] == 0) continue;
+          cum += c->uni_ep[i][j];
+          end_wk = trunc_int(cum * 1000 + 0.5);
+          if (end_wk > 1000) end_wk = 1000;
+          for (k = start_wk; k <= end_wk; k++) c->qs_freq[i][k] = (uint8_t)j;
+          if (end_wk >= 1000) break;
+          start_wk = end_wk + 1;
+        }
+        c->mod_freq[i] = end_wk;
+      }
+    }
+  } else {
+    /* ref: :3708-3789 */
+    for (i = accuracy_min; i <= accuracy_max; i++) {
+      if (c->exist[i] == 0) continue;
+      start_wk = 1;
+      cum = 0.0;
+      for (j = 1; j <= c->state_max[i]; j++) {
+        if (IP(i, j) == 0) continue;
+        cum += IP(i, j);
+        end_wk = trunc_int(cum * 1000 + 0.5);
+        if (end_wk > 1000) end_wk = 1000;
+        for (k = start_wk; k <= end_wk; k++) c->er_init[i][k] = (uint8_t)j;
+        if (end_wk >= 1000) break;
+        start_wk = end_wk + 1;
+      }
+      c->mod_init[i] = end_wk;
+      for (j = 1; j <= c->state_max[i]; j++) {
+        start_wk = 1;
+        cum = 0.0;
+        c->er_del[i][j] = trunc_int(EP(i, j, 3) * 1000 + 0.5);
+        for (k = 0; k <= 2; k++) {
+          if (EP(i, j, k) <= 0) continue;
+          cum += EP(i, j, k);
+          end_wk = trunc_int(cum * 1000 + 0.5);
+          if (end_wk > 1000) end_wk = 1000;
+          for (l = start_wk; l <= end_wk; l++) c->er_emis[i][j][l] = (uint8_t)k;
+          if (end_wk >= 1000) break;
+          start_wk = end_wk + 1;
+        }
+        c->mod_emis[i][j] = end_wk;
+      }
+      for (j = 1; j <= c->state_max[i]; j++) {
+        start_wk = 1;
+        cum = 0.0;
+        for (k = 1; k <= ORC_STATE_MAX; k++) {
+          if (TP(i, j, k) == 0) continue;
+          cum += TP(i, j, k);
+          end_wk = trunc_int(cum * 1000 + 0.5);
+          if (end_wk > 1000) end_wk = 1000;
+          for (l = start_wk; l <= end_wk; l++) c->er_tran[i][j][l] = (uint8_t)k;
+          if (end_wk >= 1000) break;
+          start_wk = end_wk + 1;
+        }
+        c->mod_tran[i][j] = end_wk;
+      }
+    }
+  }
+  c->tables_built = 1;
+  return 0;
+}
+
+/* ------------------------------------------------------------------ genome */
+
+/* ref: get_genome_seq :1035-1065 — upper-case, then per-base homopolymer length with the
+ * reference's counter quirk (nnum>11 -> 10, so runs >= 11 alternate 11,10,11,...), N runs
+ * get hp=1.  hpfreq[nnum]++ with nnum==11 writes one past hpfreq[11], which in the
+ * reference build (g++ 13.3 -O2, struct genome_t :93-103) is hp_del_bias[0]; we keep the
+ * same aliasing in hpfreq[11] and derive bias[0] from it in refresh_bias0(). */
+static void hp_scan(orc_ctx *c, char *seq, int64_t len, int16_t *hp) {
+  int64_t i, j, nstart = 0, nend = 0;
+  int16_t nnum = 1;
+  for (i = 0; i < len; i++) {
+    char ch = seq[i];
+    if (ch >= 'a' && ch <= 'z') seq[i] = (char)(ch - 'a' + 'A'); /* toupper in the C locale */
+  }
+  for (i = 1; i <= len; i++) {
+    if ((i < len) && (seq[i - 1] == seq[i])) {
+      nend = i;
+      nnum++;
+      if (nnum > 11) nnum = 10;
+    } else {
+      if (seq[i - 1] == 'N') {
+        for (j = nstart; j <= nend; j++) {
+          if (hp) hp[j] = 1;
+          c->hpfreq[1]++;
+        }
+      } else {
+        for (j = nstart; j <= nend; j++) {
+          if (hp) hp[j] = nnum;
+          c->hpfreq[nnum]++;
+        }
+      }
+      nstart = i;
+      nend = nstart;
+      nnum = 1;
+    }
+  }
+}
+
+/* bias[0] is the double whose bit pattern is the long hpfreq[11] (see above); bias[11] reads
+ * the zero padding after `genome` in the reference build -> 0.0. */
+static void refresh_bias0(orc_ctx *c) {
+  int64_t bits = (int64_t)c->hpfreq[11];
+  memcpy(&c->bias[0], &bits, sizeof(double));
+  c->bias[11] = 0.0;
+}
+
+int orc_prepass_sequence(orc_ctx *c, const char *seq, int64_t len) {
+  char *tmp = (char *)malloc((size_t)len + 1);
+  memcpy(tmp, seq, (size_t)len);
+  tmp[len] = 0;
+  hp_scan(c, tmp, len, NULL);
+  free(tmp);
+  return 0;
+}
+
+/* ref: main :678-697.  Called before the first prepass_sequence it zeroes hpfreq[0..10]
+ * (not [11]); called with finish=1 it computes the normalised bias. */
+int orc_finish_bias(orc_ctx *c) {
+  long sum1 = 0, sum2 = 0;
+  double rate;
+  int i;
+  for (i = 1; i <= 10; i++) {
+    c->bias[i] = 1 + (c->hp_del_bias_opt - 1) / 9 * (i - 1);
+    sum1 += c->hpfreq[i] * c->bias[i];
+    sum2 += c->hpfreq[i];
+  }
+  rate = (double)sum2 / sum1;
+  for (i = 1; i <= 10; i++) c->bias[i] *= rate;
+  refresh_bias0(c);
+  return 0;
+}
+
+int orc_set_sequence(orc_ctx *c, const char *seq, int64_t len, int seq_num) {
+  free(c->seq);
+  free(c->hp_alloc);
+  c->seq = (char *)malloc((size_t)len + 1);
+  memcpy(c->seq, seq, (size_t)len);
+  c->seq[len] = 0;
+  c->hp_alloc = (int16_t *)calloc((size_t)len + 2, sizeof(int16_t));
+  c->hp = c->hp_alloc + 1;
+  c->glen = len;
+  c->seq_num = seq_num;
+  hp_scan(c, c->seq, len, c->hp);
+  refresh_bias0(c);
+  return 0;
+}
+
+void orc_get_bias(orc_ctx *c, double bias[12]) { memcpy(bias, c->bias, sizeof c->bias); }
+const int16_t *orc_get_hp(orc_ctx *c, int64_t *n) { *n = c->glen; return c->hp; }
+const char *orc_get_seq(orc_ctx *c, int64_t *n) { *n = c->glen; return c->seq; }
+
+/* ------------------------------------------------------------------ draw source setup */
+int orc_rng_glibc(orc_ctx *c, uint32_t seed) {
+  c->rng.mode = RNG_GLIBC;
+  orc_glibc_srand(&c->rng.g, seed);
+  c->rng.cur = 0;
+  c->rng.exhausted = 0;
+  return 0;
+}
+int orc_rng_replay(orc_ctx *c, const int32_t *log, int64_t n) {
+  c->rng.mode = RNG_REPLAY;
+  c->rng.log = log;
+  c->rng.nlog = n;
+  c->rng.cur = 0;
+  c->rng.exhausted = 0;
+  return 0;
+}
+int orc_rng_philox(orc_ctx *c, uint32_t seed) {
+  c->rng.mode = RNG_PHILOX;
+  c->rng.key[0] = seed;
+  c->rng.key[1] = 0;
+  c->rng.cur = 0;
+  c->rng.exhausted = 0;
+  return 0;
+}
+
+/* ------------------------------------------------------------------ helpers */
+
+/* ref: count_digit :5823-5835 */
+static int count_digit(long num) {
+  int digit = 1;
+  int quotient = (int)(num / 10);
+  while (quotient != 0) {
+    digit++;
+    quotient = (int)(quotient / 10);
+  }
+  return digit;
+}
+
+/* ref: revcomp :5841-5864 — reverse, then complement upper-case A/T/G/C only */
+static void revcomp_n(char *s, int64_t len) {
+  int64_t i;
+  for (i = 0; i < len / 2; i++) {
+    char t = s[i];
+    s[i] = s[len - i - 1];
+    s[len - i - 1] = t;
+  }
+  for (i = 0; i < len; i++) {
+    switch (s[i]) {
+      case 'A': s[i] = 'T'; break;
+      case 'T': s[i] = 'A'; break;
+      case 'G': s[i] = 'C'; break;
+      case 'C': s[i] = 'G'; break;
+      default: break;
+    }
+  }
+}
+
+static void ensure_window(orc_ctx *c, int64_t wlen) {
+  int64_t cap = 4 * wlen + 4096; /* the reference uses 2*len_max+1 and overflows silently */
+  if (cap <= c->w_cap) return;
+  c->w_cap = cap;
+  c->w_seq = (char *)realloc(c->w_seq, (size_t)cap);
+  c->read_seq = (char *)realloc(c->read_seq, (size_t)cap);
+  c->qual = (char *)realloc(c->qual, (size_t)cap);
+  c->maf_seq = (char *)realloc(c->maf_seq, (size_t)cap);
+  c->maf_ref = (char *)realloc(c->maf_ref, (size_t)cap);
+  free(c->w_hp_alloc);
+  c->w_hp_alloc = (int16_t *)calloc((size_t)cap + 1, sizeof(int16_t));
+  c->w_hp = c->w_hp_alloc + 1; /* w_hp[-1] == 0: ref reads mut.hp[-1] (malloc header, 0) :2269 */
+}
+
+static const char SUB_A[] = "TGC", SUB_T[] = "AGC", SUB_G[] = "ATC", SUB_C[] = "ATG", NT4[] = "ATGC"; /* ref: :5481-5486 */
+
+static char substitute(rng_t *r, char nt) {
+  uint32_t index = d_choice3(r); /* drawn even when the base is not ACGT (ref: :2235-2246) */
+  switch (nt) {
+    case 'A': return SUB_A[index];
+    case 'T': return SUB_T[index];
+    case 'G': return SUB_G[index];
+    case 'C': return SUB_C[index];
+    default: return NT4[d_choice4(r)];
+  }
+}
+
+static void push_info(orc_ctx *c, const orc_readinfo_t *ri) {
+  if (c->info_n >= c->info_cap) {
+    c->info_cap = c->info_cap ? c->info_cap * 2 : 1024;
+    c->info = (orc_readinfo_t *)realloc(c->info, (size_t)c->info_cap * sizeof(orc_readinfo_t));
+  }
+  c->info[c->info_n++] = *ri;
+}
+
+/* ref: record emission :2318-2383 (= :4012-4078): FASTQ or SAM, then MAF */
+static void emit_records(orc_ctx *c, long read_num, long pass, long offset, long wlen, char strand,
+                         long len, long ncol) {
+  char id[512];
+  int d1[4], d2[4], dn[4], i;
+  buf_t *o = &c->out_reads, *m = &c->out_maf;
+  if (c->pass_num == 1) {
+    snprintf(id, sizeof id, "%s%d_%ld", c->id_prefix, c->seq_num, read_num);
+    buf_puts(o, "@"); buf_puts(o, id); buf_puts(o, "\n");
+    buf_put(o, c->read_seq, len);
+    buf_puts(o, "\n+"); buf_puts(o, id); buf_puts(o, "\n");
+    buf_put(o, c->qual, len);
+    buf_puts(o, "\n");
+  } else {
+    char tail[256];
+    snprintf(id, sizeof id, "%s%d/%ld/%ld", c->id_prefix, c->seq_num, read_num, pass);
+    buf_puts(o, id);
+    buf_puts(o, "\t4\t*\t0\t255\t*\t*\t0\t0\t");
+    buf_put(o, c->read_seq, len);
+    buf_puts(o, "\t");
+    buf_put(o, c->qual, len);
+    buf_puts(o, "\tcx:i:3\tip:B:C");
+    for (i = 0; i < len; i++) buf_put(o, ",9", 2);
+    buf_puts(o, "\tnp:i:1\tpw:B:C");
+    for (i = 0; i < len; i++) buf_put(o, ",9", 2);
+    snprintf(tail, sizeof tail, "\tqs:i:0\tqe:i:%ld\trq:f:%f\tsn:B:f,10.0,10.0,10.0,10.0\tzm:i:%ld\tRG:Z:ffffffff\n",
+             (long)(int)(len - 1), c->accuracy_mean, read_num);
+    buf_puts(o, tail);
+  }
+  d1[0] = 3;                      d2[0] = 1 + count_digit(read_num);
+  d1[1] = count_digit(offset);    d2[1] = 1;
+  d1[2] = count_digit(wlen);      d2[2] = count_digit(len);
+  d1[3] = count_digit(c->glen);   d2[3] = count_digit(len);
+  for (i = 0; i < 4; i++) dn[i] = d1[i] >= d2[i] ? d1[i] : d2[i];
+  buf_puts(m, "a\ns ref");
+  buf_pad(m, dn[0] - d1[0]);
+  buf_pad(m, dn[1] - d1[1]);
+  buf_long(m, " ", offset, "");
+  buf_pad(m, dn[2] - d1[2]);
+  buf_long(m, " ", wlen, " +");
+  buf_pad(m, dn[3] - d1[3]);
+  buf_long(m, " ", (long)c->glen, " ");
+  buf_put(m, c->maf_ref, ncol);
+  buf_puts(m, "\ns ");
+  buf_puts(m, id);
+  buf_pad(m, dn[0] - d2[0]);
+  buf_pad(m, dn[1] - d2[1]);
+  buf_puts(m, " 0");
+  buf_pad(m, dn[2] - d2[2]);
+  buf_long(m, " ", len, strand == '+' ? " +" : " -");
+  buf_pad(m, dn[3] - d2[3]);
+  buf_long(m, " ", len, " ");
+  buf_put(m, c->maf_seq, ncol);
+  buf_puts(m, "\n\n");
+}
+
+/* ------------------------------------------------------------------ per-pass generators */
+
+typedef struct {
+  long rlen, ncol, nsub, nins, ndel;
+} pass_out_t;
+
+/* ref: simulate_by_qshmm inner loops :2210-2286 */
+static void qshmm_pass(orc_ctx *c, rng_t *r, uint32_t pass, int acc, long wlen, pass_out_t *po) {
+  long ref_offset = 0, read_offset = 0, maf_offset = 0;
+  long state = 0, index, qv, rand_value;
+  char nt;
+  po->nsub = po->nins = po->ndel = 0;
+  while (ref_offset < wlen) {
+    d_begin(r, pass, (uint32_t)read_offset);
+    if (c->exist[acc] == 1) {
+      if (read_offset == 0) {
+        index = d_w0(r, (uint32_t)c->mod_init[acc]) + 1;
+        state = c->qs_init[acc][index];
+      } else {
+        index = d_w0(r, (uint32_t)c->mod_tran[acc][state]) + 1;
+        state = c->qs_tran[acc][state][index];
+      }
+      index = d_w1(r, (uint32_t)c->mod_emis[acc][state]) + 1;
+      qv = c->qs_emis[acc][state][index];
+    } else {
+      index = d_w0(r, (uint32_t)c->mod_freq[acc]) + 1;
+      qv = c->qs_freq[acc][index];
+    }
+    c->qual[read_offset] = (char)(qv + 33);
+    nt = c->w_seq[ref_offset];
+    rand_value = d_w2(r, 1000000);
+    if (rand_value < c->sub_thre[qv]) {
+      po->nsub++;
+      c->read_seq[read_offset] = substitute(r, nt);
+      c->maf_ref[maf_offset] = nt;
+      ref_offset++;
+    } else if (rand_value < c->ins_thre[qv]) {
+      po->nins++;
+      index = d_choice8(r);
+      c->read_seq[read_offset] = (index >= 4) ? nt : NT4[index];
+      c->maf_ref[maf_offset] = '-';
+    } else {
+      c->read_seq[read_offset] = nt;
+      c->maf_ref[maf_offset] = nt;
+      ref_offset++;
+    }
+    c->maf_seq[maf_offset] = c->read_seq[read_offset];
+    maf_offset++;
+    read_offset++;
+    {
+      uint32_t j = 0;
+      while (ref_offset < wlen) {
+        int hp = c->w_hp[ref_offset - 1];
+        rand_value = d_del(r, j++);
+        if (rand_value < c->del_thre[qv] * c->bias[hp]) {
+          po->ndel++;
+          c->maf_seq[maf_offset] = '-';
+          c->maf_ref[maf_offset] = c->w_seq[ref_offset];
+          maf_offset++;
+          ref_offset++;
+        } else {
+          break;
+        }
+      }
+    }
+  }
+  po->rlen = read_offset;
+  po->ncol = maf_offset;
+}
+
+/* ref: simulate_by_errhmm inner loops :3836-3976 */
+static void errhmm_pass(orc_ctx *c, rng_t *r, uint32_t pass, int acc, int rate_mag, long wlen, pass_out_t *po) {
+  long ref_offset = 0, read_offset = 0, maf_offset = 0, i;
+  long state = 0, index, index2;
+  int tacc, hp;
+  char nt;
+  po->nsub = po->nins = po->ndel = 0;
+  if (acc == 100) {
+    for (i = 0; i < wlen; i++) {
+      nt = c->w_seq[i];
+      c->read_seq[i] = nt;
+      c->maf_ref[i] = nt;
+      c->maf_seq[i] = nt;
+    }
+    po->rlen = wlen;
+    po->ncol = wlen;
+    return;
+  }
+  /* which accuracy's tables drive the chain (ref: :3852, :3872, :3900) */
+  if (c->exist[acc] == 1) tacc = acc;
+  else if (acc < c->acc_min) tacc = c->acc_min;
+  else tacc = c->acc_max;
+  while (ref_offset < wlen) {
+    nt = c->w_seq[ref_offset];
+    d_begin(r, pass, (uint32_t)maf_offset);
+    if (read_offset == 0) {
+      index = d_w0(r, (uint32_t)c->mod_init[tacc]) + 1;
+      state = c->er_init[tacc][index];
+    } else {
+      index = d_w0(r, (uint32_t)c->mod_tran[tacc][state]) + 1;
+      state = c->er_tran[tacc][state][index];
+    }
+    hp = c->w_hp[ref_offset];
+    index = d_w1(r, 1000) + 1;
+    if (index <= c->er_del[tacc][state] * c->bias[hp]) {
+      index = 3;
+    } else {
+      if (c->mod_emis[tacc][state] == 0) {
+        index = d_w2(r, 3);
+      } else {
+        index = d_w2(r, (uint32_t)c->mod_emis[tacc][state]) + 1;
+        index = c->er_emis[tacc][state][index];
+      }
+    }
+    if (c->exist[acc] != 1) {
+      if (acc < c->acc_min) {
+        if (index == 0) { /* ref: :3892-3899 thicken errors */
+          index = d_w3(r, 100) + 1;
+          if (index <= rate_mag) index = d_mag3(r);
+          else index = 0;
+        }
+      } else {
+        if (index != 0) { /* ref: :3920-3925 thin errors */
+          index2 = d_w3(r, 100) + 1;
+          if (index2 <= rate_mag) index = 0;
+        }
+      }
+    }
+    if (index == 0) {
+      c->read_seq[read_offset] = nt;
+      c->maf_seq[maf_offset] = nt;
+      c->maf_ref[maf_offset] = nt;
+      ref_offset++;
+      read_offset++;
+    } else if (index == 1) {
+      po->nsub++;
+      c->read_seq[read_offset] = substitute(r, nt);
+      c->maf_seq[maf_offset] = c->read_seq[read_offset];
+      c->maf_ref[maf_offset] = nt;
+      ref_offset++;
+      read_offset++;
+    } else if (index == 2) {
+      po->nins++;
+      index = d_choice8(r);
+      c->read_seq[read_offset] = (index >= 4) ? nt : NT4[index];
+      c->maf_seq[maf_offset] = c->read_seq[read_offset];
+      c->maf_ref[maf_offset] = '-';
+      read_offset++;
+    } else {
+      po->ndel++;
+      c->maf_seq[maf_offset] = '-';
+      c->maf_ref[maf_offset] = nt;
+      ref_offset++;
+    }
+    maf_offset++;
+  }
+  po->rlen = read_offset;
+  po->ncol = maf_offset;
+}
+
+/* ------------------------------------------------------------------ WGS driver */
+
+void orc_reset_outputs(orc_ctx *c) {
+  c->out_reads.n = 0;
+  c->out_maf.n = 0;
+  c->info_n = 0;
+}
+
+/* ref: simulate_by_qshmm :2172-2410, simulate_by_errhmm :3791-4105, with init_sim_res :1437
+ * and the quota from main :705. */
+int orc_simulate_wgs(orc_ctx *c, double depth) {
+  long long len_quota, len_total = 0;
+  double accuracy_total = 0.0, variance, value;
+  long h, i, len;
+  rng_t *r = &c->rng;
+  orc_stats_t *st = &c->st;
+
+  if (!c->tables_built) return fail(c, "tables not built");
+  if (!c->seq) return fail(c, "no sequence");
+  if (r->mode == RNG_PHILOX) r->key[1] = (uint32_t)c->seq_num;
+
+  memset(st, 0, sizeof *st);
+  st->res_len_min = LONG_MAX;
+  memset(c->freq_len, 0, (size_t)c->freq_len_n * sizeof(int64_t));
+  memset(c->freq_acc, 0, 100001 * sizeof(int64_t));
+  len_quota = (long long)(depth * c->glen);
+
+  while (len_total < len_quota) {
+    long index, wlen, offset;
+    int acc, rate_mag = 0;
+    char strand;
+    int64_t start_draw = r->cur;
+
+    d_plan_begin(r, (uint32_t)(st->res_num + 1));
+    index = d_plan_len(r, (uint32_t)c->len_rand_value) + 1;
+    wlen = c->prob2len[index];
+    if (len_total + wlen > len_quota) {
+      wlen = (long)(len_quota - len_total);
+      if (wlen < c->len_min) wlen = c->len_min;
+    }
+    index = d_plan_acc(r, (uint32_t)c->accuracy_rand_value) + 1;
+    acc = (int)c->prob2acc[index];
+    if (wlen >= c->glen) {
+      offset = 0;
+      wlen = (long)c->glen;
+    } else {
+      offset = (long)d_plan_off(r, (uint64_t)(c->glen - wlen + 1));
+    }
+    st->res_num++;
+
+    ensure_window(c, wlen);
+    for (i = 0; i < wlen; i++) {
+      c->w_seq[i] = c->seq[offset + i];
+      c->w_hp[i] = c->hp[offset + i];
+    }
+    c->w_seq[wlen] = '\0';
+    if (st->res_num % 2 == 1) {
+      strand = '+';
+    } else {
+      strand = '-';
+      revcomp_n(c->w_seq, wlen);
+      for (i = 0; i < wlen / 2; i++) { /* ref: revshort :5870-5879 */
+        int16_t t = c->w_hp[i];
+        c->w_hp[i] = c->w_hp[wlen - i - 1];
+        c->w_hp[wlen - i - 1] = t;
+      }
+    }
+
+    if (c->method == ORC_METHOD_ERR) { /* ref: :3829-3833 */
+      if (acc < c->acc_min) rate_mag = (int)((double)(c->acc_min - acc) / c->acc_min * 100);
+      else if (acc > c->acc_max) rate_mag = (int)((double)(acc - c->acc_max) / (100 - c->acc_max) * 100);
+    }
+
+    for (h = 0; h < c->pass_num; h++) {
+      pass_out_t po;
+      orc_readinfo_t ri;
+      int64_t pass_start = (h == 0) ? start_draw : r->cur;
+      if (c->method == ORC_METHOD_QS) qshmm_pass(c, r, (uint32_t)h, acc, wlen, &po);
+      else errhmm_pass(c, r, (uint32_t)h, acc, rate_mag, wlen, &po);
+      len = po.rlen;
+      if (strand == '-') {
+        revcomp_n(c->maf_seq, po.ncol);
+        revcomp_n(c->maf_ref, po.ncol);
+      }
+      st->res_sub_num += po.nsub;
+      st->res_ins_num += po.nins;
+      st->res_del_num += po.ndel;
+      st->res_len_total += len;
+      if (h == 0) len_total += len;
+      if (len >= 0 && len < c->freq_len_n) c->freq_len[len]++;
+      if (len > st->res_len_max) st->res_len_max = len;
+      if (len < st->res_len_min) st->res_len_min = len;
+      if (c->method == ORC_METHOD_QS) { /* ref: :2309-2316 accuracy from emitted qualities */
+        double prob = 0.0;
+        for (i = 0; i < len; i++) prob += c->qc_prob[(int)c->qual[i] - 33];
+        value = 1.0 - (prob / len);
+      } else { /* ref: :4002 accuracy from realised errors; qualities all '!' :4007-4010 */
+        value = 1.0 - ((double)(po.nsub + po.nins + po.ndel) / len);
+        for (i = 0; i < len; i++) c->qual[i] = '!';
+      }
+      accuracy_total += value;
+      {
+        long acc_wk = trunc_int(value * 100000 + 0.5);
+        if (acc_wk >= 0 && acc_wk <= 100000) c->freq_acc[acc_wk]++;
+      }
+      emit_records(c, (long)st->res_num, h, offset, wlen, strand, len, po.ncol);
+      ri.read_id = st->res_num; ri.pass = (int32_t)h; ri.acc = acc; ri.offset = offset; ri.wlen = wlen;
+      ri.rlen = len; ri.ncol = po.ncol; ri.strand = strand; ri.nsub = (int32_t)po.nsub;
+      ri.nins = (int32_t)po.nins; ri.ndel = (int32_t)po.ndel; ri.draw_start = pass_start; ri.accuracy = value;
+      push_info(c, &ri);
+    }
+    if (r->exhausted) return fail(c, "draw log exhausted");
+  }
+
+  /* ref: :2387-2410 */
+  st->res_pass_num = st->res_num * c->pass_num;
+  st->res_len_mean = (double)st->res_len_total / st->res_pass_num;
+  st->res_accuracy_mean = accuracy_total / st->res_pass_num;
+  st->accuracy_total = accuracy_total;
+  if (st->res_pass_num == 1) {
+    st->res_len_sd = 0.0;
+    st->res_accuracy_sd = 0.0;
+  } else {
+    variance = 0.0;
+    for (i = 0; i <= c->len_max; i++)
+      if (c->freq_len[i] > 0) variance += pow((st->res_len_mean - i), 2) * c->freq_len[i];
+    st->res_len_sd = sqrt(variance / st->res_pass_num);
+    variance = 0.0;
+    for (i = 0; i <= 100000; i++)
+      if (c->freq_acc[i] > 0) variance += pow((st->res_accuracy_mean - i * 0.00001), 2) * c->freq_acc[i];
+    st->res_accuracy_sd = sqrt(variance / st->res_pass_num);
+  }
+  /* ref: print_simulation_stats :5543, :5557-5559 */
+  st->res_depth = (double)st->res_len_total / c->glen / c->pass_num;
+  st->res_sub_rate = (double)st->res_sub_num / st->res_len_total;
+  st->res_ins_rate = (double)st->res_ins_num / st->res_len_total;
+  st->res_del_rate = (double)st->res_del_num / st->res_len_total;
+  return 0;
+}
+
+/* ------------------------------------------------------------------ getters */
+const char *orc_out_reads(orc_ctx *c, int64_t *n) { *n = c->out_reads.n; return c->out_reads.p; }
+const char *orc_out_maf(orc_ctx *c, int64_t *n) { *n = c->out_maf.n; return c->out_maf.p; }
+void orc_get_stats(orc_ctx *c, orc_stats_t *st) { *st = c->st; }
+const orc_readinfo_t *orc_get_readinfo(orc_ctx *c, int64_t *n) { *n = c->info_n; return c->info; }
+const int32_t *orc_get_draw_log(orc_ctx *c, int64_t *n) { *n = c->rng.cur; return c->rng.rec; }
+int64_t orc_draws_consumed(orc_ctx *c) { return c->rng.cur; }
+const int64_t *orc_get_freq_len(orc_ctx *c, int64_t *n) { *n = c->freq_len_n; return c->freq_len; }
+const int64_t *orc_get_freq_accuracy(orc_ctx *c, int64_t *n) { *n = 100001; return c->freq_acc; }
+
+int64_t orc_get_table(orc_ctx *c, int which, int acc, int state, int32_t *out, int64_t cap) {
+  int64_t n = 0, k;
+  int err = (c->method == ORC_METHOD_ERR);
+  switch (which) {
+    case 0: n = c->len_rand_value; for (k = 0; k < n && k < cap; k++) out[k] = (int32_t)c->prob2len[k + 1]; break;
+    case 1: n = c->accuracy_rand_value; for (k = 0; k < n && k < cap; k++) out[k] = (int32_t)c->prob2acc[k + 1]; break;
+    case 2: n = c->mod_init[acc];
+      for (k = 0; k < n && k < cap; k++) out[k] = err ? c->er_init[acc][k + 1] : c->qs_init[acc][k + 1];
+      break;
+    case 3: n = c->mod_emis[acc][state];
+      for (k = 0; k < n && k < cap; k++) out[k] = err ? c->er_emis[acc][state][k + 1] : c->qs_emis[acc][state][k + 1];
+      break;
+    case 4: n = c->mod_tran[acc][state];
+      for (k = 0; k < n && k < cap; k++) out[k] = err ? c->er_tran[acc][state][k + 1] : c->qs_tran[acc][state][k + 1];
+      break;
+    case 5: n = c->mod_freq[acc]; for (k = 0; k < n && k < cap; k++) out[k] = c->qs_freq[acc][k + 1]; break;
+    default: break;
+  }
+  return n;
+}
+int orc_get_emis2del(orc_ctx *c, int acc, int state) { return (int)c->er_del[acc][state]; }
+void orc_get_thresholds(orc_ctx *c, int64_t sub[94], int64_t ins[94], int64_t del[94]) {
+  int i;
+  for (i = 0; i < 94; i++) { sub[i] = c->sub_thre[i]; ins[i] = c->ins_thre[i]; del[i] = c->del_thre[i]; }
+}
+int orc_model_exists(orc_ctx *c, int acc) { return c->exist[acc]; }
+void orc_model_range(orc_ctx *c, int *acc_min, int *acc_max, int *tab_acc_lo, int *tab_acc_hi) {
+  *acc_min = c->acc_min; *acc_max = c->acc_max; *tab_acc_lo = (int)c->tab_acc_lo; *tab_acc_hi = (int)c->tab_acc_hi;
+}

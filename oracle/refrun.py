@@ -1,0 +1,144 @@
+"""TEST INFRASTRUCTURE — run the UNMODIFIED reference binary (oracle/_ref/pbsim*), built by
+`make -C oracle ref` from /root/reference/src/pbsim.cpp, and collect what it wrote.
+
+The reference pipes its text through popen("gzip > f") / popen("samtools view -b -o f -")
+(pbsim.cpp:708-730); PATH shims (oracle/_ref/shims) turn both into `cat`, so the files
+hold the uncompressed FASTQ / SAM / MAF text the generator produced.
+"""
+import glob
+import os
+import shutil
+import subprocess
+import tempfile
+import time
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF_DIR = os.path.join(HERE, "_ref")
+REF_BIN = os.path.join(REF_DIR, "pbsim")
+REF_BIN_LOG = os.path.join(REF_DIR, "pbsim_logrand")
+SHIMS = os.path.join(REF_DIR, "shims")
+REF_SRC = "/root/reference/src/pbsim.cpp"
+REF_DATA = "/root/reference/data"
+
+
+def have_reference_binary():
+    return os.path.exists(REF_BIN) and os.path.exists(os.path.join(SHIMS, "gzip"))
+
+
+def build_reference():
+    """Compile the reference where it lies (only possible where /root/reference exists)."""
+    if not os.path.exists(REF_SRC):
+        return False
+    subprocess.check_call(["make", "-C", HERE, "ref"], stdout=subprocess.DEVNULL)
+    return True
+
+
+def synth_genome(seed, contigs, n_runs=0, hp_plants=0, lowercase_frac=0.0, iupac=0):
+    """Seeded synthetic genome: i.i.d. ACGT, optional N runs, planted homopolymers (2..15),
+    lower-case stretches and isolated IUPAC codes.  Returns [(name, bytes)]."""
+    rng = np.random.default_rng(seed)
+    out = []
+    alphabet = np.frombuffer(b"ACGT", dtype=np.uint8)
+    for name, n in contigs:
+        s = alphabet[rng.integers(0, 4, size=n)].copy()
+        for _ in range(hp_plants):
+            L = int(rng.integers(2, 16))
+            p = int(rng.integers(0, max(1, n - L)))
+            s[p:p + L] = alphabet[int(rng.integers(0, 4))]
+        for _ in range(n_runs):
+            L = int(rng.integers(1, 40))
+            p = int(rng.integers(0, max(1, n - L)))
+            s[p:p + L] = ord("N")
+        for _ in range(iupac):
+            p = int(rng.integers(0, n))
+            s[p] = b"RYKMSWBDHV"[int(rng.integers(0, 10))]
+        if lowercase_frac > 0:
+            k = int(n * lowercase_frac)
+            p = int(rng.integers(0, max(1, n - k)))
+            seg = s[p:p + k]
+            up = (seg >= 65) & (seg <= 90)
+            seg[up] += 32
+        out.append((name, s.tobytes()))
+    return out
+
+
+def write_fasta(path, contigs, width=70):
+    with open(path, "wb") as f:
+        for name, s in contigs:
+            f.write(b">" + name.encode() + b"\n")
+            for i in range(0, len(s), width):
+                f.write(s[i:i + width] + b"\n")
+
+
+def read_fasta(path):
+    """Restates how get_genome_inf/get_genome_seq see a FASTA (pbsim.cpp:914-965, :1014-1029):
+    header = text after '>' (truncated to 128 chars), body = lines concatenated as-is."""
+    import gzip
+    op = gzip.open if path.endswith(".gz") else open
+    contigs, name, parts = [], None, []
+    with op(path, "rb") as f:
+        for line in f:
+            line = line.rstrip(b"\n")
+            if line.startswith(b">"):
+                if name is not None:
+                    contigs.append((name, b"".join(parts)))
+                name, parts = line[1:129].decode(), []
+            else:
+                parts.append(line)
+    if name is not None:
+        contigs.append((name, b"".join(parts)))
+    return contigs
+
+
+def run_reference(args, logrand=False, keep_dir=None, real_gzip=False, timeout=3600):
+    """Run the reference with `args` (list, without --prefix) in a scratch dir.
+    Returns dict: stderr(str), files{name: bytes}, draws(int32 array)|None, marks(int64 array)|None,
+    wall(seconds)."""
+    work = keep_dir or tempfile.mkdtemp(prefix="pbsim_ref_")
+    os.makedirs(work, exist_ok=True)
+    done_dir = os.path.join(work, "done")
+    os.makedirs(done_dir, exist_ok=True)
+    env = dict(os.environ)
+    if not real_gzip:
+        env["PATH"] = SHIMS + ":" + env.get("PATH", "")
+    env["PBSIM_SHIM_DONE_DIR"] = done_dir
+    if logrand:
+        env["PBSIM_DRAW_LOG"] = os.path.join(work, "draws.bin")
+        env["PBSIM_MARK_LOG"] = os.path.join(work, "marks.bin")
+    exe = REF_BIN_LOG if logrand else REF_BIN
+    t0 = time.time()
+    p = subprocess.run([exe] + list(args) + ["--prefix", "out"], cwd=work, env=env,
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=timeout)
+    wall = time.time() - t0
+    stderr = p.stderr.decode(errors="replace")
+    res = {"stderr": stderr, "returncode": p.returncode, "wall": wall, "files": {}, "draws": None, "marks": None}
+    # the reference fclose()s its popen streams and exits without waiting for the children
+    # (pbsim.cpp:748-753): wait until every shim has finished writing
+    outs = [f for f in glob.glob(os.path.join(work, "out*")) if not f.endswith(".ref")]
+    if not real_gzip:
+        deadline = time.time() + 60
+        while len(os.listdir(done_dir)) < len(outs) and time.time() < deadline:
+            time.sleep(0.02)
+            outs = [f for f in glob.glob(os.path.join(work, "out*")) if not f.endswith(".ref")]
+    for f in sorted(glob.glob(os.path.join(work, "out*"))):
+        with open(f, "rb") as fh:
+            res["files"][os.path.basename(f)] = fh.read()
+    if logrand:
+        res["draws"] = np.fromfile(os.path.join(work, "draws.bin"), dtype=np.int32)
+        res["marks"] = np.fromfile(os.path.join(work, "marks.bin"), dtype=np.int64)
+    if keep_dir is None:
+        shutil.rmtree(work, ignore_errors=True)
+    return res
+
+
+def split_stats_blocks(stderr):
+    """{seq_num: text of ':::: Simulation stats (ref.N) ::::' block}"""
+    blocks = {}
+    parts = stderr.split(":::: Simulation stats (ref.")
+    for part in parts[1:]:
+        num = int(part.split(")")[0])
+        body = part.split(":::: System utilization")[0]
+        blocks[num] = ":::: Simulation stats (ref." + body
+    return blocks
