@@ -1,0 +1,214 @@
+/* libpbsim_cuda — C ABI of the B200 read-generation engine.
+ *
+ * The reference (yukiteruono/pbsim3) has no plugin / FFI interface: the hot path is reached
+ * through the internal seam  `int simulate_by_qshmm()` / `int simulate_by_errhmm()`
+ * (src/pbsim.cpp:1955, :3594), called by main() once per reference sequence
+ * (src/pbsim.cpp:699-754) and communicating through file-scope globals
+ * (src/pbsim.cpp:184-197).  This header is that seam made explicit: every entry point
+ * names the reference lines it replaces.  Plain pointers and sizes only.
+ *
+ *   host front end (pbsim_host_*)      replaces set_qshmm/set_errhmm/set_mut and the table
+ *                                      builders inlined in simulate_by_* (host, runs once)
+ *   engine         (pbsim_cuda_*)      replaces get_genome_seq's in-memory products, the
+ *                                      read loop, the per-position chain, record emission
+ *                                      and the statistics accumulation (GPU)
+ *
+ * All functions return 0 on success and a negative PBSIM_E_* code on failure;
+ * pbsim_cuda_last_error() returns the message the reference would have printed (or a
+ * CUDA error string).  One engine per GPU; calls on one engine come from one host thread.
+ * There is no CPU fallback: if no CUDA device is usable pbsim_cuda_create fails.
+ */
+#ifndef PBSIM_CUDA_H
+#define PBSIM_CUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PBSIM_ABI_VERSION 1
+
+#define PBSIM_E_INVALID   (-1)  /* bad argument / call order                            */
+#define PBSIM_E_CUDA      (-2)  /* CUDA runtime error                                   */
+#define PBSIM_E_IO        (-3)  /* cannot open / parse a file                           */
+#define PBSIM_E_PARAM     (-4)  /* "length/accuracy parameters are not appropriate"     */
+#define PBSIM_E_REPLAY    (-5)  /* replay log exhausted or inconsistent with the run    */
+#define PBSIM_E_OVERFLOW  (-6)  /* a read outgrew its scratch slot even after regrowth  */
+
+#define PBSIM_METHOD_QSHMM  1   /* --method qshmm  (METHOD_QS,  pbsim.cpp:37) */
+#define PBSIM_METHOD_ERRHMM 2   /* --method errhmm (METHOD_ERR, pbsim.cpp:38) */
+
+#define PBSIM_RNG_PHILOX 0      /* Philox4x32-10 keyed by (seed, sequence, read id); engine-native */
+#define PBSIM_RNG_REPLAY 1      /* consume a log of the reference's own rand() draws              */
+
+#define PBSIM_NQV 94            /* quality codes 0..93 (pbsim.cpp:191) */
+#define PBSIM_NACC 101          /* accuracies 0..100  (ACCURACY_MAX, pbsim.cpp:42) */
+
+/* ------------------------------------------------------------------------------------------
+ * Quantised model: exactly the integer lookup tables the reference builds at the top of every
+ * simulate_by_* call, 0-based (table[k] here is the reference's table[k+1]).
+ * ---------------------------------------------------------------------------------------- */
+
+/* one accuracy row of the HMM tables.
+ * qshmm : init2state / emis2qc / tran2state, resolution 100  (pbsim.cpp:2066-2144)
+ *         or, when the model has no such accuracy, freq2qc, resolution 1000 (:2145-2169)
+ * errhmm: init2state / emis2err / emis2del / tran2state, resolution 1000 (:3708-3789) */
+typedef struct {
+  int32_t exists;          /* exist_hmm[acc]                                              */
+  int32_t nstates;         /* rows 1..nstates are valid (row 0 unused)                    */
+  int32_t resolution;      /* row stride of tran[] / emis[]: 100 or 1000                  */
+  int32_t init_mod;        /* qc_rand_value_init / err_rand_value_init                    */
+  const uint8_t *init;     /* [init_mod] -> state                                         */
+  const int32_t *tran_mod; /* [nstates+1] row modulus                                     */
+  const uint8_t *tran;     /* [(nstates+1)*resolution] -> next state                      */
+  const int32_t *emis_mod; /* [nstates+1]                                                 */
+  const uint8_t *emis;     /* [(nstates+1)*resolution] -> QV (qshmm) | 0,1,2 (errhmm)     */
+  const int32_t *emis_del; /* errhmm: emis2del[state] on the 1..1000 scale, else NULL     */
+  int32_t freq_mod;        /* qshmm without model: qc_rand_value_freq                     */
+  const uint8_t *freq;     /* [freq_mod] -> QV                                            */
+} pbsim_hmm_row;
+
+typedef struct {
+  int32_t method;                  /* PBSIM_METHOD_*                                         */
+  int32_t pass_num;                /* --pass-num                                             */
+  int64_t len_min, len_max;        /* --length-min/max                                       */
+  double accuracy_mean;            /* after set_sim_param truncation; printed as rq:f (:2333) */
+  char id_prefix[128];             /* --id-prefix                                            */
+  /* length / accuracy samplers (pbsim.cpp:1991-2064) */
+  const int32_t *prob2len;         /* [len_rand_value]                                       */
+  int32_t len_rand_value;
+  const uint8_t *prob2accuracy;    /* [accuracy_rand_value]                                  */
+  int32_t accuracy_rand_value;
+  int32_t acc_lo, acc_hi;          /* accuracy_min / accuracy_max the sampler can return     */
+  /* set_mut thresholds on the 0..999999 scale (pbsim.cpp:5474-5479) and Phred probs (:546) */
+  int32_t sub_thre[PBSIM_NQV], ins_thre[PBSIM_NQV], del_thre[PBSIM_NQV];
+  double qc_prob[PBSIM_NQV];
+  /* HMM */
+  int32_t model_acc_min, model_acc_max; /* errhmm.acc_min / acc_max (pbsim.cpp:5665-5678)    */
+  pbsim_hmm_row rows[PBSIM_NACC];
+} pbsim_model;
+
+/* one reference sequence as get_genome_seq leaves it (pbsim.cpp:997-1068) */
+typedef struct {
+  const char *bases;       /* ASCII, any case (upper-cased on the device like :1035-1037)   */
+  int64_t len;
+  int32_t seq_num;         /* genome.num, 1-based; part of read ids and of the Philox key   */
+  double hp_del_bias[12];  /* genome.hp_del_bias[0..10] plus the two cells the reference    *
+                            * reads out of bounds ([0] for hp[-1], [11] for runs >= 11)     */
+} pbsim_sequence;
+
+typedef struct {
+  int32_t rng_mode;              /* PBSIM_RNG_*                                              */
+  uint32_t seed;                 /* --seed                                                   */
+  int64_t len_quota;             /* sim.len_quota = depth * genome.len (pbsim.cpp:705)       */
+  int64_t first_read;            /* number of reads already simulated for this sequence      *
+                                  * (0 for a whole-sequence run; >0 when read-id ranges are  *
+                                  * sharded across GPUs)                                     */
+  int64_t len_total_start;       /* emitted bases of those earlier reads                     */
+  int64_t max_reads;             /* stop after this many reads even if the quota is not met  *
+                                  * (0 = run to the quota)                                   */
+  int64_t batch_reads;           /* reads per chunk (0 = engine default)                     */
+  /* replay mode: the reference's draw stream and where every (read, pass) starts in it */
+  const int32_t *replay_draws;
+  int64_t replay_ndraws;
+  const int64_t *replay_starts;  /* [replay_nsubreads]                                       */
+  int64_t replay_nsubreads;
+} pbsim_run;
+
+/* a chunk = the records of a contiguous range of reads, in read order, exactly the bytes the
+ * reference fprintf()s to fp_fq|fp_sam and fp_maf (pbsim.cpp:2318-2383) */
+typedef struct {
+  const char *reads;        /* FASTQ (pass_num == 1) or SAM records (no @HD/@RG header)      */
+  int64_t reads_bytes;
+  const char *maf;
+  int64_t maf_bytes;
+  int64_t first_read, n_reads;   /* 1-based id of the first read, number of reads            */
+  int64_t bases;                 /* emitted read bases in this chunk, all passes             */
+  int32_t on_device;             /* 1: pointers are device pointers                          */
+} pbsim_chunk;
+
+/* sim.res_* (pbsim.cpp:63-70) after the run; histograms are freq_len / freq_accuracy (:195-196) */
+typedef struct {
+  int64_t res_num, res_pass_num;
+  int64_t res_len_total;
+  int64_t res_len_min, res_len_max;
+  int64_t res_sub_num, res_ins_num, res_del_num;
+  double accuracy_total;         /* running sum of per-read accuracies, in read order        */
+  double res_len_mean, res_len_sd;
+  double res_accuracy_mean, res_accuracy_sd;
+  double gen_seconds;            /* device time spent generating (CUDA events)               */
+  int64_t kernel_launches;       /* number of engine kernels launched during the run         */
+} pbsim_stats;
+
+typedef struct pbsim_engine pbsim_engine;
+
+/* ------------------------------------------------------------------------------------------
+ * engine
+ * ---------------------------------------------------------------------------------------- */
+int pbsim_cuda_abi_version(void);
+const char *pbsim_cuda_last_error(const pbsim_engine *e); /* e may be NULL: last create error */
+
+int pbsim_cuda_create(pbsim_engine **out, int device);
+void pbsim_cuda_destroy(pbsim_engine *e);
+
+/* replaces: the static tables of simulate_by_qshmm/errhmm + set_mut (host -> device upload) */
+int pbsim_cuda_set_model(pbsim_engine *e, const pbsim_model *m);
+
+/* replaces: get_genome_seq's genome.seq / genome.hp (pbsim.cpp:1032-1065): uploads the ASCII
+ * sequence, upper-cases, computes homopolymer lengths, packs to 2 bits per base */
+int pbsim_cuda_set_sequence(pbsim_engine *e, const pbsim_sequence *s);
+/* synthetic i.i.d. ACGT sequence generated on the device (benchmarks; no host transfer) */
+int pbsim_cuda_set_synthetic_sequence(pbsim_engine *e, int64_t len, int32_t seq_num, uint64_t seed);
+/* homopolymer histogram of the current sequence, genome.hpfreq[0..10] plus the aliased [11] */
+int pbsim_cuda_get_hpfreq(pbsim_engine *e, int64_t hpfreq[12]);
+
+/* replaces: one simulate_by_qshmm() / simulate_by_errhmm() call for the current sequence */
+int pbsim_cuda_simulate_begin(pbsim_engine *e, const pbsim_run *run);
+/* 1: chunk filled (host pointers into pinned staging, valid until the next call); 0: finished */
+int pbsim_cuda_next_chunk(pbsim_engine *e, pbsim_chunk *c);
+/* same, records stay in HBM (c->on_device = 1) */
+int pbsim_cuda_next_chunk_device(pbsim_engine *e, pbsim_chunk *c);
+/* stats; freq_len has len_max*2+2 cells, freq_accuracy 100001; either may be NULL */
+int pbsim_cuda_simulate_end(pbsim_engine *e, pbsim_stats *st, int64_t *freq_len, int64_t freq_len_cells,
+                            int64_t *freq_accuracy);
+/* device pointer + cell count of the int64 stats block {counters[16], freq_accuracy[100001],
+ * freq_len[2*len_max+2]} so that a multi-GPU driver can ncclAllReduce it in place */
+int pbsim_cuda_stats_device_block(pbsim_engine *e, void **dptr, int64_t *cells);
+
+/* debugging / tests: per-(read, pass) results of the last chunk, 8 int64 per subread:
+ * {read_id, pass, acc, offset, wlen, rlen, ncol, strand} */
+int pbsim_cuda_last_chunk_info(pbsim_engine *e, int64_t *out, int64_t cap_subreads, int64_t *n_subreads);
+
+/* ------------------------------------------------------------------------------------------
+ * host front end (no GPU needed)
+ * ---------------------------------------------------------------------------------------- */
+typedef struct pbsim_host_model pbsim_host_model;
+
+/* sim_t subset that shapes the tables; accuracy_mean must already be truncated like
+ * set_sim_param does (pbsim.cpp:1660) */
+typedef struct {
+  int32_t method;
+  int32_t pass_num;
+  int64_t len_min, len_max;
+  double len_mean, len_sd;
+  double accuracy_mean;
+  int64_t sub_ratio, ins_ratio, del_ratio;
+  char id_prefix[128];
+} pbsim_host_params;
+
+/* replaces set_qshmm / set_errhmm (pbsim.cpp:5570-5714) + set_mut (:5471) + the table builders
+ * (:1991-2170, :3633-3789).  On failure *err (if not NULL) receives a static message. */
+int pbsim_host_model_load(pbsim_host_model **out, const pbsim_host_params *p, const char *model_path,
+                          const char **err);
+const pbsim_model *pbsim_host_model_get(const pbsim_host_model *m);
+void pbsim_host_model_free(pbsim_host_model *m);
+
+/* main()'s --hp-del-bias handling (pbsim.cpp:673-697): hpfreq accumulated over all sequences ->
+ * bias[1..10]; bias[0]/bias[11] are the out-of-bounds cells (see DESIGN.md "reference quirks") */
+void pbsim_host_hp_del_bias(double hp_del_bias_opt, const int64_t hpfreq[12], double bias[12]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,245 @@
+// Device image of a pbsim_model: per-accuracy table blobs in the layout sim_core.cuh reads.
+// Built on the host by the engine (engine.cu) when pbsim_cuda_set_model / set_sequence is called.
+// Table semantics: see QsView / ErView in sim_core.cuh.
+#pragma once
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/pbsim_cuda.h"
+
+namespace pb {
+
+constexpr uint32_t kQsRows = 51;  // states 0..50, row 0 = init2state
+
+struct AccEntry {          // one per accuracy 0..100, mirrored on the device
+  uint32_t blob_off;       // byte offset of the table blob inside ModelImage::blob (16-aligned)
+  uint32_t blob_bytes;     // multiple of 16 (TMA bulk copy size)
+  uint32_t bias_off;       // errhmm: offset (in uint16 cells) into the per-sequence bias table
+  uint32_t nstates;
+  uint32_t has_model;      // qshmm: 1 = HMM tables, 0 = freq2qc
+  uint32_t init_mod;
+  uint32_t freq_mod;
+  uint32_t mode;           // errhmm: 0 exact, 1 below model range, 2 above, 3 verbatim (acc 100)
+  uint32_t rate_mag;
+  uint32_t valid;          // 1 if reads of this accuracy can be simulated
+  uint32_t table_acc;      // errhmm: accuracy whose tables drive the chain
+  uint32_t pad;
+};
+
+// blob layouts (all sections 16-byte aligned)
+struct QsBlobLayout {
+  static constexpr uint32_t t2_off = 0;                                   // uint16[51*100]
+  static constexpr uint32_t emis_off = ((kQsRows * 100 * 2 + 15) / 16) * 16;  // uint8[51*100]
+  static constexpr uint32_t emod_off = emis_off + ((kQsRows * 100 + 15) / 16) * 16;  // uint8[51]
+  static constexpr uint32_t bytes = emod_off + 64;
+  static constexpr uint32_t freq_bytes = 1008;                            // uint8[1000] padded
+};
+
+inline uint32_t er_blob_bytes(uint32_t nst, uint32_t *t2_off, uint32_t *emis_off, uint32_t *emod_off) {
+  const uint32_t rows = nst + 1;
+  uint32_t o = 0;
+  *t2_off = o;   o += ((rows * 1000 * 2 + 15) / 16) * 16;
+  *emis_off = o; o += ((rows * 1000 + 15) / 16) * 16;
+  *emod_off = o; o += ((rows * 2 + 15) / 16) * 16;
+  return o;
+}
+
+struct ModelImage {
+  int method = 0;
+  std::vector<uint8_t> blob;
+  AccEntry acc[PBSIM_NACC];
+  // per-sequence, bias dependent
+  std::vector<uint32_t> qs_thr;      // [94*4]
+  std::vector<uint32_t> qs_thr_hp;   // [94*12]
+  std::vector<uint16_t> er_bias;     // per table accuracy: edel[rows] then edel_hp[rows*12]
+  std::string error;
+  bool uniform_bias = true;          // hp_del_bias[1..10] all exactly 1
+
+  bool build(const pbsim_model &m) {
+    method = m.method;
+    blob.clear();
+    std::memset(acc, 0, sizeof acc);
+    uint32_t bias_cells = 0;
+    for (int a = 0; a < PBSIM_NACC; ++a) acc[a].table_acc = a;
+    if (method == PBSIM_METHOD_QSHMM) {
+      for (int a = m.acc_lo; a <= m.acc_hi; ++a) {
+        if (a < 0 || a >= PBSIM_NACC) continue;
+        const pbsim_hmm_row &r = m.rows[a];
+        AccEntry &e = acc[a];
+        e.blob_off = (uint32_t)blob.size();
+        if (r.exists) {
+          if (!r.tran || !r.emis || !r.init || r.nstates + 1 > (int)kQsRows || r.resolution != 100) {
+            error = "qshmm row malformed";
+            return false;
+          }
+          blob.resize(blob.size() + QsBlobLayout::bytes, 0);
+          uint8_t *b = blob.data() + e.blob_off;
+          uint16_t *t2 = reinterpret_cast<uint16_t *>(b + QsBlobLayout::t2_off);
+          uint8_t *em = b + QsBlobLayout::emis_off;
+          uint8_t *emod = b + QsBlobLayout::emod_off;
+          auto tmod = [&](int s) -> uint32_t {
+            int v = (s >= 1 && s <= r.nstates) ? r.tran_mod[s] : 1;
+            return (uint32_t)(v < 1 ? 1 : (v > 255 ? 255 : v));
+          };
+          for (int k = 0; k < r.init_mod && k < 100; ++k) t2[k] = (uint16_t)(r.init[k] | (tmod(r.init[k]) << 8));
+          for (int s = 1; s <= r.nstates; ++s) {
+            for (int k = 0; k < 100; ++k) {
+              const uint8_t nx = r.tran[s * 100 + k];
+              t2[s * 100 + k] = (uint16_t)(nx | (tmod(nx) << 8));
+              em[s * 100 + k] = r.emis[s * 100 + k];
+            }
+            emod[s] = (uint8_t)(r.emis_mod[s] < 1 ? 1 : r.emis_mod[s]);
+          }
+          emod[0] = 1;
+          e.blob_bytes = QsBlobLayout::bytes;
+          e.has_model = 1;
+          e.nstates = (uint32_t)r.nstates;
+          e.init_mod = (uint32_t)(r.init_mod < 1 ? 1 : r.init_mod);
+          e.valid = 1;
+        } else {
+          if (!r.freq || r.freq_mod < 1) {
+            error = "qshmm freq row missing";
+            return false;
+          }
+          blob.resize(blob.size() + QsBlobLayout::freq_bytes, 0);
+          std::memcpy(blob.data() + e.blob_off, r.freq, (size_t)r.freq_mod);
+          e.blob_bytes = QsBlobLayout::freq_bytes;
+          e.has_model = 0;
+          e.freq_mod = (uint32_t)r.freq_mod;
+          e.valid = 1;
+        }
+      }
+    } else {
+      // blobs for modelled accuracies inside the sampler's range
+      for (int a = m.acc_lo; a <= m.acc_hi; ++a) {
+        if (a < 0 || a >= PBSIM_NACC) continue;
+        const pbsim_hmm_row &r = m.rows[a];
+        if (!r.exists || r.nstates < 1 || !r.tran) continue;
+        if (r.resolution != 1000 || r.nstates > 50) {
+          error = "errhmm row malformed";
+          return false;
+        }
+        AccEntry &e = acc[a];
+        uint32_t t2o, emo, emodo;
+        const uint32_t bytes = er_blob_bytes((uint32_t)r.nstates, &t2o, &emo, &emodo);
+        e.blob_off = (uint32_t)blob.size();
+        blob.resize(blob.size() + bytes, 0);
+        uint8_t *b = blob.data() + e.blob_off;
+        uint16_t *t2 = reinterpret_cast<uint16_t *>(b + t2o);
+        uint8_t *em = b + emo;
+        uint16_t *emod = reinterpret_cast<uint16_t *>(b + emodo);
+        auto tmod = [&](int s) -> uint32_t {
+          int v = (s >= 1 && s <= r.nstates) ? r.tran_mod[s] : 1;
+          return (uint32_t)(v < 1 ? 1 : (v > 1000 ? 1000 : v));
+        };
+        for (int k = 0; k < r.init_mod && k < 1000; ++k) t2[k] = (uint16_t)(r.init[k] | (tmod(r.init[k]) << 6));
+        for (int s = 1; s <= r.nstates; ++s) {
+          for (int k = 0; k < 1000; ++k) {
+            const uint8_t nx = r.tran[s * 1000 + k];
+            t2[s * 1000 + k] = (uint16_t)(nx | (tmod(nx) << 6));
+            em[s * 1000 + k] = r.emis[s * 1000 + k];
+          }
+          emod[s] = (uint16_t)(r.emis_mod[s] < 0 ? 0 : r.emis_mod[s]);
+        }
+        e.blob_bytes = bytes;
+        e.nstates = (uint32_t)r.nstates;
+        e.init_mod = (uint32_t)(r.init_mod < 1 ? 1 : r.init_mod);
+        e.bias_off = bias_cells;
+        bias_cells += (((uint32_t)(r.nstates + 1) * 13u + 7u) / 8u) * 8u;  // keep regions 16-byte aligned
+        e.valid = 1;
+      }
+      // every accuracy the sampler can return borrows the tables of a modelled one (:3852-3926)
+      for (int a = m.acc_lo; a <= m.acc_hi; ++a) {
+        if (a < 0 || a >= PBSIM_NACC) continue;
+        AccEntry &e = acc[a];
+        if (a == 100) {  // verbatim copy (:3837-3845)
+          e.valid = 1;
+          e.mode = 3;
+          e.blob_bytes = 0;
+          continue;
+        }
+        if (m.rows[a].exists) {
+          e.mode = 0;
+          continue;
+        }
+        int ta;
+        if (a < m.model_acc_min) {
+          ta = m.model_acc_min;
+          e.mode = 1;
+          e.rate_mag = (uint32_t)(int)((double)(m.model_acc_min - a) / m.model_acc_min * 100);
+        } else {
+          ta = m.model_acc_max;
+          e.mode = 2;
+          e.rate_mag = (uint32_t)(int)((double)(a - m.model_acc_max) / (100 - m.model_acc_max) * 100);
+        }
+        if (ta < 0 || ta >= PBSIM_NACC || !acc[ta].valid || acc[ta].mode == 3) {
+          // the reference would read tables it never built (undefined); refuse instead
+          e.valid = 0;
+          continue;
+        }
+        const uint32_t mode = e.mode, mag = e.rate_mag;
+        e = acc[ta];
+        e.mode = mode;
+        e.rate_mag = mag;
+        e.table_acc = (uint32_t)ta;
+      }
+      er_bias.assign(bias_cells, 0);
+    }
+    return true;
+  }
+
+  // thresholds that depend on genome.hp_del_bias (per sequence)
+  void apply_bias(const pbsim_model &m, const double bias[12]) {
+    uniform_bias = true;
+    for (int h = 1; h <= 10; ++h)
+      if (bias[h] != 1.0) uniform_bias = false;
+    if (method == PBSIM_METHOD_QSHMM) {
+      qs_thr.assign(PBSIM_NQV * 4, 0);
+      qs_thr_hp.assign(PBSIM_NQV * 12, 0);
+      for (int q = 0; q < PBSIM_NQV; ++q) {
+        uint32_t mx = 0;
+        for (int h = 0; h < 12; ++h) {
+          // reference test: rand_value < del_thre[qv] * hp_del_bias[hp]   (long < double, :2272)
+          const double x = (double)m.del_thre[q] * bias[h];
+          double c = std::ceil(x);
+          if (!(c >= 0)) c = 0;
+          if (c > 1000000.0) c = 1000000.0;
+          const uint32_t t = (uint32_t)c;
+          qs_thr_hp[q * 12 + h] = t;
+          if (t > mx) mx = t;
+        }
+        qs_thr[q * 4 + 0] = (uint32_t)m.sub_thre[q];
+        qs_thr[q * 4 + 1] = (uint32_t)m.ins_thre[q];
+        qs_thr[q * 4 + 2] = mx;
+        qs_thr[q * 4 + 3] = qs_thr_hp[q * 12 + 0];
+      }
+    } else {
+      for (int a = 0; a < PBSIM_NACC; ++a) {
+        const AccEntry &e = acc[a];
+        if (!e.valid || e.mode == 3 || e.table_acc != (uint32_t)a) continue;
+        const pbsim_hmm_row &r = m.rows[a];
+        uint16_t *edel = er_bias.data() + e.bias_off;
+        uint16_t *edel_hp = edel + (e.nstates + 1);
+        for (uint32_t s = 0; s <= e.nstates; ++s) {
+          uint32_t mx = 0;
+          for (int h = 0; h < 12; ++h) {
+            // reference test: index <= emis2del[state] * hp_del_bias[hp]   (long <= double, :3862)
+            const double x = (s >= 1 ? (double)r.emis_del[s] : 0.0) * bias[h];
+            double f = std::floor(x);
+            if (!(f >= 0)) f = 0;
+            if (f > 65535.0) f = 65535.0;
+            const uint32_t t = (uint32_t)f;
+            edel_hp[s * 12 + h] = (uint16_t)t;
+            if (t > mx) mx = t;
+          }
+          edel[s] = (uint16_t)mx;
+        }
+      }
+    }
+  }
+};
+
+}  // namespace pb

@@ -1,0 +1,459 @@
+// Per-read simulation core of the B200 engine: read planning, the qshmm quality chain and the
+// errhmm error-state chain, written once for both draw sources (PHILOX / REPLAY).
+//
+// Pass 1 of the engine: one GPU thread runs the inherently sequential chain of one (read, pass)
+// and emits a compact, fixed-rate EVENT STREAM instead of text:
+//     qshmm : one uint16 per read position   qv | kind<<7 | info<<9 | ndel<<12
+//     errhmm: one uint8  per alignment column kind | info<<2
+// plus a checkpoint (column, ref offset, read offset) every PB_TILE entries so that pass 2
+// (emit.cuh) can format any tile of any read independently with coalesced loads and stores.
+// Reads that touch no non-ACGT base and no bias-relevant homopolymer never look at the genome
+// here: substitution / insertion choices are recorded as indices and resolved in pass 2.
+//
+// Reference behaviour restated (yukiteruono/pbsim3 src/pbsim.cpp):
+//     read planning            :2174-2190 (= :3793-3809)
+//     qshmm per-position step  :2213-2282
+//     errhmm per-column step   :3836-3975
+//
+// The file compiles as plain C++ as well (tests/hostsim builds it with g++ to check the logic
+// against the oracle without a GPU); the product only ever runs it inside CUDA kernels.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define PB_HD __host__ __device__ __forceinline__
+#define PB_HD_NOINLINE __host__ __device__ __noinline__
+#else
+#define PB_HD inline
+#define PB_HD_NOINLINE
+#endif
+
+#define PB_TILE 1024u        // entries per pass-2 tile / checkpoint interval
+#define PB_QS_ROW 100u       // qshmm table resolution
+#define PB_ER_ROW 1000u      // errhmm table resolution
+#define PB_KIND_MATCH 0u
+#define PB_KIND_SUB 1u
+#define PB_KIND_INS 2u
+#define PB_KIND_DEL 3u       // errhmm column kind; in the qshmm stream kind 3 marks a continuation entry
+#define PB_QS_DEL_SAT 15u    // qshmm entry: 15 deletions + "continuation entry follows"
+#define PB_QS_CONT_SAT 16383u
+
+namespace pb {
+
+PB_HD uint32_t mulhi32(uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+  return __umulhi(a, b);
+#else
+  return (uint32_t)(((uint64_t)a * b) >> 32);
+#endif
+}
+
+PB_HD uint64_t mulhi64(uint64_t a, uint64_t b) {
+#if defined(__CUDA_ARCH__)
+  return __umul64hi(a, b);
+#else
+  return (uint64_t)(((unsigned __int128)a * b) >> 64);
+#endif
+}
+
+// Philox4x32-10 (Salmon et al., SC'11).  Draw addressing:
+//   key = (seed, sequence number)   counter = (position, block | pass << 16, read id, domain)
+struct Philox {
+  uint32_t k0, k1;
+  PB_HD void block(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t out[4]) const {
+    uint32_t a = k0, b = k1;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+      const uint32_t h0 = mulhi32(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+      const uint32_t h1 = mulhi32(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+      c0 = h1 ^ c1 ^ a;
+      c1 = l1;
+      c2 = h0 ^ c3 ^ b;
+      c3 = l0;
+      a += 0x9E3779B9u;
+      b += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// draw sources.  Purpose-named draws: REPLAY consumes the reference's rand() stream in the
+// reference's order (`rand() % m`); PHILOX maps every purpose to a fixed word of the block
+// addressed by the position, so results do not depend on scheduling or GPU count.
+// ---------------------------------------------------------------------------------------------
+struct PhiloxDraw {
+  Philox ph;
+  uint32_t read_id, pass, pos;
+  uint32_t w[4];
+  PB_HD void plan_begin() { ph.block(0u, 0u, read_id, 0u, w); }
+  PB_HD uint32_t plan_len(uint32_t m) { return mulhi32(w[0], m); }
+  PB_HD uint32_t plan_acc(uint32_t m) { return mulhi32(w[1], m); }
+  PB_HD uint32_t plan_off(uint32_t span) { return (uint32_t)mulhi64(((uint64_t)w[2] << 32) | w[3], span); }
+  PB_HD void begin(uint32_t p) {
+    pos = p;
+    ph.block(p, pass << 16, read_id, 1u, w);
+  }
+  PB_HD uint32_t w0(uint32_t m) { return mulhi32(w[0], m); }
+  PB_HD uint32_t w1(uint32_t m) { return mulhi32(w[1], m); }
+  PB_HD uint32_t w2(uint32_t m) { return mulhi32(w[2], m); }
+  PB_HD uint32_t w3(uint32_t m) { return mulhi32(w[3], m); }
+  PB_HD uint32_t choice3() { return ((w[0] & 0xFFFu) * 3u) >> 12; }
+  PB_HD uint32_t choice4() { return (w[0] >> 12) & 3u; }
+  PB_HD uint32_t choice8() { return w[1] & 7u; }
+  PB_HD uint32_t mag3() { return (((w[3] & 0xFFFu) * 3u) >> 12) + 1u; }
+  // j-th deletion draw after the current position, on the 0..999999 scale
+  PB_HD uint32_t del(uint32_t j) {
+    if (j == 0) return mulhi32(w[3], 1000000u);
+    uint32_t x[4];
+    ph.block(pos, (1u + (j - 1u) / 4u) | (pass << 16), read_id, 1u, x);
+    return mulhi32(x[(j - 1u) & 3u], 1000000u);
+  }
+  PB_HD uint32_t consumed() const { return 0; }
+};
+
+struct ReplayDraw {
+  const int32_t *log;  // the reference's draws
+  int64_t cur, end, start;
+  PB_HD uint32_t next() {
+    const uint32_t v = (cur < end) ? (uint32_t)log[cur] : 0u;
+    ++cur;
+    return v;
+  }
+  PB_HD void plan_begin() {}
+  PB_HD uint32_t plan_len(uint32_t m) { return next() % m; }
+  PB_HD uint32_t plan_acc(uint32_t m) { return next() % m; }
+  PB_HD uint32_t plan_off(uint32_t span) { return next() % span; }
+  PB_HD void begin(uint32_t) {}
+  PB_HD uint32_t w0(uint32_t m) { return next() % m; }
+  PB_HD uint32_t w1(uint32_t m) { return next() % m; }
+  PB_HD uint32_t w2(uint32_t m) { return next() % m; }
+  PB_HD uint32_t w3(uint32_t m) { return next() % m; }
+  PB_HD uint32_t choice3() { return next() % 3u; }
+  PB_HD uint32_t choice4() { return next() % 4u; }
+  PB_HD uint32_t choice8() { return next() % 8u; }
+  PB_HD uint32_t mag3() { return next() % 3u + 1u; }
+  PB_HD uint32_t del(uint32_t) { return next() % 1000000u; }
+  PB_HD uint32_t consumed() const { return (uint32_t)(cur - start); }
+};
+
+// ---------------------------------------------------------------------------------------------
+// read planning
+// ---------------------------------------------------------------------------------------------
+struct PlanTables {
+  const int32_t *prob2len;
+  const uint8_t *prob2acc;
+  uint32_t len_rand_value, acc_rand_value;
+  uint32_t len_min;
+};
+
+struct ReadPlan {
+  uint32_t raw_len;  // prob2len draw before any clipping (the quota test uses it, :2176)
+  uint32_t wlen;     // mut.len
+  uint32_t offset;   // mut.offset
+  uint32_t acc;      // mut.acc
+};
+
+// clip_room < 0: no quota clipping (bulk batches); otherwise quota - len_total for this read
+template <class Draw>
+PB_HD ReadPlan plan_read(const PlanTables &T, Draw &d, uint32_t glen, int64_t clip_room) {
+  ReadPlan p;
+  d.plan_begin();
+  uint32_t len = (uint32_t)T.prob2len[d.plan_len(T.len_rand_value)];
+  p.raw_len = len;
+  if (clip_room >= 0 && (int64_t)len > clip_room) {
+    len = (uint32_t)clip_room;
+    if (len < T.len_min) len = T.len_min;
+  }
+  p.acc = T.prob2acc[d.plan_acc(T.acc_rand_value)];
+  if (len >= glen) {
+    p.offset = 0;
+    len = glen;
+  } else {
+    p.offset = d.plan_off(glen - len + 1u);
+  }
+  p.wlen = len;
+  return p;
+}
+
+// ---------------------------------------------------------------------------------------------
+// slow-path genome access (only reads whose window touches a non-ACGT base or a homopolymer
+// with a non-unit deletion bias, or every read when --hp-del-bias != 1)
+// ---------------------------------------------------------------------------------------------
+struct WindowRef {
+  const uint8_t *ascii;   // upper-cased sequence
+  const uint8_t *hp4;     // 4-bit homopolymer length per base (low nibble = even index)
+  uint32_t offset, wlen;
+  uint32_t minus;         // 1: window is the reverse complement
+  PB_HD uint32_t gidx(uint32_t r) const { return minus ? offset + wlen - 1u - r : offset + r; }
+  PB_HD bool nonacgt(uint32_t r) const {
+    const uint8_t c = ascii[gidx(r)];
+    return !(c == 'A' || c == 'C' || c == 'G' || c == 'T');
+  }
+  PB_HD uint32_t hp(uint32_t r) const {
+    const uint32_t g = gidx(r);
+    return (hp4[g >> 1] >> ((g & 1u) * 4u)) & 15u;
+  }
+};
+
+struct SubreadResult {
+  uint32_t n_entries, rlen, ncol, nsub, nins, ndel;
+  uint32_t overflow;
+  double accuracy;
+};
+
+struct Ckpt {
+  uint32_t col, ref, read, pad;
+};
+
+// ---------------------------------------------------------------------------------------------
+// qshmm
+// ---------------------------------------------------------------------------------------------
+// Tables of ONE accuracy (staged in shared memory by the kernel).
+//   t2[s*100 + k]  : next state | modulus(next state) << 8 ; row 0 is init2state
+//   emis[s*100 + k]: QV ; emod[s] its modulus
+//   freq[k]        : QV when the model has no such accuracy (resolution 1000)
+//   thr[qv]        : {sub_thre, ins_thre, max_hp del threshold, del threshold for hp[-1]}
+//   thr_hp[qv*12+h]: exact deletion threshold ceil(del_thre[qv] * hp_del_bias[h])
+struct QsView {
+  const uint16_t *t2;
+  const uint8_t *emis;
+  const uint8_t *emod;
+  const uint8_t *freq;
+  uint32_t has_model, init_mod, freq_mod;
+  const uint32_t *thr;      // [94*4]
+  const uint32_t *thr_hp;   // [94*12]
+  const double *qc_prob;    // [94]
+};
+
+struct QsSink {
+  uint16_t *ev;
+  Ckpt *ck;
+  uint32_t n, cap;
+  uint64_t acc;
+  PB_HD void init(uint16_t *e, Ckpt *c, uint32_t capacity) { ev = e; ck = c; n = 0; cap = capacity; acc = 0; }
+  PB_HD bool full() const { return n + 2u > cap; }
+  PB_HD void checkpoint(uint32_t col, uint32_t ref, uint32_t read) {
+    if ((n & (PB_TILE - 1u)) == 0u) {
+      Ckpt c; c.col = col; c.ref = ref; c.read = read; c.pad = 0;
+      ck[n / PB_TILE] = c;
+    }
+  }
+  PB_HD void push(uint32_t e) {
+    acc |= (uint64_t)e << (16u * (n & 3u));
+    ++n;
+    if ((n & 3u) == 0u) {
+      *reinterpret_cast<uint64_t *>(ev + n - 4u) = acc;
+      acc = 0;
+    }
+  }
+  PB_HD void flush() {
+    const uint32_t rem = n & 3u;
+    for (uint32_t i = 0; i < rem; ++i) ev[n - rem + i] = (uint16_t)(acc >> (16u * i));
+  }
+};
+
+template <class Draw>
+PB_HD void qshmm_simulate(const QsView &T, Draw &d, const WindowRef &win, bool slow, uint32_t wlen,
+                          QsSink &sink, SubreadResult &res) {
+  uint32_t R = 0, P = 0, C = 0;
+  uint32_t state = 0, mod = T.init_mod;
+  uint32_t nsub = 0, nins = 0, ndel = 0;
+  double prob = 0.0;
+  res.overflow = 0;
+  while (R < wlen) {
+    if (sink.full()) { res.overflow = 1; break; }
+    sink.checkpoint(C, R, P);
+    d.begin(P);
+    uint32_t qv;
+    if (T.has_model) {
+      const uint32_t t = T.t2[state * PB_QS_ROW + d.w0(mod)];
+      state = t & 0xFFu;
+      mod = t >> 8;
+      qv = T.emis[state * PB_QS_ROW + d.w1(T.emod[state])];
+    } else {
+      qv = T.freq[d.w0(T.freq_mod)];
+    }
+    prob += T.qc_prob[qv];
+    const uint32_t th_sub = T.thr[qv * 4u + 0u], th_ins = T.thr[qv * 4u + 1u];
+    const uint32_t th_del = T.thr[qv * 4u + 2u], th_del0 = T.thr[qv * 4u + 3u];
+    const uint32_t r = d.w2(1000000u);
+    uint32_t kind, info;
+    if (r < th_sub) {
+      kind = PB_KIND_SUB;
+      ++nsub;
+      info = d.choice3();
+      if (slow && win.nonacgt(R)) info = d.choice4();
+      ++R;
+    } else if (r < th_ins) {
+      kind = PB_KIND_INS;
+      ++nins;
+      info = d.choice8();
+    } else {
+      kind = PB_KIND_MATCH;
+      info = 0;
+      ++R;
+    }
+    ++P;
+    ++C;
+    uint32_t nd = 0;
+    while (R < wlen) {
+      const uint32_t rd = d.del(nd);
+      bool hit = rd < th_del;
+      if (hit) {
+        if (R == 0u) hit = rd < th_del0;                                   // mut.hp[-1] (:2269)
+        else if (slow) hit = rd < T.thr_hp[qv * 12u + win.hp(R - 1u)];
+      }
+      if (!hit) break;
+      ++nd;
+      ++R;
+    }
+    ndel += nd;
+    C += nd;
+    const uint32_t base = qv | (kind << 7) | (info << 9);
+    if (nd < PB_QS_DEL_SAT) {
+      sink.push(base | (nd << 12));
+    } else {
+      sink.push(base | (PB_QS_DEL_SAT << 12));
+      uint32_t rest = nd - PB_QS_DEL_SAT;
+      for (;;) {  // continuation entries: 14-bit counts, 16383 = "more follows"
+        if (sink.full()) { res.overflow = 1; break; }
+        sink.checkpoint(C, R, P);
+        const uint32_t c = rest < PB_QS_CONT_SAT ? rest : PB_QS_CONT_SAT;
+        sink.push((c & 0x7Fu) | (3u << 7) | ((c >> 7) << 9));
+        if (c < PB_QS_CONT_SAT) break;
+        rest -= PB_QS_CONT_SAT;
+      }
+      if (res.overflow) break;
+    }
+  }
+  sink.flush();
+  res.n_entries = sink.n;
+  res.rlen = P;
+  res.ncol = C;
+  res.nsub = nsub;
+  res.nins = nins;
+  res.ndel = ndel;
+  res.accuracy = 1.0 - (prob / (double)P);  // :2313 (accuracy from the emitted qualities)
+}
+
+// ---------------------------------------------------------------------------------------------
+// errhmm
+// ---------------------------------------------------------------------------------------------
+// Tables of the accuracy that drives the chain (the read's own, or the model's nearest one):
+//   t2[s*1000 + k]  : next state | modulus(next state) << 6 ; row 0 is init2state
+//   emis[s*1000 + k]: 0 match, 1 substitution, 2 insertion ; emod[s] its modulus (0: uniform %3)
+//   edel[s]         : max over hp of floor(emis2del[s] * hp_del_bias[hp])  (1..1000 scale)
+//   edel_hp[s*12+h] : exact floor(emis2del[s] * hp_del_bias[h])
+//   mode            : 0 modelled accuracy, 1 below the model range (errors added, :3892-3899),
+//                     2 above it (errors removed, :3920-3925), 3 accuracy 100: verbatim copy (:3837)
+struct ErView {
+  const uint16_t *t2;
+  const uint8_t *emis;
+  const uint16_t *emod;
+  const uint16_t *edel;
+  const uint16_t *edel_hp;
+  uint32_t init_mod, mode, rate_mag;
+};
+
+struct ErSink {
+  uint8_t *ev;
+  Ckpt *ck;
+  uint32_t n, cap;
+  uint64_t acc;
+  PB_HD void init(uint8_t *e, Ckpt *c, uint32_t capacity) { ev = e; ck = c; n = 0; cap = capacity; acc = 0; }
+  PB_HD bool full() const { return n + 1u > cap; }
+  PB_HD void checkpoint(uint32_t col, uint32_t ref, uint32_t read) {
+    if ((n & (PB_TILE - 1u)) == 0u) {
+      Ckpt c; c.col = col; c.ref = ref; c.read = read; c.pad = 0;
+      ck[n / PB_TILE] = c;
+    }
+  }
+  PB_HD void push(uint32_t e) {
+    acc |= (uint64_t)e << (8u * (n & 7u));
+    ++n;
+    if ((n & 7u) == 0u) {
+      *reinterpret_cast<uint64_t *>(ev + n - 8u) = acc;
+      acc = 0;
+    }
+  }
+  PB_HD void flush() {
+    const uint32_t rem = n & 7u;
+    for (uint32_t i = 0; i < rem; ++i) ev[n - rem + i] = (uint8_t)(acc >> (8u * i));
+  }
+};
+
+template <class Draw>
+PB_HD void errhmm_simulate(const ErView &T, Draw &d, const WindowRef &win, bool slow, uint32_t wlen,
+                           ErSink &sink, SubreadResult &res) {
+  uint32_t R = 0, P = 0, C = 0;
+  uint32_t state = 0, mod = T.init_mod;
+  uint32_t nsub = 0, nins = 0, ndel = 0;
+  res.overflow = 0;
+  if (T.mode == 3u) {
+    while (R < wlen) {
+      if (sink.full()) { res.overflow = 1; break; }
+      sink.checkpoint(C, R, P);
+      sink.push(PB_KIND_MATCH);
+      ++R; ++P; ++C;
+    }
+  } else {
+    while (R < wlen) {
+      if (sink.full()) { res.overflow = 1; break; }
+      sink.checkpoint(C, R, P);
+      d.begin(C);
+      const uint32_t row = (P == 0u) ? 0u : state;           // init is re-drawn while read_offset == 0 (:3853)
+      const uint32_t m = (P == 0u) ? T.init_mod : mod;
+      const uint32_t t = T.t2[row * PB_ER_ROW + d.w0(m)];
+      state = t & 63u;
+      mod = t >> 6;
+      const uint32_t x = d.w1(1000u) + 1u;
+      bool isdel = x <= T.edel[state];
+      if (isdel && slow) isdel = x <= T.edel_hp[state * 12u + win.hp(R)];   // hp at the current base (:3860)
+      uint32_t kind;
+      if (isdel) {
+        kind = PB_KIND_DEL;
+      } else {
+        const uint32_t em = T.emod[state];
+        kind = (em == 0u) ? d.w2(3u) : (uint32_t)T.emis[state * PB_ER_ROW + d.w2(em)];
+      }
+      if (T.mode == 1u) {
+        if (kind == PB_KIND_MATCH) {
+          if (d.w3(100u) + 1u <= T.rate_mag) kind = d.mag3();
+        }
+      } else if (T.mode == 2u) {
+        if (kind != PB_KIND_MATCH) {
+          if (d.w3(100u) + 1u <= T.rate_mag) kind = PB_KIND_MATCH;
+        }
+      }
+      uint32_t info = 0;
+      if (kind == PB_KIND_MATCH) {
+        ++R; ++P;
+      } else if (kind == PB_KIND_SUB) {
+        ++nsub;
+        info = d.choice3();
+        if (slow && win.nonacgt(R)) info = d.choice4();
+        ++R; ++P;
+      } else if (kind == PB_KIND_INS) {
+        ++nins;
+        info = d.choice8();
+        ++P;
+      } else {
+        ++ndel;
+        ++R;
+      }
+      ++C;
+      sink.push(kind | (info << 2));
+    }
+  }
+  sink.flush();
+  res.n_entries = sink.n;
+  res.rlen = P;
+  res.ncol = C;
+  res.nsub = nsub;
+  res.nins = nins;
+  res.ndel = ndel;
+  res.accuracy = 1.0 - ((double)(nsub + nins + ndel) / (double)P);  // :4002
+}
+
+}  // namespace pb

@@ -1,0 +1,142 @@
+// TEST HARNESS (not product): compiles the engine's per-read core (pbsim_b200/csrc/sim_core.cuh)
+// and table image builder (model_image.hpp) as plain C++ and runs them sequentially, read by
+// read, so that the pass-1 logic (planning, chains, event encoding, both draw sources) can be
+// checked against the oracle on a box without a GPU.  The product never runs this code path:
+// libpbsim_cuda executes the same header only inside CUDA kernels.
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "../../include/pbsim_cuda.h"
+#include "../../pbsim_b200/csrc/model_image.hpp"
+#include "../../pbsim_b200/csrc/sim_core.cuh"
+
+struct HostSimOut {
+  std::vector<int64_t> info;     // 12 per subread: read_id, pass, acc, offset, wlen, rlen, ncol, minus, n_entries, ev_off, draw_start, overflow
+  std::vector<uint32_t> counts;  // 3 per subread: nsub, nins, ndel
+  std::vector<double> accuracy;
+  std::vector<uint8_t> events;   // qshmm: uint16 entries (little endian), errhmm: uint8 entries
+  std::vector<pb::Ckpt> ckpts;
+  std::vector<int64_t> ck_off;
+};
+
+static HostSimOut g_out;
+
+extern "C" {
+
+// returns number of subreads, <0 on error
+long hostsim_run(const pbsim_model *m, const uint8_t *ascii_upper, const int16_t *hp, long glen, int seq_num,
+                 const double bias[12], int rng_mode, uint32_t seed, const int32_t *draws, long ndraws,
+                 long long len_quota, long max_reads) {
+  pb::ModelImage img;
+  if (!img.build(*m)) { fprintf(stderr, "hostsim: %s\n", img.error.c_str()); return -1; }
+  img.apply_bias(*m, bias);
+  std::vector<uint8_t> hp4((size_t)glen / 2 + 2, 0);
+  for (long i = 0; i < glen; ++i) hp4[i >> 1] |= (uint8_t)((hp[i] & 15) << ((i & 1) * 4));
+  bool any_exc = !img.uniform_bias;
+  std::vector<uint8_t> exc((size_t)glen, 0);
+  for (long i = 0; i < glen; ++i) {
+    const uint8_t c = ascii_upper[i];
+    const bool acgt = (c == 'A' || c == 'C' || c == 'G' || c == 'T');
+    exc[i] = (!acgt) || (bias[hp[i] & 15] != 1.0);
+  }
+  g_out = HostSimOut();
+  pb::PlanTables pt;
+  pt.prob2len = m->prob2len;
+  pt.prob2acc = m->prob2accuracy;
+  pt.len_rand_value = (uint32_t)m->len_rand_value;
+  pt.acc_rand_value = (uint32_t)m->accuracy_rand_value;
+  pt.len_min = (uint32_t)m->len_min;
+
+  long long len_total = 0;
+  long read_id = 0;
+  int64_t cursor = 0;
+  while (len_total < len_quota && (max_reads <= 0 || read_id < max_reads)) {
+    ++read_id;
+    pb::PhiloxDraw pd;
+    pb::ReplayDraw rd;
+    pb::ReadPlan plan;
+    const int64_t read_start = cursor;
+    if (rng_mode == PBSIM_RNG_PHILOX) {
+      pd.ph.k0 = seed; pd.ph.k1 = (uint32_t)seq_num; pd.read_id = (uint32_t)read_id; pd.pass = 0;
+      plan = pb::plan_read(pt, pd, (uint32_t)glen, len_quota - len_total);
+    } else {
+      rd.log = draws; rd.cur = cursor; rd.end = ndraws; rd.start = cursor;
+      plan = pb::plan_read(pt, rd, (uint32_t)glen, len_quota - len_total);
+      cursor = rd.cur;
+    }
+    const pb::AccEntry &ae = img.acc[plan.acc];
+    if (!ae.valid) { fprintf(stderr, "hostsim: accuracy %u has no tables\n", plan.acc); return -2; }
+    const uint32_t minus = (read_id % 2 == 0);
+    pb::WindowRef win;
+    win.ascii = ascii_upper; win.hp4 = hp4.data(); win.offset = plan.offset; win.wlen = plan.wlen; win.minus = minus;
+    bool slow = any_exc;
+    for (uint32_t i = 0; i < plan.wlen && !slow; ++i) slow = exc[plan.offset + i];
+    for (int pass = 0; pass < m->pass_num; ++pass) {
+      const uint32_t cap = plan.wlen * 4 + 4096;
+      pb::SubreadResult res;
+      const size_t ck_base = g_out.ckpts.size();
+      g_out.ckpts.resize(ck_base + cap / PB_TILE + 2);
+      const int64_t draw_start = (pass == 0) ? read_start : cursor;
+      size_t ev_off = g_out.events.size();
+      ev_off = (ev_off + 15) / 16 * 16;
+      if (m->method == PBSIM_METHOD_QSHMM) {
+        g_out.events.resize(ev_off + (size_t)cap * 2);
+        pb::QsView T;
+        const uint8_t *b = img.blob.data() + ae.blob_off;
+        T.t2 = reinterpret_cast<const uint16_t *>(b + pb::QsBlobLayout::t2_off);
+        T.emis = b + pb::QsBlobLayout::emis_off;
+        T.emod = b + pb::QsBlobLayout::emod_off;
+        T.freq = b;
+        T.has_model = ae.has_model; T.init_mod = ae.init_mod; T.freq_mod = ae.freq_mod;
+        T.thr = img.qs_thr.data(); T.thr_hp = img.qs_thr_hp.data(); T.qc_prob = m->qc_prob;
+        pb::QsSink sink;
+        sink.init(reinterpret_cast<uint16_t *>(g_out.events.data() + ev_off), g_out.ckpts.data() + ck_base, cap);
+        if (rng_mode == PBSIM_RNG_PHILOX) { pd.pass = (uint32_t)pass; pb::qshmm_simulate(T, pd, win, slow, plan.wlen, sink, res); }
+        else { rd.cur = cursor; pb::qshmm_simulate(T, rd, win, slow, plan.wlen, sink, res); cursor = rd.cur; }
+        g_out.events.resize(ev_off + (size_t)res.n_entries * 2);
+      } else {
+        g_out.events.resize(ev_off + (size_t)cap);
+        pb::ErView T;
+        std::memset(&T, 0, sizeof T);
+        T.mode = ae.mode; T.rate_mag = ae.rate_mag; T.init_mod = ae.init_mod;
+        if (ae.mode != 3) {
+          uint32_t t2o, emo, emodo;
+          pb::er_blob_bytes(ae.nstates, &t2o, &emo, &emodo);
+          const uint8_t *b = img.blob.data() + ae.blob_off;
+          T.t2 = reinterpret_cast<const uint16_t *>(b + t2o);
+          T.emis = b + emo;
+          T.emod = reinterpret_cast<const uint16_t *>(b + emodo);
+          T.edel = img.er_bias.data() + ae.bias_off;
+          T.edel_hp = T.edel + (ae.nstates + 1);
+        }
+        pb::ErSink sink;
+        sink.init(g_out.events.data() + ev_off, g_out.ckpts.data() + ck_base, cap);
+        if (rng_mode == PBSIM_RNG_PHILOX) { pd.pass = (uint32_t)pass; pb::errhmm_simulate(T, pd, win, slow, plan.wlen, sink, res); }
+        else { rd.cur = cursor; pb::errhmm_simulate(T, rd, win, slow, plan.wlen, sink, res); cursor = rd.cur; }
+        g_out.events.resize(ev_off + (size_t)res.n_entries);
+      }
+      g_out.ckpts.resize(ck_base + (res.n_entries + PB_TILE - 1) / PB_TILE);
+      int64_t rec[12] = {read_id, pass, (int64_t)plan.acc, (int64_t)plan.offset, (int64_t)plan.wlen, (int64_t)res.rlen,
+                         (int64_t)res.ncol, (int64_t)minus, (int64_t)res.n_entries, (int64_t)ev_off, draw_start,
+                         (int64_t)res.overflow};
+      g_out.info.insert(g_out.info.end(), rec, rec + 12);
+      g_out.ck_off.push_back((int64_t)ck_base);
+      g_out.counts.push_back(res.nsub); g_out.counts.push_back(res.nins); g_out.counts.push_back(res.ndel);
+      g_out.accuracy.push_back(res.accuracy);
+      if (pass == 0) len_total += res.rlen;
+    }
+  }
+  return (long)(g_out.info.size() / 12);
+}
+
+const int64_t *hostsim_info() { return g_out.info.data(); }
+const uint32_t *hostsim_counts() { return g_out.counts.data(); }
+const double *hostsim_accuracy() { return g_out.accuracy.data(); }
+const uint8_t *hostsim_events(long *nbytes) { *nbytes = (long)g_out.events.size(); return g_out.events.data(); }
+const pb::Ckpt *hostsim_ckpts(long *n) { *n = (long)g_out.ckpts.size(); return g_out.ckpts.data(); }
+const int64_t *hostsim_ck_off() { return g_out.ck_off.data(); }
+long hostsim_draws_consumed_total() { return 0; }
+
+}  // extern "C"

@@ -1,0 +1,130 @@
+"""CPU checks of the product's host front end (pbsim_b200/csrc/host_model.cpp, model_image.hpp) and of
+the engine's pass-1 core (sim_core.cuh, compiled as plain C++ by tests/hostsim) against the oracle and the
+reference's golden outputs.  The GPU tests (-m gpu) then check the CUDA engine end to end."""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from pbsim_b200 import capi
+from tests import hostsim_util as H
+from tests.golden_util import Case, case_names
+
+
+def load_product_model(c):
+    return capi.HostModel(H.lib(), capi.host_params(c.method, **c.okw), c.model)
+
+
+@pytest.mark.parametrize("name", case_names())
+def test_host_tables_equal_oracle_tables(name):
+    """KAT: quantised tables of the product's builder == the oracle's (which reproduces the reference)."""
+    c = Case(name)
+    o = c.new_oracle()
+    hm = load_product_model(c)
+    v = hm.view
+    t, n = o.table(0)
+    assert v.len_rand_value == n and np.array_equal(np.ctypeslib.as_array(v.prob2len, shape=(n,)), t)
+    t, n = o.table(1)
+    assert v.accuracy_rand_value == n and np.array_equal(np.ctypeslib.as_array(v.prob2accuracy, shape=(n,)), t)
+    s, i, d = o.thresholds()
+    assert list(v.sub_thre) == s.tolist() and list(v.ins_thre) == i.tolist() and list(v.del_thre) == d.tolist()
+    amin, amax, lo, hi = o.model_range()
+    assert (v.acc_lo, v.acc_hi) == (lo, hi)
+    err = c.method == "errhmm"
+    if err:
+        assert (v.model_acc_min, v.model_acc_max) == (amin, amax)
+    checked = 0
+    for a in range(lo, hi + 1):
+        r = v.rows[a]
+        assert bool(r.exists) == o.model_exists(a)
+        if not r.exists:
+            if not err:
+                t, n = o.table(5, a, cap=1001)
+                assert r.freq_mod == n and np.array_equal(np.ctypeslib.as_array(r.freq, shape=(n,)), t)
+                checked += 1
+            continue
+        res = r.resolution
+        t, n = o.table(2, a, cap=1001)
+        assert r.init_mod == n and np.array_equal(np.ctypeslib.as_array(r.init, shape=(n,)), t)
+        for st in range(1, r.nstates + 1):
+            t, n = o.table(3, a, st, cap=1001)
+            assert r.emis_mod[st] == n, (a, st)
+            if 0 < n <= res:
+                assert np.array_equal(np.ctypeslib.as_array(r.emis, shape=((r.nstates + 1) * res,))[st * res:st * res + n], t)
+            t, n = o.table(4, a, st, cap=1001)
+            assert r.tran_mod[st] == n, (a, st)
+            if 0 < n <= res:
+                assert np.array_equal(np.ctypeslib.as_array(r.tran, shape=((r.nstates + 1) * res,))[st * res:st * res + n], t)
+            if err:
+                assert r.emis_del[st] == o.emis2del(a, st)
+            checked += 1
+    assert checked > 0
+
+
+def test_hp_del_bias_front_end_matches_oracle():
+    c = Case("qs_ont_hpbias")
+    out, o = c.run_oracle("glibc")
+    L = H.lib()
+    # hpfreq over all sequences, as main's prepass accumulates it (pbsim.cpp:678-685)
+    hpfreq = np.zeros(12, dtype=np.int64)
+    o2 = c.new_oracle()
+    for i, (_, s) in enumerate(c.contigs, start=1):
+        o2.set_sequence(s, i)
+        hp = o2.hp()
+        up = np.frombuffer(o2.seq_upper(), dtype=np.uint8)
+        for h in range(1, 12):
+            hpfreq[h] += int(np.count_nonzero(hp == h))
+    bias = capi.hp_del_bias(L, c.okw["hp_del_bias"], hpfreq)
+    # oracle bias during the first sequence: [1..10] identical; [0] aliases the running hp==11 count
+    assert np.allclose(bias[1:11], out[0]["bias"][1:11], rtol=0, atol=0)
+
+
+def _replay_case(c, rng):
+    """Run hostsim over all sequences of a case; returns per-sequence (reads, maf, subreads)."""
+    out, o = c.run_oracle("glibc" if rng == "replay" else "philox")
+    log = o.draw_log() if rng == "replay" else None
+    hm = load_product_model(c)
+    res = []
+    o2 = c.new_oracle()
+    if c.okw.get("hp_del_bias", 1.0) != 1.0:
+        o2.hp_bias_prepass([s for _, s in c.contigs])
+    cursor = 0
+    for i, (_, s) in enumerate(c.contigs, start=1):
+        o2.set_sequence(s, i)
+        up, hp, bias = o2.seq_upper(), o2.hp(), o2.bias()
+        quota = int(c.depth * len(s))
+        if rng == "replay":
+            sub = H.run(hm, up, hp, i, bias, capi.RNG_REPLAY, 0, log[cursor:], quota)
+            for sr in sub:
+                sr["draw_start"] += cursor
+            cursor = out[i - 1]["draws_end"]
+        else:
+            sub = H.run(hm, up, hp, i, bias, capi.RNG_PHILOX, c.seed, None, quota)
+        reads, maf = H.records_from_events(hm, sub, up, i)
+        res.append((reads, maf, sub))
+    return out, res
+
+
+@pytest.mark.parametrize("name", case_names())
+def test_core_replay_reproduces_reference(name):
+    """pass-1 core fed the reference's own draws + the pass-2 specification == reference bytes."""
+    c = Case(name)
+    out, res = _replay_case(c, "replay")
+    for i, ((reads, maf, sub), oref) in enumerate(zip(res, out), start=1):
+        assert reads == c.reads(i), "reads differ, seq %d" % i
+        assert maf == c.maf(i), "maf differs, seq %d" % i
+        info = oref["info"]
+        assert [s["draw_start"] for s in sub] == info["draw_start"].tolist()
+        assert [s["nsub"] for s in sub] == info["nsub"].tolist()
+        assert [s["ndel"] for s in sub] == info["ndel"].tolist()
+        assert np.array_equal(np.array([s["accuracy"] for s in sub]), info["accuracy"])
+        assert not any(s["overflow"] for s in sub)
+
+
+@pytest.mark.parametrize("name", ["qs_rsii_quirks", "qs_ont_hpbias", "err_onthq_basic", "err_sequel_hiacc",
+                                  "qs_rsii_multipass"])
+def test_core_philox_equals_oracle_philox(name):
+    c = Case(name)
+    out, res = _replay_case(c, "philox")
+    for (reads, maf, sub), oref in zip(res, out):
+        assert reads == oref["reads"]
+        assert maf == oref["maf"]
