@@ -152,7 +152,8 @@ const char *pbsim_cuda_last_error(const pbsim_engine *e); /* e may be NULL: last
 int pbsim_cuda_create(pbsim_engine **out, int device);
 void pbsim_cuda_destroy(pbsim_engine *e);
 
-/* replaces: the static tables of simulate_by_qshmm/errhmm + set_mut (host -> device upload) */
+/* replaces: the static tables of simulate_by_qshmm/errhmm + set_mut (host -> device upload).
+ * The pbsim_model (and the tables it points to) must stay alive while the engine uses it. */
 int pbsim_cuda_set_model(pbsim_engine *e, const pbsim_model *m);
 
 /* replaces: get_genome_seq's genome.seq / genome.hp (pbsim.cpp:1032-1065): uploads the ASCII
@@ -160,6 +161,9 @@ int pbsim_cuda_set_model(pbsim_engine *e, const pbsim_model *m);
 int pbsim_cuda_set_sequence(pbsim_engine *e, const pbsim_sequence *s);
 /* synthetic i.i.d. ACGT sequence generated on the device (benchmarks; no host transfer) */
 int pbsim_cuda_set_synthetic_sequence(pbsim_engine *e, int64_t len, int32_t seq_num, uint64_t seed);
+/* replace hp_del_bias of the current sequence without re-ingesting it (bias[0] is only known once the
+ * sequence's own hpfreq[11] is, see pbsim_host_hp_del_bias); the set of cells equal to 1 must not change */
+int pbsim_cuda_update_hp_del_bias(pbsim_engine *e, const double hp_del_bias[12]);
 /* homopolymer histogram of the current sequence, genome.hpfreq[0..10] plus the aliased [11] */
 int pbsim_cuda_get_hpfreq(pbsim_engine *e, int64_t hpfreq[12]);
 

@@ -137,7 +137,7 @@ HOST_EXPORTS = ["pbsim_host_model_load", "pbsim_host_model_get", "pbsim_host_mod
 ENGINE_EXPORTS = [
     "pbsim_cuda_abi_version", "pbsim_cuda_last_error", "pbsim_cuda_create", "pbsim_cuda_destroy",
     "pbsim_cuda_set_model", "pbsim_cuda_set_sequence", "pbsim_cuda_set_synthetic_sequence",
-    "pbsim_cuda_get_hpfreq", "pbsim_cuda_simulate_begin", "pbsim_cuda_next_chunk",
+    "pbsim_cuda_update_hp_del_bias", "pbsim_cuda_get_hpfreq", "pbsim_cuda_simulate_begin", "pbsim_cuda_next_chunk",
     "pbsim_cuda_next_chunk_device", "pbsim_cuda_simulate_end", "pbsim_cuda_stats_device_block",
     "pbsim_cuda_last_chunk_info",
 ]
@@ -167,6 +167,7 @@ def declare_engine(L):
     L.pbsim_cuda_set_model.argtypes = [C.c_void_p, C.POINTER(Model)]
     L.pbsim_cuda_set_sequence.argtypes = [C.c_void_p, C.POINTER(Sequence)]
     L.pbsim_cuda_set_synthetic_sequence.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_uint64]
+    L.pbsim_cuda_update_hp_del_bias.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
     L.pbsim_cuda_get_hpfreq.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
     L.pbsim_cuda_simulate_begin.argtypes = [C.c_void_p, C.POINTER(Run)]
     L.pbsim_cuda_next_chunk.argtypes = [C.c_void_p, C.POINTER(Chunk)]

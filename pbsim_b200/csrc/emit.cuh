@@ -1,0 +1,472 @@
+// K4 — pass 2: event streams -> FASTQ / SAM / MAF bytes, written in read order.
+// Replaces the reference's record emission (pbsim.cpp:2318-2383 = :4012-4078), count_digit (:5823)
+// and the three revcomp calls per minus-strand read (:5841): minus-strand reads are generated on the
+// reverse-complemented window and their MAF rows are mirrored back while being written.
+//
+// Work unit: one warp formats one tile of PB_TILE events of one (read, pass).  Tiles are independent
+// thanks to the checkpoints pass 1 left; output positions come from warp ballots / a warp prefix
+// scan over deletion counts, so every store lands at its final byte and consecutive lanes write
+// consecutive bytes.  The genome is read from the 2-bit packed array (coalesced; neighbouring lanes
+// share words); tiles that touch an exceptional 1024-base block read the ASCII copy instead.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "k0_genome.cuh"
+#include "sim_kernels.cuh"
+
+namespace pb {
+
+constexpr int kEmitThreads = 256;
+constexpr int kEmitWarps = kEmitThreads / 32;
+
+struct EmitParams {
+  uint32_t pass_num;
+  uint32_t sam;            // 1: SAM records (pass_num > 1), 0: FASTQ
+  uint32_t id_head_len;    // strlen(id_prefix + seq_num)
+  char id_head[160];       // "<id_prefix><seq_num>"
+  uint32_t rq_len;
+  char rq[32];             // printf("%f", accuracy_mean)
+  uint32_t glen;
+};
+
+struct EmitArgs {
+  DeviceGenome G;
+  Batch B;
+  EmitParams P;
+  const uint8_t *ev;
+  const Ckpt *ck;
+  uint32_t n_sub;              // valid subreads (after the quota cut)
+  uint64_t n_tiles;
+  const uint64_t *tile_start;  // [n_sub + 1]
+  const uint64_t *reads_off;   // [n_sub + 1]
+  const uint64_t *maf_off;     // [n_sub + 1]
+  uint8_t *out_reads;
+  uint8_t *out_maf;
+};
+
+__host__ __device__ __forceinline__ uint32_t ndigits(uint64_t v) {  // count_digit (:5823)
+  uint32_t d = 1;
+  while (v >= 10) {
+    v /= 10;
+    ++d;
+  }
+  return d;
+}
+
+struct RecLayout {
+  uint32_t idlen, d_rid, d_pass;
+  uint64_t seq_rel, qual_rel, ip_rel, pw_rel, tail_rel, reads_size;
+  uint32_t pa[4], pb_[4];  // MAF padding of the ref row / the read row fields
+  uint32_t d_off, d_wlen, d_glen, d_rlen;
+  uint64_t refrow_rel, readrow_rel, maf_size;
+};
+
+#define PB_SAM_S1 "\t4\t*\t0\t255\t*\t*\t0\t0\t"
+#define PB_SAM_S2 "\tcx:i:3\tip:B:C"
+#define PB_SAM_S3 "\tnp:i:1\tpw:B:C"
+#define PB_SAM_S4 "\tqs:i:0\tqe:i:"
+#define PB_SAM_S5 "\trq:f:"
+#define PB_SAM_S6 "\tsn:B:f,10.0,10.0,10.0,10.0\tzm:i:"
+#define PB_SAM_S7 "\tRG:Z:ffffffff\n"
+#define PB_LEN(s) ((uint32_t)(sizeof(s) - 1))
+
+__host__ __device__ __forceinline__ RecLayout rec_layout(const EmitParams &P, uint64_t read_id, uint32_t pass,
+                                                         uint32_t offset, uint32_t wlen, uint32_t rlen,
+                                                         uint32_t ncol) {
+  RecLayout L;
+  L.d_rid = ndigits(read_id);
+  L.d_pass = ndigits(pass);
+  const uint32_t qe_digits = rlen == 0 ? 2u : ndigits(rlen - 1u);  // "-1" when the read is empty
+  if (!P.sam) {
+    L.idlen = P.id_head_len + 1u + L.d_rid;  // "<head>_<read>"
+    L.seq_rel = 1u + L.idlen + 1u;
+    L.qual_rel = L.seq_rel + rlen + 2u + L.idlen + 1u;
+    L.reads_size = L.qual_rel + rlen + 1u;
+    L.ip_rel = L.pw_rel = L.tail_rel = 0;
+  } else {
+    L.idlen = P.id_head_len + 1u + L.d_rid + 1u + L.d_pass;  // "<head>/<read>/<pass>"
+    L.seq_rel = L.idlen + PB_LEN(PB_SAM_S1);
+    L.qual_rel = L.seq_rel + rlen + 1u;
+    L.ip_rel = L.qual_rel + rlen + PB_LEN(PB_SAM_S2);
+    L.pw_rel = L.ip_rel + 2ull * rlen + PB_LEN(PB_SAM_S3);
+    L.tail_rel = L.pw_rel + 2ull * rlen;
+    L.reads_size = L.tail_rel + PB_LEN(PB_SAM_S4) + qe_digits + PB_LEN(PB_SAM_S5) + P.rq_len + PB_LEN(PB_SAM_S6) +
+                   L.d_rid + PB_LEN(PB_SAM_S7);
+  }
+  // MAF field widths (:2336-2350); note the name column assumes an id of 1 + digits(read number)
+  L.d_off = ndigits(offset);
+  L.d_wlen = ndigits(wlen);
+  L.d_glen = ndigits(P.glen);
+  L.d_rlen = ndigits(rlen);
+  const uint32_t d1[4] = {3u, L.d_off, L.d_wlen, L.d_glen};
+  const uint32_t d2[4] = {1u + L.d_rid, 1u, L.d_rlen, L.d_rlen};
+  for (int i = 0; i < 4; ++i) {
+    const uint32_t dn = d1[i] > d2[i] ? d1[i] : d2[i];
+    L.pa[i] = dn - d1[i];
+    L.pb_[i] = dn - d2[i];
+  }
+  // "a\ns ref" pa0 pa1 " off" pa2 " wlen +" pa3 " glen " ROW "\n"
+  L.refrow_rel = 7u + L.pa[0] + L.pa[1] + 1u + L.d_off + L.pa[2] + 1u + L.d_wlen + 2u + L.pa[3] + 1u + L.d_glen + 1u;
+  // "s " id pb0 pb1 " 0" pb2 " rlen S" pb3 " rlen " ROW "\n\n"
+  L.readrow_rel = L.refrow_rel + ncol + 1u + 2u + L.idlen + L.pb_[0] + L.pb_[1] + 2u + L.pb_[2] + 1u + L.d_rlen + 2u +
+                  L.pb_[3] + 1u + L.d_rlen + 1u;
+  L.maf_size = L.readrow_rel + ncol + 2u;
+  return L;
+}
+
+// record sizes and tile counts of every valid subread
+__global__ void k_sizes(Batch B, EmitParams P, uint32_t n_sub, uint64_t *reads_size, uint64_t *maf_size,
+                        uint64_t *ntiles) {
+  const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_sub) return;
+  const uint32_t r = s / P.pass_num, pass = s % P.pass_num;
+  const RecLayout L = rec_layout(P, B.first_read + 1u + r, pass, B.plan_off[r], B.plan_wlen[r], B.rlen[s], B.ncol[s]);
+  reads_size[s] = L.reads_size;
+  maf_size[s] = L.maf_size;
+  const uint32_t ne = B.nent[s];
+  ntiles[s] = ne == 0 ? 1u : (ne + PB_TILE - 1u) / PB_TILE;
+}
+
+__device__ __forceinline__ uint8_t *put_dec(uint8_t *p, uint64_t v, uint32_t nd) {
+  for (uint32_t i = 0; i < nd; ++i) {
+    p[nd - 1u - i] = (uint8_t)('0' + v % 10);
+    v /= 10;
+  }
+  return p + nd;
+}
+__device__ __forceinline__ uint8_t *put_mem(uint8_t *p, const char *s, uint32_t n) {
+  for (uint32_t i = 0; i < n; ++i) p[i] = (uint8_t)s[i];
+  return p + n;
+}
+__device__ __forceinline__ uint8_t *put_pad(uint8_t *p, uint32_t n) {
+  for (uint32_t i = 0; i < n; ++i) p[i] = ' ';
+  return p + n;
+}
+#define PB_PUT_LIT(p, lit) put_mem((p), (lit), PB_LEN(lit))
+
+__device__ __forceinline__ uint8_t *put_id(uint8_t *p, const EmitParams &P, uint64_t read_id, uint32_t pass,
+                                           const RecLayout &L) {
+  p = put_mem(p, P.id_head, P.id_head_len);
+  if (!P.sam) {
+    *p++ = '_';
+    p = put_dec(p, read_id, L.d_rid);
+  } else {
+    *p++ = '/';
+    p = put_dec(p, read_id, L.d_rid);
+    *p++ = '/';
+    p = put_dec(p, pass, L.d_pass);
+  }
+  return p;
+}
+
+// everything of a record that is not a per-base row: written once, by one lane
+__device__ __noinline__ void write_headers(const EmitParams &P, const RecLayout &L, uint8_t *rd, uint8_t *mf,
+                                           uint64_t read_id, uint32_t pass, uint32_t offset, uint32_t wlen,
+                                           uint32_t rlen, uint32_t ncol, uint32_t minus) {
+  uint8_t *p = rd;
+  if (!P.sam) {
+    *p++ = '@';
+    p = put_id(p, P, read_id, pass, L);
+    *p++ = '\n';
+    p = rd + L.seq_rel + rlen;
+    *p++ = '\n';
+    *p++ = '+';
+    p = put_id(p, P, read_id, pass, L);
+    *p++ = '\n';
+    rd[L.qual_rel + rlen] = '\n';
+  } else {
+    p = put_id(p, P, read_id, pass, L);
+    p = PB_PUT_LIT(p, PB_SAM_S1);
+    rd[L.seq_rel + rlen] = '\t';
+    PB_PUT_LIT(rd + L.qual_rel + rlen, PB_SAM_S2);
+    PB_PUT_LIT(rd + L.ip_rel + 2ull * rlen, PB_SAM_S3);
+    p = rd + L.tail_rel;
+    p = PB_PUT_LIT(p, PB_SAM_S4);
+    if (rlen == 0) {
+      *p++ = '-';
+      *p++ = '1';
+    } else {
+      p = put_dec(p, rlen - 1u, ndigits(rlen - 1u));
+    }
+    p = PB_PUT_LIT(p, PB_SAM_S5);
+    p = put_mem(p, P.rq, P.rq_len);
+    p = PB_PUT_LIT(p, PB_SAM_S6);
+    p = put_dec(p, read_id, L.d_rid);
+    p = PB_PUT_LIT(p, PB_SAM_S7);
+  }
+  p = mf;
+  p = PB_PUT_LIT(p, "a\ns ref");
+  p = put_pad(p, L.pa[0] + L.pa[1]);
+  *p++ = ' ';
+  p = put_dec(p, offset, L.d_off);
+  p = put_pad(p, L.pa[2]);
+  *p++ = ' ';
+  p = put_dec(p, wlen, L.d_wlen);
+  *p++ = ' ';
+  *p++ = '+';
+  p = put_pad(p, L.pa[3]);
+  *p++ = ' ';
+  p = put_dec(p, P.glen, L.d_glen);
+  *p++ = ' ';
+  p = mf + L.refrow_rel + ncol;
+  *p++ = '\n';
+  *p++ = 's';
+  *p++ = ' ';
+  p = put_id(p, P, read_id, pass, L);
+  p = put_pad(p, L.pb_[0] + L.pb_[1]);
+  *p++ = ' ';
+  *p++ = '0';
+  p = put_pad(p, L.pb_[2]);
+  *p++ = ' ';
+  p = put_dec(p, rlen, L.d_rlen);
+  *p++ = ' ';
+  *p++ = minus ? '-' : '+';
+  p = put_pad(p, L.pb_[3]);
+  *p++ = ' ';
+  p = put_dec(p, rlen, L.d_rlen);
+  *p++ = ' ';
+  p = mf + L.readrow_rel + ncol;
+  *p++ = '\n';
+  *p++ = '\n';
+}
+
+__device__ __forceinline__ uint8_t comp_char(uint8_t c) {  // revcomp's complement (:5853-5863)
+  switch (c) {
+    case 'A': return 'T';
+    case 'T': return 'A';
+    case 'G': return 'C';
+    case 'C': return 'G';
+    default: return c;
+  }
+}
+
+struct RefFetch {
+  const uint32_t *__restrict__ pk;
+  const uint8_t *__restrict__ ascii;
+  uint32_t offset, wlen, minus;
+  bool slow;
+  // window index r -> forward genome char, window-strand char, window-strand code, ACGT flag
+  __device__ __forceinline__ void get(uint32_t r, uint8_t &gch, uint8_t &wch, uint32_t &wc, bool &acgt) const {
+    const uint32_t g = minus ? offset + wlen - 1u - r : offset + r;
+    const uint32_t lut = 0x54474341u;  // "ACGT"
+    if (!slow) {
+      const uint32_t gc = (__ldg(&pk[g >> 4]) >> ((g & 15u) * 2u)) & 3u;
+      wc = gc ^ (minus ? 3u : 0u);
+      gch = (uint8_t)(lut >> (8u * gc));
+      wch = (uint8_t)(lut >> (8u * wc));
+      acgt = true;
+    } else {
+      gch = __ldg(&ascii[g]);
+      uint32_t gc = 0;
+      acgt = true;
+      switch (gch) {
+        case 'A': gc = 0; break;
+        case 'C': gc = 1; break;
+        case 'G': gc = 2; break;
+        case 'T': gc = 3; break;
+        default: acgt = false; break;
+      }
+      wc = gc ^ (minus ? 3u : 0u);
+      wch = acgt ? (uint8_t)(lut >> (8u * wc)) : gch;
+    }
+  }
+};
+
+// read base from the event (window strand); substitution alphabets of set_mut (:5481-5486)
+__device__ __forceinline__ uint8_t read_base(uint32_t kind, uint32_t info, uint8_t wch, uint32_t wc, bool acgt) {
+  const uint32_t nt4 = 0x43475441u;  // "ATGC"
+  if (kind == PB_KIND_MATCH) return wch;
+  if (kind == PB_KIND_SUB) {
+    if (!acgt) return (uint8_t)(nt4 >> (8u * (info & 3u)));
+    // by window code A=0 C=1 G=2 T=3: A->"TGC" C->"ATG" G->"ATC" T->"AGC"
+    const uint32_t subA = 0x00434754u, subC = 0x00475441u, subG = 0x00435441u, subT = 0x00434741u;
+    const uint32_t tab = wc == 0u ? subA : (wc == 1u ? subC : (wc == 2u ? subG : subT));
+    return (uint8_t)(tab >> (8u * (info > 2u ? 2u : info)));
+  }
+  // insertion: half of the time a copy of the current (not yet consumed) reference base (:2252-2257)
+  return info >= 4u ? wch : (uint8_t)(nt4 >> (8u * info));
+}
+
+template <int METHOD>
+__global__ void __launch_bounds__(kEmitThreads) k_emit(EmitArgs A) {
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  const uint64_t warp0 = (uint64_t)blockIdx.x * kEmitWarps + (threadIdx.x >> 5);
+  const uint64_t nwarps = (uint64_t)gridDim.x * kEmitWarps;
+  for (uint64_t t = warp0; t < A.n_tiles; t += nwarps) {
+    // subread of this tile: largest s with tile_start[s] <= t
+    uint32_t lo = 0, hi = A.n_sub;
+    while (hi - lo > 1u) {
+      const uint32_t mid = (lo + hi) >> 1;
+      if (__ldg(&A.tile_start[mid]) <= t) lo = mid; else hi = mid;
+    }
+    const uint32_t s = lo;
+    const uint32_t tile = (uint32_t)(t - __ldg(&A.tile_start[s]));
+    const uint32_t r = s / A.P.pass_num, pass = s % A.P.pass_num;
+    const uint64_t read_id = A.B.first_read + 1u + r;
+    const uint32_t offset = A.B.plan_off[r], wlen = A.B.plan_wlen[r];
+    const uint32_t minus = (A.B.plan_meta[r] >> 8) & 1u;
+    const uint32_t nent = A.B.nent[s], rlen = A.B.rlen[s], ncol = A.B.ncol[s];
+    const RecLayout L = rec_layout(A.P, read_id, pass, offset, wlen, rlen, ncol);
+    uint8_t *rd = A.out_reads + A.reads_off[s];
+    uint8_t *mf = A.out_maf + A.maf_off[s];
+    if (tile == 0 && lane == 0) write_headers(A.P, L, rd, mf, read_id, pass, offset, wlen, rlen, ncol, minus);
+    if (nent == 0) continue;
+    const uint32_t e0 = tile * PB_TILE;
+    const uint32_t e1 = min(nent, e0 + PB_TILE);
+    const Ckpt *ckp = A.ck + A.B.ck_off[s];
+    const Ckpt c0 = ckp[tile];
+    uint32_t C0 = c0.col, R0 = c0.ref, P0 = c0.read;
+    RefFetch rf;
+    rf.pk = A.G.pk;
+    rf.ascii = A.G.ascii;
+    rf.offset = offset;
+    rf.wlen = wlen;
+    rf.minus = minus;
+    {
+      // reference range this tile can touch: [R0, Rend] (an insertion at the tile's end looks at Rend)
+      const uint32_t Rnext = (e1 < nent) ? ckp[tile + 1].ref : wlen;
+      const uint32_t Rend = min(Rnext, wlen - 1u);
+      const uint32_t g0 = minus ? offset + wlen - 1u - Rend : offset + R0;
+      const uint32_t g1 = minus ? offset + wlen - 1u - R0 : offset + Rend;
+      rf.slow = range_exceptional(A.G.xm, g0, g1);
+    }
+    uint8_t *seq = rd + L.seq_rel, *qual = rd + L.qual_rel;
+    uint8_t *ip = rd + L.ip_rel, *pw = rd + L.pw_rel;
+    uint8_t *mref = mf + L.refrow_rel, *mread = mf + L.readrow_rel;
+
+    for (uint32_t i = e0; i < e1; i += 32u) {
+      const uint32_t e = i + lane;
+      const bool valid = e < e1;
+      uint32_t kind = 0, info = 0, qv = 0, nd = 0;
+      bool isbase = false;
+      if (METHOD == PBSIM_METHOD_QSHMM) {
+        const uint32_t v = valid ? (uint32_t)__ldg(reinterpret_cast<const uint16_t *>(A.ev) + A.B.ev_off[s] + e) : 0u;
+        kind = (v >> 7) & 3u;
+        const bool cont = valid && kind == 3u;
+        qv = v & 0x7Fu;
+        info = (v >> 9) & 7u;
+        nd = cont ? ((v & 0x7Fu) | ((v >> 9) << 7)) : ((v >> 12) & 15u);
+        if (!valid) nd = 0;
+        isbase = valid && !cont;
+      } else {
+        const uint32_t v = valid ? (uint32_t)__ldg(A.ev + A.B.ev_off[s] + e) : 0u;
+        kind = v & 3u;
+        info = (v >> 2) & 7u;
+        isbase = valid && kind != PB_KIND_DEL;  // column carries a read base
+        nd = (valid && kind == PB_KIND_DEL) ? 1u : 0u;  // column is a deletion
+      }
+      // ref advance: qshmm base entries that are not insertions, plus deletions
+      const bool adv = (METHOD == PBSIM_METHOD_QSHMM) ? (isbase && kind != PB_KIND_INS)
+                                                      : (valid && kind != PB_KIND_INS && kind != PB_KIND_DEL);
+      const uint32_t m_base = __ballot_sync(0xFFFFFFFFu, isbase);
+      const uint32_t m_adv = __ballot_sync(0xFFFFFFFFu, adv);
+      uint32_t pre_d, tot_d;
+      if (METHOD == PBSIM_METHOD_QSHMM) {
+        uint32_t x = nd;  // inclusive warp scan of deletion counts
+        if (__any_sync(0xFFFFFFFFu, nd != 0u)) {
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o);
+            if (lane >= (uint32_t)o) x += y;
+          }
+          tot_d = __shfl_sync(0xFFFFFFFFu, x, 31);
+          pre_d = x - nd;
+        } else {
+          pre_d = tot_d = 0;
+        }
+      } else {
+        const uint32_t m_del = __ballot_sync(0xFFFFFFFFu, nd != 0u);
+        pre_d = __popc(m_del & lt_mask);
+        tot_d = __popc(m_del);
+      }
+      const uint32_t Pp = P0 + __popc(m_base & lt_mask);
+      const uint32_t Rr = R0 + __popc(m_adv & lt_mask) + pre_d;
+      const uint32_t Cc = C0 + __popc(m_base & lt_mask) + pre_d;
+      if (isbase) {
+        uint8_t gch, wch;
+        uint32_t wc;
+        bool acgt;
+        rf.get(Rr, gch, wch, wc, acgt);
+        const uint8_t rb = read_base(kind, info, wch, wc, acgt);
+        seq[Pp] = rb;
+        qual[Pp] = (METHOD == PBSIM_METHOD_QSHMM) ? (uint8_t)(qv + 33u) : (uint8_t)'!';
+        if (A.P.sam) {
+          ip[2ull * Pp] = ',';
+          ip[2ull * Pp + 1] = '9';
+          pw[2ull * Pp] = ',';
+          pw[2ull * Pp + 1] = '9';
+        }
+        const uint32_t col = minus ? ncol - 1u - Cc : Cc;
+        mread[col] = minus ? comp_char(rb) : rb;
+        mref[col] = (kind == PB_KIND_INS) ? (uint8_t)'-' : gch;
+      }
+      if (nd != 0u) {
+        // deletion columns: '-' in the read row, the reference base in the ref row
+        const uint32_t cbase = Cc + (isbase ? 1u : 0u);
+        const uint32_t rbase = Rr + (adv ? 1u : 0u);
+        for (uint32_t j = 0; j < nd; ++j) {
+          uint8_t gch, wch;
+          uint32_t wc;
+          bool acgt;
+          rf.get(rbase + j, gch, wch, wc, acgt);
+          const uint32_t col = minus ? ncol - 1u - (cbase + j) : cbase + j;
+          mread[col] = '-';
+          mref[col] = gch;
+        }
+      }
+      P0 += __popc(m_base);
+      R0 += __popc(m_adv) + tot_d;
+      C0 += __popc(m_base) + tot_d;
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// K6: statistics of the valid subreads (pbsim.cpp:2293-2316): counters, min/max, the two histograms
+// stats block layout (int64): [0] res_num(reads) [1] res_pass_num [2] len_total [3] len_min [4] len_max
+//                             [5] sub [6] ins [7] del [8..15] spare, then freq_accuracy[100001], freq_len[...]
+// ----------------------------------------------------------------------------------------------
+constexpr int kStatCounters = 16;
+
+__global__ void k_stats(Batch B, uint32_t n_sub, uint32_t pass_num, unsigned long long *blk, int64_t freq_len_cells) {
+  const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long len = 0, nsub = 0, nins = 0, ndel = 0;
+  if (s < n_sub) {
+    len = B.rlen[s];
+    nsub = B.nsub[s];
+    nins = B.nins[s];
+    ndel = B.ndel[s];
+    atomicMin(reinterpret_cast<long long *>(blk + 3), (long long)len);
+    atomicMax(reinterpret_cast<long long *>(blk + 4), (long long)len);
+    unsigned long long *freq_acc = blk + kStatCounters;
+    unsigned long long *freq_len = freq_acc + 100001;
+    if ((int64_t)len < freq_len_cells) atomicAdd(&freq_len[len], 1ull);
+    // acc_wk = (int)(value * 100000 + 0.5)  (:2315), without FMA contraction
+    const double v = __dadd_rn(__dmul_rn(B.accuracy[s], 100000.0), 0.5);
+    if (v > -1.0 && v < 100001.0) {
+      const int idx = (int)v;
+      if (idx >= 0 && idx <= 100000) atomicAdd(&freq_acc[idx], 1ull);
+    }
+  }
+  // warp-aggregate the sums
+  for (int o = 16; o > 0; o >>= 1) {
+    len += __shfl_down_sync(0xFFFFFFFFu, len, o);
+    nsub += __shfl_down_sync(0xFFFFFFFFu, nsub, o);
+    nins += __shfl_down_sync(0xFFFFFFFFu, nins, o);
+    ndel += __shfl_down_sync(0xFFFFFFFFu, ndel, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (len) atomicAdd(blk + 2, len);
+    if (nsub) atomicAdd(blk + 5, nsub);
+    if (nins) atomicAdd(blk + 6, nins);
+    if (ndel) atomicAdd(blk + 7, ndel);
+  }
+  if (s == 0) {
+    atomicAdd(blk + 0, (unsigned long long)(n_sub / pass_num));
+    atomicAdd(blk + 1, (unsigned long long)n_sub);
+  }
+}
+
+}  // namespace pb

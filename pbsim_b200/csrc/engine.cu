@@ -1,0 +1,937 @@
+// libpbsim_cuda — engine orchestration and the C ABI (include/pbsim_cuda.h).
+//
+// One engine = one GPU.  A simulate_by_* call of the reference (pbsim.cpp:1955 / :3594) becomes
+//   simulate_begin -> { next_chunk }* -> simulate_end
+// and every chunk runs, on one stream:
+//   K1 k_plan            per-read length / accuracy / offset / strand            (sim_kernels.cuh)
+//      radix sort        (accuracy, length desc) -> pass-1 schedule              (CUB, plumbing)
+//   K2 k_sim_qshmm | K3 k_sim_errhmm   chains -> event streams                   (sim_kernels.cuh)
+//      quota scan        which read crosses sim.len_quota (pbsim.cpp:2173-2181)  (CUB + k_find_cut)
+//   K4 k_sizes, k_emit   record placement and text emission                      (emit.cuh)
+//   K6 k_stats           counters and histograms                                 (emit.cuh)
+// There is no CPU implementation of any of these steps in this library.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <climits>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+#include <string>
+#include <vector>
+
+#include "../../include/pbsim_cuda.h"
+#include "emit.cuh"
+#include "k0_genome.cuh"
+#include "model_image.hpp"
+#include "sim_kernels.cuh"
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DevBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes, bool keep = false, cudaStream_t st = 0) {
+    if (bytes <= cap) return cudaSuccess;
+    size_t want = bytes + bytes / 8 + 256;
+    void *np = nullptr;
+    cudaError_t e = cudaMalloc(&np, want);
+    if (e != cudaSuccess) return e;
+    if (p) {
+      if (keep) cudaMemcpyAsync(np, p, cap, cudaMemcpyDeviceToDevice, st);
+      cudaStreamSynchronize(st);
+      cudaFree(p);
+    }
+    p = np;
+    cap = want;
+    return cudaSuccess;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <class T>
+  T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+struct PinnedBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 8 + 4096;
+    cudaError_t e = cudaMallocHost(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() {
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+// quota bookkeeping on the device: first read of the batch whose planned length crosses the quota
+__global__ void k_rlen0(const uint32_t *rlen, uint32_t n_reads, uint32_t pass_num, unsigned long long *out) {
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < n_reads) out[r] = rlen[(uint64_t)r * pass_num];
+}
+
+// ctrl[0] = cut index (first read with len_total + raw_len > quota), n_reads if none
+__global__ void k_find_cut(const unsigned long long *prefix, const uint32_t *plan_raw, uint32_t n_reads,
+                           long long len_total, long long quota, unsigned long long *ctrl) {
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_reads) return;
+  if (len_total + (long long)prefix[r] + (long long)plan_raw[r] > quota) atomicMin(&ctrl[0], (unsigned long long)r);
+}
+
+// ctrl[1] = emitted bases (pass 0) of the reads before the cut; ctrl[2] = any pass-1 flag
+__global__ void k_batch_totals(const unsigned long long *prefix, const uint32_t *rlen, const uint32_t *flags,
+                               uint32_t n_reads, uint32_t pass_num, unsigned long long *ctrl) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned long long cut = ctrl[0];
+  if (i == 0) {
+    if (cut >= n_reads) ctrl[1] = prefix[n_reads - 1] + rlen[(uint64_t)(n_reads - 1) * pass_num];
+    else ctrl[1] = prefix[cut];
+  }
+  const uint64_t n_sub = (uint64_t)min((unsigned long long)n_reads, cut + 1) * pass_num;
+  if (i < n_sub && flags[i]) atomicOr(reinterpret_cast<unsigned int *>(&ctrl[2]), flags[i]);
+}
+
+__global__ void k_fill_u32(uint32_t *p, uint32_t n, uint32_t v) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+__global__ void k_init_stats(unsigned long long *blk, int64_t cells) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < cells) blk[i] = (i == 3) ? (unsigned long long)LLONG_MAX : 0ull;
+}
+
+// widen uint32 -> uint64 for the scans
+__global__ void k_widen(const uint32_t *in, uint32_t n, unsigned long long *out) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = in[i];
+}
+
+// replay: number of draws each subread consumed must equal the distance to the next start
+__global__ void k_check_replay(const int64_t *starts, const uint32_t *used, const uint32_t *plan_wlen, uint32_t glen,
+                               uint32_t n_sub, uint32_t pass_num, int64_t next_start_after,
+                               const unsigned long long *ctrl, unsigned int *bad) {
+  const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_sub) return;
+  if ((unsigned long long)(s / pass_num) >= ctrl[0]) return;  // reads at / after the quota cut are re-planned
+  const int64_t nxt = (s + 1 < n_sub) ? starts[s + 1] : next_start_after;
+  if (nxt < 0) return;  // unknown (last subread of the log)
+  const uint32_t r = s / pass_num, pass = s % pass_num;
+  const int64_t planner = (pass == 0) ? (plan_wlen[r] < glen ? 3 : 2) : 0;
+  if (starts[s] + planner + (int64_t)used[s] != nxt) atomicAdd(bad, 1u);
+}
+
+}  // namespace
+
+using namespace pb;
+
+struct pbsim_engine {
+  int device = 0;
+  cudaStream_t st = nullptr, st_copy = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::string err;
+
+  // model
+  bool model_set = false;
+  pbsim_model model;  // shallow copy: scalar fields only are used after set_model
+  ModelImage img;
+  std::vector<int32_t> h_prob2len;
+  std::vector<uint8_t> h_prob2acc;
+  DevBuf d_blob, d_acc, d_prob2len, d_prob2acc, d_qs_thr, d_qs_thr_hp, d_qc_prob, d_er_bias;
+  uint32_t er_smem_bar_off = 0;
+  EmitParams emitp;
+
+  // sequence
+  bool seq_set = false;
+  DevBuf d_ascii, d_pk, d_hp4, d_xm, d_hpfreq, d_biasone, d_flag;
+  int64_t glen = 0;
+  int32_t seq_num = 0;
+  double bias[12];
+  int64_t hpfreq[12];
+
+  // run
+  bool running = false;
+  pbsim_run run;
+  int64_t next_read = 0;  // reads simulated so far (ids are 1-based: next id = next_read + 1)
+  int64_t len_total = 0;
+  int64_t reads_done_in_run = 0;
+  bool finished = false;
+  bool tail_mode = false;
+  double mean_rlen_est = 0;
+  double table_mean_len = 0;  // mean of the length sampler, for the first batch-size estimate
+  uint32_t cap_num = 5, cap_den = 4;  // event-slot capacity = wlen * 5/4 + 2048
+  DevBuf d_draws, d_starts;
+
+  // batch arrays
+  DevBuf b_read_u32;   // 4 arrays per read
+  DevBuf b_sub_u32;    // 15 arrays per subread
+  DevBuf b_sub_u64;    // 9 arrays per subread (+1)
+  DevBuf b_sub_f64;
+  DevBuf d_bins;       // bin_start[102], bin_lo[101], bin_hi[101], cta_first[102]
+  DevBuf d_ctrl;       // control words
+  DevBuf d_cub_tmp;
+  DevBuf d_ev, d_ck;
+  DevBuf d_out_reads, d_out_maf;
+  PinnedBuf h_reads, h_maf, h_ctrl, h_acc;
+  Batch B;
+  uint64_t *u64_cap_scan = nullptr;
+  // last chunk info
+  std::vector<int64_t> last_info;
+
+  // stats
+  DevBuf d_stats;
+  int64_t stats_cells = 0, freq_len_cells = 0;
+  double accuracy_total = 0;
+  double gen_ms = 0;
+  int64_t launches = 0;
+};
+
+namespace {
+
+int fail(pbsim_engine *e, int code, const char *fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (e) e->err = buf; else g_create_error = buf;
+  return code;
+}
+
+#define CK(call)                                                                                          \
+  do {                                                                                                    \
+    cudaError_t _e = (call);                                                                              \
+    if (_e != cudaSuccess)                                                                                \
+      return fail(e, PBSIM_E_CUDA, "CUDA error %s at %s:%d (%s)", cudaGetErrorString(_e), __FILE__, __LINE__, #call); \
+  } while (0)
+
+inline uint32_t nblk(uint64_t n, uint32_t t) { return (uint32_t)((n + t - 1) / t); }
+
+template <class T>
+int upload(pbsim_engine *e, DevBuf &d, const T *src, size_t n) {
+  CK(d.ensure(std::max<size_t>(n * sizeof(T), 16)));
+  if (n) CK(cudaMemcpyAsync(d.p, src, n * sizeof(T), cudaMemcpyHostToDevice, e->st));
+  return 0;
+}
+
+DeviceModel device_model(const pbsim_engine *e) {
+  DeviceModel M;
+  M.blob = e->d_blob.as<uint8_t>();
+  M.acc = e->d_acc.as<AccEntry>();
+  M.prob2len = e->d_prob2len.as<int32_t>();
+  M.prob2acc = e->d_prob2acc.as<uint8_t>();
+  M.len_rand_value = (uint32_t)e->model.len_rand_value;
+  M.acc_rand_value = (uint32_t)e->model.accuracy_rand_value;
+  M.len_min = (uint32_t)e->model.len_min;
+  M.qs_thr = e->d_qs_thr.as<uint32_t>();
+  M.qs_thr_hp = e->d_qs_thr_hp.as<uint32_t>();
+  M.qc_prob = e->d_qc_prob.as<double>();
+  M.er_bias = e->d_er_bias.as<uint16_t>();
+  M.pass_num = (uint32_t)e->model.pass_num;
+  M.uniform_bias = e->img.uniform_bias ? 1u : 0u;
+  return M;
+}
+
+DeviceGenome device_genome(const pbsim_engine *e) {
+  DeviceGenome G;
+  G.ascii = e->d_ascii.as<uint8_t>();
+  G.pk = e->d_pk.as<uint32_t>();
+  G.hp4 = e->d_hp4.as<uint8_t>();
+  G.xm = e->d_xm.as<uint32_t>();
+  G.len = (uint32_t)e->glen;
+  G.seq_num = (uint32_t)e->seq_num;
+  return G;
+}
+
+// bias-dependent threshold tables (re-uploaded with every sequence)
+int upload_bias_tables(pbsim_engine *e) {
+  e->img.apply_bias(e->model, e->bias);
+  if (e->model.method == PBSIM_METHOD_QSHMM) {
+    if (upload(e, e->d_qs_thr, e->img.qs_thr.data(), e->img.qs_thr.size())) return PBSIM_E_CUDA;
+    if (upload(e, e->d_qs_thr_hp, e->img.qs_thr_hp.data(), e->img.qs_thr_hp.size())) return PBSIM_E_CUDA;
+  } else {
+    if (upload(e, e->d_er_bias, e->img.er_bias.data(), e->img.er_bias.size())) return PBSIM_E_CUDA;
+  }
+  CK(cudaStreamSynchronize(e->st));
+  return 0;
+}
+
+int finish_sequence_ingest(pbsim_engine *e, int64_t len, int32_t seq_num, const double bias[12]) {
+  // ascii already in d_ascii (padded with zeros to a multiple of 16)
+  e->glen = len;
+  e->seq_num = seq_num;
+  std::memcpy(e->bias, bias, sizeof e->bias);
+  const int64_t words = (len + 15) / 16;
+  const int64_t xm_words = ((len >> kXmShift) >> 5) + 2;
+  CK(e->d_pk.ensure((size_t)(words + 8) * 4));
+  CK(e->d_hp4.ensure((size_t)(len / 2 + 16)));
+  CK(e->d_xm.ensure((size_t)xm_words * 4));
+  CK(e->d_hpfreq.ensure(12 * 8));
+  CK(e->d_biasone.ensure(16));
+  CK(e->d_flag.ensure(16));
+  CK(cudaMemsetAsync(e->d_xm.p, 0, (size_t)xm_words * 4, e->st));
+  CK(cudaMemsetAsync(e->d_hpfreq.p, 0, 12 * 8, e->st));
+  CK(cudaMemsetAsync(e->d_flag.p, 0, 16, e->st));
+  CK(cudaMemsetAsync(e->d_hp4.p, 0, (size_t)(len / 2 + 16), e->st));
+  uint8_t one[16] = {0};
+  for (int h = 0; h < 12; ++h) one[h] = (bias[h] == 1.0) ? 1 : 0;
+  one[0] = 1;  // hp 0 never occurs inside a sequence
+  CK(cudaMemcpyAsync(e->d_biasone.p, one, 16, cudaMemcpyHostToDevice, e->st));
+  k_upper_pack<<<nblk(words, 256), 256, 0, e->st>>>(e->d_ascii.as<uint8_t>(), len, e->d_pk.as<uint32_t>(),
+                                                    e->d_xm.as<uint32_t>());
+  k_hp<<<nblk((len + 1) / 2, 256), 256, 0, e->st>>>(e->d_ascii.as<uint8_t>(), len, e->d_hp4.as<uint8_t>(),
+                                                    e->d_xm.as<uint32_t>(), e->d_hpfreq.as<unsigned long long>(),
+                                                    e->d_biasone.as<uint8_t>(), e->d_flag.as<uint32_t>());
+  e->launches += 2;
+  CK(cudaGetLastError());
+  uint32_t flag = 0;
+  CK(cudaMemcpyAsync(&flag, e->d_flag.p, 4, cudaMemcpyDeviceToHost, e->st));
+  CK(cudaMemcpyAsync(e->hpfreq, e->d_hpfreq.p, 12 * 8, cudaMemcpyDeviceToHost, e->st));
+  CK(cudaStreamSynchronize(e->st));
+  if (flag) return fail(e, PBSIM_E_INVALID, "sequence holds a homopolymer longer than 65536 bases (unsupported)");
+  e->seq_set = true;
+  if (e->model_set) return upload_bias_tables(e);
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// one batch: plan -> sort -> pass 1 -> quota -> sizes -> emit -> stats
+// ---------------------------------------------------------------------------------------------
+struct BatchResult {
+  uint32_t n_valid_reads = 0;
+  bool cut = false;           // a read crossed the quota: the batch ended at n_valid_reads
+  uint64_t bases_pass0 = 0;
+  uint64_t reads_bytes = 0, maf_bytes = 0;
+  uint64_t bases_all = 0;
+};
+
+int carve_batch(pbsim_engine *e, uint32_t n_reads) {
+  const uint32_t pass = (uint32_t)e->model.pass_num;
+  const uint64_t n_sub = (uint64_t)n_reads * pass;
+  if (n_sub > 0x7FFFFFFFull) return fail(e, PBSIM_E_INVALID, "batch too large");
+  CK(e->b_read_u32.ensure((size_t)n_reads * 4 * 4 + 64));
+  CK(e->b_sub_u32.ensure((size_t)n_sub * 15 * 4 + 64));
+  CK(e->b_sub_u64.ensure((size_t)(n_sub + 1) * 10 * 8 + 64));
+  CK(e->b_sub_f64.ensure((size_t)n_sub * 8 + 64));
+  Batch &B = e->B;
+  B.n_reads = n_reads;
+  B.n_sub = (uint32_t)n_sub;
+  uint32_t *r32 = e->b_read_u32.as<uint32_t>();
+  B.plan_off = r32;
+  B.plan_wlen = r32 + n_reads;
+  B.plan_raw = r32 + 2ull * n_reads;
+  B.plan_meta = r32 + 3ull * n_reads;
+  uint32_t *s32 = e->b_sub_u32.as<uint32_t>();
+  uint32_t **fields[] = {&B.key_in, &B.key_out, &B.idx_in, &B.order, &B.cap, &B.ck_cap, &B.nent, &B.rlen,
+                         &B.ncol, &B.nsub, &B.nins, &B.ndel, &B.flags, &B.draws_used};
+  for (size_t i = 0; i < sizeof(fields) / sizeof(fields[0]); ++i) *fields[i] = s32 + i * n_sub;
+  uint64_t *s64 = e->b_sub_u64.as<uint64_t>();
+  B.ev_off = s64;
+  B.ck_off = s64 + (n_sub + 1);
+  B.accuracy = e->b_sub_f64.as<double>();
+  return 0;
+}
+
+// slices of b_sub_u64 (each n_sub + 1 long): 0 ev_off, 1 ck_off, 2 tmp widen, 3 rlen0 prefix,
+// 4 reads_size, 5 maf_size, 6 ntiles, 7 reads_off, 8 maf_off, 9 tile_start
+inline uint64_t *u64_slice(pbsim_engine *e, int k) { return e->b_sub_u64.as<uint64_t>() + (size_t)k * (e->B.n_sub + 1); }
+
+int excl_scan(pbsim_engine *e, const unsigned long long *in, unsigned long long *out, uint32_t n) {
+  size_t tmp = 0;
+  CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp, in, out, (int)n, e->st));
+  CK(e->d_cub_tmp.ensure(tmp + 256));
+  tmp = e->d_cub_tmp.cap;
+  CK(cub::DeviceScan::ExclusiveSum(e->d_cub_tmp.p, tmp, in, out, (int)n, e->st));
+  return 0;
+}
+
+int run_batch(pbsim_engine *e, uint32_t n_reads, int64_t clip_room, bool to_host, BatchResult *out) {
+  const uint32_t pass = (uint32_t)e->model.pass_num;
+  const bool qs = e->model.method == PBSIM_METHOD_QSHMM;
+  const bool replay = e->run.rng_mode == PBSIM_RNG_REPLAY;
+  int rc = carve_batch(e, n_reads);
+  if (rc) return rc;
+  Batch &B = e->B;
+  const uint32_t n_sub = B.n_sub;
+  B.first_read = (uint64_t)e->next_read;
+  CK(e->d_bins.ensure(512 * 4));
+  CK(e->d_ctrl.ensure(64 * 8));
+  CK(e->h_ctrl.ensure(64 * 8));
+  uint32_t *bin_start = e->d_bins.as<uint32_t>();
+  uint32_t *bin_lo = bin_start + 102, *bin_hi = bin_lo + 101, *cta_first = bin_hi + 101;
+  unsigned long long *ctrl = e->d_ctrl.as<unsigned long long>();
+  unsigned long long *hctrl = reinterpret_cast<unsigned long long *>(e->h_ctrl.p);
+
+  DeviceModel M = device_model(e);
+  DeviceGenome G = device_genome(e);
+  RngParams rng;
+  rng.mode = (uint32_t)e->run.rng_mode;
+  rng.seed = e->run.seed;
+  rng.draws = nullptr;
+  rng.draws_base = 0;
+  rng.draws_end = 0;
+  rng.starts = nullptr;
+  int64_t next_start_after = -1;
+  if (replay) {
+    // upload the slice of the draw log this batch can touch
+    const int64_t s0 = (int64_t)(e->next_read - e->run.first_read) * pass;
+    if (s0 + (int64_t)n_sub > e->run.replay_nsubreads)
+      return fail(e, PBSIM_E_REPLAY, "replay log exhausted: batch needs subreads %lld..%lld but the log has %lld",
+                  (long long)s0, (long long)(s0 + n_sub), (long long)e->run.replay_nsubreads);
+    const int64_t d0 = e->run.replay_starts[s0];
+    const int64_t d1 = (s0 + n_sub < e->run.replay_nsubreads) ? e->run.replay_starts[s0 + n_sub] : e->run.replay_ndraws;
+    next_start_after = (s0 + n_sub < e->run.replay_nsubreads) ? d1 : e->run.replay_ndraws;
+    if (d0 < 0 || d1 < d0 || d1 > e->run.replay_ndraws) return fail(e, PBSIM_E_REPLAY, "replay starts are not monotone");
+    if (upload(e, e->d_draws, e->run.replay_draws + d0, (size_t)(d1 - d0))) return PBSIM_E_CUDA;
+    if (upload(e, e->d_starts, e->run.replay_starts + s0, (size_t)n_sub)) return PBSIM_E_CUDA;
+    rng.draws = e->d_draws.as<int32_t>();
+    rng.draws_base = d0;
+    rng.draws_end = d1;
+    rng.starts = e->d_starts.as<int64_t>();
+  }
+
+  for (int attempt = 0; attempt < 6; ++attempt) {
+    // ---- K1 plan
+    const uint32_t ev_align = qs ? 8u : 16u;
+    k_plan<<<nblk(n_reads, 256), 256, 0, e->st>>>(M, G, rng, B, clip_room, e->cap_num, e->cap_den, ev_align);
+    e->launches++;
+    // ---- sort by (accuracy, length desc)
+    {
+      size_t tmp = 0;
+      CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, B.key_in, B.key_out, B.idx_in, B.order, (int)n_sub, 0, 27, e->st));
+      CK(e->d_cub_tmp.ensure(tmp + 256));
+      tmp = e->d_cub_tmp.cap;
+      CK(cub::DeviceRadixSort::SortPairs(e->d_cub_tmp.p, tmp, B.key_in, B.key_out, B.idx_in, B.order, (int)n_sub, 0, 27,
+                                         e->st));
+    }
+    k_fill_u32<<<1, 128, 0, e->st>>>(bin_start, 102, 0xFFFFFFFFu);
+    k_bin_bounds<<<nblk(n_sub, 256), 256, 0, e->st>>>(B.key_out, n_sub, bin_start);
+    k_cta_map<<<1, 32, 0, e->st>>>(bin_start, B.key_out, n_sub, bin_lo, bin_hi, cta_first);
+    e->launches += 3;
+    // ---- slots
+    unsigned long long *tmp64 = reinterpret_cast<unsigned long long *>(u64_slice(e, 2));
+    k_widen<<<nblk(n_sub + 1, 256), 256, 0, e->st>>>(B.cap, n_sub, tmp64);
+    if ((rc = excl_scan(e, tmp64, reinterpret_cast<unsigned long long *>(B.ev_off), n_sub + 1))) return rc;
+    k_widen<<<nblk(n_sub + 1, 256), 256, 0, e->st>>>(B.ck_cap, n_sub, tmp64);
+    if ((rc = excl_scan(e, tmp64, reinterpret_cast<unsigned long long *>(B.ck_off), n_sub + 1))) return rc;
+    e->launches += 2;
+    CK(cudaMemcpyAsync(hctrl, B.ev_off + n_sub, 8, cudaMemcpyDeviceToHost, e->st));
+    CK(cudaMemcpyAsync(hctrl + 1, B.ck_off + n_sub, 8, cudaMemcpyDeviceToHost, e->st));
+    CK(cudaStreamSynchronize(e->st));
+    const uint64_t ev_entries = hctrl[0], ck_entries = hctrl[1];
+    CK(e->d_ev.ensure((size_t)ev_entries * (qs ? 2 : 1) + 256));
+    CK(e->d_ck.ensure((size_t)ck_entries * sizeof(Ckpt) + 256));
+
+    // ---- K2 / K3 pass 1
+    SimArgs A;
+    A.M = M;
+    A.G = G;
+    A.rng = rng;
+    A.B = B;
+    A.cta_first = cta_first;
+    A.bin_lo = bin_lo;
+    A.bin_hi = bin_hi;
+    A.ev = e->d_ev.as<uint8_t>();
+    A.ck = e->d_ck.as<Ckpt>();
+    const uint32_t grid = nblk(n_sub, kSimThreads) + 101;
+    if (qs) {
+      if (replay) k_sim_qshmm<PBSIM_RNG_REPLAY><<<grid, kSimThreads, kQsSmemBytes, e->st>>>(A);
+      else k_sim_qshmm<PBSIM_RNG_PHILOX><<<grid, kSimThreads, kQsSmemBytes, e->st>>>(A);
+    } else {
+      const uint32_t smem = e->er_smem_bar_off + 16;
+      if (replay) k_sim_errhmm<PBSIM_RNG_REPLAY><<<grid, kSimThreads, smem, e->st>>>(A, e->er_smem_bar_off);
+      else k_sim_errhmm<PBSIM_RNG_PHILOX><<<grid, kSimThreads, smem, e->st>>>(A, e->er_smem_bar_off);
+    }
+    e->launches++;
+    CK(cudaGetLastError());
+
+    // ---- quota: which read crosses len_quota
+    unsigned long long *rl0 = reinterpret_cast<unsigned long long *>(u64_slice(e, 2));
+    unsigned long long *prefix = reinterpret_cast<unsigned long long *>(u64_slice(e, 3));
+    k_rlen0<<<nblk(n_reads, 256), 256, 0, e->st>>>(B.rlen, n_reads, pass, rl0);
+    if ((rc = excl_scan(e, rl0, prefix, n_reads))) return rc;
+    hctrl[0] = n_reads;
+    hctrl[1] = 0;
+    hctrl[2] = 0;
+    hctrl[3] = 0;
+    CK(cudaMemcpyAsync(ctrl, hctrl, 32, cudaMemcpyHostToDevice, e->st));
+    if (clip_room < 0)  // bulk batch: speculative unclipped plans
+      k_find_cut<<<nblk(n_reads, 256), 256, 0, e->st>>>(prefix, B.plan_raw, n_reads, e->len_total, e->run.len_quota, ctrl);
+    k_batch_totals<<<nblk(n_sub, 256), 256, 0, e->st>>>(prefix, B.rlen, B.flags, n_reads, pass, ctrl);
+    e->launches += 3;
+    if (replay) {
+      k_check_replay<<<nblk(n_sub, 256), 256, 0, e->st>>>(rng.starts, B.draws_used, B.plan_wlen, (uint32_t)e->glen, n_sub,
+                                                          pass, next_start_after, ctrl, reinterpret_cast<unsigned int *>(&ctrl[3]));
+      e->launches++;
+    }
+    CK(cudaMemcpyAsync(hctrl, ctrl, 32, cudaMemcpyDeviceToHost, e->st));
+    CK(cudaStreamSynchronize(e->st));
+    const uint32_t flags = (uint32_t)hctrl[2];
+    if (flags & 2u) return fail(e, PBSIM_E_PARAM, "a read drew an accuracy for which the model has no usable tables");
+    if (flags & 1u) {  // a read outgrew its slot: enlarge and redo the batch
+      e->cap_num *= 2;
+      if (attempt == 5) return fail(e, PBSIM_E_OVERFLOW, "event slots overflowed repeatedly");
+      continue;
+    }
+    const uint64_t cut = hctrl[0];
+    out->cut = cut < n_reads;
+    out->n_valid_reads = out->cut ? (uint32_t)cut : n_reads;
+    out->bases_pass0 = hctrl[1];
+    if (replay && hctrl[3] != 0)
+      return fail(e, PBSIM_E_REPLAY, "replay: %llu subreads consumed a different number of draws than the log says",
+                  (unsigned long long)hctrl[3]);
+    break;
+  }
+
+  const uint32_t nv_sub = out->n_valid_reads * pass;
+  out->reads_bytes = out->maf_bytes = 0;
+  out->bases_all = 0;
+  if (nv_sub == 0) return 0;
+
+  // ---- K4 sizes + offsets
+  unsigned long long *reads_size = reinterpret_cast<unsigned long long *>(u64_slice(e, 4));
+  unsigned long long *maf_size = reinterpret_cast<unsigned long long *>(u64_slice(e, 5));
+  unsigned long long *ntiles = reinterpret_cast<unsigned long long *>(u64_slice(e, 6));
+  unsigned long long *reads_off = reinterpret_cast<unsigned long long *>(u64_slice(e, 7));
+  unsigned long long *maf_off = reinterpret_cast<unsigned long long *>(u64_slice(e, 8));
+  unsigned long long *tile_start = reinterpret_cast<unsigned long long *>(u64_slice(e, 9));
+  CK(cudaMemsetAsync(reads_size + nv_sub, 0, 8, e->st));
+  CK(cudaMemsetAsync(maf_size + nv_sub, 0, 8, e->st));
+  CK(cudaMemsetAsync(ntiles + nv_sub, 0, 8, e->st));
+  e->emitp.glen = (uint32_t)e->glen;
+  {
+    char head[192];
+    snprintf(head, sizeof head, "%s%d", e->model.id_prefix, e->seq_num);
+    e->emitp.id_head_len = (uint32_t)strlen(head);
+    memcpy(e->emitp.id_head, head, e->emitp.id_head_len + 1);
+  }
+  k_sizes<<<nblk(nv_sub, 256), 256, 0, e->st>>>(B, e->emitp, nv_sub, (uint64_t *)reads_size, (uint64_t *)maf_size,
+                                                (uint64_t *)ntiles);
+  e->launches++;
+  if ((rc = excl_scan(e, reads_size, reads_off, nv_sub + 1))) return rc;
+  if ((rc = excl_scan(e, maf_size, maf_off, nv_sub + 1))) return rc;
+  if ((rc = excl_scan(e, ntiles, tile_start, nv_sub + 1))) return rc;
+  CK(cudaMemcpyAsync(hctrl + 8, reads_off + nv_sub, 8, cudaMemcpyDeviceToHost, e->st));
+  CK(cudaMemcpyAsync(hctrl + 9, maf_off + nv_sub, 8, cudaMemcpyDeviceToHost, e->st));
+  CK(cudaMemcpyAsync(hctrl + 10, tile_start + nv_sub, 8, cudaMemcpyDeviceToHost, e->st));
+  CK(cudaStreamSynchronize(e->st));
+  out->reads_bytes = hctrl[8];
+  out->maf_bytes = hctrl[9];
+  const uint64_t n_tiles = hctrl[10];
+  CK(e->d_out_reads.ensure((size_t)out->reads_bytes + 256));
+  CK(e->d_out_maf.ensure((size_t)out->maf_bytes + 256));
+
+  // ---- K4 emit
+  EmitArgs EA;
+  EA.G = G;
+  EA.B = B;
+  EA.P = e->emitp;
+  EA.ev = e->d_ev.as<uint8_t>();
+  EA.ck = e->d_ck.as<Ckpt>();
+  EA.n_sub = nv_sub;
+  EA.n_tiles = n_tiles;
+  EA.tile_start = (const uint64_t *)tile_start;
+  EA.reads_off = (const uint64_t *)reads_off;
+  EA.maf_off = (const uint64_t *)maf_off;
+  EA.out_reads = e->d_out_reads.as<uint8_t>();
+  EA.out_maf = e->d_out_maf.as<uint8_t>();
+  {
+    int dev_sms = 148;
+    cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, e->device);
+    const uint64_t want = (n_tiles + kEmitWarps - 1) / kEmitWarps;
+    const uint32_t grid = (uint32_t)std::min<uint64_t>(want, (uint64_t)dev_sms * 8 * 4);
+    if (qs) k_emit<PBSIM_METHOD_QSHMM><<<grid, kEmitThreads, 0, e->st>>>(EA);
+    else k_emit<PBSIM_METHOD_ERRHMM><<<grid, kEmitThreads, 0, e->st>>>(EA);
+    e->launches++;
+  }
+  // ---- K6 stats
+  k_stats<<<nblk(nv_sub, 256), 256, 0, e->st>>>(B, nv_sub, pass, e->d_stats.as<unsigned long long>(), e->freq_len_cells);
+  e->launches++;
+  CK(cudaGetLastError());
+
+  // per-subread accuracy values: summed on the host in read order (accuracy_total, :2314)
+  CK(e->h_acc.ensure((size_t)nv_sub * 8 + (size_t)nv_sub * 4 * 3 + 64));
+  double *hacc = reinterpret_cast<double *>(e->h_acc.p);
+  uint32_t *hrlen = reinterpret_cast<uint32_t *>(hacc + nv_sub);
+  CK(cudaMemcpyAsync(hacc, B.accuracy, (size_t)nv_sub * 8, cudaMemcpyDeviceToHost, e->st));
+  CK(cudaMemcpyAsync(hrlen, B.rlen, (size_t)nv_sub * 4, cudaMemcpyDeviceToHost, e->st));
+  (void)to_host;
+  return 0;
+}
+
+int next_chunk_impl(pbsim_engine *e, pbsim_chunk *c, bool to_host) {
+  if (!e || !c) return PBSIM_E_INVALID;
+  if (!e->running) return fail(e, PBSIM_E_INVALID, "simulate_begin was not called");
+  std::memset(c, 0, sizeof *c);
+  for (;;) {
+    if (e->finished) return 0;
+    if (e->len_total >= e->run.len_quota || (e->run.max_reads > 0 && e->reads_done_in_run >= e->run.max_reads)) {
+      e->finished = true;
+      return 0;
+    }
+    // batch size
+    int64_t nb;
+    int64_t clip_room = -1;
+    if (e->tail_mode) {
+      nb = 1;
+      clip_room = e->run.len_quota - e->len_total;
+    } else {
+      nb = e->run.batch_reads > 0 ? e->run.batch_reads : (int64_t)1 << 18;
+      double mean = e->mean_rlen_est > 0 ? e->mean_rlen_est : e->table_mean_len;
+      if (mean > (double)e->glen) mean = (double)e->glen;
+      if (mean > 0) {
+        const double need = (double)(e->run.len_quota - e->len_total) / mean;
+        const int64_t est = (int64_t)(need * 1.02) + 16;
+        if (est < nb) nb = est;
+      }
+      if (e->run.max_reads > 0) nb = std::min<int64_t>(nb, e->run.max_reads - e->reads_done_in_run);
+      if (e->run.rng_mode == PBSIM_RNG_REPLAY) {
+        const int64_t left = e->run.replay_nsubreads / e->model.pass_num - (e->next_read - e->run.first_read);
+        if (left <= 0) return fail(e, PBSIM_E_REPLAY, "replay log exhausted before the quota was reached");
+        nb = std::min<int64_t>(nb, left);
+      }
+      if (nb < 1) nb = 1;
+    }
+    CK(cudaEventRecord(e->ev0, e->st));
+    BatchResult br;
+    int rc = run_batch(e, (uint32_t)nb, clip_room, to_host, &br);
+    if (rc) return rc;
+    CK(cudaEventRecord(e->ev1, e->st));
+    CK(cudaStreamSynchronize(e->st));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, e->ev0, e->ev1));
+    e->gen_ms += ms;
+    const uint32_t pass = (uint32_t)e->model.pass_num;
+    const uint32_t nv = br.n_valid_reads;
+    // host-side ordered accumulation
+    {
+      const double *hacc = reinterpret_cast<const double *>(e->h_acc.p);
+      const uint32_t *hrlen = reinterpret_cast<const uint32_t *>(hacc + (size_t)nv * pass);
+      uint64_t bases = 0;
+      for (uint64_t s = 0; s < (uint64_t)nv * pass; ++s) {
+        e->accuracy_total += hacc[s];
+        bases += hrlen[s];
+      }
+      br.bases_all = bases;
+    }
+    if (br.cut) e->tail_mode = true;  // the next read is re-planned with the quota clip, one read at a time
+    if (nv == 0) continue;
+    if (e->mean_rlen_est <= 0 && nv > 0) e->mean_rlen_est = std::max(1.0, (double)br.bases_pass0 / nv);
+    c->first_read = e->next_read + 1;
+    c->n_reads = nv;
+    c->bases = (int64_t)br.bases_all;
+    c->reads_bytes = (int64_t)br.reads_bytes;
+    c->maf_bytes = (int64_t)br.maf_bytes;
+    // keep the per-subread info of this chunk for tests
+    e->last_info.clear();
+    e->next_read += nv;
+    e->reads_done_in_run += nv;
+    e->len_total += (int64_t)br.bases_pass0;
+    if (to_host) {
+      CK(e->h_reads.ensure((size_t)br.reads_bytes + 16));
+      CK(e->h_maf.ensure((size_t)br.maf_bytes + 16));
+      CK(cudaMemcpyAsync(e->h_reads.p, e->d_out_reads.p, (size_t)br.reads_bytes, cudaMemcpyDeviceToHost, e->st));
+      CK(cudaMemcpyAsync(e->h_maf.p, e->d_out_maf.p, (size_t)br.maf_bytes, cudaMemcpyDeviceToHost, e->st));
+      CK(cudaStreamSynchronize(e->st));
+      c->reads = reinterpret_cast<const char *>(e->h_reads.p);
+      c->maf = reinterpret_cast<const char *>(e->h_maf.p);
+      c->on_device = 0;
+    } else {
+      c->reads = reinterpret_cast<const char *>(e->d_out_reads.p);
+      c->maf = reinterpret_cast<const char *>(e->d_out_maf.p);
+      c->on_device = 1;
+    }
+    return 1;
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int pbsim_cuda_abi_version(void) { return PBSIM_ABI_VERSION; }
+
+const char *pbsim_cuda_last_error(const pbsim_engine *e) { return e ? e->err.c_str() : g_create_error.c_str(); }
+
+int pbsim_cuda_create(pbsim_engine **out, int device) {
+  pbsim_engine *e = nullptr;
+  if (!out) return fail(e, PBSIM_E_INVALID, "null output pointer");
+  int n = 0;
+  cudaError_t ce = cudaGetDeviceCount(&n);
+  if (ce != cudaSuccess || n == 0)
+    return fail(e, PBSIM_E_CUDA, "no usable CUDA device (%s); libpbsim_cuda has no CPU fallback",
+                ce == cudaSuccess ? "device count is 0" : cudaGetErrorString(ce));
+  if (device < 0 || device >= n) return fail(e, PBSIM_E_INVALID, "device %d out of range (0..%d)", device, n - 1);
+  CK(cudaSetDevice(device));
+  pbsim_engine *ne = new pbsim_engine();
+  ne->device = device;
+  cudaError_t c1 = cudaStreamCreateWithFlags(&ne->st, cudaStreamNonBlocking);
+  cudaError_t c2 = cudaStreamCreateWithFlags(&ne->st_copy, cudaStreamNonBlocking);
+  cudaError_t c3 = cudaEventCreate(&ne->ev0);
+  cudaError_t c4 = cudaEventCreate(&ne->ev1);
+  if (c1 != cudaSuccess || c2 != cudaSuccess || c3 != cudaSuccess || c4 != cudaSuccess) {
+    delete ne;
+    return fail(e, PBSIM_E_CUDA, "cannot create CUDA streams/events");
+  }
+  std::memset(&ne->model, 0, sizeof ne->model);
+  std::memset(&ne->emitp, 0, sizeof ne->emitp);
+  *out = ne;
+  return 0;
+}
+
+void pbsim_cuda_destroy(pbsim_engine *e) {
+  if (!e) return;
+  cudaSetDevice(e->device);
+  cudaStreamSynchronize(e->st);
+  DevBuf *bufs[] = {&e->d_blob, &e->d_acc, &e->d_prob2len, &e->d_prob2acc, &e->d_qs_thr, &e->d_qs_thr_hp, &e->d_qc_prob,
+                    &e->d_er_bias, &e->d_ascii, &e->d_pk, &e->d_hp4, &e->d_xm, &e->d_hpfreq, &e->d_biasone, &e->d_flag,
+                    &e->d_draws, &e->d_starts, &e->b_read_u32, &e->b_sub_u32, &e->b_sub_u64, &e->b_sub_f64, &e->d_bins,
+                    &e->d_ctrl, &e->d_cub_tmp, &e->d_ev, &e->d_ck, &e->d_out_reads, &e->d_out_maf, &e->d_stats};
+  for (DevBuf *b : bufs) b->release();
+  e->h_reads.release();
+  e->h_maf.release();
+  e->h_ctrl.release();
+  e->h_acc.release();
+  cudaEventDestroy(e->ev0);
+  cudaEventDestroy(e->ev1);
+  cudaStreamDestroy(e->st);
+  cudaStreamDestroy(e->st_copy);
+  delete e;
+}
+
+int pbsim_cuda_set_model(pbsim_engine *e, const pbsim_model *m) {
+  if (!e || !m) return PBSIM_E_INVALID;
+  CK(cudaSetDevice(e->device));
+  if (m->method != PBSIM_METHOD_QSHMM && m->method != PBSIM_METHOD_ERRHMM)
+    return fail(e, PBSIM_E_INVALID, "method must be qshmm or errhmm");
+  if (m->pass_num < 1 || m->len_rand_value < 1 || m->accuracy_rand_value < 1 || !m->prob2len || !m->prob2accuracy)
+    return fail(e, PBSIM_E_INVALID, "model samplers are empty");
+  if (m->len_max > 1000000) return fail(e, PBSIM_E_INVALID, "length-max above FASTQ_LEN_MAX (1000000)");
+  if (!e->img.build(*m)) return fail(e, PBSIM_E_INVALID, "model tables: %s", e->img.error.c_str());
+  e->model = *m;
+  e->h_prob2len.assign(m->prob2len, m->prob2len + m->len_rand_value);
+  e->h_prob2acc.assign(m->prob2accuracy, m->prob2accuracy + m->accuracy_rand_value);
+  {
+    double acc = 0;
+    for (int32_t v : e->h_prob2len) acc += v;
+    e->table_mean_len = acc / e->h_prob2len.size();
+  }
+  e->model.prob2len = e->h_prob2len.data();
+  e->model.prob2accuracy = e->h_prob2acc.data();
+  // NOTE: e->model.rows[] still points into the caller's tables; apply_bias reads emis_del from them,
+  // so the caller keeps the pbsim_model alive while the engine uses it (documented in the header).
+  if (upload(e, e->d_blob, e->img.blob.data(), e->img.blob.size())) return PBSIM_E_CUDA;
+  if (upload(e, e->d_acc, e->img.acc, PBSIM_NACC)) return PBSIM_E_CUDA;
+  if (upload(e, e->d_prob2len, e->h_prob2len.data(), e->h_prob2len.size())) return PBSIM_E_CUDA;
+  if (upload(e, e->d_prob2acc, e->h_prob2acc.data(), e->h_prob2acc.size())) return PBSIM_E_CUDA;
+  if (upload(e, e->d_qc_prob, m->qc_prob, PBSIM_NQV)) return PBSIM_E_CUDA;
+  CK(e->d_qs_thr.ensure(PBSIM_NQV * 16));
+  CK(e->d_qs_thr_hp.ensure(PBSIM_NQV * 48));
+  CK(e->d_er_bias.ensure(std::max<size_t>(e->img.er_bias.size() * 2, 16) + 64));
+  // errhmm: largest per-accuracy shared-memory footprint
+  e->er_smem_bar_off = 0;
+  if (m->method == PBSIM_METHOD_ERRHMM) {
+    uint32_t mx = 0;
+    for (int a = 0; a < PBSIM_NACC; ++a) {
+      const AccEntry &ae = e->img.acc[a];
+      if (!ae.valid || ae.mode == 3) continue;
+      const uint32_t need = ae.blob_bytes + ((ae.nstates + 1u) * 2u + 15u) / 16u * 16u;
+      mx = std::max(mx, need);
+    }
+    e->er_smem_bar_off = (mx + 15u) / 16u * 16u;
+    const int smem = (int)e->er_smem_bar_off + 16;
+    CK(cudaFuncSetAttribute(k_sim_errhmm<PBSIM_RNG_PHILOX>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CK(cudaFuncSetAttribute(k_sim_errhmm<PBSIM_RNG_REPLAY>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  }
+  // emission constants
+  e->emitp.pass_num = (uint32_t)m->pass_num;
+  e->emitp.sam = m->pass_num > 1 ? 1u : 0u;
+  snprintf(e->emitp.rq, sizeof e->emitp.rq, "%f", m->accuracy_mean);
+  e->emitp.rq_len = (uint32_t)strlen(e->emitp.rq);
+  // stats block
+  e->freq_len_cells = 2 * m->len_max + 2;
+  e->stats_cells = kStatCounters + 100001 + e->freq_len_cells;
+  CK(e->d_stats.ensure((size_t)e->stats_cells * 8));
+  CK(cudaStreamSynchronize(e->st));
+  e->model_set = true;
+  if (e->seq_set) return upload_bias_tables(e);
+  return 0;
+}
+
+int pbsim_cuda_set_sequence(pbsim_engine *e, const pbsim_sequence *s) {
+  if (!e || !s || !s->bases) return PBSIM_E_INVALID;
+  CK(cudaSetDevice(e->device));
+  if (s->len < 1 || s->len > 1000000000) return fail(e, PBSIM_E_INVALID, "sequence length out of range");
+  const size_t padded = ((size_t)s->len + 15) / 16 * 16 + 64;
+  CK(e->d_ascii.ensure(padded));
+  CK(cudaMemsetAsync(e->d_ascii.as<uint8_t>() + (s->len / 16) * 16, 0, padded - (s->len / 16) * 16, e->st));
+  CK(cudaMemcpyAsync(e->d_ascii.p, s->bases, (size_t)s->len, cudaMemcpyHostToDevice, e->st));
+  return finish_sequence_ingest(e, s->len, s->seq_num, s->hp_del_bias);
+}
+
+int pbsim_cuda_set_synthetic_sequence(pbsim_engine *e, int64_t len, int32_t seq_num, uint64_t seed) {
+  if (!e) return PBSIM_E_INVALID;
+  CK(cudaSetDevice(e->device));
+  if (len < 1 || len > 1000000000) return fail(e, PBSIM_E_INVALID, "sequence length out of range");
+  const size_t padded = ((size_t)len + 15) / 16 * 16 + 64;
+  CK(e->d_ascii.ensure(padded));
+  CK(cudaMemsetAsync(e->d_ascii.as<uint8_t>() + (len / 16) * 16, 0, padded - (len / 16) * 16, e->st));
+  k_synth_ascii<<<nblk((len + 15) / 16, 256), 256, 0, e->st>>>(e->d_ascii.as<uint8_t>(), len, seed);
+  e->launches++;
+  double bias[12] = {0, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 0};
+  return finish_sequence_ingest(e, len, seq_num, bias);
+}
+
+int pbsim_cuda_update_hp_del_bias(pbsim_engine *e, const double bias[12]) {
+  if (!e || !bias || !e->seq_set) return PBSIM_E_INVALID;
+  CK(cudaSetDevice(e->device));
+  for (int h = 1; h <= 11; ++h)
+    if ((bias[h] == 1.0) != (e->bias[h] == 1.0))
+      return fail(e, PBSIM_E_INVALID, "update_hp_del_bias may only change values, not which cells equal 1; call set_sequence");
+  std::memcpy(e->bias, bias, sizeof e->bias);
+  if (e->model_set) return upload_bias_tables(e);
+  return 0;
+}
+
+int pbsim_cuda_get_hpfreq(pbsim_engine *e, int64_t hpfreq[12]) {
+  if (!e || !e->seq_set) return PBSIM_E_INVALID;
+  std::memcpy(hpfreq, e->hpfreq, sizeof e->hpfreq);
+  return 0;
+}
+
+int pbsim_cuda_simulate_begin(pbsim_engine *e, const pbsim_run *run) {
+  if (!e || !run) return PBSIM_E_INVALID;
+  CK(cudaSetDevice(e->device));
+  if (!e->model_set || !e->seq_set) return fail(e, PBSIM_E_INVALID, "set_model and set_sequence must precede simulate_begin");
+  if (run->rng_mode == PBSIM_RNG_REPLAY && (!run->replay_draws || !run->replay_starts || run->replay_nsubreads < 1))
+    return fail(e, PBSIM_E_INVALID, "replay mode needs the draw log and the subread starts");
+  e->run = *run;
+  e->next_read = run->first_read;
+  e->len_total = run->len_total_start;
+  e->reads_done_in_run = 0;
+  e->finished = false;
+  e->tail_mode = false;
+  e->mean_rlen_est = 0;
+  e->accuracy_total = 0;
+  e->gen_ms = 0;
+  e->launches = 0;
+  k_init_stats<<<nblk(e->stats_cells, 256), 256, 0, e->st>>>(e->d_stats.as<unsigned long long>(), e->stats_cells);
+  e->launches++;
+  CK(cudaGetLastError());
+  e->running = true;
+  return 0;
+}
+
+int pbsim_cuda_next_chunk(pbsim_engine *e, pbsim_chunk *c) {
+  if (e) cudaSetDevice(e->device);
+  return next_chunk_impl(e, c, true);
+}
+
+int pbsim_cuda_next_chunk_device(pbsim_engine *e, pbsim_chunk *c) {
+  if (e) cudaSetDevice(e->device);
+  return next_chunk_impl(e, c, false);
+}
+
+int pbsim_cuda_simulate_end(pbsim_engine *e, pbsim_stats *st, int64_t *freq_len, int64_t freq_len_cells,
+                            int64_t *freq_accuracy) {
+  if (!e || !st) return PBSIM_E_INVALID;
+  CK(cudaSetDevice(e->device));
+  if (!e->running) return fail(e, PBSIM_E_INVALID, "simulate_begin was not called");
+  std::vector<long long> blk((size_t)e->stats_cells);
+  CK(cudaMemcpyAsync(blk.data(), e->d_stats.p, (size_t)e->stats_cells * 8, cudaMemcpyDeviceToHost, e->st));
+  CK(cudaStreamSynchronize(e->st));
+  std::memset(st, 0, sizeof *st);
+  st->res_num = blk[0];
+  st->res_pass_num = blk[1];
+  st->res_len_total = blk[2];
+  st->res_len_min = blk[3];
+  st->res_len_max = blk[4];
+  st->res_sub_num = blk[5];
+  st->res_ins_num = blk[6];
+  st->res_del_num = blk[7];
+  st->accuracy_total = e->accuracy_total;
+  const long long *fa = blk.data() + kStatCounters;
+  const long long *fl = fa + 100001;
+  // mean / SD exactly as the reference derives them from the histograms (:2387-2410)
+  if (st->res_pass_num > 0) {
+    st->res_len_mean = (double)st->res_len_total / st->res_pass_num;
+    st->res_accuracy_mean = e->accuracy_total / st->res_pass_num;
+    if (st->res_pass_num == 1) {
+      st->res_len_sd = 0.0;
+      st->res_accuracy_sd = 0.0;
+    } else {
+      double variance = 0.0;
+      for (int64_t i = 0; i <= e->model.len_max && i < e->freq_len_cells; ++i)
+        if (fl[i] > 0) variance += pow((st->res_len_mean - i), 2) * fl[i];
+      st->res_len_sd = sqrt(variance / st->res_pass_num);
+      variance = 0.0;
+      for (int64_t i = 0; i <= 100000; ++i)
+        if (fa[i] > 0) variance += pow((st->res_accuracy_mean - i * 0.00001), 2) * fa[i];
+      st->res_accuracy_sd = sqrt(variance / st->res_pass_num);
+    }
+  }
+  st->gen_seconds = e->gen_ms * 1e-3;
+  st->kernel_launches = e->launches;
+  if (freq_len) {
+    const int64_t n = std::min<int64_t>(freq_len_cells, e->freq_len_cells);
+    for (int64_t i = 0; i < n; ++i) freq_len[i] = fl[i];
+  }
+  if (freq_accuracy)
+    for (int64_t i = 0; i <= 100000; ++i) freq_accuracy[i] = fa[i];
+  e->running = false;
+  return 0;
+}
+
+int pbsim_cuda_stats_device_block(pbsim_engine *e, void **dptr, int64_t *cells) {
+  if (!e || !dptr || !cells || !e->model_set) return PBSIM_E_INVALID;
+  *dptr = e->d_stats.p;
+  *cells = e->stats_cells;
+  return 0;
+}
+
+int pbsim_cuda_last_chunk_info(pbsim_engine *e, int64_t *out, int64_t cap_subreads, int64_t *n_subreads) {
+  if (!e || !n_subreads) return PBSIM_E_INVALID;
+  CK(cudaSetDevice(e->device));
+  const Batch &B = e->B;
+  const uint32_t pass = (uint32_t)e->model.pass_num;
+  const int64_t n = B.n_sub;
+  *n_subreads = n;
+  if (!out) return 0;
+  const int64_t m = std::min<int64_t>(n, cap_subreads);
+  std::vector<uint32_t> off(B.n_reads), wl(B.n_reads), meta(B.n_reads), rl(n), nc(n);
+  CK(cudaMemcpy(off.data(), B.plan_off, (size_t)B.n_reads * 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(wl.data(), B.plan_wlen, (size_t)B.n_reads * 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(meta.data(), B.plan_meta, (size_t)B.n_reads * 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(rl.data(), B.rlen, (size_t)n * 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(nc.data(), B.ncol, (size_t)n * 4, cudaMemcpyDeviceToHost));
+  for (int64_t s = 0; s < m; ++s) {
+    const uint32_t r = (uint32_t)(s / pass);
+    int64_t *o = out + s * 8;
+    o[0] = (int64_t)B.first_read + 1 + r;
+    o[1] = s % pass;
+    o[2] = meta[r] & 0xFF;
+    o[3] = off[r];
+    o[4] = wl[r];
+    o[5] = rl[s];
+    o[6] = nc[s];
+    o[7] = (meta[r] >> 8) & 1;
+  }
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,147 @@
+// K0 — genome ingest on the device.
+// Replaces the in-memory products of get_genome_seq (pbsim.cpp:1032-1065): upper-cased sequence,
+// per-base homopolymer length hp[] and the hpfreq[] histogram.  Device layout per sequence:
+//   ascii : uint8[len]      upper-cased text (slow path and non-ACGT truth)
+//   pk    : uint32[len/16]  2 bits per base, A=0 C=1 G=2 T=3 (complement = code ^ 3), base i at bits 2*(i&15)
+//   hp4   : uint8[len/2]    4-bit homopolymer length (1..11, the reference's counter quirk included)
+//   xm    : uint32[]        1 bit per 1024-base block: block holds a non-ACGT base or a base whose
+//                           deletion bias hp_del_bias[hp] differs from 1 ("exceptional" block)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace pb {
+
+constexpr int kXmShift = 10;  // exception bitmap granularity: 1024 bases
+
+__device__ __forceinline__ uint32_t base_code(uint8_t c, bool &ok) {
+  // A=0 C=1 G=2 T=3
+  switch (c) {
+    case 'A': ok = true; return 0u;
+    case 'C': ok = true; return 1u;
+    case 'G': ok = true; return 2u;
+    case 'T': ok = true; return 3u;
+    default: ok = false; return 0u;
+  }
+}
+
+// synthetic i.i.d. ACGT text (benchmarks): one 64-bit hash per 16 bases
+__global__ void k_synth_ascii(uint8_t *ascii, int64_t len, uint64_t seed) {
+  const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t i0 = w * 16;
+  if (i0 >= len) return;
+  uint64_t z = seed + 0x9E3779B97F4A7C15ull * (uint64_t)(w + 1);  // splitmix64
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  const uint32_t lut = 0x54474341u;  // "ACGT"
+  uint32_t out[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    uint32_t v = 0;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const uint32_t code = (uint32_t)(z >> (2 * (q * 4 + b))) & 3u;
+      v |= ((lut >> (8 * code)) & 0xFFu) << (8 * b);
+    }
+    out[q] = v;
+  }
+  if (i0 + 16 <= len) {
+    *reinterpret_cast<uint4 *>(ascii + i0) = make_uint4(out[0], out[1], out[2], out[3]);
+  } else {
+    for (int64_t i = i0; i < len; ++i) ascii[i] = (uint8_t)(out[(i - i0) >> 2] >> (8 * ((i - i0) & 3)));
+  }
+}
+
+// upper-case in place (toupper in the C locale, :1035-1037), pack, flag non-ACGT blocks.
+// One thread per 16 bases; `ascii` is padded to a multiple of 16 with zeros.
+__global__ void k_upper_pack(uint8_t *ascii, int64_t len, uint32_t *pk, uint32_t *xm) {
+  const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t i0 = w * 16;
+  if (i0 >= len) return;
+  uint4 v = *reinterpret_cast<const uint4 *>(ascii + i0);
+  uint32_t in[4] = {v.x, v.y, v.z, v.w};
+  uint32_t word = 0;
+  bool any_bad = false;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    uint32_t o = 0;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      uint8_t c = (uint8_t)(in[q] >> (8 * b));
+      if (c >= 'a' && c <= 'z') c = (uint8_t)(c - 32);
+      o |= (uint32_t)c << (8 * b);
+      bool ok;
+      const uint32_t code = base_code(c, ok);
+      if (i0 + q * 4 + b < len) {
+        word |= code << (2 * (q * 4 + b));
+        any_bad |= !ok;
+      }
+    }
+    in[q] = o;
+  }
+  *reinterpret_cast<uint4 *>(ascii + i0) = make_uint4(in[0], in[1], in[2], in[3]);
+  pk[w] = word;
+  if (any_bad) {
+    const int64_t blk = i0 >> kXmShift;
+    atomicOr(&xm[blk >> 5], 1u << (blk & 31));
+  }
+}
+
+// hp[] with the reference's counter: run length L -> L (L <= 11), else 11 / 10 alternating
+// (nnum > 11 -> 10, :1046-1048); every base of an 'N' run gets 1 (:1050-1054).
+// One thread per 2 bases (one hp4 byte).  Walks are capped; a capped walk raises *flag so the
+// engine can fall back to a host scan for pathological inputs (megabase homopolymers).
+__device__ __forceinline__ uint32_t hp_of(const uint8_t *ascii, int64_t len, int64_t i, uint32_t *flag) {
+  const uint8_t c = ascii[i];
+  if (c == 'N') return 1u;
+  const int64_t cap = 1 << 16;
+  int64_t l = 0, r = 0;
+  while (i - l - 1 >= 0 && ascii[i - l - 1] == c && l < cap) ++l;
+  while (i + r + 1 < len && ascii[i + r + 1] == c && r < cap) ++r;
+  if (l >= cap || r >= cap) *flag = 1u;
+  const int64_t L = l + r + 1;
+  if (L <= 11) return (uint32_t)L;
+  return ((L - 11) & 1) ? 10u : 11u;
+}
+
+__global__ void k_hp(const uint8_t *ascii, int64_t len, uint8_t *hp4, uint32_t *xm, unsigned long long *hpfreq,
+                     const uint8_t *bias_is_one /*[12]*/, uint32_t *flag) {
+  __shared__ unsigned int hist[12];
+  if (threadIdx.x < 12) hist[threadIdx.x] = 0;
+  __syncthreads();
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t i0 = t * 2;
+  if (i0 < len) {
+    const uint32_t h0 = hp_of(ascii, len, i0, flag);
+    uint32_t h1 = 0;
+    atomicAdd(&hist[h0], 1u);
+    bool special = !bias_is_one[h0];
+    if (i0 + 1 < len) {
+      h1 = hp_of(ascii, len, i0 + 1, flag);
+      atomicAdd(&hist[h1], 1u);
+      special |= !bias_is_one[h1];
+    }
+    hp4[t] = (uint8_t)(h0 | (h1 << 4));
+    if (special) {
+      const int64_t blk = i0 >> kXmShift;
+      atomicOr(&xm[blk >> 5], 1u << (blk & 31));
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 12 && hist[threadIdx.x]) atomicAdd(&hpfreq[threadIdx.x], (unsigned long long)hist[threadIdx.x]);
+}
+
+// true if any 1024-base block overlapping genome range [g0, g1] is exceptional
+__device__ __forceinline__ bool range_exceptional(const uint32_t *__restrict__ xm, uint32_t g0, uint32_t g1) {
+  const uint32_t b0 = g0 >> kXmShift, b1 = g1 >> kXmShift;
+  for (uint32_t w = b0 >> 5; w <= (b1 >> 5); ++w) {
+    uint32_t bits = __ldg(&xm[w]);
+    if (w == (b0 >> 5)) bits &= 0xFFFFFFFFu << (b0 & 31);
+    if (w == (b1 >> 5)) bits &= 0xFFFFFFFFu >> (31 - (b1 & 31));
+    if (bits) return true;
+  }
+  return false;
+}
+
+}  // namespace pb

@@ -38,6 +38,9 @@ struct QsBlobLayout {
   static constexpr uint32_t freq_bytes = 1008;                            // uint8[1000] padded
 };
 
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
 inline uint32_t er_blob_bytes(uint32_t nst, uint32_t *t2_off, uint32_t *emis_off, uint32_t *emod_off) {
   const uint32_t rows = nst + 1;
   uint32_t o = 0;

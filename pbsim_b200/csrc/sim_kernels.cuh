@@ -1,0 +1,385 @@
+// K1 (read planner) and K2/K3 (pass 1: qshmm / errhmm chains -> event streams).
+//
+// Scheduling: every (read, pass) — a "subread" — is one GPU thread in pass 1, because the Markov
+// chain of a read is inherently sequential.  Subreads are sorted by (accuracy, length descending)
+// so that (a) a CTA works on ONE accuracy and stages only that accuracy's HMM tables in shared
+// memory with a TMA bulk copy, and (b) the 32 lanes of a warp run reads of near-equal length
+// (length-binned scheduling; longest first so the tail of the grid is made of short reads).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "k0_genome.cuh"
+#include "model_image.hpp"
+#include "sim_core.cuh"
+
+namespace pb {
+
+constexpr int kSimThreads = 256;  // subreads per pass-1 CTA
+
+struct DeviceModel {
+  const uint8_t *blob;
+  const AccEntry *acc;        // [101]
+  const int32_t *prob2len;
+  const uint8_t *prob2acc;
+  uint32_t len_rand_value, acc_rand_value, len_min;
+  const uint32_t *qs_thr;     // [94*4]
+  const uint32_t *qs_thr_hp;  // [94*12]
+  const double *qc_prob;      // [94]
+  const uint16_t *er_bias;
+  uint32_t pass_num;
+  uint32_t uniform_bias;
+};
+
+struct DeviceGenome {
+  const uint8_t *ascii;
+  const uint32_t *pk;
+  const uint8_t *hp4;
+  const uint32_t *xm;
+  uint32_t len;
+  uint32_t seq_num;
+};
+
+struct RngParams {
+  uint32_t mode;           // PBSIM_RNG_*
+  uint32_t seed;
+  const int32_t *draws;    // replay: device copy of the slice of the log this batch needs
+  int64_t draws_base;      // index in the full log of draws[0]
+  int64_t draws_end;       // one past the last available draw (full-log index)
+  const int64_t *starts;   // replay: first draw of every subread of this batch (full-log index)
+};
+
+// per-batch arrays (device)
+struct Batch {
+  uint32_t n_reads, n_sub;
+  uint64_t first_read;     // id of read 0 of the batch minus 1 (ids are first_read + 1 + r)
+  // per read
+  uint32_t *plan_off, *plan_wlen, *plan_raw, *plan_meta;  // meta: acc | minus<<8 | slow<<9 | invalid<<10
+  // per subread
+  uint32_t *key_in, *key_out, *idx_in, *order;
+  uint32_t *cap;           // event-slot capacity (entries)
+  uint64_t *ev_off;        // exclusive scan of cap
+  uint32_t *ck_cap;        // checkpoint slots
+  uint64_t *ck_off;
+  uint32_t *nent, *rlen, *ncol, *nsub, *nins, *ndel, *flags, *draws_used;
+  double *accuracy;
+};
+
+// ----------------------------------------------------------------------------------------------
+// K1: plan.  One thread per read.  clip_room >= 0 only for single-read tail batches.
+// ----------------------------------------------------------------------------------------------
+__global__ void k_plan(DeviceModel M, DeviceGenome G, RngParams rng, Batch B, int64_t clip_room, uint32_t cap_num,
+                       uint32_t cap_den, uint32_t ev_align) {
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= B.n_reads) return;
+  PlanTables T;
+  T.prob2len = M.prob2len;
+  T.prob2acc = M.prob2acc;
+  T.len_rand_value = M.len_rand_value;
+  T.acc_rand_value = M.acc_rand_value;
+  T.len_min = M.len_min;
+  const uint64_t read_id = B.first_read + 1u + r;
+  ReadPlan p;
+  if (rng.mode == PBSIM_RNG_PHILOX) {
+    PhiloxDraw d;
+    d.ph.k0 = rng.seed;
+    d.ph.k1 = G.seq_num;
+    d.read_id = (uint32_t)read_id;
+    d.pass = 0;
+    p = plan_read(T, d, G.len, clip_room);
+  } else {
+    ReplayDraw d;
+    d.log = rng.draws - rng.draws_base;
+    d.cur = rng.starts[(uint64_t)r * M.pass_num];
+    d.start = d.cur;
+    d.end = rng.draws_end;
+    p = plan_read(T, d, G.len, clip_room);
+  }
+  const uint32_t minus = (read_id & 1u) ? 0u : 1u;  // res_num odd -> '+', even -> '-' (:2201-2207)
+  bool slow = !M.uniform_bias;
+  if (!slow) slow = range_exceptional(G.xm, p.offset, p.offset + p.wlen - 1u);
+  const AccEntry ae = M.acc[p.acc];
+  B.plan_off[r] = p.offset;
+  B.plan_wlen[r] = p.wlen;
+  B.plan_raw[r] = p.raw_len;
+  B.plan_meta[r] = p.acc | (minus << 8) | ((slow ? 1u : 0u) << 9) | ((ae.valid ? 0u : 1u) << 10);
+  // event-slot capacity: wlen * cap_num/cap_den + slack, rounded so that slots stay 16-byte aligned
+  uint64_t cap = (uint64_t)p.wlen * cap_num / cap_den + 2048u;
+  cap = (cap + ev_align - 1u) / ev_align * ev_align;
+  const uint32_t ckc = (uint32_t)(cap / PB_TILE) + 2u;
+  for (uint32_t h = 0; h < M.pass_num; ++h) {
+    const uint32_t s = r * M.pass_num + h;
+    B.key_in[s] = (p.acc << 20) | (0xFFFFFu - (p.wlen > 0xFFFFFu ? 0xFFFFFu : p.wlen));
+    B.idx_in[s] = s;
+    B.cap[s] = (uint32_t)cap;
+    B.ck_cap[s] = ckc;
+  }
+}
+
+// accuracy-bin boundaries in the sorted order, then the CTA map
+__global__ void k_bin_bounds(const uint32_t *key_sorted, uint32_t n, uint32_t *bin_start /*[102]*/) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t a = key_sorted[i] >> 20;
+  if (i == 0 || (key_sorted[i - 1] >> 20) != a) bin_start[a] = i;
+}
+
+// cta_first[a] = first pass-1 CTA of accuracy a; cta_first[101] = total
+__global__ void k_cta_map(const uint32_t *bin_start, const uint32_t *key_sorted, uint32_t n, uint32_t *bin_lo,
+                          uint32_t *bin_hi, uint32_t *cta_first) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  // bin_start holds 0xFFFFFFFF for empty bins
+  uint32_t next_lo = n, total = 0;
+  for (int a = 100; a >= 0; --a) {
+    const uint32_t lo = bin_start[a];
+    if (lo == 0xFFFFFFFFu) {
+      bin_lo[a] = bin_hi[a] = 0;
+    } else {
+      bin_lo[a] = lo;
+      bin_hi[a] = next_lo;
+      next_lo = lo;
+    }
+  }
+  for (int a = 0; a <= 100; ++a) {
+    cta_first[a] = total;
+    total += (bin_hi[a] - bin_lo[a] + kSimThreads - 1) / kSimThreads;
+  }
+  cta_first[101] = total;
+}
+
+// ----------------------------------------------------------------------------------------------
+// TMA (bulk async copy) staging of tables into shared memory
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+// which accuracy bin does this CTA serve?  returns false if the CTA is beyond the map
+__device__ __forceinline__ bool cta_assignment(const uint32_t *cta_first, const uint32_t *bin_lo, const uint32_t *bin_hi,
+                                               uint32_t *acc, uint32_t *lo, uint32_t *hi) {
+  __shared__ uint32_t s_acc, s_lo, s_hi, s_ok;
+  if (threadIdx.x == 0) {
+    const uint32_t b = blockIdx.x;
+    s_ok = 0;
+    if (b < cta_first[101]) {
+      uint32_t a = 0;
+      while (a < 100 && cta_first[a + 1] <= b) ++a;
+      const uint32_t local = b - cta_first[a];
+      s_acc = a;
+      s_lo = bin_lo[a] + local * kSimThreads;
+      s_hi = min(bin_hi[a], s_lo + kSimThreads);
+      s_ok = 1;
+    }
+  }
+  __syncthreads();
+  *acc = s_acc;
+  *lo = s_lo;
+  *hi = s_hi;
+  return s_ok != 0;
+}
+
+struct SimArgs {
+  DeviceModel M;
+  DeviceGenome G;
+  RngParams rng;
+  Batch B;
+  const uint32_t *cta_first, *bin_lo, *bin_hi;
+  uint8_t *ev;   // event arena
+  Ckpt *ck;      // checkpoint arena
+};
+
+__device__ __forceinline__ void store_result(const Batch &B, uint32_t s, const SubreadResult &res, uint32_t used) {
+  B.nent[s] = res.n_entries;
+  B.rlen[s] = res.rlen;
+  B.ncol[s] = res.ncol;
+  B.nsub[s] = res.nsub;
+  B.nins[s] = res.nins;
+  B.ndel[s] = res.ndel;
+  B.flags[s] = res.overflow;
+  B.draws_used[s] = used;
+  B.accuracy[s] = res.accuracy;
+}
+
+// chain draws of subread (r, h) in replay mode start after the planner's 2 or 3 draws for pass 0
+__device__ __forceinline__ void replay_setup(ReplayDraw &d, const RngParams &rng, uint32_t s, uint32_t pass,
+                                             bool offset_drawn) {
+  d.log = rng.draws - rng.draws_base;
+  d.start = rng.starts[s];
+  d.cur = d.start + (pass == 0 ? (offset_drawn ? 3 : 2) : 0);
+  d.end = rng.draws_end;
+}
+
+// ----------------------------------------------------------------------------------------------
+// K2: qshmm pass 1
+// shared memory: [table blob | thr 94*16 | qc_prob 94*8 | mbarrier]
+// ----------------------------------------------------------------------------------------------
+constexpr uint32_t kQsSmemThr = QsBlobLayout::bytes;
+constexpr uint32_t kQsSmemProb = kQsSmemThr + PBSIM_NQV * 16;
+constexpr uint32_t kQsSmemBar = kQsSmemProb + PBSIM_NQV * 8;
+constexpr uint32_t kQsSmemBytes = kQsSmemBar + 16;
+
+template <int RNG_MODE>
+__global__ void __launch_bounds__(kSimThreads) k_sim_qshmm(SimArgs A) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint32_t acc, lo, hi;
+  if (!cta_assignment(A.cta_first, A.bin_lo, A.bin_hi, &acc, &lo, &hi)) return;
+  const AccEntry ae = A.M.acc[acc];
+  uint64_t *bar = reinterpret_cast<uint64_t *>(smem + kQsSmemBar);
+  if (threadIdx.x == 0) mbar_init(bar, 1);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(bar, ae.blob_bytes + PBSIM_NQV * 16 + PBSIM_NQV * 8);
+    tma_bulk_g2s(smem, A.M.blob + ae.blob_off, ae.blob_bytes, bar);
+    tma_bulk_g2s(smem + kQsSmemThr, A.M.qs_thr, PBSIM_NQV * 16, bar);
+    tma_bulk_g2s(smem + kQsSmemProb, A.M.qc_prob, PBSIM_NQV * 8, bar);
+  }
+  mbar_wait(bar, 0);
+
+  const uint32_t k = lo + threadIdx.x;
+  if (k >= hi) return;
+  const uint32_t s = A.B.order[k];
+  const uint32_t r = s / A.M.pass_num, pass = s % A.M.pass_num;
+  const uint32_t meta = A.B.plan_meta[r];
+  const uint32_t wlen = A.B.plan_wlen[r];
+  if (meta & (1u << 10)) {  // accuracy without tables: flagged, reported by the host
+    SubreadResult z = {};
+    z.overflow = 2;
+    store_result(A.B, s, z, 0);
+    return;
+  }
+  QsView T;
+  T.t2 = reinterpret_cast<const uint16_t *>(smem + QsBlobLayout::t2_off);
+  T.emis = smem + QsBlobLayout::emis_off;
+  T.emod = smem + QsBlobLayout::emod_off;
+  T.freq = smem;
+  T.has_model = ae.has_model;
+  T.init_mod = ae.init_mod;
+  T.freq_mod = ae.freq_mod;
+  T.thr = reinterpret_cast<const uint32_t *>(smem + kQsSmemThr);
+  T.thr_hp = A.M.qs_thr_hp;
+  T.qc_prob = reinterpret_cast<const double *>(smem + kQsSmemProb);
+  WindowRef win;
+  win.ascii = A.G.ascii;
+  win.hp4 = A.G.hp4;
+  win.offset = A.B.plan_off[r];
+  win.wlen = wlen;
+  win.minus = (meta >> 8) & 1u;
+  const bool slow = (meta >> 9) & 1u;
+  QsSink sink;
+  sink.init(reinterpret_cast<uint16_t *>(A.ev) + A.B.ev_off[s], A.ck + A.B.ck_off[s], A.B.cap[s]);
+  SubreadResult res;
+  uint32_t used = 0;
+  if (RNG_MODE == PBSIM_RNG_PHILOX) {
+    PhiloxDraw d;
+    d.ph.k0 = A.rng.seed;
+    d.ph.k1 = A.G.seq_num;
+    d.read_id = (uint32_t)(A.B.first_read + 1u + r);
+    d.pass = pass;
+    qshmm_simulate(T, d, win, slow, wlen, sink, res);
+  } else {
+    ReplayDraw d;
+    replay_setup(d, A.rng, s, pass, wlen < A.G.len);
+    qshmm_simulate(T, d, win, slow, wlen, sink, res);
+    used = d.consumed();
+  }
+  store_result(A.B, s, res, used);
+}
+
+// ----------------------------------------------------------------------------------------------
+// K3: errhmm pass 1
+// shared memory: [table blob (t2 | emis | emod) | edel (nst+1)*2 rounded | mbarrier]
+// ----------------------------------------------------------------------------------------------
+template <int RNG_MODE>
+__global__ void __launch_bounds__(kSimThreads) k_sim_errhmm(SimArgs A, uint32_t smem_bar_off) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint32_t acc, lo, hi;
+  if (!cta_assignment(A.cta_first, A.bin_lo, A.bin_hi, &acc, &lo, &hi)) return;
+  const AccEntry ae = A.M.acc[acc];
+  uint64_t *bar = reinterpret_cast<uint64_t *>(smem + smem_bar_off);
+  const uint32_t edel_bytes = ((ae.nstates + 1u) * 2u + 15u) / 16u * 16u;
+  if (threadIdx.x == 0) mbar_init(bar, 1);
+  __syncthreads();
+  if (ae.valid && ae.mode != 3u) {
+    if (threadIdx.x == 0) {
+      mbar_expect_tx(bar, ae.blob_bytes + edel_bytes);
+      tma_bulk_g2s(smem, A.M.blob + ae.blob_off, ae.blob_bytes, bar);
+      tma_bulk_g2s(smem + ae.blob_bytes, A.M.er_bias + ae.bias_off, edel_bytes, bar);
+    }
+    mbar_wait(bar, 0);
+  }
+  const uint32_t k = lo + threadIdx.x;
+  if (k >= hi) return;
+  const uint32_t s = A.B.order[k];
+  const uint32_t r = s / A.M.pass_num, pass = s % A.M.pass_num;
+  const uint32_t meta = A.B.plan_meta[r];
+  const uint32_t wlen = A.B.plan_wlen[r];
+  if (meta & (1u << 10)) {
+    SubreadResult z = {};
+    z.overflow = 2;
+    store_result(A.B, s, z, 0);
+    return;
+  }
+  ErView T;
+  uint32_t t2o, emo, emodo;
+  er_blob_bytes(ae.nstates, &t2o, &emo, &emodo);
+  T.t2 = reinterpret_cast<const uint16_t *>(smem + t2o);
+  T.emis = smem + emo;
+  T.emod = reinterpret_cast<const uint16_t *>(smem + emodo);
+  T.edel = reinterpret_cast<const uint16_t *>(smem + ae.blob_bytes);
+  T.edel_hp = A.M.er_bias + ae.bias_off + (ae.nstates + 1u);
+  T.init_mod = ae.init_mod;
+  T.mode = ae.mode;
+  T.rate_mag = ae.rate_mag;
+  WindowRef win;
+  win.ascii = A.G.ascii;
+  win.hp4 = A.G.hp4;
+  win.offset = A.B.plan_off[r];
+  win.wlen = wlen;
+  win.minus = (meta >> 8) & 1u;
+  const bool slow = (meta >> 9) & 1u;
+  ErSink sink;
+  sink.init(A.ev + A.B.ev_off[s], A.ck + A.B.ck_off[s], A.B.cap[s]);
+  SubreadResult res;
+  uint32_t used = 0;
+  if (RNG_MODE == PBSIM_RNG_PHILOX) {
+    PhiloxDraw d;
+    d.ph.k0 = A.rng.seed;
+    d.ph.k1 = A.G.seq_num;
+    d.read_id = (uint32_t)(A.B.first_read + 1u + r);
+    d.pass = pass;
+    errhmm_simulate(T, d, win, slow, wlen, sink, res);
+  } else {
+    ReplayDraw d;
+    replay_setup(d, A.rng, s, pass, wlen < A.G.len);
+    errhmm_simulate(T, d, win, slow, wlen, sink, res);
+    used = d.consumed();
+  }
+  store_result(A.B, s, res, used);
+}
+
+}  // namespace pb

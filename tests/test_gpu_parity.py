@@ -1,0 +1,92 @@
+"""GPU parity tests (run with -m gpu on the B200 box).  Everything goes through the C ABI
+(libpbsim_cuda.so); the oracle / golden fixtures are only the checker.
+
+  replay mode  : engine fed the reference's own rand() draws  == reference bytes (tests/golden)
+  philox mode  : engine                                        == CPU oracle running the same Philox addressing
+"""
+import numpy as np
+import pytest
+
+from pbsim_b200 import capi, simulator
+from tests.golden_util import Case, case_names
+from tests.gpu_util import engine_model, run_case_on_gpu
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    e = simulator.Engine(0)
+    yield e
+    e.close()
+
+
+@pytest.mark.parametrize("name", case_names())
+def test_replay_reproduces_reference_bytes(eng, name):
+    c = Case(name)
+    out, _ = c.run_oracle("glibc")
+    res = run_case_on_gpu(c, eng, "replay", oracle_out=out)
+    for i, (reads, maf, st, text) in enumerate(res, start=1):
+        assert reads == c.reads(i), "FASTQ/SAM differs from the reference, seq %d" % i
+        assert maf == c.maf(i), "MAF differs from the reference, seq %d" % i
+        assert text == c.stats_blocks[i], "stats block differs, seq %d" % i
+
+
+@pytest.mark.parametrize("name", case_names())
+def test_philox_equals_oracle_philox(eng, name):
+    c = Case(name)
+    out, _ = c.run_oracle("philox")
+    res = run_case_on_gpu(c, eng, "philox")
+    for i, ((reads, maf, st, text), o) in enumerate(zip(res, out), start=1):
+        assert reads == o["reads"], "reads differ from the oracle, seq %d" % i
+        assert maf == o["maf"], "maf differs from the oracle, seq %d" % i
+        assert text == o["stats_text"]
+
+
+@pytest.mark.parametrize("name", ["qs_rsii_quirks", "err_sequel_multipass"])
+@pytest.mark.parametrize("batch", [1, 7, 64])
+def test_output_is_independent_of_batching(eng, name, batch):
+    """chunking (and therefore the speculative-plan / quota-cut / tail logic) must not change a byte"""
+    c = Case(name)
+    ref = run_case_on_gpu(c, eng, "philox")
+    got = run_case_on_gpu(c, eng, "philox", batch_reads=batch)
+    for a, b in zip(ref, got):
+        assert a[0] == b[0] and a[1] == b[1] and a[3] == b[3]
+
+
+def test_replay_batched_still_reproduces_reference(eng):
+    c = Case("qs_rsii_basic")
+    out, _ = c.run_oracle("glibc")
+    res = run_case_on_gpu(c, eng, "replay", oracle_out=out, batch_reads=13)
+    for i, (reads, maf, st, text) in enumerate(res, start=1):
+        assert reads == c.reads(i) and maf == c.maf(i) and text == c.stats_blocks[i]
+
+
+def test_histograms_equal_oracle(eng):
+    c = Case("qs_rsii_basic")
+    out, _ = c.run_oracle("philox")
+    hm = engine_model(c)
+    eng.set_model(hm)
+    _, s = c.contigs[0]
+    eng.set_sequence(s, 1, [0.0] + [1.0] * 10 + [0.0])
+    reads, maf, (st, fl, fa), n = eng.simulate(int(c.depth * len(s)), rng_mode=capi.RNG_PHILOX, seed=c.seed,
+                                               want_hist=True)
+    assert np.array_equal(fl[:len(out[0]["freq_len"])], out[0]["freq_len"][:len(fl)])
+    assert np.array_equal(fa, out[0]["freq_accuracy"])
+    assert st.res_num == out[0]["stats"].res_num
+    assert st.res_sub_num == out[0]["stats"].res_sub_num
+    assert st.accuracy_total == out[0]["stats"].accuracy_total
+
+
+def test_genome_ingest_matches_oracle_hp(eng):
+    """K0: hpfreq of the device ingest == the oracle's get_genome_seq restatement"""
+    c = Case("qs_rsii_quirks")
+    o = c.new_oracle()
+    hm = engine_model(c)
+    eng.set_model(hm)
+    for i, (_, s) in enumerate(c.contigs, start=1):
+        o.set_sequence(s, i)
+        hp = o.hp()
+        want = [int(np.count_nonzero(hp == h)) for h in range(12)]
+        eng.set_sequence(s, i, [0.0] + [1.0] * 10 + [0.0])
+        assert eng.hpfreq() == want
