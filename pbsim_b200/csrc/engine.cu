@@ -131,9 +131,8 @@ __global__ void k_check_replay(const int64_t *starts, const uint32_t *used, cons
   if ((unsigned long long)(s / pass_num) >= ctrl[0]) return;  // reads at / after the quota cut are re-planned
   const int64_t nxt = (s + 1 < n_sub) ? starts[s + 1] : next_start_after;
   if (nxt < 0) return;  // unknown (last subread of the log)
-  const uint32_t r = s / pass_num, pass = s % pass_num;
-  const int64_t planner = (pass == 0) ? (plan_wlen[r] < glen ? 3 : 2) : 0;
-  if (starts[s] + planner + (int64_t)used[s] != nxt) atomicAdd(bad, 1u);
+  // `used` counts from the subread's start, i.e. it already includes the planner's 2 or 3 draws of pass 0
+  if (starts[s] + (int64_t)used[s] != nxt) atomicAdd(bad, 1u);
 }
 
 }  // namespace
