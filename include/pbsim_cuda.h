@@ -137,7 +137,9 @@ typedef struct {
   double accuracy_total;         /* running sum of per-read accuracies, in read order        */
   double res_len_mean, res_len_sd;
   double res_accuracy_mean, res_accuracy_sd;
-  double gen_seconds;            /* device time spent generating (CUDA events)               */
+  double gen_seconds;            /* device time of all generation steps (CUDA events)        */
+  double sim_seconds;            /* ... of which pass 1 (k_sim_qshmm / k_sim_errhmm)          */
+  double emit_seconds;           /* ... of which pass 2 (k_emit)                             */
   int64_t kernel_launches;       /* number of engine kernels launched during the run         */
 } pbsim_stats;
 
@@ -164,18 +166,29 @@ int pbsim_cuda_set_synthetic_sequence(pbsim_engine *e, int64_t len, int32_t seq_
 /* replace hp_del_bias of the current sequence without re-ingesting it (bias[0] is only known once the
  * sequence's own hpfreq[11] is, see pbsim_host_hp_del_bias); the set of cells equal to 1 must not change */
 int pbsim_cuda_update_hp_del_bias(pbsim_engine *e, const double hp_del_bias[12]);
+/* upper-cased text of the current sequence (tests, benchmarks) */
+int pbsim_cuda_get_sequence_ascii(pbsim_engine *e, char *dst, int64_t cap);
 /* homopolymer histogram of the current sequence, genome.hpfreq[0..10] plus the aliased [11] */
 int pbsim_cuda_get_hpfreq(pbsim_engine *e, int64_t hpfreq[12]);
 
 /* replaces: one simulate_by_qshmm() / simulate_by_errhmm() call for the current sequence */
 int pbsim_cuda_simulate_begin(pbsim_engine *e, const pbsim_run *run);
-/* 1: chunk filled (host pointers into pinned staging, valid until the next call); 0: finished */
+/* 1: chunk filled, 0: finished.  Host delivery: the records of a batch of reads stay in HBM and are
+ * handed out as consecutive PIECES of at most `stage_bytes` per stream through double-buffered pinned
+ * staging (pointers valid until the next call); concatenating the pieces gives the byte streams in
+ * read order.  first_read / n_reads / bases are set on the first piece of every batch. */
 int pbsim_cuda_next_chunk(pbsim_engine *e, pbsim_chunk *c);
 /* same, records stay in HBM (c->on_device = 1) */
 int pbsim_cuda_next_chunk_device(pbsim_engine *e, pbsim_chunk *c);
 /* stats; freq_len has len_max*2+2 cells, freq_accuracy 100001; either may be NULL */
 int pbsim_cuda_simulate_end(pbsim_engine *e, pbsim_stats *st, int64_t *freq_len, int64_t freq_len_cells,
                             int64_t *freq_accuracy);
+/* CUDA-event timer on the engine's stream: stop=0 records the start, stop=1 records the stop,
+ * waits for it and returns the elapsed device milliseconds */
+int pbsim_cuda_device_timer(pbsim_engine *e, int stop, double *ms);
+/* tunables: "stage_bytes" (pinned staging per stream and slot, default 128 MiB),
+ * "target_batch_bases" (emitted bases per batch of reads, default 6 Gi) */
+int pbsim_cuda_set_option(pbsim_engine *e, const char *name, int64_t value);
 /* device pointer + cell count of the int64 stats block {counters[16], freq_accuracy[100001],
  * freq_len[2*len_max+2]} so that a multi-GPU driver can ncclAllReduce it in place */
 int pbsim_cuda_stats_device_block(pbsim_engine *e, void **dptr, int64_t *cells);

@@ -153,18 +153,22 @@ static uint32_t d_choice8(rng_t *r) {
 static uint32_t d_mag3(rng_t *r) { /* errhmm: rand()%3+1 (ref: :3895) */
   return r->mode == RNG_PHILOX ? (((r->w[3] & 0xFFFu) * 3u) >> 12) + 1 : stream_next(r) % 3 + 1;
 }
-/* qshmm deletion draw number j (0-based) after the current position (ref: :2270) */
+/* murmur3 finaliser (bijection on 32 bits) */
+static uint32_t fmix32(uint32_t h) {
+  h ^= h >> 16;
+  h *= 0x85EBCA6Bu;
+  h ^= h >> 13;
+  h *= 0xC2B2AE35u;
+  h ^= h >> 16;
+  return h;
+}
+/* qshmm deletion draw number j (0-based) after the current position (ref: :2270).
+ * PHILOX mode: j = 0 is word 3 of the position's block; the rare later draws are derived from it
+ * through the finaliser (engine definition, DESIGN.md "Philox draw addressing"). */
 static uint32_t d_del(rng_t *r, uint32_t j) {
   if (r->mode != RNG_PHILOX) return stream_next(r) % 1000000;
   if (j == 0) return mulhi32(r->w[3], 1000000);
-  {
-    uint32_t blk = 1 + (j - 1) / 4;
-    if (blk != r->xblk) {
-      philox_at(r, r->pos, blk, 1, r->xw);
-      r->xblk = blk;
-    }
-    return mulhi32(r->xw[(j - 1) % 4], 1000000);
-  }
+  return mulhi32(fmix32(r->w[3] + j * 0x9E3779B9u), 1000000);
 }
 
 /* ------------------------------------------------------------------ context */

@@ -113,6 +113,8 @@ class Stats(C.Structure):
         ("res_accuracy_mean", C.c_double),
         ("res_accuracy_sd", C.c_double),
         ("gen_seconds", C.c_double),
+        ("sim_seconds", C.c_double),
+        ("emit_seconds", C.c_double),
         ("kernel_launches", C.c_int64),
     ]
 
@@ -137,9 +139,9 @@ HOST_EXPORTS = ["pbsim_host_model_load", "pbsim_host_model_get", "pbsim_host_mod
 ENGINE_EXPORTS = [
     "pbsim_cuda_abi_version", "pbsim_cuda_last_error", "pbsim_cuda_create", "pbsim_cuda_destroy",
     "pbsim_cuda_set_model", "pbsim_cuda_set_sequence", "pbsim_cuda_set_synthetic_sequence",
-    "pbsim_cuda_update_hp_del_bias", "pbsim_cuda_get_hpfreq", "pbsim_cuda_simulate_begin", "pbsim_cuda_next_chunk",
+    "pbsim_cuda_update_hp_del_bias", "pbsim_cuda_get_sequence_ascii", "pbsim_cuda_get_hpfreq", "pbsim_cuda_simulate_begin", "pbsim_cuda_next_chunk",
     "pbsim_cuda_next_chunk_device", "pbsim_cuda_simulate_end", "pbsim_cuda_stats_device_block",
-    "pbsim_cuda_last_chunk_info",
+    "pbsim_cuda_last_chunk_info", "pbsim_cuda_device_timer", "pbsim_cuda_set_option",
 ]
 
 
@@ -168,12 +170,15 @@ def declare_engine(L):
     L.pbsim_cuda_set_sequence.argtypes = [C.c_void_p, C.POINTER(Sequence)]
     L.pbsim_cuda_set_synthetic_sequence.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_uint64]
     L.pbsim_cuda_update_hp_del_bias.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+    L.pbsim_cuda_get_sequence_ascii.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
     L.pbsim_cuda_get_hpfreq.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
     L.pbsim_cuda_simulate_begin.argtypes = [C.c_void_p, C.POINTER(Run)]
     L.pbsim_cuda_next_chunk.argtypes = [C.c_void_p, C.POINTER(Chunk)]
     L.pbsim_cuda_next_chunk_device.argtypes = [C.c_void_p, C.POINTER(Chunk)]
     L.pbsim_cuda_simulate_end.argtypes = [C.c_void_p, C.POINTER(Stats), C.c_void_p, C.c_int64, C.c_void_p]
     L.pbsim_cuda_stats_device_block.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]
+    L.pbsim_cuda_device_timer.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double)]
+    L.pbsim_cuda_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int64]
     L.pbsim_cuda_last_chunk_info.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]
     return L
 

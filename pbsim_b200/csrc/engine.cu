@@ -186,7 +186,22 @@ struct pbsim_engine {
   DevBuf d_cub_tmp;
   DevBuf d_ev, d_ck;
   DevBuf d_out_reads, d_out_maf;
-  PinnedBuf h_reads, h_maf, h_ctrl, h_acc;
+  PinnedBuf h_ctrl, h_acc;
+  // host delivery: the records of a batch stay in HBM and are handed out in pieces through two
+  // pinned staging buffers per stream (D2H of piece i+1 overlaps the caller consuming piece i)
+  PinnedBuf h_stage[2][2];          // [stream: 0 reads, 1 maf][slot]
+  size_t stage_bytes = (size_t)128 << 20;
+  struct Pending {
+    bool active = false;
+    uint64_t total[2] = {0, 0}, issued[2] = {0, 0};
+    uint64_t inflight[2] = {0, 0};  // bytes being copied into slot `slot`
+    int slot = 0;
+    bool first = true;
+    int64_t first_read = 0, n_reads = 0, bases = 0;
+  } pend;
+  cudaEvent_t ev_copy = nullptr, ev_k[4] = {nullptr, nullptr, nullptr, nullptr}, ev_user[2] = {nullptr, nullptr};
+  double sim_ms = 0, emit_ms = 0;
+  int64_t target_batch_bases = (int64_t)6 << 30;
   Batch B;
   uint64_t *u64_cap_scan = nullptr;
   // last chunk info
@@ -448,6 +463,7 @@ int run_batch(pbsim_engine *e, uint32_t n_reads, int64_t clip_room, bool to_host
     A.ev = e->d_ev.as<uint8_t>();
     A.ck = e->d_ck.as<Ckpt>();
     const uint32_t grid = nblk(n_sub, kSimThreads) + 101;
+    CK(cudaEventRecord(e->ev_k[0], e->st));
     if (qs) {
       if (replay) k_sim_qshmm<PBSIM_RNG_REPLAY><<<grid, kSimThreads, kQsSmemBytes, e->st>>>(A);
       else k_sim_qshmm<PBSIM_RNG_PHILOX><<<grid, kSimThreads, kQsSmemBytes, e->st>>>(A);
@@ -457,6 +473,7 @@ int run_batch(pbsim_engine *e, uint32_t n_reads, int64_t clip_room, bool to_host
       else k_sim_errhmm<PBSIM_RNG_PHILOX><<<grid, kSimThreads, smem, e->st>>>(A, e->er_smem_bar_off);
     }
     e->launches++;
+    CK(cudaEventRecord(e->ev_k[1], e->st));
     CK(cudaGetLastError());
 
     // ---- quota: which read crosses len_quota
@@ -482,6 +499,11 @@ int run_batch(pbsim_engine *e, uint32_t n_reads, int64_t clip_room, bool to_host
     CK(cudaStreamSynchronize(e->st));
     const uint32_t flags = (uint32_t)hctrl[2];
     if (flags & 2u) return fail(e, PBSIM_E_PARAM, "a read drew an accuracy for which the model has no usable tables");
+    {
+      float ms = 0;
+      CK(cudaEventElapsedTime(&ms, e->ev_k[0], e->ev_k[1]));
+      e->sim_ms += ms;
+    }
     if (flags & 1u) {  // a read outgrew its slot: enlarge and redo the batch
       e->cap_num *= 2;
       if (attempt == 5) return fail(e, PBSIM_E_OVERFLOW, "event slots overflowed repeatedly");
@@ -554,8 +576,10 @@ int run_batch(pbsim_engine *e, uint32_t n_reads, int64_t clip_room, bool to_host
     cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, e->device);
     const uint64_t want = (n_tiles + kEmitWarps - 1) / kEmitWarps;
     const uint32_t grid = (uint32_t)std::min<uint64_t>(want, (uint64_t)dev_sms * 8 * 4);
+    CK(cudaEventRecord(e->ev_k[2], e->st));
     if (qs) k_emit<PBSIM_METHOD_QSHMM><<<grid, kEmitThreads, 0, e->st>>>(EA);
     else k_emit<PBSIM_METHOD_ERRHMM><<<grid, kEmitThreads, 0, e->st>>>(EA);
+    CK(cudaEventRecord(e->ev_k[3], e->st));
     e->launches++;
   }
   // ---- K6 stats
@@ -573,31 +597,84 @@ int run_batch(pbsim_engine *e, uint32_t n_reads, int64_t clip_room, bool to_host
   return 0;
 }
 
+// hand out the next piece of the batch held in HBM (host delivery); returns 1 if a piece was produced
+int deliver_piece(pbsim_engine *e, pbsim_chunk *c) {
+  pbsim_engine::Pending &p = e->pend;
+  if (!p.active) return 0;
+  for (int k = 0; k < 2; ++k)
+    for (int slot = 0; slot < 2; ++slot) CK(e->h_stage[k][slot].ensure(e->stage_bytes));
+  const uint8_t *src[2] = {e->d_out_reads.as<uint8_t>(), e->d_out_maf.as<uint8_t>()};
+  auto issue = [&](int slot) -> int {
+    for (int k = 0; k < 2; ++k) {
+      const uint64_t n = std::min<uint64_t>(e->stage_bytes, p.total[k] - p.issued[k]);
+      p.inflight[k] = n;
+      if (n) CK(cudaMemcpyAsync(e->h_stage[k][slot].p, src[k] + p.issued[k], n, cudaMemcpyDeviceToHost, e->st_copy));
+      p.issued[k] += n;
+    }
+    CK(cudaEventRecord(e->ev_copy, e->st_copy));
+    return 0;
+  };
+  if (p.first) {
+    int rc = issue(p.slot);
+    if (rc) return rc;
+  }
+  CK(cudaEventSynchronize(e->ev_copy));
+  std::memset(c, 0, sizeof *c);
+  c->reads = reinterpret_cast<const char *>(e->h_stage[0][p.slot].p);
+  c->reads_bytes = (int64_t)p.inflight[0];
+  c->maf = reinterpret_cast<const char *>(e->h_stage[1][p.slot].p);
+  c->maf_bytes = (int64_t)p.inflight[1];
+  c->on_device = 0;
+  if (p.first) {
+    c->first_read = p.first_read;
+    c->n_reads = p.n_reads;
+    c->bases = p.bases;
+    p.first = false;
+  }
+  if (p.issued[0] < p.total[0] || p.issued[1] < p.total[1]) {
+    p.slot ^= 1;  // prefetch the next piece into the other slot while the caller consumes this one
+    int rc = issue(p.slot);
+    if (rc) return rc;
+  } else {
+    p.active = false;
+  }
+  return 1;
+}
+
 int next_chunk_impl(pbsim_engine *e, pbsim_chunk *c, bool to_host) {
   if (!e || !c) return PBSIM_E_INVALID;
   if (!e->running) return fail(e, PBSIM_E_INVALID, "simulate_begin was not called");
   std::memset(c, 0, sizeof *c);
   for (;;) {
+    if (e->pend.active) {
+      if (!to_host) return fail(e, PBSIM_E_INVALID, "host pieces of the previous batch are still pending");
+      return deliver_piece(e, c);
+    }
     if (e->finished) return 0;
     if (e->len_total >= e->run.len_quota || (e->run.max_reads > 0 && e->reads_done_in_run >= e->run.max_reads)) {
       e->finished = true;
       return 0;
     }
-    // batch size
+    // batch size: enough reads for ~target_batch_bases emitted bases, never more than the quota needs
     int64_t nb;
     int64_t clip_room = -1;
     if (e->tail_mode) {
       nb = 1;
       clip_room = e->run.len_quota - e->len_total;
     } else {
-      nb = e->run.batch_reads > 0 ? e->run.batch_reads : (int64_t)1 << 18;
       double mean = e->mean_rlen_est > 0 ? e->mean_rlen_est : e->table_mean_len;
       if (mean > (double)e->glen) mean = (double)e->glen;
-      if (mean > 0) {
-        const double need = (double)(e->run.len_quota - e->len_total) / mean;
-        const int64_t est = (int64_t)(need * 1.02) + 16;
-        if (est < nb) nb = est;
+      if (mean < 1) mean = 1;
+      if (e->run.batch_reads > 0) {
+        nb = e->run.batch_reads;
+      } else {
+        nb = (int64_t)((double)e->target_batch_bases / (mean * e->model.pass_num));
+        nb = std::max<int64_t>(nb, 1 << 12);
+        nb = std::min<int64_t>(nb, 1 << 22);
       }
+      const double need = (double)(e->run.len_quota - e->len_total) / mean;
+      const int64_t est = (int64_t)(need * 1.02) + 16;
+      if (est < nb) nb = est;
       if (e->run.max_reads > 0) nb = std::min<int64_t>(nb, e->run.max_reads - e->reads_done_in_run);
       if (e->run.rng_mode == PBSIM_RNG_REPLAY) {
         const int64_t left = e->run.replay_nsubreads / e->model.pass_num - (e->next_read - e->run.first_read);
@@ -606,6 +683,7 @@ int next_chunk_impl(pbsim_engine *e, pbsim_chunk *c, bool to_host) {
       }
       if (nb < 1) nb = 1;
     }
+    // the previous batch's D2H pieces read d_out_*: they were all consumed (pend inactive) before we overwrite
     CK(cudaEventRecord(e->ev0, e->st));
     BatchResult br;
     int rc = run_batch(e, (uint32_t)nb, clip_room, to_host, &br);
@@ -617,7 +695,11 @@ int next_chunk_impl(pbsim_engine *e, pbsim_chunk *c, bool to_host) {
     e->gen_ms += ms;
     const uint32_t pass = (uint32_t)e->model.pass_num;
     const uint32_t nv = br.n_valid_reads;
-    // host-side ordered accumulation
+    if (nv > 0) {
+      CK(cudaEventElapsedTime(&ms, e->ev_k[2], e->ev_k[3]));
+      e->emit_ms += ms;
+    }
+    // host-side ordered accumulation of accuracy_total (:2314)
     {
       const double *hacc = reinterpret_cast<const double *>(e->h_acc.p);
       const uint32_t *hrlen = reinterpret_cast<const uint32_t *>(hacc + (size_t)nv * pass);
@@ -631,30 +713,29 @@ int next_chunk_impl(pbsim_engine *e, pbsim_chunk *c, bool to_host) {
     if (br.cut) e->tail_mode = true;  // the next read is re-planned with the quota clip, one read at a time
     if (nv == 0) continue;
     if (e->mean_rlen_est <= 0 && nv > 0) e->mean_rlen_est = std::max(1.0, (double)br.bases_pass0 / nv);
-    c->first_read = e->next_read + 1;
-    c->n_reads = nv;
-    c->bases = (int64_t)br.bases_all;
-    c->reads_bytes = (int64_t)br.reads_bytes;
-    c->maf_bytes = (int64_t)br.maf_bytes;
-    // keep the per-subread info of this chunk for tests
-    e->last_info.clear();
+    const int64_t first_read = e->next_read + 1;
     e->next_read += nv;
     e->reads_done_in_run += nv;
     e->len_total += (int64_t)br.bases_pass0;
     if (to_host) {
-      CK(e->h_reads.ensure((size_t)br.reads_bytes + 16));
-      CK(e->h_maf.ensure((size_t)br.maf_bytes + 16));
-      CK(cudaMemcpyAsync(e->h_reads.p, e->d_out_reads.p, (size_t)br.reads_bytes, cudaMemcpyDeviceToHost, e->st));
-      CK(cudaMemcpyAsync(e->h_maf.p, e->d_out_maf.p, (size_t)br.maf_bytes, cudaMemcpyDeviceToHost, e->st));
-      CK(cudaStreamSynchronize(e->st));
-      c->reads = reinterpret_cast<const char *>(e->h_reads.p);
-      c->maf = reinterpret_cast<const char *>(e->h_maf.p);
-      c->on_device = 0;
-    } else {
-      c->reads = reinterpret_cast<const char *>(e->d_out_reads.p);
-      c->maf = reinterpret_cast<const char *>(e->d_out_maf.p);
-      c->on_device = 1;
+      pbsim_engine::Pending &p = e->pend;
+      p = pbsim_engine::Pending();
+      p.active = true;
+      p.total[0] = br.reads_bytes;
+      p.total[1] = br.maf_bytes;
+      p.first_read = first_read;
+      p.n_reads = nv;
+      p.bases = (int64_t)br.bases_all;
+      return deliver_piece(e, c);
     }
+    c->first_read = first_read;
+    c->n_reads = nv;
+    c->bases = (int64_t)br.bases_all;
+    c->reads_bytes = (int64_t)br.reads_bytes;
+    c->maf_bytes = (int64_t)br.maf_bytes;
+    c->reads = reinterpret_cast<const char *>(e->d_out_reads.p);
+    c->maf = reinterpret_cast<const char *>(e->d_out_maf.p);
+    c->on_device = 1;
     return 1;
   }
 }
@@ -687,6 +768,9 @@ int pbsim_cuda_create(pbsim_engine **out, int device) {
     delete ne;
     return fail(e, PBSIM_E_CUDA, "cannot create CUDA streams/events");
   }
+  cudaEventCreate(&ne->ev_copy);
+  for (auto &ev : ne->ev_k) cudaEventCreate(&ev);
+  for (auto &ev : ne->ev_user) cudaEventCreate(&ev);
   std::memset(&ne->model, 0, sizeof ne->model);
   std::memset(&ne->emitp, 0, sizeof ne->emitp);
   *out = ne;
@@ -702,8 +786,11 @@ void pbsim_cuda_destroy(pbsim_engine *e) {
                     &e->d_draws, &e->d_starts, &e->b_read_u32, &e->b_sub_u32, &e->b_sub_u64, &e->b_sub_f64, &e->d_bins,
                     &e->d_ctrl, &e->d_cub_tmp, &e->d_ev, &e->d_ck, &e->d_out_reads, &e->d_out_maf, &e->d_stats};
   for (DevBuf *b : bufs) b->release();
-  e->h_reads.release();
-  e->h_maf.release();
+  for (auto &a : e->h_stage)
+    for (auto &b : a) b.release();
+  cudaEventDestroy(e->ev_copy);
+  for (auto &ev : e->ev_k) cudaEventDestroy(ev);
+  for (auto &ev : e->ev_user) cudaEventDestroy(ev);
   e->h_ctrl.release();
   e->h_acc.release();
   cudaEventDestroy(e->ev0);
@@ -807,6 +894,14 @@ int pbsim_cuda_update_hp_del_bias(pbsim_engine *e, const double bias[12]) {
   return 0;
 }
 
+int pbsim_cuda_get_sequence_ascii(pbsim_engine *e, char *dst, int64_t cap) {
+  if (!e || !dst || !e->seq_set || cap < e->glen) return PBSIM_E_INVALID;
+  CK(cudaSetDevice(e->device));
+  CK(cudaMemcpyAsync(dst, e->d_ascii.p, (size_t)e->glen, cudaMemcpyDeviceToHost, e->st));
+  CK(cudaStreamSynchronize(e->st));
+  return 0;
+}
+
 int pbsim_cuda_get_hpfreq(pbsim_engine *e, int64_t hpfreq[12]) {
   if (!e || !e->seq_set) return PBSIM_E_INVALID;
   std::memcpy(hpfreq, e->hpfreq, sizeof e->hpfreq);
@@ -828,6 +923,9 @@ int pbsim_cuda_simulate_begin(pbsim_engine *e, const pbsim_run *run) {
   e->mean_rlen_est = 0;
   e->accuracy_total = 0;
   e->gen_ms = 0;
+  e->sim_ms = 0;
+  e->emit_ms = 0;
+  e->pend = pbsim_engine::Pending();
   e->launches = 0;
   k_init_stats<<<nblk(e->stats_cells, 256), 256, 0, e->st>>>(e->d_stats.as<unsigned long long>(), e->stats_cells);
   e->launches++;
@@ -885,6 +983,8 @@ int pbsim_cuda_simulate_end(pbsim_engine *e, pbsim_stats *st, int64_t *freq_len,
     }
   }
   st->gen_seconds = e->gen_ms * 1e-3;
+  st->sim_seconds = e->sim_ms * 1e-3;
+  st->emit_seconds = e->emit_ms * 1e-3;
   st->kernel_launches = e->launches;
   if (freq_len) {
     const int64_t n = std::min<int64_t>(freq_len_cells, e->freq_len_cells);
@@ -894,6 +994,40 @@ int pbsim_cuda_simulate_end(pbsim_engine *e, pbsim_stats *st, int64_t *freq_len,
     for (int64_t i = 0; i <= 100000; ++i) freq_accuracy[i] = fa[i];
   e->running = false;
   return 0;
+}
+
+int pbsim_cuda_device_timer(pbsim_engine *e, int stop, double *ms) {
+  if (!e) return PBSIM_E_INVALID;
+  CK(cudaSetDevice(e->device));
+  if (!stop) {
+    CK(cudaStreamSynchronize(e->st));
+    CK(cudaEventRecord(e->ev_user[0], e->st));
+    return 0;
+  }
+  CK(cudaEventRecord(e->ev_user[1], e->st));
+  CK(cudaEventSynchronize(e->ev_user[1]));
+  float f = 0;
+  CK(cudaEventElapsedTime(&f, e->ev_user[0], e->ev_user[1]));
+  if (ms) *ms = f;
+  return 0;
+}
+
+int pbsim_cuda_set_option(pbsim_engine *e, const char *name, int64_t value) {
+  if (!e || !name) return PBSIM_E_INVALID;
+  if (!strcmp(name, "stage_bytes")) {
+    if (value < 4096) return fail(e, PBSIM_E_INVALID, "stage_bytes too small");
+    if (e->pend.active) return fail(e, PBSIM_E_INVALID, "cannot resize staging while pieces are pending");
+    e->stage_bytes = (size_t)value;
+    for (auto &a : e->h_stage)
+      for (auto &b : a) b.release();
+    return 0;
+  }
+  if (!strcmp(name, "target_batch_bases")) {
+    if (value < 1) return fail(e, PBSIM_E_INVALID, "target_batch_bases must be positive");
+    e->target_batch_bases = value;
+    return 0;
+  }
+  return fail(e, PBSIM_E_INVALID, "unknown option %s", name);
 }
 
 int pbsim_cuda_stats_device_block(pbsim_engine *e, void **dptr, int64_t *cells) {

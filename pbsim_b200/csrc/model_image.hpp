@@ -31,10 +31,9 @@ struct AccEntry {          // one per accuracy 0..100, mirrored on the device
 
 // blob layouts (all sections 16-byte aligned)
 struct QsBlobLayout {
-  static constexpr uint32_t t2_off = 0;                                   // uint16[51*100]
-  static constexpr uint32_t emis_off = ((kQsRows * 100 * 2 + 15) / 16) * 16;  // uint8[51*100]
-  static constexpr uint32_t emod_off = emis_off + ((kQsRows * 100 + 15) / 16) * 16;  // uint8[51]
-  static constexpr uint32_t bytes = emod_off + 64;
+  static constexpr uint32_t t2_off = 0;                                   // uint32[51*100]
+  static constexpr uint32_t emis_off = ((kQsRows * 100 * 4 + 15) / 16) * 16;  // uint8[51*100]
+  static constexpr uint32_t bytes = emis_off + ((kQsRows * 100 + 15) / 16) * 16;
   static constexpr uint32_t freq_bytes = 1008;                            // uint8[1000] padded
 };
 
@@ -80,23 +79,24 @@ struct ModelImage {
           }
           blob.resize(blob.size() + QsBlobLayout::bytes, 0);
           uint8_t *b = blob.data() + e.blob_off;
-          uint16_t *t2 = reinterpret_cast<uint16_t *>(b + QsBlobLayout::t2_off);
+          uint32_t *t2 = reinterpret_cast<uint32_t *>(b + QsBlobLayout::t2_off);
           uint8_t *em = b + QsBlobLayout::emis_off;
-          uint8_t *emod = b + QsBlobLayout::emod_off;
-          auto tmod = [&](int s) -> uint32_t {
-            int v = (s >= 1 && s <= r.nstates) ? r.tran_mod[s] : 1;
-            return (uint32_t)(v < 1 ? 1 : (v > 255 ? 255 : v));
+          // moduli of the state an entry leads to travel with the entry: one shared-memory load per step
+          auto mods = [&](int s) -> uint32_t {
+            int tm = (s >= 1 && s <= r.nstates) ? r.tran_mod[s] : 1;
+            int emd = (s >= 1 && s <= r.nstates) ? r.emis_mod[s] : 1;
+            tm = tm < 1 ? 1 : (tm > 255 ? 255 : tm);
+            emd = emd < 1 ? 1 : (emd > 255 ? 255 : emd);
+            return ((uint32_t)tm << 8) | ((uint32_t)emd << 16);
           };
-          for (int k = 0; k < r.init_mod && k < 100; ++k) t2[k] = (uint16_t)(r.init[k] | (tmod(r.init[k]) << 8));
+          for (int k = 0; k < r.init_mod && k < 100; ++k) t2[k] = (uint32_t)r.init[k] | mods(r.init[k]);
           for (int s = 1; s <= r.nstates; ++s) {
             for (int k = 0; k < 100; ++k) {
               const uint8_t nx = r.tran[s * 100 + k];
-              t2[s * 100 + k] = (uint16_t)(nx | (tmod(nx) << 8));
+              t2[s * 100 + k] = (uint32_t)nx | mods(nx);
               em[s * 100 + k] = r.emis[s * 100 + k];
             }
-            emod[s] = (uint8_t)(r.emis_mod[s] < 1 ? 1 : r.emis_mod[s]);
           }
-          emod[0] = 1;
           e.blob_bytes = QsBlobLayout::bytes;
           e.has_model = 1;
           e.nstates = (uint32_t)r.nstates;

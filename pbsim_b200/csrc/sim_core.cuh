@@ -77,22 +77,41 @@ struct Philox {
   }
 };
 
+// murmur3 finaliser: a bijection on 32 bits with full avalanche; derives the (rare) second and later
+// deletion draws of a position from the Philox word of the first one
+PB_HD uint32_t fmix32(uint32_t h) {
+  h ^= h >> 16;
+  h *= 0x85EBCA6Bu;
+  h ^= h >> 13;
+  h *= 0xC2B2AE35u;
+  h ^= h >> 16;
+  return h;
+}
+
+#define PB_GROUP 4u  // positions whose Philox blocks are computed together (instruction-level parallelism)
+
 // ---------------------------------------------------------------------------------------------
 // draw sources.  Purpose-named draws: REPLAY consumes the reference's rand() stream in the
 // reference's order (`rand() % m`); PHILOX maps every purpose to a fixed word of the block
 // addressed by the position, so results do not depend on scheduling or GPU count.
 // ---------------------------------------------------------------------------------------------
 struct PhiloxDraw {
+  static constexpr bool kCounter = true;  // draws are addressed, not consumed: both branches of a select may be evaluated
   Philox ph;
-  uint32_t read_id, pass, pos;
+  uint32_t read_id, pass;
   uint32_t w[4];
+  uint32_t g[PB_GROUP][4];
   PB_HD void plan_begin() { ph.block(0u, 0u, read_id, 0u, w); }
   PB_HD uint32_t plan_len(uint32_t m) { return mulhi32(w[0], m); }
   PB_HD uint32_t plan_acc(uint32_t m) { return mulhi32(w[1], m); }
   PB_HD uint32_t plan_off(uint32_t span) { return (uint32_t)mulhi64(((uint64_t)w[2] << 32) | w[3], span); }
-  PB_HD void begin(uint32_t p) {
-    pos = p;
-    ph.block(p, pass << 16, read_id, 1u, w);
+  // blocks of positions p .. p+PB_GROUP-1: independent dependency chains the scheduler can interleave
+  PB_HD void prefetch(uint32_t p) {
+#pragma unroll
+    for (uint32_t u = 0; u < PB_GROUP; ++u) ph.block(p + u, pass << 16, read_id, 1u, g[u]);
+  }
+  PB_HD void begin(uint32_t u) {  // u: index inside the prefetched group (compile-time constant after unrolling)
+    w[0] = g[u][0]; w[1] = g[u][1]; w[2] = g[u][2]; w[3] = g[u][3];
   }
   PB_HD uint32_t w0(uint32_t m) { return mulhi32(w[0], m); }
   PB_HD uint32_t w1(uint32_t m) { return mulhi32(w[1], m); }
@@ -104,15 +123,14 @@ struct PhiloxDraw {
   PB_HD uint32_t mag3() { return (((w[3] & 0xFFFu) * 3u) >> 12) + 1u; }
   // j-th deletion draw after the current position, on the 0..999999 scale
   PB_HD uint32_t del(uint32_t j) {
-    if (j == 0) return mulhi32(w[3], 1000000u);
-    uint32_t x[4];
-    ph.block(pos, (1u + (j - 1u) / 4u) | (pass << 16), read_id, 1u, x);
-    return mulhi32(x[(j - 1u) & 3u], 1000000u);
+    const uint32_t x = (j == 0u) ? w[3] : fmix32(w[3] + j * 0x9E3779B9u);
+    return mulhi32(x, 1000000u);
   }
   PB_HD uint32_t consumed() const { return 0; }
 };
 
 struct ReplayDraw {
+  static constexpr bool kCounter = false;  // a stream: every draw call consumes one value, in the reference's order
   const int32_t *log;  // the reference's draws
   int64_t cur, end, start;
   PB_HD uint32_t next() {
@@ -124,6 +142,7 @@ struct ReplayDraw {
   PB_HD uint32_t plan_len(uint32_t m) { return next() % m; }
   PB_HD uint32_t plan_acc(uint32_t m) { return next() % m; }
   PB_HD uint32_t plan_off(uint32_t span) { return next() % span; }
+  PB_HD void prefetch(uint32_t) {}
   PB_HD void begin(uint32_t) {}
   PB_HD uint32_t w0(uint32_t m) { return next() % m; }
   PB_HD uint32_t w1(uint32_t m) { return next() % m; }
@@ -210,18 +229,21 @@ struct Ckpt {
 // qshmm
 // ---------------------------------------------------------------------------------------------
 // Tables of ONE accuracy (staged in shared memory by the kernel).
-//   t2[s*100 + k]  : next state | modulus(next state) << 8 ; row 0 is init2state
-//   emis[s*100 + k]: QV ; emod[s] its modulus
+//   t2[s*100 + k]  : next state | transition modulus(next) << 8 | emission modulus(next) << 16 ; row 0 is init2state
+//   emis[s*100 + k]: QV
 //   freq[k]        : QV when the model has no such accuracy (resolution 1000)
 //   thr[qv]        : {sub_thre, ins_thre, max_hp del threshold, del threshold for hp[-1]}
 //   thr_hp[qv*12+h]: exact deletion threshold ceil(del_thre[qv] * hp_del_bias[h])
+struct QsThr {
+  uint32_t sub, ins, del, del0;
+};
+
 struct QsView {
-  const uint16_t *t2;
+  const uint32_t *t2;
   const uint8_t *emis;
-  const uint8_t *emod;
   const uint8_t *freq;
   uint32_t has_model, init_mod, freq_mod;
-  const uint32_t *thr;      // [94*4]
+  const QsThr *thr;         // [94]
   const uint32_t *thr_hp;   // [94*12]
   const double *qc_prob;    // [94]
 };
@@ -257,75 +279,80 @@ template <class Draw>
 PB_HD void qshmm_simulate(const QsView &T, Draw &d, const WindowRef &win, bool slow, uint32_t wlen,
                           QsSink &sink, SubreadResult &res) {
   uint32_t R = 0, P = 0, C = 0;
-  uint32_t state = 0, mod = T.init_mod;
+  uint32_t state = 0, mod = T.init_mod, emod = 1;
   uint32_t nsub = 0, nins = 0, ndel = 0;
   double prob = 0.0;
   res.overflow = 0;
   while (R < wlen) {
-    if (sink.full()) { res.overflow = 1; break; }
-    sink.checkpoint(C, R, P);
-    d.begin(P);
-    uint32_t qv;
-    if (T.has_model) {
-      const uint32_t t = T.t2[state * PB_QS_ROW + d.w0(mod)];
-      state = t & 0xFFu;
-      mod = t >> 8;
-      qv = T.emis[state * PB_QS_ROW + d.w1(T.emod[state])];
-    } else {
-      qv = T.freq[d.w0(T.freq_mod)];
-    }
-    prob += T.qc_prob[qv];
-    const uint32_t th_sub = T.thr[qv * 4u + 0u], th_ins = T.thr[qv * 4u + 1u];
-    const uint32_t th_del = T.thr[qv * 4u + 2u], th_del0 = T.thr[qv * 4u + 3u];
-    const uint32_t r = d.w2(1000000u);
-    uint32_t kind, info;
-    if (r < th_sub) {
-      kind = PB_KIND_SUB;
-      ++nsub;
-      info = d.choice3();
-      if (slow && win.nonacgt(R)) info = d.choice4();
-      ++R;
-    } else if (r < th_ins) {
-      kind = PB_KIND_INS;
-      ++nins;
-      info = d.choice8();
-    } else {
-      kind = PB_KIND_MATCH;
-      info = 0;
-      ++R;
-    }
-    ++P;
-    ++C;
-    uint32_t nd = 0;
-    while (R < wlen) {
-      const uint32_t rd = d.del(nd);
-      bool hit = rd < th_del;
-      if (hit) {
-        if (R == 0u) hit = rd < th_del0;                                   // mut.hp[-1] (:2269)
-        else if (slow) hit = rd < T.thr_hp[qv * 12u + win.hp(R - 1u)];
+    d.prefetch(P);
+#pragma unroll
+    for (uint32_t u = 0; u < PB_GROUP; ++u) {
+      if (R >= wlen) break;
+      if (sink.full()) { res.overflow = 1; break; }
+      sink.checkpoint(C, R, P);
+      d.begin(u);
+      uint32_t qv;
+      if (T.has_model) {
+        const uint32_t t = T.t2[state * PB_QS_ROW + d.w0(mod)];
+        state = t & 0xFFu;
+        mod = (t >> 8) & 0xFFu;
+        emod = t >> 16;
+        qv = T.emis[state * PB_QS_ROW + d.w1(emod)];
+      } else {
+        qv = T.freq[d.w0(T.freq_mod)];
       }
-      if (!hit) break;
-      ++nd;
-      ++R;
-    }
-    ndel += nd;
-    C += nd;
-    const uint32_t base = qv | (kind << 7) | (info << 9);
-    if (nd < PB_QS_DEL_SAT) {
-      sink.push(base | (nd << 12));
-    } else {
-      sink.push(base | (PB_QS_DEL_SAT << 12));
-      uint32_t rest = nd - PB_QS_DEL_SAT;
-      for (;;) {  // continuation entries: 14-bit counts, 16383 = "more follows"
-        if (sink.full()) { res.overflow = 1; break; }
-        sink.checkpoint(C, R, P);
-        const uint32_t c = rest < PB_QS_CONT_SAT ? rest : PB_QS_CONT_SAT;
-        sink.push((c & 0x7Fu) | (3u << 7) | ((c >> 7) << 9));
-        if (c < PB_QS_CONT_SAT) break;
-        rest -= PB_QS_CONT_SAT;
+      prob += T.qc_prob[qv];
+      const QsThr th = T.thr[qv];
+      const uint32_t r = d.w2(1000000u);
+      const bool is_sub = r < th.sub;
+      const bool is_ins = !is_sub && r < th.ins;
+      uint32_t info;
+      if (Draw::kCounter) {
+        info = is_sub ? d.choice3() : (is_ins ? d.choice8() : 0u);
+      } else {
+        info = 0;
+        if (is_sub) info = d.choice3();
+        else if (is_ins) info = d.choice8();
       }
-      if (res.overflow) break;
+      if (slow && is_sub && win.nonacgt(R)) info = d.choice4();  // the %3 draw is still consumed (:2235-2246)
+      const uint32_t kind = is_sub ? PB_KIND_SUB : (is_ins ? PB_KIND_INS : PB_KIND_MATCH);
+      nsub += is_sub ? 1u : 0u;
+      nins += is_ins ? 1u : 0u;
+      R += is_ins ? 0u : 1u;
+      ++P;
+      ++C;
+      uint32_t nd = 0;
+      while (R < wlen) {
+        const uint32_t rd = d.del(nd);
+        bool hit = rd < th.del;
+        if (hit) {
+          if (R == 0u) hit = rd < th.del0;                                   // mut.hp[-1] (:2269)
+          else if (slow) hit = rd < T.thr_hp[qv * 12u + win.hp(R - 1u)];
+        }
+        if (!hit) break;
+        ++nd;
+        ++R;
+      }
+      ndel += nd;
+      C += nd;
+      const uint32_t base = qv | (kind << 7) | (info << 9);
+      if (nd < PB_QS_DEL_SAT) {
+        sink.push(base | (nd << 12));
+      } else {
+        sink.push(base | (PB_QS_DEL_SAT << 12));
+        uint32_t rest = nd - PB_QS_DEL_SAT;
+        for (;;) {  // continuation entries: 14-bit counts, 16383 = "more follows"
+          if (sink.full()) { res.overflow = 1; break; }
+          sink.checkpoint(C, R, P);
+          const uint32_t c = rest < PB_QS_CONT_SAT ? rest : PB_QS_CONT_SAT;
+          sink.push((c & 0x7Fu) | (3u << 7) | ((c >> 7) << 9));
+          if (c < PB_QS_CONT_SAT) break;
+          rest -= PB_QS_CONT_SAT;
+        }
+        if (res.overflow) break;
+      }
     }
+    if (res.overflow) break;
   }
   sink.flush();
   res.n_entries = sink.n;
@@ -399,51 +426,58 @@ PB_HD void errhmm_simulate(const ErView &T, Draw &d, const WindowRef &win, bool 
     }
   } else {
     while (R < wlen) {
-      if (sink.full()) { res.overflow = 1; break; }
-      sink.checkpoint(C, R, P);
-      d.begin(C);
-      const uint32_t row = (P == 0u) ? 0u : state;           // init is re-drawn while read_offset == 0 (:3853)
-      const uint32_t m = (P == 0u) ? T.init_mod : mod;
-      const uint32_t t = T.t2[row * PB_ER_ROW + d.w0(m)];
-      state = t & 63u;
-      mod = t >> 6;
-      const uint32_t x = d.w1(1000u) + 1u;
-      bool isdel = x <= T.edel[state];
-      if (isdel && slow) isdel = x <= T.edel_hp[state * 12u + win.hp(R)];   // hp at the current base (:3860)
-      uint32_t kind;
-      if (isdel) {
-        kind = PB_KIND_DEL;
-      } else {
-        const uint32_t em = T.emod[state];
-        kind = (em == 0u) ? d.w2(3u) : (uint32_t)T.emis[state * PB_ER_ROW + d.w2(em)];
-      }
-      if (T.mode == 1u) {
-        if (kind == PB_KIND_MATCH) {
-          if (d.w3(100u) + 1u <= T.rate_mag) kind = d.mag3();
+      d.prefetch(C);
+#pragma unroll
+      for (uint32_t u = 0; u < PB_GROUP; ++u) {
+        if (R >= wlen) break;
+        if (sink.full()) { res.overflow = 1; break; }
+        sink.checkpoint(C, R, P);
+        d.begin(u);
+        const uint32_t row = (P == 0u) ? 0u : state;           // init is re-drawn while read_offset == 0 (:3853)
+        const uint32_t m = (P == 0u) ? T.init_mod : mod;
+        const uint32_t t = T.t2[row * PB_ER_ROW + d.w0(m)];
+        state = t & 63u;
+        mod = t >> 6;
+        const uint32_t x = d.w1(1000u) + 1u;
+        bool isdel = x <= T.edel[state];
+        if (isdel && slow) isdel = x <= T.edel_hp[state * 12u + win.hp(R)];   // hp at the current base (:3860)
+        uint32_t kind;
+        if (Draw::kCounter) {
+          const uint32_t em = T.emod[state];
+          const uint32_t k2 = (em == 0u) ? d.w2(3u) : (uint32_t)T.emis[state * PB_ER_ROW + d.w2(em == 0u ? 1u : em)];
+          kind = isdel ? PB_KIND_DEL : k2;
+        } else if (isdel) {
+          kind = PB_KIND_DEL;
+        } else {
+          const uint32_t em = T.emod[state];
+          kind = (em == 0u) ? d.w2(3u) : (uint32_t)T.emis[state * PB_ER_ROW + d.w2(em)];
         }
-      } else if (T.mode == 2u) {
-        if (kind != PB_KIND_MATCH) {
-          if (d.w3(100u) + 1u <= T.rate_mag) kind = PB_KIND_MATCH;
+        if (T.mode == 1u) {
+          if (kind == PB_KIND_MATCH) {
+            if (d.w3(100u) + 1u <= T.rate_mag) kind = d.mag3();
+          }
+        } else if (T.mode == 2u) {
+          if (kind != PB_KIND_MATCH) {
+            if (d.w3(100u) + 1u <= T.rate_mag) kind = PB_KIND_MATCH;
+          }
         }
+        uint32_t info = 0;
+        if (Draw::kCounter) {
+          info = (kind == PB_KIND_SUB) ? d.choice3() : ((kind == PB_KIND_INS) ? d.choice8() : 0u);
+        } else {
+          if (kind == PB_KIND_SUB) info = d.choice3();
+          else if (kind == PB_KIND_INS) info = d.choice8();
+        }
+        if (slow && kind == PB_KIND_SUB && win.nonacgt(R)) info = d.choice4();
+        nsub += (kind == PB_KIND_SUB) ? 1u : 0u;
+        nins += (kind == PB_KIND_INS) ? 1u : 0u;
+        ndel += (kind == PB_KIND_DEL) ? 1u : 0u;
+        R += (kind == PB_KIND_INS) ? 0u : 1u;
+        P += (kind == PB_KIND_DEL) ? 0u : 1u;
+        ++C;
+        sink.push(kind | (info << 2));
       }
-      uint32_t info = 0;
-      if (kind == PB_KIND_MATCH) {
-        ++R; ++P;
-      } else if (kind == PB_KIND_SUB) {
-        ++nsub;
-        info = d.choice3();
-        if (slow && win.nonacgt(R)) info = d.choice4();
-        ++R; ++P;
-      } else if (kind == PB_KIND_INS) {
-        ++nins;
-        info = d.choice8();
-        ++P;
-      } else {
-        ++ndel;
-        ++R;
-      }
-      ++C;
-      sink.push(kind | (info << 2));
+      if (res.overflow) break;
     }
   }
   sink.flush();

@@ -273,14 +273,13 @@ __global__ void __launch_bounds__(kSimThreads) k_sim_qshmm(SimArgs A) {
     return;
   }
   QsView T;
-  T.t2 = reinterpret_cast<const uint16_t *>(smem + QsBlobLayout::t2_off);
+  T.t2 = reinterpret_cast<const uint32_t *>(smem + QsBlobLayout::t2_off);
   T.emis = smem + QsBlobLayout::emis_off;
-  T.emod = smem + QsBlobLayout::emod_off;
   T.freq = smem;
   T.has_model = ae.has_model;
   T.init_mod = ae.init_mod;
   T.freq_mod = ae.freq_mod;
-  T.thr = reinterpret_cast<const uint32_t *>(smem + kQsSmemThr);
+  T.thr = reinterpret_cast<const QsThr *>(smem + kQsSmemThr);
   T.thr_hp = A.M.qs_thr_hp;
   T.qc_prob = reinterpret_cast<const double *>(smem + kQsSmemProb);
   WindowRef win;

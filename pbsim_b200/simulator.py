@@ -57,8 +57,38 @@ class Engine:
         self._chk(self.L.pbsim_cuda_set_synthetic_sequence(self.h, length, seq_num, seed), "set_synthetic_sequence")
         self.glen = length
 
+    def set_sequence_ptr(self, ptr, length, seq_num, bias):
+        """same as set_sequence, from a raw host pointer (e.g. pinned memory)"""
+        s = capi.Sequence()
+        s.bases = C.cast(ptr, C.c_char_p)
+        s.len = length
+        s.seq_num = seq_num
+        s.hp_del_bias = (C.c_double * 12)(*bias)
+        self._chk(self.L.pbsim_cuda_set_sequence(self.h, C.byref(s)), "set_sequence")
+        self.glen = length
+
+    def get_sequence_ascii(self, dst_ptr, cap):
+        self._chk(self.L.pbsim_cuda_get_sequence_ascii(self.h, dst_ptr, cap), "get_sequence_ascii")
+
     def update_bias(self, bias):
         self._chk(self.L.pbsim_cuda_update_hp_del_bias(self.h, (C.c_double * 12)(*bias)), "update_hp_del_bias")
+
+    def set_option(self, name, value):
+        self._chk(self.L.pbsim_cuda_set_option(self.h, name.encode(), int(value)), "set_option")
+
+    def timer_start(self):
+        self._chk(self.L.pbsim_cuda_device_timer(self.h, 0, None), "device_timer")
+
+    def timer_stop(self):
+        ms = C.c_double()
+        self._chk(self.L.pbsim_cuda_device_timer(self.h, 1, C.byref(ms)), "device_timer")
+        return ms.value
+
+    def stats_block(self):
+        ptr = C.c_void_p()
+        cells = C.c_int64()
+        self._chk(self.L.pbsim_cuda_stats_device_block(self.h, C.byref(ptr), C.byref(cells)), "stats_device_block")
+        return ptr.value, cells.value
 
     def hpfreq(self):
         out = (C.c_int64 * 12)()

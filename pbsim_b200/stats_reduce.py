@@ -1,0 +1,59 @@
+"""Multi-GPU plumbing of the path: reads shard across ranks with no data-path
+collective; the ONE exchange is the statistics block (sim.res_* counters, freq_len, freq_accuracy —
+pbsim.cpp:2293-2316, :2387-2410), all-reduced once per reference sequence, plus an all-gather of one
+int64 per rank when a sequence's read-id range is split and the quota cut needs the global prefix.
+torch.distributed is only the transport (NCCL on GPUs, gloo in the CPU tests)."""
+import torch
+
+# layout of the engine's stats block (emit.cuh k_stats): int64 cells
+CELL_LEN_MIN = 3
+CELL_LEN_MAX = 4
+
+
+class _DeviceCells:
+    """view of raw device memory for torch.as_tensor (CUDA array interface v2)"""
+
+    def __init__(self, ptr, cells):
+        self.__cuda_array_interface__ = {"shape": (int(cells),), "typestr": "<i8", "data": (int(ptr), False),
+                                         "version": 2}
+
+
+def reduce_stats_tensor(t, dist):
+    """in-place: sum every cell over ranks, except res_len_min (MIN) and res_len_max (MAX)"""
+    mn = t[CELL_LEN_MIN:CELL_LEN_MIN + 1].clone()
+    mx = t[CELL_LEN_MAX:CELL_LEN_MAX + 1].clone()
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    dist.all_reduce(mn, op=dist.ReduceOp.MIN)
+    dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+    t[CELL_LEN_MIN] = mn[0]
+    t[CELL_LEN_MAX] = mx[0]
+    return t
+
+
+def allreduce_stats_block(engine, dist):
+    ptr, cells = engine.stats_block()
+    t = torch.as_tensor(_DeviceCells(ptr, cells), device="cuda")
+    return reduce_stats_tensor(t, dist)
+
+
+def contigs_for_rank(n_contigs, rank, world):
+    """partition by sequence (many-contig genomes): rank r simulates contigs r, r+world, ..."""
+    return list(range(rank, n_contigs, world))
+
+
+def read_range_for_rank(n_reads, rank, world):
+    """partition by read-index range inside one sequence: contiguous, sizes differ by at most 1"""
+    base, extra = divmod(n_reads, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def emitted_prefix(my_emitted_bases, dist, device="cpu"):
+    """exclusive scan over ranks of the emitted bases of each rank's read range: len_total_start of
+    this rank, needed to place the quota cut (pbsim.cpp:2173-2181) when a sequence is split"""
+    world = dist.get_world_size()
+    mine = torch.tensor([int(my_emitted_bases)], dtype=torch.int64, device=device)
+    allv = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(allv, mine)
+    vals = [int(v.item()) for v in allv]
+    return sum(vals[:dist.get_rank()]), sum(vals)

@@ -85,12 +85,11 @@ long hostsim_run(const pbsim_model *m, const uint8_t *ascii_upper, const int16_t
         g_out.events.resize(ev_off + (size_t)cap * 2);
         pb::QsView T;
         const uint8_t *b = img.blob.data() + ae.blob_off;
-        T.t2 = reinterpret_cast<const uint16_t *>(b + pb::QsBlobLayout::t2_off);
+        T.t2 = reinterpret_cast<const uint32_t *>(b + pb::QsBlobLayout::t2_off);
         T.emis = b + pb::QsBlobLayout::emis_off;
-        T.emod = b + pb::QsBlobLayout::emod_off;
         T.freq = b;
         T.has_model = ae.has_model; T.init_mod = ae.init_mod; T.freq_mod = ae.freq_mod;
-        T.thr = img.qs_thr.data(); T.thr_hp = img.qs_thr_hp.data(); T.qc_prob = m->qc_prob;
+        T.thr = reinterpret_cast<const pb::QsThr *>(img.qs_thr.data()); T.thr_hp = img.qs_thr_hp.data(); T.qc_prob = m->qc_prob;
         pb::QsSink sink;
         sink.init(reinterpret_cast<uint16_t *>(g_out.events.data() + ev_off), g_out.ckpts.data() + ck_base, cap);
         if (rng_mode == PBSIM_RNG_PHILOX) { pd.pass = (uint32_t)pass; pb::qshmm_simulate(T, pd, win, slow, plan.wlen, sink, res); }

@@ -90,3 +90,49 @@ def test_genome_ingest_matches_oracle_hp(eng):
         want = [int(np.count_nonzero(hp == h)) for h in range(12)]
         eng.set_sequence(s, i, [0.0] + [1.0] * 10 + [0.0])
         assert eng.hpfreq() == want
+
+
+def test_host_delivery_in_small_pieces_is_byte_identical(eng):
+    """pinned staging of 4 KiB: the records arrive as many pieces; concatenation must not change a byte"""
+    c = Case("qs_rsii_basic")
+    ref = run_case_on_gpu(c, eng, "philox")
+    eng.set_option("stage_bytes", 4096)
+    try:
+        got = run_case_on_gpu(c, eng, "philox")
+    finally:
+        eng.set_option("stage_bytes", 128 << 20)
+    for a, b in zip(ref, got):
+        assert a[0] == b[0] and a[1] == b[1]
+
+
+def test_synthetic_sequence_roundtrip_properties(eng):
+    """size-independent properties on a device-generated 3 Mbp contig: every MAF block re-derives the FASTQ
+    read (read row minus gaps == read, reverse-complemented for '-') and the genome window (ref row minus gaps)"""
+    import ctypes as C
+    c = Case("qs_rsii_basic")
+    hm = engine_model(c)
+    eng.set_model(hm)
+    n = 3000000
+    eng.set_synthetic_sequence(n, 1, 99)
+    buf = (C.c_char * n)()
+    eng.get_sequence_ascii(C.addressof(buf), n)
+    genome = bytes(buf)
+    reads, maf, st, _ = eng.simulate(2 * n, rng_mode=capi.RNG_PHILOX, seed=5)
+    fq = reads.split(b"\n")
+    blocks = maf.split(b"\n\n")[:-1]
+    assert len(fq) // 4 == len(blocks) == st.res_num
+    comp = bytes.maketrans(b"ACGT", b"TGCA")
+    total = 0
+    for k, blk in enumerate(blocks):
+        l1, l2 = blk.split(b"\n")[1:3]
+        f1, f2 = l1.split(), l2.split()
+        off, wlen, refrow = int(f1[2]), int(f1[3]), f1[6]
+        rlen, strand, readrow = int(f2[3]), f2[4], f2[6]
+        assert len(refrow) == len(readrow)
+        assert refrow.replace(b"-", b"") == genome[off:off + wlen]
+        seq = fq[4 * k + 1]
+        assert len(seq) == rlen == len(fq[4 * k + 3])
+        rr = readrow.replace(b"-", b"")
+        assert (rr if strand == b"+" else rr.translate(comp)[::-1]) == seq
+        total += rlen
+    assert total == st.res_len_total >= 2 * n
