@@ -253,8 +253,18 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0, help="shrink contigs (debugging only; reported in config)")
     ap.add_argument("--e2e-steps", type=int, default=-1, help="steps of the host-buffer arm (default: all)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--len-sd", type=float, default=None, help="diagnostics: override --length-sd (0 = equal-length reads)")
+    ap.add_argument("--len-mean", type=float, default=None, help="diagnostics: override --length-mean")
+    ap.add_argument("--batch-bases", type=float, default=None, help="diagnostics: engine target_batch_bases")
     args = ap.parse_args()
-    wl = WORKLOADS[args.workload]
+    wl = dict(WORKLOADS[args.workload])
+    if args.len_sd is not None or args.len_mean is not None:
+        wl["params"] = dict(wl["params"])
+        if args.len_sd is not None:
+            wl["params"]["len_sd"] = args.len_sd
+        if args.len_mean is not None:
+            wl["params"]["len_mean"] = args.len_mean
+        wl["name"] += " [diagnostic override: len_mean=%s len_sd=%s]" % (args.len_mean, args.len_sd)
     if args.impl == "reference":
         reference_arm(args, wl)
         return
@@ -280,6 +290,8 @@ def main():
     hm = capi.HostModel(L, capi.host_params(wl["method"], **wl["params"]), model_path(wl["model"]))
     eng = simulator.Engine(local)
     eng.set_model(hm)
+    if args.batch_bases:
+        eng.set_option("target_batch_bases", int(args.batch_bases))
     depth = wl["depth"]
     contigs = [max(200000, int(m * 1000000 * args.scale)) for m in CONTIG_MBP]
     bias = [0.0] + [1.0] * 10 + [0.0]

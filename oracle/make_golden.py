@@ -37,6 +37,8 @@ G_PLAIN = dict(seed=1, contigs=[("chrA", 20000), ("chrB", 5000)])
 G_QUIRK = dict(seed=2, contigs=[("c1", 30000), ("c2", 150), ("c3", 8000)], n_runs=6, hp_plants=40,
                lowercase_frac=0.1, iupac=5)
 
+G_LONGHP = dict(seed=3, contigs=[("h1", 20000)], long_runs=[12, 14, 16, 18, 20, 22, 24, 26, 28, 30, 34, 38, 40, 46] * 3)
+
 CASES = {
     # name: (method, model, genome spec, depth, seed, extra CLI args, oracle kwargs)
     "qs_rsii_basic": ("qshmm", "QSHMM-RSII.model", G_PLAIN, 5, 42,
@@ -63,6 +65,18 @@ CASES = {
     "qs_rsii_multipass": ("qshmm", "QSHMM-RSII.model", G_PLAIN, 2, 6,
                           ["--length-mean", "800", "--length-sd", "600", "--pass-num", "2", "--id-prefix", "XY"],
                           dict(len_mean=800.0, len_sd=600.0, pass_num=2, id_prefix="XY")),
+    # every base QV 0, deletions dominate: runs of >= 15 deletions after one read position (continuation entries)
+    "qs_delheavy_uniform": ("qshmm", "QSHMM-RSII.model", G_PLAIN, 8, 31,
+                            ["--length-mean", "1500", "--length-sd", "900", "--accuracy-mean", "0.0",
+                             "--difference-ratio", "1:1:1000"],
+                            dict(len_mean=1500.0, len_sd=900.0, accuracy_mean=0.0, accuracy_mean_set=True,
+                                 ratio=(1, 1, 1000))),
+    # the same through the homopolymer-bias path: long even-length homopolymers are deleted wholesale
+    "qs_delheavy_bias": ("qshmm", "QSHMM-RSII.model", G_LONGHP, 6, 32,
+                         ["--length-mean", "1500", "--length-sd", "900", "--accuracy-mean", "0.3",
+                          "--difference-ratio", "1:1:1000", "--hp-del-bias", "10"],
+                         dict(len_mean=1500.0, len_sd=900.0, accuracy_mean=0.3, accuracy_mean_set=True,
+                              ratio=(1, 1, 1000), hp_del_bias=10.0)),
     "qs_rsii_fixedlen": ("qshmm", "QSHMM-RSII.model", G_PLAIN, 3, 21,
                          ["--length-mean", "500", "--length-sd", "0", "--accuracy-mean", "0.9",
                           "--length-min", "50", "--length-max", "5000"],

@@ -35,7 +35,7 @@ def build_reference():
     return True
 
 
-def synth_genome(seed, contigs, n_runs=0, hp_plants=0, lowercase_frac=0.0, iupac=0):
+def synth_genome(seed, contigs, n_runs=0, hp_plants=0, lowercase_frac=0.0, iupac=0, long_runs=()):
     """Seeded synthetic genome: i.i.d. ACGT, optional N runs, planted homopolymers (2..15),
     lower-case stretches and isolated IUPAC codes.  Returns [(name, bytes)]."""
     rng = np.random.default_rng(seed)
@@ -45,6 +45,9 @@ def synth_genome(seed, contigs, n_runs=0, hp_plants=0, lowercase_frac=0.0, iupac
         s = alphabet[rng.integers(0, 4, size=n)].copy()
         for _ in range(hp_plants):
             L = int(rng.integers(2, 16))
+            p = int(rng.integers(0, max(1, n - L)))
+            s[p:p + L] = alphabet[int(rng.integers(0, 4))]
+        for L in long_runs:  # long homopolymers of chosen lengths (deletion-run stress)
             p = int(rng.integers(0, max(1, n - L)))
             s[p:p + L] = alphabet[int(rng.integers(0, 4))]
         for _ in range(n_runs):

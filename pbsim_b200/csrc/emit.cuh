@@ -288,10 +288,214 @@ __device__ __forceinline__ uint8_t read_base(uint32_t kind, uint32_t info, uint8
   return info >= 4u ? wch : (uint8_t)(nt4 >> (8u * info));
 }
 
+// ---- fast tile path -------------------------------------------------------------------------
+// Everything in 2-bit code space (A=0 C=1 G=2 T=3, complement = ^3), converted to characters with
+// one byte-permute per output.  Substitution alphabets of set_mut (:5481-5486) as 2-bit codes:
+//   A -> T,G,C   C -> A,T,G   G -> A,T,C   T -> A,G,C      index = window code * 3 + choice
+__device__ __forceinline__ uint32_t sub_code(uint32_t wc, uint32_t choice) {
+  // codes packed 2 bits each, entry (wc*3 + choice):  A:3,2,1  C:0,3,2  G:0,3,1  T:0,2,1
+  const uint32_t tab = (3u) | (2u << 2) | (1u << 4) | (0u << 6) | (3u << 8) | (2u << 10) | (0u << 12) | (3u << 14) |
+                       (1u << 16) | (0u << 18) | (2u << 20) | (1u << 22);
+  return (tab >> ((wc * 3u + choice) * 2u)) & 3u;
+}
+// "ATGC"[i] (insertion alphabet, :5486) as a code: A T G C -> 0 3 2 1
+__device__ __forceinline__ uint32_t ins_code(uint32_t i) { return (0x6Cu >> (i * 2u)) & 3u; }  // 0b01101100
+__device__ __forceinline__ uint8_t code_char(uint32_t code) { return (uint8_t)__byte_perm(0x54474341u, 0u, code); }
+
+// read-base code of an event given the window code of the current reference base
+__device__ __forceinline__ uint32_t read_code(uint32_t kind, uint32_t info, uint32_t wc) {
+  const uint32_t s = sub_code(wc, info > 2u ? 2u : info);
+  const uint32_t i = info >= 4u ? wc : ins_code(info & 3u);
+  return kind == PB_KIND_MATCH ? wc : (kind == PB_KIND_SUB ? s : i);
+}
+
+constexpr uint32_t kEmitPerLane = 4;                    // entries per lane per iteration
+constexpr uint32_t kEmitStep = 32u * kEmitPerLane;      // entries per warp iteration
+
+// One tile whose reference range holds only ACGT: 4 entries per lane, one packed warp scan per 128 entries.
+template <int METHOD>
+__device__ __forceinline__ void emit_tile_fast(const uint8_t *__restrict__ evbase, uint32_t e0, uint32_t e1,
+                                               const uint32_t *__restrict__ pk, uint32_t offset, uint32_t wlen,
+                                               uint32_t minus, uint32_t ncol, uint32_t C0, uint32_t R0, uint32_t P0,
+                                               uint8_t *__restrict__ seq, uint8_t *__restrict__ qual,
+                                               uint8_t *__restrict__ mref, uint8_t *__restrict__ mread, uint32_t lane) {
+  const uint32_t flip = minus ? 3u : 0u;
+  for (uint32_t i = e0; i < e1; i += kEmitStep) {
+    const uint32_t eb = i + lane * kEmitPerLane;
+    // ---- load 4 entries (tile starts are 16-byte aligned, so the vector load is aligned; entries past e1 are
+    //      masked: the slot behind them is padded scratch)
+    uint32_t raw[kEmitPerLane];
+    if (METHOD == PBSIM_METHOD_QSHMM) {
+      const uint2 v = __ldg(reinterpret_cast<const uint2 *>(evbase + 2ull * eb));
+      raw[0] = v.x & 0xFFFFu; raw[1] = v.x >> 16; raw[2] = v.y & 0xFFFFu; raw[3] = v.y >> 16;
+    } else {
+      const uint32_t v = __ldg(reinterpret_cast<const uint32_t *>(evbase + eb));
+      raw[0] = v & 0xFFu; raw[1] = (v >> 8) & 0xFFu; raw[2] = (v >> 16) & 0xFFu; raw[3] = v >> 24;
+    }
+    uint32_t kind[kEmitPerLane], info[kEmitPerLane], nd[kEmitPerLane], isb[kEmitPerLane], adv[kEmitPerLane];
+    uint32_t lb = 0, la = 0, ld = 0;  // this lane's totals: read bases, ref advances by bases, deletions
+#pragma unroll
+    for (uint32_t k = 0; k < kEmitPerLane; ++k) {
+      const bool valid = eb + k < e1;
+      const uint32_t v = raw[k];
+      if (METHOD == PBSIM_METHOD_QSHMM) {
+        kind[k] = (v >> 7) & 3u;
+        info[k] = (v >> 9) & 7u;
+        const bool cont = kind[k] == 3u;
+        nd[k] = valid ? (cont ? ((v & 0x7Fu) | ((v >> 9) << 7)) : (v >> 12)) : 0u;
+        isb[k] = (valid && !cont) ? 1u : 0u;
+        adv[k] = (isb[k] && kind[k] != PB_KIND_INS) ? 1u : 0u;
+      } else {
+        kind[k] = v & 3u;
+        info[k] = (v >> 2) & 7u;
+        nd[k] = (valid && kind[k] == PB_KIND_DEL) ? 1u : 0u;
+        isb[k] = (valid && kind[k] != PB_KIND_DEL) ? 1u : 0u;
+        adv[k] = (isb[k] && kind[k] != PB_KIND_INS) ? 1u : 0u;
+      }
+      lb += isb[k];
+      la += adv[k];
+      ld += nd[k];
+    }
+    // ---- one warp scan over the packed per-lane totals: bases (8 bit) | advances (8 bit) | deletions (16 bit)
+    // deletion counts that do not fit (long continuation runs) take the wide scan
+    uint32_t pre_b, pre_a, pre_d, tot_b, tot_a, tot_d;
+    if (__any_sync(0xFFFFFFFFu, ld >= 2048u)) {
+      uint32_t xb = lb, xa = la, xd = ld;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t yb = __shfl_up_sync(0xFFFFFFFFu, xb, o), ya = __shfl_up_sync(0xFFFFFFFFu, xa, o),
+                       yd = __shfl_up_sync(0xFFFFFFFFu, xd, o);
+        if (lane >= (uint32_t)o) { xb += yb; xa += ya; xd += yd; }
+      }
+      tot_b = __shfl_sync(0xFFFFFFFFu, xb, 31); tot_a = __shfl_sync(0xFFFFFFFFu, xa, 31);
+      tot_d = __shfl_sync(0xFFFFFFFFu, xd, 31);
+      pre_b = xb - lb; pre_a = xa - la; pre_d = xd - ld;
+    } else {
+      const uint32_t mine = lb | (la << 8) | (ld << 16);
+      uint32_t x = mine;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o);
+        if (lane >= (uint32_t)o) x += y;
+      }
+      const uint32_t tot = __shfl_sync(0xFFFFFFFFu, x, 31);
+      const uint32_t pre = x - mine;
+      pre_b = pre & 0xFFu; pre_a = (pre >> 8) & 0xFFu; pre_d = pre >> 16;
+      tot_b = tot & 0xFFu; tot_a = (tot >> 8) & 0xFFu; tot_d = tot >> 16;
+    }
+    uint32_t Pp = P0 + pre_b, Rr = R0 + pre_a + pre_d, Cc = C0 + pre_b + pre_d;
+    // ---- reference bases this lane may need: window positions Rr .. Rr+3 (+ deletions, fetched on demand)
+#pragma unroll
+    for (uint32_t k = 0; k < kEmitPerLane; ++k) {
+      if (isb[k]) {
+        const uint32_t g = minus ? offset + wlen - 1u - Rr : offset + Rr;
+        const uint32_t gc = (__ldg(&pk[g >> 4]) >> ((g & 15u) * 2u)) & 3u;
+        const uint32_t wc = gc ^ flip;
+        const uint32_t rc = read_code(kind[k], info[k], wc);
+        seq[Pp] = code_char(rc);
+        if (METHOD == PBSIM_METHOD_QSHMM) qual[Pp] = (uint8_t)((raw[k] & 0x7Fu) + 33u);
+        else qual[Pp] = (uint8_t)'!';
+        const uint32_t col = minus ? ncol - 1u - Cc : Cc;
+        mread[col] = code_char(rc ^ flip);
+        mref[col] = (kind[k] == PB_KIND_INS) ? (uint8_t)'-' : code_char(gc);
+        ++Pp;
+        ++Cc;
+        Rr += adv[k];
+      }
+      if (nd[k] != 0u) {
+        for (uint32_t j = 0; j < nd[k]; ++j) {
+          const uint32_t g = minus ? offset + wlen - 1u - Rr : offset + Rr;
+          const uint32_t gc = (__ldg(&pk[g >> 4]) >> ((g & 15u) * 2u)) & 3u;
+          const uint32_t col = minus ? ncol - 1u - Cc : Cc;
+          mread[col] = '-';
+          mref[col] = code_char(gc);
+          ++Cc;
+          ++Rr;
+        }
+      }
+    }
+    P0 += tot_b;
+    R0 += tot_a + tot_d;
+    C0 += tot_b + tot_d;
+  }
+}
+
+// generic tile path: reads the ASCII copy where the tile touches non-ACGT bases; one entry per lane
+template <int METHOD>
+__device__ __noinline__ void emit_tile_generic(const uint8_t *evbase, uint32_t e0, uint32_t e1, const RefFetch &rf,
+                                               uint32_t minus, uint32_t ncol, uint32_t C0, uint32_t R0, uint32_t P0,
+                                               uint8_t *seq, uint8_t *qual, uint8_t *mref, uint8_t *mread,
+                                               uint32_t lane) {
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  for (uint32_t i = e0; i < e1; i += 32u) {
+    const uint32_t e = i + lane;
+    const bool valid = e < e1;
+    uint32_t kind = 0, info = 0, qv = 0, nd = 0;
+    bool isbase = false;
+    if (METHOD == PBSIM_METHOD_QSHMM) {
+      const uint32_t v = valid ? (uint32_t)__ldg(reinterpret_cast<const uint16_t *>(evbase) + e) : 0u;
+      kind = (v >> 7) & 3u;
+      const bool cont = valid && kind == 3u;
+      qv = v & 0x7Fu;
+      info = (v >> 9) & 7u;
+      nd = cont ? ((v & 0x7Fu) | ((v >> 9) << 7)) : ((v >> 12) & 15u);
+      if (!valid) nd = 0;
+      isbase = valid && !cont;
+    } else {
+      const uint32_t v = valid ? (uint32_t)__ldg(evbase + e) : 0u;
+      kind = v & 3u;
+      info = (v >> 2) & 7u;
+      isbase = valid && kind != PB_KIND_DEL;
+      nd = (valid && kind == PB_KIND_DEL) ? 1u : 0u;
+    }
+    const bool adv = isbase && kind != PB_KIND_INS;
+    const uint32_t m_base = __ballot_sync(0xFFFFFFFFu, isbase);
+    const uint32_t m_adv = __ballot_sync(0xFFFFFFFFu, adv);
+    uint32_t x = nd;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o);
+      if (lane >= (uint32_t)o) x += y;
+    }
+    const uint32_t tot_d = __shfl_sync(0xFFFFFFFFu, x, 31);
+    const uint32_t pre_d = x - nd;
+    const uint32_t Pp = P0 + __popc(m_base & lt_mask);
+    const uint32_t Rr = R0 + __popc(m_adv & lt_mask) + pre_d;
+    const uint32_t Cc = C0 + __popc(m_base & lt_mask) + pre_d;
+    if (isbase) {
+      uint8_t gch, wch;
+      uint32_t wc;
+      bool acgt;
+      rf.get(Rr, gch, wch, wc, acgt);
+      const uint8_t rb = read_base(kind, info, wch, wc, acgt);
+      seq[Pp] = rb;
+      qual[Pp] = (METHOD == PBSIM_METHOD_QSHMM) ? (uint8_t)(qv + 33u) : (uint8_t)'!';
+      const uint32_t col = minus ? ncol - 1u - Cc : Cc;
+      mread[col] = minus ? comp_char(rb) : rb;
+      mref[col] = (kind == PB_KIND_INS) ? (uint8_t)'-' : gch;
+    }
+    if (nd != 0u) {
+      const uint32_t cbase = Cc + (isbase ? 1u : 0u);
+      const uint32_t rbase = Rr + (adv ? 1u : 0u);
+      for (uint32_t j = 0; j < nd; ++j) {
+        uint8_t gch, wch;
+        uint32_t wc;
+        bool acgt;
+        rf.get(rbase + j, gch, wch, wc, acgt);
+        const uint32_t col = minus ? ncol - 1u - (cbase + j) : cbase + j;
+        mread[col] = '-';
+        mref[col] = gch;
+      }
+    }
+    P0 += __popc(m_base);
+    R0 += __popc(m_adv) + tot_d;
+    C0 += __popc(m_base) + tot_d;
+  }
+}
+
 template <int METHOD>
 __global__ void __launch_bounds__(kEmitThreads) k_emit(EmitArgs A) {
   const uint32_t lane = threadIdx.x & 31u;
-  const uint32_t lt_mask = (1u << lane) - 1u;
   const uint64_t warp0 = (uint64_t)blockIdx.x * kEmitWarps + (threadIdx.x >> 5);
   const uint64_t nwarps = (uint64_t)gridDim.x * kEmitWarps;
   for (uint64_t t = warp0; t < A.n_tiles; t += nwarps) {
@@ -317,108 +521,38 @@ __global__ void __launch_bounds__(kEmitThreads) k_emit(EmitArgs A) {
     const uint32_t e1 = min(nent, e0 + PB_TILE);
     const Ckpt *ckp = A.ck + A.B.ck_off[s];
     const Ckpt c0 = ckp[tile];
-    uint32_t C0 = c0.col, R0 = c0.ref, P0 = c0.read;
-    RefFetch rf;
-    rf.pk = A.G.pk;
-    rf.ascii = A.G.ascii;
-    rf.offset = offset;
-    rf.wlen = wlen;
-    rf.minus = minus;
-    {
-      // reference range this tile can touch: [R0, Rend] (an insertion at the tile's end looks at Rend)
-      const uint32_t Rnext = (e1 < nent) ? ckp[tile + 1].ref : wlen;
-      const uint32_t Rend = min(Rnext, wlen - 1u);
-      const uint32_t g0 = minus ? offset + wlen - 1u - Rend : offset + R0;
-      const uint32_t g1 = minus ? offset + wlen - 1u - R0 : offset + Rend;
-      rf.slow = range_exceptional(A.G.xm, g0, g1);
-    }
+    // reference range this tile can touch: [R0, Rend] (an insertion at the tile's end looks at Rend)
+    const uint32_t Rnext = (e1 < nent) ? ckp[tile + 1].ref : wlen;
+    const uint32_t Rend = min(Rnext, wlen - 1u);
+    const uint32_t g0 = minus ? offset + wlen - 1u - Rend : offset + c0.ref;
+    const uint32_t g1 = minus ? offset + wlen - 1u - c0.ref : offset + Rend;
+    const bool slow = range_exceptional(A.G.xm, g0, g1);
     uint8_t *seq = rd + L.seq_rel, *qual = rd + L.qual_rel;
-    uint8_t *ip = rd + L.ip_rel, *pw = rd + L.pw_rel;
     uint8_t *mref = mf + L.refrow_rel, *mread = mf + L.readrow_rel;
-
-    for (uint32_t i = e0; i < e1; i += 32u) {
-      const uint32_t e = i + lane;
-      const bool valid = e < e1;
-      uint32_t kind = 0, info = 0, qv = 0, nd = 0;
-      bool isbase = false;
-      if (METHOD == PBSIM_METHOD_QSHMM) {
-        const uint32_t v = valid ? (uint32_t)__ldg(reinterpret_cast<const uint16_t *>(A.ev) + A.B.ev_off[s] + e) : 0u;
-        kind = (v >> 7) & 3u;
-        const bool cont = valid && kind == 3u;
-        qv = v & 0x7Fu;
-        info = (v >> 9) & 7u;
-        nd = cont ? ((v & 0x7Fu) | ((v >> 9) << 7)) : ((v >> 12) & 15u);
-        if (!valid) nd = 0;
-        isbase = valid && !cont;
-      } else {
-        const uint32_t v = valid ? (uint32_t)__ldg(A.ev + A.B.ev_off[s] + e) : 0u;
-        kind = v & 3u;
-        info = (v >> 2) & 7u;
-        isbase = valid && kind != PB_KIND_DEL;  // column carries a read base
-        nd = (valid && kind == PB_KIND_DEL) ? 1u : 0u;  // column is a deletion
+    const uint8_t *evbase = A.ev + A.B.ev_off[s] * (METHOD == PBSIM_METHOD_QSHMM ? 2ull : 1ull);
+    if (!slow) {
+      emit_tile_fast<METHOD>(evbase, e0, e1, A.G.pk, offset, wlen, minus, ncol, c0.col, c0.ref, c0.read, seq, qual, mref,
+                             mread, lane);
+    } else {
+      RefFetch rf;
+      rf.pk = A.G.pk;
+      rf.ascii = A.G.ascii;
+      rf.offset = offset;
+      rf.wlen = wlen;
+      rf.minus = minus;
+      rf.slow = true;
+      emit_tile_generic<METHOD>(evbase, e0, e1, rf, minus, ncol, c0.col, c0.ref, c0.read, seq, qual, mref, mread, lane);
+    }
+    if (A.P.sam) {
+      // ip:B:C / pw:B:C arrays: ",9" per read base of this tile (:2324-2331)
+      const uint32_t p0 = c0.read;
+      const uint32_t p1 = (e1 < nent) ? ckp[tile + 1].read : rlen;
+      uint8_t *ip = rd + L.ip_rel, *pw = rd + L.pw_rel;
+      for (uint32_t j = 2u * p0 + lane; j < 2u * p1; j += 32u) {
+        const uint8_t ch = (j & 1u) ? (uint8_t)'9' : (uint8_t)',';
+        ip[j] = ch;
+        pw[j] = ch;
       }
-      // ref advance: qshmm base entries that are not insertions, plus deletions
-      const bool adv = (METHOD == PBSIM_METHOD_QSHMM) ? (isbase && kind != PB_KIND_INS)
-                                                      : (valid && kind != PB_KIND_INS && kind != PB_KIND_DEL);
-      const uint32_t m_base = __ballot_sync(0xFFFFFFFFu, isbase);
-      const uint32_t m_adv = __ballot_sync(0xFFFFFFFFu, adv);
-      uint32_t pre_d, tot_d;
-      if (METHOD == PBSIM_METHOD_QSHMM) {
-        uint32_t x = nd;  // inclusive warp scan of deletion counts
-        if (__any_sync(0xFFFFFFFFu, nd != 0u)) {
-#pragma unroll
-          for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o);
-            if (lane >= (uint32_t)o) x += y;
-          }
-          tot_d = __shfl_sync(0xFFFFFFFFu, x, 31);
-          pre_d = x - nd;
-        } else {
-          pre_d = tot_d = 0;
-        }
-      } else {
-        const uint32_t m_del = __ballot_sync(0xFFFFFFFFu, nd != 0u);
-        pre_d = __popc(m_del & lt_mask);
-        tot_d = __popc(m_del);
-      }
-      const uint32_t Pp = P0 + __popc(m_base & lt_mask);
-      const uint32_t Rr = R0 + __popc(m_adv & lt_mask) + pre_d;
-      const uint32_t Cc = C0 + __popc(m_base & lt_mask) + pre_d;
-      if (isbase) {
-        uint8_t gch, wch;
-        uint32_t wc;
-        bool acgt;
-        rf.get(Rr, gch, wch, wc, acgt);
-        const uint8_t rb = read_base(kind, info, wch, wc, acgt);
-        seq[Pp] = rb;
-        qual[Pp] = (METHOD == PBSIM_METHOD_QSHMM) ? (uint8_t)(qv + 33u) : (uint8_t)'!';
-        if (A.P.sam) {
-          ip[2ull * Pp] = ',';
-          ip[2ull * Pp + 1] = '9';
-          pw[2ull * Pp] = ',';
-          pw[2ull * Pp + 1] = '9';
-        }
-        const uint32_t col = minus ? ncol - 1u - Cc : Cc;
-        mread[col] = minus ? comp_char(rb) : rb;
-        mref[col] = (kind == PB_KIND_INS) ? (uint8_t)'-' : gch;
-      }
-      if (nd != 0u) {
-        // deletion columns: '-' in the read row, the reference base in the ref row
-        const uint32_t cbase = Cc + (isbase ? 1u : 0u);
-        const uint32_t rbase = Rr + (adv ? 1u : 0u);
-        for (uint32_t j = 0; j < nd; ++j) {
-          uint8_t gch, wch;
-          uint32_t wc;
-          bool acgt;
-          rf.get(rbase + j, gch, wch, wc, acgt);
-          const uint32_t col = minus ? ncol - 1u - (cbase + j) : cbase + j;
-          mread[col] = '-';
-          mref[col] = gch;
-        }
-      }
-      P0 += __popc(m_base);
-      R0 += __popc(m_adv) + tot_d;
-      C0 += __popc(m_base) + tot_d;
     }
   }
 }

@@ -181,7 +181,7 @@ struct pbsim_engine {
   DevBuf b_sub_u32;    // 15 arrays per subread
   DevBuf b_sub_u64;    // 9 arrays per subread (+1)
   DevBuf b_sub_f64;
-  DevBuf d_bins;       // bin_start[102], bin_lo[101], bin_hi[101], cta_first[102]
+  DevBuf d_bins;       // bin_start[kBins+1], bin_lo[kBins], bin_hi[kBins], cta_first[kBins+1]
   DevBuf d_ctrl;       // control words
   DevBuf d_cub_tmp;
   DevBuf d_ev, d_ck;
@@ -383,11 +383,14 @@ int run_batch(pbsim_engine *e, uint32_t n_reads, int64_t clip_room, bool to_host
   Batch &B = e->B;
   const uint32_t n_sub = B.n_sub;
   B.first_read = (uint64_t)e->next_read;
-  CK(e->d_bins.ensure(512 * 4));
+  const uint32_t cta_slots = nblk(n_sub, kSimThreads) + kBins;
+  CK(e->d_bins.ensure((4 * kBins + 8) * 4 + (size_t)cta_slots * 4 * 4));
   CK(e->d_ctrl.ensure(64 * 8));
   CK(e->h_ctrl.ensure(64 * 8));
   uint32_t *bin_start = e->d_bins.as<uint32_t>();
-  uint32_t *bin_lo = bin_start + 102, *bin_hi = bin_lo + 101, *cta_first = bin_hi + 101;
+  uint32_t *bin_lo = bin_start + kBins + 1, *bin_hi = bin_lo + kBins, *cta_first = bin_hi + kBins;
+  uint32_t *cta_key = cta_first + kBins + 1, *cta_id = cta_key + cta_slots, *cta_key_s = cta_id + cta_slots,
+           *cta_order = cta_key_s + cta_slots;
   unsigned long long *ctrl = e->d_ctrl.as<unsigned long long>();
   unsigned long long *hctrl = reinterpret_cast<unsigned long long *>(e->h_ctrl.p);
 
@@ -427,16 +430,25 @@ int run_batch(pbsim_engine *e, uint32_t n_reads, int64_t clip_room, bool to_host
     // ---- sort by (accuracy, length desc)
     {
       size_t tmp = 0;
-      CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, B.key_in, B.key_out, B.idx_in, B.order, (int)n_sub, 0, 27, e->st));
+      CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, B.key_in, B.key_out, B.idx_in, B.order, (int)n_sub, 0, 28, e->st));
       CK(e->d_cub_tmp.ensure(tmp + 256));
       tmp = e->d_cub_tmp.cap;
-      CK(cub::DeviceRadixSort::SortPairs(e->d_cub_tmp.p, tmp, B.key_in, B.key_out, B.idx_in, B.order, (int)n_sub, 0, 27,
+      CK(cub::DeviceRadixSort::SortPairs(e->d_cub_tmp.p, tmp, B.key_in, B.key_out, B.idx_in, B.order, (int)n_sub, 0, 28,
                                          e->st));
     }
-    k_fill_u32<<<1, 128, 0, e->st>>>(bin_start, 102, 0xFFFFFFFFu);
+    k_fill_u32<<<1, 256, 0, e->st>>>(bin_start, kBins + 1, 0xFFFFFFFFu);
     k_bin_bounds<<<nblk(n_sub, 256), 256, 0, e->st>>>(B.key_out, n_sub, bin_start);
     k_cta_map<<<1, 32, 0, e->st>>>(bin_start, B.key_out, n_sub, bin_lo, bin_hi, cta_first);
-    e->launches += 3;
+    k_cta_keys<<<nblk(cta_slots, 256), 256, 0, e->st>>>(B.key_out, bin_lo, cta_first, cta_slots, cta_key, cta_id);
+    {
+      size_t tmp = 0;
+      CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, cta_key, cta_key_s, cta_id, cta_order, (int)cta_slots, 0, 21, e->st));
+      CK(e->d_cub_tmp.ensure(tmp + 256));
+      tmp = e->d_cub_tmp.cap;
+      CK(cub::DeviceRadixSort::SortPairs(e->d_cub_tmp.p, tmp, cta_key, cta_key_s, cta_id, cta_order, (int)cta_slots, 0, 21,
+                                         e->st));
+    }
+    e->launches += 4;
     // ---- slots
     unsigned long long *tmp64 = reinterpret_cast<unsigned long long *>(u64_slice(e, 2));
     k_widen<<<nblk(n_sub + 1, 256), 256, 0, e->st>>>(B.cap, n_sub, tmp64);
@@ -453,16 +465,18 @@ int run_batch(pbsim_engine *e, uint32_t n_reads, int64_t clip_room, bool to_host
 
     // ---- K2 / K3 pass 1
     SimArgs A;
+    A.keys.init(rng.seed, (uint32_t)e->seq_num);
     A.M = M;
     A.G = G;
     A.rng = rng;
     A.B = B;
+    A.cta_order = cta_order;
     A.cta_first = cta_first;
     A.bin_lo = bin_lo;
     A.bin_hi = bin_hi;
     A.ev = e->d_ev.as<uint8_t>();
     A.ck = e->d_ck.as<Ckpt>();
-    const uint32_t grid = nblk(n_sub, kSimThreads) + 101;
+    const uint32_t grid = cta_slots;
     CK(cudaEventRecord(e->ev_k[0], e->st));
     if (qs) {
       if (replay) k_sim_qshmm<PBSIM_RNG_REPLAY><<<grid, kSimThreads, kQsSmemBytes, e->st>>>(A);

@@ -81,19 +81,20 @@ struct ModelImage {
           uint8_t *b = blob.data() + e.blob_off;
           uint32_t *t2 = reinterpret_cast<uint32_t *>(b + QsBlobLayout::t2_off);
           uint8_t *em = b + QsBlobLayout::emis_off;
-          // moduli of the state an entry leads to travel with the entry: one shared-memory load per step
-          auto mods = [&](int s) -> uint32_t {
+          // an entry carries the ROW OFFSET (state*100) and both moduli of the state it leads to:
+          // one shared-memory load per chain step, no multiply for the next address
+          auto entry = [&](int s) -> uint32_t {
             int tm = (s >= 1 && s <= r.nstates) ? r.tran_mod[s] : 1;
             int emd = (s >= 1 && s <= r.nstates) ? r.emis_mod[s] : 1;
             tm = tm < 1 ? 1 : (tm > 255 ? 255 : tm);
             emd = emd < 1 ? 1 : (emd > 255 ? 255 : emd);
-            return ((uint32_t)tm << 8) | ((uint32_t)emd << 16);
+            const int st = (s >= 0 && s <= r.nstates) ? s : 0;
+            return (uint32_t)(st * 100) | ((uint32_t)tm << 16) | ((uint32_t)emd << 24);
           };
-          for (int k = 0; k < r.init_mod && k < 100; ++k) t2[k] = (uint32_t)r.init[k] | mods(r.init[k]);
+          for (int k = 0; k < r.init_mod && k < 100; ++k) t2[k] = entry(r.init[k]);
           for (int s = 1; s <= r.nstates; ++s) {
             for (int k = 0; k < 100; ++k) {
-              const uint8_t nx = r.tran[s * 100 + k];
-              t2[s * 100 + k] = (uint32_t)nx | mods(nx);
+              t2[s * 100 + k] = entry(r.tran[s * 100 + k]);
               em[s * 100 + k] = r.emis[s * 100 + k];
             }
           }

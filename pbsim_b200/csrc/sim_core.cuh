@@ -64,12 +64,12 @@ struct Philox {
     uint32_t a = k0, b = k1;
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
-      const uint32_t h0 = mulhi32(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
-      const uint32_t h1 = mulhi32(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
-      c0 = h1 ^ c1 ^ a;
-      c1 = l1;
-      c2 = h0 ^ c3 ^ b;
-      c3 = l0;
+      const uint64_t p0 = (uint64_t)0xD2511F53u * c0;  // one IMAD.WIDE gives both halves
+      const uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+      c0 = (uint32_t)(p1 >> 32) ^ c1 ^ a;
+      c1 = (uint32_t)p1;
+      c2 = (uint32_t)(p0 >> 32) ^ c3 ^ b;
+      c3 = (uint32_t)p0;
       a += 0x9E3779B9u;
       b += 0xBB67AE85u;
     }
@@ -156,6 +156,33 @@ struct ReplayDraw {
   PB_HD uint32_t consumed() const { return (uint32_t)(cur - start); }
 };
 
+// Round keys of Philox4x32-10 for one (seed, sequence): identical for every thread of a launch, so the
+// fast path takes them from kernel parameters (constant bank operands) instead of re-deriving them.
+struct PhiloxKeys {
+  uint32_t k[10][2];
+#if !defined(__CUDACC__) || defined(__CUDA_ARCH__) || 1
+  PB_HD void init(uint32_t k0, uint32_t k1) {
+    for (int r = 0; r < 10; ++r) {
+      k[r][0] = k0 + (uint32_t)r * 0x9E3779B9u;
+      k[r][1] = k1 + (uint32_t)r * 0xBB67AE85u;
+    }
+  }
+#endif
+};
+
+PB_HD void philox_block_keys(const PhiloxKeys &K, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t out[4]) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+    const uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+    c0 = (uint32_t)(p1 >> 32) ^ c1 ^ K.k[r][0];
+    c1 = (uint32_t)p1;
+    c2 = (uint32_t)(p0 >> 32) ^ c3 ^ K.k[r][1];
+    c3 = (uint32_t)p0;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
 // ---------------------------------------------------------------------------------------------
 // read planning
 // ---------------------------------------------------------------------------------------------
@@ -229,8 +256,9 @@ struct Ckpt {
 // qshmm
 // ---------------------------------------------------------------------------------------------
 // Tables of ONE accuracy (staged in shared memory by the kernel).
-//   t2[s*100 + k]  : next state | transition modulus(next) << 8 | emission modulus(next) << 16 ; row 0 is init2state
-//   emis[s*100 + k]: QV
+//   t2[row + k]    : row offset of the next state (= state*100, 16 bit) | transition modulus(next) << 16
+//                    | emission modulus(next) << 24 ; row offset 0 is init2state
+//   emis[row + k]  : QV
 //   freq[k]        : QV when the model has no such accuracy (resolution 1000)
 //   thr[qv]        : {sub_thre, ins_thre, max_hp del threshold, del threshold for hp[-1]}
 //   thr_hp[qv*12+h]: exact deletion threshold ceil(del_thre[qv] * hp_del_bias[h])
@@ -279,7 +307,7 @@ template <class Draw>
 PB_HD void qshmm_simulate(const QsView &T, Draw &d, const WindowRef &win, bool slow, uint32_t wlen,
                           QsSink &sink, SubreadResult &res) {
   uint32_t R = 0, P = 0, C = 0;
-  uint32_t state = 0, mod = T.init_mod, emod = 1;
+  uint32_t row = 0, mod = T.init_mod, emod = 1;
   uint32_t nsub = 0, nins = 0, ndel = 0;
   double prob = 0.0;
   res.overflow = 0;
@@ -293,11 +321,11 @@ PB_HD void qshmm_simulate(const QsView &T, Draw &d, const WindowRef &win, bool s
       d.begin(u);
       uint32_t qv;
       if (T.has_model) {
-        const uint32_t t = T.t2[state * PB_QS_ROW + d.w0(mod)];
-        state = t & 0xFFu;
-        mod = (t >> 8) & 0xFFu;
-        emod = t >> 16;
-        qv = T.emis[state * PB_QS_ROW + d.w1(emod)];
+        const uint32_t t = T.t2[row + d.w0(mod)];
+        row = t & 0xFFFFu;
+        mod = (t >> 16) & 0xFFu;
+        emod = t >> 24;
+        qv = T.emis[row + d.w1(emod)];
       } else {
         qv = T.freq[d.w0(T.freq_mod)];
       }
@@ -343,7 +371,7 @@ PB_HD void qshmm_simulate(const QsView &T, Draw &d, const WindowRef &win, bool s
         uint32_t rest = nd - PB_QS_DEL_SAT;
         for (;;) {  // continuation entries: 14-bit counts, 16383 = "more follows"
           if (sink.full()) { res.overflow = 1; break; }
-          sink.checkpoint(C, R, P);
+          sink.checkpoint(C - rest, R - rest, P);  // a tile may start here: state before these deletions
           const uint32_t c = rest < PB_QS_CONT_SAT ? rest : PB_QS_CONT_SAT;
           sink.push((c & 0x7Fu) | (3u << 7) | ((c >> 7) << 9));
           if (c < PB_QS_CONT_SAT) break;
@@ -362,6 +390,114 @@ PB_HD void qshmm_simulate(const QsView &T, Draw &d, const WindowRef &win, bool s
   res.nins = nins;
   res.ndel = ndel;
   res.accuracy = 1.0 - (prob / (double)P);  // :2313 (accuracy from the emitted qualities)
+}
+
+// ---------------------------------------------------------------------------------------------
+// qshmm fast path: PHILOX draws, reads that never need the genome in pass 1 (not `slow`).
+// Same results as qshmm_simulate<PhiloxDraw> entry for entry, except that the stream is padded with
+// no-op entries (continuation entries with count 0) to a multiple of PB_GROUP, which lets every group of
+// 4 positions be packed in registers and written with one 8-byte store, checks run once per group and the
+// common path stay free of divergent branches.
+// ---------------------------------------------------------------------------------------------
+#define PB_QS_PAD (3u << 7)  // continuation entry, count 0
+
+PB_HD void qshmm_simulate_fast(const QsView &T, const PhiloxKeys &K, uint32_t read_id, uint32_t pass,
+                               uint32_t wlen, uint16_t *ev, Ckpt *ck, uint32_t cap, SubreadResult &res) {
+  uint32_t R = 0, P = 0, n = 0;
+  uint32_t row = 0, mod = T.init_mod, emod = 1;
+  uint32_t nsub = 0, ndel = 0;
+  double prob = 0.0;
+  res.overflow = 0;
+  const uint32_t c1 = pass << 16;
+  while (R < wlen) {
+    if (n + 2u * PB_GROUP > cap) { res.overflow = 1; break; }
+    if ((n & (PB_TILE - 1u)) == 0u) {
+      Ckpt c; c.col = P + ndel; c.ref = R; c.read = P; c.pad = 0;
+      ck[n / PB_TILE] = c;
+    }
+    uint32_t g[PB_GROUP][4];
+#pragma unroll
+    for (uint32_t u = 0; u < PB_GROUP; ++u) philox_block_keys(K, P + u, c1, read_id, 1u, g[u]);
+    uint32_t e[PB_GROUP];
+    uint32_t big_u = PB_GROUP, big_nd = 0;  // rare: an entry with >= 15 deletions ends the group early
+#pragma unroll
+    for (uint32_t u = 0; u < PB_GROUP; ++u) {
+      e[u] = PB_QS_PAD;
+      if (R < wlen && big_u == PB_GROUP) {
+        const uint32_t w0 = g[u][0], w1 = g[u][1], w2 = g[u][2], w3 = g[u][3];
+        uint32_t qv;
+        if (T.has_model) {
+          const uint32_t t = T.t2[row + mulhi32(w0, mod)];
+          row = t & 0xFFFFu;
+          mod = (t >> 16) & 0xFFu;
+          emod = t >> 24;
+          qv = T.emis[row + mulhi32(w1, emod)];
+        } else {
+          qv = T.freq[mulhi32(w0, T.freq_mod)];
+        }
+        prob += T.qc_prob[qv];
+        const QsThr th = T.thr[qv];
+        const uint32_t r = mulhi32(w2, 1000000u);
+        const bool is_sub = r < th.sub;
+        const bool is_err = r < th.ins;  // substitution or insertion (ins_thre is cumulative)
+        const uint32_t c3 = ((w0 & 0xFFFu) * 3u) >> 12, c8 = w1 & 7u;
+        const uint32_t info = is_sub ? c3 : (is_err ? c8 : 0u);
+        const uint32_t kind = is_sub ? PB_KIND_SUB : (is_err ? PB_KIND_INS : PB_KIND_MATCH);
+        nsub += is_sub ? 1u : 0u;
+        R += (is_err && !is_sub) ? 0u : 1u;
+        ++P;
+        uint32_t nd = 0;
+        const uint32_t rd0 = mulhi32(w3, 1000000u);
+        if (R < wlen && rd0 < (R != 0u ? th.del : th.del0)) {
+          nd = 1;
+          ++R;
+          while (R < wlen && mulhi32(fmix32(w3 + nd * 0x9E3779B9u), 1000000u) < th.del) {
+            ++nd;
+            ++R;
+          }
+        }
+        ndel += nd;
+        const uint32_t base = qv | (kind << 7) | (info << 9);
+        if (nd < PB_QS_DEL_SAT) {
+          e[u] = base | (nd << 12);
+        } else {
+          e[u] = base | (PB_QS_DEL_SAT << 12);
+          big_u = u;
+          big_nd = nd - PB_QS_DEL_SAT;
+        }
+      }
+    }
+    uint64_t *dst = reinterpret_cast<uint64_t *>(ev + n);
+    *dst = (uint64_t)(e[0] | (e[1] << 16)) | ((uint64_t)(e[2] | (e[3] << 16)) << 32);
+    n += PB_GROUP;
+    if (big_u != PB_GROUP) {
+      // continuation entries must directly follow their entry: rewrite the tail of this group generically
+      n -= PB_GROUP - 1u - big_u;          // drop the pads after the big entry
+      uint32_t rest = big_nd;
+      for (;;) {
+        if (n + 2u * PB_GROUP > cap) { res.overflow = 1; break; }
+        if ((n & (PB_TILE - 1u)) == 0u) {  // a tile may start here: state before these deletions
+          Ckpt c; c.col = P + ndel - rest; c.ref = R - rest; c.read = P; c.pad = 0;
+          ck[n / PB_TILE] = c;
+        }
+        const uint32_t c = rest < PB_QS_CONT_SAT ? rest : PB_QS_CONT_SAT;
+        ev[n++] = (uint16_t)((c & 0x7Fu) | (3u << 7) | ((c >> 7) << 9));
+        if (c < PB_QS_CONT_SAT) break;
+        rest -= PB_QS_CONT_SAT;
+      }
+      while (n & (PB_GROUP - 1u)) {         // re-align; a checkpoint can only fall on a group boundary
+        ev[n++] = (uint16_t)PB_QS_PAD;
+      }
+      if (res.overflow) break;
+    }
+  }
+  res.n_entries = n;
+  res.rlen = P;
+  res.ncol = P + ndel;
+  res.nsub = nsub;
+  res.ndel = ndel;
+  res.nins = P + ndel - R;  // C = P + ndel and R = P - nins + ndel
+  res.accuracy = 1.0 - (prob / (double)P);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -15,7 +15,8 @@
 
 namespace pb {
 
-constexpr int kSimThreads = 256;  // subreads per pass-1 CTA
+constexpr int kSimThreads = 128;  // subreads per pass-1 CTA
+constexpr int kBins = 202;        // schedule bins: accuracy * 2 + slow  (slow reads get CTAs of their own)
 
 struct DeviceModel {
   const uint8_t *blob;
@@ -109,7 +110,7 @@ __global__ void k_plan(DeviceModel M, DeviceGenome G, RngParams rng, Batch B, in
   const uint32_t ckc = (uint32_t)(cap / PB_TILE) + 2u;
   for (uint32_t h = 0; h < M.pass_num; ++h) {
     const uint32_t s = r * M.pass_num + h;
-    B.key_in[s] = (p.acc << 20) | (0xFFFFFu - (p.wlen > 0xFFFFFu ? 0xFFFFFu : p.wlen));
+    B.key_in[s] = (p.acc << 21) | ((slow ? 1u : 0u) << 20) | (0xFFFFFu - (p.wlen > 0xFFFFFu ? 0xFFFFFu : p.wlen));
     B.idx_in[s] = s;
     B.cap[s] = (uint32_t)cap;
     B.ck_cap[s] = ckc;
@@ -117,20 +118,20 @@ __global__ void k_plan(DeviceModel M, DeviceGenome G, RngParams rng, Batch B, in
 }
 
 // accuracy-bin boundaries in the sorted order, then the CTA map
-__global__ void k_bin_bounds(const uint32_t *key_sorted, uint32_t n, uint32_t *bin_start /*[102]*/) {
+__global__ void k_bin_bounds(const uint32_t *key_sorted, uint32_t n, uint32_t *bin_start /*[kBins]*/) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const uint32_t a = key_sorted[i] >> 20;
   if (i == 0 || (key_sorted[i - 1] >> 20) != a) bin_start[a] = i;
 }
 
-// cta_first[a] = first pass-1 CTA of accuracy a; cta_first[101] = total
+// cta_first[b] = first pass-1 CTA of bin b; cta_first[kBins] = total
 __global__ void k_cta_map(const uint32_t *bin_start, const uint32_t *key_sorted, uint32_t n, uint32_t *bin_lo,
                           uint32_t *bin_hi, uint32_t *cta_first) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   // bin_start holds 0xFFFFFFFF for empty bins
   uint32_t next_lo = n, total = 0;
-  for (int a = 100; a >= 0; --a) {
+  for (int a = kBins - 1; a >= 0; --a) {
     const uint32_t lo = bin_start[a];
     if (lo == 0xFFFFFFFFu) {
       bin_lo[a] = bin_hi[a] = 0;
@@ -140,11 +141,33 @@ __global__ void k_cta_map(const uint32_t *bin_start, const uint32_t *key_sorted,
       next_lo = lo;
     }
   }
-  for (int a = 0; a <= 100; ++a) {
+  for (int a = 0; a < kBins; ++a) {
     cta_first[a] = total;
     total += (bin_hi[a] - bin_lo[a] + kSimThreads - 1) / kSimThreads;
   }
-  cta_first[101] = total;
+  cta_first[kBins] = total;
+}
+
+// Global longest-first dispatch: CTA b of the (bin-ordered) map gets the key "longest read it holds"
+// (low 20 bits of the sort key, smaller = longer); the engine sorts CTAs by it and pass 1 runs
+// CTA cta_order[blockIdx.x].  Slots beyond the map get the largest key and exit immediately.
+__global__ void k_cta_keys(const uint32_t *key_sorted, const uint32_t *bin_lo, const uint32_t *cta_first,
+                           uint32_t n_slots, uint32_t *cta_key, uint32_t *cta_id) {
+  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= n_slots) return;
+  cta_id[b] = b;
+  if (b >= cta_first[kBins]) {
+    cta_key[b] = 0x100000u;
+    return;
+  }
+  uint32_t lo = 0, hi = kBins;  // largest bin a with cta_first[a] <= b
+  while (hi - lo > 1u) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (cta_first[mid] <= b) lo = mid; else hi = mid;
+  }
+  // empty bins share cta_first with their successor: step to the last bin that starts at or before b
+  const uint32_t first = bin_lo[lo] + (b - cta_first[lo]) * kSimThreads;
+  cta_key[b] = key_sorted[first] & 0xFFFFFu;
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -180,17 +203,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 }
 
 // which accuracy bin does this CTA serve?  returns false if the CTA is beyond the map
-__device__ __forceinline__ bool cta_assignment(const uint32_t *cta_first, const uint32_t *bin_lo, const uint32_t *bin_hi,
+__device__ __forceinline__ bool cta_assignment(const uint32_t *cta_order, const uint32_t *cta_first,
+                                               const uint32_t *bin_lo, const uint32_t *bin_hi,
                                                uint32_t *acc, uint32_t *lo, uint32_t *hi) {
   __shared__ uint32_t s_acc, s_lo, s_hi, s_ok;
   if (threadIdx.x == 0) {
-    const uint32_t b = blockIdx.x;
+    const uint32_t b = cta_order[blockIdx.x];
     s_ok = 0;
-    if (b < cta_first[101]) {
+    if (b < cta_first[kBins]) {
       uint32_t a = 0;
-      while (a < 100 && cta_first[a + 1] <= b) ++a;
+      while (a < kBins - 1 && cta_first[a + 1] <= b) ++a;
       const uint32_t local = b - cta_first[a];
-      s_acc = a;
+      s_acc = a >> 1;
       s_lo = bin_lo[a] + local * kSimThreads;
       s_hi = min(bin_hi[a], s_lo + kSimThreads);
       s_ok = 1;
@@ -204,11 +228,12 @@ __device__ __forceinline__ bool cta_assignment(const uint32_t *cta_first, const 
 }
 
 struct SimArgs {
+  PhiloxKeys keys;  // round keys of (seed, sequence): constant-bank operands of the fast path
   DeviceModel M;
   DeviceGenome G;
   RngParams rng;
   Batch B;
-  const uint32_t *cta_first, *bin_lo, *bin_hi;
+  const uint32_t *cta_order, *cta_first, *bin_lo, *bin_hi;
   uint8_t *ev;   // event arena
   Ckpt *ck;      // checkpoint arena
 };
@@ -247,7 +272,7 @@ template <int RNG_MODE>
 __global__ void __launch_bounds__(kSimThreads) k_sim_qshmm(SimArgs A) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint32_t acc, lo, hi;
-  if (!cta_assignment(A.cta_first, A.bin_lo, A.bin_hi, &acc, &lo, &hi)) return;
+  if (!cta_assignment(A.cta_order, A.cta_first, A.bin_lo, A.bin_hi, &acc, &lo, &hi)) return;
   const AccEntry ae = A.M.acc[acc];
   uint64_t *bar = reinterpret_cast<uint64_t *>(smem + kQsSmemBar);
   if (threadIdx.x == 0) mbar_init(bar, 1);
@@ -294,12 +319,16 @@ __global__ void __launch_bounds__(kSimThreads) k_sim_qshmm(SimArgs A) {
   SubreadResult res;
   uint32_t used = 0;
   if (RNG_MODE == PBSIM_RNG_PHILOX) {
-    PhiloxDraw d;
-    d.ph.k0 = A.rng.seed;
-    d.ph.k1 = A.G.seq_num;
-    d.read_id = (uint32_t)(A.B.first_read + 1u + r);
-    d.pass = pass;
-    qshmm_simulate(T, d, win, slow, wlen, sink, res);
+    if (!slow) {
+      qshmm_simulate_fast(T, A.keys, (uint32_t)(A.B.first_read + 1u + r), pass, wlen, sink.ev, sink.ck, sink.cap, res);
+    } else {
+      PhiloxDraw d;
+      d.ph.k0 = A.rng.seed;
+      d.ph.k1 = A.G.seq_num;
+      d.read_id = (uint32_t)(A.B.first_read + 1u + r);
+      d.pass = pass;
+      qshmm_simulate(T, d, win, slow, wlen, sink, res);
+    }
   } else {
     ReplayDraw d;
     replay_setup(d, A.rng, s, pass, wlen < A.G.len);
@@ -317,7 +346,7 @@ template <int RNG_MODE>
 __global__ void __launch_bounds__(kSimThreads) k_sim_errhmm(SimArgs A, uint32_t smem_bar_off) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint32_t acc, lo, hi;
-  if (!cta_assignment(A.cta_first, A.bin_lo, A.bin_hi, &acc, &lo, &hi)) return;
+  if (!cta_assignment(A.cta_order, A.cta_first, A.bin_lo, A.bin_hi, &acc, &lo, &hi)) return;
   const AccEntry ae = A.M.acc[acc];
   uint64_t *bar = reinterpret_cast<uint64_t *>(smem + smem_bar_off);
   const uint32_t edel_bytes = ((ae.nstates + 1u) * 2u + 15u) / 16u * 16u;

@@ -22,6 +22,8 @@ struct HostSimOut {
 };
 
 static HostSimOut g_out;
+static int use_fast = 1;
+extern "C" void hostsim_use_fast(int v) { use_fast = v; }
 
 extern "C" {
 
@@ -92,7 +94,12 @@ long hostsim_run(const pbsim_model *m, const uint8_t *ascii_upper, const int16_t
         T.thr = reinterpret_cast<const pb::QsThr *>(img.qs_thr.data()); T.thr_hp = img.qs_thr_hp.data(); T.qc_prob = m->qc_prob;
         pb::QsSink sink;
         sink.init(reinterpret_cast<uint16_t *>(g_out.events.data() + ev_off), g_out.ckpts.data() + ck_base, cap);
-        if (rng_mode == PBSIM_RNG_PHILOX) { pd.pass = (uint32_t)pass; pb::qshmm_simulate(T, pd, win, slow, plan.wlen, sink, res); }
+        if (rng_mode == PBSIM_RNG_PHILOX && !slow && use_fast) {
+          pb::PhiloxKeys K;
+          K.init(seed, (uint32_t)seq_num);
+          pb::qshmm_simulate_fast(T, K, (uint32_t)read_id, (uint32_t)pass, plan.wlen,
+                                  reinterpret_cast<uint16_t *>(g_out.events.data() + ev_off), g_out.ckpts.data() + ck_base, cap, res);
+        } else if (rng_mode == PBSIM_RNG_PHILOX) { pd.pass = (uint32_t)pass; pb::qshmm_simulate(T, pd, win, slow, plan.wlen, sink, res); }
         else { rd.cur = cursor; pb::qshmm_simulate(T, rd, win, slow, plan.wlen, sink, res); cursor = rd.cur; }
         g_out.events.resize(ev_off + (size_t)res.n_entries * 2);
       } else {

@@ -121,10 +121,28 @@ def test_core_replay_reproduces_reference(name):
 
 
 @pytest.mark.parametrize("name", ["qs_rsii_quirks", "qs_ont_hpbias", "err_onthq_basic", "err_sequel_hiacc",
-                                  "qs_rsii_multipass"])
+                                  "qs_rsii_multipass", "qs_delheavy_uniform", "qs_delheavy_bias", "qs_rsii_basic"])
 def test_core_philox_equals_oracle_philox(name):
     c = Case(name)
     out, res = _replay_case(c, "philox")
     for (reads, maf, sub), oref in zip(res, out):
         assert reads == oref["reads"]
         assert maf == oref["maf"]
+
+
+def test_fast_path_equals_generic_path():
+    """qshmm_simulate_fast (what the GPU runs for PHILOX reads that never touch the genome in pass 1) expands to
+    the same records as the generic per-draw path"""
+    for name in ("qs_rsii_basic", "qs_delheavy_uniform"):
+        c = Case(name)
+        H.lib().hostsim_use_fast(1)
+        _, fast = _replay_case(c, "philox")
+        H.lib().hostsim_use_fast(0)
+        try:
+            _, gen = _replay_case(c, "philox")
+        finally:
+            H.lib().hostsim_use_fast(1)
+        for (r1, m1, s1), (r2, m2, s2) in zip(fast, gen):
+            assert r1 == r2 and m1 == m2
+            assert [x["nins"] for x in s1] == [x["nins"] for x in s2]
+            assert [x["ndel"] for x in s1] == [x["ndel"] for x in s2]
