@@ -1,0 +1,615 @@
+// pbsim (B200) — host driver: the reference's command line and file layout in front of libpbsim_cuda.
+//
+// Keeps the CLI surface of yukiteruono/pbsim3 (23 long options, pbsim.cpp:257-530), its defaults and
+// validation (set_sim_param :1451-1688), the stderr report blocks (:5397-5465, :902-978, :5541-5564,
+// :871-873) and the output layout <prefix>_NNNN.ref / .fq.gz / .maf.gz (:708-730, :939); the read
+// generation itself is one simulate call per reference sequence into the CUDA engine (the seam of
+// main :699-754).  Compression is in-process (zlib gzip members from a thread pool) instead of
+// popen("gzip > file"); concatenated gzip members decompress to the same text.
+//
+// Engine-only options (additive): --gpu N, --rng philox|replay, --replay-draws F --replay-marks F,
+// --threads N (compression).  Not built yet in this driver: --strategy trans/templ, --method sample,
+// BAM encoding for --pass-num > 1 (SAM text is written as <prefix>_NNNN.sam.gz instead).
+#include <getopt.h>
+#include <sys/resource.h>
+#include <sys/time.h>
+#include <zlib.h>
+
+#include <algorithm>
+#include <condition_variable>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <ctime>
+#include <deque>
+#include <map>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/pbsim_cuda.h"
+
+namespace {
+
+constexpr size_t kBufSize = 10240;          // BUF_SIZE
+constexpr int kRefIdLenMax = 128;           // REF_ID_LEN_MAX
+constexpr long kRefSeqNumMax = 9999;        // REF_SEQ_NUM_MAX
+constexpr long kRefSeqLenMax = 1000000000;  // REF_SEQ_LEN_MAX
+constexpr long kRefSeqLenMin = 100;         // REF_SEQ_LEN_MIN
+constexpr int kFastqLenMax = 1000000;       // FASTQ_LEN_MAX
+constexpr int kRatioMax = 1000;
+
+struct Options {
+  int set_flg[40] = {0};
+  std::string strategy, method;
+  std::string genome, transcript, templ, sample, profile_id, qshmm, errhmm;
+  std::string prefix = "sd", id_prefix = "S";
+  double depth = 20.0;
+  long len_min = 100, len_max = 1000000;
+  long sub_ratio = 6, ins_ratio = 55, del_ratio = 39;
+  unsigned int seed = 0;
+  double accuracy_min = 0.75, accuracy_max = 1.0, accuracy_mean = 0.85;
+  double len_mean = 9000, len_sd = 7000;
+  int pass_num = 1;
+  double hp_del_bias = 1;
+  // engine-only
+  int gpu = 0;
+  std::string rng = "philox", replay_draws, replay_marks;
+  int threads = 0;
+};
+
+[[noreturn]] void die(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vfprintf(stderr, fmt, ap);
+  va_end(ap);
+  exit(-1);
+}
+
+long now_cpu() {
+  struct rusage ru;
+  getrusage(RUSAGE_SELF, &ru);
+  return ru.ru_utime.tv_sec;
+}
+long now_wall() {
+  struct timeval tv;
+  gettimeofday(&tv, nullptr);
+  return tv.tv_sec;
+}
+
+// ------------------------------------------------------------------------------------------
+// ordered, multi-threaded gzip writer: every submitted block becomes one gzip member
+// ------------------------------------------------------------------------------------------
+class GzipWriter {
+ public:
+  GzipWriter(const std::string &path, int threads, int level = 1) : level_(level) {
+    fp_ = fopen(path.c_str(), "wb");
+    if (!fp_) die("ERROR: Cannot open output file: %s\n", path.c_str());
+    for (int i = 0; i < std::max(1, threads); ++i) workers_.emplace_back([this] { work(); });
+    writer_ = std::thread([this] { write(); });
+  }
+  void submit(const char *data, size_t n) {
+    if (n == 0) return;
+    std::unique_lock<std::mutex> lk(mu_);
+    cv_space_.wait(lk, [this] { return pending_.size() + done_.size() < 64; });
+    Job j;
+    j.seq = next_seq_++;
+    j.in.assign(data, data + n);
+    pending_.push_back(std::move(j));
+    cv_work_.notify_one();
+  }
+  void close() {
+    {
+      std::unique_lock<std::mutex> lk(mu_);
+      closing_ = true;
+      cv_work_.notify_all();
+      cv_done_.notify_all();
+    }
+    for (auto &t : workers_) t.join();
+    writer_.join();
+    fclose(fp_);
+  }
+  uint64_t bytes_in = 0, bytes_out = 0;
+
+ private:
+  struct Job {
+    uint64_t seq;
+    std::vector<char> in, out;
+  };
+  void work() {
+    for (;;) {
+      Job j;
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_work_.wait(lk, [this] { return closing_ || !pending_.empty(); });
+        if (pending_.empty()) return;
+        j = std::move(pending_.front());
+        pending_.pop_front();
+      }
+      z_stream zs;
+      memset(&zs, 0, sizeof zs);
+      deflateInit2(&zs, level_, Z_DEFLATED, 15 + 16, 8, Z_DEFAULT_STRATEGY);
+      j.out.resize(deflateBound(&zs, j.in.size()) + 64);
+      zs.next_in = reinterpret_cast<Bytef *>(j.in.data());
+      zs.avail_in = (uInt)j.in.size();
+      zs.next_out = reinterpret_cast<Bytef *>(j.out.data());
+      zs.avail_out = (uInt)j.out.size();
+      deflate(&zs, Z_FINISH);
+      j.out.resize(zs.total_out);
+      deflateEnd(&zs);
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        bytes_in += j.in.size();
+        j.in.clear();
+        j.in.shrink_to_fit();
+        done_[j.seq] = std::move(j);
+        cv_done_.notify_one();
+      }
+    }
+  }
+  void write() {
+    uint64_t want = 0;
+    for (;;) {
+      Job j;
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_done_.wait(lk, [&] { return done_.count(want) || (closing_ && pending_.empty() && want == next_seq_); });
+        if (!done_.count(want)) return;
+        j = std::move(done_[want]);
+        done_.erase(want);
+        ++want;
+        cv_space_.notify_all();
+      }
+      fwrite(j.out.data(), 1, j.out.size(), fp_);
+      bytes_out += j.out.size();
+    }
+  }
+  FILE *fp_;
+  int level_;
+  std::mutex mu_;
+  std::condition_variable cv_work_, cv_done_, cv_space_;
+  std::deque<Job> pending_;
+  std::map<uint64_t, Job> done_;
+  uint64_t next_seq_ = 0;
+  bool closing_ = false;
+  std::vector<std::thread> workers_;
+  std::thread writer_;
+};
+
+// blocks for the compressor are cut at record-independent sizes; 8 MiB keeps members reasonably large
+void stream_to(GzipWriter &w, const char *p, int64_t n) {
+  const int64_t blk = 8 << 20;
+  for (int64_t o = 0; o < n; o += blk) w.submit(p + o, (size_t)std::min(blk, n - o));
+}
+
+struct RefSeq {
+  std::string id;
+  long len = 0;
+};
+
+// get_genome_inf (:896-991): split the multi-FASTA into <prefix>_NNNN.ref, collect lengths, print the block
+std::vector<RefSeq> genome_inf(const Options &o) {
+  fprintf(stderr, ":::: Reference stats ::::\n\n");
+  fprintf(stderr, "file name : %s\n", o.genome.c_str());
+  fprintf(stderr, "\n");
+  FILE *fp = fopen(o.genome.c_str(), "r");
+  if (!fp) die("ERROR: Cannot open file: %s\n", o.genome.c_str());
+  std::vector<RefSeq> seqs;
+  std::vector<char> line(kBufSize);
+  FILE *out = nullptr;
+  auto trim = [&](char *s) {
+    size_t n = strlen(s);
+    if (n && s[n - 1] == '\n') {
+      s[n - 1] = '\0';
+      return 1;
+    }
+    return 0;
+  };
+  auto finish = [&]() {
+    if (seqs.back().len < kRefSeqLenMin) die("ERROR: Reference is too short. Acceptable length >= %ld.\n", kRefSeqLenMin);
+    fprintf(stderr, "ref.%zu (len:%ld) : %s\n", seqs.size(), seqs.back().len, seqs.back().id.c_str());
+    fclose(out);
+  };
+  while (fgets(line.data(), (int)kBufSize, fp)) {
+    int ret = trim(line.data());
+    if (line[0] == '>') {
+      if (!seqs.empty()) finish();
+      if ((long)seqs.size() + 1 > kRefSeqNumMax) die("ERROR: References are too many. Max number of reference is %ld.\n", kRefSeqNumMax);
+      RefSeq r;
+      r.id.assign(line.data() + 1, strnlen(line.data() + 1, kRefIdLenMax));
+      seqs.push_back(r);
+      char name[4096];
+      snprintf(name, sizeof name, "%s_%04zu.ref", o.prefix.c_str(), seqs.size());
+      out = fopen(name, "w");
+      if (!out) die("ERROR: Cannot open output file: %s\n", name);
+      while (ret != 1) {  // header longer than the buffer: skip its continuation
+        if (!fgets(line.data(), (int)kBufSize, fp)) break;
+        ret = trim(line.data());
+      }
+      fprintf(out, ">%s\n", seqs.back().id.c_str());
+    } else {
+      if (seqs.empty()) continue;  // text before the first header (the reference would crash here)
+      seqs.back().len += (long)strlen(line.data());
+      if (seqs.back().len > kRefSeqLenMax) die("ERROR: Reference is too long. Acceptable length <= %ld.\n", kRefSeqLenMax);
+      fprintf(out, "%s\n", line.data());
+    }
+  }
+  fclose(fp);
+  if (seqs.empty()) die("ERROR: Reference is too short. Acceptable length >= %ld.\n", kRefSeqLenMin);
+  finish();
+  fprintf(stderr, "\n");
+  return seqs;
+}
+
+// get_genome_seq (:997-1033): re-read <prefix>_NNNN.ref, concatenate the body lines
+std::string genome_seq(const Options &o, size_t num) {
+  char name[4096];
+  snprintf(name, sizeof name, "%s_%04zu.ref", o.prefix.c_str(), num);
+  FILE *fp = fopen(name, "r");
+  if (!fp) die("ERROR: Cannot open file: %s\n", name);
+  std::string seq;
+  std::vector<char> line(kBufSize);
+  while (fgets(line.data(), (int)kBufSize, fp)) {
+    size_t n = strlen(line.data());
+    int ret = 0;
+    if (n && line[n - 1] == '\n') {
+      line[n - 1] = '\0';
+      ret = 1;
+      --n;
+    }
+    if (line[0] == '>') {
+      while (ret != 1) {
+        if (!fgets(line.data(), (int)kBufSize, fp)) break;
+        size_t m = strlen(line.data());
+        ret = (m && line[m - 1] == '\n') ? 1 : 0;
+      }
+    } else {
+      seq.append(line.data(), n);
+    }
+  }
+  fclose(fp);
+  return seq;
+}
+
+void print_help() {
+  fprintf(stderr,
+          "\nUSAGE: pbsim [options] \n\n [general options]\n\n"
+          "  --prefix             prefix of output files (sd).\n"
+          "  --id-prefix          prefix of read ID (S).\n"
+          "  --seed               for a pseudorandom number generator (Unix time).\n\n"
+          " [options for whole genome sequencing]\n\n"
+          "  --strategy           wgs\n"
+          "  --genome             FASTA format file (text file only).\n"
+          "  --depth              depth of coverage (20.0).\n"
+          "  --length-min         minimum length (100).\n"
+          "  --length-max         maximum length (1000000).\n\n"
+          " [options for quality score model]\n\n"
+          "  --method             qshmm\n"
+          "  --qshmm              quality score model.\n"
+          "  --length-mean        mean length (9000.0).\n"
+          "  --length-sd          standard deviation of length (7000.0).\n"
+          "  --accuracy-mean      mean accuracy (0.85).\n"
+          "  --pass-num           number of sequencing passes (1).\n"
+          "  --difference-ratio   difference (error) ratio (6:55:39).\n"
+          "  --hp-del-bias        bias intensity of deletion in homopolymer (1).\n\n"
+          " [options for error model]\n\n"
+          "  --method             errhmm\n"
+          "  --errhmm             error model.\n\n"
+          " [B200 engine]\n\n"
+          "  --gpu                CUDA device ordinal (0).\n"
+          "  --rng                philox (default) | replay\n"
+          "  --replay-draws       int32 log of the reference's rand() draws (replay mode).\n"
+          "  --replay-marks       int64 draw count after every (read, pass) (replay mode).\n"
+          "  --threads            compression threads (hardware concurrency).\n\n"
+          " --strategy trans/templ and --method sample are not built in this driver yet.\n\n");
+}
+
+template <class T>
+std::vector<T> read_binary(const std::string &path) {
+  FILE *fp = fopen(path.c_str(), "rb");
+  if (!fp) die("ERROR: Cannot open file: %s\n", path.c_str());
+  fseek(fp, 0, SEEK_END);
+  long n = ftell(fp);
+  fseek(fp, 0, SEEK_SET);
+  std::vector<T> v((size_t)n / sizeof(T));
+  if (!v.empty() && fread(v.data(), sizeof(T), v.size(), fp) != v.size()) die("ERROR: short read: %s\n", path.c_str());
+  fclose(fp);
+  return v;
+}
+
+}  // namespace
+
+int main(int argc, char **argv) {
+  const long rst1 = now_cpu(), t1 = now_wall();
+  Options o;
+  o.seed = (unsigned int)time(nullptr);
+  static struct option long_options[] = {
+      {"strategy", 1, nullptr, 0},   {"method", 1, nullptr, 0},         {"genome", 1, nullptr, 0},
+      {"transcript", 1, nullptr, 0}, {"prefix", 1, nullptr, 0},         {"id-prefix", 1, nullptr, 0},
+      {"depth", 1, nullptr, 0},      {"length-min", 1, nullptr, 0},     {"length-max", 1, nullptr, 0},
+      {"difference-ratio", 1, nullptr, 0}, {"seed", 1, nullptr, 0},     {"sample", 1, nullptr, 0},
+      {"sample-profile-id", 1, nullptr, 0}, {"accuracy-min", 1, nullptr, 0}, {"accuracy-max", 1, nullptr, 0},
+      {"qshmm", 1, nullptr, 0},      {"errhmm", 1, nullptr, 0},         {"length-mean", 1, nullptr, 0},
+      {"length-sd", 1, nullptr, 0},  {"accuracy-mean", 1, nullptr, 0},  {"pass-num", 1, nullptr, 0},
+      {"template", 1, nullptr, 0},   {"hp-del-bias", 1, nullptr, 0},
+      // engine-only
+      {"gpu", 1, nullptr, 0},        {"rng", 1, nullptr, 0},            {"replay-draws", 1, nullptr, 0},
+      {"replay-marks", 1, nullptr, 0}, {"threads", 1, nullptr, 0},      {nullptr, 0, nullptr, 0}};
+  int opt, idx = 0;
+  while ((opt = getopt_long(argc, argv, "", long_options, &idx)) != -1) {
+    if (opt != 0) exit(-1);
+    o.set_flg[idx] = 1;
+    const char *a = optarg;
+    switch (idx) {
+      case 0:
+        if (!strncmp(a, "wgs", 3)) o.strategy = "wgs";
+        else if (!strncmp(a, "trans", 5)) o.strategy = "trans";
+        else if (!strncmp(a, "templ", 5)) o.strategy = "templ";
+        else die("ERROR (strategy: %s): Acceptable value: wgs, trans, templ.\n", a);
+        break;
+      case 1:
+        if (!strncmp(a, "qshmm", 5)) o.method = "qshmm";
+        else if (!strncmp(a, "errhmm", 6)) o.method = "errhmm";
+        else if (!strncmp(a, "sample", 6)) o.method = "sample";
+        else die("ERROR (method: %s): Acceptable value: qshmm, errhmm, sample.\n", a);
+        break;
+      case 2: o.genome = a; break;
+      case 3: o.transcript = a; break;
+      case 4: o.prefix = a; break;
+      case 5: o.id_prefix = a; break;
+      case 6:
+        o.depth = atof(a);
+        if (o.depth <= 0.0) die("ERROR (depth: %s): Acceptable range is more than 0.\n", a);
+        break;
+      case 7:
+        if (strlen(a) >= 8) die("ERROR (length-min: %s): Acceptable range is 1-%d.\n", a, kFastqLenMax);
+        o.len_min = atoi(a);
+        if (o.len_min < 1 || o.len_min > kFastqLenMax) die("ERROR (length-min: %s): Acceptable range is 1-%d.\n", a, kFastqLenMax);
+        break;
+      case 8:
+        if (strlen(a) >= 8) die("ERROR (length-max: %s): Acceptable range is 1-%d.\n", a, kFastqLenMax);
+        o.len_max = atoi(a);
+        if (o.len_max < 1 || o.len_max > kFastqLenMax) die("ERROR (length-max: %s): Acceptable range is 1-%d.\n", a, kFastqLenMax);
+        break;
+      case 9: {
+        std::string tmp(a);
+        char *save = nullptr;
+        char *tp = strtok_r(&tmp[0], ":", &save);
+        for (int num = 0; num < 3; ++num) {
+          if (!tp) die("ERROR (difference-ratio: %s): Format is sub:ins:del.\n", a);
+          if (strlen(tp) >= 5) die("ERROR (difference-ratio: %s): Acceptable range is 0-%d.\n", a, kRatioMax);
+          long r = atoi(tp);
+          if (r < 0 || r > kRatioMax) die("ERROR (difference-ratio: %s): Acceptable range is 0-%d.\n", a, kRatioMax);
+          (num == 0 ? o.sub_ratio : num == 1 ? o.ins_ratio : o.del_ratio) = r;
+          tp = strtok_r(nullptr, ":", &save);
+        }
+        break;
+      }
+      case 10: o.seed = (unsigned int)atoi(a); break;
+      case 11: o.sample = a; break;
+      case 12: o.profile_id = a; break;
+      case 13:
+        o.accuracy_min = atof(a);
+        if (o.accuracy_min < 0.0 || o.accuracy_min > 1.0) die("ERROR (accuracy-min: %s): Acceptable range is 0.0-1.0.\n", a);
+        break;
+      case 14:
+        o.accuracy_max = atof(a);
+        if (o.accuracy_max < 0.0 || o.accuracy_max > 1.0) die("ERROR (accuracy-max: %s): Acceptable range is 0.0-1.0.\n", a);
+        break;
+      case 15: o.qshmm = a; break;
+      case 16: o.errhmm = a; break;
+      case 17:
+        o.len_mean = atof(a);
+        if (o.len_mean < 1 || o.len_mean > kFastqLenMax) die("ERROR (length-mean: %s): Acceptable range is 1-%d.\n", a, kFastqLenMax);
+        break;
+      case 18:
+        o.len_sd = atof(a);
+        if (o.len_sd < 0 || o.len_sd > kFastqLenMax) die("ERROR (length-sd: %s): Acceptable range is 0-%d.\n", a, kFastqLenMax);
+        break;
+      case 19:
+        o.accuracy_mean = atof(a);
+        if (o.accuracy_mean < 0.0 || o.accuracy_mean > 1.0) die("ERROR (accuracy-mean: %s): Acceptable range is 0.0-1.0.\n", a);
+        break;
+      case 20:
+        o.pass_num = atoi(a);
+        if (o.pass_num < 1) die("ERROR (pass_num: %s): Acceptable range is more than 1.\n", a);
+        break;
+      case 21: o.templ = a; break;
+      case 22:
+        if (strlen(a) >= 8) die("ERROR (hp-del-bias: %s): Acceptable range is 1-10.\n", a);
+        o.hp_del_bias = atof(a);
+        if (o.hp_del_bias < 1 || o.hp_del_bias > 10) die("ERROR (hp-del-bias: %s): Acceptable range is 1-10.\n", a);
+        break;
+      case 23: o.gpu = atoi(a); break;
+      case 24: o.rng = a; break;
+      case 25: o.replay_draws = a; break;
+      case 26: o.replay_marks = a; break;
+      case 27: o.threads = atoi(a); break;
+      default: break;
+    }
+  }
+  if (argc == 1) {
+    print_help();
+    exit(-1);
+  }
+  // ---- set_sim_param (:1451-1688)
+  if (!o.set_flg[0] || !o.set_flg[1]) die("ERROR: --strategy and --method must be set.\n");
+  if (o.strategy != "wgs" && o.method == "sample") die("ERROR: sampling-based simulation is possible only for wgs strategy.\n");
+  if (o.strategy == "wgs" && !o.set_flg[2]) die("ERROR: for --strategy wgs, --genome must be set.\n");
+  if (o.strategy == "trans" && !o.set_flg[3]) die("ERROR: for --strategy trans, --transcript must be set.\n");
+  if (o.strategy == "templ" && !o.set_flg[21]) die("ERROR: for --strategy templ, --template must be set.\n");
+  if (o.method == "qshmm" && !o.set_flg[15]) die("ERROR: for --method qshmm, --qshmm must be set.\n");
+  if (o.method == "errhmm" && !o.set_flg[16]) die("ERROR: for --method errhmm, --errhmm must be set.\n");
+  if (o.set_flg[13]) o.accuracy_min = int(o.accuracy_min * 100) * 0.01;
+  if (o.set_flg[14]) o.accuracy_max = int(o.accuracy_max * 100) * 0.01;
+  if (o.set_flg[19]) o.accuracy_mean = int(o.accuracy_mean * 100) * 0.01;
+  if (o.len_min > o.len_max) die("ERROR: length min(%ld) is greater than max(%ld).\n", o.len_min, o.len_max);
+  if (o.strategy != "wgs" || o.method == "sample")
+    die("ERROR: this B200 driver builds --strategy wgs with --method qshmm|errhmm; %s/%s is not built yet.\n",
+        o.strategy.c_str(), o.method.c_str());
+  const bool qs = o.method == "qshmm";
+
+  // ---- print_sim_param (:5397-5465)
+  fprintf(stderr, ":::: Simulation parameters :::\n\n");
+  fprintf(stderr, "strategy : wgs\n");
+  fprintf(stderr, "method : %s\n", o.method.c_str());
+  fprintf(stderr, "%s : %s\n", o.method.c_str(), qs ? o.qshmm.c_str() : o.errhmm.c_str());
+  fprintf(stderr, "genome : %s\n", o.genome.c_str());
+  fprintf(stderr, "prefix : %s\n", o.prefix.c_str());
+  fprintf(stderr, "id-prefix : %s\n", o.id_prefix.c_str());
+  fprintf(stderr, "depth : %lf\n", o.depth);
+  fprintf(stderr, "length-mean : %f\n", o.len_mean);
+  fprintf(stderr, "length-sd : %f\n", o.len_sd);
+  fprintf(stderr, "length-min : %ld\n", o.len_min);
+  fprintf(stderr, "length-max : %ld\n", o.len_max);
+  if (qs) fprintf(stderr, "difference-ratio : %ld:%ld:%ld\n", o.sub_ratio, o.ins_ratio, o.del_ratio);
+  fprintf(stderr, "seed : %d\n", o.seed);
+  fprintf(stderr, "accuracy-mean : %f\n", o.accuracy_mean);
+  fprintf(stderr, "pass_num : %d\n", o.pass_num);
+  fprintf(stderr, "hp-del-bias : %f\n", o.hp_del_bias);
+  fprintf(stderr, "\n");
+
+  // ---- model + tables (set_qshmm/set_errhmm/set_mut + table builders)
+  pbsim_host_params hp;
+  memset(&hp, 0, sizeof hp);
+  hp.method = qs ? PBSIM_METHOD_QSHMM : PBSIM_METHOD_ERRHMM;
+  hp.pass_num = o.pass_num;
+  hp.len_min = o.len_min;
+  hp.len_max = o.len_max;
+  hp.len_mean = o.len_mean;
+  hp.len_sd = o.len_sd;
+  hp.accuracy_mean = o.accuracy_mean;
+  hp.sub_ratio = o.sub_ratio;
+  hp.ins_ratio = o.ins_ratio;
+  hp.del_ratio = o.del_ratio;
+  snprintf(hp.id_prefix, sizeof hp.id_prefix, "%s", o.id_prefix.c_str());
+  pbsim_host_model *hm = nullptr;
+  const char *err = nullptr;
+  const std::string model_path = qs ? o.qshmm : o.errhmm;
+  if (pbsim_host_model_load(&hm, &hp, model_path.c_str(), &err) != 0) {
+    if (strstr(err, "Cannot open")) die("ERROR: Cannot open file: %s\n", model_path.c_str());
+    die("%s\n", err);
+  }
+  pbsim_engine *eng = nullptr;
+  if (pbsim_cuda_create(&eng, o.gpu) != 0) die("ERROR: %s\n", pbsim_cuda_last_error(nullptr));
+  if (pbsim_cuda_set_model(eng, pbsim_host_model_get(hm)) != 0) die("ERROR: %s\n", pbsim_cuda_last_error(eng));
+
+  // ---- genome (get_genome_inf)
+  const std::vector<RefSeq> seqs = genome_inf(o);
+
+  // ---- replay inputs
+  std::vector<int32_t> draws;
+  std::vector<int64_t> marks, starts;
+  const bool replay = o.rng == "replay";
+  if (replay) {
+    draws = read_binary<int32_t>(o.replay_draws);
+    marks = read_binary<int64_t>(o.replay_marks);
+    starts.resize(marks.size());
+    for (size_t i = 0; i < marks.size(); ++i) starts[i] = i == 0 ? 0 : marks[i - 1];
+  }
+  size_t replay_pos = 0;
+
+  // ---- hp-del-bias (main :673-697)
+  double bias[12] = {0, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 0};
+  int64_t hp11_running = 0;
+  auto ingest = [&](size_t num, const double b[12], int64_t hpfreq[12]) {
+    const std::string seq = genome_seq(o, num);
+    pbsim_sequence s;
+    s.bases = seq.data();
+    s.len = (int64_t)seq.size();
+    s.seq_num = (int32_t)num;
+    memcpy(s.hp_del_bias, b, sizeof s.hp_del_bias);
+    if (pbsim_cuda_set_sequence(eng, &s) != 0) die("ERROR: %s\n", pbsim_cuda_last_error(eng));
+    pbsim_cuda_get_hpfreq(eng, hpfreq);
+    return (int64_t)seq.size();
+  };
+  if (o.hp_del_bias != 1) {
+    int64_t tot[12] = {0};
+    for (size_t n = 1; n <= seqs.size(); ++n) {
+      int64_t f[12];
+      ingest(n, bias, f);
+      for (int k = 0; k < 12; ++k) tot[k] += f[k];
+    }
+    hp11_running = tot[11];
+    pbsim_host_hp_del_bias(o.hp_del_bias, tot, bias);
+  }
+  const int threads = o.threads > 0 ? o.threads : std::max(2u, std::thread::hardware_concurrency());
+
+  double gen_seconds = 0;
+  int64_t total_bases = 0;
+  for (size_t n = 1; n <= seqs.size(); ++n) {
+    int64_t f[12];
+    const int64_t glen = ingest(n, bias, f);
+    hp11_running += f[11];
+    double b[12];
+    memcpy(b, bias, sizeof b);
+    memcpy(&b[0], &hp11_running, sizeof(double));  // the cell genome.hpfreq[11] aliases in the reference build
+    if (pbsim_cuda_update_hp_del_bias(eng, b) != 0) die("ERROR: %s\n", pbsim_cuda_last_error(eng));
+
+    char name[4096];
+    snprintf(name, sizeof name, "%s_%04zu.%s", o.prefix.c_str(), n, o.pass_num == 1 ? "fq.gz" : "sam.gz");
+    GzipWriter reads_out(name, std::max(1, threads / 2));
+    snprintf(name, sizeof name, "%s_%04zu.maf.gz", o.prefix.c_str(), n);
+    GzipWriter maf_out(name, std::max(1, threads / 2));
+    if (o.pass_num > 1) {  // SAM header (:721-722)
+      char hdr[1024];
+      int m = snprintf(hdr, sizeof hdr,
+                       "@HD\tVN:1.5\tSO:unknown\tpb:3.0.7\n@RG\tID:ffffffff\tPL:PACBIO\tDS:READTYPE=SUBREAD;Ipd:CodecV1=ip;"
+                       "PulseWidth:CodecV1=pw;BINDINGKIT=101-789-500;SEQUENCINGKIT=101-826-100;BASECALLERVERSION=5.0.0;"
+                       "FRAMERATEHZ=100.000000\tPU:%s%zu\tPM:SEQUELII\n",
+                       o.id_prefix.c_str(), n);
+      reads_out.submit(hdr, (size_t)m);
+    }
+    pbsim_run run;
+    memset(&run, 0, sizeof run);
+    run.rng_mode = replay ? PBSIM_RNG_REPLAY : PBSIM_RNG_PHILOX;
+    run.seed = o.seed;
+    run.len_quota = (int64_t)(o.depth * glen);  // sim.len_quota (:705)
+    if (replay) {
+      run.replay_draws = draws.data();
+      run.replay_ndraws = (int64_t)draws.size();
+      run.replay_starts = starts.data() + replay_pos;
+      run.replay_nsubreads = (int64_t)(starts.size() - replay_pos);
+    }
+    if (pbsim_cuda_simulate_begin(eng, &run) != 0) die("ERROR: %s\n", pbsim_cuda_last_error(eng));
+    for (;;) {
+      pbsim_chunk c;
+      const int rc = pbsim_cuda_next_chunk(eng, &c);
+      if (rc < 0) die("ERROR: %s\n", pbsim_cuda_last_error(eng));
+      if (rc == 0) break;
+      stream_to(reads_out, c.reads, c.reads_bytes);
+      stream_to(maf_out, c.maf, c.maf_bytes);
+    }
+    pbsim_stats st;
+    if (pbsim_cuda_simulate_end(eng, &st, nullptr, 0, nullptr) != 0) die("ERROR: %s\n", pbsim_cuda_last_error(eng));
+    reads_out.close();
+    maf_out.close();
+    replay_pos += (size_t)st.res_pass_num;
+    gen_seconds += st.gen_seconds;
+    total_bases += st.res_len_total;
+    // print_simulation_stats (:5541-5564)
+    fprintf(stderr, ":::: Simulation stats (ref.%zu) ::::\n\n", n);
+    fprintf(stderr, "read num. : %ld\n", (long)st.res_num);
+    fprintf(stderr, "depth : %lf\n", (double)st.res_len_total / glen / o.pass_num);
+    fprintf(stderr, "read length mean (SD) : %f (%f)\n", st.res_len_mean, st.res_len_sd);
+    fprintf(stderr, "read length min : %ld\n", (long)st.res_len_min);
+    fprintf(stderr, "read length max : %ld\n", (long)st.res_len_max);
+    fprintf(stderr, "read accuracy mean (SD) : %f (%f)\n", st.res_accuracy_mean, st.res_accuracy_sd);
+    fprintf(stderr, "substitution rate. : %f\n", (double)st.res_sub_num / st.res_len_total);
+    fprintf(stderr, "insertion rate. : %f\n", (double)st.res_ins_num / st.res_len_total);
+    fprintf(stderr, "deletion rate. : %f\n", (double)st.res_del_num / st.res_len_total);
+    fprintf(stderr, "\n");
+  }
+  pbsim_cuda_destroy(eng);
+  pbsim_host_model_free(hm);
+  fprintf(stderr, ":::: System utilization ::::\n\n");
+  fprintf(stderr, "CPU time(s) : %ld\n", now_cpu() - rst1);
+  fprintf(stderr, "Elapsed time(s) : %ld\n", now_wall() - t1);
+  fprintf(stderr, "\n:::: B200 engine ::::\n\n");
+  fprintf(stderr, "generation device time(s) : %.3f\n", gen_seconds);
+  fprintf(stderr, "simulated Gbp/s (generation only) : %.3f\n", gen_seconds > 0 ? total_bases / gen_seconds / 1e9 : 0.0);
+  return 0;
+}

@@ -1,0 +1,57 @@
+"""GPU test of the C++ host driver (pbsim_b200/bin/pbsim): same command line as the reference, outputs
+compared byte for byte with the reference's golden run (replay mode) and with the oracle (philox mode)."""
+import gzip
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import __graft_entry__ as G
+from oracle import oracle as O
+from tests.golden_util import Case
+
+pytestmark = pytest.mark.gpu
+
+
+def _run_cli(c, tmp_path, extra):
+    exe = G.build_driver()
+    fa = tmp_path / "genome.fa"
+    with gzip.open(os.path.join(c.dir, "genome.fa.gz"), "rb") as f:
+        fa.write_bytes(f.read())
+    args = [exe, "--strategy", "wgs", "--method", c.method, "--" + c.method, c.model, "--genome", "genome.fa",
+            "--depth", str(c.depth), "--seed", str(c.seed)] + list(c.meta["extra_args"]) + ["--prefix", "out"] + extra
+    p = subprocess.run(args, cwd=tmp_path, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=600)
+    assert p.returncode == 0, p.stderr.decode()
+    return p.stderr.decode()
+
+
+@pytest.mark.parametrize("name", ["qs_rsii_quirks", "qs_ont_hpbias", "err_sequel_multipass"])
+def test_cli_replay_reproduces_reference_files(name, tmp_path):
+    c = Case(name)
+    O.glibc_rand(c.seed, c.ndraws).tofile(tmp_path / "draws.bin")
+    c.marks.astype(np.int64).tofile(tmp_path / "marks.bin")
+    stderr = _run_cli(c, tmp_path, ["--rng", "replay", "--replay-draws", "draws.bin", "--replay-marks", "marks.bin"])
+    for i in range(1, len(c.contigs) + 1):
+        ext = "fq.gz" if c.pass_num == 1 else "sam.gz"
+        got = gzip.open(tmp_path / ("out_%04d.%s" % (i, ext)), "rb").read()
+        want = gzip.open(os.path.join(c.dir, "seq%d.reads.gz" % i), "rb").read()  # SAM: header included
+        assert got == want, "reads file differs, seq %d" % i
+        assert gzip.open(tmp_path / ("out_%04d.maf.gz" % i), "rb").read() == c.maf(i)
+        ref = (tmp_path / ("out_%04d.ref" % i)).read_bytes()
+        assert ref == gzip.open(os.path.join(c.dir, "seq%d.ref.gz" % i), "rb").read()
+    # stderr: identical up to the "System utilization" block (timings) and the engine's own trailer
+    def norm(text):  # the echoed model path differs (tests unpack the model to a temp dir)
+        head = text.split(":::: System utilization ::::")[0]
+        return "\n".join(("%s : <model>" % c.method) if ln.startswith(c.method + " : ") else ln
+                         for ln in head.split("\n"))
+    assert norm(stderr) == norm(c.stderr)
+
+
+def test_cli_philox_equals_oracle(tmp_path):
+    c = Case("qs_rsii_basic")
+    out, _ = c.run_oracle("philox")
+    _run_cli(c, tmp_path, [])
+    for i, o in enumerate(out, start=1):
+        assert gzip.open(tmp_path / ("out_%04d.fq.gz" % i), "rb").read() == o["reads"]
+        assert gzip.open(tmp_path / ("out_%04d.maf.gz" % i), "rb").read() == o["maf"]
