@@ -85,6 +85,12 @@ CASES = {
 }
 
 
+STATS_CASES = {
+    "qs_rsii_len3k": ("qshmm", "QSHMM-RSII.model", ["--length-mean", "3000", "--length-sd", "2300"]),
+    "err_onthq_len3k": ("errhmm", "ERRHMM-ONT-HQ.model", ["--length-mean", "3000", "--length-sd", "2300"]),
+}
+
+
 def toolchain_stamp():
     gxx = subprocess.run(["g++", "--version"], stdout=subprocess.PIPE).stdout.decode().splitlines()[0]
     libc = " ".join(platform.libc_ver())
@@ -138,6 +144,30 @@ def main():
             json.dump(case, f, indent=1, sort_keys=True)
         print("golden", name, {k: len(v) for k, v in plain["files"].items() if not k.endswith(".ref")},
               "draws", len(logged["draws"]))
+
+    # distribution fixtures for the PHILOX-mode statistical parity tests: larger reference runs, reduced to
+    # histograms (tests/stats_util.py) so that only a few KB are committed
+    from tests import stats_util as SU
+    sdir = os.path.join(GOLDEN, "stats")
+    os.makedirs(sdir, exist_ok=True)
+    import tempfile
+    for sname, (method, model, extra) in STATS_CASES.items():
+        tmp = tempfile.mkdtemp()
+        fa = os.path.join(tmp, "g.fa")
+        R.write_fasta(fa, R.synth_genome(77, [("s1", 1500000)]))
+        args = ["--strategy", "wgs", "--method", method, "--" + method, os.path.join(DATA, model), "--genome", fa,
+                "--depth", "8", "--seed", "2024"] + extra
+        res = R.run_reference(args)
+        assert res["returncode"] == 0, res["stderr"]
+        st = SU.parse_outputs(res["files"]["out_0001.fq.gz"], res["files"]["out_0001.maf.gz"])
+        np.savez_compressed(os.path.join(sdir, sname + ".npz"), lengths=st["lengths"].astype(np.int32),
+                            accuracy=st["accuracy"].astype(np.float32), err_accuracy=st["err_accuracy"].astype(np.float32),
+                            qv_hist=st["qv_hist"], events=st["events"], per_read=st["per_read"].astype(np.int32),
+                            plus=st["plus"], n=st["n"])
+        with open(os.path.join(sdir, sname + ".json"), "w") as f:
+            json.dump(dict(method=method, model=model, extra_args=extra, depth=8, seed=2024, genome_bp=1500000,
+                           toolchain=stamp), f, indent=1)
+        print("stats", sname, st["n"], "reads", st["events"].tolist())
 
     # the reference's data/*.model files are INPUT DATA of the path (HMM parameters), not code;
     # carried gz-compressed so that the -m gpu tests and bench.py can run where /root/reference is absent

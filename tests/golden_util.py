@@ -31,7 +31,7 @@ def model_path(name):
 
 def case_names():
     return sorted(d for d in os.listdir(GOLDEN)
-                  if os.path.isdir(os.path.join(GOLDEN, d)) and d != "models")
+                  if os.path.isdir(os.path.join(GOLDEN, d)) and d not in ("models", "stats"))
 
 
 def gz_read(path):
