@@ -1093,7 +1093,18 @@ int orc_simulate_wgs(orc_ctx *c, double depth) {
       if (len < st->res_len_min) st->res_len_min = len;
       if (c->method == ORC_METHOD_QS) { /* ref: :2309-2316 accuracy from emitted qualities */
         double prob = 0.0;
-        for (i = 0; i < len; i++) prob += c->qc_prob[(int)c->qual[i] - 33];
+        if (r->mode == RNG_PHILOX) {
+          /* engine definition for PHILOX mode: the sum is taken per block of 1024 read positions and the
+           * block sums are added in order (the order the segment-parallel pass 1 produces) */
+          double blk = 0.0;
+          for (i = 0; i < len; i++) {
+            if ((i & 1023) == 0) { prob += blk; blk = 0.0; }
+            blk += c->qc_prob[(int)c->qual[i] - 33];
+          }
+          prob += blk;
+        } else {
+          for (i = 0; i < len; i++) prob += c->qc_prob[(int)c->qual[i] - 33];
+        }
         value = 1.0 - (prob / len);
       } else { /* ref: :4002 accuracy from realised errors; qualities all '!' :4007-4010 */
         value = 1.0 - ((double)(po.nsub + po.nins + po.ndel) / len);

@@ -26,14 +26,17 @@ struct AccEntry {          // one per accuracy 0..100, mirrored on the device
   uint32_t rate_mag;
   uint32_t valid;          // 1 if reads of this accuracy can be simulated
   uint32_t table_acc;      // errhmm: accuracy whose tables drive the chain
-  uint32_t pad;
+  uint32_t seg_ok;         // qshmm: chain couples fast enough for the segment-parallel pass 1
+  uint64_t reach;          // qshmm: states reachable from init2state (bit s)
 };
 
 // blob layouts (all sections 16-byte aligned)
 struct QsBlobLayout {
   static constexpr uint32_t t2_off = 0;                                   // uint32[51*100]
   static constexpr uint32_t emis_off = ((kQsRows * 100 * 4 + 15) / 16) * 16;  // uint8[51*100]
-  static constexpr uint32_t bytes = emis_off + ((kQsRows * 100 + 15) / 16) * 16;
+  static constexpr uint32_t tmod_off = emis_off + ((kQsRows * 100 + 15) / 16) * 16;  // uint8[51] (+pad to 64)
+  static constexpr uint32_t emodv_off = tmod_off + 64;                               // uint8[51] (+pad to 64)
+  static constexpr uint32_t bytes = emodv_off + 64;
   static constexpr uint32_t freq_bytes = 1008;                            // uint8[1000] padded
 };
 
@@ -47,6 +50,31 @@ inline uint32_t er_blob_bytes(uint32_t nst, uint32_t *t2_off, uint32_t *emis_off
   *emis_off = o; o += ((rows * 1000 + 15) / 16) * 16;
   *emod_off = o; o += ((rows * 2 + 15) / 16) * 16;
   return o;
+}
+
+// Does the chain of this accuracy forget its past quickly?  32 trials of the grand coupling (all reachable
+// states driven by the same uniform draws): segment-parallel pass 1 is enabled when every trial coalesces
+// within 512 steps.  Only a performance switch: results are identical on either path.
+inline bool coupling_screen(const pbsim_hmm_row &r, uint64_t reach) {
+  uint64_t x = 0x9E3779B97F4A7C15ull;
+  for (int trial = 0; trial < 32; ++trial) {
+    uint64_t mask = reach;
+    int t = 0;
+    for (; t < 512 && (mask & (mask - 1)); ++t) {
+      x ^= x << 13; x ^= x >> 7; x ^= x << 17;  // xorshift64
+      const uint32_t u = (uint32_t)(x >> 32);
+      uint64_t next = 0;
+      for (uint64_t m = mask; m; m &= m - 1) {
+        const int s = __builtin_ctzll(m);
+        if (s < 1 || s > r.nstates) { next |= 1ull << s; continue; }
+        const int tm = r.tran_mod[s] < 1 ? 1 : r.tran_mod[s];
+        next |= 1ull << r.tran[s * 100 + (int)(((uint64_t)u * (uint32_t)tm) >> 32)];
+      }
+      mask = next;
+    }
+    if (mask & (mask - 1)) return false;
+  }
+  return true;
 }
 
 struct ModelImage {
@@ -98,6 +126,28 @@ struct ModelImage {
               em[s * 100 + k] = r.emis[s * 100 + k];
             }
           }
+          uint8_t *tmodv = b + QsBlobLayout::tmod_off, *emodv = b + QsBlobLayout::emodv_off;
+          for (int s2 = 0; s2 <= 50; ++s2) {
+            const uint32_t en = entry(s2);
+            tmodv[s2] = (uint8_t)((en >> 16) & 0xFFu);
+            emodv[s2] = (uint8_t)(en >> 24);
+          }
+          // reachable closure from the init row, then a Monte-Carlo screen of the grand coupling time
+          uint64_t reach = 0, frontier = 0;
+          for (int k = 0; k < r.init_mod && k < 100; ++k) frontier |= 1ull << r.init[k];
+          while (frontier) {
+            const int s2 = __builtin_ctzll(frontier);
+            frontier &= frontier - 1;
+            if (reach >> s2 & 1ull) continue;
+            reach |= 1ull << s2;
+            if (s2 >= 1 && s2 <= r.nstates)
+              for (int k = 0; k < r.tran_mod[s2] && k < 100; ++k) {
+                const int nx = r.tran[s2 * 100 + k];
+                if (!(reach >> nx & 1ull)) frontier |= 1ull << nx;
+              }
+          }
+          e.reach = reach;
+          e.seg_ok = coupling_screen(r, reach) ? 1u : 0u;
           e.blob_bytes = QsBlobLayout::bytes;
           e.has_model = 1;
           e.nstates = (uint32_t)r.nstates;
@@ -111,6 +161,7 @@ struct ModelImage {
           blob.resize(blob.size() + QsBlobLayout::freq_bytes, 0);
           std::memcpy(blob.data() + e.blob_off, r.freq, (size_t)r.freq_mod);
           e.blob_bytes = QsBlobLayout::freq_bytes;
+          e.seg_ok = 1;  // no chain at all: positions are independent
           e.has_model = 0;
           e.freq_mod = (uint32_t)r.freq_mod;
           e.valid = 1;

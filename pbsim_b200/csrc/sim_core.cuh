@@ -309,7 +309,7 @@ PB_HD void qshmm_simulate(const QsView &T, Draw &d, const WindowRef &win, bool s
   uint32_t R = 0, P = 0, C = 0;
   uint32_t row = 0, mod = T.init_mod, emod = 1;
   uint32_t nsub = 0, nins = 0, ndel = 0;
-  double prob = 0.0;
+  double prob = 0.0, prob_blk = 0.0;  // counter mode sums per 1024-position block (the segment-parallel order)
   res.overflow = 0;
   while (R < wlen) {
     d.prefetch(P);
@@ -329,7 +329,12 @@ PB_HD void qshmm_simulate(const QsView &T, Draw &d, const WindowRef &win, bool s
       } else {
         qv = T.freq[d.w0(T.freq_mod)];
       }
-      prob += T.qc_prob[qv];
+      if (Draw::kCounter) {
+        if ((P & (PB_TILE - 1u)) == 0u) { prob += prob_blk; prob_blk = 0.0; }
+        prob_blk += T.qc_prob[qv];
+      } else {
+        prob += T.qc_prob[qv];
+      }
       const QsThr th = T.thr[qv];
       const uint32_t r = d.w2(1000000u);
       const bool is_sub = r < th.sub;
@@ -383,6 +388,7 @@ PB_HD void qshmm_simulate(const QsView &T, Draw &d, const WindowRef &win, bool s
     if (res.overflow) break;
   }
   sink.flush();
+  prob += prob_blk;
   res.n_entries = sink.n;
   res.rlen = P;
   res.ncol = C;
@@ -406,7 +412,7 @@ PB_HD void qshmm_simulate_fast(const QsView &T, const PhiloxKeys &K, uint32_t re
   uint32_t R = 0, P = 0, n = 0;
   uint32_t row = 0, mod = T.init_mod, emod = 1;
   uint32_t nsub = 0, ndel = 0;
-  double prob = 0.0;
+  double prob = 0.0, prob_blk = 0.0;
   res.overflow = 0;
   const uint32_t c1 = pass << 16;
   while (R < wlen) {
@@ -435,7 +441,8 @@ PB_HD void qshmm_simulate_fast(const QsView &T, const PhiloxKeys &K, uint32_t re
         } else {
           qv = T.freq[mulhi32(w0, T.freq_mod)];
         }
-        prob += T.qc_prob[qv];
+        if ((P & (PB_TILE - 1u)) == 0u) { prob += prob_blk; prob_blk = 0.0; }  // block order of the segment-parallel path
+        prob_blk += T.qc_prob[qv];
         const QsThr th = T.thr[qv];
         const uint32_t r = mulhi32(w2, 1000000u);
         const bool is_sub = r < th.sub;
@@ -491,6 +498,7 @@ PB_HD void qshmm_simulate_fast(const QsView &T, const PhiloxKeys &K, uint32_t re
       if (res.overflow) break;
     }
   }
+  prob += prob_blk;
   res.n_entries = n;
   res.rlen = P;
   res.ncol = P + ndel;
@@ -498,6 +506,257 @@ PB_HD void qshmm_simulate_fast(const QsView &T, const PhiloxKeys &K, uint32_t re
   res.ndel = ndel;
   res.nins = P + ndel - R;  // C = P + ndel and R = P - nins + ndel
   res.accuracy = 1.0 - (prob / (double)P);
+}
+
+// ---------------------------------------------------------------------------------------------
+// qshmm SEGMENT-PARALLEL pass 1 (PHILOX, reads that never need the genome in pass 1).
+// A read is cut into segments of PB_TILE read positions.  Because every draw is addressed by its
+// position, a segment can be simulated by itself once the chain state entering it is known, and that
+// state is recovered EXACTLY by backward coupling: run every reachable state through the positions
+// just before the segment with those positions' own draws; as soon as all images coincide the state is
+// independent of the earlier history (if the window reaches position 0 the init draw decides).  Segments
+// are simulated "unbounded" (they cannot know the reference offset they start at); find_end then locates
+// the position at which the window is used up, clips the last deletion run and drops the rest, which is
+// what the sequential loop `while (ref_offset < mut.len)` (:2213, :2268) does.
+// ---------------------------------------------------------------------------------------------
+#define PB_SEG_SLACK 64u                       // extra entries per segment slot (continuation entries, pads)
+#define PB_SEG_STRIDE (PB_TILE + PB_SEG_SLACK) // entries between consecutive segment slots of a read
+
+struct QsSegAux {            // per accuracy, beside the QsView tables
+  const uint8_t *tmod;       // [51] transition modulus of a state
+  const uint8_t *emodv;      // [51] emission modulus of a state
+  uint64_t reach;            // states reachable from the init distribution (bit s)
+};
+
+struct SegResult {
+  uint32_t n_entries, ref_adv, nsub, ndel;
+  uint32_t flags;            // 1: slot overflow, 2: coupling window exhausted
+  double prob;
+};
+
+PB_HD uint32_t qs_state_of_row(uint32_t row) { return (row * 41944u) >> 22; }  // row / 100 for row <= 5100
+
+// state entering position p_start (>= 1): returns false if no coalescence within max_window positions
+PB_HD bool qshmm_segment_start(const QsView &T, const QsSegAux &A, const PhiloxKeys &K, uint32_t read_id,
+                               uint32_t pass, uint32_t p_start, uint32_t max_window, uint32_t &row, uint32_t &mod,
+                               uint32_t &emod) {
+  const uint32_t c1 = pass << 16;
+  for (uint32_t B = 32u;; B *= 2u) {
+    const bool from_zero = p_start <= B;
+    const uint32_t p0 = from_zero ? 0u : p_start - B;
+    uint64_t mask = from_zero ? 1ull : A.reach;  // from position 0: the virtual state 0 (row 0 = init2state)
+    uint32_t s_row = 0, s_mod = T.init_mod, s_emod = 1;
+    bool single = from_zero;
+    for (uint32_t p = p0; p < p_start; ++p) {
+      uint32_t w[4];
+      philox_block_keys(K, p, c1, read_id, 1u, w);
+      if (single) {
+        const uint32_t t = T.t2[s_row + mulhi32(w[0], s_mod)];
+        s_row = t & 0xFFFFu;
+        s_mod = (t >> 16) & 0xFFu;
+        s_emod = t >> 24;
+      } else {
+        uint64_t next = 0;
+        uint32_t last_t = 0;
+        for (uint64_t m = mask; m; m &= m - 1ull) {
+#if defined(__CUDA_ARCH__)
+          const uint32_t s = (uint32_t)__ffsll((long long)m) - 1u;
+#else
+          const uint32_t s = (uint32_t)__builtin_ctzll(m);
+#endif
+          last_t = T.t2[s * PB_QS_ROW + mulhi32(w[0], A.tmod[s])];
+          next |= 1ull << qs_state_of_row(last_t & 0xFFFFu);
+        }
+        mask = next;
+        if ((mask & (mask - 1ull)) == 0ull) {  // coalesced: one image left
+          single = true;
+          s_row = last_t & 0xFFFFu;
+          s_mod = (last_t >> 16) & 0xFFu;
+          s_emod = last_t >> 24;
+        }
+      }
+    }
+    if (single) {
+      row = s_row; mod = s_mod; emod = s_emod;
+      return true;
+    }
+    if (B >= max_window) return false;
+  }
+}
+
+// simulate positions [p_start, p_start + PB_TILE) of a read, unbounded in the reference direction.
+// first_segment: the reference offset is 0 at p_start (the `hp[-1]` rule of :2269 applies while it stays 0).
+PB_HD void qshmm_simulate_segment(const QsView &T, const PhiloxKeys &K, uint32_t read_id, uint32_t pass,
+                                  uint32_t p_start, bool first_segment, uint32_t row, uint32_t mod, uint32_t emod,
+                                  uint16_t *ev, SegResult &res) {
+  uint32_t R = first_segment ? 0u : 1u;  // only "is it still 0" matters; ref_adv is counted separately
+  uint32_t radv = 0, n = 0, nsub = 0, ndel = 0;
+  double prob = 0.0;
+  const uint32_t c1 = pass << 16;
+  res.flags = 0;
+  const uint32_t p_end = p_start + PB_TILE;
+  for (uint32_t P = p_start; P < p_end;) {
+    if (n + 2u * PB_GROUP > PB_SEG_STRIDE) { res.flags |= 1u; break; }
+    uint32_t g[PB_GROUP][4];
+#pragma unroll
+    for (uint32_t u = 0; u < PB_GROUP; ++u) philox_block_keys(K, P + u, c1, read_id, 1u, g[u]);
+    uint32_t e[PB_GROUP];
+    uint32_t big_u = PB_GROUP, big_nd = 0;
+#pragma unroll
+    for (uint32_t u = 0; u < PB_GROUP; ++u) {
+      e[u] = PB_QS_PAD;
+      if (big_u == PB_GROUP && P < p_end) {  // a group can be misaligned after a >= 15 deletion run
+        const uint32_t w0 = g[u][0], w1 = g[u][1], w2 = g[u][2], w3 = g[u][3];
+        uint32_t qv;
+        if (T.has_model) {
+          const uint32_t t = T.t2[row + mulhi32(w0, mod)];
+          row = t & 0xFFFFu;
+          mod = (t >> 16) & 0xFFu;
+          emod = t >> 24;
+          qv = T.emis[row + mulhi32(w1, emod)];
+        } else {
+          qv = T.freq[mulhi32(w0, T.freq_mod)];
+        }
+        prob += T.qc_prob[qv];
+        const QsThr th = T.thr[qv];
+        const uint32_t r = mulhi32(w2, 1000000u);
+        const bool is_sub = r < th.sub;
+        const bool is_err = r < th.ins;
+        const uint32_t c3 = ((w0 & 0xFFFu) * 3u) >> 12, c8 = w1 & 7u;
+        const uint32_t info = is_sub ? c3 : (is_err ? c8 : 0u);
+        const uint32_t kind = is_sub ? PB_KIND_SUB : (is_err ? PB_KIND_INS : PB_KIND_MATCH);
+        nsub += is_sub ? 1u : 0u;
+        const uint32_t a = (is_err && !is_sub) ? 0u : 1u;
+        R += a;
+        radv += a;
+        ++P;
+        uint32_t nd = 0;
+        const uint32_t rd0 = mulhi32(w3, 1000000u);
+        if (rd0 < (R != 0u ? th.del : th.del0)) {
+          nd = 1;
+          while (nd < (1u << 20) && mulhi32(fmix32(w3 + nd * 0x9E3779B9u), 1000000u) < th.del) ++nd;
+          R += nd;
+          radv += nd;
+        }
+        ndel += nd;
+        const uint32_t base = qv | (kind << 7) | (info << 9);
+        if (nd < PB_QS_DEL_SAT) {
+          e[u] = base | (nd << 12);
+        } else {
+          e[u] = base | (PB_QS_DEL_SAT << 12);
+          big_u = u;
+          big_nd = nd - PB_QS_DEL_SAT;
+        }
+      }
+    }
+    uint64_t *dst = reinterpret_cast<uint64_t *>(ev + n);
+    *dst = (uint64_t)(e[0] | (e[1] << 16)) | ((uint64_t)(e[2] | (e[3] << 16)) << 32);
+    n += PB_GROUP;
+    if (big_u != PB_GROUP) {
+      n -= PB_GROUP - 1u - big_u;
+      uint32_t rest = big_nd;
+      for (;;) {
+        if (n + 2u * PB_GROUP > PB_SEG_STRIDE) { res.flags |= 1u; break; }
+        const uint32_t c = rest < PB_QS_CONT_SAT ? rest : PB_QS_CONT_SAT;
+        ev[n++] = (uint16_t)((c & 0x7Fu) | (3u << 7) | ((c >> 7) << 9));
+        if (c < PB_QS_CONT_SAT) break;
+        rest -= PB_QS_CONT_SAT;
+      }
+      while (n & (PB_GROUP - 1u)) ev[n++] = (uint16_t)PB_QS_PAD;
+      if (res.flags) break;
+    }
+  }
+  res.n_entries = n;
+  res.ref_adv = radv;
+  res.nsub = nsub;
+  res.ndel = ndel;
+  res.prob = prob;
+}
+
+// Locate the end of a segmented read: walk the entries of the segment in which the cumulative reference
+// advance reaches wlen, clip the last deletion run, return the totals of the included part of that segment.
+struct SegTail {
+  uint32_t n_entries, positions, ref_adv, nsub, ndel;
+  double prob;
+};
+
+PB_HD SegTail qshmm_find_end_in_segment(uint16_t *ev, uint32_t n_entries, uint32_t ref_room /* wlen - R before */,
+                                        const double *qc_prob) {
+  SegTail t;
+  t.n_entries = 0; t.positions = 0; t.ref_adv = 0; t.nsub = 0; t.ndel = 0; t.prob = 0.0;
+  for (uint32_t i = 0; i < n_entries; ++i) {
+    const uint32_t v = ev[i];
+    const uint32_t kind = (v >> 7) & 3u;
+    const bool cont = kind == 3u;
+    uint32_t nd = cont ? ((v & 0x7Fu) | ((v >> 9) << 7)) : (v >> 12);
+    if (!cont) {
+      if (t.ref_adv >= ref_room) break;  // `while (ref_offset < mut.len)` (:2213): no further read position
+      t.prob += qc_prob[v & 0x7Fu];
+      t.positions += 1u;
+      t.nsub += (kind == PB_KIND_SUB) ? 1u : 0u;
+      t.ref_adv += (kind == PB_KIND_INS) ? 0u : 1u;
+    }
+    const uint32_t room = ref_room - t.ref_adv;
+    if (nd >= room) {  // the deletion loop stops when the window is used up (:2268)
+      nd = room;
+      if (cont) ev[i] = (uint16_t)((nd & 0x7Fu) | (3u << 7) | ((nd >> 7) << 9));
+      else ev[i] = (uint16_t)((v & 0x0FFFu) | (nd << 12));  // room < 15 here or nd was 15 and stays 15
+      t.ndel += nd;
+      t.ref_adv += nd;
+      t.n_entries = i + 1u;
+      if (t.ref_adv >= ref_room) return t;
+      continue;
+    }
+    t.ndel += nd;
+    t.ref_adv += nd;
+    t.n_entries = i + 1u;
+  }
+  return t;
+}
+
+// Combine the segments of one read: prefix over the per-segment totals, find the segment in which the window
+// is used up, clip it, write the tile checkpoints (pad = entries of the tile) and the read's totals.
+// flags: 1 slot overflow, 2 coupling failed, 4 not enough segments provisioned, 8 a later segment started
+// at reference offset 0 (the hp[-1] rule would apply there) -> the engine redoes the batch sequentially.
+struct SegRead {
+  uint32_t n_tiles, rlen, ncol, nsub, nins, ndel, flags;
+  double accuracy;
+};
+
+PB_HD uint32_t qshmm_segments_for(uint32_t wlen) {  // provisioned segments: 10 % + 512 positions of headroom
+  const uint64_t need = (uint64_t)wlen + wlen / 10u + 512u;
+  return (uint32_t)((need + PB_TILE - 1u) / PB_TILE);
+}
+
+PB_HD void qshmm_finish_segmented(uint16_t *ev_base, const SegResult *seg, uint32_t n_seg, uint32_t wlen,
+                                  const double *qc_prob, Ckpt *ck, SegRead &out) {
+  uint32_t R = 0, P = 0, D = 0, nsub = 0;
+  double prob = 0.0;
+  out.flags = 0;
+  out.n_tiles = 0;
+  bool done = false;
+  for (uint32_t k = 0; k < n_seg && !done; ++k) {
+    out.flags |= seg[k].flags;
+    if (k >= 1u && R == 0u) out.flags |= 8u;
+    Ckpt c; c.col = P + D; c.ref = R; c.read = P; c.pad = seg[k].n_entries;
+    if ((uint64_t)R + seg[k].ref_adv >= wlen) {
+      const SegTail t = qshmm_find_end_in_segment(ev_base + (uint64_t)k * PB_SEG_STRIDE, seg[k].n_entries, wlen - R, qc_prob);
+      c.pad = t.n_entries;
+      P += t.positions; R += t.ref_adv; D += t.ndel; nsub += t.nsub; prob += t.prob;
+      out.n_tiles = k + 1u;
+      done = true;
+    } else {
+      P += PB_TILE; R += seg[k].ref_adv; D += seg[k].ndel; nsub += seg[k].nsub; prob += seg[k].prob;
+    }
+    ck[k] = c;
+  }
+  if (!done) out.flags |= 4u;
+  out.rlen = P;
+  out.ncol = P + D;
+  out.nsub = nsub;
+  out.ndel = D;
+  out.nins = P + D - R;
+  out.accuracy = 1.0 - (prob / (double)P);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -22,8 +22,50 @@ struct HostSimOut {
 };
 
 static HostSimOut g_out;
-static int use_fast = 1;
+static int use_fast = 1, use_seg = 0, seg_min_len = 2048;
+static long seg_reads = 0, seg_fallbacks = 0;
 extern "C" void hostsim_use_fast(int v) { use_fast = v; }
+extern "C" void hostsim_use_segments(int v, int min_len) { use_seg = v; seg_min_len = min_len; }
+extern "C" long hostsim_seg_reads() { return seg_reads; }
+extern "C" long hostsim_seg_fallbacks() { return seg_fallbacks; }
+
+// the segment-parallel pass 1 as the kernels run it (k_sim_seg + k_find_end), sequentially on the host;
+// returns false if the read must fall back to the sequential path
+static bool run_segmented(const pb::QsView &T, const pb::QsSegAux &A, uint32_t seed, uint32_t seq_num, uint32_t read_id,
+                          uint32_t pass, uint32_t wlen, std::vector<uint8_t> &events, size_t ev_off,
+                          std::vector<pb::Ckpt> &ckpts, size_t ck_base, pb::SubreadResult &res) {
+  pb::PhiloxKeys K;
+  K.init(seed, seq_num);
+  const uint32_t n_seg = pb::qshmm_segments_for(wlen);
+  std::vector<uint16_t> slots((size_t)n_seg * PB_SEG_STRIDE + 16, 0);
+  std::vector<pb::SegResult> seg(n_seg);
+  for (uint32_t k = 0; k < n_seg; ++k) {
+    uint32_t row = 0, mod = T.init_mod, emod = 1;
+    if (k > 0 && T.has_model) {
+      if (!pb::qshmm_segment_start(T, A, K, read_id, pass, k * PB_TILE, 4096, row, mod, emod)) return false;
+    }
+    pb::qshmm_simulate_segment(T, K, read_id, pass, k * PB_TILE, k == 0, row, mod, emod, slots.data() + (size_t)k * PB_SEG_STRIDE,
+                               seg[k]);
+  }
+  std::vector<pb::Ckpt> ck(n_seg);
+  pb::SegRead sr;
+  pb::qshmm_finish_segmented(slots.data(), seg.data(), n_seg, wlen, T.qc_prob, ck.data(), sr);
+  if (sr.flags) return false;
+  // linearise the tiles for the Python expander
+  size_t total = 0;
+  for (uint32_t k = 0; k < sr.n_tiles; ++k) total += ck[k].pad;
+  events.resize(ev_off + total * 2);
+  uint16_t *dst = reinterpret_cast<uint16_t *>(events.data() + ev_off);
+  for (uint32_t k = 0; k < sr.n_tiles; ++k) {
+    memcpy(dst, slots.data() + (size_t)k * PB_SEG_STRIDE, (size_t)ck[k].pad * 2);
+    dst += ck[k].pad;
+  }
+  ckpts.resize(ck_base + sr.n_tiles);
+  for (uint32_t k = 0; k < sr.n_tiles; ++k) ckpts[ck_base + k] = ck[k];
+  res.n_entries = (uint32_t)total; res.rlen = sr.rlen; res.ncol = sr.ncol; res.nsub = sr.nsub; res.nins = sr.nins;
+  res.ndel = sr.ndel; res.overflow = 0; res.accuracy = sr.accuracy;
+  return true;
+}
 
 extern "C" {
 
@@ -94,14 +136,26 @@ long hostsim_run(const pbsim_model *m, const uint8_t *ascii_upper, const int16_t
         T.thr = reinterpret_cast<const pb::QsThr *>(img.qs_thr.data()); T.thr_hp = img.qs_thr_hp.data(); T.qc_prob = m->qc_prob;
         pb::QsSink sink;
         sink.init(reinterpret_cast<uint16_t *>(g_out.events.data() + ev_off), g_out.ckpts.data() + ck_base, cap);
-        if (rng_mode == PBSIM_RNG_PHILOX && !slow && use_fast) {
+        bool seg_done = false;
+        if (rng_mode == PBSIM_RNG_PHILOX && !slow && use_seg && ae.seg_ok && (int)plan.wlen >= seg_min_len) {
+          pb::QsSegAux A;
+          A.tmod = b + pb::QsBlobLayout::tmod_off;
+          A.emodv = b + pb::QsBlobLayout::emodv_off;
+          A.reach = ae.reach;
+          ++seg_reads;
+          seg_done = run_segmented(T, A, seed, (uint32_t)seq_num, (uint32_t)read_id, (uint32_t)pass, plan.wlen, g_out.events, ev_off,
+                                   g_out.ckpts, ck_base, res);
+          if (!seg_done) ++seg_fallbacks;
+        }
+        if (seg_done) {
+        } else if (rng_mode == PBSIM_RNG_PHILOX && !slow && use_fast) {
           pb::PhiloxKeys K;
           K.init(seed, (uint32_t)seq_num);
           pb::qshmm_simulate_fast(T, K, (uint32_t)read_id, (uint32_t)pass, plan.wlen,
                                   reinterpret_cast<uint16_t *>(g_out.events.data() + ev_off), g_out.ckpts.data() + ck_base, cap, res);
         } else if (rng_mode == PBSIM_RNG_PHILOX) { pd.pass = (uint32_t)pass; pb::qshmm_simulate(T, pd, win, slow, plan.wlen, sink, res); }
         else { rd.cur = cursor; pb::qshmm_simulate(T, rd, win, slow, plan.wlen, sink, res); cursor = rd.cur; }
-        g_out.events.resize(ev_off + (size_t)res.n_entries * 2);
+        if (!seg_done) g_out.events.resize(ev_off + (size_t)res.n_entries * 2);
       } else {
         g_out.events.resize(ev_off + (size_t)cap);
         pb::ErView T;
@@ -123,7 +177,8 @@ long hostsim_run(const pbsim_model *m, const uint8_t *ascii_upper, const int16_t
         else { rd.cur = cursor; pb::errhmm_simulate(T, rd, win, slow, plan.wlen, sink, res); cursor = rd.cur; }
         g_out.events.resize(ev_off + (size_t)res.n_entries);
       }
-      g_out.ckpts.resize(ck_base + (res.n_entries + PB_TILE - 1) / PB_TILE);
+      if (!(m->method == PBSIM_METHOD_QSHMM && g_out.ckpts.size() != ck_base + cap / PB_TILE + 2))
+        g_out.ckpts.resize(ck_base + (res.n_entries + PB_TILE - 1) / PB_TILE);
       int64_t rec[12] = {read_id, pass, (int64_t)plan.acc, (int64_t)plan.offset, (int64_t)plan.wlen, (int64_t)res.rlen,
                          (int64_t)res.ncol, (int64_t)minus, (int64_t)res.n_entries, (int64_t)ev_off, draw_start,
                          (int64_t)res.overflow};

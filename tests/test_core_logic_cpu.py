@@ -146,3 +146,24 @@ def test_fast_path_equals_generic_path():
             assert r1 == r2 and m1 == m2
             assert [x["nins"] for x in s1] == [x["nins"] for x in s2]
             assert [x["ndel"] for x in s1] == [x["ndel"] for x in s2]
+
+
+@pytest.mark.parametrize("name", ["qs_rsii_basic", "qs_rsii_quirks", "qs_delheavy_uniform", "qs_rsii_multipass",
+                                  "qs_rsii_fixedlen"])
+def test_segment_parallel_pass1_equals_oracle(name):
+    """segment-parallel pass 1 (backward coupling + unbounded segments + find_end) gives the oracle's bytes"""
+    c = Case(name)
+    L = H.lib()
+    L.hostsim_seg_reads.restype = L.hostsim_seg_fallbacks.restype = __import__("ctypes").c_long
+    L.hostsim_use_segments(1, 1025)
+    try:
+        out, res = _replay_case(c, "philox")
+    finally:
+        L.hostsim_use_segments(0, 2048)
+    for (reads, maf, sub), oref in zip(res, out):
+        assert reads == oref["reads"]
+        assert maf == oref["maf"]
+        assert np.array_equal(np.array([s["accuracy"] for s in sub]), oref["info"]["accuracy"])
+        assert [s["nins"] for s in sub] == oref["info"]["nins"].tolist()
+    if name != "qs_rsii_fixedlen":
+        assert L.hostsim_seg_reads() > 0
