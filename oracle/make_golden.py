@@ -39,6 +39,8 @@ G_QUIRK = dict(seed=2, contigs=[("c1", 30000), ("c2", 150), ("c3", 8000)], n_run
 
 G_LONGHP = dict(seed=3, contigs=[("h1", 20000)], long_runs=[12, 14, 16, 18, 20, 22, 24, 26, 28, 30, 34, 38, 40, 46] * 3)
 
+G_HP11 = dict(seed=4, contigs=[("h11", 30000)], long_runs=[11, 13, 15, 17, 11, 13, 21, 11, 12, 14] * 12, n_runs=8, iupac=12)
+
 CASES = {
     # name: (method, model, genome spec, depth, seed, extra CLI args, oracle kwargs)
     "qs_rsii_basic": ("qshmm", "QSHMM-RSII.model", G_PLAIN, 5, 42,
@@ -77,6 +79,13 @@ CASES = {
                           "--difference-ratio", "1:1:1000", "--hp-del-bias", "10"],
                          dict(len_mean=1500.0, len_sd=900.0, accuracy_mean=0.3, accuracy_mean_set=True,
                               ratio=(1, 1, 1000), hp_del_bias=10.0)),
+    # default bias, many homopolymers >= 11 and N runs, deletion-rich: exercises the deletion-run repair of the
+    # segment-parallel path (a deletion cannot follow a base of an 11/13/15..-run: hp_del_bias[11] is 0)
+    "qs_hp11_uniform": ("qshmm", "QSHMM-RSII.model", G_HP11, 6, 33,
+                        ["--length-mean", "3000", "--length-sd", "1500", "--accuracy-mean", "0.7",
+                         "--difference-ratio", "10:20:70"],
+                        dict(len_mean=3000.0, len_sd=1500.0, accuracy_mean=0.7, accuracy_mean_set=True,
+                             ratio=(10, 20, 70))),
     "qs_rsii_fixedlen": ("qshmm", "QSHMM-RSII.model", G_PLAIN, 3, 21,
                          ["--length-mean", "500", "--length-sd", "0", "--accuracy-mean", "0.9",
                           "--length-min", "50", "--length-max", "5000"],

@@ -31,6 +31,8 @@ struct EmitParams {
 };
 
 struct EmitArgs {
+  PhiloxKeys keys;             // PHILOX mode: pass 2 re-derives the 4-way choice of substitutions on non-ACGT bases
+  uint32_t philox;
   DeviceGenome G;
   Batch B;
   EmitParams P;
@@ -125,7 +127,8 @@ __global__ void k_sizes(Batch B, EmitParams P, uint32_t n_sub, uint64_t *reads_s
   reads_size[s] = L.reads_size;
   maf_size[s] = L.maf_size;
   const uint32_t ne = B.nent[s];
-  ntiles[s] = ne == 0 ? 1u : (ne + PB_TILE - 1u) / PB_TILE;
+  if ((B.plan_meta[r] >> 11) & 1u) ntiles[s] = ne == 0 ? 1u : ne;  // segmented: nent holds the tile count
+  else ntiles[s] = ne == 0 ? 1u : (ne + PB_TILE - 1u) / PB_TILE;
 }
 
 __device__ __forceinline__ uint8_t *put_dec(uint8_t *p, uint64_t v, uint32_t nd) {
@@ -425,7 +428,7 @@ template <int METHOD>
 __device__ __noinline__ void emit_tile_generic(const uint8_t *evbase, uint32_t e0, uint32_t e1, const RefFetch &rf,
                                                uint32_t minus, uint32_t ncol, uint32_t C0, uint32_t R0, uint32_t P0,
                                                uint8_t *seq, uint8_t *qual, uint8_t *mref, uint8_t *mread,
-                                               uint32_t lane) {
+                                               uint32_t lane, const PhiloxKeys *keys, uint32_t read_id, uint32_t pass) {
   const uint32_t lt_mask = (1u << lane) - 1u;
   for (uint32_t i = e0; i < e1; i += 32u) {
     const uint32_t e = i + lane;
@@ -467,6 +470,13 @@ __device__ __noinline__ void emit_tile_generic(const uint8_t *evbase, uint32_t e
       uint32_t wc;
       bool acgt;
       rf.get(Rr, gch, wch, wc, acgt);
+      if (keys != nullptr && kind == PB_KIND_SUB && !acgt) {
+        // PHILOX mode: choice4 of this position = bits 12-13 of word 0 of its block (qshmm: position = read
+        // position, errhmm: alignment column)
+        uint32_t w[4];
+        philox_block_keys(*keys, METHOD == PBSIM_METHOD_QSHMM ? Pp : Cc, pass << 16, read_id, 1u, w);
+        info = (w[0] >> 12) & 3u;
+      }
       const uint8_t rb = read_base(kind, info, wch, wc, acgt);
       seq[Pp] = rb;
       qual[Pp] = (METHOD == PBSIM_METHOD_QSHMM) ? (uint8_t)(qv + 33u) : (uint8_t)'!';
@@ -517,19 +527,24 @@ __global__ void __launch_bounds__(kEmitThreads) k_emit(EmitArgs A) {
     uint8_t *mf = A.out_maf + A.maf_off[s];
     if (tile == 0 && lane == 0) write_headers(A.P, L, rd, mf, read_id, pass, offset, wlen, rlen, ncol, minus);
     if (nent == 0) continue;
-    const uint32_t e0 = tile * PB_TILE;
-    const uint32_t e1 = min(nent, e0 + PB_TILE);
     const Ckpt *ckp = A.ck + A.B.ck_off[s];
     const Ckpt c0 = ckp[tile];
+    // sequential pass 1: one contiguous stream, tile = entries [1024 t, 1024 (t+1)); segment-parallel pass 1:
+    // tile t lives in its own slot (stride PB_SEG_STRIDE) and its entry count is in the checkpoint
+    const bool segmented = (A.B.plan_meta[r] >> 11) & 1u;
+    const uint32_t e0 = segmented ? 0u : tile * PB_TILE;
+    const uint32_t e1 = segmented ? c0.pad : min(nent, e0 + PB_TILE);
+    const bool has_next = segmented ? (tile + 1u < nent) : (e1 < nent);
     // reference range this tile can touch: [R0, Rend] (an insertion at the tile's end looks at Rend)
-    const uint32_t Rnext = (e1 < nent) ? ckp[tile + 1].ref : wlen;
+    const uint32_t Rnext = has_next ? ckp[tile + 1].ref : wlen;
     const uint32_t Rend = min(Rnext, wlen - 1u);
     const uint32_t g0 = minus ? offset + wlen - 1u - Rend : offset + c0.ref;
     const uint32_t g1 = minus ? offset + wlen - 1u - c0.ref : offset + Rend;
     const bool slow = range_exceptional(A.G.xm, g0, g1);
     uint8_t *seq = rd + L.seq_rel, *qual = rd + L.qual_rel;
     uint8_t *mref = mf + L.refrow_rel, *mread = mf + L.readrow_rel;
-    const uint8_t *evbase = A.ev + A.B.ev_off[s] * (METHOD == PBSIM_METHOD_QSHMM ? 2ull : 1ull);
+    const uint8_t *evbase = A.ev + (A.B.ev_off[s] + (segmented ? (uint64_t)tile * PB_SEG_STRIDE : 0ull)) *
+                                       (METHOD == PBSIM_METHOD_QSHMM ? 2ull : 1ull);
     if (!slow) {
       emit_tile_fast<METHOD>(evbase, e0, e1, A.G.pk, offset, wlen, minus, ncol, c0.col, c0.ref, c0.read, seq, qual, mref,
                              mread, lane);
@@ -541,12 +556,13 @@ __global__ void __launch_bounds__(kEmitThreads) k_emit(EmitArgs A) {
       rf.wlen = wlen;
       rf.minus = minus;
       rf.slow = true;
-      emit_tile_generic<METHOD>(evbase, e0, e1, rf, minus, ncol, c0.col, c0.ref, c0.read, seq, qual, mref, mread, lane);
+      emit_tile_generic<METHOD>(evbase, e0, e1, rf, minus, ncol, c0.col, c0.ref, c0.read, seq, qual, mref, mread, lane,
+                                A.philox ? &A.keys : nullptr, (uint32_t)read_id, pass);
     }
     if (A.P.sam) {
       // ip:B:C / pw:B:C arrays: ",9" per read base of this tile (:2324-2331)
       const uint32_t p0 = c0.read;
-      const uint32_t p1 = (e1 < nent) ? ckp[tile + 1].read : rlen;
+      const uint32_t p1 = has_next ? ckp[tile + 1].read : rlen;
       uint8_t *ip = rd + L.ip_rel, *pw = rd + L.pw_rel;
       for (uint32_t j = 2u * p0 + lane; j < 2u * p1; j += 32u) {
         const uint8_t ch = (j & 1u) ? (uint8_t)'9' : (uint8_t)',';

@@ -26,6 +26,7 @@
 #include "emit.cuh"
 #include "k0_genome.cuh"
 #include "model_image.hpp"
+#include "seg_kernels.cuh"
 #include "sim_kernels.cuh"
 
 namespace {
@@ -104,6 +105,11 @@ __global__ void k_batch_totals(const unsigned long long *prefix, const uint32_t 
   }
   const uint64_t n_sub = (uint64_t)min((unsigned long long)n_reads, cut + 1) * pass_num;
   if (i < n_sub && flags[i]) atomicOr(reinterpret_cast<unsigned int *>(&ctrl[2]), flags[i]);
+}
+
+__global__ void k_iota_u32(uint32_t *p, uint32_t n) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = i;
 }
 
 __global__ void k_fill_u32(uint32_t *p, uint32_t n, uint32_t v) {
@@ -185,6 +191,10 @@ struct pbsim_engine {
   DevBuf d_ctrl;       // control words
   DevBuf d_cub_tmp;
   DevBuf d_ev, d_ck;
+  DevBuf d_seg, d_seg_bins;       // segment-parallel pass 1: segment lists / results, CTA map
+  int seg_enabled = 1;            // option "segments"
+  int64_t seg_min_len = 4096;     // option "seg_min_len": shorter reads stay on the sequential path
+  int64_t seg_batches = 0, seg_fallback_batches = 0;
   DevBuf d_out_reads, d_out_maf;
   PinnedBuf h_ctrl, h_acc;
   // host delivery: the records of a batch stay in HBM and are handed out in pieces through two
@@ -339,8 +349,8 @@ int carve_batch(pbsim_engine *e, uint32_t n_reads) {
   const uint64_t n_sub = (uint64_t)n_reads * pass;
   if (n_sub > 0x7FFFFFFFull) return fail(e, PBSIM_E_INVALID, "batch too large");
   CK(e->b_read_u32.ensure((size_t)n_reads * 4 * 4 + 64));
-  CK(e->b_sub_u32.ensure((size_t)n_sub * 15 * 4 + 64));
-  CK(e->b_sub_u64.ensure((size_t)(n_sub + 1) * 10 * 8 + 64));
+  CK(e->b_sub_u32.ensure((size_t)n_sub * 16 * 4 + 64));
+  CK(e->b_sub_u64.ensure((size_t)(n_sub + 1) * 11 * 8 + 64));
   CK(e->b_sub_f64.ensure((size_t)n_sub * 8 + 64));
   Batch &B = e->B;
   B.n_reads = n_reads;
@@ -352,7 +362,7 @@ int carve_batch(pbsim_engine *e, uint32_t n_reads) {
   B.plan_meta = r32 + 3ull * n_reads;
   uint32_t *s32 = e->b_sub_u32.as<uint32_t>();
   uint32_t **fields[] = {&B.key_in, &B.key_out, &B.idx_in, &B.order, &B.cap, &B.ck_cap, &B.nent, &B.rlen,
-                         &B.ncol, &B.nsub, &B.nins, &B.ndel, &B.flags, &B.draws_used};
+                         &B.ncol, &B.nsub, &B.nins, &B.ndel, &B.flags, &B.draws_used, &B.nseg};
   for (size_t i = 0; i < sizeof(fields) / sizeof(fields[0]); ++i) *fields[i] = s32 + i * n_sub;
   uint64_t *s64 = e->b_sub_u64.as<uint64_t>();
   B.ev_off = s64;
@@ -362,7 +372,7 @@ int carve_batch(pbsim_engine *e, uint32_t n_reads) {
 }
 
 // slices of b_sub_u64 (each n_sub + 1 long): 0 ev_off, 1 ck_off, 2 tmp widen, 3 rlen0 prefix,
-// 4 reads_size, 5 maf_size, 6 ntiles, 7 reads_off, 8 maf_off, 9 tile_start
+// 4 reads_size, 5 maf_size, 6 ntiles, 7 reads_off, 8 maf_off, 9 tile_start, 10 seg_off
 inline uint64_t *u64_slice(pbsim_engine *e, int k) { return e->b_sub_u64.as<uint64_t>() + (size_t)k * (e->B.n_sub + 1); }
 
 int excl_scan(pbsim_engine *e, const unsigned long long *in, unsigned long long *out, uint32_t n) {
@@ -422,10 +432,12 @@ int run_batch(pbsim_engine *e, uint32_t n_reads, int64_t clip_room, bool to_host
     rng.starts = e->d_starts.as<int64_t>();
   }
 
+  bool use_segments = qs && !replay && e->seg_enabled && clip_room < 0;
   for (int attempt = 0; attempt < 6; ++attempt) {
     // ---- K1 plan
     const uint32_t ev_align = qs ? 8u : 16u;
-    k_plan<<<nblk(n_reads, 256), 256, 0, e->st>>>(M, G, rng, B, clip_room, e->cap_num, e->cap_den, ev_align);
+    k_plan<<<nblk(n_reads, 256), 256, 0, e->st>>>(M, G, rng, B, clip_room, e->cap_num, e->cap_den, ev_align,
+                                                   use_segments ? (uint32_t)e->seg_min_len : 0u);
     e->launches++;
     // ---- sort by (accuracy, length desc)
     {
@@ -456,10 +468,20 @@ int run_batch(pbsim_engine *e, uint32_t n_reads, int64_t clip_room, bool to_host
     k_widen<<<nblk(n_sub + 1, 256), 256, 0, e->st>>>(B.ck_cap, n_sub, tmp64);
     if ((rc = excl_scan(e, tmp64, reinterpret_cast<unsigned long long *>(B.ck_off), n_sub + 1))) return rc;
     e->launches += 2;
+    unsigned long long *seg_off = reinterpret_cast<unsigned long long *>(u64_slice(e, 10));
+    hctrl[2] = 0;
+    if (use_segments) {
+      k_widen<<<nblk(n_sub + 1, 256), 256, 0, e->st>>>(B.nseg, n_sub, tmp64);
+      if ((rc = excl_scan(e, tmp64, seg_off, n_sub + 1))) return rc;
+      e->launches++;
+      CK(cudaMemcpyAsync(hctrl + 2, seg_off + n_sub, 8, cudaMemcpyDeviceToHost, e->st));
+    }
     CK(cudaMemcpyAsync(hctrl, B.ev_off + n_sub, 8, cudaMemcpyDeviceToHost, e->st));
     CK(cudaMemcpyAsync(hctrl + 1, B.ck_off + n_sub, 8, cudaMemcpyDeviceToHost, e->st));
     CK(cudaStreamSynchronize(e->st));
     const uint64_t ev_entries = hctrl[0], ck_entries = hctrl[1];
+    const uint64_t n_seg_total = use_segments ? hctrl[2] : 0;
+    if (n_seg_total > 0x7FFFFFF0ull) return fail(e, PBSIM_E_INVALID, "too many segments in one batch");
     CK(e->d_ev.ensure((size_t)ev_entries * (qs ? 2 : 1) + 256));
     CK(e->d_ck.ensure((size_t)ck_entries * sizeof(Ckpt) + 256));
 
@@ -487,6 +509,58 @@ int run_batch(pbsim_engine *e, uint32_t n_reads, int64_t clip_room, bool to_host
       else k_sim_errhmm<PBSIM_RNG_PHILOX><<<grid, kSimThreads, smem, e->st>>>(A, e->er_smem_bar_off);
     }
     e->launches++;
+    if (n_seg_total > 0) {
+      // ---- segment-parallel pass 1 for the long reads (seg_kernels.cuh)
+      const uint32_t nseg = (uint32_t)n_seg_total;
+      const uint32_t seg_slots = nblk(nseg, kSimThreads) + kBins;
+      CK(e->d_seg.ensure((size_t)nseg * (5 * 4 + sizeof(SegResult)) + 256));
+      CK(e->d_seg_bins.ensure((4 * kBins + 8) * 4 + (size_t)seg_slots * 4 + 64));
+      SegBatch S;
+      S.n_seg_total = nseg;
+      S.seg_off = (const uint64_t *)seg_off;
+      S.seg_res = e->d_seg.as<SegResult>();
+      uint32_t *u = reinterpret_cast<uint32_t *>(S.seg_res + nseg);
+      S.seg_sub = u;
+      S.seg_key_in = u + nseg;
+      S.seg_key_out = u + 2ull * nseg;
+      S.seg_id_in = u + 3ull * nseg;
+      S.seg_order = u + 4ull * nseg;
+      uint32_t *sb_start = e->d_seg_bins.as<uint32_t>();
+      uint32_t *sb_lo = sb_start + kBins + 1, *sb_hi = sb_lo + kBins, *sb_first = sb_hi + kBins, *sb_order = sb_first + kBins + 1;
+      k_seg_fill<<<nblk(n_sub, 256), 256, 0, e->st>>>(B, S, pass);
+      {
+        size_t tmp = 0;
+        CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, S.seg_key_in, S.seg_key_out, S.seg_id_in, S.seg_order, (int)nseg, 21,
+                                           28, e->st));
+        CK(e->d_cub_tmp.ensure(tmp + 256));
+        tmp = e->d_cub_tmp.cap;
+        CK(cub::DeviceRadixSort::SortPairs(e->d_cub_tmp.p, tmp, S.seg_key_in, S.seg_key_out, S.seg_id_in, S.seg_order,
+                                           (int)nseg, 21, 28, e->st));
+      }
+      k_fill_u32<<<1, 256, 0, e->st>>>(sb_start, kBins + 1, 0xFFFFFFFFu);
+      k_bin_bounds<<<nblk(nseg, 256), 256, 0, e->st>>>(S.seg_key_out, nseg, sb_start);
+      k_cta_map<<<1, 32, 0, e->st>>>(sb_start, S.seg_key_out, nseg, sb_lo, sb_hi, sb_first);
+      k_iota_u32<<<nblk(seg_slots, 256), 256, 0, e->st>>>(sb_order, seg_slots);
+      SegArgs SA;
+      SA.keys = A.keys;
+      SA.M = M;
+      SA.B = B;
+      SA.S = S;
+      SA.cta_order = sb_order;
+      SA.cta_first = sb_first;
+      SA.bin_lo = sb_lo;
+      SA.bin_hi = sb_hi;
+      SA.ev = e->d_ev.as<uint8_t>();
+      SA.max_window = getenv("PBSIM_EXPERIMENT_NOCOUPLE") ? 0u : 4096u;  // timing experiment only: wrong states
+      k_sim_seg<<<seg_slots, kSimThreads, kQsSmemBytes, e->st>>>(SA);
+      k_find_end<<<nblk(n_sub, 128), 128, 0, e->st>>>(B, S, G, e->d_biasone.as<uint8_t>(), pass, e->d_ev.as<uint8_t>(),
+                                                     e->d_ck.as<Ckpt>(), e->d_qc_prob.as<double>());
+      k_find_end_repair<<<nblk((uint64_t)n_sub * 32, 128), 128, 0, e->st>>>(B, S, G, e->d_biasone.as<uint8_t>(), pass,
+                                                                         e->d_ev.as<uint8_t>(), e->d_ck.as<Ckpt>(),
+                                                                         e->d_qc_prob.as<double>());
+      e->launches += 8;
+      e->seg_batches++;
+    }
     CK(cudaEventRecord(e->ev_k[1], e->st));
     CK(cudaGetLastError());
 
@@ -517,6 +591,18 @@ int run_batch(pbsim_engine *e, uint32_t n_reads, int64_t clip_room, bool to_host
       float ms = 0;
       CK(cudaEventElapsedTime(&ms, e->ev_k[0], e->ev_k[1]));
       e->sim_ms += ms;
+    }
+    if (getenv("PBSIM_DEBUG")) {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, e->ev_k[0], e->ev_k[1]);
+      fprintf(stderr, "[pbsim] batch reads=%u sub=%u segments=%llu flags=%u pass1_ms=%.2f attempt=%d\n", n_reads, n_sub,
+              (unsigned long long)n_seg_total, flags, ms, attempt);
+    }
+    if (flags & 4u) {  // a segmented read could not be completed: redo the batch on the sequential path
+      use_segments = false;
+      e->seg_fallback_batches++;
+      if (attempt == 5) return fail(e, PBSIM_E_OVERFLOW, "segment-parallel pass 1 failed repeatedly");
+      continue;
     }
     if (flags & 1u) {  // a read outgrew its slot: enlarge and redo the batch
       e->cap_num *= 2;
@@ -583,6 +669,8 @@ int run_batch(pbsim_engine *e, uint32_t n_reads, int64_t clip_room, bool to_host
   EA.tile_start = (const uint64_t *)tile_start;
   EA.reads_off = (const uint64_t *)reads_off;
   EA.maf_off = (const uint64_t *)maf_off;
+  EA.keys.init(e->run.seed, (uint32_t)e->seq_num);
+  EA.philox = replay ? 0u : 1u;
   EA.out_reads = e->d_out_reads.as<uint8_t>();
   EA.out_maf = e->d_out_maf.as<uint8_t>();
   {
@@ -798,7 +886,8 @@ void pbsim_cuda_destroy(pbsim_engine *e) {
   DevBuf *bufs[] = {&e->d_blob, &e->d_acc, &e->d_prob2len, &e->d_prob2acc, &e->d_qs_thr, &e->d_qs_thr_hp, &e->d_qc_prob,
                     &e->d_er_bias, &e->d_ascii, &e->d_pk, &e->d_hp4, &e->d_xm, &e->d_hpfreq, &e->d_biasone, &e->d_flag,
                     &e->d_draws, &e->d_starts, &e->b_read_u32, &e->b_sub_u32, &e->b_sub_u64, &e->b_sub_f64, &e->d_bins,
-                    &e->d_ctrl, &e->d_cub_tmp, &e->d_ev, &e->d_ck, &e->d_out_reads, &e->d_out_maf, &e->d_stats};
+                    &e->d_ctrl, &e->d_cub_tmp, &e->d_ev, &e->d_ck, &e->d_out_reads, &e->d_out_maf, &e->d_stats, &e->d_seg,
+                    &e->d_seg_bins};
   for (DevBuf *b : bufs) b->release();
   for (auto &a : e->h_stage)
     for (auto &b : a) b.release();
@@ -1034,6 +1123,15 @@ int pbsim_cuda_set_option(pbsim_engine *e, const char *name, int64_t value) {
     e->stage_bytes = (size_t)value;
     for (auto &a : e->h_stage)
       for (auto &b : a) b.release();
+    return 0;
+  }
+  if (!strcmp(name, "segments")) {
+    e->seg_enabled = value != 0;
+    return 0;
+  }
+  if (!strcmp(name, "seg_min_len")) {
+    if (value < (int64_t)PB_TILE) return fail(e, PBSIM_E_INVALID, "seg_min_len must be at least %u", PB_TILE);
+    e->seg_min_len = value;
     return 0;
   }
   if (!strcmp(name, "target_batch_bases")) {

@@ -28,6 +28,8 @@ struct AccEntry {          // one per accuracy 0..100, mirrored on the device
   uint32_t table_acc;      // errhmm: accuracy whose tables drive the chain
   uint32_t seg_ok;         // qshmm: chain couples fast enough for the segment-parallel pass 1
   uint64_t reach;          // qshmm: states reachable from init2state (bit s)
+  float rho;               // qshmm: estimated read positions per reference base (segment provisioning)
+  uint32_t pad2;
 };
 
 // blob layouts (all sections 16-byte aligned)
@@ -54,13 +56,15 @@ inline uint32_t er_blob_bytes(uint32_t nst, uint32_t *t2_off, uint32_t *emis_off
 
 // Does the chain of this accuracy forget its past quickly?  32 trials of the grand coupling (all reachable
 // states driven by the same uniform draws): segment-parallel pass 1 is enabled when every trial coalesces
-// within 512 steps.  Only a performance switch: results are identical on either path.
+// within 2048 steps and the median is below 512.  Only a performance switch: results are identical either way
+// (the backward search itself never fails, it just gets longer).
 inline bool coupling_screen(const pbsim_hmm_row &r, uint64_t reach) {
   uint64_t x = 0x9E3779B97F4A7C15ull;
+  int below = 0;
   for (int trial = 0; trial < 32; ++trial) {
     uint64_t mask = reach;
     int t = 0;
-    for (; t < 512 && (mask & (mask - 1)); ++t) {
+    for (; t < 2048 && (mask & (mask - 1)); ++t) {
       x ^= x << 13; x ^= x >> 7; x ^= x << 17;  // xorshift64
       const uint32_t u = (uint32_t)(x >> 32);
       uint64_t next = 0;
@@ -73,8 +77,35 @@ inline bool coupling_screen(const pbsim_hmm_row &r, uint64_t reach) {
       mask = next;
     }
     if (mask & (mask - 1)) return false;
+    if (t < 512) ++below;
   }
-  return true;
+  return below >= 16;
+}
+
+// Estimated read positions per consumed reference base for one accuracy (Monte Carlo over the quantised
+// tables, 1<<15 positions): only used to provision segments, never affects results.
+inline float estimate_rho(const pbsim_model &m, const pbsim_hmm_row &r) {
+  uint64_t x = 0xD1B54A32D192ED03ull;
+  auto u32 = [&]() { x ^= x << 13; x ^= x >> 7; x ^= x << 17; return (uint32_t)(x >> 32); };
+  auto pick = [&](uint32_t mod) { return (uint32_t)(((uint64_t)u32() * (mod < 1 ? 1 : mod)) >> 32); };
+  uint64_t ref = 0;
+  const int N = 1 << 15;
+  int state = 0;
+  for (int p = 0; p < N; ++p) {
+    int qv;
+    if (r.exists) {
+      state = (p == 0 || state < 1 || state > r.nstates) ? r.init[pick(r.init_mod)] : r.tran[state * 100 + pick(r.tran_mod[state])];
+      if (state < 1 || state > r.nstates) state = r.init[pick(r.init_mod)];
+      qv = r.emis[state * 100 + pick(r.emis_mod[state])];
+    } else {
+      qv = r.freq[pick(r.freq_mod)];
+    }
+    const uint32_t e = pick(1000000);
+    if (!(e >= (uint32_t)m.sub_thre[qv] && e < (uint32_t)m.ins_thre[qv])) ++ref;  // not an insertion
+    int guard = 0;
+    while (pick(1000000) < (uint32_t)m.del_thre[qv] && ++guard < 64) ++ref;
+  }
+  return ref ? (float)((double)N / (double)ref) : 1.0f;
 }
 
 struct ModelImage {
@@ -148,6 +179,7 @@ struct ModelImage {
           }
           e.reach = reach;
           e.seg_ok = coupling_screen(r, reach) ? 1u : 0u;
+          e.rho = estimate_rho(m, r);
           e.blob_bytes = QsBlobLayout::bytes;
           e.has_model = 1;
           e.nstates = (uint32_t)r.nstates;
@@ -162,6 +194,7 @@ struct ModelImage {
           std::memcpy(blob.data() + e.blob_off, r.freq, (size_t)r.freq_mod);
           e.blob_bytes = QsBlobLayout::freq_bytes;
           e.seg_ok = 1;  // no chain at all: positions are independent
+          e.rho = estimate_rho(m, r);
           e.has_model = 0;
           e.freq_mod = (uint32_t)r.freq_mod;
           e.valid = 1;

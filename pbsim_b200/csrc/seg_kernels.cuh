@@ -1,0 +1,269 @@
+// Segment-parallel pass 1 for qshmm (PHILOX mode).  See sim_core.cuh "qshmm SEGMENT-PARALLEL pass 1".
+//
+// Long reads are cut into segments of PB_TILE read positions; one GPU thread simulates ONE SEGMENT, so every
+// thread of the grid does the same amount of work whatever the read lengths are (1 kb or 1 Mb), which removes
+// the sequential critical path a whole-read-per-thread schedule has.  The chain state entering a segment is
+// recovered exactly by backward coupling over that segment's predecessors' position-addressed draws.
+//   k_seg_fill   : (sub-read, k) list of all segments of the batch + accuracy sort key
+//   k_sim_seg    : one thread per segment: coupling + PB_TILE positions -> entries in the segment's slot
+//   k_find_end   : one thread per segmented sub-read: prefix over its segments, clip at the window end,
+//                  tile checkpoints, totals
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "sim_kernels.cuh"
+
+namespace pb {
+
+struct SegBatch {
+  uint32_t n_seg_total;
+  const uint64_t *seg_off;   // [n_sub + 1] exclusive scan of segments per sub-read (0 for sequential sub-reads)
+  uint32_t *seg_sub;         // [n_seg_total] sub-read of a segment
+  uint32_t *seg_key_in;      // [n_seg_total] accuracy << 21 (same bin arithmetic as the sequential schedule)
+  uint32_t *seg_key_out;
+  uint32_t *seg_id_in;
+  uint32_t *seg_order;       // segments sorted by accuracy
+  SegResult *seg_res;        // [n_seg_total] indexed by segment id
+};
+
+// thread per sub-read: write its segments' descriptors
+__global__ void k_seg_fill(Batch B, SegBatch S, uint32_t pass_num) {
+  const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= B.n_sub) return;
+  const uint64_t lo = S.seg_off[s], hi = S.seg_off[s + 1];
+  if (hi == lo) return;
+  const uint32_t acc = B.plan_meta[s / pass_num] & 0xFFu;
+  for (uint64_t i = lo; i < hi; ++i) {
+    S.seg_sub[i] = s;
+    S.seg_key_in[i] = acc << 21;
+    S.seg_id_in[i] = (uint32_t)i;
+  }
+}
+
+struct SegArgs {
+  PhiloxKeys keys;
+  DeviceModel M;
+  Batch B;
+  SegBatch S;
+  const uint32_t *cta_order, *cta_first, *bin_lo, *bin_hi;
+  uint8_t *ev;
+  uint32_t max_window;
+};
+
+// shared memory: [table blob | thr 94*16 | qc_prob 94*8 | mbarrier]  (same layout as k_sim_qshmm)
+__global__ void __launch_bounds__(kSimThreads) k_sim_seg(SegArgs A) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint32_t acc, lo, hi;
+  if (!cta_assignment(A.cta_order, A.cta_first, A.bin_lo, A.bin_hi, &acc, &lo, &hi)) return;
+  const AccEntry ae = A.M.acc[acc];
+  uint64_t *bar = reinterpret_cast<uint64_t *>(smem + kQsSmemBar);
+  if (threadIdx.x == 0) mbar_init(bar, 1);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(bar, ae.blob_bytes + PBSIM_NQV * 16 + PBSIM_NQV * 8);
+    tma_bulk_g2s(smem, A.M.blob + ae.blob_off, ae.blob_bytes, bar);
+    tma_bulk_g2s(smem + kQsSmemThr, A.M.qs_thr, PBSIM_NQV * 16, bar);
+    tma_bulk_g2s(smem + kQsSmemProb, A.M.qc_prob, PBSIM_NQV * 8, bar);
+  }
+  mbar_wait(bar, 0);
+  const uint32_t i = lo + threadIdx.x;
+  if (i >= hi) return;
+  const uint32_t seg = A.S.seg_order[i];
+  const uint32_t s = A.S.seg_sub[seg];
+  const uint32_t k = seg - (uint32_t)A.S.seg_off[s];
+  const uint32_t r = s / A.M.pass_num, pass = s % A.M.pass_num;
+  const uint32_t read_id = (uint32_t)(A.B.first_read + 1u + r);
+  QsView T;
+  T.t2 = reinterpret_cast<const uint32_t *>(smem + QsBlobLayout::t2_off);
+  T.emis = smem + QsBlobLayout::emis_off;
+  T.freq = smem;
+  T.has_model = ae.has_model;
+  T.init_mod = ae.init_mod;
+  T.freq_mod = ae.freq_mod;
+  T.thr = reinterpret_cast<const QsThr *>(smem + kQsSmemThr);
+  T.thr_hp = A.M.qs_thr_hp;
+  T.qc_prob = reinterpret_cast<const double *>(smem + kQsSmemProb);
+  QsSegAux X;
+  X.tmod = smem + QsBlobLayout::tmod_off;
+  X.emodv = smem + QsBlobLayout::emodv_off;
+  X.reach = ae.reach;
+  uint32_t row = 0, mod = ae.init_mod, emod = 1;
+  SegResult res;
+  res.n_entries = 0; res.ref_adv = 0; res.nsub = 0; res.ndel = 0; res.flags = 0; res.prob = 0.0;
+  bool ok = true;
+  if (k > 0 && ae.has_model && A.max_window != 0u) ok = qshmm_segment_start(T, X, A.keys, read_id, pass, k * PB_TILE, 64u, row, mod, emod);
+  // the coupling loops leave the lanes of a warp at different points; without an explicit reconvergence the
+  // compiler keeps them apart for the whole segment loop (ncu: 13.7 of 32 threads active per instruction)
+  __syncwarp();
+  if (!ok) {
+    res.flags = 2u;
+  } else {
+    uint16_t *ev = reinterpret_cast<uint16_t *>(A.ev) + A.B.ev_off[s] + (uint64_t)k * PB_SEG_STRIDE;
+    qshmm_simulate_segment(T, A.keys, read_id, pass, k * PB_TILE, k == 0, row, mod, emod, ev, res);
+  }
+  A.S.seg_res[seg] = res;
+}
+
+// thread per sub-read (segmented ones only do work)
+__global__ void k_find_end(Batch B, SegBatch S, DeviceGenome G, const uint8_t *bias_one, uint32_t pass_num, uint8_t *ev,
+                           Ckpt *ck, const double *qc_prob) {
+  const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= B.n_sub) return;
+  const uint64_t lo = S.seg_off[s], hi = S.seg_off[s + 1];
+  if (hi == lo) return;
+  const uint32_t r = s / pass_num;
+  const uint32_t meta = B.plan_meta[r];
+  if ((meta >> 9) & 1u) return;   // reads that may need deletion-run repairs: k_find_end_repair (one warp each)
+  HpProbe hp;
+  hp.enabled = 0u;
+  hp.win.ascii = G.ascii;
+  hp.win.hp4 = G.hp4;
+  hp.win.offset = B.plan_off[r];
+  hp.win.wlen = B.plan_wlen[r];
+  hp.win.minus = (meta >> 8) & 1u;
+  hp.xm = G.xm;
+  hp.bias_one = bias_one;
+  SegRead out;
+  qshmm_finish_segmented(reinterpret_cast<uint16_t *>(ev) + B.ev_off[s], S.seg_res + lo, (uint32_t)(hi - lo), B.plan_wlen[r],
+                         qc_prob, hp, ck + B.ck_off[s], out);
+  B.nent[s] = out.n_tiles;  // segmented sub-reads: number of tiles (entries per tile live in the checkpoints)
+  B.rlen[s] = out.rlen;
+  B.ncol[s] = out.ncol;
+  B.nsub[s] = out.nsub;
+  B.nins[s] = out.nins;
+  B.ndel[s] = out.ndel;
+  B.flags[s] = out.flags ? (4u | (out.flags << 8)) : 0u;  // any problem: the engine redoes the batch sequentially
+  B.draws_used[s] = 0;
+  B.accuracy[s] = out.accuracy;
+}
+
+// One WARP per segmented sub-read whose window touches an exceptional block.  Same result as
+// qshmm_finish_segmented with the probe enabled, but the exact walk over ALL entries of the read is done 32
+// entries at a time: a warp scan gives every entry its reference offset; only groups in which the window ends or
+// a deletion run meets a flagged block are walked sequentially (by lane 0, with qshmm_walk_tile).
+__global__ void __launch_bounds__(128) k_find_end_repair(Batch B, SegBatch S, DeviceGenome G, const uint8_t *bias_one,
+                                                         uint32_t pass_num, uint8_t *ev, Ckpt *ck, const double *qc_prob) {
+  const uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t lane = threadIdx.x & 31u;
+  if (s >= B.n_sub) return;
+  const uint64_t lo = S.seg_off[s], hi = S.seg_off[s + 1];
+  if (hi == lo) return;
+  const uint32_t r = s / pass_num;
+  const uint32_t meta = B.plan_meta[r];
+  if (((meta >> 9) & 1u) == 0u) return;
+  const uint32_t wlen = B.plan_wlen[r];
+  HpProbe hp;
+  hp.enabled = 1u;
+  hp.win.ascii = G.ascii;
+  hp.win.hp4 = G.hp4;
+  hp.win.offset = B.plan_off[r];
+  hp.win.wlen = wlen;
+  hp.win.minus = (meta >> 8) & 1u;
+  hp.xm = G.xm;
+  hp.bias_one = bias_one;
+  uint16_t *ev_base = reinterpret_cast<uint16_t *>(ev) + B.ev_off[s];
+  const SegResult *seg = S.seg_res + lo;
+  Ckpt *ckp = ck + B.ck_off[s];
+  const uint32_t n_seg = (uint32_t)(hi - lo);
+  uint32_t R = 0, P = 0, D = 0, nsub = 0, flags = 0, n_tiles = 0;
+  double prob = 0.0;
+  bool done = false;
+  for (uint32_t k = 0; k < n_seg && !done; ++k) {
+    flags |= seg[k].flags;
+    if (k >= 1u && R == 0u) flags |= 8u;
+    uint16_t *e = ev_base + (uint64_t)k * PB_SEG_STRIDE;
+    const uint32_t n = seg[k].n_entries;
+    const uint32_t R_tile = R, P_tile = P, D_tile = D;
+    uint32_t n_incl = n, blocked = 0;
+    bool ended = false;
+    for (uint32_t i = 0; i < n && !ended; i += 32u) {
+      const uint32_t idx = i + lane;
+      const bool valid = idx < n;
+      const uint32_t v = valid ? (uint32_t)e[idx] : (uint32_t)PB_QS_PAD;
+      const uint32_t kind = (v >> 7) & 3u;
+      const bool cont = kind == 3u;
+      const uint32_t part = cont ? ((v & 0x7Fu) | ((v >> 9) << 7)) : (v >> 12);
+      const uint32_t a = (!cont && kind != PB_KIND_INS) ? 1u : 0u;
+      uint32_t x = a + part;  // inclusive scan of reference advances
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o);
+        if (lane >= (uint32_t)o) x += y;
+      }
+      const uint32_t total = __shfl_sync(0xFFFFFFFFu, x, 31);
+      const uint32_t Rb = R + x - (a + part);  // reference offset in front of this entry
+      // does any deletion of this entry follow a base of a flagged block?  (window indices Rb+a-1 .. Rb+a+part-2)
+      bool touch = false;
+      if (part != 0u) {
+        const uint32_t w0 = Rb + a, w1 = Rb + a + part - 1u;  // bases whose predecessor matters: w0-1 .. w1-1
+        const uint32_t lo_w = w0 == 0u ? 0u : w0 - 1u, hi_w = min(w1 == 0u ? 0u : w1 - 1u, wlen - 1u);
+        const uint32_t g0 = hp.win.minus ? hp.win.gidx(hi_w) : hp.win.gidx(lo_w);
+        const uint32_t g1 = hp.win.minus ? hp.win.gidx(lo_w) : hp.win.gidx(hi_w);
+        touch = range_exceptional(G.xm, g0, g1);
+      }
+      const bool need = __any_sync(0xFFFFFFFFu, touch) || (R + total >= wlen) || blocked != 0u;
+      if (!need) {
+        const uint32_t mb = __ballot_sync(0xFFFFFFFFu, valid && !cont);
+        const uint32_t ms = __ballot_sync(0xFFFFFFFFu, valid && kind == PB_KIND_SUB);
+        uint32_t dsum = part;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) dsum += __shfl_down_sync(0xFFFFFFFFu, dsum, o);
+        dsum = __shfl_sync(0xFFFFFFFFu, dsum, 0);
+        P += __popc(mb);
+        nsub += __popc(ms);
+        D += dsum;
+        R += total;
+      } else {
+        // exact sequential walk of these (at most 32) entries
+        uint32_t res[6];
+        if (lane == 0) {
+          const TileWalk t = qshmm_walk_tile(e + i, min(32u, n - i), R, wlen, qc_prob, hp, &blocked);
+          res[0] = t.n_entries; res[1] = t.positions; res[2] = t.ref_adv; res[3] = t.nsub; res[4] = t.ndel;
+          res[5] = t.ended | (blocked << 1);
+        }
+#pragma unroll
+        for (int q = 0; q < 6; ++q) res[q] = __shfl_sync(0xFFFFFFFFu, res[q], 0);
+        __syncwarp();
+        P += res[1]; R += res[2]; nsub += res[3]; D += res[4];
+        blocked = res[5] >> 1;
+        if (res[5] & 1u) {
+          ended = true;
+          n_incl = i + res[0];
+        }
+      }
+    }
+    if (lane == 0) {
+      Ckpt c; c.col = P_tile + D_tile; c.ref = R_tile; c.read = P_tile; c.pad = n_incl;
+      ckp[k] = c;
+    }
+    if (ended) {
+      // accuracy sum of the partial tile, in entry order (same order as every other path)
+      double pp = 0.0;
+      if (lane == 0)
+        for (uint32_t i = 0; i < n_incl; ++i) {
+          const uint32_t v = e[i];
+          if (((v >> 7) & 3u) != 3u) pp += qc_prob[v & 0x7Fu];
+        }
+      prob += pp;
+      n_tiles = k + 1u;
+      done = true;
+    } else {
+      prob += seg[k].prob;
+    }
+  }
+  if (!done) flags |= 4u;
+  if (lane == 0) {
+    B.nent[s] = n_tiles;
+    B.rlen[s] = P;
+    B.ncol[s] = P + D;
+    B.nsub[s] = nsub;
+    B.nins[s] = P + D - R;
+    B.ndel[s] = D;
+    B.flags[s] = flags ? (4u | (flags << 8)) : 0u;
+    B.draws_used[s] = 0;
+    B.accuracy[s] = 1.0 - (prob / (double)P);
+  }
+}
+
+}  // namespace pb

@@ -18,6 +18,7 @@
 // The file compiles as plain C++ as well (tests/hostsim builds it with g++ to check the logic
 // against the oracle without a GPU); the product only ever runs it inside CUDA kernels.
 #pragma once
+#include <math.h>
 #include <stdint.h>
 
 #if defined(__CUDACC__)
@@ -536,12 +537,13 @@ struct SegResult {
 
 PB_HD uint32_t qs_state_of_row(uint32_t row) { return (row * 41944u) >> 22; }  // row / 100 for row <= 5100
 
-// state entering position p_start (>= 1): returns false if no coalescence within max_window positions
+// state entering position p_start (>= 1).  The window doubles until all images coalesce; when it reaches
+// position 0 the init draw decides, so the search always ends with the exact state.
 PB_HD bool qshmm_segment_start(const QsView &T, const QsSegAux &A, const PhiloxKeys &K, uint32_t read_id,
-                               uint32_t pass, uint32_t p_start, uint32_t max_window, uint32_t &row, uint32_t &mod,
+                               uint32_t pass, uint32_t p_start, uint32_t first_window, uint32_t &row, uint32_t &mod,
                                uint32_t &emod) {
   const uint32_t c1 = pass << 16;
-  for (uint32_t B = 32u;; B *= 2u) {
+  for (uint32_t B = first_window;; B *= 2u) {
     const bool from_zero = p_start <= B;
     const uint32_t p0 = from_zero ? 0u : p_start - B;
     uint64_t mask = from_zero ? 1ull : A.reach;  // from position 0: the virtual state 0 (row 0 = init2state)
@@ -580,7 +582,6 @@ PB_HD bool qshmm_segment_start(const QsView &T, const QsSegAux &A, const PhiloxK
       row = s_row; mod = s_mod; emod = s_emod;
       return true;
     }
-    if (B >= max_window) return false;
   }
 }
 
@@ -673,44 +674,76 @@ PB_HD void qshmm_simulate_segment(const QsView &T, const PhiloxKeys &K, uint32_t
   res.prob = prob;
 }
 
-// Locate the end of a segmented read: walk the entries of the segment in which the cumulative reference
-// advance reaches wlen, clip the last deletion run, return the totals of the included part of that segment.
-struct SegTail {
+// Reference bases after which no deletion can follow: in the default bias mode hp_del_bias[hp] is 1 for hp 1..10
+// and 0 for the cells the reference reads out of bounds (hp 11, i.e. homopolymers >= 11), so the
+// effect of the homopolymer table on a read is exactly "a deletion run stops in front of such a base".  Segments are
+// simulated without knowing their reference offset; the walk below, which does know it, repairs those runs.
+struct HpProbe {
+  uint32_t enabled;         // 0: the read touches no exceptional block, nothing to repair
+  WindowRef win;
+  const uint32_t *xm;       // 1 bit per 1024-base block holding an exceptional base
+  const uint8_t *bias_one;  // [12] hp_del_bias[h] == 1
+  PB_HD bool suppress(uint32_t r_prev) const {
+    const uint32_t g = win.gidx(r_prev);
+    const uint32_t blk = g >> 10;
+    if (((xm[blk >> 5] >> (blk & 31u)) & 1u) == 0u) return false;
+    return bias_one[win.hp(r_prev)] == 0;
+  }
+};
+
+struct TileWalk {
   uint32_t n_entries, positions, ref_adv, nsub, ndel;
+  uint32_t ended;           // the reference window was used up inside this tile
   double prob;
 };
 
-PB_HD SegTail qshmm_find_end_in_segment(uint16_t *ev, uint32_t n_entries, uint32_t ref_room /* wlen - R before */,
-                                        const double *qc_prob) {
-  SegTail t;
-  t.n_entries = 0; t.positions = 0; t.ref_adv = 0; t.nsub = 0; t.ndel = 0; t.prob = 0.0;
+// Walk the entries of one tile knowing the reference offset it starts at: stop where the window is used up
+// (`while (ref_offset < mut.len)`, :2213 and :2268), clip the last deletion run, and (HpProbe) cut deletion runs
+// in front of suppressing bases.  Entries are rewritten in place; entries after the end are not counted.
+PB_HD TileWalk qshmm_walk_tile(uint16_t *ev, uint32_t n_entries, uint32_t R_start, uint32_t wlen,
+                               const double *qc_prob, const HpProbe &hp, uint32_t *blocked_io = nullptr) {
+  TileWalk t;
+  t.n_entries = 0; t.positions = 0; t.ref_adv = 0; t.nsub = 0; t.ndel = 0; t.ended = 0; t.prob = 0.0;
+  uint32_t R = R_start;
+  // the current deletion run has ended (window end or suppressing base); carried between calls when a tile is
+  // walked in pieces, because continuation entries of that run may follow in the next piece
+  bool blocked = blocked_io ? (*blocked_io != 0u) : false;
   for (uint32_t i = 0; i < n_entries; ++i) {
     const uint32_t v = ev[i];
     const uint32_t kind = (v >> 7) & 3u;
     const bool cont = kind == 3u;
-    uint32_t nd = cont ? ((v & 0x7Fu) | ((v >> 9) << 7)) : (v >> 12);
+    const uint32_t part = cont ? ((v & 0x7Fu) | ((v >> 9) << 7)) : (v >> 12);
     if (!cont) {
-      if (t.ref_adv >= ref_room) break;  // `while (ref_offset < mut.len)` (:2213): no further read position
+      if (R >= wlen) { t.ended = 1; break; }
       t.prob += qc_prob[v & 0x7Fu];
       t.positions += 1u;
       t.nsub += (kind == PB_KIND_SUB) ? 1u : 0u;
-      t.ref_adv += (kind == PB_KIND_INS) ? 0u : 1u;
+      R += (kind == PB_KIND_INS) ? 0u : 1u;
+      blocked = false;
     }
-    const uint32_t room = ref_room - t.ref_adv;
-    if (nd >= room) {  // the deletion loop stops when the window is used up (:2268)
-      nd = room;
-      if (cont) ev[i] = (uint16_t)((nd & 0x7Fu) | (3u << 7) | ((nd >> 7) << 9));
-      else ev[i] = (uint16_t)((v & 0x0FFFu) | (nd << 12));  // room < 15 here or nd was 15 and stays 15
-      t.ndel += nd;
-      t.ref_adv += nd;
-      t.n_entries = i + 1u;
-      if (t.ref_adv >= ref_room) return t;
-      continue;
+    uint32_t take = 0;
+    if (!blocked) {
+      const uint32_t room = wlen - R;
+      uint32_t lim = part < room ? part : room;
+      if (hp.enabled) {
+        for (uint32_t j = 0; j < lim; ++j) {
+          if (R + j != 0u && hp.suppress(R + j - 1u)) { lim = j; break; }
+        }
+      }
+      take = lim;
+      if (take < part) blocked = true;
     }
-    t.ndel += nd;
-    t.ref_adv += nd;
+    if (take != part) {
+      if (cont) ev[i] = (uint16_t)((take & 0x7Fu) | (3u << 7) | ((take >> 7) << 9));
+      else ev[i] = (uint16_t)((v & 0x0FFFu) | (take << 12));
+    }
+    t.ndel += take;
+    R += take;
     t.n_entries = i + 1u;
+    if (R >= wlen) { t.ended = 1; break; }
   }
+  t.ref_adv = R - R_start;
+  if (blocked_io) *blocked_io = blocked ? 1u : 0u;
   return t;
 }
 
@@ -723,13 +756,15 @@ struct SegRead {
   double accuracy;
 };
 
-PB_HD uint32_t qshmm_segments_for(uint32_t wlen) {  // provisioned segments: 10 % + 512 positions of headroom
-  const uint64_t need = (uint64_t)wlen + wlen / 10u + 512u;
-  return (uint32_t)((need + PB_TILE - 1u) / PB_TILE);
+// provisioned segments: expected positions (rho per reference base) + 1.5 % + 8 sqrt(wlen) + 64 of headroom.
+// Under-provisioning is detected (flag 4) and the engine redoes the batch without segments.
+PB_HD uint32_t qshmm_segments_for(uint32_t wlen, float rho) {
+  const double need = (double)wlen * (double)rho * 1.015 + 8.0 * sqrt((double)wlen) + 64.0;
+  return (uint32_t)((need + (double)(PB_TILE - 1u)) / (double)PB_TILE);
 }
 
 PB_HD void qshmm_finish_segmented(uint16_t *ev_base, const SegResult *seg, uint32_t n_seg, uint32_t wlen,
-                                  const double *qc_prob, Ckpt *ck, SegRead &out) {
+                                  const double *qc_prob, const HpProbe &hp, Ckpt *ck, SegRead &out) {
   uint32_t R = 0, P = 0, D = 0, nsub = 0;
   double prob = 0.0;
   out.flags = 0;
@@ -739,12 +774,17 @@ PB_HD void qshmm_finish_segmented(uint16_t *ev_base, const SegResult *seg, uint3
     out.flags |= seg[k].flags;
     if (k >= 1u && R == 0u) out.flags |= 8u;
     Ckpt c; c.col = P + D; c.ref = R; c.read = P; c.pad = seg[k].n_entries;
-    if ((uint64_t)R + seg[k].ref_adv >= wlen) {
-      const SegTail t = qshmm_find_end_in_segment(ev_base + (uint64_t)k * PB_SEG_STRIDE, seg[k].n_entries, wlen - R, qc_prob);
+    const bool may_end = (uint64_t)R + seg[k].ref_adv >= wlen;
+    if (may_end || hp.enabled) {
+      // exact walk: the last tile of every read, and every tile of a read that may need deletion-run repairs
+      const TileWalk t = qshmm_walk_tile(ev_base + (uint64_t)k * PB_SEG_STRIDE, seg[k].n_entries, R, wlen, qc_prob, hp);
       c.pad = t.n_entries;
-      P += t.positions; R += t.ref_adv; D += t.ndel; nsub += t.nsub; prob += t.prob;
-      out.n_tiles = k + 1u;
-      done = true;
+      P += t.positions; R += t.ref_adv; D += t.ndel; nsub += t.nsub;
+      prob += t.ended ? t.prob : seg[k].prob;  // a full tile's sum is the segment's own (same order, same value)
+      if (t.ended) {
+        out.n_tiles = k + 1u;
+        done = true;
+      }
     } else {
       P += PB_TILE; R += seg[k].ref_adv; D += seg[k].ndel; nsub += seg[k].nsub; prob += seg[k].prob;
     }

@@ -63,6 +63,7 @@ struct Batch {
   uint32_t *ck_cap;        // checkpoint slots
   uint64_t *ck_off;
   uint32_t *nent, *rlen, *ncol, *nsub, *nins, *ndel, *flags, *draws_used;
+  uint32_t *nseg;          // segments provisioned (0: the sub-read runs on the sequential pass-1 path)
   double *accuracy;
 };
 
@@ -70,7 +71,7 @@ struct Batch {
 // K1: plan.  One thread per read.  clip_room >= 0 only for single-read tail batches.
 // ----------------------------------------------------------------------------------------------
 __global__ void k_plan(DeviceModel M, DeviceGenome G, RngParams rng, Batch B, int64_t clip_room, uint32_t cap_num,
-                       uint32_t cap_den, uint32_t ev_align) {
+                       uint32_t cap_den, uint32_t ev_align, uint32_t seg_min_len /* 0: segments off */) {
   const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= B.n_reads) return;
   PlanTables T;
@@ -103,17 +104,29 @@ __global__ void k_plan(DeviceModel M, DeviceGenome G, RngParams rng, Batch B, in
   B.plan_off[r] = p.offset;
   B.plan_wlen[r] = p.wlen;
   B.plan_raw[r] = p.raw_len;
-  B.plan_meta[r] = p.acc | (minus << 8) | ((slow ? 1u : 0u) << 9) | ((ae.valid ? 0u : 1u) << 10);
+  // segment-parallel pass 1: PHILOX qshmm reads that never need the genome in pass 1, long enough, and whose
+  // accuracy's chain couples fast (AccEntry::seg_ok)
+  // (reads touching exceptional blocks qualify too in the default bias mode: k_find_end repairs their deletion
+  // runs with the exact reference offset, pass 2 re-derives choices on non-ACGT bases)
+  const bool segmented = seg_min_len != 0u && rng.mode == PBSIM_RNG_PHILOX && (!slow || M.uniform_bias) && ae.valid &&
+                         ae.seg_ok && p.wlen >= seg_min_len;
+  const uint32_t nseg = segmented ? qshmm_segments_for(p.wlen, ae.rho) : 0u;
+  B.plan_meta[r] = p.acc | (minus << 8) | ((slow ? 1u : 0u) << 9) | ((ae.valid ? 0u : 1u) << 10) |
+                   ((segmented ? 1u : 0u) << 11);
   // event-slot capacity: wlen * cap_num/cap_den + slack, rounded so that slots stay 16-byte aligned
   uint64_t cap = (uint64_t)p.wlen * cap_num / cap_den + 2048u;
+  if (segmented) cap = (uint64_t)nseg * PB_SEG_STRIDE + 64u;
   cap = (cap + ev_align - 1u) / ev_align * ev_align;
-  const uint32_t ckc = (uint32_t)(cap / PB_TILE) + 2u;
+  const uint32_t ckc = segmented ? nseg + 2u : (uint32_t)(cap / PB_TILE) + 2u;
   for (uint32_t h = 0; h < M.pass_num; ++h) {
     const uint32_t s = r * M.pass_num + h;
-    B.key_in[s] = (p.acc << 21) | ((slow ? 1u : 0u) << 20) | (0xFFFFFu - (p.wlen > 0xFFFFFu ? 0xFFFFFu : p.wlen));
+    // segmented sub-reads get the out-of-range bin kBins: the sequential schedule skips them
+    B.key_in[s] = segmented ? ((uint32_t)kBins << 20)
+                            : ((p.acc << 21) | ((slow ? 1u : 0u) << 20) | (0xFFFFFu - (p.wlen > 0xFFFFFu ? 0xFFFFFu : p.wlen)));
     B.idx_in[s] = s;
     B.cap[s] = (uint32_t)cap;
     B.ck_cap[s] = ckc;
+    B.nseg[s] = nseg;
   }
 }
 
@@ -129,8 +142,9 @@ __global__ void k_bin_bounds(const uint32_t *key_sorted, uint32_t n, uint32_t *b
 __global__ void k_cta_map(const uint32_t *bin_start, const uint32_t *key_sorted, uint32_t n, uint32_t *bin_lo,
                           uint32_t *bin_hi, uint32_t *cta_first) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  // bin_start holds 0xFFFFFFFF for empty bins
-  uint32_t next_lo = n, total = 0;
+  // bin_start holds 0xFFFFFFFF for empty bins; bin kBins collects the sub-reads that are NOT scheduled here
+  // (segment-parallel pass 1), they sort behind every real bin
+  uint32_t next_lo = (bin_start[kBins] != 0xFFFFFFFFu) ? bin_start[kBins] : n, total = 0;
   for (int a = kBins - 1; a >= 0; --a) {
     const uint32_t lo = bin_start[a];
     if (lo == 0xFFFFFFFFu) {

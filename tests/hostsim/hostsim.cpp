@@ -32,25 +32,44 @@ extern "C" long hostsim_seg_fallbacks() { return seg_fallbacks; }
 // the segment-parallel pass 1 as the kernels run it (k_sim_seg + k_find_end), sequentially on the host;
 // returns false if the read must fall back to the sequential path
 static bool run_segmented(const pb::QsView &T, const pb::QsSegAux &A, uint32_t seed, uint32_t seq_num, uint32_t read_id,
-                          uint32_t pass, uint32_t wlen, std::vector<uint8_t> &events, size_t ev_off,
-                          std::vector<pb::Ckpt> &ckpts, size_t ck_base, pb::SubreadResult &res) {
+                          uint32_t pass, uint32_t wlen, float rho, const pb::HpProbe &hp, std::vector<uint8_t> &events,
+                          size_t ev_off, std::vector<pb::Ckpt> &ckpts, size_t ck_base, pb::SubreadResult &res) {
   pb::PhiloxKeys K;
   K.init(seed, seq_num);
-  const uint32_t n_seg = pb::qshmm_segments_for(wlen);
+  const uint32_t n_seg = pb::qshmm_segments_for(wlen, rho);
   std::vector<uint16_t> slots((size_t)n_seg * PB_SEG_STRIDE + 16, 0);
   std::vector<pb::SegResult> seg(n_seg);
   for (uint32_t k = 0; k < n_seg; ++k) {
     uint32_t row = 0, mod = T.init_mod, emod = 1;
     if (k > 0 && T.has_model) {
-      if (!pb::qshmm_segment_start(T, A, K, read_id, pass, k * PB_TILE, 4096, row, mod, emod)) return false;
+      if (!pb::qshmm_segment_start(T, A, K, read_id, pass, k * PB_TILE, 64, row, mod, emod)) return false;
     }
     pb::qshmm_simulate_segment(T, K, read_id, pass, k * PB_TILE, k == 0, row, mod, emod, slots.data() + (size_t)k * PB_SEG_STRIDE,
                                seg[k]);
   }
   std::vector<pb::Ckpt> ck(n_seg);
   pb::SegRead sr;
-  pb::qshmm_finish_segmented(slots.data(), seg.data(), n_seg, wlen, T.qc_prob, ck.data(), sr);
+  pb::qshmm_finish_segmented(slots.data(), seg.data(), n_seg, wlen, T.qc_prob, hp, ck.data(), sr);
   if (sr.flags) return false;
+  if (hp.enabled) {
+    // what pass 2 does in PHILOX mode: the 4-way choice of a substitution on a non-ACGT base is recomputed from
+    // the position's own Philox block (the segment could not know the base)
+    for (uint32_t k = 0; k < sr.n_tiles; ++k) {
+      uint32_t R = ck[k].ref, P = ck[k].read;
+      uint16_t *e = slots.data() + (size_t)k * PB_SEG_STRIDE;
+      for (uint32_t i = 0; i < ck[k].pad; ++i) {
+        const uint32_t v = e[i], kind = (v >> 7) & 3u;
+        if (kind == 3u) { R += (v & 0x7Fu) | ((v >> 9) << 7); continue; }
+        if (kind == PB_KIND_SUB && hp.win.nonacgt(R)) {
+          uint32_t w[4];
+          pb::philox_block_keys(K, P, pass << 16, read_id, 1u, w);
+          e[i] = (uint16_t)((v & ~(7u << 9)) | (((w[0] >> 12) & 3u) << 9));
+        }
+        R += (kind == PB_KIND_INS ? 0u : 1u) + (v >> 12);
+        ++P;
+      }
+    }
+  }
   // linearise the tiles for the Python expander
   size_t total = 0;
   for (uint32_t k = 0; k < sr.n_tiles; ++k) total += ck[k].pad;
@@ -85,6 +104,12 @@ long hostsim_run(const pbsim_model *m, const uint8_t *ascii_upper, const int16_t
     const bool acgt = (c == 'A' || c == 'C' || c == 'G' || c == 'T');
     exc[i] = (!acgt) || (bias[hp[i] & 15] != 1.0);
   }
+  std::vector<uint32_t> xm(((size_t)glen >> 15) + 2, 0);  // 1 bit per 1024-base block with an exceptional base
+  for (long i = 0; i < glen; ++i)
+    if (exc[i]) xm[(i >> 10) >> 5] |= 1u << ((i >> 10) & 31);
+  uint8_t bias_one[12];
+  for (int h = 0; h < 12; ++h) bias_one[h] = (bias[h] == 1.0) ? 1 : 0;
+  bias_one[0] = 1;
   g_out = HostSimOut();
   pb::PlanTables pt;
   pt.prob2len = m->prob2len;
@@ -137,13 +162,19 @@ long hostsim_run(const pbsim_model *m, const uint8_t *ascii_upper, const int16_t
         pb::QsSink sink;
         sink.init(reinterpret_cast<uint16_t *>(g_out.events.data() + ev_off), g_out.ckpts.data() + ck_base, cap);
         bool seg_done = false;
-        if (rng_mode == PBSIM_RNG_PHILOX && !slow && use_seg && ae.seg_ok && (int)plan.wlen >= seg_min_len) {
+        if (rng_mode == PBSIM_RNG_PHILOX && (!slow || img.uniform_bias) && use_seg && ae.seg_ok &&
+            (int)plan.wlen >= seg_min_len) {
+          pb::HpProbe hpp;
+          hpp.enabled = slow ? 1u : 0u;
+          hpp.win = win;
+          hpp.xm = xm.data();
+          hpp.bias_one = bias_one;
           pb::QsSegAux A;
           A.tmod = b + pb::QsBlobLayout::tmod_off;
           A.emodv = b + pb::QsBlobLayout::emodv_off;
           A.reach = ae.reach;
           ++seg_reads;
-          seg_done = run_segmented(T, A, seed, (uint32_t)seq_num, (uint32_t)read_id, (uint32_t)pass, plan.wlen, g_out.events, ev_off,
+          seg_done = run_segmented(T, A, seed, (uint32_t)seq_num, (uint32_t)read_id, (uint32_t)pass, plan.wlen, ae.rho, hpp, g_out.events, ev_off,
                                    g_out.ckpts, ck_base, res);
           if (!seg_done) ++seg_fallbacks;
         }

@@ -136,3 +136,40 @@ def test_synthetic_sequence_roundtrip_properties(eng):
         assert (rr if strand == b"+" else rr.translate(comp)[::-1]) == seq
         total += rlen
     assert total == st.res_len_total >= 2 * n
+
+
+@pytest.mark.parametrize("name", ["qs_rsii_basic", "qs_rsii_quirks", "qs_delheavy_uniform", "qs_rsii_multipass",
+                                  "qs_ont_hpbias", "qs_hp11_uniform"])
+def test_segment_parallel_pass1_equals_oracle(eng, name):
+    """segment-parallel pass 1 forced onto every read longer than one segment: same bytes as the oracle"""
+    c = Case(name)
+    out, _ = c.run_oracle("philox")
+    eng.set_option("seg_min_len", 1024)
+    try:
+        res = run_case_on_gpu(c, eng, "philox")
+    finally:
+        eng.set_option("seg_min_len", 4096)
+    for i, ((reads, maf, st, text), o) in enumerate(zip(res, out), start=1):
+        assert reads == o["reads"], "reads differ from the oracle, seq %d" % i
+        assert maf == o["maf"], "maf differs from the oracle, seq %d" % i
+        assert text == o["stats_text"]
+
+
+def test_segments_on_and_off_give_identical_bytes(eng):
+    """3 Mbp device-generated contig, RSII defaults (mean 9 kb): the segment-parallel and the sequential pass 1
+    must agree byte for byte, statistics included"""
+    c = Case("qs_rsii_basic")
+    L = capi.load()
+    hm = capi.HostModel(L, capi.host_params("qshmm"), c.model)
+    eng.set_model(hm)
+    n = 3000000
+    eng.set_synthetic_sequence(n, 1, 7)
+    outs = []
+    for on in (1, 0):
+        eng.set_option("segments", on)
+        reads, maf, (st, fl, fa), _ = eng.simulate(3 * n, rng_mode=capi.RNG_PHILOX, seed=11, want_hist=True)
+        outs.append((reads, maf, st.res_num, st.res_len_total, st.accuracy_total, st.res_sub_num, st.res_ins_num,
+                     st.res_del_num, fa.tobytes()))
+    eng.set_option("segments", 1)
+    assert outs[0][2] > 500
+    assert outs[0] == outs[1]
