@@ -66,8 +66,9 @@ typedef struct {
   uint32_t key[2];
   uint32_t read_id, pass, pos;
   uint32_t w[4];  /* block 0 of the current position */
-  uint32_t xw[4]; /* cached extra block */
-  uint32_t xblk;
+  uint32_t cw[4]; /* chain block: state draws of positions 4*cidx .. 4*cidx+3 */
+  uint32_t cidx;
+  int cvalid;
 } rng_t;
 
 static uint32_t stream_next(rng_t *r) {
@@ -106,6 +107,7 @@ static void philox_at(const rng_t *r, uint32_t pos, uint32_t blk, uint32_t domai
 static void d_plan_begin(rng_t *r, uint32_t read_id) {
   r->read_id = read_id;
   r->pass = 0;
+  r->cvalid = 0;
   if (r->mode == RNG_PHILOX) philox_at(r, 0, 0, 0, r->w);
 }
 static uint32_t d_plan_len(rng_t *r, uint32_t mod) {
@@ -124,10 +126,22 @@ static uint64_t d_plan_off(rng_t *r, uint64_t span) {
 
 /* per-position draws */
 static void d_begin(rng_t *r, uint32_t pass, uint32_t pos) {
+  if (r->pass != pass) r->cvalid = 0;
   r->pass = pass;
   r->pos = pos;
-  r->xblk = 0;
   if (r->mode == RNG_PHILOX) philox_at(r, pos, 0, 1, r->w);
+}
+/* HMM state draw (init2state / tran2state index) of the current position.  PHILOX mode: the chain has its own
+ * stream, domain 2, one block per 4 consecutive positions (block pos>>2, word pos&3), so that the state chain can
+ * be advanced without generating the other draws of a position. */
+static uint32_t d_state(rng_t *r, uint32_t mod) {
+  if (r->mode != RNG_PHILOX) return stream_next(r) % mod;
+  if (!r->cvalid || r->cidx != (r->pos >> 2)) {
+    philox_at(r, r->pos >> 2, 0, 2, r->cw);
+    r->cidx = r->pos >> 2;
+    r->cvalid = 1;
+  }
+  return mulhi32(r->cw[r->pos & 3u], mod);
 }
 static uint32_t d_w0(rng_t *r, uint32_t mod) { /* state / freq draw */
   return r->mode == RNG_PHILOX ? mulhi32(r->w[0], mod) : stream_next(r) % mod;
@@ -855,10 +869,10 @@ static void qshmm_pass(orc_ctx *c, rng_t *r, uint32_t pass, int acc, long wlen, 
     d_begin(r, pass, (uint32_t)read_offset);
     if (c->exist[acc] == 1) {
       if (read_offset == 0) {
-        index = d_w0(r, (uint32_t)c->mod_init[acc]) + 1;
+        index = d_state(r, (uint32_t)c->mod_init[acc]) + 1;
         state = c->qs_init[acc][index];
       } else {
-        index = d_w0(r, (uint32_t)c->mod_tran[acc][state]) + 1;
+        index = d_state(r, (uint32_t)c->mod_tran[acc][state]) + 1;
         state = c->qs_tran[acc][state][index];
       }
       index = d_w1(r, (uint32_t)c->mod_emis[acc][state]) + 1;
@@ -935,10 +949,10 @@ static void errhmm_pass(orc_ctx *c, rng_t *r, uint32_t pass, int acc, int rate_m
     nt = c->w_seq[ref_offset];
     d_begin(r, pass, (uint32_t)maf_offset);
     if (read_offset == 0) {
-      index = d_w0(r, (uint32_t)c->mod_init[tacc]) + 1;
+      index = d_state(r, (uint32_t)c->mod_init[tacc]) + 1;
       state = c->er_init[tacc][index];
     } else {
-      index = d_w0(r, (uint32_t)c->mod_tran[tacc][state]) + 1;
+      index = d_state(r, (uint32_t)c->mod_tran[tacc][state]) + 1;
       state = c->er_tran[tacc][state][index];
     }
     hp = c->w_hp[ref_offset];

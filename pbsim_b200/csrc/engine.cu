@@ -193,7 +193,7 @@ struct pbsim_engine {
   DevBuf d_ev, d_ck;
   DevBuf d_seg, d_seg_bins;       // segment-parallel pass 1: segment lists / results, CTA map
   int seg_enabled = 1;            // option "segments"
-  int64_t seg_min_len = 4096;     // option "seg_min_len": shorter reads stay on the sequential path
+  int64_t seg_min_len = 2048;     // option "seg_min_len": shorter reads stay on the sequential path
   int64_t seg_batches = 0, seg_fallback_batches = 0;
   DevBuf d_out_reads, d_out_maf;
   PinnedBuf h_ctrl, h_acc;
@@ -485,8 +485,12 @@ int run_batch(pbsim_engine *e, uint32_t n_reads, int64_t clip_room, bool to_host
     CK(e->d_ev.ensure((size_t)ev_entries * (qs ? 2 : 1) + 256));
     CK(e->d_ck.ensure((size_t)ck_entries * sizeof(Ckpt) + 256));
 
+    if (n_seg_total > 0) CK(e->d_seg.ensure((size_t)n_seg_total * (6 * 4 + sizeof(SegResult)) + 256));
     // ---- K2 / K3 pass 1
     SimArgs A;
+    A.seg_off = (const uint64_t *)seg_off;
+    A.seg_state = n_seg_total > 0 ? reinterpret_cast<uint32_t *>(e->d_seg.as<SegResult>() + n_seg_total) + 5ull * n_seg_total
+                                  : nullptr;
     A.keys.init(rng.seed, (uint32_t)e->seq_num);
     A.M = M;
     A.G = G;
@@ -513,7 +517,6 @@ int run_batch(pbsim_engine *e, uint32_t n_reads, int64_t clip_room, bool to_host
       // ---- segment-parallel pass 1 for the long reads (seg_kernels.cuh)
       const uint32_t nseg = (uint32_t)n_seg_total;
       const uint32_t seg_slots = nblk(nseg, kSimThreads) + kBins;
-      CK(e->d_seg.ensure((size_t)nseg * (5 * 4 + sizeof(SegResult)) + 256));
       CK(e->d_seg_bins.ensure((4 * kBins + 8) * 4 + (size_t)seg_slots * 4 + 64));
       SegBatch S;
       S.n_seg_total = nseg;
@@ -525,6 +528,7 @@ int run_batch(pbsim_engine *e, uint32_t n_reads, int64_t clip_room, bool to_host
       S.seg_key_out = u + 2ull * nseg;
       S.seg_id_in = u + 3ull * nseg;
       S.seg_order = u + 4ull * nseg;
+      S.seg_state = u + 5ull * nseg;
       uint32_t *sb_start = e->d_seg_bins.as<uint32_t>();
       uint32_t *sb_lo = sb_start + kBins + 1, *sb_hi = sb_lo + kBins, *sb_first = sb_hi + kBins, *sb_order = sb_first + kBins + 1;
       k_seg_fill<<<nblk(n_sub, 256), 256, 0, e->st>>>(B, S, pass);
@@ -553,12 +557,10 @@ int run_batch(pbsim_engine *e, uint32_t n_reads, int64_t clip_room, bool to_host
       SA.ev = e->d_ev.as<uint8_t>();
       SA.max_window = getenv("PBSIM_EXPERIMENT_NOCOUPLE") ? 0u : 4096u;  // timing experiment only: wrong states
       k_sim_seg<<<seg_slots, kSimThreads, kQsSmemBytes, e->st>>>(SA);
-      k_find_end<<<nblk(n_sub, 128), 128, 0, e->st>>>(B, S, G, e->d_biasone.as<uint8_t>(), pass, e->d_ev.as<uint8_t>(),
-                                                     e->d_ck.as<Ckpt>(), e->d_qc_prob.as<double>());
-      k_find_end_repair<<<nblk((uint64_t)n_sub * 32, 128), 128, 0, e->st>>>(B, S, G, e->d_biasone.as<uint8_t>(), pass,
+      k_find_end<<<nblk((uint64_t)n_sub * 32, 128), 128, 0, e->st>>>(B, S, G, e->d_biasone.as<uint8_t>(), pass,
                                                                          e->d_ev.as<uint8_t>(), e->d_ck.as<Ckpt>(),
                                                                          e->d_qc_prob.as<double>());
-      e->launches += 8;
+      e->launches += 7;
       e->seg_batches++;
     }
     CK(cudaEventRecord(e->ev_k[1], e->st));

@@ -6,8 +6,8 @@
 // recovered exactly by backward coupling over that segment's predecessors' position-addressed draws.
 //   k_seg_fill   : (sub-read, k) list of all segments of the batch + accuracy sort key
 //   k_sim_seg    : one thread per segment: coupling + PB_TILE positions -> entries in the segment's slot
-//   k_find_end   : one thread per segmented sub-read: prefix over its segments, clip at the window end,
-//                  tile checkpoints, totals
+//   k_find_end   : one warp per segmented sub-read: prefix over its segments, deletion-run repairs, clip at the
+//                  window end, tile checkpoints, totals
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -25,6 +25,7 @@ struct SegBatch {
   uint32_t *seg_id_in;
   uint32_t *seg_order;       // segments sorted by accuracy
   SegResult *seg_res;        // [n_seg_total] indexed by segment id
+  uint32_t *seg_state;       // [n_seg_total] chain state in front of a segment (chain-only prepass; sticky chains)
 };
 
 // thread per sub-read: write its segments' descriptors
@@ -92,7 +93,16 @@ __global__ void __launch_bounds__(kSimThreads) k_sim_seg(SegArgs A) {
   SegResult res;
   res.n_entries = 0; res.ref_adv = 0; res.nsub = 0; res.ndel = 0; res.flags = 0; res.prob = 0.0;
   bool ok = true;
-  if (k > 0 && ae.has_model && A.max_window != 0u) ok = qshmm_segment_start(T, X, A.keys, read_id, pass, k * PB_TILE, 64u, row, mod, emod);
+  if (k > 0 && ae.has_model) {
+    if ((A.B.plan_meta[r] >> 12) & 1u) {  // recorded by the chain-only prepass
+      const uint32_t t = A.S.seg_state[seg];
+      row = t & 0xFFFFu;
+      mod = (t >> 16) & 0xFFu;
+      emod = t >> 24;
+    } else if (A.max_window != 0u) {
+      ok = qshmm_segment_start(T, X, A.keys, read_id, pass, k * PB_TILE, 64u, row, mod, emod);
+    }
+  }
   // the coupling loops leave the lanes of a warp at different points; without an explicit reconvergence the
   // compiler keeps them apart for the whole segment loop (ncu: 13.7 of 32 threads active per instruction)
   __syncwarp();
@@ -105,44 +115,11 @@ __global__ void __launch_bounds__(kSimThreads) k_sim_seg(SegArgs A) {
   A.S.seg_res[seg] = res;
 }
 
-// thread per sub-read (segmented ones only do work)
-__global__ void k_find_end(Batch B, SegBatch S, DeviceGenome G, const uint8_t *bias_one, uint32_t pass_num, uint8_t *ev,
-                           Ckpt *ck, const double *qc_prob) {
-  const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= B.n_sub) return;
-  const uint64_t lo = S.seg_off[s], hi = S.seg_off[s + 1];
-  if (hi == lo) return;
-  const uint32_t r = s / pass_num;
-  const uint32_t meta = B.plan_meta[r];
-  if ((meta >> 9) & 1u) return;   // reads that may need deletion-run repairs: k_find_end_repair (one warp each)
-  HpProbe hp;
-  hp.enabled = 0u;
-  hp.win.ascii = G.ascii;
-  hp.win.hp4 = G.hp4;
-  hp.win.offset = B.plan_off[r];
-  hp.win.wlen = B.plan_wlen[r];
-  hp.win.minus = (meta >> 8) & 1u;
-  hp.xm = G.xm;
-  hp.bias_one = bias_one;
-  SegRead out;
-  qshmm_finish_segmented(reinterpret_cast<uint16_t *>(ev) + B.ev_off[s], S.seg_res + lo, (uint32_t)(hi - lo), B.plan_wlen[r],
-                         qc_prob, hp, ck + B.ck_off[s], out);
-  B.nent[s] = out.n_tiles;  // segmented sub-reads: number of tiles (entries per tile live in the checkpoints)
-  B.rlen[s] = out.rlen;
-  B.ncol[s] = out.ncol;
-  B.nsub[s] = out.nsub;
-  B.nins[s] = out.nins;
-  B.ndel[s] = out.ndel;
-  B.flags[s] = out.flags ? (4u | (out.flags << 8)) : 0u;  // any problem: the engine redoes the batch sequentially
-  B.draws_used[s] = 0;
-  B.accuracy[s] = out.accuracy;
-}
-
-// One WARP per segmented sub-read whose window touches an exceptional block.  Same result as
-// qshmm_finish_segmented with the probe enabled, but the exact walk over ALL entries of the read is done 32
+// One WARP per segmented sub-read.  Same result as qshmm_finish_segmented (sim_core.cuh, the sequential
+// statement the CPU harness runs); the exact walk over the entries of a tile is done 32
 // entries at a time: a warp scan gives every entry its reference offset; only groups in which the window ends or
 // a deletion run meets a flagged block are walked sequentially (by lane 0, with qshmm_walk_tile).
-__global__ void __launch_bounds__(128) k_find_end_repair(Batch B, SegBatch S, DeviceGenome G, const uint8_t *bias_one,
+__global__ void __launch_bounds__(128) k_find_end(Batch B, SegBatch S, DeviceGenome G, const uint8_t *bias_one,
                                                          uint32_t pass_num, uint8_t *ev, Ckpt *ck, const double *qc_prob) {
   const uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint32_t lane = threadIdx.x & 31u;
@@ -151,10 +128,9 @@ __global__ void __launch_bounds__(128) k_find_end_repair(Batch B, SegBatch S, De
   if (hi == lo) return;
   const uint32_t r = s / pass_num;
   const uint32_t meta = B.plan_meta[r];
-  if (((meta >> 9) & 1u) == 0u) return;
   const uint32_t wlen = B.plan_wlen[r];
   HpProbe hp;
-  hp.enabled = 1u;
+  hp.enabled = (meta >> 9) & 1u;  // window touches an exceptional block: deletion runs may need repairing
   hp.win.ascii = G.ascii;
   hp.win.hp4 = G.hp4;
   hp.win.offset = B.plan_off[r];
@@ -175,6 +151,15 @@ __global__ void __launch_bounds__(128) k_find_end_repair(Batch B, SegBatch S, De
     uint16_t *e = ev_base + (uint64_t)k * PB_SEG_STRIDE;
     const uint32_t n = seg[k].n_entries;
     const uint32_t R_tile = R, P_tile = P, D_tile = D;
+    if (!hp.enabled && (uint64_t)R + seg[k].ref_adv < wlen) {
+      // nothing to repair and the window cannot end here: the segment's own totals are exact
+      if (lane == 0) {
+        Ckpt c; c.col = P + D; c.ref = R; c.read = P; c.pad = n;
+        ckp[k] = c;
+      }
+      P += PB_TILE; R += seg[k].ref_adv; D += seg[k].ndel; nsub += seg[k].nsub; prob += seg[k].prob;
+      continue;
+    }
     uint32_t n_incl = n, blocked = 0;
     bool ended = false;
     for (uint32_t i = 0; i < n && !ended; i += 32u) {
@@ -195,7 +180,7 @@ __global__ void __launch_bounds__(128) k_find_end_repair(Batch B, SegBatch S, De
       const uint32_t Rb = R + x - (a + part);  // reference offset in front of this entry
       // does any deletion of this entry follow a base of a flagged block?  (window indices Rb+a-1 .. Rb+a+part-2)
       bool touch = false;
-      if (part != 0u) {
+      if (hp.enabled && part != 0u) {
         const uint32_t w0 = Rb + a, w1 = Rb + a + part - 1u;  // bases whose predecessor matters: w0-1 .. w1-1
         const uint32_t lo_w = w0 == 0u ? 0u : w0 - 1u, hi_w = min(w1 == 0u ? 0u : w1 - 1u, wlen - 1u);
         const uint32_t g0 = hp.win.minus ? hp.win.gidx(hi_w) : hp.win.gidx(lo_w);

@@ -58,7 +58,8 @@ PB_HD uint64_t mulhi64(uint64_t a, uint64_t b) {
 }
 
 // Philox4x32-10 (Salmon et al., SC'11).  Draw addressing:
-//   key = (seed, sequence number)   counter = (position, block | pass << 16, read id, domain)
+//   key = (seed, sequence number)   counter = (position, pass << 16, read id, domain)
+//   domain 0 planner, 1 the draws of one position, 2 the HMM state draws (one block per 4 positions)
 struct Philox {
   uint32_t k0, k1;
   PB_HD void block(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t out[4]) const {
@@ -102,6 +103,18 @@ struct PhiloxDraw {
   uint32_t read_id, pass;
   uint32_t w[4];
   uint32_t g[PB_GROUP][4];
+  uint32_t c0w, c1w, c2w, c3w, cidx = 0xFFFFFFFFu;  // chain block (state draws of positions 4*cidx .. 4*cidx+3)
+  // state draw of position p: own stream so that the chain can be advanced alone (segment-parallel pass 1)
+  PB_HD uint32_t wc(uint32_t p, uint32_t m) {
+    if ((p >> 2) != cidx) {
+      uint32_t t[4];
+      ph.block(p >> 2, pass << 16, read_id, 2u, t);
+      c0w = t[0]; c1w = t[1]; c2w = t[2]; c3w = t[3];
+      cidx = p >> 2;
+    }
+    const uint32_t k = p & 3u;
+    return mulhi32(k == 0u ? c0w : (k == 1u ? c1w : (k == 2u ? c2w : c3w)), m);
+  }
   PB_HD void plan_begin() { ph.block(0u, 0u, read_id, 0u, w); }
   PB_HD uint32_t plan_len(uint32_t m) { return mulhi32(w[0], m); }
   PB_HD uint32_t plan_acc(uint32_t m) { return mulhi32(w[1], m); }
@@ -145,6 +158,7 @@ struct ReplayDraw {
   PB_HD uint32_t plan_off(uint32_t span) { return next() % span; }
   PB_HD void prefetch(uint32_t) {}
   PB_HD void begin(uint32_t) {}
+  PB_HD uint32_t wc(uint32_t, uint32_t m) { return next() % m; }
   PB_HD uint32_t w0(uint32_t m) { return next() % m; }
   PB_HD uint32_t w1(uint32_t m) { return next() % m; }
   PB_HD uint32_t w2(uint32_t m) { return next() % m; }
@@ -182,6 +196,22 @@ PB_HD void philox_block_keys(const PhiloxKeys &K, uint32_t c0, uint32_t c1, uint
     c3 = (uint32_t)p0;
   }
   out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// state-draw words (domain 2) of the PB_GROUP positions starting at p; one block when p is a multiple of 4
+PB_HD void chain_words(const PhiloxKeys &K, uint32_t read_id, uint32_t c1, uint32_t p, uint32_t cw[PB_GROUP]) {
+  if ((p & 3u) == 0u) {
+    philox_block_keys(K, p >> 2, c1, read_id, 2u, cw);
+  } else {  // misaligned group (only after a run of >= 15 deletions): two blocks
+    uint32_t a[4], b[4];
+    philox_block_keys(K, p >> 2, c1, read_id, 2u, a);
+    philox_block_keys(K, (p >> 2) + 1u, c1, read_id, 2u, b);
+#pragma unroll
+    for (uint32_t u = 0; u < PB_GROUP; ++u) {
+      const uint32_t q = (p & 3u) + u;  // 1..6
+      cw[u] = q == 1u ? a[1] : (q == 2u ? a[2] : (q == 3u ? a[3] : (q == 4u ? b[0] : (q == 5u ? b[1] : b[2]))));
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -322,7 +352,7 @@ PB_HD void qshmm_simulate(const QsView &T, Draw &d, const WindowRef &win, bool s
       d.begin(u);
       uint32_t qv;
       if (T.has_model) {
-        const uint32_t t = T.t2[row + d.w0(mod)];
+        const uint32_t t = T.t2[row + d.wc(P, mod)];
         row = t & 0xFFFFu;
         mod = (t >> 16) & 0xFFu;
         emod = t >> 24;
@@ -422,9 +452,10 @@ PB_HD void qshmm_simulate_fast(const QsView &T, const PhiloxKeys &K, uint32_t re
       Ckpt c; c.col = P + ndel; c.ref = R; c.read = P; c.pad = 0;
       ck[n / PB_TILE] = c;
     }
-    uint32_t g[PB_GROUP][4];
+    uint32_t g[PB_GROUP][4], cw[PB_GROUP];
 #pragma unroll
     for (uint32_t u = 0; u < PB_GROUP; ++u) philox_block_keys(K, P + u, c1, read_id, 1u, g[u]);
+    if (T.has_model) chain_words(K, read_id, c1, P, cw);
     uint32_t e[PB_GROUP];
     uint32_t big_u = PB_GROUP, big_nd = 0;  // rare: an entry with >= 15 deletions ends the group early
 #pragma unroll
@@ -434,7 +465,7 @@ PB_HD void qshmm_simulate_fast(const QsView &T, const PhiloxKeys &K, uint32_t re
         const uint32_t w0 = g[u][0], w1 = g[u][1], w2 = g[u][2], w3 = g[u][3];
         uint32_t qv;
         if (T.has_model) {
-          const uint32_t t = T.t2[row + mulhi32(w0, mod)];
+          const uint32_t t = T.t2[row + mulhi32(cw[u], mod)];
           row = t & 0xFFFFu;
           mod = (t >> 16) & 0xFFu;
           emod = t >> 24;
@@ -549,11 +580,13 @@ PB_HD bool qshmm_segment_start(const QsView &T, const QsSegAux &A, const PhiloxK
     uint64_t mask = from_zero ? 1ull : A.reach;  // from position 0: the virtual state 0 (row 0 = init2state)
     uint32_t s_row = 0, s_mod = T.init_mod, s_emod = 1;
     bool single = from_zero;
+    uint32_t cwb[4] = {0, 0, 0, 0};
     for (uint32_t p = p0; p < p_start; ++p) {
-      uint32_t w[4];
-      philox_block_keys(K, p, c1, read_id, 1u, w);
+      if (p == p0 || (p & 3u) == 0u) philox_block_keys(K, p >> 2, c1, read_id, 2u, cwb);
+      const uint32_t k4 = p & 3u;
+      const uint32_t wdraw = k4 == 0u ? cwb[0] : (k4 == 1u ? cwb[1] : (k4 == 2u ? cwb[2] : cwb[3]));
       if (single) {
-        const uint32_t t = T.t2[s_row + mulhi32(w[0], s_mod)];
+        const uint32_t t = T.t2[s_row + mulhi32(wdraw, s_mod)];
         s_row = t & 0xFFFFu;
         s_mod = (t >> 16) & 0xFFu;
         s_emod = t >> 24;
@@ -566,7 +599,7 @@ PB_HD bool qshmm_segment_start(const QsView &T, const QsSegAux &A, const PhiloxK
 #else
           const uint32_t s = (uint32_t)__builtin_ctzll(m);
 #endif
-          last_t = T.t2[s * PB_QS_ROW + mulhi32(w[0], A.tmod[s])];
+          last_t = T.t2[s * PB_QS_ROW + mulhi32(wdraw, A.tmod[s])];
           next |= 1ull << qs_state_of_row(last_t & 0xFFFFu);
         }
         mask = next;
@@ -585,6 +618,29 @@ PB_HD bool qshmm_segment_start(const QsView &T, const QsSegAux &A, const PhiloxK
   }
 }
 
+// Chain-only prepass for accuracies whose chain does not couple quickly (sticky states): advance just the state
+// chain over the read (one Philox block per 4 positions, one table lookup per position) and record the packed
+// table entry (row | modulus << 16 | emission modulus << 24) in front of every segment k >= 1.
+PB_HD void qshmm_chain_only(const QsView &T, const PhiloxKeys &K, uint32_t read_id, uint32_t pass, uint32_t n_seg,
+                            uint32_t *seg_state) {
+  uint32_t row = 0, mod = T.init_mod, emod = 1;
+  const uint32_t c1 = pass << 16;
+  for (uint32_t k = 1; k < n_seg; ++k) {
+    for (uint32_t p = (k - 1u) * PB_TILE; p < k * PB_TILE; p += 4u) {
+      uint32_t cw[4];
+      philox_block_keys(K, p >> 2, c1, read_id, 2u, cw);
+#pragma unroll
+      for (uint32_t u = 0; u < 4u; ++u) {
+        const uint32_t t = T.t2[row + mulhi32(cw[u], mod)];
+        row = t & 0xFFFFu;
+        mod = (t >> 16) & 0xFFu;
+        emod = t >> 24;
+      }
+    }
+    seg_state[k] = row | (mod << 16) | (emod << 24);
+  }
+}
+
 // simulate positions [p_start, p_start + PB_TILE) of a read, unbounded in the reference direction.
 // first_segment: the reference offset is 0 at p_start (the `hp[-1]` rule of :2269 applies while it stays 0).
 PB_HD void qshmm_simulate_segment(const QsView &T, const PhiloxKeys &K, uint32_t read_id, uint32_t pass,
@@ -598,9 +654,10 @@ PB_HD void qshmm_simulate_segment(const QsView &T, const PhiloxKeys &K, uint32_t
   const uint32_t p_end = p_start + PB_TILE;
   for (uint32_t P = p_start; P < p_end;) {
     if (n + 2u * PB_GROUP > PB_SEG_STRIDE) { res.flags |= 1u; break; }
-    uint32_t g[PB_GROUP][4];
+    uint32_t g[PB_GROUP][4], cw[PB_GROUP];
 #pragma unroll
     for (uint32_t u = 0; u < PB_GROUP; ++u) philox_block_keys(K, P + u, c1, read_id, 1u, g[u]);
+    if (T.has_model) chain_words(K, read_id, c1, P, cw);
     uint32_t e[PB_GROUP];
     uint32_t big_u = PB_GROUP, big_nd = 0;
 #pragma unroll
@@ -610,7 +667,7 @@ PB_HD void qshmm_simulate_segment(const QsView &T, const PhiloxKeys &K, uint32_t
         const uint32_t w0 = g[u][0], w1 = g[u][1], w2 = g[u][2], w3 = g[u][3];
         uint32_t qv;
         if (T.has_model) {
-          const uint32_t t = T.t2[row + mulhi32(w0, mod)];
+          const uint32_t t = T.t2[row + mulhi32(cw[u], mod)];
           row = t & 0xFFFFu;
           mod = (t >> 16) & 0xFFu;
           emod = t >> 24;
@@ -870,7 +927,7 @@ PB_HD void errhmm_simulate(const ErView &T, Draw &d, const WindowRef &win, bool 
         d.begin(u);
         const uint32_t row = (P == 0u) ? 0u : state;           // init is re-drawn while read_offset == 0 (:3853)
         const uint32_t m = (P == 0u) ? T.init_mod : mod;
-        const uint32_t t = T.t2[row * PB_ER_ROW + d.w0(m)];
+        const uint32_t t = T.t2[row * PB_ER_ROW + d.wc(C, m)];
         state = t & 63u;
         mod = t >> 6;
         const uint32_t x = d.w1(1000u) + 1u;

@@ -109,10 +109,13 @@ __global__ void k_plan(DeviceModel M, DeviceGenome G, RngParams rng, Batch B, in
   // (reads touching exceptional blocks qualify too in the default bias mode: k_find_end repairs their deletion
   // runs with the exact reference offset, pass 2 re-derives choices on non-ACGT bases)
   const bool segmented = seg_min_len != 0u && rng.mode == PBSIM_RNG_PHILOX && (!slow || M.uniform_bias) && ae.valid &&
-                         ae.seg_ok && p.wlen >= seg_min_len;
+                         p.wlen >= seg_min_len;
+  // chains with sticky states do not couple quickly: their segment start states come from a chain-only prepass
+  // that k_sim_qshmm runs for them (they keep their place in the sequential schedule for that)
+  const bool needs_chain = segmented && ae.has_model && !ae.seg_ok;
   const uint32_t nseg = segmented ? qshmm_segments_for(p.wlen, ae.rho) : 0u;
   B.plan_meta[r] = p.acc | (minus << 8) | ((slow ? 1u : 0u) << 9) | ((ae.valid ? 0u : 1u) << 10) |
-                   ((segmented ? 1u : 0u) << 11);
+                   ((segmented ? 1u : 0u) << 11) | ((needs_chain ? 1u : 0u) << 12);
   // event-slot capacity: wlen * cap_num/cap_den + slack, rounded so that slots stay 16-byte aligned
   uint64_t cap = (uint64_t)p.wlen * cap_num / cap_den + 2048u;
   if (segmented) cap = (uint64_t)nseg * PB_SEG_STRIDE + 64u;
@@ -121,7 +124,7 @@ __global__ void k_plan(DeviceModel M, DeviceGenome G, RngParams rng, Batch B, in
   for (uint32_t h = 0; h < M.pass_num; ++h) {
     const uint32_t s = r * M.pass_num + h;
     // segmented sub-reads get the out-of-range bin kBins: the sequential schedule skips them
-    B.key_in[s] = segmented ? ((uint32_t)kBins << 20)
+    B.key_in[s] = (segmented && !needs_chain) ? ((uint32_t)kBins << 20)
                             : ((p.acc << 21) | ((slow ? 1u : 0u) << 20) | (0xFFFFFu - (p.wlen > 0xFFFFFu ? 0xFFFFFu : p.wlen)));
     B.idx_in[s] = s;
     B.cap[s] = (uint32_t)cap;
@@ -248,6 +251,8 @@ struct SimArgs {
   RngParams rng;
   Batch B;
   const uint32_t *cta_order, *cta_first, *bin_lo, *bin_hi;
+  const uint64_t *seg_off;  // segment-parallel pass 1: first segment of a sub-read
+  uint32_t *seg_state;      // ... and the chain state in front of every segment (chain-only prepass)
   uint8_t *ev;   // event arena
   Ckpt *ck;      // checkpoint arena
 };
@@ -328,6 +333,11 @@ __global__ void __launch_bounds__(kSimThreads) k_sim_qshmm(SimArgs A) {
   win.wlen = wlen;
   win.minus = (meta >> 8) & 1u;
   const bool slow = (meta >> 9) & 1u;
+  if (RNG_MODE == PBSIM_RNG_PHILOX && ((meta >> 12) & 1u)) {
+    // chain-only prepass: this sub-read is simulated by k_sim_seg, which needs the state in front of every segment
+    qshmm_chain_only(T, A.keys, (uint32_t)(A.B.first_read + 1u + r), pass, A.B.nseg[s], A.seg_state + A.seg_off[s]);
+    return;
+  }
   QsSink sink;
   sink.init(reinterpret_cast<uint16_t *>(A.ev) + A.B.ev_off[s], A.ck + A.B.ck_off[s], A.B.cap[s]);
   SubreadResult res;

@@ -32,17 +32,24 @@ extern "C" long hostsim_seg_fallbacks() { return seg_fallbacks; }
 // the segment-parallel pass 1 as the kernels run it (k_sim_seg + k_find_end), sequentially on the host;
 // returns false if the read must fall back to the sequential path
 static bool run_segmented(const pb::QsView &T, const pb::QsSegAux &A, uint32_t seed, uint32_t seq_num, uint32_t read_id,
-                          uint32_t pass, uint32_t wlen, float rho, const pb::HpProbe &hp, std::vector<uint8_t> &events,
+                          uint32_t pass, uint32_t wlen, float rho, bool seg_ok, const pb::HpProbe &hp,
+                          std::vector<uint8_t> &events,
                           size_t ev_off, std::vector<pb::Ckpt> &ckpts, size_t ck_base, pb::SubreadResult &res) {
   pb::PhiloxKeys K;
   K.init(seed, seq_num);
   const uint32_t n_seg = pb::qshmm_segments_for(wlen, rho);
   std::vector<uint16_t> slots((size_t)n_seg * PB_SEG_STRIDE + 16, 0);
   std::vector<pb::SegResult> seg(n_seg);
+  std::vector<uint32_t> seg_state(n_seg + 1, 0);
+  if (T.has_model && !seg_ok) pb::qshmm_chain_only(T, K, read_id, pass, n_seg, seg_state.data());
   for (uint32_t k = 0; k < n_seg; ++k) {
     uint32_t row = 0, mod = T.init_mod, emod = 1;
     if (k > 0 && T.has_model) {
-      if (!pb::qshmm_segment_start(T, A, K, read_id, pass, k * PB_TILE, 64, row, mod, emod)) return false;
+      if (!seg_ok) {
+        row = seg_state[k] & 0xFFFFu; mod = (seg_state[k] >> 16) & 0xFFu; emod = seg_state[k] >> 24;
+      } else if (!pb::qshmm_segment_start(T, A, K, read_id, pass, k * PB_TILE, 64, row, mod, emod)) {
+        return false;
+      }
     }
     pb::qshmm_simulate_segment(T, K, read_id, pass, k * PB_TILE, k == 0, row, mod, emod, slots.data() + (size_t)k * PB_SEG_STRIDE,
                                seg[k]);
@@ -162,8 +169,7 @@ long hostsim_run(const pbsim_model *m, const uint8_t *ascii_upper, const int16_t
         pb::QsSink sink;
         sink.init(reinterpret_cast<uint16_t *>(g_out.events.data() + ev_off), g_out.ckpts.data() + ck_base, cap);
         bool seg_done = false;
-        if (rng_mode == PBSIM_RNG_PHILOX && (!slow || img.uniform_bias) && use_seg && ae.seg_ok &&
-            (int)plan.wlen >= seg_min_len) {
+        if (rng_mode == PBSIM_RNG_PHILOX && (!slow || img.uniform_bias) && use_seg && (int)plan.wlen >= seg_min_len) {
           pb::HpProbe hpp;
           hpp.enabled = slow ? 1u : 0u;
           hpp.win = win;
@@ -174,7 +180,8 @@ long hostsim_run(const pbsim_model *m, const uint8_t *ascii_upper, const int16_t
           A.emodv = b + pb::QsBlobLayout::emodv_off;
           A.reach = ae.reach;
           ++seg_reads;
-          seg_done = run_segmented(T, A, seed, (uint32_t)seq_num, (uint32_t)read_id, (uint32_t)pass, plan.wlen, ae.rho, hpp, g_out.events, ev_off,
+          seg_done = run_segmented(T, A, seed, (uint32_t)seq_num, (uint32_t)read_id, (uint32_t)pass, plan.wlen, ae.rho, ae.seg_ok != 0, hpp,
+                                   g_out.events, ev_off,
                                    g_out.ckpts, ck_base, res);
           if (!seg_done) ++seg_fallbacks;
         }
@@ -184,7 +191,7 @@ long hostsim_run(const pbsim_model *m, const uint8_t *ascii_upper, const int16_t
           K.init(seed, (uint32_t)seq_num);
           pb::qshmm_simulate_fast(T, K, (uint32_t)read_id, (uint32_t)pass, plan.wlen,
                                   reinterpret_cast<uint16_t *>(g_out.events.data() + ev_off), g_out.ckpts.data() + ck_base, cap, res);
-        } else if (rng_mode == PBSIM_RNG_PHILOX) { pd.pass = (uint32_t)pass; pb::qshmm_simulate(T, pd, win, slow, plan.wlen, sink, res); }
+        } else if (rng_mode == PBSIM_RNG_PHILOX) { pd.pass = (uint32_t)pass; pd.cidx = 0xFFFFFFFFu; pb::qshmm_simulate(T, pd, win, slow, plan.wlen, sink, res); }
         else { rd.cur = cursor; pb::qshmm_simulate(T, rd, win, slow, plan.wlen, sink, res); cursor = rd.cur; }
         if (!seg_done) g_out.events.resize(ev_off + (size_t)res.n_entries * 2);
       } else {
@@ -204,7 +211,7 @@ long hostsim_run(const pbsim_model *m, const uint8_t *ascii_upper, const int16_t
         }
         pb::ErSink sink;
         sink.init(g_out.events.data() + ev_off, g_out.ckpts.data() + ck_base, cap);
-        if (rng_mode == PBSIM_RNG_PHILOX) { pd.pass = (uint32_t)pass; pb::errhmm_simulate(T, pd, win, slow, plan.wlen, sink, res); }
+        if (rng_mode == PBSIM_RNG_PHILOX) { pd.pass = (uint32_t)pass; pd.cidx = 0xFFFFFFFFu; pb::errhmm_simulate(T, pd, win, slow, plan.wlen, sink, res); }
         else { rd.cur = cursor; pb::errhmm_simulate(T, rd, win, slow, plan.wlen, sink, res); cursor = rd.cur; }
         g_out.events.resize(ev_off + (size_t)res.n_entries);
       }

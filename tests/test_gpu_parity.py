@@ -148,7 +148,7 @@ def test_segment_parallel_pass1_equals_oracle(eng, name):
     try:
         res = run_case_on_gpu(c, eng, "philox")
     finally:
-        eng.set_option("seg_min_len", 4096)
+        eng.set_option("seg_min_len", 2048)
     for i, ((reads, maf, st, text), o) in enumerate(zip(res, out), start=1):
         assert reads == o["reads"], "reads differ from the oracle, seq %d" % i
         assert maf == o["maf"], "maf differs from the oracle, seq %d" % i
