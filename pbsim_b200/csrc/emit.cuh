@@ -28,6 +28,7 @@ struct EmitParams {
   uint32_t rq_len;
   char rq[32];             // printf("%f", accuracy_mean)
   uint32_t glen;
+  uint32_t qs_segments;    // method is qshmm: segmented sub-reads use one slot per tile
 };
 
 struct EmitArgs {
@@ -127,7 +128,8 @@ __global__ void k_sizes(Batch B, EmitParams P, uint32_t n_sub, uint64_t *reads_s
   reads_size[s] = L.reads_size;
   maf_size[s] = L.maf_size;
   const uint32_t ne = B.nent[s];
-  if ((B.plan_meta[r] >> 11) & 1u) ntiles[s] = ne == 0 ? 1u : ne;  // segmented: nent holds the tile count
+  // segmented qshmm sub-reads: nent holds the tile count (errhmm tiles stay one contiguous stream)
+  if (P.qs_segments && ((B.plan_meta[r] >> 11) & 1u)) ntiles[s] = ne == 0 ? 1u : ne;
   else ntiles[s] = ne == 0 ? 1u : (ne + PB_TILE - 1u) / PB_TILE;
 }
 
@@ -531,7 +533,7 @@ __global__ void __launch_bounds__(kEmitThreads) k_emit(EmitArgs A) {
     const Ckpt c0 = ckp[tile];
     // sequential pass 1: one contiguous stream, tile = entries [1024 t, 1024 (t+1)); segment-parallel pass 1:
     // tile t lives in its own slot (stride PB_SEG_STRIDE) and its entry count is in the checkpoint
-    const bool segmented = (A.B.plan_meta[r] >> 11) & 1u;
+    const bool segmented = METHOD == PBSIM_METHOD_QSHMM && ((A.B.plan_meta[r] >> 11) & 1u);
     const uint32_t e0 = segmented ? 0u : tile * PB_TILE;
     const uint32_t e1 = segmented ? c0.pad : min(nent, e0 + PB_TILE);
     const bool has_next = segmented ? (tile + 1u < nent) : (e1 < nent);

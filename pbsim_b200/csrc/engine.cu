@@ -268,6 +268,7 @@ DeviceModel device_model(const pbsim_engine *e) {
   M.er_bias = e->d_er_bias.as<uint16_t>();
   M.pass_num = (uint32_t)e->model.pass_num;
   M.uniform_bias = e->img.uniform_bias ? 1u : 0u;
+  M.method = (uint32_t)e->model.method;
   return M;
 }
 
@@ -432,7 +433,7 @@ int run_batch(pbsim_engine *e, uint32_t n_reads, int64_t clip_room, bool to_host
     rng.starts = e->d_starts.as<int64_t>();
   }
 
-  bool use_segments = qs && !replay && e->seg_enabled && clip_room < 0;
+  bool use_segments = !replay && e->seg_enabled && clip_room < 0;
   for (int attempt = 0; attempt < 6; ++attempt) {
     // ---- K1 plan
     const uint32_t ev_align = qs ? 8u : 16u;
@@ -489,6 +490,7 @@ int run_batch(pbsim_engine *e, uint32_t n_reads, int64_t clip_room, bool to_host
     // ---- K2 / K3 pass 1
     SimArgs A;
     A.seg_off = (const uint64_t *)seg_off;
+    A.bias_one = e->d_biasone.as<uint8_t>();
     A.seg_state = n_seg_total > 0 ? reinterpret_cast<uint32_t *>(e->d_seg.as<SegResult>() + n_seg_total) + 5ull * n_seg_total
                                   : nullptr;
     A.keys.init(rng.seed, (uint32_t)e->seq_num);
@@ -556,10 +558,16 @@ int run_batch(pbsim_engine *e, uint32_t n_reads, int64_t clip_room, bool to_host
       SA.bin_hi = sb_hi;
       SA.ev = e->d_ev.as<uint8_t>();
       SA.max_window = getenv("PBSIM_EXPERIMENT_NOCOUPLE") ? 0u : 4096u;  // timing experiment only: wrong states
-      k_sim_seg<<<seg_slots, kSimThreads, kQsSmemBytes, e->st>>>(SA);
-      k_find_end<<<nblk((uint64_t)n_sub * 32, 128), 128, 0, e->st>>>(B, S, G, e->d_biasone.as<uint8_t>(), pass,
-                                                                         e->d_ev.as<uint8_t>(), e->d_ck.as<Ckpt>(),
-                                                                         e->d_qc_prob.as<double>());
+      if (qs) {
+        k_sim_seg<<<seg_slots, kSimThreads, kQsSmemBytes, e->st>>>(SA);
+        k_find_end<<<nblk((uint64_t)n_sub * 32, 128), 128, 0, e->st>>>(B, S, G, e->d_biasone.as<uint8_t>(), pass,
+                                                                       e->d_ev.as<uint8_t>(), e->d_ck.as<Ckpt>(),
+                                                                       e->d_qc_prob.as<double>());
+      } else {
+        k_sim_seg_err<<<seg_slots, kSimThreads, e->er_smem_bar_off + 16, e->st>>>(SA, e->er_smem_bar_off);
+        k_find_end_err<<<nblk((uint64_t)n_sub * 32, 128), 128, 0, e->st>>>(B, S, G, SA.keys, e->d_biasone.as<uint8_t>(), pass,
+                                                                           e->d_ev.as<uint8_t>(), e->d_ck.as<Ckpt>());
+      }
       e->launches += 7;
       e->seg_batches++;
     }
@@ -637,6 +645,7 @@ int run_batch(pbsim_engine *e, uint32_t n_reads, int64_t clip_room, bool to_host
   CK(cudaMemsetAsync(maf_size + nv_sub, 0, 8, e->st));
   CK(cudaMemsetAsync(ntiles + nv_sub, 0, 8, e->st));
   e->emitp.glen = (uint32_t)e->glen;
+  e->emitp.qs_segments = qs ? 1u : 0u;
   {
     char head[192];
     snprintf(head, sizeof head, "%s%d", e->model.id_prefix, e->seq_num);
@@ -948,6 +957,7 @@ int pbsim_cuda_set_model(pbsim_engine *e, const pbsim_model *m) {
     const int smem = (int)e->er_smem_bar_off + 16;
     CK(cudaFuncSetAttribute(k_sim_errhmm<PBSIM_RNG_PHILOX>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     CK(cudaFuncSetAttribute(k_sim_errhmm<PBSIM_RNG_REPLAY>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CK(cudaFuncSetAttribute(k_sim_seg_err, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   }
   // emission constants
   e->emitp.pass_num = (uint32_t)m->pass_num;

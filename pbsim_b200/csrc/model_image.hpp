@@ -50,7 +50,7 @@ inline uint32_t er_blob_bytes(uint32_t nst, uint32_t *t2_off, uint32_t *emis_off
   uint32_t o = 0;
   *t2_off = o;   o += ((rows * 1000 * 2 + 15) / 16) * 16;
   *emis_off = o; o += ((rows * 1000 + 15) / 16) * 16;
-  *emod_off = o; o += ((rows * 2 + 15) / 16) * 16;
+  *emod_off = o; o += ((rows * 4 + 15) / 16) * 16;  // emod[rows] then tmod[rows] (uint16 each)
   return o;
 }
 
@@ -104,6 +104,28 @@ inline float estimate_rho(const pbsim_model &m, const pbsim_hmm_row &r) {
     if (!(e >= (uint32_t)m.sub_thre[qv] && e < (uint32_t)m.ins_thre[qv])) ++ref;  // not an insertion
     int guard = 0;
     while (pick(1000000) < (uint32_t)m.del_thre[qv] && ++guard < 64) ++ref;
+  }
+  return ref ? (float)((double)N / (double)ref) : 1.0f;
+}
+
+// errhmm: estimated alignment columns per consumed reference base (segment provisioning only)
+inline float estimate_rho_err(const pbsim_hmm_row &r, uint32_t mode, uint32_t rate_mag) {
+  uint64_t x = 0xA0761D6478BD642Full;
+  auto u32 = [&]() { x ^= x << 13; x ^= x >> 7; x ^= x << 17; return (uint32_t)(x >> 32); };
+  auto pick = [&](uint32_t mod) { return (uint32_t)(((uint64_t)u32() * (mod < 1 ? 1 : mod)) >> 32); };
+  const int N = 1 << 15;
+  uint64_t ref = 0;
+  int state = 0;
+  for (int c = 0; c < N; ++c) {
+    state = (c == 0 || state < 1 || state > r.nstates) ? r.init[pick(r.init_mod)] : r.tran[state * 1000 + pick(r.tran_mod[state])];
+    if (state < 1 || state > r.nstates) state = r.init[pick(r.init_mod)];
+    uint32_t kind;
+    if (pick(1000) + 1 <= (uint32_t)r.emis_del[state]) kind = 3;
+    else kind = r.emis_mod[state] == 0 ? pick(3) : r.emis[state * 1000 + pick(r.emis_mod[state])];
+    const uint32_t mag = pick(100) + 1;
+    if (mode == 1 && kind == 0 && mag <= rate_mag) kind = pick(3) + 1;
+    if (mode == 2 && kind != 0 && mag <= rate_mag) kind = 0;
+    if (kind != 2) ++ref;
   }
   return ref ? (float)((double)N / (double)ref) : 1.0f;
 }
@@ -231,7 +253,9 @@ struct ModelImage {
             em[s * 1000 + k] = r.emis[s * 1000 + k];
           }
           emod[s] = (uint16_t)(r.emis_mod[s] < 0 ? 0 : r.emis_mod[s]);
+          emod[(r.nstates + 1) + s] = (uint16_t)tmod(s);  // per-state transition modulus (chain-only prepass)
         }
+        e.rho = 1.0f;
         e.blob_bytes = bytes;
         e.nstates = (uint32_t)r.nstates;
         e.init_mod = (uint32_t)(r.init_mod < 1 ? 1 : r.init_mod);
@@ -273,6 +297,13 @@ struct ModelImage {
         e.mode = mode;
         e.rate_mag = mag;
         e.table_acc = (uint32_t)ta;
+      }
+      for (int a = m.acc_lo; a <= m.acc_hi; ++a) {
+        if (a < 0 || a >= PBSIM_NACC) continue;
+        AccEntry &e = acc[a];
+        if (!e.valid || e.mode == 3) continue;
+        e.rho = estimate_rho_err(m.rows[e.table_acc], e.mode, e.rate_mag);
+        e.seg_ok = 0;  // errhmm start states always come from the chain-only prepass
       }
       er_bias.assign(bias_cells, 0);
     }

@@ -251,4 +251,147 @@ __global__ void __launch_bounds__(128) k_find_end(Batch B, SegBatch S, DeviceGen
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// errhmm
+// ---------------------------------------------------------------------------------------------
+// shared memory: [table blob (t2 | emis | emod,tmod) | edel rounded | mbarrier]  (same layout as k_sim_errhmm)
+__global__ void __launch_bounds__(kSimThreads) k_sim_seg_err(SegArgs A, uint32_t smem_bar_off) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint32_t acc, lo, hi;
+  if (!cta_assignment(A.cta_order, A.cta_first, A.bin_lo, A.bin_hi, &acc, &lo, &hi)) return;
+  const AccEntry ae = A.M.acc[acc];
+  uint64_t *bar = reinterpret_cast<uint64_t *>(smem + smem_bar_off);
+  const uint32_t edel_bytes = ((ae.nstates + 1u) * 2u + 15u) / 16u * 16u;
+  if (threadIdx.x == 0) mbar_init(bar, 1);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(bar, ae.blob_bytes + edel_bytes);
+    tma_bulk_g2s(smem, A.M.blob + ae.blob_off, ae.blob_bytes, bar);
+    tma_bulk_g2s(smem + ae.blob_bytes, A.M.er_bias + ae.bias_off, edel_bytes, bar);
+  }
+  mbar_wait(bar, 0);
+  const uint32_t i = lo + threadIdx.x;
+  if (i >= hi) return;
+  const uint32_t seg = A.S.seg_order[i];
+  const uint32_t s = A.S.seg_sub[seg];
+  const uint32_t k = seg - (uint32_t)A.S.seg_off[s];
+  const uint32_t r = s / A.M.pass_num, pass = s % A.M.pass_num;
+  const uint32_t read_id = (uint32_t)(A.B.first_read + 1u + r);
+  ErView T;
+  uint32_t t2o, emo, emodo;
+  er_blob_bytes(ae.nstates, &t2o, &emo, &emodo);
+  T.t2 = reinterpret_cast<const uint16_t *>(smem + t2o);
+  T.emis = smem + emo;
+  T.emod = reinterpret_cast<const uint16_t *>(smem + emodo);
+  T.edel = reinterpret_cast<const uint16_t *>(smem + ae.blob_bytes);
+  T.edel_hp = A.M.er_bias + ae.bias_off + (ae.nstates + 1u);
+  T.init_mod = ae.init_mod;
+  T.mode = ae.mode;
+  T.rate_mag = ae.rate_mag;
+  uint32_t state = 0, mod = ae.init_mod;
+  bool pzero = true;
+  if (k > 0) {
+    const uint32_t t = A.S.seg_state[seg];
+    state = t & 63u;
+    mod = (t >> 6) & 0x3FFu;
+    pzero = (t >> 31) != 0u;
+  }
+  SegResult res;
+  errhmm_simulate_segment(T, A.keys, read_id, pass, k * PB_TILE, pzero, state, mod, A.ev + A.B.ev_off[s] + (uint64_t)k * PB_TILE,
+                          res);
+  A.S.seg_res[seg] = res;
+}
+
+// One warp per segmented errhmm sub-read: same result as errhmm_finish_segmented (sim_core.cuh)
+__global__ void __launch_bounds__(128) k_find_end_err(Batch B, SegBatch S, DeviceGenome G, PhiloxKeys K,
+                                                      const uint8_t *bias_one, uint32_t pass_num, uint8_t *ev, Ckpt *ck) {
+  const uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t lane = threadIdx.x & 31u;
+  if (s >= B.n_sub) return;
+  const uint64_t lo = S.seg_off[s], hi = S.seg_off[s + 1];
+  if (hi == lo) return;
+  const uint32_t r = s / pass_num, pass = s % pass_num;
+  const uint32_t meta = B.plan_meta[r];
+  const uint32_t wlen = B.plan_wlen[r];
+  const uint32_t read_id = (uint32_t)(B.first_read + 1u + r);
+  HpProbe hp;
+  hp.enabled = (meta >> 9) & 1u;
+  hp.win.ascii = G.ascii;
+  hp.win.hp4 = G.hp4;
+  hp.win.offset = B.plan_off[r];
+  hp.win.wlen = wlen;
+  hp.win.minus = (meta >> 8) & 1u;
+  hp.xm = G.xm;
+  hp.bias_one = bias_one;
+  uint8_t *ev_base = ev + B.ev_off[s];
+  const SegResult *seg = S.seg_res + lo;
+  Ckpt *ckp = ck + B.ck_off[s];
+  const uint32_t n_seg = (uint32_t)(hi - lo);
+  const uint32_t lt = (1u << lane) - 1u;
+  uint32_t R = 0, P = 0, C = 0, nsub = 0, nins = 0, ndel = 0, flags = 0;
+  bool done = false;
+  for (uint32_t k = 0; k < n_seg && !done; ++k) {
+    flags |= seg[k].flags;
+    if (lane == 0) {
+      Ckpt c; c.col = C; c.ref = R; c.read = P; c.pad = PB_TILE;
+      ckp[k] = c;
+    }
+    if (!hp.enabled && (uint64_t)R + seg[k].ref_adv < wlen) {
+      P += PB_TILE - seg[k].ndel; R += seg[k].ref_adv; nsub += seg[k].nsub; nins += (uint32_t)seg[k].prob;
+      ndel += seg[k].ndel; C += PB_TILE;
+      continue;
+    }
+    uint8_t *e = ev_base + (uint64_t)k * PB_TILE;
+    for (uint32_t i = 0; i < PB_TILE && !done; i += 32u) {
+      const uint32_t v = e[i + lane];
+      const uint32_t kind = v & 3u;
+      const bool adv = kind != PB_KIND_INS;
+      const uint32_t m_adv = __ballot_sync(0xFFFFFFFFu, adv);
+      const uint32_t Rb = R + __popc(m_adv & lt);
+      const uint32_t total = __popc(m_adv);
+      bool touch = false;
+      if (hp.enabled && (v & 0x80u) && Rb < wlen) {
+        const uint32_t g = hp.win.gidx(Rb);
+        touch = range_exceptional(G.xm, g, g);
+      }
+      const bool need = __any_sync(0xFFFFFFFFu, touch) || (R + total >= wlen);
+      if (!need) {
+        const uint32_t m_del = __ballot_sync(0xFFFFFFFFu, kind == PB_KIND_DEL);
+        const uint32_t m_sub = __ballot_sync(0xFFFFFFFFu, kind == PB_KIND_SUB);
+        P += 32u - __popc(m_del);
+        R += total;
+        nsub += __popc(m_sub);
+        nins += 32u - total;
+        ndel += __popc(m_del);
+        C += 32u;
+      } else {
+        uint32_t res[8];
+        if (lane == 0) {
+          const ErTileWalk t = errhmm_walk_tile(e + i, 32u, R, P, wlen, hp, K, read_id, pass, k * PB_TILE + i);
+          res[0] = t.n_entries; res[1] = t.positions; res[2] = t.ref_adv; res[3] = t.nsub; res[4] = t.nins;
+          res[5] = t.ndel; res[6] = t.ended; res[7] = t.early_repair;
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) res[q] = __shfl_sync(0xFFFFFFFFu, res[q], 0);
+        __syncwarp();
+        P += res[1]; R += res[2]; nsub += res[3]; nins += res[4]; ndel += res[5]; C += res[0];
+        if (res[7]) flags |= 8u;
+        if (res[6]) done = true;
+      }
+    }
+  }
+  if (!done) flags |= 4u;
+  if (lane == 0) {
+    B.nent[s] = C;  // errhmm tiles are contiguous: total number of columns
+    B.rlen[s] = P;
+    B.ncol[s] = C;
+    B.nsub[s] = nsub;
+    B.nins[s] = nins;
+    B.ndel[s] = ndel;
+    B.flags[s] = flags ? (4u | (flags << 8)) : 0u;
+    B.draws_used[s] = 0;
+    B.accuracy[s] = 1.0 - ((double)(nsub + nins + ndel) / (double)P);
+  }
+}
+
 }  // namespace pb

@@ -902,6 +902,175 @@ struct ErSink {
   }
 };
 
+// ---------------------------------------------------------------------------------------------
+// errhmm SEGMENT-PARALLEL pass 1 (PHILOX).  Same idea as for qshmm; a segment is PB_TILE alignment columns and
+// every column is exactly one entry, so the tiles of a read stay one contiguous stream.  Start states always come
+// from the chain-only prepass.  A column whose deletion test succeeded also records what it would have been had
+// the homopolymer table suppressed the deletion (bits 5-6, flag bit 7), so that the walk that knows the reference
+// offset can repair it without tables:   entry = kind | info << 2 | alt_kind << 5 | deletion-test flag << 7
+// ---------------------------------------------------------------------------------------------
+PB_HD uint32_t er_apply_mag(uint32_t kind, uint32_t mode, uint32_t rate_mag, uint32_t mag, uint32_t mag3) {
+  if (mode == 1u) return (kind == PB_KIND_MATCH && mag <= rate_mag) ? mag3 : kind;       // :3892-3899
+  if (mode == 2u) return (kind != PB_KIND_MATCH && mag <= rate_mag) ? PB_KIND_MATCH : kind;  // :3920-3925
+  return kind;
+}
+
+// Chain-only prepass: the state (state | modulus << 6 | "no read base yet" << 31) in front of every segment k >= 1.
+// While no read base has been produced the init row is drawn again at every column (:3853), so the leading
+// columns are evaluated completely (deletion test included); after the first read base only the chain advances.
+PB_HD void errhmm_chain_only(const ErView &T, const PhiloxKeys &K, const HpProbe &hp, uint32_t read_id,
+                             uint32_t pass, uint32_t n_seg, uint32_t *seg_state) {
+  uint32_t state = 0, mod = T.init_mod;
+  const uint32_t c1 = pass << 16;
+  const uint32_t c_end = (n_seg - 1u) * PB_TILE;
+  uint32_t cw[4] = {0, 0, 0, 0};
+  bool pzero = true;
+  for (uint32_t c = 0; c < c_end; ++c) {
+    if (c == 0u || (c & 3u) == 0u) philox_block_keys(K, c >> 2, c1, read_id, 2u, cw);
+    const uint32_t k4 = c & 3u;
+    const uint32_t wdraw = k4 == 0u ? cw[0] : (k4 == 1u ? cw[1] : (k4 == 2u ? cw[2] : cw[3]));
+    const uint32_t row = pzero ? 0u : state;
+    const uint32_t m = pzero ? T.init_mod : mod;
+    const uint32_t t = T.t2[row * PB_ER_ROW + mulhi32(wdraw, m)];
+    state = t & 63u;
+    mod = t >> 6;
+    if (pzero) {
+      // does this column produce a read base?  (reference offset == column index while only deletions came)
+      uint32_t w[4];
+      philox_block_keys(K, c, c1, read_id, 1u, w);
+      const uint32_t x = mulhi32(w[1], 1000u) + 1u;
+      bool isdel = x <= T.edel[state];
+      if (isdel && hp.enabled && hp.suppress(c)) isdel = false;
+      const uint32_t em = T.emod[state];
+      const uint32_t k2 = (em == 0u) ? mulhi32(w[2], 3u) : (uint32_t)T.emis[state * PB_ER_ROW + mulhi32(w[2], em == 0u ? 1u : em)];
+      const uint32_t mag = mulhi32(w[3], 100u) + 1u, mag3 = (((w[3] & 0xFFFu) * 3u) >> 12) + 1u;
+      const uint32_t kind = er_apply_mag(isdel ? PB_KIND_DEL : k2, T.mode, T.rate_mag, mag, mag3);
+      if (kind != PB_KIND_DEL) pzero = false;
+    }
+    if (((c + 1u) & (PB_TILE - 1u)) == 0u) seg_state[(c + 1u) / PB_TILE] = state | (mod << 6) | (pzero ? 0x80000000u : 0u);
+  }
+}
+
+PB_HD void errhmm_simulate_segment(const ErView &T, const PhiloxKeys &K, uint32_t read_id, uint32_t pass,
+                                   uint32_t c_start, bool pzero_in, uint32_t state, uint32_t mod, uint8_t *ev,
+                                   SegResult &res) {
+  uint32_t radv = 0, nsub = 0, ndel = 0, nins = 0;
+  bool pzero = pzero_in;  // no read base yet: the init row is drawn again (:3853)
+  const uint32_t c1 = pass << 16;
+  for (uint32_t C = c_start; C < c_start + PB_TILE; C += PB_GROUP) {
+    uint32_t g[PB_GROUP][4], cw[PB_GROUP];
+#pragma unroll
+    for (uint32_t u = 0; u < PB_GROUP; ++u) philox_block_keys(K, C + u, c1, read_id, 1u, g[u]);
+    philox_block_keys(K, C >> 2, c1, read_id, 2u, cw);
+    uint32_t packed = 0;
+#pragma unroll
+    for (uint32_t u = 0; u < PB_GROUP; ++u) {
+      const uint32_t w0 = g[u][0], w1 = g[u][1], w2 = g[u][2], w3 = g[u][3];
+      const uint32_t row = pzero ? 0u : state;
+      const uint32_t m = pzero ? T.init_mod : mod;
+      const uint32_t t = T.t2[row * PB_ER_ROW + mulhi32(cw[u], m)];
+      state = t & 63u;
+      mod = t >> 6;
+      const uint32_t x = mulhi32(w1, 1000u) + 1u;
+      const bool isdel = x <= T.edel[state];
+      const uint32_t em = T.emod[state];
+      const uint32_t k2 = (em == 0u) ? mulhi32(w2, 3u) : (uint32_t)T.emis[state * PB_ER_ROW + mulhi32(w2, em == 0u ? 1u : em)];
+      const uint32_t mag = mulhi32(w3, 100u) + 1u, mag3 = (((w3 & 0xFFFu) * 3u) >> 12) + 1u;
+      const uint32_t kind = er_apply_mag(isdel ? PB_KIND_DEL : k2, T.mode, T.rate_mag, mag, mag3);
+      const uint32_t alt = er_apply_mag(k2, T.mode, T.rate_mag, mag, mag3);
+      const uint32_t c3 = ((w0 & 0xFFFu) * 3u) >> 12, c8 = w1 & 7u;
+      const uint32_t info = kind == PB_KIND_SUB ? c3 : (kind == PB_KIND_INS ? c8 : 0u);
+      const uint32_t e = kind | (info << 2) | (isdel ? ((alt << 5) | 0x80u) : 0u);
+      packed |= e << (8u * u);
+      nsub += (kind == PB_KIND_SUB) ? 1u : 0u;
+      nins += (kind == PB_KIND_INS) ? 1u : 0u;
+      ndel += (kind == PB_KIND_DEL) ? 1u : 0u;
+      radv += (kind == PB_KIND_INS) ? 0u : 1u;
+      if (kind != PB_KIND_DEL) pzero = false;
+    }
+    *reinterpret_cast<uint32_t *>(ev + (C - c_start)) = packed;
+  }
+  res.n_entries = PB_TILE;
+  res.ref_adv = radv;
+  res.nsub = nsub;
+  res.ndel = ndel;
+  res.flags = 0;
+  res.prob = (double)nins;       // errhmm: the insertion count travels in the otherwise unused field
+}
+
+struct ErTileWalk {
+  uint32_t n_entries, positions, ref_adv, nsub, nins, ndel, ended;
+  uint32_t early_repair;  // a suppressed deletion before the first read base: init-row bookkeeping is off -> redo
+};
+
+// exact walk of columns [0, n) of a tile that starts at reference offset R_start: stops where the window is used up
+// (:3850) and, for reads touching exceptional blocks, turns deletion columns that the homopolymer table suppresses
+// (hp at the CURRENT base, :3860) into their recorded alternative
+PB_HD ErTileWalk errhmm_walk_tile(uint8_t *ev, uint32_t n, uint32_t R_start, uint32_t P_start, uint32_t wlen,
+                                  const HpProbe &hp, const PhiloxKeys &K, uint32_t read_id, uint32_t pass,
+                                  uint32_t c_abs) {
+  ErTileWalk t;
+  t.n_entries = 0; t.positions = 0; t.ref_adv = 0; t.nsub = 0; t.nins = 0; t.ndel = 0; t.ended = 0; t.early_repair = 0;
+  uint32_t R = R_start;
+  for (uint32_t i = 0; i < n; ++i) {
+    if (R >= wlen) { t.ended = 1; break; }
+    uint32_t v = ev[i];
+    uint32_t kind = v & 3u;
+    if (hp.enabled && (v & 0x80u) && hp.suppress(R)) {
+      if (P_start + t.positions == 0u) t.early_repair = 1u;
+      kind = (v >> 5) & 3u;
+      uint32_t w[4];
+      philox_block_keys(K, c_abs + i, pass << 16, read_id, 1u, w);
+      const uint32_t info = kind == PB_KIND_SUB ? (((w[0] & 0xFFFu) * 3u) >> 12) : (kind == PB_KIND_INS ? (w[1] & 7u) : 0u);
+      v = kind | (info << 2);
+      ev[i] = (uint8_t)v;
+    }
+    t.positions += (kind == PB_KIND_DEL) ? 0u : 1u;
+    t.nsub += (kind == PB_KIND_SUB) ? 1u : 0u;
+    t.nins += (kind == PB_KIND_INS) ? 1u : 0u;
+    t.ndel += (kind == PB_KIND_DEL) ? 1u : 0u;
+    R += (kind == PB_KIND_INS) ? 0u : 1u;
+    t.n_entries = i + 1u;
+    if (R >= wlen) { t.ended = 1; break; }
+  }
+  t.ref_adv = R - R_start;
+  return t;
+}
+
+// sequential statement of the errhmm find_end (the GPU runs a warp-cooperative version, seg_kernels.cuh)
+PB_HD void errhmm_finish_segmented(uint8_t *ev_base, const SegResult *seg, uint32_t n_seg, uint32_t wlen,
+                                   const HpProbe &hp, const PhiloxKeys &K, uint32_t read_id, uint32_t pass, Ckpt *ck,
+                                   SegRead &out) {
+  uint32_t R = 0, P = 0, nsub = 0, nins = 0, ndel = 0, C = 0;
+  out.flags = 0;
+  out.n_tiles = 0;
+  bool done = false;
+  for (uint32_t k = 0; k < n_seg && !done; ++k) {
+    out.flags |= seg[k].flags;
+    Ckpt c; c.col = C; c.ref = R; c.read = P; c.pad = PB_TILE;
+    ck[k] = c;
+    if (hp.enabled || (uint64_t)R + seg[k].ref_adv >= wlen) {
+      const ErTileWalk t = errhmm_walk_tile(ev_base + (uint64_t)k * PB_TILE, PB_TILE, R, P, wlen, hp, K, read_id, pass, k * PB_TILE);
+      if (t.early_repair) out.flags |= 8u;
+      P += t.positions; R += t.ref_adv; nsub += t.nsub; nins += t.nins; ndel += t.ndel; C += t.n_entries;
+      if (t.ended) {
+        out.n_tiles = k + 1u;
+        done = true;
+      }
+    } else {
+      const uint32_t si = (uint32_t)seg[k].prob;
+      P += PB_TILE - seg[k].ndel; R += seg[k].ref_adv; nsub += seg[k].nsub; nins += si; ndel += seg[k].ndel; C += PB_TILE;
+    }
+  }
+  if (!done) out.flags |= 4u;
+  out.rlen = P;
+  out.ncol = C;
+  out.nsub = nsub;
+  out.nins = nins;
+  out.ndel = ndel;
+  out.accuracy = 1.0 - ((double)(nsub + nins + ndel) / (double)P);
+}
+
 template <class Draw>
 PB_HD void errhmm_simulate(const ErView &T, Draw &d, const WindowRef &win, bool slow, uint32_t wlen,
                            ErSink &sink, SubreadResult &res) {

@@ -30,6 +30,7 @@ struct DeviceModel {
   const uint16_t *er_bias;
   uint32_t pass_num;
   uint32_t uniform_bias;
+  uint32_t method;            // PBSIM_METHOD_*
 };
 
 struct DeviceGenome {
@@ -108,17 +109,18 @@ __global__ void k_plan(DeviceModel M, DeviceGenome G, RngParams rng, Batch B, in
   // accuracy's chain couples fast (AccEntry::seg_ok)
   // (reads touching exceptional blocks qualify too in the default bias mode: k_find_end repairs their deletion
   // runs with the exact reference offset, pass 2 re-derives choices on non-ACGT bases)
+  const bool errm = M.method == PBSIM_METHOD_ERRHMM;
   const bool segmented = seg_min_len != 0u && rng.mode == PBSIM_RNG_PHILOX && (!slow || M.uniform_bias) && ae.valid &&
-                         p.wlen >= seg_min_len;
-  // chains with sticky states do not couple quickly: their segment start states come from a chain-only prepass
-  // that k_sim_qshmm runs for them (they keep their place in the sequential schedule for that)
-  const bool needs_chain = segmented && ae.has_model && !ae.seg_ok;
+                         p.wlen >= seg_min_len && !(errm && ae.mode == 3u);
+  // chains with sticky states do not couple quickly (and errhmm never uses coupling): their segment start states
+  // come from a chain-only prepass that the sequential kernel runs for them (they keep their place in its schedule)
+  const bool needs_chain = segmented && (errm || (ae.has_model && !ae.seg_ok));
   const uint32_t nseg = segmented ? qshmm_segments_for(p.wlen, ae.rho) : 0u;
   B.plan_meta[r] = p.acc | (minus << 8) | ((slow ? 1u : 0u) << 9) | ((ae.valid ? 0u : 1u) << 10) |
                    ((segmented ? 1u : 0u) << 11) | ((needs_chain ? 1u : 0u) << 12);
   // event-slot capacity: wlen * cap_num/cap_den + slack, rounded so that slots stay 16-byte aligned
   uint64_t cap = (uint64_t)p.wlen * cap_num / cap_den + 2048u;
-  if (segmented) cap = (uint64_t)nseg * PB_SEG_STRIDE + 64u;
+  if (segmented) cap = (uint64_t)nseg * (errm ? PB_TILE : PB_SEG_STRIDE) + 64u;
   cap = (cap + ev_align - 1u) / ev_align * ev_align;
   const uint32_t ckc = segmented ? nseg + 2u : (uint32_t)(cap / PB_TILE) + 2u;
   for (uint32_t h = 0; h < M.pass_num; ++h) {
@@ -253,6 +255,7 @@ struct SimArgs {
   const uint32_t *cta_order, *cta_first, *bin_lo, *bin_hi;
   const uint64_t *seg_off;  // segment-parallel pass 1: first segment of a sub-read
   uint32_t *seg_state;      // ... and the chain state in front of every segment (chain-only prepass)
+  const uint8_t *bias_one;  // [12] hp_del_bias[h] == 1
   uint8_t *ev;   // event arena
   Ckpt *ck;      // checkpoint arena
 };
@@ -414,6 +417,16 @@ __global__ void __launch_bounds__(kSimThreads) k_sim_errhmm(SimArgs A, uint32_t 
   win.wlen = wlen;
   win.minus = (meta >> 8) & 1u;
   const bool slow = (meta >> 9) & 1u;
+  if (RNG_MODE == PBSIM_RNG_PHILOX && ((meta >> 12) & 1u)) {
+    // chain-only prepass for the segment-parallel path (seg_kernels.cuh)
+    HpProbe hp;
+    hp.enabled = slow ? 1u : 0u;
+    hp.win = win;
+    hp.xm = A.G.xm;
+    hp.bias_one = A.bias_one;
+    errhmm_chain_only(T, A.keys, hp, (uint32_t)(A.B.first_read + 1u + r), pass, A.B.nseg[s], A.seg_state + A.seg_off[s]);
+    return;
+  }
   ErSink sink;
   sink.init(A.ev + A.B.ev_off[s], A.ck + A.B.ck_off[s], A.B.cap[s]);
   SubreadResult res;

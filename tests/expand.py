@@ -84,7 +84,7 @@ def expand_qshmm(ev, genome_upper, offset, wlen, minus):
 
 
 def expand_errhmm(ev, genome_upper, offset, wlen, minus):
-    ev = np.asarray(ev, dtype=np.uint8).astype(np.int64)
+    ev = np.asarray(ev, dtype=np.uint8).astype(np.int64) & 0x1F  # bits 5-7: pass-1 bookkeeping of the segment path
     kind = ev & 3
     info = (ev >> 2) & 7
     ref_adv = (kind != 2).astype(np.int64)

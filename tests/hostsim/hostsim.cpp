@@ -211,9 +211,58 @@ long hostsim_run(const pbsim_model *m, const uint8_t *ascii_upper, const int16_t
         }
         pb::ErSink sink;
         sink.init(g_out.events.data() + ev_off, g_out.ckpts.data() + ck_base, cap);
-        if (rng_mode == PBSIM_RNG_PHILOX) { pd.pass = (uint32_t)pass; pd.cidx = 0xFFFFFFFFu; pb::errhmm_simulate(T, pd, win, slow, plan.wlen, sink, res); }
+        bool seg_done = false;
+        if (rng_mode == PBSIM_RNG_PHILOX && (!slow || img.uniform_bias) && use_seg && ae.mode != 3 &&
+            (int)plan.wlen >= seg_min_len) {
+          // segment-parallel errhmm as the kernels run it: chain-only prepass, segments, find_end
+          pb::HpProbe hpp;
+          hpp.enabled = slow ? 1u : 0u;
+          hpp.win = win; hpp.xm = xm.data(); hpp.bias_one = bias_one;
+          pb::PhiloxKeys K;
+          K.init(seed, (uint32_t)seq_num);
+          const uint32_t n_seg = pb::qshmm_segments_for(plan.wlen, ae.rho);
+          std::vector<uint32_t> seg_state(n_seg + 1, 0);
+          pb::errhmm_chain_only(T, K, hpp, (uint32_t)read_id, (uint32_t)pass, n_seg, seg_state.data());
+          std::vector<uint8_t> slots((size_t)n_seg * PB_TILE + 16, 0);
+          std::vector<pb::SegResult> seg(n_seg);
+          for (uint32_t k = 0; k < n_seg; ++k) {
+            const uint32_t st = k == 0 ? 0u : (seg_state[k] & 63u), md = k == 0 ? T.init_mod : ((seg_state[k] >> 6) & 0x3FFu);
+            const bool pz = k == 0 ? true : (seg_state[k] >> 31) != 0;
+            pb::errhmm_simulate_segment(T, K, (uint32_t)read_id, (uint32_t)pass, k * PB_TILE, pz, st, md,
+                                        slots.data() + (size_t)k * PB_TILE, seg[k]);
+          }
+          std::vector<pb::Ckpt> ck(n_seg);
+          pb::SegRead sr;
+          pb::errhmm_finish_segmented(slots.data(), seg.data(), n_seg, plan.wlen, hpp, K, (uint32_t)read_id, (uint32_t)pass,
+                                      ck.data(), sr);
+          ++seg_reads;
+          if (sr.flags == 0) {
+            seg_done = true;
+            g_out.events.resize(ev_off + sr.ncol);
+            memcpy(g_out.events.data() + ev_off, slots.data(), sr.ncol);
+            if (hpp.enabled) {  // pass 2's re-derivation of the 4-way choice on non-ACGT bases
+              uint32_t R = 0;
+              for (uint32_t i = 0; i < sr.ncol; ++i) {
+                uint8_t &v = g_out.events[ev_off + i];
+                const uint32_t kind = v & 3u;
+                if (kind == PB_KIND_SUB && win.nonacgt(R)) {
+                  uint32_t w[4];
+                  pb::philox_block_keys(K, i, (uint32_t)pass << 16, (uint32_t)read_id, 1u, w);
+                  v = (uint8_t)(kind | (((w[0] >> 12) & 3u) << 2));
+                }
+                R += kind == PB_KIND_INS ? 0u : 1u;
+              }
+            }
+            res.n_entries = sr.ncol; res.rlen = sr.rlen; res.ncol = sr.ncol; res.nsub = sr.nsub; res.nins = sr.nins;
+            res.ndel = sr.ndel; res.overflow = 0; res.accuracy = sr.accuracy;
+          } else {
+            ++seg_fallbacks;
+          }
+        }
+        if (seg_done) {
+        } else if (rng_mode == PBSIM_RNG_PHILOX) { pd.pass = (uint32_t)pass; pd.cidx = 0xFFFFFFFFu; pb::errhmm_simulate(T, pd, win, slow, plan.wlen, sink, res); }
         else { rd.cur = cursor; pb::errhmm_simulate(T, rd, win, slow, plan.wlen, sink, res); cursor = rd.cur; }
-        g_out.events.resize(ev_off + (size_t)res.n_entries);
+        if (!seg_done) g_out.events.resize(ev_off + (size_t)res.n_entries);
       }
       if (!(m->method == PBSIM_METHOD_QSHMM && g_out.ckpts.size() != ck_base + cap / PB_TILE + 2))
         g_out.ckpts.resize(ck_base + (res.n_entries + PB_TILE - 1) / PB_TILE);

@@ -149,7 +149,8 @@ def test_fast_path_equals_generic_path():
 
 
 @pytest.mark.parametrize("name", ["qs_rsii_basic", "qs_rsii_quirks", "qs_delheavy_uniform", "qs_rsii_multipass",
-                                  "qs_rsii_fixedlen", "qs_hp11_uniform"])
+                                  "qs_rsii_fixedlen", "qs_hp11_uniform", "err_onthq_basic", "err_sequel_multipass",
+                                  "err_sequel_hiacc"])
 def test_segment_parallel_pass1_equals_oracle(name):
     """segment-parallel pass 1 (backward coupling + unbounded segments + find_end) gives the oracle's bytes"""
     c = Case(name)

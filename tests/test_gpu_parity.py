@@ -139,7 +139,8 @@ def test_synthetic_sequence_roundtrip_properties(eng):
 
 
 @pytest.mark.parametrize("name", ["qs_rsii_basic", "qs_rsii_quirks", "qs_delheavy_uniform", "qs_rsii_multipass",
-                                  "qs_ont_hpbias", "qs_hp11_uniform"])
+                                  "qs_ont_hpbias", "qs_hp11_uniform", "err_onthq_basic", "err_sequel_multipass",
+                                  "err_sequel_hiacc"])
 def test_segment_parallel_pass1_equals_oracle(eng, name):
     """segment-parallel pass 1 forced onto every read longer than one segment: same bytes as the oracle"""
     c = Case(name)
@@ -155,12 +156,13 @@ def test_segment_parallel_pass1_equals_oracle(eng, name):
         assert text == o["stats_text"]
 
 
-def test_segments_on_and_off_give_identical_bytes(eng):
-    """3 Mbp device-generated contig, RSII defaults (mean 9 kb): the segment-parallel and the sequential pass 1
+@pytest.mark.parametrize("method,model", [("qshmm", "QSHMM-RSII.model"), ("errhmm", "ERRHMM-ONT-HQ.model")])
+def test_segments_on_and_off_give_identical_bytes(eng, method, model):
+    """3 Mbp device-generated contig, default lengths (mean 9 kb): the segment-parallel and the sequential pass 1
     must agree byte for byte, statistics included"""
-    c = Case("qs_rsii_basic")
+    from tests.golden_util import model_path
     L = capi.load()
-    hm = capi.HostModel(L, capi.host_params("qshmm"), c.model)
+    hm = capi.HostModel(L, capi.host_params(method), model_path(model))
     eng.set_model(hm)
     n = 3000000
     eng.set_synthetic_sequence(n, 1, 7)
