@@ -550,6 +550,8 @@ int run_batch(pbsim_engine *e, uint32_t n_reads, int64_t clip_room, bool to_host
       SegArgs SA;
       SA.keys = A.keys;
       SA.M = M;
+      SA.G = G;
+      SA.bias_one = e->d_biasone.as<uint8_t>();
       SA.B = B;
       SA.S = S;
       SA.cta_order = sb_order;

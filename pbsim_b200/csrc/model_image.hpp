@@ -58,9 +58,11 @@ inline uint32_t er_blob_bytes(uint32_t nst, uint32_t *t2_off, uint32_t *emis_off
 // states driven by the same uniform draws): segment-parallel pass 1 is enabled when every trial coalesces
 // within 2048 steps and the median is below 512.  Only a performance switch: results are identical either way
 // (the backward search itself never fails, it just gets longer).
-inline bool coupling_screen(const pbsim_hmm_row &r, uint64_t reach) {
+inline uint32_t coupling_screen(const pbsim_hmm_row &r, uint64_t reach) {
   uint64_t x = 0x9E3779B97F4A7C15ull;
   int below = 0;
+  int times[32];
+  const int res = r.resolution;
   for (int trial = 0; trial < 32; ++trial) {
     uint64_t mask = reach;
     int t = 0;
@@ -72,14 +74,41 @@ inline bool coupling_screen(const pbsim_hmm_row &r, uint64_t reach) {
         const int s = __builtin_ctzll(m);
         if (s < 1 || s > r.nstates) { next |= 1ull << s; continue; }
         const int tm = r.tran_mod[s] < 1 ? 1 : r.tran_mod[s];
-        next |= 1ull << r.tran[s * 100 + (int)(((uint64_t)u * (uint32_t)tm) >> 32)];
+        next |= 1ull << r.tran[s * res + (int)(((uint64_t)u * (uint32_t)tm) >> 32)];
       }
       mask = next;
     }
-    if (mask & (mask - 1)) return false;
+    if (mask & (mask - 1)) return 0;
     if (t < 512) ++below;
+    times[trial] = t;
   }
-  return below >= 16;
+  if (below < 16) return 0;
+  // first backward window: a bit above the ~90th percentile of the observed coalescence times, power of two
+  for (int i = 0; i < 32; ++i)
+    for (int j = i + 1; j < 32; ++j)
+      if (times[j] < times[i]) { const int tt = times[i]; times[i] = times[j]; times[j] = tt; }
+  uint32_t w = 16;
+  while (w < (uint32_t)times[28] + 8u && w < 2048u) w *= 2u;
+  return w;
+}
+
+// states reachable from the init row (bit s)
+inline uint64_t reachable_states(const pbsim_hmm_row &r) {
+  uint64_t reach = 0, frontier = 0;
+  const int res = r.resolution;
+  for (int k = 0; k < r.init_mod && k < res; ++k) frontier |= 1ull << r.init[k];
+  while (frontier) {
+    const int s2 = __builtin_ctzll(frontier);
+    frontier &= frontier - 1;
+    if (reach >> s2 & 1ull) continue;
+    reach |= 1ull << s2;
+    if (s2 >= 1 && s2 <= r.nstates)
+      for (int k = 0; k < r.tran_mod[s2] && k < res; ++k) {
+        const int nx = r.tran[s2 * res + k];
+        if (!(reach >> nx & 1ull)) frontier |= 1ull << nx;
+      }
+  }
+  return reach;
 }
 
 // Estimated read positions per consumed reference base for one accuracy (Monte Carlo over the quantised
@@ -186,21 +215,9 @@ struct ModelImage {
             emodv[s2] = (uint8_t)(en >> 24);
           }
           // reachable closure from the init row, then a Monte-Carlo screen of the grand coupling time
-          uint64_t reach = 0, frontier = 0;
-          for (int k = 0; k < r.init_mod && k < 100; ++k) frontier |= 1ull << r.init[k];
-          while (frontier) {
-            const int s2 = __builtin_ctzll(frontier);
-            frontier &= frontier - 1;
-            if (reach >> s2 & 1ull) continue;
-            reach |= 1ull << s2;
-            if (s2 >= 1 && s2 <= r.nstates)
-              for (int k = 0; k < r.tran_mod[s2] && k < 100; ++k) {
-                const int nx = r.tran[s2 * 100 + k];
-                if (!(reach >> nx & 1ull)) frontier |= 1ull << nx;
-              }
-          }
+          const uint64_t reach = reachable_states(r);
           e.reach = reach;
-          e.seg_ok = coupling_screen(r, reach) ? 1u : 0u;
+          e.seg_ok = coupling_screen(r, reach);  // 0, or the first backward-coupling window
           e.rho = estimate_rho(m, r);
           e.blob_bytes = QsBlobLayout::bytes;
           e.has_model = 1;
@@ -303,7 +320,8 @@ struct ModelImage {
         AccEntry &e = acc[a];
         if (!e.valid || e.mode == 3) continue;
         e.rho = estimate_rho_err(m.rows[e.table_acc], e.mode, e.rate_mag);
-        e.seg_ok = 0;  // errhmm start states always come from the chain-only prepass
+        e.reach = reachable_states(m.rows[e.table_acc]);
+        e.seg_ok = coupling_screen(m.rows[e.table_acc], e.reach);
       }
       er_bias.assign(bias_cells, 0);
     }

@@ -45,6 +45,8 @@ __global__ void k_seg_fill(Batch B, SegBatch S, uint32_t pass_num) {
 struct SegArgs {
   PhiloxKeys keys;
   DeviceModel M;
+  DeviceGenome G;
+  const uint8_t *bias_one;
   Batch B;
   SegBatch S;
   const uint32_t *cta_order, *cta_first, *bin_lo, *bin_hi;
@@ -100,7 +102,7 @@ __global__ void __launch_bounds__(kSimThreads) k_sim_seg(SegArgs A) {
       mod = (t >> 16) & 0xFFu;
       emod = t >> 24;
     } else if (A.max_window != 0u) {
-      ok = qshmm_segment_start(T, X, A.keys, read_id, pass, k * PB_TILE, 64u, row, mod, emod);
+      ok = qshmm_segment_start(T, X, A.keys, read_id, pass, k * PB_TILE, ae.seg_ok, row, mod, emod);
     }
   }
   // the coupling loops leave the lanes of a warp at different points; without an explicit reconvergence the
@@ -290,13 +292,36 @@ __global__ void __launch_bounds__(kSimThreads) k_sim_seg_err(SegArgs A, uint32_t
   T.rate_mag = ae.rate_mag;
   uint32_t state = 0, mod = ae.init_mod;
   bool pzero = true;
+  bool ok = true;
   if (k > 0) {
-    const uint32_t t = A.S.seg_state[seg];
-    state = t & 63u;
-    mod = (t >> 6) & 0x3FFu;
-    pzero = (t >> 31) != 0u;
+    if ((A.B.plan_meta[r] >> 12) & 1u) {  // recorded by the chain-only prepass
+      const uint32_t t = A.S.seg_state[seg];
+      state = t & 63u;
+      mod = (t >> 6) & 0x3FFu;
+      pzero = (t >> 31) != 0u;
+    } else {
+      HpProbe hp;
+      const uint32_t meta = A.B.plan_meta[r];
+      hp.enabled = (meta >> 9) & 1u;
+      hp.win.ascii = A.G.ascii;
+      hp.win.hp4 = A.G.hp4;
+      hp.win.offset = A.B.plan_off[r];
+      hp.win.wlen = A.B.plan_wlen[r];
+      hp.win.minus = (meta >> 8) & 1u;
+      hp.xm = A.G.xm;
+      hp.bias_one = A.bias_one;
+      // tmod[] sits behind emod[] in the blob
+      errhmm_segment_start(T, T.emod + (ae.nstates + 1u), ae.reach, A.keys, hp, read_id, pass, k * PB_TILE, ae.seg_ok, state,
+                           mod, pzero);
+    }
   }
+  __syncwarp();
   SegResult res;
+  if (!ok) {
+    res.n_entries = 0; res.ref_adv = 0; res.nsub = 0; res.ndel = 0; res.flags = 2u; res.prob = 0.0;
+    A.S.seg_res[seg] = res;
+    return;
+  }
   errhmm_simulate_segment(T, A.keys, read_id, pass, k * PB_TILE, pzero, state, mod, A.ev + A.B.ev_off[s] + (uint64_t)k * PB_TILE,
                           res);
   A.S.seg_res[seg] = res;

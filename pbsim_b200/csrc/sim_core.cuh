@@ -915,17 +915,17 @@ PB_HD uint32_t er_apply_mag(uint32_t kind, uint32_t mode, uint32_t rate_mag, uin
   return kind;
 }
 
-// Chain-only prepass: the state (state | modulus << 6 | "no read base yet" << 31) in front of every segment k >= 1.
-// While no read base has been produced the init row is drawn again at every column (:3853), so the leading
-// columns are evaluated completely (deletion test included); after the first read base only the chain advances.
-PB_HD void errhmm_chain_only(const ErView &T, const PhiloxKeys &K, const HpProbe &hp, uint32_t read_id,
-                             uint32_t pass, uint32_t n_seg, uint32_t *seg_state) {
+// Exact chain state in front of column c_target, computed from column 0.  While no read base has been produced
+// the init row is drawn again at every column (:3853), so the leading columns are evaluated completely (deletion
+// test included); after the first read base only the chain advances.  `rec`, if given, receives
+// state | modulus << 6 | "no read base yet" << 31 in front of every segment k >= 1 passed on the way.
+PB_HD void errhmm_state_at(const ErView &T, const PhiloxKeys &K, const HpProbe &hp, uint32_t read_id, uint32_t pass,
+                           uint32_t c_target, uint32_t &state_out, uint32_t &mod_out, bool &pzero_out, uint32_t *rec) {
   uint32_t state = 0, mod = T.init_mod;
   const uint32_t c1 = pass << 16;
-  const uint32_t c_end = (n_seg - 1u) * PB_TILE;
   uint32_t cw[4] = {0, 0, 0, 0};
   bool pzero = true;
-  for (uint32_t c = 0; c < c_end; ++c) {
+  for (uint32_t c = 0; c < c_target; ++c) {
     if (c == 0u || (c & 3u) == 0u) philox_block_keys(K, c >> 2, c1, read_id, 2u, cw);
     const uint32_t k4 = c & 3u;
     const uint32_t wdraw = k4 == 0u ? cw[0] : (k4 == 1u ? cw[1] : (k4 == 2u ? cw[2] : cw[3]));
@@ -947,7 +947,73 @@ PB_HD void errhmm_chain_only(const ErView &T, const PhiloxKeys &K, const HpProbe
       const uint32_t kind = er_apply_mag(isdel ? PB_KIND_DEL : k2, T.mode, T.rate_mag, mag, mag3);
       if (kind != PB_KIND_DEL) pzero = false;
     }
-    if (((c + 1u) & (PB_TILE - 1u)) == 0u) seg_state[(c + 1u) / PB_TILE] = state | (mod << 6) | (pzero ? 0x80000000u : 0u);
+    if (rec && ((c + 1u) & (PB_TILE - 1u)) == 0u) rec[(c + 1u) / PB_TILE] = state | (mod << 6) | (pzero ? 0x80000000u : 0u);
+  }
+  state_out = state;
+  mod_out = mod;
+  pzero_out = pzero;
+}
+
+// Chain-only prepass (sticky chains): states in front of every segment k >= 1
+PB_HD void errhmm_chain_only(const ErView &T, const PhiloxKeys &K, const HpProbe &hp, uint32_t read_id,
+                             uint32_t pass, uint32_t n_seg, uint32_t *seg_state) {
+  uint32_t st, md;
+  bool pz;
+  errhmm_state_at(T, K, hp, read_id, pass, (n_seg - 1u) * PB_TILE, st, md, pz, seg_state);
+}
+
+// Backward coupling for errhmm: state entering column c_start (>= PB_TILE), assuming a read base exists before the
+// window (transition rows only).  A window never reaches below column 512 (then the exact walk from column 0 is
+// taken instead); segment 0 reports reads whose first read base comes later than that (flag 32 -> sequential
+// redo), so the assumption is checked, not hoped for.
+PB_HD void errhmm_segment_start(const ErView &T, const uint16_t *tmodv, uint64_t reach, const PhiloxKeys &K,
+                                const HpProbe &hp, uint32_t read_id, uint32_t pass, uint32_t c_start,
+                                uint32_t first_window, uint32_t &state, uint32_t &mod, bool &pzero) {
+  const uint32_t c1 = pass << 16;
+  for (uint32_t B = first_window;; B *= 2u) {
+    if (c_start < B + 512u) {
+      errhmm_state_at(T, K, hp, read_id, pass, c_start, state, mod, pzero, nullptr);
+      return;
+    }
+    const uint32_t c0 = c_start - B;
+    uint64_t mask = reach;
+    uint32_t s_state = 0, s_mod = 1;
+    bool single = false;
+    uint32_t cwb[4] = {0, 0, 0, 0};
+    for (uint32_t c = c0; c < c_start; ++c) {
+      if (c == c0 || (c & 3u) == 0u) philox_block_keys(K, c >> 2, c1, read_id, 2u, cwb);
+      const uint32_t k4 = c & 3u;
+      const uint32_t wdraw = k4 == 0u ? cwb[0] : (k4 == 1u ? cwb[1] : (k4 == 2u ? cwb[2] : cwb[3]));
+      if (single) {
+        const uint32_t t = T.t2[s_state * PB_ER_ROW + mulhi32(wdraw, s_mod)];
+        s_state = t & 63u;
+        s_mod = t >> 6;
+      } else {
+        uint64_t next = 0;
+        uint32_t last_t = 0;
+        for (uint64_t m = mask; m; m &= m - 1ull) {
+#if defined(__CUDA_ARCH__)
+          const uint32_t s = (uint32_t)__ffsll((long long)m) - 1u;
+#else
+          const uint32_t s = (uint32_t)__builtin_ctzll(m);
+#endif
+          last_t = T.t2[s * PB_ER_ROW + mulhi32(wdraw, tmodv[s])];
+          next |= 1ull << (last_t & 63u);
+        }
+        mask = next;
+        if ((mask & (mask - 1ull)) == 0ull) {
+          single = true;
+          s_state = last_t & 63u;
+          s_mod = last_t >> 6;
+        }
+      }
+    }
+    if (single) {
+      state = s_state;
+      mod = s_mod;
+      pzero = false;
+      return;
+    }
   }
 }
 
@@ -955,6 +1021,7 @@ PB_HD void errhmm_simulate_segment(const ErView &T, const PhiloxKeys &K, uint32_
                                    uint32_t c_start, bool pzero_in, uint32_t state, uint32_t mod, uint8_t *ev,
                                    SegResult &res) {
   uint32_t radv = 0, nsub = 0, ndel = 0, nins = 0;
+  bool late = false;
   bool pzero = pzero_in;  // no read base yet: the init row is drawn again (:3853)
   const uint32_t c1 = pass << 16;
   for (uint32_t C = c_start; C < c_start + PB_TILE; C += PB_GROUP) {
@@ -989,12 +1056,13 @@ PB_HD void errhmm_simulate_segment(const ErView &T, const PhiloxKeys &K, uint32_
       if (kind != PB_KIND_DEL) pzero = false;
     }
     *reinterpret_cast<uint32_t *>(ev + (C - c_start)) = packed;
+    if (pzero && C - c_start + PB_GROUP >= 512u) late = true;
   }
   res.n_entries = PB_TILE;
   res.ref_adv = radv;
   res.nsub = nsub;
   res.ndel = ndel;
-  res.flags = 0;
+  res.flags = (late && pzero_in) ? 32u : 0u;  // no read base in the first 512 columns: coupling assumptions void
   res.prob = (double)nins;       // errhmm: the insertion count travels in the otherwise unused field
 }
 

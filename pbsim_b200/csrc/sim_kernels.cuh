@@ -114,7 +114,10 @@ __global__ void k_plan(DeviceModel M, DeviceGenome G, RngParams rng, Batch B, in
                          p.wlen >= seg_min_len && !(errm && ae.mode == 3u);
   // chains with sticky states do not couple quickly (and errhmm never uses coupling): their segment start states
   // come from a chain-only prepass that the sequential kernel runs for them (they keep their place in its schedule)
-  const bool needs_chain = segmented && (errm || (ae.has_model && !ae.seg_ok));
+  // Which way a segment learns its start state: backward coupling costs a window per SEGMENT (a quarter to a half
+  // of the segment for typical chains), the prepass one cheap pass per READ but sequentially.  Reads up to 32 k
+  // positions take the prepass (its critical path is short), longer reads coupling where the chain allows it.
+  const bool needs_chain = segmented && (errm || ae.has_model) && (!ae.seg_ok || p.wlen < 32768u);
   const uint32_t nseg = segmented ? qshmm_segments_for(p.wlen, ae.rho) : 0u;
   B.plan_meta[r] = p.acc | (minus << 8) | ((slow ? 1u : 0u) << 9) | ((ae.valid ? 0u : 1u) << 10) |
                    ((segmented ? 1u : 0u) << 11) | ((needs_chain ? 1u : 0u) << 12);

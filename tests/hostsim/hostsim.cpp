@@ -32,7 +32,7 @@ extern "C" long hostsim_seg_fallbacks() { return seg_fallbacks; }
 // the segment-parallel pass 1 as the kernels run it (k_sim_seg + k_find_end), sequentially on the host;
 // returns false if the read must fall back to the sequential path
 static bool run_segmented(const pb::QsView &T, const pb::QsSegAux &A, uint32_t seed, uint32_t seq_num, uint32_t read_id,
-                          uint32_t pass, uint32_t wlen, float rho, bool seg_ok, const pb::HpProbe &hp,
+                          uint32_t pass, uint32_t wlen, float rho, bool seg_ok, uint32_t first_window, const pb::HpProbe &hp,
                           std::vector<uint8_t> &events,
                           size_t ev_off, std::vector<pb::Ckpt> &ckpts, size_t ck_base, pb::SubreadResult &res) {
   pb::PhiloxKeys K;
@@ -47,7 +47,7 @@ static bool run_segmented(const pb::QsView &T, const pb::QsSegAux &A, uint32_t s
     if (k > 0 && T.has_model) {
       if (!seg_ok) {
         row = seg_state[k] & 0xFFFFu; mod = (seg_state[k] >> 16) & 0xFFu; emod = seg_state[k] >> 24;
-      } else if (!pb::qshmm_segment_start(T, A, K, read_id, pass, k * PB_TILE, 64, row, mod, emod)) {
+      } else if (!pb::qshmm_segment_start(T, A, K, read_id, pass, k * PB_TILE, first_window, row, mod, emod)) {
         return false;
       }
     }
@@ -180,7 +180,7 @@ long hostsim_run(const pbsim_model *m, const uint8_t *ascii_upper, const int16_t
           A.emodv = b + pb::QsBlobLayout::emodv_off;
           A.reach = ae.reach;
           ++seg_reads;
-          seg_done = run_segmented(T, A, seed, (uint32_t)seq_num, (uint32_t)read_id, (uint32_t)pass, plan.wlen, ae.rho, ae.seg_ok != 0, hpp,
+          seg_done = run_segmented(T, A, seed, (uint32_t)seq_num, (uint32_t)read_id, (uint32_t)pass, plan.wlen, ae.rho, ae.seg_ok != 0, ae.seg_ok, hpp,
                                    g_out.events, ev_off,
                                    g_out.ckpts, ck_base, res);
           if (!seg_done) ++seg_fallbacks;
@@ -222,12 +222,17 @@ long hostsim_run(const pbsim_model *m, const uint8_t *ascii_upper, const int16_t
           K.init(seed, (uint32_t)seq_num);
           const uint32_t n_seg = pb::qshmm_segments_for(plan.wlen, ae.rho);
           std::vector<uint32_t> seg_state(n_seg + 1, 0);
-          pb::errhmm_chain_only(T, K, hpp, (uint32_t)read_id, (uint32_t)pass, n_seg, seg_state.data());
+          if (!ae.seg_ok) pb::errhmm_chain_only(T, K, hpp, (uint32_t)read_id, (uint32_t)pass, n_seg, seg_state.data());
           std::vector<uint8_t> slots((size_t)n_seg * PB_TILE + 16, 0);
           std::vector<pb::SegResult> seg(n_seg);
+          bool couple_fail = false;
           for (uint32_t k = 0; k < n_seg; ++k) {
-            const uint32_t st = k == 0 ? 0u : (seg_state[k] & 63u), md = k == 0 ? T.init_mod : ((seg_state[k] >> 6) & 0x3FFu);
-            const bool pz = k == 0 ? true : (seg_state[k] >> 31) != 0;
+            uint32_t st = k == 0 ? 0u : (seg_state[k] & 63u), md = k == 0 ? T.init_mod : ((seg_state[k] >> 6) & 0x3FFu);
+            bool pz = k == 0 ? true : (seg_state[k] >> 31) != 0;
+            if (k > 0 && ae.seg_ok) {
+              pb::errhmm_segment_start(T, T.emod + (ae.nstates + 1u), ae.reach, K, hpp, (uint32_t)read_id, (uint32_t)pass,
+                                       k * PB_TILE, ae.seg_ok, st, md, pz);
+            }
             pb::errhmm_simulate_segment(T, K, (uint32_t)read_id, (uint32_t)pass, k * PB_TILE, pz, st, md,
                                         slots.data() + (size_t)k * PB_TILE, seg[k]);
           }
@@ -236,7 +241,7 @@ long hostsim_run(const pbsim_model *m, const uint8_t *ascii_upper, const int16_t
           pb::errhmm_finish_segmented(slots.data(), seg.data(), n_seg, plan.wlen, hpp, K, (uint32_t)read_id, (uint32_t)pass,
                                       ck.data(), sr);
           ++seg_reads;
-          if (sr.flags == 0) {
+          if (sr.flags == 0 && !couple_fail) {
             seg_done = true;
             g_out.events.resize(ev_off + sr.ncol);
             memcpy(g_out.events.data() + ev_off, slots.data(), sr.ncol);
