@@ -394,7 +394,8 @@ int run_batch(pbsim_engine *e, uint32_t n_reads, int64_t clip_room, bool to_host
   Batch &B = e->B;
   const uint32_t n_sub = B.n_sub;
   B.first_read = (uint64_t)e->next_read;
-  const uint32_t cta_slots = nblk(n_sub, kSimThreads) + kBins;
+  const uint32_t cta_threads = qs ? kSimThreads : kErrThreads;
+  const uint32_t cta_slots = nblk(n_sub, cta_threads) + kBins;
   CK(e->d_bins.ensure((4 * kBins + 8) * 4 + (size_t)cta_slots * 4 * 4));
   CK(e->d_ctrl.ensure(64 * 8));
   CK(e->h_ctrl.ensure(64 * 8));
@@ -451,8 +452,8 @@ int run_batch(pbsim_engine *e, uint32_t n_reads, int64_t clip_room, bool to_host
     }
     k_fill_u32<<<1, 256, 0, e->st>>>(bin_start, kBins + 1, 0xFFFFFFFFu);
     k_bin_bounds<<<nblk(n_sub, 256), 256, 0, e->st>>>(B.key_out, n_sub, bin_start);
-    k_cta_map<<<1, 32, 0, e->st>>>(bin_start, B.key_out, n_sub, bin_lo, bin_hi, cta_first);
-    k_cta_keys<<<nblk(cta_slots, 256), 256, 0, e->st>>>(B.key_out, bin_lo, cta_first, cta_slots, cta_key, cta_id);
+    k_cta_map<<<1, 32, 0, e->st>>>(bin_start, B.key_out, n_sub, bin_lo, bin_hi, cta_first, cta_threads);
+    k_cta_keys<<<nblk(cta_slots, 256), 256, 0, e->st>>>(B.key_out, bin_lo, cta_first, cta_slots, cta_key, cta_id, cta_threads);
     {
       size_t tmp = 0;
       CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, cta_key, cta_key_s, cta_id, cta_order, (int)cta_slots, 0, 21, e->st));
@@ -511,14 +512,14 @@ int run_batch(pbsim_engine *e, uint32_t n_reads, int64_t clip_room, bool to_host
       else k_sim_qshmm<PBSIM_RNG_PHILOX><<<grid, kSimThreads, kQsSmemBytes, e->st>>>(A);
     } else {
       const uint32_t smem = e->er_smem_bar_off + 16;
-      if (replay) k_sim_errhmm<PBSIM_RNG_REPLAY><<<grid, kSimThreads, smem, e->st>>>(A, e->er_smem_bar_off);
-      else k_sim_errhmm<PBSIM_RNG_PHILOX><<<grid, kSimThreads, smem, e->st>>>(A, e->er_smem_bar_off);
+      if (replay) k_sim_errhmm<PBSIM_RNG_REPLAY><<<grid, kErrThreads, smem, e->st>>>(A, e->er_smem_bar_off);
+      else k_sim_errhmm<PBSIM_RNG_PHILOX><<<grid, kErrThreads, smem, e->st>>>(A, e->er_smem_bar_off);
     }
     e->launches++;
     if (n_seg_total > 0) {
       // ---- segment-parallel pass 1 for the long reads (seg_kernels.cuh)
       const uint32_t nseg = (uint32_t)n_seg_total;
-      const uint32_t seg_slots = nblk(nseg, kSimThreads) + kBins;
+      const uint32_t seg_slots = nblk(nseg, cta_threads) + kBins;
       CK(e->d_seg_bins.ensure((4 * kBins + 8) * 4 + (size_t)seg_slots * 4 + 64));
       SegBatch S;
       S.n_seg_total = nseg;
@@ -545,7 +546,7 @@ int run_batch(pbsim_engine *e, uint32_t n_reads, int64_t clip_room, bool to_host
       }
       k_fill_u32<<<1, 256, 0, e->st>>>(sb_start, kBins + 1, 0xFFFFFFFFu);
       k_bin_bounds<<<nblk(nseg, 256), 256, 0, e->st>>>(S.seg_key_out, nseg, sb_start);
-      k_cta_map<<<1, 32, 0, e->st>>>(sb_start, S.seg_key_out, nseg, sb_lo, sb_hi, sb_first);
+      k_cta_map<<<1, 32, 0, e->st>>>(sb_start, S.seg_key_out, nseg, sb_lo, sb_hi, sb_first, cta_threads);
       k_iota_u32<<<nblk(seg_slots, 256), 256, 0, e->st>>>(sb_order, seg_slots);
       SegArgs SA;
       SA.keys = A.keys;
@@ -566,7 +567,7 @@ int run_batch(pbsim_engine *e, uint32_t n_reads, int64_t clip_room, bool to_host
                                                                        e->d_ev.as<uint8_t>(), e->d_ck.as<Ckpt>(),
                                                                        e->d_qc_prob.as<double>());
       } else {
-        k_sim_seg_err<<<seg_slots, kSimThreads, e->er_smem_bar_off + 16, e->st>>>(SA, e->er_smem_bar_off);
+        k_sim_seg_err<<<seg_slots, kErrThreads, e->er_smem_bar_off + 16, e->st>>>(SA, e->er_smem_bar_off);
         k_find_end_err<<<nblk((uint64_t)n_sub * 32, 128), 128, 0, e->st>>>(B, S, G, SA.keys, e->d_biasone.as<uint8_t>(), pass,
                                                                            e->d_ev.as<uint8_t>(), e->d_ck.as<Ckpt>());
       }

@@ -257,7 +257,7 @@ __global__ void __launch_bounds__(128) k_find_end(Batch B, SegBatch S, DeviceGen
 // errhmm
 // ---------------------------------------------------------------------------------------------
 // shared memory: [table blob (t2 | emis | emod,tmod) | edel rounded | mbarrier]  (same layout as k_sim_errhmm)
-__global__ void __launch_bounds__(kSimThreads) k_sim_seg_err(SegArgs A, uint32_t smem_bar_off) {
+__global__ void __launch_bounds__(kErrThreads) k_sim_seg_err(SegArgs A, uint32_t smem_bar_off) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint32_t acc, lo, hi;
   if (!cta_assignment(A.cta_order, A.cta_first, A.bin_lo, A.bin_hi, &acc, &lo, &hi)) return;

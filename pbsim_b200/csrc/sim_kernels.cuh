@@ -15,7 +15,8 @@
 
 namespace pb {
 
-constexpr int kSimThreads = 128;  // subreads per pass-1 CTA
+constexpr int kSimThreads = 128;  // qshmm: sub-reads / segments per pass-1 CTA (tables: 28 KB of shared memory)
+constexpr int kErrThreads = 512;  // errhmm: its 1000-resolution tables take 60-90 KB, so more threads share them
 constexpr int kBins = 202;        // schedule bins: accuracy * 2 + slow  (slow reads get CTAs of their own)
 
 struct DeviceModel {
@@ -148,7 +149,7 @@ __global__ void k_bin_bounds(const uint32_t *key_sorted, uint32_t n, uint32_t *b
 
 // cta_first[b] = first pass-1 CTA of bin b; cta_first[kBins] = total
 __global__ void k_cta_map(const uint32_t *bin_start, const uint32_t *key_sorted, uint32_t n, uint32_t *bin_lo,
-                          uint32_t *bin_hi, uint32_t *cta_first) {
+                          uint32_t *bin_hi, uint32_t *cta_first, uint32_t cta_threads) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   // bin_start holds 0xFFFFFFFF for empty bins; bin kBins collects the sub-reads that are NOT scheduled here
   // (segment-parallel pass 1), they sort behind every real bin
@@ -165,7 +166,7 @@ __global__ void k_cta_map(const uint32_t *bin_start, const uint32_t *key_sorted,
   }
   for (int a = 0; a < kBins; ++a) {
     cta_first[a] = total;
-    total += (bin_hi[a] - bin_lo[a] + kSimThreads - 1) / kSimThreads;
+    total += (bin_hi[a] - bin_lo[a] + cta_threads - 1) / cta_threads;
   }
   cta_first[kBins] = total;
 }
@@ -174,7 +175,7 @@ __global__ void k_cta_map(const uint32_t *bin_start, const uint32_t *key_sorted,
 // (low 20 bits of the sort key, smaller = longer); the engine sorts CTAs by it and pass 1 runs
 // CTA cta_order[blockIdx.x].  Slots beyond the map get the largest key and exit immediately.
 __global__ void k_cta_keys(const uint32_t *key_sorted, const uint32_t *bin_lo, const uint32_t *cta_first,
-                           uint32_t n_slots, uint32_t *cta_key, uint32_t *cta_id) {
+                           uint32_t n_slots, uint32_t *cta_key, uint32_t *cta_id, uint32_t cta_threads) {
   const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= n_slots) return;
   cta_id[b] = b;
@@ -188,7 +189,7 @@ __global__ void k_cta_keys(const uint32_t *key_sorted, const uint32_t *bin_lo, c
     if (cta_first[mid] <= b) lo = mid; else hi = mid;
   }
   // empty bins share cta_first with their successor: step to the last bin that starts at or before b
-  const uint32_t first = bin_lo[lo] + (b - cta_first[lo]) * kSimThreads;
+  const uint32_t first = bin_lo[lo] + (b - cta_first[lo]) * cta_threads;
   cta_key[b] = key_sorted[first] & 0xFFFFFu;
 }
 
@@ -237,8 +238,8 @@ __device__ __forceinline__ bool cta_assignment(const uint32_t *cta_order, const 
       while (a < kBins - 1 && cta_first[a + 1] <= b) ++a;
       const uint32_t local = b - cta_first[a];
       s_acc = a >> 1;
-      s_lo = bin_lo[a] + local * kSimThreads;
-      s_hi = min(bin_hi[a], s_lo + kSimThreads);
+      s_lo = bin_lo[a] + local * blockDim.x;
+      s_hi = min(bin_hi[a], s_lo + blockDim.x);
       s_ok = 1;
     }
   }
@@ -373,7 +374,7 @@ __global__ void __launch_bounds__(kSimThreads) k_sim_qshmm(SimArgs A) {
 // shared memory: [table blob (t2 | emis | emod) | edel (nst+1)*2 rounded | mbarrier]
 // ----------------------------------------------------------------------------------------------
 template <int RNG_MODE>
-__global__ void __launch_bounds__(kSimThreads) k_sim_errhmm(SimArgs A, uint32_t smem_bar_off) {
+__global__ void __launch_bounds__(kErrThreads) k_sim_errhmm(SimArgs A, uint32_t smem_bar_off) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint32_t acc, lo, hi;
   if (!cta_assignment(A.cta_order, A.cta_first, A.bin_lo, A.bin_hi, &acc, &lo, &hi)) return;
