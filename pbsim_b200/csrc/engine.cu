@@ -19,7 +19,11 @@
 #include <cstring>
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
+#include <condition_variable>
+#include <deque>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/pbsim_cuda.h"
@@ -195,20 +199,51 @@ struct pbsim_engine {
   int seg_enabled = 1;            // option "segments"
   int64_t seg_min_len = 2048;     // option "seg_min_len": shorter reads stay on the sequential path
   int64_t seg_batches = 0, seg_fallback_batches = 0;
-  DevBuf d_out_reads, d_out_maf;
+  // the records of a batch live in one of two output sets in HBM: with the pipeline on, a producer
+  // thread generates batch k+1 into the other set while batch k is handed to the caller
+  struct OutSet {
+    DevBuf reads, maf;
+  } out[2];
+  int cur_set = 0;                  // the set run_batch writes
   PinnedBuf h_ctrl, h_acc;
-  // host delivery: the records of a batch stay in HBM and are handed out in pieces through two
-  // pinned staging buffers per stream (D2H of piece i+1 overlaps the caller consuming piece i)
+  struct BatchItem {
+    int rc = 1;                     // 1 = a batch, 0 = the run is finished, < 0 = error (message in err)
+    std::string err;
+    int set = 0;
+    int64_t first_read = 0, n_reads = 0, bases = 0;
+    uint64_t reads_bytes = 0, maf_bytes = 0;
+  };
+  int pipeline = 1;                 // option "pipeline": 0 off, 1 host delivery only, 2 always
+  int64_t host_batch_bases = (int64_t)1 << 30;  // option: batch size of pipelined host delivery
+  bool mode_set = false, mode_to_host = false, pipelined = false;
+  std::thread producer;
+  std::mutex mu;
+  std::condition_variable cv;
+  std::deque<BatchItem> queue;
+  int free_sets = 2;
+  bool stop = false;
+  int held_set = -1;                // device delivery: the set the caller's chunk points into
+  // host delivery: records are handed out in pieces through two pinned staging buffers per
+  // stream (D2H of piece i+1, possibly the first of the next batch, overlaps the caller consuming piece i)
   PinnedBuf h_stage[2][2];          // [stream: 0 reads, 1 maf][slot]
   size_t stage_bytes = (size_t)128 << 20;
-  struct Pending {
+  struct Pending {                  // the batch pieces are being issued from
     bool active = false;
+    int set = 0;
     uint64_t total[2] = {0, 0}, issued[2] = {0, 0};
-    uint64_t inflight[2] = {0, 0};  // bytes being copied into slot `slot`
-    int slot = 0;
     bool first = true;
     int64_t first_read = 0, n_reads = 0, bases = 0;
   } pend;
+  struct Piece {                    // the piece in flight into h_stage[*][slot]
+    bool valid = false;
+    int slot = 0;
+    uint64_t bytes[2] = {0, 0};
+    bool first = false;
+    int64_t first_read = 0, n_reads = 0, bases = 0;
+    int release_set = -1;           // last piece of its batch: the set is free once this copy is done
+  } piece;
+  int next_slot = 0;
+  std::mutex err_mu;
   cudaEvent_t ev_copy = nullptr, ev_k[4] = {nullptr, nullptr, nullptr, nullptr}, ev_user[2] = {nullptr, nullptr};
   double sim_ms = 0, emit_ms = 0;
   int64_t target_batch_bases = (int64_t)6 << 30;
@@ -233,7 +268,12 @@ int fail(pbsim_engine *e, int code, const char *fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(buf, sizeof buf, fmt, ap);
   va_end(ap);
-  if (e) e->err = buf; else g_create_error = buf;
+  if (e) {
+    std::lock_guard<std::mutex> lk(e->err_mu);
+    e->err = buf;
+  } else {
+    g_create_error = buf;
+  }
   return code;
 }
 
@@ -385,7 +425,7 @@ int excl_scan(pbsim_engine *e, const unsigned long long *in, unsigned long long 
   return 0;
 }
 
-int run_batch(pbsim_engine *e, uint32_t n_reads, int64_t clip_room, bool to_host, BatchResult *out) {
+int run_batch(pbsim_engine *e, uint32_t n_reads, int64_t clip_room, BatchResult *out) {
   const uint32_t pass = (uint32_t)e->model.pass_num;
   const bool qs = e->model.method == PBSIM_METHOD_QSHMM;
   const bool replay = e->run.rng_mode == PBSIM_RNG_REPLAY;
@@ -668,8 +708,9 @@ int run_batch(pbsim_engine *e, uint32_t n_reads, int64_t clip_room, bool to_host
   out->reads_bytes = hctrl[8];
   out->maf_bytes = hctrl[9];
   const uint64_t n_tiles = hctrl[10];
-  CK(e->d_out_reads.ensure((size_t)out->reads_bytes + 256));
-  CK(e->d_out_maf.ensure((size_t)out->maf_bytes + 256));
+  pbsim_engine::OutSet &O = e->out[e->cur_set];
+  CK(O.reads.ensure((size_t)out->reads_bytes + 256));
+  CK(O.maf.ensure((size_t)out->maf_bytes + 256));
 
   // ---- K4 emit
   EmitArgs EA;
@@ -685,8 +726,8 @@ int run_batch(pbsim_engine *e, uint32_t n_reads, int64_t clip_room, bool to_host
   EA.maf_off = (const uint64_t *)maf_off;
   EA.keys.init(e->run.seed, (uint32_t)e->seq_num);
   EA.philox = replay ? 0u : 1u;
-  EA.out_reads = e->d_out_reads.as<uint8_t>();
-  EA.out_maf = e->d_out_maf.as<uint8_t>();
+  EA.out_reads = O.reads.as<uint8_t>();
+  EA.out_maf = O.maf.as<uint8_t>();
   {
     int dev_sms = 148;
     cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, e->device);
@@ -709,69 +750,18 @@ int run_batch(pbsim_engine *e, uint32_t n_reads, int64_t clip_room, bool to_host
   uint32_t *hrlen = reinterpret_cast<uint32_t *>(hacc + nv_sub);
   CK(cudaMemcpyAsync(hacc, B.accuracy, (size_t)nv_sub * 8, cudaMemcpyDeviceToHost, e->st));
   CK(cudaMemcpyAsync(hrlen, B.rlen, (size_t)nv_sub * 4, cudaMemcpyDeviceToHost, e->st));
-  (void)to_host;
   return 0;
 }
 
-// hand out the next piece of the batch held in HBM (host delivery); returns 1 if a piece was produced
-int deliver_piece(pbsim_engine *e, pbsim_chunk *c) {
-  pbsim_engine::Pending &p = e->pend;
-  if (!p.active) return 0;
-  for (int k = 0; k < 2; ++k)
-    for (int slot = 0; slot < 2; ++slot) CK(e->h_stage[k][slot].ensure(e->stage_bytes));
-  const uint8_t *src[2] = {e->d_out_reads.as<uint8_t>(), e->d_out_maf.as<uint8_t>()};
-  auto issue = [&](int slot) -> int {
-    for (int k = 0; k < 2; ++k) {
-      const uint64_t n = std::min<uint64_t>(e->stage_bytes, p.total[k] - p.issued[k]);
-      p.inflight[k] = n;
-      if (n) CK(cudaMemcpyAsync(e->h_stage[k][slot].p, src[k] + p.issued[k], n, cudaMemcpyDeviceToHost, e->st_copy));
-      p.issued[k] += n;
-    }
-    CK(cudaEventRecord(e->ev_copy, e->st_copy));
-    return 0;
-  };
-  if (p.first) {
-    int rc = issue(p.slot);
-    if (rc) return rc;
-  }
-  CK(cudaEventSynchronize(e->ev_copy));
-  std::memset(c, 0, sizeof *c);
-  c->reads = reinterpret_cast<const char *>(e->h_stage[0][p.slot].p);
-  c->reads_bytes = (int64_t)p.inflight[0];
-  c->maf = reinterpret_cast<const char *>(e->h_stage[1][p.slot].p);
-  c->maf_bytes = (int64_t)p.inflight[1];
-  c->on_device = 0;
-  if (p.first) {
-    c->first_read = p.first_read;
-    c->n_reads = p.n_reads;
-    c->bases = p.bases;
-    p.first = false;
-  }
-  if (p.issued[0] < p.total[0] || p.issued[1] < p.total[1]) {
-    p.slot ^= 1;  // prefetch the next piece into the other slot while the caller consumes this one
-    int rc = issue(p.slot);
-    if (rc) return rc;
-  } else {
-    p.active = false;
-  }
-  return 1;
-}
+// ---------------------------------------------------------------------------------------------
+// batch production (the quota loop of pbsim.cpp:2173 / :3792 in batches) and delivery
+// ---------------------------------------------------------------------------------------------
 
-int next_chunk_impl(pbsim_engine *e, pbsim_chunk *c, bool to_host) {
-  if (!e || !c) return PBSIM_E_INVALID;
-  if (!e->running) return fail(e, PBSIM_E_INVALID, "simulate_begin was not called");
-  std::memset(c, 0, sizeof *c);
+// generate the next batch of the run into output set `set`; 1 = produced, 0 = run finished, < 0 = error
+int produce_one(pbsim_engine *e, int set, pbsim_engine::BatchItem *it) {
   for (;;) {
-    if (e->pend.active) {
-      if (!to_host) return fail(e, PBSIM_E_INVALID, "host pieces of the previous batch are still pending");
-      return deliver_piece(e, c);
-    }
-    if (e->finished) return 0;
-    if (e->len_total >= e->run.len_quota || (e->run.max_reads > 0 && e->reads_done_in_run >= e->run.max_reads)) {
-      e->finished = true;
-      return 0;
-    }
-    // batch size: enough reads for ~target_batch_bases emitted bases, never more than the quota needs
+    if (e->len_total >= e->run.len_quota || (e->run.max_reads > 0 && e->reads_done_in_run >= e->run.max_reads)) return 0;
+    // batch size: enough reads for the target number of emitted bases, never more than the quota needs
     int64_t nb;
     int64_t clip_room = -1;
     if (e->tail_mode) {
@@ -784,7 +774,9 @@ int next_chunk_impl(pbsim_engine *e, pbsim_chunk *c, bool to_host) {
       if (e->run.batch_reads > 0) {
         nb = e->run.batch_reads;
       } else {
-        nb = (int64_t)((double)e->target_batch_bases / (mean * e->model.pass_num));
+        const int64_t target = (e->pipelined && e->mode_to_host) ? std::min(e->target_batch_bases, e->host_batch_bases)
+                                                                 : e->target_batch_bases;
+        nb = (int64_t)((double)target / (mean * e->model.pass_num));
         nb = std::max<int64_t>(nb, 1 << 12);
         nb = std::min<int64_t>(nb, 1 << 22);
       }
@@ -799,10 +791,10 @@ int next_chunk_impl(pbsim_engine *e, pbsim_chunk *c, bool to_host) {
       }
       if (nb < 1) nb = 1;
     }
-    // the previous batch's D2H pieces read d_out_*: they were all consumed (pend inactive) before we overwrite
+    e->cur_set = set;
     CK(cudaEventRecord(e->ev0, e->st));
     BatchResult br;
-    int rc = run_batch(e, (uint32_t)nb, clip_room, to_host, &br);
+    int rc = run_batch(e, (uint32_t)nb, clip_room, &br);
     if (rc) return rc;
     CK(cudaEventRecord(e->ev1, e->st));
     CK(cudaStreamSynchronize(e->st));
@@ -828,32 +820,196 @@ int next_chunk_impl(pbsim_engine *e, pbsim_chunk *c, bool to_host) {
     }
     if (br.cut) e->tail_mode = true;  // the next read is re-planned with the quota clip, one read at a time
     if (nv == 0) continue;
-    if (e->mean_rlen_est <= 0 && nv > 0) e->mean_rlen_est = std::max(1.0, (double)br.bases_pass0 / nv);
-    const int64_t first_read = e->next_read + 1;
+    if (e->mean_rlen_est <= 0) e->mean_rlen_est = std::max(1.0, (double)br.bases_pass0 / nv);
+    it->rc = 1;
+    it->set = set;
+    it->first_read = e->next_read + 1;
+    it->n_reads = nv;
+    it->bases = (int64_t)br.bases_all;
+    it->reads_bytes = br.reads_bytes;
+    it->maf_bytes = br.maf_bytes;
     e->next_read += nv;
     e->reads_done_in_run += nv;
     e->len_total += (int64_t)br.bases_pass0;
-    if (to_host) {
-      pbsim_engine::Pending &p = e->pend;
-      p = pbsim_engine::Pending();
-      p.active = true;
-      p.total[0] = br.reads_bytes;
-      p.total[1] = br.maf_bytes;
-      p.first_read = first_read;
-      p.n_reads = nv;
-      p.bases = (int64_t)br.bases_all;
-      return deliver_piece(e, c);
-    }
-    c->first_read = first_read;
-    c->n_reads = nv;
-    c->bases = (int64_t)br.bases_all;
-    c->reads_bytes = (int64_t)br.reads_bytes;
-    c->maf_bytes = (int64_t)br.maf_bytes;
-    c->reads = reinterpret_cast<const char *>(e->d_out_reads.p);
-    c->maf = reinterpret_cast<const char *>(e->d_out_maf.p);
-    c->on_device = 1;
     return 1;
   }
+}
+
+// producer thread of the pipeline: fills the output sets alternately, at most one batch ahead of delivery
+void producer_main(pbsim_engine *e) {
+  cudaSetDevice(e->device);
+  for (uint64_t seq = 0;; ++seq) {
+    {
+      std::unique_lock<std::mutex> lk(e->mu);
+      e->cv.wait(lk, [&] { return e->free_sets > 0 || e->stop; });
+      if (e->stop) return;
+      e->free_sets--;
+    }
+    pbsim_engine::BatchItem it;
+    const int rc = produce_one(e, (int)(seq & 1), &it);
+    if (rc != 1) {
+      it.rc = rc;
+      if (rc < 0) {
+        std::lock_guard<std::mutex> lk(e->err_mu);
+        it.err = e->err;
+      }
+    }
+    {
+      std::lock_guard<std::mutex> lk(e->mu);
+      if (rc != 1) e->free_sets++;
+      e->queue.push_back(std::move(it));
+    }
+    e->cv.notify_all();
+    if (rc != 1) return;
+  }
+}
+
+void release_set(pbsim_engine *e) {
+  if (!e->pipelined) return;
+  {
+    std::lock_guard<std::mutex> lk(e->mu);
+    e->free_sets++;
+  }
+  e->cv.notify_all();
+}
+
+void stop_producer(pbsim_engine *e) {
+  if (e->producer.joinable()) {
+    {
+      std::lock_guard<std::mutex> lk(e->mu);
+      e->stop = true;
+    }
+    e->cv.notify_all();
+    e->producer.join();
+  }
+  e->queue.clear();
+  e->free_sets = 2;
+  e->stop = false;
+}
+
+// next batch for delivery: 1 = *it is a batch, 0 = finished (or, with block == false, nothing ready yet), < 0 = error
+int fetch_batch(pbsim_engine *e, bool block, pbsim_engine::BatchItem *it) {
+  if (e->finished) return 0;
+  if (!e->pipelined) {
+    if (!block) return 0;
+    const int rc = produce_one(e, 0, it);
+    if (rc == 0) e->finished = true;
+    return rc;
+  }
+  std::unique_lock<std::mutex> lk(e->mu);
+  if (block) e->cv.wait(lk, [&] { return !e->queue.empty(); });
+  if (e->queue.empty() || (!block && e->queue.front().rc != 1)) return 0;  // end / error surface on a blocking call
+  *it = std::move(e->queue.front());
+  e->queue.pop_front();
+  lk.unlock();
+  if (it->rc == 0) e->finished = true;
+  if (it->rc < 0) {
+    e->finished = true;
+    std::lock_guard<std::mutex> g(e->err_mu);
+    e->err = it->err;
+  }
+  return it->rc;
+}
+
+// host delivery: start the D2H copy of the next piece into staging slot next_slot
+// 1 = a piece is in flight, 0 = nothing to issue (finished, or not ready and !block), < 0 = error
+int issue_piece(pbsim_engine *e, bool block) {
+  pbsim_engine::Pending &p = e->pend;
+  if (!p.active) {
+    pbsim_engine::BatchItem it;
+    const int rc = fetch_batch(e, block, &it);
+    if (rc != 1) return rc;
+    p = pbsim_engine::Pending();
+    p.active = true;
+    p.set = it.set;
+    p.total[0] = it.reads_bytes;
+    p.total[1] = it.maf_bytes;
+    p.first_read = it.first_read;
+    p.n_reads = it.n_reads;
+    p.bases = it.bases;
+  }
+  for (int k = 0; k < 2; ++k)
+    for (int slot = 0; slot < 2; ++slot) CK(e->h_stage[k][slot].ensure(e->stage_bytes));
+  const uint8_t *src[2] = {e->out[p.set].reads.as<uint8_t>(), e->out[p.set].maf.as<uint8_t>()};
+  pbsim_engine::Piece &q = e->piece;
+  q = pbsim_engine::Piece();
+  q.valid = true;
+  q.slot = e->next_slot;
+  for (int k = 0; k < 2; ++k) {
+    const uint64_t n = std::min<uint64_t>(e->stage_bytes, p.total[k] - p.issued[k]);
+    q.bytes[k] = n;
+    if (n) CK(cudaMemcpyAsync(e->h_stage[k][q.slot].p, src[k] + p.issued[k], n, cudaMemcpyDeviceToHost, e->st_copy));
+    p.issued[k] += n;
+  }
+  CK(cudaEventRecord(e->ev_copy, e->st_copy));
+  if (p.first) {
+    q.first = true;
+    q.first_read = p.first_read;
+    q.n_reads = p.n_reads;
+    q.bases = p.bases;
+    p.first = false;
+  }
+  if (p.issued[0] >= p.total[0] && p.issued[1] >= p.total[1]) {
+    q.release_set = p.set;
+    p.active = false;
+  }
+  e->next_slot ^= 1;
+  return 1;
+}
+
+int next_chunk_impl(pbsim_engine *e, pbsim_chunk *c, bool to_host) {
+  if (!e || !c) return PBSIM_E_INVALID;
+  if (!e->running) return fail(e, PBSIM_E_INVALID, "simulate_begin was not called");
+  std::memset(c, 0, sizeof *c);
+  if (!e->mode_set) {
+    e->mode_set = true;
+    e->mode_to_host = to_host;
+    e->pipelined = e->pipeline == 2 || (e->pipeline == 1 && to_host);
+    if (e->pipelined) e->producer = std::thread(producer_main, e);
+  } else if (e->mode_to_host != to_host) {
+    return fail(e, PBSIM_E_INVALID, "host and device delivery cannot be mixed within one run");
+  }
+  if (to_host) {
+    if (!e->piece.valid) {
+      const int rc = issue_piece(e, true);
+      if (rc != 1) return rc;
+    }
+    pbsim_engine::Piece q = e->piece;
+    CK(cudaEventSynchronize(e->ev_copy));
+    e->piece.valid = false;
+    if (q.release_set >= 0) release_set(e);  // the batch has left HBM: the producer may overwrite its set
+    c->reads = reinterpret_cast<const char *>(e->h_stage[0][q.slot].p);
+    c->reads_bytes = (int64_t)q.bytes[0];
+    c->maf = reinterpret_cast<const char *>(e->h_stage[1][q.slot].p);
+    c->maf_bytes = (int64_t)q.bytes[1];
+    c->on_device = 0;
+    if (q.first) {
+      c->first_read = q.first_read;
+      c->n_reads = q.n_reads;
+      c->bases = q.bases;
+    }
+    // prefetch the next piece into the other slot while the caller consumes this one
+    const int rc = issue_piece(e, false);
+    if (rc < 0) return rc;
+    return 1;
+  }
+  if (e->held_set >= 0) {  // the caller is done with the previous device chunk
+    release_set(e);
+    e->held_set = -1;
+  }
+  pbsim_engine::BatchItem it;
+  const int rc = fetch_batch(e, true, &it);
+  if (rc != 1) return rc;
+  e->held_set = it.set;
+  c->first_read = it.first_read;
+  c->n_reads = it.n_reads;
+  c->bases = it.bases;
+  c->reads_bytes = (int64_t)it.reads_bytes;
+  c->maf_bytes = (int64_t)it.maf_bytes;
+  c->reads = reinterpret_cast<const char *>(e->out[it.set].reads.p);
+  c->maf = reinterpret_cast<const char *>(e->out[it.set].maf.p);
+  c->on_device = 1;
+  return 1;
 }
 
 }  // namespace
@@ -896,11 +1052,13 @@ int pbsim_cuda_create(pbsim_engine **out, int device) {
 void pbsim_cuda_destroy(pbsim_engine *e) {
   if (!e) return;
   cudaSetDevice(e->device);
+  stop_producer(e);
+  cudaStreamSynchronize(e->st_copy);
   cudaStreamSynchronize(e->st);
   DevBuf *bufs[] = {&e->d_blob, &e->d_acc, &e->d_prob2len, &e->d_prob2acc, &e->d_qs_thr, &e->d_qs_thr_hp, &e->d_qc_prob,
                     &e->d_er_bias, &e->d_ascii, &e->d_pk, &e->d_hp4, &e->d_xm, &e->d_hpfreq, &e->d_biasone, &e->d_flag,
                     &e->d_draws, &e->d_starts, &e->b_read_u32, &e->b_sub_u32, &e->b_sub_u64, &e->b_sub_f64, &e->d_bins,
-                    &e->d_ctrl, &e->d_cub_tmp, &e->d_ev, &e->d_ck, &e->d_out_reads, &e->d_out_maf, &e->d_stats, &e->d_seg,
+                    &e->d_ctrl, &e->d_cub_tmp, &e->d_ev, &e->d_ck, &e->out[0].reads, &e->out[0].maf, &e->out[1].reads, &e->out[1].maf, &e->d_stats, &e->d_seg,
                     &e->d_seg_bins};
   for (DevBuf *b : bufs) b->release();
   for (auto &a : e->h_stage)
@@ -1043,7 +1201,13 @@ int pbsim_cuda_simulate_begin(pbsim_engine *e, const pbsim_run *run) {
   e->gen_ms = 0;
   e->sim_ms = 0;
   e->emit_ms = 0;
+  stop_producer(e);  // a run abandoned without simulate_end
   e->pend = pbsim_engine::Pending();
+  e->piece = pbsim_engine::Piece();
+  e->next_slot = 0;
+  e->held_set = -1;
+  e->mode_set = false;
+  e->pipelined = false;
   e->launches = 0;
   k_init_stats<<<nblk(e->stats_cells, 256), 256, 0, e->st>>>(e->d_stats.as<unsigned long long>(), e->stats_cells);
   e->launches++;
@@ -1067,6 +1231,8 @@ int pbsim_cuda_simulate_end(pbsim_engine *e, pbsim_stats *st, int64_t *freq_len,
   if (!e || !st) return PBSIM_E_INVALID;
   CK(cudaSetDevice(e->device));
   if (!e->running) return fail(e, PBSIM_E_INVALID, "simulate_begin was not called");
+  stop_producer(e);
+  CK(cudaStreamSynchronize(e->st_copy));
   std::vector<long long> blk((size_t)e->stats_cells);
   CK(cudaMemcpyAsync(blk.data(), e->d_stats.p, (size_t)e->stats_cells * 8, cudaMemcpyDeviceToHost, e->st));
   CK(cudaStreamSynchronize(e->st));
@@ -1134,7 +1300,7 @@ int pbsim_cuda_set_option(pbsim_engine *e, const char *name, int64_t value) {
   if (!e || !name) return PBSIM_E_INVALID;
   if (!strcmp(name, "stage_bytes")) {
     if (value < 4096) return fail(e, PBSIM_E_INVALID, "stage_bytes too small");
-    if (e->pend.active) return fail(e, PBSIM_E_INVALID, "cannot resize staging while pieces are pending");
+    if (e->pend.active || e->piece.valid) return fail(e, PBSIM_E_INVALID, "cannot resize staging while pieces are pending");
     e->stage_bytes = (size_t)value;
     for (auto &a : e->h_stage)
       for (auto &b : a) b.release();
@@ -1147,6 +1313,17 @@ int pbsim_cuda_set_option(pbsim_engine *e, const char *name, int64_t value) {
   if (!strcmp(name, "seg_min_len")) {
     if (value < (int64_t)PB_TILE) return fail(e, PBSIM_E_INVALID, "seg_min_len must be at least %u", PB_TILE);
     e->seg_min_len = value;
+    return 0;
+  }
+  if (!strcmp(name, "pipeline")) {
+    if (value < 0 || value > 2) return fail(e, PBSIM_E_INVALID, "pipeline must be 0, 1 or 2");
+    if (e->running) return fail(e, PBSIM_E_INVALID, "pipeline cannot change during a run");
+    e->pipeline = (int)value;
+    return 0;
+  }
+  if (!strcmp(name, "host_batch_bases")) {
+    if (value < 1) return fail(e, PBSIM_E_INVALID, "host_batch_bases must be positive");
+    e->host_batch_bases = value;
     return 0;
   }
   if (!strcmp(name, "target_batch_bases")) {
@@ -1167,6 +1344,7 @@ int pbsim_cuda_stats_device_block(pbsim_engine *e, void **dptr, int64_t *cells) 
 int pbsim_cuda_last_chunk_info(pbsim_engine *e, int64_t *out, int64_t cap_subreads, int64_t *n_subreads) {
   if (!e || !n_subreads) return PBSIM_E_INVALID;
   CK(cudaSetDevice(e->device));
+  if (e->pipelined) return fail(e, PBSIM_E_INVALID, "last_chunk_info needs option pipeline = 0 (the producer has moved on)");
   const Batch &B = e->B;
   const uint32_t pass = (uint32_t)e->model.pass_num;
   const int64_t n = B.n_sub;

@@ -175,3 +175,70 @@ def test_segments_on_and_off_give_identical_bytes(eng, method, model):
     eng.set_option("segments", 1)
     assert outs[0][2] > 500
     assert outs[0] == outs[1]
+
+
+def _device_bytes(ptr, n):
+    """copy n bytes out of HBM with the CUDA runtime (device delivery hands out raw device pointers)"""
+    import ctypes as C
+    rt = C.CDLL("libcudart.so.12")
+    rt.cudaMemcpy.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]
+    buf = C.create_string_buffer(n)
+    assert rt.cudaMemcpy(buf, ptr, n, 2) == 0
+    return buf.raw[:n]
+
+
+@pytest.mark.parametrize("method,model", [("qshmm", "QSHMM-RSII.model"), ("errhmm", "ERRHMM-ONT-HQ.model")])
+def test_pipelined_delivery_is_byte_identical(eng, method, model):
+    """the producer thread (batch k+1 generated while batch k leaves HBM) must not change a byte: host delivery
+    with the pipeline off / on, many small batches and pieces, and pipelined device delivery"""
+    from tests.golden_util import model_path
+    L = capi.load()
+    hm = capi.HostModel(L, capi.host_params(method), model_path(model))
+    eng.set_model(hm)
+    n = 2000000
+    eng.set_synthetic_sequence(n, 1, 13)
+    outs = []
+    try:
+        eng.set_option("stage_bytes", 1 << 16)
+        for pipe in (0, 1):
+            eng.set_option("pipeline", pipe)
+            reads, maf, st, nchunks = eng.simulate(3 * n, rng_mode=capi.RNG_PHILOX, seed=3, batch_reads=64)
+            outs.append((reads, maf, st.res_num, st.res_len_total, st.accuracy_total))
+            assert nchunks > 20
+        # device delivery, pipelined: the chunk of batch k stays valid while batch k+1 is being generated
+        eng.set_option("pipeline", 2)
+        eng.begin(3 * n, rng_mode=capi.RNG_PHILOX, seed=3, batch_reads=64)
+        reads, maf, nb = [], [], 0
+        while True:
+            c = eng.next_chunk(device=True)
+            if c is None:
+                break
+            assert c.on_device == 1
+            reads.append(_device_bytes(c.reads, c.reads_bytes))
+            maf.append(_device_bytes(c.maf, c.maf_bytes))
+            nb += 1
+        st = eng.end()
+        assert nb > 5
+        outs.append((b"".join(reads), b"".join(maf), st.res_num, st.res_len_total, st.accuracy_total))
+    finally:
+        eng.set_option("pipeline", 1)
+        eng.set_option("stage_bytes", 128 << 20)
+    assert outs[0][2] > 300
+    assert outs[0] == outs[1] == outs[2]
+
+
+def test_abandoned_run_then_new_run(eng):
+    """begin / a few chunks / begin again without draining: the producer is stopped and the next run is clean"""
+    c = Case("qs_rsii_basic")
+    ref = run_case_on_gpu(c, eng, "philox")
+    hm = engine_model(c)
+    eng.set_model(hm)
+    eng.set_sequence(c.contigs[0][1], 1, [0.0] + [1.0] * 10 + [0.0])
+    eng.begin(10 * len(c.contigs[0][1]), rng_mode=capi.RNG_PHILOX, seed=c.seed, batch_reads=8)
+    assert eng.next_chunk() is not None
+    eng.end()
+    eng.begin(10 * len(c.contigs[0][1]), rng_mode=capi.RNG_PHILOX, seed=c.seed, batch_reads=8)
+    assert eng.next_chunk() is not None
+    got = run_case_on_gpu(c, eng, "philox")  # begins again over the abandoned run
+    for a, b in zip(ref, got):
+        assert a[0] == b[0] and a[1] == b[1] and a[3] == b[3]
