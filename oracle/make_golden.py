@@ -94,6 +94,34 @@ CASES = {
 }
 
 
+# transcript / template strategies: name: (strategy, method, model, synth_set kwargs, seed, extra CLI args, oracle kwargs)
+SET_CASES = {
+    "tr_qs_rsii_basic": ("trans", "qshmm", "QSHMM-RSII.model", dict(seed=3, n=12), 3, [], {}),
+    "tr_err_onthq_basic": ("trans", "errhmm", "ERRHMM-ONT-HQ.model", dict(seed=4, n=12), 4, [], {}),
+    "tm_qs_rsii_basic": ("templ", "qshmm", "QSHMM-RSII.model", dict(seed=5, n=12, long_every=4), 5, [], {}),
+    # lower-case sequences: only simulate_by_qshmm_trans upper-cases the first base (:2774 vs :3330, :4474)
+    "tm_err_sequel_multipass": ("templ", "errhmm", "ERRHMM-SEQUEL.model",
+                                dict(seed=10, n=10, lowercase_first=0.5, hp_plants=2), 10,
+                                ["--pass-num", "3"], dict(pass_num=3)),
+    "tr_qs_ont_hpbias": ("trans", "qshmm", "QSHMM-ONT.model",
+                         dict(seed=7, n=12, hp_plants=3, lowercase_first=0.5, iupac=0.01), 7,
+                         ["--hp-del-bias", "3", "--difference-ratio", "39:24:36"],
+                         dict(hp_del_bias=3.0, ratio=(39, 24, 36))),
+    "tr_err_ont_hpbias": ("trans", "errhmm", "ERRHMM-ONT.model",
+                          dict(seed=8, n=12, hp_plants=3, lowercase_first=0.5, iupac=0.01), 8,
+                          ["--hp-del-bias", "2"], dict(hp_del_bias=2.0)),
+    "tm_qs_rsii_quirks": ("templ", "qshmm", "QSHMM-RSII.model",
+                          dict(seed=9, n=12, lowercase_first=0.5, hp_plants=3, iupac=0.01), 9, [], {}),
+    # transcripts longer than one fgets buffer (BUF_SIZE 10240), two passes, short length distribution
+    "tr_qs_rsii_multipass_long": ("trans", "qshmm", "QSHMM-RSII.model", dict(seed=11, n=8, long_every=4), 11,
+                                  ["--pass-num", "2", "--length-mean", "2500", "--length-sd", "2000",
+                                   "--id-prefix", "Q"],
+                                  dict(pass_num=2, len_mean=2500.0, len_sd=2000.0, id_prefix="Q")),
+    "tm_qs_rsii_hpbias": ("templ", "qshmm", "QSHMM-RSII.model", dict(seed=12, n=12, hp_plants=3), 12,
+                          ["--hp-del-bias", "3"], dict(hp_del_bias=3.0)),
+}
+
+
 STATS_CASES = {
     "qs_rsii_len3k": ("qshmm", "QSHMM-RSII.model", ["--length-mean", "3000", "--length-sd", "2300"]),
     "err_onthq_len3k": ("errhmm", "ERRHMM-ONT-HQ.model", ["--length-mean", "3000", "--length-sd", "2300"]),
@@ -153,6 +181,38 @@ def main():
             json.dump(case, f, indent=1, sort_keys=True)
         print("golden", name, {k: len(v) for k, v in plain["files"].items() if not k.endswith(".ref")},
               "draws", len(logged["draws"]))
+
+    for name, (strategy, method, model, skw, seed, extra, okw) in SET_CASES.items():
+        d = os.path.join(GOLDEN, "sets", name)
+        os.makedirs(d, exist_ok=True)
+        seqset = R.synth_set(**skw)
+        fn = os.path.join(d, "input.txt")
+        (R.write_transcripts if strategy == "trans" else R.write_templates)(fn, seqset)
+        args = ["--strategy", strategy, "--method", method, "--" + method, os.path.join(DATA, model),
+                "--transcript" if strategy == "trans" else "--template", fn, "--seed", str(seed)] + extra
+        plain = R.run_reference(args, logrand=False)
+        logged = R.run_reference(args, logrand=True)
+        assert plain["returncode"] == 0, plain["stderr"]
+        assert plain["files"] == logged["files"], "interposed rand() changed the reference's output"
+        pass_num = okw.get("pass_num", 1)
+        gz_write(os.path.join(d, "reads.gz"), plain["files"]["out.fq.gz" if pass_num == 1 else "out.bam"])
+        gz_write(os.path.join(d, "maf.gz"), plain["files"]["out.maf.gz"])
+        with open(fn, "rb") as f:
+            gz_write(fn + ".gz", f.read())
+        os.remove(fn)
+        with open(os.path.join(d, "stderr.txt"), "w") as f:
+            f.write(plain["stderr"].replace(fn, "input.txt"))
+        np.save(os.path.join(d, "marks.npy"), logged["marks"])
+        with open(os.path.join(d, "ndraws.txt"), "w") as f:
+            f.write("%d\n" % len(logged["draws"]))
+        case = dict(name=name, strategy=strategy, method=method, model=model, seed=seed, extra_args=extra,
+                    oracle_kwargs=okw, set_spec=skw, n_seq=len(seqset), pass_num=pass_num, toolchain=stamp,
+                    command="pbsim --strategy %s --method %s --%s data/%s --%s input.txt --seed %d %s"
+                            % (strategy, method, method, model, "transcript" if strategy == "trans" else "template",
+                               seed, " ".join(extra)))
+        with open(os.path.join(d, "case.json"), "w") as f:
+            json.dump(case, f, indent=1, sort_keys=True)
+        print("golden set", name, {k: len(v) for k, v in plain["files"].items()}, "draws", len(logged["draws"]))
 
     # distribution fixtures for the PHILOX-mode statistical parity tests: larger reference runs, reduced to
     # histograms (tests/stats_util.py) so that only a few KB are committed

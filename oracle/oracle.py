@@ -96,6 +96,10 @@ def lib():
         L.orc_rng_philox.argtypes = [C.c_void_p, C.c_uint32]
         L.orc_simulate_wgs.argtypes = [C.c_void_p, C.c_double]
         L.orc_reset_outputs.argtypes = [C.c_void_p]
+        L.orc_simulate_set.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.c_char_p, C.c_void_p]
+        L.orc_get_ssp.restype = C.c_int64
+        L.orc_get_ssp.argtypes = [C.c_int, C.c_void_p, C.c_void_p]
         for name in ("orc_out_reads", "orc_out_maf"):
             getattr(L, name).restype = C.POINTER(C.c_char)
             getattr(L, name).argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
@@ -227,6 +231,23 @@ class Oracle:
         self.L.orc_get_stats(self.h, C.byref(st))
         return reads, maf, st
 
+    def simulate_set(self, strategy, seqset, reset=True):
+        """strategy 'trans' | 'templ'; seqset = list of (name, plus, minus, bases) (plus/minus ignored for templ)"""
+        if reset:
+            self.L.orc_reset_outputs(self.h)
+        bases, start, plus, minus, ids, id_start = pack_set(seqset)
+        self._chk(self.L.orc_simulate_set(self.h, 1 if strategy == "trans" else 2, len(seqset), bases,
+                                          start.ctypes.data, plus.ctypes.data, minus.ctypes.data, ids,
+                                          id_start.ctypes.data))
+        n = C.c_int64()
+        p = self.L.orc_out_reads(self.h, C.byref(n))
+        reads = C.string_at(p, n.value)
+        p = self.L.orc_out_maf(self.h, C.byref(n))
+        maf = C.string_at(p, n.value)
+        st = Stats()
+        self.L.orc_get_stats(self.h, C.byref(st))
+        return reads, maf, st
+
     def readinfo(self):
         n = C.c_int64()
         p = self.L.orc_get_readinfo(self.h, C.byref(n))
@@ -278,6 +299,43 @@ class Oracle:
         v = [C.c_int() for _ in range(4)]
         self.L.orc_model_range(self.h, *[C.byref(x) for x in v])
         return tuple(x.value for x in v)
+
+
+def pack_set(seqset):
+    """[(name, plus, minus, bases)] -> (bases, start[n+1], plus[n], minus[n], ids, id_start[n+1])"""
+    bases = b"".join(x[3] for x in seqset)
+    start = np.zeros(len(seqset) + 1, dtype=np.int64)
+    start[1:] = np.cumsum([len(x[3]) for x in seqset])
+    plus = np.array([x[1] for x in seqset], dtype=np.int32)
+    minus = np.array([x[2] for x in seqset], dtype=np.int32)
+    names = [x[0].encode() if isinstance(x[0], str) else x[0] for x in seqset]
+    ids = b"".join(names)
+    id_start = np.zeros(len(seqset) + 1, dtype=np.int32)
+    id_start[1:] = np.cumsum([len(x) for x in names])
+    return bases, start, plus, minus, ids, id_start
+
+
+def ssp_table(rank_max):
+    ends = np.full((rank_max + 1) * 21, -1, dtype=np.int32)
+    mod = np.zeros(rank_max + 1, dtype=np.int32)
+    lib().orc_get_ssp(rank_max, ends.ctypes.data, mod.ctypes.data)
+    return ends.reshape(rank_max + 1, 21), mod
+
+
+def format_stats_set(st):
+    """print_simulation_stats for the transcript / template strategies (pbsim.cpp:5547-5564)."""
+    return (
+        ":::: Simulation stats ::::\n\n"
+        + "read num. : %d\n" % st.res_num
+        + "read length mean (SD) : %f (%f)\n" % (st.res_len_mean, st.res_len_sd)
+        + "read length min : %d\n" % st.res_len_min
+        + "read length max : %d\n" % st.res_len_max
+        + "read accuracy mean (SD) : %f (%f)\n" % (st.res_accuracy_mean, st.res_accuracy_sd)
+        + "substitution rate. : %f\n" % st.res_sub_rate
+        + "insertion rate. : %f\n" % st.res_ins_rate
+        + "deletion rate. : %f\n" % st.res_del_rate
+        + "\n"
+    )
 
 
 def format_stats(st, seq_num):

@@ -237,6 +237,11 @@ struct orc_ctx {
   int seq_num;
   long hpfreq[12];  /* [11] aliases hp_del_bias[0] in the reference build, see set_sequence */
   double bias[12];
+  /* record naming: WGS writes "ref" and ids "<prefix><seqnum>_<read>"; the transcript / template
+   * strategies write the sequence's own name and ids "<prefix>_<read>" (ref: :2951, :2968-2986, :3469, :3486) */
+  int set_mode;            /* 0 WGS, 1 transcript, 2 template */
+  const char *rec_name;
+  int rec_name_width;      /* digit_num1[0]: strlen(id) for transcripts, 3 otherwise */
   /* window scratch */
   char *w_seq, *read_seq, *qual, *maf_seq, *maf_ref;
   int16_t *w_hp_alloc, *w_hp;
@@ -621,10 +626,14 @@ int orc_build_tables(orc_ctx *c) {
  * get hp=1.  hpfreq[nnum]++ with nnum==11 writes one past hpfreq[11], which in the
  * reference build (g++ 13.3 -O2, struct genome_t :93-103) is hp_del_bias[0]; we keep the
  * same aliasing in hpfreq[11] and derive bias[0] from it in refresh_bias0(). */
-static void hp_scan(orc_ctx *c, char *seq, int64_t len, int16_t *hp) {
+/* upper_from: first index toupper() is applied to.  get_genome_seq (:1035) and simulate_by_qshmm_trans (:2774)
+ * start at 0; simulate_by_qshmm_templ (:3330), simulate_by_errhmm_trans (:4474) and simulate_by_errhmm_templ
+ * loop i = 1..len, so the FIRST base of the sequence keeps its case there.
+ * weight: transcripts count every run read_num times in the bias prepass (:2714-2718). */
+static void hp_scan_w(orc_ctx *c, char *seq, int64_t len, int16_t *hp, int upper_from, long weight, int count) {
   int64_t i, j, nstart = 0, nend = 0;
   int16_t nnum = 1;
-  for (i = 0; i < len; i++) {
+  for (i = upper_from; i < len; i++) {
     char ch = seq[i];
     if (ch >= 'a' && ch <= 'z') seq[i] = (char)(ch - 'a' + 'A'); /* toupper in the C locale */
   }
@@ -634,23 +643,19 @@ static void hp_scan(orc_ctx *c, char *seq, int64_t len, int16_t *hp) {
       nnum++;
       if (nnum > 11) nnum = 10;
     } else {
-      if (seq[i - 1] == 'N') {
-        for (j = nstart; j <= nend; j++) {
-          if (hp) hp[j] = 1;
-          c->hpfreq[1]++;
-        }
-      } else {
-        for (j = nstart; j <= nend; j++) {
-          if (hp) hp[j] = nnum;
-          c->hpfreq[nnum]++;
-        }
+      int bin = (seq[i - 1] == 'N') ? 1 : nnum;
+      for (j = nstart; j <= nend; j++) {
+        if (hp) hp[j] = (int16_t)bin;
       }
+      if (count) c->hpfreq[bin] += weight * (long)(nend - nstart + 1);
       nstart = i;
       nend = nstart;
       nnum = 1;
     }
   }
 }
+
+static void hp_scan(orc_ctx *c, char *seq, int64_t len, int16_t *hp) { hp_scan_w(c, seq, len, hp, 0, 1, 1); }
 
 /* bias[0] is the double whose bit pattern is the long hpfreq[11] (see above); bias[11] reads
  * the zero padding after `genome` in the reference build -> 0.0. */
@@ -803,8 +808,10 @@ static void emit_records(orc_ctx *c, long read_num, long pass, long offset, long
   char id[512];
   int d1[4], d2[4], dn[4], i;
   buf_t *o = &c->out_reads, *m = &c->out_maf;
+  const char *name = c->set_mode ? c->rec_name : "ref";
   if (c->pass_num == 1) {
-    snprintf(id, sizeof id, "%s%d_%ld", c->id_prefix, c->seq_num, read_num);
+    if (c->set_mode) snprintf(id, sizeof id, "%s_%ld", c->id_prefix, read_num);
+    else snprintf(id, sizeof id, "%s%d_%ld", c->id_prefix, c->seq_num, read_num);
     buf_puts(o, "@"); buf_puts(o, id); buf_puts(o, "\n");
     buf_put(o, c->read_seq, len);
     buf_puts(o, "\n+"); buf_puts(o, id); buf_puts(o, "\n");
@@ -812,7 +819,8 @@ static void emit_records(orc_ctx *c, long read_num, long pass, long offset, long
     buf_puts(o, "\n");
   } else {
     char tail[256];
-    snprintf(id, sizeof id, "%s%d/%ld/%ld", c->id_prefix, c->seq_num, read_num, pass);
+    if (c->set_mode) snprintf(id, sizeof id, "%s/%ld/%ld", c->id_prefix, read_num, pass);
+    else snprintf(id, sizeof id, "%s%d/%ld/%ld", c->id_prefix, c->seq_num, read_num, pass);
     buf_puts(o, id);
     buf_puts(o, "\t4\t*\t0\t255\t*\t*\t0\t0\t");
     buf_put(o, c->read_seq, len);
@@ -826,12 +834,14 @@ static void emit_records(orc_ctx *c, long read_num, long pass, long offset, long
              (long)(int)(len - 1), c->accuracy_mean, read_num);
     buf_puts(o, tail);
   }
-  d1[0] = 3;                      d2[0] = 1 + count_digit(read_num);
+  d1[0] = c->set_mode ? c->rec_name_width : 3;
+  d2[0] = 1 + count_digit(read_num);
   d1[1] = count_digit(offset);    d2[1] = 1;
   d1[2] = count_digit(wlen);      d2[2] = count_digit(len);
   d1[3] = count_digit(c->glen);   d2[3] = count_digit(len);
   for (i = 0; i < 4; i++) dn[i] = d1[i] >= d2[i] ? d1[i] : d2[i];
-  buf_puts(m, "a\ns ref");
+  buf_puts(m, "a\ns ");
+  buf_puts(m, name);
   buf_pad(m, dn[0] - d1[0]);
   buf_pad(m, dn[1] - d1[1]);
   buf_long(m, " ", offset, "");
@@ -1021,28 +1031,144 @@ void orc_reset_outputs(orc_ctx *c) {
   c->info_n = 0;
 }
 
+/* copies the window [offset, offset+wlen) of the current sequence, reverse-complemented for '-'
+ * (ref: :2193-2207 = :2874-2886) */
+static void load_window(orc_ctx *c, long offset, long wlen, char strand) {
+  long i;
+  ensure_window(c, wlen);
+  for (i = 0; i < wlen; i++) {
+    c->w_seq[i] = c->seq[offset + i];
+    c->w_hp[i] = c->hp[offset + i];
+  }
+  c->w_seq[wlen] = '\0';
+  if (strand == '-') {
+    revcomp_n(c->w_seq, wlen);
+    for (i = 0; i < wlen / 2; i++) { /* ref: revshort :5870-5879 */
+      int16_t t = c->w_hp[i];
+      c->w_hp[i] = c->w_hp[wlen - i - 1];
+      c->w_hp[wlen - i - 1] = t;
+    }
+  }
+}
+
+/* all passes of one read: chains, per-read statistics, records (ref: :2209-2383 = :2888-3017 = :3366-3530,
+ * errhmm :3836-4078).  *len_total_pass0 receives the emitted length of pass 0 (the WGS quota counter). */
+static void run_read_passes(orc_ctx *c, long offset, long wlen, char strand, int acc, int64_t start_draw,
+                            long *len_pass0, double *accuracy_total) {
+  rng_t *r = &c->rng;
+  orc_stats_t *st = &c->st;
+  int rate_mag = 0;
+  long h, i, len;
+  double value;
+  if (c->method == ORC_METHOD_ERR) { /* ref: :3829-3833 */
+    if (acc < c->acc_min) rate_mag = (int)((double)(c->acc_min - acc) / c->acc_min * 100);
+    else if (acc > c->acc_max) rate_mag = (int)((double)(acc - c->acc_max) / (100 - c->acc_max) * 100);
+  }
+  for (h = 0; h < c->pass_num; h++) {
+    pass_out_t po;
+    orc_readinfo_t ri;
+    int64_t pass_start = (h == 0) ? start_draw : r->cur;
+    if (c->method == ORC_METHOD_QS) qshmm_pass(c, r, (uint32_t)h, acc, wlen, &po);
+    else errhmm_pass(c, r, (uint32_t)h, acc, rate_mag, wlen, &po);
+    len = po.rlen;
+    if (strand == '-') {
+      revcomp_n(c->maf_seq, po.ncol);
+      revcomp_n(c->maf_ref, po.ncol);
+    }
+    st->res_sub_num += po.nsub;
+    st->res_ins_num += po.nins;
+    st->res_del_num += po.ndel;
+    st->res_len_total += len;
+    if (h == 0) *len_pass0 = len;
+    if (len >= 0 && len < c->freq_len_n) c->freq_len[len]++;
+    if (len > st->res_len_max) st->res_len_max = len;
+    if (len < st->res_len_min) st->res_len_min = len;
+    if (c->method == ORC_METHOD_QS) { /* ref: :2309-2316 accuracy from emitted qualities */
+      double prob = 0.0;
+      if (r->mode == RNG_PHILOX) {
+        /* engine definition for PHILOX mode: the sum is taken per block of 1024 read positions and the
+         * block sums are added in order (the order the segment-parallel pass 1 produces) */
+        double blk = 0.0;
+        for (i = 0; i < len; i++) {
+          if ((i & 1023) == 0) { prob += blk; blk = 0.0; }
+          blk += c->qc_prob[(int)c->qual[i] - 33];
+        }
+        prob += blk;
+      } else {
+        for (i = 0; i < len; i++) prob += c->qc_prob[(int)c->qual[i] - 33];
+      }
+      value = 1.0 - (prob / len);
+    } else { /* ref: :4002 accuracy from realised errors; qualities all '!' :4007-4010 */
+      value = 1.0 - ((double)(po.nsub + po.nins + po.ndel) / len);
+      for (i = 0; i < len; i++) c->qual[i] = '!';
+    }
+    *accuracy_total += value;
+    {
+      long acc_wk = trunc_int(value * 100000 + 0.5);
+      if (acc_wk >= 0 && acc_wk <= 100000) c->freq_acc[acc_wk]++;
+    }
+    emit_records(c, (long)st->res_num, h, offset, wlen, strand, len, po.ncol);
+    ri.read_id = st->res_num; ri.pass = (int32_t)h; ri.acc = acc; ri.offset = offset; ri.wlen = wlen;
+    ri.rlen = len; ri.ncol = po.ncol; ri.strand = strand; ri.nsub = (int32_t)po.nsub;
+    ri.nins = (int32_t)po.nins; ri.ndel = (int32_t)po.ndel; ri.draw_start = pass_start; ri.accuracy = value;
+    push_info(c, &ri);
+  }
+}
+
+static void begin_stats(orc_ctx *c) {
+  orc_stats_t *st = &c->st;
+  memset(st, 0, sizeof *st);
+  st->res_len_min = LONG_MAX;
+  memset(c->freq_len, 0, (size_t)c->freq_len_n * sizeof(int64_t));
+  memset(c->freq_acc, 0, 100001 * sizeof(int64_t));
+}
+
+/* ref: :2387-2410 (= :3023-3047) and print_simulation_stats :5543, :5557-5559 */
+static void finish_stats(orc_ctx *c, double accuracy_total, int64_t depth_len) {
+  orc_stats_t *st = &c->st;
+  double variance;
+  long i;
+  st->res_pass_num = st->res_num * c->pass_num;
+  st->res_len_mean = (double)st->res_len_total / st->res_pass_num;
+  st->res_accuracy_mean = accuracy_total / st->res_pass_num;
+  st->accuracy_total = accuracy_total;
+  if (st->res_pass_num == 1) {
+    st->res_len_sd = 0.0;
+    st->res_accuracy_sd = 0.0;
+  } else {
+    variance = 0.0;
+    for (i = 0; i <= c->len_max; i++)
+      if (c->freq_len[i] > 0) variance += pow((st->res_len_mean - i), 2) * c->freq_len[i];
+    st->res_len_sd = sqrt(variance / st->res_pass_num);
+    variance = 0.0;
+    for (i = 0; i <= 100000; i++)
+      if (c->freq_acc[i] > 0) variance += pow((st->res_accuracy_mean - i * 0.00001), 2) * c->freq_acc[i];
+    st->res_accuracy_sd = sqrt(variance / st->res_pass_num);
+  }
+  st->res_depth = depth_len > 0 ? (double)st->res_len_total / depth_len / c->pass_num : 0.0;
+  st->res_sub_rate = (double)st->res_sub_num / st->res_len_total;
+  st->res_ins_rate = (double)st->res_ins_num / st->res_len_total;
+  st->res_del_rate = (double)st->res_del_num / st->res_len_total;
+}
+
 /* ref: simulate_by_qshmm :2172-2410, simulate_by_errhmm :3791-4105, with init_sim_res :1437
  * and the quota from main :705. */
 int orc_simulate_wgs(orc_ctx *c, double depth) {
   long long len_quota, len_total = 0;
-  double accuracy_total = 0.0, variance, value;
-  long h, i, len;
+  double accuracy_total = 0.0;
   rng_t *r = &c->rng;
   orc_stats_t *st = &c->st;
 
   if (!c->tables_built) return fail(c, "tables not built");
   if (!c->seq) return fail(c, "no sequence");
   if (r->mode == RNG_PHILOX) r->key[1] = (uint32_t)c->seq_num;
-
-  memset(st, 0, sizeof *st);
-  st->res_len_min = LONG_MAX;
-  memset(c->freq_len, 0, (size_t)c->freq_len_n * sizeof(int64_t));
-  memset(c->freq_acc, 0, 100001 * sizeof(int64_t));
+  c->set_mode = 0;
+  begin_stats(c);
   len_quota = (long long)(depth * c->glen);
 
   while (len_total < len_quota) {
-    long index, wlen, offset;
-    int acc, rate_mag = 0;
+    long index, wlen, offset, len0 = 0;
+    int acc;
     char strand;
     int64_t start_draw = r->cur;
 
@@ -1062,106 +1188,174 @@ int orc_simulate_wgs(orc_ctx *c, double depth) {
       offset = (long)d_plan_off(r, (uint64_t)(c->glen - wlen + 1));
     }
     st->res_num++;
-
-    ensure_window(c, wlen);
-    for (i = 0; i < wlen; i++) {
-      c->w_seq[i] = c->seq[offset + i];
-      c->w_hp[i] = c->hp[offset + i];
-    }
-    c->w_seq[wlen] = '\0';
-    if (st->res_num % 2 == 1) {
-      strand = '+';
-    } else {
-      strand = '-';
-      revcomp_n(c->w_seq, wlen);
-      for (i = 0; i < wlen / 2; i++) { /* ref: revshort :5870-5879 */
-        int16_t t = c->w_hp[i];
-        c->w_hp[i] = c->w_hp[wlen - i - 1];
-        c->w_hp[wlen - i - 1] = t;
-      }
-    }
-
-    if (c->method == ORC_METHOD_ERR) { /* ref: :3829-3833 */
-      if (acc < c->acc_min) rate_mag = (int)((double)(c->acc_min - acc) / c->acc_min * 100);
-      else if (acc > c->acc_max) rate_mag = (int)((double)(acc - c->acc_max) / (100 - c->acc_max) * 100);
-    }
-
-    for (h = 0; h < c->pass_num; h++) {
-      pass_out_t po;
-      orc_readinfo_t ri;
-      int64_t pass_start = (h == 0) ? start_draw : r->cur;
-      if (c->method == ORC_METHOD_QS) qshmm_pass(c, r, (uint32_t)h, acc, wlen, &po);
-      else errhmm_pass(c, r, (uint32_t)h, acc, rate_mag, wlen, &po);
-      len = po.rlen;
-      if (strand == '-') {
-        revcomp_n(c->maf_seq, po.ncol);
-        revcomp_n(c->maf_ref, po.ncol);
-      }
-      st->res_sub_num += po.nsub;
-      st->res_ins_num += po.nins;
-      st->res_del_num += po.ndel;
-      st->res_len_total += len;
-      if (h == 0) len_total += len;
-      if (len >= 0 && len < c->freq_len_n) c->freq_len[len]++;
-      if (len > st->res_len_max) st->res_len_max = len;
-      if (len < st->res_len_min) st->res_len_min = len;
-      if (c->method == ORC_METHOD_QS) { /* ref: :2309-2316 accuracy from emitted qualities */
-        double prob = 0.0;
-        if (r->mode == RNG_PHILOX) {
-          /* engine definition for PHILOX mode: the sum is taken per block of 1024 read positions and the
-           * block sums are added in order (the order the segment-parallel pass 1 produces) */
-          double blk = 0.0;
-          for (i = 0; i < len; i++) {
-            if ((i & 1023) == 0) { prob += blk; blk = 0.0; }
-            blk += c->qc_prob[(int)c->qual[i] - 33];
-          }
-          prob += blk;
-        } else {
-          for (i = 0; i < len; i++) prob += c->qc_prob[(int)c->qual[i] - 33];
-        }
-        value = 1.0 - (prob / len);
-      } else { /* ref: :4002 accuracy from realised errors; qualities all '!' :4007-4010 */
-        value = 1.0 - ((double)(po.nsub + po.nins + po.ndel) / len);
-        for (i = 0; i < len; i++) c->qual[i] = '!';
-      }
-      accuracy_total += value;
-      {
-        long acc_wk = trunc_int(value * 100000 + 0.5);
-        if (acc_wk >= 0 && acc_wk <= 100000) c->freq_acc[acc_wk]++;
-      }
-      emit_records(c, (long)st->res_num, h, offset, wlen, strand, len, po.ncol);
-      ri.read_id = st->res_num; ri.pass = (int32_t)h; ri.acc = acc; ri.offset = offset; ri.wlen = wlen;
-      ri.rlen = len; ri.ncol = po.ncol; ri.strand = strand; ri.nsub = (int32_t)po.nsub;
-      ri.nins = (int32_t)po.nins; ri.ndel = (int32_t)po.ndel; ri.draw_start = pass_start; ri.accuracy = value;
-      push_info(c, &ri);
-    }
+    strand = (st->res_num % 2 == 1) ? '+' : '-';
+    load_window(c, offset, wlen, strand);
+    run_read_passes(c, offset, wlen, strand, acc, start_draw, &len0, &accuracy_total);
+    len_total += len0;
     if (r->exhausted) return fail(c, "draw log exhausted");
   }
-
-  /* ref: :2387-2410 */
-  st->res_pass_num = st->res_num * c->pass_num;
-  st->res_len_mean = (double)st->res_len_total / st->res_pass_num;
-  st->res_accuracy_mean = accuracy_total / st->res_pass_num;
-  st->accuracy_total = accuracy_total;
-  if (st->res_pass_num == 1) {
-    st->res_len_sd = 0.0;
-    st->res_accuracy_sd = 0.0;
-  } else {
-    variance = 0.0;
-    for (i = 0; i <= c->len_max; i++)
-      if (c->freq_len[i] > 0) variance += pow((st->res_len_mean - i), 2) * c->freq_len[i];
-    st->res_len_sd = sqrt(variance / st->res_pass_num);
-    variance = 0.0;
-    for (i = 0; i <= 100000; i++)
-      if (c->freq_acc[i] > 0) variance += pow((st->res_accuracy_mean - i * 0.00001), 2) * c->freq_acc[i];
-    st->res_accuracy_sd = sqrt(variance / st->res_pass_num);
-  }
-  /* ref: print_simulation_stats :5543, :5557-5559 */
-  st->res_depth = (double)st->res_len_total / c->glen / c->pass_num;
-  st->res_sub_rate = (double)st->res_sub_num / st->res_len_total;
-  st->res_ins_rate = (double)st->res_ins_num / st->res_len_total;
-  st->res_del_rate = (double)st->res_del_num / st->res_len_total;
+  finish_stats(c, accuracy_total, c->glen);
   return 0;
+}
+
+/* ------------------------------------------------------------------ transcript / template strategies */
+
+/* ref: the "sequencing start pos distribution" table :2504-2528 (= :4193-4217).  ends[rank*21 + j-1] is the
+ * cumulative table position of outcome j (start fraction (j-1)*5 %), mod[rank] the row modulus. */
+static void build_ssp(int rank_max, long *ends, long *mod) {
+  long i, j;
+  for (i = 1; i <= rank_max; i++) {
+    double sum = 0, value = (double)1 / i, ssp_prob_total = 0.0;
+    long end_wk = 0;
+    for (j = 1; j <= 21; j++) sum += value / pow(j, (1 + value));
+    for (j = 1; j <= 21; j++) ends[i * 21 + j - 1] = -1;
+    for (j = 1; j <= 21; j++) {
+      ssp_prob_total += (value / pow(j, (1 + value))) / sum;
+      end_wk = trunc_int(ssp_prob_total * 1000 + 0.5);
+      if (end_wk > 1000) end_wk = 1000;
+      ends[i * 21 + j - 1] = end_wk;
+      if (end_wk >= 1000) break;
+    }
+    mod[i] = end_wk;
+  }
+}
+
+static long ssp_lookup(const long *ends, int rank, long index /* 1-based */) {
+  int j;
+  for (j = 1; j <= 21; j++) {
+    long e = ends[rank * 21 + j - 1];
+    if (e < 0) break;
+    if (index <= e) return (j - 1) * 5;
+  }
+  return 100; /* unreachable: index <= modulus = last end */
+}
+
+/* ref: simulate_by_{qshmm,errhmm}_trans :2419 / :4114 (strategy 1) and _templ :3055 / :4807 (strategy 2).
+ * The file parsing of the reference (get_transcript_inf :1075, get_templ_inf :1366 and the fgets loops) is the
+ * caller's: sequences arrive concatenated in `bases` with start[n+1]; names in `ids` with id_start[n+1]. */
+int orc_simulate_set(orc_ctx *c, int strategy, int64_t n, const char *bases, const int64_t *start,
+                     const int32_t *plus_exp, const int32_t *minus_exp, const char *ids, const int32_t *id_start) {
+  rng_t *r = &c->rng;
+  orc_stats_t *st = &c->st;
+  double accuracy_total = 0.0;
+  int64_t t, max_len = 0;
+  long *ssp_ends = NULL, *ssp_mod = NULL;
+  int rank_max = 0, i;
+  /* which loops upper-case from index 0 (see hp_scan_w) */
+  const int upper_from = (strategy == 1 && c->method == ORC_METHOD_QS) ? 0 : 1;
+  char name[256];
+
+  if (!c->tables_built) return fail(c, "tables not built");
+  if (strategy != 1 && strategy != 2) return fail(c, "strategy must be 1 (transcript) or 2 (template)");
+  if (r->mode == RNG_PHILOX) r->key[1] = 0;
+  c->set_mode = strategy;
+  for (t = 0; t < n; t++)
+    if (start[t + 1] - start[t] > max_len) max_len = start[t + 1] - start[t];
+  if (strategy == 1) {
+    rank_max = (int)ceil((float)max_len / 1000); /* ref: :1137 */
+    ssp_ends = (long *)malloc((size_t)(rank_max + 1) * 21 * sizeof(long));
+    ssp_mod = (long *)calloc((size_t)rank_max + 1, sizeof(long));
+    build_ssp(rank_max, ssp_ends, ssp_mod);
+  }
+  begin_stats(c);
+
+  /* --hp-del-bias != 1: frequency prepass over the whole file (ref: :2671-2746 trans, :3244-3310 templ).
+   * hpfreq[0..10] are zeroed, [11] (which aliases hp_del_bias[0]) is not. */
+  if (c->hp_del_bias_opt == 1) {
+    for (i = 1; i <= 10; i++) c->bias[i] = 1;
+  } else {
+    for (i = 0; i <= 10; i++) c->hpfreq[i] = 0;
+    for (t = 0; t < n; t++) {
+      int64_t len = start[t + 1] - start[t];
+      long weight = strategy == 1 ? (long)plus_exp[t] + (long)minus_exp[t] : 1;
+      char *tmp = (char *)malloc((size_t)len + 1);
+      memcpy(tmp, bases + start[t], (size_t)len);
+      tmp[len] = 0;
+      hp_scan_w(c, tmp, len, NULL, upper_from, weight, 1);
+      free(tmp);
+    }
+    orc_finish_bias(c);
+  }
+  refresh_bias0(c);
+
+  for (t = 0; t < n; t++) {
+    int64_t len = start[t + 1] - start[t];
+    long read_num = strategy == 1 ? (long)plus_exp[t] + (long)minus_exp[t] : 1, k;
+    int idn = id_start[t + 1] - id_start[t];
+    if (idn > 128) idn = 128; /* TRANS_ID_LEN_MAX / REF_ID_LEN_MAX */
+    memcpy(name, ids + id_start[t], (size_t)idn);
+    name[idn] = 0;
+    c->rec_name = name;
+    c->rec_name_width = strategy == 1 ? idn : 3; /* ref: :2968 vs :3486 */
+    /* the sequence becomes the "genome" of its reads */
+    free(c->seq);
+    free(c->hp_alloc);
+    c->seq = (char *)malloc((size_t)len + 1);
+    memcpy(c->seq, bases + start[t], (size_t)len);
+    c->seq[len] = 0;
+    c->hp_alloc = (int16_t *)calloc((size_t)len + 2, sizeof(int16_t));
+    c->hp = c->hp_alloc + 1;
+    c->glen = len;
+    hp_scan_w(c, c->seq, len, c->hp, upper_from, 1, 0);
+
+    for (k = 1; k <= read_num; k++) {
+      long index, wlen, offset, len0 = 0;
+      int acc;
+      char strand;
+      int64_t start_draw = r->cur;
+      d_plan_begin(r, (uint32_t)(st->res_num + 1));
+      if (strategy == 1) { /* ref: :2842-2866 */
+        int rank;
+        long ssp;
+        double value;
+        index = d_plan_len(r, (uint32_t)c->len_rand_value) + 1;
+        wlen = c->prob2len[index];
+        index = d_plan_acc(r, (uint32_t)c->accuracy_rand_value) + 1;
+        acc = (int)c->prob2acc[index];
+        rank = (int)ceil((double)len / 1000);
+        index = (long)d_plan_off(r, (uint64_t)ssp_mod[rank]) + 1;
+        ssp = ssp_lookup(ssp_ends, rank, index);
+        value = ssp == 0 ? 0.0 : ((double)ssp - 2.5) / 100;
+        offset = trunc_int((double)len * value + 0.5);
+        if (offset + wlen > len) wlen = (long)len - offset;
+        strand = (k <= plus_exp[t]) ? '+' : '-';
+      } else { /* ref: :3359-3364 */
+        index = d_plan_acc(r, (uint32_t)c->accuracy_rand_value) + 1;
+        acc = (int)c->prob2acc[index];
+        offset = 0;
+        wlen = (long)len;
+        strand = '+';
+      }
+      if (wlen < 1) {
+        free(ssp_ends); free(ssp_mod);
+        return fail(c, "empty read window: the reference divides by zero here (sequences must be longer than 20 bases)");
+      }
+      st->res_num++;
+      load_window(c, offset, wlen, strand);
+      run_read_passes(c, offset, wlen, strand, acc, start_draw, &len0, &accuracy_total);
+      if (r->exhausted) {
+        free(ssp_ends); free(ssp_mod);
+        return fail(c, "draw log exhausted");
+      }
+    }
+  }
+  free(ssp_ends);
+  free(ssp_mod);
+  c->rec_name = NULL;
+  finish_stats(c, accuracy_total, 0);
+  return 0;
+}
+
+int64_t orc_get_ssp(int rank_max, int32_t *ends /* [(rank_max+1)*21] */, int32_t *mod /* [rank_max+1] */) {
+  long *e = (long *)malloc((size_t)(rank_max + 1) * 21 * sizeof(long));
+  long *m = (long *)calloc((size_t)rank_max + 1, sizeof(long));
+  int64_t i;
+  build_ssp(rank_max, e, m);
+  for (i = 21; i < (int64_t)(rank_max + 1) * 21; i++) ends[i] = (int32_t)e[i];
+  for (i = 1; i <= rank_max; i++) mod[i] = (int32_t)m[i];
+  free(e);
+  free(m);
+  return rank_max;
 }
 
 /* ------------------------------------------------------------------ getters */

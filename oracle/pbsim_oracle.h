@@ -98,6 +98,14 @@ int orc_rng_philox(orc_ctx *c, uint32_t seed);                    /* engine PHIL
 int orc_simulate_wgs(orc_ctx *c, double depth);
 void orc_reset_outputs(orc_ctx *c);
 
+/* simulate_by_{qshmm,errhmm}_trans (strategy 1, pbsim.cpp:2419 / :4114) and _templ (strategy 2, :3055 / :4807)
+ * over n sequences given concatenated (bases/start[n+1], ids/id_start[n+1]); plus_exp / minus_exp are the
+ * expression counts of the transcript table (ignored for templates: one '+' read each). */
+int orc_simulate_set(orc_ctx *c, int strategy, int64_t n, const char *bases, const int64_t *start,
+                     const int32_t *plus_exp, const int32_t *minus_exp, const char *ids, const int32_t *id_start);
+/* start-position table (pbsim.cpp:2504-2528) for KATs: ends[rank*21 + j-1], mod[rank], rank = 1..rank_max */
+int64_t orc_get_ssp(int rank_max, int32_t *ends, int32_t *mod);
+
 const char *orc_out_reads(orc_ctx *c, int64_t *n); /* FASTQ (pass_num==1) or SAM records */
 const char *orc_out_maf(orc_ctx *c, int64_t *n);
 void orc_get_stats(orc_ctx *c, orc_stats_t *st);

@@ -95,6 +95,43 @@ def read_fasta(path):
     return contigs
 
 
+def synth_set(seed, n, len_lo=300, len_hi=4000, max_exp=4, lowercase_first=0.0, iupac=0.0, hp_plants=0,
+              long_every=0):
+    """Deterministic transcript / template set: [(name, plus, minus, bases)].  lowercase_first: share of
+    sequences whose text is lower-case (exercises the toupper-from-1 quirk); hp_plants: homopolymers of 9-14."""
+    rng = np.random.default_rng(seed)
+    out = []
+    for t in range(n):
+        ln = int(rng.integers(len_lo, len_hi))
+        if long_every and t % long_every == long_every - 1:
+            ln = int(rng.integers(11000, 14000))  # longer than one fgets buffer (BUF_SIZE 10240)
+        s = rng.integers(0, 4, ln).astype(np.uint8)
+        s = np.frombuffer(b"ACGT", dtype=np.uint8)[s].copy()
+        for _ in range(hp_plants):
+            k = int(rng.integers(9, 15))
+            p = int(rng.integers(0, max(1, ln - k)))
+            s[p:p + k] = s[p]
+        if iupac > 0:
+            m = rng.random(ln) < iupac
+            s[m] = np.frombuffer(b"NRYKM", dtype=np.uint8)[rng.integers(0, 5, int(m.sum()))]
+        b = s.tobytes()
+        if rng.random() < lowercase_first:
+            b = b.lower()
+        out.append(("TR%05d.%d" % (t + 1, t % 7), int(rng.integers(0, max_exp + 1)), int(rng.integers(0, max_exp + 1)), b))
+    return out
+
+
+def write_transcripts(path, seqset):
+    """the 4-column table get_transcript_inf reads (pbsim.cpp:1095-1120): id, plus, minus, sequence"""
+    with open(path, "wb") as f:
+        for name, plus, minus, s in seqset:
+            f.write(name.encode() + b"\t%d\t%d\t" % (plus, minus) + s + b"\n")
+
+
+def write_templates(path, seqset, width=70):
+    write_fasta(path, [(x[0], x[3]) for x in seqset], width)
+
+
 def run_reference(args, logrand=False, keep_dir=None, real_gzip=False, timeout=3600):
     """Run the reference with `args` (list, without --prefix) in a scratch dir.
     Returns dict: stderr(str), files{name: bytes}, draws(int32 array)|None, marks(int64 array)|None,
@@ -134,6 +171,12 @@ def run_reference(args, logrand=False, keep_dir=None, real_gzip=False, timeout=3
     if keep_dir is None:
         shutil.rmtree(work, ignore_errors=True)
     return res
+
+
+def set_stats_block(stderr):
+    """the ':::: Simulation stats ::::' block of a transcript / template run"""
+    body = stderr.split(":::: Simulation stats ::::")[1].split(":::: System utilization")[0]
+    return ":::: Simulation stats ::::" + body
 
 
 def split_stats_blocks(stderr):

@@ -31,7 +31,7 @@ def model_path(name):
 
 def case_names():
     return sorted(d for d in os.listdir(GOLDEN)
-                  if os.path.isdir(os.path.join(GOLDEN, d)) and d not in ("models", "stats"))
+                  if os.path.isdir(os.path.join(GOLDEN, d)) and d not in ("models", "stats", "sets"))
 
 
 def gz_read(path):
@@ -99,3 +99,74 @@ class Case:
                             info=o.readinfo(), bias=o.bias(), freq_len=o.freq_len(),
                             freq_accuracy=o.freq_accuracy(), draws_end=o.draws_consumed()))
         return out, o
+
+
+def set_case_names():
+    return sorted(os.listdir(os.path.join(GOLDEN, "sets")))
+
+
+def read_transcripts(path):
+    """The 4-column table as get_transcript_inf / simulate_by_*_trans see it (pbsim.cpp:1095-1120, :2748-2772):
+    id (truncated to 128 chars), plus, minus, sequence."""
+    out = []
+    with gzip.open(path, "rb") as f:
+        for line in f:
+            name, plus, minus, seq = line.rstrip(b"\n").split(b"\t")
+            out.append((name[:128].decode(), int(plus), int(minus), seq))
+    return out
+
+
+class SetCase:
+    """tests/golden/sets/<name>: a transcript (--strategy trans) or template (--strategy templ) run of the reference"""
+
+    def __init__(self, name):
+        self.name = name
+        self.dir = os.path.join(GOLDEN, "sets", name)
+        with open(os.path.join(self.dir, "case.json")) as f:
+            self.meta = json.load(f)
+        self.strategy = self.meta["strategy"]
+        self.method = self.meta["method"]
+        self.model = model_path(self.meta["model"])
+        self.seed = self.meta["seed"]
+        self.pass_num = self.meta["pass_num"]
+        self.okw = dict(self.meta["oracle_kwargs"])
+        if "ratio" in self.okw:
+            self.okw["ratio"] = tuple(self.okw["ratio"])
+        inp = os.path.join(self.dir, "input.txt.gz")
+        if self.strategy == "trans":
+            self.seqset = read_transcripts(inp)
+        else:
+            self.seqset = [(n, 1, 0, s) for n, s in R.read_fasta(inp)]
+        with open(os.path.join(self.dir, "stderr.txt")) as f:
+            self.stderr = f.read()
+        self.stats_text = R.set_stats_block(self.stderr)
+        self.marks = np.load(os.path.join(self.dir, "marks.npy"))
+        with open(os.path.join(self.dir, "ndraws.txt")) as f:
+            self.ndraws = int(f.read())
+
+    def reads(self):
+        data = gz_read(os.path.join(self.dir, "reads.gz"))
+        if self.pass_num > 1:
+            end = data.index(b"PM:SEQUELII\n") + len(b"PM:SEQUELII\n")
+            data = data[end:]
+        return data
+
+    def sam_header(self):
+        data = gz_read(os.path.join(self.dir, "reads.gz"))
+        return data[:data.index(b"PM:SEQUELII\n") + len(b"PM:SEQUELII\n")]
+
+    def maf(self):
+        return gz_read(os.path.join(self.dir, "maf.gz"))
+
+    def run_oracle(self, rng="glibc", log=None):
+        o = O.Oracle(self.method, self.model, **self.okw)
+        if rng == "glibc":
+            o.rng_glibc(self.seed)
+        elif rng == "replay":
+            o.rng_replay(log)
+        else:
+            o.rng_philox(self.seed)
+        reads, maf, st = o.simulate_set(self.strategy, self.seqset)
+        return dict(reads=reads, maf=maf, stats=st, stats_text=O.format_stats_set(st), info=o.readinfo(),
+                    bias=o.bias(), freq_len=o.freq_len(), freq_accuracy=o.freq_accuracy(),
+                    draws_end=o.draws_consumed()), o

@@ -4,7 +4,9 @@ stats block, the number of rand() calls and the per-(read, pass) draw offsets.""
 import numpy as np
 import pytest
 
-from tests.golden_util import Case, case_names
+from oracle import oracle as O
+
+from tests.golden_util import Case, SetCase, case_names, set_case_names
 
 
 @pytest.mark.parametrize("name", case_names())
@@ -41,3 +43,25 @@ def test_philox_mode_is_deterministic_and_differs_from_glibc():
     g, _ = c.run_oracle("glibc")
     assert a[0]["reads"] == b[0]["reads"] and a[0]["maf"] == b[0]["maf"]
     assert a[0]["reads"] != g[0]["reads"]
+
+
+@pytest.mark.parametrize("name", set_case_names())
+def test_oracle_reproduces_reference_transcript_and_template_runs(name):
+    """--strategy trans / templ (pbsim.cpp:2419, :3055, :4114, :4807): same bytes, stats block and rand() count"""
+    c = SetCase(name)
+    res, o = c.run_oracle("glibc")
+    assert res["reads"] == c.reads()
+    assert res["maf"] == c.maf()
+    assert res["stats_text"] == c.stats_text
+    assert o.draws_consumed() == c.ndraws
+    starts = res["info"]["draw_start"]
+    assert len(starts) == len(c.marks)
+    assert np.array_equal(starts[1:], c.marks[:-1])
+
+
+def test_start_position_table_known_answers():
+    """prob2ssp (pbsim.cpp:2504-2528): rank 1 puts 62.6 % of the reads at the 5' end, higher ranks fewer"""
+    ends, mod = O.ssp_table(14)
+    assert mod[1:].tolist() == [1000] * 14
+    assert all(np.all(np.diff(ends[r][ends[r] >= 0]) >= 0) for r in range(1, 15))
+    assert ends[1][0] == 626 and ends[2][0] == 458 and ends[10][0] == 310  # 1 / sum_{j<=21} j^-2 = 0.6256
