@@ -42,6 +42,10 @@ extern "C" {
 #define PBSIM_RNG_PHILOX 0      /* Philox4x32-10 keyed by (seed, sequence, read id); engine-native */
 #define PBSIM_RNG_REPLAY 1      /* consume a log of the reference's own rand() draws              */
 
+#define PBSIM_STRATEGY_WGS   0   /* --strategy wgs   (STRATEGY_WGS,   pbsim.cpp:33) */
+#define PBSIM_STRATEGY_TRANS 1   /* --strategy trans (STRATEGY_TRANS, pbsim.cpp:34) */
+#define PBSIM_STRATEGY_TEMPL 2   /* --strategy templ (STRATEGY_TEMPL, pbsim.cpp:35) */
+
 #define PBSIM_NQV 94            /* quality codes 0..93 (pbsim.cpp:191) */
 #define PBSIM_NACC 101          /* accuracies 0..100  (ACCURACY_MAX, pbsim.cpp:42) */
 
@@ -97,6 +101,25 @@ typedef struct {
   double hp_del_bias[12];  /* genome.hp_del_bias[0..10] plus the two cells the reference    *
                             * reads out of bounds ([0] for hp[-1], [11] for runs >= 11)     */
 } pbsim_sequence;
+
+/* a set of sequences simulated in one run: the transcript table of --strategy trans as
+ * get_transcript_inf and the fgets loops of simulate_by_*_trans read it (pbsim.cpp:1075-1140,
+ * :2748-2772), or the template FASTA of --strategy templ (:1366-1417, :3312-3329).  The caller
+ * parses the file; sequences arrive concatenated.  Reads are numbered 1.. through the whole set
+ * (sim.res_num): transcript t yields plus_exp[t] '+' reads then minus_exp[t] '-' reads, each a
+ * window of it (length, accuracy and start position drawn, :2842-2866); a template yields one
+ * '+' read covering it (:3359-3364). */
+typedef struct {
+  int32_t strategy;          /* PBSIM_STRATEGY_TRANS or PBSIM_STRATEGY_TEMPL                  */
+  int64_t n;                 /* sequences                                                     */
+  const char *bases;         /* concatenated text, case as in the file                        */
+  const int64_t *start;      /* [n+1] offsets into bases; total < 2^32 - 2^16                 */
+  const int32_t *plus_exp;   /* [n] trans only (may be NULL for templates)                    */
+  const int32_t *minus_exp;  /* [n]                                                           */
+  const char *ids;           /* concatenated names (transcript.id / templ.id, <= 128 chars)   */
+  const int32_t *id_start;   /* [n+1]                                                         */
+  double hp_del_bias[12];    /* transcript.hp_del_bias / templ.hp_del_bias, cells as above    */
+} pbsim_seqset;
 
 typedef struct {
   int32_t rng_mode;              /* PBSIM_RNG_*                                              */
@@ -161,6 +184,12 @@ int pbsim_cuda_set_model(pbsim_engine *e, const pbsim_model *m);
 /* replaces: get_genome_seq's genome.seq / genome.hp (pbsim.cpp:1032-1065): uploads the ASCII
  * sequence, upper-cases, computes homopolymer lengths, packs to 2 bits per base */
 int pbsim_cuda_set_sequence(pbsim_engine *e, const pbsim_sequence *s);
+/* replaces: the per-sequence ingest of simulate_by_{qshmm,errhmm}_{trans,templ} (upper-casing with the
+ * reference's first-base quirk, homopolymer lengths per sequence) for a whole set at once; needs set_model
+ * first (which of the four functions is restated depends on the method).  After it, simulate_begin runs
+ * the set: pbsim_run.len_quota is ignored, first_read / max_reads select a range of read numbers.
+ * get_hpfreq then returns the expression-weighted histogram of the --hp-del-bias prepass (:2671-2746). */
+int pbsim_cuda_set_seqset(pbsim_engine *e, const pbsim_seqset *s);
 /* synthetic i.i.d. ACGT sequence generated on the device (benchmarks; no host transfer) */
 int pbsim_cuda_set_synthetic_sequence(pbsim_engine *e, int64_t len, int32_t seq_num, uint64_t seed);
 /* replace hp_del_bias of the current sequence without re-ingesting it (bias[0] is only known once the
@@ -225,6 +254,10 @@ void pbsim_host_model_free(pbsim_host_model *m);
 
 /* main()'s --hp-del-bias handling (pbsim.cpp:673-697): hpfreq accumulated over all sequences ->
  * bias[1..10]; bias[0]/bias[11] are the out-of-bounds cells (see DESIGN.md "reference quirks") */
+/* the "sequencing start pos distribution" of --strategy trans (pbsim.cpp:2504-2528): for rank 1..rank_max,
+ * ends[rank*21 + j] = last table position (1..1000) of start fraction 5*j percent, 0xFFFF after the row
+ * ended; mod[rank] = ssp_rand_value[rank].  ends has (rank_max+1)*21 cells, mod rank_max+1. */
+void pbsim_host_ssp_table(int32_t rank_max, uint16_t *ends, uint16_t *mod);
 void pbsim_host_hp_del_bias(double hp_del_bias_opt, const int64_t hpfreq[12], double bias[12]);
 
 #ifdef __cplusplus

@@ -68,6 +68,23 @@ class Sequence(C.Structure):
     ]
 
 
+STRATEGY_WGS, STRATEGY_TRANS, STRATEGY_TEMPL = 0, 1, 2
+
+
+class SeqSet(C.Structure):
+    _fields_ = [
+        ("strategy", C.c_int32),
+        ("n", C.c_int64),
+        ("bases", C.c_void_p),
+        ("start", C.c_void_p),
+        ("plus_exp", C.c_void_p),
+        ("minus_exp", C.c_void_p),
+        ("ids", C.c_void_p),
+        ("id_start", C.c_void_p),
+        ("hp_del_bias", C.c_double * 12),
+    ]
+
+
 class Run(C.Structure):
     _fields_ = [
         ("rng_mode", C.c_int32),
@@ -135,10 +152,11 @@ class HostParams(C.Structure):
     ]
 
 
-HOST_EXPORTS = ["pbsim_host_model_load", "pbsim_host_model_get", "pbsim_host_model_free", "pbsim_host_hp_del_bias"]
+HOST_EXPORTS = ["pbsim_host_model_load", "pbsim_host_model_get", "pbsim_host_model_free", "pbsim_host_hp_del_bias",
+                "pbsim_host_ssp_table"]
 ENGINE_EXPORTS = [
     "pbsim_cuda_abi_version", "pbsim_cuda_last_error", "pbsim_cuda_create", "pbsim_cuda_destroy",
-    "pbsim_cuda_set_model", "pbsim_cuda_set_sequence", "pbsim_cuda_set_synthetic_sequence",
+    "pbsim_cuda_set_model", "pbsim_cuda_set_sequence", "pbsim_cuda_set_seqset", "pbsim_cuda_set_synthetic_sequence",
     "pbsim_cuda_update_hp_del_bias", "pbsim_cuda_get_sequence_ascii", "pbsim_cuda_get_hpfreq", "pbsim_cuda_simulate_begin", "pbsim_cuda_next_chunk",
     "pbsim_cuda_next_chunk_device", "pbsim_cuda_simulate_end", "pbsim_cuda_stats_device_block",
     "pbsim_cuda_last_chunk_info", "pbsim_cuda_device_timer", "pbsim_cuda_set_option",
@@ -156,6 +174,8 @@ def declare_host(L):
     L.pbsim_host_model_free.argtypes = [C.c_void_p]
     L.pbsim_host_hp_del_bias.restype = None
     L.pbsim_host_hp_del_bias.argtypes = [C.c_double, C.POINTER(C.c_int64), C.POINTER(C.c_double)]
+    L.pbsim_host_ssp_table.restype = None
+    L.pbsim_host_ssp_table.argtypes = [C.c_int32, C.c_void_p, C.c_void_p]
     return L
 
 
@@ -168,6 +188,7 @@ def declare_engine(L):
     L.pbsim_cuda_destroy.argtypes = [C.c_void_p]
     L.pbsim_cuda_set_model.argtypes = [C.c_void_p, C.POINTER(Model)]
     L.pbsim_cuda_set_sequence.argtypes = [C.c_void_p, C.POINTER(Sequence)]
+    L.pbsim_cuda_set_seqset.argtypes = [C.c_void_p, C.POINTER(SeqSet)]
     L.pbsim_cuda_set_synthetic_sequence.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_uint64]
     L.pbsim_cuda_update_hp_del_bias.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
     L.pbsim_cuda_get_sequence_ascii.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]

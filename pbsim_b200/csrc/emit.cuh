@@ -31,7 +31,37 @@ struct EmitParams {
   uint32_t qs_segments;    // method is qshmm: segmented sub-reads use one slot per tile
 };
 
+// the reference-row naming of a record: WGS writes "ref" and the sequence length; the transcript / template
+// strategies the sequence's own name, positions relative to it and its length (pbsim.cpp:2968-2996, :3486-3514)
+struct RefName {
+  const uint8_t *ptr;   // nullptr: "ref"
+  uint32_t len;         // characters written
+  uint32_t width;       // digit_num1[0]: strlen(id) for transcripts, 3 for WGS and (sic) templates
+  uint32_t src_len;     // genome.len / transcript.len / templ.len
+  uint32_t off;         // mut.seq_left - 1
+};
+
+__device__ __forceinline__ RefName ref_name(const DeviceSet &S, const Batch &B, uint32_t r, uint32_t glen) {
+  RefName N;
+  if (S.strategy == PBSIM_STRATEGY_WGS) {
+    N.ptr = nullptr;
+    N.len = 3u;
+    N.width = 3u;
+    N.src_len = glen;
+    N.off = B.plan_off[r];
+    return N;
+  }
+  const uint32_t t = B.plan_tr[r];
+  N.ptr = S.ids + S.id_start[t];
+  N.len = S.id_start[t + 1] - S.id_start[t];
+  N.width = S.strategy == PBSIM_STRATEGY_TRANS ? N.len : 3u;
+  N.src_len = S.start[t + 1] - S.start[t];
+  N.off = B.plan_off[r] - S.start[t];
+  return N;
+}
+
 struct EmitArgs {
+  DeviceSet S;
   PhiloxKeys keys;             // PHILOX mode: pass 2 re-derives the 4-way choice of substitutions on non-ACGT bases
   uint32_t philox;
   DeviceGenome G;
@@ -74,9 +104,9 @@ struct RecLayout {
 #define PB_SAM_S7 "\tRG:Z:ffffffff\n"
 #define PB_LEN(s) ((uint32_t)(sizeof(s) - 1))
 
-__host__ __device__ __forceinline__ RecLayout rec_layout(const EmitParams &P, uint64_t read_id, uint32_t pass,
-                                                         uint32_t offset, uint32_t wlen, uint32_t rlen,
-                                                         uint32_t ncol) {
+__device__ __forceinline__ RecLayout rec_layout(const EmitParams &P, const RefName &N, uint64_t read_id, uint32_t pass,
+                                                uint32_t wlen, uint32_t rlen, uint32_t ncol) {
+  const uint32_t offset = N.off;
   RecLayout L;
   L.d_rid = ndigits(read_id);
   L.d_pass = ndigits(pass);
@@ -100,17 +130,17 @@ __host__ __device__ __forceinline__ RecLayout rec_layout(const EmitParams &P, ui
   // MAF field widths (:2336-2350); note the name column assumes an id of 1 + digits(read number)
   L.d_off = ndigits(offset);
   L.d_wlen = ndigits(wlen);
-  L.d_glen = ndigits(P.glen);
+  L.d_glen = ndigits(N.src_len);
   L.d_rlen = ndigits(rlen);
-  const uint32_t d1[4] = {3u, L.d_off, L.d_wlen, L.d_glen};
+  const uint32_t d1[4] = {N.width, L.d_off, L.d_wlen, L.d_glen};
   const uint32_t d2[4] = {1u + L.d_rid, 1u, L.d_rlen, L.d_rlen};
   for (int i = 0; i < 4; ++i) {
     const uint32_t dn = d1[i] > d2[i] ? d1[i] : d2[i];
     L.pa[i] = dn - d1[i];
     L.pb_[i] = dn - d2[i];
   }
-  // "a\ns ref" pa0 pa1 " off" pa2 " wlen +" pa3 " glen " ROW "\n"
-  L.refrow_rel = 7u + L.pa[0] + L.pa[1] + 1u + L.d_off + L.pa[2] + 1u + L.d_wlen + 2u + L.pa[3] + 1u + L.d_glen + 1u;
+  // "a\ns " name pa0 pa1 " off" pa2 " wlen +" pa3 " glen " ROW "\n"
+  L.refrow_rel = 4u + N.len + L.pa[0] + L.pa[1] + 1u + L.d_off + L.pa[2] + 1u + L.d_wlen + 2u + L.pa[3] + 1u + L.d_glen + 1u;
   // "s " id pb0 pb1 " 0" pb2 " rlen S" pb3 " rlen " ROW "\n\n"
   L.readrow_rel = L.refrow_rel + ncol + 1u + 2u + L.idlen + L.pb_[0] + L.pb_[1] + 2u + L.pb_[2] + 1u + L.d_rlen + 2u +
                   L.pb_[3] + 1u + L.d_rlen + 1u;
@@ -119,12 +149,13 @@ __host__ __device__ __forceinline__ RecLayout rec_layout(const EmitParams &P, ui
 }
 
 // record sizes and tile counts of every valid subread
-__global__ void k_sizes(Batch B, EmitParams P, uint32_t n_sub, uint64_t *reads_size, uint64_t *maf_size,
+__global__ void k_sizes(Batch B, EmitParams P, DeviceSet S, uint32_t n_sub, uint64_t *reads_size, uint64_t *maf_size,
                         uint64_t *ntiles) {
   const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n_sub) return;
   const uint32_t r = s / P.pass_num, pass = s % P.pass_num;
-  const RecLayout L = rec_layout(P, B.first_read + 1u + r, pass, B.plan_off[r], B.plan_wlen[r], B.rlen[s], B.ncol[s]);
+  const RefName N = ref_name(S, B, r, P.glen);
+  const RecLayout L = rec_layout(P, N, B.first_read + 1u + r, pass, B.plan_wlen[r], B.rlen[s], B.ncol[s]);
   reads_size[s] = L.reads_size;
   maf_size[s] = L.maf_size;
   const uint32_t ne = B.nent[s];
@@ -166,9 +197,10 @@ __device__ __forceinline__ uint8_t *put_id(uint8_t *p, const EmitParams &P, uint
 }
 
 // everything of a record that is not a per-base row: written once, by one lane
-__device__ __noinline__ void write_headers(const EmitParams &P, const RecLayout &L, uint8_t *rd, uint8_t *mf,
-                                           uint64_t read_id, uint32_t pass, uint32_t offset, uint32_t wlen,
+__device__ __noinline__ void write_headers(const EmitParams &P, const RefName &N, const RecLayout &L, uint8_t *rd,
+                                           uint8_t *mf, uint64_t read_id, uint32_t pass, uint32_t wlen,
                                            uint32_t rlen, uint32_t ncol, uint32_t minus) {
+  const uint32_t offset = N.off;
   uint8_t *p = rd;
   if (!P.sam) {
     *p++ = '@';
@@ -201,7 +233,9 @@ __device__ __noinline__ void write_headers(const EmitParams &P, const RecLayout 
     p = PB_PUT_LIT(p, PB_SAM_S7);
   }
   p = mf;
-  p = PB_PUT_LIT(p, "a\ns ref");
+  p = PB_PUT_LIT(p, "a\ns ");
+  if (N.ptr) p = put_mem(p, reinterpret_cast<const char *>(N.ptr), N.len);
+  else p = PB_PUT_LIT(p, "ref");
   p = put_pad(p, L.pa[0] + L.pa[1]);
   *p++ = ' ';
   p = put_dec(p, offset, L.d_off);
@@ -212,7 +246,7 @@ __device__ __noinline__ void write_headers(const EmitParams &P, const RecLayout 
   *p++ = '+';
   p = put_pad(p, L.pa[3]);
   *p++ = ' ';
-  p = put_dec(p, P.glen, L.d_glen);
+  p = put_dec(p, N.src_len, L.d_glen);
   *p++ = ' ';
   p = mf + L.refrow_rel + ncol;
   *p++ = '\n';
@@ -524,10 +558,11 @@ __global__ void __launch_bounds__(kEmitThreads) k_emit(EmitArgs A) {
     const uint32_t offset = A.B.plan_off[r], wlen = A.B.plan_wlen[r];
     const uint32_t minus = (A.B.plan_meta[r] >> 8) & 1u;
     const uint32_t nent = A.B.nent[s], rlen = A.B.rlen[s], ncol = A.B.ncol[s];
-    const RecLayout L = rec_layout(A.P, read_id, pass, offset, wlen, rlen, ncol);
+    const RefName N = ref_name(A.S, A.B, r, A.P.glen);
+    const RecLayout L = rec_layout(A.P, N, read_id, pass, wlen, rlen, ncol);
     uint8_t *rd = A.out_reads + A.reads_off[s];
     uint8_t *mf = A.out_maf + A.maf_off[s];
-    if (tile == 0 && lane == 0) write_headers(A.P, L, rd, mf, read_id, pass, offset, wlen, rlen, ncol, minus);
+    if (tile == 0 && lane == 0) write_headers(A.P, N, L, rd, mf, read_id, pass, wlen, rlen, ncol, minus);
     if (nent == 0) continue;
     const Ckpt *ckp = A.ck + A.B.ck_off[s];
     const Ckpt c0 = ckp[tile];

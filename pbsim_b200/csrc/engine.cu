@@ -14,6 +14,7 @@
 
 #include <algorithm>
 #include <climits>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -173,6 +174,13 @@ struct pbsim_engine {
   double bias[12];
   int64_t hpfreq[12];
 
+  // sequence set (--strategy trans / templ); strategy WGS when a plain sequence is loaded
+  int strategy = PBSIM_STRATEGY_WGS;
+  int64_t set_n = 0, set_total_reads = 0;
+  double set_mean_len = 0;
+  int32_t set_rank_max = 0;
+  DevBuf d_set_start, d_set_rprefix, d_set_plus, d_set_ids, d_set_idstart, d_set_ssp_ends, d_set_ssp_mod, d_set_first;
+
   // run
   bool running = false;
   pbsim_run run;
@@ -323,6 +331,22 @@ DeviceGenome device_genome(const pbsim_engine *e) {
   return G;
 }
 
+DeviceSet device_set(const pbsim_engine *e) {
+  DeviceSet S;
+  std::memset(&S, 0, sizeof S);
+  S.strategy = (uint32_t)e->strategy;
+  if (e->strategy == PBSIM_STRATEGY_WGS) return S;
+  S.n = (uint32_t)e->set_n;
+  S.start = e->d_set_start.as<uint32_t>();
+  S.rprefix = e->d_set_rprefix.as<uint64_t>();
+  S.plus = e->d_set_plus.as<uint32_t>();
+  S.ssp_ends = e->d_set_ssp_ends.as<uint16_t>();
+  S.ssp_mod = e->d_set_ssp_mod.as<uint16_t>();
+  S.ids = e->d_set_ids.as<uint8_t>();
+  S.id_start = e->d_set_idstart.as<uint32_t>();
+  return S;
+}
+
 // bias-dependent threshold tables (re-uploaded with every sequence)
 int upload_bias_tables(pbsim_engine *e) {
   e->img.apply_bias(e->model, e->bias);
@@ -336,8 +360,10 @@ int upload_bias_tables(pbsim_engine *e) {
   return 0;
 }
 
-int finish_sequence_ingest(pbsim_engine *e, int64_t len, int32_t seq_num, const double bias[12]) {
+// keep_first: sequence sets whose first base keeps its case (see k_set_restore_first)
+int finish_sequence_ingest(pbsim_engine *e, int64_t len, int32_t seq_num, const double bias[12], bool keep_first = false) {
   // ascii already in d_ascii (padded with zeros to a multiple of 16)
+  const bool set = e->strategy != PBSIM_STRATEGY_WGS;
   e->glen = len;
   e->seq_num = seq_num;
   std::memcpy(e->bias, bias, sizeof e->bias);
@@ -357,11 +383,33 @@ int finish_sequence_ingest(pbsim_engine *e, int64_t len, int32_t seq_num, const 
   for (int h = 0; h < 12; ++h) one[h] = (bias[h] == 1.0) ? 1 : 0;
   one[0] = 1;  // hp 0 never occurs inside a sequence
   CK(cudaMemcpyAsync(e->d_biasone.p, one, 16, cudaMemcpyHostToDevice, e->st));
+  const uint32_t sn = (uint32_t)e->set_n;
+  if (set && keep_first) {
+    CK(e->d_set_first.ensure((size_t)sn + 16));
+    k_set_save_first<<<nblk(sn, 256), 256, 0, e->st>>>(e->d_ascii.as<uint8_t>(), e->d_set_start.as<uint32_t>(), sn,
+                                                       e->d_set_first.as<uint8_t>());
+    e->launches++;
+  }
   k_upper_pack<<<nblk(words, 256), 256, 0, e->st>>>(e->d_ascii.as<uint8_t>(), len, e->d_pk.as<uint32_t>(),
                                                     e->d_xm.as<uint32_t>());
-  k_hp<<<nblk((len + 1) / 2, 256), 256, 0, e->st>>>(e->d_ascii.as<uint8_t>(), len, e->d_hp4.as<uint8_t>(),
-                                                    e->d_xm.as<uint32_t>(), e->d_hpfreq.as<unsigned long long>(),
-                                                    e->d_biasone.as<uint8_t>(), e->d_flag.as<uint32_t>());
+  if (set) {
+    if (keep_first) {
+      k_set_restore_first<<<nblk(sn, 256), 256, 0, e->st>>>(e->d_ascii.as<uint8_t>(), e->d_set_start.as<uint32_t>(), sn,
+                                                            e->d_set_first.as<uint8_t>(), e->d_pk.as<uint32_t>(),
+                                                            e->d_xm.as<uint32_t>());
+      e->launches++;
+    }
+    // transcripts count every base once per read of the transcript (the rprefix differences)
+    k_hp_set<<<nblk((len + 1) / 2, 256), 256, 0, e->st>>>(
+        e->d_ascii.as<uint8_t>(), len, e->d_set_start.as<uint32_t>(), sn,
+        e->strategy == PBSIM_STRATEGY_TRANS ? e->d_set_plus.as<uint32_t>() + sn : nullptr, e->d_hp4.as<uint8_t>(),
+        e->d_xm.as<uint32_t>(), e->d_hpfreq.as<unsigned long long>(), e->d_biasone.as<uint8_t>(),
+        e->d_flag.as<uint32_t>());
+  } else {
+    k_hp<<<nblk((len + 1) / 2, 256), 256, 0, e->st>>>(e->d_ascii.as<uint8_t>(), len, e->d_hp4.as<uint8_t>(),
+                                                      e->d_xm.as<uint32_t>(), e->d_hpfreq.as<unsigned long long>(),
+                                                      e->d_biasone.as<uint8_t>(), e->d_flag.as<uint32_t>());
+  }
   e->launches += 2;
   CK(cudaGetLastError());
   uint32_t flag = 0;
@@ -389,7 +437,7 @@ int carve_batch(pbsim_engine *e, uint32_t n_reads) {
   const uint32_t pass = (uint32_t)e->model.pass_num;
   const uint64_t n_sub = (uint64_t)n_reads * pass;
   if (n_sub > 0x7FFFFFFFull) return fail(e, PBSIM_E_INVALID, "batch too large");
-  CK(e->b_read_u32.ensure((size_t)n_reads * 4 * 4 + 64));
+  CK(e->b_read_u32.ensure((size_t)n_reads * 5 * 4 + 64));
   CK(e->b_sub_u32.ensure((size_t)n_sub * 16 * 4 + 64));
   CK(e->b_sub_u64.ensure((size_t)(n_sub + 1) * 11 * 8 + 64));
   CK(e->b_sub_f64.ensure((size_t)n_sub * 8 + 64));
@@ -401,6 +449,7 @@ int carve_batch(pbsim_engine *e, uint32_t n_reads) {
   B.plan_wlen = r32 + n_reads;
   B.plan_raw = r32 + 2ull * n_reads;
   B.plan_meta = r32 + 3ull * n_reads;
+  B.plan_tr = r32 + 4ull * n_reads;
   uint32_t *s32 = e->b_sub_u32.as<uint32_t>();
   uint32_t **fields[] = {&B.key_in, &B.key_out, &B.idx_in, &B.order, &B.cap, &B.ck_cap, &B.nent, &B.rlen,
                          &B.ncol, &B.nsub, &B.nins, &B.ndel, &B.flags, &B.draws_used, &B.nseg};
@@ -478,7 +527,7 @@ int run_batch(pbsim_engine *e, uint32_t n_reads, int64_t clip_room, BatchResult 
   for (int attempt = 0; attempt < 6; ++attempt) {
     // ---- K1 plan
     const uint32_t ev_align = qs ? 8u : 16u;
-    k_plan<<<nblk(n_reads, 256), 256, 0, e->st>>>(M, G, rng, B, clip_room, e->cap_num, e->cap_den, ev_align,
+    k_plan<<<nblk(n_reads, 256), 256, 0, e->st>>>(M, G, device_set(e), rng, B, clip_room, e->cap_num, e->cap_den, ev_align,
                                                    use_segments ? (uint32_t)e->seg_min_len : 0u);
     e->launches++;
     // ---- sort by (accuracy, length desc)
@@ -532,6 +581,7 @@ int run_batch(pbsim_engine *e, uint32_t n_reads, int64_t clip_room, BatchResult 
     SimArgs A;
     A.seg_off = (const uint64_t *)seg_off;
     A.bias_one = e->d_biasone.as<uint8_t>();
+    A.plan_draws = e->strategy == PBSIM_STRATEGY_TRANS ? 3u : (e->strategy == PBSIM_STRATEGY_TEMPL ? 1u : 0u);
     A.seg_state = n_seg_total > 0 ? reinterpret_cast<uint32_t *>(e->d_seg.as<SegResult>() + n_seg_total) + 5ull * n_seg_total
                                   : nullptr;
     A.keys.init(rng.seed, (uint32_t)e->seq_num);
@@ -691,11 +741,12 @@ int run_batch(pbsim_engine *e, uint32_t n_reads, int64_t clip_room, BatchResult 
   e->emitp.qs_segments = qs ? 1u : 0u;
   {
     char head[192];
-    snprintf(head, sizeof head, "%s%d", e->model.id_prefix, e->seq_num);
+    if (e->strategy == PBSIM_STRATEGY_WGS) snprintf(head, sizeof head, "%s%d", e->model.id_prefix, e->seq_num);
+    else snprintf(head, sizeof head, "%s", e->model.id_prefix);  // "<prefix>_<read>" (:2951, :3469)
     e->emitp.id_head_len = (uint32_t)strlen(head);
     memcpy(e->emitp.id_head, head, e->emitp.id_head_len + 1);
   }
-  k_sizes<<<nblk(nv_sub, 256), 256, 0, e->st>>>(B, e->emitp, nv_sub, (uint64_t *)reads_size, (uint64_t *)maf_size,
+  k_sizes<<<nblk(nv_sub, 256), 256, 0, e->st>>>(B, e->emitp, device_set(e), nv_sub, (uint64_t *)reads_size, (uint64_t *)maf_size,
                                                 (uint64_t *)ntiles);
   e->launches++;
   if ((rc = excl_scan(e, reads_size, reads_off, nv_sub + 1))) return rc;
@@ -714,6 +765,7 @@ int run_batch(pbsim_engine *e, uint32_t n_reads, int64_t clip_room, BatchResult 
 
   // ---- K4 emit
   EmitArgs EA;
+  EA.S = device_set(e);
   EA.G = G;
   EA.B = B;
   EA.P = e->emitp;
@@ -769,6 +821,8 @@ int produce_one(pbsim_engine *e, int set, pbsim_engine::BatchItem *it) {
       clip_room = e->run.len_quota - e->len_total;
     } else {
       double mean = e->mean_rlen_est > 0 ? e->mean_rlen_est : e->table_mean_len;
+      if (e->strategy != PBSIM_STRATEGY_WGS && e->mean_rlen_est <= 0) mean = std::min(mean, e->set_mean_len);
+      if (e->strategy == PBSIM_STRATEGY_TEMPL && e->mean_rlen_est <= 0) mean = e->set_mean_len;
       if (mean > (double)e->glen) mean = (double)e->glen;
       if (mean < 1) mean = 1;
       if (e->run.batch_reads > 0) {
@@ -1059,7 +1113,8 @@ void pbsim_cuda_destroy(pbsim_engine *e) {
                     &e->d_er_bias, &e->d_ascii, &e->d_pk, &e->d_hp4, &e->d_xm, &e->d_hpfreq, &e->d_biasone, &e->d_flag,
                     &e->d_draws, &e->d_starts, &e->b_read_u32, &e->b_sub_u32, &e->b_sub_u64, &e->b_sub_f64, &e->d_bins,
                     &e->d_ctrl, &e->d_cub_tmp, &e->d_ev, &e->d_ck, &e->out[0].reads, &e->out[0].maf, &e->out[1].reads, &e->out[1].maf, &e->d_stats, &e->d_seg,
-                    &e->d_seg_bins};
+                    &e->d_seg_bins, &e->d_set_start, &e->d_set_rprefix, &e->d_set_plus, &e->d_set_ids, &e->d_set_idstart,
+                    &e->d_set_ssp_ends, &e->d_set_ssp_mod, &e->d_set_first};
   for (DevBuf *b : bufs) b->release();
   for (auto &a : e->h_stage)
     for (auto &b : a) b.release();
@@ -1143,7 +1198,84 @@ int pbsim_cuda_set_sequence(pbsim_engine *e, const pbsim_sequence *s) {
   CK(e->d_ascii.ensure(padded));
   CK(cudaMemsetAsync(e->d_ascii.as<uint8_t>() + (s->len / 16) * 16, 0, padded - (s->len / 16) * 16, e->st));
   CK(cudaMemcpyAsync(e->d_ascii.p, s->bases, (size_t)s->len, cudaMemcpyHostToDevice, e->st));
+  e->strategy = PBSIM_STRATEGY_WGS;
   return finish_sequence_ingest(e, s->len, s->seq_num, s->hp_del_bias);
+}
+
+int pbsim_cuda_set_seqset(pbsim_engine *e, const pbsim_seqset *s) {
+  if (!e || !s || !s->bases || !s->start || !s->ids || !s->id_start) return PBSIM_E_INVALID;
+  CK(cudaSetDevice(e->device));
+  if (!e->model_set) return fail(e, PBSIM_E_INVALID, "set_model must precede set_seqset");
+  if (s->strategy != PBSIM_STRATEGY_TRANS && s->strategy != PBSIM_STRATEGY_TEMPL)
+    return fail(e, PBSIM_E_INVALID, "seqset strategy must be PBSIM_STRATEGY_TRANS or PBSIM_STRATEGY_TEMPL");
+  const bool trans = s->strategy == PBSIM_STRATEGY_TRANS;
+  if (trans && (!s->plus_exp || !s->minus_exp)) return fail(e, PBSIM_E_INVALID, "transcripts need plus_exp and minus_exp");
+  if (s->n < 1 || s->n > 100000000) return fail(e, PBSIM_E_INVALID, "number of sequences out of range");
+  const int64_t total = s->start[s->n];
+  if (s->start[0] != 0 || total < 1 || total > 0xFFFF0000ll)
+    return fail(e, PBSIM_E_INVALID, "sequence set too large for one engine (%lld bases; limit 2^32 - 2^16)", (long long)total);
+  const uint32_t n = (uint32_t)s->n;
+  std::vector<uint32_t> start(n + 1), plus_w(2 * (size_t)n, 0u), idst(n + 1);
+  std::vector<uint64_t> rprefix(n + 1);
+  int64_t max_len = 0;
+  uint64_t reads = 0;
+  for (uint32_t t = 0; t < n; ++t) {
+    const int64_t len = s->start[t + 1] - s->start[t];
+    if (len < 0) return fail(e, PBSIM_E_INVALID, "start[] must not decrease");
+    // TEMPLATE_LEN_MAX :29; transcripts: prob2ssp has TR_RANK_MAX = 1000 rows, rank = ceil(len / 1000) (:44, :2507)
+    if (len > (trans ? 999000 : 1000000))
+      return fail(e, PBSIM_E_INVALID, "sequence %u is too long (%lld bases)", t + 1, (long long)len);
+    uint64_t nr = 1;
+    if (trans) {
+      if (s->plus_exp[t] < 0 || s->minus_exp[t] < 0) return fail(e, PBSIM_E_INVALID, "negative expression value");
+      nr = (uint64_t)s->plus_exp[t] + (uint64_t)s->minus_exp[t];
+      plus_w[t] = (uint32_t)s->plus_exp[t];
+      plus_w[n + t] = (uint32_t)nr;  // weight of the sequence in the --hp-del-bias prepass (:2714)
+    }
+    // a window can be empty when a start fraction of 97.5 % meets a transcript of <= 20 bases (:2860-2866); the
+    // reference then divides by zero and indexes freq_accuracy with the result: undefined there, refused here
+    if (nr > 0 && len < (trans ? 21 : 1))
+      return fail(e, PBSIM_E_INVALID, "sequence %u has %lld bases: %s", t + 1, (long long)len,
+                  trans ? "transcripts that are read must be longer than 20 bases" : "empty template");
+    start[t] = (uint32_t)s->start[t];
+    idst[t] = (uint32_t)s->id_start[t];
+    if (s->id_start[t + 1] < s->id_start[t] || s->id_start[t + 1] - s->id_start[t] > 128)
+      return fail(e, PBSIM_E_INVALID, "name of sequence %u is longer than 128 characters", t + 1);
+    rprefix[t] = reads;
+    reads += nr;
+    max_len = std::max(max_len, len);
+  }
+  start[n] = (uint32_t)total;
+  idst[n] = (uint32_t)s->id_start[n];
+  rprefix[n] = reads;
+  if (reads < 1) return fail(e, PBSIM_E_INVALID, "the set yields no reads");
+  if (reads > 0xFFFFFFF0ull) return fail(e, PBSIM_E_INVALID, "too many reads for one run");
+  e->strategy = s->strategy;
+  e->set_n = n;
+  e->set_total_reads = (int64_t)reads;
+  e->set_mean_len = (double)total / n;
+  int rc;
+  if ((rc = upload(e, e->d_set_start, start.data(), start.size()))) return rc;
+  if ((rc = upload(e, e->d_set_rprefix, rprefix.data(), rprefix.size()))) return rc;
+  if ((rc = upload(e, e->d_set_plus, plus_w.data(), plus_w.size()))) return rc;
+  if ((rc = upload(e, e->d_set_idstart, idst.data(), idst.size()))) return rc;
+  if ((rc = upload(e, e->d_set_ids, reinterpret_cast<const uint8_t *>(s->ids), (size_t)idst[n]))) return rc;
+  if (trans) {
+    e->set_rank_max = (int32_t)std::ceil((float)max_len / 1000);  // transcript.rank_max (:1137)
+    std::vector<uint16_t> ends((size_t)(e->set_rank_max + 1) * 21), mod((size_t)e->set_rank_max + 1);
+    pbsim_host_ssp_table(e->set_rank_max, ends.data(), mod.data());
+    if ((rc = upload(e, e->d_set_ssp_ends, ends.data(), ends.size()))) return rc;
+    if ((rc = upload(e, e->d_set_ssp_mod, mod.data(), mod.size()))) return rc;
+    CK(cudaStreamSynchronize(e->st));  // the vectors go out of scope
+  }
+  const size_t padded = ((size_t)total + 15) / 16 * 16 + 64;
+  CK(e->d_ascii.ensure(padded));
+  CK(cudaMemsetAsync(e->d_ascii.as<uint8_t>() + (total / 16) * 16, 0, padded - (total / 16) * 16, e->st));
+  CK(cudaMemcpyAsync(e->d_ascii.p, s->bases, (size_t)total, cudaMemcpyHostToDevice, e->st));
+  // only simulate_by_qshmm_trans upper-cases the first base (:2774; :3330, :4474, :5049 start at 1)
+  const bool keep_first = !(trans && e->model.method == PBSIM_METHOD_QSHMM);
+  rc = finish_sequence_ingest(e, total, 0, s->hp_del_bias, keep_first);
+  return rc;
 }
 
 int pbsim_cuda_set_synthetic_sequence(pbsim_engine *e, int64_t len, int32_t seq_num, uint64_t seed) {
@@ -1156,6 +1288,7 @@ int pbsim_cuda_set_synthetic_sequence(pbsim_engine *e, int64_t len, int32_t seq_
   k_synth_ascii<<<nblk((len + 15) / 16, 256), 256, 0, e->st>>>(e->d_ascii.as<uint8_t>(), len, seed);
   e->launches++;
   double bias[12] = {0, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 0};
+  e->strategy = PBSIM_STRATEGY_WGS;
   return finish_sequence_ingest(e, len, seq_num, bias);
 }
 
@@ -1191,8 +1324,17 @@ int pbsim_cuda_simulate_begin(pbsim_engine *e, const pbsim_run *run) {
   if (run->rng_mode == PBSIM_RNG_REPLAY && (!run->replay_draws || !run->replay_starts || run->replay_nsubreads < 1))
     return fail(e, PBSIM_E_INVALID, "replay mode needs the draw log and the subread starts");
   e->run = *run;
+  if (e->strategy != PBSIM_STRATEGY_WGS) {
+    // the whole set (or the requested range of its read numbers) is the run; there is no quota (:2841, :3312)
+    if (run->first_read < 0 || run->first_read >= e->set_total_reads)
+      return fail(e, PBSIM_E_INVALID, "first_read is outside the set's %lld reads", (long long)e->set_total_reads);
+    const int64_t left = e->set_total_reads - run->first_read;
+    e->run.len_quota = INT64_MAX / 4;
+    e->run.len_total_start = 0;
+    e->run.max_reads = run->max_reads > 0 ? std::min(run->max_reads, left) : left;
+  }
   e->next_read = run->first_read;
-  e->len_total = run->len_total_start;
+  e->len_total = e->run.len_total_start;
   e->reads_done_in_run = 0;
   e->finished = false;
   e->tail_mode = false;

@@ -355,6 +355,34 @@ const pbsim_model *pbsim_host_model_get(const pbsim_host_model *m) { return m ? 
 
 void pbsim_host_model_free(pbsim_host_model *m) { delete m; }
 
+// prob2ssp / ssp_rand_value of simulate_by_*_trans (pbsim.cpp:2504-2528 = :4193-4217): for rank r the start
+// fraction 5*j % (j = 0..20) has probability (1/r) / (j+1)^(1 + 1/r), normalised over the 21 outcomes and quantised
+// to 1000 table positions like every other table of the reference.
+void pbsim_host_ssp_table(int32_t rank_max, uint16_t *ends, uint16_t *mod) {
+  for (int j = 0; j < 21; ++j) ends[j] = 0xFFFF;
+  mod[0] = 0;
+  for (int32_t i = 1; i <= rank_max; ++i) {
+    double sum = 0;
+    const double value = static_cast<double>(1) / i;
+    for (int j = 1; j <= 21; ++j) sum += value / pow(j, (1 + value));
+    double total = 0.0;
+    long end_wk = 0;
+    bool ended = false;
+    for (int j = 1; j <= 21; ++j) {
+      if (ended) {
+        ends[i * 21 + j - 1] = 0xFFFF;
+        continue;
+      }
+      total += (value / pow(j, (1 + value))) / sum;
+      end_wk = static_cast<int>(total * 1000 + 0.5);
+      if (end_wk > 1000) end_wk = 1000;
+      ends[i * 21 + j - 1] = static_cast<uint16_t>(end_wk);
+      if (end_wk >= 1000) ended = true;
+    }
+    mod[i] = static_cast<uint16_t>(end_wk);
+  }
+}
+
 void pbsim_host_hp_del_bias(double opt, const int64_t hpfreq[12], double bias[12]) {
   for (int i = 0; i < 12; ++i) bias[i] = 0.0;
   if (opt == 1) {

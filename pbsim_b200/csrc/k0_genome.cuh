@@ -132,6 +132,87 @@ __global__ void k_hp(const uint8_t *ascii, int64_t len, uint8_t *hp4, uint32_t *
   if (threadIdx.x < 12 && hist[threadIdx.x]) atomicAdd(&hpfreq[threadIdx.x], (unsigned long long)hist[threadIdx.x]);
 }
 
+// ---- sequence sets (--strategy trans / templ): many short sequences concatenated into one device text ----------
+// start[n+1]: first base of every sequence in the concatenation.  Homopolymer runs end at sequence boundaries and
+// windows never cross them, so everything downstream of K0 treats the concatenation like one genome.
+
+// index of the sequence holding base i (largest t with start[t] <= i)
+__device__ __forceinline__ uint32_t set_find(const uint32_t *__restrict__ start, uint32_t n, uint32_t i) {
+  uint32_t lo = 0, hi = n;  // start[lo] <= i < start[hi]
+  while (hi - lo > 1u) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (__ldg(&start[mid]) <= i) lo = mid;
+    else hi = mid;
+  }
+  return lo;
+}
+
+// The reference upper-cases these sequences with `for (i = 1; i <= len; i++)` everywhere except in
+// simulate_by_qshmm_trans (pbsim.cpp:3330, :4474, :5049 vs :2774): the first base keeps its case.
+__global__ void k_set_save_first(const uint8_t *ascii, const uint32_t *start, uint32_t n, uint8_t *first) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) first[t] = ascii[start[t]];
+}
+__global__ void k_set_restore_first(uint8_t *ascii, const uint32_t *start, uint32_t n, const uint8_t *first,
+                                    uint32_t *pk, uint32_t *xm) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const uint8_t c = first[t];
+  if (c < 'a' || c > 'z') return;
+  const uint32_t i = start[t];
+  if (start[t + 1] == i) return;  // empty sequence
+  ascii[i] = c;                   // a lower-case letter is not one of A, C, G, T: the base is exceptional
+  atomicAnd(&pk[i >> 4], ~(3u << (2u * (i & 15u))));
+  const uint32_t blk = i >> kXmShift;
+  atomicOr(&xm[blk >> 5], 1u << (blk & 31));
+}
+
+__device__ __forceinline__ uint32_t hp_of_bounded(const uint8_t *ascii, int64_t lo, int64_t hi, int64_t i,
+                                                  uint32_t *flag) {
+  const uint8_t c = ascii[i];
+  if (c == 'N') return 1u;
+  const int64_t cap = 1 << 16;
+  int64_t l = 0, r = 0;
+  while (i - l - 1 >= lo && ascii[i - l - 1] == c && l < cap) ++l;
+  while (i + r + 1 < hi && ascii[i + r + 1] == c && r < cap) ++r;
+  if (l >= cap || r >= cap) *flag = 1u;
+  const int64_t L = l + r + 1;
+  if (L <= 11) return (uint32_t)L;
+  return ((L - 11) & 1) ? 10u : 11u;
+}
+
+// k_hp for a sequence set; hpfreq counts every base weight[t] times (transcripts: plus + minus reads, the
+// --hp-del-bias prepass of pbsim.cpp:2714-2718; templates: weight == nullptr, 1)
+__global__ void k_hp_set(const uint8_t *ascii, int64_t len, const uint32_t *start, uint32_t n, const uint32_t *weight,
+                         uint8_t *hp4, uint32_t *xm, unsigned long long *hpfreq, const uint8_t *bias_is_one,
+                         uint32_t *flag) {
+  __shared__ unsigned long long hist[12];
+  if (threadIdx.x < 12) hist[threadIdx.x] = 0;
+  __syncthreads();
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t i0 = t * 2;
+  if (i0 < len) {
+    uint32_t q = set_find(start, n, (uint32_t)i0);
+    uint32_t h[2] = {0, 0};
+    bool special = false;
+    for (int k = 0; k < 2; ++k) {
+      const int64_t i = i0 + k;
+      if (i >= len) break;
+      while (i >= (int64_t)start[q + 1]) ++q;  // skips empty sequences too
+      h[k] = hp_of_bounded(ascii, start[q], start[q + 1], i, flag);
+      atomicAdd(&hist[h[k]], (unsigned long long)(weight ? weight[q] : 1u));
+      special |= !bias_is_one[h[k]];
+    }
+    hp4[t] = (uint8_t)(h[0] | (h[1] << 4));
+    if (special) {
+      const int64_t blk = i0 >> kXmShift;
+      atomicOr(&xm[blk >> 5], 1u << (blk & 31));
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 12 && hist[threadIdx.x]) atomicAdd(&hpfreq[threadIdx.x], hist[threadIdx.x]);
+}
+
 // true if any 1024-base block overlapping genome range [g0, g1] is exceptional
 __device__ __forceinline__ bool range_exceptional(const uint32_t *__restrict__ xm, uint32_t g0, uint32_t g1) {
   const uint32_t b0 = g0 >> kXmShift, b1 = g1 >> kXmShift;

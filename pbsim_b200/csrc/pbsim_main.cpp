@@ -7,9 +7,12 @@
 // main :699-754).  Compression is in-process (zlib gzip members from a thread pool) instead of
 // popen("gzip > file"); concatenated gzip members decompress to the same text.
 //
+// --strategy trans / templ (main :760-868) parse the transcript table / template FASTA here and hand the
+// whole set to the engine (pbsim_cuda_set_seqset); outputs <prefix>.fq.gz / .maf.gz (:771-788).
+//
 // Engine-only options (additive): --gpu N, --rng philox|replay, --replay-draws F --replay-marks F,
-// --threads N (compression).  Not built yet in this driver: --strategy trans/templ, --method sample,
-// BAM encoding for --pass-num > 1 (SAM text is written as <prefix>_NNNN.sam.gz instead).
+// --threads N (compression).  Not built yet in this driver: --method sample,
+// BAM encoding for --pass-num > 1 (SAM text is written as <prefix>[_NNNN].sam.gz instead).
 #include <getopt.h>
 #include <sys/resource.h>
 #include <sys/time.h>
@@ -274,6 +277,123 @@ std::string genome_seq(const Options &o, size_t num) {
   return seq;
 }
 
+// ---- --strategy trans / templ: the sequence set the engine simulates in one run --------------------------------
+struct SeqSetHost {
+  std::vector<std::string> ids;
+  std::vector<int32_t> plus, minus;
+  std::string bases;
+  std::vector<int64_t> start{0};
+  long num = 0;             // transcript.num_seq / templ.num
+  long total_exp = 0;       // transcript.total_exp
+  long long len_total = 0;  // templ.len_total
+};
+
+int trim_line(char *s) {  // trim (:882-891)
+  const size_t n = strlen(s);
+  if (n && s[n - 1] == '\n') {
+    s[n - 1] = '\0';
+    return 1;
+  }
+  return 0;
+}
+
+// The transcript table as get_transcript_inf (:1075-1140) and the fgets loops of simulate_by_*_trans (:2748-2772)
+// read it: one record per line, id <TAB> plus <TAB> minus <TAB> sequence, fields split the way strtok does (runs of
+// tabs collapse); a line longer than the 10 KB buffer continues in the next fgets chunk, which is appended whole.
+SeqSetHost read_transcripts(const Options &o) {
+  FILE *fp = fopen(o.transcript.c_str(), "r");
+  if (!fp) die("ERROR: Cannot open file: %s\n", o.transcript.c_str());
+  SeqSetHost S;
+  std::vector<char> line(kBufSize);
+  int flg1 = 1;
+  while (fgets(line.data(), (int)kBufSize, fp)) {
+    const int flg2 = trim_line(line.data());
+    if (flg1 == 1) {
+      char *save = nullptr;
+      const char *id = strtok_r(line.data(), "\t", &save);
+      const char *pl = strtok_r(nullptr, "\t", &save);
+      const char *mi = strtok_r(nullptr, "\t", &save);
+      const char *sq = strtok_r(nullptr, "\t", &save);
+      if (!id || !pl || !mi || !sq)
+        die("ERROR: transcript record %ld does not have 4 tab-separated fields: %s\n", S.num + 1, o.transcript.c_str());
+      S.num++;
+      S.ids.emplace_back(id, strnlen(id, kRefIdLenMax));  // TRANS_ID_LEN_MAX = 128
+      S.plus.push_back(atoi(pl));
+      S.minus.push_back(atoi(mi));
+      S.total_exp += S.plus.back() + S.minus.back();
+      S.bases.append(sq);
+    } else {
+      S.bases.append(line.data());
+    }
+    if (flg2 == 1) S.start.push_back((int64_t)S.bases.size());
+    flg1 = flg2;
+  }
+  fclose(fp);
+  if (flg1 == 0 && !S.ids.empty()) {  // last record without a line feed: counted in the stats, never simulated (:2773)
+    S.bases.resize((size_t)S.start.back());
+    S.ids.pop_back();
+    S.plus.pop_back();
+    S.minus.pop_back();
+  }
+  fprintf(stderr, ":::: transcript stats ::::\n\n");  // print_transcript_stats (:1142-1149)
+  fprintf(stderr, "file name : %s\n", o.transcript.c_str());
+  fprintf(stderr, "transcript num : %ld\n", S.num);
+  fprintf(stderr, "total expression value : %ld\n", S.total_exp);
+  fprintf(stderr, "\n");
+  return S;
+}
+
+// The template FASTA as get_templ_inf (:1366-1417) and simulate_by_*_templ (:3312-3329, :3560-3580) read it: header =
+// text after '>' (128 characters kept), body lines concatenated; a template ends at the next header or at EOF and is
+// simulated only if it holds at least one base.
+SeqSetHost read_templates(const Options &o) {
+  constexpr long kTemplateNumMax = 100000000, kTemplateLenMax = 1000000;  // :28-29
+  FILE *fp = fopen(o.templ.c_str(), "r");
+  if (!fp) die("ERROR: Cannot open file: %s\n", o.templ.c_str());
+  SeqSetHost S;
+  std::vector<char> line(kBufSize);
+  std::string id, seq;
+  bool have = false;
+  auto flush = [&]() {
+    if (have && !seq.empty()) {
+      S.ids.push_back(id);
+      S.plus.push_back(1);
+      S.minus.push_back(0);
+      S.bases.append(seq);
+      S.start.push_back((int64_t)S.bases.size());
+    }
+    seq.clear();
+  };
+  while (fgets(line.data(), (int)kBufSize, fp)) {
+    int ret = trim_line(line.data());
+    if (line[0] == '>') {
+      flush();
+      S.num++;
+      if (S.num > kTemplateNumMax) die("ERROR: template is too many. Max acceptable number is %ld.\n", kTemplateNumMax);
+      id.assign(line.data() + 1, strnlen(line.data() + 1, kRefIdLenMax));
+      have = true;
+      while (ret != 1) {
+        if (!fgets(line.data(), (int)kBufSize, fp)) break;
+        ret = trim_line(line.data());
+      }
+    } else {
+      const size_t n = strlen(line.data());
+      seq.append(line.data(), n);
+      S.len_total += (long long)n;
+      if ((long)seq.size() > kTemplateLenMax) die("ERROR: template is too long. Max acceptable length is %ld.\n", kTemplateLenMax);
+      have = true;  // text before the first header is a template with the (empty) id the reference starts with
+    }
+  }
+  flush();
+  fclose(fp);
+  fprintf(stderr, ":::: Template stats ::::\n\n");  // print_templ_stats (:1424-1431)
+  fprintf(stderr, "file name : %s\n", o.templ.c_str());
+  fprintf(stderr, "template num. : %ld\n", S.num);
+  fprintf(stderr, "template total length : %lld\n", S.len_total);
+  fprintf(stderr, "\n");
+  return S;
+}
+
 void print_help() {
   fprintf(stderr,
           "\nUSAGE: pbsim [options] \n\n [general options]\n\n"
@@ -304,7 +424,11 @@ void print_help() {
           "  --replay-draws       int32 log of the reference's rand() draws (replay mode).\n"
           "  --replay-marks       int64 draw count after every (read, pass) (replay mode).\n"
           "  --threads            compression threads (hardware concurrency).\n\n"
-          " --strategy trans/templ and --method sample are not built in this driver yet.\n\n");
+          " [options for transcriptome / template sequencing]\n\n"
+          "  --strategy           trans | templ\n"
+          "  --transcript         transcript table: id, plus count, minus count, sequence (tab separated).\n"
+          "  --template           FASTA file of templates; every template is read once, in full.\n\n"
+          " --method sample is not built in this driver yet.\n\n");
 }
 
 template <class T>
@@ -447,24 +571,29 @@ int main(int argc, char **argv) {
   if (o.set_flg[14]) o.accuracy_max = int(o.accuracy_max * 100) * 0.01;
   if (o.set_flg[19]) o.accuracy_mean = int(o.accuracy_mean * 100) * 0.01;
   if (o.len_min > o.len_max) die("ERROR: length min(%ld) is greater than max(%ld).\n", o.len_min, o.len_max);
-  if (o.strategy != "wgs" || o.method == "sample")
-    die("ERROR: this B200 driver builds --strategy wgs with --method qshmm|errhmm; %s/%s is not built yet.\n",
-        o.strategy.c_str(), o.method.c_str());
+  if (o.method == "sample")
+    die("ERROR: this B200 driver builds --method qshmm|errhmm; %s/%s is not built yet.\n", o.strategy.c_str(),
+        o.method.c_str());
   const bool qs = o.method == "qshmm";
+  const bool wgs = o.strategy == "wgs";
 
   // ---- print_sim_param (:5397-5465)
   fprintf(stderr, ":::: Simulation parameters :::\n\n");
-  fprintf(stderr, "strategy : wgs\n");
+  fprintf(stderr, "strategy : %s\n", o.strategy.c_str());
   fprintf(stderr, "method : %s\n", o.method.c_str());
   fprintf(stderr, "%s : %s\n", o.method.c_str(), qs ? o.qshmm.c_str() : o.errhmm.c_str());
-  fprintf(stderr, "genome : %s\n", o.genome.c_str());
+  if (wgs) fprintf(stderr, "genome : %s\n", o.genome.c_str());
+  else if (o.strategy == "trans") fprintf(stderr, "transcript : %s\n", o.transcript.c_str());
+  else fprintf(stderr, "template : %s\n", o.templ.c_str());
   fprintf(stderr, "prefix : %s\n", o.prefix.c_str());
   fprintf(stderr, "id-prefix : %s\n", o.id_prefix.c_str());
-  fprintf(stderr, "depth : %lf\n", o.depth);
-  fprintf(stderr, "length-mean : %f\n", o.len_mean);
-  fprintf(stderr, "length-sd : %f\n", o.len_sd);
-  fprintf(stderr, "length-min : %ld\n", o.len_min);
-  fprintf(stderr, "length-max : %ld\n", o.len_max);
+  if (wgs) fprintf(stderr, "depth : %lf\n", o.depth);
+  if (o.strategy != "templ") {
+    fprintf(stderr, "length-mean : %f\n", o.len_mean);
+    fprintf(stderr, "length-sd : %f\n", o.len_sd);
+    fprintf(stderr, "length-min : %ld\n", o.len_min);
+    fprintf(stderr, "length-max : %ld\n", o.len_max);
+  }
   if (qs) fprintf(stderr, "difference-ratio : %ld:%ld:%ld\n", o.sub_ratio, o.ins_ratio, o.del_ratio);
   fprintf(stderr, "seed : %d\n", o.seed);
   fprintf(stderr, "accuracy-mean : %f\n", o.accuracy_mean);
@@ -497,9 +626,6 @@ int main(int argc, char **argv) {
   if (pbsim_cuda_create(&eng, o.gpu) != 0) die("ERROR: %s\n", pbsim_cuda_last_error(nullptr));
   if (pbsim_cuda_set_model(eng, pbsim_host_model_get(hm)) != 0) die("ERROR: %s\n", pbsim_cuda_last_error(eng));
 
-  // ---- genome (get_genome_inf)
-  const std::vector<RefSeq> seqs = genome_inf(o);
-
   // ---- replay inputs
   std::vector<int32_t> draws;
   std::vector<int64_t> marks, starts;
@@ -511,63 +637,29 @@ int main(int argc, char **argv) {
     for (size_t i = 0; i < marks.size(); ++i) starts[i] = i == 0 ? 0 : marks[i - 1];
   }
   size_t replay_pos = 0;
-
-  // ---- hp-del-bias (main :673-697)
-  double bias[12] = {0, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 0};
-  int64_t hp11_running = 0;
-  auto ingest = [&](size_t num, const double b[12], int64_t hpfreq[12]) {
-    const std::string seq = genome_seq(o, num);
-    pbsim_sequence s;
-    s.bases = seq.data();
-    s.len = (int64_t)seq.size();
-    s.seq_num = (int32_t)num;
-    memcpy(s.hp_del_bias, b, sizeof s.hp_del_bias);
-    if (pbsim_cuda_set_sequence(eng, &s) != 0) die("ERROR: %s\n", pbsim_cuda_last_error(eng));
-    pbsim_cuda_get_hpfreq(eng, hpfreq);
-    return (int64_t)seq.size();
-  };
-  if (o.hp_del_bias != 1) {
-    int64_t tot[12] = {0};
-    for (size_t n = 1; n <= seqs.size(); ++n) {
-      int64_t f[12];
-      ingest(n, bias, f);
-      for (int k = 0; k < 12; ++k) tot[k] += f[k];
-    }
-    hp11_running = tot[11];
-    pbsim_host_hp_del_bias(o.hp_del_bias, tot, bias);
-  }
   const int threads = o.threads > 0 ? o.threads : std::max(2u, std::thread::hardware_concurrency());
-
   double gen_seconds = 0;
   int64_t total_bases = 0;
-  for (size_t n = 1; n <= seqs.size(); ++n) {
-    int64_t f[12];
-    const int64_t glen = ingest(n, bias, f);
-    hp11_running += f[11];
-    double b[12];
-    memcpy(b, bias, sizeof b);
-    memcpy(&b[0], &hp11_running, sizeof(double));  // the cell genome.hpfreq[11] aliases in the reference build
-    if (pbsim_cuda_update_hp_del_bias(eng, b) != 0) die("ERROR: %s\n", pbsim_cuda_last_error(eng));
+  double bias[12] = {0, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 0};
 
-    char name[4096];
-    snprintf(name, sizeof name, "%s_%04zu.%s", o.prefix.c_str(), n, o.pass_num == 1 ? "fq.gz" : "sam.gz");
-    GzipWriter reads_out(name, std::max(1, threads / 2));
-    snprintf(name, sizeof name, "%s_%04zu.maf.gz", o.prefix.c_str(), n);
-    GzipWriter maf_out(name, std::max(1, threads / 2));
-    if (o.pass_num > 1) {  // SAM header (:721-722)
+  // one simulate call of the reference: stream the engine's chunks into the two compressed files
+  auto simulate_to_files = [&](const std::string &stem, const std::string &pu, int64_t len_quota) {
+    GzipWriter reads_out((stem + (o.pass_num == 1 ? ".fq.gz" : ".sam.gz")).c_str(), std::max(1, threads / 2));
+    GzipWriter maf_out((stem + ".maf.gz").c_str(), std::max(1, threads / 2));
+    if (o.pass_num > 1) {  // SAM header (:721-722, :781-782)
       char hdr[1024];
       int m = snprintf(hdr, sizeof hdr,
                        "@HD\tVN:1.5\tSO:unknown\tpb:3.0.7\n@RG\tID:ffffffff\tPL:PACBIO\tDS:READTYPE=SUBREAD;Ipd:CodecV1=ip;"
                        "PulseWidth:CodecV1=pw;BINDINGKIT=101-789-500;SEQUENCINGKIT=101-826-100;BASECALLERVERSION=5.0.0;"
-                       "FRAMERATEHZ=100.000000\tPU:%s%zu\tPM:SEQUELII\n",
-                       o.id_prefix.c_str(), n);
+                       "FRAMERATEHZ=100.000000\tPU:%s\tPM:SEQUELII\n",
+                       pu.c_str());
       reads_out.submit(hdr, (size_t)m);
     }
     pbsim_run run;
     memset(&run, 0, sizeof run);
     run.rng_mode = replay ? PBSIM_RNG_REPLAY : PBSIM_RNG_PHILOX;
     run.seed = o.seed;
-    run.len_quota = (int64_t)(o.depth * glen);  // sim.len_quota (:705)
+    run.len_quota = len_quota;
     if (replay) {
       run.replay_draws = draws.data();
       run.replay_ndraws = (int64_t)draws.size();
@@ -590,10 +682,9 @@ int main(int argc, char **argv) {
     replay_pos += (size_t)st.res_pass_num;
     gen_seconds += st.gen_seconds;
     total_bases += st.res_len_total;
-    // print_simulation_stats (:5541-5564)
-    fprintf(stderr, ":::: Simulation stats (ref.%zu) ::::\n\n", n);
-    fprintf(stderr, "read num. : %ld\n", (long)st.res_num);
-    fprintf(stderr, "depth : %lf\n", (double)st.res_len_total / glen / o.pass_num);
+    return st;
+  };
+  auto print_stats_tail = [&](const pbsim_stats &st) {  // print_simulation_stats (:5551-5563)
     fprintf(stderr, "read length mean (SD) : %f (%f)\n", st.res_len_mean, st.res_len_sd);
     fprintf(stderr, "read length min : %ld\n", (long)st.res_len_min);
     fprintf(stderr, "read length max : %ld\n", (long)st.res_len_max);
@@ -602,14 +693,97 @@ int main(int argc, char **argv) {
     fprintf(stderr, "insertion rate. : %f\n", (double)st.res_ins_num / st.res_len_total);
     fprintf(stderr, "deletion rate. : %f\n", (double)st.res_del_num / st.res_len_total);
     fprintf(stderr, "\n");
+  };
+  auto finish = [&]() {
+    pbsim_cuda_destroy(eng);
+    pbsim_host_model_free(hm);
+    fprintf(stderr, ":::: System utilization ::::\n\n");
+    fprintf(stderr, "CPU time(s) : %ld\n", now_cpu() - rst1);
+    fprintf(stderr, "Elapsed time(s) : %ld\n", now_wall() - t1);
+    fprintf(stderr, "\n:::: B200 engine ::::\n\n");
+    fprintf(stderr, "generation device time(s) : %.3f\n", gen_seconds);
+    fprintf(stderr, "simulated Gbp/s (generation only) : %.3f\n", gen_seconds > 0 ? total_bases / gen_seconds / 1e9 : 0.0);
+    return 0;
+  };
+
+  if (!wgs) {
+    // ---- main :760-868: the whole transcript table / template file is one run
+    const bool trans = o.strategy == "trans";
+    const SeqSetHost S = trans ? read_transcripts(o) : read_templates(o);
+    std::string ids;
+    std::vector<int32_t> id_start{0};
+    for (const std::string &id : S.ids) {
+      ids += id;
+      id_start.push_back((int32_t)ids.size());
+    }
+    pbsim_seqset ss;
+    memset(&ss, 0, sizeof ss);
+    ss.strategy = trans ? PBSIM_STRATEGY_TRANS : PBSIM_STRATEGY_TEMPL;
+    ss.n = (int64_t)S.ids.size();
+    ss.bases = S.bases.data();
+    ss.start = S.start.data();
+    ss.plus_exp = S.plus.data();
+    ss.minus_exp = S.minus.data();
+    ss.ids = ids.data();
+    ss.id_start = id_start.data();
+    memcpy(ss.hp_del_bias, bias, sizeof bias);
+    if (pbsim_cuda_set_seqset(eng, &ss) != 0) die("ERROR: %s\n", pbsim_cuda_last_error(eng));
+    if (o.hp_del_bias != 1) {  // the prepass of :2671-2746 / :3244-3310: expression-weighted homopolymer histogram
+      int64_t f[12];
+      pbsim_cuda_get_hpfreq(eng, f);
+      pbsim_host_hp_del_bias(o.hp_del_bias, f, ss.hp_del_bias);
+      if (pbsim_cuda_set_seqset(eng, &ss) != 0) die("ERROR: %s\n", pbsim_cuda_last_error(eng));
+    }
+    const pbsim_stats st = simulate_to_files(o.prefix, o.id_prefix, 0);
+    fprintf(stderr, ":::: Simulation stats ::::\n\n");
+    fprintf(stderr, "read num. : %ld\n", (long)st.res_num);
+    print_stats_tail(st);
+    return finish();
   }
-  pbsim_cuda_destroy(eng);
-  pbsim_host_model_free(hm);
-  fprintf(stderr, ":::: System utilization ::::\n\n");
-  fprintf(stderr, "CPU time(s) : %ld\n", now_cpu() - rst1);
-  fprintf(stderr, "Elapsed time(s) : %ld\n", now_wall() - t1);
-  fprintf(stderr, "\n:::: B200 engine ::::\n\n");
-  fprintf(stderr, "generation device time(s) : %.3f\n", gen_seconds);
-  fprintf(stderr, "simulated Gbp/s (generation only) : %.3f\n", gen_seconds > 0 ? total_bases / gen_seconds / 1e9 : 0.0);
-  return 0;
+
+  // ---- genome (get_genome_inf)
+  const std::vector<RefSeq> seqs = genome_inf(o);
+
+  // ---- hp-del-bias (main :673-697)
+  int64_t hp11_running = 0;
+  auto ingest = [&](size_t num, const double b[12], int64_t hpfreq[12]) {
+    const std::string seq = genome_seq(o, num);
+    pbsim_sequence s;
+    s.bases = seq.data();
+    s.len = (int64_t)seq.size();
+    s.seq_num = (int32_t)num;
+    memcpy(s.hp_del_bias, b, sizeof s.hp_del_bias);
+    if (pbsim_cuda_set_sequence(eng, &s) != 0) die("ERROR: %s\n", pbsim_cuda_last_error(eng));
+    pbsim_cuda_get_hpfreq(eng, hpfreq);
+    return (int64_t)seq.size();
+  };
+  if (o.hp_del_bias != 1) {
+    int64_t tot[12] = {0};
+    for (size_t n = 1; n <= seqs.size(); ++n) {
+      int64_t f[12];
+      ingest(n, bias, f);
+      for (int k = 0; k < 12; ++k) tot[k] += f[k];
+    }
+    hp11_running = tot[11];
+    pbsim_host_hp_del_bias(o.hp_del_bias, tot, bias);
+  }
+  for (size_t n = 1; n <= seqs.size(); ++n) {
+    int64_t f[12];
+    const int64_t glen = ingest(n, bias, f);
+    hp11_running += f[11];
+    double b[12];
+    memcpy(b, bias, sizeof b);
+    memcpy(&b[0], &hp11_running, sizeof(double));  // the cell genome.hpfreq[11] aliases in the reference build
+    if (pbsim_cuda_update_hp_del_bias(eng, b) != 0) die("ERROR: %s\n", pbsim_cuda_last_error(eng));
+    char stem[4096], pu[512];
+    snprintf(stem, sizeof stem, "%s_%04zu", o.prefix.c_str(), n);
+    snprintf(pu, sizeof pu, "%s%zu", o.id_prefix.c_str(), n);
+    const pbsim_stats st = simulate_to_files(stem, pu, (int64_t)(o.depth * glen));  // sim.len_quota (:705)
+    // print_simulation_stats (:5541-5564)
+    fprintf(stderr, ":::: Simulation stats (ref.%zu) ::::\n\n", n);
+    fprintf(stderr, "read num. : %ld\n", (long)st.res_num);
+    fprintf(stderr, "depth : %lf\n", (double)st.res_len_total / glen / o.pass_num);
+    print_stats_tail(st);
+  }
+  return finish();
 }

@@ -253,6 +253,57 @@ PB_HD ReadPlan plan_read(const PlanTables &T, Draw &d, uint32_t glen, int64_t cl
   return p;
 }
 
+// --strategy trans (pbsim.cpp:2842-2866 = :4538-4562): length, accuracy, then the start position from the
+// prob2ssp table of the transcript's rank (:2504-2528); the window is clipped at the transcript's end.
+// ssp_ends[rank*21 + j]: cumulative table position of start fraction 5*j percent (0xFFFF: row ended), ssp_mod[rank]
+// the row modulus.  tlen: length of the transcript.  The returned offset is relative to the transcript.
+PB_HD double pb_mul_add_rn(double a, double b, double c) {  // a*b + c with two roundings, as the host computes it
+#ifdef __CUDA_ARCH__
+  return __dadd_rn(__dmul_rn(a, b), c);
+#else
+  volatile double m = a * b;
+  return m + c;
+#endif
+}
+
+template <class Draw>
+PB_HD ReadPlan plan_read_trans(const PlanTables &T, Draw &d, const uint16_t *ssp_ends, const uint16_t *ssp_mod,
+                               uint32_t tlen) {
+  ReadPlan p;
+  d.plan_begin();
+  uint32_t len = (uint32_t)T.prob2len[d.plan_len(T.len_rand_value)];
+  p.raw_len = len;
+  p.acc = T.prob2acc[d.plan_acc(T.acc_rand_value)];
+  const uint32_t rank = (tlen + 999u) / 1000u;  // ceil((double)transcript.len / 1000)
+  const uint32_t index = d.plan_off(ssp_mod[rank]) + 1u;
+  uint32_t ssp = 100u;
+  for (uint32_t j = 0; j < 21u; ++j) {
+    const uint32_t e = ssp_ends[rank * 21u + j];
+    if (e == 0xFFFFu) break;
+    if (index <= e) {
+      ssp = j * 5u;
+      break;
+    }
+  }
+  const double value = ssp == 0u ? 0.0 : ((double)ssp - 2.5) / 100;
+  p.offset = (uint32_t)(int)pb_mul_add_rn((double)tlen, value, 0.5);
+  if ((uint64_t)p.offset + len > tlen) len = p.offset < tlen ? tlen - p.offset : 0u;
+  p.wlen = len;
+  return p;
+}
+
+// --strategy templ (:3359-3364 = :5078-5083): one accuracy draw; the read covers the whole template
+template <class Draw>
+PB_HD ReadPlan plan_read_templ(const PlanTables &T, Draw &d, uint32_t tlen) {
+  ReadPlan p;
+  d.plan_begin();
+  p.acc = T.prob2acc[d.plan_acc(T.acc_rand_value)];
+  p.raw_len = tlen;
+  p.wlen = tlen;
+  p.offset = 0;
+  return p;
+}
+
 // ---------------------------------------------------------------------------------------------
 // slow-path genome access (only reads whose window touches a non-ACGT base or a homopolymer
 // with a non-unit deletion bias, or every read when --hp-del-bias != 1)

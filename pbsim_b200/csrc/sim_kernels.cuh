@@ -43,6 +43,20 @@ struct DeviceGenome {
   uint32_t seq_num;
 };
 
+// --strategy trans / templ: the sequences are concatenated into the device genome; reads are numbered through the
+// whole set (sim.res_num) and belong to sequence t when rprefix[t] < read id <= rprefix[t+1]
+struct DeviceSet {
+  uint32_t strategy;        // PBSIM_STRATEGY_*; WGS: every pointer below is null
+  uint32_t n;
+  const uint32_t *start;    // [n+1] first base of sequence t in the concatenation
+  const uint64_t *rprefix;  // [n+1] reads of the sequences before t (trans: plus + minus each; templ: 1 each)
+  const uint32_t *plus;     // [n]   trans: the first plus[t] reads of a transcript are '+', the rest '-'
+  const uint16_t *ssp_ends; // start-position table, see plan_read_trans
+  const uint16_t *ssp_mod;
+  const uint8_t *ids;       // names, concatenated
+  const uint32_t *id_start; // [n+1]
+};
+
 struct RngParams {
   uint32_t mode;           // PBSIM_RNG_*
   uint32_t seed;
@@ -58,6 +72,7 @@ struct Batch {
   uint64_t first_read;     // id of read 0 of the batch minus 1 (ids are first_read + 1 + r)
   // per read
   uint32_t *plan_off, *plan_wlen, *plan_raw, *plan_meta;  // meta: acc | minus<<8 | slow<<9 | invalid<<10
+  uint32_t *plan_tr;       // sequence index of the read (trans / templ; unused for WGS)
   // per subread
   uint32_t *key_in, *key_out, *idx_in, *order;
   uint32_t *cap;           // event-slot capacity (entries)
@@ -72,8 +87,16 @@ struct Batch {
 // ----------------------------------------------------------------------------------------------
 // K1: plan.  One thread per read.  clip_room >= 0 only for single-read tail batches.
 // ----------------------------------------------------------------------------------------------
-__global__ void k_plan(DeviceModel M, DeviceGenome G, RngParams rng, Batch B, int64_t clip_room, uint32_t cap_num,
-                       uint32_t cap_den, uint32_t ev_align, uint32_t seg_min_len /* 0: segments off */) {
+template <class Draw>
+__device__ __forceinline__ ReadPlan plan_any(const PlanTables &T, Draw &d, const DeviceGenome &G, const DeviceSet &S,
+                                             uint32_t tlen, int64_t clip_room) {
+  if (S.strategy == PBSIM_STRATEGY_TRANS) return plan_read_trans(T, d, S.ssp_ends, S.ssp_mod, tlen);
+  if (S.strategy == PBSIM_STRATEGY_TEMPL) return plan_read_templ(T, d, tlen);
+  return plan_read(T, d, G.len, clip_room);
+}
+
+__global__ void k_plan(DeviceModel M, DeviceGenome G, DeviceSet S, RngParams rng, Batch B, int64_t clip_room,
+                       uint32_t cap_num, uint32_t cap_den, uint32_t ev_align, uint32_t seg_min_len /* 0: segments off */) {
   const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= B.n_reads) return;
   PlanTables T;
@@ -84,22 +107,41 @@ __global__ void k_plan(DeviceModel M, DeviceGenome G, RngParams rng, Batch B, in
   T.len_min = M.len_min;
   const uint64_t read_id = B.first_read + 1u + r;
   ReadPlan p;
+  // sequence sets: which sequence the read belongs to, and its rank among that sequence's reads
+  uint32_t tr = 0, tlen = 0, tstart = 0;
+  uint64_t kth = 0;
+  if (S.strategy != PBSIM_STRATEGY_WGS) {
+    uint32_t lo = 0, hi = S.n;  // rprefix[lo] <= read_id - 1 < rprefix[hi]
+    while (hi - lo > 1u) {
+      const uint32_t mid = (lo + hi) >> 1;
+      if (S.rprefix[mid] <= read_id - 1u) lo = mid;
+      else hi = mid;
+    }
+    tr = lo;
+    kth = read_id - S.rprefix[tr];
+    tstart = S.start[tr];
+    tlen = S.start[tr + 1] - tstart;
+    B.plan_tr[r] = tr;
+  }
   if (rng.mode == PBSIM_RNG_PHILOX) {
     PhiloxDraw d;
     d.ph.k0 = rng.seed;
     d.ph.k1 = G.seq_num;
     d.read_id = (uint32_t)read_id;
     d.pass = 0;
-    p = plan_read(T, d, G.len, clip_room);
+    p = plan_any(T, d, G, S, tlen, clip_room);
   } else {
     ReplayDraw d;
     d.log = rng.draws - rng.draws_base;
     d.cur = rng.starts[(uint64_t)r * M.pass_num];
     d.start = d.cur;
     d.end = rng.draws_end;
-    p = plan_read(T, d, G.len, clip_room);
+    p = plan_any(T, d, G, S, tlen, clip_room);
   }
-  const uint32_t minus = (read_id & 1u) ? 0u : 1u;  // res_num odd -> '+', even -> '-' (:2201-2207)
+  p.offset += tstart;  // position in the concatenation
+  uint32_t minus = (read_id & 1u) ? 0u : 1u;  // res_num odd -> '+', even -> '-' (:2201-2207)
+  if (S.strategy == PBSIM_STRATEGY_TRANS) minus = kth <= S.plus[tr] ? 0u : 1u;  // i <= plus_exp -> '+' (:2880)
+  if (S.strategy == PBSIM_STRATEGY_TEMPL) minus = 0u;                           // :3363
   bool slow = !M.uniform_bias;
   if (!slow) slow = range_exceptional(G.xm, p.offset, p.offset + p.wlen - 1u);
   const AccEntry ae = M.acc[p.acc];
@@ -260,6 +302,7 @@ struct SimArgs {
   const uint64_t *seg_off;  // segment-parallel pass 1: first segment of a sub-read
   uint32_t *seg_state;      // ... and the chain state in front of every segment (chain-only prepass)
   const uint8_t *bias_one;  // [12] hp_del_bias[h] == 1
+  uint32_t plan_draws;      // replay: planner draws in front of pass 0 (0: WGS, 2 or 3; trans 3; templ 1)
   uint8_t *ev;   // event arena
   Ckpt *ck;      // checkpoint arena
 };
@@ -276,12 +319,13 @@ __device__ __forceinline__ void store_result(const Batch &B, uint32_t s, const S
   B.accuracy[s] = res.accuracy;
 }
 
-// chain draws of subread (r, h) in replay mode start after the planner's 2 or 3 draws for pass 0
+// chain draws of subread (r, h) in replay mode start after the planner's draws for pass 0: WGS 2 or 3 (:2174-2189),
+// transcripts 3 (:2842-2850), templates 1 (:3359)
 __device__ __forceinline__ void replay_setup(ReplayDraw &d, const RngParams &rng, uint32_t s, uint32_t pass,
-                                             bool offset_drawn) {
+                                             uint32_t fixed, bool offset_drawn) {
   d.log = rng.draws - rng.draws_base;
   d.start = rng.starts[s];
-  d.cur = d.start + (pass == 0 ? (offset_drawn ? 3 : 2) : 0);
+  d.cur = d.start + (pass == 0 ? (fixed ? fixed : (offset_drawn ? 3u : 2u)) : 0u);
   d.end = rng.draws_end;
 }
 
@@ -362,7 +406,7 @@ __global__ void __launch_bounds__(kSimThreads) k_sim_qshmm(SimArgs A) {
     }
   } else {
     ReplayDraw d;
-    replay_setup(d, A.rng, s, pass, wlen < A.G.len);
+    replay_setup(d, A.rng, s, pass, A.plan_draws, wlen < A.G.len);
     qshmm_simulate(T, d, win, slow, wlen, sink, res);
     used = d.consumed();
   }
@@ -444,7 +488,7 @@ __global__ void __launch_bounds__(kErrThreads) k_sim_errhmm(SimArgs A, uint32_t 
     errhmm_simulate(T, d, win, slow, wlen, sink, res);
   } else {
     ReplayDraw d;
-    replay_setup(d, A.rng, s, pass, wlen < A.G.len);
+    replay_setup(d, A.rng, s, pass, A.plan_draws, wlen < A.G.len);
     errhmm_simulate(T, d, win, slow, wlen, sink, res);
     used = d.consumed();
   }

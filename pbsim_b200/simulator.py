@@ -53,6 +53,32 @@ class Engine:
         self._chk(self.L.pbsim_cuda_set_sequence(self.h, C.byref(s)), "set_sequence")
         self.glen = len(bases)
 
+    def set_seqset(self, strategy, seqset, bias):
+        """strategy 'trans' | 'templ'; seqset = [(name, plus, minus, bases)] as parsed from the transcript table /
+        template FASTA (pbsim.cpp:1075, :1366)"""
+        names = [x[0].encode() if isinstance(x[0], str) else x[0] for x in seqset]
+        bases = b"".join(x[3] for x in seqset)
+        start = np.zeros(len(seqset) + 1, dtype=np.int64)
+        start[1:] = np.cumsum([len(x[3]) for x in seqset])
+        plus = np.array([x[1] for x in seqset], dtype=np.int32)
+        minus = np.array([x[2] for x in seqset], dtype=np.int32)
+        ids = b"".join(names)
+        id_start = np.zeros(len(seqset) + 1, dtype=np.int32)
+        id_start[1:] = np.cumsum([len(x) for x in names])
+        self._keep = [bases, start, plus, minus, ids, id_start]
+        s = capi.SeqSet()
+        s.strategy = capi.STRATEGY_TRANS if strategy == "trans" else capi.STRATEGY_TEMPL
+        s.n = len(seqset)
+        s.bases = C.cast(C.c_char_p(bases), C.c_void_p)
+        s.start = start.ctypes.data
+        s.plus_exp = plus.ctypes.data
+        s.minus_exp = minus.ctypes.data
+        s.ids = C.cast(C.c_char_p(ids), C.c_void_p)
+        s.id_start = id_start.ctypes.data
+        s.hp_del_bias = (C.c_double * 12)(*bias)
+        self._chk(self.L.pbsim_cuda_set_seqset(self.h, C.byref(s)), "set_seqset")
+        self.glen = len(bases)
+
     def set_synthetic_sequence(self, length, seq_num, seed):
         self._chk(self.L.pbsim_cuda_set_synthetic_sequence(self.h, length, seq_num, seed), "set_synthetic_sequence")
         self.glen = length
@@ -215,3 +241,42 @@ class WgsRun:
         reads, maf, st, n = self.e.simulate(quota, **kw)
         text = format_stats(st, seq_num, len(bases), self.hm.view.pass_num)
         return reads, maf, st, text
+
+
+def format_stats_set(st):
+    """print_simulation_stats for the transcript / template strategies (pbsim.cpp:5547-5564)."""
+    tot = st.res_len_total
+    return (
+        ":::: Simulation stats ::::\n\n"
+        + "read num. : %d\n" % st.res_num
+        + "read length mean (SD) : %f (%f)\n" % (st.res_len_mean, st.res_len_sd)
+        + "read length min : %d\n" % st.res_len_min
+        + "read length max : %d\n" % st.res_len_max
+        + "read accuracy mean (SD) : %f (%f)\n" % (st.res_accuracy_mean, st.res_accuracy_sd)
+        + "substitution rate. : %f\n" % (st.res_sub_num / tot)
+        + "insertion rate. : %f\n" % (st.res_ins_num / tot)
+        + "deletion rate. : %f\n" % (st.res_del_num / tot)
+        + "\n"
+    )
+
+
+class SetRun:
+    """main()'s transcript / template branches (pbsim.cpp:760-868): ingest the set, bias, simulate, stats."""
+
+    def __init__(self, engine, host_model, strategy, hp_del_bias=1.0):
+        self.e = engine
+        self.hm = host_model
+        self.strategy = strategy
+        self.opt = hp_del_bias
+        engine.set_model(host_model)
+
+    def simulate(self, seqset, **kw):
+        bias = [0.0] + [1.0] * 10 + [0.0]
+        self.e.set_seqset(self.strategy, seqset, bias)
+        if self.opt != 1.0:
+            # the --hp-del-bias prepass (:2671-2746, :3244-3310): expression-weighted homopolymer histogram; its
+            # cell [11] lands on hp_del_bias[0] in the reference build
+            bias = capi.hp_del_bias(self.e.L, self.opt, self.e.hpfreq())
+            self.e.set_seqset(self.strategy, seqset, bias)
+        reads, maf, st, n = self.e.simulate(0, **kw)
+        return reads, maf, st, format_stats_set(st)

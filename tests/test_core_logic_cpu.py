@@ -168,3 +168,20 @@ def test_segment_parallel_pass1_equals_oracle(name):
         assert [s["nins"] for s in sub] == oref["info"]["nins"].tolist()
     if name != "qs_rsii_fixedlen":
         assert L.hostsim_seg_reads() > 0
+
+
+def test_start_position_table_equals_oracle():
+    """pbsim_host_ssp_table (the product's builder of prob2ssp, pbsim.cpp:2504-2528) against the oracle's, for every
+    rank a 999 kb transcript can reach"""
+    import ctypes as C
+    from pbsim_b200 import capi
+    L = capi.load()
+    rank_max = 999
+    ends = np.zeros((rank_max + 1) * 21, dtype=np.uint16)
+    mod = np.zeros(rank_max + 1, dtype=np.uint16)
+    L.pbsim_host_ssp_table(rank_max, ends.ctypes.data, mod.ctypes.data)
+    o_ends, o_mod = O.ssp_table(rank_max)
+    ends = ends.reshape(rank_max + 1, 21).astype(np.int64)
+    ends[ends == 0xFFFF] = -1
+    assert np.array_equal(ends[1:], o_ends[1:])
+    assert np.array_equal(mod[1:], o_mod[1:])

@@ -55,3 +55,34 @@ def test_cli_philox_equals_oracle(tmp_path):
     for i, o in enumerate(out, start=1):
         assert gzip.open(tmp_path / ("out_%04d.fq.gz" % i), "rb").read() == o["reads"]
         assert gzip.open(tmp_path / ("out_%04d.maf.gz" % i), "rb").read() == o["maf"]
+
+
+@pytest.mark.parametrize("name", ["tr_qs_ont_hpbias", "tr_err_ont_hpbias", "tm_err_sequel_multipass",
+                                  "tr_qs_rsii_multipass_long", "tm_qs_rsii_hpbias"])
+def test_cli_replay_reproduces_reference_transcript_and_template_files(name, tmp_path):
+    """--strategy trans / templ: the driver parses the transcript table / template FASTA itself (long lines,
+    lower case, multi-line FASTA) and must write the reference's <prefix>.fq.gz|.bam text and <prefix>.maf.gz"""
+    from tests.golden_util import SetCase
+    c = SetCase(name)
+    exe = G.build_driver()
+    with gzip.open(os.path.join(c.dir, "input.txt.gz"), "rb") as f:
+        (tmp_path / "input.txt").write_bytes(f.read())
+    O.glibc_rand(c.seed, c.ndraws).tofile(tmp_path / "draws.bin")
+    c.marks.astype(np.int64).tofile(tmp_path / "marks.bin")
+    args = [exe, "--strategy", c.strategy, "--method", c.method, "--" + c.method, c.model,
+            "--transcript" if c.strategy == "trans" else "--template", "input.txt", "--seed", str(c.seed)] \
+        + list(c.meta["extra_args"]) + ["--prefix", "out", "--rng", "replay", "--replay-draws", "draws.bin",
+                                        "--replay-marks", "marks.bin"]
+    p = subprocess.run(args, cwd=tmp_path, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=600)
+    assert p.returncode == 0, p.stderr.decode()
+    ext = "fq.gz" if c.pass_num == 1 else "sam.gz"
+    got = gzip.open(tmp_path / ("out." + ext), "rb").read()
+    want = gzip.open(os.path.join(c.dir, "reads.gz"), "rb").read()  # SAM: header included
+    assert got == want
+    assert gzip.open(tmp_path / "out.maf.gz", "rb").read() == c.maf()
+
+    def norm(text):
+        head = text.split(":::: System utilization ::::")[0]
+        return "\n".join(("%s : <model>" % c.method) if ln.startswith(c.method + " : ") else ln
+                         for ln in head.split("\n"))
+    assert norm(p.stderr.decode()) == norm(c.stderr)
