@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py — simulated Gbp/s of the PBSIM3 read-generation hot path on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3|c1|c2] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3|c1|c2|c4|c5] [--impl reference]
 
 A STEP is one call of the reference's seam for one reference sequence: ingest the sequence
 (get_genome_seq), then simulate_by_qshmm / simulate_by_errhmm to the depth quota, records emitted
@@ -50,6 +50,15 @@ WORKLOADS = {
     # configs[1]
     "c2": dict(name="WGS errhmm ERRHMM-ONT-HQ (mean 9 kb), 3.1 Gbp synthetic genome, --depth 30",
                method="errhmm", model="ERRHMM-ONT-HQ.model", depth=30.0, params=dict(), cli=[]),
+    # configs[4]: multi-pass CLR, SAM records (pbsim.cpp:2322-2333) instead of FASTQ
+    "c5": dict(name="WGS errhmm ERRHMM-SEQUEL --pass-num 10 (mean 9 kb), 3.1 Gbp synthetic genome, --depth 20, SAM+MAF",
+               method="errhmm", model="ERRHMM-SEQUEL.model", depth=20.0, params=dict(pass_num=10),
+               cli=["--pass-num", "10"], batch_bases=3 << 30),
+    # configs[3]: transcriptome; a step is one run over the whole transcript table
+    "c4": dict(name="trans qshmm QSHMM-RSII, 200,000 synthetic transcripts (log-normal, median 1.5 kb), Zipf "
+                    "expression, 2e7 reads",
+               method="qshmm", model="QSHMM-RSII.model", depth=0.0, params=dict(), cli=[], strategy="trans",
+               n_transcripts=200000, n_reads=20000000),
 }
 
 # algorithmic bytes per emitted base: FASTQ 2.002 + MAF 2.122 written + 0.244 read (2-bit genome)
@@ -293,9 +302,30 @@ def main():
     eng.set_model(hm)
     if args.batch_bases:
         eng.set_option("target_batch_bases", int(args.batch_bases))
+    if wl.get("batch_bases") and not args.batch_bases:
+        eng.set_option("target_batch_bases", int(wl["batch_bases"]))
     depth = wl["depth"]
     contigs = [max(200000, int(m * 1000000 * args.scale)) for m in CONTIG_MBP]
     bias = [0.0] + [1.0] * 10 + [0.0]
+    seqset = None
+    if wl.get("strategy") == "trans":
+        # log-normal lengths (median 1.5 kb, capped), Zipf expression counts, both strands
+        rng = np.random.default_rng(GENOME_SEED + rank)
+        nt = max(100, int(wl["n_transcripts"] * args.scale))
+        lens = np.clip(np.exp(rng.normal(np.log(1500.0), 0.75, nt)).astype(np.int64), 200, 100000)
+        w = 1.0 / np.arange(1, nt + 1) ** 0.9
+        expr = rng.permutation(np.maximum(1, (w / w.sum() * wl["n_reads"] * args.scale)).astype(np.int64))
+        text = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, int(lens.sum()))].tobytes()
+        st0 = np.zeros(nt + 1, dtype=np.int64)
+        st0[1:] = np.cumsum(lens)
+        plus = (expr + 1) // 2
+        names = [b"T%06d" % (t + 1) for t in range(nt)]
+        id_start = np.zeros(nt + 1, dtype=np.int32)
+        id_start[1:] = np.cumsum([len(x) for x in names])
+        seqset = dict(n=nt, bases=text, start=st0, plus=plus.astype(np.int32), minus=(expr - plus).astype(np.int32),
+                      ids=b"".join(names), id_start=id_start)
+        contigs = [int(lens.sum())]
+        eng.set_seqset("trans", seqset, bias)
 
     def seq_of(step):
         return (rank + step * world) % len(contigs)
@@ -303,8 +333,9 @@ def main():
     def step_device(step):
         """ingest (synthetic text generated in HBM) + simulate to the quota, records stay in HBM"""
         k = seq_of(step)
-        eng.set_synthetic_sequence(contigs[k], k + 1, GENOME_SEED + k)
-        eng.begin(int(depth * contigs[k]), rng_mode=capi.RNG_PHILOX, seed=1)
+        if seqset is None:
+            eng.set_synthetic_sequence(contigs[k], k + 1, GENOME_SEED + k)
+        eng.begin(int(depth * contigs[k]), rng_mode=capi.RNG_PHILOX, seed=1 + (step if seqset else 0))
         bases = out_bytes = 0
         while True:
             c = eng.next_chunk(device=True)
@@ -349,7 +380,7 @@ def main():
     e2e_steps = args.steps if args.e2e_steps < 0 else args.e2e_steps
     e2e = None
     if e2e_steps > 0:
-        need = sorted({seq_of(args.warmup + k) for k in range(e2e_steps)})
+        need = sorted({seq_of(args.warmup + k) for k in range(e2e_steps)}) if seqset is None else []
         host_seq = {}
         for k in need:  # pinned host copies of the sequence text (untimed preparation)
             eng.set_synthetic_sequence(contigs[k], k + 1, GENOME_SEED + k)
@@ -362,7 +393,10 @@ def main():
         sink = 0
         for k in range(e2e_steps):
             q = seq_of(args.warmup + k)
-            eng.set_sequence_ptr(host_seq[q].data_ptr(), contigs[q], q + 1, bias)
+            if seqset is None:
+                eng.set_sequence_ptr(host_seq[q].data_ptr(), contigs[q], q + 1, bias)
+            else:
+                eng.set_seqset("trans", seqset, bias)  # the table's text goes up with every step
             h2d += contigs[q]
             eng.begin(int(depth * contigs[q]), rng_mode=capi.RNG_PHILOX, seed=1)
             while True:
@@ -415,8 +449,10 @@ def main():
             "metric": "simulated Gbp/s", "value": value, "unit": "Gbp/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": max_ms / max(1, args.steps), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-            "config": {"workload": wl["name"], "step": "one reference sequence: device ingest + simulate to depth quota, "
-                       "FASTQ+MAF emitted", "genome_bp": int(sum(contigs)), "contigs": len(contigs), "rng": "philox4x32-10",
+            "config": {"workload": wl["name"],
+                       "step": ("one run over the transcript table, FASTQ+MAF emitted" if seqset is not None else
+                                "one reference sequence: device ingest + simulate to depth quota, %s+MAF emitted"
+                                % ("SAM" if wl["params"].get("pass_num", 1) > 1 else "FASTQ")), "genome_bp": int(sum(contigs)), "contigs": len(contigs), "rng": "philox4x32-10",
                        "l2": "every step writes > 10 GB of records and events (>> 126 MB L2); no explicit flush needed",
                        "host_wall_ms_per_step": max_wall / max(1, args.steps), "scale": args.scale},
             "gpu_launches": int(tot_launches),

@@ -627,12 +627,12 @@ int run_batch(pbsim_engine *e, uint32_t n_reads, int64_t clip_room, BatchResult 
       k_seg_fill<<<nblk(n_sub, 256), 256, 0, e->st>>>(B, S, pass);
       {
         size_t tmp = 0;
-        CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, S.seg_key_in, S.seg_key_out, S.seg_id_in, S.seg_order, (int)nseg, 21,
+        CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, S.seg_key_in, S.seg_key_out, S.seg_id_in, S.seg_order, (int)nseg, 20,
                                            28, e->st));
         CK(e->d_cub_tmp.ensure(tmp + 256));
         tmp = e->d_cub_tmp.cap;
         CK(cub::DeviceRadixSort::SortPairs(e->d_cub_tmp.p, tmp, S.seg_key_in, S.seg_key_out, S.seg_id_in, S.seg_order,
-                                           (int)nseg, 21, 28, e->st));
+                                           (int)nseg, 20, 28, e->st));
       }
       k_fill_u32<<<1, 256, 0, e->st>>>(sb_start, kBins + 1, 0xFFFFFFFFu);
       k_bin_bounds<<<nblk(nseg, 256), 256, 0, e->st>>>(S.seg_key_out, nseg, sb_start);

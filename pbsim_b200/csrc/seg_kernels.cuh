@@ -34,10 +34,15 @@ __global__ void k_seg_fill(Batch B, SegBatch S, uint32_t pass_num) {
   if (s >= B.n_sub) return;
   const uint64_t lo = S.seg_off[s], hi = S.seg_off[s + 1];
   if (hi == lo) return;
-  const uint32_t acc = B.plan_meta[s / pass_num] & 0xFFu;
+  const uint32_t meta = B.plan_meta[s / pass_num];
+  const uint32_t acc = meta & 0xFFu;
+  // segments that recover their start state by backward coupling (not the first segment, not reads served by the
+  // chain-only prepass) get the odd bin of their accuracy: CTAs, and so warps, are all-coupling or coupling-free
+  // (mixed warps pay the coupling loop at a quarter of their lanes)
+  const uint32_t couples = ((meta >> 12) & 1u) ? 0u : 1u;
   for (uint64_t i = lo; i < hi; ++i) {
     S.seg_sub[i] = s;
-    S.seg_key_in[i] = acc << 21;
+    S.seg_key_in[i] = (acc << 21) | ((i > lo ? couples : 0u) << 20);
     S.seg_id_in[i] = (uint32_t)i;
   }
 }
@@ -153,7 +158,16 @@ __global__ void __launch_bounds__(128) k_find_end(Batch B, SegBatch S, DeviceGen
     uint16_t *e = ev_base + (uint64_t)k * PB_SEG_STRIDE;
     const uint32_t n = seg[k].n_entries;
     const uint32_t R_tile = R, P_tile = P, D_tile = D;
-    if (!hp.enabled && (uint64_t)R + seg[k].ref_adv < wlen) {
+    // a repair is only possible where a deletion follows a base of an exceptional block: test the segment's
+    // whole reference range first (window bases R-1 .. R+ref_adv), so that a long read pays for its few flagged
+    // segments and not for all of them
+    bool seg_touch = false;
+    if (hp.enabled && (uint64_t)R + seg[k].ref_adv < wlen) {
+      const uint32_t lo_w = R == 0u ? 0u : R - 1u, hi_w = R + seg[k].ref_adv;
+      const uint32_t ga = hp.win.gidx(lo_w), gb = hp.win.gidx(hi_w);
+      seg_touch = range_exceptional(G.xm, min(ga, gb), max(ga, gb));
+    }
+    if (!seg_touch && (uint64_t)R + seg[k].ref_adv < wlen) {
       // nothing to repair and the window cannot end here: the segment's own totals are exact
       if (lane == 0) {
         Ckpt c; c.col = P + D; c.ref = R; c.read = P; c.pad = n;
@@ -361,7 +375,12 @@ __global__ void __launch_bounds__(128) k_find_end_err(Batch B, SegBatch S, Devic
       Ckpt c; c.col = C; c.ref = R; c.read = P; c.pad = PB_TILE;
       ckp[k] = c;
     }
-    if (!hp.enabled && (uint64_t)R + seg[k].ref_adv < wlen) {
+    bool seg_touch = false;  // errhmm tests the bias of the CURRENT reference base: window bases R .. R+ref_adv
+    if (hp.enabled && (uint64_t)R + seg[k].ref_adv < wlen) {
+      const uint32_t ga = hp.win.gidx(R), gb = hp.win.gidx(R + seg[k].ref_adv);
+      seg_touch = range_exceptional(G.xm, min(ga, gb), max(ga, gb));
+    }
+    if (!seg_touch && (uint64_t)R + seg[k].ref_adv < wlen) {
       P += PB_TILE - seg[k].ndel; R += seg[k].ref_adv; nsub += seg[k].nsub; nins += (uint32_t)seg[k].prob;
       ndel += seg[k].ndel; C += PB_TILE;
       continue;

@@ -53,9 +53,9 @@ class Engine:
         self._chk(self.L.pbsim_cuda_set_sequence(self.h, C.byref(s)), "set_sequence")
         self.glen = len(bases)
 
-    def set_seqset(self, strategy, seqset, bias):
-        """strategy 'trans' | 'templ'; seqset = [(name, plus, minus, bases)] as parsed from the transcript table /
-        template FASTA (pbsim.cpp:1075, :1366)"""
+    @staticmethod
+    def pack_seqset(seqset):
+        """[(name, plus, minus, bases)] -> the concatenated arrays pbsim_seqset points to"""
         names = [x[0].encode() if isinstance(x[0], str) else x[0] for x in seqset]
         bases = b"".join(x[3] for x in seqset)
         start = np.zeros(len(seqset) + 1, dtype=np.int64)
@@ -65,19 +65,25 @@ class Engine:
         ids = b"".join(names)
         id_start = np.zeros(len(seqset) + 1, dtype=np.int32)
         id_start[1:] = np.cumsum([len(x) for x in names])
-        self._keep = [bases, start, plus, minus, ids, id_start]
+        return dict(n=len(seqset), bases=bases, start=start, plus=plus, minus=minus, ids=ids, id_start=id_start)
+
+    def set_seqset(self, strategy, seqset, bias):
+        """strategy 'trans' | 'templ'; seqset = [(name, plus, minus, bases)] as parsed from the transcript table /
+        template FASTA (pbsim.cpp:1075, :1366), or the result of pack_seqset"""
+        k = seqset if isinstance(seqset, dict) else self.pack_seqset(seqset)
+        self._keep = [k]
         s = capi.SeqSet()
         s.strategy = capi.STRATEGY_TRANS if strategy == "trans" else capi.STRATEGY_TEMPL
-        s.n = len(seqset)
-        s.bases = C.cast(C.c_char_p(bases), C.c_void_p)
-        s.start = start.ctypes.data
-        s.plus_exp = plus.ctypes.data
-        s.minus_exp = minus.ctypes.data
-        s.ids = C.cast(C.c_char_p(ids), C.c_void_p)
-        s.id_start = id_start.ctypes.data
+        s.n = k["n"]
+        s.bases = C.cast(C.c_char_p(k["bases"]), C.c_void_p)
+        s.start = k["start"].ctypes.data
+        s.plus_exp = k["plus"].ctypes.data
+        s.minus_exp = k["minus"].ctypes.data
+        s.ids = C.cast(C.c_char_p(k["ids"]), C.c_void_p)
+        s.id_start = k["id_start"].ctypes.data
         s.hp_del_bias = (C.c_double * 12)(*bias)
         self._chk(self.L.pbsim_cuda_set_seqset(self.h, C.byref(s)), "set_seqset")
-        self.glen = len(bases)
+        self.glen = len(k["bases"])
 
     def set_synthetic_sequence(self, length, seq_num, seed):
         self._chk(self.L.pbsim_cuda_set_synthetic_sequence(self.h, length, seq_num, seed), "set_synthetic_sequence")
