@@ -676,10 +676,14 @@ PB_HD void qshmm_chain_only(const QsView &T, const PhiloxKeys &K, uint32_t read_
                             uint32_t *seg_state) {
   uint32_t row = 0, mod = T.init_mod, emod = 1;
   const uint32_t c1 = pass << 16;
+  // the lookups form one dependent chain (table entry -> next row); the Philox block of the NEXT four positions
+  // does not depend on it and is computed alongside, so that the chain never waits for its draws
+  uint32_t nx[4];
+  philox_block_keys(K, 0u, c1, read_id, 2u, nx);
   for (uint32_t k = 1; k < n_seg; ++k) {
     for (uint32_t p = (k - 1u) * PB_TILE; p < k * PB_TILE; p += 4u) {
-      uint32_t cw[4];
-      philox_block_keys(K, p >> 2, c1, read_id, 2u, cw);
+      const uint32_t cw[4] = {nx[0], nx[1], nx[2], nx[3]};
+      philox_block_keys(K, (p >> 2) + 1u, c1, read_id, 2u, nx);
 #pragma unroll
       for (uint32_t u = 0; u < 4u; ++u) {
         const uint32_t t = T.t2[row + mulhi32(cw[u], mod)];
@@ -976,7 +980,10 @@ PB_HD void errhmm_state_at(const ErView &T, const PhiloxKeys &K, const HpProbe &
   const uint32_t c1 = pass << 16;
   uint32_t cw[4] = {0, 0, 0, 0};
   bool pzero = true;
-  for (uint32_t c = 0; c < c_target; ++c) {
+  uint32_t c = 0;
+  // phase 1: column by column until the first read base exists (init row, :3853) and the column index is a
+  // multiple of 4 again
+  for (; c < c_target && (pzero || (c & 3u) != 0u); ++c) {
     if (c == 0u || (c & 3u) == 0u) philox_block_keys(K, c >> 2, c1, read_id, 2u, cw);
     const uint32_t k4 = c & 3u;
     const uint32_t wdraw = k4 == 0u ? cw[0] : (k4 == 1u ? cw[1] : (k4 == 2u ? cw[2] : cw[3]));
@@ -999,6 +1006,34 @@ PB_HD void errhmm_state_at(const ErView &T, const PhiloxKeys &K, const HpProbe &
       if (kind != PB_KIND_DEL) pzero = false;
     }
     if (rec && ((c + 1u) & (PB_TILE - 1u)) == 0u) rec[(c + 1u) / PB_TILE] = state | (mod << 6) | (pzero ? 0x80000000u : 0u);
+  }
+  // phase 2: transition rows only, four columns per step; the next block of chain draws is computed while the
+  // dependent lookups of the current one run
+  if (c + 4u <= c_target) {
+    uint32_t nx[4];
+    philox_block_keys(K, c >> 2, c1, read_id, 2u, nx);
+    for (; c + 4u <= c_target; c += 4u) {
+      const uint32_t w4[4] = {nx[0], nx[1], nx[2], nx[3]};
+      philox_block_keys(K, (c >> 2) + 1u, c1, read_id, 2u, nx);
+#pragma unroll
+      for (uint32_t u = 0; u < 4u; ++u) {
+        const uint32_t t = T.t2[state * PB_ER_ROW + mulhi32(w4[u], mod)];
+        state = t & 63u;
+        mod = t >> 6;
+      }
+      if (rec && ((c + 4u) & (PB_TILE - 1u)) == 0u) rec[(c + 4u) / PB_TILE] = state | (mod << 6);
+    }
+  }
+  // tail: fewer than four columns left
+  if (c < c_target) {
+    philox_block_keys(K, c >> 2, c1, read_id, 2u, cw);
+    for (; c < c_target; ++c) {
+      const uint32_t k4 = c & 3u;
+      const uint32_t wdraw = k4 == 0u ? cw[0] : (k4 == 1u ? cw[1] : (k4 == 2u ? cw[2] : cw[3]));
+      const uint32_t t = T.t2[state * PB_ER_ROW + mulhi32(wdraw, mod)];
+      state = t & 63u;
+      mod = t >> 6;
+    }
   }
   state_out = state;
   mod_out = mod;
