@@ -217,8 +217,11 @@ int pbsim_cuda_simulate_end(pbsim_engine *e, pbsim_stats *st, int64_t *freq_len,
 int pbsim_cuda_device_timer(pbsim_engine *e, int stop, double *ms);
 /* tunables: "stage_bytes" (pinned staging per stream and slot, default 128 MiB),
  * "target_batch_bases" (emitted bases per batch of reads, default 6 Gi),
- * "segments" (1: segment-parallel pass 1 for long qshmm reads in PHILOX mode, default 1; results are identical
- * either way), "seg_min_len" (shortest read that is segmented, default 4096) */
+ * "segments" (1: segment-parallel pass 1 for long reads in PHILOX mode, default 1; results are identical
+ * either way), "seg_min_len" (shortest read that is segmented, default 2048),
+ * "pipeline" (0: batches are generated inside next_chunk; 1 (default): with host delivery a producer thread
+ * generates batch k+1 into a second record buffer while batch k is handed out; 2: also for device delivery),
+ * "host_batch_bases" (batch size of pipelined host delivery, default 1 Gi) */
 int pbsim_cuda_set_option(pbsim_engine *e, const char *name, int64_t value);
 /* device pointer + cell count of the int64 stats block {counters[16], freq_accuracy[100001],
  * freq_len[2*len_max+2]} so that a multi-GPU driver can ncclAllReduce it in place */
