@@ -387,30 +387,38 @@ def main():
             t = torch.empty(contigs[k], dtype=torch.uint8, pin_memory=True)
             eng.get_sequence_ascii(t.data_ptr(), contigs[k])
             host_seq[k] = t
-        barrier()
-        t0 = time.perf_counter()
-        e_bases = h2d = d2h = 0
-        sink = 0
-        for k in range(e2e_steps):
-            q = seq_of(args.warmup + k)
-            if seqset is None:
-                eng.set_sequence_ptr(host_seq[q].data_ptr(), contigs[q], q + 1, bias)
-            else:
-                eng.set_seqset("trans", seqset, bias)  # the table's text goes up with every step
-            h2d += contigs[q]
-            eng.begin(int(depth * contigs[q]), rng_mode=capi.RNG_PHILOX, seed=1)
-            while True:
-                c = eng.next_chunk(device=False)
-                if c is None:
-                    break
-                e_bases += c.bases
-                d2h += c.reads_bytes + c.maf_bytes
-                if c.reads_bytes:  # the consumer looks at the delivered bytes
-                    sink ^= C.c_ubyte.from_address(c.reads + c.reads_bytes - 1).value
-            eng.end()
-        barrier()
-        e_ms = (time.perf_counter() - t0) * 1e3
-        e2e = dict(bases=e_bases, ms=e_ms, h2d=h2d / e2e_steps, d2h=d2h / e2e_steps)
+        def e2e_pass():
+            barrier()
+            t0 = time.perf_counter()
+            e_bases = h2d = d2h = 0
+            sink = 0
+            for k in range(e2e_steps):
+                q = seq_of(args.warmup + k)
+                if seqset is None:
+                    eng.set_sequence_ptr(host_seq[q].data_ptr(), contigs[q], q + 1, bias)
+                else:
+                    eng.set_seqset("trans", seqset, bias)  # the table's text goes up with every step
+                h2d += contigs[q]
+                eng.begin(int(depth * contigs[q]), rng_mode=capi.RNG_PHILOX, seed=1)
+                while True:
+                    c = eng.next_chunk(device=False)
+                    if c is None:
+                        break
+                    e_bases += c.bases
+                    d2h += c.reads_bytes + c.maf_bytes
+                    if c.reads_bytes:  # the consumer looks at the delivered bytes
+                        sink ^= C.c_ubyte.from_address(c.reads + c.reads_bytes - 1).value
+                eng.end()
+            barrier()
+            e_ms = (time.perf_counter() - t0) * 1e3
+            return dict(bases=e_bases, ms=e_ms, h2d=h2d / e2e_steps, d2h=d2h / e2e_steps)
+
+        e2e = e2e_pass()
+        # the same with the records gzip-compressed on the GPU before they cross PCIe (the reference's outputs are
+        # .gz files, pbsim.cpp:708-730); reported next to the text number, not instead of it
+        eng.set_option("deflate", 1)
+        e2e_gz = e2e_pass()
+        eng.set_option("deflate", 0)
         del host_seq
 
     # ---- reduce over ranks: total units, MAX time
@@ -435,6 +443,8 @@ def main():
     if e2e:
         e2e_bases = allsum(e2e["bases"])
         e2e_ms = allmax(e2e["ms"])
+        e2e_gz_bases = allsum(e2e_gz["bases"])
+        e2e_gz_ms = allmax(e2e_gz["ms"])
     if dist is not None:
         # the one collective of the path: statistics block (counters + both histograms), NCCL all-reduce
         from pbsim_b200.stats_reduce import allreduce_stats_block
@@ -467,7 +477,12 @@ def main():
         if e2e:
             line["e2e"] = {"value": e2e_bases / (e2e_ms * 1e-3) / 1e9, "unit": "Gbp/s",
                            "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
-                           "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps}
+                           "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps, "delivered": "text records"}
+            line["e2e_gzip"] = {"value": e2e_gz_bases / (e2e_gz_ms * 1e-3) / 1e9, "unit": "Gbp/s",
+                                "h2d_bytes_per_step": e2e_gz["h2d"], "d2h_bytes_per_step": e2e_gz["d2h"],
+                                "steps": e2e_steps, "ms_per_step": e2e_gz_ms / e2e_steps,
+                                "delivered": "gzip members written by the GPU (option deflate)",
+                                "compression_ratio": e2e["d2h"] / max(1.0, e2e_gz["d2h"])}
         if not args.no_cpu_baseline:
             try:
                 line["cpu_baseline"] = cpu_baseline(wl)

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define PBSIM_ABI_VERSION 1
+#define PBSIM_ABI_VERSION 2
 
 #define PBSIM_E_INVALID   (-1)  /* bad argument / call order                            */
 #define PBSIM_E_CUDA      (-2)  /* CUDA runtime error                                   */
@@ -149,6 +149,10 @@ typedef struct {
   int64_t first_read, n_reads;   /* 1-based id of the first read, number of reads            */
   int64_t bases;                 /* emitted read bases in this chunk, all passes             */
   int32_t on_device;             /* 1: pointers are device pointers                          */
+  int32_t compressed;            /* 1: option "deflate": the bytes are gzip members (host    *
+                                  * delivery only); concatenated they gunzip to the text     */
+  int64_t reads_text_bytes;      /* text size of the batch's records (set with first_read)   */
+  int64_t maf_text_bytes;
 } pbsim_chunk;
 
 /* sim.res_* (pbsim.cpp:63-70) after the run; histograms are freq_len / freq_accuracy (:195-196) */
@@ -163,6 +167,7 @@ typedef struct {
   double gen_seconds;            /* device time of all generation steps (CUDA events)        */
   double sim_seconds;            /* ... of which pass 1 (k_sim_qshmm / k_sim_errhmm)          */
   double emit_seconds;           /* ... of which pass 2 (k_emit)                             */
+  double deflate_seconds;        /* ... of which the gzip writer (option "deflate")          */
   int64_t kernel_launches;       /* number of engine kernels launched during the run         */
 } pbsim_stats;
 
@@ -221,7 +226,10 @@ int pbsim_cuda_device_timer(pbsim_engine *e, int stop, double *ms);
  * either way), "seg_min_len" (shortest read that is segmented, default 2048),
  * "pipeline" (0: batches are generated inside next_chunk; 1 (default): with host delivery a producer thread
  * generates batch k+1 into a second record buffer while batch k is handed out; 2: also for device delivery),
- * "host_batch_bases" (batch size of pipelined host delivery, default 1 Gi) */
+ * "host_batch_bases" (batch size of pipelined host delivery, default 1 Gi),
+ * "deflate" (1: host delivery hands out gzip members written on the GPU — every 32 KiB of a record stream is one
+ * member holding one dynamic-Huffman block — instead of text: what the reference's `gzip >` children produce,
+ * pbsim.cpp:708-730; default 0) */
 int pbsim_cuda_set_option(pbsim_engine *e, const char *name, int64_t value);
 /* device pointer + cell count of the int64 stats block {counters[16], freq_accuracy[100001],
  * freq_len[2*len_max+2]} so that a multi-GPU driver can ncclAllReduce it in place */
@@ -261,6 +269,10 @@ void pbsim_host_model_free(pbsim_host_model *m);
  * ends[rank*21 + j] = last table position (1..1000) of start fraction 5*j percent, 0xFFFF after the row
  * ended; mod[rank] = ssp_rand_value[rank].  ends has (rank_max+1)*21 cells, mod rank_max+1. */
 void pbsim_host_ssp_table(int32_t rank_max, uint16_t *ends, uint16_t *mod);
+/* the literal code (bit-reversed code | length << 16 for bytes 0..255, then end-of-block) and the DEFLATE dynamic
+ * block header (LSB-first bit string) the engine's gzip writer derives from a stream's byte histogram */
+int pbsim_host_deflate_code(const int64_t hist[256], uint32_t lit[257], uint32_t *hdr_bits, uint32_t *hdr_words,
+                            int32_t cap_words);
 void pbsim_host_hp_del_bias(double hp_del_bias_opt, const int64_t hpfreq[12], double bias[12]);
 
 #ifdef __cplusplus

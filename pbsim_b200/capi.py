@@ -111,6 +111,9 @@ class Chunk(C.Structure):
         ("n_reads", C.c_int64),
         ("bases", C.c_int64),
         ("on_device", C.c_int32),
+        ("compressed", C.c_int32),
+        ("reads_text_bytes", C.c_int64),
+        ("maf_text_bytes", C.c_int64),
     ]
 
 
@@ -132,6 +135,7 @@ class Stats(C.Structure):
         ("gen_seconds", C.c_double),
         ("sim_seconds", C.c_double),
         ("emit_seconds", C.c_double),
+        ("deflate_seconds", C.c_double),
         ("kernel_launches", C.c_int64),
     ]
 
@@ -153,7 +157,7 @@ class HostParams(C.Structure):
 
 
 HOST_EXPORTS = ["pbsim_host_model_load", "pbsim_host_model_get", "pbsim_host_model_free", "pbsim_host_hp_del_bias",
-                "pbsim_host_ssp_table"]
+                "pbsim_host_ssp_table", "pbsim_host_deflate_code"]
 ENGINE_EXPORTS = [
     "pbsim_cuda_abi_version", "pbsim_cuda_last_error", "pbsim_cuda_create", "pbsim_cuda_destroy",
     "pbsim_cuda_set_model", "pbsim_cuda_set_sequence", "pbsim_cuda_set_seqset", "pbsim_cuda_set_synthetic_sequence",
@@ -174,6 +178,7 @@ def declare_host(L):
     L.pbsim_host_model_free.argtypes = [C.c_void_p]
     L.pbsim_host_hp_del_bias.restype = None
     L.pbsim_host_hp_del_bias.argtypes = [C.c_double, C.POINTER(C.c_int64), C.POINTER(C.c_double)]
+    L.pbsim_host_deflate_code.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32), C.c_void_p, C.c_int32]
     L.pbsim_host_ssp_table.restype = None
     L.pbsim_host_ssp_table.argtypes = [C.c_int32, C.c_void_p, C.c_void_p]
     return L

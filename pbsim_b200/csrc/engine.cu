@@ -29,6 +29,7 @@
 
 #include "../../include/pbsim_cuda.h"
 #include "emit.cuh"
+#include "gz_kernels.cuh"
 #include "k0_genome.cuh"
 #include "model_image.hpp"
 #include "seg_kernels.cuh"
@@ -219,8 +220,17 @@ struct pbsim_engine {
     std::string err;
     int set = 0;
     int64_t first_read = 0, n_reads = 0, bases = 0;
-    uint64_t reads_bytes = 0, maf_bytes = 0;
+    uint64_t reads_bytes = 0, maf_bytes = 0;          // bytes to deliver (gzip members when deflate is on)
+    uint64_t reads_text_bytes = 0, maf_text_bytes = 0;
+    bool gz = false;
   };
+  // option "deflate": host delivery hands out gzip members (gz_kernels.cuh) instead of text
+  int deflate = 0;
+  OutSet gz[2];
+  DevBuf d_gz_tables, d_gz_hist, d_gz_usize, d_gz_ucrc, d_gz_uoff;
+  PinnedBuf h_gz;
+  double gz_ms = 0;
+  cudaEvent_t ev_gz[2] = {nullptr, nullptr};
   int pipeline = 1;                 // option "pipeline": 0 off, 1 host delivery only, 2 always
   int64_t host_batch_bases = (int64_t)1 << 30;  // option: batch size of pipelined host delivery
   bool mode_set = false, mode_to_host = false, pipelined = false;
@@ -237,6 +247,8 @@ struct pbsim_engine {
   size_t stage_bytes = (size_t)128 << 20;
   struct Pending {                  // the batch pieces are being issued from
     bool active = false;
+    bool gz = false;
+    uint64_t text[2] = {0, 0};
     int set = 0;
     uint64_t total[2] = {0, 0}, issued[2] = {0, 0};
     bool first = true;
@@ -248,6 +260,7 @@ struct pbsim_engine {
     uint64_t bytes[2] = {0, 0};
     bool first = false;
     int64_t first_read = 0, n_reads = 0, bases = 0;
+    uint64_t text[2] = {0, 0};      // first piece of a batch: text bytes the batch's members inflate to
     int release_set = -1;           // last piece of its batch: the set is free once this copy is done
   } piece;
   int next_slot = 0;
@@ -809,6 +822,82 @@ int run_batch(pbsim_engine *e, uint32_t n_reads, int64_t clip_room, BatchResult 
 // batch production (the quota loop of pbsim.cpp:2173 / :3792 in batches) and delivery
 // ---------------------------------------------------------------------------------------------
 
+// gzip one record stream of the batch in HBM (gz_kernels.cuh): histogram -> code (host) -> member sizes -> offsets
+// -> members.  Replaces the reference's popen("gzip > file") children (pbsim.cpp:708-730).
+int gz_compress(pbsim_engine *e, const uint8_t *in, uint64_t n, DevBuf &dst, uint64_t *out_bytes) {
+  *out_bytes = 0;
+  if (n == 0) return 0;
+  static_assert(sizeof(GzTables) % 8 == 0, "GzTables is copied as words");
+  CK(e->d_gz_hist.ensure(256 * 8));
+  CK(e->d_gz_tables.ensure(sizeof(GzTables)));
+  CK(e->h_gz.ensure(256 * 8 + sizeof(GzTables) + 64));
+  unsigned long long *hh = reinterpret_cast<unsigned long long *>(e->h_gz.p);
+  GzTables *ht = reinterpret_cast<GzTables *>(hh + 256);
+  CK(cudaMemsetAsync(e->d_gz_hist.p, 0, 256 * 8, e->st));
+  int dev_sms = 148;
+  cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, e->device);
+  // streams above 64 MiB are sampled: one 16-byte chunk in 16
+  k_gz_hist<<<(uint32_t)std::min<uint64_t>((n + 4095) / 4096, (uint64_t)dev_sms * 8), 256, 0, e->st>>>(
+      in, n, n > ((uint64_t)64 << 20) ? 16u : 1u, e->d_gz_hist.as<unsigned long long>());
+  e->launches++;
+  CK(cudaMemcpyAsync(hh, e->d_gz_hist.p, 256 * 8, cudaMemcpyDeviceToHost, e->st));
+  CK(cudaStreamSynchronize(e->st));
+  {
+    uint64_t hist[256];
+    for (int i = 0; i < 256; ++i) hist[i] = hh[i];
+    GzCode code;
+    gz_build_code(hist, &code);
+    std::memset(ht, 0, sizeof *ht);
+    std::memcpy(ht->lit, code.lit, sizeof ht->lit);
+    std::memcpy(ht->hdr, code.hdr, sizeof ht->hdr);
+    std::memcpy(ht->len, code.len, sizeof ht->len);
+    ht->eob = code.eob;
+    ht->hdr_bits = code.hdr_bits;
+    gz_crc_table(ht->crc);
+    gz_x2n_table(ht->x2n);
+    // x^(8 * slice * 2^j): the shift that appends 2^j slices to a CRC
+    uint32_t p = 1u << 31;
+    for (uint64_t nn = kGzSlice, k = 3; nn; nn >>= 1, ++k)
+      if (nn & 1u) p = gz_gf_mul(ht->x2n[k & 31u], p);
+    for (int j = 0; j < 8; ++j) {
+      ht->shift[j] = p;
+      p = gz_gf_mul(p, p);
+    }
+  }
+  CK(cudaMemcpyAsync(e->d_gz_tables.p, ht, sizeof(GzTables), cudaMemcpyHostToDevice, e->st));
+  const uint64_t units = (n + kGzUnit - 1) / kGzUnit;
+  if (units > 0x7FFFFFFFull) return fail(e, PBSIM_E_INVALID, "stream too large for the gzip writer");
+  CK(e->d_gz_usize.ensure((size_t)units * 4 + 64));
+  CK(e->d_gz_ucrc.ensure((size_t)units * 4 + 64));
+  CK(e->d_gz_uoff.ensure((size_t)(units + 1) * 16 + 64));
+  unsigned long long *wide = e->d_gz_uoff.as<unsigned long long>();
+  unsigned long long *uoff = wide + (units + 1);
+  k_gz_size<<<(uint32_t)units, kGzThreads, 0, e->st>>>(in, n, e->d_gz_tables.as<GzTables>(), e->d_gz_usize.as<uint32_t>(),
+                                                     e->d_gz_ucrc.as<uint32_t>());
+  k_widen<<<nblk(units, 256), 256, 0, e->st>>>(e->d_gz_usize.as<uint32_t>(), (uint32_t)units, wide);
+  CK(cudaMemsetAsync(wide + units, 0, 8, e->st));
+  e->launches += 2;
+  int rc = excl_scan(e, wide, uoff, (uint32_t)units + 1u);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(hh, uoff + units, 8, cudaMemcpyDeviceToHost, e->st));
+  CK(cudaStreamSynchronize(e->st));
+  const uint64_t total = hh[0];
+  CK(dst.ensure((size_t)total + 256));
+  static bool attr_set = false;
+  const size_t smem = (size_t)kGzImgWords * 4 + 256 * 4;
+  if (!attr_set) {
+    CK(cudaFuncSetAttribute(k_gz_encode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  k_gz_encode<<<(uint32_t)units, kGzThreads, smem, e->st>>>(in, n, e->d_gz_tables.as<GzTables>(),
+                                                           reinterpret_cast<const uint64_t *>(uoff),
+                                                           e->d_gz_ucrc.as<uint32_t>(), dst.as<uint8_t>());
+  e->launches++;
+  CK(cudaGetLastError());
+  *out_bytes = total;
+  return 0;
+}
+
 // generate the next batch of the run into output set `set`; 1 = produced, 0 = run finished, < 0 = error
 int produce_one(pbsim_engine *e, int set, pbsim_engine::BatchItem *it) {
   for (;;) {
@@ -850,11 +939,23 @@ int produce_one(pbsim_engine *e, int set, pbsim_engine::BatchItem *it) {
     BatchResult br;
     int rc = run_batch(e, (uint32_t)nb, clip_room, &br);
     if (rc) return rc;
+    const bool gz = e->deflate && e->mode_to_host && br.n_valid_reads > 0;
+    uint64_t gz_bytes[2] = {0, 0};
+    if (gz) {
+      CK(cudaEventRecord(e->ev_gz[0], e->st));
+      if ((rc = gz_compress(e, e->out[set].reads.as<uint8_t>(), br.reads_bytes, e->gz[set].reads, &gz_bytes[0]))) return rc;
+      if ((rc = gz_compress(e, e->out[set].maf.as<uint8_t>(), br.maf_bytes, e->gz[set].maf, &gz_bytes[1]))) return rc;
+      CK(cudaEventRecord(e->ev_gz[1], e->st));
+    }
     CK(cudaEventRecord(e->ev1, e->st));
     CK(cudaStreamSynchronize(e->st));
     float ms = 0;
     CK(cudaEventElapsedTime(&ms, e->ev0, e->ev1));
     e->gen_ms += ms;
+    if (gz) {
+      CK(cudaEventElapsedTime(&ms, e->ev_gz[0], e->ev_gz[1]));
+      e->gz_ms += ms;
+    }
     const uint32_t pass = (uint32_t)e->model.pass_num;
     const uint32_t nv = br.n_valid_reads;
     if (nv > 0) {
@@ -880,8 +981,11 @@ int produce_one(pbsim_engine *e, int set, pbsim_engine::BatchItem *it) {
     it->first_read = e->next_read + 1;
     it->n_reads = nv;
     it->bases = (int64_t)br.bases_all;
-    it->reads_bytes = br.reads_bytes;
-    it->maf_bytes = br.maf_bytes;
+    it->reads_text_bytes = br.reads_bytes;
+    it->maf_text_bytes = br.maf_bytes;
+    it->reads_bytes = gz ? gz_bytes[0] : br.reads_bytes;
+    it->maf_bytes = gz ? gz_bytes[1] : br.maf_bytes;
+    it->gz = gz;
     e->next_read += nv;
     e->reads_done_in_run += nv;
     e->len_total += (int64_t)br.bases_pass0;
@@ -976,6 +1080,9 @@ int issue_piece(pbsim_engine *e, bool block) {
     p = pbsim_engine::Pending();
     p.active = true;
     p.set = it.set;
+    p.gz = it.gz;
+    p.text[0] = it.reads_text_bytes;
+    p.text[1] = it.maf_text_bytes;
     p.total[0] = it.reads_bytes;
     p.total[1] = it.maf_bytes;
     p.first_read = it.first_read;
@@ -984,7 +1091,8 @@ int issue_piece(pbsim_engine *e, bool block) {
   }
   for (int k = 0; k < 2; ++k)
     for (int slot = 0; slot < 2; ++slot) CK(e->h_stage[k][slot].ensure(e->stage_bytes));
-  const uint8_t *src[2] = {e->out[p.set].reads.as<uint8_t>(), e->out[p.set].maf.as<uint8_t>()};
+  const pbsim_engine::OutSet &O = p.gz ? e->gz[p.set] : e->out[p.set];
+  const uint8_t *src[2] = {O.reads.as<uint8_t>(), O.maf.as<uint8_t>()};
   pbsim_engine::Piece &q = e->piece;
   q = pbsim_engine::Piece();
   q.valid = true;
@@ -998,6 +1106,8 @@ int issue_piece(pbsim_engine *e, bool block) {
   CK(cudaEventRecord(e->ev_copy, e->st_copy));
   if (p.first) {
     q.first = true;
+    q.text[0] = p.text[0];
+    q.text[1] = p.text[1];
     q.first_read = p.first_read;
     q.n_reads = p.n_reads;
     q.bases = p.bases;
@@ -1037,10 +1147,13 @@ int next_chunk_impl(pbsim_engine *e, pbsim_chunk *c, bool to_host) {
     c->maf = reinterpret_cast<const char *>(e->h_stage[1][q.slot].p);
     c->maf_bytes = (int64_t)q.bytes[1];
     c->on_device = 0;
+    c->compressed = e->deflate ? 1 : 0;
     if (q.first) {
       c->first_read = q.first_read;
       c->n_reads = q.n_reads;
       c->bases = q.bases;
+      c->reads_text_bytes = (int64_t)q.text[0];
+      c->maf_text_bytes = (int64_t)q.text[1];
     }
     // prefetch the next piece into the other slot while the caller consumes this one
     const int rc = issue_piece(e, false);
@@ -1060,6 +1173,8 @@ int next_chunk_impl(pbsim_engine *e, pbsim_chunk *c, bool to_host) {
   c->bases = it.bases;
   c->reads_bytes = (int64_t)it.reads_bytes;
   c->maf_bytes = (int64_t)it.maf_bytes;
+  c->reads_text_bytes = (int64_t)it.reads_text_bytes;
+  c->maf_text_bytes = (int64_t)it.maf_text_bytes;
   c->reads = reinterpret_cast<const char *>(e->out[it.set].reads.p);
   c->maf = reinterpret_cast<const char *>(e->out[it.set].maf.p);
   c->on_device = 1;
@@ -1097,6 +1212,7 @@ int pbsim_cuda_create(pbsim_engine **out, int device) {
   cudaEventCreate(&ne->ev_copy);
   for (auto &ev : ne->ev_k) cudaEventCreate(&ev);
   for (auto &ev : ne->ev_user) cudaEventCreate(&ev);
+  for (auto &ev : ne->ev_gz) cudaEventCreate(&ev);
   std::memset(&ne->model, 0, sizeof ne->model);
   std::memset(&ne->emitp, 0, sizeof ne->emitp);
   *out = ne;
@@ -1114,13 +1230,16 @@ void pbsim_cuda_destroy(pbsim_engine *e) {
                     &e->d_draws, &e->d_starts, &e->b_read_u32, &e->b_sub_u32, &e->b_sub_u64, &e->b_sub_f64, &e->d_bins,
                     &e->d_ctrl, &e->d_cub_tmp, &e->d_ev, &e->d_ck, &e->out[0].reads, &e->out[0].maf, &e->out[1].reads, &e->out[1].maf, &e->d_stats, &e->d_seg,
                     &e->d_seg_bins, &e->d_set_start, &e->d_set_rprefix, &e->d_set_plus, &e->d_set_ids, &e->d_set_idstart,
-                    &e->d_set_ssp_ends, &e->d_set_ssp_mod, &e->d_set_first};
+                    &e->d_set_ssp_ends, &e->d_set_ssp_mod, &e->d_set_first, &e->gz[0].reads, &e->gz[0].maf, &e->gz[1].reads,
+                    &e->gz[1].maf, &e->d_gz_tables, &e->d_gz_hist, &e->d_gz_usize, &e->d_gz_ucrc, &e->d_gz_uoff};
   for (DevBuf *b : bufs) b->release();
   for (auto &a : e->h_stage)
     for (auto &b : a) b.release();
   cudaEventDestroy(e->ev_copy);
   for (auto &ev : e->ev_k) cudaEventDestroy(ev);
   for (auto &ev : e->ev_user) cudaEventDestroy(ev);
+  for (auto &ev : e->ev_gz) cudaEventDestroy(ev);
+  e->h_gz.release();
   e->h_ctrl.release();
   e->h_acc.release();
   cudaEventDestroy(e->ev0);
@@ -1343,6 +1462,7 @@ int pbsim_cuda_simulate_begin(pbsim_engine *e, const pbsim_run *run) {
   e->gen_ms = 0;
   e->sim_ms = 0;
   e->emit_ms = 0;
+  e->gz_ms = 0;
   stop_producer(e);  // a run abandoned without simulate_end
   e->pend = pbsim_engine::Pending();
   e->piece = pbsim_engine::Piece();
@@ -1411,6 +1531,7 @@ int pbsim_cuda_simulate_end(pbsim_engine *e, pbsim_stats *st, int64_t *freq_len,
   st->gen_seconds = e->gen_ms * 1e-3;
   st->sim_seconds = e->sim_ms * 1e-3;
   st->emit_seconds = e->emit_ms * 1e-3;
+  st->deflate_seconds = e->gz_ms * 1e-3;
   st->kernel_launches = e->launches;
   if (freq_len) {
     const int64_t n = std::min<int64_t>(freq_len_cells, e->freq_len_cells);
@@ -1461,6 +1582,11 @@ int pbsim_cuda_set_option(pbsim_engine *e, const char *name, int64_t value) {
     if (value < 0 || value > 2) return fail(e, PBSIM_E_INVALID, "pipeline must be 0, 1 or 2");
     if (e->running) return fail(e, PBSIM_E_INVALID, "pipeline cannot change during a run");
     e->pipeline = (int)value;
+    return 0;
+  }
+  if (!strcmp(name, "deflate")) {
+    if (e->running) return fail(e, PBSIM_E_INVALID, "deflate cannot change during a run");
+    e->deflate = value != 0;
     return 0;
   }
   if (!strcmp(name, "host_batch_bases")) {

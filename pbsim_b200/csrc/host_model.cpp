@@ -9,6 +9,7 @@
 //   HMM lookup tables                           :2066-2170 (qshmm), :3708-3789 (errhmm)
 // No GPU code here; compiled into libpbsim_cuda.so so that host drivers get one library.
 #include "../../include/pbsim_cuda.h"
+#include "gz_host.hpp"
 
 #include <climits>
 #include <cmath>
@@ -381,6 +382,23 @@ void pbsim_host_ssp_table(int32_t rank_max, uint16_t *ends, uint16_t *mod) {
     }
     mod[i] = static_cast<uint16_t>(end_wk);
   }
+}
+
+// the Huffman code and DEFLATE block header the engine's gzip writer uses for a stream with this byte histogram
+// (tests: a CPU encoder driven by these tables must produce a stream zlib inflates back to the text)
+int pbsim_host_deflate_code(const int64_t hist[256], uint32_t lit[257], uint32_t *hdr_bits, uint32_t *hdr_words,
+                            int32_t cap_words) {
+  uint64_t h[256];
+  for (int i = 0; i < 256; ++i) h[i] = hist[i] > 0 ? static_cast<uint64_t>(hist[i]) : 0;
+  pb::GzCode c;
+  pb::gz_build_code(h, &c);
+  for (int i = 0; i < 256; ++i) lit[i] = c.lit[i];
+  lit[256] = c.eob;
+  *hdr_bits = c.hdr_bits;
+  const int32_t need = static_cast<int32_t>((c.hdr_bits + 31) / 32);
+  if (need > cap_words) return PBSIM_E_INVALID;
+  for (int32_t i = 0; i < need; ++i) hdr_words[i] = c.hdr[i];
+  return 0;
 }
 
 void pbsim_host_hp_del_bias(double opt, const int64_t hpfreq[12], double bias[12]) {

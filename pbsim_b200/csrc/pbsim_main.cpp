@@ -11,7 +11,8 @@
 // whole set to the engine (pbsim_cuda_set_seqset); outputs <prefix>.fq.gz / .maf.gz (:771-788).
 //
 // Engine-only options (additive): --gpu N, --rng philox|replay, --replay-draws F --replay-marks F,
-// --threads N (compression).  Not built yet in this driver: --method sample,
+// --threads N (host compression), --gzip gpu|host (default gpu: the records are gzip-compressed on the GPU and the
+// driver only writes the members to the files).  Not built yet in this driver: --method sample,
 // BAM encoding for --pass-num > 1 (SAM text is written as <prefix>[_NNNN].sam.gz instead).
 #include <getopt.h>
 #include <sys/resource.h>
@@ -62,6 +63,7 @@ struct Options {
   int gpu = 0;
   std::string rng = "philox", replay_draws, replay_marks;
   int threads = 0;
+  std::string gzip = "gpu";  // who writes the gzip members: the GPU (gz_kernels.cuh) or zlib threads on the host
 };
 
 [[noreturn]] void die(const char *fmt, ...) {
@@ -94,12 +96,14 @@ class GzipWriter {
     for (int i = 0; i < std::max(1, threads); ++i) workers_.emplace_back([this] { work(); });
     writer_ = std::thread([this] { write(); });
   }
-  void submit(const char *data, size_t n) {
+  // raw: the bytes are gzip members already (written by the GPU, option "deflate"): kept in order, not compressed
+  void submit(const char *data, size_t n, bool raw = false) {
     if (n == 0) return;
     std::unique_lock<std::mutex> lk(mu_);
     cv_space_.wait(lk, [this] { return pending_.size() + done_.size() < 64; });
     Job j;
     j.seq = next_seq_++;
+    j.raw = raw;
     j.in.assign(data, data + n);
     pending_.push_back(std::move(j));
     cv_work_.notify_one();
@@ -120,6 +124,7 @@ class GzipWriter {
  private:
   struct Job {
     uint64_t seq;
+    bool raw = false;
     std::vector<char> in, out;
   };
   void work() {
@@ -132,17 +137,21 @@ class GzipWriter {
         j = std::move(pending_.front());
         pending_.pop_front();
       }
-      z_stream zs;
-      memset(&zs, 0, sizeof zs);
-      deflateInit2(&zs, level_, Z_DEFLATED, 15 + 16, 8, Z_DEFAULT_STRATEGY);
-      j.out.resize(deflateBound(&zs, j.in.size()) + 64);
-      zs.next_in = reinterpret_cast<Bytef *>(j.in.data());
-      zs.avail_in = (uInt)j.in.size();
-      zs.next_out = reinterpret_cast<Bytef *>(j.out.data());
-      zs.avail_out = (uInt)j.out.size();
-      deflate(&zs, Z_FINISH);
-      j.out.resize(zs.total_out);
-      deflateEnd(&zs);
+      if (j.raw) {
+        j.out = j.in;
+      } else {
+        z_stream zs;
+        memset(&zs, 0, sizeof zs);
+        deflateInit2(&zs, level_, Z_DEFLATED, 15 + 16, 8, Z_DEFAULT_STRATEGY);
+        j.out.resize(deflateBound(&zs, j.in.size()) + 64);
+        zs.next_in = reinterpret_cast<Bytef *>(j.in.data());
+        zs.avail_in = (uInt)j.in.size();
+        zs.next_out = reinterpret_cast<Bytef *>(j.out.data());
+        zs.avail_out = (uInt)j.out.size();
+        deflate(&zs, Z_FINISH);
+        j.out.resize(zs.total_out);
+        deflateEnd(&zs);
+      }
       {
         std::unique_lock<std::mutex> lk(mu_);
         bytes_in += j.in.size();
@@ -183,9 +192,9 @@ class GzipWriter {
 };
 
 // blocks for the compressor are cut at record-independent sizes; 8 MiB keeps members reasonably large
-void stream_to(GzipWriter &w, const char *p, int64_t n) {
+void stream_to(GzipWriter &w, const char *p, int64_t n, bool raw = false) {
   const int64_t blk = 8 << 20;
-  for (int64_t o = 0; o < n; o += blk) w.submit(p + o, (size_t)std::min(blk, n - o));
+  for (int64_t o = 0; o < n; o += blk) w.submit(p + o, (size_t)std::min(blk, n - o), raw);
 }
 
 struct RefSeq {
@@ -423,7 +432,8 @@ void print_help() {
           "  --rng                philox (default) | replay\n"
           "  --replay-draws       int32 log of the reference's rand() draws (replay mode).\n"
           "  --replay-marks       int64 draw count after every (read, pass) (replay mode).\n"
-          "  --threads            compression threads (hardware concurrency).\n\n"
+          "  --threads            compression threads (hardware concurrency).\n"
+          "  --gzip               gpu (default): gzip members are written on the GPU | host: zlib threads.\n\n"
           " [options for transcriptome / template sequencing]\n\n"
           "  --strategy           trans | templ\n"
           "  --transcript         transcript table: id, plus count, minus count, sequence (tab separated).\n"
@@ -461,7 +471,8 @@ int main(int argc, char **argv) {
       {"template", 1, nullptr, 0},   {"hp-del-bias", 1, nullptr, 0},
       // engine-only
       {"gpu", 1, nullptr, 0},        {"rng", 1, nullptr, 0},            {"replay-draws", 1, nullptr, 0},
-      {"replay-marks", 1, nullptr, 0}, {"threads", 1, nullptr, 0},      {nullptr, 0, nullptr, 0}};
+      {"replay-marks", 1, nullptr, 0}, {"threads", 1, nullptr, 0},      {"gzip", 1, nullptr, 0},
+      {nullptr, 0, nullptr, 0}};
   int opt, idx = 0;
   while ((opt = getopt_long(argc, argv, "", long_options, &idx)) != -1) {
     if (opt != 0) exit(-1);
@@ -552,6 +563,10 @@ int main(int argc, char **argv) {
       case 25: o.replay_draws = a; break;
       case 26: o.replay_marks = a; break;
       case 27: o.threads = atoi(a); break;
+      case 28:
+        if (!strcmp(a, "gpu") || !strcmp(a, "host")) o.gzip = a;
+        else die("ERROR (gzip: %s): Acceptable value: gpu, host.\n", a);
+        break;
       default: break;
     }
   }
@@ -625,6 +640,7 @@ int main(int argc, char **argv) {
   pbsim_engine *eng = nullptr;
   if (pbsim_cuda_create(&eng, o.gpu) != 0) die("ERROR: %s\n", pbsim_cuda_last_error(nullptr));
   if (pbsim_cuda_set_model(eng, pbsim_host_model_get(hm)) != 0) die("ERROR: %s\n", pbsim_cuda_last_error(eng));
+  if (pbsim_cuda_set_option(eng, "deflate", o.gzip == "gpu" ? 1 : 0) != 0) die("ERROR: %s\n", pbsim_cuda_last_error(eng));
 
   // ---- replay inputs
   std::vector<int32_t> draws;
@@ -672,8 +688,8 @@ int main(int argc, char **argv) {
       const int rc = pbsim_cuda_next_chunk(eng, &c);
       if (rc < 0) die("ERROR: %s\n", pbsim_cuda_last_error(eng));
       if (rc == 0) break;
-      stream_to(reads_out, c.reads, c.reads_bytes);
-      stream_to(maf_out, c.maf, c.maf_bytes);
+      stream_to(reads_out, c.reads, c.reads_bytes, c.compressed != 0);
+      stream_to(maf_out, c.maf, c.maf_bytes, c.compressed != 0);
     }
     pbsim_stats st;
     if (pbsim_cuda_simulate_end(eng, &st, nullptr, 0, nullptr) != 0) die("ERROR: %s\n", pbsim_cuda_last_error(eng));

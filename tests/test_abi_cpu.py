@@ -26,7 +26,7 @@ def test_header_symbols_are_exported(lib):
     for n in names:
         assert hasattr(lib, n), n
     assert set(names) == set(capi.HOST_EXPORTS + capi.ENGINE_EXPORTS)
-    assert lib.pbsim_cuda_abi_version() == 1
+    assert lib.pbsim_cuda_abi_version() == 2
 
 
 def test_create_fails_loudly_without_gpu(lib):
