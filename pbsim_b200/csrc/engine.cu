@@ -855,13 +855,14 @@ int gz_compress(pbsim_engine *e, const uint8_t *in, uint64_t n, DevBuf &dst, uin
     ht->hdr_bits = code.hdr_bits;
     gz_crc_table(ht->crc);
     gz_x2n_table(ht->x2n);
-    // x^(8 * slice * 2^j): the shift that appends 2^j slices to a CRC
-    uint32_t p = 1u << 31;
+    // x^(8 * slice): appends one slice to a CRC; tail[t] = that to the power of the slices behind slice t
+    uint32_t step = 1u << 31;
     for (uint64_t nn = kGzSlice, k = 3; nn; nn >>= 1, ++k)
-      if (nn & 1u) p = gz_gf_mul(ht->x2n[k & 31u], p);
-    for (int j = 0; j < 8; ++j) {
-      ht->shift[j] = p;
-      p = gz_gf_mul(p, p);
+      if (nn & 1u) step = gz_gf_mul(ht->x2n[k & 31u], step);
+    uint32_t p = 1u << 31;  // x^0
+    for (int t = (int)kGzThreads - 1; t >= 0; --t) {
+      ht->tail[t] = p;
+      p = gz_gf_mul(step, p);
     }
   }
   CK(cudaMemcpyAsync(e->d_gz_tables.p, ht, sizeof(GzTables), cudaMemcpyHostToDevice, e->st));

@@ -29,7 +29,7 @@ struct GzTables {        // device copy of GzCode + CRC constants
   uint32_t crc[256];
   uint32_t hdr[kGzHdrWords];
   uint32_t x2n[32];      // x^(2^k) mod P
-  uint32_t shift[8];     // x^(8 * kGzSlice * 2^j) mod P: CRC combine of equal halves, j = 0..7
+  uint32_t tail[kGzThreads];  // x^(8 * kGzSlice * (kGzThreads-1-t)) mod P: moves slice t's CRC to the end of a full unit
   uint32_t eob, hdr_bits;
   uint8_t len[256];
 };
@@ -58,15 +58,14 @@ __global__ void k_gz_hist(const uint8_t *__restrict__ in, uint64_t n, uint32_t s
     if (h[i]) atomicAdd(&hist[i], (unsigned long long)h[i]);
 }
 
+// a * b mod P in the reflected representation zlib's crc32_combine uses (bit 31 = x^0); branch-free, 32 steps
 __device__ __forceinline__ uint32_t gz_gf_mul_dev(uint32_t a, uint32_t b) {
-  uint32_t m = 1u << 31, p = 0;
-  for (;;) {
-    if (a & m) {
-      p ^= b;
-      if ((a & (m - 1u)) == 0u) break;
-    }
-    m >>= 1;
-    b = (b & 1u) ? (b >> 1) ^ 0xEDB88320u : b >> 1;
+  uint32_t p = 0;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    p ^= (0u - (a >> 31)) & b;
+    a <<= 1;
+    b = (b >> 1) ^ ((0u - (b & 1u)) & 0xEDB88320u);
   }
   return p;
 }
@@ -162,26 +161,18 @@ __global__ void __launch_bounds__(kGzThreads) k_gz_size(const uint8_t *__restric
   gz_slice_scan(in, u0 + s0, sn, len_s, crc_s, &bits, &crc);
   uint32_t total_bits;
   gz_block_excl_scan(bits, wt, &total_bits);
-  // CRC tree: crc(A || B) = crc(A) * x^(8 |B|) + crc(B); full units have equal halves at every level
-  red[threadIdx.x] = crc;
+  // crc(A || B) = crc(A) * x^(8 |B|) + crc(B)  =>  crc(unit) = XOR over slices of crc(slice) * x^(8 * bytes after it):
+  // one multiplication per thread (a table constant for full units), then an XOR reduction
+  const uint32_t after = un - (s0 + sn);  // bytes of the unit behind this slice
+  uint32_t part = 0;
+  if (sn != 0u) part = gz_gf_mul_dev(un == kGzUnit ? T->tail[threadIdx.x] : gz_x8n(T->x2n, after), crc);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) part ^= __shfl_xor_sync(0xFFFFFFFFu, part, o);
+  if ((threadIdx.x & 31u) == 0u) red[threadIdx.x >> 5] = part;
   __syncthreads();
-  if (un == kGzUnit) {
-#pragma unroll 1
-    for (uint32_t j = 0; j < 8u; ++j) {
-      const uint32_t step = 2u << j;
-      if ((threadIdx.x & (step - 1u)) == 0u) {
-        red[threadIdx.x] = gz_gf_mul_dev(T->shift[j], red[threadIdx.x]) ^ red[threadIdx.x + (step >> 1)];
-      }
-      __syncthreads();
-    }
-  } else if (threadIdx.x == 0) {  // the stream's last, partial unit: sequential combine with general shifts
+  if (threadIdx.x == 0) {
     uint32_t c = 0;
-    for (uint32_t t = 0; t < kGzThreads; ++t) {
-      const uint32_t t0 = t * kGzSlice;
-      const uint32_t tn = t0 >= un ? 0u : min(kGzSlice, un - t0);
-      if (tn == 0u) break;
-      c = gz_gf_mul_dev(gz_x8n(T->x2n, tn), c) ^ red[t];
-    }
+    for (uint32_t q = 0; q < kGzThreads / 32u; ++q) c ^= red[q];
     red[0] = c;
   }
   __syncthreads();
