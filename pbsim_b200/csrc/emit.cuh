@@ -60,6 +60,12 @@ __device__ __forceinline__ RefName ref_name(const DeviceSet &S, const Batch &B, 
   return N;
 }
 
+// where the per-base rows of a sub-read's records start (relative to the record); computed once per sub-read by
+// k_sizes so that the tiles of pass 2 load it instead of re-deriving digit counts
+struct EmitLay {
+  uint32_t seq_rel, qual_rel, ip_rel, pw_rel, refrow_rel, readrow_rel;
+};
+
 struct EmitArgs {
   DeviceSet S;
   PhiloxKeys keys;             // PHILOX mode: pass 2 re-derives the 4-way choice of substitutions on non-ACGT bases
@@ -72,18 +78,20 @@ struct EmitArgs {
   uint32_t n_sub;              // valid subreads (after the quota cut)
   uint64_t n_tiles;
   const uint64_t *tile_start;  // [n_sub + 1]
+  const uint32_t *tile_sub;    // [n_tiles] sub-read of a tile (k_tile_map)
+  const EmitLay *lay;          // [n_sub] row positions inside the records (k_sizes)
   const uint64_t *reads_off;   // [n_sub + 1]
   const uint64_t *maf_off;     // [n_sub + 1]
   uint8_t *out_reads;
   uint8_t *out_maf;
 };
 
-__host__ __device__ __forceinline__ uint32_t ndigits(uint64_t v) {  // count_digit (:5823)
-  uint32_t d = 1;
-  while (v >= 10) {
-    v /= 10;
-    ++d;
-  }
+__host__ __device__ __forceinline__ uint32_t ndigits(uint64_t v) {  // count_digit (:5823), without divisions
+  if (v < 100000ull) return v < 10ull ? 1u : (v < 100ull ? 2u : (v < 1000ull ? 3u : (v < 10000ull ? 4u : 5u)));
+  if (v < 10000000000ull)
+    return v < 1000000ull ? 6u : (v < 10000000ull ? 7u : (v < 100000000ull ? 8u : (v < 1000000000ull ? 9u : 10u)));
+  uint32_t d = 10;
+  for (v /= 10000000000ull; v; v /= 10) ++d;
   return d;
 }
 
@@ -150,7 +158,7 @@ __device__ __forceinline__ RecLayout rec_layout(const EmitParams &P, const RefNa
 
 // record sizes and tile counts of every valid subread
 __global__ void k_sizes(Batch B, EmitParams P, DeviceSet S, uint32_t n_sub, uint64_t *reads_size, uint64_t *maf_size,
-                        uint64_t *ntiles) {
+                        uint64_t *ntiles, EmitLay *lay) {
   const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n_sub) return;
   const uint32_t r = s / P.pass_num, pass = s % P.pass_num;
@@ -158,6 +166,10 @@ __global__ void k_sizes(Batch B, EmitParams P, DeviceSet S, uint32_t n_sub, uint
   const RecLayout L = rec_layout(P, N, B.first_read + 1u + r, pass, B.plan_wlen[r], B.rlen[s], B.ncol[s]);
   reads_size[s] = L.reads_size;
   maf_size[s] = L.maf_size;
+  EmitLay y;
+  y.seq_rel = (uint32_t)L.seq_rel; y.qual_rel = (uint32_t)L.qual_rel; y.ip_rel = (uint32_t)L.ip_rel;
+  y.pw_rel = (uint32_t)L.pw_rel; y.refrow_rel = (uint32_t)L.refrow_rel; y.readrow_rel = (uint32_t)L.readrow_rel;
+  lay[s] = y;
   const uint32_t ne = B.nent[s];
   // segmented qshmm sub-reads: nent holds the tile count (errhmm tiles stay one contiguous stream)
   if (P.qs_segments && ((B.plan_meta[r] >> 11) & 1u)) ntiles[s] = ne == 0 ? 1u : ne;
@@ -357,7 +369,8 @@ __device__ __forceinline__ void emit_tile_fast(const uint8_t *__restrict__ evbas
                                                const uint32_t *__restrict__ pk, uint32_t offset, uint32_t wlen,
                                                uint32_t minus, uint32_t ncol, uint32_t C0, uint32_t R0, uint32_t P0,
                                                uint8_t *__restrict__ seq, uint8_t *__restrict__ qual,
-                                               uint8_t *__restrict__ mref, uint8_t *__restrict__ mread, uint32_t lane) {
+                                               uint8_t *__restrict__ mref, uint8_t *__restrict__ mread, uint32_t lane,
+                                               const uint8_t *lut_s /* read_code by kind<<5 | info<<2 | window code */) {
   const uint32_t flip = minus ? 3u : 0u;
   for (uint32_t i = e0; i < e1; i += kEmitStep) {
     const uint32_t eb = i + lane * kEmitPerLane;
@@ -430,7 +443,7 @@ __device__ __forceinline__ void emit_tile_fast(const uint8_t *__restrict__ evbas
         const uint32_t g = minus ? offset + wlen - 1u - Rr : offset + Rr;
         const uint32_t gc = (__ldg(&pk[g >> 4]) >> ((g & 15u) * 2u)) & 3u;
         const uint32_t wc = gc ^ flip;
-        const uint32_t rc = read_code(kind[k], info[k], wc);
+        const uint32_t rc = lut_s[(kind[k] << 5) | (info[k] << 2) | wc];
         seq[Pp] = code_char(rc);
         if (METHOD == PBSIM_METHOD_QSHMM) qual[Pp] = (uint8_t)((raw[k] & 0x7Fu) + 33u);
         else qual[Pp] = (uint8_t)'!';
@@ -539,30 +552,43 @@ __device__ __noinline__ void emit_tile_generic(const uint8_t *evbase, uint32_t e
   }
 }
 
+// sub-read of every tile: largest s with tile_start[s] <= t.  One THREAD per tile here instead of one search per
+// WARP in k_emit.
+__global__ void k_tile_map(const uint64_t *__restrict__ tile_start, uint32_t n_sub, uint64_t n_tiles, uint32_t *tile_sub) {
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_tiles) return;
+  uint32_t lo = 0, hi = n_sub;
+  while (hi - lo > 1u) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (__ldg(&tile_start[mid]) <= t) lo = mid; else hi = mid;
+  }
+  tile_sub[t] = lo;
+}
+
 template <int METHOD>
 __global__ void __launch_bounds__(kEmitThreads) k_emit(EmitArgs A) {
+  __shared__ uint8_t lut_s[128];
+  if (threadIdx.x < 128u) lut_s[threadIdx.x] = (uint8_t)read_code((threadIdx.x >> 5) & 3u, (threadIdx.x >> 2) & 7u, threadIdx.x & 3u);
+  __syncthreads();
   const uint32_t lane = threadIdx.x & 31u;
   const uint64_t warp0 = (uint64_t)blockIdx.x * kEmitWarps + (threadIdx.x >> 5);
   const uint64_t nwarps = (uint64_t)gridDim.x * kEmitWarps;
   for (uint64_t t = warp0; t < A.n_tiles; t += nwarps) {
-    // subread of this tile: largest s with tile_start[s] <= t
-    uint32_t lo = 0, hi = A.n_sub;
-    while (hi - lo > 1u) {
-      const uint32_t mid = (lo + hi) >> 1;
-      if (__ldg(&A.tile_start[mid]) <= t) lo = mid; else hi = mid;
-    }
-    const uint32_t s = lo;
+    const uint32_t s = __ldg(&A.tile_sub[t]);
     const uint32_t tile = (uint32_t)(t - __ldg(&A.tile_start[s]));
     const uint32_t r = s / A.P.pass_num, pass = s % A.P.pass_num;
     const uint64_t read_id = A.B.first_read + 1u + r;
     const uint32_t offset = A.B.plan_off[r], wlen = A.B.plan_wlen[r];
     const uint32_t minus = (A.B.plan_meta[r] >> 8) & 1u;
     const uint32_t nent = A.B.nent[s], rlen = A.B.rlen[s], ncol = A.B.ncol[s];
-    const RefName N = ref_name(A.S, A.B, r, A.P.glen);
-    const RecLayout L = rec_layout(A.P, N, read_id, pass, wlen, rlen, ncol);
+    const EmitLay L = A.lay[s];
     uint8_t *rd = A.out_reads + A.reads_off[s];
     uint8_t *mf = A.out_maf + A.maf_off[s];
-    if (tile == 0 && lane == 0) write_headers(A.P, N, L, rd, mf, read_id, pass, wlen, rlen, ncol, minus);
+    if (tile == 0) {  // everything of the record that is not a per-base row: once per sub-read
+      const RefName N = ref_name(A.S, A.B, r, A.P.glen);
+      const RecLayout LL = rec_layout(A.P, N, read_id, pass, wlen, rlen, ncol);
+      if (lane == 0) write_headers(A.P, N, LL, rd, mf, read_id, pass, wlen, rlen, ncol, minus);
+    }
     if (nent == 0) continue;
     const Ckpt *ckp = A.ck + A.B.ck_off[s];
     const Ckpt c0 = ckp[tile];
@@ -584,7 +610,7 @@ __global__ void __launch_bounds__(kEmitThreads) k_emit(EmitArgs A) {
                                        (METHOD == PBSIM_METHOD_QSHMM ? 2ull : 1ull);
     if (!slow) {
       emit_tile_fast<METHOD>(evbase, e0, e1, A.G.pk, offset, wlen, minus, ncol, c0.col, c0.ref, c0.read, seq, qual, mref,
-                             mread, lane);
+                             mread, lane, lut_s);
     } else {
       RefFetch rf;
       rf.pk = A.G.pk;

@@ -203,7 +203,7 @@ struct pbsim_engine {
   DevBuf d_bins;       // bin_start[kBins+1], bin_lo[kBins], bin_hi[kBins], cta_first[kBins+1]
   DevBuf d_ctrl;       // control words
   DevBuf d_cub_tmp;
-  DevBuf d_ev, d_ck;
+  DevBuf d_ev, d_ck, d_lay, d_tile_sub;
   DevBuf d_seg, d_seg_bins;       // segment-parallel pass 1: segment lists / results, CTA map
   int seg_enabled = 1;            // option "segments"
   int64_t seg_min_len = 2048;     // option "seg_min_len": shorter reads stay on the sequential path
@@ -759,8 +759,9 @@ int run_batch(pbsim_engine *e, uint32_t n_reads, int64_t clip_room, BatchResult 
     e->emitp.id_head_len = (uint32_t)strlen(head);
     memcpy(e->emitp.id_head, head, e->emitp.id_head_len + 1);
   }
+  CK(e->d_lay.ensure((size_t)nv_sub * sizeof(EmitLay) + 64));
   k_sizes<<<nblk(nv_sub, 256), 256, 0, e->st>>>(B, e->emitp, device_set(e), nv_sub, (uint64_t *)reads_size, (uint64_t *)maf_size,
-                                                (uint64_t *)ntiles);
+                                                (uint64_t *)ntiles, e->d_lay.as<EmitLay>());
   e->launches++;
   if ((rc = excl_scan(e, reads_size, reads_off, nv_sub + 1))) return rc;
   if ((rc = excl_scan(e, maf_size, maf_off, nv_sub + 1))) return rc;
@@ -787,6 +788,13 @@ int run_batch(pbsim_engine *e, uint32_t n_reads, int64_t clip_room, BatchResult 
   EA.n_sub = nv_sub;
   EA.n_tiles = n_tiles;
   EA.tile_start = (const uint64_t *)tile_start;
+  CK(e->d_tile_sub.ensure((size_t)n_tiles * 4 + 64));
+  if (n_tiles > 0) {
+    k_tile_map<<<nblk(n_tiles, 256), 256, 0, e->st>>>((const uint64_t *)tile_start, nv_sub, n_tiles, e->d_tile_sub.as<uint32_t>());
+    e->launches++;
+  }
+  EA.tile_sub = e->d_tile_sub.as<uint32_t>();
+  EA.lay = e->d_lay.as<EmitLay>();
   EA.reads_off = (const uint64_t *)reads_off;
   EA.maf_off = (const uint64_t *)maf_off;
   EA.keys.init(e->run.seed, (uint32_t)e->seq_num);
@@ -1232,7 +1240,8 @@ void pbsim_cuda_destroy(pbsim_engine *e) {
                     &e->d_ctrl, &e->d_cub_tmp, &e->d_ev, &e->d_ck, &e->out[0].reads, &e->out[0].maf, &e->out[1].reads, &e->out[1].maf, &e->d_stats, &e->d_seg,
                     &e->d_seg_bins, &e->d_set_start, &e->d_set_rprefix, &e->d_set_plus, &e->d_set_ids, &e->d_set_idstart,
                     &e->d_set_ssp_ends, &e->d_set_ssp_mod, &e->d_set_first, &e->gz[0].reads, &e->gz[0].maf, &e->gz[1].reads,
-                    &e->gz[1].maf, &e->d_gz_tables, &e->d_gz_hist, &e->d_gz_usize, &e->d_gz_ucrc, &e->d_gz_uoff};
+                    &e->gz[1].maf, &e->d_gz_tables, &e->d_gz_hist, &e->d_gz_usize, &e->d_gz_ucrc, &e->d_gz_uoff,
+                    &e->d_lay, &e->d_tile_sub};
   for (DevBuf *b : bufs) b->release();
   for (auto &a : e->h_stage)
     for (auto &b : a) b.release();
