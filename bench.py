@@ -61,8 +61,9 @@ WORKLOADS = {
                n_transcripts=200000, n_reads=20000000),
 }
 
-# DRAM traffic rate of k_emit from the committed ncu captures (GB/s; None where no capture exists)
-NCU_EMIT_DRAM_GBS = {"qshmm": 1053.7, "errhmm": None}
+# DRAM traffic rate (dram__bytes_read.sum + dram__bytes_write.sum over gpu__time_duration.sum, GB/s) of the two big
+# kernels from the committed ncu captures profiles/r01_k_sim_seg_c3_v11.txt / r01_k_emit_c3_v11.txt
+NCU_DRAM_GBS = {("qshmm", "seg"): 423.2, ("qshmm", "emit"): 1496.0}
 
 # algorithmic bytes per emitted base: FASTQ 2.002 + MAF 2.122 written + 0.244 read (2-bit genome)
 ALGO_BYTES_PER_BASE = 4.37
@@ -372,7 +373,7 @@ def main():
     eng.timer_start()
     t0 = time.perf_counter()
     bases = out_bytes = launches = 0
-    sim_s = emit_s = gen_s = 0.0
+    sim_s = emit_s = gen_s = seg_s = 0.0
     for k in range(args.steps):
         b, ob, st = step_device(args.warmup + k)
         bases += b
@@ -380,6 +381,7 @@ def main():
         launches += st.kernel_launches
         sim_s += st.sim_seconds
         emit_s += st.emit_seconds
+        seg_s += st.seg_seconds
         gen_s += st.gen_seconds
     dev_ms = eng.timer_stop()
     barrier()
@@ -467,9 +469,12 @@ def main():
         kern_s = sim_s + emit_s
         # the dominant kernel is pass 2 (k_emit): it performs the path's algorithmic traffic (genome read, records
         # written); its launches are bracketed by CUDA events on the engine's stream (pbsim_stats.emit_seconds)
-        achieved = ALGO_BYTES_PER_BASE * bases / emit_s / 1e9 if emit_s > 0 else 0.0
+        seg_name = "k_sim_seg" if wl["method"] == "qshmm" else "k_sim_seg_err"
+        dom_s, dom_name = (seg_s, seg_name + " (pass 1, segment-parallel chains)") if seg_s >= emit_s else \
+                          (emit_s, "k_emit (pass 2)")
+        achieved = ALGO_BYTES_PER_BASE * bases / dom_s / 1e9 if dom_s > 0 else 0.0
         path_achieved = ALGO_BYTES_PER_BASE * bases / kern_s / 1e9 if kern_s > 0 else 0.0
-        traffic = NCU_EMIT_DRAM_GBS.get(wl["method"])
+        traffic = NCU_DRAM_GBS.get((wl["method"], "seg" if seg_s >= emit_s else "emit"))
         line = {
             "metric": "simulated Gbp/s", "value": value, "unit": "Gbp/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": max_ms / max(1, args.steps), "higher_is_better": True,
@@ -487,12 +492,13 @@ def main():
             "clocks": {"sm_mhz": clocks["sm_mhz"], "sm_max_mhz": clocks["sm_max_mhz"], "reasons": clocks["reasons"]},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak if peak else None, "traffic": traffic,
-                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one k_emit launch / its "
-                                           "duration, GB/s (ncu --set full, profiles/r01_k_emit_*)",
-                         "kernel": "k_emit (pass 2), rank 0",
+                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch of that "
+                                           "kernel / its duration, GB/s (ncu --set full, profiles/r01_k_*_c3_v11.txt)",
+                         "kernel": dom_name + ", rank 0",
                          "algorithmic_bytes_per_base": ALGO_BYTES_PER_BASE, "peak_source": peak_src,
-                         "kernel_seconds": {"sim": sim_s, "emit": emit_s, "all_generation": gen_s},
-                         "kernel_share_of_step": emit_s / (dev_ms * 1e-3) if dev_ms else None,
+                         "kernel_seconds": {"sim": sim_s, "of_which_" + seg_name: seg_s, "emit": emit_s,
+                                            "all_generation": gen_s},
+                         "kernel_share_of_step": dom_s / (dev_ms * 1e-3) if dev_ms else None,
                          "path": {"what": "pass 1 + pass 2 together (k_sim_seg, k_find_end, k_sim_%s, k_emit)"
                                           % wl["method"],
                                   "achieved": path_achieved, "frac": path_achieved / peak if peak else None,

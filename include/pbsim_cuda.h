@@ -168,6 +168,7 @@ typedef struct {
   double sim_seconds;            /* ... of which pass 1 (k_sim_qshmm / k_sim_errhmm)          */
   double emit_seconds;           /* ... of which pass 2 (k_emit)                             */
   double deflate_seconds;        /* ... of which the gzip writer (option "deflate")          */
+  double seg_seconds;            /* ... of which the segment kernel (k_sim_seg / _err) alone  */
   int64_t kernel_launches;       /* number of engine kernels launched during the run         */
 } pbsim_stats;
 

@@ -136,6 +136,7 @@ class Stats(C.Structure):
         ("sim_seconds", C.c_double),
         ("emit_seconds", C.c_double),
         ("deflate_seconds", C.c_double),
+        ("seg_seconds", C.c_double),
         ("kernel_launches", C.c_int64),
     ]
 

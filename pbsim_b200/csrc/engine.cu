@@ -229,8 +229,8 @@ struct pbsim_engine {
   OutSet gz[2];
   DevBuf d_gz_tables, d_gz_hist, d_gz_usize, d_gz_ucrc, d_gz_uoff;
   PinnedBuf h_gz;
-  double gz_ms = 0;
-  cudaEvent_t ev_gz[2] = {nullptr, nullptr};
+  double gz_ms = 0, seg_ms = 0;
+  cudaEvent_t ev_gz[2] = {nullptr, nullptr}, ev_seg[2] = {nullptr, nullptr};
   int pipeline = 1;                 // option "pipeline": 0 off, 1 host delivery only, 2 always
   int64_t host_batch_bases = (int64_t)1 << 30;  // option: batch size of pipelined host delivery
   bool mode_set = false, mode_to_host = false, pipelined = false;
@@ -609,6 +609,7 @@ int run_batch(pbsim_engine *e, uint32_t n_reads, int64_t clip_room, BatchResult 
     A.ev = e->d_ev.as<uint8_t>();
     A.ck = e->d_ck.as<Ckpt>();
     const uint32_t grid = cta_slots;
+    bool seg_timed = false;
     CK(cudaEventRecord(e->ev_k[0], e->st));
     if (qs) {
       if (replay) k_sim_qshmm<PBSIM_RNG_REPLAY><<<grid, kSimThreads, kQsSmemBytes, e->st>>>(A);
@@ -664,13 +665,17 @@ int run_batch(pbsim_engine *e, uint32_t n_reads, int64_t clip_room, BatchResult 
       SA.bin_hi = sb_hi;
       SA.ev = e->d_ev.as<uint8_t>();
       SA.max_window = getenv("PBSIM_EXPERIMENT_NOCOUPLE") ? 0u : 4096u;  // timing experiment only: wrong states
+      CK(cudaEventRecord(e->ev_seg[0], e->st));
+      seg_timed = true;
       if (qs) {
         k_sim_seg<<<seg_slots, kSimThreads, kQsSmemBytes, e->st>>>(SA);
+        CK(cudaEventRecord(e->ev_seg[1], e->st));
         k_find_end<<<nblk((uint64_t)n_sub * 32, 128), 128, 0, e->st>>>(B, S, G, e->d_biasone.as<uint8_t>(), pass,
                                                                        e->d_ev.as<uint8_t>(), e->d_ck.as<Ckpt>(),
                                                                        e->d_qc_prob.as<double>());
       } else {
         k_sim_seg_err<<<seg_slots, kErrThreads, e->er_smem_bar_off + 16, e->st>>>(SA, e->er_smem_bar_off);
+        CK(cudaEventRecord(e->ev_seg[1], e->st));
         k_find_end_err<<<nblk((uint64_t)n_sub * 32, 128), 128, 0, e->st>>>(B, S, G, SA.keys, e->d_biasone.as<uint8_t>(), pass,
                                                                            e->d_ev.as<uint8_t>(), e->d_ck.as<Ckpt>());
       }
@@ -707,6 +712,10 @@ int run_batch(pbsim_engine *e, uint32_t n_reads, int64_t clip_room, BatchResult 
       float ms = 0;
       CK(cudaEventElapsedTime(&ms, e->ev_k[0], e->ev_k[1]));
       e->sim_ms += ms;
+      if (seg_timed) {
+        CK(cudaEventElapsedTime(&ms, e->ev_seg[0], e->ev_seg[1]));
+        e->seg_ms += ms;
+      }
     }
     if (getenv("PBSIM_DEBUG")) {
       float ms = 0;
@@ -926,8 +935,10 @@ int produce_one(pbsim_engine *e, int set, pbsim_engine::BatchItem *it) {
       if (e->run.batch_reads > 0) {
         nb = e->run.batch_reads;
       } else {
-        const int64_t target = (e->pipelined && e->mode_to_host) ? std::min(e->target_batch_bases, e->host_batch_bases)
-                                                                 : e->target_batch_bases;
+        int64_t target = (e->pipelined && e->mode_to_host) ? std::min(e->target_batch_bases, e->host_batch_bases)
+                                                           : e->target_batch_bases;
+        // the first batch of a pipelined run is the only one whose generation nothing hides: keep it short
+        if (e->pipelined && e->mode_to_host && e->reads_done_in_run == 0) target = std::max<int64_t>(target / 4, 1 << 26);
         nb = (int64_t)((double)target / (mean * e->model.pass_num));
         nb = std::max<int64_t>(nb, 1 << 12);
         nb = std::min<int64_t>(nb, 1 << 22);
@@ -1222,6 +1233,7 @@ int pbsim_cuda_create(pbsim_engine **out, int device) {
   for (auto &ev : ne->ev_k) cudaEventCreate(&ev);
   for (auto &ev : ne->ev_user) cudaEventCreate(&ev);
   for (auto &ev : ne->ev_gz) cudaEventCreate(&ev);
+  for (auto &ev : ne->ev_seg) cudaEventCreate(&ev);
   std::memset(&ne->model, 0, sizeof ne->model);
   std::memset(&ne->emitp, 0, sizeof ne->emitp);
   *out = ne;
@@ -1249,6 +1261,7 @@ void pbsim_cuda_destroy(pbsim_engine *e) {
   for (auto &ev : e->ev_k) cudaEventDestroy(ev);
   for (auto &ev : e->ev_user) cudaEventDestroy(ev);
   for (auto &ev : e->ev_gz) cudaEventDestroy(ev);
+  for (auto &ev : e->ev_seg) cudaEventDestroy(ev);
   e->h_gz.release();
   e->h_ctrl.release();
   e->h_acc.release();
@@ -1473,6 +1486,7 @@ int pbsim_cuda_simulate_begin(pbsim_engine *e, const pbsim_run *run) {
   e->sim_ms = 0;
   e->emit_ms = 0;
   e->gz_ms = 0;
+  e->seg_ms = 0;
   stop_producer(e);  // a run abandoned without simulate_end
   e->pend = pbsim_engine::Pending();
   e->piece = pbsim_engine::Piece();
@@ -1542,6 +1556,7 @@ int pbsim_cuda_simulate_end(pbsim_engine *e, pbsim_stats *st, int64_t *freq_len,
   st->sim_seconds = e->sim_ms * 1e-3;
   st->emit_seconds = e->emit_ms * 1e-3;
   st->deflate_seconds = e->gz_ms * 1e-3;
+  st->seg_seconds = e->seg_ms * 1e-3;
   st->kernel_launches = e->launches;
   if (freq_len) {
     const int64_t n = std::min<int64_t>(freq_len_cells, e->freq_len_cells);

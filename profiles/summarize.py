@@ -38,6 +38,8 @@ def main(path):
         ia, isrc, isamp = hdr.index("Instructions Executed"), hdr.index("Source"), hdr.index("# Samples")
         c, s = Counter(), Counter()
         for r in rows[2:]:
+            if len(r) <= max(ia, isrc, isamp) or not r[ia].isdigit():
+                continue
             t = r[isrc].split()
             if not t:
                 continue
