@@ -208,6 +208,7 @@ struct pbsim_engine {
   int seg_enabled = 1;            // option "segments"
   int64_t seg_min_len = 2048;     // option "seg_min_len": shorter reads stay on the sequential path
   int64_t seg_batches = 0, seg_fallback_batches = 0;
+  float seg_extra = 0.0f;         // extra segment headroom (fraction), raised when a batch runs out of segments
   // the records of a batch live in one of two output sets in HBM: with the pipeline on, a producer
   // thread generates batch k+1 into the other set while batch k is handed to the caller
   struct OutSet {
@@ -537,11 +538,12 @@ int run_batch(pbsim_engine *e, uint32_t n_reads, int64_t clip_room, BatchResult 
   }
 
   bool use_segments = !replay && e->seg_enabled && clip_room < 0;
-  for (int attempt = 0; attempt < 6; ++attempt) {
+  int seg_retries = 0;
+  for (int attempt = 0; attempt < 9; ++attempt) {
     // ---- K1 plan
     const uint32_t ev_align = qs ? 8u : 16u;
     k_plan<<<nblk(n_reads, 256), 256, 0, e->st>>>(M, G, device_set(e), rng, B, clip_room, e->cap_num, e->cap_den, ev_align,
-                                                   use_segments ? (uint32_t)e->seg_min_len : 0u);
+                                                   use_segments ? (uint32_t)e->seg_min_len : 0u, e->seg_extra);
     e->launches++;
     // ---- sort by (accuracy, length desc)
     {
@@ -723,15 +725,24 @@ int run_batch(pbsim_engine *e, uint32_t n_reads, int64_t clip_room, BatchResult 
       fprintf(stderr, "[pbsim] batch reads=%u sub=%u segments=%llu flags=%u pass1_ms=%.2f attempt=%d\n", n_reads, n_sub,
               (unsigned long long)n_seg_total, flags, ms, attempt);
     }
-    if (flags & 4u) {  // a segmented read could not be completed: redo the batch on the sequential path
+    if (flags & 4u) {
+      // A segmented read could not be completed.  If the only reason is that its window outlasted the segments
+      // provisioned for it (a read that stays in an insertion-rich state of a sticky chain), provision more — the
+      // headroom stays for the batches to come; anything else redoes the batch on the sequential path.
+      const uint32_t inner = flags >> 8;
+      if (inner == 4u && e->seg_extra < 0.6f && seg_retries < 3) {
+        e->seg_extra += 0.04f;
+        ++seg_retries;
+        continue;
+      }
       use_segments = false;
       e->seg_fallback_batches++;
-      if (attempt == 5) return fail(e, PBSIM_E_OVERFLOW, "segment-parallel pass 1 failed repeatedly");
+      if (attempt >= 8) return fail(e, PBSIM_E_OVERFLOW, "segment-parallel pass 1 failed repeatedly");
       continue;
     }
     if (flags & 1u) {  // a read outgrew its slot: enlarge and redo the batch
       e->cap_num *= 2;
-      if (attempt == 5) return fail(e, PBSIM_E_OVERFLOW, "event slots overflowed repeatedly");
+      if (attempt >= 8) return fail(e, PBSIM_E_OVERFLOW, "event slots overflowed repeatedly");
       continue;
     }
     const uint64_t cut = hctrl[0];
