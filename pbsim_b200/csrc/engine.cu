@@ -1,14 +1,18 @@
 // libpbsim_cuda — engine orchestration and the C ABI (include/pbsim_cuda.h).
 //
-// One engine = one GPU.  A simulate_by_* call of the reference (pbsim.cpp:1955 / :3594) becomes
+// One engine = one GPU.  A simulate_by_* call of the reference (pbsim.cpp:1955 / :3594, and the _trans / _templ
+// variants :2419, :3055, :4114, :4807) becomes
 //   simulate_begin -> { next_chunk }* -> simulate_end
-// and every chunk runs, on one stream:
-//   K1 k_plan            per-read length / accuracy / offset / strand            (sim_kernels.cuh)
-//      radix sort        (accuracy, length desc) -> pass-1 schedule              (CUB, plumbing)
-//   K2 k_sim_qshmm | K3 k_sim_errhmm   chains -> event streams                   (sim_kernels.cuh)
-//      quota scan        which read crosses sim.len_quota (pbsim.cpp:2173-2181)  (CUB + k_find_cut)
-//   K4 k_sizes, k_emit   record placement and text emission                      (emit.cuh)
-//   K6 k_stats           counters and histograms                                 (emit.cuh)
+// and every batch of reads runs, on one stream:
+//   K1 k_plan            per-read length / accuracy / offset / strand, segment provisioning  (sim_kernels.cuh)
+//      radix sorts       (accuracy, length desc) -> pass-1 schedules                          (CUB, plumbing)
+//   K2 k_sim_qshmm | K3 k_sim_errhmm   short reads, replay mode, chain-only prepass           (sim_kernels.cuh)
+//      k_sim_seg | k_sim_seg_err, k_find_end[_err]   segment-parallel pass 1 -> event streams (seg_kernels.cuh)
+//      quota scan        which read crosses sim.len_quota (pbsim.cpp:2173-2181)               (CUB + k_find_cut)
+//   K4 k_sizes, k_tile_map, k_emit   record placement and text emission                       (emit.cuh)
+//   K6 k_stats           counters and histograms                                              (emit.cuh)
+//      k_gz_hist / k_gz_size / k_gz_encode   option "deflate": gzip members for host delivery (gz_kernels.cuh)
+// Host delivery is pipelined: a producer thread generates batch k+1 while batch k streams through pinned staging.
 // There is no CPU implementation of any of these steps in this library.
 #include <cuda_runtime.h>
 

@@ -242,3 +242,24 @@ def test_abandoned_run_then_new_run(eng):
     got = run_case_on_gpu(c, eng, "philox")  # begins again over the abandoned run
     for a, b in zip(ref, got):
         assert a[0] == b[0] and a[1] == b[1] and a[3] == b[3]
+
+
+def test_read_range_shards_concatenate_to_the_single_gpu_run(eng):
+    """multi-GPU sharding of one sequence by read-id range: rank 0 takes reads [0, k), rank 1
+    the rest, told how many bases rank 0 emitted (the all_gather of stats_reduce.emitted_prefix); the quota cut and
+    every byte must equal the one-engine run"""
+    from tests.golden_util import model_path
+    L = capi.load()
+    hm = capi.HostModel(L, capi.host_params("qshmm"), model_path("QSHMM-RSII.model"))
+    eng.set_model(hm)
+    n = 1500000
+    eng.set_synthetic_sequence(n, 1, 21)
+    quota = 3 * n
+    whole = eng.simulate(quota, rng_mode=capi.RNG_PHILOX, seed=4)
+    k = whole[2].res_num // 3
+    a = eng.simulate(quota, rng_mode=capi.RNG_PHILOX, seed=4, first_read=0, max_reads=k)
+    b = eng.simulate(quota, rng_mode=capi.RNG_PHILOX, seed=4, first_read=k, len_total_start=a[2].res_len_total)
+    assert a[2].res_num == k and a[2].res_num + b[2].res_num == whole[2].res_num
+    assert a[0] + b[0] == whole[0]
+    assert a[1] + b[1] == whole[1]
+    assert a[2].res_len_total + b[2].res_len_total == whole[2].res_len_total
