@@ -269,6 +269,7 @@ def main():
     ap.add_argument("--len-sd", type=float, default=None, help="diagnostics: override --length-sd (0 = equal-length reads)")
     ap.add_argument("--len-mean", type=float, default=None, help="diagnostics: override --length-mean")
     ap.add_argument("--batch-bases", type=float, default=None, help="diagnostics: engine target_batch_bases")
+    ap.add_argument("--couple-min-len", type=int, default=None, help="diagnostics: engine couple_min_len")
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload])
     if args.len_sd is not None or args.len_mean is not None:
@@ -306,6 +307,8 @@ def main():
     eng.set_model(hm)
     if args.batch_bases:
         eng.set_option("target_batch_bases", int(args.batch_bases))
+    if args.couple_min_len:
+        eng.set_option("couple_min_len", args.couple_min_len)
     if wl.get("batch_bases") and not args.batch_bases:
         eng.set_option("target_batch_bases", int(wl["batch_bases"]))
     depth = wl["depth"]

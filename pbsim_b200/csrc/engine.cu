@@ -212,6 +212,7 @@ struct pbsim_engine {
   int seg_enabled = 1;            // option "segments"
   int64_t seg_min_len = 2048;     // option "seg_min_len": shorter reads stay on the sequential path
   int64_t seg_batches = 0, seg_fallback_batches = 0;
+  int64_t couple_min_len = 32768;  // option "couple_min_len": reads at least this long recover segment states by coupling
   float seg_extra = 0.0f;         // extra segment headroom (fraction), raised when a batch runs out of segments
   // the records of a batch live in one of two output sets in HBM: with the pipeline on, a producer
   // thread generates batch k+1 into the other set while batch k is handed to the caller
@@ -547,7 +548,8 @@ int run_batch(pbsim_engine *e, uint32_t n_reads, int64_t clip_room, BatchResult 
     // ---- K1 plan
     const uint32_t ev_align = qs ? 8u : 16u;
     k_plan<<<nblk(n_reads, 256), 256, 0, e->st>>>(M, G, device_set(e), rng, B, clip_room, e->cap_num, e->cap_den, ev_align,
-                                                   use_segments ? (uint32_t)e->seg_min_len : 0u, e->seg_extra);
+                                                   use_segments ? (uint32_t)e->seg_min_len : 0u, e->seg_extra,
+                                                   (uint32_t)e->couple_min_len);
     e->launches++;
     // ---- sort by (accuracy, length desc)
     {
@@ -1611,6 +1613,11 @@ int pbsim_cuda_set_option(pbsim_engine *e, const char *name, int64_t value) {
   }
   if (!strcmp(name, "segments")) {
     e->seg_enabled = value != 0;
+    return 0;
+  }
+  if (!strcmp(name, "couple_min_len")) {
+    if (value < (int64_t)PB_TILE) return fail(e, PBSIM_E_INVALID, "couple_min_len must be at least %u", PB_TILE);
+    e->couple_min_len = value;
     return 0;
   }
   if (!strcmp(name, "seg_min_len")) {

@@ -97,7 +97,8 @@ __device__ __forceinline__ ReadPlan plan_any(const PlanTables &T, Draw &d, const
 
 __global__ void k_plan(DeviceModel M, DeviceGenome G, DeviceSet S, RngParams rng, Batch B, int64_t clip_room,
                        uint32_t cap_num, uint32_t cap_den, uint32_t ev_align, uint32_t seg_min_len /* 0: segments off */,
-                       float seg_extra /* extra segment headroom learnt from earlier batches */) {
+                       float seg_extra /* extra segment headroom learnt from earlier batches */,
+                       uint32_t couple_min_len /* shorter reads take the chain-only prepass */) {
   const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= B.n_reads) return;
   PlanTables T;
@@ -161,7 +162,7 @@ __global__ void k_plan(DeviceModel M, DeviceGenome G, DeviceSet S, RngParams rng
   // Which way a segment learns its start state: backward coupling costs a window per SEGMENT (a quarter to a half
   // of the segment for typical chains), the prepass one cheap pass per READ but sequentially.  Reads up to 32 k
   // positions take the prepass (its critical path is short), longer reads coupling where the chain allows it.
-  const bool needs_chain = segmented && (errm || ae.has_model) && (!ae.seg_ok || p.wlen < 32768u);
+  const bool needs_chain = segmented && (errm || ae.has_model) && (!ae.seg_ok || p.wlen < couple_min_len);
   const uint32_t nseg = segmented ? qshmm_segments_for(p.wlen, ae.rho * (1.0f + seg_extra)) : 0u;
   B.plan_meta[r] = p.acc | (minus << 8) | ((slow ? 1u : 0u) << 9) | ((ae.valid ? 0u : 1u) << 10) |
                    ((segmented ? 1u : 0u) << 11) | ((needs_chain ? 1u : 0u) << 12);
