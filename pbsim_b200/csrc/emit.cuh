@@ -372,17 +372,24 @@ __device__ __forceinline__ void emit_tile_fast(const uint8_t *__restrict__ evbas
                                                uint8_t *__restrict__ mref, uint8_t *__restrict__ mread, uint32_t lane,
                                                const uint8_t *lut_s /* read_code by kind<<5 | info<<2 | window code */) {
   const uint32_t flip = minus ? 3u : 0u;
+  // ---- 4 entries per lane and iteration (tile starts are 16-byte aligned, so the vector load is aligned; entries
+  //      past e1 are masked: the slot behind them is padded scratch).  The entries of the NEXT iteration are
+  //      requested before the current ones are processed, so the DRAM latency overlaps the formatting work.
+  auto load_entries = [&](uint32_t i) -> uint2 {
+    const uint32_t eb = i + lane * kEmitPerLane;
+    if (METHOD == PBSIM_METHOD_QSHMM) return __ldg(reinterpret_cast<const uint2 *>(evbase + 2ull * eb));
+    return make_uint2(__ldg(reinterpret_cast<const uint32_t *>(evbase + eb)), 0u);
+  };
+  uint2 nxt = load_entries(e0);
   for (uint32_t i = e0; i < e1; i += kEmitStep) {
     const uint32_t eb = i + lane * kEmitPerLane;
-    // ---- load 4 entries (tile starts are 16-byte aligned, so the vector load is aligned; entries past e1 are
-    //      masked: the slot behind them is padded scratch)
+    const uint2 v = nxt;
+    if (i + kEmitStep < e1) nxt = load_entries(i + kEmitStep);
     uint32_t raw[kEmitPerLane];
     if (METHOD == PBSIM_METHOD_QSHMM) {
-      const uint2 v = __ldg(reinterpret_cast<const uint2 *>(evbase + 2ull * eb));
       raw[0] = v.x & 0xFFFFu; raw[1] = v.x >> 16; raw[2] = v.y & 0xFFFFu; raw[3] = v.y >> 16;
     } else {
-      const uint32_t v = __ldg(reinterpret_cast<const uint32_t *>(evbase + eb));
-      raw[0] = v & 0xFFu; raw[1] = (v >> 8) & 0xFFu; raw[2] = (v >> 16) & 0xFFu; raw[3] = v >> 24;
+      raw[0] = v.x & 0xFFu; raw[1] = (v.x >> 8) & 0xFFu; raw[2] = (v.x >> 16) & 0xFFu; raw[3] = v.x >> 24;
     }
     uint32_t kind[kEmitPerLane], info[kEmitPerLane], nd[kEmitPerLane], isb[kEmitPerLane], adv[kEmitPerLane];
     uint32_t lb = 0, la = 0, ld = 0;  // this lane's totals: read bases, ref advances by bases, deletions
