@@ -230,7 +230,10 @@ int pbsim_cuda_device_timer(pbsim_engine *e, int stop, double *ms);
  * "host_batch_bases" (batch size of pipelined host delivery, default 1 Gi),
  * "deflate" (1: host delivery hands out gzip members written on the GPU — every 32 KiB of a record stream is one
  * member holding one dynamic-Huffman block — instead of text: what the reference's `gzip >` children produce,
- * pbsim.cpp:708-730; default 0) */
+ * pbsim.cpp:708-730; default 0),
+ * "bam" (1: with pass_num > 1 the reads stream holds BAM alignment records — the binary form of the reference's SAM
+ * lines, what its `samtools view -b` child writes (pbsim.cpp:715-722) — and, with "deflate", BGZF blocks; the caller
+ * adds the BAM header block in front and the BGZF end-of-file block behind; default 0) */
 int pbsim_cuda_set_option(pbsim_engine *e, const char *name, int64_t value);
 /* device pointer + cell count of the int64 stats block {counters[16], freq_accuracy[100001],
  * freq_len[2*len_max+2]} so that a multi-GPU driver can ncclAllReduce it in place */

@@ -22,11 +22,12 @@ constexpr int kEmitWarps = kEmitThreads / 32;
 
 struct EmitParams {
   uint32_t pass_num;
-  uint32_t sam;            // 1: SAM records (pass_num > 1), 0: FASTQ
+  uint32_t sam;            // 0: FASTQ, 1: SAM records (pass_num > 1), 2: BAM records (same content, binary)
   uint32_t id_head_len;    // strlen(id_prefix + seq_num)
   char id_head[160];       // "<id_prefix><seq_num>"
   uint32_t rq_len;
   char rq[32];             // printf("%f", accuracy_mean)
+  float rq_f;              // the same text read back as a float (BAM: rq:f)
   uint32_t glen;
   uint32_t qs_segments;    // method is qshmm: segmented sub-reads use one slot per tile
 };
@@ -112,6 +113,41 @@ struct RecLayout {
 #define PB_SAM_S7 "\tRG:Z:ffffffff\n"
 #define PB_LEN(s) ((uint32_t)(sizeof(s) - 1))
 
+// integer tags take the smallest type that holds the value, as htslib's SAM parser chooses it
+__device__ __forceinline__ uint32_t bam_int_width(int64_t v) {
+  if (v < 0) return v >= -128 ? 1u : (v >= -32768 ? 2u : 4u);
+  return v <= 255 ? 1u : (v <= 65535 ? 2u : 4u);
+}
+__device__ __forceinline__ uint8_t bam_int_type(int64_t v) {
+  if (v < 0) return v >= -128 ? 'c' : (v >= -32768 ? 's' : 'i');
+  return v <= 255 ? 'C' : (v <= 65535 ? 'S' : 'I');
+}
+// 4-bit base codes "=ACMGRSVTWYHKDBN" (SAM spec 4.2.3); anything else is N, lower case counts as upper case
+__device__ __forceinline__ uint32_t bam_nibble(uint8_t c) {
+  if (c >= 'a' && c <= 'z') c = (uint8_t)(c - 32);
+  switch (c) {
+    case '=': return 0u;  case 'A': return 1u;  case 'C': return 2u;  case 'M': return 3u;
+    case 'G': return 4u;  case 'R': return 5u;  case 'S': return 6u;  case 'V': return 7u;
+    case 'T': return 8u;  case 'W': return 9u;  case 'Y': return 10u; case 'H': return 11u;
+    case 'K': return 12u; case 'D': return 13u; case 'B': return 14u; default: return 15u;
+  }
+}
+// one read base into its row(s): text formats store characters; BAM packs two bases per byte (high nibble first)
+// with an atomic OR into the zeroed record, and stores the quality value itself
+template <bool BAM>
+__device__ __forceinline__ void put_read_base(uint8_t *seq, uint8_t *qual, uint32_t Pp, uint8_t ch, uint32_t nib,
+                                              uint32_t qv, bool has_qv) {
+  if (!BAM) {
+    seq[Pp] = ch;
+    qual[Pp] = has_qv ? (uint8_t)(qv + 33u) : (uint8_t)'!';
+  } else {
+    uint8_t *b = seq + (Pp >> 1);
+    const uintptr_t a = reinterpret_cast<uintptr_t>(b);
+    atomicOr(reinterpret_cast<unsigned int *>(a & ~(uintptr_t)3), (nib << ((Pp & 1u) ? 0u : 4u)) << (8u * (uint32_t)(a & 3u)));
+    qual[Pp] = has_qv ? (uint8_t)qv : (uint8_t)0;
+  }
+}
+
 __device__ __forceinline__ RecLayout rec_layout(const EmitParams &P, const RefName &N, uint64_t read_id, uint32_t pass,
                                                 uint32_t wlen, uint32_t rlen, uint32_t ncol) {
   const uint32_t offset = N.off;
@@ -125,6 +161,17 @@ __device__ __forceinline__ RecLayout rec_layout(const EmitParams &P, const RefNa
     L.qual_rel = L.seq_rel + rlen + 2u + L.idlen + 1u;
     L.reads_size = L.qual_rel + rlen + 1u;
     L.ip_rel = L.pw_rel = L.tail_rel = 0;
+  } else if (P.sam == 2u) {
+    // BAM alignment record (SAM spec 4.2) of an unmapped read: 36 fixed bytes, name + NUL, 4-bit bases, qualities,
+    // then the tags with the types samtools gives them when it converts the reference's SAM text
+    L.idlen = P.id_head_len + 1u + L.d_rid + 1u + L.d_pass;
+    L.seq_rel = 36u + L.idlen + 1u;
+    L.qual_rel = L.seq_rel + (rlen + 1u) / 2u;
+    L.ip_rel = L.qual_rel + rlen + 4u + 8u;          // cx:C (4), ip:B:C header (8)
+    L.pw_rel = L.ip_rel + rlen + 4u + 8u;            // np:C (4), pw:B:C header (8)
+    L.tail_rel = L.pw_rel + rlen;
+    const int64_t qe = (int64_t)rlen - 1;
+    L.reads_size = L.tail_rel + 4u + (3u + bam_int_width(qe)) + 7u + 24u + (3u + bam_int_width((int64_t)read_id)) + 12u;
   } else {
     L.idlen = P.id_head_len + 1u + L.d_rid + 1u + L.d_pass;  // "<head>/<read>/<pass>"
     L.seq_rel = L.idlen + PB_LEN(PB_SAM_S1);
@@ -224,6 +271,49 @@ __device__ __noinline__ void write_headers(const EmitParams &P, const RefName &N
     p = put_id(p, P, read_id, pass, L);
     *p++ = '\n';
     rd[L.qual_rel + rlen] = '\n';
+  } else if (P.sam == 2u) {
+    auto put32 = [](uint8_t *q, uint32_t v) { q[0] = (uint8_t)v; q[1] = (uint8_t)(v >> 8); q[2] = (uint8_t)(v >> 16); q[3] = (uint8_t)(v >> 24); return q + 4; };
+    auto put16 = [](uint8_t *q, uint32_t v) { q[0] = (uint8_t)v; q[1] = (uint8_t)(v >> 8); return q + 2; };
+    auto put_int_tag = [&](uint8_t *q, char t0, char t1, int64_t v) {
+      *q++ = (uint8_t)t0; *q++ = (uint8_t)t1; *q++ = bam_int_type(v);
+      const uint32_t w = bam_int_width(v);
+      for (uint32_t i = 0; i < w; ++i) *q++ = (uint8_t)((uint64_t)v >> (8u * i));
+      return q;
+    };
+    p = put32(p, (uint32_t)(L.reads_size - 4u));  // block_size
+    p = put32(p, 0xFFFFFFFFu);                    // refID -1
+    p = put32(p, 0xFFFFFFFFu);                    // pos -1 (SAM POS 0)
+    *p++ = (uint8_t)(L.idlen + 1u);               // l_read_name
+    *p++ = 255;                                   // MAPQ
+    p = put16(p, 4680u);                          // bin of an unmapped read: reg2bin(-1, 0)
+    p = put16(p, 0u);                             // n_cigar_op
+    p = put16(p, 4u);                             // FLAG: unmapped
+    p = put32(p, rlen);                           // l_seq
+    p = put32(p, 0xFFFFFFFFu);                    // next refID
+    p = put32(p, 0xFFFFFFFFu);                    // next pos
+    p = put32(p, 0u);                             // tlen
+    p = put_id(p, P, read_id, pass, L);
+    *p++ = 0;
+    p = rd + L.qual_rel + rlen;
+    *p++ = 'c'; *p++ = 'x'; *p++ = 'C'; *p++ = 3;
+    *p++ = 'i'; *p++ = 'p'; *p++ = 'B'; *p++ = 'C';
+    p = put32(p, rlen);
+    p = rd + L.ip_rel + rlen;
+    *p++ = 'n'; *p++ = 'p'; *p++ = 'C'; *p++ = 1;
+    *p++ = 'p'; *p++ = 'w'; *p++ = 'B'; *p++ = 'C';
+    p = put32(p, rlen);
+    p = rd + L.tail_rel;
+    *p++ = 'q'; *p++ = 's'; *p++ = 'C'; *p++ = 0;
+    p = put_int_tag(p, 'q', 'e', (int64_t)rlen - 1);
+    *p++ = 'r'; *p++ = 'q'; *p++ = 'f';
+    p = put32(p, __float_as_uint(P.rq_f));
+    *p++ = 's'; *p++ = 'n'; *p++ = 'B'; *p++ = 'f';
+    p = put32(p, 4u);
+    for (int i = 0; i < 4; ++i) p = put32(p, __float_as_uint(10.0f));
+    p = put_int_tag(p, 'z', 'm', (int64_t)read_id);
+    *p++ = 'R'; *p++ = 'G'; *p++ = 'Z';
+    p = put_mem(p, "ffffffff", 8);
+    *p++ = 0;
   } else {
     p = put_id(p, P, read_id, pass, L);
     p = PB_PUT_LIT(p, PB_SAM_S1);
@@ -364,7 +454,7 @@ constexpr uint32_t kEmitPerLane = 4;                    // entries per lane per 
 constexpr uint32_t kEmitStep = 32u * kEmitPerLane;      // entries per warp iteration
 
 // One tile whose reference range holds only ACGT: 4 entries per lane, one packed warp scan per 128 entries.
-template <int METHOD>
+template <int METHOD, bool BAM>
 __device__ __forceinline__ void emit_tile_fast(const uint8_t *__restrict__ evbase, uint32_t e0, uint32_t e1,
                                                const uint32_t *__restrict__ pk, uint32_t offset, uint32_t wlen,
                                                uint32_t minus, uint32_t ncol, uint32_t C0, uint32_t R0, uint32_t P0,
@@ -451,9 +541,7 @@ __device__ __forceinline__ void emit_tile_fast(const uint8_t *__restrict__ evbas
         const uint32_t gc = (__ldg(&pk[g >> 4]) >> ((g & 15u) * 2u)) & 3u;
         const uint32_t wc = gc ^ flip;
         const uint32_t rc = lut_s[(kind[k] << 5) | (info[k] << 2) | wc];
-        seq[Pp] = code_char(rc);
-        if (METHOD == PBSIM_METHOD_QSHMM) qual[Pp] = (uint8_t)((raw[k] & 0x7Fu) + 33u);
-        else qual[Pp] = (uint8_t)'!';
+        put_read_base<BAM>(seq, qual, Pp, code_char(rc), 1u << rc, raw[k] & 0x7Fu, METHOD == PBSIM_METHOD_QSHMM);
         const uint32_t col = minus ? ncol - 1u - Cc : Cc;
         mread[col] = code_char(rc ^ flip);
         mref[col] = (kind[k] == PB_KIND_INS) ? (uint8_t)'-' : code_char(gc);
@@ -480,7 +568,7 @@ __device__ __forceinline__ void emit_tile_fast(const uint8_t *__restrict__ evbas
 }
 
 // generic tile path: reads the ASCII copy where the tile touches non-ACGT bases; one entry per lane
-template <int METHOD>
+template <int METHOD, bool BAM>
 __device__ __noinline__ void emit_tile_generic(const uint8_t *evbase, uint32_t e0, uint32_t e1, const RefFetch &rf,
                                                uint32_t minus, uint32_t ncol, uint32_t C0, uint32_t R0, uint32_t P0,
                                                uint8_t *seq, uint8_t *qual, uint8_t *mref, uint8_t *mread,
@@ -534,8 +622,7 @@ __device__ __noinline__ void emit_tile_generic(const uint8_t *evbase, uint32_t e
         info = (w[0] >> 12) & 3u;
       }
       const uint8_t rb = read_base(kind, info, wch, wc, acgt);
-      seq[Pp] = rb;
-      qual[Pp] = (METHOD == PBSIM_METHOD_QSHMM) ? (uint8_t)(qv + 33u) : (uint8_t)'!';
+      put_read_base<BAM>(seq, qual, Pp, rb, BAM ? bam_nibble(rb) : 0u, qv, METHOD == PBSIM_METHOD_QSHMM);
       const uint32_t col = minus ? ncol - 1u - Cc : Cc;
       mread[col] = minus ? comp_char(rb) : rb;
       mref[col] = (kind == PB_KIND_INS) ? (uint8_t)'-' : gch;
@@ -572,7 +659,7 @@ __global__ void k_tile_map(const uint64_t *__restrict__ tile_start, uint32_t n_s
   tile_sub[t] = lo;
 }
 
-template <int METHOD>
+template <int METHOD, bool BAM>
 __global__ void __launch_bounds__(kEmitThreads) k_emit(EmitArgs A) {
   __shared__ uint8_t lut_s[128];
   if (threadIdx.x < 128u) lut_s[threadIdx.x] = (uint8_t)read_code((threadIdx.x >> 5) & 3u, (threadIdx.x >> 2) & 7u, threadIdx.x & 3u);
@@ -616,7 +703,7 @@ __global__ void __launch_bounds__(kEmitThreads) k_emit(EmitArgs A) {
     const uint8_t *evbase = A.ev + (A.B.ev_off[s] + (segmented ? (uint64_t)tile * PB_SEG_STRIDE : 0ull)) *
                                        (METHOD == PBSIM_METHOD_QSHMM ? 2ull : 1ull);
     if (!slow) {
-      emit_tile_fast<METHOD>(evbase, e0, e1, A.G.pk, offset, wlen, minus, ncol, c0.col, c0.ref, c0.read, seq, qual, mref,
+      emit_tile_fast<METHOD, BAM>(evbase, e0, e1, A.G.pk, offset, wlen, minus, ncol, c0.col, c0.ref, c0.read, seq, qual, mref,
                              mread, lane, lut_s);
     } else {
       RefFetch rf;
@@ -626,7 +713,7 @@ __global__ void __launch_bounds__(kEmitThreads) k_emit(EmitArgs A) {
       rf.wlen = wlen;
       rf.minus = minus;
       rf.slow = true;
-      emit_tile_generic<METHOD>(evbase, e0, e1, rf, minus, ncol, c0.col, c0.ref, c0.read, seq, qual, mref, mread, lane,
+      emit_tile_generic<METHOD, BAM>(evbase, e0, e1, rf, minus, ncol, c0.col, c0.ref, c0.read, seq, qual, mref, mread, lane,
                                 A.philox ? &A.keys : nullptr, (uint32_t)read_id, pass);
     }
     if (A.P.sam) {
@@ -634,10 +721,17 @@ __global__ void __launch_bounds__(kEmitThreads) k_emit(EmitArgs A) {
       const uint32_t p0 = c0.read;
       const uint32_t p1 = has_next ? ckp[tile + 1].read : rlen;
       uint8_t *ip = rd + L.ip_rel, *pw = rd + L.pw_rel;
-      for (uint32_t j = 2u * p0 + lane; j < 2u * p1; j += 32u) {
-        const uint8_t ch = (j & 1u) ? (uint8_t)'9' : (uint8_t)',';
-        ip[j] = ch;
-        pw[j] = ch;
+      if (BAM) {  // one byte of value 9 per read base
+        for (uint32_t j = p0 + lane; j < p1; j += 32u) {
+          ip[j] = 9;
+          pw[j] = 9;
+        }
+      } else {
+        for (uint32_t j = 2u * p0 + lane; j < 2u * p1; j += 32u) {
+          const uint8_t ch = (j & 1u) ? (uint8_t)'9' : (uint8_t)',';
+          ip[j] = ch;
+          pw[j] = ch;
+        }
       }
     }
   }

@@ -232,6 +232,7 @@ struct pbsim_engine {
   };
   // option "deflate": host delivery hands out gzip members (gz_kernels.cuh) instead of text
   int deflate = 0;
+  int bam = 0;                      // option "bam": multi-pass records are BAM alignment records, not SAM text
   OutSet gz[2];
   DevBuf d_gz_tables, d_gz_hist, d_gz_usize, d_gz_ucrc, d_gz_uoff;
   PinnedBuf h_gz;
@@ -777,6 +778,7 @@ int run_batch(pbsim_engine *e, uint32_t n_reads, int64_t clip_room, BatchResult 
   CK(cudaMemsetAsync(maf_size + nv_sub, 0, 8, e->st));
   CK(cudaMemsetAsync(ntiles + nv_sub, 0, 8, e->st));
   e->emitp.glen = (uint32_t)e->glen;
+  e->emitp.sam = e->model.pass_num > 1 ? (e->bam ? 2u : 1u) : 0u;
   e->emitp.qs_segments = qs ? 1u : 0u;
   {
     char head[192];
@@ -833,8 +835,14 @@ int run_batch(pbsim_engine *e, uint32_t n_reads, int64_t clip_room, BatchResult 
     const uint64_t want = (n_tiles + kEmitWarps - 1) / kEmitWarps;
     const uint32_t grid = (uint32_t)std::min<uint64_t>(want, (uint64_t)dev_sms * 8 * 4);
     CK(cudaEventRecord(e->ev_k[2], e->st));
-    if (qs) k_emit<PBSIM_METHOD_QSHMM><<<grid, kEmitThreads, 0, e->st>>>(EA);
-    else k_emit<PBSIM_METHOD_ERRHMM><<<grid, kEmitThreads, 0, e->st>>>(EA);
+    if (EA.P.sam == 2u) {  // BAM packs bases with atomic ORs: the records start zeroed
+      CK(cudaMemsetAsync(O.reads.p, 0, (size_t)out->reads_bytes, e->st));
+      if (qs) k_emit<PBSIM_METHOD_QSHMM, true><<<grid, kEmitThreads, 0, e->st>>>(EA);
+      else k_emit<PBSIM_METHOD_ERRHMM, true><<<grid, kEmitThreads, 0, e->st>>>(EA);
+    } else {
+      if (qs) k_emit<PBSIM_METHOD_QSHMM, false><<<grid, kEmitThreads, 0, e->st>>>(EA);
+      else k_emit<PBSIM_METHOD_ERRHMM, false><<<grid, kEmitThreads, 0, e->st>>>(EA);
+    }
     CK(cudaEventRecord(e->ev_k[3], e->st));
     e->launches++;
   }
@@ -858,7 +866,7 @@ int run_batch(pbsim_engine *e, uint32_t n_reads, int64_t clip_room, BatchResult 
 
 // gzip one record stream of the batch in HBM (gz_kernels.cuh): histogram -> code (host) -> member sizes -> offsets
 // -> members.  Replaces the reference's popen("gzip > file") children (pbsim.cpp:708-730).
-int gz_compress(pbsim_engine *e, const uint8_t *in, uint64_t n, DevBuf &dst, uint64_t *out_bytes) {
+int gz_compress(pbsim_engine *e, const uint8_t *in, uint64_t n, DevBuf &dst, uint64_t *out_bytes, bool bgzf = false) {
   *out_bytes = 0;
   if (n == 0) return 0;
   static_assert(sizeof(GzTables) % 8 == 0, "GzTables is copied as words");
@@ -907,8 +915,8 @@ int gz_compress(pbsim_engine *e, const uint8_t *in, uint64_t n, DevBuf &dst, uin
   CK(e->d_gz_uoff.ensure((size_t)(units + 1) * 16 + 64));
   unsigned long long *wide = e->d_gz_uoff.as<unsigned long long>();
   unsigned long long *uoff = wide + (units + 1);
-  k_gz_size<<<(uint32_t)units, kGzThreads, 0, e->st>>>(in, n, e->d_gz_tables.as<GzTables>(), e->d_gz_usize.as<uint32_t>(),
-                                                     e->d_gz_ucrc.as<uint32_t>());
+  k_gz_size<<<(uint32_t)units, kGzThreads, 0, e->st>>>(in, n, e->d_gz_tables.as<GzTables>(), bgzf ? 1u : 0u,
+                                                     e->d_gz_usize.as<uint32_t>(), e->d_gz_ucrc.as<uint32_t>());
   k_widen<<<nblk(units, 256), 256, 0, e->st>>>(e->d_gz_usize.as<uint32_t>(), (uint32_t)units, wide);
   CK(cudaMemsetAsync(wide + units, 0, 8, e->st));
   e->launches += 2;
@@ -926,7 +934,7 @@ int gz_compress(pbsim_engine *e, const uint8_t *in, uint64_t n, DevBuf &dst, uin
   }
   k_gz_encode<<<(uint32_t)units, kGzThreads, smem, e->st>>>(in, n, e->d_gz_tables.as<GzTables>(),
                                                            reinterpret_cast<const uint64_t *>(uoff),
-                                                           e->d_gz_ucrc.as<uint32_t>(), dst.as<uint8_t>());
+                                                           e->d_gz_ucrc.as<uint32_t>(), bgzf ? 1u : 0u, dst.as<uint8_t>());
   e->launches++;
   CK(cudaGetLastError());
   *out_bytes = total;
@@ -980,7 +988,9 @@ int produce_one(pbsim_engine *e, int set, pbsim_engine::BatchItem *it) {
     uint64_t gz_bytes[2] = {0, 0};
     if (gz) {
       CK(cudaEventRecord(e->ev_gz[0], e->st));
-      if ((rc = gz_compress(e, e->out[set].reads.as<uint8_t>(), br.reads_bytes, e->gz[set].reads, &gz_bytes[0]))) return rc;
+      // BAM records travel as BGZF blocks (what samtools writes), everything else as plain gzip members
+      const bool bgzf = e->bam && e->model.pass_num > 1;
+      if ((rc = gz_compress(e, e->out[set].reads.as<uint8_t>(), br.reads_bytes, e->gz[set].reads, &gz_bytes[0], bgzf))) return rc;
       if ((rc = gz_compress(e, e->out[set].maf.as<uint8_t>(), br.maf_bytes, e->gz[set].maf, &gz_bytes[1]))) return rc;
       CK(cudaEventRecord(e->ev_gz[1], e->st));
     }
@@ -1339,6 +1349,7 @@ int pbsim_cuda_set_model(pbsim_engine *e, const pbsim_model *m) {
   e->emitp.sam = m->pass_num > 1 ? 1u : 0u;
   snprintf(e->emitp.rq, sizeof e->emitp.rq, "%f", m->accuracy_mean);
   e->emitp.rq_len = (uint32_t)strlen(e->emitp.rq);
+  e->emitp.rq_f = strtof(e->emitp.rq, nullptr);  // what a SAM parser makes of "rq:f:0.850000"
   // stats block
   e->freq_len_cells = 2 * m->len_max + 2;
   e->stats_cells = kStatCounters + 100001 + e->freq_len_cells;
@@ -1629,6 +1640,11 @@ int pbsim_cuda_set_option(pbsim_engine *e, const char *name, int64_t value) {
     if (value < 0 || value > 2) return fail(e, PBSIM_E_INVALID, "pipeline must be 0, 1 or 2");
     if (e->running) return fail(e, PBSIM_E_INVALID, "pipeline cannot change during a run");
     e->pipeline = (int)value;
+    return 0;
+  }
+  if (!strcmp(name, "bam")) {
+    if (e->running) return fail(e, PBSIM_E_INVALID, "bam cannot change during a run");
+    e->bam = value != 0;
     return 0;
   }
   if (!strcmp(name, "deflate")) {

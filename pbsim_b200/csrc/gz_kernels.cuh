@@ -81,13 +81,23 @@ __device__ __forceinline__ uint32_t gz_x8n(const uint32_t *x2n, uint64_t n) {
   return p;
 }
 
-// member geometry from the body's bit count
-__device__ __forceinline__ void gz_geometry(uint32_t body_bits, uint32_t *body_bytes, uint32_t *k, uint32_t *total) {
+// member geometry from the body's bit count.  bgzf: the 18-byte BGZF header (FEXTRA with the 'BC' subfield holding
+// the block size, SAM spec 4.1; htslib insists on XLEN == 6, so no padding and no alignment), else the 10-byte header
+// with a 0-3 character FNAME that makes the member's size a multiple of 4
+__device__ __forceinline__ void gz_geometry(uint32_t body_bits, uint32_t bgzf, uint32_t *body_bytes, uint32_t *k,
+                                            uint32_t *hdr_bytes, uint32_t *total) {
   const uint32_t B = (body_bits + 7u) >> 3;
-  const uint32_t kk = (4u - ((19u + B) & 3u)) & 3u;
   *body_bytes = B;
-  *k = kk;
-  *total = 19u + kk + B;  // 10 header + k name + NUL + body + 8 trailer
+  if (bgzf) {
+    *k = 0;
+    *hdr_bytes = 18u;
+    *total = 18u + B + 8u;
+  } else {
+    const uint32_t kk = (4u - ((19u + B) & 3u)) & 3u;
+    *k = kk;
+    *hdr_bytes = 11u + kk;    // 10 header + k name + NUL
+    *total = 19u + kk + B;    // ... + body + 8 trailer
+  }
 }
 
 // CTA-wide sums / scans over kGzThreads values
@@ -145,7 +155,7 @@ __device__ __forceinline__ void gz_slice_scan(const uint8_t *__restrict__ in, ui
 
 // unit_size[u] = member bytes, unit_crc[u] = CRC-32 of the unit's text.  The input is padded to a multiple of 16.
 __global__ void __launch_bounds__(kGzThreads) k_gz_size(const uint8_t *__restrict__ in, uint64_t n, const GzTables *T,
-                                                        uint32_t *unit_size, uint32_t *unit_crc) {
+                                                        uint32_t bgzf, uint32_t *unit_size, uint32_t *unit_crc) {
   __shared__ uint8_t len_s[256];
   __shared__ uint32_t crc_s[256];
   __shared__ uint32_t red[kGzThreads];
@@ -177,8 +187,8 @@ __global__ void __launch_bounds__(kGzThreads) k_gz_size(const uint8_t *__restric
   }
   __syncthreads();
   if (threadIdx.x == 0) {
-    uint32_t B, k, total;
-    gz_geometry(T->hdr_bits + total_bits + (T->eob >> 16), &B, &k, &total);
+    uint32_t B, k, hb, total;
+    gz_geometry(T->hdr_bits + total_bits + (T->eob >> 16), bgzf, &B, &k, &hb, &total);
     unit_size[blockIdx.x] = total;
     unit_crc[blockIdx.x] = red[0];
   }
@@ -193,7 +203,7 @@ __device__ __forceinline__ void gz_put_bits(uint32_t *img, uint32_t bitpos, uint
 
 __global__ void __launch_bounds__(kGzThreads) k_gz_encode(const uint8_t *__restrict__ in, uint64_t n, const GzTables *T,
                                                           const uint64_t *unit_off, const uint32_t *unit_crc,
-                                                          uint8_t *out) {
+                                                          uint32_t bgzf, uint8_t *out) {
   extern __shared__ __align__(16) uint32_t gz_smem[];
   uint32_t *img = gz_smem;                       // [kGzImgWords]
   uint32_t *lit_s = gz_smem + kGzImgWords;       // [256]
@@ -223,17 +233,24 @@ __global__ void __launch_bounds__(kGzThreads) k_gz_encode(const uint8_t *__restr
   uint32_t total_bits;
   const uint32_t my_bits = gz_block_excl_scan(bits, wt, &total_bits);
   const uint32_t hdr_bits = T->hdr_bits, eob = T->eob;
-  uint32_t B, k, total;
-  gz_geometry(hdr_bits + total_bits + (eob >> 16), &B, &k, &total);
-  const uint32_t body0 = (11u + k) * 8u;  // bit position of the DEFLATE stream inside the member
+  uint32_t B, k, hb, total;
+  gz_geometry(hdr_bits + total_bits + (eob >> 16), bgzf, &B, &k, &hb, &total);
+  const uint32_t body0 = hb * 8u;  // bit position of the DEFLATE stream inside the member
   // header bytes, block header, end of block, trailer
   if (threadIdx.x == 0) {
-    gz_put_bits(img, 0, 0x08088B1Fu, 32);         // ID1 ID2 CM=8 FLG=FNAME
-    gz_put_bits(img, 32, 0u, 32);                 // MTIME = 0
-    gz_put_bits(img, 64, 0x0300u, 16);            // XFL = 0, OS = 3 (Unix)
-    for (uint32_t j = 0; j < k; ++j) gz_put_bits(img, 80u + 8u * j, (uint32_t)'p', 8);
+    if (bgzf) {
+      gz_put_bits(img, 0, 0x04088B1Fu, 32);       // ID1 ID2 CM=8 FLG=FEXTRA
+      gz_put_bits(img, 64, 0xFF00u, 16);          // XFL = 0, OS = 255 (unknown), as htslib writes it
+      gz_put_bits(img, 80, 6u, 16);               // XLEN
+      gz_put_bits(img, 96, 0x00024342u, 32);      // 'B' 'C' SLEN = 2
+      gz_put_bits(img, 128, total - 1u, 16);      // BSIZE: block size minus 1
+    } else {
+      gz_put_bits(img, 0, 0x08088B1Fu, 32);       // ID1 ID2 CM=8 FLG=FNAME
+      gz_put_bits(img, 64, 0x0300u, 16);          // XFL = 0, OS = 3 (Unix); MTIME stays 0
+      for (uint32_t j = 0; j < k; ++j) gz_put_bits(img, 80u + 8u * j, (uint32_t)'p', 8);
+    }
     gz_put_bits(img, body0 + hdr_bits + total_bits, eob & 0xFFFFu, eob >> 16);
-    const uint32_t tr = (11u + k + B) * 8u;
+    const uint32_t tr = (hb + B) * 8u;
     gz_put_bits(img, tr, unit_crc[blockIdx.x], 32);
     gz_put_bits(img, tr + 32u, un, 32);           // ISIZE
   }
@@ -274,10 +291,15 @@ __global__ void __launch_bounds__(kGzThreads) k_gz_encode(const uint8_t *__restr
     if (accbits) atomicOr(&img[w], (uint32_t)acc);
   }
   __syncthreads();
-  // copy the member out: whole words, the member starts 4-byte aligned and its size is a multiple of 4
-  uint32_t *dst = reinterpret_cast<uint32_t *>(out + unit_off[blockIdx.x]);
-  const uint32_t nw = total >> 2;
-  for (uint32_t i = threadIdx.x; i < nw; i += kGzThreads) dst[i] = img[i];
+  if (bgzf) {  // byte-granular placement
+    uint8_t *dst = out + unit_off[blockIdx.x];
+    const uint8_t *img8 = reinterpret_cast<const uint8_t *>(img);
+    for (uint32_t i = threadIdx.x; i < total; i += kGzThreads) dst[i] = img8[i];
+  } else {     // whole words: the member starts 4-byte aligned and its size is a multiple of 4
+    uint32_t *dst = reinterpret_cast<uint32_t *>(out + unit_off[blockIdx.x]);
+    const uint32_t nw = total >> 2;
+    for (uint32_t i = threadIdx.x; i < nw; i += kGzThreads) dst[i] = img[i];
+  }
 }
 
 }  // namespace pb
