@@ -272,6 +272,7 @@ def main():
     ap.add_argument("--len-mean", type=float, default=None, help="diagnostics: override --length-mean")
     ap.add_argument("--batch-bases", type=float, default=None, help="diagnostics: engine target_batch_bases")
     ap.add_argument("--couple-min-len", type=int, default=None, help="diagnostics: engine couple_min_len")
+    ap.add_argument("--bam", action="store_true", help="multi-pass workloads: BAM records / BGZF blocks instead of SAM text")
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload])
     if args.len_sd is not None or args.len_mean is not None:
@@ -311,6 +312,9 @@ def main():
         eng.set_option("target_batch_bases", int(args.batch_bases))
     if args.couple_min_len:
         eng.set_option("couple_min_len", args.couple_min_len)
+    if args.bam:
+        eng.set_option("bam", 1)
+        wl["name"] += " [BAM records]"
     if wl.get("batch_bases") and not args.batch_bases:
         eng.set_option("target_batch_bases", int(wl["batch_bases"]))
     depth = wl["depth"]

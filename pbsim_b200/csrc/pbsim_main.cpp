@@ -197,6 +197,33 @@ void stream_to(GzipWriter &w, const char *p, int64_t n, bool raw = false) {
   for (int64_t o = 0; o < n; o += blk) w.submit(p + o, (size_t)std::min(blk, n - o), raw);
 }
 
+// one BGZF block (SAM spec 4.1) holding `data` (at most 64 KiB): the BAM file header goes through here, the
+// alignment records arrive from the GPU as BGZF blocks already
+std::string bgzf_block(const std::string &data) {
+  z_stream zs;
+  memset(&zs, 0, sizeof zs);
+  deflateInit2(&zs, 6, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY);
+  std::string body(deflateBound(&zs, data.size()) + 16, '\0');
+  zs.next_in = reinterpret_cast<Bytef *>(const_cast<char *>(data.data()));
+  zs.avail_in = (uInt)data.size();
+  zs.next_out = reinterpret_cast<Bytef *>(&body[0]);
+  zs.avail_out = (uInt)body.size();
+  deflate(&zs, Z_FINISH);
+  body.resize(zs.total_out);
+  deflateEnd(&zs);
+  const uint32_t crc = (uint32_t)crc32(crc32(0L, Z_NULL, 0), reinterpret_cast<const Bytef *>(data.data()), (uInt)data.size());
+  const uint32_t isize = (uint32_t)data.size();
+  const uint16_t bsize = (uint16_t)(18 + body.size() + 8 - 1);
+  std::string out;
+  const unsigned char hdr[16] = {0x1f, 0x8b, 0x08, 0x04, 0, 0, 0, 0, 0, 0xff, 0x06, 0, 0x42, 0x43, 0x02, 0};
+  out.append(reinterpret_cast<const char *>(hdr), 16);
+  out.append(reinterpret_cast<const char *>(&bsize), 2);
+  out += body;
+  out.append(reinterpret_cast<const char *>(&crc), 4);
+  out.append(reinterpret_cast<const char *>(&isize), 4);
+  return out;
+}
+
 struct RefSeq {
   std::string id;
   long len = 0;
@@ -433,7 +460,8 @@ void print_help() {
           "  --replay-draws       int32 log of the reference's rand() draws (replay mode).\n"
           "  --replay-marks       int64 draw count after every (read, pass) (replay mode).\n"
           "  --threads            compression threads (hardware concurrency).\n"
-          "  --gzip               gpu (default): gzip members are written on the GPU | host: zlib threads.\n\n"
+          "  --gzip               gpu (default): gzip members / BGZF blocks are written on the GPU (multi-pass\n"
+          "                       output is <prefix>_NNNN.bam) | host: zlib threads (multi-pass: .sam.gz).\n\n"
           " [options for transcriptome / template sequencing]\n\n"
           "  --strategy           trans | templ\n"
           "  --transcript         transcript table: id, plus count, minus count, sequence (tab separated).\n"
@@ -659,8 +687,12 @@ int main(int argc, char **argv) {
   double bias[12] = {0, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 0};
 
   // one simulate call of the reference: stream the engine's chunks into the two compressed files
+  // multi-pass output: <stem>.bam like the reference (:715-722) when the GPU writes the BGZF blocks, SAM text in
+  // <stem>.sam.gz with --gzip host
+  const bool bam = o.pass_num > 1 && o.gzip == "gpu";
+  if (pbsim_cuda_set_option(eng, "bam", bam ? 1 : 0) != 0) die("ERROR: %s\n", pbsim_cuda_last_error(eng));
   auto simulate_to_files = [&](const std::string &stem, const std::string &pu, int64_t len_quota) {
-    GzipWriter reads_out((stem + (o.pass_num == 1 ? ".fq.gz" : ".sam.gz")).c_str(), std::max(1, threads / 2));
+    GzipWriter reads_out((stem + (o.pass_num == 1 ? ".fq.gz" : (bam ? ".bam" : ".sam.gz"))).c_str(), std::max(1, threads / 2));
     GzipWriter maf_out((stem + ".maf.gz").c_str(), std::max(1, threads / 2));
     if (o.pass_num > 1) {  // SAM header (:721-722, :781-782)
       char hdr[1024];
@@ -669,7 +701,18 @@ int main(int argc, char **argv) {
                        "PulseWidth:CodecV1=pw;BINDINGKIT=101-789-500;SEQUENCINGKIT=101-826-100;BASECALLERVERSION=5.0.0;"
                        "FRAMERATEHZ=100.000000\tPU:%s\tPM:SEQUELII\n",
                        pu.c_str());
-      reads_out.submit(hdr, (size_t)m);
+      if (bam) {
+        // BAM file header (SAM spec 4.2): magic, the header text, no reference sequences — as one BGZF block
+        std::string h("BAM\1", 4);
+        const uint32_t l_text = (uint32_t)m, n_ref = 0;
+        h.append(reinterpret_cast<const char *>(&l_text), 4);
+        h.append(hdr, (size_t)m);
+        h.append(reinterpret_cast<const char *>(&n_ref), 4);
+        const std::string blk = bgzf_block(h);
+        reads_out.submit(blk.data(), blk.size(), true);
+      } else {
+        reads_out.submit(hdr, (size_t)m);
+      }
     }
     pbsim_run run;
     memset(&run, 0, sizeof run);
@@ -693,6 +736,11 @@ int main(int argc, char **argv) {
     }
     pbsim_stats st;
     if (pbsim_cuda_simulate_end(eng, &st, nullptr, 0, nullptr) != 0) die("ERROR: %s\n", pbsim_cuda_last_error(eng));
+    if (bam) {  // BGZF end-of-file marker (SAM spec 4.1.2)
+      static const unsigned char eof[28] = {0x1f, 0x8b, 0x08, 0x04, 0, 0, 0, 0, 0, 0xff, 0x06, 0, 0x42, 0x43,
+                                            0x02, 0, 0x1b, 0, 0x03, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+      reads_out.submit(reinterpret_cast<const char *>(eof), sizeof eof, true);
+    }
     reads_out.close();
     maf_out.close();
     replay_pos += (size_t)st.res_pass_num;
