@@ -227,6 +227,8 @@ std::string bgzf_block(const std::string &data) {
 struct RefSeq {
   std::string id;
   long len = 0;
+  std::string text;  // the sequence as get_genome_seq would re-read it from <prefix>_NNNN.ref; kept from the split
+                     // pass so that every reference is read from disk once, not three times
 };
 
 // get_genome_inf (:896-991): split the multi-FASTA into <prefix>_NNNN.ref, collect lengths, print the block
@@ -236,6 +238,7 @@ std::vector<RefSeq> genome_inf(const Options &o) {
   fprintf(stderr, "\n");
   FILE *fp = fopen(o.genome.c_str(), "r");
   if (!fp) die("ERROR: Cannot open file: %s\n", o.genome.c_str());
+  setvbuf(fp, nullptr, _IOFBF, 8 << 20);
   std::vector<RefSeq> seqs;
   std::vector<char> line(kBufSize);
   FILE *out = nullptr;
@@ -264,6 +267,7 @@ std::vector<RefSeq> genome_inf(const Options &o) {
       snprintf(name, sizeof name, "%s_%04zu.ref", o.prefix.c_str(), seqs.size());
       out = fopen(name, "w");
       if (!out) die("ERROR: Cannot open output file: %s\n", name);
+      setvbuf(out, nullptr, _IOFBF, 8 << 20);
       while (ret != 1) {  // header longer than the buffer: skip its continuation
         if (!fgets(line.data(), (int)kBufSize, fp)) break;
         ret = trim(line.data());
@@ -271,9 +275,11 @@ std::vector<RefSeq> genome_inf(const Options &o) {
       fprintf(out, ">%s\n", seqs.back().id.c_str());
     } else {
       if (seqs.empty()) continue;  // text before the first header (the reference would crash here)
-      seqs.back().len += (long)strlen(line.data());
+      const size_t ln = strlen(line.data());
+      seqs.back().len += (long)ln;
       if (seqs.back().len > kRefSeqLenMax) die("ERROR: Reference is too long. Acceptable length <= %ld.\n", kRefSeqLenMax);
       fprintf(out, "%s\n", line.data());
+      seqs.back().text.append(line.data(), ln);
     }
   }
   fclose(fp);
@@ -281,36 +287,6 @@ std::vector<RefSeq> genome_inf(const Options &o) {
   finish();
   fprintf(stderr, "\n");
   return seqs;
-}
-
-// get_genome_seq (:997-1033): re-read <prefix>_NNNN.ref, concatenate the body lines
-std::string genome_seq(const Options &o, size_t num) {
-  char name[4096];
-  snprintf(name, sizeof name, "%s_%04zu.ref", o.prefix.c_str(), num);
-  FILE *fp = fopen(name, "r");
-  if (!fp) die("ERROR: Cannot open file: %s\n", name);
-  std::string seq;
-  std::vector<char> line(kBufSize);
-  while (fgets(line.data(), (int)kBufSize, fp)) {
-    size_t n = strlen(line.data());
-    int ret = 0;
-    if (n && line[n - 1] == '\n') {
-      line[n - 1] = '\0';
-      ret = 1;
-      --n;
-    }
-    if (line[0] == '>') {
-      while (ret != 1) {
-        if (!fgets(line.data(), (int)kBufSize, fp)) break;
-        size_t m = strlen(line.data());
-        ret = (m && line[m - 1] == '\n') ? 1 : 0;
-      }
-    } else {
-      seq.append(line.data(), n);
-    }
-  }
-  fclose(fp);
-  return seq;
 }
 
 // ---- --strategy trans / templ: the sequence set the engine simulates in one run --------------------------------
@@ -811,7 +787,9 @@ int main(int argc, char **argv) {
   // ---- hp-del-bias (main :673-697)
   int64_t hp11_running = 0;
   auto ingest = [&](size_t num, const double b[12], int64_t hpfreq[12]) {
-    const std::string seq = genome_seq(o, num);
+    // the split pass kept the text (identical to what genome_seq re-reads from <prefix>_NNNN.ref: the split writes
+    // the body lines verbatim, :953-957)
+    const std::string &seq = seqs[num - 1].text;
     pbsim_sequence s;
     s.bases = seq.data();
     s.len = (int64_t)seq.size();
