@@ -7,6 +7,7 @@
 import numpy as np
 import pytest
 
+from oracle import oracle as O
 from pbsim_b200 import capi, simulator
 from tests.golden_util import Case, case_names
 from tests.gpu_util import engine_model, run_case_on_gpu
@@ -263,3 +264,61 @@ def test_read_range_shards_concatenate_to_the_single_gpu_run(eng):
     assert a[0] + b[0] == whole[0]
     assert a[1] + b[1] == whole[1]
     assert a[2].res_len_total + b[2].res_len_total == whole[2].res_len_total
+
+
+def test_megabase_reads_equal_oracle(eng):
+    """reads at the length limit (--length-mean 900000 --length-sd 0 --length-max 1000000): ~880 segments per read,
+    backward coupling on every one of them; bytes and statistics must equal the oracle's"""
+    from tests.golden_util import model_path
+    from oracle import refrun as R
+    okw = dict(len_mean=900000.0, len_sd=0.0, len_max=1000000, ratio=(39, 24, 36))
+    contigs = R.synth_genome(31, [("big", 3000000)], n_runs=4, hp_plants=30)
+    o = O.Oracle("qshmm", model_path("QSHMM-ONT.model"), **okw)
+    o.rng_philox(17)
+    o.set_sequence(contigs[0][1], 1)
+    want_reads, want_maf, want_st = o.simulate_wgs(2.0)
+    hm = capi.HostModel(capi.load(), capi.host_params("qshmm", **okw), model_path("QSHMM-ONT.model"))
+    run = simulator.WgsRun(eng, hm, 2.0)
+    reads, maf, st, text = run.simulate_sequence(contigs[0][1], 1, rng_mode=capi.RNG_PHILOX, seed=17)
+    assert st.res_len_max > 850000
+    assert reads == want_reads
+    assert maf == want_maf
+    assert text == O.format_stats(want_st, 1)
+
+
+def test_long_read_roundtrip_properties_at_scale(eng):
+    """60 Mbp device-generated contig, QSHMM-ONT 50 kb reads (the default bench workload's parameters), depth 3:
+    every MAF block must re-derive its FASTQ read and its window of the genome; totals must match the statistics"""
+    import ctypes as C
+    from tests.golden_util import model_path
+    okw = dict(len_mean=50000.0, len_sd=35000.0, len_max=1000000, ratio=(39, 24, 36))
+    hm = capi.HostModel(capi.load(), capi.host_params("qshmm", **okw), model_path("QSHMM-ONT.model"))
+    eng.set_model(hm)
+    n = 60000000
+    eng.set_synthetic_sequence(n, 1, 123)
+    buf = (C.c_char * n)()
+    eng.get_sequence_ascii(C.addressof(buf), n)
+    genome = bytes(buf)
+    reads, maf, st, _ = eng.simulate(3 * n, rng_mode=capi.RNG_PHILOX, seed=5)
+    fq = reads.split(b"\n")
+    blocks = maf.split(b"\n\n")[:-1]
+    assert len(fq) // 4 == len(blocks) == st.res_num > 2000
+    comp = bytes.maketrans(b"ACGT", b"TGCA")
+    total = ndel = nins = 0
+    for k, blk in enumerate(blocks):
+        l1, l2 = blk.split(b"\n")[1:3]
+        f1, f2 = l1.split(), l2.split()
+        off, wlen, refrow = int(f1[2]), int(f1[3]), f1[6]
+        rlen, strand, readrow = int(f2[3]), f2[4], f2[6]
+        assert len(refrow) == len(readrow)
+        assert refrow.replace(b"-", b"") == genome[off:off + wlen]
+        seq = fq[4 * k + 1]
+        assert len(seq) == rlen == len(fq[4 * k + 3])
+        rr = readrow.replace(b"-", b"")
+        assert (rr if strand == b"+" else rr.translate(comp)[::-1]) == seq
+        assert fq[4 * k] == b"@S1_%d" % (k + 1) and (strand == b"+") == (k % 2 == 0)
+        total += rlen
+        ndel += readrow.count(b"-")
+        nins += refrow.count(b"-")
+    assert total == st.res_len_total >= 3 * n
+    assert ndel == st.res_del_num and nins == st.res_ins_num
