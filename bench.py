@@ -271,7 +271,7 @@ def main():
     ap.add_argument("--len-sd", type=float, default=None, help="diagnostics: override --length-sd (0 = equal-length reads)")
     ap.add_argument("--len-mean", type=float, default=None, help="diagnostics: override --length-mean")
     ap.add_argument("--batch-bases", type=float, default=None, help="diagnostics: engine target_batch_bases")
-    ap.add_argument("--couple-min-len", type=int, default=None, help="diagnostics: engine couple_min_len")
+    ap.add_argument("--chain-chunk", type=int, default=None, help="diagnostics: engine chain_chunk (segments per chunk)")
     ap.add_argument("--bam", action="store_true", help="multi-pass workloads: BAM records / BGZF blocks instead of SAM text")
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload])
@@ -310,8 +310,8 @@ def main():
     eng.set_model(hm)
     if args.batch_bases:
         eng.set_option("target_batch_bases", int(args.batch_bases))
-    if args.couple_min_len:
-        eng.set_option("couple_min_len", args.couple_min_len)
+    if args.chain_chunk:
+        eng.set_option("chain_chunk", args.chain_chunk)
     if args.bam:
         eng.set_option("bam", 1)
         wl["name"] += " [BAM records]"

@@ -224,7 +224,8 @@ int pbsim_cuda_device_timer(pbsim_engine *e, int stop, double *ms);
 /* tunables: "stage_bytes" (pinned staging per stream and slot, default 128 MiB),
  * "target_batch_bases" (emitted bases per batch of reads, default 6 Gi),
  * "segments" (1: segment-parallel pass 1 for long reads in PHILOX mode, default 1; results are identical
- * either way), "seg_min_len" (shortest read that is segmented, default 2048),
+ * either way), "seg_min_len" (shortest read that is segmented, default 2048), "chain_chunk" (segments whose entry
+ * states one thread of the chain-only pass recovers, default 32),
  * "pipeline" (0: batches are generated inside next_chunk; 1 (default): with host delivery a producer thread
  * generates batch k+1 into a second record buffer while batch k is handed out; 2: also for device delivery),
  * "host_batch_bases" (batch size of pipelined host delivery, default 1 Gi),

@@ -212,7 +212,8 @@ struct pbsim_engine {
   int seg_enabled = 1;            // option "segments"
   int64_t seg_min_len = 2048;     // option "seg_min_len": shorter reads stay on the sequential path
   int64_t seg_batches = 0, seg_fallback_batches = 0;
-  int64_t couple_min_len = 32768;  // option "couple_min_len": reads at least this long recover segment states by coupling
+  int64_t chain_chunk = 32;         // option "chain_chunk": segments walked by one thread of the chain-only pass
+  DevBuf d_chunk, d_chunk_bins;
   float seg_extra = 0.0f;         // extra segment headroom (fraction), raised when a batch runs out of segments
   // the records of a batch live in one of two output sets in HBM: with the pipeline on, a producer
   // thread generates batch k+1 into the other set while batch k is handed to the caller
@@ -459,7 +460,7 @@ int carve_batch(pbsim_engine *e, uint32_t n_reads) {
   if (n_sub > 0x7FFFFFFFull) return fail(e, PBSIM_E_INVALID, "batch too large");
   CK(e->b_read_u32.ensure((size_t)n_reads * 5 * 4 + 64));
   CK(e->b_sub_u32.ensure((size_t)n_sub * 16 * 4 + 64));
-  CK(e->b_sub_u64.ensure((size_t)(n_sub + 1) * 11 * 8 + 64));
+  CK(e->b_sub_u64.ensure((size_t)(n_sub + 1) * 12 * 8 + 64));
   CK(e->b_sub_f64.ensure((size_t)n_sub * 8 + 64));
   Batch &B = e->B;
   B.n_reads = n_reads;
@@ -472,7 +473,7 @@ int carve_batch(pbsim_engine *e, uint32_t n_reads) {
   B.plan_tr = r32 + 4ull * n_reads;
   uint32_t *s32 = e->b_sub_u32.as<uint32_t>();
   uint32_t **fields[] = {&B.key_in, &B.key_out, &B.idx_in, &B.order, &B.cap, &B.ck_cap, &B.nent, &B.rlen,
-                         &B.ncol, &B.nsub, &B.nins, &B.ndel, &B.flags, &B.draws_used, &B.nseg};
+                         &B.ncol, &B.nsub, &B.nins, &B.ndel, &B.flags, &B.draws_used, &B.nseg, &B.nchunk};
   for (size_t i = 0; i < sizeof(fields) / sizeof(fields[0]); ++i) *fields[i] = s32 + i * n_sub;
   uint64_t *s64 = e->b_sub_u64.as<uint64_t>();
   B.ev_off = s64;
@@ -482,7 +483,7 @@ int carve_batch(pbsim_engine *e, uint32_t n_reads) {
 }
 
 // slices of b_sub_u64 (each n_sub + 1 long): 0 ev_off, 1 ck_off, 2 tmp widen, 3 rlen0 prefix,
-// 4 reads_size, 5 maf_size, 6 ntiles, 7 reads_off, 8 maf_off, 9 tile_start, 10 seg_off
+// 4 reads_size, 5 maf_size, 6 ntiles, 7 reads_off, 8 maf_off, 9 tile_start, 10 seg_off, 11 chunk_off
 inline uint64_t *u64_slice(pbsim_engine *e, int k) { return e->b_sub_u64.as<uint64_t>() + (size_t)k * (e->B.n_sub + 1); }
 
 int excl_scan(pbsim_engine *e, const unsigned long long *in, unsigned long long *out, uint32_t n) {
@@ -550,7 +551,7 @@ int run_batch(pbsim_engine *e, uint32_t n_reads, int64_t clip_room, BatchResult 
     const uint32_t ev_align = qs ? 8u : 16u;
     k_plan<<<nblk(n_reads, 256), 256, 0, e->st>>>(M, G, device_set(e), rng, B, clip_room, e->cap_num, e->cap_den, ev_align,
                                                    use_segments ? (uint32_t)e->seg_min_len : 0u, e->seg_extra,
-                                                   (uint32_t)e->couple_min_len);
+                                                   (uint32_t)e->chain_chunk);
     e->launches++;
     // ---- sort by (accuracy, length desc)
     {
@@ -582,18 +583,25 @@ int run_batch(pbsim_engine *e, uint32_t n_reads, int64_t clip_room, BatchResult 
     if ((rc = excl_scan(e, tmp64, reinterpret_cast<unsigned long long *>(B.ck_off), n_sub + 1))) return rc;
     e->launches += 2;
     unsigned long long *seg_off = reinterpret_cast<unsigned long long *>(u64_slice(e, 10));
+    unsigned long long *chunk_off = reinterpret_cast<unsigned long long *>(u64_slice(e, 11));
     hctrl[2] = 0;
+    hctrl[4] = 0;
     if (use_segments) {
       k_widen<<<nblk(n_sub + 1, 256), 256, 0, e->st>>>(B.nseg, n_sub, tmp64);
       if ((rc = excl_scan(e, tmp64, seg_off, n_sub + 1))) return rc;
       e->launches++;
       CK(cudaMemcpyAsync(hctrl + 2, seg_off + n_sub, 8, cudaMemcpyDeviceToHost, e->st));
+      k_widen<<<nblk(n_sub + 1, 256), 256, 0, e->st>>>(B.nchunk, n_sub, tmp64);
+      if ((rc = excl_scan(e, tmp64, chunk_off, n_sub + 1))) return rc;
+      e->launches++;
+      CK(cudaMemcpyAsync(hctrl + 4, chunk_off + n_sub, 8, cudaMemcpyDeviceToHost, e->st));
     }
     CK(cudaMemcpyAsync(hctrl, B.ev_off + n_sub, 8, cudaMemcpyDeviceToHost, e->st));
     CK(cudaMemcpyAsync(hctrl + 1, B.ck_off + n_sub, 8, cudaMemcpyDeviceToHost, e->st));
     CK(cudaStreamSynchronize(e->st));
     const uint64_t ev_entries = hctrl[0], ck_entries = hctrl[1];
     const uint64_t n_seg_total = use_segments ? hctrl[2] : 0;
+    const uint64_t n_chunk_total = use_segments ? hctrl[4] : 0;
     if (n_seg_total > 0x7FFFFFF0ull) return fail(e, PBSIM_E_INVALID, "too many segments in one batch");
     CK(e->d_ev.ensure((size_t)ev_entries * (qs ? 2 : 1) + 256));
     CK(e->d_ck.ensure((size_t)ck_entries * sizeof(Ckpt) + 256));
@@ -674,6 +682,54 @@ int run_batch(pbsim_engine *e, uint32_t n_reads, int64_t clip_room, BatchResult 
       SA.bin_hi = sb_hi;
       SA.ev = e->d_ev.as<uint8_t>();
       SA.max_window = getenv("PBSIM_EXPERIMENT_NOCOUPLE") ? 0u : 4096u;  // timing experiment only: wrong states
+      if (n_chunk_total > 0) {
+        // ---- chain-only pass: the HMM state in front of every segment (k_chain_chunk), scheduled like the segments
+        const uint32_t nch = (uint32_t)n_chunk_total;
+        const uint32_t ch_slots = nblk(nch, cta_threads) + kBins;
+        CK(e->d_chunk.ensure((size_t)nch * 5 * 4 + 64));
+        CK(e->d_chunk_bins.ensure((4 * kBins + 8) * 4 + (size_t)ch_slots * 4 * 4 + 64));
+        ChunkBatch C;
+        C.n_chunks = nch;
+        C.per_chunk = (uint32_t)e->chain_chunk;
+        C.chunk_off = (const uint64_t *)chunk_off;
+        uint32_t *cu = e->d_chunk.as<uint32_t>();
+        C.sub = cu;
+        C.key_in = cu + nch;
+        C.key_out = cu + 2ull * nch;
+        C.id_in = cu + 3ull * nch;
+        C.order = cu + 4ull * nch;
+        uint32_t *cb_start = e->d_chunk_bins.as<uint32_t>();
+        uint32_t *cb_lo = cb_start + kBins + 1, *cb_hi = cb_lo + kBins, *cb_first = cb_hi + kBins;
+        uint32_t *cb_key = cb_first + kBins + 1, *cb_id = cb_key + ch_slots, *cb_key_s = cb_id + ch_slots,
+                 *cb_order = cb_key_s + ch_slots;
+        k_chunk_fill<<<nblk(n_sub, 256), 256, 0, e->st>>>(B, C, pass);
+        {
+          size_t tmp = 0;
+          CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, C.key_in, C.key_out, C.id_in, C.order, (int)nch, 0, 28, e->st));
+          CK(e->d_cub_tmp.ensure(tmp + 256));
+          tmp = e->d_cub_tmp.cap;
+          CK(cub::DeviceRadixSort::SortPairs(e->d_cub_tmp.p, tmp, C.key_in, C.key_out, C.id_in, C.order, (int)nch, 0, 28, e->st));
+        }
+        k_fill_u32<<<1, 256, 0, e->st>>>(cb_start, kBins + 1, 0xFFFFFFFFu);
+        k_bin_bounds<<<nblk(nch, 256), 256, 0, e->st>>>(C.key_out, nch, cb_start);
+        k_cta_map<<<1, 32, 0, e->st>>>(cb_start, C.key_out, nch, cb_lo, cb_hi, cb_first, cta_threads);
+        k_cta_keys<<<nblk(ch_slots, 256), 256, 0, e->st>>>(C.key_out, cb_lo, cb_first, ch_slots, cb_key, cb_id, cta_threads);
+        {
+          size_t tmp = 0;
+          CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, cb_key, cb_key_s, cb_id, cb_order, (int)ch_slots, 0, 21, e->st));
+          CK(e->d_cub_tmp.ensure(tmp + 256));
+          tmp = e->d_cub_tmp.cap;
+          CK(cub::DeviceRadixSort::SortPairs(e->d_cub_tmp.p, tmp, cb_key, cb_key_s, cb_id, cb_order, (int)ch_slots, 0, 21, e->st));
+        }
+        SegArgs CA = SA;
+        CA.cta_order = cb_order;
+        CA.cta_first = cb_first;
+        CA.bin_lo = cb_lo;
+        CA.bin_hi = cb_hi;
+        if (qs) k_chain_chunk<<<ch_slots, kSimThreads, kQsSmemBytes, e->st>>>(CA, C);
+        else k_chain_chunk_err<<<ch_slots, kErrThreads, e->er_smem_bar_off + 16, e->st>>>(CA, C, e->er_smem_bar_off);
+        e->launches += 6;
+      }
       CK(cudaEventRecord(e->ev_seg[0], e->st));
       seg_timed = true;
       if (qs) {
@@ -1280,7 +1336,7 @@ void pbsim_cuda_destroy(pbsim_engine *e) {
                     &e->d_seg_bins, &e->d_set_start, &e->d_set_rprefix, &e->d_set_plus, &e->d_set_ids, &e->d_set_idstart,
                     &e->d_set_ssp_ends, &e->d_set_ssp_mod, &e->d_set_first, &e->gz[0].reads, &e->gz[0].maf, &e->gz[1].reads,
                     &e->gz[1].maf, &e->d_gz_tables, &e->d_gz_hist, &e->d_gz_usize, &e->d_gz_ucrc, &e->d_gz_uoff,
-                    &e->d_lay, &e->d_tile_sub};
+                    &e->d_lay, &e->d_tile_sub, &e->d_chunk, &e->d_chunk_bins};
   for (DevBuf *b : bufs) b->release();
   for (auto &a : e->h_stage)
     for (auto &b : a) b.release();
@@ -1343,6 +1399,7 @@ int pbsim_cuda_set_model(pbsim_engine *e, const pbsim_model *m) {
     CK(cudaFuncSetAttribute(k_sim_errhmm<PBSIM_RNG_PHILOX>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     CK(cudaFuncSetAttribute(k_sim_errhmm<PBSIM_RNG_REPLAY>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     CK(cudaFuncSetAttribute(k_sim_seg_err, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CK(cudaFuncSetAttribute(k_chain_chunk_err, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   }
   // emission constants
   e->emitp.pass_num = (uint32_t)m->pass_num;
@@ -1626,9 +1683,9 @@ int pbsim_cuda_set_option(pbsim_engine *e, const char *name, int64_t value) {
     e->seg_enabled = value != 0;
     return 0;
   }
-  if (!strcmp(name, "couple_min_len")) {
-    if (value < (int64_t)PB_TILE) return fail(e, PBSIM_E_INVALID, "couple_min_len must be at least %u", PB_TILE);
-    e->couple_min_len = value;
+  if (!strcmp(name, "chain_chunk")) {
+    if (value < 1 || value > 65536) return fail(e, PBSIM_E_INVALID, "chain_chunk must be 1..65536 segments");
+    e->chain_chunk = value;
     return 0;
   }
   if (!strcmp(name, "seg_min_len")) {

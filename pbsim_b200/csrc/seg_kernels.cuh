@@ -36,14 +36,35 @@ __global__ void k_seg_fill(Batch B, SegBatch S, uint32_t pass_num) {
   if (hi == lo) return;
   const uint32_t meta = B.plan_meta[s / pass_num];
   const uint32_t acc = meta & 0xFFu;
-  // segments that recover their start state by backward coupling (not the first segment, not reads served by the
-  // chain-only prepass) get the odd bin of their accuracy: CTAs, and so warps, are all-coupling or coupling-free
-  // (mixed warps pay the coupling loop at a quarter of their lanes)
-  const uint32_t couples = ((meta >> 12) & 1u) ? 0u : 1u;
   for (uint64_t i = lo; i < hi; ++i) {
     S.seg_sub[i] = s;
-    S.seg_key_in[i] = (acc << 21) | ((i > lo ? couples : 0u) << 20);
+    S.seg_key_in[i] = acc << 21;
     S.seg_id_in[i] = (uint32_t)i;
+  }
+}
+
+// ---- chain chunks: the threads that recover the HMM state in front of every segment -------------------------------
+struct ChunkBatch {
+  uint32_t n_chunks, per_chunk;   // per_chunk: segments walked by one chunk (reads of sticky chains: all of them)
+  const uint64_t *chunk_off;      // [n_sub + 1] exclusive scan of Batch::nchunk
+  uint32_t *sub, *key_in, *key_out, *id_in, *order;
+};
+
+__global__ void k_chunk_fill(Batch B, ChunkBatch C, uint32_t pass_num) {
+  const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= B.n_sub) return;
+  const uint64_t lo = C.chunk_off[s], hi = C.chunk_off[s + 1];
+  if (hi == lo) return;
+  const uint32_t acc = B.plan_meta[s / pass_num] & 0xFFu;
+  const uint32_t nseg = B.nseg[s];
+  const uint32_t per = (hi - lo == 1u) ? nseg : C.per_chunk;
+  for (uint64_t i = lo; i < hi; ++i) {
+    // longest walk first inside an accuracy (the same key layout as the sequential schedule)
+    const uint32_t k_from = (uint32_t)(i - lo) * per, k_to = min(k_from + per, nseg - 1u);
+    const uint32_t work = k_to - k_from + (k_from > 0u ? 1u : 0u);
+    C.sub[i] = s;
+    C.key_in[i] = (acc << 21) | (0xFFFFFu - min(work, 0xFFFFFu));
+    C.id_in[i] = (uint32_t)i;
   }
 }
 
@@ -92,27 +113,16 @@ __global__ void __launch_bounds__(kSimThreads) k_sim_seg(SegArgs A) {
   T.thr = reinterpret_cast<const QsThr *>(smem + kQsSmemThr);
   T.thr_hp = A.M.qs_thr_hp;
   T.qc_prob = reinterpret_cast<const double *>(smem + kQsSmemProb);
-  QsSegAux X;
-  X.tmod = smem + QsBlobLayout::tmod_off;
-  X.emodv = smem + QsBlobLayout::emodv_off;
-  X.reach = ae.reach;
   uint32_t row = 0, mod = ae.init_mod, emod = 1;
   SegResult res;
   res.n_entries = 0; res.ref_adv = 0; res.nsub = 0; res.ndel = 0; res.flags = 0; res.prob = 0.0;
   bool ok = true;
-  if (k > 0 && ae.has_model) {
-    if ((A.B.plan_meta[r] >> 12) & 1u) {  // recorded by the chain-only prepass
-      const uint32_t t = A.S.seg_state[seg];
-      row = t & 0xFFFFu;
-      mod = (t >> 16) & 0xFFu;
-      emod = t >> 24;
-    } else if (A.max_window != 0u) {
-      ok = qshmm_segment_start(T, X, A.keys, read_id, pass, k * PB_TILE, ae.seg_ok, row, mod, emod);
-    }
+  if (k > 0 && ae.has_model) {  // recorded by k_chain_chunk
+    const uint32_t t = A.S.seg_state[seg];
+    row = t & 0xFFFFu;
+    mod = (t >> 16) & 0xFFu;
+    emod = t >> 24;
   }
-  // the coupling loops leave the lanes of a warp at different points; without an explicit reconvergence the
-  // compiler keeps them apart for the whole segment loop (ncu: 13.7 of 32 threads active per instruction)
-  __syncwarp();
   if (!ok) {
     res.flags = 2u;
   } else {
@@ -120,6 +130,124 @@ __global__ void __launch_bounds__(kSimThreads) k_sim_seg(SegArgs A) {
     qshmm_simulate_segment(T, A.keys, read_id, pass, k * PB_TILE, k == 0, row, mod, emod, ev, res);
   }
   A.S.seg_res[seg] = res;
+}
+
+// One thread per chain chunk (qshmm): exact state at the chunk's first position by backward coupling (init draw at
+// position 0), then the chain-only walk through the chunk's segments; k_sim_seg reads the recorded states.
+__global__ void __launch_bounds__(kSimThreads) k_chain_chunk(SegArgs A, ChunkBatch C) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint32_t acc, lo, hi;
+  if (!cta_assignment(A.cta_order, A.cta_first, A.bin_lo, A.bin_hi, &acc, &lo, &hi)) return;
+  const AccEntry ae = A.M.acc[acc];
+  uint64_t *bar = reinterpret_cast<uint64_t *>(smem + kQsSmemBar);
+  if (threadIdx.x == 0) mbar_init(bar, 1);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(bar, ae.blob_bytes);
+    tma_bulk_g2s(smem, A.M.blob + ae.blob_off, ae.blob_bytes, bar);
+  }
+  mbar_wait(bar, 0);
+  const uint32_t i = lo + threadIdx.x;
+  if (i >= hi) return;
+  const uint32_t id = C.order[i];
+  const uint32_t s = C.sub[id];
+  const uint32_t c = id - (uint32_t)C.chunk_off[s];
+  const uint32_t n_ch = (uint32_t)(C.chunk_off[s + 1] - C.chunk_off[s]);
+  const uint32_t r = s / A.M.pass_num, pass = s % A.M.pass_num;
+  const uint32_t read_id = (uint32_t)(A.B.first_read + 1u + r);
+  const uint32_t nseg = A.B.nseg[s];
+  const uint32_t per = n_ch == 1u ? nseg : C.per_chunk;   // a one-chunk read is walked whole
+  const uint32_t k_from = c * per, k_to = min(k_from + per, nseg - 1u);
+  QsView T;
+  T.t2 = reinterpret_cast<const uint32_t *>(smem + QsBlobLayout::t2_off);
+  T.emis = smem + QsBlobLayout::emis_off;
+  T.freq = smem;
+  T.has_model = ae.has_model;
+  T.init_mod = ae.init_mod;
+  T.freq_mod = ae.freq_mod;
+  T.thr = nullptr;
+  T.thr_hp = nullptr;
+  T.qc_prob = nullptr;
+  uint32_t *rec = A.S.seg_state + A.S.seg_off[s];
+  uint32_t row = 0, mod = ae.init_mod, emod = 1;
+  if (k_from > 0u) {
+    QsSegAux X;
+    X.tmod = smem + QsBlobLayout::tmod_off;
+    X.emodv = smem + QsBlobLayout::emodv_off;
+    X.reach = ae.reach;
+    qshmm_segment_start(T, X, A.keys, read_id, pass, k_from * PB_TILE, ae.seg_ok ? ae.seg_ok : 512u, row, mod, emod);
+  }
+  // the coupling loops leave the lanes of a warp at different points: reconverge before the walk
+  __syncwarp();
+  qshmm_chain_range(T, A.keys, read_id, pass, row, mod, emod, k_from, k_to, rec);
+}
+
+// the same for errhmm: chunk 0 walks from column 0 (the init row is drawn until a read base exists, :3853)
+__global__ void __launch_bounds__(kErrThreads) k_chain_chunk_err(SegArgs A, ChunkBatch C, uint32_t smem_bar_off) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint32_t acc, lo, hi;
+  if (!cta_assignment(A.cta_order, A.cta_first, A.bin_lo, A.bin_hi, &acc, &lo, &hi)) return;
+  const AccEntry ae = A.M.acc[acc];
+  uint64_t *bar = reinterpret_cast<uint64_t *>(smem + smem_bar_off);
+  const uint32_t edel_bytes = ((ae.nstates + 1u) * 2u + 15u) / 16u * 16u;
+  if (threadIdx.x == 0) mbar_init(bar, 1);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(bar, ae.blob_bytes + edel_bytes);
+    tma_bulk_g2s(smem, A.M.blob + ae.blob_off, ae.blob_bytes, bar);
+    tma_bulk_g2s(smem + ae.blob_bytes, A.M.er_bias + ae.bias_off, edel_bytes, bar);
+  }
+  mbar_wait(bar, 0);
+  const uint32_t i = lo + threadIdx.x;
+  if (i >= hi) return;
+  const uint32_t id = C.order[i];
+  const uint32_t s = C.sub[id];
+  const uint32_t c = id - (uint32_t)C.chunk_off[s];
+  const uint32_t n_ch = (uint32_t)(C.chunk_off[s + 1] - C.chunk_off[s]);
+  const uint32_t r = s / A.M.pass_num, pass = s % A.M.pass_num;
+  const uint32_t read_id = (uint32_t)(A.B.first_read + 1u + r);
+  const uint32_t nseg = A.B.nseg[s];
+  const uint32_t per = n_ch == 1u ? nseg : C.per_chunk;
+  const uint32_t k_from = c * per, k_to = min(k_from + per, nseg - 1u);
+  ErView T;
+  uint32_t t2o, emo, emodo;
+  er_blob_bytes(ae.nstates, &t2o, &emo, &emodo);
+  T.t2 = reinterpret_cast<const uint16_t *>(smem + t2o);
+  T.emis = smem + emo;
+  T.emod = reinterpret_cast<const uint16_t *>(smem + emodo);
+  T.edel = reinterpret_cast<const uint16_t *>(smem + ae.blob_bytes);
+  T.edel_hp = A.M.er_bias + ae.bias_off + (ae.nstates + 1u);
+  T.init_mod = ae.init_mod;
+  T.mode = ae.mode;
+  T.rate_mag = ae.rate_mag;
+  HpProbe hp;
+  const uint32_t meta = A.B.plan_meta[r];
+  hp.enabled = (meta >> 9) & 1u;
+  hp.win.ascii = A.G.ascii;
+  hp.win.hp4 = A.G.hp4;
+  hp.win.offset = A.B.plan_off[r];
+  hp.win.wlen = A.B.plan_wlen[r];
+  hp.win.minus = (meta >> 8) & 1u;
+  hp.xm = A.G.xm;
+  hp.bias_one = A.bias_one;
+  uint32_t *rec = A.S.seg_state + A.S.seg_off[s];
+  uint32_t state = 0, mod = ae.init_mod;
+  bool pzero = true;
+  if (k_from == 0u) {  // exact walk from column 0, leading deletions included
+    errhmm_state_at(T, A.keys, hp, read_id, pass, k_to * PB_TILE, state, mod, pzero, rec);
+    return;
+  }
+  // tmod[] sits behind emod[] in the blob
+  errhmm_segment_start(T, T.emod + (ae.nstates + 1u), ae.reach, A.keys, hp, read_id, pass, k_from * PB_TILE,
+                       ae.seg_ok ? ae.seg_ok : 512u, state, mod, pzero);
+  __syncwarp();
+  if (pzero) {
+    // no read base before the chunk (a read that starts with thousands of deletions): walk from column 0; the
+    // states in front of this chunk's segments are the only ones written twice, with the same values
+    errhmm_state_at(T, A.keys, hp, read_id, pass, k_to * PB_TILE, state, mod, pzero, rec);
+    return;
+  }
+  errhmm_chain_range(T, A.keys, read_id, pass, state, mod, k_from * PB_TILE, k_to * PB_TILE, rec);
 }
 
 // One WARP per segmented sub-read.  Same result as qshmm_finish_segmented (sim_core.cuh, the sequential
@@ -307,29 +435,12 @@ __global__ void __launch_bounds__(kErrThreads) k_sim_seg_err(SegArgs A, uint32_t
   uint32_t state = 0, mod = ae.init_mod;
   bool pzero = true;
   bool ok = true;
-  if (k > 0) {
-    if ((A.B.plan_meta[r] >> 12) & 1u) {  // recorded by the chain-only prepass
-      const uint32_t t = A.S.seg_state[seg];
-      state = t & 63u;
-      mod = (t >> 6) & 0x3FFu;
-      pzero = (t >> 31) != 0u;
-    } else {
-      HpProbe hp;
-      const uint32_t meta = A.B.plan_meta[r];
-      hp.enabled = (meta >> 9) & 1u;
-      hp.win.ascii = A.G.ascii;
-      hp.win.hp4 = A.G.hp4;
-      hp.win.offset = A.B.plan_off[r];
-      hp.win.wlen = A.B.plan_wlen[r];
-      hp.win.minus = (meta >> 8) & 1u;
-      hp.xm = A.G.xm;
-      hp.bias_one = A.bias_one;
-      // tmod[] sits behind emod[] in the blob
-      errhmm_segment_start(T, T.emod + (ae.nstates + 1u), ae.reach, A.keys, hp, read_id, pass, k * PB_TILE, ae.seg_ok, state,
-                           mod, pzero);
-    }
+  if (k > 0) {  // recorded by k_chain_chunk_err
+    const uint32_t t = A.S.seg_state[seg];
+    state = t & 63u;
+    mod = (t >> 6) & 0x3FFu;
+    pzero = (t >> 31) != 0u;
   }
-  __syncwarp();
   SegResult res;
   if (!ok) {
     res.n_entries = 0; res.ref_adv = 0; res.nsub = 0; res.ndel = 0; res.flags = 2u; res.prob = 0.0;

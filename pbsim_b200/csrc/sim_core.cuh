@@ -672,15 +672,16 @@ PB_HD bool qshmm_segment_start(const QsView &T, const QsSegAux &A, const PhiloxK
 // Chain-only prepass for accuracies whose chain does not couple quickly (sticky states): advance just the state
 // chain over the read (one Philox block per 4 positions, one table lookup per position) and record the packed
 // table entry (row | modulus << 16 | emission modulus << 24) in front of every segment k >= 1.
-PB_HD void qshmm_chain_only(const QsView &T, const PhiloxKeys &K, uint32_t read_id, uint32_t pass, uint32_t n_seg,
-                            uint32_t *seg_state) {
-  uint32_t row = 0, mod = T.init_mod, emod = 1;
+// chain-only walk over segments k_from .. k_to-1 from the state (row, mod, emod) that enters segment k_from; records
+// the packed table entry in front of segments k_from+1 .. k_to.  The lookups form one dependent chain (table entry
+// -> next row); the Philox block of the NEXT four positions does not depend on it and is computed alongside, so
+// that the chain never waits for its draws.
+PB_HD void qshmm_chain_range(const QsView &T, const PhiloxKeys &K, uint32_t read_id, uint32_t pass, uint32_t row,
+                             uint32_t mod, uint32_t emod, uint32_t k_from, uint32_t k_to, uint32_t *seg_state) {
   const uint32_t c1 = pass << 16;
-  // the lookups form one dependent chain (table entry -> next row); the Philox block of the NEXT four positions
-  // does not depend on it and is computed alongside, so that the chain never waits for its draws
   uint32_t nx[4];
-  philox_block_keys(K, 0u, c1, read_id, 2u, nx);
-  for (uint32_t k = 1; k < n_seg; ++k) {
+  philox_block_keys(K, (k_from * PB_TILE) >> 2, c1, read_id, 2u, nx);
+  for (uint32_t k = k_from + 1u; k <= k_to; ++k) {
     for (uint32_t p = (k - 1u) * PB_TILE; p < k * PB_TILE; p += 4u) {
       const uint32_t cw[4] = {nx[0], nx[1], nx[2], nx[3]};
       philox_block_keys(K, (p >> 2) + 1u, c1, read_id, 2u, nx);
@@ -694,6 +695,11 @@ PB_HD void qshmm_chain_only(const QsView &T, const PhiloxKeys &K, uint32_t read_
     }
     seg_state[k] = row | (mod << 16) | (emod << 24);
   }
+}
+
+PB_HD void qshmm_chain_only(const QsView &T, const PhiloxKeys &K, uint32_t read_id, uint32_t pass, uint32_t n_seg,
+                            uint32_t *seg_state) {
+  if (n_seg > 1u) qshmm_chain_range(T, K, read_id, pass, 0u, T.init_mod, 1u, 0u, n_seg - 1u, seg_state);
 }
 
 // simulate positions [p_start, p_start + PB_TILE) of a read, unbounded in the reference direction.
@@ -1038,6 +1044,26 @@ PB_HD void errhmm_state_at(const ErView &T, const PhiloxKeys &K, const HpProbe &
   state_out = state;
   mod_out = mod;
   pzero_out = pzero;
+}
+
+// transition rows only (a read base exists): columns [c_from, c_to), both multiples of PB_TILE; records the state in
+// front of every segment boundary passed
+PB_HD void errhmm_chain_range(const ErView &T, const PhiloxKeys &K, uint32_t read_id, uint32_t pass, uint32_t state,
+                              uint32_t mod, uint32_t c_from, uint32_t c_to, uint32_t *rec) {
+  const uint32_t c1 = pass << 16;
+  uint32_t nx[4];
+  philox_block_keys(K, c_from >> 2, c1, read_id, 2u, nx);
+  for (uint32_t c = c_from; c + 4u <= c_to; c += 4u) {
+    const uint32_t w4[4] = {nx[0], nx[1], nx[2], nx[3]};
+    philox_block_keys(K, (c >> 2) + 1u, c1, read_id, 2u, nx);
+#pragma unroll
+    for (uint32_t u = 0; u < 4u; ++u) {
+      const uint32_t t = T.t2[state * PB_ER_ROW + mulhi32(w4[u], mod)];
+      state = t & 63u;
+      mod = t >> 6;
+    }
+    if (((c + 4u) & (PB_TILE - 1u)) == 0u) rec[(c + 4u) / PB_TILE] = state | (mod << 6);
+  }
 }
 
 // Chain-only prepass (sticky chains): states in front of every segment k >= 1

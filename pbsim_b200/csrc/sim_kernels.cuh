@@ -81,6 +81,7 @@ struct Batch {
   uint64_t *ck_off;
   uint32_t *nent, *rlen, *ncol, *nsub, *nins, *ndel, *flags, *draws_used;
   uint32_t *nseg;          // segments provisioned (0: the sub-read runs on the sequential pass-1 path)
+  uint32_t *nchunk;        // chain chunks: threads of k_chain_chunk that recover the states in front of its segments
   double *accuracy;
 };
 
@@ -98,7 +99,7 @@ __device__ __forceinline__ ReadPlan plan_any(const PlanTables &T, Draw &d, const
 __global__ void k_plan(DeviceModel M, DeviceGenome G, DeviceSet S, RngParams rng, Batch B, int64_t clip_room,
                        uint32_t cap_num, uint32_t cap_den, uint32_t ev_align, uint32_t seg_min_len /* 0: segments off */,
                        float seg_extra /* extra segment headroom learnt from earlier batches */,
-                       uint32_t couple_min_len /* shorter reads take the chain-only prepass */) {
+                       uint32_t chain_chunk /* segments per chain chunk */) {
   const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= B.n_reads) return;
   PlanTables T;
@@ -157,12 +158,11 @@ __global__ void k_plan(DeviceModel M, DeviceGenome G, DeviceSet S, RngParams rng
   const bool errm = M.method == PBSIM_METHOD_ERRHMM;
   const bool segmented = seg_min_len != 0u && rng.mode == PBSIM_RNG_PHILOX && (!slow || M.uniform_bias) && ae.valid &&
                          p.wlen >= seg_min_len && !(errm && ae.mode == 3u);
-  // chains with sticky states do not couple quickly (and errhmm never uses coupling): their segment start states
-  // come from a chain-only prepass that the sequential kernel runs for them (they keep their place in its schedule)
-  // Which way a segment learns its start state: backward coupling costs a window per SEGMENT (a quarter to a half
-  // of the segment for typical chains), the prepass one cheap pass per READ but sequentially.  Reads up to 32 k
-  // positions take the prepass (its critical path is short), longer reads coupling where the chain allows it.
-  const bool needs_chain = segmented && (errm || ae.has_model) && (!ae.seg_ok || p.wlen < couple_min_len);
+  // The HMM state in front of every segment comes from a chain-only pass (k_chain_chunk): a thread per CHUNK of
+  // chain_chunk segments starts from the exact state recovered by backward coupling at the chunk's first position
+  // (position 0: the init draw) and walks just the state chain through the chunk.  Chains with sticky states do not
+  // couple quickly: their reads are one chunk.
+  const bool needs_chain = segmented && (errm || ae.has_model);
   const uint32_t nseg = segmented ? qshmm_segments_for(p.wlen, ae.rho * (1.0f + seg_extra)) : 0u;
   B.plan_meta[r] = p.acc | (minus << 8) | ((slow ? 1u : 0u) << 9) | ((ae.valid ? 0u : 1u) << 10) |
                    ((segmented ? 1u : 0u) << 11) | ((needs_chain ? 1u : 0u) << 12);
@@ -171,10 +171,13 @@ __global__ void k_plan(DeviceModel M, DeviceGenome G, DeviceSet S, RngParams rng
   if (segmented) cap = (uint64_t)nseg * (errm ? PB_TILE : PB_SEG_STRIDE) + 64u;
   cap = (cap + ev_align - 1u) / ev_align * ev_align;
   const uint32_t ckc = segmented ? nseg + 2u : (uint32_t)(cap / PB_TILE) + 2u;
+  uint32_t nchunk = 0;
+  if (needs_chain && nseg > 1u) nchunk = ae.seg_ok ? (nseg - 1u + chain_chunk - 1u) / chain_chunk : 1u;
   for (uint32_t h = 0; h < M.pass_num; ++h) {
     const uint32_t s = r * M.pass_num + h;
+    B.nchunk[s] = nchunk;
     // segmented sub-reads get the out-of-range bin kBins: the sequential schedule skips them
-    B.key_in[s] = (segmented && !needs_chain) ? ((uint32_t)kBins << 20)
+    B.key_in[s] = segmented ? ((uint32_t)kBins << 20)
                             : ((p.acc << 21) | ((slow ? 1u : 0u) << 20) | (0xFFFFFu - (p.wlen > 0xFFFFFu ? 0xFFFFFu : p.wlen)));
     B.idx_in[s] = s;
     B.cap[s] = (uint32_t)cap;
@@ -386,11 +389,6 @@ __global__ void __launch_bounds__(kSimThreads) k_sim_qshmm(SimArgs A) {
   win.wlen = wlen;
   win.minus = (meta >> 8) & 1u;
   const bool slow = (meta >> 9) & 1u;
-  if (RNG_MODE == PBSIM_RNG_PHILOX && ((meta >> 12) & 1u)) {
-    // chain-only prepass: this sub-read is simulated by k_sim_seg, which needs the state in front of every segment
-    qshmm_chain_only(T, A.keys, (uint32_t)(A.B.first_read + 1u + r), pass, A.B.nseg[s], A.seg_state + A.seg_off[s]);
-    return;
-  }
   QsSink sink;
   sink.init(reinterpret_cast<uint16_t *>(A.ev) + A.B.ev_off[s], A.ck + A.B.ck_off[s], A.B.cap[s]);
   SubreadResult res;
@@ -467,16 +465,6 @@ __global__ void __launch_bounds__(kErrThreads) k_sim_errhmm(SimArgs A, uint32_t 
   win.wlen = wlen;
   win.minus = (meta >> 8) & 1u;
   const bool slow = (meta >> 9) & 1u;
-  if (RNG_MODE == PBSIM_RNG_PHILOX && ((meta >> 12) & 1u)) {
-    // chain-only prepass for the segment-parallel path (seg_kernels.cuh)
-    HpProbe hp;
-    hp.enabled = slow ? 1u : 0u;
-    hp.win = win;
-    hp.xm = A.G.xm;
-    hp.bias_one = A.bias_one;
-    errhmm_chain_only(T, A.keys, hp, (uint32_t)(A.B.first_read + 1u + r), pass, A.B.nseg[s], A.seg_state + A.seg_off[s]);
-    return;
-  }
   ErSink sink;
   sink.init(A.ev + A.B.ev_off[s], A.ck + A.B.ck_off[s], A.B.cap[s]);
   SubreadResult res;
