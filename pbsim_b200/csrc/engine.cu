@@ -544,7 +544,8 @@ int run_batch(pbsim_engine *e, uint32_t n_reads, int64_t clip_room, BatchResult 
     rng.starts = e->d_starts.as<int64_t>();
   }
 
-  bool use_segments = !replay && e->seg_enabled && clip_room < 0;
+  // (the single, quota-clipped read of a tail batch is segmented too: on one thread a 50 kb read takes milliseconds)
+  bool use_segments = !replay && e->seg_enabled;
   int seg_retries = 0;
   for (int attempt = 0; attempt < 9; ++attempt) {
     // ---- K1 plan
