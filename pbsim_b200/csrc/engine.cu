@@ -1056,6 +1056,7 @@ int produce_one(pbsim_engine *e, int set, pbsim_engine::BatchItem *it) {
     float ms = 0;
     CK(cudaEventElapsedTime(&ms, e->ev0, e->ev1));
     e->gen_ms += ms;
+    if (getenv("PBSIM_DEBUG")) fprintf(stderr, "[pbsim] batch of %lld reads took %.3f ms on the device\n", (long long)nb, ms);
     if (gz) {
       CK(cudaEventElapsedTime(&ms, e->ev_gz[0], e->ev_gz[1]));
       e->gz_ms += ms;

@@ -322,3 +322,43 @@ def test_long_read_roundtrip_properties_at_scale(eng):
         nins += refrow.count(b"-")
     assert total == st.res_len_total >= 3 * n
     assert ndel == st.res_del_num and nins == st.res_ins_num
+
+
+@pytest.mark.parametrize("name", ["qs_rsii_basic", "qs_hp11_uniform", "qs_delheavy_uniform", "err_onthq_basic",
+                                  "err_sequel_hiacc", "err_sequel_multipass"])
+def test_one_segment_chain_chunks_equal_oracle(eng, name):
+    """chain_chunk = 1 and seg_min_len = 1024: every segment's entry state comes from a backward coupling of its own
+    (sticky chains: from the whole-read walk); bytes must still equal the oracle's"""
+    c = Case(name)
+    out, _ = c.run_oracle("philox")
+    eng.set_option("seg_min_len", 1024)
+    eng.set_option("chain_chunk", 1)
+    try:
+        res = run_case_on_gpu(c, eng, "philox")
+    finally:
+        eng.set_option("seg_min_len", 2048)
+        eng.set_option("chain_chunk", 32)
+    for i, ((reads, maf, st, text), o) in enumerate(zip(res, out), start=1):
+        assert reads == o["reads"], "reads differ from the oracle, seq %d" % i
+        assert maf == o["maf"], "maf differs from the oracle, seq %d" % i
+        assert text == o["stats_text"]
+
+
+def test_long_errhmm_reads_in_several_chunks_equal_oracle(eng):
+    """errhmm reads of 150 k columns: five chain chunks each (coupling at 32 k-column boundaries), accuracies below
+    and above the model's range included"""
+    from tests.golden_util import model_path
+    from oracle import refrun as R
+    okw = dict(len_mean=150000.0, len_sd=0.0, len_max=1000000)
+    contigs = R.synth_genome(41, [("e1", 2000000)], n_runs=3, hp_plants=20)
+    o = O.Oracle("errhmm", model_path("ERRHMM-ONT-HQ.model"), **okw)
+    o.rng_philox(23)
+    o.set_sequence(contigs[0][1], 1)
+    want_reads, want_maf, want_st = o.simulate_wgs(3.0)
+    hm = capi.HostModel(capi.load(), capi.host_params("errhmm", **okw), model_path("ERRHMM-ONT-HQ.model"))
+    run = simulator.WgsRun(eng, hm, 3.0)
+    reads, maf, st, text = run.simulate_sequence(contigs[0][1], 1, rng_mode=capi.RNG_PHILOX, seed=23)
+    assert st.res_num >= 40
+    assert reads == want_reads
+    assert maf == want_maf
+    assert text == O.format_stats(want_st, 1)
