@@ -536,6 +536,28 @@ __device__ __forceinline__ void emit_tile_fast(const uint8_t *__restrict__ evbas
     // ---- reference bases this lane may need: window positions Rr .. Rr+3 (+ deletions, fetched on demand)
 #pragma unroll
     for (uint32_t k = 0; k < kEmitPerLane; ++k) {
+      if (METHOD == PBSIM_METHOD_ERRHMM) {
+        // errhmm: an entry is one alignment column, a deletion included, so a deleted column takes the same
+        // straight-line path as a base (no per-entry deletion loop, which runs at 2 of 32 lanes)
+        if (isb[k] | nd[k]) {
+          const uint32_t g = minus ? offset + wlen - 1u - Rr : offset + Rr;
+          const uint32_t gc = (__ldg(&pk[g >> 4]) >> ((g & 15u) * 2u)) & 3u;
+          const uint32_t col = minus ? ncol - 1u - Cc : Cc;
+          if (isb[k]) {
+            const uint32_t rc = lut_s[(kind[k] << 5) | (info[k] << 2) | (gc ^ flip)];
+            put_read_base<BAM>(seq, qual, Pp, code_char(rc), 1u << rc, 0u, false);
+            mread[col] = code_char(rc ^ flip);
+            mref[col] = (kind[k] == PB_KIND_INS) ? (uint8_t)'-' : code_char(gc);
+            ++Pp;
+          } else {
+            mread[col] = '-';
+            mref[col] = code_char(gc);
+          }
+          ++Cc;
+          Rr += adv[k] + nd[k];
+        }
+        continue;
+      }
       if (isb[k]) {
         const uint32_t g = minus ? offset + wlen - 1u - Rr : offset + Rr;
         const uint32_t gc = (__ldg(&pk[g >> 4]) >> ((g & 15u) * 2u)) & 3u;
