@@ -62,8 +62,8 @@ WORKLOADS = {
 }
 
 # DRAM traffic rate (dram__bytes_read.sum + dram__bytes_write.sum over gpu__time_duration.sum, GB/s) of the two big
-# kernels from the committed ncu captures profiles/r01_k_sim_seg_c3_v11.txt / r01_k_emit_c3_v11.txt
-NCU_DRAM_GBS = {("qshmm", "seg"): 423.2, ("qshmm", "emit"): 1496.0,
+# kernels from the committed ncu captures profiles/r01_k_sim_seg_c3_v17.txt / r01_k_emit_c3_v17.txt
+NCU_DRAM_GBS = {("qshmm", "seg"): 567.0, ("qshmm", "emit"): 1602.6,
                 # profiles/r01_k_sim_seg_err_c2_v13.txt / r01_k_emit_c2_v13.txt
                 ("errhmm", "seg"): 366.7, ("errhmm", "emit"): 1385.7}
 
@@ -502,7 +502,7 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak if peak else None, "traffic": traffic,
                          "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch of that "
-                                           "kernel / its duration, GB/s (ncu --set full, profiles/r01_k_*_c3_v11.txt, *_c2_v13.txt)",
+                                           "kernel / its duration, GB/s (ncu --set full, profiles/r01_k_*_c3_v17.txt, *_c2_v13.txt)",
                          "kernel": dom_name + ", rank 0",
                          "algorithmic_bytes_per_base": ALGO_BYTES_PER_BASE, "peak_source": peak_src,
                          "kernel_seconds": {"sim": sim_s, "of_which_" + seg_name: seg_s, "emit": emit_s,
