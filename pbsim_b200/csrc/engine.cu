@@ -610,11 +610,8 @@ int run_batch(pbsim_engine *e, uint32_t n_reads, int64_t clip_room, BatchResult 
     if (n_seg_total > 0) CK(e->d_seg.ensure((size_t)n_seg_total * (6 * 4 + sizeof(SegResult)) + 256));
     // ---- K2 / K3 pass 1
     SimArgs A;
-    A.seg_off = (const uint64_t *)seg_off;
     A.bias_one = e->d_biasone.as<uint8_t>();
     A.plan_draws = e->strategy == PBSIM_STRATEGY_TRANS ? 3u : (e->strategy == PBSIM_STRATEGY_TEMPL ? 1u : 0u);
-    A.seg_state = n_seg_total > 0 ? reinterpret_cast<uint32_t *>(e->d_seg.as<SegResult>() + n_seg_total) + 5ull * n_seg_total
-                                  : nullptr;
     A.keys.init(rng.seed, (uint32_t)e->seq_num);
     A.M = M;
     A.G = G;
@@ -682,7 +679,6 @@ int run_batch(pbsim_engine *e, uint32_t n_reads, int64_t clip_room, BatchResult 
       SA.bin_lo = sb_lo;
       SA.bin_hi = sb_hi;
       SA.ev = e->d_ev.as<uint8_t>();
-      SA.max_window = getenv("PBSIM_EXPERIMENT_NOCOUPLE") ? 0u : 4096u;  // timing experiment only: wrong states
       if (n_chunk_total > 0) {
         // ---- chain-only pass: the HMM state in front of every segment (k_chain_chunk), scheduled like the segments
         const uint32_t nch = (uint32_t)n_chunk_total;

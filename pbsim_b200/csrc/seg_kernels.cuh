@@ -25,7 +25,7 @@ struct SegBatch {
   uint32_t *seg_id_in;
   uint32_t *seg_order;       // segments sorted by accuracy
   SegResult *seg_res;        // [n_seg_total] indexed by segment id
-  uint32_t *seg_state;       // [n_seg_total] chain state in front of a segment (chain-only prepass; sticky chains)
+  uint32_t *seg_state;       // [n_seg_total] chain state in front of a segment (recorded by k_chain_chunk)
 };
 
 // thread per sub-read: write its segments' descriptors
@@ -77,7 +77,6 @@ struct SegArgs {
   SegBatch S;
   const uint32_t *cta_order, *cta_first, *bin_lo, *bin_hi;
   uint8_t *ev;
-  uint32_t max_window;
 };
 
 // shared memory: [table blob | thr 94*16 | qc_prob 94*8 | mbarrier]  (same layout as k_sim_qshmm)

@@ -151,8 +151,7 @@ __global__ void k_plan(DeviceModel M, DeviceGenome G, DeviceSet S, RngParams rng
   B.plan_off[r] = p.offset;
   B.plan_wlen[r] = p.wlen;
   B.plan_raw[r] = p.raw_len;
-  // segment-parallel pass 1: PHILOX qshmm reads that never need the genome in pass 1, long enough, and whose
-  // accuracy's chain couples fast (AccEntry::seg_ok)
+  // segment-parallel pass 1: PHILOX-mode reads of at least seg_min_len positions
   // (reads touching exceptional blocks qualify too in the default bias mode: k_find_end repairs their deletion
   // runs with the exact reference offset, pass 2 re-derives choices on non-ACGT bases)
   const bool errm = M.method == PBSIM_METHOD_ERRHMM;
@@ -304,8 +303,6 @@ struct SimArgs {
   RngParams rng;
   Batch B;
   const uint32_t *cta_order, *cta_first, *bin_lo, *bin_hi;
-  const uint64_t *seg_off;  // segment-parallel pass 1: first segment of a sub-read
-  uint32_t *seg_state;      // ... and the chain state in front of every segment (chain-only prepass)
   const uint8_t *bias_one;  // [12] hp_del_bias[h] == 1
   uint32_t plan_draws;      // replay: planner draws in front of pass 0 (0: WGS, 2 or 3; trans 3; templ 1)
   uint8_t *ev;   // event arena
