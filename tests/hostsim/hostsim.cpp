@@ -26,6 +26,10 @@ static int use_fast = 1, use_seg = 0, seg_min_len = 2048;
 static long seg_reads = 0, seg_fallbacks = 0;
 extern "C" void hostsim_use_fast(int v) { use_fast = v; }
 extern "C" void hostsim_use_segments(int v, int min_len) { use_seg = v; seg_min_len = min_len; }
+// > 0: the states in front of the segments come from chain chunks of this many segments, as k_chain_chunk computes
+// them (coupling at the chunk's first position, then the chain-only walk); 0: coupling per segment / whole-read walk
+static int chain_chunk = 0;
+extern "C" void hostsim_set_chain_chunk(int g) { chain_chunk = g; }
 extern "C" long hostsim_seg_reads() { return seg_reads; }
 extern "C" long hostsim_seg_fallbacks() { return seg_fallbacks; }
 
@@ -41,11 +45,24 @@ static bool run_segmented(const pb::QsView &T, const pb::QsSegAux &A, uint32_t s
   std::vector<uint16_t> slots((size_t)n_seg * PB_SEG_STRIDE + 16, 0);
   std::vector<pb::SegResult> seg(n_seg);
   std::vector<uint32_t> seg_state(n_seg + 1, 0);
-  if (T.has_model && !seg_ok) pb::qshmm_chain_only(T, K, read_id, pass, n_seg, seg_state.data());
+  bool from_chunks = false;
+  if (T.has_model && chain_chunk > 0 && n_seg > 1) {  // k_chain_chunk
+    const uint32_t n_ch = seg_ok ? (n_seg - 1u + (uint32_t)chain_chunk - 1u) / (uint32_t)chain_chunk : 1u;
+    const uint32_t per = n_ch == 1u ? n_seg : (uint32_t)chain_chunk;
+    for (uint32_t c = 0; c < n_ch; ++c) {
+      const uint32_t k_from = c * per, k_to = std::min(k_from + per, n_seg - 1u);
+      uint32_t row = 0, mod = T.init_mod, emod = 1;
+      if (k_from > 0) pb::qshmm_segment_start(T, A, K, read_id, pass, k_from * PB_TILE, first_window ? first_window : 512u, row, mod, emod);
+      pb::qshmm_chain_range(T, K, read_id, pass, row, mod, emod, k_from, k_to, seg_state.data());
+    }
+    from_chunks = true;
+  } else if (T.has_model && !seg_ok) {
+    pb::qshmm_chain_only(T, K, read_id, pass, n_seg, seg_state.data());
+  }
   for (uint32_t k = 0; k < n_seg; ++k) {
     uint32_t row = 0, mod = T.init_mod, emod = 1;
     if (k > 0 && T.has_model) {
-      if (!seg_ok) {
+      if (!seg_ok || from_chunks) {
         row = seg_state[k] & 0xFFFFu; mod = (seg_state[k] >> 16) & 0xFFu; emod = seg_state[k] >> 24;
       } else if (!pb::qshmm_segment_start(T, A, K, read_id, pass, k * PB_TILE, first_window, row, mod, emod)) {
         return false;
@@ -222,14 +239,34 @@ long hostsim_run(const pbsim_model *m, const uint8_t *ascii_upper, const int16_t
           K.init(seed, (uint32_t)seq_num);
           const uint32_t n_seg = pb::qshmm_segments_for(plan.wlen, ae.rho);
           std::vector<uint32_t> seg_state(n_seg + 1, 0);
-          if (!ae.seg_ok) pb::errhmm_chain_only(T, K, hpp, (uint32_t)read_id, (uint32_t)pass, n_seg, seg_state.data());
+          bool from_chunks = false;
+          if (chain_chunk > 0 && n_seg > 1) {  // k_chain_chunk_err
+            const uint32_t n_ch = ae.seg_ok ? (n_seg - 1u + (uint32_t)chain_chunk - 1u) / (uint32_t)chain_chunk : 1u;
+            const uint32_t per = n_ch == 1u ? n_seg : (uint32_t)chain_chunk;
+            for (uint32_t c = 0; c < n_ch; ++c) {
+              const uint32_t k_from = c * per, k_to = std::min(k_from + per, n_seg - 1u);
+              uint32_t st = 0, md = T.init_mod;
+              bool pz = true;
+              if (k_from == 0) {
+                pb::errhmm_state_at(T, K, hpp, (uint32_t)read_id, (uint32_t)pass, k_to * PB_TILE, st, md, pz, seg_state.data());
+                continue;
+              }
+              pb::errhmm_segment_start(T, T.emod + (ae.nstates + 1u), ae.reach, K, hpp, (uint32_t)read_id, (uint32_t)pass,
+                                       k_from * PB_TILE, ae.seg_ok ? ae.seg_ok : 512u, st, md, pz);
+              if (pz) pb::errhmm_state_at(T, K, hpp, (uint32_t)read_id, (uint32_t)pass, k_to * PB_TILE, st, md, pz, seg_state.data());
+              else pb::errhmm_chain_range(T, K, (uint32_t)read_id, (uint32_t)pass, st, md, k_from * PB_TILE, k_to * PB_TILE, seg_state.data());
+            }
+            from_chunks = true;
+          } else if (!ae.seg_ok) {
+            pb::errhmm_chain_only(T, K, hpp, (uint32_t)read_id, (uint32_t)pass, n_seg, seg_state.data());
+          }
           std::vector<uint8_t> slots((size_t)n_seg * PB_TILE + 16, 0);
           std::vector<pb::SegResult> seg(n_seg);
           bool couple_fail = false;
           for (uint32_t k = 0; k < n_seg; ++k) {
             uint32_t st = k == 0 ? 0u : (seg_state[k] & 63u), md = k == 0 ? T.init_mod : ((seg_state[k] >> 6) & 0x3FFu);
             bool pz = k == 0 ? true : (seg_state[k] >> 31) != 0;
-            if (k > 0 && ae.seg_ok) {
+            if (k > 0 && ae.seg_ok && !from_chunks) {
               pb::errhmm_segment_start(T, T.emod + (ae.nstates + 1u), ae.reach, K, hpp, (uint32_t)read_id, (uint32_t)pass,
                                        k * PB_TILE, ae.seg_ok, st, md, pz);
             }

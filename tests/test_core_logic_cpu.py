@@ -185,3 +185,22 @@ def test_start_position_table_equals_oracle():
     ends[ends == 0xFFFF] = -1
     assert np.array_equal(ends[1:], o_ends[1:])
     assert np.array_equal(mod[1:], o_mod[1:])
+
+
+@pytest.mark.parametrize("chunk", [1, 2, 32])
+@pytest.mark.parametrize("name", ["qs_rsii_basic", "qs_hp11_uniform", "err_onthq_basic", "err_sequel_hiacc"])
+def test_chain_chunks_give_the_oracle_bytes(name, chunk):
+    """the states in front of the segments as k_chain_chunk recovers them (coupling at a chunk's first position,
+    chain-only walk through the chunk), run on the host with chunks of 1, 2 and 32 segments"""
+    c = Case(name)
+    L = H.lib()
+    L.hostsim_use_segments(1, 1025)
+    L.hostsim_set_chain_chunk(chunk)
+    try:
+        out, res = _replay_case(c, "philox")
+    finally:
+        L.hostsim_use_segments(0, 2048)
+        L.hostsim_set_chain_chunk(0)
+    for (reads, maf, sub), oref in zip(res, out):
+        assert reads == oref["reads"]
+        assert maf == oref["maf"]
