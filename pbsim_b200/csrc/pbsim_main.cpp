@@ -63,6 +63,8 @@ struct Options {
   int gpu = 0;
   std::string rng = "philox", replay_draws, replay_marks;
   int threads = 0;
+  int rank = 0, world = 1;   // one process per GPU: process `rank` of `world` simulates the sequences n with
+                             // (n - 1) % world == rank (their output files are independent of everything else)
   std::string gzip = "gpu";  // who writes the gzip members: the GPU (gz_kernels.cuh) or zlib threads on the host
 };
 
@@ -265,7 +267,7 @@ std::vector<RefSeq> genome_inf(const Options &o) {
       seqs.push_back(r);
       char name[4096];
       snprintf(name, sizeof name, "%s_%04zu.ref", o.prefix.c_str(), seqs.size());
-      out = fopen(name, "w");
+      out = fopen(o.rank == 0 ? name : "/dev/null", "w");  // one writer of the .ref files is enough
       if (!out) die("ERROR: Cannot open output file: %s\n", name);
       setvbuf(out, nullptr, _IOFBF, 8 << 20);
       while (ret != 1) {  // header longer than the buffer: skip its continuation
@@ -436,6 +438,8 @@ void print_help() {
           "  --replay-draws       int32 log of the reference's rand() draws (replay mode).\n"
           "  --replay-marks       int64 draw count after every (read, pass) (replay mode).\n"
           "  --threads            compression threads (hardware concurrency).\n"
+          "  --rank R --world N   one process per GPU: this process simulates the sequences n with (n-1) %% N == R\n"
+          "                       (WGS; every process reads the whole genome, files are written per sequence).\n"
           "  --gzip               gpu (default): gzip members / BGZF blocks are written on the GPU (multi-pass\n"
           "                       output is <prefix>_NNNN.bam) | host: zlib threads (multi-pass: .sam.gz).\n\n"
           " [options for transcriptome / template sequencing]\n\n"
@@ -476,7 +480,7 @@ int main(int argc, char **argv) {
       // engine-only
       {"gpu", 1, nullptr, 0},        {"rng", 1, nullptr, 0},            {"replay-draws", 1, nullptr, 0},
       {"replay-marks", 1, nullptr, 0}, {"threads", 1, nullptr, 0},      {"gzip", 1, nullptr, 0},
-      {nullptr, 0, nullptr, 0}};
+      {"rank", 1, nullptr, 0},       {"world", 1, nullptr, 0},          {nullptr, 0, nullptr, 0}};
   int opt, idx = 0;
   while ((opt = getopt_long(argc, argv, "", long_options, &idx)) != -1) {
     if (opt != 0) exit(-1);
@@ -567,6 +571,8 @@ int main(int argc, char **argv) {
       case 25: o.replay_draws = a; break;
       case 26: o.replay_marks = a; break;
       case 27: o.threads = atoi(a); break;
+      case 29: o.rank = atoi(a); break;
+      case 30: o.world = atoi(a); break;
       case 28:
         if (!strcmp(a, "gpu") || !strcmp(a, "host")) o.gzip = a;
         else die("ERROR (gzip: %s): Acceptable value: gpu, host.\n", a);
@@ -590,6 +596,9 @@ int main(int argc, char **argv) {
   if (o.set_flg[14]) o.accuracy_max = int(o.accuracy_max * 100) * 0.01;
   if (o.set_flg[19]) o.accuracy_mean = int(o.accuracy_mean * 100) * 0.01;
   if (o.len_min > o.len_max) die("ERROR: length min(%ld) is greater than max(%ld).\n", o.len_min, o.len_max);
+  if (o.world < 1 || o.rank < 0 || o.rank >= o.world) die("ERROR: --rank must be in 0..world-1.\n");
+  if (o.world > 1 && (o.strategy != "wgs" || o.rng == "replay"))
+    die("ERROR: --world > 1 shards the sequences of --strategy wgs in philox mode; shard a transcript table by read range through the library instead.\n");
   if (o.method == "sample")
     die("ERROR: this B200 driver builds --method qshmm|errhmm; %s/%s is not built yet.\n", o.strategy.c_str(),
         o.method.c_str());
@@ -812,7 +821,8 @@ int main(int argc, char **argv) {
   for (size_t n = 1; n <= seqs.size(); ++n) {
     int64_t f[12];
     const int64_t glen = ingest(n, bias, f);
-    hp11_running += f[11];
+    hp11_running += f[11];  // every process ingests every sequence: the aliased cell depends on all earlier ones
+    if ((int)((n - 1) % (size_t)o.world) != o.rank) continue;
     double b[12];
     memcpy(b, bias, sizeof b);
     memcpy(&b[0], &hp11_running, sizeof(double));  // the cell genome.hpfreq[11] aliases in the reference build

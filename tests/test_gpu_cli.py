@@ -116,3 +116,15 @@ def test_cli_host_gzip_writes_sam_text_for_multipass(tmp_path):
         got = gzip.open(tmp_path / ("out_%04d.sam.gz" % i), "rb").read()
         assert got == gzip.open(os.path.join(c.dir, "seq%d.reads.gz" % i), "rb").read()
         assert gzip.open(tmp_path / ("out_%04d.maf.gz" % i), "rb").read() == c.maf(i)
+
+
+def test_cli_two_processes_shard_the_sequences(tmp_path):
+    """--rank / --world: one process per GPU, sequences dealt round-robin; the union of the two processes' files
+    equals the files of a single process (here both run on the one GPU)"""
+    c = Case("qs_rsii_quirks")  # three contigs, homopolymers >= 11 (the aliased bias cell runs across sequences)
+    out, _ = c.run_oracle("philox")
+    for rank in (0, 1):
+        _run_cli(c, tmp_path, ["--rank", str(rank), "--world", "2"])
+    for i, o in enumerate(out, start=1):
+        assert gzip.open(tmp_path / ("out_%04d.fq.gz" % i), "rb").read() == o["reads"]
+        assert gzip.open(tmp_path / ("out_%04d.maf.gz" % i), "rb").read() == o["maf"]
