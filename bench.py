@@ -272,6 +272,8 @@ def main():
     ap.add_argument("--len-mean", type=float, default=None, help="diagnostics: override --length-mean")
     ap.add_argument("--batch-bases", type=float, default=None, help="diagnostics: engine target_batch_bases")
     ap.add_argument("--chain-chunk", type=int, default=None, help="diagnostics: engine chain_chunk (segments per chunk)")
+    ap.add_argument("--first-batch-div", type=int, default=None, help="diagnostics: engine first_batch_div")
+    ap.add_argument("--host-batch-bases", type=float, default=None, help="diagnostics: engine host_batch_bases")
     ap.add_argument("--bam", action="store_true", help="multi-pass workloads: BAM records / BGZF blocks instead of SAM text")
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload])
@@ -312,6 +314,10 @@ def main():
         eng.set_option("target_batch_bases", int(args.batch_bases))
     if args.chain_chunk:
         eng.set_option("chain_chunk", args.chain_chunk)
+    if args.first_batch_div:
+        eng.set_option("first_batch_div", args.first_batch_div)
+    if args.host_batch_bases:
+        eng.set_option("host_batch_bases", int(args.host_batch_bases))
     if args.bam:
         eng.set_option("bam", 1)
         wl["name"] += " [BAM records]"

@@ -241,6 +241,7 @@ struct pbsim_engine {
   cudaEvent_t ev_gz[2] = {nullptr, nullptr}, ev_seg[2] = {nullptr, nullptr};
   int pipeline = 1;                 // option "pipeline": 0 off, 1 host delivery only, 2 always
   int64_t host_batch_bases = (int64_t)1 << 30;  // option: batch size of pipelined host delivery
+  int64_t first_batch_div = 1;                  // option: the first batch of a pipelined run can be made this much smaller (measured: no gain)
   bool mode_set = false, mode_to_host = false, pipelined = false;
   std::thread producer;
   std::mutex mu;
@@ -1016,7 +1017,8 @@ int produce_one(pbsim_engine *e, int set, pbsim_engine::BatchItem *it) {
         int64_t target = (e->pipelined && e->mode_to_host) ? std::min(e->target_batch_bases, e->host_batch_bases)
                                                            : e->target_batch_bases;
         // the first batch of a pipelined run is the only one whose generation nothing hides: keep it short
-        if (e->pipelined && e->mode_to_host && e->reads_done_in_run == 0) target = std::max<int64_t>(target / 4, 1 << 26);
+        if (e->pipelined && e->mode_to_host && e->reads_done_in_run == 0 && e->first_batch_div > 1)
+          target = std::max<int64_t>(target / e->first_batch_div, 1 << 26);
         nb = (int64_t)((double)target / (mean * e->model.pass_num));
         nb = std::max<int64_t>(nb, 1 << 12);
         nb = std::min<int64_t>(nb, 1 << 22);
@@ -1705,6 +1707,11 @@ int pbsim_cuda_set_option(pbsim_engine *e, const char *name, int64_t value) {
   if (!strcmp(name, "deflate")) {
     if (e->running) return fail(e, PBSIM_E_INVALID, "deflate cannot change during a run");
     e->deflate = value != 0;
+    return 0;
+  }
+  if (!strcmp(name, "first_batch_div")) {
+    if (value < 1 || value > 64) return fail(e, PBSIM_E_INVALID, "first_batch_div must be 1..64");
+    e->first_batch_div = value;
     return 0;
   }
   if (!strcmp(name, "host_batch_bases")) {
