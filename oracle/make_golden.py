@@ -214,6 +214,42 @@ def main():
             json.dump(case, f, indent=1, sort_keys=True)
         print("golden set", name, {k: len(v) for k, v in plain["files"].items()}, "draws", len(logged["draws"]))
 
+    # command-line validation: what the reference prints and returns for invocations it rejects before simulating
+    # (set_sim_param :1451-1688, get_genome_inf :896-991, the file openers); the driver must say the same
+    import shutil
+    import tempfile
+    work = tempfile.mkdtemp(prefix="pbsim_cli_")
+    shutil.copy(os.path.join(DATA, "QSHMM-RSII.model"), os.path.join(work, "QSHMM-RSII.model"))
+    shutil.copy(os.path.join(DATA, "ERRHMM-ONT.model"), os.path.join(work, "ERRHMM-ONT.model"))
+    with open(os.path.join(work, "tiny.fa"), "w") as f:
+        f.write(">s\nACGTACGTAC\n")
+    qs = ["--strategy", "wgs", "--method", "qshmm", "--qshmm", "QSHMM-RSII.model", "--genome", "tiny.fa"]
+    cli_cases = [
+        ["--strategy", "foo"], ["--strategy", "wgs"], ["--strategy", "wgs", "--method", "qshmm"],
+        ["--strategy", "wgs", "--method", "qshmm", "--qshmm", "QSHMM-RSII.model"],
+        ["--strategy", "wgs", "--method", "bar", "--genome", "tiny.fa"],
+        ["--strategy", "wgs", "--method", "errhmm", "--genome", "tiny.fa"],
+        qs + ["--depth", "-1"], qs + ["--length-min", "500", "--length-max", "100"], qs + ["--difference-ratio", "1:2"],
+        qs + ["--difference-ratio", "0:0:0"], qs + ["--accuracy-mean", "1.5"], qs + ["--pass-num", "0"],
+        qs + ["--hp-del-bias", "0"], qs + ["--length-mean", "0"], qs + ["--length-sd", "-3"], qs + ["--length-max", "2000000"],
+        qs + ["--seed", "-5"], qs,
+        ["--strategy", "wgs", "--method", "qshmm", "--qshmm", "nofile.model", "--genome", "tiny.fa"],
+        ["--strategy", "wgs", "--method", "qshmm", "--qshmm", "QSHMM-RSII.model", "--genome", "nofile.fa"],
+        ["--strategy", "trans", "--method", "qshmm", "--qshmm", "QSHMM-RSII.model"],
+        ["--strategy", "trans", "--method", "qshmm", "--qshmm", "QSHMM-RSII.model", "--transcript", "nofile.tsv"],
+        ["--strategy", "templ", "--method", "errhmm", "--errhmm", "ERRHMM-ONT.model"],
+        ["--strategy", "templ", "--method", "errhmm", "--errhmm", "ERRHMM-ONT.model", "--template", "nofile.fa"],
+        ["--strategy", "trans", "--method", "sample", "--transcript", "nofile.tsv"],
+    ]
+    cli_out = []
+    for a in cli_cases:
+        p = subprocess.run([R.REF_BIN] + a, cwd=work, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+        cli_out.append(dict(args=a, returncode=p.returncode, stderr=p.stderr.decode(), stdout=p.stdout.decode()))
+    with open(os.path.join(GOLDEN, "cli_errors.json"), "w") as f:
+        json.dump(dict(toolchain=stamp, cases=cli_out), f, indent=1)
+    shutil.rmtree(work, ignore_errors=True)
+    print("cli error cases", len(cli_out))
+
     # distribution fixtures for the PHILOX-mode statistical parity tests: larger reference runs, reduced to
     # histograms (tests/stats_util.py) so that only a few KB are committed
     from tests import stats_util as SU

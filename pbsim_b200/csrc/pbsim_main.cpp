@@ -650,6 +650,15 @@ int main(int argc, char **argv) {
     if (strstr(err, "Cannot open")) die("ERROR: Cannot open file: %s\n", model_path.c_str());
     die("%s\n", err);
   }
+  // ---- the input files are read before the GPU is touched, in the reference's order (get_genome_inf :896 /
+  //      get_transcript_inf :1075 / get_templ_inf :1366 come right after the model): their errors and stats blocks
+  //      appear exactly where the reference prints them
+  const bool trans = o.strategy == "trans";
+  std::vector<RefSeq> seqs;
+  SeqSetHost S;
+  if (wgs) seqs = genome_inf(o);
+  else S = trans ? read_transcripts(o) : read_templates(o);
+
   pbsim_engine *eng = nullptr;
   if (pbsim_cuda_create(&eng, o.gpu) != 0) die("ERROR: %s\n", pbsim_cuda_last_error(nullptr));
   if (pbsim_cuda_set_model(eng, pbsim_host_model_get(hm)) != 0) die("ERROR: %s\n", pbsim_cuda_last_error(eng));
@@ -757,8 +766,6 @@ int main(int argc, char **argv) {
 
   if (!wgs) {
     // ---- main :760-868: the whole transcript table / template file is one run
-    const bool trans = o.strategy == "trans";
-    const SeqSetHost S = trans ? read_transcripts(o) : read_templates(o);
     std::string ids;
     std::vector<int32_t> id_start{0};
     for (const std::string &id : S.ids) {
@@ -790,8 +797,6 @@ int main(int argc, char **argv) {
     return finish();
   }
 
-  // ---- genome (get_genome_inf)
-  const std::vector<RefSeq> seqs = genome_inf(o);
 
   // ---- hp-del-bias (main :673-697)
   int64_t hp11_running = 0;

@@ -1,0 +1,41 @@
+"""CPU: the C++ driver rejects what the reference rejects, with the same message and exit status, before any GPU is
+touched.  tests/golden/cli_errors.json holds what the UNMODIFIED reference printed for 25 invocations (option
+validation of set_sim_param pbsim.cpp:1451-1688, missing files, a reference sequence shorter than 100 bases)."""
+import json
+import os
+import re
+import shutil
+import subprocess
+
+import pytest
+
+import __graft_entry__ as G
+from tests.golden_util import GOLDEN, model_path
+
+with open(os.path.join(GOLDEN, "cli_errors.json")) as f:
+    CASES = json.load(f)["cases"]
+
+
+@pytest.fixture(scope="module")
+def workdir(tmp_path_factory):
+    d = tmp_path_factory.mktemp("cli")
+    shutil.copy(model_path("QSHMM-RSII.model"), d / "QSHMM-RSII.model")
+    shutil.copy(model_path("ERRHMM-ONT.model"), d / "ERRHMM-ONT.model")
+    (d / "tiny.fa").write_text(">s\nACGTACGTAC\n")
+    return d
+
+
+def _norm(text, args):
+    if "--seed" not in args:  # the default seed is the Unix time (pbsim.cpp:253)
+        text = re.sub(r"(?m)^seed : -?\d+$", "seed : <time>", text)
+    return text
+
+
+@pytest.mark.parametrize("case", CASES, ids=[" ".join(c["args"][-3:]) for c in CASES])
+def test_driver_rejects_like_the_reference(case, workdir):
+    G.build_engine()
+    exe = G.build_driver()
+    p = subprocess.run([exe] + case["args"], cwd=workdir, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=120)
+    assert p.returncode == case["returncode"]
+    assert _norm(p.stderr.decode(), case["args"]) == _norm(case["stderr"], case["args"])
+    assert p.stdout.decode() == case["stdout"]
