@@ -39,3 +39,32 @@ def test_driver_rejects_like_the_reference(case, workdir):
     assert p.returncode == case["returncode"]
     assert _norm(p.stderr.decode(), case["args"]) == _norm(case["stderr"], case["args"])
     assert p.stdout.decode() == case["stdout"]
+
+
+@pytest.mark.parametrize("name", ["tr_qs_rsii_multipass_long", "tm_qs_rsii_quirks", "tr_err_ont_hpbias"])
+def test_driver_prints_the_reference_blocks_before_it_needs_a_gpu(name, tmp_path):
+    """without a GPU the driver stops at engine creation — after the parameter block and the transcript / template
+    statistics (get_transcript_inf :1075, get_templ_inf :1366), which must read like the reference's"""
+    import gzip
+    import torch
+    from tests.golden_util import SetCase
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: the run would continue")
+    c = SetCase(name)
+    G.build_engine()
+    exe = G.build_driver()
+    with gzip.open(os.path.join(c.dir, "input.txt.gz"), "rb") as f:
+        (tmp_path / "input.txt").write_bytes(f.read())
+    args = [exe, "--strategy", c.strategy, "--method", c.method, "--" + c.method, c.model,
+            "--transcript" if c.strategy == "trans" else "--template", "input.txt", "--seed", str(c.seed)] \
+        + list(c.meta["extra_args"]) + ["--prefix", "out"]
+    p = subprocess.run(args, cwd=tmp_path, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=120)
+    assert p.returncode != 0
+    got = p.stderr.decode()
+    assert "no CPU fallback" in got
+    head = got.split("ERROR: no usable CUDA device")[0]
+    want = c.stderr.split(":::: Simulation stats ::::")[0]
+
+    def norm(text):
+        return "\n".join(("%s : <model>" % c.method) if ln.startswith(c.method + " : ") else ln for ln in text.split("\n"))
+    assert norm(head) == norm(want)
