@@ -122,6 +122,22 @@ SET_CASES = {
 }
 
 
+# --method sample (pbsim.cpp:1694): the sample FASTQ is the reference's own output of the case named in `sample_of`
+SAMPLE_CASES = {
+    "sample_basic": dict(sample_of="qs_rsii_basic", genome=dict(seed=5, contigs=[("g1", 30000), ("g2", 900)], n_runs=3,
+                                                              hp_plants=20),
+                         depth=5, seed=3, extra=[], okw={}, pool={}),
+    # several copies per pool entry (the quality buffer is cut at the end of every read), deletion-rich, bias, filters
+    "sample_quirks": dict(sample_of="qs_rsii_basic", genome=dict(seed=6, contigs=[("g1", 25000), ("g2", 700)], n_runs=4,
+                                                               hp_plants=30, iupac=6),
+                          depth=14, seed=5,
+                          extra=["--hp-del-bias", "3", "--difference-ratio", "20:30:50", "--length-min", "300",
+                                 "--length-max", "2500", "--accuracy-min", "0.78", "--accuracy-max", "0.93"],
+                          okw=dict(hp_del_bias=3.0, ratio=(20, 30, 50), len_min=300, len_max=2500),
+                          pool=dict(len_min=300, len_max=2500, accuracy_min=0.78, accuracy_max=0.93)),
+}
+
+
 STATS_CASES = {
     "qs_rsii_len3k": ("qshmm", "QSHMM-RSII.model", ["--length-mean", "3000", "--length-sd", "2300"]),
     "err_onthq_len3k": ("errhmm", "ERRHMM-ONT-HQ.model", ["--length-mean", "3000", "--length-sd", "2300"]),
@@ -213,6 +229,50 @@ def main():
         with open(os.path.join(d, "case.json"), "w") as f:
             json.dump(case, f, indent=1, sort_keys=True)
         print("golden set", name, {k: len(v) for k, v in plain["files"].items()}, "draws", len(logged["draws"]))
+
+    for name, sc in SAMPLE_CASES.items():
+        d = os.path.join(GOLDEN, "sample", name)
+        os.makedirs(d, exist_ok=True)
+        src = os.path.join(GOLDEN, sc["sample_of"])
+        fq = b""
+        for i in range(1, 10):
+            pth = os.path.join(src, "seq%d.reads.gz" % i)
+            if os.path.exists(pth):
+                with gzip.open(pth, "rb") as f:
+                    fq += f.read()
+        sfq = os.path.join(d, "sample.fq")
+        with open(sfq, "wb") as f:
+            f.write(fq)
+        contigs = R.synth_genome(**sc["genome"])
+        fa = os.path.join(d, "genome.fa")
+        R.write_fasta(fa, contigs)
+        args = ["--strategy", "wgs", "--method", "sample", "--sample", sfq, "--genome", fa, "--depth", str(sc["depth"]),
+                "--seed", str(sc["seed"])] + sc["extra"]
+        plain = R.run_reference(args, logrand=False)
+        logged = R.run_reference(args, logrand=True)
+        assert plain["returncode"] == 0, plain["stderr"]
+        assert plain["files"] == logged["files"]
+        for i in range(1, len(contigs) + 1):
+            gz_write(os.path.join(d, "seq%d.reads.gz" % i), plain["files"]["out_%04d.fq.gz" % i])
+            gz_write(os.path.join(d, "seq%d.maf.gz" % i), plain["files"]["out_%04d.maf.gz" % i])
+        with open(fa, "rb") as f:
+            gz_write(fa + ".gz", f.read())
+        os.remove(fa)
+        os.remove(sfq)
+        with open(os.path.join(d, "stderr.txt"), "w") as f:
+            f.write(plain["stderr"].replace(fa, "genome.fa").replace(sfq, "sample.fq"))
+        np.save(os.path.join(d, "marks.npy"), logged["marks"])
+        with open(os.path.join(d, "ndraws.txt"), "w") as f:
+            f.write("%d\n" % len(logged["draws"]))
+        case = dict(name=name, method="sample", sample_of=sc["sample_of"], depth=sc["depth"], seed=sc["seed"],
+                    extra_args=sc["extra"], oracle_kwargs=sc["okw"], pool_kwargs=sc["pool"], genome_spec=sc["genome"],
+                    n_seq=len(contigs), toolchain=stamp,
+                    command="pbsim --strategy wgs --method sample --sample sample.fq --genome genome.fa --depth %s --seed %d %s"
+                            % (sc["depth"], sc["seed"], " ".join(sc["extra"])))
+        with open(os.path.join(d, "case.json"), "w") as f:
+            json.dump(case, f, indent=1, sort_keys=True)
+        print("golden sample", name, {k: len(v) for k, v in plain["files"].items() if not k.endswith(".ref")},
+              "draws", len(logged["draws"]))
 
     # command-line validation: what the reference prints and returns for invocations it rejects before simulating
     # (set_sim_param :1451-1688, get_genome_inf :896-991, the file openers); the driver must say the same

@@ -96,6 +96,7 @@ def lib():
         L.orc_rng_philox.argtypes = [C.c_void_p, C.c_uint32]
         L.orc_simulate_wgs.argtypes = [C.c_void_p, C.c_double]
         L.orc_reset_outputs.argtypes = [C.c_void_p]
+        L.orc_simulate_sample.argtypes = [C.c_void_p, C.c_double, C.c_int64, C.c_char_p, C.c_void_p]
         L.orc_simulate_set.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                        C.c_char_p, C.c_void_p]
         L.orc_get_ssp.restype = C.c_int64
@@ -152,7 +153,7 @@ class Oracle:
                  ratio=(6, 55, 39), hp_del_bias=1.0, id_prefix="S"):
         self.L = lib()
         self.h = C.c_void_p(self.L.orc_new())
-        self.method = METHOD_QS if method in ("qshmm", METHOD_QS) else METHOD_ERR
+        self.method = 3 if method == "sample" else (METHOD_QS if method in ("qshmm", METHOD_QS) else METHOD_ERR)
         self.pass_num = pass_num
         self.hp_del_bias = hp_del_bias
         if accuracy_mean_set:
@@ -162,8 +163,9 @@ class Oracle:
         self._chk(self.L.orc_set_params(self.h, self.method, pass_num, accuracy_mean, len_min, len_max, len_mean,
                                         len_sd, ratio[0], ratio[1], ratio[2], hp_del_bias,
                                         id_prefix.encode()))
-        self._chk(self.L.orc_load_model(self.h, model_path.encode()))
-        self._chk(self.L.orc_build_tables(self.h))
+        if method != "sample":  # --method sample has no model: thresholds only (set_mut)
+            self._chk(self.L.orc_load_model(self.h, model_path.encode()))
+            self._chk(self.L.orc_build_tables(self.h))
 
     def _chk(self, rc):
         if rc != 0:
@@ -248,6 +250,23 @@ class Oracle:
         self.L.orc_get_stats(self.h, C.byref(st))
         return reads, maf, st
 
+    def simulate_sample(self, depth, pool, reset=True):
+        """pool: the quality strings get_sample_inf kept (sample_pool()), in file order"""
+        if reset:
+            self.L.orc_reset_outputs(self.h)
+        quals = b"".join(pool)
+        qstart = np.zeros(len(pool) + 1, dtype=np.int64)
+        qstart[1:] = np.cumsum([len(x) for x in pool])
+        self._chk(self.L.orc_simulate_sample(self.h, depth, len(pool), quals, qstart.ctypes.data))
+        n = C.c_int64()
+        p = self.L.orc_out_reads(self.h, C.byref(n))
+        reads = C.string_at(p, n.value)
+        p = self.L.orc_out_maf(self.h, C.byref(n))
+        maf = C.string_at(p, n.value)
+        st = Stats()
+        self.L.orc_get_stats(self.h, C.byref(st))
+        return reads, maf, st
+
     def readinfo(self):
         n = C.c_int64()
         p = self.L.orc_get_readinfo(self.h, C.byref(n))
@@ -299,6 +318,28 @@ class Oracle:
         v = [C.c_int() for _ in range(4)]
         self.L.orc_model_range(self.h, *[C.byref(x) for x in v])
         return tuple(x.value for x in v)
+
+
+def sample_pool(fastq, len_min=100, len_max=1000000, accuracy_min=0.75, accuracy_max=1.0):
+    """get_sample_inf's filter (pbsim.cpp:1214-1275): the quality lines of the 4-line FASTQ records whose length
+    lies in [len_min, len_max] and whose accuracy 1 - mean(10^(-q/10)) lies in [accuracy_min, accuracy_max]."""
+    prob = [pow(10, i / -10) for i in range(94)]  # qc[i].prob (:549)
+    pool = []
+    lines = fastq.split(b"\n")
+    if lines and lines[-1] == b"":
+        lines.pop()
+    for k in range(3, len(lines), 4):
+        q = lines[k]
+        n = len(q)
+        if n < len_min or n > len_max:
+            continue
+        total = 0.0
+        for ch in q:
+            total += prob[ch - 33]
+        acc = 1.0 - (total / n)
+        if accuracy_min <= acc <= accuracy_max:
+            pool.append(q)
+    return pool
 
 
 def pack_set(seqset):

@@ -1358,6 +1358,169 @@ int64_t orc_get_ssp(int rank_max, int32_t *ends /* [(rank_max+1)*21] */, int32_t
   return rank_max;
 }
 
+/* ------------------------------------------------------------------ --method sample (no engine counterpart yet) */
+
+/* ref: simulate_by_sample inner loop :1775-1833.  The quality string of the sampled read gives the quality of
+ * every position; `len` bounds BOTH the window and the read (mut.len, :1756-1763), and no deletion is drawn once
+ * either is used up. */
+static void sample_pass(orc_ctx *c, rng_t *r, const char *q, long len, pass_out_t *po) {
+  long ref_offset = 0, read_offset = 0, maf_offset = 0, index, qv = 0, rand_value;
+  char nt;
+  po->nsub = po->nins = po->ndel = 0;
+  while ((ref_offset < len) && (read_offset < len)) {
+    d_begin(r, 0, (uint32_t)read_offset);
+    nt = c->w_seq[ref_offset];
+    qv = (int)q[read_offset] - 33;
+    c->qual[read_offset] = q[read_offset];
+    rand_value = d_w2(r, 1000000);
+    if (rand_value < c->sub_thre[qv]) {
+      po->nsub++;
+      c->read_seq[read_offset] = substitute(r, nt);
+      c->maf_ref[maf_offset] = nt;
+      ref_offset++;
+    } else if (rand_value < c->ins_thre[qv]) {
+      po->nins++;
+      index = d_choice8(r);
+      c->read_seq[read_offset] = (index >= 4) ? nt : NT4[index];
+      c->maf_ref[maf_offset] = '-';
+    } else {
+      c->read_seq[read_offset] = nt;
+      c->maf_ref[maf_offset] = nt;
+      ref_offset++;
+    }
+    c->maf_seq[maf_offset] = c->read_seq[read_offset];
+    maf_offset++;
+    read_offset++;
+    {
+      uint32_t j = 0;
+      while ((ref_offset < len) && (read_offset < len)) {
+        int hp = c->w_hp[ref_offset - 1];
+        rand_value = d_del(r, j++);
+        if (rand_value < c->del_thre[qv] * c->bias[hp]) {
+          po->ndel++;
+          c->maf_seq[maf_offset] = '-';
+          c->maf_ref[maf_offset] = c->w_seq[ref_offset];
+          maf_offset++;
+          ref_offset++;
+        } else {
+          break;
+        }
+      }
+    }
+  }
+  po->rlen = read_offset;
+  po->ncol = maf_offset;
+}
+
+/* the draw that starts pass p over the pool (ref: sample_value = rand() % sample.num_filtered, :1734) */
+static uint32_t d_pool_pass(rng_t *r, uint32_t p, uint32_t n) {
+  if (r->mode == RNG_PHILOX) {
+    uint32_t ctr[4] = {p, 0u, 0u, 3u}, w[4];
+    orc_philox4x32_10(ctr, r->key, w);
+    return mulhi32(w[0], n);
+  }
+  return stream_next(r) % n;
+}
+
+/* ref: simulate_by_sample :1694-1949.  The pool is what get_sample_inf (:1214-1275) leaves in fp_filtered: the
+ * quality strings that pass the length and accuracy filters, in file order (quals / qstart[n+1]).
+ * Quirk kept: the quality buffer is cut at the end of every read (mut.qc[read_offset] = 0, :1835) and measured again
+ * for the next copy of the same pool entry (mut.len = strlen(mut.qc), :1756): copy i+1 is as long as copy i's READ. */
+int orc_simulate_sample(orc_ctx *c, double depth, int64_t n, const char *quals, const int64_t *qstart) {
+  rng_t *r = &c->rng;
+  orc_stats_t *st = &c->st;
+  long long len_quota, len_total = 0, pool_total;
+  long sample_num, sample_interval, sample_value, sample_residue, num, i;
+  double accuracy_total = 0.0;
+  uint32_t pool_pass = 0;
+  int64_t j;
+
+  if (!c->seq) return fail(c, "no sequence");
+  if (n < 2) return fail(c, "the reference divides by zero with a pool of fewer than 2 reads (:1723)");
+  if (r->mode == RNG_PHILOX) r->key[1] = (uint32_t)c->seq_num;
+  c->set_mode = 0;
+  begin_stats(c);
+  pool_total = qstart[n];
+  len_quota = (long long)(depth * c->glen);
+  sample_num = (long)(len_quota / pool_total);
+  sample_residue = (long)(len_quota % pool_total);
+  if (sample_residue == 0) {
+    sample_interval = 1;
+  } else {
+    sample_interval = trunc_int((double)(pool_total / sample_residue) * 2 + 0.5);
+    if (sample_interval > (long)(n * 0.5)) sample_interval = (long)(n * 0.5);
+  }
+
+  while (len_total < len_quota) {
+    int64_t pass_draw = r->cur;
+    sample_value = (long)d_pool_pass(r, pool_pass++, (uint32_t)n);
+    for (j = 0; j < n; j++) {
+      const char *q = quals + qstart[j];
+      long curlen = (long)(qstart[j + 1] - qstart[j]);  /* strlen(mut.qc) after fgets + trim */
+      if (len_total >= len_quota) break;
+      num = (sample_value % sample_interval == 0) ? sample_num + 1 : sample_num;
+      sample_value++;
+      for (i = 0; i < num; i++) {
+        long len, offset, k;
+        char strand;
+        pass_out_t po;
+        orc_readinfo_t ri;
+        double prob = 0.0, value;
+        int64_t start_draw = pass_draw >= 0 ? pass_draw : r->cur;
+        if (len_total >= len_quota) break;
+        pass_draw = -1;
+        len = curlen;
+        d_plan_begin(r, (uint32_t)(st->res_num + 1));
+        if (len >= c->glen) {
+          offset = 0;
+          len = (long)c->glen;
+        } else {
+          offset = (long)d_plan_off(r, (uint64_t)(c->glen - len + 1));
+        }
+        st->res_num++;
+        strand = (st->res_num % 2 == 1) ? '+' : '-';
+        load_window(c, offset, len, strand);
+        sample_pass(c, r, q, len, &po);
+        curlen = po.rlen; /* the quirk: the buffer now ends where this read ended */
+        if (strand == '-') {
+          revcomp_n(c->maf_seq, po.ncol);
+          revcomp_n(c->maf_ref, po.ncol);
+        }
+        st->res_sub_num += po.nsub;
+        st->res_ins_num += po.nins;
+        st->res_del_num += po.ndel;
+        st->res_len_total += po.rlen;
+        len_total += po.rlen;
+        if (po.rlen < c->freq_len_n) c->freq_len[po.rlen]++;
+        if (po.rlen > st->res_len_max) st->res_len_max = po.rlen;
+        if (po.rlen < st->res_len_min) st->res_len_min = po.rlen;
+        for (k = 0; k < po.rlen; k++) prob += c->qc_prob[(int)c->qual[k] - 33];
+        value = 1.0 - (prob / po.rlen);
+        accuracy_total += value;
+        {
+          long acc_wk = trunc_int(value * 100000 + 0.5);
+          if (acc_wk >= 0 && acc_wk <= 100000) c->freq_acc[acc_wk]++;
+        }
+        /* the MAF reference row covers what was consumed (mut.seq_right = offset + ref_offset, :1847) */
+        emit_records(c, (long)st->res_num, 0, offset, po.ncol - po.nins, strand, po.rlen, po.ncol);
+        ri.read_id = st->res_num; ri.pass = 0; ri.acc = 0; ri.offset = offset; ri.wlen = len; ri.rlen = po.rlen;
+        ri.ncol = po.ncol; ri.strand = strand; ri.nsub = (int32_t)po.nsub; ri.nins = (int32_t)po.nins;
+        ri.ndel = (int32_t)po.ndel; ri.draw_start = start_draw; ri.accuracy = value;
+        push_info(c, &ri);
+        if (r->exhausted) return fail(c, "draw log exhausted");
+      }
+    }
+    sample_num = 0;
+  }
+  {
+    int keep = c->pass_num;
+    c->pass_num = 1; /* ref: means over res_num (:1923-1946) */
+    finish_stats(c, accuracy_total, c->glen);
+    c->pass_num = keep;
+  }
+  return 0;
+}
+
 /* ------------------------------------------------------------------ getters */
 const char *orc_out_reads(orc_ctx *c, int64_t *n) { *n = c->out_reads.n; return c->out_reads.p; }
 const char *orc_out_maf(orc_ctx *c, int64_t *n) { *n = c->out_maf.n; return c->out_maf.p; }

@@ -103,6 +103,10 @@ void orc_reset_outputs(orc_ctx *c);
  * expression counts of the transcript table (ignored for templates: one '+' read each). */
 int orc_simulate_set(orc_ctx *c, int strategy, int64_t n, const char *bases, const int64_t *start,
                      const int32_t *plus_exp, const int32_t *minus_exp, const char *ids, const int32_t *id_start);
+/* simulate_by_sample (pbsim.cpp:1694) for the current sequence; the pool holds the quality strings that passed
+ * get_sample_inf's filters (:1214-1275), in file order.  orc_set_params is enough (no model, no tables).
+ * The CUDA engine does not implement this method yet: the restatement pins the specification for it. */
+int orc_simulate_sample(orc_ctx *c, double depth, int64_t n, const char *quals, const int64_t *qstart);
 /* start-position table (pbsim.cpp:2504-2528) for KATs: ends[rank*21 + j-1], mod[rank], rank = 1..rank_max */
 int64_t orc_get_ssp(int rank_max, int32_t *ends, int32_t *mod);
 

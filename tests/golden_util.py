@@ -31,7 +31,7 @@ def model_path(name):
 
 def case_names():
     return sorted(d for d in os.listdir(GOLDEN)
-                  if os.path.isdir(os.path.join(GOLDEN, d)) and d not in ("models", "stats", "sets"))
+                  if os.path.isdir(os.path.join(GOLDEN, d)) and d not in ("models", "stats", "sets", "sample"))
 
 
 def gz_read(path):
@@ -170,3 +170,40 @@ class SetCase:
         return dict(reads=reads, maf=maf, stats=st, stats_text=O.format_stats_set(st), info=o.readinfo(),
                     bias=o.bias(), freq_len=o.freq_len(), freq_accuracy=o.freq_accuracy(),
                     draws_end=o.draws_consumed()), o
+
+
+def sample_case_names():
+    return sorted(os.listdir(os.path.join(GOLDEN, "sample")))
+
+
+class SampleCase:
+    """tests/golden/sample/<name>: a --method sample run of the reference; the sample FASTQ is the reference's own
+    output of another golden case (meta["sample_of"])"""
+
+    def __init__(self, name):
+        self.name = name
+        self.dir = os.path.join(GOLDEN, "sample", name)
+        with open(os.path.join(self.dir, "case.json")) as f:
+            self.meta = json.load(f)
+        self.depth = self.meta["depth"]
+        self.seed = self.meta["seed"]
+        self.okw = dict(self.meta["oracle_kwargs"])
+        if "ratio" in self.okw:
+            self.okw["ratio"] = tuple(self.okw["ratio"])
+        self.contigs = R.read_fasta(os.path.join(self.dir, "genome.fa.gz"))
+        src = os.path.join(GOLDEN, self.meta["sample_of"])
+        self.sample_fastq = b"".join(gz_read(os.path.join(src, "seq%d.reads.gz" % i))
+                                     for i in range(1, 10) if os.path.exists(os.path.join(src, "seq%d.reads.gz" % i)))
+        self.pool = O.sample_pool(self.sample_fastq, **self.meta["pool_kwargs"])
+        with open(os.path.join(self.dir, "stderr.txt")) as f:
+            self.stderr = f.read()
+        self.stats_blocks = R.split_stats_blocks(self.stderr)
+        self.marks = np.load(os.path.join(self.dir, "marks.npy"))
+        with open(os.path.join(self.dir, "ndraws.txt")) as f:
+            self.ndraws = int(f.read())
+
+    def reads(self, i):
+        return gz_read(os.path.join(self.dir, "seq%d.reads.gz" % i))
+
+    def maf(self, i):
+        return gz_read(os.path.join(self.dir, "seq%d.maf.gz" % i))

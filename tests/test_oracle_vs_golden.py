@@ -6,7 +6,7 @@ import pytest
 
 from oracle import oracle as O
 
-from tests.golden_util import Case, SetCase, case_names, set_case_names
+from tests.golden_util import Case, SampleCase, SetCase, case_names, sample_case_names, set_case_names
 
 
 @pytest.mark.parametrize("name", case_names())
@@ -65,3 +65,26 @@ def test_start_position_table_known_answers():
     assert mod[1:].tolist() == [1000] * 14
     assert all(np.all(np.diff(ends[r][ends[r] >= 0]) >= 0) for r in range(1, 15))
     assert ends[1][0] == 626 and ends[2][0] == 458 and ends[10][0] == 310  # 1 / sum_{j<=21} j^-2 = 0.6256
+
+
+@pytest.mark.parametrize("name", sample_case_names())
+def test_oracle_reproduces_reference_sample_method(name):
+    """--method sample (pbsim.cpp:1694; get_sample_inf's filter :1214-1275 restated in oracle.sample_pool): the
+    specification for the engine's next method, pinned byte for byte — including the quality buffer that is cut at
+    the end of every read, which makes copy i+1 of a pool entry as long as copy i's read"""
+    c = SampleCase(name)
+    o = O.Oracle("sample", None, **c.okw)
+    o.rng_glibc(c.seed)
+    if c.okw.get("hp_del_bias", 1.0) != 1.0:
+        o.hp_bias_prepass([s for _, s in c.contigs])
+    starts = []
+    for i, (_, s) in enumerate(c.contigs, start=1):
+        o.set_sequence(s, i)
+        reads, maf, st = o.simulate_sample(c.depth, c.pool)
+        assert reads == c.reads(i), "reads differ, seq %d" % i
+        assert maf == c.maf(i), "maf differs, seq %d" % i
+        assert O.format_stats(st, i) == c.stats_blocks[i]
+        starts.append(o.readinfo()["draw_start"])
+    assert o.draws_consumed() == c.ndraws
+    starts = np.concatenate(starts)
+    assert np.array_equal(starts[1:], c.marks[:-1])
