@@ -137,7 +137,7 @@ class Engine:
         run.len_total_start = len_total_start
         run.max_reads = max_reads
         run.batch_reads = batch_reads
-        if rng_mode == capi.RNG_REPLAY:
+        if rng_mode == capi.RNG_REPLAY and replay_draws is not None and replay_starts is not None:
             d = np.ascontiguousarray(replay_draws, dtype=np.int32)
             s = np.ascontiguousarray(replay_starts, dtype=np.int64)
             self._replay_keep = (d, s)
