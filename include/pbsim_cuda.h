@@ -38,6 +38,7 @@ extern "C" {
 
 #define PBSIM_METHOD_QSHMM  1   /* --method qshmm  (METHOD_QS,  pbsim.cpp:37) */
 #define PBSIM_METHOD_ERRHMM 2   /* --method errhmm (METHOD_ERR, pbsim.cpp:38) */
+#define PBSIM_METHOD_SAMPLE 3   /* --method sample (METHOD_SAM, pbsim.cpp:39): qualities copied from a pool of real reads */
 
 #define PBSIM_RNG_PHILOX 0      /* Philox4x32-10 keyed by (seed, sequence, read id); engine-native */
 #define PBSIM_RNG_REPLAY 1      /* consume a log of the reference's own rand() draws              */

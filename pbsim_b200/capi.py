@@ -14,6 +14,7 @@ NQV = 94
 NACC = 101
 METHOD_QSHMM = 1
 METHOD_ERRHMM = 2
+METHOD_SAMPLE = 3
 RNG_PHILOX = 0
 RNG_REPLAY = 1
 
@@ -235,7 +236,8 @@ def truncate_accuracy(x):
 def host_params(method, pass_num=1, accuracy_mean=0.85, accuracy_mean_set=False, len_min=100, len_max=1000000,
                 len_mean=9000.0, len_sd=7000.0, ratio=(6, 55, 39), id_prefix="S", **_ignored):
     p = HostParams()
-    p.method = METHOD_QSHMM if method in ("qshmm", METHOD_QSHMM) else METHOD_ERRHMM
+    p.method = (METHOD_SAMPLE if method in ("sample", METHOD_SAMPLE)
+                else METHOD_QSHMM if method in ("qshmm", METHOD_QSHMM) else METHOD_ERRHMM)
     p.pass_num = pass_num
     p.len_min, p.len_max = len_min, len_max
     p.len_mean, p.len_sd = len_mean, len_sd
@@ -252,7 +254,8 @@ class HostModel:
         self.L = L
         self.h = C.c_void_p()
         err = C.c_char_p()
-        rc = L.pbsim_host_model_load(C.byref(self.h), C.byref(params), model_path.encode(), C.byref(err))
+        rc = L.pbsim_host_model_load(C.byref(self.h), C.byref(params), model_path.encode() if model_path else None,
+                                     C.byref(err))
         if rc != 0:
             raise RuntimeError("pbsim_host_model_load: %s (%d)" % ((err.value or b"").decode(), rc))
         self.params = params

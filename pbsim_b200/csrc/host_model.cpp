@@ -316,17 +316,18 @@ int pbsim_host_model_load(pbsim_host_model **out, const pbsim_host_params *p, co
   static const char *dummy;
   if (!err) err = &dummy;
   *err = "";
-  if (!out || !p || !model_path) {
+  const bool sample = p && p->method == PBSIM_METHOD_SAMPLE;  // no model file: set_mut's thresholds only (:5471)
+  if (!out || !p || (!model_path && !sample)) {
     *err = "invalid argument";
     return PBSIM_E_INVALID;
   }
-  if (p->method != PBSIM_METHOD_QSHMM && p->method != PBSIM_METHOD_ERRHMM) {
-    *err = "method must be qshmm or errhmm";
+  if (p->method != PBSIM_METHOD_QSHMM && p->method != PBSIM_METHOD_ERRHMM && !sample) {
+    *err = "method must be qshmm, errhmm or sample";
     return PBSIM_E_INVALID;
   }
   pbsim_host_model *m = new pbsim_host_model();
   std::memset(&m->view, 0, sizeof m->view);
-  int rc = parse_model(model_path, p->method, m->raw, err);
+  int rc = sample ? 0 : parse_model(model_path, p->method, m->raw, err);
   if (rc) {
     delete m;
     return rc;
@@ -342,6 +343,11 @@ int pbsim_host_model_load(pbsim_host_model **out, const pbsim_host_params *p, co
   v.model_acc_max = m->raw.acc_max;
   static thread_local double uni_ep[kAccCells][PBSIM_NQV];
   build_thresholds(v, *p, uni_ep);
+  if (sample) {
+    v.model_acc_min = v.model_acc_max = 0;
+    *out = m;
+    return 0;
+  }
   rc = build_samplers(*m, *p, err);
   if (rc) {
     delete m;

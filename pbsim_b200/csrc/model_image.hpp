@@ -176,6 +176,7 @@ struct ModelImage {
     std::memset(acc, 0, sizeof acc);
     uint32_t bias_cells = 0;
     for (int a = 0; a < PBSIM_NACC; ++a) acc[a].table_acc = a;
+    if (method == PBSIM_METHOD_SAMPLE) return true;  // no HMM: the thresholds of apply_bias are all there is
     if (method == PBSIM_METHOD_QSHMM) {
       for (int a = m.acc_lo; a <= m.acc_hi; ++a) {
         if (a < 0 || a >= PBSIM_NACC) continue;
@@ -333,7 +334,7 @@ struct ModelImage {
     uniform_bias = true;
     for (int h = 1; h <= 10; ++h)
       if (bias[h] != 1.0) uniform_bias = false;
-    if (method == PBSIM_METHOD_QSHMM) {
+    if (method == PBSIM_METHOD_QSHMM || method == PBSIM_METHOD_SAMPLE) {
       qs_thr.assign(PBSIM_NQV * 4, 0);
       qs_thr_hp.assign(PBSIM_NQV * 12, 0);
       for (int q = 0; q < PBSIM_NQV; ++q) {

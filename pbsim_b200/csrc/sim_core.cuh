@@ -481,6 +481,91 @@ PB_HD void qshmm_simulate(const QsView &T, Draw &d, const WindowRef &win, bool s
 }
 
 // ---------------------------------------------------------------------------------------------
+// --method sample (simulate_by_sample, pbsim.cpp:1775-1833): the quality string of a sampled read gives
+// the quality of every position, so there is no chain; the per-position draws and the event stream are
+// those of qshmm.  `len` (mut.len, :1756-1763) bounds BOTH the window and the read, and no deletion is
+// drawn once either is used up.  The read's accuracy sums the error probabilities in read order (:1868).
+// ---------------------------------------------------------------------------------------------
+template <class Draw>
+PB_HD void sample_simulate(const QsView &T, Draw &d, const WindowRef &win, bool slow, uint32_t len,
+                           const uint8_t *quals, QsSink &sink, SubreadResult &res) {
+  uint32_t R = 0, P = 0, C = 0;
+  uint32_t nsub = 0, nins = 0, ndel = 0;
+  double prob = 0.0;
+  res.overflow = 0;
+  while (R < len && P < len) {
+    d.prefetch(P);
+#pragma unroll
+    for (uint32_t u = 0; u < PB_GROUP; ++u) {
+      if (R >= len || P >= len) break;
+      if (sink.full()) { res.overflow = 1; break; }
+      sink.checkpoint(C, R, P);
+      d.begin(u);
+      const uint32_t qv = (uint32_t)quals[P] - 33u;
+      prob += T.qc_prob[qv];
+      const QsThr th = T.thr[qv];
+      const uint32_t r = d.w2(1000000u);
+      const bool is_sub = r < th.sub;
+      const bool is_ins = !is_sub && r < th.ins;
+      uint32_t info;
+      if (Draw::kCounter) {
+        info = is_sub ? d.choice3() : (is_ins ? d.choice8() : 0u);
+      } else {
+        info = 0;
+        if (is_sub) info = d.choice3();
+        else if (is_ins) info = d.choice8();
+      }
+      if (slow && is_sub && win.nonacgt(R)) info = d.choice4();
+      const uint32_t kind = is_sub ? PB_KIND_SUB : (is_ins ? PB_KIND_INS : PB_KIND_MATCH);
+      nsub += is_sub ? 1u : 0u;
+      nins += is_ins ? 1u : 0u;
+      R += is_ins ? 0u : 1u;
+      ++P;
+      ++C;
+      uint32_t nd = 0;
+      while (R < len && P < len) {
+        const uint32_t rd = d.del(nd);
+        bool hit = rd < th.del;
+        if (hit) {
+          if (R == 0u) hit = rd < th.del0;
+          else if (slow) hit = rd < T.thr_hp[qv * 12u + win.hp(R - 1u)];
+        }
+        if (!hit) break;
+        ++nd;
+        ++R;
+      }
+      ndel += nd;
+      C += nd;
+      const uint32_t base = qv | (kind << 7) | (info << 9);
+      if (nd < PB_QS_DEL_SAT) {
+        sink.push(base | (nd << 12));
+      } else {
+        sink.push(base | (PB_QS_DEL_SAT << 12));
+        uint32_t rest = nd - PB_QS_DEL_SAT;
+        for (;;) {
+          if (sink.full()) { res.overflow = 1; break; }
+          sink.checkpoint(C - rest, R - rest, P);
+          const uint32_t c = rest < PB_QS_CONT_SAT ? rest : PB_QS_CONT_SAT;
+          sink.push((c & 0x7Fu) | (3u << 7) | ((c >> 7) << 9));
+          if (c < PB_QS_CONT_SAT) break;
+          rest -= PB_QS_CONT_SAT;
+        }
+        if (res.overflow) break;
+      }
+    }
+    if (res.overflow) break;
+  }
+  sink.flush();
+  res.n_entries = sink.n;
+  res.rlen = P;
+  res.ncol = C;
+  res.nsub = nsub;
+  res.nins = nins;
+  res.ndel = ndel;
+  res.accuracy = 1.0 - (prob / (double)P);
+}
+
+// ---------------------------------------------------------------------------------------------
 // qshmm fast path: PHILOX draws, reads that never need the genome in pass 1 (not `slow`).
 // Same results as qshmm_simulate<PhiloxDraw> entry for entry, except that the stream is padded with
 // no-op entries (continuation entries with count 0) to a multiple of PB_GROUP, which lets every group of

@@ -42,8 +42,9 @@ def _read_bases(kind, info, nt):
     return rb
 
 
-def expand_qshmm(ev, genome_upper, offset, wlen, minus):
-    """ev: uint16 entries.  Returns (seq, qual, maf_ref, maf_read) as uint8 arrays."""
+def expand_qshmm(ev, genome_upper, offset, wlen, minus, partial=False):
+    """ev: uint16 entries.  Returns (seq, qual, maf_ref, maf_read) as uint8 arrays.
+    partial: --method sample, where a read may end before its window is used up"""
     ev = np.asarray(ev, dtype=np.uint16).astype(np.int64)
     kind = (ev >> 7) & 3
     cont = kind == 3
@@ -57,7 +58,7 @@ def expand_qshmm(ev, genome_upper, offset, wlen, minus):
     R = np.cumsum(ref_adv) - ref_adv
     Ccol = np.cumsum(col_adv) - col_adv
     ncol = int(col_adv.sum())
-    assert int(ref_adv.sum()) == wlen, (int(ref_adv.sum()), wlen)
+    assert int(ref_adv.sum()) == wlen or (partial and int(ref_adv.sum()) < wlen), (int(ref_adv.sum()), wlen)
     W = window(genome_upper, offset, wlen, minus)
     b = np.nonzero(is_base)[0]
     nt = W[R[b]]

@@ -10,6 +10,7 @@
 
 #include "../../include/pbsim_cuda.h"
 #include "../../pbsim_b200/csrc/model_image.hpp"
+#include "../../pbsim_b200/csrc/sample_plan.hpp"
 #include "../../pbsim_b200/csrc/sim_core.cuh"
 
 struct HostSimOut {
@@ -317,6 +318,107 @@ long hostsim_run(const pbsim_model *m, const uint8_t *ascii_upper, const int16_t
       g_out.accuracy.push_back(res.accuracy);
       if (pass == 0) len_total += res.rlen;
     }
+  }
+  return (long)(g_out.info.size() / 12);
+}
+
+// --method sample: the engine's schedule (sample_plan.hpp: groups of copies, batches, the quota cut in read order)
+// and per-read core (sample_simulate), run sequentially.  Replay mode consumes the log in order, which is the order
+// the groups are walked in.
+long hostsim_run_sample(const pbsim_model *m, const uint8_t *ascii_upper, const int16_t *hp, long glen, int seq_num,
+                        const double bias[12], int rng_mode, uint32_t seed, const int32_t *draws, long ndraws,
+                        long long len_quota, long n, const uint8_t *quals, const int64_t *qstart, long batch_reads) {
+  pb::ModelImage img;
+  if (!img.build(*m)) { fprintf(stderr, "hostsim: %s\n", img.error.c_str()); return -1; }
+  img.apply_bias(*m, bias);
+  std::vector<uint8_t> hp4((size_t)glen / 2 + 2, 0);
+  for (long i = 0; i < glen; ++i) hp4[i >> 1] |= (uint8_t)((hp[i] & 15) << ((i & 1) * 4));
+  std::vector<uint8_t> exc((size_t)glen, 0);
+  for (long i = 0; i < glen; ++i) {
+    const uint8_t c = ascii_upper[i];
+    exc[i] = !(c == 'A' || c == 'C' || c == 'G' || c == 'T') || (bias[hp[i] & 15] != 1.0);
+  }
+  g_out = HostSimOut();
+  pb::QsView T;
+  std::memset(&T, 0, sizeof T);
+  T.thr = reinterpret_cast<const pb::QsThr *>(img.qs_thr.data());
+  T.thr_hp = img.qs_thr_hp.data();
+  T.qc_prob = m->qc_prob;
+  pb::SampleSchedule S;
+  if (!S.init(len_quota, n, qstart)) return -3;
+  long long len_total = 0;
+  long reads_done = 0;
+  int64_t cursor = 0;
+  while (len_total < len_quota) {
+    bool first_of_pass = false;
+    if (!S.pass_open) {
+      if (rng_mode == PBSIM_RNG_PHILOX) S.open_pass(pb::SampleSchedule::philox_value(seed, (uint32_t)seq_num, S.pass, (uint32_t)n));
+      else S.open_pass((cursor < ndraws ? draws[cursor] : 0) % n);
+      first_of_pass = true;
+    }
+    pb::SampleGroups G;
+    pb::sample_collect(S, batch_reads > 0 ? batch_reads : 1000, 1ll << 40, &G);
+    const size_t info0 = g_out.info.size() / 12;
+    for (size_t g = 0; g < G.entry.size(); ++g) {
+      const uint32_t j = G.entry[g];
+      uint32_t len = (uint32_t)(qstart[j + 1] - qstart[j]);
+      for (uint32_t i = G.first[g]; i < G.first[g + 1]; ++i) {
+        const long read_id = reads_done + 1 + i;
+        pb::PhiloxDraw pd;
+        pb::ReplayDraw rd;
+        const int64_t draw_start = cursor;
+        uint32_t offset = 0;
+        if (rng_mode == PBSIM_RNG_PHILOX) {
+          pd.ph.k0 = seed; pd.ph.k1 = (uint32_t)seq_num; pd.read_id = (uint32_t)read_id; pd.pass = 0;
+          pd.plan_begin();
+          if (len >= (uint32_t)glen) len = (uint32_t)glen; else offset = pd.plan_off((uint32_t)glen - len + 1u);
+        } else {
+          rd.log = draws; rd.cur = cursor + ((first_of_pass && i == 0) ? 1 : 0); rd.end = ndraws; rd.start = cursor;
+          if (len >= (uint32_t)glen) len = (uint32_t)glen; else offset = rd.plan_off((uint32_t)glen - len + 1u);
+        }
+        const uint32_t minus = (read_id % 2 == 0);
+        pb::WindowRef win;
+        win.ascii = ascii_upper; win.hp4 = hp4.data(); win.offset = offset; win.wlen = len; win.minus = minus;
+        bool slow = !img.uniform_bias;
+        for (uint32_t k = 0; k < len && !slow; ++k) slow = exc[offset + k];
+        const uint32_t cap = len * 2 + 4096;
+        const size_t ck_base = g_out.ckpts.size();
+        g_out.ckpts.resize(ck_base + cap / PB_TILE + 2);
+        size_t ev_off = (g_out.events.size() + 15) / 16 * 16;
+        g_out.events.resize(ev_off + (size_t)cap * 2);
+        pb::QsSink sink;
+        sink.init(reinterpret_cast<uint16_t *>(g_out.events.data() + ev_off), g_out.ckpts.data() + ck_base, cap);
+        pb::SubreadResult res;
+        if (rng_mode == PBSIM_RNG_PHILOX) pb::sample_simulate(T, pd, win, slow, len, quals + qstart[j], sink, res);
+        else { pb::sample_simulate(T, rd, win, slow, len, quals + qstart[j], sink, res); cursor = rd.cur; }
+        g_out.events.resize(ev_off + (size_t)res.n_entries * 2);
+        g_out.ckpts.resize(ck_base + (res.n_entries + PB_TILE - 1) / PB_TILE);
+        int64_t rec[12] = {read_id, 0, 0, (int64_t)offset, (int64_t)len, (int64_t)res.rlen, (int64_t)res.ncol,
+                           (int64_t)minus, (int64_t)res.n_entries, (int64_t)ev_off, draw_start, (int64_t)res.overflow};
+        g_out.info.insert(g_out.info.end(), rec, rec + 12);
+        g_out.ck_off.push_back((int64_t)ck_base);
+        g_out.counts.push_back(res.nsub); g_out.counts.push_back(res.nins); g_out.counts.push_back(res.ndel);
+        g_out.accuracy.push_back(res.accuracy);
+        len = res.rlen;  // the next copy is as long as this read (:1835, :1756)
+      }
+    }
+    // the quota test in front of every read (:1747, :1753), in read order
+    const size_t nb = g_out.info.size() / 12 - info0;
+    size_t keep = nb;
+    for (size_t r = 0; r < nb; ++r) {
+      if (len_total >= len_quota) { keep = r; break; }
+      len_total += g_out.info[(info0 + r) * 12 + 5];
+    }
+    if (keep < nb) {
+      g_out.info.resize((info0 + keep) * 12);
+      g_out.counts.resize((info0 + keep) * 3);
+      g_out.accuracy.resize(info0 + keep);
+      g_out.ck_off.resize(info0 + keep);
+      break;
+    }
+    reads_done += (long)nb;
+    S.j = G.j_end;
+    if (S.j >= S.n) S.next_pass();
   }
   return (long)(g_out.info.size() / 12);
 }

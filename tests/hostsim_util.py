@@ -11,7 +11,7 @@ from tests import expand
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 SRC = [os.path.join(HERE, "hostsim", "hostsim.cpp"), os.path.join(ROOT, "pbsim_b200", "csrc", "host_model.cpp")]
-DEPS = SRC + [os.path.join(ROOT, "pbsim_b200", "csrc", f) for f in ("sim_core.cuh", "model_image.hpp")] + [
+DEPS = SRC + [os.path.join(ROOT, "pbsim_b200", "csrc", f) for f in ("sim_core.cuh", "model_image.hpp", "sample_plan.hpp")] + [
     os.path.join(ROOT, "include", "pbsim_cuda.h")]
 LIB = os.path.join(HERE, "hostsim", "libhostsim.so")
 
@@ -29,6 +29,10 @@ def lib():
         L.hostsim_run.argtypes = [C.POINTER(capi.Model), C.c_void_p, C.c_void_p, C.c_long, C.c_int,
                                   C.POINTER(C.c_double), C.c_int, C.c_uint32, C.c_void_p, C.c_long,
                                   C.c_longlong, C.c_long]
+        L.hostsim_run_sample.restype = C.c_long
+        L.hostsim_run_sample.argtypes = [C.POINTER(capi.Model), C.c_void_p, C.c_void_p, C.c_long, C.c_int,
+                                         C.POINTER(C.c_double), C.c_int, C.c_uint32, C.c_void_p, C.c_long,
+                                         C.c_longlong, C.c_long, C.c_char_p, C.c_void_p, C.c_long]
         L.hostsim_info.restype = C.POINTER(C.c_int64)
         L.hostsim_counts.restype = C.POINTER(C.c_uint32)
         L.hostsim_accuracy.restype = C.POINTER(C.c_double)
@@ -38,8 +42,9 @@ def lib():
     return _lib
 
 
-def run(model, genome_upper, hp, seq_num, bias, rng_mode, seed, draws, len_quota, max_reads=0):
-    """Returns list of per-subread dicts with the event stream attached."""
+def run(model, genome_upper, hp, seq_num, bias, rng_mode, seed, draws, len_quota, max_reads=0, pool=None,
+        batch_reads=0):
+    """Returns list of per-subread dicts with the event stream attached.  pool: --method sample, the quality strings"""
     L = lib()
     g = np.frombuffer(genome_upper, dtype=np.uint8)
     hp = np.ascontiguousarray(hp, dtype=np.int16)
@@ -47,8 +52,16 @@ def run(model, genome_upper, hp, seq_num, bias, rng_mode, seed, draws, len_quota
     if draws is None:
         draws = np.zeros(1, dtype=np.int32)
     draws = np.ascontiguousarray(draws, dtype=np.int32)
-    n = L.hostsim_run(model.ptr, g.ctypes.data, hp.ctypes.data, len(g), seq_num, b, rng_mode, seed,
-                      draws.ctypes.data, len(draws), int(len_quota), max_reads)
+    if pool is not None:
+        quals = b"".join(pool)
+        qstart = np.zeros(len(pool) + 1, dtype=np.int64)
+        qstart[1:] = np.cumsum([len(x) for x in pool])
+        n = L.hostsim_run_sample(model.ptr, g.ctypes.data, hp.ctypes.data, len(g), seq_num, b, rng_mode, seed,
+                                 draws.ctypes.data, len(draws), int(len_quota), len(pool), quals, qstart.ctypes.data,
+                                 batch_reads)
+    else:
+        n = L.hostsim_run(model.ptr, g.ctypes.data, hp.ctypes.data, len(g), seq_num, b, rng_mode, seed,
+                          draws.ctypes.data, len(draws), int(len_quota), max_reads)
     if n < 0:
         raise RuntimeError("hostsim_run failed: %d" % n)
     info = np.ctypeslib.as_array(L.hostsim_info(), shape=(n, 12)).copy()
@@ -57,7 +70,7 @@ def run(model, genome_upper, hp, seq_num, bias, rng_mode, seed, draws, len_quota
     nb = C.c_long()
     evp = L.hostsim_events(C.byref(nb))
     ev = np.ctypeslib.as_array(evp, shape=(nb.value,)).copy() if nb.value else np.zeros(0, np.uint8)
-    qs = model.view.method == capi.METHOD_QSHMM
+    qs = model.view.method != capi.METHOD_ERRHMM
     out = []
     for i in range(n):
         rid, pas, a, off, wlen, rlen, ncol, minus, nent, evoff, dstart, ovf = [int(x) for x in info[i]]
@@ -74,14 +87,21 @@ def run(model, genome_upper, hp, seq_num, bias, rng_mode, seed, draws, len_quota
 def records_from_events(model, subreads, genome_upper, seq_num):
     """Expand + format every subread; returns (reads_bytes, maf_bytes)."""
     v = model.view
-    qs = v.method == capi.METHOD_QSHMM
+    qs = v.method != capi.METHOD_ERRHMM
+    sample = v.method == capi.METHOD_SAMPLE
     reads, maf = [], []
     for s in subreads:
-        f = expand.expand_qshmm if qs else expand.expand_errhmm
-        seq, qual, mref, mread = f(s["events"], genome_upper, s["offset"], s["wlen"], s["minus"])
+        if sample:  # the window may outlast the read: the MAF line reports what was consumed (:1847)
+            seq, qual, mref, mread = expand.expand_qshmm(s["events"], genome_upper, s["offset"], s["wlen"], s["minus"],
+                                                         partial=True)
+            shown = s["ncol"] - s["nins"]
+        else:
+            f = expand.expand_qshmm if qs else expand.expand_errhmm
+            seq, qual, mref, mread = f(s["events"], genome_upper, s["offset"], s["wlen"], s["minus"])
+            shown = s["wlen"]
         assert len(seq) == s["rlen"] and len(mref) == s["ncol"]
         r, m = expand.format_records(v.pass_num, v.id_prefix.decode(), seq_num, s["read_id"], s["pas"], s["offset"],
-                                     s["wlen"], len(genome_upper), s["minus"], seq, qual, mref, mread,
+                                     shown, len(genome_upper), s["minus"], seq, qual, mref, mread,
                                      v.accuracy_mean)
         reads.append(r)
         maf.append(m)

@@ -204,3 +204,59 @@ def test_chain_chunks_give_the_oracle_bytes(name, chunk):
     for (reads, maf, sub), oref in zip(res, out):
         assert reads == oref["reads"]
         assert maf == oref["maf"]
+
+
+# ---- --method sample: the engine's schedule (sample_plan.hpp) and per-read core (sample_simulate) on the host
+
+def _sample_case(c, rng, batch_reads=0):
+    from tests.golden_util import SampleCase  # noqa: F401
+    o = O.Oracle("sample", None, **c.okw)
+    if rng == "replay":
+        o.rng_glibc(c.seed)
+    else:
+        o.rng_philox(c.seed)
+    if c.okw.get("hp_del_bias", 1.0) != 1.0:
+        o.hp_bias_prepass([s for _, s in c.contigs])
+    hm = capi.HostModel(H.lib(), capi.host_params("sample", **c.okw), None)
+    out = []
+    cursor = 0
+    for i, (_, s) in enumerate(c.contigs, start=1):
+        o.set_sequence(s, i)
+        up, hp, bias = o.seq_upper(), o.hp(), o.bias()
+        oreads, omaf, ost = o.simulate_sample(c.depth, c.pool)
+        info = o.readinfo()
+        quota = int(c.depth * len(s))
+        if rng == "replay":
+            log = o.draw_log()
+            sub = H.run(hm, up, hp, i, bias, capi.RNG_REPLAY, 0, log[cursor:], quota, pool=c.pool, batch_reads=batch_reads)
+            for sr in sub:
+                sr["draw_start"] += cursor
+            cursor = o.draws_consumed()
+        else:
+            sub = H.run(hm, up, hp, i, bias, capi.RNG_PHILOX, c.seed, None, quota, pool=c.pool, batch_reads=batch_reads)
+        reads, maf = H.records_from_events(hm, sub, up, i)
+        out.append((reads, maf, sub, oreads, omaf, info))
+    return out
+
+
+@pytest.mark.parametrize("batch_reads", [0, 7])
+@pytest.mark.parametrize("name", ["sample_basic", "sample_quirks"])
+def test_sample_core_replay_reproduces_reference(name, batch_reads):
+    from tests.golden_util import SampleCase
+    c = SampleCase(name)
+    for i, (reads, maf, sub, oreads, omaf, info) in enumerate(_sample_case(c, "replay", batch_reads), start=1):
+        assert reads == c.reads(i), "reads differ, seq %d" % i
+        assert maf == c.maf(i), "maf differs, seq %d" % i
+        assert [s["draw_start"] for s in sub] == info["draw_start"].tolist()
+        assert np.array_equal(np.array([s["accuracy"] for s in sub]), info["accuracy"])
+        assert not any(s["overflow"] for s in sub)
+
+
+@pytest.mark.parametrize("name", ["sample_basic", "sample_quirks"])
+def test_sample_core_philox_equals_oracle_philox(name):
+    from tests.golden_util import SampleCase
+    c = SampleCase(name)
+    for reads, maf, sub, oreads, omaf, info in _sample_case(c, "philox", 5):
+        assert reads == oreads
+        assert maf == omaf
+        assert [s["nins"] for s in sub] == info["nins"].tolist()
