@@ -197,6 +197,13 @@ int pbsim_cuda_set_sequence(pbsim_engine *e, const pbsim_sequence *s);
  * the set: pbsim_run.len_quota is ignored, first_read / max_reads select a range of read numbers.
  * get_hpfreq then returns the expression-weighted histogram of the --hp-del-bias prepass (:2671-2746). */
 int pbsim_cuda_set_seqset(pbsim_engine *e, const pbsim_seqset *s);
+/* --method sample: the pool get_sample_inf leaves in fp_filtered (pbsim.cpp:1214-1275) — the quality strings of
+ * the sample reads that pass the length and accuracy filters, in file order, concatenated (quals, qstart[n+1]).
+ * The caller parses and filters the FASTQ (host front end: pbsim_host_sample_filter).  A run with a model of
+ * method PBSIM_METHOD_SAMPLE then replaces simulate_by_sample (:1694-1949): every read copies the qualities of a
+ * pool entry; the copies of one entry follow each other and each is as long as the previous copy's read (:1756,
+ * :1835).  Single-pass, --strategy wgs only, whole sequences only (first_read = max_reads = 0). */
+int pbsim_cuda_set_pool(pbsim_engine *e, const char *quals, const int64_t *qstart, int64_t n);
 /* synthetic i.i.d. ACGT sequence generated on the device (benchmarks; no host transfer) */
 int pbsim_cuda_set_synthetic_sequence(pbsim_engine *e, int64_t len, int32_t seq_num, uint64_t seed);
 /* replace hp_del_bias of the current sequence without re-ingesting it (bias[0] is only known once the

@@ -30,6 +30,7 @@ struct EmitParams {
   float rq_f;              // the same text read back as a float (BAM: rq:f)
   uint32_t glen;
   uint32_t qs_segments;    // method is qshmm: segmented sub-reads use one slot per tile
+  uint32_t sample;         // --method sample: the MAF line reports the bases consumed, not the window (:1847)
 };
 
 // the reference-row naming of a record: WGS writes "ref" and the sequence length; the transcript / template
@@ -210,7 +211,8 @@ __global__ void k_sizes(Batch B, EmitParams P, DeviceSet S, uint32_t n_sub, uint
   if (s >= n_sub) return;
   const uint32_t r = s / P.pass_num, pass = s % P.pass_num;
   const RefName N = ref_name(S, B, r, P.glen);
-  const RecLayout L = rec_layout(P, N, B.first_read + 1u + r, pass, B.plan_wlen[r], B.rlen[s], B.ncol[s]);
+  const uint32_t shown = P.sample ? B.ncol[s] - B.nins[s] : B.plan_wlen[r];
+  const RecLayout L = rec_layout(P, N, B.first_read + 1u + r, pass, shown, B.rlen[s], B.ncol[s]);
   reads_size[s] = L.reads_size;
   maf_size[s] = L.maf_size;
   EmitLay y;
@@ -702,8 +704,9 @@ __global__ void __launch_bounds__(kEmitThreads) k_emit(EmitArgs A) {
     uint8_t *mf = A.out_maf + A.maf_off[s];
     if (tile == 0) {  // everything of the record that is not a per-base row: once per sub-read
       const RefName N = ref_name(A.S, A.B, r, A.P.glen);
-      const RecLayout LL = rec_layout(A.P, N, read_id, pass, wlen, rlen, ncol);
-      if (lane == 0) write_headers(A.P, N, LL, rd, mf, read_id, pass, wlen, rlen, ncol, minus);
+      const uint32_t shown = A.P.sample ? ncol - A.B.nins[s] : wlen;
+      const RecLayout LL = rec_layout(A.P, N, read_id, pass, shown, rlen, ncol);
+      if (lane == 0) write_headers(A.P, N, LL, rd, mf, read_id, pass, shown, rlen, ncol, minus);
     }
     if (nent == 0) continue;
     const Ckpt *ckp = A.ck + A.B.ck_off[s];

@@ -36,6 +36,7 @@
 #include "gz_kernels.cuh"
 #include "k0_genome.cuh"
 #include "model_image.hpp"
+#include "sample_plan.hpp"
 #include "seg_kernels.cuh"
 #include "sim_kernels.cuh"
 
@@ -102,6 +103,14 @@ __global__ void k_find_cut(const unsigned long long *prefix, const uint32_t *pla
   const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n_reads) return;
   if (len_total + (long long)prefix[r] + (long long)plan_raw[r] > quota) atomicMin(&ctrl[0], (unsigned long long)r);
+}
+
+// --method sample tests the quota in front of every read and never clips one (pbsim.cpp:1747, :1753)
+__global__ void k_find_cut_sample(const unsigned long long *prefix, uint32_t n_reads, long long len_total, long long quota,
+                                  unsigned long long *ctrl) {
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_reads) return;
+  if (len_total + (long long)prefix[r] >= quota) atomicMin(&ctrl[0], (unsigned long long)r);
 }
 
 // ctrl[1] = emitted bases (pass 0) of the reads before the cut; ctrl[2] = any pass-1 flag
@@ -185,6 +194,13 @@ struct pbsim_engine {
   double set_mean_len = 0;
   int32_t set_rank_max = 0;
   DevBuf d_set_start, d_set_rprefix, d_set_plus, d_set_ids, d_set_idstart, d_set_ssp_ends, d_set_ssp_mod, d_set_first;
+
+  // --method sample: the pool of quality strings (get_sample_inf's fp_filtered) and the run's schedule
+  bool pool_set = false;
+  std::vector<int64_t> pool_start;
+  DevBuf d_pool_q, d_pool_start, d_groups;
+  SampleSchedule sched;
+  SampleGroups groups;
 
   // run
   bool running = false;
@@ -372,7 +388,7 @@ DeviceSet device_set(const pbsim_engine *e) {
 // bias-dependent threshold tables (re-uploaded with every sequence)
 int upload_bias_tables(pbsim_engine *e) {
   e->img.apply_bias(e->model, e->bias);
-  if (e->model.method == PBSIM_METHOD_QSHMM) {
+  if (e->model.method != PBSIM_METHOD_ERRHMM) {
     if (upload(e, e->d_qs_thr, e->img.qs_thr.data(), e->img.qs_thr.size())) return PBSIM_E_CUDA;
     if (upload(e, e->d_qs_thr_hp, e->img.qs_thr_hp.data(), e->img.qs_thr_hp.size())) return PBSIM_E_CUDA;
   } else {
@@ -496,9 +512,16 @@ int excl_scan(pbsim_engine *e, const unsigned long long *in, unsigned long long 
   return 0;
 }
 
-int run_batch(pbsim_engine *e, uint32_t n_reads, int64_t clip_room, BatchResult *out) {
+// sb: --method sample, the groups of this batch (n_reads = their copies); otherwise null
+int run_batch(pbsim_engine *e, uint32_t n_reads, int64_t clip_room, BatchResult *out, const SampleBatch *sb = nullptr) {
   const uint32_t pass = (uint32_t)e->model.pass_num;
-  const bool qs = e->model.method == PBSIM_METHOD_QSHMM;
+  const bool qs = e->model.method != PBSIM_METHOD_ERRHMM;  // sample reads use the qshmm event stream
+  const bool sample = e->model.method == PBSIM_METHOD_SAMPLE;
+  DevicePool Pl;
+  Pl.quals = e->d_pool_q.as<uint8_t>();
+  Pl.start = e->d_pool_start.as<uint64_t>();
+  Pl.n = (uint32_t)(e->pool_start.empty() ? 0 : e->pool_start.size() - 1);
+  if (sample && !sb) return fail(e, PBSIM_E_INVALID, "internal: sample batch without groups");
   const bool replay = e->run.rng_mode == PBSIM_RNG_REPLAY;
   int rc = carve_batch(e, n_reads);
   if (rc) return rc;
@@ -546,14 +569,17 @@ int run_batch(pbsim_engine *e, uint32_t n_reads, int64_t clip_room, BatchResult 
   }
 
   // (the single, quota-clipped read of a tail batch is segmented too: on one thread a 50 kb read takes milliseconds)
-  bool use_segments = !replay && e->seg_enabled;
+  bool use_segments = !replay && e->seg_enabled && !sample;
   int seg_retries = 0;
   for (int attempt = 0; attempt < 9; ++attempt) {
     // ---- K1 plan
     const uint32_t ev_align = qs ? 8u : 16u;
-    k_plan<<<nblk(n_reads, 256), 256, 0, e->st>>>(M, G, device_set(e), rng, B, clip_room, e->cap_num, e->cap_den, ev_align,
-                                                   use_segments ? (uint32_t)e->seg_min_len : 0u, e->seg_extra,
-                                                   (uint32_t)e->chain_chunk);
+    if (sample)
+      k_plan_sample<<<nblk(n_reads, 256), 256, 0, e->st>>>(G, Pl, *sb, B, e->cap_num, e->cap_den);
+    else
+      k_plan<<<nblk(n_reads, 256), 256, 0, e->st>>>(M, G, device_set(e), rng, B, clip_room, e->cap_num, e->cap_den, ev_align,
+                                                     use_segments ? (uint32_t)e->seg_min_len : 0u, e->seg_extra,
+                                                     (uint32_t)e->chain_chunk);
     e->launches++;
     // ---- sort by (accuracy, length desc)
     {
@@ -627,7 +653,10 @@ int run_batch(pbsim_engine *e, uint32_t n_reads, int64_t clip_room, BatchResult 
     const uint32_t grid = cta_slots;
     bool seg_timed = false;
     CK(cudaEventRecord(e->ev_k[0], e->st));
-    if (qs) {
+    if (sample) {
+      if (replay) k_sim_sample<PBSIM_RNG_REPLAY><<<grid, kSimThreads, 0, e->st>>>(A, Pl, *sb);
+      else k_sim_sample<PBSIM_RNG_PHILOX><<<grid, kSimThreads, 0, e->st>>>(A, Pl, *sb);
+    } else if (qs) {
       if (replay) k_sim_qshmm<PBSIM_RNG_REPLAY><<<grid, kSimThreads, kQsSmemBytes, e->st>>>(A);
       else k_sim_qshmm<PBSIM_RNG_PHILOX><<<grid, kSimThreads, kQsSmemBytes, e->st>>>(A);
     } else {
@@ -758,7 +787,9 @@ int run_batch(pbsim_engine *e, uint32_t n_reads, int64_t clip_room, BatchResult 
     hctrl[2] = 0;
     hctrl[3] = 0;
     CK(cudaMemcpyAsync(ctrl, hctrl, 32, cudaMemcpyHostToDevice, e->st));
-    if (clip_room < 0)  // bulk batch: speculative unclipped plans
+    if (sample)
+      k_find_cut_sample<<<nblk(n_reads, 256), 256, 0, e->st>>>(prefix, n_reads, e->len_total, e->run.len_quota, ctrl);
+    else if (clip_room < 0)  // bulk batch: speculative unclipped plans
       k_find_cut<<<nblk(n_reads, 256), 256, 0, e->st>>>(prefix, B.plan_raw, n_reads, e->len_total, e->run.len_quota, ctrl);
     k_batch_totals<<<nblk(n_sub, 256), 256, 0, e->st>>>(prefix, B.rlen, B.flags, n_reads, pass, ctrl);
     e->launches += 3;
@@ -834,6 +865,7 @@ int run_batch(pbsim_engine *e, uint32_t n_reads, int64_t clip_room, BatchResult 
   e->emitp.glen = (uint32_t)e->glen;
   e->emitp.sam = e->model.pass_num > 1 ? (e->bam ? 2u : 1u) : 0u;
   e->emitp.qs_segments = qs ? 1u : 0u;
+  e->emitp.sample = sample ? 1u : 0u;
   {
     char head[192];
     if (e->strategy == PBSIM_STRATEGY_WGS) snprintf(head, sizeof head, "%s%d", e->model.id_prefix, e->seq_num);
@@ -1002,7 +1034,48 @@ int produce_one(pbsim_engine *e, int set, pbsim_engine::BatchItem *it) {
     // batch size: enough reads for the target number of emitted bases, never more than the quota needs
     int64_t nb;
     int64_t clip_room = -1;
-    if (e->tail_mode) {
+    const bool sample = e->model.method == PBSIM_METHOD_SAMPLE;
+    SampleBatch sb;
+    if (sample) {
+      // the groups (pool entry, copies) of the current pool pass that make up this batch (sample_plan.hpp)
+      SampleSchedule &S = e->sched;
+      sb.skip_first = 0;
+      if (!S.pass_open) {
+        if (e->run.rng_mode == PBSIM_RNG_REPLAY) {
+          const int64_t s0 = e->next_read - e->run.first_read;
+          if (s0 >= e->run.replay_nsubreads) return fail(e, PBSIM_E_REPLAY, "replay log exhausted before the quota was reached");
+          const int64_t d0 = e->run.replay_starts[s0];
+          if (d0 < 0 || d0 >= e->run.replay_ndraws) return fail(e, PBSIM_E_REPLAY, "replay starts are not monotone");
+          S.open_pass((int64_t)((uint32_t)e->run.replay_draws[d0] % (uint32_t)S.n));  // sample_value (:1734)
+          sb.skip_first = 1;
+        } else {
+          S.open_pass(SampleSchedule::philox_value(e->run.seed, (uint32_t)e->seq_num, S.pass, (uint32_t)S.n));
+        }
+      }
+      const int64_t target = (e->pipelined && e->mode_to_host) ? std::min(e->target_batch_bases, e->host_batch_bases)
+                                                               : e->target_batch_bases;
+      const int64_t need = (int64_t)((double)(e->run.len_quota - e->len_total) * 1.05) + (1 << 20);
+      int64_t hard = (int64_t)1 << 30;
+      if (e->run.rng_mode == PBSIM_RNG_REPLAY) {
+        hard = e->run.replay_nsubreads - (e->next_read - e->run.first_read);
+        if (hard <= 0) return fail(e, PBSIM_E_REPLAY, "replay log exhausted before the quota was reached");
+      }
+      sample_collect(S, e->run.batch_reads > 0 ? e->run.batch_reads : (int64_t)1 << 22, std::min(target, need), hard,
+                     &e->groups);
+      const size_t G = e->groups.entry.size();
+      nb = e->groups.first[G];
+      if (nb == 0) {  // nothing left in this pass (cannot happen while sample_interval <= n / 2, kept for safety)
+        S.next_pass();
+        continue;
+      }
+      CK(e->d_groups.ensure((2 * G + 1) * 4 + 64));
+      uint32_t *dg = e->d_groups.as<uint32_t>();
+      CK(cudaMemcpyAsync(dg, e->groups.entry.data(), G * 4, cudaMemcpyHostToDevice, e->st));
+      CK(cudaMemcpyAsync(dg + G, e->groups.first.data(), (G + 1) * 4, cudaMemcpyHostToDevice, e->st));
+      sb.g_entry = dg;
+      sb.g_first = dg + G;
+      sb.n_groups = (uint32_t)G;
+    } else if (e->tail_mode) {
       nb = 1;
       clip_room = e->run.len_quota - e->len_total;
     } else {
@@ -1037,7 +1110,7 @@ int produce_one(pbsim_engine *e, int set, pbsim_engine::BatchItem *it) {
     e->cur_set = set;
     CK(cudaEventRecord(e->ev0, e->st));
     BatchResult br;
-    int rc = run_batch(e, (uint32_t)nb, clip_room, &br);
+    int rc = run_batch(e, (uint32_t)nb, clip_room, &br, sample ? &sb : nullptr);
     if (rc) return rc;
     const bool gz = e->deflate && e->mode_to_host && br.n_valid_reads > 0;
     uint64_t gz_bytes[2] = {0, 0};
@@ -1076,7 +1149,14 @@ int produce_one(pbsim_engine *e, int set, pbsim_engine::BatchItem *it) {
       }
       br.bases_all = bases;
     }
-    if (br.cut) e->tail_mode = true;  // the next read is re-planned with the quota clip, one read at a time
+    if (sample) {
+      if (!br.cut) {
+        e->sched.j = e->groups.j_end;
+        if (e->sched.j >= e->sched.n) e->sched.next_pass();
+      }
+    } else if (br.cut) {
+      e->tail_mode = true;  // the next read is re-planned with the quota clip, one read at a time
+    }
     if (nv == 0) continue;
     if (e->mean_rlen_est <= 0) e->mean_rlen_est = std::max(1.0, (double)br.bases_pass0 / nv);
     it->rc = 1;
@@ -1358,15 +1438,25 @@ void pbsim_cuda_destroy(pbsim_engine *e) {
 int pbsim_cuda_set_model(pbsim_engine *e, const pbsim_model *m) {
   if (!e || !m) return PBSIM_E_INVALID;
   CK(cudaSetDevice(e->device));
-  if (m->method != PBSIM_METHOD_QSHMM && m->method != PBSIM_METHOD_ERRHMM)
-    return fail(e, PBSIM_E_INVALID, "method must be qshmm or errhmm");
-  if (m->pass_num < 1 || m->len_rand_value < 1 || m->accuracy_rand_value < 1 || !m->prob2len || !m->prob2accuracy)
+  const bool sample = m->method == PBSIM_METHOD_SAMPLE;
+  if (m->method != PBSIM_METHOD_QSHMM && m->method != PBSIM_METHOD_ERRHMM && !sample)
+    return fail(e, PBSIM_E_INVALID, "method must be qshmm, errhmm or sample");
+  if (sample && m->pass_num != 1)
+    return fail(e, PBSIM_E_INVALID, "sampling-based simulation supports only single-pass");  // pbsim.cpp:1675-1679
+  if (!sample &&
+      (m->pass_num < 1 || m->len_rand_value < 1 || m->accuracy_rand_value < 1 || !m->prob2len || !m->prob2accuracy))
     return fail(e, PBSIM_E_INVALID, "model samplers are empty");
   if (m->len_max > 1000000) return fail(e, PBSIM_E_INVALID, "length-max above FASTQ_LEN_MAX (1000000)");
   if (!e->img.build(*m)) return fail(e, PBSIM_E_INVALID, "model tables: %s", e->img.error.c_str());
   e->model = *m;
-  e->h_prob2len.assign(m->prob2len, m->prob2len + m->len_rand_value);
-  e->h_prob2acc.assign(m->prob2accuracy, m->prob2accuracy + m->accuracy_rand_value);
+  if (sample) {  // lengths come from the pool (set_pool); there are no samplers
+    e->h_prob2len.assign(1, 0);
+    e->h_prob2acc.assign(1, 0);
+    e->model.len_rand_value = e->model.accuracy_rand_value = 1;
+  } else {
+    e->h_prob2len.assign(m->prob2len, m->prob2len + m->len_rand_value);
+    e->h_prob2acc.assign(m->prob2accuracy, m->prob2accuracy + m->accuracy_rand_value);
+  }
   {
     double acc = 0;
     for (int32_t v : e->h_prob2len) acc += v;
@@ -1414,6 +1504,31 @@ int pbsim_cuda_set_model(pbsim_engine *e, const pbsim_model *m) {
   CK(cudaStreamSynchronize(e->st));
   e->model_set = true;
   if (e->seq_set) return upload_bias_tables(e);
+  return 0;
+}
+
+int pbsim_cuda_set_pool(pbsim_engine *e, const char *quals, const int64_t *qstart, int64_t n) {
+  if (!e || !quals || !qstart) return PBSIM_E_INVALID;
+  CK(cudaSetDevice(e->device));
+  if (e->running) return fail(e, PBSIM_E_INVALID, "the pool cannot change during a run");
+  if (n < 2) return fail(e, PBSIM_E_INVALID, "the pool needs at least 2 reads (the reference divides by zero, pbsim.cpp:1723)");
+  if (n > 0xFFFFFFF0ll) return fail(e, PBSIM_E_INVALID, "too many reads in the pool");
+  if (qstart[0] != 0) return fail(e, PBSIM_E_INVALID, "qstart[0] must be 0");
+  for (int64_t j = 0; j < n; ++j) {
+    const int64_t len = qstart[j + 1] - qstart[j];
+    if (len < 1 || len > 1000000)  // FASTQ_LEN_MAX :27
+      return fail(e, PBSIM_E_INVALID, "pool read %lld has %lld qualities (1..1000000)", (long long)j + 1, (long long)len);
+  }
+  const int64_t total = qstart[n];
+  for (int64_t i = 0; i < total; ++i)
+    if ((uint8_t)quals[i] < 33 || (uint8_t)quals[i] > 126)
+      return fail(e, PBSIM_E_INVALID, "quality character out of range '!'..'~' at pool byte %lld", (long long)i);
+  e->pool_start.assign(qstart, qstart + n + 1);
+  int rc;
+  if ((rc = upload(e, e->d_pool_q, reinterpret_cast<const uint8_t *>(quals), (size_t)total))) return rc;
+  if ((rc = upload(e, e->d_pool_start, reinterpret_cast<const uint64_t *>(e->pool_start.data()), (size_t)n + 1))) return rc;
+  CK(cudaStreamSynchronize(e->st));
+  e->pool_set = true;
   return 0;
 }
 
@@ -1550,6 +1665,14 @@ int pbsim_cuda_simulate_begin(pbsim_engine *e, const pbsim_run *run) {
   if (!e->model_set || !e->seq_set) return fail(e, PBSIM_E_INVALID, "set_model and set_sequence must precede simulate_begin");
   if (run->rng_mode == PBSIM_RNG_REPLAY && (!run->replay_draws || !run->replay_starts || run->replay_nsubreads < 1))
     return fail(e, PBSIM_E_INVALID, "replay mode needs the draw log and the subread starts");
+  if (e->model.method == PBSIM_METHOD_SAMPLE) {
+    if (!e->pool_set) return fail(e, PBSIM_E_INVALID, "set_pool must precede simulate_begin for --method sample");
+    if (e->strategy != PBSIM_STRATEGY_WGS) return fail(e, PBSIM_E_INVALID, "--method sample simulates a genome (--strategy wgs)");
+    if (run->first_read != 0 || run->len_total_start != 0 || run->max_reads != 0)
+      return fail(e, PBSIM_E_INVALID, "--method sample runs whole sequences: read ranges are not supported");
+    if (!e->sched.init(run->len_quota, (int64_t)e->pool_start.size() - 1, e->pool_start.data()))
+      return fail(e, PBSIM_E_INVALID, "the pool cannot be sampled (fewer than 2 reads)");
+  }
   e->run = *run;
   if (e->strategy != PBSIM_STRATEGY_WGS) {
     // the whole set (or the requested range of its read numbers) is the run; there is no quota (:2841, :3312)

@@ -80,14 +80,19 @@ struct SampleGroups {
   int64_t j_end = 0;            // first entry after the batch
 };
 
-inline void sample_collect(const SampleSchedule &S, int64_t max_reads, int64_t max_bases, SampleGroups *out) {
+// hard_reads: never plan more reads than this (replay: the reads the log holds; the last group may be cut short,
+// its missing copies lie behind the quota cut)
+inline void sample_collect(const SampleSchedule &S, int64_t max_reads, int64_t max_bases, int64_t hard_reads,
+                           SampleGroups *out) {
   out->entry.clear();
   out->first.clear();
   int64_t reads = 0, bases = 0, j = S.j;
   for (; j < S.n; ++j) {
-    const int64_t c = S.copies(j);
+    int64_t c = S.copies(j);
     if (c == 0) continue;
     if (reads > 0 && (reads + c > max_reads || bases >= max_bases)) break;
+    if (reads + c > hard_reads) c = hard_reads - reads;
+    if (c <= 0) break;
     out->entry.push_back((uint32_t)j);
     out->first.push_back((uint32_t)reads);
     reads += c;

@@ -482,4 +482,135 @@ __global__ void __launch_bounds__(kErrThreads) k_sim_errhmm(SimArgs A, uint32_t 
   store_result(A.B, s, res, used);
 }
 
+// ----------------------------------------------------------------------------------------------
+// --method sample (simulate_by_sample, pbsim.cpp:1694-1949; schedule: sample_plan.hpp)
+// The reads of a batch are the copies of GROUPS (pool entry, pool pass) in read order; the copies of a group are
+// a chain (copy i+1 is as long as copy i's read), so ONE thread simulates a group: it plans copy 0 from the pool
+// entry's length, runs sample_simulate, plans copy 1 from the read's length, and so on.  Groups run in parallel,
+// scheduled longest-first like the sequential pass-1 bins (bin 0; copies > 0 carry the out-of-range bin).
+// ----------------------------------------------------------------------------------------------
+struct DevicePool {
+  const uint8_t *quals;    // quality strings of the filtered sample reads, concatenated (fp_filtered, :1214-1275)
+  const uint64_t *start;   // [n+1]
+  uint32_t n;
+};
+
+struct SampleBatch {
+  const uint32_t *g_entry;  // [n_groups] pool entry
+  const uint32_t *g_first;  // [n_groups+1] first read of the group inside the batch
+  uint32_t n_groups;
+  uint32_t skip_first;      // replay: read 0 of the batch is preceded by the pool-pass draw (:1734)
+};
+
+__global__ void k_plan_sample(DeviceGenome G, DevicePool Pl, SampleBatch SB, Batch B, uint32_t cap_num, uint32_t cap_den) {
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= B.n_reads) return;
+  uint32_t lo = 0, hi = SB.n_groups;  // g_first[lo] <= r < g_first[hi]
+  while (hi - lo > 1u) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (SB.g_first[mid] <= r) lo = mid;
+    else hi = mid;
+  }
+  const uint32_t copy = r - SB.g_first[lo], num = SB.g_first[lo + 1] - SB.g_first[lo];
+  const uint32_t j = SB.g_entry[lo];
+  uint32_t len0 = (uint32_t)(Pl.start[j + 1] - Pl.start[j]);
+  if (len0 > G.len) len0 = G.len;
+  B.plan_tr[r] = j;
+  B.plan_off[r] = 0;
+  B.plan_wlen[r] = len0;   // upper bound; the group's thread stores the planned window of every copy
+  B.plan_raw[r] = num;     // copy 0: copies of the group
+  B.plan_meta[r] = 0;
+  uint64_t cap = (uint64_t)len0 * cap_num / cap_den + 2048u;
+  cap = (cap + 7u) / 8u * 8u;
+  uint64_t work = (uint64_t)len0 * num / 16u;
+  if (work > 0xFFFFFu) work = 0xFFFFFu;
+  B.key_in[r] = copy == 0u ? (0xFFFFFu - (uint32_t)work) : ((uint32_t)kBins << 20);
+  B.idx_in[r] = r;
+  B.cap[r] = (uint32_t)cap;
+  B.ck_cap[r] = (uint32_t)(cap / PB_TILE) + 2u;
+  B.nseg[r] = 0;
+  B.nchunk[r] = 0;
+}
+
+// shared memory: [thr 94*16 | qc_prob 94*8]
+constexpr uint32_t kSampleSmemBytes = PBSIM_NQV * 16 + PBSIM_NQV * 8;
+
+template <int RNG_MODE>
+__global__ void __launch_bounds__(kSimThreads) k_sim_sample(SimArgs A, DevicePool Pl, SampleBatch SB) {
+  __shared__ __align__(16) uint8_t smem[kSampleSmemBytes];
+  uint32_t acc, lo, hi;
+  if (!cta_assignment(A.cta_order, A.cta_first, A.bin_lo, A.bin_hi, &acc, &lo, &hi)) return;
+  {
+    uint32_t *d = reinterpret_cast<uint32_t *>(smem);
+    for (uint32_t i = threadIdx.x; i < PBSIM_NQV * 4u; i += blockDim.x) d[i] = A.M.qs_thr[i];
+    double *q = reinterpret_cast<double *>(smem + PBSIM_NQV * 16);
+    for (uint32_t i = threadIdx.x; i < PBSIM_NQV; i += blockDim.x) q[i] = A.M.qc_prob[i];
+  }
+  __syncthreads();
+  const uint32_t k = lo + threadIdx.x;
+  if (k >= hi) return;
+  const uint32_t r0 = A.B.order[k];
+  const uint32_t num = A.B.plan_raw[r0];
+  const uint32_t j = A.B.plan_tr[r0];
+  const uint8_t *quals = Pl.quals + Pl.start[j];
+  QsView T;
+  T.t2 = nullptr;
+  T.emis = nullptr;
+  T.freq = nullptr;
+  T.has_model = 0;
+  T.init_mod = 1;
+  T.freq_mod = 1;
+  T.thr = reinterpret_cast<const QsThr *>(smem);
+  T.thr_hp = A.M.qs_thr_hp;
+  T.qc_prob = reinterpret_cast<const double *>(smem + PBSIM_NQV * 16);
+  uint32_t len = (uint32_t)(Pl.start[j + 1] - Pl.start[j]);
+  for (uint32_t i = 0; i < num; ++i) {
+    const uint32_t r = r0 + i;
+    const uint32_t read_id = (uint32_t)(A.B.first_read + 1u + r);
+    PhiloxDraw pd;
+    ReplayDraw rd;
+    uint32_t offset = 0;
+    if (RNG_MODE == PBSIM_RNG_PHILOX) {
+      pd.ph.k0 = A.rng.seed;
+      pd.ph.k1 = A.G.seq_num;
+      pd.read_id = read_id;
+      pd.pass = 0;
+      pd.plan_begin();
+      if (len >= A.G.len) len = A.G.len;                    // :1758-1763
+      else offset = pd.plan_off(A.G.len - len + 1u);
+    } else {
+      rd.log = A.rng.draws - A.rng.draws_base;
+      rd.start = A.rng.starts[r];
+      rd.cur = rd.start + ((r == 0u && SB.skip_first) ? 1 : 0);
+      rd.end = A.rng.draws_end;
+      if (len >= A.G.len) len = A.G.len;
+      else offset = rd.plan_off(A.G.len - len + 1u);
+    }
+    const uint32_t minus = (read_id & 1u) ? 0u : 1u;       // :1768-1774
+    bool slow = !A.M.uniform_bias;
+    if (!slow && len > 0u) slow = range_exceptional(A.G.xm, offset, offset + len - 1u);
+    A.B.plan_off[r] = offset;
+    A.B.plan_wlen[r] = len;
+    A.B.plan_meta[r] = (minus << 8) | ((slow ? 1u : 0u) << 9);
+    WindowRef win;
+    win.ascii = A.G.ascii;
+    win.hp4 = A.G.hp4;
+    win.offset = offset;
+    win.wlen = len;
+    win.minus = minus;
+    QsSink sink;
+    sink.init(reinterpret_cast<uint16_t *>(A.ev) + A.B.ev_off[r], A.ck + A.B.ck_off[r], A.B.cap[r]);
+    SubreadResult res;
+    uint32_t used = 0;
+    if (RNG_MODE == PBSIM_RNG_PHILOX) {
+      sample_simulate(T, pd, win, slow, len, quals, sink, res);
+    } else {
+      sample_simulate(T, rd, win, slow, len, quals, sink, res);
+      used = rd.consumed();
+    }
+    store_result(A.B, r, res, used);
+    len = res.rlen;  // mut.qc was cut where the read ended (:1835): the next copy is this long (:1756)
+  }
+}
+
 }  // namespace pb

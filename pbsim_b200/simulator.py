@@ -85,6 +85,13 @@ class Engine:
         self._chk(self.L.pbsim_cuda_set_seqset(self.h, C.byref(s)), "set_seqset")
         self.glen = len(k["bases"])
 
+    def set_pool(self, pool):
+        """--method sample: the quality strings get_sample_inf keeps (pbsim.cpp:1214-1275), in file order"""
+        quals = b"".join(pool)
+        qstart = np.zeros(len(pool) + 1, dtype=np.int64)
+        qstart[1:] = np.cumsum([len(x) for x in pool])
+        self._chk(self.L.pbsim_cuda_set_pool(self.h, quals, qstart.ctypes.data, len(pool)), "set_pool")
+
     def set_synthetic_sequence(self, length, seq_num, seed):
         self._chk(self.L.pbsim_cuda_set_synthetic_sequence(self.h, length, seq_num, seed), "set_synthetic_sequence")
         self.glen = length

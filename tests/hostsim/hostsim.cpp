@@ -357,7 +357,7 @@ long hostsim_run_sample(const pbsim_model *m, const uint8_t *ascii_upper, const 
       first_of_pass = true;
     }
     pb::SampleGroups G;
-    pb::sample_collect(S, batch_reads > 0 ? batch_reads : 1000, 1ll << 40, &G);
+    pb::sample_collect(S, batch_reads > 0 ? batch_reads : 1000, 1ll << 40, 1ll << 40, &G);
     const size_t info0 = g_out.info.size() / 12;
     for (size_t g = 0; g < G.entry.size(); ++g) {
       const uint32_t j = G.entry[g];

@@ -1,0 +1,115 @@
+"""GPU: --method sample (simulate_by_sample, pbsim.cpp:1694) through the C ABI — the reference's bytes in replay
+mode, the oracle's in PHILOX mode, for every batch size (the copies of a pool entry are a chain that one GPU thread
+walks; batches cut the pool passes anywhere between entries)."""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from pbsim_b200 import capi, simulator
+from tests.golden_util import SampleCase, sample_case_names
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle(c, rng):
+    o = O.Oracle("sample", None, **c.okw)
+    (o.rng_glibc if rng == "glibc" else o.rng_philox)(c.seed)
+    if c.okw.get("hp_del_bias", 1.0) != 1.0:
+        o.hp_bias_prepass([s for _, s in c.contigs])
+    out = []
+    for i, (_, s) in enumerate(c.contigs, start=1):
+        o.set_sequence(s, i)
+        reads, maf, st = o.simulate_sample(c.depth, c.pool)
+        out.append(dict(reads=reads, maf=maf, text=O.format_stats(st, i), n=len(o.readinfo())))
+    return out
+
+
+def _run(c):
+    hm = capi.HostModel(capi.load(), capi.host_params("sample", **c.okw), None)
+    eng = simulator.Engine(0)
+    eng.set_option("pipeline", 0)
+    run = simulator.WgsRun(eng, hm, c.depth, c.okw.get("hp_del_bias", 1.0))
+    eng.set_pool(c.pool)
+    if c.okw.get("hp_del_bias", 1.0) != 1.0:
+        run.prepass(c.contigs)
+    return eng, run
+
+
+@pytest.mark.parametrize("batch_reads", [0, 1, 7])
+@pytest.mark.parametrize("name", sample_case_names())
+def test_replay_reproduces_reference(name, batch_reads):
+    c = SampleCase(name)
+    ref = _oracle(c, "glibc")
+    draws = O.glibc_rand(c.seed, c.ndraws)
+    starts = np.concatenate([[0], c.marks[:-1]]).astype(np.int64)
+    eng, run = _run(c)
+    pos = 0
+    for i, (_, s) in enumerate(c.contigs, start=1):
+        n = ref[i - 1]["n"]
+        end = int(starts[pos + n]) if pos + n < len(starts) else c.ndraws
+        reads, maf, st, text = run.simulate_sequence(s, i, rng_mode=capi.RNG_REPLAY, replay_draws=draws[:end],
+                                                     replay_starts=starts[pos:pos + n], batch_reads=batch_reads)
+        pos += n
+        assert reads == c.reads(i), "FASTQ differs from the reference (seq %d)" % i
+        assert maf == c.maf(i), "MAF differs from the reference (seq %d)" % i
+        assert text == c.stats_blocks[i]
+
+
+@pytest.mark.parametrize("batch_reads", [0, 5])
+@pytest.mark.parametrize("name", sample_case_names())
+def test_philox_equals_oracle(name, batch_reads):
+    c = SampleCase(name)
+    ref = _oracle(c, "philox")
+    eng, run = _run(c)
+    for i, (_, s) in enumerate(c.contigs, start=1):
+        reads, maf, st, text = run.simulate_sequence(s, i, rng_mode=capi.RNG_PHILOX, seed=c.seed, batch_reads=batch_reads)
+        assert reads == ref[i - 1]["reads"]
+        assert maf == ref[i - 1]["maf"]
+        assert text == ref[i - 1]["text"]
+
+
+def test_pipelined_and_device_delivery_match():
+    c = SampleCase("sample_quirks")
+    ref = _oracle(c, "philox")
+    from tests.test_gpu_parity import _device_bytes
+    for mode in ("pipeline", "device"):
+        eng, run = _run(c)
+        eng.set_option("pipeline", 2 if mode == "pipeline" else 0)
+        for i, (_, s) in enumerate(c.contigs, start=1):
+            if mode == "pipeline":
+                reads, maf, st, text = run.simulate_sequence(s, i, rng_mode=capi.RNG_PHILOX, seed=c.seed, batch_reads=9)
+            else:
+                bias = list(run.base_bias)
+                eng.set_sequence(s, i, bias)
+                run.hp11_running += eng.hpfreq()[11]
+                bias[0] = float(np.array([run.hp11_running], dtype=np.int64).view(np.float64)[0])
+                eng.update_bias(bias)
+                eng.begin(int(c.depth * len(s)), rng_mode=capi.RNG_PHILOX, seed=c.seed, batch_reads=11)
+                rs, ms = [], []
+                while True:
+                    ch = eng.next_chunk(device=True)
+                    if ch is None:
+                        break
+                    rs.append(_device_bytes(ch.reads, ch.reads_bytes))
+                    ms.append(_device_bytes(ch.maf, ch.maf_bytes))
+                eng.end()
+                reads, maf = b"".join(rs), b"".join(ms)
+            assert reads == ref[i - 1]["reads"], mode
+            assert maf == ref[i - 1]["maf"], mode
+
+
+def test_misuse_fails_loudly():
+    c = SampleCase("sample_basic")
+    hm = capi.HostModel(capi.load(), capi.host_params("sample", **c.okw), None)
+    eng = simulator.Engine(0)
+    eng.set_model(hm)
+    eng.set_sequence(c.contigs[0][1], 1, [0.0] + [1.0] * 10 + [0.0])
+    with pytest.raises(simulator.EngineError, match="set_pool"):
+        eng.begin(1000)
+    with pytest.raises(simulator.EngineError, match="at least 2 reads"):
+        eng.set_pool([b"IIII"])
+    with pytest.raises(simulator.EngineError, match="quality character"):
+        eng.set_pool([b"II II", b"IIII"])
+    eng.set_pool(c.pool)
+    with pytest.raises(simulator.EngineError, match="read ranges"):
+        eng.begin(1000, first_read=5)
