@@ -286,6 +286,20 @@ void pbsim_host_ssp_table(int32_t rank_max, uint16_t *ends, uint16_t *mod);
  * block header (LSB-first bit string) the engine's gzip writer derives from a stream's byte histogram */
 int pbsim_host_deflate_code(const int64_t hist[256], uint32_t lit[257], uint32_t *hdr_bits, uint32_t *hdr_words,
                             int32_t cap_words);
+/* get_sample_inf (pbsim.cpp:1155-1330) over a FASTQ held in memory: every 4th '\n'-terminated line is a quality
+ * string (a last line without line feed is not counted, like fgets + trim do); strings whose length lies in
+ * [len_min, len_max] and whose accuracy 1 - mean(10^(-q/10)) lies in [accuracy_min, accuracy_max] are appended to
+ * quals (capacity: bytes) in file order, qstart[0..*n_out] are their offsets (capacity qstart_cap cells).
+ * st receives the numbers print_sample_stats shows (:1336-1358) and the sample profile stores (:1317-1326).
+ * Errors carry the reference's message in *err. */
+typedef struct {
+  int64_t num, len_total, len_min, len_max;                                         /* all reads      */
+  int64_t num_filtered, len_total_filtered, len_min_filtered, len_max_filtered;     /* filtered reads */
+  double len_mean_filtered, len_sd_filtered, accuracy_mean_filtered, accuracy_sd_filtered;
+} pbsim_sample_stats;
+int pbsim_host_sample_filter(const char *fastq, int64_t bytes, int64_t len_min, int64_t len_max, double accuracy_min,
+                             double accuracy_max, char *quals, int64_t *qstart, int64_t qstart_cap, int64_t *n_out,
+                             pbsim_sample_stats *st, const char **err);
 void pbsim_host_hp_del_bias(double hp_del_bias_opt, const int64_t hpfreq[12], double bias[12]);
 
 #ifdef __cplusplus

@@ -283,6 +283,9 @@ def main():
     shutil.copy(os.path.join(DATA, "ERRHMM-ONT.model"), os.path.join(work, "ERRHMM-ONT.model"))
     with open(os.path.join(work, "tiny.fa"), "w") as f:
         f.write(">s\nACGTACGTAC\n")
+    with open(os.path.join(work, "tiny.fq"), "w") as f:
+        f.write("@r1\nACGT\n+\nIIII\n@r2\nACGTA\n+\nIIIII\n")
+    sm = ["--strategy", "wgs", "--method", "sample", "--genome", "tiny.fa"]
     qs = ["--strategy", "wgs", "--method", "qshmm", "--qshmm", "QSHMM-RSII.model", "--genome", "tiny.fa"]
     cli_cases = [
         ["--strategy", "foo"], ["--strategy", "wgs"], ["--strategy", "wgs", "--method", "qshmm"],
@@ -300,6 +303,9 @@ def main():
         ["--strategy", "templ", "--method", "errhmm", "--errhmm", "ERRHMM-ONT.model"],
         ["--strategy", "templ", "--method", "errhmm", "--errhmm", "ERRHMM-ONT.model", "--template", "nofile.fa"],
         ["--strategy", "trans", "--method", "sample", "--transcript", "nofile.tsv"],
+        sm, sm + ["--sample", "nofile.fq"], sm + ["--sample", "tiny.fq", "--pass-num", "2"],
+        sm + ["--sample-profile-id", "nosuchprofile"], sm + ["--sample", "tiny.fq"],
+        sm + ["--sample", "tiny.fq", "--accuracy-min", "1.5"],
     ]
     cli_out = []
     for a in cli_cases:

@@ -158,7 +158,14 @@ class HostParams(C.Structure):
     ]
 
 
-HOST_EXPORTS = ["pbsim_host_model_load", "pbsim_host_model_get", "pbsim_host_model_free", "pbsim_host_hp_del_bias",
+class SampleStats(C.Structure):
+    _fields_ = [(k, C.c_int64) for k in ("num", "len_total", "len_min", "len_max", "num_filtered", "len_total_filtered",
+                                         "len_min_filtered", "len_max_filtered")] + [
+        (k, C.c_double) for k in ("len_mean_filtered", "len_sd_filtered", "accuracy_mean_filtered",
+                                  "accuracy_sd_filtered")]
+
+
+HOST_EXPORTS = ["pbsim_host_sample_filter", "pbsim_host_model_load", "pbsim_host_model_get", "pbsim_host_model_free", "pbsim_host_hp_del_bias",
                 "pbsim_host_ssp_table", "pbsim_host_deflate_code"]
 ENGINE_EXPORTS = [
     "pbsim_cuda_abi_version", "pbsim_cuda_last_error", "pbsim_cuda_create", "pbsim_cuda_destroy",
@@ -181,6 +188,9 @@ def declare_host(L):
     L.pbsim_host_hp_del_bias.restype = None
     L.pbsim_host_hp_del_bias.argtypes = [C.c_double, C.POINTER(C.c_int64), C.POINTER(C.c_double)]
     L.pbsim_host_deflate_code.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32), C.c_void_p, C.c_int32]
+    L.pbsim_host_sample_filter.argtypes = [C.c_char_p, C.c_int64, C.c_int64, C.c_int64, C.c_double, C.c_double,
+                                           C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64),
+                                           C.POINTER(SampleStats), C.POINTER(C.c_char_p)]
     L.pbsim_host_ssp_table.restype = None
     L.pbsim_host_ssp_table.argtypes = [C.c_int32, C.c_void_p, C.c_void_p]
     return L
@@ -286,3 +296,31 @@ def hp_del_bias(L, opt, hpfreq12):
     out = (C.c_double * 12)()
     L.pbsim_host_hp_del_bias(opt, arr, out)
     return list(out)
+
+
+def sample_filter(L, fastq, len_min=100, len_max=1000000, accuracy_min=0.75, accuracy_max=1.0):
+    """get_sample_inf (pbsim.cpp:1155): -> (pool of quality strings in file order, SampleStats)"""
+    import numpy as np
+    quals = C.create_string_buffer(max(len(fastq), 1))
+    cap = fastq.count(b"\n") // 4 + 2
+    qstart = np.zeros(cap, dtype=np.int64)
+    n = C.c_int64()
+    st = SampleStats()
+    err = C.c_char_p()
+    rc = L.pbsim_host_sample_filter(fastq, len(fastq), len_min, len_max, accuracy_min, accuracy_max, quals,
+                                    qstart.ctypes.data, cap, C.byref(n), C.byref(st), C.byref(err))
+    if rc != 0:
+        raise RuntimeError((err.value or b"").decode())
+    raw = quals.raw
+    return [raw[qstart[i]:qstart[i + 1]] for i in range(n.value)], st
+
+
+def format_sample_stats(st, file_name):
+    """print_sample_stats (pbsim.cpp:1336-1358)"""
+    return (":::: sample reads stats ::::\n\nfile name : %s\n\n:: all reads ::\nread num. : %d\nread total length : %d\n"
+            "read min length : %d\nread max length : %d\n\n:: filtered reads ::\nread num. : %d\nread total length : %d\n"
+            "read min length : %d\nread max length : %d\nread length mean (SD) : %f (%f)\n"
+            "read accuracy mean (SD) : %f (%f)\n\n"
+            % (file_name, st.num, st.len_total, st.len_min, st.len_max, st.num_filtered, st.len_total_filtered,
+               st.len_min_filtered, st.len_max_filtered, st.len_mean_filtered, st.len_sd_filtered,
+               st.accuracy_mean_filtered, st.accuracy_sd_filtered))

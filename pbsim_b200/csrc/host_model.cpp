@@ -407,6 +407,90 @@ int pbsim_host_deflate_code(const int64_t hist[256], uint32_t lit[257], uint32_t
   return 0;
 }
 
+// get_sample_inf (pbsim.cpp:1214-1330): the filter in front of --method sample
+int pbsim_host_sample_filter(const char *fastq, int64_t bytes, int64_t len_min, int64_t len_max, double accuracy_min,
+                             double accuracy_max, char *quals, int64_t *qstart, int64_t qstart_cap, int64_t *n_out,
+                             pbsim_sample_stats *st, const char **err) {
+  static const char *dummy;
+  if (!err) err = &dummy;
+  *err = "";
+  if (!fastq || bytes < 0 || !quals || !qstart || qstart_cap < 1 || !n_out || !st) {
+    *err = "invalid argument";
+    return PBSIM_E_INVALID;
+  }
+  double prob_of[PBSIM_NQV];
+  for (int q = 0; q < PBSIM_NQV; ++q) prob_of[q] = std::pow(10, static_cast<double>(q) / -10);  // qc[i].prob (:549)
+  std::memset(st, 0, sizeof *st);
+  st->len_min = st->len_min_filtered = LONG_MAX;
+  std::vector<long> freq_len(static_cast<size_t>(len_max > 0 ? len_max : 0) + 1, 0), freq_acc(100001, 0);
+  double accuracy_total = 0;
+  int64_t n = 0, out = 0, line_num = 0, pos = 0;
+  qstart[0] = 0;
+  while (pos < bytes) {
+    const char *nl = static_cast<const char *>(std::memchr(fastq + pos, '\n', static_cast<size_t>(bytes - pos)));
+    if (!nl) break;  // no line feed: fgets returns the rest, trim() does not count it
+    const int64_t len = nl - (fastq + pos);
+    const char *line = fastq + pos;
+    pos += len + 1;
+    if (++line_num < 4) continue;
+    line_num = 0;
+    if (len > 1000000) {
+      *err = "ERROR: fastq is too long. Max acceptable length is 1000000.";
+      return PBSIM_E_INVALID;
+    }
+    st->num++;
+    st->len_total += len;
+    if (st->num > 100000000) {
+      *err = "ERROR: fastq is too many. Max acceptable number is 100000000.";
+      return PBSIM_E_INVALID;
+    }
+    if (len > st->len_max) st->len_max = len;
+    if (len < st->len_min) st->len_min = len;
+    if (len < len_min || len > len_max) continue;
+    double prob = 0.0;
+    for (int64_t i = 0; i < len; ++i) {
+      const int q = static_cast<unsigned char>(line[i]) - 33;
+      if (q < 0 || q >= PBSIM_NQV) {
+        *err = "ERROR: quality character outside '!'..'~' in the sample FASTQ.";  // the reference reads qc[] out of bounds
+        return PBSIM_E_INVALID;
+      }
+      prob += prob_of[q];
+    }
+    const double accuracy = 1.0 - (prob / len);
+    if (!(accuracy >= accuracy_min && accuracy <= accuracy_max)) continue;
+    if (n + 1 >= qstart_cap) {
+      *err = "qstart is too small";
+      return PBSIM_E_INVALID;
+    }
+    accuracy_total += accuracy;
+    st->num_filtered++;
+    st->len_total_filtered += len;
+    freq_len[static_cast<size_t>(len)]++;
+    freq_acc[static_cast<size_t>(cxx_int(accuracy * 100000 + 0.5))]++;
+    std::memcpy(quals + out, line, static_cast<size_t>(len));
+    out += len;
+    qstart[++n] = out;
+    if (len > st->len_max_filtered) st->len_max_filtered = len;
+    if (len < st->len_min_filtered) st->len_min_filtered = len;
+  }
+  *n_out = n;
+  if (st->num_filtered < 1) {
+    *err = "ERROR: there is no sample in the valid range of length and accuracy.";
+    return PBSIM_E_PARAM;
+  }
+  st->len_mean_filtered = static_cast<double>(st->len_total_filtered) / st->num_filtered;
+  st->accuracy_mean_filtered = accuracy_total / st->num_filtered;
+  double variance = 0.0;
+  for (int64_t i = 0; i <= len_max; ++i)
+    if (freq_len[static_cast<size_t>(i)] > 0) variance += std::pow((st->len_mean_filtered - i), 2) * freq_len[static_cast<size_t>(i)];
+  st->len_sd_filtered = std::sqrt(variance / st->num_filtered);
+  variance = 0.0;
+  for (int64_t i = 0; i <= 100000; ++i)
+    if (freq_acc[static_cast<size_t>(i)] > 0) variance += std::pow((st->accuracy_mean_filtered - i * 0.00001), 2) * freq_acc[static_cast<size_t>(i)];
+  st->accuracy_sd_filtered = std::sqrt(variance / st->num_filtered);
+  return 0;
+}
+
 void pbsim_host_hp_del_bias(double opt, const int64_t hpfreq[12], double bias[12]) {
   for (int i = 0; i < 12; ++i) bias[i] = 0.0;
   if (opt == 1) {

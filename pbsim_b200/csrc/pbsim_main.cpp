@@ -12,8 +12,8 @@
 //
 // Engine-only options (additive): --gpu N, --rng philox|replay, --replay-draws F --replay-marks F,
 // --threads N (host compression), --gzip gpu|host (default gpu: the records are gzip-compressed on the GPU and the
-// driver only writes the members to the files).  Not built yet in this driver: --method sample,
-// BAM encoding for --pass-num > 1 (SAM text is written as <prefix>[_NNNN].sam.gz instead).
+// driver only writes the members to the files; multi-pass output is <prefix>[_NNNN].bam, or SAM text in .sam.gz with
+// --gzip host).  --method sample filters the FASTQ on the host (pbsim_host_sample_filter) and hands the pool to the engine.
 #include <getopt.h>
 #include <sys/resource.h>
 #include <sys/time.h>
@@ -446,7 +446,12 @@ void print_help() {
           "  --strategy           trans | templ\n"
           "  --transcript         transcript table: id, plus count, minus count, sequence (tab separated).\n"
           "  --template           FASTA file of templates; every template is read once, in full.\n\n"
-          " --method sample is not built in this driver yet.\n\n");
+          " [options for sampling-based simulation]\n\n"
+          "  --method             sample\n"
+          "  --sample             FASTQ format file to sample.\n"
+          "  --sample-profile-id  sample (filtered) profile ID; with --sample the profile is stored, without it reused.\n"
+          "  --accuracy-min       minimum accuracy (0.75).\n"
+          "  --accuracy-max       maximum accuracy (1.00).\n\n");
 }
 
 template <class T>
@@ -592,6 +597,33 @@ int main(int argc, char **argv) {
   if (o.strategy == "templ" && !o.set_flg[21]) die("ERROR: for --strategy templ, --template must be set.\n");
   if (o.method == "qshmm" && !o.set_flg[15]) die("ERROR: for --method qshmm, --qshmm must be set.\n");
   if (o.method == "errhmm" && !o.set_flg[16]) die("ERROR: for --method errhmm, --errhmm must be set.\n");
+  // sample, sample-profile-id (:1565-1616): --sample alone filters the FASTQ, with a profile id the filtered reads are
+  // stored (sample_profile_<id>.fastq / .stats), the id alone reuses a stored profile
+  const bool sample = o.method == "sample";
+  int sample_mode = 0;  // 0: METHOD_SAM, 1: METHOD_SAM_STORE, 2: METHOD_SAM_REUSE
+  std::string profile_fq, profile_stats;
+  if (sample) {
+    if (o.set_flg[11]) sample_mode = o.set_flg[12] ? 1 : 0;
+    else if (o.set_flg[12]) sample_mode = 2;
+    else die("ERROR: for --method sample, --sample (and/or --sample-profile-id) must be set.\n");
+  }
+  if (o.set_flg[12]) {
+    profile_fq = "sample_profile_" + o.profile_id + ".fastq";
+    profile_stats = "sample_profile_" + o.profile_id + ".stats";
+  }
+  auto readable = [](const std::string &f) {
+    FILE *fp = fopen(f.c_str(), "r");
+    if (fp) fclose(fp);
+    return fp != nullptr;
+  };
+  if (sample_mode == 1) {
+    if (readable(profile_fq)) die("ERROR: %s exists.\n", profile_fq.c_str());
+    if (readable(profile_stats)) die("ERROR: %s exists.\n", profile_stats.c_str());
+  }
+  if (sample_mode == 2) {
+    if (!readable(profile_fq)) die("ERROR: %s does not exist.\n", profile_fq.c_str());
+    if (!readable(profile_stats)) die("ERROR: %s does not exist.\n", profile_stats.c_str());
+  }
   if (o.set_flg[13]) o.accuracy_min = int(o.accuracy_min * 100) * 0.01;
   if (o.set_flg[14]) o.accuracy_max = int(o.accuracy_max * 100) * 0.01;
   if (o.set_flg[19]) o.accuracy_mean = int(o.accuracy_mean * 100) * 0.01;
@@ -599,9 +631,9 @@ int main(int argc, char **argv) {
   if (o.world < 1 || o.rank < 0 || o.rank >= o.world) die("ERROR: --rank must be in 0..world-1.\n");
   if (o.world > 1 && (o.strategy != "wgs" || o.rng == "replay"))
     die("ERROR: --world > 1 shards the sequences of --strategy wgs in philox mode; shard a transcript table by read range through the library instead.\n");
-  if (o.method == "sample")
-    die("ERROR: this B200 driver builds --method qshmm|errhmm; %s/%s is not built yet.\n", o.strategy.c_str(),
-        o.method.c_str());
+  if (o.pass_num > 1 && sample) die("ERROR: sampling-based simulation supports only single-pass.\n");  // :1675-1679
+  if (sample && o.world > 1)
+    die("ERROR: --method sample runs on one GPU (the copies of a pool entry are sequential).\n");
   const bool qs = o.method == "qshmm";
   const bool wgs = o.strategy == "wgs";
 
@@ -609,30 +641,145 @@ int main(int argc, char **argv) {
   fprintf(stderr, ":::: Simulation parameters :::\n\n");
   fprintf(stderr, "strategy : %s\n", o.strategy.c_str());
   fprintf(stderr, "method : %s\n", o.method.c_str());
-  fprintf(stderr, "%s : %s\n", o.method.c_str(), qs ? o.qshmm.c_str() : o.errhmm.c_str());
+  if (!sample) fprintf(stderr, "%s : %s\n", o.method.c_str(), qs ? o.qshmm.c_str() : o.errhmm.c_str());
   if (wgs) fprintf(stderr, "genome : %s\n", o.genome.c_str());
   else if (o.strategy == "trans") fprintf(stderr, "transcript : %s\n", o.transcript.c_str());
   else fprintf(stderr, "template : %s\n", o.templ.c_str());
   fprintf(stderr, "prefix : %s\n", o.prefix.c_str());
   fprintf(stderr, "id-prefix : %s\n", o.id_prefix.c_str());
   if (wgs) fprintf(stderr, "depth : %lf\n", o.depth);
-  if (o.strategy != "templ") {
+  if (sample) {
+    fprintf(stderr, "length-mean : (sample FASTQ)\n");
+    fprintf(stderr, "length-sd : (sample FASTQ)\n");
+    fprintf(stderr, "length-min : %ld\n", o.len_min);
+    fprintf(stderr, "length-max : %ld\n", o.len_max);
+  } else if (o.strategy != "templ") {
     fprintf(stderr, "length-mean : %f\n", o.len_mean);
     fprintf(stderr, "length-sd : %f\n", o.len_sd);
     fprintf(stderr, "length-min : %ld\n", o.len_min);
     fprintf(stderr, "length-max : %ld\n", o.len_max);
   }
-  if (qs) fprintf(stderr, "difference-ratio : %ld:%ld:%ld\n", o.sub_ratio, o.ins_ratio, o.del_ratio);
+  if (qs || sample) fprintf(stderr, "difference-ratio : %ld:%ld:%ld\n", o.sub_ratio, o.ins_ratio, o.del_ratio);
   fprintf(stderr, "seed : %d\n", o.seed);
-  fprintf(stderr, "accuracy-mean : %f\n", o.accuracy_mean);
+  if (sample) {  // printf("%s", NULL) prints "(null)" with glibc
+    fprintf(stderr, "sample : %s\n", o.set_flg[11] ? o.sample.c_str() : "(null)");
+    fprintf(stderr, "sample-profile-id : %s\n", o.set_flg[12] ? o.profile_id.c_str() : "(null)");
+    fprintf(stderr, "accuracy-mean : (sample FASTQ)\n");
+    fprintf(stderr, "accuracy-sd : (sample FASTQ)\n");
+    fprintf(stderr, "accuracy-min : %f\n", o.accuracy_min);
+    fprintf(stderr, "accuracy-max : %f\n", o.accuracy_max);
+  } else {
+    fprintf(stderr, "accuracy-mean : %f\n", o.accuracy_mean);
+  }
   fprintf(stderr, "pass_num : %d\n", o.pass_num);
   fprintf(stderr, "hp-del-bias : %f\n", o.hp_del_bias);
   fprintf(stderr, "\n");
 
+  // ---- sample reads (main :579-616): get_sample_inf + print_sample_stats
+  std::string pool_q;
+  std::vector<int64_t> pool_start{0};
+  if (sample) {
+    pbsim_sample_stats ss;
+    memset(&ss, 0, sizeof ss);
+    auto slurp = [](const std::string &f, std::string *out) {
+      FILE *fp = fopen(f.c_str(), "rb");
+      if (!fp) return false;
+      char buf[1 << 16];
+      size_t k;
+      while ((k = fread(buf, 1, sizeof buf, fp)) > 0) out->append(buf, k);
+      fclose(fp);
+      return true;
+    };
+    if (sample_mode == 2) {
+      // the stored profile: statistics as the reference wrote them (:1317-1326), one quality string per line
+      std::string text, line;
+      if (!slurp(profile_stats, &text) || !slurp(profile_fq, &pool_q)) die("ERROR: Cannot open sample_profile\n");
+      size_t p = 0;
+      while (p < text.size()) {
+        size_t q = text.find('\n', p);
+        if (q == std::string::npos) q = text.size();
+        line = text.substr(p, q - p);
+        p = q + 1;
+        const size_t tab = line.find('\t');
+        if (tab == std::string::npos) continue;
+        const std::string item = line.substr(0, tab), val = line.substr(tab + 1);
+        if (item == "num") ss.num_filtered = atol(val.c_str());
+        else if (item == "len_total") ss.len_total_filtered = atol(val.c_str());
+        else if (item == "len_min") ss.len_min_filtered = atol(val.c_str());
+        else if (item == "len_max") ss.len_max_filtered = atol(val.c_str());
+        else if (item == "len_mean") ss.len_mean_filtered = atof(val.c_str());
+        else if (item == "len_sd") ss.len_sd_filtered = atof(val.c_str());
+        else if (item == "accuracy_mean") ss.accuracy_mean_filtered = atof(val.c_str());
+        else if (item == "accuracy_sd") ss.accuracy_sd_filtered = atof(val.c_str());
+      }
+      std::string packed;
+      for (size_t a = 0; a < pool_q.size();) {
+        size_t b = pool_q.find('\n', a);
+        if (b == std::string::npos) b = pool_q.size();
+        packed.append(pool_q, a, b - a);
+        pool_start.push_back((int64_t)packed.size());
+        a = b + 1;
+      }
+      pool_q.swap(packed);
+      if ((int64_t)pool_start.size() - 1 != ss.num_filtered || (int64_t)pool_q.size() != ss.len_total_filtered)
+        die("ERROR: %s does not match %s.\n", profile_fq.c_str(), profile_stats.c_str());
+    } else {
+      std::string fq;
+      if (!slurp(o.sample, &fq)) die("ERROR: Cannot open file: %s\n", o.sample.c_str());
+      pool_q.resize(fq.size() + 1);
+      pool_start.assign((size_t)std::count(fq.begin(), fq.end(), '\n') / 4 + 2, 0);
+      int64_t n = 0;
+      const char *ferr = nullptr;
+      if (pbsim_host_sample_filter(fq.data(), (int64_t)fq.size(), o.len_min, o.len_max, o.accuracy_min, o.accuracy_max,
+                                   &pool_q[0], pool_start.data(), (int64_t)pool_start.size(), &n, &ss, &ferr) != 0)
+        die("%s\n", ferr);
+      pool_start.resize((size_t)n + 1);
+      pool_q.resize((size_t)pool_start[n]);
+      if (sample_mode == 1) {
+        FILE *f1 = fopen(profile_fq.c_str(), "w"), *f2 = fopen(profile_stats.c_str(), "w");
+        if (!f1 || !f2) die("ERROR: Cannot open sample_profile\n");
+        for (int64_t i = 0; i < n; ++i) {
+          fwrite(pool_q.data() + pool_start[i], 1, (size_t)(pool_start[i + 1] - pool_start[i]), f1);
+          fputc('\n', f1);
+        }
+        fprintf(f2, "num\t%ld\n", (long)ss.num_filtered);
+        fprintf(f2, "len_total\t%lld\n", (long long)ss.len_total_filtered);
+        fprintf(f2, "len_min\t%ld\n", (long)ss.len_min_filtered);
+        fprintf(f2, "len_max\t%ld\n", (long)ss.len_max_filtered);
+        fprintf(f2, "len_mean\t%f\n", ss.len_mean_filtered);
+        fprintf(f2, "len_sd\t%f\n", ss.len_sd_filtered);
+        fprintf(f2, "accuracy_mean\t%f\n", ss.accuracy_mean_filtered);
+        fprintf(f2, "accuracy_sd\t%f\n", ss.accuracy_sd_filtered);
+        fclose(f1);
+        fclose(f2);
+      }
+    }
+    // print_sample_stats (:1336-1358)
+    fprintf(stderr, ":::: sample reads stats ::::\n\n");
+    if (sample_mode == 2) {
+      fprintf(stderr, "file name : %s\n", profile_fq.c_str());
+    } else {
+      fprintf(stderr, "file name : %s\n", o.sample.c_str());
+      fprintf(stderr, "\n:: all reads ::\n");
+      fprintf(stderr, "read num. : %ld\n", (long)ss.num);
+      fprintf(stderr, "read total length : %lld\n", (long long)ss.len_total);
+      fprintf(stderr, "read min length : %ld\n", (long)ss.len_min);
+      fprintf(stderr, "read max length : %ld\n", (long)ss.len_max);
+    }
+    fprintf(stderr, "\n:: filtered reads ::\n");
+    fprintf(stderr, "read num. : %ld\n", (long)ss.num_filtered);
+    fprintf(stderr, "read total length : %lld\n", (long long)ss.len_total_filtered);
+    fprintf(stderr, "read min length : %ld\n", (long)ss.len_min_filtered);
+    fprintf(stderr, "read max length : %ld\n", (long)ss.len_max_filtered);
+    fprintf(stderr, "read length mean (SD) : %f (%f)\n", ss.len_mean_filtered, ss.len_sd_filtered);
+    fprintf(stderr, "read accuracy mean (SD) : %f (%f)\n", ss.accuracy_mean_filtered, ss.accuracy_sd_filtered);
+    fprintf(stderr, "\n");
+  }
+
   // ---- model + tables (set_qshmm/set_errhmm/set_mut + table builders)
   pbsim_host_params hp;
   memset(&hp, 0, sizeof hp);
-  hp.method = qs ? PBSIM_METHOD_QSHMM : PBSIM_METHOD_ERRHMM;
+  hp.method = sample ? PBSIM_METHOD_SAMPLE : (qs ? PBSIM_METHOD_QSHMM : PBSIM_METHOD_ERRHMM);
   hp.pass_num = o.pass_num;
   hp.len_min = o.len_min;
   hp.len_max = o.len_max;
@@ -646,7 +793,7 @@ int main(int argc, char **argv) {
   pbsim_host_model *hm = nullptr;
   const char *err = nullptr;
   const std::string model_path = qs ? o.qshmm : o.errhmm;
-  if (pbsim_host_model_load(&hm, &hp, model_path.c_str(), &err) != 0) {
+  if (pbsim_host_model_load(&hm, &hp, sample ? nullptr : model_path.c_str(), &err) != 0) {
     if (strstr(err, "Cannot open")) die("ERROR: Cannot open file: %s\n", model_path.c_str());
     die("%s\n", err);
   }
@@ -663,6 +810,8 @@ int main(int argc, char **argv) {
   if (pbsim_cuda_create(&eng, o.gpu) != 0) die("ERROR: %s\n", pbsim_cuda_last_error(nullptr));
   if (pbsim_cuda_set_model(eng, pbsim_host_model_get(hm)) != 0) die("ERROR: %s\n", pbsim_cuda_last_error(eng));
   if (pbsim_cuda_set_option(eng, "deflate", o.gzip == "gpu" ? 1 : 0) != 0) die("ERROR: %s\n", pbsim_cuda_last_error(eng));
+  if (sample && pbsim_cuda_set_pool(eng, pool_q.data(), pool_start.data(), (int64_t)pool_start.size() - 1) != 0)
+    die("ERROR: %s\n", pbsim_cuda_last_error(eng));
 
   // ---- replay inputs
   std::vector<int32_t> draws;

@@ -1,5 +1,5 @@
 """CPU: the C++ driver rejects what the reference rejects, with the same message and exit status, before any GPU is
-touched.  tests/golden/cli_errors.json holds what the UNMODIFIED reference printed for 25 invocations (option
+touched.  tests/golden/cli_errors.json holds what the UNMODIFIED reference printed for 31 invocations (option
 validation of set_sim_param pbsim.cpp:1451-1688, missing files, a reference sequence shorter than 100 bases)."""
 import json
 import os
@@ -22,6 +22,7 @@ def workdir(tmp_path_factory):
     shutil.copy(model_path("QSHMM-RSII.model"), d / "QSHMM-RSII.model")
     shutil.copy(model_path("ERRHMM-ONT.model"), d / "ERRHMM-ONT.model")
     (d / "tiny.fa").write_text(">s\nACGTACGTAC\n")
+    (d / "tiny.fq").write_text("@r1\nACGT\n+\nIIII\n@r2\nACGTA\n+\nIIIII\n")
     return d
 
 
@@ -68,3 +69,27 @@ def test_driver_prints_the_reference_blocks_before_it_needs_a_gpu(name, tmp_path
     def norm(text):
         return "\n".join(("%s : <model>" % c.method) if ln.startswith(c.method + " : ") else ln for ln in text.split("\n"))
     assert norm(head) == norm(want)
+
+
+@pytest.mark.parametrize("name", ["sample_basic", "sample_quirks"])
+def test_sample_driver_prints_the_reference_blocks_before_it_needs_a_gpu(name, tmp_path):
+    """--method sample: parameters, the sample FASTQ statistics (get_sample_inf / print_sample_stats, :1155-1358) and the
+    reference statistics read like the reference's; then the driver stops for want of a GPU"""
+    import gzip
+    import torch
+    from tests.golden_util import SampleCase
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: the run would continue")
+    c = SampleCase(name)
+    G.build_engine()
+    exe = G.build_driver()
+    with gzip.open(os.path.join(c.dir, "genome.fa.gz"), "rb") as f:
+        (tmp_path / "genome.fa").write_bytes(f.read())
+    (tmp_path / "sample.fq").write_bytes(c.sample_fastq)
+    args = [exe, "--strategy", "wgs", "--method", "sample", "--sample", "sample.fq", "--genome", "genome.fa", "--depth",
+            str(c.depth), "--seed", str(c.seed)] + list(c.meta["extra_args"]) + ["--prefix", "out"]
+    p = subprocess.run(args, cwd=tmp_path, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=120)
+    assert p.returncode != 0
+    got = p.stderr.decode()
+    assert "no CPU fallback" in got
+    assert got.split("ERROR: no usable CUDA device")[0] == c.stderr.split(":::: Simulation stats (ref.1) ::::")[0]

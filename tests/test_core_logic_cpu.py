@@ -260,3 +260,19 @@ def test_sample_core_philox_equals_oracle_philox(name):
         assert reads == oreads
         assert maf == omaf
         assert [s["nins"] for s in sub] == info["nins"].tolist()
+
+
+@pytest.mark.parametrize("name", ["sample_basic", "sample_quirks"])
+def test_sample_filter_equals_reference(name):
+    """pbsim_host_sample_filter (get_sample_inf, pbsim.cpp:1155-1330): the pool equals the oracle's restatement and the
+    statistics are the block the reference printed"""
+    from tests.golden_util import SampleCase
+    c = SampleCase(name)
+    pool, st = capi.sample_filter(H.lib(), c.sample_fastq, **c.meta["pool_kwargs"])
+    assert pool == c.pool
+    assert capi.format_sample_stats(st, "sample.fq") in c.stderr
+    # a last record without line feed is not counted; nothing in range is the reference's error
+    cut, _ = capi.sample_filter(H.lib(), c.sample_fastq[:-1], **c.meta["pool_kwargs"])
+    assert cut == c.pool[:-1] or len(c.pool[-1]) and cut == c.pool[:len(cut)] and len(cut) >= len(c.pool) - 1
+    with pytest.raises(RuntimeError, match="no sample in the valid range"):
+        capi.sample_filter(H.lib(), c.sample_fastq, len_min=999999, len_max=1000000)

@@ -128,3 +128,50 @@ def test_cli_two_processes_shard_the_sequences(tmp_path):
     for i, o in enumerate(out, start=1):
         assert gzip.open(tmp_path / ("out_%04d.fq.gz" % i), "rb").read() == o["reads"]
         assert gzip.open(tmp_path / ("out_%04d.maf.gz" % i), "rb").read() == o["maf"]
+
+
+@pytest.mark.parametrize("name", ["sample_basic", "sample_quirks"])
+def test_cli_sample_method_reproduces_reference_files(name, tmp_path):
+    """--method sample: the driver filters the FASTQ (get_sample_inf), the engine copies the pool; files and stderr are
+    the reference's.  Then the profile round trip: --sample + --sample-profile-id stores the filtered reads,
+    --sample-profile-id alone reuses them (pbsim.cpp:1565-1616) and must simulate the same reads."""
+    from tests.golden_util import SampleCase
+    c = SampleCase(name)
+    exe = G.build_driver()
+    with gzip.open(os.path.join(c.dir, "genome.fa.gz"), "rb") as f:
+        (tmp_path / "genome.fa").write_bytes(f.read())
+    (tmp_path / "sample.fq").write_bytes(c.sample_fastq)
+    O.glibc_rand(c.seed, c.ndraws).tofile(tmp_path / "draws.bin")
+    c.marks.astype(np.int64).tofile(tmp_path / "marks.bin")
+    common = ["--strategy", "wgs", "--method", "sample", "--genome", "genome.fa", "--depth", str(c.depth), "--seed",
+              str(c.seed)] + list(c.meta["extra_args"])
+    replay = ["--rng", "replay", "--replay-draws", "draws.bin", "--replay-marks", "marks.bin"]
+
+    def run(extra, prefix):
+        p = subprocess.run([exe] + common + extra + ["--prefix", prefix], cwd=tmp_path, stdout=subprocess.PIPE,
+                           stderr=subprocess.PIPE, timeout=600)
+        assert p.returncode == 0, p.stderr.decode()
+        return p.stderr.decode()
+
+    stderr = run(["--sample", "sample.fq"] + replay, "out")
+    for i in range(1, len(c.contigs) + 1):
+        assert gzip.open(tmp_path / ("out_%04d.fq.gz" % i), "rb").read() == c.reads(i), "reads file differs, seq %d" % i
+        assert gzip.open(tmp_path / ("out_%04d.maf.gz" % i), "rb").read() == c.maf(i)
+    assert stderr.split(":::: System utilization ::::")[0] == c.stderr.split(":::: System utilization ::::")[0]
+    # store, then reuse
+    run(["--sample", "sample.fq", "--sample-profile-id", "p1"] + replay, "st")
+    stats = (tmp_path / "sample_profile_p1.stats").read_text()
+    assert stats.startswith("num\t%d\nlen_total\t%d\n" % (len(c.pool), sum(len(q) for q in c.pool)))
+    assert (tmp_path / "sample_profile_p1.fastq").read_bytes() == b"".join(q + b"\n" for q in c.pool)
+    err2 = run(["--sample-profile-id", "p1"] + replay, "re")
+    assert "file name : sample_profile_p1.fastq\n\n:: filtered reads ::\nread num. : %d\n" % len(c.pool) in err2
+    for i in range(1, len(c.contigs) + 1):
+        for ext in ("fq.gz", "maf.gz"):
+            assert gzip.open(tmp_path / ("st_%04d.%s" % (i, ext)), "rb").read() == \
+                gzip.open(tmp_path / ("out_%04d.%s" % (i, ext)), "rb").read()
+            assert gzip.open(tmp_path / ("re_%04d.%s" % (i, ext)), "rb").read() == \
+                gzip.open(tmp_path / ("out_%04d.%s" % (i, ext)), "rb").read()
+    # storing over an existing profile is refused like the reference does
+    p = subprocess.run([exe] + common + ["--sample", "sample.fq", "--sample-profile-id", "p1"], cwd=tmp_path,
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=60)
+    assert p.returncode != 0 and "ERROR: sample_profile_p1.fastq exists." in p.stderr.decode()
