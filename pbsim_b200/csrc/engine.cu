@@ -201,6 +201,9 @@ struct pbsim_engine {
   DevBuf d_pool_q, d_pool_start, d_groups;
   SampleSchedule sched;
   SampleGroups groups;
+  int sample_spec = 1;            // option "sample_spec": simulate all copies at once assuming full-length reads, redo the rest
+  bool sample_spec_run = true;    // this run: switched off when most groups had to be redone
+  int64_t sample_redo_groups = 0;
 
   // run
   bool running = false;
@@ -522,6 +525,7 @@ int run_batch(pbsim_engine *e, uint32_t n_reads, int64_t clip_room, BatchResult 
   Pl.start = e->d_pool_start.as<uint64_t>();
   Pl.n = (uint32_t)(e->pool_start.empty() ? 0 : e->pool_start.size() - 1);
   if (sample && !sb) return fail(e, PBSIM_E_INVALID, "internal: sample batch without groups");
+  const bool spec = sample && e->sample_spec && e->sample_spec_run;
   const bool replay = e->run.rng_mode == PBSIM_RNG_REPLAY;
   int rc = carve_batch(e, n_reads);
   if (rc) return rc;
@@ -575,34 +579,38 @@ int run_batch(pbsim_engine *e, uint32_t n_reads, int64_t clip_room, BatchResult 
     // ---- K1 plan
     const uint32_t ev_align = qs ? 8u : 16u;
     if (sample)
-      k_plan_sample<<<nblk(n_reads, 256), 256, 0, e->st>>>(G, Pl, *sb, B, e->cap_num, e->cap_den);
+      k_plan_sample<<<nblk(n_reads, 256), 256, 0, e->st>>>(G, Pl, *sb, B, e->cap_num, e->cap_den, spec ? 1u : 0u);
     else
       k_plan<<<nblk(n_reads, 256), 256, 0, e->st>>>(M, G, device_set(e), rng, B, clip_room, e->cap_num, e->cap_den, ev_align,
                                                      use_segments ? (uint32_t)e->seg_min_len : 0u, e->seg_extra,
                                                      (uint32_t)e->chain_chunk);
     e->launches++;
-    // ---- sort by (accuracy, length desc)
-    {
-      size_t tmp = 0;
-      CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, B.key_in, B.key_out, B.idx_in, B.order, (int)n_sub, 0, 28, e->st));
-      CK(e->d_cub_tmp.ensure(tmp + 256));
-      tmp = e->d_cub_tmp.cap;
-      CK(cub::DeviceRadixSort::SortPairs(e->d_cub_tmp.p, tmp, B.key_in, B.key_out, B.idx_in, B.order, (int)n_sub, 0, 28,
-                                         e->st));
-    }
-    k_fill_u32<<<1, 256, 0, e->st>>>(bin_start, kBins + 1, 0xFFFFFFFFu);
-    k_bin_bounds<<<nblk(n_sub, 256), 256, 0, e->st>>>(B.key_out, n_sub, bin_start);
-    k_cta_map<<<1, 32, 0, e->st>>>(bin_start, B.key_out, n_sub, bin_lo, bin_hi, cta_first, cta_threads);
-    k_cta_keys<<<nblk(cta_slots, 256), 256, 0, e->st>>>(B.key_out, bin_lo, cta_first, cta_slots, cta_key, cta_id, cta_threads);
-    {
-      size_t tmp = 0;
-      CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, cta_key, cta_key_s, cta_id, cta_order, (int)cta_slots, 0, 21, e->st));
-      CK(e->d_cub_tmp.ensure(tmp + 256));
-      tmp = e->d_cub_tmp.cap;
-      CK(cub::DeviceRadixSort::SortPairs(e->d_cub_tmp.p, tmp, cta_key, cta_key_s, cta_id, cta_order, (int)cta_slots, 0, 21,
-                                         e->st));
-    }
-    e->launches += 4;
+    // ---- sort by (accuracy, length desc), bins, longest-first CTA order
+    auto schedule = [&]() -> int {
+      {
+        size_t tmp = 0;
+        CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, B.key_in, B.key_out, B.idx_in, B.order, (int)n_sub, 0, 28, e->st));
+        CK(e->d_cub_tmp.ensure(tmp + 256));
+        tmp = e->d_cub_tmp.cap;
+        CK(cub::DeviceRadixSort::SortPairs(e->d_cub_tmp.p, tmp, B.key_in, B.key_out, B.idx_in, B.order, (int)n_sub, 0, 28,
+                                           e->st));
+      }
+      k_fill_u32<<<1, 256, 0, e->st>>>(bin_start, kBins + 1, 0xFFFFFFFFu);
+      k_bin_bounds<<<nblk(n_sub, 256), 256, 0, e->st>>>(B.key_out, n_sub, bin_start);
+      k_cta_map<<<1, 32, 0, e->st>>>(bin_start, B.key_out, n_sub, bin_lo, bin_hi, cta_first, cta_threads);
+      k_cta_keys<<<nblk(cta_slots, 256), 256, 0, e->st>>>(B.key_out, bin_lo, cta_first, cta_slots, cta_key, cta_id, cta_threads);
+      {
+        size_t tmp = 0;
+        CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, cta_key, cta_key_s, cta_id, cta_order, (int)cta_slots, 0, 21, e->st));
+        CK(e->d_cub_tmp.ensure(tmp + 256));
+        tmp = e->d_cub_tmp.cap;
+        CK(cub::DeviceRadixSort::SortPairs(e->d_cub_tmp.p, tmp, cta_key, cta_key_s, cta_id, cta_order, (int)cta_slots, 0, 21,
+                                           e->st));
+      }
+      e->launches += 4;
+      return 0;
+    };
+    if ((rc = schedule())) return rc;
     // ---- slots
     unsigned long long *tmp64 = reinterpret_cast<unsigned long long *>(u64_slice(e, 2));
     k_widen<<<nblk(n_sub + 1, 256), 256, 0, e->st>>>(B.cap, n_sub, tmp64);
@@ -654,8 +662,25 @@ int run_batch(pbsim_engine *e, uint32_t n_reads, int64_t clip_room, BatchResult 
     bool seg_timed = false;
     CK(cudaEventRecord(e->ev_k[0], e->st));
     if (sample) {
-      if (replay) k_sim_sample<PBSIM_RNG_REPLAY><<<grid, kSimThreads, 0, e->st>>>(A, Pl, *sb);
-      else k_sim_sample<PBSIM_RNG_PHILOX><<<grid, kSimThreads, 0, e->st>>>(A, Pl, *sb);
+      if (replay) k_sim_sample<PBSIM_RNG_REPLAY><<<grid, kSimThreads, 0, e->st>>>(A, Pl, *sb, 0u);
+      else k_sim_sample<PBSIM_RNG_PHILOX><<<grid, kSimThreads, 0, e->st>>>(A, Pl, *sb, 0u);
+      if (spec) {
+        // which copies assumed a wrong length?  Their groups' tails are redone as chains (k_sample_redo)
+        hctrl[6] = 0;
+        CK(cudaMemsetAsync(ctrl + 6, 0, 8, e->st));
+        k_sample_redo<<<nblk(n_reads, 256), 256, 0, e->st>>>(B, ctrl + 6);
+        CK(cudaMemcpyAsync(hctrl + 6, ctrl + 6, 8, cudaMemcpyDeviceToHost, e->st));
+        CK(cudaStreamSynchronize(e->st));
+        e->launches += 2;
+        if (hctrl[6] > 0) {
+          if ((rc = schedule())) return rc;
+          if (replay) k_sim_sample<PBSIM_RNG_REPLAY><<<grid, kSimThreads, 0, e->st>>>(A, Pl, *sb, 1u);
+          else k_sim_sample<PBSIM_RNG_PHILOX><<<grid, kSimThreads, 0, e->st>>>(A, Pl, *sb, 1u);
+          e->launches++;
+          e->sample_redo_groups += (int64_t)hctrl[6];
+          if (hctrl[6] * 2 > sb->n_groups) e->sample_spec_run = false;  // deletion-rich mix: chains from the start
+        }
+      }
     } else if (qs) {
       if (replay) k_sim_qshmm<PBSIM_RNG_REPLAY><<<grid, kSimThreads, kQsSmemBytes, e->st>>>(A);
       else k_sim_qshmm<PBSIM_RNG_PHILOX><<<grid, kSimThreads, kQsSmemBytes, e->st>>>(A);
@@ -1672,6 +1697,8 @@ int pbsim_cuda_simulate_begin(pbsim_engine *e, const pbsim_run *run) {
       return fail(e, PBSIM_E_INVALID, "--method sample runs whole sequences: read ranges are not supported");
     if (!e->sched.init(run->len_quota, (int64_t)e->pool_start.size() - 1, e->pool_start.data()))
       return fail(e, PBSIM_E_INVALID, "the pool cannot be sampled (fewer than 2 reads)");
+    e->sample_spec_run = true;
+    e->sample_redo_groups = 0;
   }
   e->run = *run;
   if (e->strategy != PBSIM_STRATEGY_WGS) {
@@ -1820,6 +1847,10 @@ int pbsim_cuda_set_option(pbsim_engine *e, const char *name, int64_t value) {
     if (value < 0 || value > 2) return fail(e, PBSIM_E_INVALID, "pipeline must be 0, 1 or 2");
     if (e->running) return fail(e, PBSIM_E_INVALID, "pipeline cannot change during a run");
     e->pipeline = (int)value;
+    return 0;
+  }
+  if (!strcmp(name, "sample_spec")) {
+    e->sample_spec = value != 0;
     return 0;
   }
   if (!strcmp(name, "bam")) {

@@ -488,6 +488,13 @@ __global__ void __launch_bounds__(kErrThreads) k_sim_errhmm(SimArgs A, uint32_t 
 // a chain (copy i+1 is as long as copy i's read), so ONE thread simulates a group: it plans copy 0 from the pool
 // entry's length, runs sample_simulate, plans copy 1 from the read's length, and so on.  Groups run in parallel,
 // scheduled longest-first like the sequential pass-1 bins (bin 0; copies > 0 carry the out-of-range bin).
+//
+// Speculation (option "sample_spec", default on): with the usual error mix (more insertions than deletions) a read
+// uses up its quality string before its window, so every copy is as long as the pool entry and the chain is
+// trivial.  The engine therefore first simulates EVERY copy in its own thread assuming the entry's length
+// (critical path: one read instead of all copies of the longest entry), k_sample_redo then finds, per group, the
+// first copy whose predecessor came out shorter than assumed, and only those tails are redone as chains that start
+// from the predecessor's read length.  The result is the chain's, by construction.
 // ----------------------------------------------------------------------------------------------
 struct DevicePool {
   const uint8_t *quals;    // quality strings of the filtered sample reads, concatenated (fp_filtered, :1214-1275)
@@ -502,7 +509,8 @@ struct SampleBatch {
   uint32_t skip_first;      // replay: read 0 of the batch is preceded by the pool-pass draw (:1734)
 };
 
-__global__ void k_plan_sample(DeviceGenome G, DevicePool Pl, SampleBatch SB, Batch B, uint32_t cap_num, uint32_t cap_den) {
+__global__ void k_plan_sample(DeviceGenome G, DevicePool Pl, SampleBatch SB, Batch B, uint32_t cap_num, uint32_t cap_den,
+                              uint32_t spec) {
   const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= B.n_reads) return;
   uint32_t lo = 0, hi = SB.n_groups;  // g_first[lo] <= r < g_first[hi]
@@ -518,25 +526,47 @@ __global__ void k_plan_sample(DeviceGenome G, DevicePool Pl, SampleBatch SB, Bat
   B.plan_tr[r] = j;
   B.plan_off[r] = 0;
   B.plan_wlen[r] = len0;   // upper bound; the group's thread stores the planned window of every copy
-  B.plan_raw[r] = num;     // copy 0: copies of the group
+  B.plan_raw[r] = spec ? 1u : num;  // copies the thread scheduled for this read simulates (chain: copy 0 walks them all)
   B.plan_meta[r] = 0;
   uint64_t cap = (uint64_t)len0 * cap_num / cap_den + 2048u;
   cap = (cap + 7u) / 8u * 8u;
-  uint64_t work = (uint64_t)len0 * num / 16u;
+  uint64_t work = spec ? (uint64_t)len0 : (uint64_t)len0 * num / 16u;
   if (work > 0xFFFFFu) work = 0xFFFFFu;
-  B.key_in[r] = copy == 0u ? (0xFFFFFu - (uint32_t)work) : ((uint32_t)kBins << 20);
+  B.key_in[r] = (copy == 0u || spec) ? (0xFFFFFu - (uint32_t)work) : ((uint32_t)kBins << 20);
   B.idx_in[r] = r;
   B.cap[r] = (uint32_t)cap;
   B.ck_cap[r] = (uint32_t)(cap / PB_TILE) + 2u;
-  B.nseg[r] = 0;
-  B.nchunk[r] = 0;
+  B.nseg[r] = copy;   // (the segment fields are free for --method sample)
+  B.nchunk[r] = num;
+}
+
+// after the speculative pass: read r heads a chain to redo iff its predecessor's read is not as long as r assumed
+// and every earlier copy of the group assumed right; everything else leaves the schedule
+__global__ void k_sample_redo(Batch B, unsigned long long *n_redo) {
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= B.n_reads) return;
+  const uint32_t copy = B.nseg[r], num = B.nchunk[r];
+  bool head = copy > 0u && B.rlen[r - 1u] != B.plan_wlen[r];
+  for (uint32_t k = 1; head && k < copy; ++k)
+    if (B.rlen[r - copy + k - 1u] != B.plan_wlen[r - copy + k]) head = false;
+  uint32_t key = (uint32_t)kBins << 20;
+  if (head) {
+    uint64_t work = (uint64_t)B.plan_wlen[r] * (num - copy) / 16u;
+    if (work > 0xFFFFFu) work = 0xFFFFFu;
+    key = 0xFFFFFu - (uint32_t)work;
+    B.plan_raw[r] = num - copy;
+    atomicAdd(n_redo, 1ull);
+  }
+  B.key_in[r] = key;
+  B.idx_in[r] = r;
 }
 
 // shared memory: [thr 94*16 | qc_prob 94*8]
 constexpr uint32_t kSampleSmemBytes = PBSIM_NQV * 16 + PBSIM_NQV * 8;
 
 template <int RNG_MODE>
-__global__ void __launch_bounds__(kSimThreads) k_sim_sample(SimArgs A, DevicePool Pl, SampleBatch SB) {
+__global__ void __launch_bounds__(kSimThreads) k_sim_sample(SimArgs A, DevicePool Pl, SampleBatch SB,
+                                                            uint32_t from_prev /* redo pass: chains start at any copy */) {
   __shared__ __align__(16) uint8_t smem[kSampleSmemBytes];
   uint32_t acc, lo, hi;
   if (!cta_assignment(A.cta_order, A.cta_first, A.bin_lo, A.bin_hi, &acc, &lo, &hi)) return;
@@ -564,6 +594,7 @@ __global__ void __launch_bounds__(kSimThreads) k_sim_sample(SimArgs A, DevicePoo
   T.thr_hp = A.M.qs_thr_hp;
   T.qc_prob = reinterpret_cast<const double *>(smem + PBSIM_NQV * 16);
   uint32_t len = (uint32_t)(Pl.start[j + 1] - Pl.start[j]);
+  if (from_prev) len = A.B.rlen[r0 - 1u];  // the buffer was cut where the previous copy's read ended
   for (uint32_t i = 0; i < num; ++i) {
     const uint32_t r = r0 + i;
     const uint32_t read_id = (uint32_t)(A.B.first_read + 1u + r);

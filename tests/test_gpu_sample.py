@@ -24,10 +24,11 @@ def _oracle(c, rng):
     return out
 
 
-def _run(c):
+def _run(c, spec=1):
     hm = capi.HostModel(capi.load(), capi.host_params("sample", **c.okw), None)
     eng = simulator.Engine(0)
     eng.set_option("pipeline", 0)
+    eng.set_option("sample_spec", spec)  # 1: all copies at once assuming full-length reads, wrong tails redone as chains
     run = simulator.WgsRun(eng, hm, c.depth, c.okw.get("hp_del_bias", 1.0))
     eng.set_pool(c.pool)
     if c.okw.get("hp_del_bias", 1.0) != 1.0:
@@ -35,14 +36,15 @@ def _run(c):
     return eng, run
 
 
+@pytest.mark.parametrize("spec", [0, 1])
 @pytest.mark.parametrize("batch_reads", [0, 1, 7])
 @pytest.mark.parametrize("name", sample_case_names())
-def test_replay_reproduces_reference(name, batch_reads):
+def test_replay_reproduces_reference(name, batch_reads, spec):
     c = SampleCase(name)
     ref = _oracle(c, "glibc")
     draws = O.glibc_rand(c.seed, c.ndraws)
     starts = np.concatenate([[0], c.marks[:-1]]).astype(np.int64)
-    eng, run = _run(c)
+    eng, run = _run(c, spec)
     pos = 0
     for i, (_, s) in enumerate(c.contigs, start=1):
         n = ref[i - 1]["n"]
@@ -55,12 +57,13 @@ def test_replay_reproduces_reference(name, batch_reads):
         assert text == c.stats_blocks[i]
 
 
+@pytest.mark.parametrize("spec", [0, 1])
 @pytest.mark.parametrize("batch_reads", [0, 5])
 @pytest.mark.parametrize("name", sample_case_names())
-def test_philox_equals_oracle(name, batch_reads):
+def test_philox_equals_oracle(name, batch_reads, spec):
     c = SampleCase(name)
     ref = _oracle(c, "philox")
-    eng, run = _run(c)
+    eng, run = _run(c, spec)
     for i, (_, s) in enumerate(c.contigs, start=1):
         reads, maf, st, text = run.simulate_sequence(s, i, rng_mode=capi.RNG_PHILOX, seed=c.seed, batch_reads=batch_reads)
         assert reads == ref[i - 1]["reads"]
