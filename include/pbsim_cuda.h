@@ -242,7 +242,10 @@ int pbsim_cuda_device_timer(pbsim_engine *e, int stop, double *ms);
  * pbsim.cpp:708-730; default 0),
  * "bam" (1: with pass_num > 1 the reads stream holds BAM alignment records — the binary form of the reference's SAM
  * lines, what its `samtools view -b` child writes (pbsim.cpp:715-722) — and, with "deflate", BGZF blocks; the caller
- * adds the BAM header block in front and the BGZF end-of-file block behind; default 0) */
+ * adds the BAM header block in front and the BGZF end-of-file block behind; default 0),
+ * "sample_spec" (--method sample; 1 (default): every copy of a pool entry is first simulated in its own thread at
+ * the entry's length and only the copies that follow a shorter read are redone as chains; 0: one thread walks all
+ * copies of an entry; results are identical either way) */
 int pbsim_cuda_set_option(pbsim_engine *e, const char *name, int64_t value);
 /* device pointer + cell count of the int64 stats block {counters[16], freq_accuracy[100001],
  * freq_len[2*len_max+2]} so that a multi-GPU driver can ncclAllReduce it in place */

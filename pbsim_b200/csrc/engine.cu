@@ -1,12 +1,13 @@
 // libpbsim_cuda — engine orchestration and the C ABI (include/pbsim_cuda.h).
 //
-// One engine = one GPU.  A simulate_by_* call of the reference (pbsim.cpp:1955 / :3594, and the _trans / _templ
-// variants :2419, :3055, :4114, :4807) becomes
+// One engine = one GPU.  A simulate_by_* call of the reference (pbsim.cpp:1955 / :3594, the _trans / _templ
+// variants :2419, :3055, :4114, :4807, and simulate_by_sample :1694) becomes
 //   simulate_begin -> { next_chunk }* -> simulate_end
 // and every batch of reads runs, on one stream:
 //   K1 k_plan            per-read length / accuracy / offset / strand, segment provisioning  (sim_kernels.cuh)
 //      radix sorts       (accuracy, length desc) -> pass-1 schedules                          (CUB, plumbing)
-//   K2 k_sim_qshmm | K3 k_sim_errhmm   short reads, replay mode, chain-only prepass           (sim_kernels.cuh)
+//   K2 k_sim_qshmm | K3 k_sim_errhmm   short reads, replay mode                                (sim_kernels.cuh)
+//      k_plan_sample, k_sim_sample, k_sample_redo   --method sample: copies of pool entries     (sim_kernels.cuh)
 //      k_sim_seg | k_sim_seg_err, k_find_end[_err]   segment-parallel pass 1 -> event streams (seg_kernels.cuh)
 //      quota scan        which read crosses sim.len_quota (pbsim.cpp:2173-2181)               (CUB + k_find_cut)
 //   K4 k_sizes, k_tile_map, k_emit   record placement and text emission                       (emit.cuh)

@@ -632,8 +632,6 @@ int main(int argc, char **argv) {
   if (o.world > 1 && (o.strategy != "wgs" || o.rng == "replay"))
     die("ERROR: --world > 1 shards the sequences of --strategy wgs in philox mode; shard a transcript table by read range through the library instead.\n");
   if (o.pass_num > 1 && sample) die("ERROR: sampling-based simulation supports only single-pass.\n");  // :1675-1679
-  if (sample && o.world > 1)
-    die("ERROR: --method sample runs on one GPU (the copies of a pool entry are sequential).\n");
   const bool qs = o.method == "qshmm";
   const bool wgs = o.strategy == "wgs";
 
