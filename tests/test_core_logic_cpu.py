@@ -276,3 +276,29 @@ def test_sample_filter_equals_reference(name):
     assert cut == c.pool[:-1] or len(c.pool[-1]) and cut == c.pool[:len(cut)] and len(cut) >= len(c.pool) - 1
     with pytest.raises(RuntimeError, match="no sample in the valid range"):
         capi.sample_filter(H.lib(), c.sample_fastq, len_min=999999, len_max=1000000)
+
+
+@pytest.mark.parametrize("glen,depth,lens", [
+    (2000, 1.5, [300, 250, 200, 150, 100]),      # quota is a multiple of the pool: sample_interval = 1 (:1721)
+    (5000, 3.3, [400, 350, 120]),                # n * 0.5 truncates to 1: the interval clamp (:1727)
+    (700, 9.0, [900, 650, 300, 800, 120, 101]),  # entries longer than the sequence: offset 0, len = glen (:1758)
+    (4000, 0.2, [500, 400, 300, 200]),           # sample_num = 0: the first pool pass already copies only the extras
+    (3000, 40.0, [150, 140, 130, 120, 110, 100, 160, 170]),  # many copies per entry, several batches per group
+])
+def test_sample_schedule_edge_cases_equal_oracle(glen, depth, lens):
+    """the group schedule (sample_plan.hpp) against the oracle's sequential loop where the reference's arithmetic has
+    corners; PHILOX draws, batches of 3 reads so that groups straddle batches"""
+    rng = np.random.default_rng(glen)
+    genome = bytes(rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), glen))
+    pool = [bytes(rng.integers(33 + 5, 33 + 20, n).astype(np.uint8)) for n in lens]
+    okw = dict(ratio=(20, 30, 50), len_min=100, len_max=2500)
+    o = O.Oracle("sample", None, **okw)
+    o.rng_philox(9)
+    o.set_sequence(genome, 1)
+    oreads, omaf, ost = o.simulate_sample(depth, pool)
+    hm = capi.HostModel(H.lib(), capi.host_params("sample", **okw), None)
+    sub = H.run(hm, o.seq_upper(), o.hp(), 1, o.bias(), capi.RNG_PHILOX, 9, None, int(depth * glen), pool=pool,
+                batch_reads=3)
+    reads, maf = H.records_from_events(hm, sub, o.seq_upper(), 1)
+    assert reads == oreads and maf == omaf
+    assert len(sub) == ost.res_num

@@ -116,3 +116,31 @@ def test_misuse_fails_loudly():
     eng.set_pool(c.pool)
     with pytest.raises(simulator.EngineError, match="read ranges"):
         eng.begin(1000, first_read=5)
+
+
+@pytest.mark.parametrize("spec", [0, 1])
+@pytest.mark.parametrize("glen,depth,lens", [
+    (2000, 1.5, [300, 250, 200, 150, 100]),      # quota is a multiple of the pool: sample_interval = 1 (:1721)
+    (5000, 3.3, [400, 350, 120]),                # n * 0.5 truncates to 1: the interval clamp (:1727)
+    (700, 9.0, [900, 650, 300, 800, 120, 101]),  # entries longer than the sequence: offset 0, len = glen (:1758)
+    (4000, 0.2, [500, 400, 300, 200]),           # sample_num = 0: the first pool pass copies only the extras
+    (3000, 40.0, [150, 140, 130, 120, 110, 100, 160, 170]),  # many copies per entry, groups straddle batches
+])
+def test_schedule_corners_equal_oracle(glen, depth, lens, spec):
+    rng = np.random.default_rng(glen)
+    genome = bytes(rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), glen))
+    pool = [bytes(rng.integers(33 + 5, 33 + 20, n).astype(np.uint8)) for n in lens]
+    okw = dict(ratio=(20, 30, 50), len_min=100, len_max=2500)
+    o = O.Oracle("sample", None, **okw)
+    o.rng_philox(9)
+    o.set_sequence(genome, 1)
+    oreads, omaf, ost = o.simulate_sample(depth, pool)
+    hm = capi.HostModel(capi.load(), capi.host_params("sample", **okw), None)
+    eng = simulator.Engine(0)
+    eng.set_option("pipeline", 0)
+    eng.set_option("sample_spec", spec)
+    run = simulator.WgsRun(eng, hm, depth)
+    eng.set_pool(pool)
+    reads, maf, st, text = run.simulate_sequence(genome, 1, rng_mode=capi.RNG_PHILOX, seed=9, batch_reads=3)
+    assert reads == oreads and maf == omaf
+    assert text == O.format_stats(ost, 1)
