@@ -285,6 +285,11 @@ def main():
         f.write(">s\nACGTACGTAC\n")
     with open(os.path.join(work, "tiny.fq"), "w") as f:
         f.write("@r1\nACGT\n+\nIIII\n@r2\nACGTA\n+\nIIIII\n")
+    with open(os.path.join(work, "nonl.fq"), "w") as f:      # last record without line feed: not counted (:1218)
+        f.write("@r1\nACGTAC\n+\nIIIIII\n@r2\nACGTA\n+\n55555")
+    with open(os.path.join(work, "long.fq"), "w") as f:      # lines longer than one fgets buffer (BUF_SIZE 10240, :20)
+        f.write("@r1\n" + "ACGT" * 6250 + "\n+\n" + "5I+?" * 6250 + "\n@r2\n" + "A" * 10239 + "\n+\n" + "9" * 10239 + "\n"
+                + "@r3\nACGT\n+\n!!!!\n")
     sm = ["--strategy", "wgs", "--method", "sample", "--genome", "tiny.fa"]
     qs = ["--strategy", "wgs", "--method", "qshmm", "--qshmm", "QSHMM-RSII.model", "--genome", "tiny.fa"]
     cli_cases = [
@@ -306,6 +311,10 @@ def main():
         sm, sm + ["--sample", "nofile.fq"], sm + ["--sample", "tiny.fq", "--pass-num", "2"],
         sm + ["--sample-profile-id", "nosuchprofile"], sm + ["--sample", "tiny.fq"],
         sm + ["--sample", "tiny.fq", "--accuracy-min", "1.5"],
+        sm + ["--sample", "tiny.fq", "--length-min", "1"], sm + ["--sample", "nonl.fq", "--length-min", "1"],
+        sm + ["--sample", "long.fq", "--length-min", "1"], sm + ["--sample", "long.fq", "--length-min", "1", "--accuracy-min", "0.5"],
+        sm + ["--sample", "long.fq", "--length-min", "1", "--accuracy-max", "0.4"],
+        sm + ["--sample", "long.fq", "--length-min", "1", "--length-max", "10239", "--accuracy-min", "0"],
     ]
     cli_out = []
     for a in cli_cases:

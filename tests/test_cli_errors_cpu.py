@@ -1,6 +1,7 @@
 """CPU: the C++ driver rejects what the reference rejects, with the same message and exit status, before any GPU is
-touched.  tests/golden/cli_errors.json holds what the UNMODIFIED reference printed for 31 invocations (option
-validation of set_sim_param pbsim.cpp:1451-1688, missing files, a reference sequence shorter than 100 bases)."""
+touched.  tests/golden/cli_errors.json holds what the UNMODIFIED reference printed for 37 invocations (option
+validation of set_sim_param pbsim.cpp:1451-1688, missing files, a reference sequence shorter than 100 bases, the
+sample FASTQ filter and its statistics block on files with long lines / without a final line feed)."""
 import json
 import os
 import re
@@ -23,6 +24,9 @@ def workdir(tmp_path_factory):
     shutil.copy(model_path("ERRHMM-ONT.model"), d / "ERRHMM-ONT.model")
     (d / "tiny.fa").write_text(">s\nACGTACGTAC\n")
     (d / "tiny.fq").write_text("@r1\nACGT\n+\nIIII\n@r2\nACGTA\n+\nIIIII\n")
+    (d / "nonl.fq").write_text("@r1\nACGTAC\n+\nIIIIII\n@r2\nACGTA\n+\n55555")
+    (d / "long.fq").write_text("@r1\n" + "ACGT" * 6250 + "\n+\n" + "5I+?" * 6250 + "\n@r2\n" + "A" * 10239 + "\n+\n"
+                               + "9" * 10239 + "\n@r3\nACGT\n+\n!!!!\n")
     return d
 
 
