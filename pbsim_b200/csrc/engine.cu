@@ -220,9 +220,9 @@ struct pbsim_engine {
   DevBuf d_draws, d_starts;
 
   // batch arrays
-  DevBuf b_read_u32;   // 4 arrays per read
-  DevBuf b_sub_u32;    // 15 arrays per subread
-  DevBuf b_sub_u64;    // 9 arrays per subread (+1)
+  DevBuf b_read_u32;   // 5 arrays per read (carve_batch)
+  DevBuf b_sub_u32;    // 16 arrays per subread
+  DevBuf b_sub_u64;    // 12 slices of n_sub + 1 (u64_slice)
   DevBuf b_sub_f64;
   DevBuf d_bins;       // bin_start[kBins+1], bin_lo[kBins], bin_hi[kBins], cta_first[kBins+1]
   DevBuf d_ctrl;       // control words
