@@ -1691,6 +1691,10 @@ int pbsim_cuda_simulate_begin(pbsim_engine *e, const pbsim_run *run) {
   if (!e->model_set || !e->seq_set) return fail(e, PBSIM_E_INVALID, "set_model and set_sequence must precede simulate_begin");
   if (run->rng_mode == PBSIM_RNG_REPLAY && (!run->replay_draws || !run->replay_starts || run->replay_nsubreads < 1))
     return fail(e, PBSIM_E_INVALID, "replay mode needs the draw log and the subread starts");
+  // a run abandoned without simulate_end: its producer thread must be gone before any run state changes
+  stop_producer(e);
+  CK(cudaStreamSynchronize(e->st_copy));  // a piece of that run may still be on its way into the staging buffers
+  e->running = false;
   if (e->model.method == PBSIM_METHOD_SAMPLE) {
     if (!e->pool_set) return fail(e, PBSIM_E_INVALID, "set_pool must precede simulate_begin for --method sample");
     if (e->strategy != PBSIM_STRATEGY_WGS) return fail(e, PBSIM_E_INVALID, "--method sample simulates a genome (--strategy wgs)");
@@ -1723,7 +1727,6 @@ int pbsim_cuda_simulate_begin(pbsim_engine *e, const pbsim_run *run) {
   e->emit_ms = 0;
   e->gz_ms = 0;
   e->seg_ms = 0;
-  stop_producer(e);  // a run abandoned without simulate_end
   e->pend = pbsim_engine::Pending();
   e->piece = pbsim_engine::Piece();
   e->next_slot = 0;
