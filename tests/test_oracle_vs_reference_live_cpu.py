@@ -1,0 +1,109 @@
+"""CPU: the oracle against the UNMODIFIED reference run live (oracle/_ref/pbsim, built from /root/reference by
+`make -C oracle ref`; skipped where that binary is absent).  Seeded random configurations — the ones the engine is
+fuzzed with in tests/test_fuzz_core_cpu.py and tests/test_gpu_zz_fuzz.py — go through the reference's own command line;
+FASTQ / SAM, MAF and the statistics block of the oracle (glibc rand() restatement, same seed) must equal the
+reference's byte for byte.  This extends the pin of the oracle beyond the committed golden runs."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from oracle import refrun as R
+from tests.golden_util import model_path
+from tests.test_fuzz_core_cpu import _config
+
+pytestmark = pytest.mark.skipif(not os.path.exists(R.REF_BIN), reason="oracle/_ref/pbsim is not built here")
+
+
+@pytest.mark.parametrize("k", range(48))
+def test_oracle_equals_live_reference(k, tmp_path):
+    cfg = _config(k)
+    okw, genome, method = cfg["okw"], cfg["genome"], cfg["method"]
+    fa = str(tmp_path / "genome.fa")
+    R.write_fasta(fa, [("g", genome)])
+    args = ["--strategy", "wgs", "--method", method, "--genome", fa, "--depth", repr(cfg["depth"]), "--seed", str(cfg["seed"]),
+            "--length-min", str(okw["len_min"]), "--length-max", str(okw["len_max"]),
+            "--difference-ratio", "%d:%d:%d" % okw["ratio"], "--hp-del-bias", repr(okw["hp_del_bias"])]
+    pool = None
+    if method == "sample":
+        lens = cfg["rng"].integers(100, 3000, int(cfg["rng"].integers(4, 40)))
+        quals = [bytes(cfg["rng"].integers(33 + 3, 33 + 25, int(n)).astype(np.uint8)) for n in lens]
+        fq = b"".join(b"@r%d\n" % i + b"A" * len(q) + b"\n+\n" + q + b"\n" for i, q in enumerate(quals))
+        (tmp_path / "sample.fq").write_bytes(fq)
+        args += ["--sample", str(tmp_path / "sample.fq"), "--accuracy-min", "0", "--accuracy-max", "1"]
+        pool = O.sample_pool(fq, len_min=okw["len_min"], len_max=okw["len_max"], accuracy_min=0.0, accuracy_max=1.0)
+        assert len(pool) >= 2
+    else:
+        args += ["--" + method, model_path(cfg["model"]), "--length-mean", repr(okw["len_mean"]), "--length-sd",
+                 repr(okw["len_sd"]), "--accuracy-mean", "%.2f" % okw["accuracy_mean"], "--pass-num", str(okw["pass_num"])]
+    ref = R.run_reference(args)
+    try:
+        o = O.Oracle(method, model_path(cfg["model"]) if cfg["model"] else None, **okw)
+        o.rng_glibc(cfg["seed"])
+        if okw["hp_del_bias"] != 1.0:
+            o.hp_bias_prepass([genome])
+        o.set_sequence(genome, 1)
+        reads, maf, st = o.simulate_sample(cfg["depth"], pool) if pool is not None else o.simulate_wgs(cfg["depth"])
+    except RuntimeError as e:
+        # what the oracle refuses the reference must refuse too
+        assert ref["returncode"] != 0, "oracle failed (%s) where the reference ran" % e
+        return
+    assert ref["returncode"] == 0, ref["stderr"][-400:]
+    multi = okw.get("pass_num", 1) > 1
+    got = ref["files"]["out_0001.bam" if multi else "out_0001.fq.gz"]
+    if multi:  # the two header lines main() writes (:721-722)
+        got = got[got.index(b"PM:SEQUELII\n") + len(b"PM:SEQUELII\n"):]
+    assert reads == got, "reads differ from the live reference"
+    assert maf == ref["files"]["out_0001.maf.gz"], "MAF differs from the live reference"
+    assert O.format_stats(st, 1) == R.split_stats_blocks(ref["stderr"])[1]
+
+
+@pytest.mark.parametrize("k", range(24))
+def test_engine_core_replays_live_reference(k, tmp_path):
+    """the engine's per-read core (tests/hostsim) fed the rand() stream of a live reference run (the -include hook of
+    oracle/ref_hooks logs every draw) reproduces that run's files"""
+    from pbsim_b200 import capi
+    from tests import hostsim_util as H
+    cfg = _config(k)
+    okw, genome, method = cfg["okw"], cfg["genome"], cfg["method"]
+    if not os.path.exists(R.REF_BIN_LOG):
+        pytest.skip("oracle/_ref/pbsim_logrand is not built here")
+    fa = str(tmp_path / "genome.fa")
+    R.write_fasta(fa, [("g", genome)])
+    args = ["--strategy", "wgs", "--method", method, "--genome", fa, "--depth", repr(cfg["depth"]), "--seed", str(cfg["seed"]),
+            "--length-min", str(okw["len_min"]), "--length-max", str(okw["len_max"]),
+            "--difference-ratio", "%d:%d:%d" % okw["ratio"], "--hp-del-bias", repr(okw["hp_del_bias"])]
+    pool = None
+    if method == "sample":
+        lens = cfg["rng"].integers(100, 3000, int(cfg["rng"].integers(4, 40)))
+        quals = [bytes(cfg["rng"].integers(33 + 3, 33 + 25, int(n)).astype(np.uint8)) for n in lens]
+        fq = b"".join(b"@r%d\n" % i + b"A" * len(q) + b"\n+\n" + q + b"\n" for i, q in enumerate(quals))
+        (tmp_path / "sample.fq").write_bytes(fq)
+        args += ["--sample", str(tmp_path / "sample.fq"), "--accuracy-min", "0", "--accuracy-max", "1"]
+        pool, _ = capi.sample_filter(H.lib(), fq, len_min=okw["len_min"], len_max=okw["len_max"], accuracy_min=0.0,
+                                     accuracy_max=1.0)
+    else:
+        args += ["--" + method, model_path(cfg["model"]), "--length-mean", repr(okw["len_mean"]), "--length-sd",
+                 repr(okw["len_sd"]), "--accuracy-mean", "%.2f" % okw["accuracy_mean"], "--pass-num", str(okw["pass_num"])]
+    ref = R.run_reference(args, logrand=True)
+    if ref["returncode"] != 0:
+        pytest.skip("the reference rejects this configuration")
+    try:
+        hm = capi.HostModel(H.lib(), capi.host_params(method, **okw), model_path(cfg["model"]) if cfg["model"] else None)
+    except RuntimeError as e:
+        pytest.fail("the product's table builder fails (%s) where the reference ran" % e)
+    o = O.Oracle(method, model_path(cfg["model"]) if cfg["model"] else None, **okw)  # ingest only: upper case, hp, bias
+    if okw["hp_del_bias"] != 1.0:
+        o.hp_bias_prepass([genome])
+    o.set_sequence(genome, 1)
+    sub = H.run(hm, o.seq_upper(), o.hp(), 1, o.bias(), capi.RNG_REPLAY, 0, ref["draws"], int(cfg["depth"] * len(genome)),
+                pool=pool, batch_reads=int(cfg["rng"].integers(1, 20)))
+    reads, maf = H.records_from_events(hm, sub, o.seq_upper(), 1)
+    multi = okw.get("pass_num", 1) > 1
+    got = ref["files"]["out_0001.bam" if multi else "out_0001.fq.gz"]
+    if multi:
+        got = got[got.index(b"PM:SEQUELII\n") + len(b"PM:SEQUELII\n"):]
+    assert reads == got
+    assert maf == ref["files"]["out_0001.maf.gz"]
+    assert [s["draw_start"] for s in sub] == [0] + [int(x) for x in ref["marks"][:len(sub) - 1]]
