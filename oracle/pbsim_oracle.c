@@ -1337,6 +1337,12 @@ int orc_simulate_set(orc_ctx *c, int strategy, int64_t n, const char *bases, con
         free(ssp_ends); free(ssp_mod);
         return fail(c, "draw log exhausted");
       }
+      /* Reference quirk (simulate_by_errhmm_trans only): the verbatim copy of an accuracy-100 read is
+       * `for (i=0; i<mut.len; i++)` (:4532) with the SAME i that counts the transcript's reads (:4487), so after
+       * such a read the count continues from mut.len + 1 — usually past read_num: the transcript's remaining reads
+       * are never simulated.  Reproduced for the reference's own draw stream; PHILOX mode (the engine's numbering of
+       * reads is static) simulates every read. */
+      if (strategy == 1 && c->method == ORC_METHOD_ERR && acc == 100 && r->mode != RNG_PHILOX) k = wlen;
     }
   }
   free(ssp_ends);

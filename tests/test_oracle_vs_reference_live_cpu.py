@@ -107,3 +107,55 @@ def test_engine_core_replays_live_reference(k, tmp_path):
     assert reads == got
     assert maf == ref["files"]["out_0001.maf.gz"]
     assert [s["draw_start"] for s in sub] == [0] + [int(x) for x in ref["marks"][:len(sub) - 1]]
+
+
+@pytest.mark.parametrize("k", range(24))
+def test_oracle_equals_live_reference_on_sequence_sets(k, tmp_path):
+    """--strategy trans / templ: random transcript tables (expression counts on both strands, lower-case sequences,
+    IUPAC codes, homopolymers, lines longer than an fgets buffer) and template FASTA files"""
+    rng = np.random.default_rng(7700 + k)
+    strategy = ["trans", "templ"][k % 2]
+    method = ["qshmm", "errhmm"][(k // 2) % 2]
+    model = str(rng.choice(["QSHMM-RSII.model", "QSHMM-ONT.model", "QSHMM-ONT-HQ.model"] if method == "qshmm" else
+                           ["ERRHMM-RSII.model", "ERRHMM-ONT.model", "ERRHMM-ONT-HQ.model", "ERRHMM-SEQUEL.model"]))
+    mean = float(rng.integers(800, 4000))
+    okw = dict(len_min=100, len_max=int(rng.integers(3000, 30000)), ratio=tuple(int(x) for x in rng.integers(1, 60, 3)),
+               hp_del_bias=float(rng.choice([1.0, 1.0, 3.0])), len_mean=mean, len_sd=float(rng.uniform(0.3, 0.9)) * mean,
+               pass_num=int(rng.choice([1, 1, 3])), accuracy_mean=float(rng.integers(82, 97)) / 100.0, accuracy_mean_set=True)
+    seqset = R.synth_set(300 + k, int(rng.integers(5, 30)), len_lo=150, len_hi=int(rng.integers(600, 5000)),
+                         max_exp=int(rng.integers(1, 5)), lowercase_first=float(rng.choice([0.0, 0.3])),
+                         iupac=float(rng.choice([0.0, 0.002])), hp_plants=int(rng.integers(0, 4)),
+                         long_every=int(rng.choice([0, 7])))
+    if strategy == "templ":
+        seqset = [(n, 1, 0, s) for n, _, _, s in seqset]
+        # a template longer than --length-max overruns the reference's read buffers (malloc(len_max * 2 + 1), and half
+        # of that for mut.hp, :5488-5531): undefined behaviour there, so the comparison stays inside the buffers
+        okw["len_max"] = max(okw["len_max"], max(len(x[3]) for x in seqset) + 1)
+    seed = int(rng.integers(1, 1 << 30))
+    inp = str(tmp_path / "input.txt")
+    (R.write_transcripts if strategy == "trans" else R.write_templates)(inp, seqset)
+    args = ["--strategy", strategy, "--method", method, "--" + method, model_path(model),
+            "--transcript" if strategy == "trans" else "--template", inp, "--seed", str(seed),
+            "--difference-ratio", "%d:%d:%d" % okw["ratio"], "--hp-del-bias", repr(okw["hp_del_bias"]),
+            "--accuracy-mean", "%.2f" % okw["accuracy_mean"], "--pass-num", str(okw["pass_num"])]
+    # (templates are read in full whatever --length-max says, but the SD of the statistics block only counts
+    # lengths up to it, :3568-3575)
+    args += ["--length-min", str(okw["len_min"]), "--length-max", str(okw["len_max"])]
+    if strategy == "trans":
+        args += ["--length-mean", repr(okw["len_mean"]), "--length-sd", repr(okw["len_sd"])]
+    ref = R.run_reference(args)
+    try:
+        o = O.Oracle(method, model_path(model), **okw)
+        o.rng_glibc(seed)
+        reads, maf, st = o.simulate_set(strategy, seqset)
+    except RuntimeError as e:
+        assert ref["returncode"] != 0, "oracle failed (%s) where the reference ran" % e
+        return
+    assert ref["returncode"] == 0, ref["stderr"][-400:]
+    multi = okw["pass_num"] > 1
+    got = ref["files"]["out.bam" if multi else "out.fq.gz"]
+    if multi:
+        got = got[got.index(b"PM:SEQUELII\n") + len(b"PM:SEQUELII\n"):]
+    assert reads == got, "reads differ from the live reference"
+    assert maf == ref["files"]["out.maf.gz"], "MAF differs from the live reference"
+    assert O.format_stats_set(st) == R.set_stats_block(ref["stderr"])
