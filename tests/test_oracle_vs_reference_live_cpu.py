@@ -159,3 +159,85 @@ def test_oracle_equals_live_reference_on_sequence_sets(k, tmp_path):
     assert reads == got, "reads differ from the live reference"
     assert maf == ref["files"]["out.maf.gz"], "MAF differs from the live reference"
     assert O.format_stats_set(st) == R.set_stats_block(ref["stderr"])
+
+
+def _config_wide(k):
+    """wider corners than _config (which the GPU fuzz shares): accuracies 0.70 .. 1.00 (below / above the models' range,
+    accuracy-100 reads), fixed-length reads, genomes shorter than the reads, zero entries in the ratio, up to 4 passes"""
+    rng = np.random.default_rng(9100 + k)
+    method = ["qshmm", "errhmm"][k % 2]
+    model = str(rng.choice(["QSHMM-RSII.model", "QSHMM-ONT.model", "QSHMM-ONT-HQ.model"] if method == "qshmm" else
+                           ["ERRHMM-RSII.model", "ERRHMM-ONT.model", "ERRHMM-ONT-HQ.model", "ERRHMM-SEQUEL.model"]))
+    mean = float(rng.integers(300, 8000))
+    ratio = [int(x) for x in rng.integers(0, 60, 3)]
+    if k % 5 == 0:
+        ratio[int(rng.integers(0, 3))] = 0
+    if sum(ratio) == 0:
+        ratio[0] = 1
+    okw = dict(len_min=int(rng.choice([100, 100, 250])), len_max=int(rng.integers(3000, 40000)), ratio=tuple(ratio),
+               hp_del_bias=float(rng.choice([1.0, 1.0, 1.5, 6.0])), len_mean=mean,
+               len_sd=0.0 if k % 6 == 0 else float(rng.uniform(0.2, 0.95)) * mean, pass_num=int(rng.choice([1, 1, 2, 4])),
+               accuracy_mean=float(rng.integers(70, 101)) / 100.0, accuracy_mean_set=True)
+    glen = int(rng.integers(400, 3000)) if k % 4 == 0 else int(rng.integers(8000, 50000))
+    genome = R.synth_genome(500 + k, [("g", glen)], n_runs=int(rng.integers(0, 4)), hp_plants=int(rng.integers(0, 40)),
+                            lowercase_frac=float(rng.choice([0.0, 0.2])), iupac=int(rng.integers(0, 6)),
+                            long_runs=(12, 30) if k % 3 == 0 else ())[0][1]
+    return dict(method=method, model=model, okw=okw, genome=genome, depth=float(rng.uniform(0.5, 6.0)),
+                seed=int(rng.integers(1, 1 << 30)), rng=rng)
+
+
+@pytest.mark.parametrize("k", range(40))
+def test_wide_corners_reference_oracle_and_engine_core_agree(k, tmp_path):
+    """reference (live) == oracle (glibc) == engine core (replay of the logged draws); engine core (PHILOX) == oracle
+    (PHILOX) — on the wide corner configurations; what the reference rejects, the product's table builder rejects"""
+    from pbsim_b200 import capi
+    from tests import hostsim_util as H
+    cfg = _config_wide(k)
+    okw, genome, method = cfg["okw"], cfg["genome"], cfg["method"]
+    fa = str(tmp_path / "genome.fa")
+    R.write_fasta(fa, [("g", genome)])
+    args = ["--strategy", "wgs", "--method", method, "--genome", fa, "--depth", repr(cfg["depth"]), "--seed", str(cfg["seed"]),
+            "--length-min", str(okw["len_min"]), "--length-max", str(okw["len_max"]),
+            "--difference-ratio", "%d:%d:%d" % okw["ratio"], "--hp-del-bias", repr(okw["hp_del_bias"]),
+            "--" + method, model_path(cfg["model"]), "--length-mean", repr(okw["len_mean"]), "--length-sd",
+            repr(okw["len_sd"]), "--accuracy-mean", "%.2f" % okw["accuracy_mean"], "--pass-num", str(okw["pass_num"])]
+    ref = R.run_reference(args, logrand=True)
+    mp = model_path(cfg["model"])
+    if ref["returncode"] != 0:
+        with pytest.raises(RuntimeError):
+            o = O.Oracle(method, mp, **okw)
+            o.rng_glibc(cfg["seed"])
+            o.set_sequence(genome, 1)
+            o.simulate_wgs(cfg["depth"])
+        return
+    o = O.Oracle(method, mp, **okw)
+    o.rng_glibc(cfg["seed"])
+    if okw["hp_del_bias"] != 1.0:
+        o.hp_bias_prepass([genome])
+    o.set_sequence(genome, 1)
+    reads, maf, st = o.simulate_wgs(cfg["depth"])
+    multi = okw["pass_num"] > 1
+    got = ref["files"]["out_0001.bam" if multi else "out_0001.fq.gz"]
+    if multi:
+        got = got[got.index(b"PM:SEQUELII\n") + len(b"PM:SEQUELII\n"):]
+    assert reads == got, "oracle reads differ from the live reference"
+    assert maf == ref["files"]["out_0001.maf.gz"]
+    assert O.format_stats(st, 1) == R.split_stats_blocks(ref["stderr"])[1]
+    hm = capi.HostModel(H.lib(), capi.host_params(method, **okw), mp)
+    quota = int(cfg["depth"] * len(genome))
+    sub = H.run(hm, o.seq_upper(), o.hp(), 1, o.bias(), capi.RNG_REPLAY, 0, ref["draws"], quota)
+    r2, m2 = H.records_from_events(hm, sub, o.seq_upper(), 1)
+    assert r2 == got and m2 == ref["files"]["out_0001.maf.gz"], "engine core replay differs from the live reference"
+    # PHILOX: engine core (segments forced on) against the oracle
+    o.rng_philox(cfg["seed"])
+    preads, pmaf, _ = o.simulate_wgs(cfg["depth"])
+    L = H.lib()
+    L.hostsim_use_segments(1, 1025)
+    L.hostsim_set_chain_chunk(int(cfg["rng"].choice([0, 1, 3, 32])))
+    try:
+        sub = H.run(hm, o.seq_upper(), o.hp(), 1, o.bias(), capi.RNG_PHILOX, cfg["seed"], None, quota)
+    finally:
+        L.hostsim_use_segments(0, 2048)
+        L.hostsim_set_chain_chunk(0)
+    r3, m3 = H.records_from_events(hm, sub, o.seq_upper(), 1)
+    assert r3 == preads and m3 == pmaf, "engine core (PHILOX) differs from the oracle"
