@@ -241,3 +241,86 @@ def test_wide_corners_reference_oracle_and_engine_core_agree(k, tmp_path):
         L.hostsim_set_chain_chunk(0)
     r3, m3 = H.records_from_events(hm, sub, o.seq_upper(), 1)
     assert r3 == preads and m3 == pmaf, "engine core (PHILOX) differs from the oracle"
+
+
+@pytest.mark.parametrize("k", range(10))
+def test_driver_parses_fasta_like_the_live_reference(k, tmp_path):
+    """get_genome_inf (:896-995) through the C++ driver: random multi-FASTA files (many contigs, ragged line widths,
+    lines longer than an fgets buffer, blank lines, lower case, names with spaces and longer than 128 characters) —
+    the <prefix>_NNNN.ref files and everything printed before the first simulation must equal the reference's.  (The
+    driver stops at engine creation on a box without a GPU; with one it runs on, the comparison is the same.)"""
+    import subprocess
+    import __graft_entry__ as G
+    rng = np.random.default_rng(3300 + k)
+    n = int(rng.integers(1, 12))
+    lines = []
+    for t in range(n):
+        name = "ctg%d" % t + (" some description" if t % 3 == 0 else "") + ("x" * 150 if t % 5 == 4 else "")
+        glen = int(rng.integers(100, 30000))
+        s = np.frombuffer(b"ACGTacgtNn", dtype=np.uint8)[rng.integers(0, 10 if t % 2 else 4, glen)].tobytes()
+        lines.append(b">" + name.encode())
+        width = int(rng.choice([60, 70, 11000, 25000]))
+        for i in range(0, glen, width):
+            lines.append(s[i:i + width])
+            if rng.random() < 0.05:
+                lines.append(b"")
+    fa = tmp_path / "genome.fa"
+    fa.write_bytes(b"\n".join(lines) + (b"\n" if k % 2 == 0 else b""))
+    args = ["--strategy", "wgs", "--method", "qshmm", "--qshmm", model_path("QSHMM-RSII.model"), "--genome", "genome.fa",
+            "--depth", "0.5", "--seed", "3", "--length-mean", "500", "--length-sd", "200", "--length-min", "100"]
+    rdir, ddir = tmp_path / "r", tmp_path / "d"
+    rdir.mkdir()
+    ddir.mkdir()
+    for d in (rdir, ddir):
+        (d / "genome.fa").write_bytes(fa.read_bytes())
+    env = dict(os.environ, PATH=R.SHIMS + ":" + os.environ.get("PATH", ""))
+    pr = subprocess.run([R.REF_BIN] + args + ["--prefix", "out"], cwd=rdir, env=env, stdout=subprocess.PIPE,
+                        stderr=subprocess.PIPE, timeout=300)
+    G.build_engine()
+    pd = subprocess.run([G.build_driver()] + args + ["--prefix", "out"], cwd=ddir, stdout=subprocess.PIPE,
+                        stderr=subprocess.PIPE, timeout=300)
+    want, got = pr.stderr.decode(), pd.stderr.decode()
+    cut = ":::: Simulation stats (ref.1) ::::"
+    head_w = want.split(cut)[0]
+    head_g = got.split("ERROR: no usable CUDA device")[0].split(cut)[0]
+    assert head_g == head_w
+    if pr.returncode != 0:  # e.g. a contig shorter than 100 bases: same message, same status
+        assert pd.returncode == pr.returncode
+        return
+    refs = sorted(f for f in os.listdir(rdir) if f.endswith(".ref"))
+    assert refs and refs == sorted(f for f in os.listdir(ddir) if f.endswith(".ref"))
+    for f in refs:
+        assert (ddir / f).read_bytes() == (rdir / f).read_bytes(), f
+
+
+@pytest.mark.parametrize("k", range(8))
+def test_driver_parses_sets_like_the_live_reference(k, tmp_path):
+    """get_transcript_inf (:1075) / get_templ_inf (:1366) through the C++ driver on random tables / FASTA files: the
+    statistics blocks printed before the simulation equal the reference's"""
+    import subprocess
+    import __graft_entry__ as G
+    rng = np.random.default_rng(5500 + k)
+    strategy = ["trans", "templ"][k % 2]
+    seqset = R.synth_set(800 + k, int(rng.integers(3, 40)), len_lo=120, len_hi=int(rng.integers(500, 6000)),
+                         max_exp=int(rng.integers(1, 9)), lowercase_first=0.3, iupac=0.001, hp_plants=2,
+                         long_every=int(rng.choice([0, 5])))
+    inp = tmp_path / "input.txt"
+    if strategy == "trans":
+        R.write_transcripts(str(inp), seqset)
+    else:
+        R.write_templates(str(inp), seqset, width=int(rng.choice([60, 70, 12000])))
+    args = ["--strategy", strategy, "--method", "errhmm", "--errhmm", model_path("ERRHMM-ONT.model"),
+            "--transcript" if strategy == "trans" else "--template", "input.txt", "--seed", "5", "--length-mean", "600",
+            "--length-sd", "300"]
+    rdir, ddir = tmp_path / "r", tmp_path / "d"
+    for d in (rdir, ddir):
+        d.mkdir()
+        (d / "input.txt").write_bytes(inp.read_bytes())
+    env = dict(os.environ, PATH=R.SHIMS + ":" + os.environ.get("PATH", ""))
+    pr = subprocess.run([R.REF_BIN] + args + ["--prefix", "out"], cwd=rdir, env=env, stdout=subprocess.PIPE,
+                        stderr=subprocess.PIPE, timeout=300)
+    G.build_engine()
+    pd = subprocess.run([G.build_driver()] + args + ["--prefix", "out"], cwd=ddir, stdout=subprocess.PIPE,
+                        stderr=subprocess.PIPE, timeout=300)
+    cut = ":::: Simulation stats ::::"
+    assert pd.stderr.decode().split("ERROR: no usable CUDA device")[0].split(cut)[0] == pr.stderr.decode().split(cut)[0]
