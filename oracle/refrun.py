@@ -166,8 +166,10 @@ def run_reference(args, logrand=False, keep_dir=None, real_gzip=False, timeout=3
         with open(f, "rb") as fh:
             res["files"][os.path.basename(f)] = fh.read()
     if logrand:
-        res["draws"] = np.fromfile(os.path.join(work, "draws.bin"), dtype=np.int32)
-        res["marks"] = np.fromfile(os.path.join(work, "marks.bin"), dtype=np.int64)
+        # (a run that stops before its first rand() call leaves no log)
+        dlog, mlog = os.path.join(work, "draws.bin"), os.path.join(work, "marks.bin")
+        res["draws"] = np.fromfile(dlog, dtype=np.int32) if os.path.exists(dlog) else np.zeros(0, np.int32)
+        res["marks"] = np.fromfile(mlog, dtype=np.int64) if os.path.exists(mlog) else np.zeros(0, np.int64)
     if keep_dir is None:
         shutil.rmtree(work, ignore_errors=True)
     return res

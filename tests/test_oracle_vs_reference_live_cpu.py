@@ -324,3 +324,64 @@ def test_driver_parses_sets_like_the_live_reference(k, tmp_path):
                         stderr=subprocess.PIPE, timeout=300)
     cut = ":::: Simulation stats ::::"
     assert pd.stderr.decode().split("ERROR: no usable CUDA device")[0].split(cut)[0] == pr.stderr.decode().split(cut)[0]
+
+
+@pytest.mark.parametrize("k", range(20))
+def test_sample_method_live_with_filters(k, tmp_path):
+    """--method sample with the length and accuracy filters cutting into the FASTQ, sequences shorter than the sampled
+    reads, deletion-rich and insertion-rich mixes: product filter == reference's statistics block, oracle == reference
+    files, engine core (schedule + per-read core, replay of the logged draws) == reference files"""
+    from pbsim_b200 import capi
+    from tests import hostsim_util as H
+    rng = np.random.default_rng(6600 + k)
+    glen = int(rng.integers(300, 2500)) if k % 3 == 0 else int(rng.integers(5000, 40000))
+    genome = R.synth_genome(40 + k, [("g", glen)], n_runs=int(rng.integers(0, 3)), hp_plants=int(rng.integers(0, 30)),
+                            iupac=int(rng.integers(0, 4)), lowercase_frac=float(rng.choice([0.0, 0.15])))[0][1]
+    okw = dict(len_min=int(rng.integers(100, 600)), len_max=int(rng.integers(1500, 4000)),
+               ratio=tuple(int(x) for x in rng.integers(1, 60, 3)), hp_del_bias=float(rng.choice([1.0, 1.0, 2.0, 5.0])))
+    amin, amax = sorted(float(x) / 100 for x in rng.integers(70, 100, 2))
+    if amin == amax:
+        amax = min(1.0, amax + 0.05)
+    lens = rng.integers(50, 5000, int(rng.integers(10, 80)))
+    recs = []
+    for i, n in enumerate(lens):
+        lo = int(rng.integers(2, 15))
+        q = bytes(rng.integers(33 + lo, 33 + lo + int(rng.integers(2, 25)), int(n)).astype(np.uint8))
+        recs.append(b"@r%d\n" % i + b"C" * int(n) + b"\n+\n" + q + b"\n")
+    fq = b"".join(recs)
+    (tmp_path / "sample.fq").write_bytes(fq)
+    fa = str(tmp_path / "genome.fa")
+    R.write_fasta(fa, [("g", genome)])
+    depth = float(rng.uniform(0.5, 12.0))
+    seed = int(rng.integers(1, 1 << 30))
+    args = ["--strategy", "wgs", "--method", "sample", "--sample", str(tmp_path / "sample.fq"), "--genome", fa, "--depth",
+            repr(depth), "--seed", str(seed), "--length-min", str(okw["len_min"]), "--length-max", str(okw["len_max"]),
+            "--accuracy-min", "%.2f" % amin, "--accuracy-max", "%.2f" % amax,
+            "--difference-ratio", "%d:%d:%d" % okw["ratio"], "--hp-del-bias", repr(okw["hp_del_bias"])]
+    ref = R.run_reference(args, logrand=True)
+    tr = lambda x: int(float("%.2f" % x) * 100) * 0.01  # noqa: E731  (set_sim_param truncates to two decimals, :1620-1629)
+    try:
+        pool, ss = capi.sample_filter(H.lib(), fq, len_min=okw["len_min"], len_max=okw["len_max"], accuracy_min=tr(amin),
+                                      accuracy_max=tr(amax))
+    except RuntimeError as e:
+        assert ref["returncode"] != 0 and str(e) in ref["stderr"]
+        return
+    assert capi.format_sample_stats(ss, str(tmp_path / "sample.fq")) in ref["stderr"]
+    assert pool == O.sample_pool(fq, len_min=okw["len_min"], len_max=okw["len_max"], accuracy_min=tr(amin),
+                                 accuracy_max=tr(amax))
+    if len(pool) < 2:
+        return  # the reference divides by zero (:1723); the engine refuses the pool
+    assert ref["returncode"] == 0, ref["stderr"][-300:]
+    o = O.Oracle("sample", None, **okw)
+    o.rng_glibc(seed)
+    if okw["hp_del_bias"] != 1.0:
+        o.hp_bias_prepass([genome])
+    o.set_sequence(genome, 1)
+    reads, maf, st = o.simulate_sample(depth, pool)
+    assert reads == ref["files"]["out_0001.fq.gz"] and maf == ref["files"]["out_0001.maf.gz"]
+    assert O.format_stats(st, 1) == R.split_stats_blocks(ref["stderr"])[1]
+    hm = capi.HostModel(H.lib(), capi.host_params("sample", **okw), None)
+    sub = H.run(hm, o.seq_upper(), o.hp(), 1, o.bias(), capi.RNG_REPLAY, 0, ref["draws"], int(depth * len(genome)),
+                pool=pool, batch_reads=int(rng.integers(1, 30)))
+    r2, m2 = H.records_from_events(hm, sub, o.seq_upper(), 1)
+    assert r2 == reads and m2 == maf
