@@ -385,3 +385,49 @@ def test_sample_method_live_with_filters(k, tmp_path):
                 pool=pool, batch_reads=int(rng.integers(1, 30)))
     r2, m2 = H.records_from_events(hm, sub, o.seq_upper(), 1)
     assert r2 == reads and m2 == maf
+
+
+@pytest.mark.parametrize("k", range(10))
+def test_multi_contig_genomes_live(k, tmp_path):
+    """several sequences per run: the rand() stream, the --hp-del-bias prepass over all sequences and the hpfreq[11]
+    cell that aliases hp_del_bias[0] carry over from one sequence to the next (main :673-754)"""
+    from pbsim_b200 import capi
+    from tests import hostsim_util as H
+    rng = np.random.default_rng(8800 + k)
+    method = ["qshmm", "errhmm"][k % 2]
+    model = str(rng.choice(["QSHMM-RSII.model", "QSHMM-ONT.model"] if method == "qshmm" else ["ERRHMM-ONT.model", "ERRHMM-SEQUEL.model"]))
+    contigs = R.synth_genome(70 + k, [("c%d" % t, int(rng.integers(300, 20000))) for t in range(int(rng.integers(2, 6)))],
+                             n_runs=2, hp_plants=25, iupac=2, long_runs=(11, 12, 19, 40))
+    okw = dict(len_min=100, len_max=20000, ratio=tuple(int(x) for x in rng.integers(1, 60, 3)),
+               hp_del_bias=float(rng.choice([1.0, 2.0, 7.5])), len_mean=float(rng.integers(500, 3000)), len_sd=400.0,
+               pass_num=int(rng.choice([1, 2])), accuracy_mean=float(rng.integers(80, 99)) / 100.0, accuracy_mean_set=True)
+    depth, seed = float(rng.uniform(1.0, 4.0)), int(rng.integers(1, 1 << 30))
+    fa = str(tmp_path / "genome.fa")
+    R.write_fasta(fa, contigs)
+    args = ["--strategy", "wgs", "--method", method, "--" + method, model_path(model), "--genome", fa, "--depth", repr(depth),
+            "--seed", str(seed), "--length-min", "100", "--length-max", "20000", "--length-mean", repr(okw["len_mean"]),
+            "--length-sd", "400", "--difference-ratio", "%d:%d:%d" % okw["ratio"], "--hp-del-bias", repr(okw["hp_del_bias"]),
+            "--accuracy-mean", "%.2f" % okw["accuracy_mean"], "--pass-num", str(okw["pass_num"])]
+    ref = R.run_reference(args, logrand=True)
+    assert ref["returncode"] == 0, ref["stderr"][-300:]
+    o = O.Oracle(method, model_path(model), **okw)
+    o.rng_glibc(seed)
+    if okw["hp_del_bias"] != 1.0:
+        o.hp_bias_prepass([s for _, s in contigs])
+    hm = capi.HostModel(H.lib(), capi.host_params(method, **okw), model_path(model))
+    blocks = R.split_stats_blocks(ref["stderr"])
+    cursor = 0
+    for i, (_, s) in enumerate(contigs, start=1):
+        o.set_sequence(s, i)
+        reads, maf, st = o.simulate_wgs(depth)
+        got = ref["files"]["out_%04d.%s" % (i, "bam" if okw["pass_num"] > 1 else "fq.gz")]
+        if okw["pass_num"] > 1:
+            got = got[got.index(b"PM:SEQUELII\n") + len(b"PM:SEQUELII\n"):]
+        assert reads == got, "sequence %d: oracle reads differ from the live reference" % i
+        assert maf == ref["files"]["out_%04d.maf.gz" % i]
+        assert O.format_stats(st, i) == blocks[i]
+        sub = H.run(hm, o.seq_upper(), o.hp(), i, o.bias(), capi.RNG_REPLAY, 0, ref["draws"][cursor:], int(depth * len(s)))
+        cursor = o.draws_consumed()
+        r2, m2 = H.records_from_events(hm, sub, o.seq_upper(), i)
+        assert r2 == got and m2 == maf, "sequence %d: engine core replay differs" % i
+    assert cursor == len(ref["draws"])
