@@ -431,3 +431,36 @@ def test_multi_contig_genomes_live(k, tmp_path):
         r2, m2 = H.records_from_events(hm, sub, o.seq_upper(), i)
         assert r2 == got and m2 == maf, "sequence %d: engine core replay differs" % i
     assert cursor == len(ref["draws"])
+
+
+@pytest.mark.parametrize("k", range(6))
+def test_long_transcripts_live(k, tmp_path):
+    """transcripts of 20 k .. 600 k bases: start-position tables of high ranks (prob2ssp[rank], rank = ceil(len / 1000),
+    :2504-2528, :2855) and table lines of many fgets buffers, against the live reference"""
+    rng = np.random.default_rng(1200 + k)
+    method = ["qshmm", "errhmm"][k % 2]
+    model = "QSHMM-ONT.model" if method == "qshmm" else "ERRHMM-ONT-HQ.model"
+    seqset = []
+    for t in range(int(rng.integers(2, 6))):
+        n = int(rng.integers(20000, 600000))
+        s = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, n)].tobytes()
+        seqset.append(("LONG%d" % t, int(rng.integers(0, 4)), int(rng.integers(0, 4)), s))
+    if sum(x[1] + x[2] for x in seqset) == 0:
+        seqset[0] = (seqset[0][0], 2, 1, seqset[0][3])
+    mean = float(rng.integers(2000, 30000))
+    okw = dict(len_min=100, len_max=100000, ratio=(6, 55, 39), hp_del_bias=1.0, len_mean=mean,
+               len_sd=float(rng.uniform(0.4, 0.9)) * mean, pass_num=1, accuracy_mean=0.9, accuracy_mean_set=True)
+    seed = int(rng.integers(1, 1 << 30))
+    inp = str(tmp_path / "input.txt")
+    R.write_transcripts(inp, seqset)
+    args = ["--strategy", "trans", "--method", method, "--" + method, model_path(model), "--transcript", inp, "--seed",
+            str(seed), "--length-mean", repr(okw["len_mean"]), "--length-sd", repr(okw["len_sd"]), "--length-max", "100000",
+            "--accuracy-mean", "0.90"]
+    ref = R.run_reference(args)
+    assert ref["returncode"] == 0, ref["stderr"][-300:]
+    o = O.Oracle(method, model_path(model), **okw)
+    o.rng_glibc(seed)
+    reads, maf, st = o.simulate_set("trans", seqset)
+    assert reads == ref["files"]["out.fq.gz"]
+    assert maf == ref["files"]["out.maf.gz"]
+    assert O.format_stats_set(st) == R.set_stats_block(ref["stderr"])
