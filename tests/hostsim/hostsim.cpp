@@ -423,6 +423,37 @@ long hostsim_run_sample(const pbsim_model *m, const uint8_t *ascii_upper, const 
   return (long)(g_out.info.size() / 12);
 }
 
+// the planners of --strategy trans / templ (plan_read_trans / plan_read_templ, the functions k_plan calls) for every
+// read of a set in PHILOX mode; out: 4 per read (offset inside the sequence, window length, accuracy, minus)
+long hostsim_plan_set(const pbsim_model *m, int strategy, long n, const int64_t *tlen, const int32_t *plus,
+                      const int32_t *minus, uint32_t seed, int rank_max, int64_t *out, long cap_reads) {
+  std::vector<uint16_t> ends((size_t)(rank_max + 1) * 21), mod((size_t)rank_max + 1);
+  if (strategy == PBSIM_STRATEGY_TRANS) pbsim_host_ssp_table(rank_max, ends.data(), mod.data());
+  pb::PlanTables pt;
+  pt.prob2len = m->prob2len;
+  pt.prob2acc = m->prob2accuracy;
+  pt.len_rand_value = (uint32_t)m->len_rand_value;
+  pt.acc_rand_value = (uint32_t)m->accuracy_rand_value;
+  pt.len_min = (uint32_t)m->len_min;
+  long read_id = 0;
+  for (long t = 0; t < n; ++t) {
+    const long nr = strategy == PBSIM_STRATEGY_TRANS ? (long)plus[t] + (long)minus[t] : 1;
+    for (long k = 1; k <= nr; ++k) {
+      ++read_id;
+      if (read_id > cap_reads) return -1;
+      pb::PhiloxDraw d;
+      d.ph.k0 = seed; d.ph.k1 = 0u; d.read_id = (uint32_t)read_id; d.pass = 0;
+      const pb::ReadPlan p = strategy == PBSIM_STRATEGY_TRANS
+                                 ? pb::plan_read_trans(pt, d, ends.data(), mod.data(), (uint32_t)tlen[t])
+                                 : pb::plan_read_templ(pt, d, (uint32_t)tlen[t]);
+      int64_t *o = out + (read_id - 1) * 4;
+      o[0] = p.offset; o[1] = p.wlen; o[2] = p.acc;
+      o[3] = strategy == PBSIM_STRATEGY_TRANS ? (k <= plus[t] ? 0 : 1) : 0;
+    }
+  }
+  return read_id;
+}
+
 const int64_t *hostsim_info() { return g_out.info.data(); }
 const uint32_t *hostsim_counts() { return g_out.counts.data(); }
 const double *hostsim_accuracy() { return g_out.accuracy.data(); }

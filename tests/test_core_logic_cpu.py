@@ -302,3 +302,38 @@ def test_sample_schedule_edge_cases_equal_oracle(glen, depth, lens):
     reads, maf = H.records_from_events(hm, sub, o.seq_upper(), 1)
     assert reads == oreads and maf == omaf
     assert len(sub) == ost.res_num
+
+
+@pytest.mark.parametrize("strategy", ["trans", "templ"])
+def test_set_planners_equal_oracle_on_long_sequences(strategy):
+    """plan_read_trans / plan_read_templ (what k_plan runs per read of a sequence set) against the oracle's read plans
+    in PHILOX mode, on transcripts of up to 900 kb (start-position tables of ranks up to 900, pbsim.cpp:2504-2528,
+    :2842-2866) and with windows clipped at the transcript's end"""
+    import ctypes as C
+    from tests.golden_util import model_path
+    rng = np.random.default_rng(77)
+    lens = [int(x) for x in rng.integers(300, 900000, 14)] + [999000, 1000, 1001, 21, 22]
+    seqset = [("T%d" % i, int(rng.integers(0, 6)), int(rng.integers(0, 6)),
+               np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, n)].tobytes()) for i, n in enumerate(lens)]
+    okw = dict(len_mean=30000.0, len_sd=25000.0, len_max=1000000, accuracy_mean=0.9, accuracy_mean_set=True)
+    o = O.Oracle("qshmm", model_path("QSHMM-RSII.model"), **okw)
+    o.rng_philox(5)
+    o.simulate_set(strategy, seqset)
+    info = o.readinfo()
+    hm = capi.HostModel(H.lib(), capi.host_params("qshmm", **okw), model_path("QSHMM-RSII.model"))
+    L = H.lib()
+    L.hostsim_plan_set.restype = C.c_long
+    L.hostsim_plan_set.argtypes = [C.POINTER(capi.Model), C.c_int, C.c_long, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32,
+                                   C.c_int, C.c_void_p, C.c_long]
+    tlen = np.array(lens, dtype=np.int64)
+    plus = np.array([x[1] for x in seqset], dtype=np.int32)
+    minus = np.array([x[2] for x in seqset], dtype=np.int32)
+    out = np.zeros((len(info) + 8, 4), dtype=np.int64)
+    n = L.hostsim_plan_set(hm.ptr, capi.STRATEGY_TRANS if strategy == "trans" else capi.STRATEGY_TEMPL, len(lens),
+                           tlen.ctypes.data, plus.ctypes.data, minus.ctypes.data, 5, 1000, out.ctypes.data, len(out))
+    assert n == len(info) and n > 10
+    out = out[:n]
+    assert np.array_equal(out[:, 0], info["offset"])
+    assert np.array_equal(out[:, 1], info["wlen"])
+    assert np.array_equal(out[:, 2], info["acc"])
+    assert np.array_equal(out[:, 3], (info["strand"] == ord("-")).astype(np.int64))
