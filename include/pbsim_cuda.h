@@ -27,7 +27,8 @@
 extern "C" {
 #endif
 
-#define PBSIM_ABI_VERSION 2
+/* 3: PBSIM_METHOD_SAMPLE, pbsim_cuda_set_pool, pbsim_host_sample_filter (additive over 2) */
+#define PBSIM_ABI_VERSION 3
 
 #define PBSIM_E_INVALID   (-1)  /* bad argument / call order                            */
 #define PBSIM_E_CUDA      (-2)  /* CUDA runtime error                                   */

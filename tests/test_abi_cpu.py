@@ -26,7 +26,17 @@ def test_header_symbols_are_exported(lib):
     for n in names:
         assert hasattr(lib, n), n
     assert set(names) == set(capi.HOST_EXPORTS + capi.ENGINE_EXPORTS)
-    assert lib.pbsim_cuda_abi_version() == 2
+    assert lib.pbsim_cuda_abi_version() == 3
+
+
+def test_header_is_plain_c(tmp_path):
+    """the boundary is a C ABI: the header must compile as C99 on its own (no C++, no torch types)"""
+    import subprocess
+    src = tmp_path / "abi.c"
+    src.write_text('#include "pbsim_cuda.h"\nint main(void) { pbsim_run r; pbsim_chunk c; pbsim_stats s; pbsim_seqset q; '
+                   'pbsim_sample_stats t; (void)r; (void)c; (void)s; (void)q; (void)t; return PBSIM_ABI_VERSION == 0; }\n')
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only",
+                           "-I", os.path.join(ROOT, "include"), str(src)])
 
 
 def test_create_fails_loudly_without_gpu(lib):
