@@ -83,3 +83,30 @@ def test_kraft_equality_and_uniform_input():
     lens = (lit >> 16).astype(int)
     assert sum(2.0 ** -int(x) for x in lens) == 1.0  # complete code: 257 symbols
     roundtrip(bytes(range(256)), np.ones(256, dtype=np.int64))
+
+
+@pytest.mark.parametrize("seed", range(36))
+def test_extreme_histograms_give_valid_streams(seed):
+    """empty, single-symbol, power-of-two, Fibonacci-like (deepest Huffman trees) and heavy-tailed histograms: the code
+    stays within 12 bits, is a prefix code, and zlib inflates what it encodes — for any input bytes"""
+    rng = np.random.default_rng(50000 + seed)
+    kind = seed % 6
+    if kind == 0:
+        hist = np.zeros(256, np.int64)
+        hist[int(rng.integers(0, 256))] = int(rng.integers(1, 10 ** 15))
+    elif kind == 1:
+        hist = np.zeros(256, np.int64)
+    elif kind == 2:
+        hist = (2 ** rng.integers(0, 50, 256)).astype(np.int64) * (rng.random(256) < rng.random())
+    elif kind == 3:
+        hist = np.array([int(1.6180339 ** min(i, 80)) for i in range(256)], dtype=np.int64)
+        rng.shuffle(hist)
+    elif kind == 4:
+        hist = rng.integers(0, 3, 256).astype(np.int64)
+    else:
+        hist = (rng.pareto(0.4, 256) * 1000).astype(np.int64)
+    data = bytes(rng.integers(0, 256, int(rng.integers(0, 600)), dtype=np.uint8))
+    _, lit = roundtrip(data, hist)
+    lens = (lit >> 16).astype(int)
+    assert 1 <= lens.min() and lens.max() <= 12
+    assert sum(2.0 ** -int(x) for x in lens) <= 1.0
