@@ -1364,7 +1364,7 @@ int64_t orc_get_ssp(int rank_max, int32_t *ends /* [(rank_max+1)*21] */, int32_t
   return rank_max;
 }
 
-/* ------------------------------------------------------------------ --method sample (no engine counterpart yet) */
+/* ------------------------------------------------------------------ --method sample (engine: k_sim_sample, sample_plan.hpp) */
 
 /* ref: simulate_by_sample inner loop :1775-1833.  The quality string of the sampled read gives the quality of
  * every position; `len` bounds BOTH the window and the read (mut.len, :1756-1763), and no deletion is drawn once

@@ -70,7 +70,7 @@ def test_start_position_table_known_answers():
 @pytest.mark.parametrize("name", sample_case_names())
 def test_oracle_reproduces_reference_sample_method(name):
     """--method sample (pbsim.cpp:1694; get_sample_inf's filter :1214-1275 restated in oracle.sample_pool): the
-    specification for the engine's next method, pinned byte for byte — including the quality buffer that is cut at
+    specification of the engine's sample method, pinned byte for byte — including the quality buffer that is cut at
     the end of every read, which makes copy i+1 of a pool entry as long as copy i's read"""
     c = SampleCase(name)
     o = O.Oracle("sample", None, **c.okw)
