@@ -60,3 +60,31 @@ def test_engine_philox_matches_reference_distributions(name):
     ok, res = SU.compare(got, fix, meta["method"])
     eng.close()
     assert ok, res
+
+
+@pytest.mark.skipif(not os.path.exists(R.REF_BIN), reason="oracle/_ref/pbsim is not built here")
+def test_sample_method_philox_matches_live_reference_distributions(tmp_path):
+    """--method sample: PHILOX mode (oracle == engine byte for byte, tests/test_gpu_sample.py) against a run of the
+    unmodified reference on the same pool and another seed — same tolerances as the qshmm fixture comparison.
+    The pool is the reference's own qshmm output (as a user would make one)."""
+    glen = 600000
+    genome = R.synth_genome(321, [("s1", glen)])[0][1]
+    fa = str(tmp_path / "g.fa")
+    R.write_fasta(fa, [("s1", genome)])
+    src = R.run_reference(["--strategy", "wgs", "--method", "qshmm", "--qshmm", model_path("QSHMM-RSII.model"), "--genome", fa,
+                           "--depth", "2", "--seed", "7", "--length-mean", "3000", "--length-sd", "2000"])
+    fq = src["files"]["out_0001.fq.gz"]
+    (tmp_path / "sample.fq").write_bytes(fq)
+    ref = R.run_reference(["--strategy", "wgs", "--method", "sample", "--sample", str(tmp_path / "sample.fq"), "--genome", fa,
+                           "--depth", "8", "--seed", "2024"])
+    assert ref["returncode"] == 0
+    want = SU.parse_outputs(ref["files"]["out_0001.fq.gz"], ref["files"]["out_0001.maf.gz"])
+    pool = O.sample_pool(fq)
+    o = O.Oracle("sample", None)
+    o.rng_philox(99)
+    o.set_sequence(R.synth_genome(322, [("s1", glen)])[0][1], 1)  # an independent random genome
+    reads, maf, st = o.simulate_sample(8.0, pool)
+    got = SU.parse_outputs(reads, maf)
+    ok, res = SU.compare(got, want, "qshmm")
+    assert ok, res
+    assert got["plus"] == (got["n"] + 1) // 2
