@@ -484,7 +484,10 @@ int orc_build_tables(orc_ctx *c) {
     }
     c->len_rand_value = end_wk;
   }
-  if (c->pass_num == 1 && c->len_rand_value < 1)
+  /* the reference makes this check only with --pass-num 1 (:2022, :3664); with more passes it goes on and indexes
+   * prob2len with a draw modulo a non-positive value (a crash in practice).  The restatement stops in both cases, as
+   * the product's table builder does. */
+  if (c->len_rand_value < 1)
     return fail(c, "ERROR: length parameters are not appropriate.");
 
   /* accuracy distribution (ref: :2029-2064) */

@@ -57,3 +57,16 @@ def test_host_front_end_reports_reference_errors(lib):
         capi.HostModel(lib, p, model_path("QSHMM-RSII.model"))
     with pytest.raises(RuntimeError, match="Cannot open"):
         capi.HostModel(lib, capi.host_params("qshmm"), "/nonexistent.model")
+
+
+def test_length_parameters_are_checked_for_every_pass_number(lib):
+    """the reference tests len_rand_value only with --pass-num 1 (pbsim.cpp:2022, :3664) and crashes otherwise; the
+    product's table builder (and the oracle) refuse the parameters whatever the pass number"""
+    from oracle import oracle as O
+    from tests.golden_util import model_path
+    for method, model in (("qshmm", "QSHMM-RSII.model"), ("errhmm", "ERRHMM-ONT.model")):
+        for pass_num in (1, 2, 10):
+            with pytest.raises(RuntimeError, match="length parameters are not appropriate"):
+                capi.HostModel(lib, capi.host_params(method, len_mean=50000.0, len_sd=5000.0, pass_num=pass_num), model_path(model))
+            with pytest.raises(RuntimeError, match="length parameters are not appropriate"):
+                O.Oracle(method, model_path(model), len_mean=50000.0, len_sd=5000.0, pass_num=pass_num)
