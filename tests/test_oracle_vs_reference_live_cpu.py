@@ -464,3 +464,53 @@ def test_long_transcripts_live(k, tmp_path):
     assert reads == ref["files"]["out.fq.gz"]
     assert maf == ref["files"]["out.maf.gz"]
     assert O.format_stats_set(st) == R.set_stats_block(ref["stderr"])
+
+
+def _cli_variants():
+    qs = ["--strategy", "wgs", "--method", "qshmm", "--qshmm", "QSHMM-RSII.model", "--genome", "tiny.fa"]
+    er = ["--strategy", "wgs", "--method", "errhmm", "--errhmm", "ERRHMM-ONT.model", "--genome", "tiny.fa"]
+    out = []
+    for opt, vals in (("--depth", ["0", "0.0", "-0.5", "abc", "1e3", "1001"]),
+                      ("--length-min", ["0", "-1", "1000001", "x"]), ("--length-max", ["0", "1000001", "99"]),
+                      ("--length-mean", ["0", "-5", "1000001", "1e7"]), ("--length-sd", ["-1", "1000001"]),
+                      ("--accuracy-mean", ["-0.1", "1.01", "abc", "0"]), ("--accuracy-min", ["-1", "2"]),
+                      ("--accuracy-max", ["-1", "2"]), ("--difference-ratio", ["1001:1:1", "1:1", "a:b:c", "1:1:1:1", "-1:2:3", "0:0:0"]),
+                      ("--pass-num", ["0", "-3", "abc"]), ("--hp-del-bias", ["0", "-1", "11", "abc", "10.5"]),
+                      ("--seed", ["abc", "-1"]), ("--id-prefix", ["x" * 200]), ("--prefix", [""])):
+        for v in vals:
+            out.append(qs + [opt, v])
+            if opt in ("--depth", "--pass-num", "--hp-del-bias", "--accuracy-mean"):
+                out.append(er + [opt, v])
+    out += [["--strategy", "wgsx"] + qs[2:], ["--strategy", "w"] + qs[2:], qs[:2] + ["--method", "qshmmXYZ"] + qs[4:],
+            qs[:2] + ["--method", "q"] + qs[4:], ["--strategy", "templ", "--method", "sample", "--template", "tiny.fa"],
+            qs + ["--nonsense", "1"], qs + ["--depth"], []]
+    return out
+
+
+@pytest.mark.parametrize("idx", range(len(_cli_variants())))
+def test_driver_option_validation_equals_live_reference(idx, tmp_path):
+    """every option with out-of-range / malformed values: when the reference rejects the command line, the driver
+    prints the same text and exits with the same status (option parsing :257-530, set_sim_param :1451-1688)"""
+    import re
+    import shutil
+    import subprocess
+    import __graft_entry__ as G
+    args = _cli_variants()[idx]
+    shutil.copy(model_path("QSHMM-RSII.model"), tmp_path / "QSHMM-RSII.model")
+    shutil.copy(model_path("ERRHMM-ONT.model"), tmp_path / "ERRHMM-ONT.model")
+    (tmp_path / "tiny.fa").write_text(">s\nACGTACGTAC\n")
+    env = dict(os.environ, PATH=R.SHIMS + ":" + os.environ.get("PATH", ""))
+    pr = subprocess.run([R.REF_BIN] + args, cwd=tmp_path, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=120)
+    assert pr.returncode != 0  # (tiny.fa is shorter than 100 bases: nothing gets as far as a simulation)
+    G.build_engine()
+    pd = subprocess.run([G.build_driver()] + args, cwd=tmp_path, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=120)
+
+    def norm(t):
+        t = re.sub(r"(?m)^seed : -?\d+$", "seed : <n>", t) if "--seed" not in args else t
+        return re.sub(r"(?m)^(\S*pbsim\S*): ", "pbsim: ", t)  # getopt prefixes its messages with argv[0]
+    assert pd.returncode == pr.returncode
+    assert pd.stdout == pr.stdout
+    if not args:  # the help text: the driver's lists its additional engine options
+        assert pd.stderr.decode().startswith("\nUSAGE: pbsim [options]") and pr.stderr.decode().startswith("\nUSAGE: pbsim [options]")
+        return
+    assert norm(pd.stderr.decode()) == norm(pr.stderr.decode())
