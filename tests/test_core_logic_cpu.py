@@ -18,8 +18,23 @@ def load_product_model(c):
 def test_host_tables_equal_oracle_tables(name):
     """KAT: quantised tables of the product's builder == the oracle's (which reproduces the reference)."""
     c = Case(name)
-    o = c.new_oracle()
-    hm = load_product_model(c)
+    _compare_tables(c.new_oracle(), load_product_model(c), c.method)
+
+
+@pytest.mark.parametrize("k", range(40))
+def test_host_tables_equal_oracle_tables_on_random_options(k):
+    """the same for 40 random option sets (accuracy 0.70 .. 1.00, fixed lengths, all seven models): the configurations on
+    which tests/test_oracle_vs_reference_live_cpu.py pins the oracle to the reference"""
+    from tests.golden_util import model_path
+    from tests.test_oracle_vs_reference_live_cpu import _config_wide
+    cfg = _config_wide(k)
+    mp = model_path(cfg["model"])
+    o = O.Oracle(cfg["method"], mp, **cfg["okw"])
+    hm = capi.HostModel(H.lib(), capi.host_params(cfg["method"], **cfg["okw"]), mp)
+    _compare_tables(o, hm, cfg["method"])
+
+
+def _compare_tables(o, hm, method):
     v = hm.view
     t, n = o.table(0)
     assert v.len_rand_value == n and np.array_equal(np.ctypeslib.as_array(v.prob2len, shape=(n,)), t)
@@ -29,7 +44,7 @@ def test_host_tables_equal_oracle_tables(name):
     assert list(v.sub_thre) == s.tolist() and list(v.ins_thre) == i.tolist() and list(v.del_thre) == d.tolist()
     amin, amax, lo, hi = o.model_range()
     assert (v.acc_lo, v.acc_hi) == (lo, hi)
-    err = c.method == "errhmm"
+    err = method == "errhmm"
     if err:
         assert (v.model_acc_min, v.model_acc_max) == (amin, amax)
     checked = 0
