@@ -352,3 +352,28 @@ def test_set_planners_equal_oracle_on_long_sequences(strategy):
     assert np.array_equal(out[:, 1], info["wlen"])
     assert np.array_equal(out[:, 2], info["acc"])
     assert np.array_equal(out[:, 3], (info["strand"] == ord("-")).astype(np.int64))
+
+
+@pytest.mark.parametrize("k", range(12))
+def test_hp_del_bias_front_end_equals_oracle_on_random_genomes(k):
+    """pbsim_host_hp_del_bias (main :673-697, with its long += double truncation) on random multi-contig genomes and
+    bias options: cells 1..10 equal the oracle's after its prepass; cell 0 is the aliased hpfreq[11] counter"""
+    from oracle import refrun as R
+    rng = np.random.default_rng(31000 + k)
+    contigs = R.synth_genome(600 + k, [("c%d" % t, int(rng.integers(200, 30000))) for t in range(int(rng.integers(1, 6)))],
+                             n_runs=int(rng.integers(0, 4)), hp_plants=int(rng.integers(0, 60)), iupac=int(rng.integers(0, 4)),
+                             lowercase_frac=float(rng.choice([0.0, 0.3])), long_runs=(11, 12, 13, 26) if k % 2 else ())
+    opt = float(rng.choice([1.5, 2.0, 3.0, 7.25, 10.0]))
+    o = O.Oracle("qshmm", __import__("tests.golden_util", fromlist=["model_path"]).model_path("QSHMM-RSII.model"),
+                 hp_del_bias=opt)
+    o.hp_bias_prepass([s for _, s in contigs])
+    hpfreq = np.zeros(12, dtype=np.int64)
+    for i, (_, s) in enumerate(contigs, start=1):
+        o.set_sequence(s, i)
+        hp = o.hp()
+        for h in range(1, 12):
+            hpfreq[h] += int(np.count_nonzero(hp == h))
+    bias = capi.hp_del_bias(H.lib(), opt, hpfreq)
+    assert bias[1:11] == o.bias()[1:11].tolist()
+    assert bias[11] == 0.0
+    assert np.array([bias[0]]).view(np.int64)[0] == hpfreq[11]
