@@ -514,3 +514,43 @@ def test_driver_option_validation_equals_live_reference(idx, tmp_path):
         assert pd.stderr.decode().startswith("\nUSAGE: pbsim [options]") and pr.stderr.decode().startswith("\nUSAGE: pbsim [options]")
         return
     assert norm(pd.stderr.decode()) == norm(pr.stderr.decode())
+
+
+def test_sample_profile_files_equal_live_reference(tmp_path):
+    """--sample + --sample-profile-id stores the filtered reads and their statistics (pbsim.cpp:1317-1326, :590-602);
+    --sample-profile-id alone reuses them (:603-615): the driver writes the files the reference writes and prints the
+    blocks the reference prints (everything before the first simulation; the driver needs a GPU from there on)"""
+    import subprocess
+    import __graft_entry__ as G
+    rng = np.random.default_rng(17)
+    recs = []
+    for i in range(60):
+        n = int(rng.integers(60, 3000))
+        lo = int(rng.integers(2, 15))
+        q = bytes(rng.integers(33 + lo, 33 + lo + int(rng.integers(2, 25)), n).astype(np.uint8))
+        recs.append(b"@r%d\n" % i + b"G" * n + b"\n+\n" + q + b"\n")
+    genome = R.synth_genome(3, [("g", 4000)])[0][1]
+    G.build_engine()
+    exe = G.build_driver()
+    env = dict(os.environ, PATH=R.SHIMS + ":" + os.environ.get("PATH", ""))
+    common = ["--strategy", "wgs", "--method", "sample", "--genome", "genome.fa", "--depth", "2", "--seed", "9",
+              "--length-min", "200", "--length-max", "2500", "--accuracy-min", "0.8", "--accuracy-max", "0.97", "--prefix", "out"]
+    outs = {}
+    for who, binary in (("r", R.REF_BIN), ("d", exe)):
+        d = tmp_path / who
+        d.mkdir()
+        (d / "sample.fq").write_bytes(b"".join(recs))
+        R.write_fasta(str(d / "genome.fa"), [("g", genome)])
+        p1 = subprocess.run([binary] + common + ["--sample", "sample.fq", "--sample-profile-id", "prof"], cwd=d, env=env,
+                            stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=300)
+        p2 = subprocess.run([binary] + common + ["--sample-profile-id", "prof"], cwd=d, env=env, stdout=subprocess.PIPE,
+                            stderr=subprocess.PIPE, timeout=300)
+        p3 = subprocess.run([binary] + common + ["--sample", "sample.fq", "--sample-profile-id", "prof"], cwd=d, env=env,
+                            stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=300)
+        cut = ":::: Simulation stats (ref.1) ::::"
+        head = lambda t: t.split("ERROR: no usable CUDA device")[0].split(cut)[0]  # noqa: E731
+        outs[who] = ((d / "sample_profile_prof.fastq").read_bytes(), (d / "sample_profile_prof.stats").read_bytes(),
+                     head(p1.stderr.decode()), head(p2.stderr.decode()), p3.stderr.decode(), p3.returncode)
+    assert outs["d"] == outs["r"]
+    assert b"\n" in outs["r"][0] and outs["r"][1].startswith(b"num\t")
+    assert "exists." in outs["r"][4]
