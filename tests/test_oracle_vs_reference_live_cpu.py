@@ -554,3 +554,44 @@ def test_sample_profile_files_equal_live_reference(tmp_path):
     assert outs["d"] == outs["r"]
     assert b"\n" in outs["r"][0] and outs["r"][1].startswith(b"num\t")
     assert "exists." in outs["r"][4]
+
+
+_ODD_FASTA = {
+    "empty": b"",
+    "header_only": b">s\n",
+    "crlf": b">s desc\r\n" + b"ACGT" * 40 + b"\r\n" + b"ACGT" * 40 + b"\r\n",
+    "two_headers_empty_first": b">a\n>b\n" + b"ACGT" * 50 + b"\n",
+    "short_second": b">a\n" + b"ACGT" * 50 + b"\n>b\nACGT\n",
+    "blank_lines": b"\n\n>a\n\n" + b"ACGT" * 50 + b"\n\n",
+    "gt_in_seq": b">a\n" + b"ACGT" * 30 + b"\n" + b">" + b"\n" + b"ACGT" * 30 + b"\n",
+    "lower_n": b">a\n" + b"acgtnNRY" * 30 + b"\n",
+    "long_name": b">" + b"n" * 400 + b"\n" + b"ACGT" * 50 + b"\n",
+    "no_header": b"ACGT" * 50 + b"\n",  # the reference crashes on this one; the driver must refuse it
+}
+
+
+@pytest.mark.parametrize("name", sorted(_ODD_FASTA))
+def test_driver_handles_odd_fasta_like_the_live_reference(name, tmp_path):
+    import subprocess
+    import __graft_entry__ as G
+    G.build_engine()
+    env = dict(os.environ, PATH=R.SHIMS + ":" + os.environ.get("PATH", ""))
+    res = {}
+    for who, binary in (("r", R.REF_BIN), ("d", G.build_driver())):
+        d = tmp_path / who
+        d.mkdir()
+        (d / "g.fa").write_bytes(_ODD_FASTA[name])
+        p = subprocess.run([binary, "--strategy", "wgs", "--method", "qshmm", "--qshmm", model_path("QSHMM-RSII.model"),
+                            "--genome", "g.fa", "--depth", "0.3", "--seed", "1", "--prefix", "out"], cwd=d, env=env,
+                           stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=120)
+        err = p.stderr.decode(errors="replace")
+        head = err.split("ERROR: no usable CUDA device")[0].split(":::: Simulation stats (ref.1) ::::")[0]
+        refs = {f: (d / f).read_bytes() for f in sorted(os.listdir(d)) if f.endswith(".ref")}
+        res[who] = (head, refs, p.returncode)
+    if res["r"][2] < 0:  # killed by a signal: undefined behaviour in the reference
+        assert res["d"][2] not in (0,) and res["d"][2] > 0
+        return
+    assert res["d"][0] == res["r"][0]
+    assert res["d"][1] == res["r"][1]
+    if res["r"][2] != 0:
+        assert res["d"][2] == res["r"][2]
