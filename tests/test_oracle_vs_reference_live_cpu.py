@@ -595,3 +595,44 @@ def test_driver_handles_odd_fasta_like_the_live_reference(name, tmp_path):
     assert res["d"][1] == res["r"][1]
     if res["r"][2] != 0:
         assert res["d"][2] == res["r"][2]
+
+
+_SEQ = b"ACGT" * 100
+_ODD_SETS = {
+    "ok": (b"T1\t2\t1\t" + _SEQ + b"\nT2\t0\t0\t" + _SEQ + b"\n", "trans"),
+    "no_final_newline": (b"T1\t2\t1\t" + _SEQ + b"\nT2\t1\t1\t" + _SEQ, "trans"),
+    "empty": (b"", "trans"),
+    "non_numeric": (b"T1\tx\ty\t" + _SEQ + b"\n", "trans"),
+    "zero_expr_all": (b"T1\t0\t0\t" + _SEQ + b"\n", "trans"),
+    "short_seq": (b"T1\t1\t1\tACGTACGTAC\n", "trans"),
+    "missing_col": (b"T1\t2\t" + _SEQ + b"\n", "trans"),            # the reference crashes (strtok returns NULL)
+    "blank_line": (b"T1\t2\t1\t" + _SEQ + b"\n\nT2\t1\t1\t" + _SEQ + b"\n", "trans"),  # likewise
+    "templ_ok": (b">a\n" + _SEQ + b"\n>b\n" + _SEQ + b"\n", "templ"),
+    "templ_empty": (b"", "templ"),
+    "templ_header_only": (b">a\n", "templ"),
+    "templ_blank": (b">a\n\n" + _SEQ + b"\n\n>b\n" + _SEQ + b"\n", "templ"),
+}
+
+
+@pytest.mark.parametrize("name", sorted(_ODD_SETS))
+def test_driver_handles_odd_tables_like_the_live_reference(name, tmp_path):
+    import subprocess
+    import __graft_entry__ as G
+    G.build_engine()
+    data, strategy = _ODD_SETS[name]
+    env = dict(os.environ, PATH=R.SHIMS + ":" + os.environ.get("PATH", ""))
+    res = {}
+    for who, binary in (("r", R.REF_BIN), ("d", G.build_driver())):
+        d = tmp_path / who
+        d.mkdir()
+        (d / "in.txt").write_bytes(data)
+        p = subprocess.run([binary, "--strategy", strategy, "--method", "qshmm", "--qshmm", model_path("QSHMM-RSII.model"),
+                            "--transcript" if strategy == "trans" else "--template", "in.txt", "--seed", "1", "--prefix", "out",
+                            "--length-mean", "200", "--length-sd", "100"], cwd=d, env=env, stdout=subprocess.PIPE,
+                           stderr=subprocess.PIPE, timeout=120)
+        err = p.stderr.decode(errors="replace")
+        res[who] = (err.split("ERROR: no usable CUDA device")[0].split(":::: Simulation stats ::::")[0], p.returncode)
+    if res["r"][1] < 0:  # the reference died of a signal: the driver must stop with a message instead
+        assert res["d"][1] > 0 and "ERROR:" in res["d"][0]
+        return
+    assert res["d"][0] == res["r"][0]
