@@ -388,7 +388,7 @@ def main():
     eng.timer_start()
     t0 = time.perf_counter()
     bases = out_bytes = launches = 0
-    sim_s = emit_s = gen_s = seg_s = 0.0
+    sim_s = emit_s = gen_s = seg_s = chain_s = 0.0
     for k in range(args.steps):
         b, ob, st = step_device(args.warmup + k)
         bases += b
@@ -397,6 +397,7 @@ def main():
         sim_s += st.sim_seconds
         emit_s += st.emit_seconds
         seg_s += st.seg_seconds
+        chain_s += st.chain_seconds
         gen_s += st.gen_seconds
     dev_ms = eng.timer_stop()
     barrier()
@@ -511,7 +512,8 @@ def main():
                                            "kernel / its duration, GB/s (ncu --set full, profiles/r01_k_*_c3_v17.txt, *_c2_v13.txt)",
                          "kernel": dom_name + ", rank 0",
                          "algorithmic_bytes_per_base": ALGO_BYTES_PER_BASE, "peak_source": peak_src,
-                         "kernel_seconds": {"sim": sim_s, "of_which_" + seg_name: seg_s, "emit": emit_s,
+                         "kernel_seconds": {"sim": sim_s, "of_which_" + seg_name: seg_s,
+                                            "of_which_k_chain_chunk": chain_s, "emit": emit_s,
                                             "all_generation": gen_s},
                          "kernel_share_of_step": dom_s / (dev_ms * 1e-3) if dev_ms else None,
                          "path": {"what": "pass 1 + pass 2 together (k_sim_seg, k_find_end, k_sim_%s, k_emit)"

@@ -28,7 +28,7 @@ extern "C" {
 #endif
 
 /* 3: PBSIM_METHOD_SAMPLE, pbsim_cuda_set_pool, pbsim_host_sample_filter (additive over 2) */
-#define PBSIM_ABI_VERSION 3
+#define PBSIM_ABI_VERSION 4
 
 #define PBSIM_E_INVALID   (-1)  /* bad argument / call order                            */
 #define PBSIM_E_CUDA      (-2)  /* CUDA runtime error                                   */
@@ -172,6 +172,7 @@ typedef struct {
   double deflate_seconds;        /* ... of which the gzip writer (option "deflate")          */
   double seg_seconds;            /* ... of which the segment kernel (k_sim_seg / _err) alone  */
   int64_t kernel_launches;       /* number of engine kernels launched during the run         */
+  double chain_seconds;          /* ... of which the chain / quality kernel (k_chain_chunk / _err) alone (ABI 4) */
 } pbsim_stats;
 
 typedef struct pbsim_engine pbsim_engine;

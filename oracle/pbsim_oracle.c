@@ -69,6 +69,14 @@ typedef struct {
   uint32_t cw[4]; /* chain block: state draws of positions 4*cidx .. 4*cidx+3 */
   uint32_t cidx;
   int cvalid;
+  /* addressing scheme of the per-position draws: 0 = errhmm (one block per column + chain stream),
+   * 1 = qshmm / sample "v2" (DESIGN.md 2.5): error stream = domain 1, one block per TWO positions
+   * (block pos>>1, words 2*(pos&1) = X and 2*(pos&1)+1 = Y); quality stream = domain 2, one block per FOUR
+   * positions (block pos>>2, word pos&3 = S: high half state draw, low half emission draw) */
+  int scheme;
+  uint32_t ew[4]; /* error block of positions 2*eidx, 2*eidx+1 */
+  uint32_t eidx;
+  int evalid;
 } rng_t;
 
 static uint32_t stream_next(rng_t *r) {
@@ -108,6 +116,7 @@ static void d_plan_begin(rng_t *r, uint32_t read_id) {
   r->read_id = read_id;
   r->pass = 0;
   r->cvalid = 0;
+  r->evalid = 0;
   if (r->mode == RNG_PHILOX) philox_at(r, 0, 0, 0, r->w);
 }
 static uint32_t d_plan_len(rng_t *r, uint32_t mod) {
@@ -126,25 +135,59 @@ static uint64_t d_plan_off(rng_t *r, uint64_t span) {
 
 /* per-position draws */
 static void d_begin(rng_t *r, uint32_t pass, uint32_t pos) {
-  if (r->pass != pass) r->cvalid = 0;
+  if (r->pass != pass) r->cvalid = r->evalid = 0;
   r->pass = pass;
   r->pos = pos;
-  if (r->mode == RNG_PHILOX) philox_at(r, pos, 0, 1, r->w);
+  if (r->mode != RNG_PHILOX) return;
+  if (r->scheme == 1) {
+    if (!r->evalid || r->eidx != (pos >> 1)) {
+      philox_at(r, pos >> 1, 0, 1, r->ew);
+      r->eidx = pos >> 1;
+      r->evalid = 1;
+    }
+    r->w[0] = r->ew[(pos & 1u) * 2u];      /* X: error draw, 3-way choice in the low 12 bits */
+    r->w[1] = r->ew[(pos & 1u) * 2u + 1u]; /* Y: deletion draws, 8-way choice bits 0-2, 4-way choice bits 3-4 */
+  } else {
+    philox_at(r, pos, 0, 1, r->w);
+  }
+}
+/* quality-stream word S of the current position (scheme 1) */
+static uint32_t qs_word(rng_t *r) {
+  if (!r->cvalid || r->cidx != (r->pos >> 2)) {
+    philox_at(r, r->pos >> 2, 0, 2, r->cw);
+    r->cidx = r->pos >> 2;
+    r->cvalid = 1;
+  }
+  return r->cw[r->pos & 3u];
+}
+/* PHILOX scheme 1: a 32-bit word W "hits" a threshold of t millionths iff W < T32(t),
+ * T32(t) = min(ceil(t * 2^32 / 10^6), 2^32 - 1); for t < 10^6 that is mulhi32(W, 10^6) < t exactly. */
+static uint32_t t32_of(double thr) {
+  double c = ceil(thr);
+  uint64_t t, v;
+  if (!(c >= 0)) c = 0;
+  if (c > 1000000.0) c = 1000000.0;
+  t = (uint64_t)c;
+  v = (t * 4294967296ull + 999999ull) / 1000000ull;
+  return v > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)v;
+}
+/* does draw `d` (stream modes: a value 0..999999; scheme 1: a raw word) fall below `thr` millionths? */
+static int d_lt(const rng_t *r, uint32_t d, double thr) {
+  if (r->mode == RNG_PHILOX && r->scheme == 1) return d < t32_of(thr);
+  return (double)d < thr;
 }
 /* HMM state draw (init2state / tran2state index) of the current position.  PHILOX mode: the chain has its own
  * stream, domain 2, one block per 4 consecutive positions (block pos>>2, word pos&3), so that the state chain can
  * be advanced without generating the other draws of a position. */
 static uint32_t d_state(rng_t *r, uint32_t mod) {
   if (r->mode != RNG_PHILOX) return stream_next(r) % mod;
+  if (r->scheme == 1) return mulhi32(qs_word(r) & 0xFFFF0000u, mod); /* high half: (S >> 16) * mod >> 16 */
   if (!r->cvalid || r->cidx != (r->pos >> 2)) {
     philox_at(r, r->pos >> 2, 0, 2, r->cw);
     r->cidx = r->pos >> 2;
     r->cvalid = 1;
   }
   return mulhi32(r->cw[r->pos & 3u], mod);
-}
-static uint32_t d_w0(rng_t *r, uint32_t mod) { /* state / freq draw */
-  return r->mode == RNG_PHILOX ? mulhi32(r->w[0], mod) : stream_next(r) % mod;
 }
 static uint32_t d_w1(rng_t *r, uint32_t mod) {
   return r->mode == RNG_PHILOX ? mulhi32(r->w[1], mod) : stream_next(r) % mod;
@@ -155,11 +198,24 @@ static uint32_t d_w2(rng_t *r, uint32_t mod) {
 static uint32_t d_w3(rng_t *r, uint32_t mod) {
   return r->mode == RNG_PHILOX ? mulhi32(r->w[3], mod) : stream_next(r) % mod;
 }
+/* qshmm emission / freq2qc index (ref: :2226, :2230) */
+static uint32_t d_qs_emis(rng_t *r, uint32_t mod) {
+  if (r->mode != RNG_PHILOX) return stream_next(r) % mod;
+  return mulhi32(qs_word(r) << 16, mod); /* low half: (S & 0xFFFF) * mod >> 16 */
+}
+static uint32_t d_qs_freq(rng_t *r, uint32_t mod) {
+  return r->mode == RNG_PHILOX ? mulhi32(qs_word(r), mod) : stream_next(r) % mod;
+}
+/* qshmm / sample error draw (ref: rand() % 1000000, :2234); compare with d_lt */
+static uint32_t d_qs_err(rng_t *r) {
+  return r->mode == RNG_PHILOX ? r->w[0] : stream_next(r) % 1000000;
+}
 static uint32_t d_choice3(rng_t *r) {
   return r->mode == RNG_PHILOX ? ((r->w[0] & 0xFFFu) * 3u) >> 12 : stream_next(r) % 3;
 }
 static uint32_t d_choice4(rng_t *r) {
-  return r->mode == RNG_PHILOX ? (r->w[0] >> 12) & 3u : stream_next(r) % 4;
+  if (r->mode != RNG_PHILOX) return stream_next(r) % 4;
+  return r->scheme == 1 ? (r->w[1] >> 3) & 3u : (r->w[0] >> 12) & 3u;
 }
 static uint32_t d_choice8(rng_t *r) {
   return r->mode == RNG_PHILOX ? r->w[1] & 7u : stream_next(r) % 8;
@@ -177,10 +233,11 @@ static uint32_t fmix32(uint32_t h) {
   return h;
 }
 /* qshmm deletion draw number j (0-based) after the current position (ref: :2270).
- * PHILOX mode: j = 0 is word 3 of the position's block; the rare later draws are derived from it
+ * PHILOX mode: j = 0 is the position's word Y; the rare later draws are derived from it
  * through the finaliser (engine definition, DESIGN.md "Philox draw addressing"). */
 static uint32_t d_del(rng_t *r, uint32_t j) {
   if (r->mode != RNG_PHILOX) return stream_next(r) % 1000000;
+  if (r->scheme == 1) return j == 0 ? r->w[1] : fmix32(r->w[1] + j * 0x9E3779B9u); /* raw word: compare with d_lt */
   if (j == 0) return mulhi32(r->w[3], 1000000);
   return mulhi32(fmix32(r->w[3] + j * 0x9E3779B9u), 1000000);
 }
@@ -888,21 +945,21 @@ static void qshmm_pass(orc_ctx *c, rng_t *r, uint32_t pass, int acc, long wlen, 
         index = d_state(r, (uint32_t)c->mod_tran[acc][state]) + 1;
         state = c->qs_tran[acc][state][index];
       }
-      index = d_w1(r, (uint32_t)c->mod_emis[acc][state]) + 1;
+      index = d_qs_emis(r, (uint32_t)c->mod_emis[acc][state]) + 1;
       qv = c->qs_emis[acc][state][index];
     } else {
-      index = d_w0(r, (uint32_t)c->mod_freq[acc]) + 1;
+      index = d_qs_freq(r, (uint32_t)c->mod_freq[acc]) + 1;
       qv = c->qs_freq[acc][index];
     }
     c->qual[read_offset] = (char)(qv + 33);
     nt = c->w_seq[ref_offset];
-    rand_value = d_w2(r, 1000000);
-    if (rand_value < c->sub_thre[qv]) {
+    rand_value = d_qs_err(r);
+    if (d_lt(r, (uint32_t)rand_value, (double)c->sub_thre[qv])) {
       po->nsub++;
       c->read_seq[read_offset] = substitute(r, nt);
       c->maf_ref[maf_offset] = nt;
       ref_offset++;
-    } else if (rand_value < c->ins_thre[qv]) {
+    } else if (d_lt(r, (uint32_t)rand_value, (double)c->ins_thre[qv])) {
       po->nins++;
       index = d_choice8(r);
       c->read_seq[read_offset] = (index >= 4) ? nt : NT4[index];
@@ -920,7 +977,7 @@ static void qshmm_pass(orc_ctx *c, rng_t *r, uint32_t pass, int acc, long wlen, 
       while (ref_offset < wlen) {
         int hp = c->w_hp[ref_offset - 1];
         rand_value = d_del(r, j++);
-        if (rand_value < c->del_thre[qv] * c->bias[hp]) {
+        if (d_lt(r, (uint32_t)rand_value, c->del_thre[qv] * c->bias[hp])) {
           po->ndel++;
           c->maf_seq[maf_offset] = '-';
           c->maf_ref[maf_offset] = c->w_seq[ref_offset];
@@ -1054,6 +1111,14 @@ static void load_window(orc_ctx *c, long offset, long wlen, char strand) {
   }
 }
 
+/* PHILOX mode: sum of the error probabilities of qual[0..len) in 2^-26 fixed point (order independent) */
+static double qs_prob_sum_fixed(orc_ctx *c, long len) {
+  uint64_t acc = 0;
+  long i;
+  for (i = 0; i < len; i++) acc += (uint64_t)llround(c->qc_prob[(int)c->qual[i] - 33] * 67108864.0);
+  return (double)acc / 67108864.0;
+}
+
 /* all passes of one read: chains, per-read statistics, records (ref: :2209-2383 = :2888-3017 = :3366-3530,
  * errhmm :3836-4078).  *len_total_pass0 receives the emitted length of pass 0 (the WGS quota counter). */
 static void run_read_passes(orc_ctx *c, long offset, long wlen, char strand, int acc, int64_t start_draw,
@@ -1089,14 +1154,9 @@ static void run_read_passes(orc_ctx *c, long offset, long wlen, char strand, int
     if (c->method == ORC_METHOD_QS) { /* ref: :2309-2316 accuracy from emitted qualities */
       double prob = 0.0;
       if (r->mode == RNG_PHILOX) {
-        /* engine definition for PHILOX mode: the sum is taken per block of 1024 read positions and the
-         * block sums are added in order (the order the segment-parallel pass 1 produces) */
-        double blk = 0.0;
-        for (i = 0; i < len; i++) {
-          if ((i & 1023) == 0) { prob += blk; blk = 0.0; }
-          blk += c->qc_prob[(int)c->qual[i] - 33];
-        }
-        prob += blk;
+        /* engine definition for PHILOX mode: the error probabilities are summed in fixed point (26 fractional
+         * bits), so the sum does not depend on the order in which the position-parallel pass 1 adds them */
+        prob = qs_prob_sum_fixed(c, len);
       } else {
         for (i = 0; i < len; i++) prob += c->qc_prob[(int)c->qual[i] - 33];
       }
@@ -1165,6 +1225,7 @@ int orc_simulate_wgs(orc_ctx *c, double depth) {
   if (!c->tables_built) return fail(c, "tables not built");
   if (!c->seq) return fail(c, "no sequence");
   if (r->mode == RNG_PHILOX) r->key[1] = (uint32_t)c->seq_num;
+  r->scheme = (c->method == ORC_METHOD_ERR) ? 0 : 1;
   c->set_mode = 0;
   begin_stats(c);
   len_quota = (long long)(depth * c->glen);
@@ -1251,6 +1312,7 @@ int orc_simulate_set(orc_ctx *c, int strategy, int64_t n, const char *bases, con
   if (!c->tables_built) return fail(c, "tables not built");
   if (strategy != 1 && strategy != 2) return fail(c, "strategy must be 1 (transcript) or 2 (template)");
   if (r->mode == RNG_PHILOX) r->key[1] = 0;
+  r->scheme = (c->method == ORC_METHOD_ERR) ? 0 : 1;
   c->set_mode = strategy;
   for (t = 0; t < n; t++)
     if (start[t + 1] - start[t] > max_len) max_len = start[t + 1] - start[t];
@@ -1381,13 +1443,13 @@ static void sample_pass(orc_ctx *c, rng_t *r, const char *q, long len, pass_out_
     nt = c->w_seq[ref_offset];
     qv = (int)q[read_offset] - 33;
     c->qual[read_offset] = q[read_offset];
-    rand_value = d_w2(r, 1000000);
-    if (rand_value < c->sub_thre[qv]) {
+    rand_value = d_qs_err(r);
+    if (d_lt(r, (uint32_t)rand_value, (double)c->sub_thre[qv])) {
       po->nsub++;
       c->read_seq[read_offset] = substitute(r, nt);
       c->maf_ref[maf_offset] = nt;
       ref_offset++;
-    } else if (rand_value < c->ins_thre[qv]) {
+    } else if (d_lt(r, (uint32_t)rand_value, (double)c->ins_thre[qv])) {
       po->nins++;
       index = d_choice8(r);
       c->read_seq[read_offset] = (index >= 4) ? nt : NT4[index];
@@ -1405,7 +1467,7 @@ static void sample_pass(orc_ctx *c, rng_t *r, const char *q, long len, pass_out_
       while ((ref_offset < len) && (read_offset < len)) {
         int hp = c->w_hp[ref_offset - 1];
         rand_value = d_del(r, j++);
-        if (rand_value < c->del_thre[qv] * c->bias[hp]) {
+        if (d_lt(r, (uint32_t)rand_value, c->del_thre[qv] * c->bias[hp])) {
           po->ndel++;
           c->maf_seq[maf_offset] = '-';
           c->maf_ref[maf_offset] = c->w_seq[ref_offset];
@@ -1447,6 +1509,7 @@ int orc_simulate_sample(orc_ctx *c, double depth, int64_t n, const char *quals, 
   if (!c->seq) return fail(c, "no sequence");
   if (n < 2) return fail(c, "the reference divides by zero with a pool of fewer than 2 reads (:1723)");
   if (r->mode == RNG_PHILOX) r->key[1] = (uint32_t)c->seq_num;
+  r->scheme = 1;
   c->set_mode = 0;
   begin_stats(c);
   pool_total = qstart[n];
@@ -1503,7 +1566,8 @@ int orc_simulate_sample(orc_ctx *c, double depth, int64_t n, const char *quals, 
         if (po.rlen < c->freq_len_n) c->freq_len[po.rlen]++;
         if (po.rlen > st->res_len_max) st->res_len_max = po.rlen;
         if (po.rlen < st->res_len_min) st->res_len_min = po.rlen;
-        for (k = 0; k < po.rlen; k++) prob += c->qc_prob[(int)c->qual[k] - 33];
+        if (r->mode == RNG_PHILOX) prob = qs_prob_sum_fixed(c, po.rlen);
+        else for (k = 0; k < po.rlen; k++) prob += c->qc_prob[(int)c->qual[k] - 33];
         value = 1.0 - (prob / po.rlen);
         accuracy_total += value;
         {

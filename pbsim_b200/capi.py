@@ -139,6 +139,7 @@ class Stats(C.Structure):
         ("deflate_seconds", C.c_double),
         ("seg_seconds", C.c_double),
         ("kernel_launches", C.c_int64),
+        ("chain_seconds", C.c_double),
     ]
 
 

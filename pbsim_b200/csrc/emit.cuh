@@ -639,11 +639,17 @@ __device__ __noinline__ void emit_tile_generic(const uint8_t *evbase, uint32_t e
       bool acgt;
       rf.get(Rr, gch, wch, wc, acgt);
       if (keys != nullptr && kind == PB_KIND_SUB && !acgt) {
-        // PHILOX mode: choice4 of this position = bits 12-13 of word 0 of its block (qshmm: position = read
-        // position, errhmm: alignment column)
-        uint32_t w[4];
-        philox_block_keys(*keys, METHOD == PBSIM_METHOD_QSHMM ? Pp : Cc, pass << 16, read_id, 1u, w);
-        info = (w[0] >> 12) & 3u;
+        // PHILOX mode: the 4-way choice of this position, re-derived from its own draws (sim_core.cuh: qshmm /
+        // sample bits 3-4 of word Y of read position Pp; errhmm bits 12-13 of word 0 of alignment column Cc)
+        if (METHOD == PBSIM_METHOD_QSHMM) {
+          uint32_t x, y;
+          error_words_at(*keys, read_id, pass << 16, Pp, x, y);
+          info = (y >> 3) & 3u;
+        } else {
+          uint32_t w[4];
+          philox_block_keys(*keys, Cc, pass << 16, read_id, 1u, w);
+          info = (w[0] >> 12) & 3u;
+        }
       }
       const uint8_t rb = read_base(kind, info, wch, wc, acgt);
       put_read_base<BAM>(seq, qual, Pp, rb, BAM ? bam_nibble(rb) : 0u, qv, METHOD == PBSIM_METHOD_QSHMM);

@@ -177,7 +177,8 @@ struct pbsim_engine {
   ModelImage img;
   std::vector<int32_t> h_prob2len;
   std::vector<uint8_t> h_prob2acc;
-  DevBuf d_blob, d_acc, d_prob2len, d_prob2acc, d_qs_thr, d_qs_thr_hp, d_qc_prob, d_er_bias;
+  DevBuf d_blob, d_acc, d_prob2len, d_prob2acc, d_qs_tabs, d_qs_thr_hp, d_qs_thr_hp32, d_er_bias;
+  std::vector<uint8_t> h_qs_tabs;
   uint32_t er_smem_bar_off = 0;
   EmitParams emitp;
 
@@ -257,8 +258,8 @@ struct pbsim_engine {
   OutSet gz[2];
   DevBuf d_gz_tables, d_gz_hist, d_gz_usize, d_gz_ucrc, d_gz_uoff;
   PinnedBuf h_gz;
-  double gz_ms = 0, seg_ms = 0;
-  cudaEvent_t ev_gz[2] = {nullptr, nullptr}, ev_seg[2] = {nullptr, nullptr};
+  double gz_ms = 0, seg_ms = 0, chain_ms = 0;
+  cudaEvent_t ev_gz[2] = {nullptr, nullptr}, ev_seg[2] = {nullptr, nullptr}, ev_chain[2] = {nullptr, nullptr};
   int pipeline = 1;                 // option "pipeline": 0 off, 1 host delivery only, 2 always
   int64_t host_batch_bases = (int64_t)1 << 30;  // option: batch size of pipelined host delivery
   int64_t first_batch_div = 1;                  // option: the first batch of a pipelined run can be made this much smaller (measured: no gain)
@@ -352,9 +353,11 @@ DeviceModel device_model(const pbsim_engine *e) {
   M.len_rand_value = (uint32_t)e->model.len_rand_value;
   M.acc_rand_value = (uint32_t)e->model.accuracy_rand_value;
   M.len_min = (uint32_t)e->model.len_min;
-  M.qs_thr = e->d_qs_thr.as<uint32_t>();
+  M.qs_tabs = e->d_qs_tabs.as<uint8_t>();
   M.qs_thr_hp = e->d_qs_thr_hp.as<uint32_t>();
-  M.qc_prob = e->d_qc_prob.as<double>();
+  M.qs_thr_hp32 = e->d_qs_thr_hp32.as<uint32_t>();
+  M.qs_thr32 = reinterpret_cast<const uint32_t *>(M.qs_tabs + kQsTabThr32);
+  M.qs_fast = reinterpret_cast<const QsFast *>(M.qs_tabs + kQsTabFast);
   M.er_bias = e->d_er_bias.as<uint16_t>();
   M.pass_num = (uint32_t)e->model.pass_num;
   M.uniform_bias = e->img.uniform_bias ? 1u : 0u;
@@ -393,8 +396,15 @@ DeviceSet device_set(const pbsim_engine *e) {
 int upload_bias_tables(pbsim_engine *e) {
   e->img.apply_bias(e->model, e->bias);
   if (e->model.method != PBSIM_METHOD_ERRHMM) {
-    if (upload(e, e->d_qs_thr, e->img.qs_thr.data(), e->img.qs_thr.size())) return PBSIM_E_CUDA;
+    // thr | qc_prob | thr32 | fast as one block (one bulk copy into shared memory per CTA)
+    e->h_qs_tabs.assign(kQsTabBytes, 0);
+    std::memcpy(e->h_qs_tabs.data() + kQsTabThr, e->img.qs_thr.data(), PBSIM_NQV * 16);
+    std::memcpy(e->h_qs_tabs.data() + kQsTabProb, e->model.qc_prob, PBSIM_NQV * 8);
+    std::memcpy(e->h_qs_tabs.data() + kQsTabThr32, e->img.qs_thr32.data(), PBSIM_NQV * 16);
+    std::memcpy(e->h_qs_tabs.data() + kQsTabFast, e->img.qs_fast.data(), PBSIM_NQV * 16);
+    if (upload(e, e->d_qs_tabs, e->h_qs_tabs.data(), e->h_qs_tabs.size())) return PBSIM_E_CUDA;
     if (upload(e, e->d_qs_thr_hp, e->img.qs_thr_hp.data(), e->img.qs_thr_hp.size())) return PBSIM_E_CUDA;
+    if (upload(e, e->d_qs_thr_hp32, e->img.qs_thr_hp32.data(), e->img.qs_thr_hp32.size())) return PBSIM_E_CUDA;
   } else {
     if (upload(e, e->d_er_bias, e->img.er_bias.data(), e->img.er_bias.size())) return PBSIM_E_CUDA;
   }
@@ -660,7 +670,7 @@ int run_batch(pbsim_engine *e, uint32_t n_reads, int64_t clip_room, BatchResult 
     A.ev = e->d_ev.as<uint8_t>();
     A.ck = e->d_ck.as<Ckpt>();
     const uint32_t grid = cta_slots;
-    bool seg_timed = false;
+    bool seg_timed = false, chain_timed = false;
     CK(cudaEventRecord(e->ev_k[0], e->st));
     if (sample) {
       if (replay) k_sim_sample<PBSIM_RNG_REPLAY><<<grid, kSimThreads, 0, e->st>>>(A, Pl, *sb, 0u);
@@ -744,6 +754,7 @@ int run_batch(pbsim_engine *e, uint32_t n_reads, int64_t clip_room, BatchResult 
         ChunkBatch C;
         C.n_chunks = nch;
         C.per_chunk = (uint32_t)e->chain_chunk;
+        C.qs = qs ? 1u : 0u;
         C.chunk_off = (const uint64_t *)chunk_off;
         uint32_t *cu = e->d_chunk.as<uint32_t>();
         C.sub = cu;
@@ -779,18 +790,20 @@ int run_batch(pbsim_engine *e, uint32_t n_reads, int64_t clip_room, BatchResult 
         CA.cta_first = cb_first;
         CA.bin_lo = cb_lo;
         CA.bin_hi = cb_hi;
+        CK(cudaEventRecord(e->ev_chain[0], e->st));
         if (qs) k_chain_chunk<<<ch_slots, kSimThreads, kQsSmemBytes, e->st>>>(CA, C);
         else k_chain_chunk_err<<<ch_slots, kErrThreads, e->er_smem_bar_off + 16, e->st>>>(CA, C, e->er_smem_bar_off);
+        CK(cudaEventRecord(e->ev_chain[1], e->st));
+        chain_timed = true;
         e->launches += 6;
       }
       CK(cudaEventRecord(e->ev_seg[0], e->st));
       seg_timed = true;
       if (qs) {
-        k_sim_seg<<<seg_slots, kSimThreads, kQsSmemBytes, e->st>>>(SA);
+        k_sim_seg<<<seg_slots, kSimThreads, 0, e->st>>>(SA);
         CK(cudaEventRecord(e->ev_seg[1], e->st));
         k_find_end<<<nblk((uint64_t)n_sub * 32, 128), 128, 0, e->st>>>(B, S, G, e->d_biasone.as<uint8_t>(), pass,
-                                                                       e->d_ev.as<uint8_t>(), e->d_ck.as<Ckpt>(),
-                                                                       e->d_qc_prob.as<double>());
+                                                                       e->d_ev.as<uint8_t>(), e->d_ck.as<Ckpt>(), M.qs_fast);
       } else {
         k_sim_seg_err<<<seg_slots, kErrThreads, e->er_smem_bar_off + 16, e->st>>>(SA, e->er_smem_bar_off);
         CK(cudaEventRecord(e->ev_seg[1], e->st));
@@ -835,6 +848,10 @@ int run_batch(pbsim_engine *e, uint32_t n_reads, int64_t clip_room, BatchResult 
       if (seg_timed) {
         CK(cudaEventElapsedTime(&ms, e->ev_seg[0], e->ev_seg[1]));
         e->seg_ms += ms;
+      }
+      if (chain_timed) {
+        CK(cudaEventElapsedTime(&ms, e->ev_chain[0], e->ev_chain[1]));
+        e->chain_ms += ms;
       }
     }
     if (getenv("PBSIM_DEBUG")) {
@@ -1423,6 +1440,7 @@ int pbsim_cuda_create(pbsim_engine **out, int device) {
   for (auto &ev : ne->ev_user) cudaEventCreate(&ev);
   for (auto &ev : ne->ev_gz) cudaEventCreate(&ev);
   for (auto &ev : ne->ev_seg) cudaEventCreate(&ev);
+  for (auto &ev : ne->ev_chain) cudaEventCreate(&ev);
   std::memset(&ne->model, 0, sizeof ne->model);
   std::memset(&ne->emitp, 0, sizeof ne->emitp);
   *out = ne;
@@ -1435,7 +1453,7 @@ void pbsim_cuda_destroy(pbsim_engine *e) {
   stop_producer(e);
   cudaStreamSynchronize(e->st_copy);
   cudaStreamSynchronize(e->st);
-  DevBuf *bufs[] = {&e->d_blob, &e->d_acc, &e->d_prob2len, &e->d_prob2acc, &e->d_qs_thr, &e->d_qs_thr_hp, &e->d_qc_prob,
+  DevBuf *bufs[] = {&e->d_blob, &e->d_acc, &e->d_prob2len, &e->d_prob2acc, &e->d_qs_tabs, &e->d_qs_thr_hp, &e->d_qs_thr_hp32,
                     &e->d_er_bias, &e->d_ascii, &e->d_pk, &e->d_hp4, &e->d_xm, &e->d_hpfreq, &e->d_biasone, &e->d_flag,
                     &e->d_draws, &e->d_starts, &e->b_read_u32, &e->b_sub_u32, &e->b_sub_u64, &e->b_sub_f64, &e->d_bins,
                     &e->d_ctrl, &e->d_cub_tmp, &e->d_ev, &e->d_ck, &e->out[0].reads, &e->out[0].maf, &e->out[1].reads, &e->out[1].maf, &e->d_stats, &e->d_seg,
@@ -1451,6 +1469,7 @@ void pbsim_cuda_destroy(pbsim_engine *e) {
   for (auto &ev : e->ev_user) cudaEventDestroy(ev);
   for (auto &ev : e->ev_gz) cudaEventDestroy(ev);
   for (auto &ev : e->ev_seg) cudaEventDestroy(ev);
+  for (auto &ev : e->ev_chain) cudaEventDestroy(ev);
   e->h_gz.release();
   e->h_ctrl.release();
   e->h_acc.release();
@@ -1496,9 +1515,9 @@ int pbsim_cuda_set_model(pbsim_engine *e, const pbsim_model *m) {
   if (upload(e, e->d_acc, e->img.acc, PBSIM_NACC)) return PBSIM_E_CUDA;
   if (upload(e, e->d_prob2len, e->h_prob2len.data(), e->h_prob2len.size())) return PBSIM_E_CUDA;
   if (upload(e, e->d_prob2acc, e->h_prob2acc.data(), e->h_prob2acc.size())) return PBSIM_E_CUDA;
-  if (upload(e, e->d_qc_prob, m->qc_prob, PBSIM_NQV)) return PBSIM_E_CUDA;
-  CK(e->d_qs_thr.ensure(PBSIM_NQV * 16));
+  CK(e->d_qs_tabs.ensure(kQsTabBytes));
   CK(e->d_qs_thr_hp.ensure(PBSIM_NQV * 48));
+  CK(e->d_qs_thr_hp32.ensure(PBSIM_NQV * 48));
   CK(e->d_er_bias.ensure(std::max<size_t>(e->img.er_bias.size() * 2, 16) + 64));
   // errhmm: largest per-accuracy shared-memory footprint
   e->er_smem_bar_off = 0;
@@ -1727,6 +1746,7 @@ int pbsim_cuda_simulate_begin(pbsim_engine *e, const pbsim_run *run) {
   e->emit_ms = 0;
   e->gz_ms = 0;
   e->seg_ms = 0;
+  e->chain_ms = 0;
   e->pend = pbsim_engine::Pending();
   e->piece = pbsim_engine::Piece();
   e->next_slot = 0;
@@ -1796,6 +1816,7 @@ int pbsim_cuda_simulate_end(pbsim_engine *e, pbsim_stats *st, int64_t *freq_len,
   st->emit_seconds = e->emit_ms * 1e-3;
   st->deflate_seconds = e->gz_ms * 1e-3;
   st->seg_seconds = e->seg_ms * 1e-3;
+  st->chain_seconds = e->chain_ms * 1e-3;
   st->kernel_launches = e->launches;
   if (freq_len) {
     const int64_t n = std::min<int64_t>(freq_len_cells, e->freq_len_cells);

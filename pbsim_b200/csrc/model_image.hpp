@@ -166,6 +166,9 @@ struct ModelImage {
   // per-sequence, bias dependent
   std::vector<uint32_t> qs_thr;      // [94*4]
   std::vector<uint32_t> qs_thr_hp;   // [94*12]
+  // PHILOX mode: the same thresholds on the 32-bit scale T32(t) (sim_core.cuh), and the per-quality record of
+  // the position-parallel kernels {T32(sub), T32(ins), T32(del), error probability in 2^-26 fixed point}
+  std::vector<uint32_t> qs_thr32, qs_thr_hp32, qs_fast;
   std::vector<uint16_t> er_bias;     // per table accuracy: edel[rows] then edel_hp[rows*12]
   std::string error;
   bool uniform_bias = true;          // hp_del_bias[1..10] all exactly 1
@@ -353,6 +356,21 @@ struct ModelImage {
         qs_thr[q * 4 + 1] = (uint32_t)m.ins_thre[q];
         qs_thr[q * 4 + 2] = mx;
         qs_thr[q * 4 + 3] = qs_thr_hp[q * 12 + 0];
+      }
+      auto t32 = [](uint32_t t) -> uint32_t {
+        if (t >= 1000000u) return 0xFFFFFFFFu;
+        return (uint32_t)(((uint64_t)t * 4294967296ull + 999999ull) / 1000000ull);
+      };
+      qs_thr32.resize(qs_thr.size());
+      qs_thr_hp32.resize(qs_thr_hp.size());
+      qs_fast.assign(PBSIM_NQV * 4, 0);
+      for (size_t i = 0; i < qs_thr.size(); ++i) qs_thr32[i] = t32(qs_thr[i]);
+      for (size_t i = 0; i < qs_thr_hp.size(); ++i) qs_thr_hp32[i] = t32(qs_thr_hp[i]);
+      for (int q = 0; q < PBSIM_NQV; ++q) {
+        qs_fast[q * 4 + 0] = qs_thr32[q * 4 + 0];
+        qs_fast[q * 4 + 1] = qs_thr32[q * 4 + 1];
+        qs_fast[q * 4 + 2] = qs_thr32[q * 4 + 2];
+        qs_fast[q * 4 + 3] = (uint32_t)std::llround(m.qc_prob[q] * 67108864.0);  // 2^26
       }
     } else {
       for (int a = 0; a < PBSIM_NACC; ++a) {

@@ -1,13 +1,15 @@
-// Segment-parallel pass 1 for qshmm (PHILOX mode).  See sim_core.cuh "qshmm SEGMENT-PARALLEL pass 1".
+// Segment-parallel pass 1 (PHILOX mode).  See sim_core.cuh "qshmm SEGMENT-PARALLEL pass 1".
 //
-// Long reads are cut into segments of PB_TILE read positions; one GPU thread simulates ONE SEGMENT, so every
-// thread of the grid does the same amount of work whatever the read lengths are (1 kb or 1 Mb), which removes
-// the sequential critical path a whole-read-per-thread schedule has.  The chain state entering a segment is
-// recovered exactly by backward coupling over that segment's predecessors' position-addressed draws.
-//   k_seg_fill   : (sub-read, k) list of all segments of the batch + accuracy sort key
-//   k_sim_seg    : one thread per segment: coupling + PB_TILE positions -> entries in the segment's slot
-//   k_find_end   : one warp per segmented sub-read: prefix over its segments, deletion-run repairs, clip at the
-//                  window end, tile checkpoints, totals
+// Long reads are cut into segments of PB_TILE read positions (qshmm) / alignment columns (errhmm), so the work
+// units are the same size whatever the read lengths are (1 kb or 1 Mb), which removes the sequential critical
+// path a whole-read-per-thread schedule has.  qshmm splits the work by what is sequential and what is not:
+//   k_seg_fill    : (sub-read, k) list of all segments of the batch + accuracy sort key
+//   k_chain_chunk : QUALITY pass.  One thread per chunk of segments: exact entry state by backward coupling, then
+//                   the HMM chain + emission walk; writes the quality value of every position into its event slot
+//   k_sim_seg     : ERROR pass.  One WARP per segment, consecutive lanes on consecutive positions: error draw,
+//                   choices, deletion run of every position -> the event, in place over the quality (coalesced)
+//   k_find_end    : one warp per segmented sub-read: prefix over its segments, deletion-run repairs, clip at the
+//                   window end, tile checkpoints, totals
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -46,6 +48,7 @@ __global__ void k_seg_fill(Batch B, SegBatch S, uint32_t pass_num) {
 // ---- chain chunks: the threads that recover the HMM state in front of every segment -------------------------------
 struct ChunkBatch {
   uint32_t n_chunks, per_chunk;   // per_chunk: segments walked by one chunk (reads of sticky chains: all of them)
+  uint32_t qs;                    // 1: qshmm (the quality pass walks every segment)
   const uint64_t *chunk_off;      // [n_sub + 1] exclusive scan of Batch::nchunk
   uint32_t *sub, *key_in, *key_out, *id_in, *order;
 };
@@ -60,7 +63,10 @@ __global__ void k_chunk_fill(Batch B, ChunkBatch C, uint32_t pass_num) {
   const uint32_t per = (hi - lo == 1u) ? nseg : C.per_chunk;
   for (uint64_t i = lo; i < hi; ++i) {
     // longest walk first inside an accuracy (the same key layout as the sequential schedule)
-    const uint32_t k_from = (uint32_t)(i - lo) * per, k_to = min(k_from + per, nseg - 1u);
+    // errhmm records the state in front of segments k_from+1 .. k_to (nobody needs the one behind the last
+    // segment); the qshmm quality pass walks every segment
+    const bool qs = C.qs != 0u;
+    const uint32_t k_from = (uint32_t)(i - lo) * per, k_to = min(k_from + per, qs ? nseg : nseg - 1u);
     const uint32_t work = k_to - k_from + (k_from > 0u ? 1u : 0u);
     C.sub[i] = s;
     C.key_in[i] = (acc << 21) | (0xFFFFFu - min(work, 0xFFFFFu));
@@ -79,60 +85,105 @@ struct SegArgs {
   uint8_t *ev;
 };
 
-// shared memory: [table blob | thr 94*16 | qc_prob 94*8 | mbarrier]  (same layout as k_sim_qshmm)
+// ERROR pass of the qshmm segments: one WARP per segment, lane l of iteration i on positions 128 i + 4 l .. + 3.
+// The slot holds the qualities the quality pass wrote (accuracies without a model: computed here from the freq2qc
+// table); events replace them in place with 8-byte loads and stores, consecutive lanes on consecutive addresses.
+// A CTA serves kSimThreads segments of one accuracy (the schedule of the other pass-1 kernels), warp w the
+// segments lo + w, lo + w + 4, ...
+constexpr int kSegWarps = kSimThreads / 32;
+
 __global__ void __launch_bounds__(kSimThreads) k_sim_seg(SegArgs A) {
-  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ __align__(16) QsFast s_fast[PBSIM_NQV];
+  __shared__ __align__(16) uint8_t s_freq[QsBlobLayout::freq_bytes];
+  __shared__ __align__(16) uint8_t s_q[kSegWarps][PB_TILE];  // qualities of a segment that is redone generically
   uint32_t acc, lo, hi;
   if (!cta_assignment(A.cta_order, A.cta_first, A.bin_lo, A.bin_hi, &acc, &lo, &hi)) return;
   const AccEntry ae = A.M.acc[acc];
-  uint64_t *bar = reinterpret_cast<uint64_t *>(smem + kQsSmemBar);
-  if (threadIdx.x == 0) mbar_init(bar, 1);
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    mbar_expect_tx(bar, ae.blob_bytes + PBSIM_NQV * 16 + PBSIM_NQV * 8);
-    tma_bulk_g2s(smem, A.M.blob + ae.blob_off, ae.blob_bytes, bar);
-    tma_bulk_g2s(smem + kQsSmemThr, A.M.qs_thr, PBSIM_NQV * 16, bar);
-    tma_bulk_g2s(smem + kQsSmemProb, A.M.qc_prob, PBSIM_NQV * 8, bar);
+  {
+    uint32_t *d = reinterpret_cast<uint32_t *>(s_fast);
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(A.M.qs_fast);
+    for (uint32_t i = threadIdx.x; i < PBSIM_NQV * 4u; i += blockDim.x) d[i] = src[i];
+    if (!ae.has_model) {
+      uint32_t *f = reinterpret_cast<uint32_t *>(s_freq);
+      const uint32_t *fs = reinterpret_cast<const uint32_t *>(A.M.blob + ae.blob_off);
+      for (uint32_t i = threadIdx.x; i < QsBlobLayout::freq_bytes / 4u; i += blockDim.x) f[i] = fs[i];
+    }
   }
-  mbar_wait(bar, 0);
-  const uint32_t i = lo + threadIdx.x;
-  if (i >= hi) return;
-  const uint32_t seg = A.S.seg_order[i];
-  const uint32_t s = A.S.seg_sub[seg];
-  const uint32_t k = seg - (uint32_t)A.S.seg_off[s];
-  const uint32_t r = s / A.M.pass_num, pass = s % A.M.pass_num;
-  const uint32_t read_id = (uint32_t)(A.B.first_read + 1u + r);
+  __syncthreads();
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   QsView T;
-  T.t2 = reinterpret_cast<const uint32_t *>(smem + QsBlobLayout::t2_off);
-  T.emis = smem + QsBlobLayout::emis_off;
-  T.freq = smem;
+  T.t2 = nullptr;
+  T.emis = nullptr;
+  T.freq = s_freq;
   T.has_model = ae.has_model;
   T.init_mod = ae.init_mod;
   T.freq_mod = ae.freq_mod;
-  T.thr = reinterpret_cast<const QsThr *>(smem + kQsSmemThr);
-  T.thr_hp = A.M.qs_thr_hp;
-  T.qc_prob = reinterpret_cast<const double *>(smem + kQsSmemProb);
-  uint32_t row = 0, mod = ae.init_mod, emod = 1;
-  SegResult res;
-  res.n_entries = 0; res.ref_adv = 0; res.nsub = 0; res.ndel = 0; res.flags = 0; res.prob = 0.0;
-  bool ok = true;
-  if (k > 0 && ae.has_model) {  // recorded by k_chain_chunk
-    const uint32_t t = A.S.seg_state[seg];
-    row = t & 0xFFFFu;
-    mod = (t >> 16) & 0xFFu;
-    emod = t >> 24;
-  }
-  if (!ok) {
-    res.flags = 2u;
-  } else {
+  T.thr = nullptr;
+  T.thr_hp = nullptr;
+  T.qc_prob = nullptr;
+  T.thr32 = reinterpret_cast<const QsThr *>(A.M.qs_thr32);  // global: only the rare hp[-1] rule reads it
+  T.thr_hp32 = nullptr;
+  T.fast = s_fast;
+  for (uint32_t i = lo + warp; i < hi; i += kSegWarps) {
+    const uint32_t seg = A.S.seg_order[i];
+    const uint32_t s = A.S.seg_sub[seg];
+    const uint32_t k = seg - (uint32_t)A.S.seg_off[s];
+    const uint32_t r = s / A.M.pass_num, pass = s % A.M.pass_num;
+    const uint32_t read_id = (uint32_t)(A.B.first_read + 1u + r);
+    const uint32_t c1 = pass << 16;
     uint16_t *ev = reinterpret_cast<uint16_t *>(A.ev) + A.B.ev_off[s] + (uint64_t)k * PB_SEG_STRIDE;
-    qshmm_simulate_segment(T, A.keys, read_id, pass, k * PB_TILE, k == 0, row, mod, emod, ev, res);
+    QsLaneTotals t;
+    t.nsub = t.nins = t.ndel = t.prob = t.big = 0;
+#pragma unroll 2
+    for (uint32_t j = lane * PB_GROUP; j < PB_TILE; j += 32u * PB_GROUP) {
+      uint32_t qv[PB_GROUP], e[PB_GROUP];
+      if (ae.has_model) {
+        const uint2 v = *reinterpret_cast<const uint2 *>(ev + j);
+        qv[0] = v.x & 0x7Fu; qv[1] = (v.x >> 16) & 0x7Fu; qv[2] = v.y & 0x7Fu; qv[3] = (v.y >> 16) & 0x7Fu;
+      } else {
+        qs_freq_qualities(T, A.keys, read_id, c1, k * PB_TILE + j, qv);
+      }
+      qs_error_lane(s_fast, A.keys, read_id, c1, k * PB_TILE + j, qv, e, t);
+      *reinterpret_cast<uint2 *>(ev + j) = make_uint2(e[0] | (e[1] << 16), e[2] | (e[3] << 16));
+    }
+    const uint32_t big = __any_sync(0xFFFFFFFFu, t.big != 0u) ? 1u : 0u;
+    SegResult res;
+    if (big) {
+      // an entry with >= 15 deletions needs continuation entries: the segment is redone entry by entry
+      __syncwarp();
+      for (uint32_t j = lane; j < PB_TILE; j += 32u) s_q[warp][j] = (uint8_t)(ev[j] & 0x7Fu);
+      __syncwarp();
+      if (lane == 0) {
+        qshmm_segment_generic(T, A.keys, read_id, pass, k * PB_TILE, k == 0, s_q[warp], ev, res);
+        A.S.seg_res[seg] = res;
+      }
+      __syncwarp();
+      continue;
+    }
+    const uint32_t cnt = __reduce_add_sync(0xFFFFFFFFu, t.nsub | (t.nins << 16));
+    uint32_t ndel = __reduce_add_sync(0xFFFFFFFFu, t.ndel);
+    const uint32_t plo = __reduce_add_sync(0xFFFFFFFFu, t.prob & 0xFFFFu);
+    const uint32_t phi = __reduce_add_sync(0xFFFFFFFFu, t.prob >> 16);
+    if (k == 0) {  // leading insertions of the read: the hp[-1] rule (qs_fix_leading)
+      __syncwarp();
+      if (lane == 0) ndel -= qs_fix_leading(T, A.keys, read_id, c1, ev);
+    }
+    if (lane == 0) {
+      res.n_entries = PB_TILE;
+      res.ref_adv = PB_TILE - (cnt >> 16) + ndel;
+      res.nsub = cnt & 0xFFFFu;
+      res.ndel = ndel;
+      res.flags = 0;
+      res.pad = 0;
+      res.prob = (uint64_t)plo + ((uint64_t)phi << 16);
+      A.S.seg_res[seg] = res;
+    }
   }
-  A.S.seg_res[seg] = res;
 }
 
-// One thread per chain chunk (qshmm): exact state at the chunk's first position by backward coupling (init draw at
-// position 0), then the chain-only walk through the chunk's segments; k_sim_seg reads the recorded states.
+// QUALITY pass (qshmm): one thread per chain chunk.  Exact state at the chunk's first position by backward
+// coupling (init draw at position 0), then the chain + emission walk through the chunk's segments, which writes
+// the quality of every position into its event slot (qshmm_quality_range); k_sim_seg turns them into events.
 __global__ void __launch_bounds__(kSimThreads) k_chain_chunk(SegArgs A, ChunkBatch C) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint32_t acc, lo, hi;
@@ -156,7 +207,7 @@ __global__ void __launch_bounds__(kSimThreads) k_chain_chunk(SegArgs A, ChunkBat
   const uint32_t read_id = (uint32_t)(A.B.first_read + 1u + r);
   const uint32_t nseg = A.B.nseg[s];
   const uint32_t per = n_ch == 1u ? nseg : C.per_chunk;   // a one-chunk read is walked whole
-  const uint32_t k_from = c * per, k_to = min(k_from + per, nseg - 1u);
+  const uint32_t k_from = c * per, k_to = min(k_from + per, nseg);
   QsView T;
   T.t2 = reinterpret_cast<const uint32_t *>(smem + QsBlobLayout::t2_off);
   T.emis = smem + QsBlobLayout::emis_off;
@@ -167,7 +218,9 @@ __global__ void __launch_bounds__(kSimThreads) k_chain_chunk(SegArgs A, ChunkBat
   T.thr = nullptr;
   T.thr_hp = nullptr;
   T.qc_prob = nullptr;
-  uint32_t *rec = A.S.seg_state + A.S.seg_off[s];
+  T.thr32 = nullptr;
+  T.thr_hp32 = nullptr;
+  T.fast = nullptr;
   uint32_t row = 0, mod = ae.init_mod, emod = 1;
   if (k_from > 0u) {
     QsSegAux X;
@@ -178,7 +231,8 @@ __global__ void __launch_bounds__(kSimThreads) k_chain_chunk(SegArgs A, ChunkBat
   }
   // the coupling loops leave the lanes of a warp at different points: reconverge before the walk
   __syncwarp();
-  qshmm_chain_range(T, A.keys, read_id, pass, row, mod, emod, k_from, k_to, rec);
+  qshmm_quality_range(T, A.keys, read_id, pass, row, mod, emod, k_from, k_to,
+                      reinterpret_cast<uint16_t *>(A.ev) + A.B.ev_off[s]);
 }
 
 // the same for errhmm: chunk 0 walks from column 0 (the init row is drawn until a read base exists, :3853)
@@ -254,7 +308,7 @@ __global__ void __launch_bounds__(kErrThreads) k_chain_chunk_err(SegArgs A, Chun
 // entries at a time: a warp scan gives every entry its reference offset; only groups in which the window ends or
 // a deletion run meets a flagged block are walked sequentially (by lane 0, with qshmm_walk_tile).
 __global__ void __launch_bounds__(128) k_find_end(Batch B, SegBatch S, DeviceGenome G, const uint8_t *bias_one,
-                                                         uint32_t pass_num, uint8_t *ev, Ckpt *ck, const double *qc_prob) {
+                                                         uint32_t pass_num, uint8_t *ev, Ckpt *ck, const QsFast *fast) {
   const uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint32_t lane = threadIdx.x & 31u;
   if (s >= B.n_sub) return;
@@ -277,7 +331,7 @@ __global__ void __launch_bounds__(128) k_find_end(Batch B, SegBatch S, DeviceGen
   Ckpt *ckp = ck + B.ck_off[s];
   const uint32_t n_seg = (uint32_t)(hi - lo);
   uint32_t R = 0, P = 0, D = 0, nsub = 0, flags = 0, n_tiles = 0;
-  double prob = 0.0;
+  uint64_t prob = 0;
   bool done = false;
   for (uint32_t k = 0; k < n_seg && !done; ++k) {
     flags |= seg[k].flags;
@@ -346,7 +400,7 @@ __global__ void __launch_bounds__(128) k_find_end(Batch B, SegBatch S, DeviceGen
         // exact sequential walk of these (at most 32) entries
         uint32_t res[6];
         if (lane == 0) {
-          const TileWalk t = qshmm_walk_tile(e + i, min(32u, n - i), R, wlen, qc_prob, hp, &blocked);
+          const TileWalk t = qshmm_walk_tile(e + i, min(32u, n - i), R, wlen, fast, hp, &blocked);
           res[0] = t.n_entries; res[1] = t.positions; res[2] = t.ref_adv; res[3] = t.nsub; res[4] = t.ndel;
           res[5] = t.ended | (blocked << 1);
         }
@@ -366,14 +420,13 @@ __global__ void __launch_bounds__(128) k_find_end(Batch B, SegBatch S, DeviceGen
       ckp[k] = c;
     }
     if (ended) {
-      // accuracy sum of the partial tile, in entry order (same order as every other path)
-      double pp = 0.0;
-      if (lane == 0)
-        for (uint32_t i = 0; i < n_incl; ++i) {
-          const uint32_t v = e[i];
-          if (((v >> 7) & 3u) != 3u) pp += qc_prob[v & 0x7Fu];
-        }
-      prob += pp;
+      // fixed-point sum of the error probabilities of the partial tile (order independent)
+      uint32_t pp = 0;  // <= 32 positions per lane, each < 2^26
+      for (uint32_t i = lane; i < n_incl; i += 32u) {
+        const uint32_t v = e[i];
+        if (((v >> 7) & 3u) != 3u) pp += fast[v & 0x7Fu].prob;
+      }
+      prob += (uint64_t)__reduce_add_sync(0xFFFFFFFFu, pp & 0xFFFFu) + ((uint64_t)__reduce_add_sync(0xFFFFFFFFu, pp >> 16) << 16);
       n_tiles = k + 1u;
       done = true;
     } else {
@@ -390,7 +443,7 @@ __global__ void __launch_bounds__(128) k_find_end(Batch B, SegBatch S, DeviceGen
     B.ndel[s] = D;
     B.flags[s] = flags ? (4u | (flags << 8)) : 0u;
     B.draws_used[s] = 0;
-    B.accuracy[s] = 1.0 - (prob / (double)P);
+    B.accuracy[s] = 1.0 - (((double)prob / (double)(1u << PB_PROB_SHIFT)) / (double)P);
   }
 }
 

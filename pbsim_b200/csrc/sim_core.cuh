@@ -143,6 +143,54 @@ struct PhiloxDraw {
   PB_HD uint32_t consumed() const { return 0; }
 };
 
+// PHILOX addressing of the qshmm and sample methods ("v2"):
+//   error stream   (domain 1): block p >> 1, words 2*(p&1) = X and 2*(p&1)+1 = Y of read position p
+//       X: error draw (hit of a threshold t millionths iff X < T32(t)); 3-way choice = ((X & 0xFFF) * 3) >> 12
+//       Y: deletion draws (first: Y, j-th: fmix32(Y + j * 0x9E3779B9)); 8-way choice = Y & 7; 4-way choice = (Y >> 3) & 3
+//   quality stream (domain 2): block p >> 2, word p & 3 = S
+//       state draw = (S >> 16) * modulus >> 16; emission draw = (S & 0xFFFF) * modulus >> 16; freq2qc draw = mulhi(S, modulus)
+// T32(t) = min(ceil(t * 2^32 / 10^6), 2^32 - 1): for t < 10^6, X < T32(t) is mulhi32(X, 10^6) < t exactly.
+PB_HD uint32_t t32_of(uint32_t t) {
+  if (t >= 1000000u) return 0xFFFFFFFFu;
+  return (uint32_t)(((uint64_t)t * 4294967296ull + 999999ull) / 1000000ull);
+}
+#define PB_PROB_SHIFT 26  // PHILOX mode: error probabilities are summed in 2^-26 fixed point (order independent)
+
+struct PhiloxDrawQ {
+  static constexpr bool kCounter = true;
+  Philox ph;
+  uint32_t read_id, pass;
+  uint32_t w[4];        // planner block
+  uint32_t g[2][4];     // error blocks of the current group of PB_GROUP positions
+  uint32_t q[4];        // quality block of the group
+  uint32_t X, Y, S;
+  PB_HD void plan_begin() { ph.block(0u, 0u, read_id, 0u, w); }
+  PB_HD uint32_t plan_len(uint32_t m) { return mulhi32(w[0], m); }
+  PB_HD uint32_t plan_acc(uint32_t m) { return mulhi32(w[1], m); }
+  PB_HD uint32_t plan_off(uint32_t span) { return (uint32_t)mulhi64(((uint64_t)w[2] << 32) | w[3], span); }
+  PB_HD void prefetch(uint32_t p) {  // p is a multiple of PB_GROUP
+    ph.block(p >> 1, pass << 16, read_id, 1u, g[0]);
+    ph.block((p >> 1) + 1u, pass << 16, read_id, 1u, g[1]);
+    ph.block(p >> 2, pass << 16, read_id, 2u, q);
+  }
+  PB_HD void begin(uint32_t u) {  // u: index inside the group (compile-time constant after unrolling)
+    X = g[u >> 1][(u & 1u) * 2u];
+    Y = g[u >> 1][(u & 1u) * 2u + 1u];
+    S = q[u];
+  }
+  PB_HD uint32_t qs_state(uint32_t m) { return mulhi32(S & 0xFFFF0000u, m); }
+  PB_HD uint32_t qs_emis(uint32_t m) { return mulhi32(S << 16, m); }
+  PB_HD uint32_t qs_freq(uint32_t m) { return mulhi32(S, m); }
+  PB_HD uint32_t qs_err() { return X; }
+  PB_HD uint32_t choice3() { return ((X & 0xFFFu) * 3u) >> 12; }
+  PB_HD uint32_t choice4() { return (Y >> 3) & 3u; }
+  PB_HD uint32_t choice8() { return Y & 7u; }
+  PB_HD uint32_t del(uint32_t j) { return (j == 0u) ? Y : fmix32(Y + j * 0x9E3779B9u); }
+  // a draw against a threshold given on both scales (t6: millionths, t32 = T32(t6))
+  static PB_HD bool lt(uint32_t d, uint32_t, uint32_t t32) { return d < t32; }
+  PB_HD uint32_t consumed() const { return 0; }
+};
+
 struct ReplayDraw {
   static constexpr bool kCounter = false;  // a stream: every draw call consumes one value, in the reference's order
   const int32_t *log;  // the reference's draws
@@ -168,6 +216,11 @@ struct ReplayDraw {
   PB_HD uint32_t choice8() { return next() % 8u; }
   PB_HD uint32_t mag3() { return next() % 3u + 1u; }
   PB_HD uint32_t del(uint32_t) { return next() % 1000000u; }
+  PB_HD uint32_t qs_state(uint32_t m) { return next() % m; }
+  PB_HD uint32_t qs_emis(uint32_t m) { return next() % m; }
+  PB_HD uint32_t qs_freq(uint32_t m) { return next() % m; }
+  PB_HD uint32_t qs_err() { return next() % 1000000u; }
+  static PB_HD bool lt(uint32_t d, uint32_t t6, uint32_t) { return d < t6; }
   PB_HD uint32_t consumed() const { return (uint32_t)(cur - start); }
 };
 
@@ -348,6 +401,11 @@ struct QsThr {
   uint32_t sub, ins, del, del0;
 };
 
+struct QsFast {  // what the PHILOX fast paths load per quality value
+  uint32_t sub, ins, del;  // T32 thresholds: substitution, substitution + insertion, deletion (reference offset > 0)
+  uint32_t prob;           // error probability 10^(-qv/10) in 2^-PB_PROB_SHIFT fixed point
+};
+
 struct QsView {
   const uint32_t *t2;
   const uint8_t *emis;
@@ -356,6 +414,10 @@ struct QsView {
   const QsThr *thr;         // [94]
   const uint32_t *thr_hp;   // [94*12]
   const double *qc_prob;    // [94]
+  // PHILOX mode: the same thresholds on the 32-bit scale (T32), and what the position-parallel kernels load
+  const QsThr *thr32;       // [94] {T32(sub), T32(ins), T32(del), T32(del0)}
+  const uint32_t *thr_hp32; // [94*12]
+  const QsFast *fast;       // [94] {T32(sub), T32(ins), T32(del), error probability in 2^-26 fixed point}
 };
 
 struct QsSink {
@@ -385,14 +447,70 @@ struct QsSink {
   }
 };
 
+// one position of the qshmm / sample loop after its quality is known: error draw, choices, deletion run.
+// Returns the event's kind / info / deletion count; advances R.  Shared by qshmm_simulate and sample_simulate.
+template <class Draw, class Bound>
+PB_HD void qs_position(const QsView &T, Draw &d, const WindowRef &win, bool slow, uint32_t qv, uint32_t &R,
+                       const Bound &more, uint32_t &kind, uint32_t &info, uint32_t &nd) {
+  const QsThr th = T.thr[qv];
+  QsThr t32 = th;
+  if (Draw::kCounter) t32 = T.thr32[qv];
+  const uint32_t r = d.qs_err();
+  const bool is_sub = Draw::lt(r, th.sub, t32.sub);
+  const bool is_ins = !is_sub && Draw::lt(r, th.ins, t32.ins);
+  if (Draw::kCounter) {
+    info = is_sub ? d.choice3() : (is_ins ? d.choice8() : 0u);
+  } else {
+    info = 0;
+    if (is_sub) info = d.choice3();
+    else if (is_ins) info = d.choice8();
+  }
+  if (slow && is_sub && win.nonacgt(R)) info = d.choice4();  // the %3 draw is still consumed (:2235-2246)
+  kind = is_sub ? PB_KIND_SUB : (is_ins ? PB_KIND_INS : PB_KIND_MATCH);
+  R += is_ins ? 0u : 1u;
+  nd = 0;
+  while (more(R)) {
+    const uint32_t rd = d.del(nd);
+    bool hit = Draw::lt(rd, th.del, t32.del);
+    if (hit) {
+      if (R == 0u) hit = Draw::lt(rd, th.del0, t32.del0);                                   // mut.hp[-1] (:2269)
+      else if (slow) {
+        const uint32_t h = qv * 12u + win.hp(R - 1u);
+        hit = Draw::lt(rd, T.thr_hp[h], Draw::kCounter ? T.thr_hp32[h] : 0u);
+      }
+    }
+    if (!hit) break;
+    ++nd;
+    ++R;
+  }
+}
+
+// the accuracy of a read from its qualities (:2309-2313): the reference's sum in read order (REPLAY), or the
+// order-independent fixed-point sum of PHILOX mode
+struct QsProbSum {
+  double prob = 0.0;
+  uint64_t fx = 0;
+  template <class Draw>
+  PB_HD void add(const QsView &T, uint32_t qv) {
+    if (Draw::kCounter) fx += T.fast[qv].prob;
+    else prob += T.qc_prob[qv];
+  }
+  template <class Draw>
+  PB_HD double accuracy(uint32_t P) const {
+    const double p = Draw::kCounter ? (double)fx / (double)(1u << PB_PROB_SHIFT) : prob;
+    return 1.0 - (p / (double)P);
+  }
+};
+
 template <class Draw>
 PB_HD void qshmm_simulate(const QsView &T, Draw &d, const WindowRef &win, bool slow, uint32_t wlen,
                           QsSink &sink, SubreadResult &res) {
   uint32_t R = 0, P = 0, C = 0;
   uint32_t row = 0, mod = T.init_mod, emod = 1;
   uint32_t nsub = 0, nins = 0, ndel = 0;
-  double prob = 0.0, prob_blk = 0.0;  // counter mode sums per 1024-position block (the segment-parallel order)
+  QsProbSum ps;
   res.overflow = 0;
+  const auto more = [wlen](uint32_t r) { return r < wlen; };
   while (R < wlen) {
     d.prefetch(P);
 #pragma unroll
@@ -403,51 +521,21 @@ PB_HD void qshmm_simulate(const QsView &T, Draw &d, const WindowRef &win, bool s
       d.begin(u);
       uint32_t qv;
       if (T.has_model) {
-        const uint32_t t = T.t2[row + d.wc(P, mod)];
+        const uint32_t t = T.t2[row + d.qs_state(mod)];
         row = t & 0xFFFFu;
         mod = (t >> 16) & 0xFFu;
         emod = t >> 24;
-        qv = T.emis[row + d.w1(emod)];
+        qv = T.emis[row + d.qs_emis(emod)];
       } else {
-        qv = T.freq[d.w0(T.freq_mod)];
+        qv = T.freq[d.qs_freq(T.freq_mod)];
       }
-      if (Draw::kCounter) {
-        if ((P & (PB_TILE - 1u)) == 0u) { prob += prob_blk; prob_blk = 0.0; }
-        prob_blk += T.qc_prob[qv];
-      } else {
-        prob += T.qc_prob[qv];
-      }
-      const QsThr th = T.thr[qv];
-      const uint32_t r = d.w2(1000000u);
-      const bool is_sub = r < th.sub;
-      const bool is_ins = !is_sub && r < th.ins;
-      uint32_t info;
-      if (Draw::kCounter) {
-        info = is_sub ? d.choice3() : (is_ins ? d.choice8() : 0u);
-      } else {
-        info = 0;
-        if (is_sub) info = d.choice3();
-        else if (is_ins) info = d.choice8();
-      }
-      if (slow && is_sub && win.nonacgt(R)) info = d.choice4();  // the %3 draw is still consumed (:2235-2246)
-      const uint32_t kind = is_sub ? PB_KIND_SUB : (is_ins ? PB_KIND_INS : PB_KIND_MATCH);
-      nsub += is_sub ? 1u : 0u;
-      nins += is_ins ? 1u : 0u;
-      R += is_ins ? 0u : 1u;
+      ps.template add<Draw>(T, qv);
+      uint32_t kind, info, nd;
+      qs_position(T, d, win, slow, qv, R, more, kind, info, nd);
+      nsub += kind == PB_KIND_SUB ? 1u : 0u;
+      nins += kind == PB_KIND_INS ? 1u : 0u;
       ++P;
       ++C;
-      uint32_t nd = 0;
-      while (R < wlen) {
-        const uint32_t rd = d.del(nd);
-        bool hit = rd < th.del;
-        if (hit) {
-          if (R == 0u) hit = rd < th.del0;                                   // mut.hp[-1] (:2269)
-          else if (slow) hit = rd < T.thr_hp[qv * 12u + win.hp(R - 1u)];
-        }
-        if (!hit) break;
-        ++nd;
-        ++R;
-      }
       ndel += nd;
       C += nd;
       const uint32_t base = qv | (kind << 7) | (info << 9);
@@ -470,14 +558,13 @@ PB_HD void qshmm_simulate(const QsView &T, Draw &d, const WindowRef &win, bool s
     if (res.overflow) break;
   }
   sink.flush();
-  prob += prob_blk;
   res.n_entries = sink.n;
   res.rlen = P;
   res.ncol = C;
   res.nsub = nsub;
   res.nins = nins;
   res.ndel = ndel;
-  res.accuracy = 1.0 - (prob / (double)P);  // :2313 (accuracy from the emitted qualities)
+  res.accuracy = ps.template accuracy<Draw>(P);  // :2313 (accuracy from the emitted qualities)
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -491,7 +578,7 @@ PB_HD void sample_simulate(const QsView &T, Draw &d, const WindowRef &win, bool 
                            const uint8_t *quals, QsSink &sink, SubreadResult &res) {
   uint32_t R = 0, P = 0, C = 0;
   uint32_t nsub = 0, nins = 0, ndel = 0;
-  double prob = 0.0;
+  QsProbSum ps;
   res.overflow = 0;
   while (R < len && P < len) {
     d.prefetch(P);
@@ -502,38 +589,15 @@ PB_HD void sample_simulate(const QsView &T, Draw &d, const WindowRef &win, bool 
       sink.checkpoint(C, R, P);
       d.begin(u);
       const uint32_t qv = (uint32_t)quals[P] - 33u;
-      prob += T.qc_prob[qv];
-      const QsThr th = T.thr[qv];
-      const uint32_t r = d.w2(1000000u);
-      const bool is_sub = r < th.sub;
-      const bool is_ins = !is_sub && r < th.ins;
-      uint32_t info;
-      if (Draw::kCounter) {
-        info = is_sub ? d.choice3() : (is_ins ? d.choice8() : 0u);
-      } else {
-        info = 0;
-        if (is_sub) info = d.choice3();
-        else if (is_ins) info = d.choice8();
-      }
-      if (slow && is_sub && win.nonacgt(R)) info = d.choice4();
-      const uint32_t kind = is_sub ? PB_KIND_SUB : (is_ins ? PB_KIND_INS : PB_KIND_MATCH);
-      nsub += is_sub ? 1u : 0u;
-      nins += is_ins ? 1u : 0u;
-      R += is_ins ? 0u : 1u;
+      ps.template add<Draw>(T, qv);
       ++P;
+      const uint32_t Pn = P;
+      const auto more = [len, Pn](uint32_t r) { return r < len && Pn < len; };
+      uint32_t kind, info, nd;
+      qs_position(T, d, win, slow, qv, R, more, kind, info, nd);
+      nsub += kind == PB_KIND_SUB ? 1u : 0u;
+      nins += kind == PB_KIND_INS ? 1u : 0u;
       ++C;
-      uint32_t nd = 0;
-      while (R < len && P < len) {
-        const uint32_t rd = d.del(nd);
-        bool hit = rd < th.del;
-        if (hit) {
-          if (R == 0u) hit = rd < th.del0;
-          else if (slow) hit = rd < T.thr_hp[qv * 12u + win.hp(R - 1u)];
-        }
-        if (!hit) break;
-        ++nd;
-        ++R;
-      }
       ndel += nd;
       C += nd;
       const uint32_t base = qv | (kind << 7) | (info << 9);
@@ -562,24 +626,56 @@ PB_HD void sample_simulate(const QsView &T, Draw &d, const WindowRef &win, bool 
   res.nsub = nsub;
   res.nins = nins;
   res.ndel = ndel;
-  res.accuracy = 1.0 - (prob / (double)P);
+  res.accuracy = ps.template accuracy<Draw>(P);
 }
 
 // ---------------------------------------------------------------------------------------------
 // qshmm fast path: PHILOX draws, reads that never need the genome in pass 1 (not `slow`).
-// Same results as qshmm_simulate<PhiloxDraw> entry for entry, except that the stream is padded with
+// Same results as qshmm_simulate<PhiloxDrawQ> entry for entry, except that the stream is padded with
 // no-op entries (continuation entries with count 0) to a multiple of PB_GROUP, which lets every group of
 // 4 positions be packed in registers and written with one 8-byte store, checks run once per group and the
 // common path stay free of divergent branches.
 // ---------------------------------------------------------------------------------------------
 #define PB_QS_PAD (3u << 7)  // continuation entry, count 0
 
+// error-stream words of the PB_GROUP positions starting at p (a multiple of 4): x[u], y[u]
+PB_HD void error_words(const PhiloxKeys &K, uint32_t read_id, uint32_t c1, uint32_t p, uint32_t x[PB_GROUP], uint32_t y[PB_GROUP]) {
+  uint32_t a[4], b[4];
+  philox_block_keys(K, p >> 1, c1, read_id, 1u, a);
+  philox_block_keys(K, (p >> 1) + 1u, c1, read_id, 1u, b);
+  x[0] = a[0]; y[0] = a[1]; x[1] = a[2]; y[1] = a[3];
+  x[2] = b[0]; y[2] = b[1]; x[3] = b[2]; y[3] = b[3];
+}
+// the words of ONE position (any p): used off the hot paths
+PB_HD void error_words_at(const PhiloxKeys &K, uint32_t read_id, uint32_t c1, uint32_t p, uint32_t &x, uint32_t &y) {
+  uint32_t a[4];
+  philox_block_keys(K, p >> 1, c1, read_id, 1u, a);
+  x = (p & 1u) ? a[2] : a[0];
+  y = (p & 1u) ? a[3] : a[1];
+}
+
+// kind, info and deletion count of one position from its quality and its two error-stream words, for a position
+// whose reference offset is > 0 after the base (every position except leading insertions of a read)
+PB_HD uint32_t qs_event(const QsFast th, uint32_t qv, uint32_t X, uint32_t Y, uint32_t &kind, uint32_t &nd) {
+  const bool is_sub = X < th.sub;
+  const bool is_err = X < th.ins;  // substitution or insertion (the insertion threshold is cumulative)
+  const uint32_t c3 = ((X & 0xFFFu) * 3u) >> 12, c8 = Y & 7u;
+  const uint32_t info = is_sub ? c3 : (is_err ? c8 : 0u);
+  kind = is_sub ? PB_KIND_SUB : (is_err ? PB_KIND_INS : PB_KIND_MATCH);
+  nd = 0;
+  if (Y < th.del) {
+    nd = 1;
+    while (nd < (1u << 20) && fmix32(Y + nd * 0x9E3779B9u) < th.del) ++nd;
+  }
+  return qv | (kind << 7) | (info << 9);
+}
+
 PB_HD void qshmm_simulate_fast(const QsView &T, const PhiloxKeys &K, uint32_t read_id, uint32_t pass,
                                uint32_t wlen, uint16_t *ev, Ckpt *ck, uint32_t cap, SubreadResult &res) {
   uint32_t R = 0, P = 0, n = 0;
   uint32_t row = 0, mod = T.init_mod, emod = 1;
   uint32_t nsub = 0, ndel = 0;
-  double prob = 0.0, prob_blk = 0.0;
+  uint64_t prob = 0;
   res.overflow = 0;
   const uint32_t c1 = pass << 16;
   while (R < wlen) {
@@ -588,45 +684,41 @@ PB_HD void qshmm_simulate_fast(const QsView &T, const PhiloxKeys &K, uint32_t re
       Ckpt c; c.col = P + ndel; c.ref = R; c.read = P; c.pad = 0;
       ck[n / PB_TILE] = c;
     }
-    uint32_t g[PB_GROUP][4], cw[PB_GROUP];
-#pragma unroll
-    for (uint32_t u = 0; u < PB_GROUP; ++u) philox_block_keys(K, P + u, c1, read_id, 1u, g[u]);
-    if (T.has_model) chain_words(K, read_id, c1, P, cw);
+    // P is a multiple of PB_GROUP here: a group is only cut short by the end of the read
+    uint32_t x[PB_GROUP], y[PB_GROUP], q[PB_GROUP];
+    error_words(K, read_id, c1, P, x, y);
+    philox_block_keys(K, P >> 2, c1, read_id, 2u, q);
     uint32_t e[PB_GROUP];
     uint32_t big_u = PB_GROUP, big_nd = 0;  // rare: an entry with >= 15 deletions ends the group early
 #pragma unroll
     for (uint32_t u = 0; u < PB_GROUP; ++u) {
       e[u] = PB_QS_PAD;
       if (R < wlen && big_u == PB_GROUP) {
-        const uint32_t w0 = g[u][0], w1 = g[u][1], w2 = g[u][2], w3 = g[u][3];
         uint32_t qv;
         if (T.has_model) {
-          const uint32_t t = T.t2[row + mulhi32(cw[u], mod)];
+          const uint32_t t = T.t2[row + mulhi32(q[u] & 0xFFFF0000u, mod)];
           row = t & 0xFFFFu;
           mod = (t >> 16) & 0xFFu;
           emod = t >> 24;
-          qv = T.emis[row + mulhi32(w1, emod)];
+          qv = T.emis[row + mulhi32(q[u] << 16, emod)];
         } else {
-          qv = T.freq[mulhi32(w0, T.freq_mod)];
+          qv = T.freq[mulhi32(q[u], T.freq_mod)];
         }
-        if ((P & (PB_TILE - 1u)) == 0u) { prob += prob_blk; prob_blk = 0.0; }  // block order of the segment-parallel path
-        prob_blk += T.qc_prob[qv];
-        const QsThr th = T.thr[qv];
-        const uint32_t r = mulhi32(w2, 1000000u);
-        const bool is_sub = r < th.sub;
-        const bool is_err = r < th.ins;  // substitution or insertion (ins_thre is cumulative)
-        const uint32_t c3 = ((w0 & 0xFFFu) * 3u) >> 12, c8 = w1 & 7u;
+        const QsFast th = T.fast[qv];
+        prob += th.prob;
+        const bool is_sub = x[u] < th.sub;
+        const bool is_err = x[u] < th.ins;
+        const uint32_t c3 = ((x[u] & 0xFFFu) * 3u) >> 12, c8 = y[u] & 7u;
         const uint32_t info = is_sub ? c3 : (is_err ? c8 : 0u);
         const uint32_t kind = is_sub ? PB_KIND_SUB : (is_err ? PB_KIND_INS : PB_KIND_MATCH);
         nsub += is_sub ? 1u : 0u;
         R += (is_err && !is_sub) ? 0u : 1u;
         ++P;
         uint32_t nd = 0;
-        const uint32_t rd0 = mulhi32(w3, 1000000u);
-        if (R < wlen && rd0 < (R != 0u ? th.del : th.del0)) {
+        if (R < wlen && y[u] < (R != 0u ? th.del : T.thr32[qv].del0)) {
           nd = 1;
           ++R;
-          while (R < wlen && mulhi32(fmix32(w3 + nd * 0x9E3779B9u), 1000000u) < th.del) {
+          while (R < wlen && fmix32(y[u] + nd * 0x9E3779B9u) < th.del) {
             ++nd;
             ++R;
           }
@@ -646,8 +738,9 @@ PB_HD void qshmm_simulate_fast(const QsView &T, const PhiloxKeys &K, uint32_t re
     *dst = (uint64_t)(e[0] | (e[1] << 16)) | ((uint64_t)(e[2] | (e[3] << 16)) << 32);
     n += PB_GROUP;
     if (big_u != PB_GROUP) {
-      // continuation entries must directly follow their entry: rewrite the tail of this group generically
-      n -= PB_GROUP - 1u - big_u;          // drop the pads after the big entry
+      // continuation entries directly follow their entry, then the rest of the group follows them: the group's
+      // remaining positions are redone one entry at a time so that P stays a multiple of PB_GROUP afterwards
+      n -= PB_GROUP - 1u - big_u;          // drop the entries after the big one
       uint32_t rest = big_nd;
       for (;;) {
         if (n + 2u * PB_GROUP > cap) { res.overflow = 1; break; }
@@ -660,32 +753,87 @@ PB_HD void qshmm_simulate_fast(const QsView &T, const PhiloxKeys &K, uint32_t re
         if (c < PB_QS_CONT_SAT) break;
         rest -= PB_QS_CONT_SAT;
       }
+      if (res.overflow) break;
+      // the positions of the group behind the big entry, each followed by its own continuation entries
+      for (uint32_t u = big_u + 1u; u < PB_GROUP && R < wlen; ++u) {
+        if (n + 2u * PB_GROUP > cap) { res.overflow = 1; break; }
+        if ((n & (PB_TILE - 1u)) == 0u) {
+          Ckpt c; c.col = P + ndel; c.ref = R; c.read = P; c.pad = 0;
+          ck[n / PB_TILE] = c;
+        }
+        uint32_t qv;
+        if (T.has_model) {
+          const uint32_t t = T.t2[row + mulhi32(q[u] & 0xFFFF0000u, mod)];
+          row = t & 0xFFFFu;
+          mod = (t >> 16) & 0xFFu;
+          emod = t >> 24;
+          qv = T.emis[row + mulhi32(q[u] << 16, emod)];
+        } else {
+          qv = T.freq[mulhi32(q[u], T.freq_mod)];
+        }
+        const QsFast th = T.fast[qv];
+        prob += th.prob;
+        const bool is_sub = x[u] < th.sub;
+        const bool is_err = x[u] < th.ins;
+        const uint32_t info = is_sub ? (((x[u] & 0xFFFu) * 3u) >> 12) : (is_err ? (y[u] & 7u) : 0u);
+        const uint32_t kind = is_sub ? PB_KIND_SUB : (is_err ? PB_KIND_INS : PB_KIND_MATCH);
+        nsub += is_sub ? 1u : 0u;
+        R += (is_err && !is_sub) ? 0u : 1u;
+        ++P;
+        uint32_t nd = 0;
+        if (R < wlen && y[u] < (R != 0u ? th.del : T.thr32[qv].del0)) {
+          nd = 1;
+          ++R;
+          while (R < wlen && fmix32(y[u] + nd * 0x9E3779B9u) < th.del) { ++nd; ++R; }
+        }
+        ndel += nd;
+        const uint32_t base = qv | (kind << 7) | (info << 9);
+        ev[n++] = (uint16_t)(base | ((nd < PB_QS_DEL_SAT ? nd : PB_QS_DEL_SAT) << 12));
+        uint32_t rest2 = nd >= PB_QS_DEL_SAT ? nd - PB_QS_DEL_SAT : 0u;
+        bool cont = nd >= PB_QS_DEL_SAT;
+        while (cont) {
+          if (n + 2u * PB_GROUP > cap) { res.overflow = 1; break; }
+          if ((n & (PB_TILE - 1u)) == 0u) {
+            Ckpt c; c.col = P + ndel - rest2; c.ref = R - rest2; c.read = P; c.pad = 0;
+            ck[n / PB_TILE] = c;
+          }
+          const uint32_t c = rest2 < PB_QS_CONT_SAT ? rest2 : PB_QS_CONT_SAT;
+          ev[n++] = (uint16_t)((c & 0x7Fu) | (3u << 7) | ((c >> 7) << 9));
+          cont = c >= PB_QS_CONT_SAT;
+          rest2 -= c;
+        }
+        if (res.overflow) break;
+      }
+      if (res.overflow) break;
       while (n & (PB_GROUP - 1u)) {         // re-align; a checkpoint can only fall on a group boundary
         ev[n++] = (uint16_t)PB_QS_PAD;
       }
-      if (res.overflow) break;
     }
   }
-  prob += prob_blk;
   res.n_entries = n;
   res.rlen = P;
   res.ncol = P + ndel;
   res.nsub = nsub;
   res.ndel = ndel;
   res.nins = P + ndel - R;  // C = P + ndel and R = P - nins + ndel
-  res.accuracy = 1.0 - (prob / (double)P);
+  res.accuracy = 1.0 - (((double)prob / (double)(1u << PB_PROB_SHIFT)) / (double)P);
 }
 
 // ---------------------------------------------------------------------------------------------
 // qshmm SEGMENT-PARALLEL pass 1 (PHILOX, reads that never need the genome in pass 1).
-// A read is cut into segments of PB_TILE read positions.  Because every draw is addressed by its
-// position, a segment can be simulated by itself once the chain state entering it is known, and that
-// state is recovered EXACTLY by backward coupling: run every reachable state through the positions
-// just before the segment with those positions' own draws; as soon as all images coincide the state is
-// independent of the earlier history (if the window reaches position 0 the init draw decides).  Segments
-// are simulated "unbounded" (they cannot know the reference offset they start at); find_end then locates
-// the position at which the window is used up, clips the last deletion run and drops the rest, which is
-// what the sequential loop `while (ref_offset < mut.len)` (:2213, :2268) does.
+// A read is cut into segments of PB_TILE read positions; the work is split by what is sequential and what is not:
+//   * the QUALITY pass (k_chain_chunk): the HMM chain is the only sequential part of a read.  One thread walks a
+//     chunk of segments through the chain (its own Philox stream, one block per 4 positions) and writes the
+//     QUALITY VALUE of every position into the segment's event slot.  The state entering a chunk is recovered
+//     EXACTLY by backward coupling: run every reachable state through the positions just before the chunk with
+//     those positions' own draws; as soon as all images coincide the state is independent of the earlier history
+//     (if the window reaches position 0 the init draw decides).
+//   * the ERROR pass (k_sim_seg): given its quality, a position depends on nothing but its own two error-stream
+//     words, so one WARP handles a segment with consecutive lanes on consecutive positions (coalesced loads and
+//     stores, no divergence): error draw, choices, deletion run -> the event, written over the quality in place.
+// Segments are simulated "unbounded" (they cannot know the reference offset they start at); find_end then locates
+// the position at which the window is used up, clips the last deletion run and drops the rest, which is what the
+// sequential loop `while (ref_offset < mut.len)` (:2213, :2268) does.
 // ---------------------------------------------------------------------------------------------
 #define PB_SEG_SLACK 64u                       // extra entries per segment slot (continuation entries, pads)
 #define PB_SEG_STRIDE (PB_TILE + PB_SEG_SLACK) // entries between consecutive segment slots of a read
@@ -699,7 +847,8 @@ struct QsSegAux {            // per accuracy, beside the QsView tables
 struct SegResult {
   uint32_t n_entries, ref_adv, nsub, ndel;
   uint32_t flags;            // 1: slot overflow, 2: coupling window exhausted
-  double prob;
+  uint32_t pad;
+  uint64_t prob;             // qshmm: fixed-point sum of the error probabilities; errhmm: the insertion count
 };
 
 PB_HD uint32_t qs_state_of_row(uint32_t row) { return (row * 41944u) >> 22; }  // row / 100 for row <= 5100
@@ -720,7 +869,7 @@ PB_HD bool qshmm_segment_start(const QsView &T, const QsSegAux &A, const PhiloxK
     for (uint32_t p = p0; p < p_start; ++p) {
       if (p == p0 || (p & 3u) == 0u) philox_block_keys(K, p >> 2, c1, read_id, 2u, cwb);
       const uint32_t k4 = p & 3u;
-      const uint32_t wdraw = k4 == 0u ? cwb[0] : (k4 == 1u ? cwb[1] : (k4 == 2u ? cwb[2] : cwb[3]));
+      const uint32_t wdraw = (k4 == 0u ? cwb[0] : (k4 == 1u ? cwb[1] : (k4 == 2u ? cwb[2] : cwb[3]))) & 0xFFFF0000u;
       if (single) {
         const uint32_t t = T.t2[s_row + mulhi32(wdraw, s_mod)];
         s_row = t & 0xFFFFu;
@@ -754,111 +903,149 @@ PB_HD bool qshmm_segment_start(const QsView &T, const QsSegAux &A, const PhiloxK
   }
 }
 
-// Chain-only prepass for accuracies whose chain does not couple quickly (sticky states): advance just the state
-// chain over the read (one Philox block per 4 positions, one table lookup per position) and record the packed
-// table entry (row | modulus << 16 | emission modulus << 24) in front of every segment k >= 1.
-// chain-only walk over segments k_from .. k_to-1 from the state (row, mod, emod) that enters segment k_from; records
-// the packed table entry in front of segments k_from+1 .. k_to.  The lookups form one dependent chain (table entry
-// -> next row); the Philox block of the NEXT four positions does not depend on it and is computed alongside, so
-// that the chain never waits for its draws.
-PB_HD void qshmm_chain_range(const QsView &T, const PhiloxKeys &K, uint32_t read_id, uint32_t pass, uint32_t row,
-                             uint32_t mod, uint32_t emod, uint32_t k_from, uint32_t k_to, uint32_t *seg_state) {
+PB_HD void store_u16x8(uint16_t *dst, const uint32_t v[4]) {  // dst is 16-byte aligned
+#if defined(__CUDA_ARCH__)
+  *reinterpret_cast<uint4 *>(dst) = make_uint4(v[0], v[1], v[2], v[3]);
+#else
+  for (int i = 0; i < 4; ++i) { dst[2 * i] = (uint16_t)v[i]; dst[2 * i + 1] = (uint16_t)(v[i] >> 16); }
+#endif
+}
+
+// QUALITY pass over segments k_from .. k_to-1 of a read from the state (row, mod, emod) that enters segment k_from:
+// the quality value of every position goes into bits 0-6 of its entry in the segment's slot (uint16 per position,
+// 8 positions per 16-byte store).  The lookups form one dependent chain (table entry -> next row); the Philox
+// blocks of the NEXT eight positions do not depend on it and are computed alongside.
+PB_HD void qshmm_quality_range(const QsView &T, const PhiloxKeys &K, uint32_t read_id, uint32_t pass, uint32_t row,
+                               uint32_t mod, uint32_t emod, uint32_t k_from, uint32_t k_to, uint16_t *slots) {
   const uint32_t c1 = pass << 16;
-  uint32_t nx[4];
+  uint32_t nx[8];
   philox_block_keys(K, (k_from * PB_TILE) >> 2, c1, read_id, 2u, nx);
-  for (uint32_t k = k_from + 1u; k <= k_to; ++k) {
-    for (uint32_t p = (k - 1u) * PB_TILE; p < k * PB_TILE; p += 4u) {
-      const uint32_t cw[4] = {nx[0], nx[1], nx[2], nx[3]};
-      philox_block_keys(K, (p >> 2) + 1u, c1, read_id, 2u, nx);
+  philox_block_keys(K, ((k_from * PB_TILE) >> 2) + 1u, c1, read_id, 2u, nx + 4);
+  for (uint32_t k = k_from; k < k_to; ++k) {
+    uint16_t *slot = slots + (uint64_t)k * PB_SEG_STRIDE;
+    for (uint32_t j = 0; j < PB_TILE; j += 8u) {
+      const uint32_t p = k * PB_TILE + j;
+      uint32_t cw[8];
 #pragma unroll
-      for (uint32_t u = 0; u < 4u; ++u) {
-        const uint32_t t = T.t2[row + mulhi32(cw[u], mod)];
+      for (uint32_t u = 0; u < 8u; ++u) cw[u] = nx[u];
+      philox_block_keys(K, (p >> 2) + 2u, c1, read_id, 2u, nx);
+      philox_block_keys(K, (p >> 2) + 3u, c1, read_id, 2u, nx + 4);
+      uint32_t out[4];
+#pragma unroll
+      for (uint32_t u = 0; u < 8u; ++u) {
+        const uint32_t t = T.t2[row + mulhi32(cw[u] & 0xFFFF0000u, mod)];
         row = t & 0xFFFFu;
         mod = (t >> 16) & 0xFFu;
         emod = t >> 24;
+        const uint32_t qv = T.emis[row + mulhi32(cw[u] << 16, emod)];
+        if (u & 1u) out[u >> 1] |= qv << 16;
+        else out[u >> 1] = qv;
       }
+      store_u16x8(slot + j, out);
     }
-    seg_state[k] = row | (mod << 16) | (emod << 24);
   }
 }
 
-PB_HD void qshmm_chain_only(const QsView &T, const PhiloxKeys &K, uint32_t read_id, uint32_t pass, uint32_t n_seg,
-                            uint32_t *seg_state) {
-  if (n_seg > 1u) qshmm_chain_range(T, K, read_id, pass, 0u, T.init_mod, 1u, 0u, n_seg - 1u, seg_state);
+// the qualities of PB_GROUP positions of an accuracy WITHOUT model (freq2qc table, :2230): no chain, so the
+// error pass computes them itself
+PB_HD void qs_freq_qualities(const QsView &T, const PhiloxKeys &K, uint32_t read_id, uint32_t c1, uint32_t p,
+                             uint32_t qv[PB_GROUP]) {
+  uint32_t q[4];
+  philox_block_keys(K, p >> 2, c1, read_id, 2u, q);
+#pragma unroll
+  for (uint32_t u = 0; u < PB_GROUP; ++u) qv[u] = T.freq[mulhi32(q[u], T.freq_mod)];
 }
 
-// simulate positions [p_start, p_start + PB_TILE) of a read, unbounded in the reference direction.
-// first_segment: the reference offset is 0 at p_start (the `hp[-1]` rule of :2269 applies while it stays 0).
-PB_HD void qshmm_simulate_segment(const QsView &T, const PhiloxKeys &K, uint32_t read_id, uint32_t pass,
-                                  uint32_t p_start, bool first_segment, uint32_t row, uint32_t mod, uint32_t emod,
-                                  uint16_t *ev, SegResult &res) {
+// ERROR pass, the work of one lane: the events of positions p .. p+3 (p a multiple of 4) from their qualities.
+// Deletion counts are stored saturated at PB_QS_DEL_SAT; `big` reports that one of them was (the segment is then
+// redone by qshmm_segment_generic, which writes continuation entries).
+struct QsLaneTotals {
+  uint32_t nsub, nins, ndel, prob, big;
+};
+PB_HD void qs_error_lane(const QsFast *fast, const PhiloxKeys &K, uint32_t read_id, uint32_t c1, uint32_t p,
+                         const uint32_t qv[PB_GROUP], uint32_t e[PB_GROUP], QsLaneTotals &t) {
+  uint32_t x[PB_GROUP], y[PB_GROUP];
+  error_words(K, read_id, c1, p, x, y);
+#pragma unroll
+  for (uint32_t u = 0; u < PB_GROUP; ++u) {
+    const QsFast th = fast[qv[u]];
+    uint32_t kind, nd;
+    const uint32_t base = qs_event(th, qv[u], x[u], y[u], kind, nd);
+    t.nsub += kind == PB_KIND_SUB ? 1u : 0u;
+    t.nins += kind == PB_KIND_INS ? 1u : 0u;
+    t.ndel += nd;
+    t.prob += th.prob;
+    t.big |= nd >= PB_QS_DEL_SAT ? 1u : 0u;
+    e[u] = base | ((nd < PB_QS_DEL_SAT ? nd : PB_QS_DEL_SAT) << 12);
+  }
+}
+
+// ERROR pass, first segment of a read: while the reference offset is still 0 (leading insertions) the deletion
+// test uses the threshold of mut.hp[-1] (:2269) instead of the one qs_event applied.  Walks the leading
+// insertions of the slot, corrects their deletion counts and returns the deletions removed.
+PB_HD uint32_t qs_fix_leading(const QsView &T, const PhiloxKeys &K, uint32_t read_id, uint32_t c1, uint16_t *ev) {
+  uint32_t removed = 0;
+  for (uint32_t p = 0; p < PB_TILE; ++p) {
+    const uint32_t v = ev[p];
+    if (((v >> 7) & 3u) != PB_KIND_INS) break;     // a base that consumes the reference: offset > 0 from here on
+    uint32_t x, y;
+    error_words_at(K, read_id, c1, p, x, y);
+    if (y < T.thr32[v & 0x7Fu].del0) break;        // deleted under the hp[-1] rule as well (del0 <= del): unchanged
+    removed += v >> 12;
+    ev[p] = (uint16_t)(v & 0x0FFFu);
+  }
+  return removed;
+}
+
+// ERROR pass, generic statement for one whole segment: entries with >= PB_QS_DEL_SAT deletions get continuation
+// entries, the hp[-1] rule is applied as the positions go.  qv: the qualities of the segment's PB_TILE positions
+// (model accuracies; ignored otherwise).  Used for the rare segments qs_error_lane reports as `big`.
+PB_HD void qshmm_segment_generic(const QsView &T, const PhiloxKeys &K, uint32_t read_id, uint32_t pass,
+                                 uint32_t p_start, bool first_segment, const uint8_t *qv_in, uint16_t *ev,
+                                 SegResult &res) {
   uint32_t R = first_segment ? 0u : 1u;  // only "is it still 0" matters; ref_adv is counted separately
   uint32_t radv = 0, n = 0, nsub = 0, ndel = 0;
-  double prob = 0.0;
+  uint64_t prob = 0;
   const uint32_t c1 = pass << 16;
   res.flags = 0;
-  const uint32_t p_end = p_start + PB_TILE;
-  for (uint32_t P = p_start; P < p_end;) {
+  for (uint32_t j = 0; j < PB_TILE; ++j) {
     if (n + 2u * PB_GROUP > PB_SEG_STRIDE) { res.flags |= 1u; break; }
-    uint32_t g[PB_GROUP][4], cw[PB_GROUP];
-#pragma unroll
-    for (uint32_t u = 0; u < PB_GROUP; ++u) philox_block_keys(K, P + u, c1, read_id, 1u, g[u]);
-    if (T.has_model) chain_words(K, read_id, c1, P, cw);
-    uint32_t e[PB_GROUP];
-    uint32_t big_u = PB_GROUP, big_nd = 0;
-#pragma unroll
-    for (uint32_t u = 0; u < PB_GROUP; ++u) {
-      e[u] = PB_QS_PAD;
-      if (big_u == PB_GROUP && P < p_end) {  // a group can be misaligned after a >= 15 deletion run
-        const uint32_t w0 = g[u][0], w1 = g[u][1], w2 = g[u][2], w3 = g[u][3];
-        uint32_t qv;
-        if (T.has_model) {
-          const uint32_t t = T.t2[row + mulhi32(cw[u], mod)];
-          row = t & 0xFFFFu;
-          mod = (t >> 16) & 0xFFu;
-          emod = t >> 24;
-          qv = T.emis[row + mulhi32(w1, emod)];
-        } else {
-          qv = T.freq[mulhi32(w0, T.freq_mod)];
-        }
-        prob += T.qc_prob[qv];
-        const QsThr th = T.thr[qv];
-        const uint32_t r = mulhi32(w2, 1000000u);
-        const bool is_sub = r < th.sub;
-        const bool is_err = r < th.ins;
-        const uint32_t c3 = ((w0 & 0xFFFu) * 3u) >> 12, c8 = w1 & 7u;
-        const uint32_t info = is_sub ? c3 : (is_err ? c8 : 0u);
-        const uint32_t kind = is_sub ? PB_KIND_SUB : (is_err ? PB_KIND_INS : PB_KIND_MATCH);
-        nsub += is_sub ? 1u : 0u;
-        const uint32_t a = (is_err && !is_sub) ? 0u : 1u;
-        R += a;
-        radv += a;
-        ++P;
-        uint32_t nd = 0;
-        const uint32_t rd0 = mulhi32(w3, 1000000u);
-        if (rd0 < (R != 0u ? th.del : th.del0)) {
-          nd = 1;
-          while (nd < (1u << 20) && mulhi32(fmix32(w3 + nd * 0x9E3779B9u), 1000000u) < th.del) ++nd;
-          R += nd;
-          radv += nd;
-        }
-        ndel += nd;
-        const uint32_t base = qv | (kind << 7) | (info << 9);
-        if (nd < PB_QS_DEL_SAT) {
-          e[u] = base | (nd << 12);
-        } else {
-          e[u] = base | (PB_QS_DEL_SAT << 12);
-          big_u = u;
-          big_nd = nd - PB_QS_DEL_SAT;
-        }
-      }
+    const uint32_t P = p_start + j;
+    uint32_t qv;
+    if (T.has_model) {
+      qv = qv_in[j];
+    } else {
+      uint32_t q[4];
+      philox_block_keys(K, P >> 2, c1, read_id, 2u, q);
+      const uint32_t k4 = P & 3u;
+      qv = T.freq[mulhi32(k4 == 0u ? q[0] : (k4 == 1u ? q[1] : (k4 == 2u ? q[2] : q[3])), T.freq_mod)];
     }
-    uint64_t *dst = reinterpret_cast<uint64_t *>(ev + n);
-    *dst = (uint64_t)(e[0] | (e[1] << 16)) | ((uint64_t)(e[2] | (e[3] << 16)) << 32);
-    n += PB_GROUP;
-    if (big_u != PB_GROUP) {
-      n -= PB_GROUP - 1u - big_u;
-      uint32_t rest = big_nd;
+    uint32_t x, y;
+    error_words_at(K, read_id, c1, P, x, y);
+    const QsFast th = T.fast[qv];
+    prob += th.prob;
+    const bool is_sub = x < th.sub;
+    const bool is_err = x < th.ins;
+    const uint32_t info = is_sub ? (((x & 0xFFFu) * 3u) >> 12) : (is_err ? (y & 7u) : 0u);
+    const uint32_t kind = is_sub ? PB_KIND_SUB : (is_err ? PB_KIND_INS : PB_KIND_MATCH);
+    nsub += is_sub ? 1u : 0u;
+    const uint32_t a = (is_err && !is_sub) ? 0u : 1u;
+    R += a;
+    radv += a;
+    uint32_t nd = 0;
+    if (y < (R != 0u ? th.del : T.thr32[qv].del0)) {
+      nd = 1;
+      while (nd < (1u << 20) && fmix32(y + nd * 0x9E3779B9u) < th.del) ++nd;
+      R += nd;
+      radv += nd;
+    }
+    ndel += nd;
+    const uint32_t base = qv | (kind << 7) | (info << 9);
+    if (nd < PB_QS_DEL_SAT) {
+      ev[n++] = (uint16_t)(base | (nd << 12));
+    } else {
+      ev[n++] = (uint16_t)(base | (PB_QS_DEL_SAT << 12));
+      uint32_t rest = nd - PB_QS_DEL_SAT;
       for (;;) {
         if (n + 2u * PB_GROUP > PB_SEG_STRIDE) { res.flags |= 1u; break; }
         const uint32_t c = rest < PB_QS_CONT_SAT ? rest : PB_QS_CONT_SAT;
@@ -866,14 +1053,54 @@ PB_HD void qshmm_simulate_segment(const QsView &T, const PhiloxKeys &K, uint32_t
         if (c < PB_QS_CONT_SAT) break;
         rest -= PB_QS_CONT_SAT;
       }
-      while (n & (PB_GROUP - 1u)) ev[n++] = (uint16_t)PB_QS_PAD;
       if (res.flags) break;
     }
   }
+  while (n & (PB_GROUP - 1u)) ev[n++] = (uint16_t)PB_QS_PAD;
   res.n_entries = n;
   res.ref_adv = radv;
   res.nsub = nsub;
   res.ndel = ndel;
+  res.pad = 0;
+  res.prob = prob;
+}
+
+// ERROR pass over one segment, as the warp of k_sim_seg runs it (sequential statement for the CPU harness: the
+// 256 lane steps one after the other).  The slot holds the qualities on entry (model accuracies).
+PB_HD void qshmm_error_segment(const QsView &T, const PhiloxKeys &K, uint32_t read_id, uint32_t pass, uint32_t p_start,
+                               bool first_segment, uint16_t *ev, SegResult &res) {
+  const uint32_t c1 = pass << 16;
+  QsLaneTotals t;
+  t.nsub = t.nins = t.ndel = t.prob = t.big = 0;
+  uint64_t prob = 0;
+  uint8_t qsave[PB_TILE];
+  for (uint32_t j = 0; j < PB_TILE; j += PB_GROUP) {
+    uint32_t qv[PB_GROUP], e[PB_GROUP];
+    if (T.has_model) {
+#pragma unroll
+      for (uint32_t u = 0; u < PB_GROUP; ++u) qv[u] = ev[j + u] & 0x7Fu;
+    } else {
+      qs_freq_qualities(T, K, read_id, c1, p_start + j, qv);
+    }
+#pragma unroll
+    for (uint32_t u = 0; u < PB_GROUP; ++u) qsave[j + u] = (uint8_t)qv[u];
+    t.prob = 0;
+    qs_error_lane(T.fast, K, read_id, c1, p_start + j, qv, e, t);
+    prob += t.prob;
+#pragma unroll
+    for (uint32_t u = 0; u < PB_GROUP; ++u) ev[j + u] = (uint16_t)e[u];
+  }
+  if (t.big) {
+    qshmm_segment_generic(T, K, read_id, pass, p_start, first_segment, qsave, ev, res);
+    return;
+  }
+  if (first_segment) t.ndel -= qs_fix_leading(T, K, read_id, c1, ev);
+  res.n_entries = PB_TILE;
+  res.ref_adv = PB_TILE - t.nins + t.ndel;
+  res.nsub = t.nsub;
+  res.ndel = t.ndel;
+  res.flags = 0;
+  res.pad = 0;
   res.prob = prob;
 }
 
@@ -897,16 +1124,16 @@ struct HpProbe {
 struct TileWalk {
   uint32_t n_entries, positions, ref_adv, nsub, ndel;
   uint32_t ended;           // the reference window was used up inside this tile
-  double prob;
+  uint64_t prob;            // fixed-point sum of the error probabilities of the positions walked
 };
 
 // Walk the entries of one tile knowing the reference offset it starts at: stop where the window is used up
 // (`while (ref_offset < mut.len)`, :2213 and :2268), clip the last deletion run, and (HpProbe) cut deletion runs
 // in front of suppressing bases.  Entries are rewritten in place; entries after the end are not counted.
 PB_HD TileWalk qshmm_walk_tile(uint16_t *ev, uint32_t n_entries, uint32_t R_start, uint32_t wlen,
-                               const double *qc_prob, const HpProbe &hp, uint32_t *blocked_io = nullptr) {
+                               const QsFast *fast, const HpProbe &hp, uint32_t *blocked_io = nullptr) {
   TileWalk t;
-  t.n_entries = 0; t.positions = 0; t.ref_adv = 0; t.nsub = 0; t.ndel = 0; t.ended = 0; t.prob = 0.0;
+  t.n_entries = 0; t.positions = 0; t.ref_adv = 0; t.nsub = 0; t.ndel = 0; t.ended = 0; t.prob = 0;
   uint32_t R = R_start;
   // the current deletion run has ended (window end or suppressing base); carried between calls when a tile is
   // walked in pieces, because continuation entries of that run may follow in the next piece
@@ -918,7 +1145,7 @@ PB_HD TileWalk qshmm_walk_tile(uint16_t *ev, uint32_t n_entries, uint32_t R_star
     const uint32_t part = cont ? ((v & 0x7Fu) | ((v >> 9) << 7)) : (v >> 12);
     if (!cont) {
       if (R >= wlen) { t.ended = 1; break; }
-      t.prob += qc_prob[v & 0x7Fu];
+      t.prob += fast[v & 0x7Fu].prob;
       t.positions += 1u;
       t.nsub += (kind == PB_KIND_SUB) ? 1u : 0u;
       R += (kind == PB_KIND_INS) ? 0u : 1u;
@@ -967,9 +1194,9 @@ PB_HD uint32_t qshmm_segments_for(uint32_t wlen, float rho) {
 }
 
 PB_HD void qshmm_finish_segmented(uint16_t *ev_base, const SegResult *seg, uint32_t n_seg, uint32_t wlen,
-                                  const double *qc_prob, const HpProbe &hp, Ckpt *ck, SegRead &out) {
+                                  const QsFast *fast, const HpProbe &hp, Ckpt *ck, SegRead &out) {
   uint32_t R = 0, P = 0, D = 0, nsub = 0;
-  double prob = 0.0;
+  uint64_t prob = 0;
   out.flags = 0;
   out.n_tiles = 0;
   bool done = false;
@@ -980,7 +1207,7 @@ PB_HD void qshmm_finish_segmented(uint16_t *ev_base, const SegResult *seg, uint3
     const bool may_end = (uint64_t)R + seg[k].ref_adv >= wlen;
     if (may_end || hp.enabled) {
       // exact walk: the last tile of every read, and every tile of a read that may need deletion-run repairs
-      const TileWalk t = qshmm_walk_tile(ev_base + (uint64_t)k * PB_SEG_STRIDE, seg[k].n_entries, R, wlen, qc_prob, hp);
+      const TileWalk t = qshmm_walk_tile(ev_base + (uint64_t)k * PB_SEG_STRIDE, seg[k].n_entries, R, wlen, fast, hp);
       c.pad = t.n_entries;
       P += t.positions; R += t.ref_adv; D += t.ndel; nsub += t.nsub;
       prob += t.ended ? t.prob : seg[k].prob;  // a full tile's sum is the segment's own (same order, same value)
@@ -999,7 +1226,7 @@ PB_HD void qshmm_finish_segmented(uint16_t *ev_base, const SegResult *seg, uint3
   out.nsub = nsub;
   out.ndel = D;
   out.nins = P + D - R;
-  out.accuracy = 1.0 - (prob / (double)P);
+  out.accuracy = 1.0 - (((double)prob / (double)(1u << PB_PROB_SHIFT)) / (double)P);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1260,7 +1487,8 @@ PB_HD void errhmm_simulate_segment(const ErView &T, const PhiloxKeys &K, uint32_
   res.nsub = nsub;
   res.ndel = ndel;
   res.flags = (late && pzero_in) ? 32u : 0u;  // no read base in the first 512 columns: coupling assumptions void
-  res.prob = (double)nins;       // errhmm: the insertion count travels in the otherwise unused field
+  res.pad = 0;
+  res.prob = nins;               // errhmm: the insertion count travels in the otherwise unused field
 }
 
 struct ErTileWalk {

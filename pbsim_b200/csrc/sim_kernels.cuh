@@ -25,9 +25,11 @@ struct DeviceModel {
   const int32_t *prob2len;
   const uint8_t *prob2acc;
   uint32_t len_rand_value, acc_rand_value, len_min;
-  const uint32_t *qs_thr;     // [94*4]
+  const uint8_t *qs_tabs;     // [kQsTabBytes] thr 94*16 | qc_prob 94*8 | thr32 94*16 | fast 94*16 (one bulk copy)
   const uint32_t *qs_thr_hp;  // [94*12]
-  const double *qc_prob;      // [94]
+  const uint32_t *qs_thr_hp32;// [94*12] the same on the T32 scale (PHILOX mode)
+  const uint32_t *qs_thr32;   // [94*4]  = qs_tabs + kQsTabThr32
+  const QsFast *qs_fast;      // [94]    = qs_tabs + kQsTabFast
   const uint16_t *er_bias;
   uint32_t pass_num;
   uint32_t uniform_bias;
@@ -170,8 +172,9 @@ __global__ void k_plan(DeviceModel M, DeviceGenome G, DeviceSet S, RngParams rng
   if (segmented) cap = (uint64_t)nseg * (errm ? PB_TILE : PB_SEG_STRIDE) + 64u;
   cap = (cap + ev_align - 1u) / ev_align * ev_align;
   const uint32_t ckc = segmented ? nseg + 2u : (uint32_t)(cap / PB_TILE) + 2u;
+  // the quality pass walks EVERY provisioned segment (it writes the quality of every position)
   uint32_t nchunk = 0;
-  if (needs_chain && nseg > 1u) nchunk = ae.seg_ok ? (nseg - 1u + chain_chunk - 1u) / chain_chunk : 1u;
+  if (needs_chain && nseg > 0u) nchunk = ae.seg_ok ? (nseg + chain_chunk - 1u) / chain_chunk : 1u;
   for (uint32_t h = 0; h < M.pass_num; ++h) {
     const uint32_t s = r * M.pass_num + h;
     B.nchunk[s] = nchunk;
@@ -335,9 +338,18 @@ __device__ __forceinline__ void replay_setup(ReplayDraw &d, const RngParams &rng
 // K2: qshmm pass 1
 // shared memory: [table blob | thr 94*16 | qc_prob 94*8 | mbarrier]
 // ----------------------------------------------------------------------------------------------
+// the per-quality tables travel as one block (DeviceModel::qs_tabs): thr | qc_prob | thr32 | fast
+constexpr uint32_t kQsTabThr = 0;
+constexpr uint32_t kQsTabProb = kQsTabThr + PBSIM_NQV * 16;
+constexpr uint32_t kQsTabThr32 = kQsTabProb + PBSIM_NQV * 8;
+constexpr uint32_t kQsTabFast = kQsTabThr32 + PBSIM_NQV * 16;
+constexpr uint32_t kQsTabBytes = kQsTabFast + PBSIM_NQV * 16;
+static_assert(kQsTabBytes % 16 == 0, "bulk copy size");
 constexpr uint32_t kQsSmemThr = QsBlobLayout::bytes;
-constexpr uint32_t kQsSmemProb = kQsSmemThr + PBSIM_NQV * 16;
-constexpr uint32_t kQsSmemBar = kQsSmemProb + PBSIM_NQV * 8;
+constexpr uint32_t kQsSmemProb = kQsSmemThr + kQsTabProb;
+constexpr uint32_t kQsSmemThr32 = kQsSmemThr + kQsTabThr32;
+constexpr uint32_t kQsSmemFast = kQsSmemThr + kQsTabFast;
+constexpr uint32_t kQsSmemBar = kQsSmemThr + kQsTabBytes;
 constexpr uint32_t kQsSmemBytes = kQsSmemBar + 16;
 
 template <int RNG_MODE>
@@ -350,10 +362,9 @@ __global__ void __launch_bounds__(kSimThreads) k_sim_qshmm(SimArgs A) {
   if (threadIdx.x == 0) mbar_init(bar, 1);
   __syncthreads();
   if (threadIdx.x == 0) {
-    mbar_expect_tx(bar, ae.blob_bytes + PBSIM_NQV * 16 + PBSIM_NQV * 8);
+    mbar_expect_tx(bar, ae.blob_bytes + kQsTabBytes);
     tma_bulk_g2s(smem, A.M.blob + ae.blob_off, ae.blob_bytes, bar);
-    tma_bulk_g2s(smem + kQsSmemThr, A.M.qs_thr, PBSIM_NQV * 16, bar);
-    tma_bulk_g2s(smem + kQsSmemProb, A.M.qc_prob, PBSIM_NQV * 8, bar);
+    tma_bulk_g2s(smem + kQsSmemThr, A.M.qs_tabs, kQsTabBytes, bar);
   }
   mbar_wait(bar, 0);
 
@@ -379,6 +390,9 @@ __global__ void __launch_bounds__(kSimThreads) k_sim_qshmm(SimArgs A) {
   T.thr = reinterpret_cast<const QsThr *>(smem + kQsSmemThr);
   T.thr_hp = A.M.qs_thr_hp;
   T.qc_prob = reinterpret_cast<const double *>(smem + kQsSmemProb);
+  T.thr32 = reinterpret_cast<const QsThr *>(smem + kQsSmemThr32);
+  T.thr_hp32 = A.M.qs_thr_hp32;
+  T.fast = reinterpret_cast<const QsFast *>(smem + kQsSmemFast);
   WindowRef win;
   win.ascii = A.G.ascii;
   win.hp4 = A.G.hp4;
@@ -394,7 +408,7 @@ __global__ void __launch_bounds__(kSimThreads) k_sim_qshmm(SimArgs A) {
     if (!slow) {
       qshmm_simulate_fast(T, A.keys, (uint32_t)(A.B.first_read + 1u + r), pass, wlen, sink.ev, sink.ck, sink.cap, res);
     } else {
-      PhiloxDraw d;
+      PhiloxDrawQ d;
       d.ph.k0 = A.rng.seed;
       d.ph.k1 = A.G.seq_num;
       d.read_id = (uint32_t)(A.B.first_read + 1u + r);
@@ -561,8 +575,8 @@ __global__ void k_sample_redo(Batch B, unsigned long long *n_redo) {
   B.idx_in[r] = r;
 }
 
-// shared memory: [thr 94*16 | qc_prob 94*8]
-constexpr uint32_t kSampleSmemBytes = PBSIM_NQV * 16 + PBSIM_NQV * 8;
+// shared memory: the per-quality tables (thr | qc_prob | thr32 | fast)
+constexpr uint32_t kSampleSmemBytes = kQsTabBytes;
 
 template <int RNG_MODE>
 __global__ void __launch_bounds__(kSimThreads) k_sim_sample(SimArgs A, DevicePool Pl, SampleBatch SB,
@@ -572,9 +586,8 @@ __global__ void __launch_bounds__(kSimThreads) k_sim_sample(SimArgs A, DevicePoo
   if (!cta_assignment(A.cta_order, A.cta_first, A.bin_lo, A.bin_hi, &acc, &lo, &hi)) return;
   {
     uint32_t *d = reinterpret_cast<uint32_t *>(smem);
-    for (uint32_t i = threadIdx.x; i < PBSIM_NQV * 4u; i += blockDim.x) d[i] = A.M.qs_thr[i];
-    double *q = reinterpret_cast<double *>(smem + PBSIM_NQV * 16);
-    for (uint32_t i = threadIdx.x; i < PBSIM_NQV; i += blockDim.x) q[i] = A.M.qc_prob[i];
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(A.M.qs_tabs);
+    for (uint32_t i = threadIdx.x; i < kQsTabBytes / 4u; i += blockDim.x) d[i] = src[i];
   }
   __syncthreads();
   const uint32_t k = lo + threadIdx.x;
@@ -590,15 +603,18 @@ __global__ void __launch_bounds__(kSimThreads) k_sim_sample(SimArgs A, DevicePoo
   T.has_model = 0;
   T.init_mod = 1;
   T.freq_mod = 1;
-  T.thr = reinterpret_cast<const QsThr *>(smem);
+  T.thr = reinterpret_cast<const QsThr *>(smem + kQsTabThr);
   T.thr_hp = A.M.qs_thr_hp;
-  T.qc_prob = reinterpret_cast<const double *>(smem + PBSIM_NQV * 16);
+  T.qc_prob = reinterpret_cast<const double *>(smem + kQsTabProb);
+  T.thr32 = reinterpret_cast<const QsThr *>(smem + kQsTabThr32);
+  T.thr_hp32 = A.M.qs_thr_hp32;
+  T.fast = reinterpret_cast<const QsFast *>(smem + kQsTabFast);
   uint32_t len = (uint32_t)(Pl.start[j + 1] - Pl.start[j]);
   if (from_prev) len = A.B.rlen[r0 - 1u];  // the buffer was cut where the previous copy's read ended
   for (uint32_t i = 0; i < num; ++i) {
     const uint32_t r = r0 + i;
     const uint32_t read_id = (uint32_t)(A.B.first_read + 1u + r);
-    PhiloxDraw pd;
+    PhiloxDrawQ pd;
     ReplayDraw rd;
     uint32_t offset = 0;
     if (RNG_MODE == PBSIM_RNG_PHILOX) {

@@ -45,36 +45,22 @@ static bool run_segmented(const pb::QsView &T, const pb::QsSegAux &A, uint32_t s
   const uint32_t n_seg = pb::qshmm_segments_for(wlen, rho);
   std::vector<uint16_t> slots((size_t)n_seg * PB_SEG_STRIDE + 16, 0);
   std::vector<pb::SegResult> seg(n_seg);
-  std::vector<uint32_t> seg_state(n_seg + 1, 0);
-  bool from_chunks = false;
-  if (T.has_model && chain_chunk > 0 && n_seg > 1) {  // k_chain_chunk
-    const uint32_t n_ch = seg_ok ? (n_seg - 1u + (uint32_t)chain_chunk - 1u) / (uint32_t)chain_chunk : 1u;
-    const uint32_t per = n_ch == 1u ? n_seg : (uint32_t)chain_chunk;
+  if (T.has_model) {  // k_chain_chunk: the quality pass, one "thread" per chunk of segments
+    const uint32_t cc = chain_chunk > 0 ? (uint32_t)chain_chunk : 1u;
+    const uint32_t n_ch = seg_ok ? (n_seg + cc - 1u) / cc : 1u;
+    const uint32_t per = n_ch == 1u ? n_seg : cc;
     for (uint32_t c = 0; c < n_ch; ++c) {
-      const uint32_t k_from = c * per, k_to = std::min(k_from + per, n_seg - 1u);
+      const uint32_t k_from = c * per, k_to = std::min(k_from + per, n_seg);
       uint32_t row = 0, mod = T.init_mod, emod = 1;
       if (k_from > 0) pb::qshmm_segment_start(T, A, K, read_id, pass, k_from * PB_TILE, first_window ? first_window : 512u, row, mod, emod);
-      pb::qshmm_chain_range(T, K, read_id, pass, row, mod, emod, k_from, k_to, seg_state.data());
+      pb::qshmm_quality_range(T, K, read_id, pass, row, mod, emod, k_from, k_to, slots.data());
     }
-    from_chunks = true;
-  } else if (T.has_model && !seg_ok) {
-    pb::qshmm_chain_only(T, K, read_id, pass, n_seg, seg_state.data());
   }
-  for (uint32_t k = 0; k < n_seg; ++k) {
-    uint32_t row = 0, mod = T.init_mod, emod = 1;
-    if (k > 0 && T.has_model) {
-      if (!seg_ok || from_chunks) {
-        row = seg_state[k] & 0xFFFFu; mod = (seg_state[k] >> 16) & 0xFFu; emod = seg_state[k] >> 24;
-      } else if (!pb::qshmm_segment_start(T, A, K, read_id, pass, k * PB_TILE, first_window, row, mod, emod)) {
-        return false;
-      }
-    }
-    pb::qshmm_simulate_segment(T, K, read_id, pass, k * PB_TILE, k == 0, row, mod, emod, slots.data() + (size_t)k * PB_SEG_STRIDE,
-                               seg[k]);
-  }
+  for (uint32_t k = 0; k < n_seg; ++k)  // k_sim_seg: the error pass, one "warp" per segment
+    pb::qshmm_error_segment(T, K, read_id, pass, k * PB_TILE, k == 0, slots.data() + (size_t)k * PB_SEG_STRIDE, seg[k]);
   std::vector<pb::Ckpt> ck(n_seg);
   pb::SegRead sr;
-  pb::qshmm_finish_segmented(slots.data(), seg.data(), n_seg, wlen, T.qc_prob, hp, ck.data(), sr);
+  pb::qshmm_finish_segmented(slots.data(), seg.data(), n_seg, wlen, T.fast, hp, ck.data(), sr);
   if (sr.flags) return false;
   if (hp.enabled) {
     // what pass 2 does in PHILOX mode: the 4-way choice of a substitution on a non-ACGT base is recomputed from
@@ -86,9 +72,9 @@ static bool run_segmented(const pb::QsView &T, const pb::QsSegAux &A, uint32_t s
         const uint32_t v = e[i], kind = (v >> 7) & 3u;
         if (kind == 3u) { R += (v & 0x7Fu) | ((v >> 9) << 7); continue; }
         if (kind == PB_KIND_SUB && hp.win.nonacgt(R)) {
-          uint32_t w[4];
-          pb::philox_block_keys(K, P, pass << 16, read_id, 1u, w);
-          e[i] = (uint16_t)((v & ~(7u << 9)) | (((w[0] >> 12) & 3u) << 9));
+          uint32_t x, y;
+          pb::error_words_at(K, read_id, pass << 16, P, x, y);
+          e[i] = (uint16_t)((v & ~(7u << 9)) | (((y >> 3) & 3u) << 9));
         }
         R += (kind == PB_KIND_INS ? 0u : 1u) + (v >> 12);
         ++P;
@@ -184,6 +170,10 @@ long hostsim_run(const pbsim_model *m, const uint8_t *ascii_upper, const int16_t
         T.freq = b;
         T.has_model = ae.has_model; T.init_mod = ae.init_mod; T.freq_mod = ae.freq_mod;
         T.thr = reinterpret_cast<const pb::QsThr *>(img.qs_thr.data()); T.thr_hp = img.qs_thr_hp.data(); T.qc_prob = m->qc_prob;
+        T.thr32 = reinterpret_cast<const pb::QsThr *>(img.qs_thr32.data()); T.thr_hp32 = img.qs_thr_hp32.data();
+        T.fast = reinterpret_cast<const pb::QsFast *>(img.qs_fast.data());
+        pb::PhiloxDrawQ pq;
+        pq.ph.k0 = seed; pq.ph.k1 = (uint32_t)seq_num; pq.read_id = (uint32_t)read_id; pq.pass = (uint32_t)pass;
         pb::QsSink sink;
         sink.init(reinterpret_cast<uint16_t *>(g_out.events.data() + ev_off), g_out.ckpts.data() + ck_base, cap);
         bool seg_done = false;
@@ -209,7 +199,7 @@ long hostsim_run(const pbsim_model *m, const uint8_t *ascii_upper, const int16_t
           K.init(seed, (uint32_t)seq_num);
           pb::qshmm_simulate_fast(T, K, (uint32_t)read_id, (uint32_t)pass, plan.wlen,
                                   reinterpret_cast<uint16_t *>(g_out.events.data() + ev_off), g_out.ckpts.data() + ck_base, cap, res);
-        } else if (rng_mode == PBSIM_RNG_PHILOX) { pd.pass = (uint32_t)pass; pd.cidx = 0xFFFFFFFFu; pb::qshmm_simulate(T, pd, win, slow, plan.wlen, sink, res); }
+        } else if (rng_mode == PBSIM_RNG_PHILOX) { pb::qshmm_simulate(T, pq, win, slow, plan.wlen, sink, res); }
         else { rd.cur = cursor; pb::qshmm_simulate(T, rd, win, slow, plan.wlen, sink, res); cursor = rd.cur; }
         if (!seg_done) g_out.events.resize(ev_off + (size_t)res.n_entries * 2);
       } else {
@@ -344,6 +334,9 @@ long hostsim_run_sample(const pbsim_model *m, const uint8_t *ascii_upper, const 
   T.thr = reinterpret_cast<const pb::QsThr *>(img.qs_thr.data());
   T.thr_hp = img.qs_thr_hp.data();
   T.qc_prob = m->qc_prob;
+  T.thr32 = reinterpret_cast<const pb::QsThr *>(img.qs_thr32.data());
+  T.thr_hp32 = img.qs_thr_hp32.data();
+  T.fast = reinterpret_cast<const pb::QsFast *>(img.qs_fast.data());
   pb::SampleSchedule S;
   if (!S.init(len_quota, n, qstart)) return -3;
   long long len_total = 0;
@@ -364,7 +357,7 @@ long hostsim_run_sample(const pbsim_model *m, const uint8_t *ascii_upper, const 
       uint32_t len = (uint32_t)(qstart[j + 1] - qstart[j]);
       for (uint32_t i = G.first[g]; i < G.first[g + 1]; ++i) {
         const long read_id = reads_done + 1 + i;
-        pb::PhiloxDraw pd;
+        pb::PhiloxDrawQ pd;
         pb::ReplayDraw rd;
         const int64_t draw_start = cursor;
         uint32_t offset = 0;

@@ -26,7 +26,7 @@ def test_header_symbols_are_exported(lib):
     for n in names:
         assert hasattr(lib, n), n
     assert set(names) == set(capi.HOST_EXPORTS + capi.ENGINE_EXPORTS)
-    assert lib.pbsim_cuda_abi_version() == 3
+    assert lib.pbsim_cuda_abi_version() == 4
 
 
 def test_header_is_plain_c(tmp_path):
