@@ -591,6 +591,292 @@ __device__ __forceinline__ void emit_tile_fast(const uint8_t *__restrict__ evbas
   }
 }
 
+// ---- staged tile path -----------------------------------------------------------------------
+// The four per-base rows of a tile (read bases, qualities, MAF reference row, MAF read row) are contiguous
+// fragments of the records (the MAF fragments of a minus-strand read run backwards, but they are still one
+// range each).  The warp builds them in shared memory and then copies every fragment to HBM with 16-byte
+// stores: the staging buffer of a row starts at the same offset modulo 16 as its destination, so aligned
+// chunks of the record are aligned chunks of the buffer; only the first and last chunk of a fragment (shared
+// with the neighbouring tiles) are written bytewise.  The window bases of the tile are staged first as 2-bit
+// codes in WINDOW order (reversed and complemented for the minus strand), so a lane gets the 16 bases that
+// follow its first entry with two shared-memory loads and a funnel shift.
+constexpr uint32_t kStageCols = 1280;   // MAF columns a tile may have on this path (more: direct path)
+struct EmitStage {
+  uint8_t seq[PB_TILE + 32];
+  uint8_t qual[PB_TILE + 32];
+  uint8_t mref[kStageCols + 32];
+  uint8_t mread[kStageCols + 32];
+  uint32_t pk[kStageCols / 16 + 8];
+};
+static_assert(sizeof(EmitStage) % 16 == 0, "staging rows stay 16-byte aligned");
+
+// window codes of window positions r0 + 16 j .. r0 + 16 j + 15 (2 bits each, position r0 + 16 j in bits 0-1)
+__device__ __forceinline__ uint32_t window_word(const uint32_t *__restrict__ pk, uint32_t offset, uint32_t wlen,
+                                                uint32_t minus, uint32_t glen_words, uint32_t r) {
+  if (!minus) {
+    const uint32_t g = offset + r;
+    const uint32_t w = g >> 4, sh = (g & 15u) * 2u;
+    const uint32_t lo = __ldg(&pk[w]);
+    const uint32_t hi = (w + 1u < glen_words) ? __ldg(&pk[w + 1u]) : 0u;
+    return __funnelshift_r(lo, hi, sh);
+  }
+  // minus strand: window position r is genome position offset + wlen - 1 - r, complemented.  The 16 positions
+  // r .. r+15 are the genome positions gh-15 .. gh in reverse order.
+  const int64_t gh = (int64_t)offset + (int64_t)wlen - 1 - (int64_t)r;   // genome position of window position r
+  const int64_t gl = gh - 15;                                            // may lie before the window (never read)
+  uint32_t x;
+  if (gl >= 0) {
+    const uint32_t g = (uint32_t)gl;
+    const uint32_t w = g >> 4, sh = (g & 15u) * 2u;
+    const uint32_t lo = __ldg(&pk[w]);
+    const uint32_t hi = (w + 1u < glen_words) ? __ldg(&pk[w + 1u]) : 0u;
+    x = __funnelshift_r(lo, hi, sh);
+  } else {
+    if (gh < 0) return 0u;
+    x = __ldg(&pk[0]) << (uint32_t)(-gl * 2);                            // genome positions 0 .. gh in the top fields
+  }
+  x = __brev(x);                                                         // reverse the 16 fields ...
+  x = ((x & 0x55555555u) << 1) | ((x >> 1) & 0x55555555u);               // ... keeping the bit order inside a field
+  return ~x;                                                             // complement: code ^ 3
+}
+
+// copy `n` staged bytes to g; buf[shift + i] holds byte i and (g - shift) is 16-byte aligned.  Whole 16-byte
+// chunks go out as vectors; the bytes of the partial first and last chunk one per lane.
+__device__ __forceinline__ void flush_row(const uint8_t *buf, uint8_t *__restrict__ g, uint32_t n, uint32_t shift,
+                                          uint32_t lane) {
+  const uint32_t total = shift + n;
+  uint8_t *g0 = g - shift;
+  const uint32_t body_lo = shift ? 16u : 0u, body_hi = total & ~15u;   // [body_lo, body_hi): whole chunks (if any)
+  for (uint32_t lo = body_lo + lane * 16u; lo < body_hi; lo += 512u)
+    *reinterpret_cast<uint4 *>(g0 + lo) = *reinterpret_cast<const uint4 *>(buf + lo);
+  const uint32_t head_end = shift ? (total < 16u ? total : 16u) : 0u;  // head: bytes [shift, head_end)
+  uint32_t tail_start = body_hi > body_lo ? body_hi : body_lo;         // tail: bytes [tail_start, total)
+  if (tail_start < head_end) tail_start = head_end;
+  if (shift + lane < head_end) g0[shift + lane] = buf[shift + lane];
+  if (tail_start + lane < total) g0[tail_start + lane] = buf[tail_start + lane];
+}
+
+// byte LUTs of the staged path, index = (kind | info << 2) << 2 | window code of the current reference base
+// (kind 3 = errhmm deletion column).  seq: the read base; mread / mref: the MAF characters for the plus ([0]) and
+// the minus strand ([1], complemented because the rows are mirrored back).
+struct EmitLuts {
+  uint8_t seq[128];
+  uint8_t mread[2][128];
+  uint8_t mref[2][128];
+};
+__device__ __forceinline__ void build_emit_luts(EmitLuts &L, uint32_t t) {  // t = 0 .. 127
+  const uint32_t wc = t & 3u, kind = (t >> 2) & 3u, info = (t >> 4) & 7u;
+  const uint32_t rc = read_code(kind == 3u ? 0u : kind, info, wc);
+  L.seq[t] = code_char(rc);
+  for (uint32_t f = 0; f < 2u; ++f) {
+    const uint32_t flip = f ? 3u : 0u;
+    L.mread[f][t] = kind == 3u ? (uint8_t)'-' : code_char(rc ^ flip);
+    L.mref[f][t] = kind == PB_KIND_INS ? (uint8_t)'-' : code_char(wc ^ flip);
+  }
+}
+
+// One tile whose reference range holds only ACGT, text records.  Pn / Cn / Rn: read bases, MAF columns and window
+// bases of the tile (Cn <= kStageCols, Pn <= PB_TILE).
+template <int METHOD>
+__device__ __forceinline__ void emit_tile_staged(EmitStage &S, const EmitLuts &LU, const uint8_t *__restrict__ evbase,
+                                                 uint32_t e0, uint32_t e1, const uint32_t *__restrict__ pk,
+                                                 uint32_t glen_words, uint32_t offset, uint32_t wlen, uint32_t minus,
+                                                 uint32_t ncol, uint32_t C0, uint32_t R0, uint32_t P0, uint32_t Pn,
+                                                 uint32_t Cn, uint32_t Rn, uint8_t *__restrict__ seq,
+                                                 uint8_t *__restrict__ qual, uint8_t *__restrict__ mref,
+                                                 uint8_t *__restrict__ mread, uint32_t lane) {
+  // destinations of the four fragments and the offsets (modulo 16) their staging rows start at
+  uint8_t *g_seq = seq + P0, *g_qual = qual + P0;
+  const uint32_t cfirst = minus ? ncol - C0 - Cn : C0;   // first MAF column (in file order) of the tile
+  uint8_t *g_ref = mref + cfirst, *g_read = mread + cfirst;
+  const uint32_t sh_s = (uint32_t)(reinterpret_cast<uintptr_t>(g_seq) & 15u);
+  const uint32_t sh_q = (uint32_t)(reinterpret_cast<uintptr_t>(g_qual) & 15u);
+  const uint32_t sh_r = (uint32_t)(reinterpret_cast<uintptr_t>(g_ref) & 15u);
+  const uint32_t sh_m = (uint32_t)(reinterpret_cast<uintptr_t>(g_read) & 15u);
+  // staging addresses: column c of the tile lives at cbase + c * cdir (the minus strand's rows run backwards)
+  uint8_t *const b_seq = S.seq + sh_s, *const b_qual = S.qual + sh_q;
+  const int32_t cdir = minus ? -1 : 1;
+  uint8_t *const b_ref = S.mref + sh_r + (minus ? Cn - 1u : 0u), *const b_read = S.mread + sh_m + (minus ? Cn - 1u : 0u);
+  const uint8_t *const l_seq = LU.seq, *const l_read = LU.mread[minus], *const l_ref = LU.mref[minus];
+  // ---- window codes of the tile: positions R0 .. R0 + Rn (an insertion at the end looks at R0 + Rn) + 16 spare
+  const uint32_t nw = (Rn + 16u) / 16u + 1u;
+  for (uint32_t j = lane; j < nw; j += 32u) S.pk[j] = window_word(pk, offset, wlen, minus, glen_words, R0 + 16u * j);
+  __syncwarp();
+  auto load_entries = [&](uint32_t i) -> uint2 {
+    const uint32_t eb = i + lane * kEmitPerLane;
+    if (METHOD == PBSIM_METHOD_QSHMM) return __ldg(reinterpret_cast<const uint2 *>(evbase + 2ull * eb));
+    return make_uint2(__ldg(reinterpret_cast<const uint32_t *>(evbase + eb)), 0u);
+  };
+  auto codes_at = [&](uint32_t r) -> uint32_t {   // the 16 window bases from tile-relative position r on
+    return __funnelshift_r(S.pk[r >> 4], S.pk[(r >> 4) + 1u], (r & 15u) * 2u);
+  };
+  uint32_t Pt = 0, Rt = 0, Ct = 0;   // tile-relative totals so far
+  uint2 nxt = load_entries(e0);
+  for (uint32_t i = e0; i < e1; i += kEmitStep) {
+    const uint32_t eb = i + lane * kEmitPerLane;
+    const uint2 v = nxt;
+    if (i + kEmitStep < e1) nxt = load_entries(i + kEmitStep);
+    uint32_t raw[kEmitPerLane];
+    if (METHOD == PBSIM_METHOD_QSHMM) {
+      raw[0] = v.x & 0xFFFFu; raw[1] = v.x >> 16; raw[2] = v.y & 0xFFFFu; raw[3] = v.y >> 16;
+    } else {
+      raw[0] = v.x & 0xFFu; raw[1] = (v.x >> 8) & 0xFFu; raw[2] = (v.x >> 16) & 0xFFu; raw[3] = v.x >> 24;
+    }
+    // common case: 128 valid entries, none of them a continuation entry
+    bool plain = i + kEmitStep <= e1;
+    if (METHOD == PBSIM_METHOD_QSHMM)
+      plain = plain && !__any_sync(0xFFFFFFFFu, ((v.x & (v.x >> 1)) | (v.y & (v.y >> 1))) & 0x00800080u);  // kind == 3
+    if (plain) {
+      // ---- lane totals: insertions (no reference advance) and deletions of its four entries
+      uint32_t li = 0, ld = 0;
+      uint32_t idx[kEmitPerLane], nd[kEmitPerLane];
+#pragma unroll
+      for (uint32_t k = 0; k < kEmitPerLane; ++k) {
+        if (METHOD == PBSIM_METHOD_QSHMM) {
+          idx[k] = (raw[k] >> 5) & 0x7Cu;       // (kind | info << 2) << 2
+          nd[k] = raw[k] >> 12;
+          li += (raw[k] >> 8) & 1u;             // kind 2
+          ld += nd[k];
+        } else {
+          idx[k] = (raw[k] & 0x1Fu) << 2;
+          nd[k] = ((raw[k] & 3u) == PB_KIND_DEL) ? 1u : 0u;
+          li += ((raw[k] & 3u) == PB_KIND_INS) ? 1u : 0u;
+          ld += nd[k];
+        }
+      }
+      const uint32_t mine = li | (ld << 8);     // <= 128 insertions, <= kStageCols deletions per iteration
+      uint32_t x = mine;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o);
+        if (lane >= (uint32_t)o) x += y;
+      }
+      const uint32_t tot = __shfl_sync(0xFFFFFFFFu, x, 31);
+      const uint32_t pre = x - mine;
+      const uint32_t pre_i = pre & 0xFFu, pre_d = pre >> 8;
+      uint32_t Pp, Rr, Cc;
+      if (METHOD == PBSIM_METHOD_QSHMM) {       // an entry is a read base (+ deletions behind it)
+        Pp = Pt + lane * kEmitPerLane;
+        Rr = Rt + lane * kEmitPerLane - pre_i + pre_d;
+        Cc = Ct + lane * kEmitPerLane + pre_d;
+      } else {                                  // an entry is an alignment column
+        Cc = Ct + lane * kEmitPerLane;
+        Rr = Rt + lane * kEmitPerLane - pre_i;
+        Pp = Pt + lane * kEmitPerLane - pre_d;
+      }
+      uint32_t bits = codes_at(Rr), bbase = Rr;
+      uint8_t *pc_ref = b_ref + (int32_t)Cc * cdir, *pc_read = b_read + (int32_t)Cc * cdir;
+#pragma unroll
+      for (uint32_t k = 0; k < kEmitPerLane; ++k) {
+        if (Rr - bbase > 15u) { bits = codes_at(Rr); bbase = Rr; }   // (a lane with many deletions)
+        const uint32_t t = idx[k] | ((bits >> ((Rr - bbase) * 2u)) & 3u);
+        if (METHOD == PBSIM_METHOD_QSHMM) {
+          b_seq[Pp] = l_seq[t];
+          b_qual[Pp] = (uint8_t)((raw[k] & 0x7Fu) + 33u);
+          *pc_read = l_read[t];
+          *pc_ref = l_ref[t];
+          ++Pp;
+          pc_read += cdir;
+          pc_ref += cdir;
+          Rr += 1u - ((raw[k] >> 8) & 1u);
+          if (nd[k]) {                          // deleted reference bases behind the entry: mostly one
+            for (uint32_t j = 0; j < nd[k]; ++j) {
+              if (Rr - bbase > 15u) { bits = codes_at(Rr); bbase = Rr; }
+              *pc_read = '-';
+              *pc_ref = l_ref[(bits >> ((Rr - bbase) * 2u)) & 3u];   // index of a match on that base
+              pc_read += cdir;
+              pc_ref += cdir;
+              ++Rr;
+            }
+          }
+        } else {
+          const bool isb = nd[k] == 0u;
+          if (isb) {
+            b_seq[Pp] = l_seq[t];
+            b_qual[Pp] = '!';
+          }
+          *pc_read = l_read[t];
+          *pc_ref = l_ref[t];
+          pc_read += cdir;
+          pc_ref += cdir;
+          Pp += isb ? 1u : 0u;
+          Rr += ((raw[k] & 3u) == PB_KIND_INS) ? 0u : 1u;
+        }
+      }
+      const uint32_t tot_i = tot & 0xFFu, tot_d = tot >> 8;
+      if (METHOD == PBSIM_METHOD_QSHMM) {
+        Pt += kEmitStep; Rt += kEmitStep - tot_i + tot_d; Ct += kEmitStep + tot_d;
+      } else {
+        Ct += kEmitStep; Rt += kEmitStep - tot_i; Pt += kEmitStep - tot_d;
+      }
+      continue;
+    }
+    // ---- general iteration: entries past the end of the tile, continuation entries
+    uint32_t kind[kEmitPerLane], info[kEmitPerLane], nd[kEmitPerLane], isb[kEmitPerLane], adv[kEmitPerLane];
+    uint32_t lb = 0, la = 0, ld = 0;
+#pragma unroll
+    for (uint32_t k = 0; k < kEmitPerLane; ++k) {
+      const bool valid = eb + k < e1;
+      const uint32_t x = raw[k];
+      if (METHOD == PBSIM_METHOD_QSHMM) {
+        kind[k] = (x >> 7) & 3u;
+        info[k] = (x >> 9) & 7u;
+        const bool cont = kind[k] == 3u;
+        nd[k] = valid ? (cont ? ((x & 0x7Fu) | ((x >> 9) << 7)) : (x >> 12)) : 0u;
+        isb[k] = (valid && !cont) ? 1u : 0u;
+      } else {
+        kind[k] = x & 3u;
+        info[k] = (x >> 2) & 7u;
+        nd[k] = (valid && kind[k] == PB_KIND_DEL) ? 1u : 0u;
+        isb[k] = (valid && kind[k] != PB_KIND_DEL) ? 1u : 0u;
+      }
+      adv[k] = (isb[k] && kind[k] != PB_KIND_INS) ? 1u : 0u;
+      lb += isb[k];
+      la += adv[k];
+      ld += nd[k];
+    }
+    // one warp scan over the packed per-lane totals: bases (8 bit) | advances (8 bit) | deletions (16 bit);
+    // Cn <= kStageCols bounds every count of the tile, so the packed fields cannot overflow
+    const uint32_t mine = lb | (la << 8) | (ld << 16);
+    uint32_t x = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o);
+      if (lane >= (uint32_t)o) x += y;
+    }
+    const uint32_t tot = __shfl_sync(0xFFFFFFFFu, x, 31);
+    const uint32_t pre = x - mine;
+    uint32_t Pp = Pt + (pre & 0xFFu), Rr = Rt + ((pre >> 8) & 0xFFu) + (pre >> 16), Cc = Ct + (pre & 0xFFu) + (pre >> 16);
+    for (uint32_t k = 0; k < kEmitPerLane; ++k) {
+      if (isb[k]) {
+        const uint32_t t = ((kind[k] | (info[k] << 2)) << 2) | (codes_at(Rr) & 3u);
+        b_seq[Pp] = l_seq[t];
+        b_qual[Pp] = METHOD == PBSIM_METHOD_QSHMM ? (uint8_t)((raw[k] & 0x7Fu) + 33u) : (uint8_t)'!';
+        b_read[(int32_t)Cc * cdir] = l_read[t];
+        b_ref[(int32_t)Cc * cdir] = l_ref[t];
+        ++Pp;
+        ++Cc;
+        Rr += adv[k];
+      }
+      for (uint32_t j = 0; j < nd[k]; ++j) {
+        b_read[(int32_t)Cc * cdir] = '-';
+        b_ref[(int32_t)Cc * cdir] = l_ref[codes_at(Rr) & 3u];
+        ++Cc;
+        ++Rr;
+      }
+    }
+    Pt += tot & 0xFFu;
+    Rt += ((tot >> 8) & 0xFFu) + (tot >> 16);
+    Ct += (tot & 0xFFu) + (tot >> 16);
+  }
+  __syncwarp();
+  flush_row(S.seq, g_seq, Pn, sh_s, lane);
+  flush_row(S.qual, g_qual, Pn, sh_q, lane);
+  flush_row(S.mref, g_ref, Cn, sh_r, lane);
+  flush_row(S.mread, g_read, Cn, sh_m, lane);
+  __syncwarp();
+}
+
 // generic tile path: reads the ASCII copy where the tile touches non-ACGT bases; one entry per lane
 template <int METHOD, bool BAM>
 __device__ __noinline__ void emit_tile_generic(const uint8_t *evbase, uint32_t e0, uint32_t e1, const RefFetch &rf,
@@ -692,7 +978,12 @@ __global__ void k_tile_map(const uint64_t *__restrict__ tile_start, uint32_t n_s
 template <int METHOD, bool BAM>
 __global__ void __launch_bounds__(kEmitThreads) k_emit(EmitArgs A) {
   __shared__ uint8_t lut_s[128];
-  if (threadIdx.x < 128u) lut_s[threadIdx.x] = (uint8_t)read_code((threadIdx.x >> 5) & 3u, (threadIdx.x >> 2) & 7u, threadIdx.x & 3u);
+  __shared__ __align__(16) EmitStage stage[BAM ? 1 : kEmitWarps];
+  __shared__ EmitLuts luts;
+  if (threadIdx.x < 128u) {
+    lut_s[threadIdx.x] = (uint8_t)read_code((threadIdx.x >> 5) & 3u, (threadIdx.x >> 2) & 7u, threadIdx.x & 3u);
+    build_emit_luts(luts, threadIdx.x);
+  }
   __syncthreads();
   const uint32_t lane = threadIdx.x & 31u;
   const uint64_t warp0 = (uint64_t)blockIdx.x * kEmitWarps + (threadIdx.x >> 5);
@@ -733,7 +1024,14 @@ __global__ void __launch_bounds__(kEmitThreads) k_emit(EmitArgs A) {
     uint8_t *mref = mf + L.refrow_rel, *mread = mf + L.readrow_rel;
     const uint8_t *evbase = A.ev + (A.B.ev_off[s] + (segmented ? (uint64_t)tile * PB_SEG_STRIDE : 0ull)) *
                                        (METHOD == PBSIM_METHOD_QSHMM ? 2ull : 1ull);
-    if (!slow) {
+    // what the tile covers: read bases, MAF columns, window bases (up to the next tile's checkpoint / the read's end)
+    const uint32_t Pn = (has_next ? ckp[tile + 1].read : rlen) - c0.read;
+    const uint32_t Cn = (has_next ? ckp[tile + 1].col : ncol) - c0.col;
+    if (!slow && !BAM && Cn <= kStageCols && Pn <= PB_TILE) {
+      emit_tile_staged<METHOD>(stage[BAM ? 0 : (threadIdx.x >> 5)], luts, evbase, e0, e1, A.G.pk, (A.G.len + 15u) / 16u,
+                               offset, wlen, minus, ncol, c0.col, c0.ref, c0.read, Pn, Cn, Rnext - c0.ref, seq, qual, mref,
+                               mread, lane);
+    } else if (!slow) {
       emit_tile_fast<METHOD, BAM>(evbase, e0, e1, A.G.pk, offset, wlen, minus, ncol, c0.col, c0.ref, c0.read, seq, qual, mref,
                              mread, lane, lut_s);
     } else {
