@@ -80,7 +80,8 @@ struct EmitArgs {
   uint32_t n_sub;              // valid subreads (after the quota cut)
   uint64_t n_tiles;
   const uint64_t *tile_start;  // [n_sub + 1]
-  const uint32_t *tile_sub;    // [n_tiles] sub-read of a tile (k_tile_map)
+  const uint32_t *tile_sub;    // [n_tiles] sub-read of a tile (k_tile_desc)
+  struct TileDesc *desc;       // [n_tiles] everything pass 2 needs to know about a tile (k_tile_desc)
   const EmitLay *lay;          // [n_sub] row positions inside the records (k_sizes)
   const uint64_t *reads_off;   // [n_sub + 1]
   const uint64_t *maf_off;     // [n_sub + 1]
@@ -591,6 +592,21 @@ __device__ __forceinline__ void emit_tile_fast(const uint8_t *__restrict__ evbas
   }
 }
 
+// Everything the row kernel needs to know about a tile, gathered once by k_tile_desc (one THREAD per tile: the
+// dependent loads through tile -> sub-read -> plan / layout / checkpoints run with full memory-level parallelism
+// there instead of as a serial prologue in front of every tile).
+struct TileDesc {
+  uint64_t ev_off;          // byte offset of the tile's first entry in the event arena
+  uint64_t o_seq, o_qual;   // byte offsets in the reads stream of the tile's first read base / quality
+  uint64_t o_ref, o_read;   // byte offsets in the MAF stream of the tile's first column (file order) in both rows
+  uint32_t e1;              // entries of the tile
+  uint32_t Pn, Cn, Rn;      // read bases, MAF columns and window bases it covers
+  uint32_t wpos;            // genome index of the tile's first window base (the minus strand walks down from it)
+  uint32_t flags;           // kTile*
+};
+static_assert(sizeof(TileDesc) == 64, "four 16-byte loads");
+constexpr uint32_t kTileMinus = 1u, kTileGeneric = 2u, kTileWide = 4u, kTileEmpty = 8u;
+
 // ---- staged tile path -----------------------------------------------------------------------
 // The four per-base rows of a tile (read bases, qualities, MAF reference row, MAF read row) are contiguous
 // fragments of the records (the MAF fragments of a minus-strand read run backwards, but they are still one
@@ -604,26 +620,18 @@ constexpr uint32_t kStageCols = 1280;   // MAF columns a tile may have on this p
 struct EmitStage {
   uint8_t seq[PB_TILE + 32];
   uint8_t qual[PB_TILE + 32];
-  uint8_t mref[kStageCols + 32];
-  uint8_t mread[kStageCols + 32];
+  uint8_t mref[kStageCols + 48];
+  uint8_t mread[kStageCols + 48];
   uint32_t pk[kStageCols / 16 + 8];
 };
 static_assert(sizeof(EmitStage) % 16 == 0, "staging rows stay 16-byte aligned");
 
-// window codes of window positions r0 + 16 j .. r0 + 16 j + 15 (2 bits each, position r0 + 16 j in bits 0-1)
-__device__ __forceinline__ uint32_t window_word(const uint32_t *__restrict__ pk, uint32_t offset, uint32_t wlen,
-                                                uint32_t minus, uint32_t glen_words, uint32_t r) {
-  if (!minus) {
-    const uint32_t g = offset + r;
-    const uint32_t w = g >> 4, sh = (g & 15u) * 2u;
-    const uint32_t lo = __ldg(&pk[w]);
-    const uint32_t hi = (w + 1u < glen_words) ? __ldg(&pk[w + 1u]) : 0u;
-    return __funnelshift_r(lo, hi, sh);
-  }
-  // minus strand: window position r is genome position offset + wlen - 1 - r, complemented.  The 16 positions
-  // r .. r+15 are the genome positions gh-15 .. gh in reverse order.
-  const int64_t gh = (int64_t)offset + (int64_t)wlen - 1 - (int64_t)r;   // genome position of window position r
-  const int64_t gl = gh - 15;                                            // may lie before the window (never read)
+// window codes of the 16 window positions from tile-relative position r on (2 bits each, position r in bits 0-1);
+// wpos: genome index of the tile's window position 0
+__device__ __forceinline__ uint32_t window_word(const uint32_t *__restrict__ pk, uint32_t wpos, uint32_t minus,
+                                                uint32_t glen_words, uint32_t r) {
+  // plus strand: genome positions wpos + r .. + 15; minus strand: wpos - r - 15 .. wpos - r, reversed and complemented
+  const int64_t gl = minus ? (int64_t)wpos - (int64_t)r - 15 : (int64_t)wpos + (int64_t)r;
   uint32_t x;
   if (gl >= 0) {
     const uint32_t g = (uint32_t)gl;
@@ -632,9 +640,10 @@ __device__ __forceinline__ uint32_t window_word(const uint32_t *__restrict__ pk,
     const uint32_t hi = (w + 1u < glen_words) ? __ldg(&pk[w + 1u]) : 0u;
     x = __funnelshift_r(lo, hi, sh);
   } else {
-    if (gh < 0) return 0u;
-    x = __ldg(&pk[0]) << (uint32_t)(-gl * 2);                            // genome positions 0 .. gh in the top fields
+    if (gl < -15) return 0u;                                             // wholly in front of the genome (never read)
+    x = __ldg(&pk[0]) << (uint32_t)(-gl * 2);                            // genome positions 0 .. in the top fields
   }
+  if (!minus) return x;
   x = __brev(x);                                                         // reverse the 16 fields ...
   x = ((x & 0x55555555u) << 1) | ((x >> 1) & 0x55555555u);               // ... keeping the bit order inside a field
   return ~x;                                                             // complement: code ^ 3
@@ -675,32 +684,32 @@ __device__ __forceinline__ void build_emit_luts(EmitLuts &L, uint32_t t) {  // t
   }
 }
 
-// One tile whose reference range holds only ACGT, text records.  Pn / Cn / Rn: read bases, MAF columns and window
-// bases of the tile (Cn <= kStageCols, Pn <= PB_TILE).
+// One tile whose reference range holds only ACGT, text records (Cn <= kStageCols, Pn <= PB_TILE).
 template <int METHOD>
 __device__ __forceinline__ void emit_tile_staged(EmitStage &S, const EmitLuts &LU, const uint8_t *__restrict__ evbase,
-                                                 uint32_t e0, uint32_t e1, const uint32_t *__restrict__ pk,
-                                                 uint32_t glen_words, uint32_t offset, uint32_t wlen, uint32_t minus,
-                                                 uint32_t ncol, uint32_t C0, uint32_t R0, uint32_t P0, uint32_t Pn,
-                                                 uint32_t Cn, uint32_t Rn, uint8_t *__restrict__ seq,
-                                                 uint8_t *__restrict__ qual, uint8_t *__restrict__ mref,
-                                                 uint8_t *__restrict__ mread, uint32_t lane) {
-  // destinations of the four fragments and the offsets (modulo 16) their staging rows start at
-  uint8_t *g_seq = seq + P0, *g_qual = qual + P0;
-  const uint32_t cfirst = minus ? ncol - C0 - Cn : C0;   // first MAF column (in file order) of the tile
-  uint8_t *g_ref = mref + cfirst, *g_read = mread + cfirst;
+                                                 uint32_t e1, const uint32_t *__restrict__ pk, uint32_t glen_words,
+                                                 uint32_t wpos, uint32_t minus, uint32_t Pn, uint32_t Cn, uint32_t Rn,
+                                                 uint8_t *__restrict__ g_seq, uint8_t *__restrict__ g_qual,
+                                                 uint8_t *__restrict__ g_ref, uint8_t *__restrict__ g_read, uint32_t lane) {
+  const uint32_t e0 = 0;
+  // the offsets (modulo 16) the staging rows of the four fragments start at
   const uint32_t sh_s = (uint32_t)(reinterpret_cast<uintptr_t>(g_seq) & 15u);
   const uint32_t sh_q = (uint32_t)(reinterpret_cast<uintptr_t>(g_qual) & 15u);
   const uint32_t sh_r = (uint32_t)(reinterpret_cast<uintptr_t>(g_ref) & 15u);
   const uint32_t sh_m = (uint32_t)(reinterpret_cast<uintptr_t>(g_read) & 15u);
-  // staging addresses: column c of the tile lives at cbase + c * cdir (the minus strand's rows run backwards)
-  uint8_t *const b_seq = S.seq + sh_s, *const b_qual = S.qual + sh_q;
+  // staging indices: column c of the tile lives at S.mref[o_ref + c * cdir] (the minus strand's rows run backwards)
   const int32_t cdir = minus ? -1 : 1;
-  uint8_t *const b_ref = S.mref + sh_r + (minus ? Cn - 1u : 0u), *const b_read = S.mread + sh_m + (minus ? Cn - 1u : 0u);
-  const uint8_t *const l_seq = LU.seq, *const l_read = LU.mread[minus], *const l_ref = LU.mref[minus];
+  const uint32_t o_ref = sh_r + (minus ? Cn - 1u : 0u);
+  const uint32_t d_read = sh_m - sh_r;                           // S.mread index of a column = its S.mref index + d_read (mod 2^32)
+  const uint32_t o_dump = kStageCols + 40u;                      // scratch byte behind the rows
+  const uint32_t moff = minus ? 128u : 0u;                       // strand half of the MAF character LUTs
+  const uint32_t ref_chars = minus ? 0x41434754u : 0x54474341u;  // "TGCA" / "ACGT": MAF character of a window code
+  // the MAF read row starts as all '-': deletion columns then only need their reference character
+  for (uint32_t j = lane * 16u; j < sh_m + Cn; j += 512u)
+    *reinterpret_cast<uint4 *>(S.mread + j) = make_uint4(0x2D2D2D2Du, 0x2D2D2D2Du, 0x2D2D2D2Du, 0x2D2D2D2Du);
   // ---- window codes of the tile: positions R0 .. R0 + Rn (an insertion at the end looks at R0 + Rn) + 16 spare
   const uint32_t nw = (Rn + 16u) / 16u + 1u;
-  for (uint32_t j = lane; j < nw; j += 32u) S.pk[j] = window_word(pk, offset, wlen, minus, glen_words, R0 + 16u * j);
+  for (uint32_t j = lane; j < nw; j += 32u) S.pk[j] = window_word(pk, wpos, minus, glen_words, 16u * j);
   __syncwarp();
   auto load_entries = [&](uint32_t i) -> uint2 {
     const uint32_t eb = i + lane * kEmitPerLane;
@@ -722,29 +731,30 @@ __device__ __forceinline__ void emit_tile_staged(EmitStage &S, const EmitLuts &L
     } else {
       raw[0] = v.x & 0xFFu; raw[1] = (v.x >> 8) & 0xFFu; raw[2] = (v.x >> 16) & 0xFFu; raw[3] = v.x >> 24;
     }
-    // common case: 128 valid entries, none of them a continuation entry
-    bool plain = i + kEmitStep <= e1;
-    if (METHOD == PBSIM_METHOD_QSHMM)
-      plain = plain && !__any_sync(0xFFFFFFFFu, ((v.x & (v.x >> 1)) | (v.y & (v.y >> 1))) & 0x00800080u);  // kind == 3
-    if (plain) {
-      // ---- lane totals: insertions (no reference advance) and deletions of its four entries
-      uint32_t li = 0, ld = 0;
-      uint32_t idx[kEmitPerLane], nd[kEmitPerLane];
+    // common case: 128 valid entries, none of them a continuation entry, no lane with more than 11 deletions
+    // (so the 16 window bases a lane fetches cover everything its four entries touch)
+    uint32_t li = 0, ld = 0;
+    uint32_t idx[kEmitPerLane], nd[kEmitPerLane];
 #pragma unroll
-      for (uint32_t k = 0; k < kEmitPerLane; ++k) {
-        if (METHOD == PBSIM_METHOD_QSHMM) {
-          idx[k] = (raw[k] >> 5) & 0x7Cu;       // (kind | info << 2) << 2
-          nd[k] = raw[k] >> 12;
-          li += (raw[k] >> 8) & 1u;             // kind 2
-          ld += nd[k];
-        } else {
-          idx[k] = (raw[k] & 0x1Fu) << 2;
-          nd[k] = ((raw[k] & 3u) == PB_KIND_DEL) ? 1u : 0u;
-          li += ((raw[k] & 3u) == PB_KIND_INS) ? 1u : 0u;
-          ld += nd[k];
-        }
+    for (uint32_t k = 0; k < kEmitPerLane; ++k) {
+      if (METHOD == PBSIM_METHOD_QSHMM) {
+        idx[k] = (raw[k] >> 5) & 0x7Cu;       // (kind | info << 2) << 2
+        nd[k] = raw[k] >> 12;
+        li += (raw[k] >> 8) & 1u;             // kind 2
+      } else {
+        idx[k] = (raw[k] & 0x1Fu) << 2;
+        nd[k] = ((raw[k] & 3u) == PB_KIND_DEL) ? 1u : 0u;
+        li += ((raw[k] & 3u) == PB_KIND_INS) ? 1u : 0u;
       }
-      const uint32_t mine = li | (ld << 8);     // <= 128 insertions, <= kStageCols deletions per iteration
+      ld += nd[k];
+    }
+    bool plain = i + kEmitStep <= e1;
+    if (METHOD == PBSIM_METHOD_QSHMM) {
+      const uint32_t cont = ((v.x & (v.x >> 1)) | (v.y & (v.y >> 1))) & 0x00800080u;  // kind == 3 in one of the four
+      plain = plain && !__any_sync(0xFFFFFFFFu, (cont != 0u) || (ld > 11u));
+    }
+    if (plain) {
+      const uint32_t mine = li | (ld << 8);     // <= 128 insertions, <= 12 * 32 deletions per iteration
       uint32_t x = mine;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
@@ -764,43 +774,57 @@ __device__ __forceinline__ void emit_tile_staged(EmitStage &S, const EmitLuts &L
         Rr = Rt + lane * kEmitPerLane - pre_i;
         Pp = Pt + lane * kEmitPerLane - pre_d;
       }
-      uint32_t bits = codes_at(Rr), bbase = Rr;
-      uint8_t *pc_ref = b_ref + (int32_t)Cc * cdir, *pc_read = b_read + (int32_t)Cc * cdir;
+      uint32_t bits = codes_at(Rr);             // consumed two bits at a time as the reference advances
+      // 32-bit staging indices (generic 64-bit pointers into shared memory cost two instructions per step)
+      uint32_t oc = o_ref + Cc * (uint32_t)cdir;   // this column's byte in S.mref; S.mread: + d_read
+      if (METHOD == PBSIM_METHOD_QSHMM) {
+        const uint32_t op = Pp;
+        uint32_t multi = 0;
+        const uint32_t bits0 = bits, oc0 = oc;
 #pragma unroll
-      for (uint32_t k = 0; k < kEmitPerLane; ++k) {
-        if (Rr - bbase > 15u) { bits = codes_at(Rr); bbase = Rr; }   // (a lane with many deletions)
-        const uint32_t t = idx[k] | ((bits >> ((Rr - bbase) * 2u)) & 3u);
-        if (METHOD == PBSIM_METHOD_QSHMM) {
-          b_seq[Pp] = l_seq[t];
-          b_qual[Pp] = (uint8_t)((raw[k] & 0x7Fu) + 33u);
-          *pc_read = l_read[t];
-          *pc_ref = l_ref[t];
-          ++Pp;
-          pc_read += cdir;
-          pc_ref += cdir;
-          Rr += 1u - ((raw[k] >> 8) & 1u);
-          if (nd[k]) {                          // deleted reference bases behind the entry: mostly one
-            for (uint32_t j = 0; j < nd[k]; ++j) {
-              if (Rr - bbase > 15u) { bits = codes_at(Rr); bbase = Rr; }
-              *pc_read = '-';
-              *pc_ref = l_ref[(bits >> ((Rr - bbase) * 2u)) & 3u];   // index of a match on that base
-              pc_read += cdir;
-              pc_ref += cdir;
-              ++Rr;
-            }
+        for (uint32_t k = 0; k < kEmitPerLane; ++k) {
+          const uint32_t t = idx[k] | (bits & 3u);
+          S.seq[sh_s + op + k] = LU.seq[t];
+          S.qual[sh_q + op + k] = (uint8_t)((raw[k] & 0x7Fu) + 33u);
+          S.mread[oc + d_read] = LU.mread[0][t + moff];
+          S.mref[oc] = LU.mref[0][t + moff];
+          oc += (uint32_t)cdir;
+          if (!(raw[k] & 0x100u)) bits >>= 2;   // an insertion does not consume the reference base
+          // deleted reference bases behind the entry: the read row already holds '-' (prefilled); the first
+          // deleted base is stored without a branch (to a scratch byte when there is none)
+          const uint32_t dst = nd[k] ? oc : o_dump;
+          S.mref[dst] = (uint8_t)__byte_perm(ref_chars, 0u, bits & 3u);
+          multi |= nd[k];
+          oc += nd[k] * (uint32_t)cdir;
+          bits >>= 2u * nd[k];
+        }
+        if (multi > 1u) {   // an entry with two or more deletions (rare): their further reference characters
+          uint32_t b2 = bits0, o2 = oc0;
+#pragma unroll
+          for (uint32_t k = 0; k < kEmitPerLane; ++k) {
+            o2 += (uint32_t)cdir;
+            if (!(raw[k] & 0x100u)) b2 >>= 2;
+            for (uint32_t j = 1; j < nd[k]; ++j)
+              S.mref[o2 + j * (uint32_t)cdir] = (uint8_t)__byte_perm(ref_chars, 0u, (b2 >> (2u * j)) & 3u);
+            o2 += nd[k] * (uint32_t)cdir;
+            b2 >>= 2u * nd[k];
           }
-        } else {
+        }
+      } else {
+        uint32_t op = Pp;
+#pragma unroll
+        for (uint32_t k = 0; k < kEmitPerLane; ++k) {
+          const uint32_t t = idx[k] | (bits & 3u);
           const bool isb = nd[k] == 0u;
           if (isb) {
-            b_seq[Pp] = l_seq[t];
-            b_qual[Pp] = '!';
+            S.seq[sh_s + op] = LU.seq[t];
+            S.qual[sh_q + op] = '!';
           }
-          *pc_read = l_read[t];
-          *pc_ref = l_ref[t];
-          pc_read += cdir;
-          pc_ref += cdir;
-          Pp += isb ? 1u : 0u;
-          Rr += ((raw[k] & 3u) == PB_KIND_INS) ? 0u : 1u;
+          S.mread[oc + d_read] = LU.mread[0][t + moff];
+          S.mref[oc] = LU.mref[0][t + moff];
+          oc += (uint32_t)cdir;
+          op += isb ? 1u : 0u;
+          if ((raw[k] & 3u) != PB_KIND_INS) bits >>= 2;
         }
       }
       const uint32_t tot_i = tot & 0xFFu, tot_d = tot >> 8;
@@ -812,8 +836,9 @@ __device__ __forceinline__ void emit_tile_staged(EmitStage &S, const EmitLuts &L
       continue;
     }
     // ---- general iteration: entries past the end of the tile, continuation entries
-    uint32_t kind[kEmitPerLane], info[kEmitPerLane], nd[kEmitPerLane], isb[kEmitPerLane], adv[kEmitPerLane];
-    uint32_t lb = 0, la = 0, ld = 0;
+    uint32_t kind[kEmitPerLane], info[kEmitPerLane], isb[kEmitPerLane], adv[kEmitPerLane];
+    uint32_t lb = 0, la = 0;
+    ld = 0;
 #pragma unroll
     for (uint32_t k = 0; k < kEmitPerLane; ++k) {
       const bool valid = eb + k < e1;
@@ -850,17 +875,17 @@ __device__ __forceinline__ void emit_tile_staged(EmitStage &S, const EmitLuts &L
     for (uint32_t k = 0; k < kEmitPerLane; ++k) {
       if (isb[k]) {
         const uint32_t t = ((kind[k] | (info[k] << 2)) << 2) | (codes_at(Rr) & 3u);
-        b_seq[Pp] = l_seq[t];
-        b_qual[Pp] = METHOD == PBSIM_METHOD_QSHMM ? (uint8_t)((raw[k] & 0x7Fu) + 33u) : (uint8_t)'!';
-        b_read[(int32_t)Cc * cdir] = l_read[t];
-        b_ref[(int32_t)Cc * cdir] = l_ref[t];
+        S.seq[sh_s + Pp] = LU.seq[t];
+        S.qual[sh_q + Pp] = METHOD == PBSIM_METHOD_QSHMM ? (uint8_t)((raw[k] & 0x7Fu) + 33u) : (uint8_t)'!';
+        S.mread[o_ref + Cc * (uint32_t)cdir + d_read] = LU.mread[0][t + moff];
+        S.mref[o_ref + Cc * (uint32_t)cdir] = LU.mref[0][t + moff];
         ++Pp;
         ++Cc;
         Rr += adv[k];
       }
       for (uint32_t j = 0; j < nd[k]; ++j) {
-        b_read[(int32_t)Cc * cdir] = '-';
-        b_ref[(int32_t)Cc * cdir] = l_ref[codes_at(Rr) & 3u];
+        S.mread[o_ref + Cc * (uint32_t)cdir + d_read] = '-';
+        S.mref[o_ref + Cc * (uint32_t)cdir] = LU.mref[0][(codes_at(Rr) & 3u) + moff];
         ++Cc;
         ++Rr;
       }
@@ -962,28 +987,119 @@ __device__ __noinline__ void emit_tile_generic(const uint8_t *evbase, uint32_t e
   }
 }
 
-// sub-read of every tile: largest s with tile_start[s] <= t.  One THREAD per tile here instead of one search per
-// WARP in k_emit.
-__global__ void k_tile_map(const uint64_t *__restrict__ tile_start, uint32_t n_sub, uint64_t n_tiles, uint32_t *tile_sub) {
-  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= n_tiles) return;
-  uint32_t lo = 0, hi = n_sub;
-  while (hi - lo > 1u) {
-    const uint32_t mid = (lo + hi) >> 1;
-    if (__ldg(&tile_start[mid]) <= t) lo = mid; else hi = mid;
-  }
-  tile_sub[t] = lo;
+// what a tile covers, from the sub-read's arrays and checkpoints (shared by k_tile_desc and k_emit)
+struct TileGeom {
+  uint32_t e0, e1, has_next, Rnext, Pn, Cn, segmented, slow;
+  Ckpt c0;
+};
+template <int METHOD>
+__device__ __forceinline__ TileGeom tile_geom(const EmitArgs &A, uint32_t s, uint32_t r, uint32_t tile, uint32_t nent,
+                                              uint32_t rlen, uint32_t ncol, uint32_t offset, uint32_t wlen, uint32_t minus) {
+  TileGeom g;
+  const Ckpt *ckp = A.ck + A.B.ck_off[s];
+  g.c0 = ckp[tile];
+  // sequential pass 1: one contiguous stream, tile = entries [1024 t, 1024 (t+1)); segment-parallel pass 1:
+  // tile t lives in its own slot (stride PB_SEG_STRIDE) and its entry count is in the checkpoint
+  g.segmented = (METHOD == PBSIM_METHOD_QSHMM && ((A.B.plan_meta[r] >> 11) & 1u)) ? 1u : 0u;
+  g.e0 = g.segmented ? 0u : tile * PB_TILE;
+  g.e1 = g.segmented ? g.c0.pad : min(nent, g.e0 + PB_TILE);
+  g.has_next = (g.segmented ? (tile + 1u < nent) : (g.e1 < nent)) ? 1u : 0u;
+  // reference range this tile can touch: [R0, Rend] (an insertion at the tile's end looks at Rend)
+  Ckpt c1 = g.c0;
+  if (g.has_next) c1 = ckp[tile + 1];
+  g.Rnext = g.has_next ? c1.ref : wlen;
+  const uint32_t Rend = min(g.Rnext, wlen - 1u);
+  const uint32_t g0 = minus ? offset + wlen - 1u - Rend : offset + g.c0.ref;
+  const uint32_t g1 = minus ? offset + wlen - 1u - g.c0.ref : offset + Rend;
+  g.slow = range_exceptional(A.G.xm, g0, g1) ? 1u : 0u;
+  // what the tile covers: read bases, MAF columns (up to the next tile's checkpoint / the read's end)
+  g.Pn = (g.has_next ? c1.read : rlen) - g.c0.read;
+  g.Cn = (g.has_next ? c1.col : ncol) - g.c0.col;
+  return g;
 }
 
-template <int METHOD, bool BAM>
-__global__ void __launch_bounds__(kEmitThreads) k_emit(EmitArgs A) {
-  __shared__ uint8_t lut_s[128];
-  __shared__ __align__(16) EmitStage stage[BAM ? 1 : kEmitWarps];
-  __shared__ EmitLuts luts;
-  if (threadIdx.x < 128u) {
-    lut_s[threadIdx.x] = (uint8_t)read_code((threadIdx.x >> 5) & 3u, (threadIdx.x >> 2) & 7u, threadIdx.x & 3u);
-    build_emit_luts(luts, threadIdx.x);
+// One THREAD per tile: its sub-read (largest s with tile_start[s] <= t) and its descriptor.
+template <int METHOD>
+__global__ void k_tile_desc(const __grid_constant__ EmitArgs A, uint32_t *tile_sub) {
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= A.n_tiles) return;
+  uint32_t lo = 0, hi = A.n_sub;
+  while (hi - lo > 1u) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (__ldg(&A.tile_start[mid]) <= t) lo = mid; else hi = mid;
   }
+  const uint32_t s = lo;
+  tile_sub[t] = s;
+  const uint32_t tile = (uint32_t)(t - __ldg(&A.tile_start[s]));
+  const uint32_t r = s / A.P.pass_num;
+  const uint32_t offset = A.B.plan_off[r], wlen = A.B.plan_wlen[r];
+  const uint32_t minus = (A.B.plan_meta[r] >> 8) & 1u;
+  const uint32_t nent = A.B.nent[s], rlen = A.B.rlen[s], ncol = A.B.ncol[s];
+  TileDesc d;
+  memset(&d, 0, sizeof d);
+  if (nent == 0) {
+    d.flags = kTileEmpty;
+  } else {
+    const TileGeom g = tile_geom<METHOD>(A, s, r, tile, nent, rlen, ncol, offset, wlen, minus);
+    const EmitLay L = A.lay[s];
+    const uint64_t rd = A.reads_off[s], mf = A.maf_off[s];
+    d.ev_off = (A.B.ev_off[s] + (g.segmented ? (uint64_t)tile * PB_SEG_STRIDE : (uint64_t)g.e0)) *
+               (METHOD == PBSIM_METHOD_QSHMM ? 2ull : 1ull);
+    d.o_seq = rd + L.seq_rel + g.c0.read;
+    d.o_qual = rd + L.qual_rel + g.c0.read;
+    const uint32_t cfirst = minus ? ncol - g.c0.col - g.Cn : g.c0.col;   // first MAF column (file order) of the tile
+    d.o_ref = mf + L.refrow_rel + cfirst;
+    d.o_read = mf + L.readrow_rel + cfirst;
+    d.e1 = g.e1 - g.e0;
+    d.Pn = g.Pn;
+    d.Cn = g.Cn;
+    d.Rn = g.Rnext - g.c0.ref;
+    d.wpos = minus ? offset + wlen - 1u - g.c0.ref : offset + g.c0.ref;
+    d.flags = (minus ? kTileMinus : 0u) | (g.slow ? kTileGeneric : 0u) |
+              ((g.Cn > kStageCols || g.Pn > PB_TILE) ? kTileWide : 0u);
+  }
+  uint4 *dst = reinterpret_cast<uint4 *>(A.desc + t);
+  const uint4 *src = reinterpret_cast<const uint4 *>(&d);
+  dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; dst[3] = src[3];
+}
+
+// The ROW kernel of pass 2 (text records): one warp per tile, everything it needs in the tile's descriptor.
+// Tiles that touch exceptional bases or are too wide for the staging rows are left to k_emit, as are the record
+// headers, the SAM ip / pw arrays and BAM records.  Kept small on purpose: the loop must live in the instruction cache.
+template <int METHOD>
+__global__ void __launch_bounds__(kEmitThreads, 4) k_emit_rows(const TileDesc *__restrict__ desc, uint64_t n_tiles,
+                                                              const uint8_t *__restrict__ ev,
+                                                              const uint32_t *__restrict__ pk, uint32_t glen_words,
+                                                              uint8_t *__restrict__ out_reads,
+                                                              uint8_t *__restrict__ out_maf) {
+  __shared__ __align__(16) EmitStage stage[kEmitWarps];
+  __shared__ EmitLuts luts;
+  if (threadIdx.x < 128u) build_emit_luts(luts, threadIdx.x);
+  __syncthreads();
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint64_t warp0 = (uint64_t)blockIdx.x * kEmitWarps + (threadIdx.x >> 5);
+  const uint64_t nwarps = (uint64_t)gridDim.x * kEmitWarps;
+  for (uint64_t t = warp0; t < n_tiles; t += nwarps) {
+    const uint4 *dp = reinterpret_cast<const uint4 *>(desc + t);
+    const uint4 d0 = __ldg(dp), d1 = __ldg(dp + 1), d2 = __ldg(dp + 2), d3 = __ldg(dp + 3);
+    const uint32_t flags = d3.w;
+    if (flags & (kTileGeneric | kTileWide | kTileEmpty)) continue;
+    const uint64_t ev_off = (uint64_t)d0.x | ((uint64_t)d0.y << 32), o_seq = (uint64_t)d0.z | ((uint64_t)d0.w << 32);
+    const uint64_t o_qual = (uint64_t)d1.x | ((uint64_t)d1.y << 32), o_ref = (uint64_t)d1.z | ((uint64_t)d1.w << 32);
+    const uint64_t o_read = (uint64_t)d2.x | ((uint64_t)d2.y << 32);
+    emit_tile_staged<METHOD>(stage[threadIdx.x >> 5], luts, ev + ev_off, d2.z /* e1 */, pk, glen_words, d3.z /* wpos */,
+                             flags & kTileMinus, d2.w /* Pn */, d3.x /* Cn */, d3.y /* Rn */, out_reads + o_seq,
+                             out_reads + o_qual, out_maf + o_ref, out_maf + o_read, lane);
+  }
+}
+
+// Everything of pass 2 that is not a plain text tile: the record headers (once per sub-read), tiles that touch
+// exceptional bases or are too wide for the staging rows, the SAM ip / pw arrays, and BAM records altogether.
+template <int METHOD, bool BAM>
+__global__ void __launch_bounds__(kEmitThreads) k_emit(const __grid_constant__ EmitArgs A) {
+  __shared__ uint8_t lut_s[128];
+  if (threadIdx.x < 128u)
+    lut_s[threadIdx.x] = (uint8_t)read_code((threadIdx.x >> 5) & 3u, (threadIdx.x >> 2) & 7u, threadIdx.x & 3u);
   __syncthreads();
   const uint32_t lane = threadIdx.x & 31u;
   const uint64_t warp0 = (uint64_t)blockIdx.x * kEmitWarps + (threadIdx.x >> 5);
@@ -991,6 +1107,10 @@ __global__ void __launch_bounds__(kEmitThreads) k_emit(EmitArgs A) {
   for (uint64_t t = warp0; t < A.n_tiles; t += nwarps) {
     const uint32_t s = __ldg(&A.tile_sub[t]);
     const uint32_t tile = (uint32_t)(t - __ldg(&A.tile_start[s]));
+    // text tiles the row kernel handles: nothing to do here unless the tile opens a record or SAM arrays follow
+    const uint32_t dflags = BAM ? (kTileGeneric) : __ldg(&A.desc[t].flags);
+    const bool rows_here = (dflags & (kTileGeneric | kTileWide)) != 0u;
+    if (!rows_here && tile != 0u && !A.P.sam) continue;
     const uint32_t r = s / A.P.pass_num, pass = s % A.P.pass_num;
     const uint64_t read_id = A.B.first_read + 1u + r;
     const uint32_t offset = A.B.plan_off[r], wlen = A.B.plan_wlen[r];
@@ -1006,44 +1126,30 @@ __global__ void __launch_bounds__(kEmitThreads) k_emit(EmitArgs A) {
       if (lane == 0) write_headers(A.P, N, LL, rd, mf, read_id, pass, shown, rlen, ncol, minus);
     }
     if (nent == 0) continue;
+    const TileGeom g = tile_geom<METHOD>(A, s, r, tile, nent, rlen, ncol, offset, wlen, minus);
+    const Ckpt c0 = g.c0;
+    const uint32_t e0 = g.e0, e1 = g.e1;
+    const bool has_next = g.has_next != 0u;
     const Ckpt *ckp = A.ck + A.B.ck_off[s];
-    const Ckpt c0 = ckp[tile];
-    // sequential pass 1: one contiguous stream, tile = entries [1024 t, 1024 (t+1)); segment-parallel pass 1:
-    // tile t lives in its own slot (stride PB_SEG_STRIDE) and its entry count is in the checkpoint
-    const bool segmented = METHOD == PBSIM_METHOD_QSHMM && ((A.B.plan_meta[r] >> 11) & 1u);
-    const uint32_t e0 = segmented ? 0u : tile * PB_TILE;
-    const uint32_t e1 = segmented ? c0.pad : min(nent, e0 + PB_TILE);
-    const bool has_next = segmented ? (tile + 1u < nent) : (e1 < nent);
-    // reference range this tile can touch: [R0, Rend] (an insertion at the tile's end looks at Rend)
-    const uint32_t Rnext = has_next ? ckp[tile + 1].ref : wlen;
-    const uint32_t Rend = min(Rnext, wlen - 1u);
-    const uint32_t g0 = minus ? offset + wlen - 1u - Rend : offset + c0.ref;
-    const uint32_t g1 = minus ? offset + wlen - 1u - c0.ref : offset + Rend;
-    const bool slow = range_exceptional(A.G.xm, g0, g1);
-    uint8_t *seq = rd + L.seq_rel, *qual = rd + L.qual_rel;
-    uint8_t *mref = mf + L.refrow_rel, *mread = mf + L.readrow_rel;
-    const uint8_t *evbase = A.ev + (A.B.ev_off[s] + (segmented ? (uint64_t)tile * PB_SEG_STRIDE : 0ull)) *
-                                       (METHOD == PBSIM_METHOD_QSHMM ? 2ull : 1ull);
-    // what the tile covers: read bases, MAF columns, window bases (up to the next tile's checkpoint / the read's end)
-    const uint32_t Pn = (has_next ? ckp[tile + 1].read : rlen) - c0.read;
-    const uint32_t Cn = (has_next ? ckp[tile + 1].col : ncol) - c0.col;
-    if (!slow && !BAM && Cn <= kStageCols && Pn <= PB_TILE) {
-      emit_tile_staged<METHOD>(stage[BAM ? 0 : (threadIdx.x >> 5)], luts, evbase, e0, e1, A.G.pk, (A.G.len + 15u) / 16u,
-                               offset, wlen, minus, ncol, c0.col, c0.ref, c0.read, Pn, Cn, Rnext - c0.ref, seq, qual, mref,
-                               mread, lane);
-    } else if (!slow) {
-      emit_tile_fast<METHOD, BAM>(evbase, e0, e1, A.G.pk, offset, wlen, minus, ncol, c0.col, c0.ref, c0.read, seq, qual, mref,
-                             mread, lane, lut_s);
-    } else {
-      RefFetch rf;
-      rf.pk = A.G.pk;
-      rf.ascii = A.G.ascii;
-      rf.offset = offset;
-      rf.wlen = wlen;
-      rf.minus = minus;
-      rf.slow = true;
-      emit_tile_generic<METHOD, BAM>(evbase, e0, e1, rf, minus, ncol, c0.col, c0.ref, c0.read, seq, qual, mref, mread, lane,
-                                A.philox ? &A.keys : nullptr, (uint32_t)read_id, pass);
+    if (rows_here) {
+      uint8_t *seq = rd + L.seq_rel, *qual = rd + L.qual_rel;
+      uint8_t *mref = mf + L.refrow_rel, *mread = mf + L.readrow_rel;
+      const uint8_t *evbase = A.ev + (A.B.ev_off[s] + (g.segmented ? (uint64_t)tile * PB_SEG_STRIDE : 0ull)) *
+                                         (METHOD == PBSIM_METHOD_QSHMM ? 2ull : 1ull);
+      if (!g.slow && BAM) {
+        emit_tile_fast<METHOD, BAM>(evbase, e0, e1, A.G.pk, offset, wlen, minus, ncol, c0.col, c0.ref, c0.read, seq, qual,
+                                    mref, mread, lane, lut_s);
+      } else {
+        RefFetch rf;
+        rf.pk = A.G.pk;
+        rf.ascii = A.G.ascii;
+        rf.offset = offset;
+        rf.wlen = wlen;
+        rf.minus = minus;
+        rf.slow = true;
+        emit_tile_generic<METHOD, BAM>(evbase, e0, e1, rf, minus, ncol, c0.col, c0.ref, c0.read, seq, qual, mref, mread,
+                                       lane, A.philox ? &A.keys : nullptr, (uint32_t)read_id, pass);
+      }
     }
     if (A.P.sam) {
       // ip:B:C / pw:B:C arrays: ",9" per read base of this tile (:2324-2331)

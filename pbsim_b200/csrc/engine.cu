@@ -10,7 +10,7 @@
 //      k_plan_sample, k_sim_sample, k_sample_redo   --method sample: copies of pool entries     (sim_kernels.cuh)
 //      k_sim_seg | k_sim_seg_err, k_find_end[_err]   segment-parallel pass 1 -> event streams (seg_kernels.cuh)
 //      quota scan        which read crosses sim.len_quota (pbsim.cpp:2173-2181)               (CUB + k_find_cut)
-//   K4 k_sizes, k_tile_map, k_emit   record placement and text emission                       (emit.cuh)
+//   K4 k_sizes, k_tile_desc, k_emit_rows, k_emit   record placement and text emission          (emit.cuh)
 //   K6 k_stats           counters and histograms                                              (emit.cuh)
 //      k_gz_hist / k_gz_size / k_gz_encode   option "deflate": gzip members for host delivery (gz_kernels.cuh)
 // Host delivery is pipelined: a producer thread generates batch k+1 while batch k streams through pinned staging.
@@ -228,7 +228,7 @@ struct pbsim_engine {
   DevBuf d_bins;       // bin_start[kBins+1], bin_lo[kBins], bin_hi[kBins], cta_first[kBins+1]
   DevBuf d_ctrl;       // control words
   DevBuf d_cub_tmp;
-  DevBuf d_ev, d_ck, d_lay, d_tile_sub;
+  DevBuf d_ev, d_ck, d_lay, d_tile_sub, d_tile_desc;
   DevBuf d_seg, d_seg_bins;       // segment-parallel pass 1: segment lists / results, CTA map
   int seg_enabled = 1;            // option "segments"
   int64_t seg_min_len = 2048;     // option "seg_min_len": shorter reads stay on the sequential path
@@ -946,11 +946,9 @@ int run_batch(pbsim_engine *e, uint32_t n_reads, int64_t clip_room, BatchResult 
   EA.n_tiles = n_tiles;
   EA.tile_start = (const uint64_t *)tile_start;
   CK(e->d_tile_sub.ensure((size_t)n_tiles * 4 + 64));
-  if (n_tiles > 0) {
-    k_tile_map<<<nblk(n_tiles, 256), 256, 0, e->st>>>((const uint64_t *)tile_start, nv_sub, n_tiles, e->d_tile_sub.as<uint32_t>());
-    e->launches++;
-  }
+  CK(e->d_tile_desc.ensure((size_t)n_tiles * sizeof(TileDesc) + 64));
   EA.tile_sub = e->d_tile_sub.as<uint32_t>();
+  EA.desc = e->d_tile_desc.as<TileDesc>();
   EA.lay = e->d_lay.as<EmitLay>();
   EA.reads_off = (const uint64_t *)reads_off;
   EA.maf_off = (const uint64_t *)maf_off;
@@ -958,19 +956,37 @@ int run_batch(pbsim_engine *e, uint32_t n_reads, int64_t clip_room, BatchResult 
   EA.philox = replay ? 0u : 1u;
   EA.out_reads = O.reads.as<uint8_t>();
   EA.out_maf = O.maf.as<uint8_t>();
-  {
+  if (n_tiles > 0) {
     int dev_sms = 148;
     cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, e->device);
     const uint64_t want = (n_tiles + kEmitWarps - 1) / kEmitWarps;
     const uint32_t grid = (uint32_t)std::min<uint64_t>(want, (uint64_t)dev_sms * 8 * 4);
+    static bool carve_set = false;
+    if (!carve_set) {  // the staging rows need shared memory for 4 CTAs per SM: ask for the largest carve-out
+      CK(cudaFuncSetAttribute(k_emit_rows<PBSIM_METHOD_QSHMM>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+      CK(cudaFuncSetAttribute(k_emit_rows<PBSIM_METHOD_ERRHMM>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+      carve_set = true;
+    }
     CK(cudaEventRecord(e->ev_k[2], e->st));
+    // per-tile descriptors (and the tile -> sub-read map), then the row kernel on the plain text tiles and
+    // k_emit on everything else (headers, exceptional / wide tiles, SAM arrays, BAM records)
+    if (qs) k_tile_desc<PBSIM_METHOD_QSHMM><<<nblk(n_tiles, 256), 256, 0, e->st>>>(EA, e->d_tile_sub.as<uint32_t>());
+    else k_tile_desc<PBSIM_METHOD_ERRHMM><<<nblk(n_tiles, 256), 256, 0, e->st>>>(EA, e->d_tile_sub.as<uint32_t>());
+    e->launches++;
     if (EA.P.sam == 2u) {  // BAM packs bases with atomic ORs: the records start zeroed
       CK(cudaMemsetAsync(O.reads.p, 0, (size_t)out->reads_bytes, e->st));
       if (qs) k_emit<PBSIM_METHOD_QSHMM, true><<<grid, kEmitThreads, 0, e->st>>>(EA);
       else k_emit<PBSIM_METHOD_ERRHMM, true><<<grid, kEmitThreads, 0, e->st>>>(EA);
     } else {
-      if (qs) k_emit<PBSIM_METHOD_QSHMM, false><<<grid, kEmitThreads, 0, e->st>>>(EA);
-      else k_emit<PBSIM_METHOD_ERRHMM, false><<<grid, kEmitThreads, 0, e->st>>>(EA);
+      const uint32_t glen_words = (uint32_t)((e->glen + 15) / 16);
+      if (qs) {
+        k_emit_rows<PBSIM_METHOD_QSHMM><<<grid, kEmitThreads, 0, e->st>>>(EA.desc, n_tiles, EA.ev, G.pk, glen_words, EA.out_reads, EA.out_maf);
+        k_emit<PBSIM_METHOD_QSHMM, false><<<grid, kEmitThreads, 0, e->st>>>(EA);
+      } else {
+        k_emit_rows<PBSIM_METHOD_ERRHMM><<<grid, kEmitThreads, 0, e->st>>>(EA.desc, n_tiles, EA.ev, G.pk, glen_words, EA.out_reads, EA.out_maf);
+        k_emit<PBSIM_METHOD_ERRHMM, false><<<grid, kEmitThreads, 0, e->st>>>(EA);
+      }
+      e->launches++;
     }
     CK(cudaEventRecord(e->ev_k[3], e->st));
     e->launches++;
@@ -1460,7 +1476,7 @@ void pbsim_cuda_destroy(pbsim_engine *e) {
                     &e->d_seg_bins, &e->d_set_start, &e->d_set_rprefix, &e->d_set_plus, &e->d_set_ids, &e->d_set_idstart,
                     &e->d_set_ssp_ends, &e->d_set_ssp_mod, &e->d_set_first, &e->gz[0].reads, &e->gz[0].maf, &e->gz[1].reads,
                     &e->gz[1].maf, &e->d_gz_tables, &e->d_gz_hist, &e->d_gz_usize, &e->d_gz_ucrc, &e->d_gz_uoff,
-                    &e->d_lay, &e->d_tile_sub, &e->d_chunk, &e->d_chunk_bins};
+                    &e->d_lay, &e->d_tile_sub, &e->d_tile_desc, &e->d_chunk, &e->d_chunk_bins};
   for (DevBuf *b : bufs) b->release();
   for (auto &a : e->h_stage)
     for (auto &b : a) b.release();
