@@ -233,11 +233,15 @@ static uint32_t fmix32(uint32_t h) {
   return h;
 }
 /* qshmm deletion draw number j (0-based) after the current position (ref: :2270).
- * PHILOX mode: j = 0 is the position's word Y; the rare later draws are derived from it
- * through the finaliser (engine definition, DESIGN.md "Philox draw addressing"). */
+ * PHILOX mode: j = 0 is the position's word Y; the rare later draws are derived from it (scheme 1: a
+ * multiply-add chain, errhmm scheme 0: the murmur finaliser; engine definition, DESIGN.md "Philox draw addressing"). */
 static uint32_t d_del(rng_t *r, uint32_t j) {
   if (r->mode != RNG_PHILOX) return stream_next(r) % 1000000;
-  if (r->scheme == 1) return j == 0 ? r->w[1] : fmix32(r->w[1] + j * 0x9E3779B9u); /* raw word: compare with d_lt */
+  if (r->scheme == 1) { /* raw word (compare with d_lt): d_0 = Y, d_j = d_{j-1} * 0x9E3779B1 + 0x7F4A7C15 (one multiply-add per further draw) */
+    uint32_t d = r->w[1], k;
+    for (k = 0; k < j; k++) d = d * 0x9E3779B1u + 0x7F4A7C15u;
+    return d;
+  }
   if (j == 0) return mulhi32(r->w[3], 1000000);
   return mulhi32(fmix32(r->w[3] + j * 0x9E3779B9u), 1000000);
 }

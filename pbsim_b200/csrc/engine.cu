@@ -748,7 +748,8 @@ int run_batch(pbsim_engine *e, uint32_t n_reads, int64_t clip_room, BatchResult 
       if (n_chunk_total > 0) {
         // ---- chain-only pass: the HMM state in front of every segment (k_chain_chunk), scheduled like the segments
         const uint32_t nch = (uint32_t)n_chunk_total;
-        const uint32_t ch_slots = nblk(nch, cta_threads) + kBins;
+        const uint32_t chain_threads = qs ? (uint32_t)kChainThreads : cta_threads;
+        const uint32_t ch_slots = nblk(nch, chain_threads) + kBins;
         CK(e->d_chunk.ensure((size_t)nch * 5 * 4 + 64));
         CK(e->d_chunk_bins.ensure((4 * kBins + 8) * 4 + (size_t)ch_slots * 4 * 4 + 64));
         ChunkBatch C;
@@ -776,8 +777,8 @@ int run_batch(pbsim_engine *e, uint32_t n_reads, int64_t clip_room, BatchResult 
         }
         k_fill_u32<<<1, 256, 0, e->st>>>(cb_start, kBins + 1, 0xFFFFFFFFu);
         k_bin_bounds<<<nblk(nch, 256), 256, 0, e->st>>>(C.key_out, nch, cb_start);
-        k_cta_map<<<1, 32, 0, e->st>>>(cb_start, C.key_out, nch, cb_lo, cb_hi, cb_first, cta_threads);
-        k_cta_keys<<<nblk(ch_slots, 256), 256, 0, e->st>>>(C.key_out, cb_lo, cb_first, ch_slots, cb_key, cb_id, cta_threads);
+        k_cta_map<<<1, 32, 0, e->st>>>(cb_start, C.key_out, nch, cb_lo, cb_hi, cb_first, chain_threads);
+        k_cta_keys<<<nblk(ch_slots, 256), 256, 0, e->st>>>(C.key_out, cb_lo, cb_first, ch_slots, cb_key, cb_id, chain_threads);
         {
           size_t tmp = 0;
           CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, cb_key, cb_key_s, cb_id, cb_order, (int)ch_slots, 0, 21, e->st));
@@ -790,8 +791,13 @@ int run_batch(pbsim_engine *e, uint32_t n_reads, int64_t clip_room, BatchResult 
         CA.cta_first = cb_first;
         CA.bin_lo = cb_lo;
         CA.bin_hi = cb_hi;
+        static bool chain_carve = false;
+        if (!chain_carve) {
+          CK(cudaFuncSetAttribute(k_chain_chunk, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+          chain_carve = true;
+        }
         CK(cudaEventRecord(e->ev_chain[0], e->st));
-        if (qs) k_chain_chunk<<<ch_slots, kSimThreads, kQsSmemBytes, e->st>>>(CA, C);
+        if (qs) k_chain_chunk<<<ch_slots, kChainThreads, kQsSmemBytes, e->st>>>(CA, C);
         else k_chain_chunk_err<<<ch_slots, kErrThreads, e->er_smem_bar_off + 16, e->st>>>(CA, C, e->er_smem_bar_off);
         CK(cudaEventRecord(e->ev_chain[1], e->st));
         chain_timed = true;

@@ -91,6 +91,9 @@ struct SegArgs {
 // A CTA serves kSimThreads segments of one accuracy (the schedule of the other pass-1 kernels), warp w the
 // segments lo + w, lo + w + 4, ...
 constexpr int kSegWarps = kSimThreads / 32;
+// threads of a quality-pass CTA (they share one accuracy's tables, 28 KB: 8 CTAs per SM with the largest shared-memory
+// carve-out).  Measured: 512-thread CTAs (48 warps per SM) are slower — the pass is bound by the shared-memory pipe.
+constexpr int kChainThreads = 128;
 
 __global__ void __launch_bounds__(kSimThreads) k_sim_seg(SegArgs A) {
   __shared__ __align__(16) QsFast s_fast[PBSIM_NQV];
@@ -134,17 +137,26 @@ __global__ void __launch_bounds__(kSimThreads) k_sim_seg(SegArgs A) {
     uint16_t *ev = reinterpret_cast<uint16_t *>(A.ev) + A.B.ev_off[s] + (uint64_t)k * PB_SEG_STRIDE;
     QsLaneTotals t;
     t.nsub = t.nins = t.ndel = t.prob = t.big = 0;
-#pragma unroll 2
-    for (uint32_t j = lane * PB_GROUP; j < PB_TILE; j += 32u * PB_GROUP) {
-      uint32_t qv[PB_GROUP], e[PB_GROUP];
+    // the eight 8-byte loads of the lane are independent of everything: all in flight before the first is used
+    constexpr uint32_t kIters = PB_TILE / (32u * PB_GROUP);
+    uint2 q[kIters];
+    if (ae.has_model) {
+#pragma unroll
+      for (uint32_t it = 0; it < kIters; ++it)
+        q[it] = *reinterpret_cast<const uint2 *>(ev + lane * PB_GROUP + it * 32u * PB_GROUP);
+    }
+#pragma unroll
+    for (uint32_t it = 0; it < kIters; ++it) {
+      const uint32_t j = lane * PB_GROUP + it * 32u * PB_GROUP;
+      uint32_t qv[PB_GROUP];
       if (ae.has_model) {
-        const uint2 v = *reinterpret_cast<const uint2 *>(ev + j);
-        qv[0] = v.x & 0x7Fu; qv[1] = (v.x >> 16) & 0x7Fu; qv[2] = v.y & 0x7Fu; qv[3] = (v.y >> 16) & 0x7Fu;
+        qv[0] = q[it].x & 0x7Fu; qv[1] = (q[it].x >> 16) & 0x7Fu; qv[2] = q[it].y & 0x7Fu; qv[3] = (q[it].y >> 16) & 0x7Fu;
       } else {
         qs_freq_qualities(T, A.keys, read_id, c1, k * PB_TILE + j, qv);
       }
-      qs_error_lane(s_fast, A.keys, read_id, c1, k * PB_TILE + j, qv, e, t);
-      *reinterpret_cast<uint2 *>(ev + j) = make_uint2(e[0] | (e[1] << 16), e[2] | (e[3] << 16));
+      uint32_t w0, w1;
+      qs_error_lane(s_fast, A.keys, read_id, c1, k * PB_TILE + j, qv, w0, w1, t);
+      *reinterpret_cast<uint2 *>(ev + j) = make_uint2(w0, w1);
     }
     const uint32_t big = __any_sync(0xFFFFFFFFu, t.big != 0u) ? 1u : 0u;
     SegResult res;
@@ -184,7 +196,7 @@ __global__ void __launch_bounds__(kSimThreads) k_sim_seg(SegArgs A) {
 // QUALITY pass (qshmm): one thread per chain chunk.  Exact state at the chunk's first position by backward
 // coupling (init draw at position 0), then the chain + emission walk through the chunk's segments, which writes
 // the quality of every position into its event slot (qshmm_quality_range); k_sim_seg turns them into events.
-__global__ void __launch_bounds__(kSimThreads) k_chain_chunk(SegArgs A, ChunkBatch C) {
+__global__ void __launch_bounds__(kChainThreads) k_chain_chunk(SegArgs A, ChunkBatch C) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint32_t acc, lo, hi;
   if (!cta_assignment(A.cta_order, A.cta_first, A.bin_lo, A.bin_hi, &acc, &lo, &hi)) return;

@@ -146,7 +146,7 @@ struct PhiloxDraw {
 // PHILOX addressing of the qshmm and sample methods ("v2"):
 //   error stream   (domain 1): block p >> 1, words 2*(p&1) = X and 2*(p&1)+1 = Y of read position p
 //       X: error draw (hit of a threshold t millionths iff X < T32(t)); 3-way choice = ((X & 0xFFF) * 3) >> 12
-//       Y: deletion draws (first: Y, j-th: fmix32(Y + j * 0x9E3779B9)); 8-way choice = Y & 7; 4-way choice = (Y >> 3) & 3
+//       Y: deletion draws (d_0 = Y, d_j = d_{j-1} * 0x9E3779B1 + 0x7F4A7C15); 8-way choice = Y & 7; 4-way choice = (Y >> 3) & 3
 //   quality stream (domain 2): block p >> 2, word p & 3 = S
 //       state draw = (S >> 16) * modulus >> 16; emission draw = (S & 0xFFFF) * modulus >> 16; freq2qc draw = mulhi(S, modulus)
 // T32(t) = min(ceil(t * 2^32 / 10^6), 2^32 - 1): for t < 10^6, X < T32(t) is mulhi32(X, 10^6) < t exactly.
@@ -154,6 +154,8 @@ PB_HD uint32_t t32_of(uint32_t t) {
   if (t >= 1000000u) return 0xFFFFFFFFu;
   return (uint32_t)(((uint64_t)t * 4294967296ull + 999999ull) / 1000000ull);
 }
+// further deletion draws of a position (qshmm / sample): d_0 = Y, d_j = d_{j-1} * 0x9E3779B1 + 0x7F4A7C15
+PB_HD uint32_t del_next(uint32_t d) { return d * 0x9E3779B1u + 0x7F4A7C15u; }
 #define PB_PROB_SHIFT 26  // PHILOX mode: error probabilities are summed in 2^-26 fixed point (order independent)
 
 struct PhiloxDrawQ {
@@ -185,7 +187,11 @@ struct PhiloxDrawQ {
   PB_HD uint32_t choice3() { return ((X & 0xFFFu) * 3u) >> 12; }
   PB_HD uint32_t choice4() { return (Y >> 3) & 3u; }
   PB_HD uint32_t choice8() { return Y & 7u; }
-  PB_HD uint32_t del(uint32_t j) { return (j == 0u) ? Y : fmix32(Y + j * 0x9E3779B9u); }
+  uint32_t dcur;
+  PB_HD uint32_t del(uint32_t j) {  // called with j = 0, 1, 2, ... in order
+    dcur = (j == 0u) ? Y : del_next(dcur);
+    return dcur;
+  }
   // a draw against a threshold given on both scales (t6: millionths, t32 = T32(t6))
   static PB_HD bool lt(uint32_t d, uint32_t, uint32_t t32) { return d < t32; }
   PB_HD uint32_t consumed() const { return 0; }
@@ -655,19 +661,27 @@ PB_HD void error_words_at(const PhiloxKeys &K, uint32_t read_id, uint32_t c1, ui
 }
 
 // kind, info and deletion count of one position from its quality and its two error-stream words, for a position
-// whose reference offset is > 0 after the base (every position except leading insertions of a read)
-PB_HD uint32_t qs_event(const QsFast th, uint32_t qv, uint32_t X, uint32_t Y, uint32_t &kind, uint32_t &nd) {
+// whose reference offset is > 0 after the base (every position except leading insertions of a read).
+// The first two deletion draws are evaluated without a branch (the second is one multiply-add away from the first).
+PB_HD uint32_t qs_event(const QsFast th, uint32_t qv, uint32_t X, uint32_t Y, uint32_t &nd) {
   const bool is_sub = X < th.sub;
-  const bool is_err = X < th.ins;  // substitution or insertion (the insertion threshold is cumulative)
-  const uint32_t c3 = ((X & 0xFFFu) * 3u) >> 12, c8 = Y & 7u;
-  const uint32_t info = is_sub ? c3 : (is_err ? c8 : 0u);
-  kind = is_sub ? PB_KIND_SUB : (is_err ? PB_KIND_INS : PB_KIND_MATCH);
-  nd = 0;
-  if (Y < th.del) {
-    nd = 1;
-    while (nd < (1u << 20) && fmix32(Y + nd * 0x9E3779B9u) < th.del) ++nd;
+  const bool is_ins = !is_sub && X < th.ins;  // (the insertion threshold is cumulative)
+  const uint32_t c3 = mulhi32(X << 20, 3u);    // ((X & 0xFFF) * 3) >> 12
+  uint32_t e = qv;
+  if (is_sub) e |= (PB_KIND_SUB << 7) | (c3 << 9);
+  if (is_ins) e |= (PB_KIND_INS << 7) | ((Y & 7u) << 9);
+  const uint32_t y2 = del_next(Y);
+  const bool hit1 = Y < th.del, hit2 = hit1 && y2 < th.del;
+  nd = (hit1 ? 1u : 0u) + (hit2 ? 1u : 0u);
+  if (hit2) {
+    uint32_t d = y2;
+    while (nd < (1u << 20)) {
+      d = del_next(d);
+      if (!(d < th.del)) break;
+      ++nd;
+    }
   }
-  return qv | (kind << 7) | (info << 9);
+  return e;
 }
 
 PB_HD void qshmm_simulate_fast(const QsView &T, const PhiloxKeys &K, uint32_t read_id, uint32_t pass,
@@ -718,7 +732,7 @@ PB_HD void qshmm_simulate_fast(const QsView &T, const PhiloxKeys &K, uint32_t re
         if (R < wlen && y[u] < (R != 0u ? th.del : T.thr32[qv].del0)) {
           nd = 1;
           ++R;
-          while (R < wlen && fmix32(y[u] + nd * 0x9E3779B9u) < th.del) {
+          for (uint32_t d = del_next(y[u]); R < wlen && d < th.del; d = del_next(d)) {
             ++nd;
             ++R;
           }
@@ -784,7 +798,7 @@ PB_HD void qshmm_simulate_fast(const QsView &T, const PhiloxKeys &K, uint32_t re
         if (R < wlen && y[u] < (R != 0u ? th.del : T.thr32[qv].del0)) {
           nd = 1;
           ++R;
-          while (R < wlen && fmix32(y[u] + nd * 0x9E3779B9u) < th.del) { ++nd; ++R; }
+          for (uint32_t d = del_next(y[u]); R < wlen && d < th.del; d = del_next(d)) { ++nd; ++R; }
         }
         ndel += nd;
         const uint32_t base = qv | (kind << 7) | (info << 9);
@@ -956,28 +970,40 @@ PB_HD void qs_freq_qualities(const QsView &T, const PhiloxKeys &K, uint32_t read
   for (uint32_t u = 0; u < PB_GROUP; ++u) qv[u] = T.freq[mulhi32(q[u], T.freq_mod)];
 }
 
-// ERROR pass, the work of one lane: the events of positions p .. p+3 (p a multiple of 4) from their qualities.
-// Deletion counts are stored saturated at PB_QS_DEL_SAT; `big` reports that one of them was (the segment is then
-// redone by qshmm_segment_generic, which writes continuation entries).
+// ERROR pass, the work of one lane: the events of positions p .. p+3 (p a multiple of 4) from their qualities,
+// packed two per word (w0: positions p, p+1; w1: p+2, p+3).  Deletion counts are stored saturated at
+// PB_QS_DEL_SAT; `big` reports that one of them was (the segment is then redone by qshmm_segment_generic, which
+// writes continuation entries).  The counters are taken from the packed events (sub: bit 7, ins: bit 8, deletions:
+// bits 12-15 of every half word).
 struct QsLaneTotals {
   uint32_t nsub, nins, ndel, prob, big;
 };
+PB_HD uint32_t pb_popc(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+  return (uint32_t)__popc(x);
+#else
+  return (uint32_t)__builtin_popcount(x);
+#endif
+}
 PB_HD void qs_error_lane(const QsFast *fast, const PhiloxKeys &K, uint32_t read_id, uint32_t c1, uint32_t p,
-                         const uint32_t qv[PB_GROUP], uint32_t e[PB_GROUP], QsLaneTotals &t) {
-  uint32_t x[PB_GROUP], y[PB_GROUP];
+                         const uint32_t qv[PB_GROUP], uint32_t &w0, uint32_t &w1, QsLaneTotals &t) {
+  uint32_t x[PB_GROUP], y[PB_GROUP], e[PB_GROUP];
   error_words(K, read_id, c1, p, x, y);
 #pragma unroll
   for (uint32_t u = 0; u < PB_GROUP; ++u) {
     const QsFast th = fast[qv[u]];
-    uint32_t kind, nd;
-    const uint32_t base = qs_event(th, qv[u], x[u], y[u], kind, nd);
-    t.nsub += kind == PB_KIND_SUB ? 1u : 0u;
-    t.nins += kind == PB_KIND_INS ? 1u : 0u;
-    t.ndel += nd;
+    uint32_t nd;
+    const uint32_t base = qs_event(th, qv[u], x[u], y[u], nd);
     t.prob += th.prob;
     t.big |= nd >= PB_QS_DEL_SAT ? 1u : 0u;
     e[u] = base | ((nd < PB_QS_DEL_SAT ? nd : PB_QS_DEL_SAT) << 12);
   }
+  w0 = e[0] | (e[1] << 16);
+  w1 = e[2] | (e[3] << 16);
+  t.nsub += pb_popc((w0 & 0x00800080u) | ((w1 & 0x00800080u) << 1));
+  t.nins += pb_popc((w0 & 0x01000100u) | ((w1 & 0x01000100u) << 1));
+  const uint32_t dd = ((w0 >> 12) & 0x000F000Fu) + ((w1 >> 12) & 0x000F000Fu);
+  t.ndel += (dd & 0xFFFFu) + (dd >> 16);
 }
 
 // ERROR pass, first segment of a read: while the reference offset is still 0 (leading insertions) the deletion
@@ -1035,7 +1061,7 @@ PB_HD void qshmm_segment_generic(const QsView &T, const PhiloxKeys &K, uint32_t 
     uint32_t nd = 0;
     if (y < (R != 0u ? th.del : T.thr32[qv].del0)) {
       nd = 1;
-      while (nd < (1u << 20) && fmix32(y + nd * 0x9E3779B9u) < th.del) ++nd;
+      for (uint32_t d = del_next(y); nd < (1u << 20) && d < th.del; d = del_next(d)) ++nd;
       R += nd;
       radv += nd;
     }
@@ -1085,7 +1111,9 @@ PB_HD void qshmm_error_segment(const QsView &T, const PhiloxKeys &K, uint32_t re
 #pragma unroll
     for (uint32_t u = 0; u < PB_GROUP; ++u) qsave[j + u] = (uint8_t)qv[u];
     t.prob = 0;
-    qs_error_lane(T.fast, K, read_id, c1, p_start + j, qv, e, t);
+    uint32_t w0, w1;
+    qs_error_lane(T.fast, K, read_id, c1, p_start + j, qv, w0, w1, t);
+    e[0] = w0 & 0xFFFFu; e[1] = w0 >> 16; e[2] = w1 & 0xFFFFu; e[3] = w1 >> 16;
     prob += t.prob;
 #pragma unroll
     for (uint32_t u = 0; u < PB_GROUP; ++u) ev[j + u] = (uint16_t)e[u];
