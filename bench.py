@@ -61,12 +61,6 @@ WORKLOADS = {
                n_transcripts=200000, n_reads=20000000),
 }
 
-# DRAM traffic rate (dram__bytes_read.sum + dram__bytes_write.sum over gpu__time_duration.sum, GB/s) of the two big
-# kernels from the committed ncu captures profiles/r01_k_sim_seg_c3_v17.txt / r01_k_emit_c3_v17.txt
-NCU_DRAM_GBS = {("qshmm", "seg"): 567.0, ("qshmm", "emit"): 1602.6,
-                # profiles/r01_k_sim_seg_err_c2_v13.txt / r01_k_emit_c2_v13.txt
-                ("errhmm", "seg"): 366.7, ("errhmm", "emit"): 1385.7}
-
 # algorithmic bytes per emitted base: FASTQ 2.002 + MAF 2.122 written + 0.244 read (2-bit genome)
 ALGO_BYTES_PER_BASE = 4.37
 
@@ -227,8 +221,8 @@ def reference_arm(args, wl):
         return
     from oracle import refrun as R
     base = {"impl": "reference", "metric": "simulated Gbp/s", "unit": "Gbp/s", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
-            "data": "synthetic", "config": {"workload": wl["name"]}}
+            "warmup": args.warmup, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int32",
+            "data": "synthetic", "config": make_config(wl, args, args.gpus)}
     if not R.have_reference_binary():
         cb = cpu_baseline(wl)
         base.update(value=cb["value"], ms_per_step=None, cpu_baseline=cb,
@@ -251,13 +245,236 @@ def reference_arm(args, wl):
                               "sample": "unmodified reference binary, %d seed-split processes per step, each 5 Mbp "
                                         "synthetic contig --depth %d; gzip children replaced by cat" % (nproc, depth)},
                 e2e={"value": v, "unit": "Gbp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0})
-    base["config"].update(sample_genome_bp=5000000, processes=nproc)
     print(json.dumps(base))
 
 
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
+# DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of ONE launch of the three big kernels on the c3 workload,
+# and the read positions that launch covered, from the committed ncu captures (profiles/r02_k_*_c3.txt)
+NCU_DRAM_BYTES = {
+    "k_chain_chunk": dict(bytes=18.12e9, positions=6.73e9, src="profiles/r02_k_chain_chunk_c3_v1.txt"),
+    "k_sim_seg": dict(bytes=27.47e9, positions=6.73e9, src="profiles/r02_k_sim_seg_c3_v14.txt"),
+    "k_emit_rows": dict(bytes=39.68e9, positions=6.10e9, src="profiles/r02_k_emit_c3_v8.txt"),
+}
+# algorithmic bytes per read position of each kernel: the quality pass writes a 2-byte slot entry per position; the
+# error pass reads and rewrites it; the row kernel reads it and 0.244 B of 2-bit genome and writes the records (4.124 B)
+KERNEL_ALGO_BYTES = {"k_chain_chunk": 2.0, "k_sim_seg": 4.0, "k_emit_rows": 2.0 + 0.244 + 4.124}
+
+
+def make_config(wl, args, world):
+    """static description of the workload: identical in both arms (ours and --impl reference)"""
+    trans = wl.get("strategy") == "trans"
+    contigs = [max(200000, int(m * 1000000 * args.scale)) for m in CONTIG_MBP]
+    if trans:
+        sharding = ("strong scaling: the read numbers of the set are split into %d contiguous ranges (no quota in this "
+                    "strategy); one NCCL all-reduce of the statistics block" % world)
+    else:
+        sharding = ("strong scaling: the %d sequences of the timed steps are assigned to the ranks longest-first (LPT), "
+                    "each simulated whole by one rank to its own depth quota; no data-path collective, one NCCL "
+                    "all-reduce of the statistics block" % args.steps)
+    return {"workload": wl["name"],
+            "step": ("one run over the transcript table, FASTQ+MAF emitted" if trans else
+                     "one reference sequence: ingest + simulate to depth quota, %s+MAF emitted"
+                     % ("SAM" if wl["params"].get("pass_num", 1) > 1 else "FASTQ")),
+            "genome_bp": int(sum(contigs)) if not trans else None, "contigs": len(contigs) if not trans else 1,
+            "rng": "philox4x32-10 (ours) / libc rand() (reference)",
+            "l2": "every step writes > 10 GB of records and events (>> 126 MB L2); no explicit flush needed",
+            "scale": args.scale, "sharding": sharding}
+
+
+def lpt_assign(sizes, world):
+    """longest-processing-time-first: item indices per rank (the by-sequence split of ONE run)"""
+    loads = [0] * world
+    out = [[] for _ in range(world)]
+    for i in sorted(range(len(sizes)), key=lambda i: (-sizes[i], i)):
+        r = loads.index(min(loads))
+        loads[r] += sizes[i]
+        out[r].append(i)
+    return out
+
+
+class Workload:
+    """one engine set up for one BASELINE.json configuration"""
+
+    def __init__(self, key, args, local, rank, overrides=True):
+        import numpy as np
+        from pbsim_b200 import capi, simulator
+        from tests.golden_util import model_path
+        self.np, self.capi = np, capi
+        wl = dict(WORKLOADS[key])
+        if overrides and (args.len_sd is not None or args.len_mean is not None):
+            wl["params"] = dict(wl["params"])
+            if args.len_sd is not None:
+                wl["params"]["len_sd"] = args.len_sd
+            if args.len_mean is not None:
+                wl["params"]["len_mean"] = args.len_mean
+            wl["name"] += " [diagnostic override: len_mean=%s len_sd=%s]" % (args.len_mean, args.len_sd)
+        self.wl, self.key, self.rank = wl, key, rank
+        L = capi.load()
+        self.hm = capi.HostModel(L, capi.host_params(wl["method"], **wl["params"]), model_path(wl["model"]))
+        self.eng = eng = simulator.Engine(local)
+        eng.set_model(self.hm)
+        if overrides:
+            for opt, val in (("target_batch_bases", args.batch_bases), ("chain_chunk", args.chain_chunk),
+                             ("first_batch_div", args.first_batch_div), ("host_batch_bases", args.host_batch_bases)):
+                if val:
+                    eng.set_option(opt, int(val))
+            if args.bam:
+                eng.set_option("bam", 1)
+                wl["name"] += " [BAM records]"
+        if wl.get("batch_bases") and not (overrides and args.batch_bases):
+            eng.set_option("target_batch_bases", int(wl["batch_bases"]))
+        self.depth = wl["depth"]
+        self.contigs = [max(200000, int(m * 1000000 * args.scale)) for m in CONTIG_MBP]
+        self.bias = [0.0] + [1.0] * 10 + [0.0]
+        self.seqset = None
+        if wl.get("strategy") == "trans":
+            # SURVEY.md 8d C4: log-normal lengths (median 1.5 kb, capped), Zipf expression counts, both strands
+            rng = np.random.default_rng(GENOME_SEED)
+            nt = max(100, int(wl["n_transcripts"] * args.scale))
+            lens = np.clip(np.exp(rng.normal(np.log(1500.0), 0.75, nt)).astype(np.int64), 200, 100000)
+            w = 1.0 / np.arange(1, nt + 1) ** 0.9
+            expr = rng.permutation(np.maximum(1, (w / w.sum() * wl["n_reads"] * args.scale)).astype(np.int64))
+            text = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, int(lens.sum()))].tobytes()
+            st0 = np.zeros(nt + 1, dtype=np.int64)
+            st0[1:] = np.cumsum(lens)
+            plus = (expr + 1) // 2
+            names = [b"T%06d" % (t + 1) for t in range(nt)]
+            id_start = np.zeros(nt + 1, dtype=np.int32)
+            id_start[1:] = np.cumsum([len(x) for x in names])
+            self.seqset = dict(n=nt, bases=text, start=st0, plus=plus.astype(np.int32),
+                               minus=(expr - plus).astype(np.int32), ids=b"".join(names), id_start=id_start)
+            self.contigs = [int(lens.sum())]
+            self.total_reads = int(expr.sum())
+            eng.set_seqset("trans", self.seqset, self.bias)
+
+    def step_device(self, k, rng_seed=0, read_range=None):
+        """one step on sequence k: ingest (synthetic text generated in HBM) + simulate to the quota, records stay in
+        HBM.  read_range: (first_read, max_reads) of a sequence-set run split by read number."""
+        eng, capi = self.eng, self.capi
+        if self.seqset is None:
+            eng.set_synthetic_sequence(self.contigs[k], k + 1, GENOME_SEED + k)
+            eng.begin(int(self.depth * self.contigs[k]), rng_mode=capi.RNG_PHILOX, seed=rng_seed)
+        else:
+            fr, mr = read_range if read_range else (0, 0)
+            eng.begin(0, rng_mode=capi.RNG_PHILOX, seed=1 + rng_seed, first_read=fr, max_reads=mr)
+        bases = out_bytes = 0
+        while True:
+            c = eng.next_chunk(device=True)
+            if c is None:
+                break
+            bases += c.bases
+            out_bytes += c.reads_bytes + c.maf_bytes
+        return bases, out_bytes, eng.end()
+
+
+def measure(W, my_steps, warm_steps, e2e_steps, barrier, read_range=None, gzip_arm=True, e2e_warm=False):
+    """device-resident arm + end-to-end arm(s) over this rank's steps.  Returns a dict of local measurements."""
+    import torch
+    eng, capi = W.eng, W.capi
+    for k in warm_steps:  # warm-up (also grows every arena to its steady-state size)
+        W.step_device(k, read_range=read_range)
+    barrier()
+    eng.timer_start()
+    t0 = time.perf_counter()
+    acc = dict(bases=0, out_bytes=0, launches=0, sim=0.0, emit=0.0, seg=0.0, chain=0.0, gen=0.0)
+    for i, k in enumerate(my_steps):
+        b, ob, st = W.step_device(k, rng_seed=(i if W.seqset is not None else 0), read_range=read_range)
+        acc["bases"] += b
+        acc["out_bytes"] += ob
+        acc["launches"] += st.kernel_launches
+        acc["sim"] += st.sim_seconds
+        acc["emit"] += st.emit_seconds
+        acc["seg"] += st.seg_seconds
+        acc["chain"] += st.chain_seconds
+        acc["gen"] += st.gen_seconds
+    acc["dev_ms"] = eng.timer_stop() if my_steps else 0.0
+    barrier()
+    acc["wall_ms"] = (time.perf_counter() - t0) * 1e3
+    acc["e2e"] = acc["e2e_gz"] = None
+    steps_e = my_steps[:e2e_steps] if e2e_steps >= 0 else my_steps
+    if e2e_steps != 0:
+        host_seq = {}
+        if W.seqset is None:
+            for k in sorted(set(steps_e)):  # pinned host copies of the sequence text (untimed preparation)
+                eng.set_synthetic_sequence(W.contigs[k], k + 1, GENOME_SEED + k)
+                t = torch.empty(W.contigs[k], dtype=torch.uint8, pin_memory=True)
+                eng.get_sequence_ascii(t.data_ptr(), W.contigs[k])
+                host_seq[k] = t
+
+        def e2e_pass():
+            barrier()
+            t0 = time.perf_counter()
+            e_bases = h2d = d2h = 0
+            sink = 0
+            gen_s = gz_s = 0.0
+            for i, q in enumerate(steps_e):
+                if W.seqset is None:
+                    eng.set_sequence_ptr(host_seq[q].data_ptr(), W.contigs[q], q + 1, W.bias)
+                    eng.begin(int(W.depth * W.contigs[q]), rng_mode=capi.RNG_PHILOX, seed=0)
+                else:
+                    eng.set_seqset("trans", W.seqset, W.bias)  # the table's text goes up with every step
+                    fr, mr = read_range if read_range else (0, 0)
+                    eng.begin(0, rng_mode=capi.RNG_PHILOX, seed=1 + i, first_read=fr, max_reads=mr)
+                h2d += W.contigs[q]
+                while True:
+                    c = eng.next_chunk(device=False)
+                    if c is None:
+                        break
+                    e_bases += c.bases
+                    d2h += c.reads_bytes + c.maf_bytes
+                    if c.reads_bytes:  # the consumer looks at the delivered bytes
+                        sink ^= C.c_ubyte.from_address(c.reads + c.reads_bytes - 1).value
+                st = eng.end()
+                gen_s += st.gen_seconds
+                gz_s += st.deflate_seconds
+            barrier()
+            return dict(bases=e_bases, ms=(time.perf_counter() - t0) * 1e3, h2d=h2d, d2h=d2h, steps=len(steps_e),
+                        gen_s=gen_s, gz_s=gz_s)
+
+        if e2e_warm:  # untimed pass: pinned staging buffers and record buffers reach their steady-state size
+            e2e_pass()
+        acc["e2e"] = e2e_pass()
+        if gzip_arm:
+            # the same with the records gzip-compressed on the GPU before they cross PCIe (the reference's outputs
+            # are .gz files, pbsim.cpp:708-730); reported next to the text number, not instead of it
+            eng.set_option("deflate", 1)
+            acc["e2e_gz"] = e2e_pass()
+            eng.set_option("deflate", 0)
+        del host_seq
+    return acc
+
+
+def roofline_block(method, acc, peak, peak_src):
+    """whole-step fraction on top; per-kernel fractions (each kernel against its OWN algorithmic bytes) below"""
+    bases = acc["bases"]
+    dev_s = acc["dev_ms"] * 1e-3
+    achieved = ALGO_BYTES_PER_BASE * bases / dev_s / 1e9 if dev_s > 0 else 0.0
+    chain_name = "k_chain_chunk" if method == "qshmm" else "k_chain_chunk_err"
+    seg_name = "k_sim_seg" if method == "qshmm" else "k_sim_seg_err"
+    kern = {}
+    for name, key, secs in ((chain_name, "k_chain_chunk", acc["chain"]), (seg_name, "k_sim_seg", acc["seg"]),
+                            ("k_tile_desc + k_emit_rows + k_emit (pass 2)", "k_emit_rows", acc["emit"])):
+        ab = KERNEL_ALGO_BYTES[key] if method == "qshmm" or key == "k_emit_rows" else KERNEL_ALGO_BYTES[key] / 2.0
+        a = ab * bases / secs / 1e9 if secs > 0 else 0.0
+        ncu = NCU_DRAM_BYTES[key] if method == "qshmm" else None
+        kern[name] = {"seconds": secs, "algorithmic_bytes_per_base": ab, "achieved": a, "frac": a / peak if peak else None,
+                      "share_of_step": secs / dev_s if dev_s else None,
+                      "traffic": ncu["bytes"] if ncu else None,
+                      "traffic_per_base": ncu["bytes"] / ncu["positions"] if ncu else None,
+                      "traffic_source": (ncu["src"] + ": dram__bytes_read.sum + dram__bytes_write.sum of one launch")
+                      if ncu else None}
+    dom = max(kern, key=lambda n: kern[n]["seconds"])
+    return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
+            "what": "whole step: %.2f algorithmic bytes per emitted base x bases / device time of the timed steps"
+                    % ALGO_BYTES_PER_BASE,
+            "traffic": kern[dom]["traffic"], "kernel": dom + ", rank 0", "algorithmic_bytes_per_base": ALGO_BYTES_PER_BASE,
+            "peak_source": peak_src, "dominant_kernel": dict(kern[dom], name=dom), "kernels": kern,
+            "kernel_seconds": {"sim": acc["sim"], "emit": acc["emit"], "all_generation": acc["gen"]}}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -268,6 +485,8 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0, help="shrink contigs (debugging only; reported in config)")
     ap.add_argument("--e2e-steps", type=int, default=-1, help="steps of the host-buffer arm (default: all)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the short runs of the other BASELINE configurations")
+    ap.add_argument("--extra-steps", type=int, default=3)
     ap.add_argument("--len-sd", type=float, default=None, help="diagnostics: override --length-sd (0 = equal-length reads)")
     ap.add_argument("--len-mean", type=float, default=None, help="diagnostics: override --length-mean")
     ap.add_argument("--batch-bases", type=float, default=None, help="diagnostics: engine target_batch_bases")
@@ -276,22 +495,11 @@ def main():
     ap.add_argument("--host-batch-bases", type=float, default=None, help="diagnostics: engine host_batch_bases")
     ap.add_argument("--bam", action="store_true", help="multi-pass workloads: BAM records / BGZF blocks instead of SAM text")
     args = ap.parse_args()
-    wl = dict(WORKLOADS[args.workload])
-    if args.len_sd is not None or args.len_mean is not None:
-        wl["params"] = dict(wl["params"])
-        if args.len_sd is not None:
-            wl["params"]["len_sd"] = args.len_sd
-        if args.len_mean is not None:
-            wl["params"]["len_mean"] = args.len_mean
-        wl["name"] += " [diagnostic override: len_mean=%s len_sd=%s]" % (args.len_mean, args.len_sd)
     if args.impl == "reference":
-        reference_arm(args, wl)
+        reference_arm(args, dict(WORKLOADS[args.workload]))
         return
 
-    import numpy as np
     import torch
-    from pbsim_b200 import capi, simulator
-    from tests.golden_util import model_path
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -299,78 +507,14 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
     torch.cuda.set_device(local)
+    pin_to_gpu_numa_node(local)
     dist = None
     if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line
+        # NCCL's own log (whatever level the caller asked for) goes to stderr: stdout carries the one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         import torch.distributed as dist_mod
         dist = dist_mod
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-
-    L = capi.load()
-    hm = capi.HostModel(L, capi.host_params(wl["method"], **wl["params"]), model_path(wl["model"]))
-    eng = simulator.Engine(local)
-    eng.set_model(hm)
-    if args.batch_bases:
-        eng.set_option("target_batch_bases", int(args.batch_bases))
-    if args.chain_chunk:
-        eng.set_option("chain_chunk", args.chain_chunk)
-    if args.first_batch_div:
-        eng.set_option("first_batch_div", args.first_batch_div)
-    if args.host_batch_bases:
-        eng.set_option("host_batch_bases", int(args.host_batch_bases))
-    if args.bam:
-        eng.set_option("bam", 1)
-        wl["name"] += " [BAM records]"
-    if wl.get("batch_bases") and not args.batch_bases:
-        eng.set_option("target_batch_bases", int(wl["batch_bases"]))
-    depth = wl["depth"]
-    contigs = [max(200000, int(m * 1000000 * args.scale)) for m in CONTIG_MBP]
-    bias = [0.0] + [1.0] * 10 + [0.0]
-    seqset = None
-    if wl.get("strategy") == "trans":
-        # log-normal lengths (median 1.5 kb, capped), Zipf expression counts, both strands
-        rng = np.random.default_rng(GENOME_SEED + rank)
-        nt = max(100, int(wl["n_transcripts"] * args.scale))
-        lens = np.clip(np.exp(rng.normal(np.log(1500.0), 0.75, nt)).astype(np.int64), 200, 100000)
-        w = 1.0 / np.arange(1, nt + 1) ** 0.9
-        expr = rng.permutation(np.maximum(1, (w / w.sum() * wl["n_reads"] * args.scale)).astype(np.int64))
-        text = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, int(lens.sum()))].tobytes()
-        st0 = np.zeros(nt + 1, dtype=np.int64)
-        st0[1:] = np.cumsum(lens)
-        plus = (expr + 1) // 2
-        names = [b"T%06d" % (t + 1) for t in range(nt)]
-        id_start = np.zeros(nt + 1, dtype=np.int32)
-        id_start[1:] = np.cumsum([len(x) for x in names])
-        seqset = dict(n=nt, bases=text, start=st0, plus=plus.astype(np.int32), minus=(expr - plus).astype(np.int32),
-                      ids=b"".join(names), id_start=id_start)
-        contigs = [int(lens.sum())]
-        eng.set_seqset("trans", seqset, bias)
-
-    # multi-GPU: reads shard by read-id range with no data-path collective.  Every rank walks
-    # the same contigs and simulates its own range of read ids of each (first_read = rank << 26; results depend only
-    # on (seed, sequence, read id)), to the full depth quota: per-GPU work is fixed as N grows (weak scaling) and
-    # equal across ranks.
-    first_read = rank << 26
-
-    def seq_of(step):
-        return step % len(contigs)
-
-    def step_device(step):
-        """ingest (synthetic text generated in HBM) + simulate to the quota, records stay in HBM"""
-        k = seq_of(step)
-        if seqset is None:
-            eng.set_synthetic_sequence(contigs[k], k + 1, GENOME_SEED + k)
-        eng.begin(int(depth * contigs[k]), rng_mode=capi.RNG_PHILOX, seed=1 + ((step + 1000 * rank) if seqset else 0),
-                  first_read=first_read if seqset is None else 0)
-        bases = out_bytes = 0
-        while True:
-            c = eng.next_chunk(device=True)
-            if c is None:
-                break
-            bases += c.bases
-            out_bytes += c.reads_bytes + c.maf_bytes
-        st = eng.end()
-        return bases, out_bytes, st
 
     def barrier():
         torch.cuda.synchronize()
@@ -378,79 +522,6 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- warm-up (also grows every arena to its steady-state size)
-    for w in range(args.warmup):
-        step_device(w)
-    # ---- timed: device-resident arm
-    sampler = ClockSampler(local)
-    sampler.start()
-    barrier()
-    eng.timer_start()
-    t0 = time.perf_counter()
-    bases = out_bytes = launches = 0
-    sim_s = emit_s = gen_s = seg_s = chain_s = 0.0
-    for k in range(args.steps):
-        b, ob, st = step_device(args.warmup + k)
-        bases += b
-        out_bytes += ob
-        launches += st.kernel_launches
-        sim_s += st.sim_seconds
-        emit_s += st.emit_seconds
-        seg_s += st.seg_seconds
-        chain_s += st.chain_seconds
-        gen_s += st.gen_seconds
-    dev_ms = eng.timer_stop()
-    barrier()
-    wall_ms = (time.perf_counter() - t0) * 1e3
-    clocks = sampler.stop()
-
-    # ---- timed: end-to-end arm (host buffers both ways)
-    e2e_steps = args.steps if args.e2e_steps < 0 else args.e2e_steps
-    e2e = None
-    if e2e_steps > 0:
-        need = sorted({seq_of(args.warmup + k) for k in range(e2e_steps)}) if seqset is None else []
-        host_seq = {}
-        for k in need:  # pinned host copies of the sequence text (untimed preparation)
-            eng.set_synthetic_sequence(contigs[k], k + 1, GENOME_SEED + k)
-            t = torch.empty(contigs[k], dtype=torch.uint8, pin_memory=True)
-            eng.get_sequence_ascii(t.data_ptr(), contigs[k])
-            host_seq[k] = t
-        def e2e_pass():
-            barrier()
-            t0 = time.perf_counter()
-            e_bases = h2d = d2h = 0
-            sink = 0
-            for k in range(e2e_steps):
-                q = seq_of(args.warmup + k)
-                if seqset is None:
-                    eng.set_sequence_ptr(host_seq[q].data_ptr(), contigs[q], q + 1, bias)
-                else:
-                    eng.set_seqset("trans", seqset, bias)  # the table's text goes up with every step
-                h2d += contigs[q]
-                eng.begin(int(depth * contigs[q]), rng_mode=capi.RNG_PHILOX, seed=1 + (rank if seqset else 0),
-                          first_read=first_read if seqset is None else 0)
-                while True:
-                    c = eng.next_chunk(device=False)
-                    if c is None:
-                        break
-                    e_bases += c.bases
-                    d2h += c.reads_bytes + c.maf_bytes
-                    if c.reads_bytes:  # the consumer looks at the delivered bytes
-                        sink ^= C.c_ubyte.from_address(c.reads + c.reads_bytes - 1).value
-                eng.end()
-            barrier()
-            e_ms = (time.perf_counter() - t0) * 1e3
-            return dict(bases=e_bases, ms=e_ms, h2d=h2d / e2e_steps, d2h=d2h / e2e_steps)
-
-        e2e = e2e_pass()
-        # the same with the records gzip-compressed on the GPU before they cross PCIe (the reference's outputs are
-        # .gz files, pbsim.cpp:708-730); reported next to the text number, not instead of it
-        eng.set_option("deflate", 1)
-        e2e_gz = e2e_pass()
-        eng.set_option("deflate", 0)
-        del host_seq
-
-    # ---- reduce over ranks: total units, MAX time
     def allsum(x):
         if dist is None:
             return x
@@ -465,71 +536,87 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return t.item()
 
-    tot_bases = allsum(bases)
-    max_ms = allmax(dev_ms)
-    max_wall = allmax(wall_ms)
-    tot_launches = allsum(launches)
-    if e2e:
-        e2e_bases = allsum(e2e["bases"])
-        e2e_ms = allmax(e2e["ms"])
-        e2e_gz_bases = allsum(e2e_gz["bases"])
-        e2e_gz_ms = allmax(e2e_gz["ms"])
+    W = Workload(args.workload, args, local, rank)
+    wl = W.wl
+    # ---- ONE run split over the ranks (strong scaling): the timed steps are the sequences (warmup + k) mod 24,
+    #      k < steps; rank r simulates the ones the longest-first assignment gives it, whole (its own quota, its own
+    #      output files: pbsim.cpp:699-754).  A sequence set (--strategy trans) is one step: split by read-number range.
+    read_range = None
+    if W.seqset is None:
+        step_ids = [(args.warmup + k) % len(W.contigs) for k in range(args.steps)]
+        mine = [step_ids[i] for i in lpt_assign([W.contigs[k] for k in step_ids], world)[rank]]
+        warm = [max(mine, key=lambda k: W.contigs[k])] * args.warmup if mine else []
+    else:
+        from pbsim_b200.stats_reduce import read_range_for_rank
+        lo, hi = read_range_for_rank(W.total_reads, rank, world)
+        read_range = (lo, hi - lo)
+        mine = [0] * args.steps
+        warm = [0] * args.warmup
+    sampler = ClockSampler(local)
+    sampler.start()
+    acc = measure(W, mine, warm, args.e2e_steps, barrier, read_range=read_range)
+    clocks = sampler.stop()
+
+    tot_bases = allsum(acc["bases"])
+    max_ms = allmax(acc["dev_ms"])
+    max_wall = allmax(acc["wall_ms"])
+    tot_launches = allsum(acc["launches"])
+    e2e_line = {}
+    for key in ("e2e", "e2e_gz"):
+        if acc[key] is not None or world > 1 and args.e2e_steps != 0:
+            e = acc[key] or dict(bases=0, ms=0.0, h2d=0, d2h=0, steps=0, gen_s=0.0, gz_s=0.0)
+            e2e_line[key] = dict(bases=allsum(e["bases"]), ms=allmax(e["ms"]), h2d=allsum(e["h2d"]), d2h=allsum(e["d2h"]),
+                                 steps=allsum(e["steps"]), gen_s=allmax(e["gen_s"]), gz_s=allmax(e["gz_s"]))
     if dist is not None:
         # the one collective of the path: statistics block (counters + both histograms), NCCL all-reduce
         from pbsim_b200.stats_reduce import allreduce_stats_block
-        allreduce_stats_block(eng, dist)
+        allreduce_stats_block(W.eng, dist)
 
     if rank == 0:
         peak, peak_src = measured_peak()
-        value = tot_bases / (max_ms * 1e-3) / 1e9
-        kern_s = sim_s + emit_s
-        # the dominant kernel is pass 2 (k_emit): it performs the path's algorithmic traffic (genome read, records
-        # written); its launches are bracketed by CUDA events on the engine's stream (pbsim_stats.emit_seconds)
-        seg_name = "k_sim_seg" if wl["method"] == "qshmm" else "k_sim_seg_err"
-        dom_s, dom_name = (seg_s, seg_name + " (pass 1, segment-parallel chains)") if seg_s >= emit_s else \
-                          (emit_s, "k_emit (pass 2)")
-        achieved = ALGO_BYTES_PER_BASE * bases / dom_s / 1e9 if dom_s > 0 else 0.0
-        path_achieved = ALGO_BYTES_PER_BASE * bases / kern_s / 1e9 if kern_s > 0 else 0.0
-        traffic = NCU_DRAM_GBS.get((wl["method"], "seg" if seg_s >= emit_s else "emit"))
+        value = tot_bases / (max_ms * 1e-3) / 1e9 if max_ms > 0 else 0.0
+        nsteps = max(1, args.steps)
+        config = make_config(wl, args, world)
         line = {
             "metric": "simulated Gbp/s", "value": value, "unit": "Gbp/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": max_ms / max(1, args.steps), "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-            "config": {"workload": wl["name"],
-                       "step": ("one run over the transcript table, FASTQ+MAF emitted" if seqset is not None else
-                                "one reference sequence: device ingest + simulate to depth quota, %s+MAF emitted"
-                                % ("SAM" if wl["params"].get("pass_num", 1) > 1 else "FASTQ")), "genome_bp": int(sum(contigs)), "contigs": len(contigs), "rng": "philox4x32-10",
-                       "l2": "every step writes > 10 GB of records and events (>> 126 MB L2); no explicit flush needed",
-                       "host_wall_ms_per_step": max_wall / max(1, args.steps), "scale": args.scale,
-                       "sharding": "every rank simulates its own read-id range (first_read = rank << 26) of the same "
-                                   "contig to the full depth quota; no data-path collective, one NCCL all-reduce of "
-                                   "the statistics block"},
+            "warmup": args.warmup, "ms_per_step": max_ms / nsteps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+            "config": config, "host_wall_ms_per_step": max_wall / nsteps,
             "gpu_launches": int(tot_launches),
             "clocks": {"sm_mhz": clocks["sm_mhz"], "sm_max_mhz": clocks["sm_max_mhz"], "reasons": clocks["reasons"]},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak if peak else None, "traffic": traffic,
-                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch of that "
-                                           "kernel / its duration, GB/s (ncu --set full, profiles/r01_k_*_c3_v17.txt, *_c2_v13.txt)",
-                         "kernel": dom_name + ", rank 0",
-                         "algorithmic_bytes_per_base": ALGO_BYTES_PER_BASE, "peak_source": peak_src,
-                         "kernel_seconds": {"sim": sim_s, "of_which_" + seg_name: seg_s,
-                                            "of_which_k_chain_chunk": chain_s, "emit": emit_s,
-                                            "all_generation": gen_s},
-                         "kernel_share_of_step": dom_s / (dev_ms * 1e-3) if dev_ms else None,
-                         "path": {"what": "pass 1 + pass 2 together (k_sim_seg, k_find_end, k_sim_%s, k_emit)"
-                                          % wl["method"],
-                                  "achieved": path_achieved, "frac": path_achieved / peak if peak else None,
-                                  "share_of_step": kern_s / (dev_ms * 1e-3) if dev_ms else None}},
+            "roofline": roofline_block(wl["method"], acc, peak, peak_src),
         }
-        if e2e:
-            line["e2e"] = {"value": e2e_bases / (e2e_ms * 1e-3) / 1e9, "unit": "Gbp/s",
-                           "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
-                           "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps, "delivered": "text records"}
-            line["e2e_gzip"] = {"value": e2e_gz_bases / (e2e_gz_ms * 1e-3) / 1e9, "unit": "Gbp/s",
-                                "h2d_bytes_per_step": e2e_gz["h2d"], "d2h_bytes_per_step": e2e_gz["d2h"],
-                                "steps": e2e_steps, "ms_per_step": e2e_gz_ms / e2e_steps,
-                                "delivered": "gzip members written by the GPU (option deflate)",
-                                "compression_ratio": e2e["d2h"] / max(1.0, e2e_gz["d2h"])}
+        for key, name, what in (("e2e", "e2e", "text records"),
+                                ("e2e_gz", "e2e_gzip", "gzip members written by the GPU (option deflate)")):
+            if key in e2e_line and e2e_line[key]["ms"] > 0:
+                e = e2e_line[key]
+                st = max(1.0, e["steps"])
+                line[name] = {"value": e["bases"] / (e["ms"] * 1e-3) / 1e9, "unit": "Gbp/s",
+                              "h2d_bytes_per_step": e["h2d"] / st, "d2h_bytes_per_step": e["d2h"] / st,
+                              "steps": int(e["steps"]), "ms_per_step": e["ms"] / (st / world), "delivered": what,
+                              "d2h_gb_per_s": e["d2h"] / (e["ms"] * 1e-3) / 1e9,
+                              "device_seconds": {"generation_incl_deflate": e["gen_s"], "of_which_deflate": e["gz_s"],
+                                                 "wall": e["ms"] * 1e-3}}
+        if "e2e_gzip" in line and "e2e" in line:
+            line["e2e_gzip"]["compression_ratio"] = line["e2e"]["d2h_bytes_per_step"] / max(1.0, line["e2e_gzip"]["d2h_bytes_per_step"])
+        # ---- short runs of the other BASELINE configurations (one GPU): value + roofline each
+        if world == 1 and not args.no_extras and args.workload == "c3":
+            W.eng.close()
+            line["extra"] = {}
+            for key in ("c1", "c2", "c4", "c5"):
+                try:
+                    X = Workload(key, args, local, rank, overrides=False)
+                    ns = args.extra_steps if X.seqset is None else 1
+                    st_ids = [(2 + k) % len(X.contigs) for k in range(ns)]  # mid-sized contigs
+                    a = measure(X, st_ids, st_ids[:1], 1, barrier, gzip_arm=False, e2e_warm=True)
+                    line["extra"][key] = {
+                        "workload": X.wl["name"], "steps": ns,
+                        "value": a["bases"] / (a["dev_ms"] * 1e-3) / 1e9, "unit": "Gbp/s",
+                        "e2e": a["e2e"]["bases"] / (a["e2e"]["ms"] * 1e-3) / 1e9 if a["e2e"] else None,
+                        "roofline": roofline_block(X.wl["method"], a, peak, peak_src)}
+                    X.eng.close()
+                except Exception as ex:  # an extra must never cost the headline
+                    line["extra"][key] = {"error": repr(ex)}
         if not args.no_cpu_baseline:
             try:
                 line["cpu_baseline"] = cpu_baseline(wl)
@@ -540,6 +627,40 @@ def main():
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def pin_to_gpu_numa_node(local):
+    """host side of the delivery path: run this rank (and allocate its pinned staging buffers) on the NUMA node its
+    GPU hangs off, so that 8 ranks do not all stage through node 0"""
+    try:
+        import torch
+        bdf = None
+        pr = torch.cuda.get_device_properties(local)
+        if hasattr(pr, "pci_bus_id") and hasattr(pr, "pci_device_id"):
+            bdf = "%04x:%02x:%02x.0" % (getattr(pr, "pci_domain_id", 0), pr.pci_bus_id, pr.pci_device_id)
+        if bdf is None or not os.path.exists("/sys/bus/pci/devices/%s/numa_node" % bdf):
+            out = subprocess.run(["nvidia-smi", "-i", str(local), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, timeout=20).stdout.decode().strip()
+            bdf = out[-12:].lower() if len(out) >= 12 else None  # 00000000:1B:00.0 -> 0000:1b:00.0
+        if not bdf:
+            return None
+        node_path = "/sys/bus/pci/devices/%s/numa_node" % bdf
+        node = int(open(node_path).read().strip())
+        if node < 0:
+            return None
+        cpus = open("/sys/devices/system/node/node%d/cpulist" % node).read().strip()
+        ids = []
+        for part in cpus.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                ids.extend(range(int(a), int(b) + 1))
+            elif part:
+                ids.append(int(part))
+        if ids:
+            os.sched_setaffinity(0, ids)
+        return node
+    except Exception:
+        return None
 
 
 if __name__ == "__main__":

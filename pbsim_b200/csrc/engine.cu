@@ -127,6 +127,14 @@ __global__ void k_batch_totals(const unsigned long long *prefix, const uint32_t 
   if (i < n_sub && flags[i]) atomicOr(reinterpret_cast<unsigned int *>(&ctrl[2]), flags[i]);
 }
 
+// Control read-backs (a few words per batch) are written by a kernel straight into pinned host memory instead of
+// going through cudaMemcpyAsync: a D2H memcpy on the compute stream queues on the same DMA engine as the delivery
+// stream's 128 MiB record copies and waits milliseconds behind them, several times per batch.
+__global__ void k_peek(const uint32_t *__restrict__ src, uint32_t *__restrict__ host_dst, uint64_t words) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < words) host_dst[i] = src[i];
+}
+
 __global__ void k_iota_u32(uint32_t *p, uint32_t n) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = i;
@@ -256,7 +264,7 @@ struct pbsim_engine {
   int deflate = 0;
   int bam = 0;                      // option "bam": multi-pass records are BAM alignment records, not SAM text
   OutSet gz[2];
-  DevBuf d_gz_tables, d_gz_hist, d_gz_usize, d_gz_ucrc, d_gz_uoff;
+  DevBuf d_gz_tables, d_gz_hist, d_gz_usize, d_gz_ucrc, d_gz_uoff, d_gz_usel, d_gz_sbits;
   PinnedBuf h_gz;
   double gz_ms = 0, seg_ms = 0, chain_ms = 0;
   cudaEvent_t ev_gz[2] = {nullptr, nullptr}, ev_seg[2] = {nullptr, nullptr}, ev_chain[2] = {nullptr, nullptr};
@@ -341,6 +349,17 @@ template <class T>
 int upload(pbsim_engine *e, DevBuf &d, const T *src, size_t n) {
   CK(d.ensure(std::max<size_t>(n * sizeof(T), 16)));
   if (n) CK(cudaMemcpyAsync(d.p, src, n * sizeof(T), cudaMemcpyHostToDevice, e->st));
+  return 0;
+}
+
+// device -> pinned host, by a kernel on the engine's stream (see k_peek); host_dst must be pinned memory, both
+// pointers 4-byte aligned, bytes a multiple of 4
+int peek(pbsim_engine *e, void *host_dst, const void *dev_src, size_t bytes) {
+  if (!bytes) return 0;
+  const uint64_t words = (bytes + 3) / 4;
+  k_peek<<<nblk(words, 256), 256, 0, e->st>>>(reinterpret_cast<const uint32_t *>(dev_src), reinterpret_cast<uint32_t *>(host_dst),
+                                              words);
+  CK(cudaGetLastError());
   return 0;
 }
 
@@ -637,14 +656,14 @@ int run_batch(pbsim_engine *e, uint32_t n_reads, int64_t clip_room, BatchResult 
       k_widen<<<nblk(n_sub + 1, 256), 256, 0, e->st>>>(B.nseg, n_sub, tmp64);
       if ((rc = excl_scan(e, tmp64, seg_off, n_sub + 1))) return rc;
       e->launches++;
-      CK(cudaMemcpyAsync(hctrl + 2, seg_off + n_sub, 8, cudaMemcpyDeviceToHost, e->st));
+      if (peek(e, hctrl + 2, seg_off + n_sub, 8)) return PBSIM_E_CUDA;
       k_widen<<<nblk(n_sub + 1, 256), 256, 0, e->st>>>(B.nchunk, n_sub, tmp64);
       if ((rc = excl_scan(e, tmp64, chunk_off, n_sub + 1))) return rc;
       e->launches++;
-      CK(cudaMemcpyAsync(hctrl + 4, chunk_off + n_sub, 8, cudaMemcpyDeviceToHost, e->st));
+      if (peek(e, hctrl + 4, chunk_off + n_sub, 8)) return PBSIM_E_CUDA;
     }
-    CK(cudaMemcpyAsync(hctrl, B.ev_off + n_sub, 8, cudaMemcpyDeviceToHost, e->st));
-    CK(cudaMemcpyAsync(hctrl + 1, B.ck_off + n_sub, 8, cudaMemcpyDeviceToHost, e->st));
+    if (peek(e, hctrl, B.ev_off + n_sub, 8)) return PBSIM_E_CUDA;
+    if (peek(e, hctrl + 1, B.ck_off + n_sub, 8)) return PBSIM_E_CUDA;
     CK(cudaStreamSynchronize(e->st));
     const uint64_t ev_entries = hctrl[0], ck_entries = hctrl[1];
     const uint64_t n_seg_total = use_segments ? hctrl[2] : 0;
@@ -680,7 +699,7 @@ int run_batch(pbsim_engine *e, uint32_t n_reads, int64_t clip_room, BatchResult 
         hctrl[6] = 0;
         CK(cudaMemsetAsync(ctrl + 6, 0, 8, e->st));
         k_sample_redo<<<nblk(n_reads, 256), 256, 0, e->st>>>(B, ctrl + 6);
-        CK(cudaMemcpyAsync(hctrl + 6, ctrl + 6, 8, cudaMemcpyDeviceToHost, e->st));
+        if (peek(e, hctrl + 6, ctrl + 6, 8)) return PBSIM_E_CUDA;
         CK(cudaStreamSynchronize(e->st));
         e->launches += 2;
         if (hctrl[6] > 0) {
@@ -843,7 +862,7 @@ int run_batch(pbsim_engine *e, uint32_t n_reads, int64_t clip_room, BatchResult 
                                                           pass, next_start_after, ctrl, reinterpret_cast<unsigned int *>(&ctrl[3]));
       e->launches++;
     }
-    CK(cudaMemcpyAsync(hctrl, ctrl, 32, cudaMemcpyDeviceToHost, e->st));
+    if (peek(e, hctrl, ctrl, 32)) return PBSIM_E_CUDA;
     CK(cudaStreamSynchronize(e->st));
     const uint32_t flags = (uint32_t)hctrl[2];
     if (flags & 2u) return fail(e, PBSIM_E_PARAM, "a read drew an accuracy for which the model has no usable tables");
@@ -929,9 +948,9 @@ int run_batch(pbsim_engine *e, uint32_t n_reads, int64_t clip_room, BatchResult 
   if ((rc = excl_scan(e, reads_size, reads_off, nv_sub + 1))) return rc;
   if ((rc = excl_scan(e, maf_size, maf_off, nv_sub + 1))) return rc;
   if ((rc = excl_scan(e, ntiles, tile_start, nv_sub + 1))) return rc;
-  CK(cudaMemcpyAsync(hctrl + 8, reads_off + nv_sub, 8, cudaMemcpyDeviceToHost, e->st));
-  CK(cudaMemcpyAsync(hctrl + 9, maf_off + nv_sub, 8, cudaMemcpyDeviceToHost, e->st));
-  CK(cudaMemcpyAsync(hctrl + 10, tile_start + nv_sub, 8, cudaMemcpyDeviceToHost, e->st));
+  if (peek(e, hctrl + 8, reads_off + nv_sub, 8)) return PBSIM_E_CUDA;
+  if (peek(e, hctrl + 9, maf_off + nv_sub, 8)) return PBSIM_E_CUDA;
+  if (peek(e, hctrl + 10, tile_start + nv_sub, 8)) return PBSIM_E_CUDA;
   CK(cudaStreamSynchronize(e->st));
   out->reads_bytes = hctrl[8];
   out->maf_bytes = hctrl[9];
@@ -1006,8 +1025,8 @@ int run_batch(pbsim_engine *e, uint32_t n_reads, int64_t clip_room, BatchResult 
   CK(e->h_acc.ensure((size_t)nv_sub * 8 + (size_t)nv_sub * 4 * 3 + 64));
   double *hacc = reinterpret_cast<double *>(e->h_acc.p);
   uint32_t *hrlen = reinterpret_cast<uint32_t *>(hacc + nv_sub);
-  CK(cudaMemcpyAsync(hacc, B.accuracy, (size_t)nv_sub * 8, cudaMemcpyDeviceToHost, e->st));
-  CK(cudaMemcpyAsync(hrlen, B.rlen, (size_t)nv_sub * 4, cudaMemcpyDeviceToHost, e->st));
+  if (peek(e, hacc, B.accuracy, (size_t)nv_sub * 8)) return PBSIM_E_CUDA;
+  if (peek(e, hrlen, B.rlen, (size_t)nv_sub * 4)) return PBSIM_E_CUDA;
   return 0;
 }
 
@@ -1021,31 +1040,35 @@ int gz_compress(pbsim_engine *e, const uint8_t *in, uint64_t n, DevBuf &dst, uin
   *out_bytes = 0;
   if (n == 0) return 0;
   static_assert(sizeof(GzTables) % 8 == 0, "GzTables is copied as words");
-  CK(e->d_gz_hist.ensure(256 * 8));
+  CK(e->d_gz_hist.ensure(512 * 8));
   CK(e->d_gz_tables.ensure(sizeof(GzTables)));
-  CK(e->h_gz.ensure(256 * 8 + sizeof(GzTables) + 64));
+  CK(e->h_gz.ensure(512 * 8 + sizeof(GzTables) + 64));
   unsigned long long *hh = reinterpret_cast<unsigned long long *>(e->h_gz.p);
-  GzTables *ht = reinterpret_cast<GzTables *>(hh + 256);
-  CK(cudaMemsetAsync(e->d_gz_hist.p, 0, 256 * 8, e->st));
+  GzTables *ht = reinterpret_cast<GzTables *>(hh + 512);
+  CK(cudaMemsetAsync(e->d_gz_hist.p, 0, 512 * 8, e->st));
   int dev_sms = 148;
   cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, e->device);
   // streams above 64 MiB are sampled: one 16-byte chunk in 16
   k_gz_hist<<<(uint32_t)std::min<uint64_t>((n + 4095) / 4096, (uint64_t)dev_sms * 8), 256, 0, e->st>>>(
       in, n, n > ((uint64_t)64 << 20) ? 16u : 1u, e->d_gz_hist.as<unsigned long long>());
   e->launches++;
-  CK(cudaMemcpyAsync(hh, e->d_gz_hist.p, 256 * 8, cudaMemcpyDeviceToHost, e->st));
+  if (peek(e, hh, e->d_gz_hist.p, 512 * 8)) return PBSIM_E_CUDA;
   CK(cudaStreamSynchronize(e->st));
   {
-    uint64_t hist[256];
-    for (int i = 0; i < 256; ++i) hist[i] = hh[i];
-    GzCode code;
-    gz_build_code(hist, &code);
+    // three codes per stream: code 0 from the sequence-like text, code 1 from the rest, code 2 from all of it
+    // (gz_kernels.cuh)
     std::memset(ht, 0, sizeof *ht);
-    std::memcpy(ht->lit, code.lit, sizeof ht->lit);
-    std::memcpy(ht->hdr, code.hdr, sizeof ht->hdr);
-    std::memcpy(ht->len, code.len, sizeof ht->len);
-    ht->eob = code.eob;
-    ht->hdr_bits = code.hdr_bits;
+    for (uint32_t c = 0; c < kGzCodes; ++c) {
+      uint64_t hist[256];
+      for (int i = 0; i < 256; ++i) hist[i] = c < 2 ? hh[c * 256 + i] : hh[i] + hh[256 + i];
+      GzCode code;
+      gz_build_code(hist, &code);
+      std::memcpy(ht->lit[c], code.lit, sizeof ht->lit[c]);
+      std::memcpy(ht->hdr[c], code.hdr, sizeof ht->hdr[c]);
+      for (int i = 0; i < 256; ++i) ht->len3[i] |= (unsigned long long)code.len[i] << (16 * c);
+      ht->eob[c] = code.eob;
+      ht->hdr_bits[c] = code.hdr_bits;
+    }
     gz_crc_table(ht->crc);
     gz_x2n_table(ht->x2n);
     // x^(8 * slice): appends one slice to a CRC; tail[t] = that to the power of the slices behind slice t
@@ -1063,29 +1086,33 @@ int gz_compress(pbsim_engine *e, const uint8_t *in, uint64_t n, DevBuf &dst, uin
   if (units > 0x7FFFFFFFull) return fail(e, PBSIM_E_INVALID, "stream too large for the gzip writer");
   CK(e->d_gz_usize.ensure((size_t)units * 4 + 64));
   CK(e->d_gz_ucrc.ensure((size_t)units * 4 + 64));
+  CK(e->d_gz_usel.ensure((size_t)units * 2 + 64));
+  CK(e->d_gz_sbits.ensure((size_t)units * kGzThreads * 2 + 64));
   CK(e->d_gz_uoff.ensure((size_t)(units + 1) * 16 + 64));
   unsigned long long *wide = e->d_gz_uoff.as<unsigned long long>();
   unsigned long long *uoff = wide + (units + 1);
   k_gz_size<<<(uint32_t)units, kGzThreads, 0, e->st>>>(in, n, e->d_gz_tables.as<GzTables>(), bgzf ? 1u : 0u,
-                                                     e->d_gz_usize.as<uint32_t>(), e->d_gz_ucrc.as<uint32_t>());
+                                                     e->d_gz_usize.as<uint32_t>(), e->d_gz_ucrc.as<uint32_t>(),
+                                                     e->d_gz_usel.as<uint16_t>(), e->d_gz_sbits.as<uint16_t>());
   k_widen<<<nblk(units, 256), 256, 0, e->st>>>(e->d_gz_usize.as<uint32_t>(), (uint32_t)units, wide);
   CK(cudaMemsetAsync(wide + units, 0, 8, e->st));
   e->launches += 2;
   int rc = excl_scan(e, wide, uoff, (uint32_t)units + 1u);
   if (rc) return rc;
-  CK(cudaMemcpyAsync(hh, uoff + units, 8, cudaMemcpyDeviceToHost, e->st));
+  if (peek(e, hh, uoff + units, 8)) return PBSIM_E_CUDA;
   CK(cudaStreamSynchronize(e->st));
   const uint64_t total = hh[0];
   CK(dst.ensure((size_t)total + 256));
   static bool attr_set = false;
-  const size_t smem = (size_t)kGzImgWords * 4 + 256 * 4;
+  const size_t smem = (size_t)kGzImgWords * 4 + kGzCodes * 256 * 4;
   if (!attr_set) {
     CK(cudaFuncSetAttribute(k_gz_encode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
   k_gz_encode<<<(uint32_t)units, kGzThreads, smem, e->st>>>(in, n, e->d_gz_tables.as<GzTables>(),
                                                            reinterpret_cast<const uint64_t *>(uoff),
-                                                           e->d_gz_ucrc.as<uint32_t>(), bgzf ? 1u : 0u, dst.as<uint8_t>());
+                                                           e->d_gz_ucrc.as<uint32_t>(), e->d_gz_usel.as<uint16_t>(),
+                                                           e->d_gz_sbits.as<uint16_t>(), bgzf ? 1u : 0u, dst.as<uint8_t>());
   e->launches++;
   CK(cudaGetLastError());
   *out_bytes = total;
@@ -1481,7 +1508,7 @@ void pbsim_cuda_destroy(pbsim_engine *e) {
                     &e->d_ctrl, &e->d_cub_tmp, &e->d_ev, &e->d_ck, &e->out[0].reads, &e->out[0].maf, &e->out[1].reads, &e->out[1].maf, &e->d_stats, &e->d_seg,
                     &e->d_seg_bins, &e->d_set_start, &e->d_set_rprefix, &e->d_set_plus, &e->d_set_ids, &e->d_set_idstart,
                     &e->d_set_ssp_ends, &e->d_set_ssp_mod, &e->d_set_first, &e->gz[0].reads, &e->gz[0].maf, &e->gz[1].reads,
-                    &e->gz[1].maf, &e->d_gz_tables, &e->d_gz_hist, &e->d_gz_usize, &e->d_gz_ucrc, &e->d_gz_uoff,
+                    &e->gz[1].maf, &e->d_gz_tables, &e->d_gz_hist, &e->d_gz_usize, &e->d_gz_ucrc, &e->d_gz_uoff, &e->d_gz_usel, &e->d_gz_sbits,
                     &e->d_lay, &e->d_tile_sub, &e->d_tile_desc, &e->d_chunk, &e->d_chunk_bins};
   for (DevBuf *b : bufs) b->release();
   for (auto &a : e->h_stage)
