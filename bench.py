@@ -284,6 +284,20 @@ def make_config(wl, args, world):
             "scale": args.scale, "sharding": sharding}
 
 
+def host_d2h_ceiling(world):
+    """aggregate GB/s of N concurrent bare pinned device-to-host copy loops on this pool's 8-GPU host
+    (tools/d2h_ceiling.py, committed as profiles/r02_d2h_ceiling_8gpu.json): what the delivery path can reach at best"""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r02_d2h_ceiling_8gpu.json")) as f:
+            runs = json.load(f)["runs"]
+        for r in runs:
+            if r["n"] == world and not r["numa_pinned"]:
+                return r["aggregate_gb_s"]
+    except Exception:
+        pass
+    return None
+
+
 def lpt_assign(sizes, world):
     """longest-processing-time-first: item indices per rank (the by-sequence split of ONE run)"""
     loads = [0] * world
@@ -597,6 +611,10 @@ def main():
                               "d2h_gb_per_s": e["d2h"] / (e["ms"] * 1e-3) / 1e9,
                               "device_seconds": {"generation_incl_deflate": e["gen_s"], "of_which_deflate": e["gz_s"],
                                                  "wall": e["ms"] * 1e-3}}
+                ceil = host_d2h_ceiling(world)
+                if ceil:
+                    line[name]["host_d2h_ceiling_gb_per_s"] = ceil
+                    line[name]["d2h_frac_of_host_ceiling"] = line[name]["d2h_gb_per_s"] / ceil
         if "e2e_gzip" in line and "e2e" in line:
             line["e2e_gzip"]["compression_ratio"] = line["e2e"]["d2h_bytes_per_step"] / max(1.0, line["e2e_gzip"]["d2h_bytes_per_step"])
         # ---- short runs of the other BASELINE configurations (one GPU): value + roofline each

@@ -121,6 +121,21 @@ def synth_set(seed, n, len_lo=300, len_hi=4000, max_exp=4, lowercase_first=0.0, 
     return out
 
 
+def synth_transcripts(seed, n, n_reads):
+    """BASELINE config 4 in small: log-normal lengths (median 1.5 kb), Zipf expression, both strands.
+    Returns [(name, plus, minus, bases)] with sum(plus + minus) ~ n_reads."""
+    rng = np.random.default_rng(seed)
+    lens = np.clip(np.exp(rng.normal(np.log(1500.0), 0.75, n)).astype(np.int64), 200, 100000)
+    w = 1.0 / np.arange(1, n + 1) ** 0.9
+    expr = rng.permutation(np.maximum(1, (w / w.sum() * n_reads)).astype(np.int64))
+    out = []
+    for t in range(n):
+        s = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, int(lens[t]))].tobytes()
+        plus = int((expr[t] + 1) // 2)
+        out.append(("T%06d" % (t + 1), plus, int(expr[t] - plus), s))
+    return out
+
+
 def write_transcripts(path, seqset):
     """the 4-column table get_transcript_inf reads (pbsim.cpp:1095-1120): id, plus, minus, sequence"""
     with open(path, "wb") as f:

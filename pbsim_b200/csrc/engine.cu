@@ -204,6 +204,11 @@ struct pbsim_engine {
   double set_mean_len = 0;
   int32_t set_rank_max = 0;
   DevBuf d_set_start, d_set_rprefix, d_set_plus, d_set_ids, d_set_idstart, d_set_ssp_ends, d_set_ssp_mod, d_set_first;
+  // host copies for the replay read map of simulate_by_errhmm_trans (build_replay_read_map)
+  std::vector<uint32_t> h_set_start, h_set_nr;
+  std::vector<uint16_t> h_ssp_ends, h_ssp_mod;
+  DevBuf d_map_tr, d_map_k;
+  bool replay_map = false;
 
   // --method sample: the pool of quality strings (get_sample_inf's fp_filtered) and the run's schedule
   bool pool_set = false;
@@ -408,6 +413,8 @@ DeviceSet device_set(const pbsim_engine *e) {
   S.ssp_mod = e->d_set_ssp_mod.as<uint16_t>();
   S.ids = e->d_set_ids.as<uint8_t>();
   S.id_start = e->d_set_idstart.as<uint32_t>();
+  S.map_tr = e->replay_map ? e->d_map_tr.as<uint32_t>() : nullptr;
+  S.map_k = e->replay_map ? e->d_map_k.as<uint32_t>() : nullptr;
   return S;
 }
 
@@ -1456,6 +1463,61 @@ int next_chunk_impl(pbsim_engine *e, pbsim_chunk *c, bool to_host) {
   return 1;
 }
 
+// Replay of simulate_by_errhmm_trans: the reference copies an accuracy-100 read with `for (i=0; i<mut.len; i++)`
+// (pbsim.cpp:4532) using the SAME i that counts the transcript's reads (:4487), so after such a read the count
+// continues from mut.len + 1 and the transcript's remaining reads are (usually) never simulated.  Which reads exist
+// therefore depends on the draws.  The log holds them: walk it with the planner's three draws per read (:4538-4562)
+// and record the transcript and the rank of every logged read.
+int build_replay_read_map(pbsim_engine *e) {
+  const pbsim_run &run = e->run;
+  const int64_t pass = e->model.pass_num;
+  const int64_t n_logged = run.replay_nsubreads / pass;
+  std::vector<uint32_t> map_tr, map_k;
+  map_tr.reserve((size_t)n_logged);
+  map_k.reserve((size_t)n_logged);
+  int64_t idx = 0;
+  for (uint32_t t = 0; t < (uint32_t)e->set_n && idx < n_logged; ++t) {
+    const uint32_t tlen = e->h_set_start[t + 1] - e->h_set_start[t];
+    const uint32_t rank = (tlen + 999u) / 1000u;
+    for (uint64_t k = 1; k <= e->h_set_nr[t] && idx < n_logged; ++k) {
+      const int64_t st = run.replay_starts[idx * pass];
+      if (st < 0 || st + 3 > run.replay_ndraws) return fail(e, PBSIM_E_REPLAY, "replay log exhausted while mapping the reads of the set");
+      const uint32_t d0 = (uint32_t)run.replay_draws[st], d1 = (uint32_t)run.replay_draws[st + 1],
+                     d2 = (uint32_t)run.replay_draws[st + 2];
+      uint32_t len = (uint32_t)e->h_prob2len[d0 % (uint32_t)e->model.len_rand_value];
+      const uint32_t acc = e->h_prob2acc[d1 % (uint32_t)e->model.accuracy_rand_value];
+      const uint32_t index = d2 % e->h_ssp_mod[rank] + 1u;
+      uint32_t ssp = 100u;
+      for (uint32_t j = 0; j < 21u; ++j) {
+        const uint32_t en = e->h_ssp_ends[rank * 21u + j];
+        if (en == 0xFFFFu) break;
+        if (index <= en) {
+          ssp = j * 5u;
+          break;
+        }
+      }
+      const double value = ssp == 0u ? 0.0 : ((double)ssp - 2.5) / 100;
+      volatile double prod = (double)tlen * value;  // two roundings, as plan_read_trans computes it
+      const uint32_t offset = (uint32_t)(int)(prod + 0.5);
+      if ((uint64_t)offset + len > tlen) len = offset < tlen ? tlen - offset : 0u;
+      map_tr.push_back(t);
+      map_k.push_back((uint32_t)k);
+      ++idx;
+      if (acc == 100u) k = len;  // the loop variable was the copy loop's too: the count resumes behind mut.len
+    }
+  }
+  if (idx != n_logged)
+    return fail(e, PBSIM_E_REPLAY, "the replay log holds %lld reads but the set accounts for %lld", (long long)n_logged,
+                (long long)idx);
+  int rc;
+  if ((rc = upload(e, e->d_map_tr, map_tr.data(), map_tr.size()))) return rc;
+  if ((rc = upload(e, e->d_map_k, map_k.data(), map_k.size()))) return rc;
+  CK(cudaStreamSynchronize(e->st));
+  e->replay_map = true;
+  e->run.max_reads = idx;
+  return 0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -1507,7 +1569,7 @@ void pbsim_cuda_destroy(pbsim_engine *e) {
                     &e->d_draws, &e->d_starts, &e->b_read_u32, &e->b_sub_u32, &e->b_sub_u64, &e->b_sub_f64, &e->d_bins,
                     &e->d_ctrl, &e->d_cub_tmp, &e->d_ev, &e->d_ck, &e->out[0].reads, &e->out[0].maf, &e->out[1].reads, &e->out[1].maf, &e->d_stats, &e->d_seg,
                     &e->d_seg_bins, &e->d_set_start, &e->d_set_rprefix, &e->d_set_plus, &e->d_set_ids, &e->d_set_idstart,
-                    &e->d_set_ssp_ends, &e->d_set_ssp_mod, &e->d_set_first, &e->gz[0].reads, &e->gz[0].maf, &e->gz[1].reads,
+                    &e->d_set_ssp_ends, &e->d_set_ssp_mod, &e->d_set_first, &e->d_map_tr, &e->d_map_k, &e->gz[0].reads, &e->gz[0].maf, &e->gz[1].reads,
                     &e->gz[1].maf, &e->d_gz_tables, &e->d_gz_hist, &e->d_gz_usize, &e->d_gz_ucrc, &e->d_gz_uoff, &e->d_gz_usel, &e->d_gz_sbits,
                     &e->d_lay, &e->d_tile_sub, &e->d_tile_desc, &e->d_chunk, &e->d_chunk_bins};
   for (DevBuf *b : bufs) b->release();
@@ -1689,6 +1751,10 @@ int pbsim_cuda_set_seqset(pbsim_engine *e, const pbsim_seqset *s) {
   e->strategy = s->strategy;
   e->set_n = n;
   e->set_total_reads = (int64_t)reads;
+  e->h_set_start = start;
+  e->h_set_nr.assign(n, 1u);
+  if (trans)
+    for (uint32_t t = 0; t < n; ++t) e->h_set_nr[t] = plus_w[n + t];
   e->set_mean_len = (double)total / n;
   int rc;
   if ((rc = upload(e, e->d_set_start, start.data(), start.size()))) return rc;
@@ -1700,6 +1766,8 @@ int pbsim_cuda_set_seqset(pbsim_engine *e, const pbsim_seqset *s) {
     e->set_rank_max = (int32_t)std::ceil((float)max_len / 1000);  // transcript.rank_max (:1137)
     std::vector<uint16_t> ends((size_t)(e->set_rank_max + 1) * 21), mod((size_t)e->set_rank_max + 1);
     pbsim_host_ssp_table(e->set_rank_max, ends.data(), mod.data());
+    e->h_ssp_ends = ends;
+    e->h_ssp_mod = mod;
     if ((rc = upload(e, e->d_set_ssp_ends, ends.data(), ends.size()))) return rc;
     if ((rc = upload(e, e->d_set_ssp_mod, mod.data(), mod.size()))) return rc;
     CK(cudaStreamSynchronize(e->st));  // the vectors go out of scope
@@ -1774,6 +1842,7 @@ int pbsim_cuda_simulate_begin(pbsim_engine *e, const pbsim_run *run) {
     e->sample_redo_groups = 0;
   }
   e->run = *run;
+  e->replay_map = false;
   if (e->strategy != PBSIM_STRATEGY_WGS) {
     // the whole set (or the requested range of its read numbers) is the run; there is no quota (:2841, :3312)
     if (run->first_read < 0 || run->first_read >= e->set_total_reads)
@@ -1782,6 +1851,12 @@ int pbsim_cuda_simulate_begin(pbsim_engine *e, const pbsim_run *run) {
     e->run.len_quota = INT64_MAX / 4;
     e->run.len_total_start = 0;
     e->run.max_reads = run->max_reads > 0 ? std::min(run->max_reads, left) : left;
+    if (run->rng_mode == PBSIM_RNG_REPLAY && e->strategy == PBSIM_STRATEGY_TRANS && e->model.method == PBSIM_METHOD_ERRHMM) {
+      if (run->first_read != 0)
+        return fail(e, PBSIM_E_INVALID, "a replay of simulate_by_errhmm_trans starts at read 0 (its read numbering depends on the draws)");
+      const int rc = build_replay_read_map(e);
+      if (rc) return rc;
+    }
   }
   e->next_read = run->first_read;
   e->len_total = e->run.len_total_start;

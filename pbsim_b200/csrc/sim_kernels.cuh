@@ -57,6 +57,10 @@ struct DeviceSet {
   const uint16_t *ssp_mod;
   const uint8_t *ids;       // names, concatenated
   const uint32_t *id_start; // [n+1]
+  // replay of simulate_by_errhmm_trans only: sequence and rank of every logged read (null otherwise).  The
+  // reference's read counter of a transcript jumps after an accuracy-100 read (pbsim.cpp:4487, :4532), so which reads
+  // exist depends on the draws; the host works the sequence out from the log (engine.cu build_replay_read_map).
+  const uint32_t *map_tr, *map_k;
 };
 
 struct RngParams {
@@ -116,14 +120,19 @@ __global__ void k_plan(DeviceModel M, DeviceGenome G, DeviceSet S, RngParams rng
   uint32_t tr = 0, tlen = 0, tstart = 0;
   uint64_t kth = 0;
   if (S.strategy != PBSIM_STRATEGY_WGS) {
-    uint32_t lo = 0, hi = S.n;  // rprefix[lo] <= read_id - 1 < rprefix[hi]
-    while (hi - lo > 1u) {
-      const uint32_t mid = (lo + hi) >> 1;
-      if (S.rprefix[mid] <= read_id - 1u) lo = mid;
-      else hi = mid;
+    if (S.map_tr != nullptr) {
+      tr = S.map_tr[read_id - 1u];
+      kth = S.map_k[read_id - 1u];
+    } else {
+      uint32_t lo = 0, hi = S.n;  // rprefix[lo] <= read_id - 1 < rprefix[hi]
+      while (hi - lo > 1u) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (S.rprefix[mid] <= read_id - 1u) lo = mid;
+        else hi = mid;
+      }
+      tr = lo;
+      kth = read_id - S.rprefix[tr];
     }
-    tr = lo;
-    kth = read_id - S.rprefix[tr];
     tstart = S.start[tr];
     tlen = S.start[tr + 1] - tstart;
     B.plan_tr[r] = tr;

@@ -62,6 +62,98 @@ def test_engine_philox_matches_reference_distributions(name):
     assert ok, res
 
 
+# ---- the BASELINE.json configurations (fixtures: oracle/make_stats_fixtures.py, two reference seeds each) -----------
+BASELINE_CASES = ["c3_qs_ont_50k", "c2_err_onthq_default", "c5_err_sequel_pass10", "c4_trans_qs_rsii"]
+ALPHA = 0.002   # every KS / chi-square test; 4 configurations x 7 tests: a true-null failure in about 1 run in 18
+
+
+def _split(fix, tag):
+    keys = ("lengths", "accuracy", "err_accuracy", "qv_hist", "qv_thin", "events", "per_read", "plus", "n")
+    out = {k: fix[tag + k] for k in keys}
+    out["lengths"] = out["lengths"].astype(np.int64)
+    return out
+
+
+def _pass0(st, stride):
+    """multi-pass runs: the passes of a read share its window and accuracy, so the read-level tests use pass 0 only"""
+    if stride == 1:
+        return st
+    out = dict(st)
+    for k in ("lengths", "accuracy", "err_accuracy", "per_read"):
+        out[k] = st[k][::stride]
+    out["events"] = out["per_read"].sum(0)
+    return out
+
+
+def _okw_baseline(meta):
+    a = meta["extra"]
+    kw = {}
+    if "--length-mean" in a:
+        kw.update(len_mean=float(a[a.index("--length-mean") + 1]), len_sd=float(a[a.index("--length-sd") + 1]),
+                  len_max=int(a[a.index("--length-max") + 1]))
+    if "--difference-ratio" in a:
+        kw["ratio"] = tuple(int(x) for x in a[a.index("--difference-ratio") + 1].split(":"))
+    if "--pass-num" in a:
+        kw["pass_num"] = int(a[a.index("--pass-num") + 1])
+    return kw
+
+
+@pytest.mark.parametrize("name", BASELINE_CASES)
+def test_reference_seed_to_seed_passes_the_same_bars(name):
+    """calibration: two runs of the UNMODIFIED reference with different seeds pass the comparison the engine has to pass"""
+    meta, fix = load_fixture(name)
+    stride = _okw_baseline(meta).get("pass_num", 1)
+    ok, res = SU.compare(_pass0(_split(fix, "b_"), stride), _pass0(_split(fix, ""), stride), meta["method"], alpha=ALPHA)
+    assert ok, res
+
+
+def _oracle_run(meta, seed):
+    kw = _okw_baseline(meta)
+    o = O.Oracle(meta["method"], model_path(meta["model"]), **kw)
+    o.rng_philox(seed)
+    if meta["strategy"] == "wgs":
+        o.set_sequence(R.synth_genome(78, [("s1", meta["genome_bp"])])[0][1], 1)  # an independent random genome
+        reads, maf, st = o.simulate_wgs(meta["depth"])
+    else:
+        reads, maf, st = o.simulate_set("trans", R.synth_transcripts(4242, meta["n_transcripts"], meta["n_reads"]))
+    if kw.get("pass_num", 1) > 1:
+        reads = SU.sam_to_fastq(reads)
+    return SU.parse_outputs(reads, maf), kw.get("pass_num", 1)
+
+
+@pytest.mark.parametrize("name", BASELINE_CASES)
+def test_oracle_philox_matches_reference_on_baseline_configs(name):
+    meta, fix = load_fixture(name)
+    got, stride = _oracle_run(meta, 99)
+    ok, res = SU.compare(_pass0(got, stride), _pass0(_split(fix, ""), stride), meta["method"], alpha=ALPHA)
+    assert ok, res
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", BASELINE_CASES)
+def test_engine_philox_matches_reference_on_baseline_configs(name):
+    from pbsim_b200 import capi, simulator
+    meta, fix = load_fixture(name)
+    kw = _okw_baseline(meta)
+    L = capi.load()
+    hm = capi.HostModel(L, capi.host_params(meta["method"], **kw), model_path(meta["model"]))
+    eng = simulator.Engine(0)
+    eng.set_model(hm)
+    if meta["strategy"] == "wgs":
+        eng.set_synthetic_sequence(meta["genome_bp"], 1, 4242)
+        reads, maf, st, _ = eng.simulate(int(meta["depth"] * meta["genome_bp"]), rng_mode=capi.RNG_PHILOX, seed=123)
+    else:
+        eng.set_seqset("trans", R.synth_transcripts(4242, meta["n_transcripts"], meta["n_reads"]), [0.0] + [1.0] * 10 + [0.0])
+        reads, maf, st, _ = eng.simulate(0, rng_mode=capi.RNG_PHILOX, seed=123)
+    eng.close()
+    stride = kw.get("pass_num", 1)
+    if stride > 1:
+        reads = SU.sam_to_fastq(reads)
+    got = SU.parse_outputs(reads, maf)
+    ok, res = SU.compare(_pass0(got, stride), _pass0(_split(fix, ""), stride), meta["method"], alpha=ALPHA)
+    assert ok, res
+
+
 @pytest.mark.skipif(not os.path.exists(R.REF_BIN), reason="oracle/_ref/pbsim is not built here")
 def test_sample_method_philox_matches_live_reference_distributions(tmp_path):
     """--method sample: PHILOX mode (oracle == engine byte for byte, tests/test_gpu_sample.py) against a run of the
