@@ -299,14 +299,8 @@ def host_d2h_ceiling(world):
 
 
 def lpt_assign(sizes, world):
-    """longest-processing-time-first: item indices per rank (the by-sequence split of ONE run)"""
-    loads = [0] * world
-    out = [[] for _ in range(world)]
-    for i in sorted(range(len(sizes)), key=lambda i: (-sizes[i], i)):
-        r = loads.index(min(loads))
-        loads[r] += sizes[i]
-        out[r].append(i)
-    return out
+    from pbsim_b200.stats_reduce import lpt_assign as f
+    return f(sizes, world)
 
 
 class Workload:

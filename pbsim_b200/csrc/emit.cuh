@@ -1175,7 +1175,8 @@ __global__ void __launch_bounds__(kEmitThreads) k_emit(const __grid_constant__ E
 // ----------------------------------------------------------------------------------------------
 // K6: statistics of the valid subreads (pbsim.cpp:2293-2316): counters, min/max, the two histograms
 // stats block layout (int64): [0] res_num(reads) [1] res_pass_num [2] len_total [3] len_min [4] len_max
-//                             [5] sub [6] ins [7] del [8..15] spare, then freq_accuracy[100001], freq_len[...]
+//                             [5] sub [6] ins [7] del [8] accuracy sum (2^-40 fixed point) [9..15] spare,
+//                             then freq_accuracy[100001], freq_len[...]
 // ----------------------------------------------------------------------------------------------
 constexpr int kStatCounters = 16;
 
@@ -1206,7 +1207,16 @@ __global__ void k_stats(Batch B, uint32_t n_sub, uint32_t pass_num, unsigned lon
     nins += __shfl_down_sync(0xFFFFFFFFu, nins, o);
     ndel += __shfl_down_sync(0xFFFFFFFFu, ndel, o);
   }
+  // [8]: sum of the per-read accuracies in 2^-40 fixed point — reducible over ranks (pbsim_stats.accuracy_total is
+  // the reference's floating-point sum in read order, which is not)
+  unsigned long long accfx = 0;
+  if (s < n_sub) {
+    const double a = B.accuracy[s];
+    if (a > 0.0 && a <= 1.0) accfx = (unsigned long long)__double2ll_rn(a * 1099511627776.0);
+  }
+  for (int o = 16; o > 0; o >>= 1) accfx += __shfl_down_sync(0xFFFFFFFFu, accfx, o);
   if ((threadIdx.x & 31) == 0) {
+    if (accfx) atomicAdd(blk + 8, accfx);
     if (len) atomicAdd(blk + 2, len);
     if (nsub) atomicAdd(blk + 5, nsub);
     if (nins) atomicAdd(blk + 6, nins);

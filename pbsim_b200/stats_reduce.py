@@ -36,6 +36,45 @@ def allreduce_stats_block(engine, dist):
     return reduce_stats_tensor(t, dist)
 
 
+CELL_ACC_FX = 8          # sum of the per-read accuracies, 2^-40 fixed point (emit.cuh k_stats)
+N_COUNTERS = 16
+
+
+def merged_summary(cells, len_max, pass_num=1):
+    """The reference's end-of-run numbers (pbsim.cpp:2387-2410, :5541-5564) from a REDUCED stats block (host array of
+    int64 cells).  The accuracy mean comes from the fixed-point sum in the block: pbsim_stats.accuracy_total of one
+    engine is the reference's floating-point sum in read order and cannot be combined across ranks."""
+    import numpy as np
+    c = np.asarray(cells, dtype=np.int64)
+    res_num, res_pass, total = int(c[0]), int(c[1]), int(c[2])
+    fa = c[N_COUNTERS:N_COUNTERS + 100001].astype(np.float64)
+    fl = c[N_COUNTERS + 100001:].astype(np.float64)
+    out = dict(res_num=res_num, res_pass_num=res_pass, res_len_total=total, res_len_min=int(c[CELL_LEN_MIN]),
+               res_len_max=int(c[CELL_LEN_MAX]), res_sub_num=int(c[5]), res_ins_num=int(c[6]), res_del_num=int(c[7]))
+    if res_pass > 0:
+        out["res_len_mean"] = total / res_pass
+        out["res_accuracy_mean"] = int(c[CELL_ACC_FX]) / 1099511627776.0 / res_pass
+        if res_pass == 1:
+            out["res_len_sd"] = out["res_accuracy_sd"] = 0.0
+        else:
+            i = np.arange(min(len(fl), len_max + 1), dtype=np.float64)
+            out["res_len_sd"] = float(np.sqrt((((out["res_len_mean"] - i) ** 2) * fl[:len(i)]).sum() / res_pass))
+            j = np.arange(100001, dtype=np.float64) * 0.00001
+            out["res_accuracy_sd"] = float(np.sqrt((((out["res_accuracy_mean"] - j) ** 2) * fa).sum() / res_pass))
+    return out
+
+
+def lpt_assign(sizes, world):
+    """by-sequence split of ONE run over the ranks: longest-processing-time-first, item indices per rank"""
+    loads = [0] * world
+    out = [[] for _ in range(world)]
+    for i in sorted(range(len(sizes)), key=lambda i: (-sizes[i], i)):
+        r = loads.index(min(loads))
+        loads[r] += sizes[i]
+        out[r].append(i)
+    return out
+
+
 def contigs_for_rank(n_contigs, rank, world):
     """partition by sequence (many-contig genomes): rank r simulates contigs r, r+world, ..."""
     return list(range(rank, n_contigs, world))

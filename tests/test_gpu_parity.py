@@ -266,6 +266,44 @@ def test_read_range_shards_concatenate_to_the_single_gpu_run(eng):
     assert a[2].res_len_total + b[2].res_len_total == whole[2].res_len_total
 
 
+def test_merged_statistics_of_a_split_run_equal_the_single_engine_statistics(eng):
+    """the stats blocks of a 2-way read-range split, summed as the NCCL all-reduce sums them, give the one-engine
+    statistics text: the accuracy mean comes from the block's fixed-point sum (pbsim_stats.accuracy_total, the
+    reference's floating-point sum in read order, cannot be combined across ranks)"""
+    import ctypes as C
+    import torch
+    from pbsim_b200 import stats_reduce as SR
+    from tests.golden_util import model_path
+    hm = capi.HostModel(capi.load(), capi.host_params("qshmm"), model_path("QSHMM-RSII.model"))
+    eng.set_model(hm)
+    n = 1200000
+    eng.set_synthetic_sequence(n, 1, 33)
+    quota = 3 * n
+
+    def block():
+        ptr, cells = eng.stats_block()
+        return torch.as_tensor(SR._DeviceCells(ptr, cells), device="cuda").cpu().numpy().copy()
+
+    whole = eng.simulate(quota, rng_mode=capi.RNG_PHILOX, seed=9)
+    blk_whole = block()
+    k = whole[2].res_num // 2
+    a = eng.simulate(quota, rng_mode=capi.RNG_PHILOX, seed=9, first_read=0, max_reads=k)
+    blk_a = block()
+    b = eng.simulate(quota, rng_mode=capi.RNG_PHILOX, seed=9, first_read=k, len_total_start=a[2].res_len_total)
+    blk_b = block()
+    merged = blk_a + blk_b
+    merged[SR.CELL_LEN_MIN] = min(blk_a[SR.CELL_LEN_MIN], blk_b[SR.CELL_LEN_MIN])
+    merged[SR.CELL_LEN_MAX] = max(blk_a[SR.CELL_LEN_MAX], blk_b[SR.CELL_LEN_MAX])
+    assert (merged == blk_whole).all()          # every cell, the fixed-point accuracy sum included
+    m = SR.merged_summary(merged, hm.view.len_max)
+    st = whole[2]
+    assert m["res_num"] == st.res_num and m["res_len_total"] == st.res_len_total
+    assert abs(m["res_accuracy_mean"] - st.res_accuracy_mean) < 1e-9
+    assert abs(m["res_accuracy_sd"] - st.res_accuracy_sd) < 1e-9
+    assert abs(m["res_len_sd"] - st.res_len_sd) < 1e-6 * max(1.0, st.res_len_sd)
+    assert "%f (%f)" % (m["res_accuracy_mean"], m["res_accuracy_sd"]) == "%f (%f)" % (st.res_accuracy_mean, st.res_accuracy_sd)
+
+
 def test_megabase_reads_equal_oracle(eng):
     """reads at the length limit (--length-mean 900000 --length-sd 0 --length-max 1000000): ~880 segments per read,
     backward coupling on every one of them; bytes and statistics must equal the oracle's"""

@@ -66,3 +66,27 @@ def test_sharding_helpers_cover_everything_once():
             assert all(a[1] == b[0] for a, b in zip(ranges, ranges[1:]))
             sizes = [b - a for a, b in ranges]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_lpt_split_covers_every_sequence_once_and_balances():
+    sizes = [248, 242, 198, 190, 182, 171, 159, 145, 138, 134, 135, 133, 114, 107, 102, 90, 83, 80, 59, 64, 47, 51, 156, 57]
+    for world in (1, 2, 4, 8):
+        parts = SR.lpt_assign(sizes, world)
+        assert sorted(i for p in parts for i in p) == list(range(len(sizes)))
+        loads = [sum(sizes[i] for i in p) for p in parts]
+        assert sum(sizes) / world / max(loads) > 0.95   # the 24 human-sized contigs balance to > 95 % on 8 ranks
+
+
+def test_merged_summary_from_a_reduced_block():
+    import numpy as np
+    cells = np.zeros(16 + 100001 + 2002, dtype=np.int64)
+    # two reads: lengths 100 and 300, accuracies 0.80 and 0.90
+    cells[0] = 2; cells[1] = 2; cells[2] = 400; cells[3] = 100; cells[4] = 300
+    cells[5], cells[6], cells[7] = 4, 8, 12
+    cells[SR.CELL_ACC_FX] = int(round(0.8 * 2 ** 40)) + int(round(0.9 * 2 ** 40))
+    cells[16 + 80000] = 1; cells[16 + 90000] = 1
+    cells[16 + 100001 + 100] = 1; cells[16 + 100001 + 300] = 1
+    m = SR.merged_summary(cells, 1000)
+    assert m["res_num"] == 2 and m["res_len_mean"] == 200.0
+    assert abs(m["res_accuracy_mean"] - 0.85) < 1e-12 and abs(m["res_accuracy_sd"] - 0.05) < 1e-9
+    assert abs(m["res_len_sd"] - 100.0) < 1e-9
