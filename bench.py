@@ -270,10 +270,17 @@ def make_config(wl, args, world):
     if trans:
         sharding = ("strong scaling: the read numbers of the set are split into %d contiguous ranges (no quota in this "
                     "strategy); one NCCL all-reduce of the statistics block" % world)
-    else:
+    elif getattr(args, "no_split", False) or world == 1:
         sharding = ("strong scaling: the %d sequences of the timed steps are assigned to the ranks longest-first (LPT), "
                     "each simulated whole by one rank to its own depth quota; no data-path collective, one NCCL "
                     "all-reduce of the statistics block" % args.steps)
+    else:
+        sharding = ("strong scaling: ONE run of %d sequences, each to its own depth quota; the line of all their reads is "
+                    "cut into %d pieces of equal estimated work (a rank owns whole sequences plus at most one leading "
+                    "and one trailing read range of a sequence shared with a neighbour); results depend only on (seed, "
+                    "sequence, read number), so the parts concatenate to the 1-GPU bytes; the quota cut of a shared "
+                    "sequence takes the emitted bases of its earlier parts from one asynchronous NCCL all-reduce (an "
+                    "int64 per sequence), plus one NCCL all-reduce of the statistics block" % (args.steps, world))
     return {"workload": wl["name"],
             "step": ("one run over the transcript table, FASTQ+MAF emitted" if trans else
                      "one reference sequence: ingest + simulate to depth quota, %s+MAF emitted"
@@ -358,38 +365,94 @@ class Workload:
             self.total_reads = int(expr.sum())
             eng.set_seqset("trans", self.seqset, self.bias)
 
-    def step_device(self, k, rng_seed=0, read_range=None):
-        """one step on sequence k: ingest (synthetic text generated in HBM) + simulate to the quota, records stay in
-        HBM.  read_range: (first_read, max_reads) of a sequence-set run split by read number."""
+    def run_part(self, part, rng_seed=0, read_range=None, prefix=0, host_seq=None, sink=None, on_chunk=None):
+        """one part of the run: WGS — a sequence, or a read range of one (part = dict(seq, first_read, max_reads, last),
+        stats_reduce.plan_line_split; prefix = emitted bases of the sequence's earlier parts when this is its dependent
+        last part); sequence sets — the whole table or this rank's read-number range of it.
+        host_seq = None: the sequence text is generated in HBM and the records stay there (device arm);
+        otherwise the text is uploaded from that pinned host buffer and every record byte is delivered to host memory.
+        Returns (bases, record bytes, stats)."""
         eng, capi = self.eng, self.capi
+        device = host_seq is None
         if self.seqset is None:
-            eng.set_synthetic_sequence(self.contigs[k], k + 1, GENOME_SEED + k)
-            eng.begin(int(self.depth * self.contigs[k]), rng_mode=capi.RNG_PHILOX, seed=rng_seed)
+            k = part["seq"]
+            if device:
+                eng.set_synthetic_sequence(self.contigs[k], k + 1, GENOME_SEED + k)
+            else:
+                eng.set_sequence_ptr(host_seq.data_ptr(), self.contigs[k], k + 1, self.bias)
+            eng.begin(int(self.depth * self.contigs[k]), rng_mode=capi.RNG_PHILOX, seed=0,
+                      first_read=part["first_read"], max_reads=part["max_reads"], len_total_start=prefix)
         else:
+            if not device:
+                eng.set_seqset("trans", self.seqset, self.bias)  # the table's text goes up with every step
             fr, mr = read_range if read_range else (0, 0)
             eng.begin(0, rng_mode=capi.RNG_PHILOX, seed=1 + rng_seed, first_read=fr, max_reads=mr)
         bases = out_bytes = 0
         while True:
-            c = eng.next_chunk(device=True)
+            c = eng.next_chunk(device=device)
             if c is None:
                 break
             bases += c.bases
             out_bytes += c.reads_bytes + c.maf_bytes
-        return bases, out_bytes, eng.end()
+            if sink is not None and c.reads_bytes:  # the consumer looks at the delivered bytes
+                sink[0] ^= C.c_ubyte.from_address(c.reads + c.reads_bytes - 1).value
+            if on_chunk is not None:
+                on_chunk(c)
+        st = eng.end()
+        if self.seqset is None and not part["last"]:
+            if st.res_num != part["max_reads"] or st.len_total_end >= int(self.depth * self.contigs[part["seq"]]):
+                raise RuntimeError("line split: a part that is not the last one of sequence %d reached the quota "
+                                   "(the read-count estimate was off by more than the snap margin)" % (part["seq"] + 1))
+        return bases, out_bytes, st
+
+    def pilot_mean_emitted(self, k, n_reads=16384):
+        """emitted bases per read, from the first n_reads reads of sequence k (a few ms): what the line split needs to
+        turn a quota into an estimated read count.  Reads depend only on (seed, sequence, read number), so every rank
+        gets the same number without talking to the others."""
+        b, _, st = self.run_part(dict(seq=k, first_read=0, max_reads=n_reads, last=True))
+        return st.len_total_end / max(1, st.res_num)
 
 
-def measure(W, my_steps, warm_steps, e2e_steps, barrier, read_range=None, gzip_arm=True, e2e_warm=False):
-    """device-resident arm + end-to-end arm(s) over this rank's steps.  Returns a dict of local measurements."""
+def whole_parts(step_ids):
+    return [dict(seq=k, first_read=0, max_reads=0, last=True, est=0.0) for k in step_ids]
+
+
+def run_parts(W, parts, dist, device, on_part, read_range=None, host_seq=None, sink=None, on_chunk=None):
+    """this rank's parts in the order of stats_reduce.split_order: feeders, publish (asynchronous all-reduce of the
+    emitted bases per sequence), whole sequences, dependent last parts (each told its len_total_start)."""
+    from pbsim_b200 import stats_reduce as SR
+    feeders, whole, dependent = SR.split_order(parts)
+    ex = None
+    if W.seqset is None and dist is not None:
+        ex = SR.SplitExchange(len(W.contigs), dist, device="cuda")
+    i = 0
+    for phase, plist in (("feed", feeders), ("whole", whole), ("dep", dependent)):
+        if phase == "whole" and ex is not None:
+            ex.publish()
+        for p in plist:
+            prefix = ex.prefix(p["seq"]) if phase == "dep" else 0
+            if on_chunk is not None:
+                on_chunk(p)  # a new part begins
+            b, ob, st = W.run_part(p, rng_seed=(i if W.seqset is not None else 0), read_range=read_range, prefix=prefix,
+                                   host_seq=None if host_seq is None else host_seq[p["seq"]], sink=sink, on_chunk=on_chunk)
+            if phase == "feed":
+                ex.add(p["seq"], st.len_total_end)
+            on_part(p, b, ob, st)
+            i += 1
+
+
+def measure(W, my_parts, warm_parts, e2e_steps, barrier, dist=None, read_range=None, gzip_arm=True, e2e_warm=False):
+    """device-resident arm + end-to-end arm(s) over this rank's parts.  Returns a dict of local measurements."""
     import torch
     eng, capi = W.eng, W.capi
-    for k in warm_steps:  # warm-up (also grows every arena to its steady-state size)
-        W.step_device(k, read_range=read_range)
+    for p in warm_parts:  # warm-up (also grows every arena to its steady-state size)
+        W.run_part(dict(p, first_read=0, last=True, max_reads=p["max_reads"]), read_range=read_range)
     barrier()
     eng.timer_start()
     t0 = time.perf_counter()
     acc = dict(bases=0, out_bytes=0, launches=0, sim=0.0, emit=0.0, seg=0.0, chain=0.0, gen=0.0)
-    for i, k in enumerate(my_steps):
-        b, ob, st = W.step_device(k, rng_seed=(i if W.seqset is not None else 0), read_range=read_range)
+
+    def on_part(p, b, ob, st):
         acc["bases"] += b
         acc["out_bytes"] += ob
         acc["launches"] += st.kernel_launches
@@ -398,49 +461,47 @@ def measure(W, my_steps, warm_steps, e2e_steps, barrier, read_range=None, gzip_a
         acc["seg"] += st.seg_seconds
         acc["chain"] += st.chain_seconds
         acc["gen"] += st.gen_seconds
-    acc["dev_ms"] = eng.timer_stop() if my_steps else 0.0
+
+    run_parts(W, my_parts, dist, True, on_part, read_range=read_range)
+    acc["dev_ms"] = eng.timer_stop() if my_parts else 0.0
     barrier()
     acc["wall_ms"] = (time.perf_counter() - t0) * 1e3
     acc["e2e"] = acc["e2e_gz"] = None
-    steps_e = my_steps[:e2e_steps] if e2e_steps >= 0 else my_steps
+    # the host-buffer arm runs the same parts (a prefix of the run's sequences when --e2e-steps asks for fewer)
+    if e2e_steps >= 0 and W.seqset is None:
+        keep = set(sorted(set(p["seq"] for p in my_parts), key=lambda k: [q["seq"] for q in my_parts].index(k))[:e2e_steps])
+        parts_e = [p for p in my_parts if p["seq"] in keep] if dist is None else my_parts
+    else:
+        parts_e = my_parts[:e2e_steps] if e2e_steps >= 0 else my_parts
     if e2e_steps != 0:
         host_seq = {}
         if W.seqset is None:
-            for k in sorted(set(steps_e)):  # pinned host copies of the sequence text (untimed preparation)
+            for k in sorted(set(p["seq"] for p in parts_e)):  # pinned host copies of the sequence text (untimed preparation)
                 eng.set_synthetic_sequence(W.contigs[k], k + 1, GENOME_SEED + k)
                 t = torch.empty(W.contigs[k], dtype=torch.uint8, pin_memory=True)
                 eng.get_sequence_ascii(t.data_ptr(), W.contigs[k])
                 host_seq[k] = t
+        else:
+            host_seq[0] = True
+            parts_e = [dict(p, seq=0) for p in parts_e]
 
         def e2e_pass():
             barrier()
             t0 = time.perf_counter()
-            e_bases = h2d = d2h = 0
-            sink = 0
-            gen_s = gz_s = 0.0
-            for i, q in enumerate(steps_e):
-                if W.seqset is None:
-                    eng.set_sequence_ptr(host_seq[q].data_ptr(), W.contigs[q], q + 1, W.bias)
-                    eng.begin(int(W.depth * W.contigs[q]), rng_mode=capi.RNG_PHILOX, seed=0)
-                else:
-                    eng.set_seqset("trans", W.seqset, W.bias)  # the table's text goes up with every step
-                    fr, mr = read_range if read_range else (0, 0)
-                    eng.begin(0, rng_mode=capi.RNG_PHILOX, seed=1 + i, first_read=fr, max_reads=mr)
-                h2d += W.contigs[q]
-                while True:
-                    c = eng.next_chunk(device=False)
-                    if c is None:
-                        break
-                    e_bases += c.bases
-                    d2h += c.reads_bytes + c.maf_bytes
-                    if c.reads_bytes:  # the consumer looks at the delivered bytes
-                        sink ^= C.c_ubyte.from_address(c.reads + c.reads_bytes - 1).value
-                st = eng.end()
-                gen_s += st.gen_seconds
-                gz_s += st.deflate_seconds
+            e = dict(bases=0, h2d=0, d2h=0, gen_s=0.0, gz_s=0.0)
+            sink = [0]
+
+            def on_e(p, b, ob, st):
+                e["bases"] += b
+                e["d2h"] += ob
+                e["h2d"] += W.contigs[p["seq"]]
+                e["gen_s"] += st.gen_seconds
+                e["gz_s"] += st.deflate_seconds
+
+            run_parts(W, parts_e, dist, False, on_e, read_range=read_range, host_seq=host_seq, sink=sink)
             barrier()
-            return dict(bases=e_bases, ms=(time.perf_counter() - t0) * 1e3, h2d=h2d, d2h=d2h, steps=len(steps_e),
-                        gen_s=gen_s, gz_s=gz_s)
+            return dict(e, ms=(time.perf_counter() - t0) * 1e3, steps=len(set(p["seq"] for p in parts_e)) if W.seqset is None
+                        else len(parts_e))
 
         if e2e_warm:  # untimed pass: pinned staging buffers and record buffers reach their steady-state size
             e2e_pass()
@@ -453,6 +514,95 @@ def measure(W, my_steps, warm_steps, e2e_steps, barrier, read_range=None, gzip_a
             eng.set_option("deflate", 0)
         del host_seq
     return acc
+
+
+def verify_split(W, my_parts, dist, rank):
+    """the parts of every sequence shared by several ranks, delivered as text to host memory, against the same sequence
+    simulated whole by rank 0: CRC-32 and byte count of every part's FASTQ and MAF bytes must equal those of the whole
+    run's bytes cut at the parts' byte counts.  Untimed; meant for a reduced --scale."""
+    import zlib
+    import torch
+    eng = W.eng
+    allparts = [None] * dist.get_world_size()
+    dist.all_gather_object(allparts, [dict(p) for p in my_parts])
+    nparts = {}
+    for plist in allparts:
+        for p in plist:
+            nparts[p["seq"]] = nparts.get(p["seq"], 0) + 1
+    shared = sorted(k for k, n in nparts.items() if n > 1)
+    host_seq = {}
+    for k in shared:
+        eng.set_synthetic_sequence(W.contigs[k], k + 1, GENOME_SEED + k)
+        t = torch.empty(W.contigs[k], dtype=torch.uint8, pin_memory=True)
+        eng.get_sequence_ascii(t.data_ptr(), W.contigs[k])
+        host_seq[k] = t
+    recs = []
+    cur = [None]
+
+    def on_chunk(c):
+        if isinstance(c, dict):  # a new part
+            cur[0] = dict(seq=c["seq"], first_read=c["first_read"], fq_len=0, fq_crc=0, maf_len=0, maf_crc=0)
+            recs.append(cur[0])
+            return
+        r = cur[0]
+        if c.reads_bytes:
+            r["fq_crc"] = zlib.crc32((C.c_char * c.reads_bytes).from_address(c.reads), r["fq_crc"])
+            r["fq_len"] += c.reads_bytes
+        if c.maf_bytes:
+            r["maf_crc"] = zlib.crc32((C.c_char * c.maf_bytes).from_address(c.maf), r["maf_crc"])
+            r["maf_len"] += c.maf_bytes
+
+    mine = [p for p in my_parts if p["seq"] in shared]
+    run_parts(W, mine, dist, False, lambda *a: None, host_seq=host_seq, on_chunk=on_chunk)
+    allrecs = [None] * dist.get_world_size()
+    dist.all_gather_object(allrecs, recs)
+    out = None
+    if rank == 0:
+        ok, checked, nbytes = True, 0, 0
+        for k in shared:
+            parts = sorted((r for rl in allrecs for r in rl if r["seq"] == k), key=lambda r: r["first_read"])
+            # the whole sequence, streamed; the running CRCs restart at every part boundary
+            state = dict(fq_i=0, maf_i=0, got=[dict(fq_crc=0, maf_crc=0, fq_len=0, maf_len=0) for _ in parts])
+
+            def feed(ptr, n, which):  # every stream (FASTQ, MAF) walks the part list on its own
+                off = 0
+                key_i = which + "_i"
+                while n > 0:
+                    i = state[key_i]
+                    if i >= len(parts):
+                        state["overflow"] = True
+                        return
+                    room = parts[i][which + "_len"] - state["got"][i][which + "_len"]
+                    if room == 0:
+                        state[key_i] = i + 1
+                        continue
+                    take = min(room, n)
+                    g = state["got"][i]
+                    g[which + "_crc"] = zlib.crc32((C.c_char * take).from_address(ptr + off), g[which + "_crc"])
+                    g[which + "_len"] += take
+                    off += take
+                    n -= take
+
+            def on_whole(c):
+                if isinstance(c, dict):
+                    return
+                if c.reads_bytes:
+                    feed(c.reads, c.reads_bytes, "fq")
+                if c.maf_bytes:
+                    feed(c.maf, c.maf_bytes, "maf")
+
+            W.run_part(dict(seq=k, first_read=0, max_reads=0, last=True), host_seq=host_seq[k], on_chunk=on_whole)
+            for pr, g in zip(parts, state["got"]):
+                checked += 1
+                nbytes += g["fq_len"] + g["maf_len"]
+                if (pr["fq_len"], pr["fq_crc"], pr["maf_len"], pr["maf_crc"]) != (g["fq_len"], g["fq_crc"], g["maf_len"], g["maf_crc"]):
+                    ok = False
+            if state.get("overflow"):
+                ok = False
+        out = {"ok": ok, "shared_sequences": len(shared), "parts_checked": checked, "bytes_compared": nbytes,
+               "how": "CRC-32 + length of every part's FASTQ and MAF bytes == the 1-GPU run's bytes cut at the same offsets"}
+    dist.barrier()
+    return out
 
 
 def roofline_block(method, acc, peak, peak_src):
@@ -502,6 +652,11 @@ def main():
     ap.add_argument("--first-batch-div", type=int, default=None, help="diagnostics: engine first_batch_div")
     ap.add_argument("--host-batch-bases", type=float, default=None, help="diagnostics: engine host_batch_bases")
     ap.add_argument("--bam", action="store_true", help="multi-pass workloads: BAM records / BGZF blocks instead of SAM text")
+    ap.add_argument("--no-split", action="store_true",
+                    help="N > 1: assign whole sequences to ranks (longest first) instead of cutting the line of reads")
+    ap.add_argument("--verify-split", action="store_true",
+                    help="N > 1: after the timed runs, rank 0 simulates every shared sequence whole and compares the "
+                         "CRC-32 of its bytes, cut at the parts' byte counts, with what the ranks delivered")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args, dict(WORKLOADS[args.workload]))
@@ -546,25 +701,47 @@ def main():
 
     W = Workload(args.workload, args, local, rank)
     wl = W.wl
-    # ---- ONE run split over the ranks (strong scaling): the timed steps are the sequences (warmup + k) mod 24,
-    #      k < steps; rank r simulates the ones the longest-first assignment gives it, whole (its own quota, its own
-    #      output files: pbsim.cpp:699-754).  A sequence set (--strategy trans) is one step: split by read-number range.
+    # ---- ONE run split over the ranks (strong scaling).  The timed steps are the sequences (warmup + k) mod 24, k < steps,
+    #      each simulated to its own depth quota into its own output files (pbsim.cpp:699-754).  All their reads laid on
+    #      one line are cut into `world` pieces of equal estimated work (stats_reduce.plan_line_split): a rank owns whole
+    #      sequences plus at most one leading and one trailing read range of a sequence it shares with a neighbour; the
+    #      quota cut of a shared sequence needs the emitted bases of its earlier parts: one asynchronous all-reduce.
+    #      A sequence set (--strategy trans) is one step and has no quota: split by read-number range.
     read_range = None
+    split_info = None
     if W.seqset is None:
+        from pbsim_b200 import stats_reduce as SR
         step_ids = [(args.warmup + k) % len(W.contigs) for k in range(args.steps)]
-        mine = [step_ids[i] for i in lpt_assign([W.contigs[k] for k in step_ids], world)[rank]]
-        warm = [max(mine, key=lambda k: W.contigs[k])] * args.warmup if mine else []
+        if world > 1 and not args.no_split:
+            mean_emit = W.pilot_mean_emitted(step_ids[0])
+            reads_est = [W.depth * W.contigs[k] / mean_emit for k in step_ids]
+            plan = SR.plan_line_split(reads_est, world, weights=[float(W.contigs[k]) for k in step_ids])
+            for r in plan:
+                for p in r:
+                    p["seq"] = step_ids[p["seq"]]
+            mine = plan[rank]
+            split_info = {"mean_emitted_bases_per_read": mean_emit,
+                          "parts_per_rank": [len(r) for r in plan],
+                          "sequences_shared_by_two_ranks": sum(1 for r in plan for p in r if not p["last"])}
+        else:
+            mine = whole_parts([step_ids[i] for i in lpt_assign([W.contigs[k] for k in step_ids], world)[rank]])
+            for p in mine:
+                p["est"] = float(W.contigs[p["seq"]])
+        warm = [max(mine, key=lambda p: p["est"])] * args.warmup if mine else []
     else:
         from pbsim_b200.stats_reduce import read_range_for_rank
         lo, hi = read_range_for_rank(W.total_reads, rank, world)
         read_range = (lo, hi - lo)
-        mine = [0] * args.steps
-        warm = [0] * args.warmup
+        mine = whole_parts([0] * args.steps)
+        warm = whole_parts([0] * args.warmup)
     sampler = ClockSampler(local)
     sampler.start()
-    acc = measure(W, mine, warm, args.e2e_steps, barrier, read_range=read_range)
+    acc = measure(W, mine, warm, args.e2e_steps, barrier, dist=dist, read_range=read_range)
     clocks = sampler.stop()
 
+    verified = None
+    if args.verify_split and dist is not None and split_info is not None:
+        verified = verify_split(W, mine, dist, rank)
     tot_bases = allsum(acc["bases"])
     max_ms = allmax(acc["dev_ms"])
     max_wall = allmax(acc["wall_ms"])
@@ -574,7 +751,8 @@ def main():
         if acc[key] is not None or world > 1 and args.e2e_steps != 0:
             e = acc[key] or dict(bases=0, ms=0.0, h2d=0, d2h=0, steps=0, gen_s=0.0, gz_s=0.0)
             e2e_line[key] = dict(bases=allsum(e["bases"]), ms=allmax(e["ms"]), h2d=allsum(e["h2d"]), d2h=allsum(e["d2h"]),
-                                 steps=allsum(e["steps"]), gen_s=allmax(e["gen_s"]), gz_s=allmax(e["gz_s"]))
+                                 steps=(args.steps if world > 1 else e["steps"]), gen_s=allmax(e["gen_s"]),
+                                 gz_s=allmax(e["gz_s"]))
     if dist is not None:
         # the one collective of the path: statistics block (counters + both histograms), NCCL all-reduce
         from pbsim_b200.stats_reduce import allreduce_stats_block
@@ -594,6 +772,10 @@ def main():
             "clocks": {"sm_mhz": clocks["sm_mhz"], "sm_max_mhz": clocks["sm_max_mhz"], "reasons": clocks["reasons"]},
             "roofline": roofline_block(wl["method"], acc, peak, peak_src),
         }
+        if split_info is not None:
+            line["split"] = split_info
+            if verified is not None:
+                line["split"]["verified"] = verified
         for key, name, what in (("e2e", "e2e", "text records"),
                                 ("e2e_gz", "e2e_gzip", "gzip members written by the GPU (option deflate)")):
             if key in e2e_line and e2e_line[key]["ms"] > 0:
@@ -620,7 +802,8 @@ def main():
                     X = Workload(key, args, local, rank, overrides=False)
                     ns = args.extra_steps if X.seqset is None else 1
                     st_ids = [(2 + k) % len(X.contigs) for k in range(ns)]  # mid-sized contigs
-                    a = measure(X, st_ids, st_ids[:1], 1, barrier, gzip_arm=False, e2e_warm=True)
+                    xp = whole_parts(st_ids if X.seqset is None else [0] * ns)
+                    a = measure(X, xp, xp[:1], 1, barrier, gzip_arm=False, e2e_warm=True)
                     line["extra"][key] = {
                         "workload": X.wl["name"], "steps": ns,
                         "value": a["bases"] / (a["dev_ms"] * 1e-3) / 1e9, "unit": "Gbp/s",

@@ -173,6 +173,8 @@ typedef struct {
   double seg_seconds;            /* ... of which the segment kernel (k_sim_seg / _err) alone  */
   int64_t kernel_launches;       /* number of engine kernels launched during the run         */
   double chain_seconds;          /* ... of which the chain / quality kernel (k_chain_chunk / _err) alone (ABI 4) */
+  int64_t len_total_end;         /* the quota counter when the run ended: len_total_start + the bases this run's *
+                                  * reads emitted in pass 0 (:2297) = len_total_start of the next read range (ABI 4) */
 } pbsim_stats;
 
 typedef struct pbsim_engine pbsim_engine;

@@ -140,6 +140,7 @@ class Stats(C.Structure):
         ("seg_seconds", C.c_double),
         ("kernel_launches", C.c_int64),
         ("chain_seconds", C.c_double),
+        ("len_total_end", C.c_int64),
     ]
 
 

@@ -246,7 +246,15 @@ struct pbsim_engine {
   int seg_enabled = 1;            // option "segments"
   int64_t seg_min_len = 2048;     // option "seg_min_len": shorter reads stay on the sequential path
   int64_t seg_batches = 0, seg_fallback_batches = 0;
-  int64_t chain_chunk = 32;         // option "chain_chunk": segments walked by one thread of the chain-only pass
+  // option "chain_chunk": segments walked by one thread of the chain pass; 0 = by method.  Measured on B200 (bench.py,
+  // chunks of 2 / 4 / 6 / 8 / 12 / 16 / 24 / 32 / 64 segments): the qshmm quality pass, which walks every position, is
+  // fastest with short chunks (more threads hide the dependent shared-memory lookups: c3 108.2 / 107.5 Gbp/s at 4 / 8
+  // against 102.0 at 32; c1 88.1 / 89.2 against 85.7); errhmm, whose chunk threads only record states and pay a
+  // costlier coupling, with long ones (c2 77.3 at 32 against 74.8 at 8; c5 70.3 against 66.3)
+  int64_t chain_chunk = 0;
+  uint32_t chain_chunk_eff() const {
+    return chain_chunk > 0 ? (uint32_t)chain_chunk : (model.method == PBSIM_METHOD_QSHMM ? 8u : 32u);
+  }
   DevBuf d_chunk, d_chunk_bins;
   float seg_extra = 0.0f;         // extra segment headroom (fraction), raised when a batch runs out of segments
   // the records of a batch live in one of two output sets in HBM: with the pipeline on, a producer
@@ -255,7 +263,7 @@ struct pbsim_engine {
     DevBuf reads, maf;
   } out[2];
   int cur_set = 0;                  // the set run_batch writes
-  PinnedBuf h_ctrl, h_acc;
+  PinnedBuf h_ctrl, h_acc, h_stats;
   struct BatchItem {
     int rc = 1;                     // 1 = a batch, 0 = the run is finished, < 0 = error (message in err)
     std::string err;
@@ -620,7 +628,7 @@ int run_batch(pbsim_engine *e, uint32_t n_reads, int64_t clip_room, BatchResult 
     else
       k_plan<<<nblk(n_reads, 256), 256, 0, e->st>>>(M, G, device_set(e), rng, B, clip_room, e->cap_num, e->cap_den, ev_align,
                                                      use_segments ? (uint32_t)e->seg_min_len : 0u, e->seg_extra,
-                                                     (uint32_t)e->chain_chunk);
+                                                     e->chain_chunk_eff());
     e->launches++;
     // ---- sort by (accuracy, length desc), bins, longest-first CTA order
     auto schedule = [&]() -> int {
@@ -780,7 +788,7 @@ int run_batch(pbsim_engine *e, uint32_t n_reads, int64_t clip_room, BatchResult 
         CK(e->d_chunk_bins.ensure((4 * kBins + 8) * 4 + (size_t)ch_slots * 4 * 4 + 64));
         ChunkBatch C;
         C.n_chunks = nch;
-        C.per_chunk = (uint32_t)e->chain_chunk;
+        C.per_chunk = e->chain_chunk_eff();
         C.qs = qs ? 1u : 0u;
         C.chunk_off = (const uint64_t *)chunk_off;
         uint32_t *cu = e->d_chunk.as<uint32_t>();
@@ -1584,6 +1592,7 @@ void pbsim_cuda_destroy(pbsim_engine *e) {
   e->h_gz.release();
   e->h_ctrl.release();
   e->h_acc.release();
+  e->h_stats.release();
   cudaEventDestroy(e->ev0);
   cudaEventDestroy(e->ev1);
   cudaStreamDestroy(e->st);
@@ -1902,8 +1911,13 @@ int pbsim_cuda_simulate_end(pbsim_engine *e, pbsim_stats *st, int64_t *freq_len,
   if (!e->running) return fail(e, PBSIM_E_INVALID, "simulate_begin was not called");
   stop_producer(e);
   CK(cudaStreamSynchronize(e->st_copy));
-  std::vector<long long> blk((size_t)e->stats_cells);
-  CK(cudaMemcpyAsync(blk.data(), e->d_stats.p, (size_t)e->stats_cells * 8, cudaMemcpyDeviceToHost, e->st));
+  // The block is 16 + 100001 + 2 len_max + 2 cells (16.8 MB with --length-max 1000000) and the GPU idles while the host
+  // looks at it: fetch the counters and the accuracy histogram into pinned memory first, then only the occupied range
+  // [res_len_min, res_len_max] of the length histogram.
+  CK(e->h_stats.ensure((size_t)e->stats_cells * 8));
+  long long *blk = reinterpret_cast<long long *>(e->h_stats.p);
+  const size_t head_cells = (size_t)kStatCounters + 100001;
+  CK(cudaMemcpyAsync(blk, e->d_stats.p, head_cells * 8, cudaMemcpyDeviceToHost, e->st));
   CK(cudaStreamSynchronize(e->st));
   std::memset(st, 0, sizeof *st);
   st->res_num = blk[0];
@@ -1915,9 +1929,20 @@ int pbsim_cuda_simulate_end(pbsim_engine *e, pbsim_stats *st, int64_t *freq_len,
   st->res_ins_num = blk[6];
   st->res_del_num = blk[7];
   st->accuracy_total = e->accuracy_total;
-  const long long *fa = blk.data() + kStatCounters;
-  const long long *fl = fa + 100001;
-  // mean / SD exactly as the reference derives them from the histograms (:2387-2410)
+  const long long *fa = blk + kStatCounters;
+  long long *fl = blk + head_cells;
+  int64_t fl_lo = 0, fl_hi = 0;  // occupied cells of freq_len: [fl_lo, fl_hi)
+  if (st->res_pass_num > 0) {
+    fl_lo = std::min<int64_t>(std::max<int64_t>(st->res_len_min, 0), e->freq_len_cells);
+    fl_hi = std::min<int64_t>(std::max<int64_t>(st->res_len_max + 1, fl_lo), e->freq_len_cells);
+    if (fl_hi > fl_lo) {
+      CK(cudaMemcpyAsync(fl + fl_lo, reinterpret_cast<const long long *>(e->d_stats.p) + head_cells + fl_lo,
+                         (size_t)(fl_hi - fl_lo) * 8, cudaMemcpyDeviceToHost, e->st));
+      CK(cudaStreamSynchronize(e->st));
+    }
+  }
+  // mean / SD exactly as the reference derives them from the histograms (:2387-2410); cells outside the occupied range
+  // are zero and add nothing
   if (st->res_pass_num > 0) {
     st->res_len_mean = (double)st->res_len_total / st->res_pass_num;
     st->res_accuracy_mean = e->accuracy_total / st->res_pass_num;
@@ -1926,7 +1951,7 @@ int pbsim_cuda_simulate_end(pbsim_engine *e, pbsim_stats *st, int64_t *freq_len,
       st->res_accuracy_sd = 0.0;
     } else {
       double variance = 0.0;
-      for (int64_t i = 0; i <= e->model.len_max && i < e->freq_len_cells; ++i)
+      for (int64_t i = fl_lo; i <= e->model.len_max && i < fl_hi; ++i)
         if (fl[i] > 0) variance += pow((st->res_len_mean - i), 2) * fl[i];
       st->res_len_sd = sqrt(variance / st->res_pass_num);
       variance = 0.0;
@@ -1942,9 +1967,10 @@ int pbsim_cuda_simulate_end(pbsim_engine *e, pbsim_stats *st, int64_t *freq_len,
   st->seg_seconds = e->seg_ms * 1e-3;
   st->chain_seconds = e->chain_ms * 1e-3;
   st->kernel_launches = e->launches;
+  st->len_total_end = e->len_total;
   if (freq_len) {
     const int64_t n = std::min<int64_t>(freq_len_cells, e->freq_len_cells);
-    for (int64_t i = 0; i < n; ++i) freq_len[i] = fl[i];
+    for (int64_t i = 0; i < n; ++i) freq_len[i] = (i >= fl_lo && i < fl_hi) ? fl[i] : 0;
   }
   if (freq_accuracy)
     for (int64_t i = 0; i <= 100000; ++i) freq_accuracy[i] = fa[i];
@@ -1983,7 +2009,7 @@ int pbsim_cuda_set_option(pbsim_engine *e, const char *name, int64_t value) {
     return 0;
   }
   if (!strcmp(name, "chain_chunk")) {
-    if (value < 1 || value > 65536) return fail(e, PBSIM_E_INVALID, "chain_chunk must be 1..65536 segments");
+    if (value < 0 || value > 65536) return fail(e, PBSIM_E_INVALID, "chain_chunk must be 0 (by method) or 1..65536 segments");
     e->chain_chunk = value;
     return 0;
   }

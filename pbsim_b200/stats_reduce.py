@@ -96,3 +96,99 @@ def emitted_prefix(my_emitted_bases, dist, device="cpu"):
     dist.all_gather(allv, mine)
     vals = [int(v.item()) for v in allv]
     return sum(vals[:dist.get_rank()]), sum(vals)
+
+
+# ---- one run split over the ranks inside sequences ("line split") ----------------------------------------------------
+# The reference simulates a sequence until its quota of emitted bases is met (pbsim.cpp:2173-2181): how many reads a
+# sequence gets is only known once every earlier read has been simulated.  Reads themselves depend on nothing but
+# (seed, sequence, read number), so every part of a sequence EXCEPT ITS LAST can be simulated without knowing anything
+# about the others (`max_reads` reads from `first_read`, the quota is far away); the last part runs to the quota and
+# needs one number, the emitted bases of all parts before it (`len_total_start`).  The plan below lays all reads of the
+# run on one line (sequences in order), cuts it into `world` pieces of equal estimated work, and lets every rank run
+# its feeders first, the sequences it owns whole next and its dependent last parts at the end: by then the sums it
+# needs have long been published by ONE asynchronous all-reduce of an int64 per sequence (SplitExchange).
+
+def plan_line_split(reads_est, world, weights=None, snap_lo=0.02, snap_hi=0.04):
+    """reads_est[k]: estimated read count of sequence k (quota / mean emitted bases per read); weights[k]: estimated
+    work (default: reads_est).  Returns for every rank its parts in line order, each a dict
+      seq, first_read, max_reads (0: run to the quota), last (the part that meets the quota), est (estimated work).
+    A cut that falls into the first snap_lo or the last snap_hi of a sequence moves to the sequence's boundary: the
+    estimate of a sequence's read count is good to a per cent or so, and a part that is not the last one must end
+    safely in front of the quota."""
+    n = len(reads_est)
+    w = [float(x) for x in (weights if weights is not None else reads_est)]
+    total = sum(w)
+    start = [0.0] * (n + 1)
+    for k in range(n):
+        start[k + 1] = start[k] + w[k]
+    cut_in = {k: [] for k in range(n)}   # read indices at which sequence k is cut
+    rank_cut_after = []  # for every rank boundary r (1..world-1): (k, read); (k, 0) = in front of sequence k
+    for r in range(1, world):
+        x = total * r / world
+        k = 0
+        while k + 1 < n and start[k + 1] <= x:
+            k += 1
+        f = (x - start[k]) / w[k] if w[k] > 0 else 0.0
+        if f < snap_lo:
+            rank_cut_after.append((k, 0))
+        elif f > 1.0 - snap_hi:
+            rank_cut_after.append((k + 1, 0))
+        else:
+            rd = int(f * reads_est[k])
+            if rd <= 0:
+                rank_cut_after.append((k, 0))
+            else:
+                rank_cut_after.append((k, rd))
+                if rd not in cut_in[k]:
+                    cut_in[k].append(rd)
+    out = [[] for _ in range(world)]
+    for k in range(n):
+        marks = [0] + sorted(cut_in[k])
+        for i, lo in enumerate(marks):
+            last = i + 1 == len(marks)
+            hi = 0 if last else marks[i + 1]
+            frac = ((reads_est[k] if last else hi) - lo) / max(1.0, float(reads_est[k]))
+            piece = dict(seq=k, first_read=int(lo), max_reads=int(0 if last else hi - lo), last=last,
+                         est=w[k] * max(0.0, frac))
+            # owner: the number of rank boundaries at or in front of this piece's start
+            r = sum(1 for (ck, crd) in rank_cut_after if (ck, crd) <= (k, lo))
+            out[min(r, world - 1)].append(piece)
+    return out
+
+
+def split_order(parts):
+    """execution order on one rank: feeders (parts others wait for), whole sequences, dependent last parts"""
+    feeders = [p for p in parts if not p["last"]]
+    whole = [p for p in parts if p["last"] and p["first_read"] == 0]
+    dependent = [p for p in parts if p["last"] and p["first_read"] > 0]
+    return feeders, whole, dependent
+
+
+class SplitExchange:
+    """the one data-dependent exchange of a line-split run: per sequence, the emitted bases of all parts that are not
+    the last one.  Every rank adds what its feeders emitted and calls publish() once; the all-reduce runs
+    asynchronously (NCCL on its own stream, gloo in the CPU tests) while the rank simulates the sequences it owns whole;
+    prefix(k) waits for it (once) and returns len_total_start of sequence k's last part."""
+
+    def __init__(self, n_seq, dist=None, device="cpu"):
+        self.n, self.dist, self.device = n_seq, dist, device
+        self.mine = [0] * n_seq
+        self.work = self.t = self.sums = None
+
+    def add(self, seq, emitted_bases):
+        assert self.t is None, "SplitExchange.add after publish"
+        self.mine[seq] += int(emitted_bases)
+
+    def publish(self):
+        self.t = torch.tensor(self.mine, dtype=torch.int64, device=self.device)
+        if self.dist is not None:
+            self.work = self.dist.all_reduce(self.t, op=self.dist.ReduceOp.SUM, async_op=True)
+
+    def prefix(self, seq):
+        if self.sums is None:
+            if self.t is None:
+                raise RuntimeError("SplitExchange.prefix before publish")
+            if self.work is not None:
+                self.work.wait()
+            self.sums = [int(v) for v in self.t.cpu().tolist()]
+        return self.sums[seq]

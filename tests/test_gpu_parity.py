@@ -304,6 +304,54 @@ def test_merged_statistics_of_a_split_run_equal_the_single_engine_statistics(eng
     assert "%f (%f)" % (m["res_accuracy_mean"], m["res_accuracy_sd"]) == "%f (%f)" % (st.res_accuracy_mean, st.res_accuracy_sd)
 
 
+def test_line_split_of_a_multi_sequence_run_concatenates_to_the_single_gpu_bytes(eng):
+    """bench.py --gpus N / stats_reduce.plan_line_split: ONE run of several sequences cut into `world` pieces of equal
+    estimated work.  The ranks are emulated one after the other on this GPU in the order a real run imposes (every
+    rank's feeders, the exchange of emitted bases, then whole sequences and dependent last parts); the parts of every
+    sequence, concatenated in read order, must be the bytes of the sequence simulated whole, and the summed statistics
+    blocks the whole run's."""
+    from pbsim_b200 import stats_reduce as SR
+    from tests.golden_util import model_path
+    hm = capi.HostModel(capi.load(), capi.host_params("qshmm"), model_path("QSHMM-RSII.model"))
+    eng.set_model(hm)
+    lens = [900000, 400000, 1300000, 700000, 250000]
+    depth = 3
+
+    def run(k, **kw):
+        eng.set_synthetic_sequence(lens[k], k + 1, 100 + k)
+        return eng.simulate(depth * lens[k], rng_mode=capi.RNG_PHILOX, seed=6, **kw)
+
+    whole = [run(k) for k in range(len(lens))]
+    pilot = run(0, max_reads=64)
+    mean_emit = pilot[2].len_total_end / pilot[2].res_num
+    for world in (2, 3, 7):
+        plan = SR.plan_line_split([depth * n / mean_emit for n in lens], world, weights=[float(n) for n in lens])
+        ex = SR.SplitExchange(len(lens))
+        got = {}
+        order = [SR.split_order(parts) for parts in plan]
+        for f, _, _ in order:
+            for p in f:
+                r = run(p["seq"], first_read=p["first_read"], max_reads=p["max_reads"])
+                assert r[2].res_num == p["max_reads"] and r[2].len_total_end < depth * lens[p["seq"]]
+                ex.add(p["seq"], r[2].len_total_end)
+                got[(p["seq"], p["first_read"])] = r
+        ex.publish()
+        for _, w, d in order:
+            for p in w:
+                got[(p["seq"], 0)] = run(p["seq"])
+            for p in d:
+                got[(p["seq"], p["first_read"])] = run(p["seq"], first_read=p["first_read"],
+                                                       len_total_start=ex.prefix(p["seq"]))
+        assert any(k[1] > 0 for k in got)   # something was split
+        for k in range(len(lens)):
+            parts = [got[key] for key in sorted(got) if key[0] == k]
+            assert b"".join(p[0] for p in parts) == whole[k][0]
+            assert b"".join(p[1] for p in parts) == whole[k][1]
+            assert sum(p[2].res_num for p in parts) == whole[k][2].res_num
+            assert sum(p[2].res_len_total for p in parts) == whole[k][2].res_len_total
+            assert parts[-1][2].len_total_end == whole[k][2].len_total_end
+
+
 def test_megabase_reads_equal_oracle(eng):
     """reads at the length limit (--length-mean 900000 --length-sd 0 --length-max 1000000): ~880 segments per read,
     backward coupling on every one of them; bytes and statistics must equal the oracle's"""
@@ -375,7 +423,7 @@ def test_one_segment_chain_chunks_equal_oracle(eng, name):
         res = run_case_on_gpu(c, eng, "philox")
     finally:
         eng.set_option("seg_min_len", 2048)
-        eng.set_option("chain_chunk", 32)
+        eng.set_option("chain_chunk", 0)
     for i, ((reads, maf, st, text), o) in enumerate(zip(res, out), start=1):
         assert reads == o["reads"], "reads differ from the oracle, seq %d" % i
         assert maf == o["maf"], "maf differs from the oracle, seq %d" % i

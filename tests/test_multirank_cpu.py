@@ -90,3 +90,84 @@ def test_merged_summary_from_a_reduced_block():
     assert m["res_num"] == 2 and m["res_len_mean"] == 200.0
     assert abs(m["res_accuracy_mean"] - 0.85) < 1e-12 and abs(m["res_accuracy_sd"] - 0.05) < 1e-9
     assert abs(m["res_len_sd"] - 100.0) < 1e-9
+
+
+def _check_plan(reads_est, world, plan):
+    # every sequence is covered exactly once by consecutive read ranges; the last part runs to the quota
+    by_seq = {}
+    for r, parts in enumerate(plan):
+        for p in parts:
+            by_seq.setdefault(p["seq"], []).append((p["first_read"], p["max_reads"], p["last"], r))
+    assert sorted(by_seq) == list(range(len(reads_est)))
+    for k, parts in by_seq.items():
+        parts.sort()
+        assert parts[0][0] == 0
+        for a, b in zip(parts, parts[1:]):
+            assert not a[2] and a[1] > 0 and a[0] + a[1] == b[0]      # feeders are bounded and contiguous
+            assert a[3] <= b[3]                                       # line order follows rank order
+        assert parts[-1][2] and parts[-1][1] == 0
+        # a part that is not the last one ends safely in front of the estimated end of the sequence
+        if len(parts) > 1:
+            assert parts[-1][0] <= 0.961 * reads_est[k]
+            assert parts[1][0] >= 0.0199 * reads_est[k]
+    # ranks own contiguous pieces of the line
+    flat = [(p["seq"], p["first_read"]) for parts in plan for p in parts]
+    assert flat == sorted(flat)
+
+
+def test_line_split_plans():
+    sizes = [248, 242, 198, 190, 182, 171, 159, 145, 138, 134, 135, 133, 114, 107, 102, 90, 83, 80, 59, 64, 47, 51, 156, 57]
+    reads = [s * 1000.0 for s in sizes]
+    for world in (1, 2, 3, 4, 8, 16, 40):
+        for n in (1, 2, 5, 20, 24):
+            plan = SR.plan_line_split(reads[:n], world)
+            assert len(plan) == world
+            _check_plan(reads[:n], world, plan)
+            if world <= 8 and n >= 20:
+                loads = [sum(p["est"] for p in parts) for parts in plan]
+                assert min(loads) / max(loads) > 0.90   # LPT over whole sequences reaches 0.93 of the mean at best
+            if world == 1:
+                assert all(p["last"] and p["first_read"] == 0 for p in plan[0])
+    # a sequence much longer than a rank's share is cut several times: all parts but the last are independent
+    plan = SR.plan_line_split([1000000.0], 8)
+    assert sum(len(p) for p in plan) == 8 and sum(1 for parts in plan for p in parts if p["last"]) == 1
+
+
+def test_split_order_runs_feeders_first_and_dependents_last():
+    plan = SR.plan_line_split([1000.0, 900.0, 800.0, 700.0], 3)
+    for parts in plan:
+        f, w, d = SR.split_order(parts)
+        assert all(not p["last"] for p in f)
+        assert all(p["last"] and p["first_read"] == 0 for p in w)
+        assert all(p["last"] and p["first_read"] > 0 for p in d)
+        assert len(f) + len(w) + len(d) == len(parts)
+
+
+def _exchange_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    ex = SR.SplitExchange(3, dist)
+    if rank == 0:
+        ex.add(1, 12345)       # rank 0 simulated the first part of sequence 1 ...
+        ex.add(2, 100)
+    else:
+        ex.add(2, 23)          # ... and both ranks a part of sequence 2
+    ex.publish()
+    q.put((rank, ex.prefix(0), ex.prefix(1), ex.prefix(2)))
+    dist.destroy_process_group()
+
+
+def test_split_exchange_world2():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    ps = [ctx.Process(target=_exchange_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in ps:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in ps:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res == [(0, 0, 12345, 123), (1, 0, 12345, 123)]
