@@ -291,18 +291,25 @@ def make_config(wl, args, world):
             "scale": args.scale, "sharding": sharding}
 
 
-def host_d2h_ceiling(world):
-    """aggregate GB/s of N concurrent bare pinned device-to-host copy loops on this pool's 8-GPU host
-    (tools/d2h_ceiling.py, committed as profiles/r02_d2h_ceiling_8gpu.json): what the delivery path can reach at best"""
+def host_d2h_ceiling(barrier, allsum, reps=8, nbytes=256 << 20):
+    """what the delivery path can reach at best on THIS box: aggregate GB/s of bare device -> pinned host copies issued
+    by all ranks at once (measured in this run; tools/d2h_ceiling.py is the stand-alone version, its numbers for the
+    pool's 8-GPU host are in profiles/r02_d2h_ceiling_8gpu.json)"""
+    import torch
     try:
-        with open(os.path.join(ROOT, "profiles", "r02_d2h_ceiling_8gpu.json")) as f:
-            runs = json.load(f)["runs"]
-        for r in runs:
-            if r["n"] == world and not r["numa_pinned"]:
-                return r["aggregate_gb_s"]
+        d = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+        h = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+        h.copy_(d, non_blocking=True)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            h.copy_(d, non_blocking=True)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        barrier()
+        return allsum(nbytes * reps / dt / 1e9)
     except Exception:
-        pass
-    return None
+        return None
 
 
 def lpt_assign(sizes, world):
@@ -452,7 +459,15 @@ def measure(W, my_parts, warm_parts, e2e_steps, barrier, dist=None, read_range=N
     t0 = time.perf_counter()
     acc = dict(bases=0, out_bytes=0, launches=0, sim=0.0, emit=0.0, seg=0.0, chain=0.0, gen=0.0)
 
+    tp = [time.perf_counter()]
+
     def on_part(p, b, ob, st):
+        if os.environ.get("PBSIM_BENCH_DEBUG"):
+            t = time.perf_counter()
+            sys.stderr.write("[bench] rank %d part seq %d first_read %d max_reads %d last %s: %.3f Gbase, %.2f ms wall, "
+                             "%.2f ms generation\n" % (W.rank, p["seq"] + 1, p["first_read"], p["max_reads"], p["last"],
+                                                       b / 1e9, (t - tp[0]) * 1e3, st.gen_seconds * 1e3))
+            tp[0] = t
         acc["bases"] += b
         acc["out_bytes"] += ob
         acc["launches"] += st.kernel_launches
@@ -652,6 +667,9 @@ def main():
     ap.add_argument("--first-batch-div", type=int, default=None, help="diagnostics: engine first_batch_div")
     ap.add_argument("--host-batch-bases", type=float, default=None, help="diagnostics: engine host_batch_bases")
     ap.add_argument("--bam", action="store_true", help="multi-pass workloads: BAM records / BGZF blocks instead of SAM text")
+    ap.add_argument("--part-overhead-gbase", type=float, default=0.3,
+                    help="line split: fixed cost of one run in units of emitted Gbase (balances ranks that own many "
+                         "short sequences against ranks that own few long ones)")
     ap.add_argument("--no-split", action="store_true",
                     help="N > 1: assign whole sequences to ranks (longest first) instead of cutting the line of reads")
     ap.add_argument("--verify-split", action="store_true",
@@ -715,7 +733,10 @@ def main():
         if world > 1 and not args.no_split:
             mean_emit = W.pilot_mean_emitted(step_ids[0])
             reads_est = [W.depth * W.contigs[k] / mean_emit for k in step_ids]
-            plan = SR.plan_line_split(reads_est, world, weights=[float(W.contigs[k]) for k in step_ids])
+            # work of a sequence = its bases + a fixed cost per run (ingest, the quota's tail reads, the last partly
+            # filled batch: about 3 ms, measured with PBSIM_BENCH_DEBUG=1 on one GPU) expressed in bases
+            plan = SR.plan_line_split(reads_est, world,
+                                      weights=[W.depth * W.contigs[k] + args.part_overhead_gbase * 1e9 for k in step_ids])
             for r in plan:
                 for p in r:
                     p["seq"] = step_ids[p["seq"]]
@@ -739,9 +760,18 @@ def main():
     acc = measure(W, mine, warm, args.e2e_steps, barrier, dist=dist, read_range=read_range)
     clocks = sampler.stop()
 
+    d2h_ceiling = host_d2h_ceiling(barrier, allsum) if args.e2e_steps != 0 else None
     verified = None
     if args.verify_split and dist is not None and split_info is not None:
         verified = verify_split(W, mine, dist, rank)
+    per_rank = None
+    if dist is not None:
+        import torch as _t
+        mine_t = _t.tensor([acc["dev_ms"], acc["bases"] / 1e9, float(len(mine))], dtype=_t.float64, device="cuda")
+        allv = [_t.zeros_like(mine_t) for _ in range(world)]
+        dist.all_gather(allv, mine_t)
+        per_rank = {"dev_ms": [round(float(v[0]), 2) for v in allv], "gbases": [round(float(v[1]), 3) for v in allv],
+                    "parts": [int(v[2]) for v in allv]}
     tot_bases = allsum(acc["bases"])
     max_ms = allmax(acc["dev_ms"])
     max_wall = allmax(acc["wall_ms"])
@@ -772,6 +802,8 @@ def main():
             "clocks": {"sm_mhz": clocks["sm_mhz"], "sm_max_mhz": clocks["sm_max_mhz"], "reasons": clocks["reasons"]},
             "roofline": roofline_block(wl["method"], acc, peak, peak_src),
         }
+        if per_rank is not None:
+            line["per_rank"] = per_rank
         if split_info is not None:
             line["split"] = split_info
             if verified is not None:
@@ -787,7 +819,7 @@ def main():
                               "d2h_gb_per_s": e["d2h"] / (e["ms"] * 1e-3) / 1e9,
                               "device_seconds": {"generation_incl_deflate": e["gen_s"], "of_which_deflate": e["gz_s"],
                                                  "wall": e["ms"] * 1e-3}}
-                ceil = host_d2h_ceiling(world)
+                ceil = d2h_ceiling
                 if ceil:
                     line[name]["host_d2h_ceiling_gb_per_s"] = ceil
                     line[name]["d2h_frac_of_host_ceiling"] = line[name]["d2h_gb_per_s"] / ceil

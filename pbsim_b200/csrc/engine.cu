@@ -492,7 +492,7 @@ int finish_sequence_ingest(pbsim_engine *e, int64_t len, int32_t seq_num, const 
         e->d_xm.as<uint32_t>(), e->d_hpfreq.as<unsigned long long>(), e->d_biasone.as<uint8_t>(),
         e->d_flag.as<uint32_t>());
   } else {
-    k_hp<<<nblk((len + 1) / 2, 256), 256, 0, e->st>>>(e->d_ascii.as<uint8_t>(), len, e->d_hp4.as<uint8_t>(),
+    k_hp<<<(unsigned)std::min<int64_t>(nblk((len + 7) / 8, kHpThreads), 148 * 8), kHpThreads, 0, e->st>>>(e->d_ascii.as<uint8_t>(), len, e->d_hp4.as<uint8_t>(),
                                                       e->d_xm.as<uint32_t>(), e->d_hpfreq.as<unsigned long long>(),
                                                       e->d_biasone.as<uint8_t>(), e->d_flag.as<uint32_t>());
   }

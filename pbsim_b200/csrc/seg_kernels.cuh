@@ -345,30 +345,60 @@ __global__ void __launch_bounds__(128) k_find_end(Batch B, SegBatch S, DeviceGen
   uint32_t R = 0, P = 0, D = 0, nsub = 0, flags = 0, n_tiles = 0;
   uint64_t prob = 0;
   bool done = false;
-  for (uint32_t k = 0; k < n_seg && !done; ++k) {
+  uint32_t k = 0;
+  while (k < n_seg && !done) {
+    // ---- up to 32 segments at once: lane j looks at segment k + j.  A segment whose reference range neither reaches
+    //      the window's end nor touches an exceptional block keeps its own totals: prefix sums over the lanes give
+    //      every such segment its checkpoint.  The first segment that needs the exact treatment ends the group.
+    {
+      const uint32_t kk = k + lane;
+      const bool in = kk < n_seg;
+      SegResult sr;
+      if (in) sr = seg[kk];
+      else sr.n_entries = sr.ref_adv = sr.nsub = sr.ndel = sr.flags = sr.pad = 0u, sr.prob = 0ull;
+      uint32_t xr = sr.ref_adv, xd = sr.ndel;  // inclusive scans
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t yr = __shfl_up_sync(0xFFFFFFFFu, xr, o), yd = __shfl_up_sync(0xFFFFFFFFu, xd, o);
+        if (lane >= (uint32_t)o) xr += yr, xd += yd;
+      }
+      // (a group that would overflow 32 bits holds a segment that reaches the window's end: 64-bit test)
+      const uint64_t Rk64 = (uint64_t)R + xr - sr.ref_adv;
+      const uint32_t Rk = (uint32_t)Rk64, Dk = D + xd - sr.ndel;
+      bool simple = in && Rk64 + sr.ref_adv < wlen;
+      if (simple && hp.enabled) {
+        const uint32_t lo_w = Rk == 0u ? 0u : Rk - 1u, hi_w = Rk + sr.ref_adv;
+        const uint32_t ga = hp.win.gidx(lo_w), gb = hp.win.gidx(hi_w);
+        simple = !range_exceptional(G.xm, min(ga, gb), max(ga, gb));
+      }
+      const uint32_t bad = __ballot_sync(0xFFFFFFFFu, !simple);
+      const uint32_t cnt = bad ? (uint32_t)__ffs((int)bad) - 1u : 32u;
+      if (cnt > 0u) {
+        const bool mine = lane < cnt;
+        uint32_t f = mine ? sr.flags : 0u;
+        if (mine && kk >= 1u && Rk == 0u) f |= 8u;
+        flags |= __reduce_or_sync(0xFFFFFFFFu, f);
+        if (mine) {
+          Ckpt c; c.col = P + lane * PB_TILE + Dk; c.ref = Rk; c.read = P + lane * PB_TILE; c.pad = sr.n_entries;
+          ckp[kk] = c;
+        }
+        R += __shfl_sync(0xFFFFFFFFu, xr, cnt - 1u);
+        D += __shfl_sync(0xFFFFFFFFu, xd, cnt - 1u);
+        nsub += __reduce_add_sync(0xFFFFFFFFu, mine ? sr.nsub : 0u);
+        // prob < 2^36 per segment: 24 + 12 bits
+        prob += (uint64_t)__reduce_add_sync(0xFFFFFFFFu, mine ? (uint32_t)(sr.prob & 0xFFFFFFu) : 0u) +
+                ((uint64_t)__reduce_add_sync(0xFFFFFFFFu, mine ? (uint32_t)(sr.prob >> 24) : 0u) << 24);
+        P += cnt * PB_TILE;
+        k += cnt;
+        continue;
+      }
+    }
+    // ---- segment k: the window may end in it, or a deletion run may need a repair
     flags |= seg[k].flags;
     if (k >= 1u && R == 0u) flags |= 8u;
     uint16_t *e = ev_base + (uint64_t)k * PB_SEG_STRIDE;
     const uint32_t n = seg[k].n_entries;
     const uint32_t R_tile = R, P_tile = P, D_tile = D;
-    // a repair is only possible where a deletion follows a base of an exceptional block: test the segment's
-    // whole reference range first (window bases R-1 .. R+ref_adv), so that a long read pays for its few flagged
-    // segments and not for all of them
-    bool seg_touch = false;
-    if (hp.enabled && (uint64_t)R + seg[k].ref_adv < wlen) {
-      const uint32_t lo_w = R == 0u ? 0u : R - 1u, hi_w = R + seg[k].ref_adv;
-      const uint32_t ga = hp.win.gidx(lo_w), gb = hp.win.gidx(hi_w);
-      seg_touch = range_exceptional(G.xm, min(ga, gb), max(ga, gb));
-    }
-    if (!seg_touch && (uint64_t)R + seg[k].ref_adv < wlen) {
-      // nothing to repair and the window cannot end here: the segment's own totals are exact
-      if (lane == 0) {
-        Ckpt c; c.col = P + D; c.ref = R; c.read = P; c.pad = n;
-        ckp[k] = c;
-      }
-      P += PB_TILE; R += seg[k].ref_adv; D += seg[k].ndel; nsub += seg[k].nsub; prob += seg[k].prob;
-      continue;
-    }
     uint32_t n_incl = n, blocked = 0;
     bool ended = false;
     for (uint32_t i = 0; i < n && !ended; i += 32u) {
@@ -444,6 +474,7 @@ __global__ void __launch_bounds__(128) k_find_end(Batch B, SegBatch S, DeviceGen
     } else {
       prob += seg[k].prob;
     }
+    ++k;
   }
   if (!done) flags |= 4u;
   if (lane == 0) {
