@@ -14,12 +14,18 @@
 // --threads N (host compression), --gzip gpu|host (default gpu: the records are gzip-compressed on the GPU and the
 // driver only writes the members to the files; multi-pass output is <prefix>[_NNNN].bam, or SAM text in .sam.gz with
 // --gzip host).  --method sample filters the FASTQ on the host (pbsim_host_sample_filter) and hands the pool to the engine.
+#include <fcntl.h>
 #include <getopt.h>
+#include <sys/mman.h>
 #include <sys/resource.h>
+#include <sys/stat.h>
 #include <sys/time.h>
+#include <unistd.h>
 #include <zlib.h>
 
 #include <algorithm>
+#include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <cstdarg>
 #include <cstdint>
@@ -68,11 +74,14 @@ struct Options {
   std::string gzip = "gpu";  // who writes the gzip members: the GPU (gz_kernels.cuh) or zlib threads on the host
 };
 
+std::thread *g_background = nullptr;  // a thread that must have ended before the process exits (CUDA start-up)
+
 [[noreturn]] void die(const char *fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
   vfprintf(stderr, fmt, ap);
   va_end(ap);
+  if (g_background && g_background->joinable() && g_background->get_id() != std::this_thread::get_id()) g_background->join();
   exit(-1);
 }
 
@@ -87,20 +96,138 @@ long now_wall() {
   return tv.tv_sec;
 }
 
+double now_seconds() {
+  return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
 // ------------------------------------------------------------------------------------------
-// ordered, multi-threaded gzip writer: every submitted block becomes one gzip member
+// a few threads that copy byte ranges to file offsets: the gzip members the GPU wrote go from the engine's pinned
+// staging buffers straight into the files, several 4 MiB blocks at a time.  The copies go through a shared mapping of
+// the file (grown ahead with ftruncate, cut to its size at the end): write()/pwrite() on one file are serialised by
+// the inode lock (3.5 GB/s measured on a RAM disk for the two output files together), page faults on a mapping are not.
+// The reference's writers are the two `gzip > file` children (:708-730).
+// ------------------------------------------------------------------------------------------
+class WritePool {
+ public:
+  struct Range {
+    int fd;
+    const char *p;
+    size_t n;
+    uint64_t off;
+  };
+  explicit WritePool(int threads) {
+    for (int i = 0; i < std::max(1, threads); ++i) workers_.emplace_back([this] { work(); });
+  }
+  ~WritePool() {
+    {
+      std::unique_lock<std::mutex> lk(mu_);
+      closing_ = true;
+      cv_work_.notify_all();
+    }
+    for (auto &t : workers_) t.join();
+  }
+  // returns when every byte is in the file (the caller's buffers are only valid until then); false on an I/O error.
+  // The files must be large enough (GzipWriter::direct_range grows them).
+  bool run(const std::vector<Range> &ranges) {
+    constexpr size_t kBlock = 4 << 20;
+    const size_t page = (size_t)sysconf(_SC_PAGESIZE);
+    struct Map {
+      char *base;
+      size_t len;
+    };
+    std::vector<Map> maps;
+    bool ok = true;
+    {
+      std::unique_lock<std::mutex> lk(mu_);
+      for (const Range &r : ranges) {
+        if (r.n == 0) continue;
+        const uint64_t a = r.off / page * page;
+        const size_t len = (size_t)(r.off + r.n - a);
+        void *m = mmap(nullptr, len, PROT_READ | PROT_WRITE, MAP_SHARED, r.fd, (off_t)a);
+        if (m == MAP_FAILED) {  // a file that cannot be mapped (a pipe, some network file systems): plain pwrite
+          for (size_t o = 0; o < r.n; o += kBlock) {
+            queue_.push_back(Job{r.fd, nullptr, r.p + o, std::min(kBlock, r.n - o), r.off + o});
+            ++open_;
+          }
+          continue;
+        }
+        maps.push_back(Map{static_cast<char *>(m), len});
+        char *dst = static_cast<char *>(m) + (r.off - a);
+        for (size_t o = 0; o < r.n; o += kBlock) {
+          queue_.push_back(Job{-1, dst + o, r.p + o, std::min(kBlock, r.n - o), 0});
+          ++open_;
+        }
+      }
+      cv_work_.notify_all();
+      cv_done_.wait(lk, [this] { return open_ == 0; });
+      ok = !failed_;
+    }
+    for (const Map &m : maps) munmap(m.base, m.len);
+    return ok;
+  }
+
+ private:
+  struct Job {
+    int fd;
+    char *dst;
+    const char *src;
+    size_t n;
+    uint64_t off;
+  };
+  void work() {
+    for (;;) {
+      Job j;
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_work_.wait(lk, [this] { return closing_ || !queue_.empty(); });
+        if (queue_.empty()) return;
+        j = queue_.front();
+        queue_.pop_front();
+      }
+      bool ok = true;
+      if (j.dst) {
+        memcpy(j.dst, j.src, j.n);
+      } else {
+        while (j.n > 0) {
+          const ssize_t w = pwrite(j.fd, j.src, j.n, (off_t)j.off);
+          if (w <= 0) {
+            ok = false;
+            break;
+          }
+          j.src += w;
+          j.n -= (size_t)w;
+          j.off += (uint64_t)w;
+        }
+      }
+      std::unique_lock<std::mutex> lk(mu_);
+      if (!ok) failed_ = true;
+      if (--open_ == 0) cv_done_.notify_all();
+    }
+  }
+  std::mutex mu_;
+  std::condition_variable cv_work_, cv_done_;
+  std::deque<Job> queue_;
+  size_t open_ = 0;
+  bool closing_ = false, failed_ = false;
+  std::vector<std::thread> workers_;
+};
+
+// ------------------------------------------------------------------------------------------
+// ordered gzip writer of one output file.  Text blocks (--gzip host, the SAM header) are compressed by zlib threads,
+// one gzip member per block, and written in order; members that arrive compressed from the GPU bypass all of that
+// (append_direct).  Every write is a pwrite at the file's running offset; an I/O or zlib error ends the run in close().
 // ------------------------------------------------------------------------------------------
 class GzipWriter {
  public:
-  GzipWriter(const std::string &path, int threads, int level = 1) : level_(level) {
-    fp_ = fopen(path.c_str(), "wb");
-    if (!fp_) die("ERROR: Cannot open output file: %s\n", path.c_str());
-    for (int i = 0; i < std::max(1, threads); ++i) workers_.emplace_back([this] { work(); });
-    writer_ = std::thread([this] { write(); });
+  GzipWriter(const std::string &path, int threads, int level = 1) : path_(path), level_(level) {
+    fd_ = open(path.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
+    if (fd_ < 0) die("ERROR: Cannot open output file: %s\n", path.c_str());
+    nthreads_ = std::max(1, threads);
   }
-  // raw: the bytes are gzip members already (written by the GPU, option "deflate"): kept in order, not compressed
+  // raw: the bytes are gzip members already: kept in order, not compressed
   void submit(const char *data, size_t n, bool raw = false) {
     if (n == 0) return;
+    start_threads();
     std::unique_lock<std::mutex> lk(mu_);
     cv_space_.wait(lk, [this] { return pending_.size() + done_.size() < 64; });
     Job j;
@@ -110,6 +237,28 @@ class GzipWriter {
     pending_.push_back(std::move(j));
     cv_work_.notify_one();
   }
+  // everything submitted so far is in the file
+  void drain() {
+    std::unique_lock<std::mutex> lk(mu_);
+    cv_space_.wait(lk, [this] { return written_ == next_seq_; });
+  }
+  // the range WritePool::run needs to append n bytes behind what was submitted (drain() first)
+  WritePool::Range direct_range(const char *p, size_t n) {
+    WritePool::Range r{fd_, p, n, off_};
+    off_ += n;
+    bytes_out += n;
+    // the pool copies through a mapping: the file has to be that long already (lengthened 1 GiB ahead; a file that
+    // cannot be lengthened — a device, a pipe — is written with pwrite by the pool).  Measured on the GPU box's RAM disk
+    // (profiles/r02_cli_wallclock.log): 16 threads copying into the two mapped files 4.3 GB/s, 16 pwrite threads 3.5
+    // GB/s, allocating ahead with fallocate from a thread per file 3 GB/s — page allocation inside ONE file is
+    // serialised by the file system (16 dd writers of 16 files: 45 GB/s), and the two output files are the layout
+    if (off_ > size_) {
+      size_ = (off_ + ((uint64_t)1 << 30)) & ~(((uint64_t)1 << 30) - 1);
+      if (ftruncate(fd_, (off_t)size_) != 0) size_ = 0;
+    }
+    return r;
+  }
+  void fail() { failed_ = true; }
   void close() {
     {
       std::unique_lock<std::mutex> lk(mu_);
@@ -118,8 +267,10 @@ class GzipWriter {
       cv_done_.notify_all();
     }
     for (auto &t : workers_) t.join();
-    writer_.join();
-    fclose(fp_);
+    if (writer_.joinable()) writer_.join();
+    if (size_ > off_ && ftruncate(fd_, (off_t)off_) != 0) failed_ = true;
+    if (::close(fd_) != 0) failed_ = true;
+    if (failed_) die("ERROR: Cannot write output file: %s\n", path_.c_str());
   }
   uint64_t bytes_in = 0, bytes_out = 0;
 
@@ -129,6 +280,11 @@ class GzipWriter {
     bool raw = false;
     std::vector<char> in, out;
   };
+  void start_threads() {
+    if (!workers_.empty()) return;
+    for (int i = 0; i < nthreads_; ++i) workers_.emplace_back([this] { work(); });
+    writer_ = std::thread([this] { write(); });
+  }
   void work() {
     for (;;) {
       Job j;
@@ -139,24 +295,28 @@ class GzipWriter {
         j = std::move(pending_.front());
         pending_.pop_front();
       }
+      bool ok = true;
       if (j.raw) {
-        j.out = j.in;
+        j.out.swap(j.in);
       } else {
         z_stream zs;
         memset(&zs, 0, sizeof zs);
-        deflateInit2(&zs, level_, Z_DEFLATED, 15 + 16, 8, Z_DEFAULT_STRATEGY);
-        j.out.resize(deflateBound(&zs, j.in.size()) + 64);
-        zs.next_in = reinterpret_cast<Bytef *>(j.in.data());
-        zs.avail_in = (uInt)j.in.size();
-        zs.next_out = reinterpret_cast<Bytef *>(j.out.data());
-        zs.avail_out = (uInt)j.out.size();
-        deflate(&zs, Z_FINISH);
-        j.out.resize(zs.total_out);
-        deflateEnd(&zs);
+        ok = deflateInit2(&zs, level_, Z_DEFLATED, 15 + 16, 8, Z_DEFAULT_STRATEGY) == Z_OK;
+        if (ok) {
+          j.out.resize(deflateBound(&zs, j.in.size()) + 64);
+          zs.next_in = reinterpret_cast<Bytef *>(j.in.data());
+          zs.avail_in = (uInt)j.in.size();
+          zs.next_out = reinterpret_cast<Bytef *>(j.out.data());
+          zs.avail_out = (uInt)j.out.size();
+          ok = deflate(&zs, Z_FINISH) == Z_STREAM_END;
+          j.out.resize(zs.total_out);
+          deflateEnd(&zs);
+        }
       }
       {
         std::unique_lock<std::mutex> lk(mu_);
-        bytes_in += j.in.size();
+        if (!ok) failed_ = true;
+        bytes_in += j.raw ? j.out.size() : j.in.size();
         j.in.clear();
         j.in.shrink_to_fit();
         done_[j.seq] = std::move(j);
@@ -175,20 +335,38 @@ class GzipWriter {
         j = std::move(done_[want]);
         done_.erase(want);
         ++want;
-        cv_space_.notify_all();
       }
-      fwrite(j.out.data(), 1, j.out.size(), fp_);
+      const char *p = j.out.data();
+      size_t n = j.out.size();
+      bool ok = true;
+      while (n > 0) {
+        const ssize_t w = pwrite(fd_, p, n, (off_t)off_);
+        if (w <= 0) {
+          ok = false;
+          break;
+        }
+        p += w;
+        n -= (size_t)w;
+        off_ += (uint64_t)w;
+      }
+      std::unique_lock<std::mutex> lk(mu_);
+      if (!ok) failed_ = true;
       bytes_out += j.out.size();
+      written_ = want;
+      cv_space_.notify_all();
     }
   }
-  FILE *fp_;
-  int level_;
+  std::string path_;
+  int fd_ = -1;
+  int level_, nthreads_ = 1;
+  uint64_t size_ = 0;  // length the file was grown to for the mapped copies (cut back to off_ in close)
+  uint64_t off_ = 0;  // the file's running offset: the writer thread's while jobs are pending, the caller's after drain()
   std::mutex mu_;
   std::condition_variable cv_work_, cv_done_, cv_space_;
   std::deque<Job> pending_;
   std::map<uint64_t, Job> done_;
-  uint64_t next_seq_ = 0;
-  bool closing_ = false;
+  uint64_t next_seq_ = 0, written_ = 0;
+  bool closing_ = false, failed_ = false;
   std::vector<std::thread> workers_;
   std::thread writer_;
 };
@@ -233,8 +411,9 @@ struct RefSeq {
                      // pass so that every reference is read from disk once, not three times
 };
 
-// get_genome_inf (:896-991): split the multi-FASTA into <prefix>_NNNN.ref, collect lengths, print the block
-std::vector<RefSeq> genome_inf(const Options &o) {
+// get_genome_inf (:896-991): split the multi-FASTA into <prefix>_NNNN.ref, collect lengths, print the block.
+// The statement of the reference's fgets loop, line by line: the reader of files the parallel one declines.
+std::vector<RefSeq> genome_inf_sequential(const Options &o) {
   fprintf(stderr, ":::: Reference stats ::::\n\n");
   fprintf(stderr, "file name : %s\n", o.genome.c_str());
   fprintf(stderr, "\n");
@@ -289,6 +468,154 @@ std::vector<RefSeq> genome_inf(const Options &o) {
   finish();
   fprintf(stderr, "\n");
   return seqs;
+}
+
+// The same for ordinary FASTA files, in parallel (the 3.1 Gbp human genome is 44 million lines; the loop above spends
+// 4-5 s on them).  The file is mapped; a first parallel scan finds the header lines ('>' at the start of a line), the
+// longest line and any NUL byte; when every line fits one fgets buffer (so that the reference's chunking of long lines
+// and its '>' test on chunk starts cannot matter) and no NUL cuts a line short, the records are independent: a thread
+// per record collects its text and writes its .ref file (the body lines verbatim, which is what the fgets loop writes).
+// Messages and errors are then replayed in the reference's order.  Returns false when the file is not of that kind.
+bool genome_inf_parallel(const Options &o, int threads, std::vector<RefSeq> &seqs) {
+  const int fd = open(o.genome.c_str(), O_RDONLY);
+  if (fd < 0) return false;  // the sequential reader reports it
+  struct stat sb;
+  const char *min_env = getenv("PBSIM_INGEST_PARALLEL_MIN");  // tests: take this path for small files too
+  const long min_bytes = min_env ? std::max(1L, atol(min_env)) : (1L << 16);  // small files: nothing to gain
+  if (fstat(fd, &sb) != 0 || !S_ISREG(sb.st_mode) || sb.st_size < min_bytes) {
+    close(fd);
+    return false;
+  }
+  const size_t n = (size_t)sb.st_size;
+  void *mp = mmap(nullptr, n, PROT_READ, MAP_PRIVATE, fd, 0);
+  close(fd);
+  if (mp == MAP_FAILED) return false;
+  madvise(mp, n, MADV_WILLNEED);
+  const char *p = static_cast<const char *>(mp);
+  const int T = std::max(1, std::min(threads, (int)(n >> 22) + 1));
+  struct Slice {
+    std::vector<size_t> headers;
+    size_t first_nl = SIZE_MAX, last_nl = SIZE_MAX, max_gap = 0;
+    bool nul = false;
+  };
+  std::vector<Slice> sl((size_t)T);
+  {
+    std::vector<std::thread> th;
+    for (int t = 0; t < T; ++t)
+      th.emplace_back([&, t] {
+        const size_t a = n * (size_t)t / (size_t)T, b = n * (size_t)(t + 1) / (size_t)T;
+        Slice &S = sl[(size_t)t];
+        if (memchr(p + a, 0, b - a)) S.nul = true;
+        size_t prev = SIZE_MAX;
+        for (const char *q = p + a; q < p + b;) {
+          const char *nl = static_cast<const char *>(memchr(q, '\n', (size_t)(p + b - q)));
+          if (!nl) break;
+          const size_t i = (size_t)(nl - p);
+          if (prev == SIZE_MAX) S.first_nl = i;
+          else S.max_gap = std::max(S.max_gap, i - prev - 1);
+          prev = i;
+          if (i + 1 < n && p[i + 1] == '>') S.headers.push_back(i + 1);
+          q = nl + 1;
+        }
+        S.last_nl = prev;
+      });
+    for (auto &t : th) t.join();
+  }
+  std::vector<size_t> heads;
+  if (p[0] == '>') heads.push_back(0);
+  size_t longest = 0, prev = SIZE_MAX;  // prev: the newline in front of the current line (SIZE_MAX: start of file)
+  bool nul = false;
+  for (const Slice &S : sl) {
+    nul |= S.nul;
+    heads.insert(heads.end(), S.headers.begin(), S.headers.end());
+    longest = std::max(longest, S.max_gap);
+    if (S.first_nl != SIZE_MAX) {
+      longest = std::max(longest, prev == SIZE_MAX ? S.first_nl : S.first_nl - prev - 1);
+      prev = S.last_nl;
+    }
+  }
+  longest = std::max(longest, prev == SIZE_MAX ? n : n - prev - 1);
+  if (nul || longest > kBufSize - 2 || heads.empty()) {
+    munmap(mp, n);
+    return false;
+  }
+  const size_t R = std::min(heads.size(), (size_t)kRefSeqNumMax);  // the reader dies at header 10000 (below)
+  seqs.assign(R, RefSeq());
+  std::vector<int> open_failed(R, 0), write_failed(R, 0);
+  std::atomic<size_t> next(0);
+  auto parse = [&] {
+    for (;;) {
+      const size_t r = next.fetch_add(1);
+      if (r >= R) return;
+      const size_t a = heads[r], b = r + 1 < heads.size() ? heads[r + 1] : n;
+      const char *hl = static_cast<const char *>(memchr(p + a, '\n', b - a));
+      const size_t hend = hl ? (size_t)(hl - p) : b;  // end of the header line's text
+      RefSeq &q = seqs[r];
+      q.id.assign(p + a + 1, std::min(hend - a - 1, (size_t)kRefIdLenMax));
+      const size_t body = hl ? hend + 1 : b;
+      q.text.reserve(b - body);
+      for (size_t i = body; i < b;) {
+        const char *nl = static_cast<const char *>(memchr(p + i, '\n', b - i));
+        const size_t e = nl ? (size_t)(nl - p) : b;
+        q.text.append(p + i, e - i);
+        i = e + 1;
+      }
+      q.len = (long)q.text.size();
+      if (o.rank == 0) {  // one writer of the .ref files is enough
+        char name[4096];
+        snprintf(name, sizeof name, "%s_%04zu.ref", o.prefix.c_str(), r + 1);
+        const int out = open(name, O_WRONLY | O_CREAT | O_TRUNC, 0644);
+        if (out < 0) {
+          open_failed[r] = 1;
+          continue;
+        }
+        std::string head = ">" + q.id + "\n";
+        bool ok = write(out, head.data(), head.size()) == (ssize_t)head.size();
+        for (size_t i = body; ok && i < b;) {
+          const ssize_t w = write(out, p + i, std::min(b - i, (size_t)1 << 30));
+          if (w <= 0) ok = false;
+          else i += (size_t)w;
+        }
+        if (ok && b > body && p[b - 1] != '\n') ok = write(out, "\n", 1) == 1;  // a last line without line feed
+        if (close(out) != 0) ok = false;
+        if (!ok) write_failed[r] = 1;
+      }
+    }
+  };
+  {
+    std::vector<std::thread> th;
+    for (int t = 0; t < std::max(1, std::min(threads, (int)R)); ++t) th.emplace_back(parse);
+    for (auto &t : th) t.join();
+  }
+  munmap(mp, n);
+  // the report and the checks, in the order the sequential loop makes them
+  fprintf(stderr, ":::: Reference stats ::::\n\n");
+  fprintf(stderr, "file name : %s\n", o.genome.c_str());
+  fprintf(stderr, "\n");
+  auto drop_later_refs = [&](size_t r) {  // the sequential reader has not come to the records behind r when it stops
+    for (size_t q = r + 1; q < R && o.rank == 0; ++q) {
+      char name[4096];
+      snprintf(name, sizeof name, "%s_%04zu.ref", o.prefix.c_str(), q + 1);
+      unlink(name);
+    }
+  };
+  for (size_t r = 0; r < R; ++r) {
+    if (open_failed[r] || write_failed[r] || seqs[r].len > kRefSeqLenMax || seqs[r].len < kRefSeqLenMin) drop_later_refs(r);
+    if (open_failed[r]) die("ERROR: Cannot open output file: %s_%04zu.ref\n", o.prefix.c_str(), r + 1);
+    if (write_failed[r]) die("ERROR: Cannot write output file: %s_%04zu.ref\n", o.prefix.c_str(), r + 1);
+    if (seqs[r].len > kRefSeqLenMax) die("ERROR: Reference is too long. Acceptable length <= %ld.\n", kRefSeqLenMax);
+    if (seqs[r].len < kRefSeqLenMin) die("ERROR: Reference is too short. Acceptable length >= %ld.\n", kRefSeqLenMin);
+    fprintf(stderr, "ref.%zu (len:%ld) : %s\n", r + 1, seqs[r].len, seqs[r].id.c_str());
+  }
+  if (heads.size() > (size_t)kRefSeqNumMax) die("ERROR: References are too many. Max number of reference is %ld.\n", kRefSeqNumMax);
+  fprintf(stderr, "\n");
+  return true;
+}
+
+std::vector<RefSeq> genome_inf(const Options &o, int threads) {
+  std::vector<RefSeq> seqs;
+  if (genome_inf_parallel(o, threads, seqs)) return seqs;
+  return genome_inf_sequential(o);
 }
 
 // ---- --strategy trans / templ: the sequence set the engine simulates in one run --------------------------------
@@ -801,11 +1128,23 @@ int main(int argc, char **argv) {
   const bool trans = o.strategy == "trans";
   std::vector<RefSeq> seqs;
   SeqSetHost S;
-  if (wgs) seqs = genome_inf(o);
-  else S = trans ? read_transcripts(o) : read_templates(o);
-
+  // (the CUDA context comes up on a thread of its own meanwhile; its outcome is looked at afterwards)
+  const int threads = o.threads > 0 ? o.threads : std::max(2u, std::thread::hardware_concurrency());
   pbsim_engine *eng = nullptr;
-  if (pbsim_cuda_create(&eng, o.gpu) != 0) die("ERROR: %s\n", pbsim_cuda_last_error(nullptr));
+  int create_rc = 0;
+  std::string create_err;
+  std::thread creator([&] {
+    create_rc = pbsim_cuda_create(&eng, o.gpu);
+    if (create_rc != 0) create_err = pbsim_cuda_last_error(nullptr);  // thread-local in the library: read it here
+  });
+  g_background = &creator;
+  const double t_load0 = now_seconds();
+  if (wgs) seqs = genome_inf(o, threads);
+  else S = trans ? read_transcripts(o) : read_templates(o);
+  const double load_seconds = now_seconds() - t_load0;
+  creator.join();
+  g_background = nullptr;
+  if (create_rc != 0) die("ERROR: %s\n", create_err.c_str());
   if (pbsim_cuda_set_model(eng, pbsim_host_model_get(hm)) != 0) die("ERROR: %s\n", pbsim_cuda_last_error(eng));
   if (pbsim_cuda_set_option(eng, "deflate", o.gzip == "gpu" ? 1 : 0) != 0) die("ERROR: %s\n", pbsim_cuda_last_error(eng));
   if (sample && pbsim_cuda_set_pool(eng, pool_q.data(), pool_start.data(), (int64_t)pool_start.size() - 1) != 0)
@@ -822,8 +1161,9 @@ int main(int argc, char **argv) {
     for (size_t i = 0; i < marks.size(); ++i) starts[i] = i == 0 ? 0 : marks[i - 1];
   }
   size_t replay_pos = 0;
-  const int threads = o.threads > 0 ? o.threads : std::max(2u, std::thread::hardware_concurrency());
-  double gen_seconds = 0;
+  WritePool pool(std::min(threads, 16));
+  double gen_seconds = 0, write_seconds = 0, chunk_wait_seconds = 0;
+  int64_t written_bytes = 0;
   int64_t total_bases = 0;
   double bias[12] = {0, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 0};
 
@@ -869,11 +1209,29 @@ int main(int argc, char **argv) {
     if (pbsim_cuda_simulate_begin(eng, &run) != 0) die("ERROR: %s\n", pbsim_cuda_last_error(eng));
     for (;;) {
       pbsim_chunk c;
+      const double tc = now_seconds();
       const int rc = pbsim_cuda_next_chunk(eng, &c);
+      chunk_wait_seconds += now_seconds() - tc;
       if (rc < 0) die("ERROR: %s\n", pbsim_cuda_last_error(eng));
       if (rc == 0) break;
-      stream_to(reads_out, c.reads, c.reads_bytes, c.compressed != 0);
-      stream_to(maf_out, c.maf, c.maf_bytes, c.compressed != 0);
+      if (c.compressed) {
+        // gzip members / BGZF blocks written by the GPU: from the engine's pinned staging straight into the files
+        reads_out.drain();
+        maf_out.drain();
+        std::vector<WritePool::Range> ranges;
+        if (c.reads_bytes) ranges.push_back(reads_out.direct_range(c.reads, (size_t)c.reads_bytes));
+        if (c.maf_bytes) ranges.push_back(maf_out.direct_range(c.maf, (size_t)c.maf_bytes));
+        const double tw = now_seconds();
+        if (!pool.run(ranges)) {
+          reads_out.fail();
+          maf_out.fail();
+        }
+        write_seconds += now_seconds() - tw;
+        written_bytes += c.reads_bytes + c.maf_bytes;
+      } else {
+        stream_to(reads_out, c.reads, c.reads_bytes);
+        stream_to(maf_out, c.maf, c.maf_bytes);
+      }
     }
     pbsim_stats st;
     if (pbsim_cuda_simulate_end(eng, &st, nullptr, 0, nullptr) != 0) die("ERROR: %s\n", pbsim_cuda_last_error(eng));
@@ -906,6 +1264,9 @@ int main(int argc, char **argv) {
     fprintf(stderr, "CPU time(s) : %ld\n", now_cpu() - rst1);
     fprintf(stderr, "Elapsed time(s) : %ld\n", now_wall() - t1);
     fprintf(stderr, "\n:::: B200 engine ::::\n\n");
+    fprintf(stderr, "input load time(s) : %.3f\n", load_seconds);
+    fprintf(stderr, "waiting for record pieces (generation + device-to-host copies) (s) : %.3f\n", chunk_wait_seconds);
+    fprintf(stderr, "copying gzip members into the output files (s) : %.3f (%.2f GB)\n", write_seconds, written_bytes / 1e9);
     fprintf(stderr, "generation device time(s) : %.3f\n", gen_seconds);
     fprintf(stderr, "simulated Gbp/s (generation only) : %.3f\n", gen_seconds > 0 ? total_bases / gen_seconds / 1e9 : 0.0);
     return 0;

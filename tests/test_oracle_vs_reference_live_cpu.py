@@ -277,7 +277,10 @@ def test_driver_parses_fasta_like_the_live_reference(k, tmp_path):
     pr = subprocess.run([R.REF_BIN] + args + ["--prefix", "out"], cwd=rdir, env=env, stdout=subprocess.PIPE,
                         stderr=subprocess.PIPE, timeout=300)
     G.build_engine()
+    # even k: the parallel reader (mapped file, a thread per record) is forced onto these small files; it declines
+    # files with lines longer than an fgets buffer and leaves them to the line-by-line reader
     pd = subprocess.run([G.build_driver()] + args + ["--prefix", "out"], cwd=ddir, stdout=subprocess.PIPE,
+                        env=dict(os.environ, PBSIM_INGEST_PARALLEL_MIN="1") if k % 2 == 0 else dict(os.environ),
                         stderr=subprocess.PIPE, timeout=300)
     want, got = pr.stderr.decode(), pd.stderr.decode()
     cut = ":::: Simulation stats (ref.1) ::::"
@@ -577,17 +580,20 @@ def test_driver_handles_odd_fasta_like_the_live_reference(name, tmp_path):
     G.build_engine()
     env = dict(os.environ, PATH=R.SHIMS + ":" + os.environ.get("PATH", ""))
     res = {}
-    for who, binary in (("r", R.REF_BIN), ("d", G.build_driver())):
+    # "p": the driver's parallel reader (mapped file, a thread per record), which small files normally do not take
+    for who, binary in (("r", R.REF_BIN), ("d", G.build_driver()), ("p", G.build_driver())):
         d = tmp_path / who
         d.mkdir()
         (d / "g.fa").write_bytes(_ODD_FASTA[name])
         p = subprocess.run([binary, "--strategy", "wgs", "--method", "qshmm", "--qshmm", model_path("QSHMM-RSII.model"),
-                            "--genome", "g.fa", "--depth", "0.3", "--seed", "1", "--prefix", "out"], cwd=d, env=env,
+                            "--genome", "g.fa", "--depth", "0.3", "--seed", "1", "--prefix", "out"], cwd=d,
+                           env=dict(env, PBSIM_INGEST_PARALLEL_MIN="1") if who == "p" else env,
                            stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=120)
         err = p.stderr.decode(errors="replace")
         head = err.split("ERROR: no usable CUDA device")[0].split(":::: Simulation stats (ref.1) ::::")[0]
         refs = {f: (d / f).read_bytes() for f in sorted(os.listdir(d)) if f.endswith(".ref")}
         res[who] = (head, refs, p.returncode)
+    assert res["p"] == res["d"]
     if res["r"][2] < 0:  # killed by a signal: undefined behaviour in the reference
         assert res["d"][2] not in (0,) and res["d"][2] > 0
         return
