@@ -5,14 +5,17 @@
 
 A STEP is one call of the reference's seam for one reference sequence: ingest the sequence
 (get_genome_seq), then simulate_by_qshmm / simulate_by_errhmm to the depth quota, records emitted
-(FASTQ + MAF).  Sequences are the 24 contigs of a synthetic 3.1 Gbp human-sized genome; step i works on
-contig i mod 24, and with N GPUs every rank simulates its own range of read ids of that contig.  Default workload "c3" = BASELINE.json configs[2]
-(WGS qshmm, QSHMM-ONT ultra-long reads, 3.1 Gbp genome, --depth 50): the configuration the metric
-"simulated Gbp/s (WGS qshmm, 3.1 Gbp genome)" is quoted on.
+(FASTQ + MAF).  Sequences are the 24 contigs of a synthetic 3.1 Gbp human-sized genome; the timed steps are the
+sequences (warmup + k) mod 24.  With N GPUs the steps are ONE run split over the ranks: the line of all their reads
+is cut into N pieces of equal estimated work (whole sequences plus read ranges of the sequences two ranks share).
+Default workload "c3" = BASELINE.json configs[2] (WGS qshmm, QSHMM-ONT ultra-long reads, 3.1 Gbp genome, --depth 50):
+the configuration the metric "simulated Gbp/s (WGS qshmm, 3.1 Gbp genome)" is quoted on.
 
-  value : emitted bases / device time, sequence text already resident in HBM, records left in HBM
-  e2e   : same steps through the C ABI with HOST buffers: the sequence text is uploaded from pinned
-          host memory and every record byte is delivered to pinned host memory inside the timed region
+  value    : emitted bases / device time, sequence text already resident in HBM, records left in HBM
+  e2e      : same steps through the C ABI with HOST buffers: the sequence text is uploaded from pinned host memory and
+             every record byte is delivered to pinned host memory inside the timed region, as gzip members written by
+             the GPU — the reference's output files are .fq.gz / .maf.gz (pbsim.cpp:708-730)
+  e2e_text : the same delivering the uncompressed text (4.1 bytes per base over PCIe instead of 1.6)
   roofline / cpu_baseline : see DESIGN.md "Measurement"
 
 --impl reference times the UNMODIFIED reference binary (oracle/_ref/pbsim, compiled from
@@ -336,18 +339,20 @@ class Workload:
         self.wl, self.key, self.rank = wl, key, rank
         L = capi.load()
         self.hm = capi.HostModel(L, capi.host_params(wl["method"], **wl["params"]), model_path(wl["model"]))
-        self.eng = eng = simulator.Engine(local)
-        eng.set_model(self.hm)
+        self.local, self.simulator = local, simulator
+        self.options = []
         if overrides:
             for opt, val in (("target_batch_bases", args.batch_bases), ("chain_chunk", args.chain_chunk),
                              ("first_batch_div", args.first_batch_div), ("host_batch_bases", args.host_batch_bases)):
                 if val:
-                    eng.set_option(opt, int(val))
+                    self.options.append((opt, int(val)))
             if args.bam:
-                eng.set_option("bam", 1)
+                self.options.append(("bam", 1))
                 wl["name"] += " [BAM records]"
         if wl.get("batch_bases") and not (overrides and args.batch_bases):
-            eng.set_option("target_batch_bases", int(wl["batch_bases"]))
+            self.options.append(("target_batch_bases", int(wl["batch_bases"])))
+        self.engines = []
+        self.eng = eng = self.engine(0)
         self.depth = wl["depth"]
         self.contigs = [max(200000, int(m * 1000000 * args.scale)) for m in CONTIG_MBP]
         self.bias = [0.0] + [1.0] * 10 + [0.0]
@@ -372,14 +377,31 @@ class Workload:
             self.total_reads = int(expr.sum())
             eng.set_seqset("trans", self.seqset, self.bias)
 
-    def run_part(self, part, rng_seed=0, read_range=None, prefix=0, host_seq=None, sink=None, on_chunk=None):
+    def engine(self, lane):
+        """engine number `lane` of this GPU (the host-delivery arm drives two, see run_parts)"""
+        while len(self.engines) <= lane:
+            e = self.simulator.Engine(self.local)
+            e.set_model(self.hm)
+            for opt, val in self.options:
+                e.set_option(opt, val)
+            if self.engines and getattr(self, "seqset", None) is not None:
+                e.set_seqset("trans", self.seqset, self.bias)
+            self.engines.append(e)
+        return self.engines[lane]
+
+    def close(self):
+        for e in self.engines:
+            e.close()
+        self.engines = []
+
+    def run_part(self, part, rng_seed=0, read_range=None, prefix=0, host_seq=None, sink=None, on_chunk=None, eng=None):
         """one part of the run: WGS — a sequence, or a read range of one (part = dict(seq, first_read, max_reads, last),
         stats_reduce.plan_line_split; prefix = emitted bases of the sequence's earlier parts when this is its dependent
         last part); sequence sets — the whole table or this rank's read-number range of it.
         host_seq = None: the sequence text is generated in HBM and the records stay there (device arm);
         otherwise the text is uploaded from that pinned host buffer and every record byte is delivered to host memory.
         Returns (bases, record bytes, stats)."""
-        eng, capi = self.eng, self.capi
+        eng, capi = eng or self.eng, self.capi
         device = host_seq is None
         if self.seqset is None:
             k = part["seq"]
@@ -424,31 +446,67 @@ def whole_parts(step_ids):
     return [dict(seq=k, first_read=0, max_reads=0, last=True, est=0.0) for k in step_ids]
 
 
-def run_parts(W, parts, dist, device, on_part, read_range=None, host_seq=None, sink=None, on_chunk=None):
+def run_parts(W, parts, dist, device, on_part, read_range=None, host_seq=None, sink=None, on_chunk=None, lanes=1):
     """this rank's parts in the order of stats_reduce.split_order: feeders, publish (asynchronous all-reduce of the
-    emitted bases per sequence), whole sequences, dependent last parts (each told its len_total_start)."""
+    emitted bases per sequence), whole sequences, dependent last parts (each told its len_total_start).
+    lanes = 2 (host delivery): two engines on this GPU, each driven by its own host thread, take the parts of a phase
+    alternately — while one run drains its last records over PCIe and the next sequence is ingested and its first batch
+    generated, the other engine's copies keep the link busy (a run has nothing to copy for its first 15-20 ms)."""
     from pbsim_b200 import stats_reduce as SR
     feeders, whole, dependent = SR.split_order(parts)
     ex = None
     if W.seqset is None and dist is not None:
         ex = SR.SplitExchange(len(W.contigs), dist, device="cuda")
-    i = 0
+    lock = threading.Lock()
+    base = 0
     for phase, plist in (("feed", feeders), ("whole", whole), ("dep", dependent)):
         if phase == "whole" and ex is not None:
             ex.publish()
-        for p in plist:
-            prefix = ex.prefix(p["seq"]) if phase == "dep" else 0
-            if on_chunk is not None:
-                on_chunk(p)  # a new part begins
-            b, ob, st = W.run_part(p, rng_seed=(i if W.seqset is not None else 0), read_range=read_range, prefix=prefix,
-                                   host_seq=None if host_seq is None else host_seq[p["seq"]], sink=sink, on_chunk=on_chunk)
-            if phase == "feed":
-                ex.add(p["seq"], st.len_total_end)
-            on_part(p, b, ob, st)
-            i += 1
+        nxt = [0]
+        errors = []
+
+        def worker(lane):
+            try:
+                import torch
+                torch.cuda.set_device(W.local)  # the current device is a per-thread setting
+                while True:
+                    with lock:
+                        j = nxt[0]
+                        nxt[0] += 1
+                    if j >= len(plist) or errors:
+                        return
+                    p = plist[j]
+                    prefix = ex.prefix(p["seq"]) if phase == "dep" else 0
+                    if on_chunk is not None:
+                        on_chunk(p)  # a new part begins
+                    b, ob, st = W.run_part(p, rng_seed=(base + j if W.seqset is not None else 0), read_range=read_range,
+                                           prefix=prefix, host_seq=None if host_seq is None else host_seq[p["seq"]],
+                                           sink=sink, on_chunk=on_chunk, eng=W.engine(lane))
+                    with lock:
+                        if phase == "feed":
+                            ex.add(p["seq"], st.len_total_end)
+                        on_part(p, b, ob, st)
+            except Exception as ex_:  # noqa: BLE001 - re-raised on the calling thread
+                errors.append(ex_)
+
+        n_lanes = min(lanes, len(plist)) if on_chunk is None else 1
+        if n_lanes <= 1:
+            worker(0)
+        else:
+            for lane in range(n_lanes):
+                W.engine(lane)  # created on this thread, before the clocks of the workers start
+            ts = [threading.Thread(target=worker, args=(lane,)) for lane in range(n_lanes)]
+            for t in ts:
+                t.start()
+            for t in ts:
+                t.join()
+        if errors:
+            raise errors[0]
+        base += len(plist)
 
 
-def measure(W, my_parts, warm_parts, e2e_steps, barrier, dist=None, read_range=None, gzip_arm=True, e2e_warm=False):
+def measure(W, my_parts, warm_parts, e2e_steps, barrier, dist=None, read_range=None, gzip_arm=True, text_arm=True,
+            e2e_warm=False, e2e_lanes=2):
     """device-resident arm + end-to-end arm(s) over this rank's parts.  Returns a dict of local measurements."""
     import torch
     eng, capi = W.eng, W.capi
@@ -513,20 +571,31 @@ def measure(W, my_parts, warm_parts, e2e_steps, barrier, dist=None, read_range=N
                 e["gen_s"] += st.gen_seconds
                 e["gz_s"] += st.deflate_seconds
 
-            run_parts(W, parts_e, dist, False, on_e, read_range=read_range, host_seq=host_seq, sink=sink)
+            run_parts(W, parts_e, dist, False, on_e, read_range=read_range, host_seq=host_seq, sink=sink, lanes=e2e_lanes)
             barrier()
             return dict(e, ms=(time.perf_counter() - t0) * 1e3, steps=len(set(p["seq"] for p in parts_e)) if W.seqset is None
                         else len(parts_e))
 
-        if e2e_warm:  # untimed pass: pinned staging buffers and record buffers reach their steady-state size
-            e2e_pass()
-        acc["e2e"] = e2e_pass()
+        # untimed: one run through every engine of the arm, so that pinned staging buffers and record buffers exist
+        if parts_e:
+            big = max(parts_e, key=lambda p: p.get("est", 0.0))
+            for lane in range(e2e_lanes if len(parts_e) > 1 else 1):
+                W.run_part(dict(big, first_read=0, last=True), read_range=read_range, host_seq=host_seq[big["seq"]],
+                           eng=W.engine(lane))
+        if text_arm:
+            if e2e_warm:  # untimed pass: every buffer reaches its steady-state size
+                e2e_pass()
+            acc["e2e"] = e2e_pass()
         if gzip_arm:
-            # the same with the records gzip-compressed on the GPU before they cross PCIe (the reference's outputs
-            # are .gz files, pbsim.cpp:708-730); reported next to the text number, not instead of it
-            eng.set_option("deflate", 1)
+            # the records gzip-compressed on the GPU before they cross PCIe (the reference's outputs are .gz files,
+            # pbsim.cpp:708-730)
+            for e_ in W.engines:
+                e_.set_option("deflate", 1)
+            if e2e_warm:
+                e2e_pass()
             acc["e2e_gz"] = e2e_pass()
-            eng.set_option("deflate", 0)
+            for e_ in W.engines:
+                e_.set_option("deflate", 0)
         del host_seq
     return acc
 
@@ -670,6 +739,8 @@ def main():
     ap.add_argument("--part-overhead-gbase", type=float, default=0.3,
                     help="line split: fixed cost of one run in units of emitted Gbase (balances ranks that own many "
                          "short sequences against ranks that own few long ones)")
+    ap.add_argument("--e2e-lanes", type=int, default=2, choices=[1, 2],
+                    help="engines per GPU in the host-delivery arm (2: one run's start-up hides behind the other's copies)")
     ap.add_argument("--no-split", action="store_true",
                     help="N > 1: assign whole sequences to ranks (longest first) instead of cutting the line of reads")
     ap.add_argument("--verify-split", action="store_true",
@@ -757,7 +828,7 @@ def main():
         warm = whole_parts([0] * args.warmup)
     sampler = ClockSampler(local)
     sampler.start()
-    acc = measure(W, mine, warm, args.e2e_steps, barrier, dist=dist, read_range=read_range)
+    acc = measure(W, mine, warm, args.e2e_steps, barrier, dist=dist, read_range=read_range, e2e_lanes=args.e2e_lanes)
     clocks = sampler.stop()
 
     d2h_ceiling = host_d2h_ceiling(barrier, allsum) if args.e2e_steps != 0 else None
@@ -808,8 +879,12 @@ def main():
             line["split"] = split_info
             if verified is not None:
                 line["split"]["verified"] = verified
-        for key, name, what in (("e2e", "e2e", "text records"),
-                                ("e2e_gz", "e2e_gzip", "gzip members written by the GPU (option deflate)")):
+        # e2e delivers what the reference's run delivers: gzip-compressed record files (its FASTQ / MAF streams go
+        # through `gzip` children into <prefix>_NNNN.fq.gz / .maf.gz, pbsim.cpp:708-730); the engine writes the gzip
+        # members on the GPU (option "deflate").  e2e_text is the same run delivering the uncompressed text.
+        for key, name, what in (("e2e_gz", "e2e", "gzip members written by the GPU (option deflate): the format of the "
+                                                  "reference's output files (.fq.gz / .maf.gz, pbsim.cpp:708-730)"),
+                                ("e2e", "e2e_text", "uncompressed text records")):
             if key in e2e_line and e2e_line[key]["ms"] > 0:
                 e = e2e_line[key]
                 st = max(1.0, e["steps"])
@@ -823,11 +898,12 @@ def main():
                 if ceil:
                     line[name]["host_d2h_ceiling_gb_per_s"] = ceil
                     line[name]["d2h_frac_of_host_ceiling"] = line[name]["d2h_gb_per_s"] / ceil
-        if "e2e_gzip" in line and "e2e" in line:
-            line["e2e_gzip"]["compression_ratio"] = line["e2e"]["d2h_bytes_per_step"] / max(1.0, line["e2e_gzip"]["d2h_bytes_per_step"])
+        if "e2e_text" in line and "e2e" in line:
+            line["e2e"]["compression_ratio"] = line["e2e_text"]["d2h_bytes_per_step"] / max(1.0, line["e2e"]["d2h_bytes_per_step"])
+            line["e2e"]["engines_per_gpu"] = line["e2e_text"]["engines_per_gpu"] = args.e2e_lanes
         # ---- short runs of the other BASELINE configurations (one GPU): value + roofline each
         if world == 1 and not args.no_extras and args.workload == "c3":
-            W.eng.close()
+            W.close()
             line["extra"] = {}
             for key in ("c1", "c2", "c4", "c5"):
                 try:
@@ -835,13 +911,13 @@ def main():
                     ns = args.extra_steps if X.seqset is None else 1
                     st_ids = [(2 + k) % len(X.contigs) for k in range(ns)]  # mid-sized contigs
                     xp = whole_parts(st_ids if X.seqset is None else [0] * ns)
-                    a = measure(X, xp, xp[:1], 1, barrier, gzip_arm=False, e2e_warm=True)
+                    a = measure(X, xp, xp[:1], 1, barrier, gzip_arm=True, text_arm=False, e2e_warm=True)
                     line["extra"][key] = {
                         "workload": X.wl["name"], "steps": ns,
                         "value": a["bases"] / (a["dev_ms"] * 1e-3) / 1e9, "unit": "Gbp/s",
-                        "e2e": a["e2e"]["bases"] / (a["e2e"]["ms"] * 1e-3) / 1e9 if a["e2e"] else None,
+                        "e2e": a["e2e_gz"]["bases"] / (a["e2e_gz"]["ms"] * 1e-3) / 1e9 if a["e2e_gz"] else None,
                         "roofline": roofline_block(X.wl["method"], a, peak, peak_src)}
-                    X.eng.close()
+                    X.close()
                 except Exception as ex:  # an extra must never cost the headline
                     line["extra"][key] = {"error": repr(ex)}
         if not args.no_cpu_baseline:

@@ -92,8 +92,12 @@ struct SegArgs {
 // segments lo + w, lo + w + 4, ...
 constexpr int kSegWarps = kSimThreads / 32;
 // threads of a quality-pass CTA (they share one accuracy's tables, 28 KB: 8 CTAs per SM with the largest shared-memory
-// carve-out).  Measured: 512-thread CTAs (48 warps per SM) are slower — the pass is bound by the shared-memory pipe.
-constexpr int kChainThreads = 128;
+// carve-out).  Measured: 256-thread CTAs (48 warps per SM) are 15 % slower on the pass (c3 and c1, chunks of 8
+// segments), 512-thread CTAs likewise with chunks of 32 — more warps only queue up behind the shared-memory pipe.
+#ifndef PB_CHAIN_THREADS
+#define PB_CHAIN_THREADS 128
+#endif
+constexpr int kChainThreads = PB_CHAIN_THREADS;
 
 __global__ void __launch_bounds__(kSimThreads) k_sim_seg(SegArgs A) {
   __shared__ __align__(16) QsFast s_fast[PBSIM_NQV];
