@@ -255,11 +255,12 @@ def reference_arm(args, wl):
 # our arm
 # ------------------------------------------------------------------------------------------------
 # DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of ONE launch of the three big kernels on the c3 workload,
-# and the read positions that launch covered, from the committed ncu captures (profiles/r02_k_*_c3.txt)
+# and the read positions that launch covered, from the committed ncu captures (profiles/r02_k_*_c3_final.txt)
 NCU_DRAM_BYTES = {
-    "k_chain_chunk": dict(bytes=18.12e9, positions=6.73e9, src="profiles/r02_k_chain_chunk_c3_v1.txt"),
-    "k_sim_seg": dict(bytes=27.47e9, positions=6.73e9, src="profiles/r02_k_sim_seg_c3_v14.txt"),
-    "k_emit_rows": dict(bytes=39.68e9, positions=6.10e9, src="profiles/r02_k_emit_c3_v8.txt"),
+    # one batch of 128,851 reads: 6,565,276 segments = 6.72e9 simulated positions, 6.34e9 emitted bases
+    "k_chain_chunk": dict(bytes=16.81e9, positions=6.72e9, src="profiles/r02_k_chain_chunk_c3_final.txt"),
+    "k_sim_seg": dict(bytes=27.96e9, positions=6.72e9, src="profiles/r02_k_sim_seg_c3_final.txt"),
+    "k_emit_rows": dict(bytes=41.26e9, positions=6.34e9, src="profiles/r02_k_emit_rows_c3_final.txt"),
 }
 # algorithmic bytes per read position of each kernel: the quality pass writes a 2-byte slot entry per position; the
 # error pass reads and rewrites it; the row kernel reads it and 0.244 B of 2-bit genome and writes the records (4.124 B)
