@@ -311,9 +311,10 @@ def host_d2h_ceiling(barrier, allsum, reps=8, nbytes=256 << 20):
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         barrier()
-        return allsum(nbytes * reps / dt / 1e9)
+        mine = nbytes * reps / dt / 1e9
+        return allsum(mine), mine
     except Exception:
-        return None
+        return None, None
 
 
 def lpt_assign(sizes, world):
@@ -507,7 +508,7 @@ def run_parts(W, parts, dist, device, on_part, read_range=None, host_seq=None, s
 
 
 def measure(W, my_parts, warm_parts, e2e_steps, barrier, dist=None, read_range=None, gzip_arm=True, text_arm=True,
-            e2e_warm=False, e2e_lanes=2):
+            e2e_warm=False, e2e_lanes=2, parts_e=None):
     """device-resident arm + end-to-end arm(s) over this rank's parts.  Returns a dict of local measurements."""
     import torch
     eng, capi = W.eng, W.capi
@@ -542,7 +543,9 @@ def measure(W, my_parts, warm_parts, e2e_steps, barrier, dist=None, read_range=N
     acc["wall_ms"] = (time.perf_counter() - t0) * 1e3
     acc["e2e"] = acc["e2e_gz"] = None
     # the host-buffer arm runs the same parts (a prefix of the run's sequences when --e2e-steps asks for fewer)
-    if e2e_steps >= 0 and W.seqset is None:
+    if parts_e is not None:
+        pass  # the caller's plan for the host-delivery arm (pieces proportional to every rank's delivery rate)
+    elif e2e_steps >= 0 and W.seqset is None:
         keep = set(sorted(set(p["seq"] for p in my_parts), key=lambda k: [q["seq"] for q in my_parts].index(k))[:e2e_steps])
         parts_e = [p for p in my_parts if p["seq"] in keep] if dist is None else my_parts
     else:
@@ -737,7 +740,7 @@ def main():
     ap.add_argument("--first-batch-div", type=int, default=None, help="diagnostics: engine first_batch_div")
     ap.add_argument("--host-batch-bases", type=float, default=None, help="diagnostics: engine host_batch_bases")
     ap.add_argument("--bam", action="store_true", help="multi-pass workloads: BAM records / BGZF blocks instead of SAM text")
-    ap.add_argument("--part-overhead-gbase", type=float, default=0.3,
+    ap.add_argument("--part-overhead-gbase", type=float, default=0.45,
                     help="line split: fixed cost of one run in units of emitted Gbase (balances ranks that own many "
                          "short sequences against ranks that own few long ones)")
     ap.add_argument("--e2e-lanes", type=int, default=2, choices=[1, 2],
@@ -799,6 +802,8 @@ def main():
     #      A sequence set (--strategy trans) is one step and has no quota: split by read-number range.
     read_range = None
     split_info = None
+    parts_e = None
+    d2h_ceiling, my_d2h = host_d2h_ceiling(barrier, allsum) if args.e2e_steps != 0 else (None, None)
     if W.seqset is None:
         from pbsim_b200 import stats_reduce as SR
         step_ids = [(args.warmup + k) % len(W.contigs) for k in range(args.steps)]
@@ -806,7 +811,7 @@ def main():
             mean_emit = W.pilot_mean_emitted(step_ids[0])
             reads_est = [W.depth * W.contigs[k] / mean_emit for k in step_ids]
             # work of a sequence = its bases + a fixed cost per run (ingest, the quota's tail reads, the last partly
-            # filled batch: about 3 ms, measured with PBSIM_BENCH_DEBUG=1 on one GPU) expressed in bases
+            # filled batch: about 4 ms, measured with PBSIM_BENCH_DEBUG=1 on one GPU) expressed in bases
             plan = SR.plan_line_split(reads_est, world,
                                       weights=[W.depth * W.contigs[k] + args.part_overhead_gbase * 1e9 for k in step_ids])
             for r in plan:
@@ -816,6 +821,23 @@ def main():
             split_info = {"mean_emitted_bases_per_read": mean_emit,
                           "parts_per_rank": [len(r) for r in plan],
                           "sequences_shared_by_two_ranks": sum(1 for r in plan for p in r if not p["last"])}
+            if my_d2h:
+                # the host-delivery arm is bound by every rank's device-to-host path, and those differ (on this pool's
+                # 8-GPU hosts four GPUs reach 8 GB/s and four 18 GB/s when all copy at once): its pieces are
+                # proportional to the rates just measured
+                import torch as _t
+                rt = _t.tensor([my_d2h], dtype=_t.float64, device="cuda")
+                allr = [_t.zeros_like(rt) for _ in range(world)]
+                dist.all_gather(allr, rt)
+                rates = [float(v[0]) for v in allr]
+                plan_e = SR.plan_line_split(reads_est, world, shares=rates,
+                                            weights=[W.depth * W.contigs[k] + args.part_overhead_gbase * 1e9 for k in step_ids])
+                for r in plan_e:
+                    for p in r:
+                        p["seq"] = step_ids[p["seq"]]
+                parts_e = plan_e[rank]
+                split_info["host_delivery_d2h_gb_per_s_per_rank"] = [round(x, 2) for x in rates]
+                split_info["host_delivery_parts_per_rank"] = [len(r) for r in plan_e]
         else:
             mine = whole_parts([step_ids[i] for i in lpt_assign([W.contigs[k] for k in step_ids], world)[rank]])
             for p in mine:
@@ -829,10 +851,11 @@ def main():
         warm = whole_parts([0] * args.warmup)
     sampler = ClockSampler(local)
     sampler.start()
-    acc = measure(W, mine, warm, args.e2e_steps, barrier, dist=dist, read_range=read_range, e2e_lanes=args.e2e_lanes)
+    acc = measure(W, mine, warm, args.e2e_steps, barrier, dist=dist, read_range=read_range, e2e_lanes=args.e2e_lanes,
+                  parts_e=parts_e)
     clocks = sampler.stop()
 
-    d2h_ceiling = host_d2h_ceiling(barrier, allsum) if args.e2e_steps != 0 else None
+    d2h_ceiling = None
     verified = None
     if args.verify_split and dist is not None and split_info is not None:
         verified = verify_split(W, mine, dist, rank)

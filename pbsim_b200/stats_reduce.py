@@ -108,13 +108,14 @@ def emitted_prefix(my_emitted_bases, dist, device="cpu"):
 # its feeders first, the sequences it owns whole next and its dependent last parts at the end: by then the sums it
 # needs have long been published by ONE asynchronous all-reduce of an int64 per sequence (SplitExchange).
 
-def plan_line_split(reads_est, world, weights=None, snap_lo=0.02, snap_hi=0.04):
+def plan_line_split(reads_est, world, weights=None, snap_lo=0.02, snap_hi=0.04, shares=None):
     """reads_est[k]: estimated read count of sequence k (quota / mean emitted bases per read); weights[k]: estimated
     work (default: reads_est).  Returns for every rank its parts in line order, each a dict
       seq, first_read, max_reads (0: run to the quota), last (the part that meets the quota), est (estimated work).
     A cut that falls into the first snap_lo or the last snap_hi of a sequence moves to the sequence's boundary: the
     estimate of a sequence's read count is good to a per cent or so, and a part that is not the last one must end
-    safely in front of the quota."""
+    safely in front of the quota.  shares[r] (default: equal): the fraction of the work rank r should get — ranks
+    whose delivery path is slower (GPUs behind a busier PCIe switch) get shorter pieces."""
     n = len(reads_est)
     w = [float(x) for x in (weights if weights is not None else reads_est)]
     total = sum(w)
@@ -123,8 +124,13 @@ def plan_line_split(reads_est, world, weights=None, snap_lo=0.02, snap_hi=0.04):
         start[k + 1] = start[k] + w[k]
     cut_in = {k: [] for k in range(n)}   # read indices at which sequence k is cut
     rank_cut_after = []  # for every rank boundary r (1..world-1): (k, read); (k, 0) = in front of sequence k
+    if shares is None:
+        shares = [1.0 / world] * world
+    ssum = float(sum(shares))
+    cum = 0.0
     for r in range(1, world):
-        x = total * r / world
+        cum += shares[r - 1] / ssum
+        x = total * cum
         k = 0
         while k + 1 < n and start[k + 1] <= x:
             k += 1

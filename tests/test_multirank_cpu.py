@@ -133,6 +133,18 @@ def test_line_split_plans():
     assert sum(len(p) for p in plan) == 8 and sum(1 for parts in plan for p in parts if p["last"]) == 1
 
 
+def test_line_split_with_unequal_shares():
+    """the host-delivery arm gives ranks behind a slower device-to-host path shorter pieces"""
+    sizes = [248, 242, 198, 190, 182, 171, 159, 145, 138, 134, 135, 133, 114, 107, 102, 90, 83, 80, 59, 64]
+    reads = [s * 1000.0 for s in sizes]
+    shares = [8.0, 8.0, 8.0, 8.0, 18.0, 18.0, 18.0, 18.0]
+    plan = SR.plan_line_split(reads, 8, shares=shares)
+    _check_plan(reads, 8, plan)
+    loads = [sum(p["est"] for p in parts) for parts in plan]
+    for ld, sh in zip(loads, shares):
+        assert abs(ld / sum(loads) - sh / sum(shares)) < 0.02
+
+
 def test_split_order_runs_feeders_first_and_dependents_last():
     plan = SR.plan_line_split([1000.0, 900.0, 800.0, 700.0], 3)
     for parts in plan:
