@@ -508,14 +508,19 @@ def run_parts(W, parts, dist, device, on_part, read_range=None, host_seq=None, s
 
 
 def measure(W, my_parts, warm_parts, e2e_steps, barrier, dist=None, read_range=None, gzip_arm=True, text_arm=True,
-            e2e_warm=False, e2e_lanes=2, parts_e=None):
+            e2e_warm=False, e2e_lanes=2, parts_e=None, dev_lanes=1):
     """device-resident arm + end-to-end arm(s) over this rank's parts.  Returns a dict of local measurements."""
     import torch
     eng, capi = W.eng, W.capi
     for p in warm_parts:  # warm-up (also grows every arena to its steady-state size)
         W.run_part(dict(p, first_read=0, last=True, max_reads=p["max_reads"]), read_range=read_range)
+    dev_lanes = min(dev_lanes, max(1, len(my_parts)))
+    for lane in range(1, dev_lanes):  # every engine of the device arm warmed on this rank's largest part
+        for p in warm_parts[:1]:
+            W.run_part(dict(p, first_read=0, last=True, max_reads=p["max_reads"]), read_range=read_range, eng=W.engine(lane))
     barrier()
-    eng.timer_start()
+    for lane in range(dev_lanes):
+        W.engine(lane).timer_start()
     t0 = time.perf_counter()
     acc = dict(bases=0, out_bytes=0, launches=0, sim=0.0, emit=0.0, seg=0.0, chain=0.0, gen=0.0)
 
@@ -537,8 +542,10 @@ def measure(W, my_parts, warm_parts, e2e_steps, barrier, dist=None, read_range=N
         acc["chain"] += st.chain_seconds
         acc["gen"] += st.gen_seconds
 
-    run_parts(W, my_parts, dist, True, on_part, read_range=read_range)
-    acc["dev_ms"] = eng.timer_stop() if my_parts else 0.0
+    run_parts(W, my_parts, dist, True, on_part, read_range=read_range, lanes=dev_lanes)
+    # CUDA events on every engine's own stream, all started behind the same device-wide synchronisation: the span of
+    # the timed steps is the longest of them
+    acc["dev_ms"] = max(W.engine(lane).timer_stop() for lane in range(dev_lanes)) if my_parts else 0.0
     barrier()
     acc["wall_ms"] = (time.perf_counter() - t0) * 1e3
     acc["e2e"] = acc["e2e_gz"] = None
@@ -743,6 +750,8 @@ def main():
     ap.add_argument("--part-overhead-gbase", type=float, default=0.45,
                     help="line split: fixed cost of one run in units of emitted Gbase (balances ranks that own many "
                          "short sequences against ranks that own few long ones)")
+    ap.add_argument("--lanes", type=int, default=2, choices=[1, 2, 3, 4],
+                    help="engines per GPU in the device-resident arm, each driven by its own host thread on alternate parts")
     ap.add_argument("--e2e-lanes", type=int, default=2, choices=[1, 2],
                     help="engines per GPU in the host-delivery arm (2: one run's start-up hides behind the other's copies)")
     ap.add_argument("--no-split", action="store_true",
@@ -852,7 +861,7 @@ def main():
     sampler = ClockSampler(local)
     sampler.start()
     acc = measure(W, mine, warm, args.e2e_steps, barrier, dist=dist, read_range=read_range, e2e_lanes=args.e2e_lanes,
-                  parts_e=parts_e)
+                  parts_e=parts_e, dev_lanes=args.lanes)
     clocks = sampler.stop()
 
     d2h_ceiling = None

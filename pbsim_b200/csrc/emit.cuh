@@ -620,8 +620,8 @@ constexpr uint32_t kStageCols = 1280;   // MAF columns a tile may have on this p
 struct EmitStage {
   uint8_t seq[PB_TILE + 32];
   uint8_t qual[PB_TILE + 32];
-  uint8_t mref[kStageCols + 48];
-  uint8_t mread[kStageCols + 48];
+  uint8_t mref[kStageCols + 80];   // rows end before + 32; bytes + 48 .. + 79: one scratch byte per lane
+  uint8_t mread[kStageCols + 80];
   uint32_t pk[kStageCols / 16 + 8];
 };
 static_assert(sizeof(EmitStage) % 16 == 0, "staging rows stay 16-byte aligned");
@@ -701,7 +701,7 @@ __device__ __forceinline__ void emit_tile_staged(EmitStage &S, const EmitLuts &L
   const int32_t cdir = minus ? -1 : 1;
   const uint32_t o_ref = sh_r + (minus ? Cn - 1u : 0u);
   const uint32_t d_read = sh_m - sh_r;                           // S.mread index of a column = its S.mref index + d_read (mod 2^32)
-  const uint32_t o_dump = kStageCols + 40u;                      // scratch byte behind the rows
+  const uint32_t o_dump = kStageCols + 48u + lane;               // this lane's scratch byte behind the rows
   const uint32_t moff = minus ? 128u : 0u;                       // strand half of the MAF character LUTs
   const uint32_t ref_chars = minus ? 0x41434754u : 0x54474341u;  // "TGCA" / "ACGT": MAF character of a window code
   // the MAF read row starts as all '-': deletion columns then only need their reference character

@@ -292,8 +292,14 @@ __device__ __forceinline__ bool cta_assignment(const uint32_t *cta_order, const 
     const uint32_t b = cta_order[blockIdx.x];
     s_ok = 0;
     if (b < cta_first[kBins]) {
-      uint32_t a = 0;
-      while (a < kBins - 1 && cta_first[a + 1] <= b) ++a;
+      // the last bin whose first CTA is <= b (cta_first is non-decreasing; empty bins repeat a value): binary search,
+      // 8 dependent loads instead of a walk over up to kBins of them in front of every CTA's barrier
+      uint32_t a = 0, top = kBins;
+      while (top - a > 1u) {
+        const uint32_t mid = (a + top) >> 1;
+        if (cta_first[mid] <= b) a = mid;
+        else top = mid;
+      }
       const uint32_t local = b - cta_first[a];
       s_acc = a >> 1;
       s_lo = bin_lo[a] + local * blockDim.x;
