@@ -892,7 +892,6 @@ def main():
                   parts_e=parts_e, dev_lanes=args.lanes)
     clocks = sampler.stop()
 
-    d2h_ceiling = None
     verified = None
     if args.verify_split and dist is not None and split_info is not None:
         verified = verify_split(W, mine, dist, rank)
