@@ -58,6 +58,11 @@ WORKLOADS = {
     "c5": dict(name="WGS errhmm ERRHMM-SEQUEL --pass-num 10 (mean 9 kb), 3.1 Gbp synthetic genome, --depth 20, SAM+MAF",
                method="errhmm", model="ERRHMM-SEQUEL.model", depth=20.0, params=dict(pass_num=10),
                cli=["--pass-num", "10"], batch_bases=3 << 30),
+    # --method sample: qualities copied from a pool of real reads; the pool is made the way a user would make
+    # it (reads simulated with QSHMM-RSII, filtered by pbsim_host_sample_filter)
+    "cs": dict(name="WGS --method sample (pool: simulated QSHMM-RSII reads of a 30 Mbp sequence x 20, mean 9 kb), 3.1 Gbp "
+                    "synthetic genome, --depth 20",
+               method="sample", model=None, depth=20.0, params=dict(), cli=[]),
     # configs[3]: transcriptome; a step is one run over the whole transcript table
     "c4": dict(name="trans qshmm QSHMM-RSII, 200,000 synthetic transcripts (log-normal, median 1.5 kb), Zipf "
                     "expression, 2e7 reads",
@@ -223,6 +228,9 @@ def reference_arm(args, wl):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    if wl["method"] == "sample":
+        print(json.dumps({"impl": "reference", "unavailable": "the reference arm is set up for the qshmm / errhmm workloads"}))
+        return
     from oracle import refrun as R
     base = {"impl": "reference", "metric": "simulated Gbp/s", "unit": "Gbp/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int32",
@@ -344,7 +352,16 @@ class Workload:
             wl["name"] += " [diagnostic override: len_mean=%s len_sd=%s]" % (args.len_mean, args.len_sd)
         self.wl, self.key, self.rank = wl, key, rank
         L = capi.load()
-        self.hm = capi.HostModel(L, capi.host_params(wl["method"], **wl["params"]), model_path(wl["model"]))
+        self.pool = None
+        if wl["method"] == "sample":
+            pe = simulator.Engine(local)
+            pe.set_model(capi.HostModel(L, capi.host_params("qshmm"), model_path("QSHMM-RSII.model")))
+            pe.set_synthetic_sequence(30000000, 1, 7)
+            fastq, _, _, _ = pe.simulate(int(20.0 * 30000000), rng_mode=capi.RNG_PHILOX, seed=11)
+            pe.close()
+            self.pool, _ = capi.sample_filter(L, fastq)
+        self.hm = capi.HostModel(L, capi.host_params(wl["method"], **wl["params"]),
+                                 model_path(wl["model"]) if wl["model"] else None)
         self.local, self.simulator = local, simulator
         self.options = []
         if overrides:
@@ -390,6 +407,8 @@ class Workload:
             e.set_model(self.hm)
             for opt, val in self.options:
                 e.set_option(opt, val)
+            if self.pool is not None:
+                e.set_pool(self.pool)
             if self.engines and getattr(self, "seqset", None) is not None:
                 e.set_seqset("trans", self.seqset, self.bias)
             self.engines.append(e)
@@ -732,12 +751,17 @@ def roofline_block(method, acc, peak, peak_src):
         bases, dev_s = acc["bases"], acc["dev_ms"] * 1e-3
         kern_note = ("single-engine pass of %d steps after the timed region (in the timed steps two engines share the "
                      "GPU and their kernels overlap)" % acc["steps"])
-    chain_name = "k_chain_chunk" if method == "qshmm" else "k_chain_chunk_err"
-    seg_name = "k_sim_seg" if method == "qshmm" else "k_sim_seg_err"
+    qs_events = method in ("qshmm", "sample")   # 2-byte events per read position
+    chain_name = "k_chain_chunk" if qs_events else "k_chain_chunk_err"
+    seg_name = "k_sim_seg" if qs_events else "k_sim_seg_err"
     kern = {}
     for name, key, secs in ((chain_name, "k_chain_chunk", acc["chain"]), (seg_name, "k_sim_seg", acc["seg"]),
                             ("k_tile_desc + k_emit_rows + k_emit (pass 2)", "k_emit_rows", acc["emit"])):
-        ab = KERNEL_ALGO_BYTES[key] if method == "qshmm" or key == "k_emit_rows" else KERNEL_ALGO_BYTES[key] / 2.0
+        if secs <= 0:   # --method sample has no chain
+            continue
+        ab = KERNEL_ALGO_BYTES[key] if qs_events or key == "k_emit_rows" else KERNEL_ALGO_BYTES[key] / 2.0
+        if method == "sample" and key == "k_sim_seg":
+            ab = 3.0    # reads a quality byte of the pool entry, writes the 2-byte event
         a = ab * bases / secs / 1e9 if secs > 0 else 0.0
         ncu = NCU_DRAM_BYTES[key] if method == "qshmm" else None
         kern[name] = {"seconds": secs, "algorithmic_bytes_per_base": ab, "achieved": a, "frac": a / peak if peak else None,
@@ -965,7 +989,7 @@ def main():
         if world == 1 and not args.no_extras and args.workload == "c3":
             W.close()
             line["extra"] = {}
-            for key in ("c1", "c2", "c4", "c5"):
+            for key in ("c1", "c2", "c4", "c5", "cs"):
                 try:
                     X = Workload(key, args, local, rank, overrides=False)
                     ns = args.extra_steps if X.seqset is None else 1

@@ -1007,7 +1007,9 @@ __device__ __forceinline__ TileGeom tile_geom(const EmitArgs &A, uint32_t s, uin
   // reference range this tile can touch: [R0, Rend] (an insertion at the tile's end looks at Rend)
   Ckpt c1 = g.c0;
   if (g.has_next) c1 = ckp[tile + 1];
-  g.Rnext = g.has_next ? c1.ref : wlen;
+  // (--method sample: a read that is as long as its quality string ends with window bases left over, :1775-1833;
+  // the reference bases it consumed are its columns minus its insertions)
+  g.Rnext = g.has_next ? c1.ref : (A.P.sample ? min(wlen, ncol - A.B.nins[s]) : wlen);
   const uint32_t Rend = min(g.Rnext, wlen - 1u);
   const uint32_t g0 = minus ? offset + wlen - 1u - Rend : offset + g.c0.ref;
   const uint32_t g1 = minus ? offset + wlen - 1u - g.c0.ref : offset + Rend;
@@ -1056,7 +1058,7 @@ __global__ void k_tile_desc(const __grid_constant__ EmitArgs A, uint32_t *tile_s
     d.Rn = g.Rnext - g.c0.ref;
     d.wpos = minus ? offset + wlen - 1u - g.c0.ref : offset + g.c0.ref;
     d.flags = (minus ? kTileMinus : 0u) | (g.slow ? kTileGeneric : 0u) |
-              ((g.Cn > kStageCols || g.Pn > PB_TILE) ? kTileWide : 0u);
+              ((g.Cn > kStageCols || g.Pn > PB_TILE || d.Rn > kStageCols) ? kTileWide : 0u);
   }
   uint4 *dst = reinterpret_cast<uint4 *>(A.desc + t);
   const uint4 *src = reinterpret_cast<const uint4 *>(&d);

@@ -523,7 +523,7 @@ int carve_batch(pbsim_engine *e, uint32_t n_reads) {
   const uint32_t pass = (uint32_t)e->model.pass_num;
   const uint64_t n_sub = (uint64_t)n_reads * pass;
   if (n_sub > 0x7FFFFFFFull) return fail(e, PBSIM_E_INVALID, "batch too large");
-  CK(e->b_read_u32.ensure((size_t)n_reads * 5 * 4 + 64));
+  CK(e->b_read_u32.ensure((size_t)n_reads * 7 * 4 + 64));
   CK(e->b_sub_u32.ensure((size_t)n_sub * 16 * 4 + 64));
   CK(e->b_sub_u64.ensure((size_t)(n_sub + 1) * 12 * 8 + 64));
   CK(e->b_sub_f64.ensure((size_t)n_sub * 8 + 64));
@@ -536,6 +536,8 @@ int carve_batch(pbsim_engine *e, uint32_t n_reads) {
   B.plan_raw = r32 + 2ull * n_reads;
   B.plan_meta = r32 + 3ull * n_reads;
   B.plan_tr = r32 + 4ull * n_reads;
+  B.grp_copy = r32 + 5ull * n_reads;
+  B.grp_num = r32 + 6ull * n_reads;
   uint32_t *s32 = e->b_sub_u32.as<uint32_t>();
   uint32_t **fields[] = {&B.key_in, &B.key_out, &B.idx_in, &B.order, &B.cap, &B.ck_cap, &B.nent, &B.rlen,
                          &B.ncol, &B.nsub, &B.nins, &B.ndel, &B.flags, &B.draws_used, &B.nseg, &B.nchunk};
@@ -618,13 +620,16 @@ int run_batch(pbsim_engine *e, uint32_t n_reads, int64_t clip_room, BatchResult 
   }
 
   // (the single, quota-clipped read of a tail batch is segmented too: on one thread a 50 kb read takes milliseconds)
-  bool use_segments = !replay && e->seg_enabled && !sample;
+  // (--method sample: the speculative pass of PHILOX runs; the chains that have to be redone stay sequential)
+  bool use_segments = !replay && e->seg_enabled && (!sample || spec);
   int seg_retries = 0;
   for (int attempt = 0; attempt < 9; ++attempt) {
     // ---- K1 plan
     const uint32_t ev_align = qs ? 8u : 16u;
     if (sample)
-      k_plan_sample<<<nblk(n_reads, 256), 256, 0, e->st>>>(G, Pl, *sb, B, e->cap_num, e->cap_den, spec ? 1u : 0u);
+      k_plan_sample<<<nblk(n_reads, 256), 256, 0, e->st>>>(G, Pl, *sb, B, e->cap_num, e->cap_den, spec ? 1u : 0u, rng.seed,
+                                                           M.uniform_bias ? 1u : 0u,
+                                                           use_segments ? (uint32_t)e->seg_min_len : 0u);
     else
       k_plan<<<nblk(n_reads, 256), 256, 0, e->st>>>(M, G, device_set(e), rng, B, clip_room, e->cap_num, e->cap_den, ev_align,
                                                      use_segments ? (uint32_t)e->seg_min_len : 0u, e->seg_extra,
@@ -709,23 +714,6 @@ int run_batch(pbsim_engine *e, uint32_t n_reads, int64_t clip_room, BatchResult 
     if (sample) {
       if (replay) k_sim_sample<PBSIM_RNG_REPLAY><<<grid, kSimThreads, 0, e->st>>>(A, Pl, *sb, 0u);
       else k_sim_sample<PBSIM_RNG_PHILOX><<<grid, kSimThreads, 0, e->st>>>(A, Pl, *sb, 0u);
-      if (spec) {
-        // which copies assumed a wrong length?  Their groups' tails are redone as chains (k_sample_redo)
-        hctrl[6] = 0;
-        CK(cudaMemsetAsync(ctrl + 6, 0, 8, e->st));
-        k_sample_redo<<<nblk(n_reads, 256), 256, 0, e->st>>>(B, ctrl + 6);
-        if (peek(e, hctrl + 6, ctrl + 6, 8)) return PBSIM_E_CUDA;
-        CK(cudaStreamSynchronize(e->st));
-        e->launches += 2;
-        if (hctrl[6] > 0) {
-          if ((rc = schedule())) return rc;
-          if (replay) k_sim_sample<PBSIM_RNG_REPLAY><<<grid, kSimThreads, 0, e->st>>>(A, Pl, *sb, 1u);
-          else k_sim_sample<PBSIM_RNG_PHILOX><<<grid, kSimThreads, 0, e->st>>>(A, Pl, *sb, 1u);
-          e->launches++;
-          e->sample_redo_groups += (int64_t)hctrl[6];
-          if (hctrl[6] * 2 > sb->n_groups) e->sample_spec_run = false;  // deletion-rich mix: chains from the start
-        }
-      }
     } else if (qs) {
       if (replay) k_sim_qshmm<PBSIM_RNG_REPLAY><<<grid, kSimThreads, kQsSmemBytes, e->st>>>(A);
       else k_sim_qshmm<PBSIM_RNG_PHILOX><<<grid, kSimThreads, kQsSmemBytes, e->st>>>(A);
@@ -779,6 +767,8 @@ int run_batch(pbsim_engine *e, uint32_t n_reads, int64_t clip_room, BatchResult 
       SA.bin_lo = sb_lo;
       SA.bin_hi = sb_hi;
       SA.ev = e->d_ev.as<uint8_t>();
+      SA.pool_q = Pl.quals;
+      SA.pool_start = Pl.start;
       if (n_chunk_total > 0) {
         // ---- chain-only pass: the HMM state in front of every segment (k_chain_chunk), scheduled like the segments
         const uint32_t nch = (uint32_t)n_chunk_total;
@@ -840,10 +830,12 @@ int run_batch(pbsim_engine *e, uint32_t n_reads, int64_t clip_room, BatchResult 
       CK(cudaEventRecord(e->ev_seg[0], e->st));
       seg_timed = true;
       if (qs) {
-        k_sim_seg<<<seg_slots, kSimThreads, 0, e->st>>>(SA);
+        if (sample) k_sim_seg<true><<<seg_slots, kSimThreads, 0, e->st>>>(SA);
+        else k_sim_seg<false><<<seg_slots, kSimThreads, 0, e->st>>>(SA);
         CK(cudaEventRecord(e->ev_seg[1], e->st));
         k_find_end<<<nblk((uint64_t)n_sub * 32, 128), 128, 0, e->st>>>(B, S, G, e->d_biasone.as<uint8_t>(), pass,
-                                                                       e->d_ev.as<uint8_t>(), e->d_ck.as<Ckpt>(), M.qs_fast);
+                                                                       e->d_ev.as<uint8_t>(), e->d_ck.as<Ckpt>(), M.qs_fast,
+                                                                       sample ? 1u : 0u);
       } else {
         k_sim_seg_err<<<seg_slots, kErrThreads, e->er_smem_bar_off + 16, e->st>>>(SA, e->er_smem_bar_off);
         CK(cudaEventRecord(e->ev_seg[1], e->st));
@@ -852,6 +844,24 @@ int run_batch(pbsim_engine *e, uint32_t n_reads, int64_t clip_room, BatchResult 
       }
       e->launches += 7;
       e->seg_batches++;
+    }
+    if (sample && spec) {
+      // which copies assumed a wrong length?  Their groups' tails are redone as chains (k_sample_redo), one thread per
+      // chain, in the sequential slot layout (k_sim_sample clears the reads' "segmented" mark)
+      hctrl[6] = 0;
+      CK(cudaMemsetAsync(ctrl + 6, 0, 8, e->st));
+      k_sample_redo<<<nblk(n_reads, 256), 256, 0, e->st>>>(B, ctrl + 6);
+      if (peek(e, hctrl + 6, ctrl + 6, 8)) return PBSIM_E_CUDA;
+      CK(cudaStreamSynchronize(e->st));
+      e->launches += 2;
+      if (hctrl[6] > 0) {
+        if ((rc = schedule())) return rc;
+        if (replay) k_sim_sample<PBSIM_RNG_REPLAY><<<grid, kSimThreads, 0, e->st>>>(A, Pl, *sb, 1u);
+        else k_sim_sample<PBSIM_RNG_PHILOX><<<grid, kSimThreads, 0, e->st>>>(A, Pl, *sb, 1u);
+        e->launches++;
+        e->sample_redo_groups += (int64_t)hctrl[6];
+        if (hctrl[6] * 2 > sb->n_groups) e->sample_spec_run = false;  // deletion-rich mix: chains from the start
+      }
     }
     CK(cudaEventRecord(e->ev_k[1], e->st));
     CK(cudaGetLastError());

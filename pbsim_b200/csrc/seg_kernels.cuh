@@ -83,6 +83,9 @@ struct SegArgs {
   SegBatch S;
   const uint32_t *cta_order, *cta_first, *bin_lo, *bin_hi;
   uint8_t *ev;
+  // --method sample: the pool of quality strings (the qualities of a read's positions are its pool entry's bytes)
+  const uint8_t *pool_q;
+  const uint64_t *pool_start;
 };
 
 // ERROR pass of the qshmm segments: one WARP per segment, lane l of iteration i on positions 128 i + 4 l .. + 3.
@@ -99,18 +102,22 @@ constexpr int kSegWarps = kSimThreads / 32;
 #endif
 constexpr int kChainThreads = PB_CHAIN_THREADS;
 
+// SAMPLE (--method sample, speculative pass): the quality of position p is byte p of the read's pool entry
+// (simulate_by_sample, :1775-1833); positions behind the entry's end are filled with quality 0 and dropped by k_find_end.
+template <bool SAMPLE>
 __global__ void __launch_bounds__(kSimThreads) k_sim_seg(SegArgs A) {
   __shared__ __align__(16) QsFast s_fast[PBSIM_NQV];
   __shared__ __align__(16) uint8_t s_freq[QsBlobLayout::freq_bytes];
   __shared__ __align__(16) uint8_t s_q[kSegWarps][PB_TILE];  // qualities of a segment that is redone generically
   uint32_t acc, lo, hi;
   if (!cta_assignment(A.cta_order, A.cta_first, A.bin_lo, A.bin_hi, &acc, &lo, &hi)) return;
-  const AccEntry ae = A.M.acc[acc];
+  AccEntry ae = A.M.acc[SAMPLE ? 0u : acc];
+  if (SAMPLE) ae.has_model = 1;  // "the qualities are given": the generic redo of a segment takes them from s_q
   {
     uint32_t *d = reinterpret_cast<uint32_t *>(s_fast);
     const uint32_t *src = reinterpret_cast<const uint32_t *>(A.M.qs_fast);
     for (uint32_t i = threadIdx.x; i < PBSIM_NQV * 4u; i += blockDim.x) d[i] = src[i];
-    if (!ae.has_model) {
+    if (!SAMPLE && !ae.has_model) {
       uint32_t *f = reinterpret_cast<uint32_t *>(s_freq);
       const uint32_t *fs = reinterpret_cast<const uint32_t *>(A.M.blob + ae.blob_off);
       for (uint32_t i = threadIdx.x; i < QsBlobLayout::freq_bytes / 4u; i += blockDim.x) f[i] = fs[i];
@@ -144,7 +151,18 @@ __global__ void __launch_bounds__(kSimThreads) k_sim_seg(SegArgs A) {
     // the eight 8-byte loads of the lane are independent of everything: all in flight before the first is used
     constexpr uint32_t kIters = PB_TILE / (32u * PB_GROUP);
     uint2 q[kIters];
-    if (ae.has_model) {
+    if (SAMPLE) {
+      const uint8_t *qp = A.pool_q + A.pool_start[A.B.plan_tr[r]];
+      const uint32_t len = A.B.plan_wlen[r];
+#pragma unroll
+      for (uint32_t it = 0; it < kIters; ++it) {
+        const uint32_t p = k * PB_TILE + lane * PB_GROUP + it * 32u * PB_GROUP;
+        uint32_t b[PB_GROUP];
+#pragma unroll
+        for (uint32_t u = 0; u < PB_GROUP; ++u) b[u] = p + u < len ? (uint32_t)__ldg(qp + p + u) - 33u : 0u;
+        q[it] = make_uint2(b[0] | (b[1] << 16), b[2] | (b[3] << 16));
+      }
+    } else if (ae.has_model) {
 #pragma unroll
       for (uint32_t it = 0; it < kIters; ++it)
         q[it] = *reinterpret_cast<const uint2 *>(ev + lane * PB_GROUP + it * 32u * PB_GROUP);
@@ -153,7 +171,7 @@ __global__ void __launch_bounds__(kSimThreads) k_sim_seg(SegArgs A) {
     for (uint32_t it = 0; it < kIters; ++it) {
       const uint32_t j = lane * PB_GROUP + it * 32u * PB_GROUP;
       uint32_t qv[PB_GROUP];
-      if (ae.has_model) {
+      if (SAMPLE || ae.has_model) {
         qv[0] = q[it].x & 0x7Fu; qv[1] = (q[it].x >> 16) & 0x7Fu; qv[2] = q[it].y & 0x7Fu; qv[3] = (q[it].y >> 16) & 0x7Fu;
       } else {
         qs_freq_qualities(T, A.keys, read_id, c1, k * PB_TILE + j, qv);
@@ -323,8 +341,11 @@ __global__ void __launch_bounds__(kErrThreads) k_chain_chunk_err(SegArgs A, Chun
 // statement the CPU harness runs); the exact walk over the entries of a tile is done 32
 // entries at a time: a warp scan gives every entry its reference offset; only groups in which the window ends or
 // a deletion run meets a flagged block are walked sequentially (by lane 0, with qshmm_walk_tile).
+// sample != 0 (--method sample): the read is also over when it is as long as its quality string (= the window length);
+// that last position draws no deletion (qshmm_walk_tile, p_left).
 __global__ void __launch_bounds__(128) k_find_end(Batch B, SegBatch S, DeviceGenome G, const uint8_t *bias_one,
-                                                         uint32_t pass_num, uint8_t *ev, Ckpt *ck, const QsFast *fast) {
+                                                         uint32_t pass_num, uint8_t *ev, Ckpt *ck, const QsFast *fast,
+                                                         uint32_t sample) {
   const uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint32_t lane = threadIdx.x & 31u;
   if (s >= B.n_sub) return;
@@ -370,6 +391,7 @@ __global__ void __launch_bounds__(128) k_find_end(Batch B, SegBatch S, DeviceGen
       const uint64_t Rk64 = (uint64_t)R + xr - sr.ref_adv;
       const uint32_t Rk = (uint32_t)Rk64, Dk = D + xd - sr.ndel;
       bool simple = in && Rk64 + sr.ref_adv < wlen;
+      if (sample && (uint64_t)(kk + 1u) * PB_TILE >= wlen) simple = false;  // holds the read's last position
       if (simple && hp.enabled) {
         const uint32_t lo_w = Rk == 0u ? 0u : Rk - 1u, hi_w = Rk + sr.ref_adv;
         const uint32_t ga = hp.win.gidx(lo_w), gb = hp.win.gidx(hi_w);
@@ -430,9 +452,10 @@ __global__ void __launch_bounds__(128) k_find_end(Batch B, SegBatch S, DeviceGen
         const uint32_t g1 = hp.win.minus ? hp.win.gidx(lo_w) : hp.win.gidx(hi_w);
         touch = range_exceptional(G.xm, g0, g1);
       }
-      const bool need = __any_sync(0xFFFFFFFFu, touch) || (R + total >= wlen) || blocked != 0u;
+      const uint32_t mb = __ballot_sync(0xFFFFFFFFu, valid && !cont);
+      const bool need = __any_sync(0xFFFFFFFFu, touch) || (R + total >= wlen) || blocked != 0u ||
+                        (sample && P + (uint32_t)__popc(mb) >= wlen);
       if (!need) {
-        const uint32_t mb = __ballot_sync(0xFFFFFFFFu, valid && !cont);
         const uint32_t ms = __ballot_sync(0xFFFFFFFFu, valid && kind == PB_KIND_SUB);
         uint32_t dsum = part;
 #pragma unroll
@@ -446,7 +469,8 @@ __global__ void __launch_bounds__(128) k_find_end(Batch B, SegBatch S, DeviceGen
         // exact sequential walk of these (at most 32) entries
         uint32_t res[6];
         if (lane == 0) {
-          const TileWalk t = qshmm_walk_tile(e + i, min(32u, n - i), R, wlen, fast, hp, &blocked);
+          const TileWalk t = qshmm_walk_tile(e + i, min(32u, n - i), R, wlen, fast, hp, &blocked,
+                                             sample ? wlen - P : 0xFFFFFFFFu);
           res[0] = t.n_entries; res[1] = t.positions; res[2] = t.ref_adv; res[3] = t.nsub; res[4] = t.ndel;
           res[5] = t.ended | (blocked << 1);
         }

@@ -1160,8 +1160,11 @@ struct TileWalk {
 // Walk the entries of one tile knowing the reference offset it starts at: stop where the window is used up
 // (`while (ref_offset < mut.len)`, :2213 and :2268), clip the last deletion run, and (HpProbe) cut deletion runs
 // in front of suppressing bases.  Entries are rewritten in place; entries after the end are not counted.
+// p_left (--method sample): read positions left before the read is as long as its quality string; that last position
+// draws no deletion and ends the read (`while (ref_offset < len && read_offset < len)`, :1775-1833).
 PB_HD TileWalk qshmm_walk_tile(uint16_t *ev, uint32_t n_entries, uint32_t R_start, uint32_t wlen,
-                               const QsFast *fast, const HpProbe &hp, uint32_t *blocked_io = nullptr) {
+                               const QsFast *fast, const HpProbe &hp, uint32_t *blocked_io = nullptr,
+                               uint32_t p_left = 0xFFFFFFFFu) {
   TileWalk t;
   t.n_entries = 0; t.positions = 0; t.ref_adv = 0; t.nsub = 0; t.ndel = 0; t.ended = 0; t.prob = 0;
   uint32_t R = R_start;
@@ -1173,13 +1176,15 @@ PB_HD TileWalk qshmm_walk_tile(uint16_t *ev, uint32_t n_entries, uint32_t R_star
     const uint32_t kind = (v >> 7) & 3u;
     const bool cont = kind == 3u;
     const uint32_t part = cont ? ((v & 0x7Fu) | ((v >> 9) << 7)) : (v >> 12);
+    bool last_position = false;
     if (!cont) {
-      if (R >= wlen) { t.ended = 1; break; }
+      if (R >= wlen || t.positions >= p_left) { t.ended = 1; break; }
       t.prob += fast[v & 0x7Fu].prob;
       t.positions += 1u;
       t.nsub += (kind == PB_KIND_SUB) ? 1u : 0u;
       R += (kind == PB_KIND_INS) ? 0u : 1u;
       blocked = false;
+      if (t.positions == p_left) blocked = last_position = true;
     }
     uint32_t take = 0;
     if (!blocked) {
@@ -1200,7 +1205,7 @@ PB_HD TileWalk qshmm_walk_tile(uint16_t *ev, uint32_t n_entries, uint32_t R_star
     t.ndel += take;
     R += take;
     t.n_entries = i + 1u;
-    if (R >= wlen) { t.ended = 1; break; }
+    if (R >= wlen || last_position) { t.ended = 1; break; }
   }
   t.ref_adv = R - R_start;
   if (blocked_io) *blocked_io = blocked ? 1u : 0u;

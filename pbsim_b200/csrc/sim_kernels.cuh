@@ -89,6 +89,8 @@ struct Batch {
   uint32_t *nseg;          // segments provisioned (0: the sub-read runs on the sequential pass-1 path)
   uint32_t *nchunk;        // chain chunks: threads of k_chain_chunk that recover the states in front of its segments
   double *accuracy;
+  // --method sample, per read: which copy of its group (pool entry, pool pass) a read is, and the group's size
+  uint32_t *grp_copy, *grp_num;
 };
 
 // ----------------------------------------------------------------------------------------------
@@ -538,8 +540,11 @@ struct SampleBatch {
   uint32_t skip_first;      // replay: read 0 of the batch is preceded by the pool-pass draw (:1734)
 };
 
+// seg_min_len != 0 (speculative pass, PHILOX draws): reads of at least that many positions that touch no exceptional
+// block are planned here completely (offset, strand: what k_sim_sample does for the others) and cut into segments of
+// PB_TILE positions for the error pass (k_sim_seg<true>: the qualities come from the pool entry) and k_find_end.
 __global__ void k_plan_sample(DeviceGenome G, DevicePool Pl, SampleBatch SB, Batch B, uint32_t cap_num, uint32_t cap_den,
-                              uint32_t spec) {
+                              uint32_t spec, uint32_t seed, uint32_t uniform_bias, uint32_t seg_min_len) {
   const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= B.n_reads) return;
   uint32_t lo = 0, hi = SB.n_groups;  // g_first[lo] <= r < g_first[hi]
@@ -550,23 +555,46 @@ __global__ void k_plan_sample(DeviceGenome G, DevicePool Pl, SampleBatch SB, Bat
   }
   const uint32_t copy = r - SB.g_first[lo], num = SB.g_first[lo + 1] - SB.g_first[lo];
   const uint32_t j = SB.g_entry[lo];
-  uint32_t len0 = (uint32_t)(Pl.start[j + 1] - Pl.start[j]);
+  const uint32_t entry_len = (uint32_t)(Pl.start[j + 1] - Pl.start[j]);
+  uint32_t len0 = entry_len;
   if (len0 > G.len) len0 = G.len;
   B.plan_tr[r] = j;
   B.plan_off[r] = 0;
   B.plan_wlen[r] = len0;   // upper bound; the group's thread stores the planned window of every copy
   B.plan_raw[r] = spec ? 1u : num;  // copies the thread scheduled for this read simulates (chain: copy 0 walks them all)
   B.plan_meta[r] = 0;
+  bool segmented = false;
+  if (seg_min_len != 0u && spec && len0 >= seg_min_len && uniform_bias) {
+    const uint32_t read_id = (uint32_t)(B.first_read + 1u + r);
+    PhiloxDrawQ pd;
+    pd.ph.k0 = seed;
+    pd.ph.k1 = G.seq_num;
+    pd.read_id = read_id;
+    pd.pass = 0;
+    pd.plan_begin();
+    const uint32_t offset = entry_len >= G.len ? 0u : pd.plan_off(G.len - len0 + 1u);  // :1758-1763
+    if (!range_exceptional(G.xm, offset, offset + len0 - 1u)) {
+      segmented = true;
+      const uint32_t minus = (read_id & 1u) ? 0u : 1u;  // :1768-1774
+      B.plan_off[r] = offset;
+      B.plan_meta[r] = (minus << 8) | (1u << 11);
+    }
+  }
   uint64_t cap = (uint64_t)len0 * cap_num / cap_den + 2048u;
+  const uint32_t nseg = segmented ? (len0 + PB_TILE - 1u) / PB_TILE : 0u;
+  if (segmented) cap = (uint64_t)nseg * PB_SEG_STRIDE + 64u;
   cap = (cap + 7u) / 8u * 8u;
   uint64_t work = spec ? (uint64_t)len0 : (uint64_t)len0 * num / 16u;
   if (work > 0xFFFFFu) work = 0xFFFFFu;
-  B.key_in[r] = (copy == 0u || spec) ? (0xFFFFFu - (uint32_t)work) : ((uint32_t)kBins << 20);
+  // segmented reads carry the out-of-range bin: the sequential schedule skips them (as it skips copies > 0 of a chain)
+  B.key_in[r] = (!segmented && (copy == 0u || spec)) ? (0xFFFFFu - (uint32_t)work) : ((uint32_t)kBins << 20);
   B.idx_in[r] = r;
   B.cap[r] = (uint32_t)cap;
-  B.ck_cap[r] = (uint32_t)(cap / PB_TILE) + 2u;
-  B.nseg[r] = copy;   // (the segment fields are free for --method sample)
-  B.nchunk[r] = num;
+  B.ck_cap[r] = segmented ? nseg + 2u : (uint32_t)(cap / PB_TILE) + 2u;
+  B.nseg[r] = nseg;
+  B.nchunk[r] = 0;
+  B.grp_copy[r] = copy;
+  B.grp_num[r] = num;
 }
 
 // after the speculative pass: read r heads a chain to redo iff its predecessor's read is not as long as r assumed
@@ -574,7 +602,7 @@ __global__ void k_plan_sample(DeviceGenome G, DevicePool Pl, SampleBatch SB, Bat
 __global__ void k_sample_redo(Batch B, unsigned long long *n_redo) {
   const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= B.n_reads) return;
-  const uint32_t copy = B.nseg[r], num = B.nchunk[r];
+  const uint32_t copy = B.grp_copy[r], num = B.grp_num[r];
   bool head = copy > 0u && B.rlen[r - 1u] != B.plan_wlen[r];
   for (uint32_t k = 1; head && k < copy; ++k)
     if (B.rlen[r - copy + k - 1u] != B.plan_wlen[r - copy + k]) head = false;

@@ -144,3 +144,32 @@ def test_schedule_corners_equal_oracle(glen, depth, lens, spec):
     reads, maf, st, text = run.simulate_sequence(genome, 1, rng_mode=capi.RNG_PHILOX, seed=9, batch_reads=3)
     assert reads == oreads and maf == omaf
     assert text == O.format_stats(ost, 1)
+
+
+@pytest.mark.parametrize("segments", [1, 0])
+@pytest.mark.parametrize("glen,depth,lens,ratio", [
+    # long pool entries: the speculative pass runs them through the error pass (k_sim_seg<true>) in segments of 1024
+    # positions and k_find_end; lengths around the segment size, a multiple of it, and one entry longer than the sequence
+    (60000, 6.0, [5000, 3072, 2048, 2049, 4095, 9000, 1500, 300, 70000], (20, 50, 30)),  # insertion-rich: reads end first
+    (60000, 6.0, [5000, 3072, 2048, 2049, 4095, 9000, 1500, 300], (20, 20, 60)),   # deletion-rich: windows end first, chains redone
+    (30000, 12.0, [8000, 6000, 2500], (6, 55, 39)),                                # several copies per entry
+])
+def test_long_entries_on_segments_equal_oracle(glen, depth, lens, ratio, segments):
+    rng = np.random.default_rng(glen + len(lens))
+    genome = bytes(rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), glen))
+    pool = [bytes(rng.integers(33 + 3, 33 + 25, n).astype(np.uint8)) for n in lens]
+    okw = dict(ratio=ratio, len_min=100, len_max=100000)
+    o = O.Oracle("sample", None, **okw)
+    o.rng_philox(21)
+    o.set_sequence(genome, 1)
+    oreads, omaf, ost = o.simulate_sample(depth, pool)
+    hm = capi.HostModel(capi.load(), capi.host_params("sample", **okw), None)
+    eng = simulator.Engine(0)
+    eng.set_option("pipeline", 0)
+    eng.set_option("segments", segments)
+    run = simulator.WgsRun(eng, hm, depth)
+    eng.set_pool(pool)
+    reads, maf, st, text = run.simulate_sequence(genome, 1, rng_mode=capi.RNG_PHILOX, seed=21)
+    assert reads == oreads and maf == omaf
+    assert text == O.format_stats(ost, 1)
+    assert st.res_len_max >= 8000
