@@ -540,8 +540,8 @@ struct SampleBatch {
   uint32_t skip_first;      // replay: read 0 of the batch is preceded by the pool-pass draw (:1734)
 };
 
-// seg_min_len != 0 (speculative pass, PHILOX draws): reads of at least that many positions that touch no exceptional
-// block are planned here completely (offset, strand: what k_sim_sample does for the others) and cut into segments of
+// seg_min_len != 0 (speculative pass, PHILOX draws, --hp-del-bias 1): reads of at least that many positions are planned
+// here completely (offset, strand: what k_sim_sample does for the others) and cut into segments of
 // PB_TILE positions for the error pass (k_sim_seg<true>: the qualities come from the pool entry) and k_find_end.
 __global__ void k_plan_sample(DeviceGenome G, DevicePool Pl, SampleBatch SB, Batch B, uint32_t cap_num, uint32_t cap_den,
                               uint32_t spec, uint32_t seed, uint32_t uniform_bias, uint32_t seg_min_len) {
@@ -573,12 +573,13 @@ __global__ void k_plan_sample(DeviceGenome G, DevicePool Pl, SampleBatch SB, Bat
     pd.pass = 0;
     pd.plan_begin();
     const uint32_t offset = entry_len >= G.len ? 0u : pd.plan_off(G.len - len0 + 1u);  // :1758-1763
-    if (!range_exceptional(G.xm, offset, offset + len0 - 1u)) {
-      segmented = true;
-      const uint32_t minus = (read_id & 1u) ? 0u : 1u;  // :1768-1774
-      B.plan_off[r] = offset;
-      B.plan_meta[r] = (minus << 8) | (1u << 11);
-    }
+    // a window that touches an exceptional block (a non-ACGT base, a homopolymer of 11 or more) is segmented too, as
+    // for qshmm: k_find_end repairs its deletion runs with the exact reference offset, pass 2 takes the generic path
+    const bool slow = range_exceptional(G.xm, offset, offset + len0 - 1u);
+    segmented = true;
+    const uint32_t minus = (read_id & 1u) ? 0u : 1u;  // :1768-1774
+    B.plan_off[r] = offset;
+    B.plan_meta[r] = (minus << 8) | ((slow ? 1u : 0u) << 9) | (1u << 11);
   }
   uint64_t cap = (uint64_t)len0 * cap_num / cap_den + 2048u;
   const uint32_t nseg = segmented ? (len0 + PB_TILE - 1u) / PB_TILE : 0u;

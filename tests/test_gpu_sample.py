@@ -156,7 +156,12 @@ def test_schedule_corners_equal_oracle(glen, depth, lens, spec):
 ])
 def test_long_entries_on_segments_equal_oracle(glen, depth, lens, ratio, segments):
     rng = np.random.default_rng(glen + len(lens))
-    genome = bytes(rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), glen))
+    g = bytearray(rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), glen).tobytes())
+    # exceptional blocks: homopolymers of 11 and more (no deletion may follow them), N runs, IUPAC codes, lower case
+    for k, at in enumerate(rng.integers(100, glen - 100, 14)):
+        run = [b"A" * 12, b"T" * 15, b"NNNNN", b"R", b"c" * 11, b"G" * 30, b"y"][k % 7]
+        g[at:at + len(run)] = run
+    genome = bytes(g)
     pool = [bytes(rng.integers(33 + 3, 33 + 25, n).astype(np.uint8)) for n in lens]
     okw = dict(ratio=ratio, len_min=100, len_max=100000)
     o = O.Oracle("sample", None, **okw)
