@@ -474,60 +474,73 @@ def whole_parts(step_ids):
 def run_parts(W, parts, dist, device, on_part, read_range=None, host_seq=None, sink=None, on_chunk=None, lanes=1):
     """this rank's parts in the order of stats_reduce.split_order: feeders, publish (asynchronous all-reduce of the
     emitted bases per sequence), whole sequences, dependent last parts (each told its len_total_start).
-    lanes = 2 (host delivery): two engines on this GPU, each driven by its own host thread, take the parts of a phase
-    alternately — while one run drains its last records over PCIe and the next sequence is ingested and its first batch
-    generated, the other engine's copies keep the link busy (a run has nothing to copy for its first 15-20 ms)."""
+    lanes = 2: two engines on this GPU, each driven by its own host thread, take the parts alternately — in the
+    host-delivery arm one run's start-up (the next sequence ingested, its first batch generated: nothing to copy for
+    15-20 ms) hides behind the other engine's copies; in the device arm kernels bound by different things overlap."""
     from pbsim_b200 import stats_reduce as SR
     feeders, whole, dependent = SR.split_order(parts)
     ex = None
     if W.seqset is None and dist is not None:
         ex = SR.SplitExchange(len(W.contigs), dist, device="cuda")
     lock = threading.Lock()
-    base = 0
-    for phase, plist in (("feed", feeders), ("whole", whole), ("dep", dependent)):
-        if phase == "whole" and ex is not None:
-            ex.publish()
-        nxt = [0]
-        errors = []
+    # one queue in the order feeders, whole sequences, dependent last parts: a lane that runs out of feeders goes on
+    # with the whole sequences while the other still feeds; the lane that finishes the LAST feeder publishes
+    queue = [("feed", p) for p in feeders] + [("whole", p) for p in whole] + [("dep", p) for p in dependent]
+    published = threading.Event()
+    state = dict(next=0, feed_left=len(feeders))
+    errors = []
+    if ex is None:
+        published.set()
+    elif not feeders:
+        ex.publish()
+        published.set()
 
-        def worker(lane):
-            try:
-                import torch
-                torch.cuda.set_device(W.local)  # the current device is a per-thread setting
-                while True:
+    def worker(lane):
+        try:
+            import torch
+            torch.cuda.set_device(W.local)  # the current device is a per-thread setting
+            while True:
+                with lock:
+                    j = state["next"]
+                    state["next"] += 1
+                if j >= len(queue) or errors:
+                    return
+                phase, p = queue[j]
+                prefix = 0
+                if phase == "dep":
+                    published.wait()
                     with lock:
-                        j = nxt[0]
-                        nxt[0] += 1
-                    if j >= len(plist) or errors:
-                        return
-                    p = plist[j]
-                    prefix = ex.prefix(p["seq"]) if phase == "dep" else 0
-                    if on_chunk is not None:
-                        on_chunk(p)  # a new part begins
-                    b, ob, st = W.run_part(p, rng_seed=(base + j if W.seqset is not None else 0), read_range=read_range,
-                                           prefix=prefix, host_seq=None if host_seq is None else host_seq[p["seq"]],
-                                           sink=sink, on_chunk=on_chunk, eng=W.engine(lane))
-                    with lock:
-                        if phase == "feed":
-                            ex.add(p["seq"], st.len_total_end)
-                        on_part(p, b, ob, st)
-            except Exception as ex_:  # noqa: BLE001 - re-raised on the calling thread
-                errors.append(ex_)
+                        prefix = ex.prefix(p["seq"])
+                if on_chunk is not None:
+                    on_chunk(p)  # a new part begins
+                b, ob, st = W.run_part(p, rng_seed=(j if W.seqset is not None else 0), read_range=read_range,
+                                       prefix=prefix, host_seq=None if host_seq is None else host_seq[p["seq"]],
+                                       sink=sink, on_chunk=on_chunk, eng=W.engine(lane))
+                with lock:
+                    if phase == "feed" and ex is not None:
+                        ex.add(p["seq"], st.len_total_end)
+                        state["feed_left"] -= 1
+                        if state["feed_left"] == 0:
+                            ex.publish()
+                            published.set()
+                    on_part(p, b, ob, st)
+        except Exception as ex_:  # noqa: BLE001 - re-raised on the calling thread
+            errors.append(ex_)
+            published.set()
 
-        n_lanes = min(lanes, len(plist)) if on_chunk is None else 1
-        if n_lanes <= 1:
-            worker(0)
-        else:
-            for lane in range(n_lanes):
-                W.engine(lane)  # created on this thread, before the clocks of the workers start
-            ts = [threading.Thread(target=worker, args=(lane,)) for lane in range(n_lanes)]
-            for t in ts:
-                t.start()
-            for t in ts:
-                t.join()
-        if errors:
-            raise errors[0]
-        base += len(plist)
+    n_lanes = min(lanes, len(queue)) if on_chunk is None else 1
+    if n_lanes <= 1:
+        worker(0)
+    else:
+        for lane in range(n_lanes):
+            W.engine(lane)  # created on this thread, before the clocks of the workers start
+        ts = [threading.Thread(target=worker, args=(lane,)) for lane in range(n_lanes)]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+    if errors:
+        raise errors[0]
 
 
 def measure(W, my_parts, warm_parts, e2e_steps, barrier, dist=None, read_range=None, gzip_arm=True, text_arm=True,
