@@ -483,17 +483,25 @@ def run_parts(W, parts, dist, device, on_part, read_range=None, host_seq=None, s
     if W.seqset is None and dist is not None:
         ex = SR.SplitExchange(len(W.contigs), dist, device="cuda")
     lock = threading.Lock()
-    # one queue in the order feeders, whole sequences, dependent last parts: a lane that runs out of feeders goes on
-    # with the whole sequences while the other still feeds; the lane that finishes the LAST feeder publishes
-    queue = [("feed", p) for p in feeders] + [("whole", p) for p in whole] + [("dep", p) for p in dependent]
+    # Feeders run first and alone: other ranks wait for what they emit (measured on 8 GPUs: a feeder that shares its
+    # GPU with a whole sequence on the other lane doubles its time, and a rank that starts with a dependent part then
+    # idles that long).  Whole sequences and dependent last parts follow in one queue, dependents last.
+    plock = threading.Lock()
     published = threading.Event()
-    state = dict(next=0, feed_left=len(feeders))
     errors = []
     if ex is None:
         published.set()
-    elif not feeders:
-        ex.publish()
-        published.set()
+    for queue in ([("feed", p) for p in feeders], [("whole", p) for p in whole] + [("dep", p) for p in dependent]):
+        run_queue(W, queue, dict(next=0), lanes, ex, lock, plock, errors, on_part, on_chunk, read_range, host_seq, sink)
+        if errors:
+            raise errors[0]
+        if not published.is_set():   # the feeders of this rank are done (or it has none)
+            ex.publish()
+            published.set()
+
+
+def run_queue(W, queue, state, lanes, ex, lock, plock, errors, on_part, on_chunk, read_range, host_seq, sink):
+    """the parts of `queue` in order, on up to `lanes` engines of this GPU (a host thread each)"""
 
     def worker(lane):
         try:
@@ -508,8 +516,7 @@ def run_parts(W, parts, dist, device, on_part, read_range=None, host_seq=None, s
                 phase, p = queue[j]
                 prefix = 0
                 if phase == "dep":
-                    published.wait()
-                    with lock:
+                    with plock:  # (waits for the all-reduce once; the other lane goes on meanwhile)
                         prefix = ex.prefix(p["seq"])
                 if on_chunk is not None:
                     on_chunk(p)  # a new part begins
@@ -519,14 +526,9 @@ def run_parts(W, parts, dist, device, on_part, read_range=None, host_seq=None, s
                 with lock:
                     if phase == "feed" and ex is not None:
                         ex.add(p["seq"], st.len_total_end)
-                        state["feed_left"] -= 1
-                        if state["feed_left"] == 0:
-                            ex.publish()
-                            published.set()
                     on_part(p, b, ob, st)
         except Exception as ex_:  # noqa: BLE001 - re-raised on the calling thread
             errors.append(ex_)
-            published.set()
 
     n_lanes = min(lanes, len(queue)) if on_chunk is None else 1
     if n_lanes <= 1:
@@ -539,8 +541,6 @@ def run_parts(W, parts, dist, device, on_part, read_range=None, host_seq=None, s
             t.start()
         for t in ts:
             t.join()
-    if errors:
-        raise errors[0]
 
 
 def measure(W, my_parts, warm_parts, e2e_steps, barrier, dist=None, read_range=None, gzip_arm=True, text_arm=True,
