@@ -474,73 +474,65 @@ def whole_parts(step_ids):
 def run_parts(W, parts, dist, device, on_part, read_range=None, host_seq=None, sink=None, on_chunk=None, lanes=1):
     """this rank's parts in the order of stats_reduce.split_order: feeders, publish (asynchronous all-reduce of the
     emitted bases per sequence), whole sequences, dependent last parts (each told its len_total_start).
-    lanes = 2: two engines on this GPU, each driven by its own host thread, take the parts alternately — in the
-    host-delivery arm one run's start-up (the next sequence ingested, its first batch generated: nothing to copy for
-    15-20 ms) hides behind the other engine's copies; in the device arm kernels bound by different things overlap."""
+    lanes = 2: two engines on this GPU, each driven by its own host thread, take the parts of a PHASE alternately — in
+    the host-delivery arm one run's start-up (the next sequence ingested, its first batch generated: nothing to copy for
+    15-20 ms) hides behind the other engine's copies; in the device arm kernels bound by different things overlap.
+    The phases stay separate on purpose.  Measured on 8 B200 (value of the c3 run): phases 823.7 Gbp/s; one queue over all
+    three phases 490 (a feeder that shares its GPU with a whole sequence takes twice as long, and every rank that starts
+    with a dependent part waits for the slowest feeder anywhere); feeders alone, then one queue of whole sequences and
+    dependent parts 629 (the dependent part is picked up at once and waits for the all-reduce while it could have run
+    behind the whole sequences)."""
     from pbsim_b200 import stats_reduce as SR
     feeders, whole, dependent = SR.split_order(parts)
     ex = None
     if W.seqset is None and dist is not None:
         ex = SR.SplitExchange(len(W.contigs), dist, device="cuda")
     lock = threading.Lock()
-    # Feeders run first and alone: other ranks wait for what they emit (measured on 8 GPUs: a feeder that shares its
-    # GPU with a whole sequence on the other lane doubles its time, and a rank that starts with a dependent part then
-    # idles that long).  Whole sequences and dependent last parts follow in one queue, dependents last.
-    plock = threading.Lock()
-    published = threading.Event()
-    errors = []
-    if ex is None:
-        published.set()
-    for queue in ([("feed", p) for p in feeders], [("whole", p) for p in whole] + [("dep", p) for p in dependent]):
-        run_queue(W, queue, dict(next=0), lanes, ex, lock, plock, errors, on_part, on_chunk, read_range, host_seq, sink)
+    base = 0
+    for phase, plist in (("feed", feeders), ("whole", whole), ("dep", dependent)):
+        if phase == "whole" and ex is not None:
+            ex.publish()
+        nxt = [0]
+        errors = []
+
+        def worker(lane):
+            try:
+                import torch
+                torch.cuda.set_device(W.local)  # the current device is a per-thread setting
+                while True:
+                    with lock:
+                        j = nxt[0]
+                        nxt[0] += 1
+                    if j >= len(plist) or errors:
+                        return
+                    p = plist[j]
+                    prefix = ex.prefix(p["seq"]) if phase == "dep" else 0
+                    if on_chunk is not None:
+                        on_chunk(p)  # a new part begins
+                    b, ob, st = W.run_part(p, rng_seed=(base + j if W.seqset is not None else 0), read_range=read_range,
+                                           prefix=prefix, host_seq=None if host_seq is None else host_seq[p["seq"]],
+                                           sink=sink, on_chunk=on_chunk, eng=W.engine(lane))
+                    with lock:
+                        if phase == "feed":
+                            ex.add(p["seq"], st.len_total_end)
+                        on_part(p, b, ob, st)
+            except Exception as ex_:  # noqa: BLE001 - re-raised on the calling thread
+                errors.append(ex_)
+
+        n_lanes = min(lanes, len(plist)) if on_chunk is None else 1
+        if n_lanes <= 1:
+            worker(0)
+        else:
+            for lane in range(n_lanes):
+                W.engine(lane)  # created on this thread, before the clocks of the workers start
+            ts = [threading.Thread(target=worker, args=(lane,)) for lane in range(n_lanes)]
+            for t in ts:
+                t.start()
+            for t in ts:
+                t.join()
         if errors:
             raise errors[0]
-        if not published.is_set():   # the feeders of this rank are done (or it has none)
-            ex.publish()
-            published.set()
-
-
-def run_queue(W, queue, state, lanes, ex, lock, plock, errors, on_part, on_chunk, read_range, host_seq, sink):
-    """the parts of `queue` in order, on up to `lanes` engines of this GPU (a host thread each)"""
-
-    def worker(lane):
-        try:
-            import torch
-            torch.cuda.set_device(W.local)  # the current device is a per-thread setting
-            while True:
-                with lock:
-                    j = state["next"]
-                    state["next"] += 1
-                if j >= len(queue) or errors:
-                    return
-                phase, p = queue[j]
-                prefix = 0
-                if phase == "dep":
-                    with plock:  # (waits for the all-reduce once; the other lane goes on meanwhile)
-                        prefix = ex.prefix(p["seq"])
-                if on_chunk is not None:
-                    on_chunk(p)  # a new part begins
-                b, ob, st = W.run_part(p, rng_seed=(j if W.seqset is not None else 0), read_range=read_range,
-                                       prefix=prefix, host_seq=None if host_seq is None else host_seq[p["seq"]],
-                                       sink=sink, on_chunk=on_chunk, eng=W.engine(lane))
-                with lock:
-                    if phase == "feed" and ex is not None:
-                        ex.add(p["seq"], st.len_total_end)
-                    on_part(p, b, ob, st)
-        except Exception as ex_:  # noqa: BLE001 - re-raised on the calling thread
-            errors.append(ex_)
-
-    n_lanes = min(lanes, len(queue)) if on_chunk is None else 1
-    if n_lanes <= 1:
-        worker(0)
-    else:
-        for lane in range(n_lanes):
-            W.engine(lane)  # created on this thread, before the clocks of the workers start
-        ts = [threading.Thread(target=worker, args=(lane,)) for lane in range(n_lanes)]
-        for t in ts:
-            t.start()
-        for t in ts:
-            t.join()
+        base += len(plist)
 
 
 def measure(W, my_parts, warm_parts, e2e_steps, barrier, dist=None, read_range=None, gzip_arm=True, text_arm=True,
