@@ -1228,8 +1228,11 @@ PB_HD uint32_t qshmm_segments_for(uint32_t wlen, float rho) {
   return (uint32_t)((need + (double)(PB_TILE - 1u)) / (double)PB_TILE);
 }
 
+// p_len (--method sample): the read also ends when it is p_len positions long (its quality string; k_find_end's
+// `sample` rule).
 PB_HD void qshmm_finish_segmented(uint16_t *ev_base, const SegResult *seg, uint32_t n_seg, uint32_t wlen,
-                                  const QsFast *fast, const HpProbe &hp, Ckpt *ck, SegRead &out) {
+                                  const QsFast *fast, const HpProbe &hp, Ckpt *ck, SegRead &out,
+                                  uint32_t p_len = 0xFFFFFFFFu) {
   uint32_t R = 0, P = 0, D = 0, nsub = 0;
   uint64_t prob = 0;
   out.flags = 0;
@@ -1239,10 +1242,11 @@ PB_HD void qshmm_finish_segmented(uint16_t *ev_base, const SegResult *seg, uint3
     out.flags |= seg[k].flags;
     if (k >= 1u && R == 0u) out.flags |= 8u;
     Ckpt c; c.col = P + D; c.ref = R; c.read = P; c.pad = seg[k].n_entries;
-    const bool may_end = (uint64_t)R + seg[k].ref_adv >= wlen;
+    const bool may_end = (uint64_t)R + seg[k].ref_adv >= wlen || (uint64_t)(k + 1u) * PB_TILE >= p_len;
     if (may_end || hp.enabled) {
       // exact walk: the last tile of every read, and every tile of a read that may need deletion-run repairs
-      const TileWalk t = qshmm_walk_tile(ev_base + (uint64_t)k * PB_SEG_STRIDE, seg[k].n_entries, R, wlen, fast, hp);
+      const TileWalk t = qshmm_walk_tile(ev_base + (uint64_t)k * PB_SEG_STRIDE, seg[k].n_entries, R, wlen, fast, hp, nullptr,
+                                         p_len == 0xFFFFFFFFu ? 0xFFFFFFFFu : p_len - P);
       c.pad = t.n_entries;
       P += t.positions; R += t.ref_adv; D += t.ndel; nsub += t.nsub;
       prob += t.ended ? t.prob : seg[k].prob;  // a full tile's sum is the segment's own (same order, same value)

@@ -97,6 +97,62 @@ static bool run_segmented(const pb::QsView &T, const pb::QsSegAux &A, uint32_t s
   return true;
 }
 
+// --method sample, the speculative pass of a long read as the kernels run it: the qualities of the segments' positions
+// come from the pool entry (k_sim_seg<true>), the error pass is qshmm's, and the read ends where its window is used up
+// or where it is as long as its quality string (k_find_end with sample != 0).  Returns false: fall back.
+static bool run_segmented_sample(pb::QsView T, uint32_t seed, uint32_t seq_num, uint32_t read_id, uint32_t len,
+                                 const uint8_t *quals, const pb::HpProbe &hp, std::vector<uint8_t> &events, size_t ev_off,
+                                 std::vector<pb::Ckpt> &ckpts, size_t ck_base, pb::SubreadResult &res) {
+  pb::PhiloxKeys K;
+  K.init(seed, seq_num);
+  const uint32_t n_seg = (len + PB_TILE - 1u) / PB_TILE;
+  std::vector<uint16_t> slots((size_t)n_seg * PB_SEG_STRIDE + 16, 0);
+  std::vector<pb::SegResult> seg(n_seg);
+  T.has_model = 1;  // "the qualities are in the slot"
+  for (uint32_t k = 0; k < n_seg; ++k) {
+    uint16_t *slot = slots.data() + (size_t)k * PB_SEG_STRIDE;
+    for (uint32_t j = 0; j < PB_TILE; ++j) {
+      const uint32_t p = k * PB_TILE + j;
+      slot[j] = p < len ? (uint16_t)(quals[p] - 33u) : 0u;
+    }
+    pb::qshmm_error_segment(T, K, read_id, 0u, k * PB_TILE, k == 0, slot, seg[k]);
+  }
+  std::vector<pb::Ckpt> ck(n_seg);
+  pb::SegRead sr;
+  pb::qshmm_finish_segmented(slots.data(), seg.data(), n_seg, len, T.fast, hp, ck.data(), sr, len);
+  if (sr.flags) return false;
+  if (hp.enabled) {  // pass 2's re-derivation of the 4-way choice of a substitution on a non-ACGT base
+    for (uint32_t k = 0; k < sr.n_tiles; ++k) {
+      uint32_t R = ck[k].ref, P = ck[k].read;
+      uint16_t *e = slots.data() + (size_t)k * PB_SEG_STRIDE;
+      for (uint32_t i = 0; i < ck[k].pad; ++i) {
+        const uint32_t v = e[i], kind = (v >> 7) & 3u;
+        if (kind == 3u) { R += (v & 0x7Fu) | ((v >> 9) << 7); continue; }
+        if (kind == PB_KIND_SUB && hp.win.nonacgt(R)) {
+          uint32_t x, y;
+          pb::error_words_at(K, read_id, 0u, P, x, y);
+          e[i] = (uint16_t)((v & ~(7u << 9)) | (((y >> 3) & 3u) << 9));
+        }
+        R += (kind == PB_KIND_INS ? 0u : 1u) + (v >> 12);
+        ++P;
+      }
+    }
+  }
+  size_t total = 0;
+  for (uint32_t k = 0; k < sr.n_tiles; ++k) total += ck[k].pad;
+  events.resize(ev_off + total * 2);
+  uint16_t *dst = reinterpret_cast<uint16_t *>(events.data() + ev_off);
+  for (uint32_t k = 0; k < sr.n_tiles; ++k) {
+    memcpy(dst, slots.data() + (size_t)k * PB_SEG_STRIDE, (size_t)ck[k].pad * 2);
+    dst += ck[k].pad;
+  }
+  ckpts.resize(ck_base + sr.n_tiles);
+  for (uint32_t k = 0; k < sr.n_tiles; ++k) ckpts[ck_base + k] = ck[k];
+  res.n_entries = (uint32_t)total; res.rlen = sr.rlen; res.ncol = sr.ncol; res.nsub = sr.nsub; res.nins = sr.nins;
+  res.ndel = sr.ndel; res.overflow = 0; res.accuracy = sr.accuracy;
+  return true;
+}
+
 extern "C" {
 
 // returns number of subreads, <0 on error
@@ -328,6 +384,12 @@ long hostsim_run_sample(const pbsim_model *m, const uint8_t *ascii_upper, const 
     const uint8_t c = ascii_upper[i];
     exc[i] = !(c == 'A' || c == 'C' || c == 'G' || c == 'T') || (bias[hp[i] & 15] != 1.0);
   }
+  std::vector<uint32_t> xm(((size_t)glen >> 15) + 2, 0);  // 1 bit per 1024-base block with an exceptional base
+  for (long i = 0; i < glen; ++i)
+    if (exc[i]) xm[(i >> 10) >> 5] |= 1u << ((i >> 10) & 31);
+  uint8_t bias_one[12];
+  for (int h = 0; h < 12; ++h) bias_one[h] = (bias[h] == 1.0) ? 1 : 0;
+  bias_one[0] = 1;
   g_out = HostSimOut();
   pb::QsView T;
   std::memset(&T, 0, sizeof T);
@@ -382,10 +444,30 @@ long hostsim_run_sample(const pbsim_model *m, const uint8_t *ascii_upper, const 
         pb::QsSink sink;
         sink.init(reinterpret_cast<uint16_t *>(g_out.events.data() + ev_off), g_out.ckpts.data() + ck_base, cap);
         pb::SubreadResult res;
-        if (rng_mode == PBSIM_RNG_PHILOX) pb::sample_simulate(T, pd, win, slow, len, quals + qstart[j], sink, res);
-        else { pb::sample_simulate(T, rd, win, slow, len, quals + qstart[j], sink, res); cursor = rd.cur; }
-        g_out.events.resize(ev_off + (size_t)res.n_entries * 2);
-        g_out.ckpts.resize(ck_base + (res.n_entries + PB_TILE - 1) / PB_TILE);
+        bool seg_done = false;
+        if (rng_mode == PBSIM_RNG_PHILOX && use_seg && img.uniform_bias && (int)len >= seg_min_len) {
+          // (the engine segments a copy only when it assumed the right length; here every copy's length is known)
+          pb::HpProbe hpp;
+          hpp.enabled = slow ? 1u : 0u;
+          hpp.win = win;
+          hpp.xm = xm.data();
+          hpp.bias_one = bias_one;
+          ++seg_reads;
+          seg_done = run_segmented_sample(T, seed, (uint32_t)seq_num, (uint32_t)read_id, len, quals + qstart[j], hpp,
+                                          g_out.events, ev_off, g_out.ckpts, ck_base, res);
+          if (!seg_done) ++seg_fallbacks;
+        }
+        if (seg_done) {
+        } else if (rng_mode == PBSIM_RNG_PHILOX) {
+          g_out.events.resize(ev_off + (size_t)cap * 2);
+          g_out.ckpts.resize(ck_base + cap / PB_TILE + 2);
+          sink.init(reinterpret_cast<uint16_t *>(g_out.events.data() + ev_off), g_out.ckpts.data() + ck_base, cap);
+          pb::sample_simulate(T, pd, win, slow, len, quals + qstart[j], sink, res);
+        } else { pb::sample_simulate(T, rd, win, slow, len, quals + qstart[j], sink, res); cursor = rd.cur; }
+        if (!seg_done) {
+          g_out.events.resize(ev_off + (size_t)res.n_entries * 2);
+          g_out.ckpts.resize(ck_base + (res.n_entries + PB_TILE - 1) / PB_TILE);
+        }
         int64_t rec[12] = {read_id, 0, 0, (int64_t)offset, (int64_t)len, (int64_t)res.rlen, (int64_t)res.ncol,
                            (int64_t)minus, (int64_t)res.n_entries, (int64_t)ev_off, draw_start, (int64_t)res.overflow};
         g_out.info.insert(g_out.info.end(), rec, rec + 12);

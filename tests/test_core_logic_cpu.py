@@ -319,6 +319,42 @@ def test_sample_schedule_edge_cases_equal_oracle(glen, depth, lens):
     assert len(sub) == ost.res_num
 
 
+@pytest.mark.parametrize("glen,depth,lens,ratio", [
+    (60000, 6.0, [5000, 3072, 2048, 2049, 4095, 9000, 1500, 300, 70000], (20, 50, 30)),  # insertion-rich: reads end first
+    (60000, 6.0, [5000, 3072, 2048, 2049, 4095, 9000, 1500, 300], (20, 20, 60)),         # deletion-rich: windows end first
+    (30000, 12.0, [8000, 6000, 2500], (6, 55, 39)),
+])
+def test_sample_long_entries_on_segments_equal_oracle(glen, depth, lens, ratio):
+    """--method sample, long pool entries on the segment path as the kernels run it (hostsim run_segmented_sample: the
+    qualities of a segment's positions from the pool entry, qshmm's error pass, the read ended where its window is
+    used up or where it is as long as its quality string: qshmm_finish_segmented / qshmm_walk_tile with p_left), on a
+    genome with homopolymers of 11 and more, N runs, IUPAC codes and lower case; the oracle's sequential loop decides"""
+    rng = np.random.default_rng(glen + len(lens))
+    g = bytearray(rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), glen).tobytes())
+    for k, at in enumerate(rng.integers(100, glen - 100, 14)):
+        run = [b"A" * 12, b"T" * 15, b"NNNNN", b"R", b"c" * 11, b"G" * 30, b"y"][k % 7]
+        g[at:at + len(run)] = run
+    genome = bytes(g)
+    pool = [bytes(rng.integers(33 + 3, 33 + 25, n).astype(np.uint8)) for n in lens]
+    okw = dict(ratio=ratio, len_min=100, len_max=100000)
+    o = O.Oracle("sample", None, **okw)
+    o.rng_philox(21)
+    o.set_sequence(genome, 1)
+    oreads, omaf, ost = o.simulate_sample(depth, pool)
+    hm = capi.HostModel(H.lib(), capi.host_params("sample", **okw), None)
+    L = H.lib()
+    L.hostsim_use_segments(1, 2048)
+    try:
+        before = L.hostsim_seg_reads()
+        sub = H.run(hm, o.seq_upper(), o.hp(), 1, o.bias(), capi.RNG_PHILOX, 21, None, int(depth * glen), pool=pool)
+        assert L.hostsim_seg_reads() - before >= 10 and L.hostsim_seg_fallbacks() == 0
+    finally:
+        L.hostsim_use_segments(0, 2048)
+    reads, maf = H.records_from_events(hm, sub, o.seq_upper(), 1)
+    assert reads == oreads and maf == omaf
+    assert len(sub) == ost.res_num
+
+
 @pytest.mark.parametrize("strategy", ["trans", "templ"])
 def test_set_planners_equal_oracle_on_long_sequences(strategy):
     """plan_read_trans / plan_read_templ (what k_plan runs per read of a sequence set) against the oracle's read plans
