@@ -486,7 +486,8 @@ def run_parts(W, parts, dist, device, on_part, read_range=None, host_seq=None, s
     feeders, whole, dependent = SR.split_order(parts)
     ex = None
     if W.seqset is None and dist is not None:
-        ex = SR.SplitExchange(len(W.contigs), dist, device="cuda")
+        import torch
+        ex = SR.SplitExchange(len(W.contigs), dist, device="cuda" if torch.cuda.is_available() else "cpu")
     lock = threading.Lock()
     base = 0
     for phase, plist in (("feed", feeders), ("whole", whole), ("dep", dependent)):
@@ -498,7 +499,8 @@ def run_parts(W, parts, dist, device, on_part, read_range=None, host_seq=None, s
         def worker(lane):
             try:
                 import torch
-                torch.cuda.set_device(W.local)  # the current device is a per-thread setting
+                if torch.cuda.is_available():
+                    torch.cuda.set_device(W.local)  # the current device is a per-thread setting
                 while True:
                     with lock:
                         j = nxt[0]

@@ -183,3 +183,77 @@ def test_split_exchange_world2():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert res == [(0, 0, 12345, 123), (1, 0, 12345, 123)]
+
+
+class _FakeStats:
+    def __init__(self, len_total_end, res_num):
+        self.len_total_end, self.res_num = len_total_end, res_num
+        self.kernel_launches = 1
+        self.sim_seconds = self.emit_seconds = self.seg_seconds = self.chain_seconds = self.gen_seconds = 0.0
+
+
+class _FakeWorkload:
+    """stands in for bench.Workload: every read emits exactly 10 bases, a sequence's quota is 10 x its read count"""
+
+    def __init__(self, reads_per_seq, rank):
+        self.seqset, self.local, self.rank = None, 0, rank
+        self.contigs = list(reads_per_seq)
+        self.log = []
+
+    def engine(self, lane):
+        return lane
+
+    def run_part(self, part, rng_seed=0, read_range=None, prefix=0, host_seq=None, sink=None, on_chunk=None, eng=None):
+        import time
+        time.sleep(0.01)
+        total = self.contigs[part["seq"]]
+        n = part["max_reads"] if not part["last"] else total - part["first_read"]
+        # a dependent last part must have been told what the parts in front of it emitted
+        assert prefix == (10 * part["first_read"] if part["last"] else 0), (part, prefix)
+        self.log.append((part["seq"], part["first_read"], n, eng))
+        return 10 * n, 0, _FakeStats(prefix + 10 * n if part["last"] else 10 * n, n)
+
+
+def _run_parts_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import bench
+    reads = [1000, 400, 700, 300, 900]
+    plan = SR.plan_line_split([float(r) for r in reads], world)
+    W = _FakeWorkload(reads, rank)
+    got = []
+    for lanes in (1, 2):
+        bases = [0]
+        bench.run_parts(W, plan[rank], dist, True, lambda p, b, ob, st: bases.__setitem__(0, bases[0] + b), lanes=lanes)
+        got.append(bases[0])
+    q.put((rank, got, sorted(W.log)))
+    dist.destroy_process_group()
+
+
+def test_bench_run_parts_orders_feeders_exchange_and_dependents_world2():
+    """bench.run_parts on two ranks (gloo) with a fake workload, one and two lanes: every read of every sequence is
+    simulated exactly once, and every dependent last part starts from the emitted bases of the parts in front of it"""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    ps = [ctx.Process(target=_run_parts_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in ps:
+        p.start()
+    res = sorted(q.get(timeout=180) for _ in range(world))
+    for p in ps:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    reads = [1000, 400, 700, 300, 900]
+    for lanes_i in (0, 1):
+        assert sum(r[1][lanes_i] for r in res) == 10 * sum(reads)
+    covered = {}
+    for _, _, log in res:
+        for seq, first, n, _ in log[::1]:
+            covered.setdefault(seq, []).append((first, n))
+    for k, total in enumerate(reads):
+        spans = sorted(set(covered[k]))
+        assert spans[0][0] == 0 and sum(n for _, n in spans) == total
+        assert all(a[0] + a[1] == b[0] for a, b in zip(spans, spans[1:]))
+    assert any(len(set(v)) > 1 for v in covered.values())   # a sequence was shared by the two ranks
