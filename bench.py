@@ -875,7 +875,8 @@ def main():
     if W.seqset is None:
         from pbsim_b200 import stats_reduce as SR
         step_ids = [(args.warmup + k) % len(W.contigs) for k in range(args.steps)]
-        if world > 1 and not args.no_split:
+        # (--method sample runs whole sequences: its pool passes make the read numbers depend on the quota)
+        if world > 1 and not args.no_split and wl["method"] != "sample":
             mean_emit = W.pilot_mean_emitted(step_ids[0])
             reads_est = [W.depth * W.contigs[k] / mean_emit for k in step_ids]
             # work of a sequence = its bases + a fixed cost per run (ingest, the quota's tail reads, the last partly
