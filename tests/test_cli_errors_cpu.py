@@ -97,3 +97,45 @@ def test_sample_driver_prints_the_reference_blocks_before_it_needs_a_gpu(name, t
     got = p.stderr.decode()
     assert "no CPU fallback" in got
     assert got.split("ERROR: no usable CUDA device")[0] == c.stderr.split(":::: Simulation stats (ref.1) ::::")[0]
+
+
+def test_parallel_fasta_reader_equals_the_line_by_line_reader_on_a_large_file(tmp_path):
+    """the driver's two FASTA readers (mapped file + a thread per record; the fgets loop that restates
+    get_genome_inf, pbsim.cpp:896-991) on a 40 MB multi-FASTA with ragged line widths, blank lines, CRLF records,
+    lower case and a last line without line feed: same .ref files, same report.  (Without a GPU the driver stops at
+    engine creation, after the input files are read.)"""
+    import subprocess
+    import numpy as np
+    import __graft_entry__ as G
+    from tests.golden_util import model_path
+    G.build_engine()
+    drv = G.build_driver()
+    rng = np.random.default_rng(5)
+    chunks = []
+    for t in range(37):
+        glen = int(rng.integers(200, 2500000))
+        s = np.frombuffer(b"ACGTacgtNn", dtype=np.uint8)[rng.integers(0, 10 if t % 4 == 0 else 4, glen)].tobytes()
+        width = int(rng.choice([50, 60, 70, 80, 1000, 10000]))
+        eol = b"\r\n" if t % 9 == 3 else b"\n"
+        chunks.append(b">contig_%d some text" % t + (b" x" * 80 if t % 11 == 5 else b"") + eol)
+        for i in range(0, glen, width):
+            chunks.append(s[i:i + width] + eol)
+            if rng.random() < 0.001:
+                chunks.append(eol)
+    data = b"".join(chunks)[:-1]  # the last line has no line feed
+    args = ["--strategy", "wgs", "--method", "qshmm", "--qshmm", model_path("QSHMM-RSII.model"), "--genome", "g.fa",
+            "--depth", "0.1", "--seed", "1", "--prefix", "out"]
+    res = {}
+    for who, env in (("parallel", {"PBSIM_INGEST_PARALLEL_MIN": "1"}), ("sequential", {"PBSIM_INGEST_PARALLEL_MIN": "1000000000000"})):
+        d = tmp_path / who
+        d.mkdir()
+        (d / "g.fa").write_bytes(data)
+        p = subprocess.run([drv] + args, cwd=d, env=dict(os.environ, **env), stdout=subprocess.PIPE, stderr=subprocess.PIPE,
+                           timeout=300)
+        head = p.stderr.decode(errors="replace").split("ERROR: no usable CUDA device")[0].split(":::: Simulation stats")[0]
+        refs = {f: (d / f).read_bytes() for f in sorted(os.listdir(d)) if f.endswith(".ref")}
+        res[who] = (head, refs)
+    assert len(res["parallel"][1]) == 37
+    assert res["parallel"][0] == res["sequential"][0]
+    assert res["parallel"][1] == res["sequential"][1]
+    assert "ref.37 (len:" in res["parallel"][0]
