@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py — simulated Gbp/s of the PBSIM3 read-generation hot path on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3|c1|c2|c4|c5] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3|c1|c2|c4|c5|cs] [--impl reference]
 
 A STEP is one call of the reference's seam for one reference sequence: ingest the sequence
 (get_genome_seq), then simulate_by_qshmm / simulate_by_errhmm to the depth quota, records emitted

@@ -236,20 +236,21 @@ int pbsim_cuda_device_timer(pbsim_engine *e, int stop, double *ms);
 /* tunables: "stage_bytes" (pinned staging per stream and slot, default 128 MiB),
  * "target_batch_bases" (emitted bases per batch of reads, default 6 Gi),
  * "segments" (1: segment-parallel pass 1 for long reads in PHILOX mode, default 1; results are identical
- * either way), "seg_min_len" (shortest read that is segmented, default 2048), "chain_chunk" (segments whose entry
- * states one thread of the chain-only pass recovers, default 32),
+ * either way), "seg_min_len" (shortest read that is segmented, default 2048), "chain_chunk" (segments one thread of the
+ * chain / quality pass walks; 0 (default): by method — 8 for qshmm, 32 for errhmm; results are identical for any value),
  * "pipeline" (0: batches are generated inside next_chunk; 1 (default): with host delivery a producer thread
  * generates batch k+1 into a second record buffer while batch k is handed out; 2: also for device delivery),
  * "host_batch_bases" (batch size of pipelined host delivery, default 1 Gi),
  * "deflate" (1: host delivery hands out gzip members written on the GPU — every 32 KiB of a record stream is one
- * member holding one dynamic-Huffman block — instead of text: what the reference's `gzip >` children produce,
+ * member holding up to eight dynamic-Huffman blocks of literals — instead of text: what the reference's `gzip >` children produce,
  * pbsim.cpp:708-730; default 0),
  * "bam" (1: with pass_num > 1 the reads stream holds BAM alignment records — the binary form of the reference's SAM
  * lines, what its `samtools view -b` child writes (pbsim.cpp:715-722) — and, with "deflate", BGZF blocks; the caller
  * adds the BAM header block in front and the BGZF end-of-file block behind; default 0),
  * "sample_spec" (--method sample; 1 (default): every copy of a pool entry is first simulated in its own thread at
  * the entry's length and only the copies that follow a shorter read are redone as chains; 0: one thread walks all
- * copies of an entry; results are identical either way) */
+ * copies of an entry; results are identical either way; with "segments" the speculative pass of reads of at least
+ * "seg_min_len" positions runs on the segment kernels) */
 int pbsim_cuda_set_option(pbsim_engine *e, const char *name, int64_t value);
 /* device pointer + cell count of the int64 stats block {counters[16], freq_accuracy[100001],
  * freq_len[2*len_max+2]} so that a multi-GPU driver can ncclAllReduce it in place */
