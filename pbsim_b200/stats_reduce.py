@@ -108,13 +108,14 @@ def emitted_prefix(my_emitted_bases, dist, device="cpu"):
 # its feeders first, the sequences it owns whole next and its dependent last parts at the end: by then the sums it
 # needs have long been published by ONE asynchronous all-reduce of an int64 per sequence (SplitExchange).
 
-def plan_line_split(reads_est, world, weights=None, snap_lo=0.02, snap_hi=0.04, shares=None):
+def plan_line_split(reads_est, world, weights=None, snap_lo=0.02, snap_hi=0.04, shares=None, min_cut_reads=2000):
     """reads_est[k]: estimated read count of sequence k (quota / mean emitted bases per read); weights[k]: estimated
     work (default: reads_est).  Returns for every rank its parts in line order, each a dict
       seq, first_read, max_reads (0: run to the quota), last (the part that meets the quota), est (estimated work).
     A cut that falls into the first snap_lo or the last snap_hi of a sequence moves to the sequence's boundary: the
     estimate of a sequence's read count is good to a per cent or so, and a part that is not the last one must end
-    safely in front of the quota.  shares[r] (default: equal): the fraction of the work rank r should get — ranks
+    safely in front of the quota; a sequence of fewer than min_cut_reads reads is never cut (the sum of a few hundred
+    read lengths scatters by several per cent).  shares[r] (default: equal): the fraction of the work rank r should get — ranks
     whose delivery path is slower (GPUs behind a busier PCIe switch) get shorter pieces."""
     n = len(reads_est)
     w = [float(x) for x in (weights if weights is not None else reads_est)]
@@ -135,6 +136,8 @@ def plan_line_split(reads_est, world, weights=None, snap_lo=0.02, snap_hi=0.04, 
         while k + 1 < n and start[k + 1] <= x:
             k += 1
         f = (x - start[k]) / w[k] if w[k] > 0 else 0.0
+        if reads_est[k] < min_cut_reads:
+            f = 0.0 if f < 0.5 else 1.0
         if f < snap_lo:
             rank_cut_after.append((k, 0))
         elif f > 1.0 - snap_hi:

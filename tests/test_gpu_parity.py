@@ -325,7 +325,9 @@ def test_line_split_of_a_multi_sequence_run_concatenates_to_the_single_gpu_bytes
     pilot = run(0, max_reads=64)
     mean_emit = pilot[2].len_total_end / pilot[2].res_num
     for world in (2, 3, 7):
-        plan = SR.plan_line_split([depth * n / mean_emit for n in lens], world, weights=[float(n) for n in lens])
+        # (sequences of a few hundred reads: the planner would not cut them on its own)
+        plan = SR.plan_line_split([depth * n / mean_emit for n in lens], world, weights=[float(n) for n in lens],
+                                  min_cut_reads=0)
         ex = SR.SplitExchange(len(lens))
         got = {}
         order = [SR.split_order(parts) for parts in plan]
